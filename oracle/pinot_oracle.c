@@ -1,0 +1,1202 @@
+/*
+ * pinot_oracle.c — CPU restatement (plain C) of Apache Pinot's per-segment
+ * DocIdSetOperator / filter operators / ProjectionOperator / GroupByOperator /
+ * AggregationOperator path, block-at-a-time like the reference.
+ *
+ * TEST INFRASTRUCTURE ONLY (see pinot_oracle.h).  Every function names the
+ * reference file:line whose behaviour it restates.
+ *   CTR  = pinot-core/src/main/java/org/apache/pinot/core
+ *   SEGL = pinot-segment-local/src/main/java/org/apache/pinot/segment/local
+ */
+#include "pinot_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_EOF (-1)                   /* Constants.EOF */
+#define MAX_DOC_PER_CALL 10000         /* CTR/plan/DocIdSetPlanNode.java:29 */
+#define SCAN_BATCH 256                 /* BlockDocIdIterator.OPTIMAL_ITERATOR_BATCH_SIZE */
+
+static __thread char g_err[512];
+const char* orc_last_error(void) { return g_err; }
+static void set_err(const char* m) { snprintf(g_err, sizeof g_err, "%s", m); }
+void orc_free(void* p) { free(p); }
+
+/* ------------------------------------------------------------------ */
+/* big-endian primitive reads (PinotDataBuffer is BIG_ENDIAN)          */
+/* ------------------------------------------------------------------ */
+static inline uint32_t be32(const uint8_t* p) {
+  return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+}
+static inline uint64_t be64(const uint8_t* p) { return ((uint64_t)be32(p) << 32) | be32(p + 4); }
+static inline float be_f32(const uint8_t* p) { uint32_t u = be32(p); float f; memcpy(&f, &u, 4); return f; }
+static inline double be_f64(const uint8_t* p) { uint64_t u = be64(p); double d; memcpy(&d, &u, 8); return d; }
+
+/* SEGL/io/util/PinotDataBitSet.java:61-72 */
+int32_t orc_num_bits_per_value(int32_t max_value) {
+  if (max_value <= 1) return 1;
+  int32_t n = 0;
+  uint32_t v = (uint32_t)max_value;
+  while (v) { n++; v >>= 1; }
+  return n;
+}
+
+/* SEGL/io/util/PinotDataBitSet.java:80-102 (readInt): MSB-first big-endian bitstream */
+int32_t orc_read_dict_id(const uint8_t* fwd, int32_t bits, int64_t doc) {
+  int64_t bit_offset = doc * (int64_t)bits;
+  int64_t byte_offset = bit_offset / 8;
+  int32_t in_first = (int32_t)(bit_offset % 8);
+  int32_t cur = fwd[byte_offset] & (0xff >> in_first);
+  int32_t left = bits - (8 - in_first);
+  if (left <= 0) return cur >> -left;
+  while (left > 8) {
+    byte_offset++;
+    cur = (cur << 8) | fwd[byte_offset];
+    left -= 8;
+  }
+  return (int32_t)(((uint32_t)cur << left) | (uint32_t)(fwd[byte_offset + 1] >> (8 - left)));
+}
+
+/* ------------------------------------------------------------------ */
+/* column readers                                                      */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  const orc_column* c;
+  int32_t num_docs;
+  int64_t raw_data_start;   /* raw forward index: offset of the first value */
+} col_reader;
+
+/* SEGL/segment/index/readers/forward/BaseChunkForwardIndexReader.java:61-104 */
+static int col_reader_init(col_reader* r, const orc_column* c, int32_t num_docs) {
+  r->c = c; r->num_docs = num_docs; r->raw_data_start = 0;
+  if (!c->has_dictionary) {
+    const uint8_t* b = c->forward_index;
+    int32_t version = (int32_t)be32(b);
+    int32_t num_chunks = (int32_t)be32(b + 4);
+    int32_t off = 16;
+    int32_t data_header_start = off;
+    if (version > 1) {
+      int32_t compression = (int32_t)be32(b + off + 4);
+      if (compression != 0) { set_err("raw forward index is compressed (only PASS_THROUGH supported)"); return -1; }
+      data_header_start = (int32_t)be32(b + off + 8);
+    } else { set_err("raw forward index v1 (snappy) unsupported"); return -1; }
+    int32_t entry = version <= 2 ? 4 : 8;
+    r->raw_data_start = (int64_t)data_header_start + (int64_t)num_chunks * entry;
+  }
+  return 0;
+}
+
+/* SEGL/segment/index/readers/sorted/SortedIndexReaderImpl.java:37-116 */
+static inline int32_t sorted_start(const orc_column* c, int32_t dict_id) { return (int32_t)be32(c->forward_index + 8 * (int64_t)dict_id); }
+static inline int32_t sorted_end(const orc_column* c, int32_t dict_id) { return (int32_t)be32(c->forward_index + 8 * (int64_t)dict_id + 4); }
+static int32_t sorted_dict_id_of_doc(const orc_column* c, int32_t doc) {
+  int32_t lo = 0, hi = c->cardinality - 1;
+  while (lo < hi) {
+    int32_t mid = (lo + hi) >> 1;
+    if (sorted_end(c, mid) < doc) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+/* dictId of a doc: FixedBitSVForwardIndexReaderV2.readDictIds
+ * (SEGL/segment/index/readers/forward/FixedBitSVForwardIndexReaderV2.java:65-99) or sorted index */
+static inline int32_t dict_id_of(const col_reader* r, int32_t doc) {
+  const orc_column* c = r->c;
+  if (c->is_sorted) return sorted_dict_id_of_doc(c, doc);
+  /* fast 64-bit window; equal to orc_read_dict_id (checked in tests) */
+  int64_t bit = (int64_t)doc * c->bits_per_element;
+  int64_t byte = bit >> 3;
+  int32_t sh = (int32_t)(bit & 7);
+  uint64_t w;
+  if (byte + 8 <= c->forward_index_len) w = be64(c->forward_index + byte);
+  else {
+    uint8_t tmp[8] = {0};
+    memcpy(tmp, c->forward_index + byte, (size_t)(c->forward_index_len - byte));
+    w = be64(tmp);
+  }
+  return (int32_t)((w << sh) >> (64 - c->bits_per_element));
+}
+
+/* dictionary value reads: SEGL/segment/index/readers/BaseImmutableDictionary.java:45-58,124-139 */
+static inline int64_t dict_long(const orc_column* c, int32_t id) {
+  return c->data_type == ORC_INT ? (int64_t)(int32_t)be32(c->dictionary + 4 * (int64_t)id)
+                                 : (int64_t)be64(c->dictionary + 8 * (int64_t)id);
+}
+static inline double dict_double(const orc_column* c, int32_t id) {
+  switch (c->data_type) {
+    case ORC_INT: return (double)(int32_t)be32(c->dictionary + 4 * (int64_t)id);
+    case ORC_LONG: return (double)(int64_t)be64(c->dictionary + 8 * (int64_t)id);
+    case ORC_FLOAT: return (double)be_f32(c->dictionary + 4 * (int64_t)id);
+    default: return be_f64(c->dictionary + 8 * (int64_t)id);
+  }
+}
+static inline int64_t raw_long(const col_reader* r, int32_t doc) {
+  const orc_column* c = r->c;
+  return c->data_type == ORC_INT ? (int64_t)(int32_t)be32(c->forward_index + r->raw_data_start + 4 * (int64_t)doc)
+                                 : (int64_t)be64(c->forward_index + r->raw_data_start + 8 * (int64_t)doc);
+}
+static inline double raw_double(const col_reader* r, int32_t doc) {
+  const orc_column* c = r->c;
+  const uint8_t* p = c->forward_index + r->raw_data_start;
+  switch (c->data_type) {
+    case ORC_INT: return (double)(int32_t)be32(p + 4 * (int64_t)doc);
+    case ORC_LONG: return (double)(int64_t)be64(p + 8 * (int64_t)doc);
+    case ORC_FLOAT: return (double)be_f32(p + 4 * (int64_t)doc);
+    default: return be_f64(p + 8 * (int64_t)doc);
+  }
+}
+/* BlockValSet.getDoubleValuesSV for one doc (CTR/common/DataFetcher.java:376-386) */
+static inline double value_as_double(const col_reader* r, int32_t doc) {
+  return r->c->has_dictionary ? dict_double(r->c, dict_id_of(r, doc)) : raw_double(r, doc);
+}
+
+/* Dictionary.insertionIndexOf: Arrays.binarySearch convention
+ * (SEGL/segment/index/readers/BaseImmutableDictionary.java:141-260) */
+static int32_t dict_insertion_index_long(const orc_column* c, int64_t v) {
+  int32_t lo = 0, hi = c->cardinality - 1;
+  while (lo <= hi) {
+    int32_t mid = (int32_t)(((uint32_t)lo + (uint32_t)hi) >> 1);
+    int64_t m = dict_long(c, mid);
+    if (m < v) lo = mid + 1; else if (m > v) hi = mid - 1; else return mid;
+  }
+  return -(lo + 1);
+}
+static int32_t dict_insertion_index_double(const orc_column* c, double v) {
+  int32_t lo = 0, hi = c->cardinality - 1;
+  while (lo <= hi) {
+    int32_t mid = (int32_t)(((uint32_t)lo + (uint32_t)hi) >> 1);
+    double m = c->data_type == ORC_FLOAT ? (double)be_f32(c->dictionary + 4 * (int64_t)mid)
+                                         : be_f64(c->dictionary + 8 * (int64_t)mid);
+    if (m < v) lo = mid + 1; else if (m > v) hi = mid - 1; else return mid;
+  }
+  return -(lo + 1);
+}
+/* padded fixed-width string compare (pad byte 0 sorts first, as in the sorted dictionary) */
+static int str_cmp_entry(const orc_column* c, int32_t id, const char* s) {
+  const uint8_t* e = c->dictionary + (int64_t)id * c->dict_entry_bytes;
+  int32_t n = c->dict_entry_bytes;
+  int32_t elen = 0;
+  while (elen < n && e[elen] != 0) elen++;
+  size_t slen = strlen(s);
+  size_t m = (size_t)elen < slen ? (size_t)elen : slen;
+  int r = memcmp(e, s, m);
+  if (r != 0) return r;
+  return (elen > (int32_t)slen) - (elen < (int32_t)slen);
+}
+static int32_t dict_insertion_index_string(const orc_column* c, const char* s) {
+  int32_t lo = 0, hi = c->cardinality - 1;
+  while (lo <= hi) {
+    int32_t mid = (int32_t)(((uint32_t)lo + (uint32_t)hi) >> 1);
+    int r = str_cmp_entry(c, mid, s);
+    if (r < 0) lo = mid + 1; else if (r > 0) hi = mid - 1; else return mid;
+  }
+  return -(lo + 1);
+}
+static int32_t dict_insertion_index(const orc_column* c, const orc_predicate* p, int32_t vi) {
+  switch (c->data_type) {
+    case ORC_INT: case ORC_LONG: return dict_insertion_index_long(c, p->int_values[vi]);
+    case ORC_FLOAT: case ORC_DOUBLE: return dict_insertion_index_double(c, p->double_values[vi]);
+    default: return dict_insertion_index_string(c, p->string_values[vi]);
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* flat doc bitmaps (stand-in for RoaringBitmap set semantics)         */
+/* ------------------------------------------------------------------ */
+typedef struct { uint64_t* w; int64_t nwords; int32_t num_docs; } bitmap;
+static bitmap bm_new(int32_t num_docs) {
+  bitmap b; b.num_docs = num_docs; b.nwords = ((int64_t)num_docs + 63) / 64;
+  b.w = (uint64_t*)calloc((size_t)(b.nwords > 0 ? b.nwords : 1), 8); return b;
+}
+static void bm_free(bitmap* b) { free(b->w); b->w = NULL; }
+static inline void bm_set(bitmap* b, int32_t d) { b->w[d >> 6] |= 1ull << (d & 63); }
+static inline int bm_get(const bitmap* b, int32_t d) { return (int)((b->w[d >> 6] >> (d & 63)) & 1); }
+static void bm_set_range(bitmap* b, int32_t lo, int32_t hi_incl) { for (int32_t d = lo; d <= hi_incl; d++) bm_set(b, d); }
+static void bm_flip(bitmap* b) {   /* flip(0, numDocs) */
+  for (int64_t i = 0; i < b->nwords; i++) b->w[i] = ~b->w[i];
+  int32_t tail = b->num_docs & 63;
+  if (tail && b->nwords) b->w[b->nwords - 1] &= (1ull << tail) - 1ull;
+}
+static int64_t bm_card(const bitmap* b) { int64_t n = 0; for (int64_t i = 0; i < b->nwords; i++) n += __builtin_popcountll(b->w[i]); return n; }
+static int32_t bm_next(const bitmap* b, int32_t from) {   /* first set bit >= from, or EOF */
+  if (from >= b->num_docs) return ORC_EOF;
+  int64_t wi = from >> 6;
+  uint64_t cur = b->w[wi] & (~0ull << (from & 63));
+  while (1) {
+    if (cur) { int32_t d = (int32_t)(wi * 64 + __builtin_ctzll(cur)); return d < b->num_docs ? d : ORC_EOF; }
+    if (++wi >= b->nwords) return ORC_EOF;
+    cur = b->w[wi];
+  }
+}
+
+/* RoaringBitmap portable format -> docIds (third-party spec, RoaringBitmap 1.3.0; reached through
+ * SEGL/segment/index/readers/BitmapInvertedIndexReader.java:45-62) */
+static inline uint32_t le16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+static inline uint32_t le32(const uint8_t* p) { return le16(p) | (le16(p + 2) << 16); }
+typedef void (*doc_sink)(void* ctx, uint32_t doc);
+static int roaring_for_each(const uint8_t* blob, int64_t len, doc_sink sink, void* ctx) {
+  if (len < 4) return -1;
+  uint32_t cookie = le32(blob);
+  int64_t p;
+  uint32_t n;
+  const uint8_t* run_bitmap = NULL;
+  int has_offsets;
+  if ((cookie & 0xffff) == 12347u) {
+    n = (cookie >> 16) + 1;
+    run_bitmap = blob + 4;
+    p = 4 + (n + 7) / 8;
+    has_offsets = n >= 4;
+  } else if (cookie == 12346u) {
+    n = le32(blob + 4);
+    p = 8;
+    has_offsets = 1;
+  } else return -1;
+  const uint8_t* hdr = blob + p;
+  p += 4 * (int64_t)n;
+  if (has_offsets) p += 4 * (int64_t)n;
+  for (uint32_t c = 0; c < n; c++) {
+    uint32_t key = le16(hdr + 4 * c);
+    uint32_t card = le16(hdr + 4 * c + 2) + 1;
+    int is_run = run_bitmap && ((run_bitmap[c / 8] >> (c % 8)) & 1);
+    uint32_t base = key << 16;
+    if (is_run) {
+      uint32_t nr = le16(blob + p); p += 2;
+      for (uint32_t r = 0; r < nr; r++) {
+        uint32_t s = le16(blob + p), l = le16(blob + p + 2); p += 4;
+        for (uint32_t k = 0; k <= l; k++) sink(ctx, base | (s + k));
+      }
+    } else if (card <= 4096) {
+      for (uint32_t k = 0; k < card; k++) { sink(ctx, base | le16(blob + p)); p += 2; }
+    } else {
+      for (uint32_t wv = 0; wv < 1024; wv++) {
+        uint64_t word = (uint64_t)le32(blob + p) | ((uint64_t)le32(blob + p + 4) << 32); p += 8;
+        while (word) { int b = __builtin_ctzll(word); sink(ctx, base | (wv * 64 + (uint32_t)b)); word &= word - 1; }
+      }
+    }
+    if (p > len) return -1;
+  }
+  return 0;
+}
+typedef struct { uint32_t* out; int64_t n, cap; } list_ctx;
+static void list_sink(void* ctx, uint32_t d) { list_ctx* l = (list_ctx*)ctx; if (l->n < l->cap) l->out[l->n] = d; l->n++; }
+int64_t orc_roaring_to_doc_ids(const uint8_t* blob, int64_t len, uint32_t* out, int64_t cap) {
+  list_ctx l = {out, 0, cap};
+  if (roaring_for_each(blob, len, list_sink, &l) != 0) return -1;
+  return l.n;
+}
+static void bm_sink(void* ctx, uint32_t d) { bitmap* b = (bitmap*)ctx; if ((int32_t)d < b->num_docs) bm_set(b, (int32_t)d); }
+/* BitmapInvertedIndexReader.getDocIds(dictId): offsets are big-endian, relative to the first one */
+static int inverted_or_into(const orc_column* c, int32_t dict_id, bitmap* b) {
+  const uint8_t* inv = c->inverted_index;
+  uint32_t first = be32(inv);
+  uint32_t s = be32(inv + 4 * (int64_t)dict_id), e = be32(inv + 4 * (int64_t)dict_id + 4);
+  int64_t base = 4 * ((int64_t)c->cardinality + 1);
+  return roaring_for_each(inv + base + (s - first), (int64_t)(e - s), bm_sink, b);
+}
+
+/* ------------------------------------------------------------------ */
+/* predicate evaluators                                                */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  const orc_predicate* p;
+  const orc_column* c;
+  col_reader reader;
+  int dict_based;
+  int always_true, always_false;
+  int exclusive;            /* NEQ / NOT_IN */
+  int is_range;
+  int32_t start_dict_id, end_dict_id;   /* sorted-dictionary RANGE: [start, end) */
+  int32_t* dict_ids; int32_t n_dict_ids;  /* EQ/IN: matching ids; NEQ/NOT_IN: non-matching ids (sorted) */
+  uint8_t* dict_member;     /* membership over the dictionary for dict_ids */
+  /* raw-value evaluators */
+  int64_t ilo, ihi;         /* inclusive bounds (INT/LONG) */
+  double dlo, dhi; int dlo_incl, dhi_incl;
+} pred_eval;
+
+static int cmp_i32(const void* a, const void* b) { int32_t x = *(const int32_t*)a, y = *(const int32_t*)b; return (x > y) - (x < y); }
+
+/* CTR/operator/filter/predicate/PredicateEvaluatorProvider.java:45-95 and the per-type factories:
+ * RangePredicateEvaluatorFactory.java:119-169 (sorted dictionary range), :326-400 (raw ranges, bounds
+ * made inclusive :334-345); EqualsPredicateEvaluatorFactory.java:83-110; NotEqualsPredicateEvaluatorFactory.java:83-110;
+ * InPredicateEvaluatorFactory.java:158-188; NotInPredicateEvaluatorFactory.java:155-172 */
+static int pred_eval_init(pred_eval* e, const orc_segment* seg, const orc_predicate* p) {
+  memset(e, 0, sizeof *e);
+  e->p = p; e->c = &seg->columns[p->column];
+  const orc_column* c = e->c;
+  if (col_reader_init(&e->reader, c, seg->num_docs) != 0) return -1;
+  e->dict_based = c->has_dictionary;
+  e->exclusive = (p->type == ORC_NEQ || p->type == ORC_NOT_IN);
+  e->is_range = (p->type == ORC_RANGE);
+  if (c->has_dictionary) {
+    int32_t card = c->cardinality;
+    if (p->type == ORC_RANGE) {
+      if (p->lower_unbounded) e->start_dict_id = 0;
+      else {
+        int32_t ii = dict_insertion_index(c, p, 0);
+        e->start_dict_id = ii < 0 ? -(ii + 1) : (p->lower_inclusive ? ii : ii + 1);
+      }
+      if (p->upper_unbounded) e->end_dict_id = card;
+      else {
+        int32_t ii = dict_insertion_index(c, p, 1);
+        e->end_dict_id = ii < 0 ? -(ii + 1) : (p->upper_inclusive ? ii + 1 : ii);
+      }
+      int32_t nm = e->end_dict_id - e->start_dict_id; if (nm < 0) nm = 0;
+      if (nm == 0) e->always_false = 1; else if (nm == card) e->always_true = 1;
+    } else {
+      e->dict_ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)(p->num_values > 0 ? p->num_values : 1));
+      e->dict_member = (uint8_t*)calloc((size_t)card + 1, 1);
+      for (int32_t i = 0; i < p->num_values; i++) {
+        int32_t id = dict_insertion_index(c, p, i);     /* Dictionary.indexOf */
+        if (id >= 0 && !e->dict_member[id]) { e->dict_member[id] = 1; e->dict_ids[e->n_dict_ids++] = id; }
+      }
+      qsort(e->dict_ids, (size_t)e->n_dict_ids, sizeof(int32_t), cmp_i32);
+      if (!e->exclusive) { if (e->n_dict_ids == 0) e->always_false = 1; else if (e->n_dict_ids == card) e->always_true = 1; }
+      else { if (e->n_dict_ids == 0) e->always_true = 1; else if (e->n_dict_ids == card) e->always_false = 1; }
+    }
+  } else {
+    if (c->data_type == ORC_STRING) { set_err("raw STRING predicate unsupported"); return -1; }
+    int is_int = (c->data_type == ORC_INT || c->data_type == ORC_LONG);
+    if (p->type == ORC_RANGE) {
+      if (is_int) {
+        int64_t tmin = c->data_type == ORC_INT ? INT32_MIN : INT64_MIN;
+        int64_t tmax = c->data_type == ORC_INT ? INT32_MAX : INT64_MAX;
+        if (p->lower_unbounded) e->ilo = tmin;
+        else { e->ilo = p->int_values[0]; if (!p->lower_inclusive) { if (e->ilo == tmax) e->always_false = 1; else e->ilo++; } }
+        if (p->upper_unbounded) e->ihi = tmax;
+        else { e->ihi = p->int_values[1]; if (!p->upper_inclusive) { if (e->ihi == tmin) e->always_false = 1; else e->ihi--; } }
+        if (e->ilo > e->ihi) e->always_false = 1;
+      } else {
+        e->dlo = p->lower_unbounded ? -INFINITY : p->double_values[0];
+        e->dhi = p->upper_unbounded ? INFINITY : p->double_values[1];
+        e->dlo_incl = p->lower_unbounded || p->lower_inclusive;
+        e->dhi_incl = p->upper_unbounded || p->upper_inclusive;
+      }
+    }
+  }
+  return 0;
+}
+static void pred_eval_free(pred_eval* e) { free(e->dict_ids); free(e->dict_member); }
+
+/* PredicateEvaluator.applySV(dictId) / applySV(value) */
+static inline int pred_match_dict_id(const pred_eval* e, int32_t id) {
+  if (e->is_range) return e->start_dict_id <= id && e->end_dict_id > id;
+  return e->exclusive ? !e->dict_member[id] : e->dict_member[id];
+}
+static int pred_match_doc(const pred_eval* e, int32_t doc) {
+  if (e->dict_based) return pred_match_dict_id(e, dict_id_of(&e->reader, doc));
+  const orc_column* c = e->c; const orc_predicate* p = e->p;
+  if (c->data_type == ORC_INT || c->data_type == ORC_LONG) {
+    int64_t v = raw_long(&e->reader, doc);
+    if (e->is_range) return v >= e->ilo && v <= e->ihi;
+    int found = 0;
+    for (int32_t i = 0; i < p->num_values; i++) if (p->int_values[i] == v) { found = 1; break; }
+    return e->exclusive ? !found : found;
+  } else {
+    double v = raw_double(&e->reader, doc);
+    if (e->is_range) {
+      int lo_ok = e->dlo_incl ? v >= e->dlo : v > e->dlo;
+      int hi_ok = e->dhi_incl ? v <= e->dhi : v < e->dhi;
+      return lo_ok && hi_ok;
+    }
+    int found = 0;
+    for (int32_t i = 0; i < p->num_values; i++) {
+      double q = c->data_type == ORC_FLOAT ? (double)(float)p->double_values[i] : p->double_values[i];
+      if (q == v) { found = 1; break; }
+    }
+    return e->exclusive ? !found : found;
+  }
+}
+
+/* ------------------------------------------------------------------ */
+/* filter operators and docId iterators                                */
+/* ------------------------------------------------------------------ */
+enum { OP_EMPTY, OP_MATCH_ALL, OP_SORTED, OP_BITMAP, OP_SCAN, OP_AND, OP_OR, OP_NOT };
+typedef struct { int32_t lo, hi; } irange;   /* inclusive */
+
+typedef struct fop {
+  int kind;
+  int32_t num_docs;
+  /* OP_SORTED */ irange* ranges; int32_t n_ranges;
+  /* OP_BITMAP */ bitmap bm;
+  /* OP_SCAN   */ pred_eval* ev;
+  /* AND/OR/NOT */ struct fop** kids; int32_t n_kids;
+} fop;
+
+static fop* fop_new(int kind, int32_t num_docs) { fop* f = (fop*)calloc(1, sizeof(fop)); f->kind = kind; f->num_docs = num_docs; return f; }
+static void fop_free(fop* f) {
+  if (!f) return;
+  for (int32_t i = 0; i < f->n_kids; i++) fop_free(f->kids[i]);
+  free(f->kids); free(f->ranges);
+  if (f->kind == OP_BITMAP) bm_free(&f->bm);
+  if (f->ev) { pred_eval_free(f->ev); free(f->ev); }
+  free(f);
+}
+
+/* CTR/operator/filter/SortedIndexBasedFilterOperator.java:53-131 */
+static fop* make_sorted_op(pred_eval* e, int32_t num_docs) {
+  const orc_column* c = e->c;
+  fop* f = fop_new(OP_SORTED, num_docs);
+  if (e->is_range) {
+    f->ranges = (irange*)malloc(sizeof(irange)); f->n_ranges = 1;
+    f->ranges[0].lo = sorted_start(c, e->start_dict_id);
+    f->ranges[0].hi = sorted_end(c, e->end_dict_id - 1);
+    return f;
+  }
+  int32_t n = e->n_dict_ids;
+  irange* r = (irange*)malloc(sizeof(irange) * (size_t)(n + 2));
+  int32_t nr = 0;
+  irange last = { sorted_start(c, e->dict_ids[0]), sorted_end(c, e->dict_ids[0]) };
+  for (int32_t i = 1; i < n; i++) {
+    irange cur = { sorted_start(c, e->dict_ids[i]), sorted_end(c, e->dict_ids[i]) };
+    if (cur.lo == last.hi + 1) last.hi = cur.hi; else { r[nr++] = last; last = cur; }
+  }
+  r[nr++] = last;
+  if (e->exclusive) {
+    irange* inv = (irange*)malloc(sizeof(irange) * (size_t)(nr + 2));
+    int32_t ni = 0;
+    if (r[0].lo > 0) { inv[ni].lo = 0; inv[ni].hi = r[0].lo - 1; ni++; }
+    for (int32_t i = 0; i + 1 < nr; i++) { inv[ni].lo = r[i].hi + 1; inv[ni].hi = r[i + 1].lo - 1; ni++; }
+    if (r[nr - 1].hi < num_docs - 1) { inv[ni].lo = r[nr - 1].hi + 1; inv[ni].hi = num_docs - 1; ni++; }
+    free(r); r = inv; nr = ni;
+  }
+  f->ranges = r; f->n_ranges = nr;
+  return f;
+}
+
+/* CTR/operator/filter/InvertedIndexFilterOperator.java:60-96 */
+static fop* make_inverted_op(pred_eval* e, int32_t num_docs) {
+  if (e->n_dict_ids == 0) return fop_new(OP_EMPTY, num_docs);
+  fop* f = fop_new(OP_BITMAP, num_docs);
+  f->bm = bm_new(num_docs);
+  for (int32_t i = 0; i < e->n_dict_ids; i++) inverted_or_into(e->c, e->dict_ids[i], &f->bm);
+  if (e->exclusive) bm_flip(&f->bm);
+  return f;
+}
+
+/* CTR/operator/filter/FilterOperatorUtils.java:74-133 (index selection) */
+static fop* make_leaf_op(const orc_segment* seg, const orc_query* q, const orc_predicate* p) {
+  pred_eval* e = (pred_eval*)malloc(sizeof(pred_eval));
+  if (pred_eval_init(e, seg, p) != 0) { free(e); return NULL; }
+  int32_t n = seg->num_docs;
+  fop* f;
+  if (e->always_false) f = fop_new(OP_EMPTY, n);
+  else if (e->always_true) f = fop_new(OP_MATCH_ALL, n);
+  else if (e->c->is_sorted && e->c->has_dictionary) f = make_sorted_op(e, n);
+  else if (p->type != ORC_RANGE && e->c->inverted_index != NULL && !q->skip_inverted_index) f = make_inverted_op(e, n);
+  else { f = fop_new(OP_SCAN, n); f->ev = e; return f; }
+  pred_eval_free(e); free(e);
+  return f;
+}
+
+static int fop_priority(const fop* f) {   /* FilterOperatorUtils.java:205-252 */
+  switch (f->kind) {
+    case OP_SORTED: return 0;
+    case OP_BITMAP: return 100;
+    case OP_AND: return 300;
+    case OP_OR: return 400;
+    case OP_NOT: return fop_priority(f->kids[0]);
+    case OP_SCAN: return 500;
+    default: return 10000;
+  }
+}
+
+/* FilterOperatorUtils.java:136-195 */
+static fop* make_and_op(fop** kids, int32_t n, int32_t num_docs) {
+  fop** keep = (fop**)malloc(sizeof(fop*) * (size_t)(n > 0 ? n : 1));
+  int32_t nk = 0;
+  for (int32_t i = 0; i < n; i++) {
+    if (kids[i]->kind == OP_EMPTY) {
+      for (int32_t j = 0; j < n; j++) fop_free(kids[j]);
+      free(keep); return fop_new(OP_EMPTY, num_docs);
+    }
+  }
+  for (int32_t i = 0; i < n; i++) { if (kids[i]->kind == OP_MATCH_ALL) fop_free(kids[i]); else keep[nk++] = kids[i]; }
+  if (nk == 0) { free(keep); return fop_new(OP_MATCH_ALL, num_docs); }
+  if (nk == 1) { fop* r = keep[0]; free(keep); return r; }
+  /* stable sort by priority (List.sort is a stable merge sort) */
+  for (int32_t i = 1; i < nk; i++) {
+    fop* x = keep[i]; int px = fop_priority(x); int32_t j = i - 1;
+    while (j >= 0 && fop_priority(keep[j]) > px) { keep[j + 1] = keep[j]; j--; }
+    keep[j + 1] = x;
+  }
+  fop* f = fop_new(OP_AND, num_docs); f->kids = keep; f->n_kids = nk; return f;
+}
+static fop* make_or_op(fop** kids, int32_t n, int32_t num_docs) {
+  fop** keep = (fop**)malloc(sizeof(fop*) * (size_t)(n > 0 ? n : 1));
+  int32_t nk = 0;
+  for (int32_t i = 0; i < n; i++) {
+    if (kids[i]->kind == OP_MATCH_ALL) {
+      for (int32_t j = 0; j < n; j++) fop_free(kids[j]);
+      free(keep); return fop_new(OP_MATCH_ALL, num_docs);
+    }
+  }
+  for (int32_t i = 0; i < n; i++) { if (kids[i]->kind == OP_EMPTY) fop_free(kids[i]); else keep[nk++] = kids[i]; }
+  if (nk == 0) { free(keep); return fop_new(OP_EMPTY, num_docs); }
+  if (nk == 1) { fop* r = keep[0]; free(keep); return r; }
+  fop* f = fop_new(OP_OR, num_docs); f->kids = keep; f->n_kids = nk; return f;
+}
+static fop* make_not_op(fop* kid, int32_t num_docs) {
+  if (kid->kind == OP_MATCH_ALL) { fop_free(kid); return fop_new(OP_EMPTY, num_docs); }
+  if (kid->kind == OP_EMPTY) { fop_free(kid); return fop_new(OP_MATCH_ALL, num_docs); }
+  fop* f = fop_new(OP_NOT, num_docs); f->kids = (fop**)malloc(sizeof(fop*)); f->kids[0] = kid; f->n_kids = 1; return f;
+}
+
+/* CTR/plan/FilterPlanNode.java:195-320 (constructPhysicalOperator) from the postfix tree */
+static fop* build_filter(const orc_segment* seg, const orc_query* q) {
+  int32_t n = seg->num_docs;
+  if (q->num_filter_nodes == 0) return fop_new(OP_MATCH_ALL, n);
+  fop** stack = (fop**)malloc(sizeof(fop*) * (size_t)q->num_filter_nodes);
+  int32_t sp = 0;
+  for (int32_t i = 0; i < q->num_filter_nodes; i++) {
+    const orc_filter_node* nd = &q->filter_nodes[i];
+    if (nd->kind == ORC_PRED) {
+      fop* f = make_leaf_op(seg, q, &q->predicates[nd->predicate]);
+      if (!f) { for (int32_t j = 0; j < sp; j++) fop_free(stack[j]); free(stack); return NULL; }
+      stack[sp++] = f;
+    } else if (nd->kind == ORC_NOT) {
+      stack[sp - 1] = make_not_op(stack[sp - 1], n);
+    } else {
+      int32_t k = nd->n_children;
+      fop* f = nd->kind == ORC_AND ? make_and_op(&stack[sp - k], k, n) : make_or_op(&stack[sp - k], k, n);
+      sp -= k; stack[sp++] = f;
+    }
+  }
+  fop* root = stack[0];
+  free(stack);
+  return root;
+}
+
+/* ---- iterators (CTR/operator/dociditerators) ---- */
+enum { IT_EMPTY, IT_MATCH_ALL, IT_SORTED, IT_BITMAP, IT_SCAN, IT_AND, IT_OR, IT_NOT };
+typedef struct dit {
+  int kind;
+  int32_t num_docs;
+  int32_t next_doc;                       /* MATCH_ALL, SORTED, BITMAP, AND, NOT */
+  const irange* ranges; int32_t n_ranges; int32_t cur_range;     /* SORTED */
+  bitmap* bm; int owns_bm;                /* BITMAP */
+  const pred_eval* ev;                    /* SCAN */
+  int32_t batch[SCAN_BATCH]; int32_t first_mismatch, cursor; int64_t entries;   /* SCAN */
+  struct dit** kids; int32_t n_kids;      /* AND / OR / NOT */
+  int32_t* next_ids; int32_t n_live; int32_t prev_doc;          /* OR */
+  int32_t next_non_matching;              /* NOT */
+} dit;
+
+static int32_t dit_next(dit* it);
+static int32_t dit_advance(dit* it, int32_t target);
+
+static dit* dit_new(int kind, int32_t num_docs) { dit* d = (dit*)calloc(1, sizeof(dit)); d->kind = kind; d->num_docs = num_docs; return d; }
+static void dit_free(dit* d) {
+  if (!d) return;
+  for (int32_t i = 0; i < d->n_kids; i++) dit_free(d->kids[i]);
+  free(d->kids); free(d->next_ids);
+  if (d->owns_bm && d->bm) { bm_free(d->bm); free(d->bm); }
+  free(d);
+}
+static int64_t dit_entries(const dit* d) {
+  int64_t n = d->kind == IT_SCAN ? d->entries : 0;
+  for (int32_t i = 0; i < d->n_kids; i++) n += dit_entries(d->kids[i]);
+  return n;
+}
+
+/* SVScanDocIdIterator.java:76-98 (next), :101-113 (advance) */
+static int32_t scan_next(dit* it) {
+  if (it->cursor >= it->first_mismatch) {
+    int32_t limit, bs = 0;
+    do {
+      limit = it->num_docs - it->next_doc; if (limit > SCAN_BATCH) limit = SCAN_BATCH;
+      if (limit > 0) {
+        bs = 0;
+        for (int32_t i = 0; i < limit; i++) if (pred_match_doc(it->ev, it->next_doc + i)) it->batch[bs++] = it->next_doc + i;
+        it->next_doc += limit;
+        it->entries += limit;
+      }
+    } while (limit > 0 && bs == 0);
+    it->first_mismatch = bs; it->cursor = 0;
+    if (bs == 0) return ORC_EOF;
+  }
+  return it->batch[it->cursor++];
+}
+static int32_t scan_advance(dit* it, int32_t target) {
+  it->next_doc = target; it->first_mismatch = 0;
+  while (it->next_doc < it->num_docs) {
+    int32_t d = it->next_doc++;
+    it->entries++;
+    if (pred_match_doc(it->ev, d)) return d;
+  }
+  return ORC_EOF;
+}
+/* SortedDocIdIterator */
+static int32_t sorted_next(dit* it) {
+  while (it->cur_range < it->n_ranges) {
+    const irange* r = &it->ranges[it->cur_range];
+    if (it->next_doc < r->lo) it->next_doc = r->lo;
+    if (it->next_doc <= r->hi) return it->next_doc++;
+    it->cur_range++;
+  }
+  return ORC_EOF;
+}
+/* AndDocIdIterator.java:40-68 */
+static int32_t and_next(dit* it) {
+  int32_t max_doc = it->next_doc, max_idx = -1, idx = 0;
+  while (idx < it->n_kids) {
+    if (idx == max_idx) { idx++; continue; }
+    int32_t d = dit_advance(it->kids[idx], max_doc);
+    if (d == ORC_EOF) return ORC_EOF;
+    if (d == max_doc) idx++; else { max_doc = d; max_idx = idx; idx = 0; }
+  }
+  it->next_doc = max_doc;
+  return it->next_doc++;
+}
+/* OrDocIdIterator.java:51-117 */
+static void or_remove_exhausted(dit* it) {
+  int32_t i = 0;
+  while (i < it->n_live) {
+    if (it->next_ids[i] == ORC_EOF) {
+      it->n_live--;
+      dit* t = it->kids[i]; it->kids[i] = it->kids[it->n_live]; it->kids[it->n_live] = t;
+      it->next_ids[i] = it->next_ids[it->n_live];
+    } else i++;
+  }
+}
+static int32_t or_step(dit* it, int use_target, int32_t target) {
+  int32_t best = INT32_MAX; int exhausted = 0;
+  for (int32_t i = 0; i < it->n_live; i++) {
+    int32_t d = it->next_ids[i];
+    if (use_target ? (d < target) : (d == it->prev_doc)) {
+      d = use_target ? dit_advance(it->kids[i], target) : dit_next(it->kids[i]);
+      it->next_ids[i] = d;
+      if (d == ORC_EOF) { exhausted = 1; continue; }
+    }
+    if (d < best) best = d;
+  }
+  if (exhausted) or_remove_exhausted(it);
+  if (best != INT32_MAX) { it->prev_doc = best; return best; }
+  return ORC_EOF;
+}
+/* NotDocIdIterator.java:30-75 */
+static int32_t not_next(dit* it) {
+  if (it->next_doc >= it->num_docs) return ORC_EOF;
+  while (it->next_doc == it->next_non_matching) {
+    it->next_doc++;
+    int32_t n = dit_next(it->kids[0]);
+    it->next_non_matching = n == ORC_EOF ? it->num_docs : n;
+  }
+  if (it->next_doc >= it->num_docs) return ORC_EOF;
+  return it->next_doc++;
+}
+
+static int32_t dit_next(dit* it) {
+  switch (it->kind) {
+    case IT_EMPTY: return ORC_EOF;
+    case IT_MATCH_ALL: return it->next_doc < it->num_docs ? it->next_doc++ : ORC_EOF;
+    case IT_SORTED: return sorted_next(it);
+    case IT_BITMAP: { int32_t d = bm_next(it->bm, it->next_doc); if (d == ORC_EOF) { it->next_doc = it->num_docs; return ORC_EOF; } it->next_doc = d + 1; return d; }
+    case IT_SCAN: return scan_next(it);
+    case IT_AND: return and_next(it);
+    case IT_OR: return or_step(it, 0, 0);
+    default: return not_next(it);
+  }
+}
+static int32_t dit_advance(dit* it, int32_t target) {
+  switch (it->kind) {
+    case IT_EMPTY: return ORC_EOF;
+    case IT_MATCH_ALL: it->next_doc = target; return dit_next(it);
+    case IT_SORTED:
+      /* SortedDocIdIterator.advance: move to the range containing / following target */
+      while (it->cur_range < it->n_ranges && it->ranges[it->cur_range].hi < target) it->cur_range++;
+      if (target > it->next_doc) it->next_doc = target;
+      return sorted_next(it);
+    case IT_BITMAP: it->next_doc = target; return dit_next(it);
+    case IT_SCAN: return scan_advance(it, target);
+    case IT_AND: it->next_doc = target; return and_next(it);
+    case IT_OR: return or_step(it, 1, target);
+    default:
+      it->next_doc = target;
+      if (target > it->next_non_matching) {
+        int32_t n = dit_advance(it->kids[0], target);
+        it->next_non_matching = n == ORC_EOF ? it->num_docs : n;
+      }
+      return not_next(it);
+  }
+}
+
+static dit* make_iterator(fop* f, int64_t* extra_entries);
+
+/* AndDocIdSet.iterator(): CTR/operator/docidsets/AndDocIdSet.java:72-186 */
+static dit* make_and_iterator(fop* f, int64_t* extra_entries) {
+  int32_t n = f->n_kids, num_docs = f->num_docs;
+  dit** all = (dit**)malloc(sizeof(dit*) * (size_t)n);
+  int32_t n_sorted = 0, n_bitmap = 0, n_scan = 0, n_rem = 0;
+  for (int32_t i = 0; i < n; i++) {
+    all[i] = make_iterator(f->kids[i], extra_entries);
+    switch (all[i]->kind) { case IT_SORTED: n_sorted++; break; case IT_BITMAP: n_bitmap++; break; case IT_SCAN: n_scan++; break; default: n_rem++; }
+  }
+  int32_t n_index = n_sorted + n_bitmap;
+  if ((n_index > 0 && n_scan > 0) || n_index > 1) {
+    bitmap* acc = (bitmap*)malloc(sizeof(bitmap)); *acc = bm_new(num_docs);
+    int first = 1;
+    /* sorted ranges: intersect (SortedRangeIntersection) then -> bitmap */
+    for (int32_t i = 0; i < n; i++) if (all[i]->kind == IT_SORTED) {
+      bitmap t = bm_new(num_docs);
+      for (int32_t r = 0; r < all[i]->n_ranges; r++) bm_set_range(&t, all[i]->ranges[r].lo, all[i]->ranges[r].hi);
+      if (first) { memcpy(acc->w, t.w, (size_t)acc->nwords * 8); first = 0; }
+      else for (int64_t k = 0; k < acc->nwords; k++) acc->w[k] &= t.w[k];
+      bm_free(&t);
+    }
+    for (int32_t i = 0; i < n; i++) if (all[i]->kind == IT_BITMAP) {
+      if (first) { memcpy(acc->w, all[i]->bm->w, (size_t)acc->nwords * 8); first = 0; }
+      else for (int64_t k = 0; k < acc->nwords; k++) acc->w[k] &= all[i]->bm->w[k];
+    }
+    /* scans restricted to survivors: SVScanDocIdIterator.applyAnd (:115-142): entries += incoming docs */
+    for (int32_t i = 0; i < n; i++) if (all[i]->kind == IT_SCAN) {
+      int64_t incoming = bm_card(acc);
+      if (incoming == 0) continue;                 /* !docIdIterator.hasNext() */
+      for (int32_t d = bm_next(acc, 0); d != ORC_EOF; d = bm_next(acc, d + 1))
+        if (!pred_match_doc(all[i]->ev, d)) acc->w[d >> 6] &= ~(1ull << (d & 63));
+      *extra_entries += incoming;
+    }
+    dit* merged = dit_new(IT_BITMAP, num_docs); merged->bm = acc; merged->owns_bm = 1;
+    dit* result;
+    if (n_rem == 0) result = merged;
+    else {
+      result = dit_new(IT_AND, num_docs);
+      result->kids = (dit**)malloc(sizeof(dit*) * (size_t)(n_rem + 1));
+      result->kids[result->n_kids++] = merged;
+      for (int32_t i = 0; i < n; i++) if (all[i]->kind != IT_SORTED && all[i]->kind != IT_BITMAP && all[i]->kind != IT_SCAN) { result->kids[result->n_kids++] = all[i]; all[i] = NULL; }
+    }
+    for (int32_t i = 0; i < n; i++) dit_free(all[i]);
+    free(all);
+    return result;
+  }
+  dit* result = dit_new(IT_AND, num_docs);
+  result->kids = all; result->n_kids = n;
+  return result;
+}
+
+/* OrDocIdSet.iterator(): CTR/operator/docidsets/OrDocIdSet.java:63-127 */
+static dit* make_or_iterator(fop* f, int64_t* extra_entries) {
+  int32_t n = f->n_kids, num_docs = f->num_docs;
+  dit** all = (dit**)malloc(sizeof(dit*) * (size_t)n);
+  int32_t n_index = 0;
+  for (int32_t i = 0; i < n; i++) {
+    all[i] = make_iterator(f->kids[i], extra_entries);
+    if (all[i]->kind == IT_SORTED || all[i]->kind == IT_BITMAP) n_index++;
+  }
+  dit* result = dit_new(IT_OR, num_docs);
+  if (n_index > 1) {
+    bitmap* acc = (bitmap*)malloc(sizeof(bitmap)); *acc = bm_new(num_docs);
+    for (int32_t i = 0; i < n; i++) {
+      if (all[i]->kind == IT_SORTED) for (int32_t r = 0; r < all[i]->n_ranges; r++) bm_set_range(acc, all[i]->ranges[r].lo, all[i]->ranges[r].hi);
+      else if (all[i]->kind == IT_BITMAP) for (int64_t k = 0; k < acc->nwords; k++) acc->w[k] |= all[i]->bm->w[k];
+    }
+    dit* merged = dit_new(IT_BITMAP, num_docs); merged->bm = acc; merged->owns_bm = 1;
+    int32_t n_rem = n - n_index;
+    if (n_rem == 0) { for (int32_t i = 0; i < n; i++) dit_free(all[i]); free(all); dit_free(result); return merged; }
+    result->kids = (dit**)malloc(sizeof(dit*) * (size_t)(n_rem + 1));
+    result->kids[result->n_kids++] = merged;
+    for (int32_t i = 0; i < n; i++) {
+      if (all[i]->kind == IT_SORTED || all[i]->kind == IT_BITMAP) dit_free(all[i]); else result->kids[result->n_kids++] = all[i];
+    }
+    free(all);
+  } else { result->kids = all; result->n_kids = n; }
+  result->n_live = result->n_kids;
+  result->next_ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)result->n_kids);
+  for (int32_t i = 0; i < result->n_kids; i++) result->next_ids[i] = -1;
+  result->prev_doc = -1;
+  return result;
+}
+
+static dit* make_iterator(fop* f, int64_t* extra_entries) {
+  switch (f->kind) {
+    case OP_EMPTY: return dit_new(IT_EMPTY, f->num_docs);
+    case OP_MATCH_ALL: return dit_new(IT_MATCH_ALL, f->num_docs);
+    case OP_SORTED: { dit* d = dit_new(IT_SORTED, f->num_docs); d->ranges = f->ranges; d->n_ranges = f->n_ranges; return d; }
+    case OP_BITMAP: { dit* d = dit_new(IT_BITMAP, f->num_docs); d->bm = &f->bm; return d; }
+    case OP_SCAN: { dit* d = dit_new(IT_SCAN, f->num_docs); d->ev = f->ev; return d; }
+    case OP_AND: return make_and_iterator(f, extra_entries);
+    case OP_OR: return make_or_iterator(f, extra_entries);
+    default: {
+      dit* d = dit_new(IT_NOT, f->num_docs);
+      d->kids = (dit**)malloc(sizeof(dit*)); d->kids[0] = make_iterator(f->kids[0], extra_entries); d->n_kids = 1;
+      int32_t first = dit_next(d->kids[0]);
+      d->next_non_matching = first == ORC_EOF ? f->num_docs : first;
+      return d;
+    }
+  }
+}
+
+int64_t orc_filter_doc_ids(const orc_segment* seg, const orc_query* q, int32_t** out, int64_t* entries_scanned) {
+  fop* root = build_filter(seg, q);
+  if (!root) return -1;
+  int64_t extra = 0;
+  dit* it = make_iterator(root, &extra);
+  int64_t cap = 1024, n = 0;
+  int32_t* docs = (int32_t*)malloc(sizeof(int32_t) * (size_t)cap);
+  for (int32_t d = dit_next(it); d != ORC_EOF; d = dit_next(it)) {
+    if (n == cap) { cap *= 2; docs = (int32_t*)realloc(docs, sizeof(int32_t) * (size_t)cap); }
+    docs[n++] = d;
+  }
+  if (entries_scanned) *entries_scanned = extra + dit_entries(it);
+  dit_free(it); fop_free(root);
+  *out = docs;
+  return n;
+}
+
+/* ------------------------------------------------------------------ */
+/* group-by / aggregation                                              */
+/* ------------------------------------------------------------------ */
+struct orc_result {
+  int32_t num_groups, num_group_by, num_aggs;
+  orc_stats stats;
+  int64_t* group_keys;          /* [num_groups][num_group_by] */
+  double** dbl;                 /* per agg */
+  int64_t** lng;                /* per agg */
+  int64_t** dc_offsets;         /* per agg (DISTINCTCOUNT) */
+  int32_t** dc_ids;
+};
+
+void orc_result_free(orc_result* r) {
+  if (!r) return;
+  for (int32_t a = 0; a < r->num_aggs; a++) {
+    if (r->dbl) free(r->dbl[a]);
+    if (r->lng) free(r->lng[a]);
+    if (r->dc_offsets) free(r->dc_offsets[a]);
+    if (r->dc_ids) free(r->dc_ids[a]);
+  }
+  free(r->dbl); free(r->lng); free(r->dc_offsets); free(r->dc_ids); free(r->group_keys); free(r);
+}
+int32_t orc_result_num_groups(const orc_result* r) { return r->num_groups; }
+const orc_stats* orc_result_stats(const orc_result* r) { return &r->stats; }
+const int64_t* orc_result_group_keys(const orc_result* r) { return r->group_keys; }
+const double* orc_result_double(const orc_result* r, int32_t a) { return r->dbl[a]; }
+const int64_t* orc_result_long(const orc_result* r, int32_t a) { return r->lng[a]; }
+const int64_t* orc_result_distinct_offsets(const orc_result* r, int32_t a) { return r->dc_offsets[a]; }
+const int32_t* orc_result_distinct_dict_ids(const orc_result* r, int32_t a) { return r->dc_ids[a]; }
+
+/* tuple-keyed open-addressing map, ids in first-seen order — stands in for IntGroupIdMap /
+ * Long2IntOpenHashMap / Object2IntOpenHashMap<IntArray> (DictionaryBasedGroupKeyGenerator.java:416-495,
+ * 629-705, 809-885, 993-1138) and the NoDictionary*GroupKeyGenerator maps.  Iteration order is not
+ * part of the contract (tests look groups up by key: CTEST QueriesTestUtils.java:61-83). */
+typedef struct {
+  int32_t arity;
+  int64_t cap, size;
+  int32_t* slot_id;     /* -1 empty */
+  int64_t* keys;        /* [size][arity], in id order */
+  int64_t keys_cap;
+} gmap;
+static void gmap_init(gmap* m, int32_t arity) {
+  m->arity = arity; m->cap = 1024; m->size = 0;
+  m->slot_id = (int32_t*)malloc(sizeof(int32_t) * (size_t)m->cap);
+  memset(m->slot_id, 0xff, sizeof(int32_t) * (size_t)m->cap);
+  m->keys_cap = 1024; m->keys = (int64_t*)malloc(sizeof(int64_t) * (size_t)(m->keys_cap * arity));
+}
+static void gmap_free(gmap* m) { free(m->slot_id); free(m->keys); }
+static inline uint64_t gmap_hash(const int64_t* k, int32_t arity) {
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+  for (int32_t i = 0; i < arity; i++) { h ^= (uint64_t)k[i]; h *= 0xff51afd7ed558ccdull; h ^= h >> 32; }
+  return h;
+}
+static void gmap_grow(gmap* m) {
+  int64_t ncap = m->cap * 2;
+  int32_t* ns = (int32_t*)malloc(sizeof(int32_t) * (size_t)ncap);
+  memset(ns, 0xff, sizeof(int32_t) * (size_t)ncap);
+  for (int64_t id = 0; id < m->size; id++) {
+    uint64_t s = gmap_hash(m->keys + id * m->arity, m->arity) & (uint64_t)(ncap - 1);
+    while (ns[s] >= 0) s = (s + 1) & (uint64_t)(ncap - 1);
+    ns[s] = (int32_t)id;
+  }
+  free(m->slot_id); m->slot_id = ns; m->cap = ncap;
+}
+/* returns group id, or -1 (INVALID_ID) when the key is new and the limit is reached
+ * (DictionaryBasedGroupKeyGenerator.java:1033-1035, 660-668) */
+static int32_t gmap_get_or_add(gmap* m, const int64_t* key, int64_t limit) {
+  uint64_t s = gmap_hash(key, m->arity) & (uint64_t)(m->cap - 1);
+  while (m->slot_id[s] >= 0) {
+    if (memcmp(m->keys + (int64_t)m->slot_id[s] * m->arity, key, sizeof(int64_t) * (size_t)m->arity) == 0) return m->slot_id[s];
+    s = (s + 1) & (uint64_t)(m->cap - 1);
+  }
+  if (m->size >= limit) return -1;
+  if (m->size == m->keys_cap) { m->keys_cap *= 2; m->keys = (int64_t*)realloc(m->keys, sizeof(int64_t) * (size_t)(m->keys_cap * m->arity)); }
+  memcpy(m->keys + m->size * m->arity, key, sizeof(int64_t) * (size_t)m->arity);
+  int32_t id = (int32_t)m->size++;
+  m->slot_id[s] = id;
+  if (m->size * 4 > m->cap * 3) gmap_grow(m);
+  return id;
+}
+
+typedef struct { double* v; int64_t cap; double dflt; } dholder;   /* DoubleGroupByResultHolder.java:42-98 */
+static void dholder_ensure(dholder* h, int64_t n) {
+  if (n <= h->cap) return;
+  int64_t nc = h->cap ? h->cap : 16; while (nc < n) nc *= 2;
+  h->v = (double*)realloc(h->v, sizeof(double) * (size_t)nc);
+  for (int64_t i = h->cap; i < nc; i++) h->v[i] = h->dflt;
+  h->cap = nc;
+}
+typedef struct { uint64_t** sets; int64_t cap; int64_t words; } bholder;   /* per-group dictId bitmaps */
+static void bholder_ensure(bholder* h, int64_t n) {
+  if (n <= h->cap) return;
+  int64_t nc = h->cap ? h->cap : 16; while (nc < n) nc *= 2;
+  h->sets = (uint64_t**)realloc(h->sets, sizeof(uint64_t*) * (size_t)nc);
+  for (int64_t i = h->cap; i < nc; i++) h->sets[i] = NULL;
+  h->cap = nc;
+}
+
+orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
+  g_err[0] = 0;
+  const int32_t nG = q->num_group_by, nA = q->num_aggregations, num_docs = seg->num_docs;
+  fop* root = build_filter(seg, q);
+  if (!root) return NULL;
+  int64_t extra_entries = 0;
+  dit* it = make_iterator(root, &extra_entries);
+
+  col_reader* greaders = (col_reader*)calloc((size_t)(nG > 0 ? nG : 1), sizeof(col_reader));
+  col_reader* areaders = (col_reader*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(col_reader));
+  int all_dict = 1;
+  for (int32_t j = 0; j < nG; j++) {
+    if (col_reader_init(&greaders[j], &seg->columns[q->group_by_columns[j]], num_docs) != 0) goto fail;
+    if (!greaders[j].c->has_dictionary) all_dict = 0;
+  }
+  for (int32_t a = 0; a < nA; a++) {
+    if (q->aggregations[a].column >= 0) {
+      if (col_reader_init(&areaders[a], &seg->columns[q->aggregations[a].column], num_docs) != 0) goto fail;
+      if (q->aggregations[a].op == ORC_DISTINCTCOUNT && !areaders[a].c->has_dictionary) { set_err("DISTINCTCOUNT on raw column unsupported in oracle"); goto fail; }
+      if (q->aggregations[a].op != ORC_DISTINCTCOUNT && areaders[a].c->data_type == ORC_STRING) { set_err("numeric aggregation on STRING"); goto fail; }
+    }
+  }
+
+  /* key-holder strategy: DictionaryBasedGroupKeyGenerator.java:120-185; DefaultGroupByExecutor.java:106-121 */
+  int holder = 0; int64_t card_product = 1; int overflow = 0;
+  if (nG > 0) {
+    if (!all_dict) holder = 5;
+    else {
+      for (int32_t j = 0; j < nG; j++) {
+        int64_t card = greaders[j].c->cardinality;
+        if (!overflow) { if (card_product > INT64_MAX / card) overflow = 1; else card_product *= card; }
+      }
+      if (overflow) holder = 4;
+      else if (card_product > INT32_MAX) holder = 3;
+      else if (card_product > q->max_initial_result_holder_capacity || q->num_groups_limit < card_product) holder = 2;
+      else holder = 1;
+    }
+  }
+  const int64_t limit = q->num_groups_limit;
+
+  gmap map; int have_map = 0;
+  uint8_t* array_flags = NULL;       /* ArrayBasedHolder._flags */
+  int64_t num_keys = 0;              /* number of groups created */
+  if (holder >= 2) { gmap_init(&map, nG); have_map = 1; }
+  else if (holder == 1) array_flags = (uint8_t*)calloc((size_t)card_product, 1);
+
+  dholder* dh = (dholder*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(dholder));   /* SUM/MIN/MAX/COUNT(double)/AVG sum */
+  dholder* ch = (dholder*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(dholder));   /* AVG count */
+  bholder* bh = (bholder*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(bholder));
+  for (int32_t a = 0; a < nA; a++) {
+    int op = q->aggregations[a].op;
+    dh[a].dflt = op == ORC_MIN ? INFINITY : (op == ORC_MAX ? -INFINITY : 0.0);
+    ch[a].dflt = 0.0;
+    if (op == ORC_DISTINCTCOUNT) bh[a].words = ((int64_t)areaders[a].c->cardinality + 63) / 64;
+  }
+  /* keyless native-type MIN/MAX state (MinAggregationFunction.java:69-148) */
+  int64_t* kl_long = (int64_t*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int64_t));
+  int* kl_long_set = (int*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int));
+  int64_t kl_count = 0;
+
+  int32_t* doc_ids = (int32_t*)malloc(sizeof(int32_t) * MAX_DOC_PER_CALL);
+  int32_t* group_ids = (int32_t*)malloc(sizeof(int32_t) * MAX_DOC_PER_CALL);
+  double* values = (double*)malloc(sizeof(double) * MAX_DOC_PER_CALL);
+  int32_t* dict_buf = (int32_t*)malloc(sizeof(int32_t) * MAX_DOC_PER_CALL);
+  int64_t key[64];
+  if (nG > 64) { set_err("too many group-by columns"); goto fail2; }
+  int64_t num_docs_scanned = 0;
+  if (nG == 0) for (int32_t a = 0; a < nA; a++) { dholder_ensure(&dh[a], 1); dholder_ensure(&ch[a], 1); bholder_ensure(&bh[a], 1); }
+
+  /* GroupByOperator.getNextBlock (CTR/operator/query/GroupByOperator.java:101-140) /
+   * AggregationOperator.getNextBlock (CTR/operator/query/AggregationOperator.java:64-80) */
+  while (1) {
+    /* DocIdSetOperator.getNextBlock: CTR/operator/DocIdSetOperator.java:59-86 */
+    int32_t len = 0;
+    for (; len < MAX_DOC_PER_CALL; len++) { int32_t d = dit_next(it); if (d == ORC_EOF) break; doc_ids[len] = d; }
+    if (len == 0) break;
+    num_docs_scanned += len;
+
+    if (nG > 0) {
+      /* generateKeysForBlock: DictionaryBasedGroupKeyGenerator.java:210-217, 290-305, 341-347, 424-446 */
+      for (int32_t i = 0; i < len; i++) {
+        int32_t d = doc_ids[i];
+        if (holder == 1) {
+          int64_t raw = 0, mult = 1;
+          for (int32_t j = 0; j < nG; j++) { raw += (int64_t)dict_id_of(&greaders[j], d) * mult; mult *= greaders[j].c->cardinality; }
+          if (!array_flags[raw]) { array_flags[raw] = 1; num_keys++; }
+          group_ids[i] = (int32_t)raw;
+        } else {
+          for (int32_t j = 0; j < nG; j++) {
+            const col_reader* r = &greaders[j];
+            if (r->c->has_dictionary) key[j] = dict_id_of(r, d);
+            else if (r->c->data_type == ORC_INT || r->c->data_type == ORC_LONG) key[j] = raw_long(r, d);
+            else { double v = raw_double(r, d); memcpy(&key[j], &v, 8); }
+          }
+          group_ids[i] = gmap_get_or_add(&map, key, limit);
+        }
+      }
+      int64_t need = holder == 1 ? card_product : map.size;
+      for (int32_t a = 0; a < nA; a++) {
+        int op = q->aggregations[a].op;
+        dholder_ensure(&dh[a], need);
+        if (op == ORC_AVG) dholder_ensure(&ch[a], need);
+        if (op == ORC_DISTINCTCOUNT) bholder_ensure(&bh[a], need);
+        if (op == ORC_COUNT) {   /* CountAggregationFunction.java:178-185 */
+          for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0) dh[a].v[group_ids[i]] += 1.0;
+          continue;
+        }
+        if (op == ORC_DISTINCTCOUNT) {  /* BaseDistinctAggregateAggregationFunction.java:306-321 */
+          for (int32_t i = 0; i < len; i++) {
+            int32_t g = group_ids[i]; if (g < 0) continue;
+            if (!bh[a].sets[g]) bh[a].sets[g] = (uint64_t*)calloc((size_t)bh[a].words, 8);
+            int32_t id = dict_id_of(&areaders[a], doc_ids[i]);
+            bh[a].sets[g][id >> 6] |= 1ull << (id & 63);
+          }
+          continue;
+        }
+        for (int32_t i = 0; i < len; i++) values[i] = value_as_double(&areaders[a], doc_ids[i]);
+        double* hv = dh[a].v;
+        switch (op) {
+          case ORC_SUM:  /* SumAggregationFunction.java:160-179 */
+            for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0) hv[group_ids[i]] += values[i];
+            break;
+          case ORC_MIN:  /* MinAggregationFunction.java:163-188: strict < in double */
+            for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0 && values[i] < hv[group_ids[i]]) hv[group_ids[i]] = values[i];
+            break;
+          case ORC_MAX:
+            for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0 && values[i] > hv[group_ids[i]]) hv[group_ids[i]] = values[i];
+            break;
+          case ORC_AVG:  /* AvgAggregationFunction.java:106-127 */
+            for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0) { hv[group_ids[i]] += values[i]; ch[a].v[group_ids[i]] += 1.0; }
+            break;
+          default: break;
+        }
+      }
+    } else {
+      kl_count += len;
+      for (int32_t a = 0; a < nA; a++) {
+        int op = q->aggregations[a].op;
+        if (op == ORC_COUNT) { dh[a].v[0] += (double)len; continue; }   /* CountAggregationFunction.java:110-116 */
+        const col_reader* r = &areaders[a];
+        if (op == ORC_DISTINCTCOUNT) {   /* BaseDistinctAggregateAggregationFunction.java:144-155 */
+          if (!bh[a].sets[0]) bh[a].sets[0] = (uint64_t*)calloc((size_t)bh[a].words, 8);
+          for (int32_t i = 0; i < len; i++) { int32_t id = dict_id_of(r, doc_ids[i]); bh[a].sets[0][id >> 6] |= 1ull << (id & 63); }
+          continue;
+        }
+        int is_long_typed = (r->c->data_type == ORC_INT || r->c->data_type == ORC_LONG);
+        if ((op == ORC_MIN || op == ORC_MAX) && is_long_typed) {
+          /* keyless MIN/MAX fold in the native type, then doubleValue() */
+          for (int32_t i = 0; i < len; i++) {
+            int64_t v = r->c->has_dictionary ? dict_long(r->c, dict_id_of(r, doc_ids[i])) : raw_long(r, doc_ids[i]);
+            if (!kl_long_set[a] || (op == ORC_MIN ? v < kl_long[a] : v > kl_long[a])) { kl_long[a] = v; kl_long_set[a] = 1; }
+          }
+          dh[a].v[0] = (double)kl_long[a];
+          continue;
+        }
+        for (int32_t i = 0; i < len; i++) values[i] = value_as_double(r, doc_ids[i]);
+        if (op == ORC_SUM || op == ORC_AVG) {   /* SumAggregationFunction.java:69-145: per-block innerSum */
+          double inner = 0; for (int32_t i = 0; i < len; i++) inner += values[i];
+          dh[a].v[0] += inner;
+          if (op == ORC_AVG) ch[a].v[0] += (double)len;
+        } else if (op == ORC_MIN) { for (int32_t i = 0; i < len; i++) if (values[i] < dh[a].v[0]) dh[a].v[0] = values[i]; }
+        else if (op == ORC_MAX) { for (int32_t i = 0; i < len; i++) if (values[i] > dh[a].v[0]) dh[a].v[0] = values[i]; }
+        (void)dict_buf;
+      }
+    }
+  }
+
+  /* ---- build the result ---- */
+  orc_result* res = (orc_result*)calloc(1, sizeof(orc_result));
+  res->num_group_by = nG; res->num_aggs = nA;
+  int64_t ng;
+  int32_t* id_of_group = NULL;    /* result row -> holder index */
+  if (nG == 0) ng = 1;
+  else if (holder == 1) {
+    ng = num_keys;
+    id_of_group = (int32_t*)malloc(sizeof(int32_t) * (size_t)(ng > 0 ? ng : 1));
+    int64_t k = 0;
+    for (int64_t raw = 0; raw < card_product; raw++) if (array_flags[raw]) id_of_group[k++] = (int32_t)raw;
+  } else ng = map.size;
+  res->num_groups = (int32_t)ng;
+  res->group_keys = (int64_t*)calloc((size_t)((ng > 0 ? ng : 1) * (nG > 0 ? nG : 1)), sizeof(int64_t));
+  for (int64_t g = 0; g < ng && nG > 0; g++) {
+    if (holder == 1) {   /* decode: DictionaryBasedGroupKeyGenerator.java:578-591 */
+      int64_t raw = id_of_group[g];
+      for (int32_t j = 0; j < nG; j++) { int64_t card = greaders[j].c->cardinality; res->group_keys[g * nG + j] = raw % card; raw /= card; }
+    } else memcpy(res->group_keys + g * nG, map.keys + g * nG, sizeof(int64_t) * (size_t)nG);
+  }
+  res->dbl = (double**)calloc((size_t)(nA > 0 ? nA : 1), sizeof(double*));
+  res->lng = (int64_t**)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int64_t*));
+  res->dc_offsets = (int64_t**)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int64_t*));
+  res->dc_ids = (int32_t**)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int32_t*));
+  for (int32_t a = 0; a < nA; a++) {
+    int op = q->aggregations[a].op;
+    res->dbl[a] = (double*)calloc((size_t)(ng > 0 ? ng : 1), sizeof(double));
+    res->lng[a] = (int64_t*)calloc((size_t)(ng > 0 ? ng : 1), sizeof(int64_t));
+    if (op == ORC_DISTINCTCOUNT) res->dc_offsets[a] = (int64_t*)calloc((size_t)ng + 1, sizeof(int64_t));
+    int64_t total_ids = 0;
+    for (int64_t g = 0; g < ng; g++) {
+      int64_t h = (nG > 0 && holder == 1) ? id_of_group[g] : g;
+      switch (op) {
+        case ORC_COUNT: res->lng[a][g] = (int64_t)dh[a].v[h]; res->dbl[a][g] = dh[a].v[h]; break;
+        case ORC_AVG: res->dbl[a][g] = dh[a].v[h]; res->lng[a][g] = (int64_t)ch[a].v[h]; break;
+        case ORC_DISTINCTCOUNT: {
+          int64_t n = 0;
+          if (bh[a].sets[h]) for (int64_t w = 0; w < bh[a].words; w++) n += __builtin_popcountll(bh[a].sets[h][w]);
+          res->lng[a][g] = n; total_ids += n; res->dc_offsets[a][g + 1] = total_ids;
+          break;
+        }
+        default: res->dbl[a][g] = dh[a].v[h]; break;
+      }
+    }
+    if (op == ORC_DISTINCTCOUNT) {
+      res->dc_ids[a] = (int32_t*)malloc(sizeof(int32_t) * (size_t)(total_ids > 0 ? total_ids : 1));
+      int64_t k = 0;
+      for (int64_t g = 0; g < ng; g++) {
+        int64_t h = (nG > 0 && holder == 1) ? id_of_group[g] : g;
+        if (!bh[a].sets[h]) continue;
+        for (int64_t w = 0; w < bh[a].words; w++) { uint64_t x = bh[a].sets[h][w]; while (x) { res->dc_ids[a][k++] = (int32_t)(w * 64 + __builtin_ctzll(x)); x &= x - 1; } }
+      }
+    }
+  }
+  /* ExecutionStatistics: GroupByOperator.java:148-153; ProjectPlanNode.java:69-78 (distinct projected columns) */
+  {
+    int32_t cols[128]; int32_t nc = 0;
+    for (int32_t j = 0; j < nG; j++) { int32_t c = q->group_by_columns[j]; int seen = 0; for (int32_t k = 0; k < nc; k++) if (cols[k] == c) seen = 1; if (!seen && nc < 128) cols[nc++] = c; }
+    for (int32_t a = 0; a < nA; a++) { int32_t c = q->aggregations[a].column; if (c < 0) continue; int seen = 0; for (int32_t k = 0; k < nc; k++) if (cols[k] == c) seen = 1; if (!seen && nc < 128) cols[nc++] = c; }
+    res->stats.num_docs_scanned = num_docs_scanned;
+    res->stats.num_entries_scanned_in_filter = extra_entries + dit_entries(it);
+    res->stats.num_entries_scanned_post_filter = num_docs_scanned * nc;
+    res->stats.num_total_docs = num_docs;
+    res->stats.num_groups_limit_reached = (nG > 0 && ng >= limit) ? 1 : 0;   /* GroupByOperator.java:116 */
+    res->stats.key_holder = holder;
+  }
+  free(id_of_group);
+  free(doc_ids); free(group_ids); free(values); free(dict_buf);
+  for (int32_t a = 0; a < nA; a++) {
+    free(dh[a].v); free(ch[a].v);
+    for (int64_t i = 0; i < bh[a].cap; i++) free(bh[a].sets[i]);
+    free(bh[a].sets);
+  }
+  free(dh); free(ch); free(bh); free(kl_long); free(kl_long_set);
+  if (have_map) gmap_free(&map);
+  free(array_flags); free(greaders); free(areaders);
+  dit_free(it); fop_free(root);
+  (void)kl_count;
+  return res;
+
+fail2:
+  free(doc_ids); free(group_ids); free(values); free(dict_buf);
+  free(dh); free(ch); free(bh); free(kl_long); free(kl_long_set);
+  if (have_map) gmap_free(&map);
+  free(array_flags);
+fail:
+  free(greaders); free(areaders);
+  dit_free(it); fop_free(root);
+  return NULL;
+}

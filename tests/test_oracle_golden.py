@@ -1,0 +1,120 @@
+"""Pin the oracle to the reference's own golden values.
+
+Every expected number below is a literal quoted from the reference's tests (CTEST =
+pinot-core/src/test/java/org/apache/pinot/queries):
+  InnerSegmentAggregationSingleValueQueriesTest.java:43-177   (per-segment operator results + ExecutionStatistics)
+  InterSegmentAggregationSingleValueQueriesTest.java:47-258   (4 identical segments merged)
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from pinot_b200.query import parse_sql
+from tests.fixtures import FILTER, sv_segment
+
+AGG = "SELECT COUNT(*), SUM(column1), MAX(column3), MIN(column6), AVG(column7) FROM testTable"
+
+
+def _inner(sql):
+    seg = sv_segment()
+    return oracle.execute(seg, parse_sql(sql))
+
+
+def _check_agg(r, g, expected):
+    assert int(r.longs[0][g]) == expected[0]
+    assert int(r.doubles[1][g]) == expected[1]
+    assert int(r.doubles[2][g]) == expected[2]
+    assert int(r.doubles[3][g]) == expected[3]
+    assert int(r.doubles[4][g]) == expected[4]
+    assert int(r.longs[4][g]) == expected[5]
+
+
+def _stats(r):
+    s = r.stats
+    return (s["num_docs_scanned"], s["num_entries_scanned_in_filter"], s["num_entries_scanned_post_filter"],
+            s["num_total_docs"])
+
+
+def test_aggregation_only():   # InnerSegment...Test.java:43-60
+    r = _inner(AGG)
+    assert _stats(r) == (30000, 0, 120000, 30000)
+    _check_agg(r, 0, (30000, 32317185437847, 2147419555, 1689277, 28175373944314, 30000))
+    r = _inner(AGG + FILTER)
+    assert _stats(r) == (6129, 63064, 24516, 30000)
+    _check_agg(r, 0, (6129, 6875947596072, 999813884, 1980174, 4699510391301, 6129))
+
+
+def _find(r, key):
+    keys = r.decoded_keys()
+    assert key in keys, f"group {key} not found"
+    return keys.index(key)
+
+
+@pytest.mark.parametrize("group_by,holder,post,post_f,key,exp,key_f,exp_f", [
+    # :96-111 ARRAY_BASED
+    (" GROUP BY column9", 1, 150000, 30645, (11270,), (1, 815409257, 1215316262, 1328642550, 788414092, 1),
+     (242920,), (3, 4348938306, 407993712, 296467636, 5803888725, 3)),
+    # :115-131 INT_MAP_BASED
+    (" GROUP BY column9, column11, column12", 2, 210000, 42903, (1813102948, b"P", b"HEuxNvH"),
+     (4, 2062187196, 1988589001, 394608493, 4782388964, 4),
+     (1176631727, b"P", b"KrNxpdycSiwoRohEiTIlLqDHnx"), (1, 716185211, 489993380, 371110078, 487714191, 1)),
+    # :135-152 LONG_MAP_BASED
+    (" GROUP BY column1, column6, column9, column11, column12", 3, 210000, 42903,
+     (484569489, 16200443, 1159557463, b"P", b"MaztCmmxxgguBUxPti"), (2, 969138978, 995355481, 16200443, 2222394270, 2),
+     (1318761745, 353175528, 1172307870, b"P", b"HEuxNvH"), (2, 2637523490, 557154208, 353175528, 2427862396, 2)),
+    # :156-174 ARRAY_MAP_BASED
+    (" GROUP BY column1, column3, column6, column7, column9, column11, column12, column17, column18", 4, 270000, 55161,
+     (1784773968, 204243323, 628170461, 1985159279, 296467636, b"P", b"HEuxNvH", 402773817, 2047180536),
+     (1, 1784773968, 204243323, 628170461, 1985159279, 1),
+     (1361199163, 178133991, 296467636, 788414092, 1719301234, b"P", b"MaztCmmxxgguBUxPti", 1284373442, 752388855),
+     (1, 1361199163, 178133991, 296467636, 788414092, 1)),
+])
+def test_group_by(group_by, holder, post, post_f, key, exp, key_f, exp_f):
+    r = _inner(AGG + group_by)
+    assert r.stats["key_holder"] == holder
+    assert _stats(r) == (30000, 0, post, 30000)
+    _check_agg(r, _find(r, key), exp)
+    r = _inner(AGG + FILTER + group_by)
+    assert _stats(r) == (6129, 63064, post_f, 30000)
+    _check_agg(r, _find(r, key_f), exp_f)
+
+
+def _inter(sql):
+    """BaseQueriesTest.getBrokerResponse: 2 segment objects x 2 'servers' = 4 identical segments."""
+    seg = sv_segment()
+    q = parse_sql(sql)
+    r = oracle.execute(seg, q)
+    return oracle.combine([r, r, r, r]), q
+
+
+def test_inter_segment_count():   # InterSegment...Test.java:47-88
+    t, _ = _inter("SELECT COUNT(*) FROM testTable")
+    assert t[()][0] == 120000
+    t, _ = _inter("SELECT COUNT(*) FROM testTable" + FILTER)
+    assert t[()][0] == 24516
+    t, _ = _inter("SELECT COUNT(*) FROM testTable GROUP BY column9")
+    assert max(v[0] for v in t.values()) == 64420
+    t, _ = _inter("SELECT COUNT(*) FROM testTable" + FILTER + " GROUP BY column9")
+    assert max(v[0] for v in t.values()) == 17080
+
+
+def test_inter_segment_min_max():   # :92-147
+    t, _ = _inter("SELECT MAX(column1), MAX(column3) FROM testTable")
+    assert t[()] == [2146952047.0, 2147419555.0]
+    t, _ = _inter("SELECT MAX(column1), MAX(column3) FROM testTable" + FILTER)
+    assert t[()] == [2146952047.0, 999813884.0]
+    t, _ = _inter("SELECT MIN(column1), MIN(column3) FROM testTable")
+    assert t[()] == [240528.0, 17891.0]
+
+
+def test_inter_segment_distinct_count():   # :235-258
+    t, _ = _inter("SELECT DISTINCTCOUNT(column1), DISTINCTCOUNT(column3) FROM testTable")
+    assert [len(s) for s in t[()]] == [6582, 21910]
+    t, _ = _inter("SELECT DISTINCTCOUNT(column1), DISTINCTCOUNT(column3) FROM testTable" + FILTER)
+    assert [len(s) for s in t[()]] == [1872, 4556]
+    t, _ = _inter("SELECT DISTINCTCOUNT(column1), DISTINCTCOUNT(column3) FROM testTable GROUP BY column9")
+    assert max(len(v[0]) for v in t.values()) == 3495
+    assert max(len(v[1]) for v in t.values()) == 11961
+    t, _ = _inter("SELECT DISTINCTCOUNT(column1), DISTINCTCOUNT(column3) FROM testTable" + FILTER + " GROUP BY column9")
+    assert max(len(v[0]) for v in t.values()) == 1272
+    assert max(len(v[1]) for v in t.values()) == 3289
