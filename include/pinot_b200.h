@@ -1,0 +1,214 @@
+/*
+ * pinot_b200.h — C ABI of libpinot_b200.so, the B200-native executor for Apache Pinot's per-segment
+ * scan -> filter -> project -> group-by/aggregate path.
+ *
+ * This is the boundary a JNI shim binds (jni/pinot_b200_jni.c).  Plain pointers and
+ * sizes only.  Every entry point names the reference interface it stands in for
+ * (CTR  = pinot-core/src/main/java/org/apache/pinot/core,
+ *  SEGL = pinot-segment-local/src/main/java/org/apache/pinot/segment/local,
+ *  SPI  = pinot-segment-spi/src/main/java/org/apache/pinot/segment/spi).
+ *
+ * Division of labour: the host side (Java in a Pinot server; pinot_b200/csrc/host in
+ * this repo) runs the reference's own PredicateEvaluator lowering and FilterOperatorUtils index
+ * selection, and hands over (a) the segment's index buffers exactly as mmap'd and (b) a filter tree
+ * whose leaves are already in dictId / docId-range / bitmap form.  Everything per-row happens on the GPU.
+ *
+ * Threading: all functions are thread-safe; one call = one CUDA stream.  Errors: 0 = PB_OK, negative
+ * code otherwise with a thread-local message in pb_last_error().  The library never aborts and never
+ * falls back to a CPU implementation.
+ */
+#ifndef PINOT_B200_H
+#define PINOT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_OK 0
+#define PB_ERR_INVALID (-1)       /* malformed descriptor */
+#define PB_ERR_UNSUPPORTED (-2)   /* outside the eligible set: the plan maker must decline to the CPU plan */
+#define PB_ERR_CUDA (-3)
+#define PB_ERR_OOM (-4)
+#define PB_ERR_STATE (-5)
+
+/* FieldSpec.DataType stored types (pinot-spi/.../data/FieldSpec.java) on this path */
+enum { PB_INT = 0, PB_LONG = 1, PB_FLOAT = 2, PB_DOUBLE = 3, PB_STRING = 4 };
+
+/* AggregationFunctionType subset (CTR/query/aggregation/function) */
+enum { PB_AGG_COUNT = 0, PB_AGG_SUM = 1, PB_AGG_MIN = 2, PB_AGG_MAX = 3, PB_AGG_AVG = 4, PB_AGG_DISTINCTCOUNT = 5 };
+
+/* Filter tree node kinds.  Leaves are the OUTPUT of PredicateEvaluator + FilterOperatorUtils:
+ *   SCAN_*      ScanBasedFilterOperator  (CTR/operator/filter/ScanBasedFilterOperator.java:59-66)
+ *   INVERTED    InvertedIndexFilterOperator (…/InvertedIndexFilterOperator.java:60-96)
+ *   SORTED      SortedIndexBasedFilterOperator (…/SortedIndexBasedFilterOperator.java:53-131)
+ *   BITMAP      BitmapBasedFilterOperator (…/BitmapBasedFilterOperator.java:42-60), e.g. upsert validDocIds
+ *   AND/OR/NOT  And/Or/NotFilterOperator */
+enum {
+  PB_F_AND = 0, PB_F_OR = 1, PB_F_NOT = 2, PB_F_MATCH_ALL = 3, PB_F_EMPTY = 4,
+  PB_F_SCAN_DICT_RANGE = 5,   /* dictionary column, lo <= dictId < hi                                   */
+  PB_F_SCAN_DICT_SET = 6,     /* dictionary column, dictId in ids[] (exclusive: NOT in)                 */
+  PB_F_SCAN_RAW_RANGE = 7,    /* raw column: INT/LONG lo..hi inclusive; FLOAT/DOUBLE dlo..dhi + flags   */
+  PB_F_SCAN_RAW_SET = 8,      /* raw column: value in raw_values[] (exclusive: NOT in); doubles as bits */
+  PB_F_INVERTED = 9,          /* bitmap inverted index: OR of the bitmaps of ids[] (exclusive: flipped) */
+  PB_F_SORTED = 10,           /* sorted index: ids[] holds num_ids inclusive (start,end) docId pairs    */
+  PB_F_BITMAP = 11            /* caller-supplied RoaringBitmap portable blob (exclusive: flipped)       */
+};
+
+typedef struct pb_segment_s* pb_segment_handle;
+typedef struct pb_group_s* pb_segment_group_handle;
+typedef struct pb_result_s* pb_result_handle;
+
+/* One column's index buffers, exactly as sliced out of columns.psf
+ * (SPI/store/SegmentDirectory.java:179 getIndexFor; big-endian Pinot layouts). */
+typedef struct pb_column_desc {
+  const char* name;
+  int32_t stored_type;         /* PB_INT .. PB_STRING */
+  int32_t has_dictionary;
+  int32_t is_sorted;
+  int32_t cardinality;         /* column.<name>.cardinality (dictionary columns) */
+  int32_t bits_per_element;    /* column.<name>.bitsPerElement */
+  int32_t dict_entry_bytes;    /* 4/8 for numerics, lengthOfEachEntry for STRING */
+  const void* forward_index;   /* .sv.unsorted.fwd | .sv.sorted.fwd | .sv.raw.fwd (PASS_THROUGH only) */
+  uint64_t forward_index_len;
+  const void* dictionary;      /* .dict, NULL for raw columns */
+  uint64_t dictionary_len;
+  const void* inverted_index;  /* .bitmap.inv, NULL when absent */
+  uint64_t inverted_index_len;
+} pb_column_desc;
+
+typedef struct pb_segment_desc {
+  const char* segment_name;
+  int32_t num_docs;            /* segment.total.docs */
+  int32_t num_columns;
+  const pb_column_desc* columns;
+} pb_segment_desc;
+
+typedef struct pb_filter_node {
+  int32_t kind;                /* PB_F_* */
+  int32_t column;              /* index into pb_segment_desc.columns (leaves on a column) */
+  int32_t num_children;        /* AND / OR: operand count (postfix); NOT: 1 */
+  int32_t exclusive;           /* NEQ / NOT_IN semantics for *_SET, INVERTED, BITMAP */
+  int64_t lo, hi;              /* SCAN_DICT_RANGE: [lo,hi) dictIds; SCAN_RAW_RANGE (INT/LONG): [lo,hi] */
+  double dlo, dhi;             /* SCAN_RAW_RANGE (FLOAT/DOUBLE) */
+  int32_t dlo_inclusive, dhi_inclusive;
+  const int32_t* ids;          /* dictIds (sorted ascending) or docId pairs */
+  int32_t num_ids;
+  int32_t num_raw_values;
+  const int64_t* raw_values;   /* SCAN_RAW_SET: INT/LONG values; FLOAT/DOUBLE as IEEE-754 double bits */
+  const void* blob;            /* PB_F_BITMAP */
+  uint64_t blob_len;
+} pb_filter_node;
+
+/* Per-segment part of a query: the filter in postfix order (empty = match all).  It is per segment
+ * because dictIds are segment-local (FilterPlanNode.run is per segment: CTR/plan/FilterPlanNode.java:88-106). */
+typedef struct pb_segment_query {
+  const pb_filter_node* filter;
+  int32_t num_filter_nodes;
+} pb_segment_query;
+
+typedef struct pb_aggregation_desc {
+  int32_t op;                  /* PB_AGG_* */
+  const char* column;          /* NULL for COUNT(*) */
+} pb_aggregation_desc;
+
+#define PB_Q_COMBINE 1u            /* one merged table over all segments (GroupByCombineOperator semantics, on device) */
+#define PB_Q_DEFER_FINALIZE 2u     /* leave tables on the device for a cross-GPU reduce; call pb_result_finalize */
+#define PB_Q_GENERIC_KERNEL 4u     /* force the width-generic predicate path (testing / A-B measurement) */
+#define PB_Q_NO_TMA 8u             /* stage tiles with ld.global/st.shared instead of cp.async.bulk (testing) */
+
+typedef struct pb_query_desc {
+  int32_t num_group_by;
+  const char* const* group_by_columns;
+  int32_t num_aggregations;
+  const pb_aggregation_desc* aggregations;
+  int32_t num_groups_limit;                     /* InstancePlanMakerImplV2.java:79 (default 100000) */
+  int32_t max_initial_result_holder_capacity;   /* InstancePlanMakerImplV2.java:70 (default 10000) */
+  uint32_t flags;                               /* PB_Q_* */
+} pb_query_desc;
+
+/* ExecutionStatistics (CTR/operator/ExecutionStatistics.java:28-65) */
+typedef struct pb_exec_stats {
+  int64_t num_docs_scanned;
+  int64_t num_entries_scanned_in_filter;
+  int64_t num_entries_scanned_post_filter;
+  int64_t num_total_docs;
+  int32_t num_groups_limit_reached;
+  int32_t num_segments;
+} pb_exec_stats;
+
+/* -------- lifecycle -------- */
+int pb_init(const int* device_ids, int n_devices, size_t hbm_cache_bytes);
+int pb_shutdown(void);
+const char* pb_last_error(void);
+int pb_device_count(void);
+
+/* -------- segment staging: replaces the DataSource / ForwardIndexReader / Dictionary / InvertedIndexReader
+ * objects the operators pull from IndexSegment.getDataSource (SPI/datasource/DataSource.java:38-60).
+ * Copies the buffers to HBM once; the handle is valid until pb_segment_release. -------- */
+int pb_segment_stage(const pb_segment_desc* desc, int device_index, pb_segment_handle* out);
+int pb_segment_release(pb_segment_handle seg);
+int64_t pb_segment_device_bytes(pb_segment_handle seg);
+
+/* A set of segments queried together.  Holds the per-column global dictionaries (sorted union of the
+ * segment dictionaries) and local->global dictId remaps that make a device-side cross-segment merge
+ * possible (the reference merges by decoded value: CTR/operator/combine/GroupByCombineOperator.java:132-147). */
+int pb_segment_group_create(const pb_segment_handle* segs, int n_segs, pb_segment_group_handle* out);
+int pb_segment_group_release(pb_segment_group_handle g);
+/* Cross-process agreement on a column's global dictionary (multi-GPU): export this group's union, and
+ * install the union over all ranks.  values are native-endian stored-type values (STRING: fixed-width
+ * padded entries of entry_bytes each). */
+int pb_segment_group_export_dictionary(pb_segment_group_handle g, const char* column, const void** values,
+                                       int64_t* num_values, int32_t* entry_bytes);
+int pb_segment_group_set_global_dictionary(pb_segment_group_handle g, const char* column, const void* values,
+                                           int64_t num_values, int32_t entry_bytes);
+
+/* -------- execution: replaces GroupByOperator.getNextBlock / AggregationOperator.getNextBlock
+ * (CTR/operator/query/GroupByOperator.java:101-140, AggregationOperator.java:64-80) for every segment of
+ * the group in one call.  seg_queries[i] belongs to the i-th segment of the group. -------- */
+int pb_query_execute(pb_segment_group_handle g, const pb_segment_query* seg_queries, const pb_query_desc* q,
+                     pb_result_handle* out);
+
+/* -------- results: the contents of GroupByResultsBlock / AggregationResultsBlock
+ * (CTR/operator/blocks/results/GroupByResultsBlock.java:68-139, AggregationGroupByResult.java:31-57).
+ * Without PB_Q_COMBINE there is one table per segment (table index = segment index); with it, one.
+ * All returned pointers are pinned host memory owned by the result handle. -------- */
+int32_t pb_result_num_tables(pb_result_handle r);
+int64_t pb_result_num_groups(pb_result_handle r, int32_t table);          /* 1 for keyless aggregation */
+/* group key of column gb: dictIds (segment-local without COMBINE, global with it); NULL for raw key columns */
+const int32_t* pb_result_group_dict_ids(pb_result_handle r, int32_t table, int32_t gb);
+/* decoded key values (GroupKeyGenerator.GroupKey._keys): native-endian stored-type values; STRING keys are
+ * fixed-width padded entries.  *stored_type / *entry_bytes describe the array. */
+const void* pb_result_group_key_values(pb_result_handle r, int32_t table, int32_t gb, int32_t* stored_type,
+                                       int32_t* entry_bytes);
+/* per aggregation arrays [num_groups]: SUM/MIN/MAX value, AVG sum -> double; COUNT, AVG count,
+ * DISTINCTCOUNT size -> long */
+const double* pb_result_double(pb_result_handle r, int32_t table, int32_t agg);
+const int64_t* pb_result_long(pb_result_handle r, int32_t table, int32_t agg);
+/* DISTINCTCOUNT intermediate value sets (BaseDistinctAggregateAggregationFunction.java:760-806):
+ * offsets[num_groups+1] into dictIds (ascending per group; local without COMBINE, global with it) */
+const int64_t* pb_result_distinct_offsets(pb_result_handle r, int32_t table, int32_t agg);
+const int32_t* pb_result_distinct_dict_ids(pb_result_handle r, int32_t table, int32_t agg);
+const pb_exec_stats* pb_result_stats(pb_result_handle r, int32_t table);
+/* device time (CUDA events around the kernels of this call), and the scan kernel alone */
+double pb_result_device_ms(pb_result_handle r);
+double pb_result_scan_kernel_ms(pb_result_handle r);
+int32_t pb_result_kernel_launches(pb_result_handle r);
+void pb_result_free(pb_result_handle r);
+
+/* -------- multi-GPU (PB_Q_COMBINE | PB_Q_DEFER_FINALIZE): device-resident table arrays for an
+ * NCCL all-reduce issued by the caller (torch.distributed), then finalize on the root.
+ * which: 0 = row counts (int64, SUM); 1 = per-aggregation double sums (float64, SUM);
+ *        2 = per-aggregation min/max in order-preserving int64 encoding (int64, MIN or MAX);
+ *        3 = per-aggregation distinct bitset words (int32; OR == MAX over 0/1 is NOT valid — all-gather + pb_or) -------- */
+int pb_result_device_buffer(pb_result_handle r, int32_t which, int32_t agg, void** device_ptr, int64_t* num_elements);
+int pb_result_finalize(pb_result_handle r);
+/* the CUDA stream (cudaStream_t) this result's work was issued on */
+void* pb_result_stream(pb_result_handle r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINOT_B200_H */

@@ -1,0 +1,433 @@
+// pb_host.cpp — the host planning layer above the C ABI, class for class after the reference
+// (in a Pinot server these steps run in Java; see include/pinot_b200_host.h and INTEGRATION.md).
+//
+//   Dictionary                     SEGL/segment/index/readers/BaseImmutableDictionary.java:45-260
+//   PredicateEvaluatorProvider     CTR/operator/filter/predicate/PredicateEvaluatorProvider.java:45-95
+//     RANGE  (sorted dictionary)   …/RangePredicateEvaluatorFactory.java:119-169   raw: :326-400
+//     EQ / NOT_EQ                  …/EqualsPredicateEvaluatorFactory.java:83-110, NotEqualsPredicateEvaluatorFactory.java:83-110
+//     IN / NOT_IN                  …/InPredicateEvaluatorFactory.java:158-188, NotInPredicateEvaluatorFactory.java:155-172
+//   FilterOperatorUtils            CTR/operator/filter/FilterOperatorUtils.java:74-252
+//   FilterPlanNode                 CTR/plan/FilterPlanNode.java:195-320
+//   SortedIndexBasedFilterOperator CTR/operator/filter/SortedIndexBasedFilterOperator.java:53-131
+//   B200PlanMaker eligibility      SURVEY.md §8b (override of InstancePlanMakerImplV2.makeSegmentPlanNode :275-294)
+#include "../../../include/pinot_b200_host.h"
+#include "../pb_internal.h"
+
+#include <algorithm>
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace pinot_b200 {
+
+static inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+static inline uint64_t be64(const uint8_t* p) { return ((uint64_t)be32(p) << 32) | be32(p + 4); }
+
+struct BadQuery { std::string msg; };   // BadQueryRequestException
+
+// ---------------------------------------------------------------------------------------------- Dictionary
+class Dictionary {
+ public:
+  explicit Dictionary(const PbColumnView& c) : _c(c) {}
+  int length() const { return _c.card; }
+  long long getLong(int id) const { return _c.type == PB_INT ? (long long)(int32_t)be32(_c.dict + 4ull * id) : (long long)be64(_c.dict + 8ull * id); }
+  double getDouble(int id) const {
+    if (_c.type == PB_FLOAT) { uint32_t u = be32(_c.dict + 4ull * id); float f; memcpy(&f, &u, 4); return f; }
+    uint64_t u = be64(_c.dict + 8ull * id); double d; memcpy(&d, &u, 8); return d;
+  }
+  // Arrays.binarySearch convention: index if found, else -(insertionPoint + 1)
+  int insertionIndexOf(const std::string& v) const {
+    switch (_c.type) {
+      case PB_INT: case PB_LONG: {
+        long long iv; double dv;
+        if (parseIntegral(v, &iv)) return search([&](int m) { long long x = getLong(m); return (x > iv) - (x < iv); });
+        dv = parseDouble(v);   // fractional literal against an integral dictionary: never equal
+        return search([&](int m) { double x = (double)getLong(m); return (x > dv) - (x < dv); });
+      }
+      case PB_FLOAT: { float fv = (float)parseDouble(v); return search([&](int m) { float x = (float)getDouble(m); return (x > fv) - (x < fv); }); }
+      case PB_DOUBLE: { double dv = parseDouble(v); return search([&](int m) { double x = getDouble(m); return (x > dv) - (x < dv); }); }
+      default:
+        return search([&](int m) {
+          const uint8_t* e = _c.dict + (size_t)m * _c.entry_bytes;
+          size_t el = 0; while (el < (size_t)_c.entry_bytes && e[el]) el++;
+          size_t n = std::min(el, v.size());
+          int r = memcmp(e, v.data(), n);
+          if (r) return r;
+          return (el > v.size()) - (el < v.size());
+        });
+    }
+  }
+  int indexOf(const std::string& v) const { int i = insertionIndexOf(v); return i >= 0 ? i : -1; }
+
+  static bool parseIntegral(const std::string& s, long long* out) {
+    errno = 0; char* end = nullptr;
+    long long v = strtoll(s.c_str(), &end, 10);
+    if (errno || end == s.c_str() || *end) return false;
+    *out = v; return true;
+  }
+  static double parseDouble(const std::string& s) {
+    errno = 0; char* end = nullptr;
+    double v = strtod(s.c_str(), &end);
+    if (end == s.c_str() || *end) throw BadQuery{"cannot parse numeric literal '" + s + "'"};
+    return v;
+  }
+
+ private:
+  template <class Cmp> int search(Cmp cmp) const {
+    int lo = 0, hi = _c.card - 1;
+    while (lo <= hi) {
+      int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1);
+      int r = cmp(mid);
+      if (r < 0) lo = mid + 1; else if (r > 0) hi = mid - 1; else return mid;
+    }
+    return -(lo + 1);
+  }
+  const PbColumnView& _c;
+};
+
+// ---------------------------------------------------------------------------------------------- PredicateEvaluator
+struct PredicateEvaluator {
+  int type = 0;               // PBH_*
+  int column = -1;
+  bool dictionaryBased = false;
+  bool alwaysTrue = false, alwaysFalse = false;
+  bool exclusive = false;     // NOT_EQ / NOT_IN
+  // dictionary based
+  int startDictId = 0, endDictId = 0;          // RANGE: [start, end)
+  std::vector<int32_t> dictIds;                // EQ/IN: matching; NOT_EQ/NOT_IN: non-matching; sorted, unique
+  // raw value based
+  long long ilo = 0, ihi = 0; double dlo = 0, dhi = 0; bool dloIncl = false, dhiIncl = false;
+  std::vector<int64_t> rawValues;
+  bool isRange() const { return type == PBH_RANGE; }
+};
+
+class PredicateEvaluatorProvider {
+ public:
+  static PredicateEvaluator getPredicateEvaluator(const pbh_predicate& p, const PbColumnView& c, int columnIndex) {
+    PredicateEvaluator e;
+    e.type = p.type; e.column = columnIndex; e.dictionaryBased = c.has_dict; e.exclusive = p.type == PBH_NOT_EQ || p.type == PBH_NOT_IN;
+    if (c.has_dict) {
+      Dictionary dict(c);
+      const int card = dict.length();
+      if (p.type == PBH_RANGE) {
+        if (!p.lower) e.startDictId = 0;
+        else { int ii = dict.insertionIndexOf(p.lower); e.startDictId = ii < 0 ? -(ii + 1) : (p.lower_inclusive ? ii : ii + 1); }
+        if (!p.upper) e.endDictId = card;
+        else { int ii = dict.insertionIndexOf(p.upper); e.endDictId = ii < 0 ? -(ii + 1) : (p.upper_inclusive ? ii + 1 : ii); }
+        int n = std::max(e.endDictId - e.startDictId, 0);
+        if (n == 0) e.alwaysFalse = true; else if (n == card) e.alwaysTrue = true;
+      } else {
+        for (int i = 0; i < p.num_values; i++) { int id = dict.indexOf(p.values[i]); if (id >= 0) e.dictIds.push_back(id); }
+        std::sort(e.dictIds.begin(), e.dictIds.end());
+        e.dictIds.erase(std::unique(e.dictIds.begin(), e.dictIds.end()), e.dictIds.end());
+        const int n = (int)e.dictIds.size();
+        if (!e.exclusive) { if (n == 0) e.alwaysFalse = true; else if (n == card) e.alwaysTrue = true; }
+        else { if (n == 0) e.alwaysTrue = true; else if (n == card) e.alwaysFalse = true; }
+      }
+      return e;
+    }
+    // raw value based
+    if (c.type == PB_STRING) throw BadQuery{"raw STRING predicate on column " + c.name};
+    const bool integral = c.type == PB_INT || c.type == PB_LONG;
+    if (p.type == PBH_RANGE) {
+      if (integral) {
+        const long long tmin = c.type == PB_INT ? INT32_MIN : INT64_MIN, tmax = c.type == PB_INT ? INT32_MAX : INT64_MAX;
+        auto parse = [&](const char* s) { long long v; if (!Dictionary::parseIntegral(s, &v)) throw BadQuery{std::string("cannot parse integral literal '") + s + "'"}; return v; };
+        e.ilo = p.lower ? parse(p.lower) : tmin; e.ihi = p.upper ? parse(p.upper) : tmax;
+        if (p.lower && !p.lower_inclusive) { if (e.ilo == tmax) e.alwaysFalse = true; else e.ilo++; }   // RangePredicateEvaluatorFactory.java:334-345
+        if (p.upper && !p.upper_inclusive) { if (e.ihi == tmin) e.alwaysFalse = true; else e.ihi--; }
+        if (e.ilo > e.ihi) e.alwaysFalse = true;
+      } else {
+        e.dlo = p.lower ? Dictionary::parseDouble(p.lower) : -INFINITY; e.dhi = p.upper ? Dictionary::parseDouble(p.upper) : INFINITY;
+        if (c.type == PB_FLOAT) { e.dlo = (double)(float)e.dlo; e.dhi = (double)(float)e.dhi; }
+        e.dloIncl = !p.lower || p.lower_inclusive; e.dhiIncl = !p.upper || p.upper_inclusive;
+      }
+    } else {
+      for (int i = 0; i < p.num_values; i++) {
+        if (integral) { long long v; if (!Dictionary::parseIntegral(p.values[i], &v)) throw BadQuery{std::string("cannot parse integral literal '") + p.values[i] + "'"}; e.rawValues.push_back(v); }
+        else { double d = Dictionary::parseDouble(p.values[i]); if (c.type == PB_FLOAT) d = (double)(float)d; int64_t b; memcpy(&b, &d, 8); e.rawValues.push_back(b); }
+      }
+    }
+    return e;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- filter operators
+enum OpKind { OP_EMPTY, OP_MATCH_ALL, OP_SORTED, OP_INVERTED, OP_SCAN, OP_AND, OP_OR, OP_NOT };
+struct FilterOperator {
+  OpKind kind = OP_EMPTY;
+  PredicateEvaluator ev;
+  std::vector<int32_t> docIdRanges;   // OP_SORTED: inclusive (start,end) pairs
+  std::vector<std::unique_ptr<FilterOperator>> children;
+};
+using OpPtr = std::unique_ptr<FilterOperator>;
+static OpPtr mk(OpKind k) { OpPtr p(new FilterOperator()); p->kind = k; return p; }
+
+class SortedIndexBasedFilterOperator {
+ public:
+  static OpPtr create(const PredicateEvaluator& ev, const PbColumnView& c, int numDocs) {
+    OpPtr op = mk(OP_SORTED);
+    auto start = [&](int id) { return c.sorted_pairs[2 * id]; };
+    auto end = [&](int id) { return c.sorted_pairs[2 * id + 1]; };
+    if (ev.isRange()) { op->docIdRanges = {start(ev.startDictId), end(ev.endDictId - 1)}; return op; }
+    std::vector<int32_t> r;
+    int32_t ls = start(ev.dictIds[0]), le = end(ev.dictIds[0]);
+    for (size_t i = 1; i < ev.dictIds.size(); i++) {
+      int32_t s = start(ev.dictIds[i]), e = end(ev.dictIds[i]);
+      if (s == le + 1) le = e; else { r.push_back(ls); r.push_back(le); ls = s; le = e; }
+    }
+    r.push_back(ls); r.push_back(le);
+    if (ev.exclusive) {   // invert over [0, numDocs)
+      std::vector<int32_t> inv;
+      if (r[0] > 0) { inv.push_back(0); inv.push_back(r[0] - 1); }
+      for (size_t i = 0; i + 2 < r.size(); i += 2) { inv.push_back(r[i + 1] + 1); inv.push_back(r[i + 2] - 1); }
+      if (r[r.size() - 1] < numDocs - 1) { inv.push_back(r[r.size() - 1] + 1); inv.push_back(numDocs - 1); }
+      r.swap(inv);
+    }
+    op->docIdRanges = r;
+    return op;
+  }
+};
+
+class FilterOperatorUtils {
+ public:
+  // getLeafFilterOperator: sorted > inverted > scan (RANGE never uses the inverted index); range-index/text/json/H3 are out of scope
+  static OpPtr getLeafFilterOperator(const PredicateEvaluator& ev, const PbColumnView& c, int numDocs, bool skipInverted) {
+    if (ev.alwaysFalse) return mk(OP_EMPTY);
+    if (ev.alwaysTrue) return mk(OP_MATCH_ALL);
+    if (c.is_sorted && c.has_dict) return SortedIndexBasedFilterOperator::create(ev, c, numDocs);
+    OpPtr op;
+    if (!ev.isRange() && c.has_inverted && c.has_dict && !skipInverted) op = mk(OP_INVERTED); else op = mk(OP_SCAN);
+    op->ev = ev;
+    return op;
+  }
+  static int getPriority(const FilterOperator& f) {   // PrioritizedFilterOperator constants
+    switch (f.kind) {
+      case OP_SORTED: return 0;
+      case OP_INVERTED: return 100;
+      case OP_AND: return 300;
+      case OP_OR: return 400;
+      case OP_NOT: return getPriority(*f.children[0]);
+      case OP_SCAN: return 500;
+      default: return 10000;
+    }
+  }
+  static OpPtr getAndFilterOperator(std::vector<OpPtr> ops) {
+    std::vector<OpPtr> kids;
+    for (auto& o : ops) if (o->kind == OP_EMPTY) return mk(OP_EMPTY);
+    for (auto& o : ops) if (o->kind != OP_MATCH_ALL) kids.push_back(std::move(o));
+    if (kids.empty()) return mk(OP_MATCH_ALL);
+    if (kids.size() == 1) return std::move(kids[0]);
+    std::stable_sort(kids.begin(), kids.end(), [](const OpPtr& a, const OpPtr& b) { return getPriority(*a) < getPriority(*b); });
+    OpPtr op = mk(OP_AND); op->children = std::move(kids); return op;
+  }
+  static OpPtr getOrFilterOperator(std::vector<OpPtr> ops) {
+    std::vector<OpPtr> kids;
+    for (auto& o : ops) if (o->kind == OP_MATCH_ALL) return mk(OP_MATCH_ALL);
+    for (auto& o : ops) if (o->kind != OP_EMPTY) kids.push_back(std::move(o));
+    if (kids.empty()) return mk(OP_EMPTY);
+    if (kids.size() == 1) return std::move(kids[0]);
+    OpPtr op = mk(OP_OR); op->children = std::move(kids); return op;
+  }
+  static OpPtr getNotFilterOperator(OpPtr o) {
+    if (o->kind == OP_MATCH_ALL) return mk(OP_EMPTY);
+    if (o->kind == OP_EMPTY) return mk(OP_MATCH_ALL);
+    OpPtr op = mk(OP_NOT); op->children.push_back(std::move(o)); return op;
+  }
+};
+
+static int findColumn(const PbSegmentView& s, const char* name) {
+  for (size_t i = 0; i < s.cols.size(); i++) if (s.cols[i].name == name) return (int)i;
+  return -1;
+}
+
+class FilterPlanNode {
+ public:
+  // constructPhysicalOperator over the postfix FilterContext
+  static OpPtr run(const PbSegmentView& seg, const pbh_query_context& q) {
+    if (q.num_filter_nodes == 0) return mk(OP_MATCH_ALL);
+    std::vector<OpPtr> stack;
+    for (int i = 0; i < q.num_filter_nodes; i++) {
+      const pbh_filter_node& n = q.filter_nodes[i];
+      if (n.kind == PBH_PREDICATE) {
+        const pbh_predicate& p = q.predicates[n.predicate];
+        int ci = findColumn(seg, p.column);
+        if (ci < 0) throw BadQuery{std::string("unknown column ") + p.column};
+        bool skipInv = false;
+        for (int k = 0; k < q.num_skip_inverted; k++) if (seg.cols[ci].name == q.skip_inverted_columns[k]) skipInv = true;
+        PredicateEvaluator ev = PredicateEvaluatorProvider::getPredicateEvaluator(p, seg.cols[ci], ci);
+        stack.push_back(FilterOperatorUtils::getLeafFilterOperator(ev, seg.cols[ci], seg.num_docs, skipInv));
+      } else if (n.kind == PBH_NOT) {
+        if (stack.empty()) throw BadQuery{"malformed filter"};
+        OpPtr c = std::move(stack.back()); stack.pop_back();
+        stack.push_back(FilterOperatorUtils::getNotFilterOperator(std::move(c)));
+      } else {
+        if ((int)stack.size() < n.num_children || n.num_children < 1) throw BadQuery{"malformed filter"};
+        std::vector<OpPtr> kids;
+        for (size_t k = stack.size() - n.num_children; k < stack.size(); k++) kids.push_back(std::move(stack[k]));
+        stack.resize(stack.size() - n.num_children);
+        stack.push_back(n.kind == PBH_AND ? FilterOperatorUtils::getAndFilterOperator(std::move(kids)) : FilterOperatorUtils::getOrFilterOperator(std::move(kids)));
+      }
+    }
+    if (stack.size() != 1) throw BadQuery{"malformed filter"};
+    return std::move(stack[0]);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------- lowering to the C ABI
+struct LoweredSegment {
+  std::vector<pb_filter_node> nodes;
+  std::vector<std::unique_ptr<std::vector<int32_t>>> idStore;
+  std::vector<std::unique_ptr<std::vector<int64_t>>> rawStore;
+};
+
+static void emit(const FilterOperator& f, const PbSegmentView& seg, LoweredSegment& out) {
+  pb_filter_node n;
+  memset(&n, 0, sizeof n);
+  switch (f.kind) {
+    case OP_EMPTY: n.kind = PB_F_EMPTY; break;
+    case OP_MATCH_ALL: n.kind = PB_F_MATCH_ALL; break;
+    case OP_SORTED: {
+      out.idStore.emplace_back(new std::vector<int32_t>(f.docIdRanges));
+      n.kind = PB_F_SORTED; n.ids = out.idStore.back()->data(); n.num_ids = (int32_t)(f.docIdRanges.size() / 2);
+      break;
+    }
+    case OP_INVERTED: {
+      out.idStore.emplace_back(new std::vector<int32_t>(f.ev.dictIds));
+      n.kind = PB_F_INVERTED; n.column = f.ev.column; n.exclusive = f.ev.exclusive; n.ids = out.idStore.back()->data(); n.num_ids = (int32_t)f.ev.dictIds.size();
+      break;
+    }
+    case OP_SCAN: {
+      const PredicateEvaluator& e = f.ev;
+      n.column = e.column;
+      if (e.dictionaryBased) {
+        if (e.isRange()) { n.kind = PB_F_SCAN_DICT_RANGE; n.lo = e.startDictId; n.hi = e.endDictId; }
+        else {
+          out.idStore.emplace_back(new std::vector<int32_t>(e.dictIds));
+          n.kind = PB_F_SCAN_DICT_SET; n.exclusive = e.exclusive; n.ids = out.idStore.back()->data(); n.num_ids = (int32_t)e.dictIds.size();
+        }
+      } else if (e.isRange()) {
+        n.kind = PB_F_SCAN_RAW_RANGE; n.lo = e.ilo; n.hi = e.ihi; n.dlo = e.dlo; n.dhi = e.dhi; n.dlo_inclusive = e.dloIncl; n.dhi_inclusive = e.dhiIncl;
+      } else {
+        out.rawStore.emplace_back(new std::vector<int64_t>(e.rawValues));
+        n.kind = PB_F_SCAN_RAW_SET; n.exclusive = e.exclusive; n.raw_values = out.rawStore.back()->data(); n.num_raw_values = (int32_t)e.rawValues.size();
+      }
+      break;
+    }
+    case OP_NOT: emit(*f.children[0], seg, out); n.kind = PB_F_NOT; n.num_children = 1; break;
+    default:
+      for (auto& c : f.children) emit(*c, seg, out);
+      n.kind = f.kind == OP_AND ? PB_F_AND : PB_F_OR; n.num_children = (int32_t)f.children.size();
+      break;
+  }
+  out.nodes.push_back(n);
+}
+
+static void explain(const FilterOperator& f, const PbSegmentView& seg, int depth, std::string& out) {
+  static const char* names[] = {"FILTER_EMPTY", "FILTER_MATCH_ENTIRE_SEGMENT", "FILTER_SORTED_INDEX", "FILTER_INVERTED_INDEX", "FILTER_FULL_SCAN", "FILTER_AND", "FILTER_OR", "FILTER_NOT"};
+  out.append((size_t)depth * 2, ' ');
+  out += names[f.kind];
+  if (f.kind == OP_SCAN || f.kind == OP_INVERTED) {
+    char buf[160];
+    static const char* pt[] = {"EQ", "NOT_EQ", "IN", "NOT_IN", "RANGE"};
+    if (f.ev.dictionaryBased && f.ev.isRange()) snprintf(buf, sizeof buf, "(%s %s dictIds[%d,%d))", seg.cols[f.ev.column].name.c_str(), pt[f.ev.type], f.ev.startDictId, f.ev.endDictId);
+    else snprintf(buf, sizeof buf, "(%s %s n=%zu)", seg.cols[f.ev.column].name.c_str(), pt[f.ev.type], f.ev.dictionaryBased ? f.ev.dictIds.size() : f.ev.rawValues.size());
+    out += buf;
+  }
+  if (f.kind == OP_SORTED) { char buf[64]; snprintf(buf, sizeof buf, "(%zu docId ranges)", f.docIdRanges.size() / 2); out += buf; }
+  out += "\n";
+  for (auto& c : f.children) explain(*c, seg, depth + 1, out);
+}
+
+// ---------------------------------------------------------------------------------------------- B200PlanMaker
+class B200PlanMaker {
+ public:
+  // the (segment, query) pairs this executor accepts; everything else keeps the stock CPU plan
+  static void checkEligible(const PbSegmentView& seg, const pbh_query_context& q) {
+    if (q.num_aggregations <= 0) throw BadQuery{"not an aggregation query"};
+    for (int j = 0; j < q.num_group_by; j++) {
+      int ci = findColumn(seg, q.group_by_columns[j]);
+      if (ci < 0) throw BadQuery{std::string("unknown group-by column ") + q.group_by_columns[j]};
+      if (!seg.cols[ci].has_dict && seg.cols[ci].type == PB_STRING) throw BadQuery{"raw STRING group-by key"};
+    }
+    for (int a = 0; a < q.num_aggregations; a++) {
+      const pb_aggregation_desc& ad = q.aggregations[a];
+      if (ad.op < PB_AGG_COUNT || ad.op > PB_AGG_DISTINCTCOUNT) throw BadQuery{"aggregation function not offloaded"};
+      if (ad.op == PB_AGG_COUNT) continue;
+      int ci = ad.column ? findColumn(seg, ad.column) : -1;
+      if (ci < 0) throw BadQuery{"unknown aggregation column"};
+      if (ad.op == PB_AGG_DISTINCTCOUNT) { if (!seg.cols[ci].has_dict) throw BadQuery{"DISTINCTCOUNT on a raw column"}; }
+      else if (seg.cols[ci].type == PB_STRING) throw BadQuery{"numeric aggregation on STRING"};
+    }
+  }
+};
+
+}  // namespace pinot_b200
+
+using namespace pinot_b200;
+
+extern "C" int pbh_is_eligible(pb_segment_group_handle g, const pbh_query_context* q) {
+  std::vector<pb_segment_handle> segs;
+  int rc = pbi_group_segments(g, &segs);
+  if (rc) return rc;
+  if (!q) return pbi_fail(PB_ERR_INVALID, "null query");
+  try {
+    for (auto s : segs) {
+      PbSegmentView v;
+      if ((rc = pbi_segment_view(s, &v))) return rc;
+      B200PlanMaker::checkEligible(v, *q);
+      FilterPlanNode::run(v, *q);
+    }
+  } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
+  return PB_OK;
+}
+
+extern "C" int pbh_execute(pb_segment_group_handle g, const pbh_query_context* q, uint32_t flags, pb_result_handle* out) {
+  std::vector<pb_segment_handle> segs;
+  int rc = pbi_group_segments(g, &segs);
+  if (rc) return rc;
+  if (!q || !out) return pbi_fail(PB_ERR_INVALID, "null argument");
+  std::vector<LoweredSegment> lowered(segs.size());
+  std::vector<pb_segment_query> sq(segs.size());
+  try {
+    for (size_t i = 0; i < segs.size(); i++) {
+      PbSegmentView v;
+      if ((rc = pbi_segment_view(segs[i], &v))) return rc;
+      B200PlanMaker::checkEligible(v, *q);
+      OpPtr root = FilterPlanNode::run(v, *q);
+      if (root->kind != OP_MATCH_ALL) emit(*root, v, lowered[i]);
+      sq[i].filter = lowered[i].nodes.data();
+      sq[i].num_filter_nodes = (int32_t)lowered[i].nodes.size();
+    }
+  } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
+  pb_query_desc d;
+  memset(&d, 0, sizeof d);
+  d.num_group_by = q->num_group_by; d.group_by_columns = q->group_by_columns;
+  d.num_aggregations = q->num_aggregations; d.aggregations = q->aggregations;
+  d.num_groups_limit = q->num_groups_limit > 0 ? q->num_groups_limit : 100000;
+  d.max_initial_result_holder_capacity = q->max_initial_result_holder_capacity > 0 ? q->max_initial_result_holder_capacity : 10000;
+  d.flags = flags;
+  return pb_query_execute(g, sq.data(), &d, out);
+}
+
+extern "C" int pbh_explain_filter(pb_segment_group_handle g, int32_t si, const pbh_query_context* q, char* buf, int32_t cap) {
+  std::vector<pb_segment_handle> segs;
+  int rc = pbi_group_segments(g, &segs);
+  if (rc) return rc;
+  if (!q || !buf || cap <= 0 || si < 0 || si >= (int)segs.size()) return pbi_fail(PB_ERR_INVALID, "bad argument");
+  try {
+    PbSegmentView v;
+    if ((rc = pbi_segment_view(segs[si], &v))) return rc;
+    OpPtr root = FilterPlanNode::run(v, *q);
+    std::string s;
+    explain(*root, v, 0, s);
+    int n = (int)std::min<size_t>(s.size(), (size_t)cap - 1);
+    memcpy(buf, s.data(), (size_t)n); buf[n] = 0;
+    return n;
+  } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
+}

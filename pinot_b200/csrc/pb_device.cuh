@@ -1,0 +1,880 @@
+// pb_device.cuh — device-side data model and kernels of the B200 segment executor (sm_100a).
+//
+// One persistent kernel (pb_scan_kernel) runs the whole per-segment operator chain for every segment of
+// a query:  DocIdSetOperator/filter operators -> ProjectionOperator -> GroupByOperator/AggregationOperator
+// (reference: CTR/operator/query/GroupByOperator.java:101-140 and the call stack in SURVEY.md §3.1).
+//
+//   tile (8 x 1024 docs) of every scan-predicate column  --cp.async.bulk (TMA) + mbarrier, 3 stages-->  smem
+//   warp = 1024-doc chunk, lane = 32 consecutive docs: unpack big-endian bit-packed dictIds from smem,
+//     evaluate the predicate tree on 32-bit doc masks (one mask word per lane == packed docId bitmap)
+//   matching docs -> per-warp queue -> 32 at a time: gather group-key / metric dictIds straight from HBM
+//     (only the sectors that hold matching rows are touched), dictionary decode, accumulate into the
+//     group table with native L2 reductions (RED.ADD.F64 / RED.MIN.S64 / RED.MAX.S64 / RED.OR.B32).
+//
+// No tensor cores: the path is integer / gather / atomic bound (BASELINE.json north_star).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PB_NTHREADS 256
+#define PB_NWARPS 8
+#define PB_CHUNK_DOCS 1024          // docs per warp-chunk (lane owns 32)
+#define PB_NSTAGE 3
+#define PB_MAX_LEAVES 16
+#define PB_MAX_NODES 32
+#define PB_MAX_GROUP_BY 16
+#define PB_MAX_AGGS 16
+#define PB_MAX_SCAN_SLOTS 8
+#define PB_SET_SMEM_WORDS 1024      // 4 KB of dictId-set bitsets cached in smem per segment
+#define PB_WQ_CAP 64                // per-warp match queue entries
+
+enum { L_TRUE = 0, L_FALSE = 1, L_DICT_RANGE = 2, L_DICT_SET = 3, L_RAW_RANGE_I = 4, L_RAW_RANGE_F = 5,
+       L_RAW_SET = 6, L_BITMAP = 7 };
+enum { N_LEAF = 0, N_AND = 1, N_OR = 2, N_NOT = 3 };
+enum { T_KEYLESS = 0, T_DENSE = 1, T_HASH = 2 };
+
+#define PB_HASH_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+struct DevLeaf {
+  int32_t kind;
+  int32_t slot;            // scan slot (tile-staged column) for scan leaves
+  int32_t bits;            // dictionary column: bits per element
+  int32_t raw_width;       // raw column: 4 or 8
+  int32_t data_type;
+  int32_t exclusive;
+  uint32_t lo, span;       // L_DICT_RANGE: match iff (dictId - lo) < span (unsigned)
+  int32_t set_smem_off;    // L_DICT_SET: word offset into the smem set cache, -1 = read from global
+  int32_t set_words;
+  const uint32_t* set_bits;   // L_DICT_SET: bitset over dictIds
+  int64_t ilo, ihi;        // L_RAW_RANGE_I inclusive
+  double dlo, dhi;         // L_RAW_RANGE_F
+  int32_t dlo_incl, dhi_incl;
+  const int64_t* raw_set;  // L_RAW_SET
+  int32_t n_raw_set;
+  int32_t pad0;
+  const uint32_t* bitmap;  // L_BITMAP: flat doc bitmap of this segment (bit d&31 of word d>>5)
+};
+
+struct DevScanCol {        // a column staged tile-by-tile through smem
+  const uint8_t* base;     // first byte of doc 0
+  int32_t bits_per_doc;    // bits per element (dict) or 8*raw_width
+  int32_t pad;
+  uint64_t bytes_total;    // readable bytes from base (16-byte padded)
+};
+
+struct DevKeyCol {         // group-by column (gathered per matching doc)
+  const uint8_t* fwd;
+  const int32_t* remap;    // local -> global dictId (combined mode), may be null
+  int32_t bits;
+  int32_t raw_width;       // 0 for dictionary columns
+  int32_t data_type;
+  int32_t shift;           // T_HASH: bit position of this column in the composite key
+  uint64_t mult;           // T_DENSE: mixed-radix multiplier
+};
+
+struct DevAggCol {
+  const uint8_t* fwd;
+  const double* dict_f64;  // dictionary decoded to double
+  const int32_t* remap;    // DISTINCTCOUNT in combined mode: local -> global dictId
+  int32_t bits;
+  int32_t raw_width;
+  int32_t data_type;
+  int32_t pad;
+};
+
+struct DevSegQuery {
+  int32_t num_docs;
+  int32_t n_nodes;
+  int32_t n_scan;
+  int32_t table;           // result table index
+  uint64_t tile_begin;     // global index of this segment's first tile
+  int8_t node_kind[PB_MAX_NODES];
+  int8_t node_arg[PB_MAX_NODES];
+  DevLeaf leaves[PB_MAX_LEAVES];
+  DevScanCol scan[PB_MAX_SCAN_SLOTS];
+  DevKeyCol keys[PB_MAX_GROUP_BY];
+  DevAggCol aggs[PB_MAX_AGGS];
+};
+
+struct DevTable {
+  int32_t mode;
+  int32_t pad;
+  uint64_t capacity;                 // dense: number of groups; hash: slots (power of two)
+  unsigned long long* hkeys;         // hash: slot keys (PB_HASH_EMPTY = free)
+  unsigned long long* rowcnt;        // rows per slot
+  double* sum[PB_MAX_AGGS];
+  long long* mm[PB_MAX_AGGS];        // order-preserving int64 encoding of the double min / max
+  uint32_t* dc_bits[PB_MAX_AGGS];    // DISTINCTCOUNT: per-slot bitset over (global) dictIds
+  uint64_t dc_words[PB_MAX_AGGS];
+  unsigned int* num_groups;          // hash: groups created so far
+  unsigned int* limit_reached;
+  unsigned long long* docs_matched;  // numDocsScanned
+  uint32_t num_groups_limit;
+  uint32_t pad2;
+};
+
+struct DevQuery {
+  int32_t n_segs;
+  int32_t n_group_by;
+  int32_t n_aggs;
+  int32_t table_mode;
+  int32_t agg_op[PB_MAX_AGGS];
+  int32_t slot_off[PB_MAX_SCAN_SLOTS];   // byte offset of each scan slot inside a stage
+  int32_t stage_bytes;                   // bytes per stage
+  int32_t tile_chunks;                   // chunks (1024 docs) per tile
+  int32_t use_tma;
+  int32_t generic;                       // 1 = width-generic predicate path only
+  uint64_t n_tiles;
+  const DevSegQuery* segs;
+  DevTable* tables;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pb_bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+
+// order-preserving int64 encoding of a double (signed compare == double compare)
+__device__ __forceinline__ long long pb_enc_f64(double v) {
+  long long b = __double_as_longlong(v);
+  return b >= 0 ? b : (b ^ 0x7fffffffffffffffLL);
+}
+__host__ __device__ __forceinline__ double pb_dec_f64(long long e) {
+  long long b = e >= 0 ? e : (e ^ 0x7fffffffffffffffLL);
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double(b);
+#else
+  double d; memcpy(&d, &b, 8); return d;
+#endif
+}
+
+// dictId of `doc` from a big-endian MSB-first bitstream in global memory
+// (FixedBitSVForwardIndexReaderV2.readDictIds, SEGL/segment/index/readers/forward/FixedBitSVForwardIndexReaderV2.java:65-99;
+//  bit layout SEGL/io/util/PinotDataBitSet.java:80-102).  The buffer is 4-byte aligned and padded by >= 8 bytes.
+__device__ __forceinline__ uint32_t pb_unpack_at(const uint8_t* __restrict__ fwd, uint32_t doc, int bits) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(fwd);
+  unsigned long long bit = (unsigned long long)doc * (unsigned)bits;
+  unsigned long long wi = bit >> 5;
+  uint32_t s = (uint32_t)bit & 31u;
+  uint32_t hi = pb_bswap32(__ldg(w + wi));
+  uint32_t lo = pb_bswap32(__ldg(w + wi + 1));
+  return __funnelshift_l(lo, hi, s) >> (32 - bits);
+}
+
+// raw PASS_THROUGH forward index value (FixedByteChunkSVForwardIndexReader.java:53-61): big-endian
+__device__ __forceinline__ long long pb_raw_i64(const uint8_t* __restrict__ fwd, uint32_t doc, int width, int data_type) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(fwd);
+  if (width == 4) return (long long)(int32_t)pb_bswap32(__ldg(w + doc));
+  uint32_t hi = pb_bswap32(__ldg(w + 2ull * doc)), lo = pb_bswap32(__ldg(w + 2ull * doc + 1));
+  return (long long)(((unsigned long long)hi << 32) | lo);
+}
+__device__ __forceinline__ double pb_raw_f64(const uint8_t* __restrict__ fwd, uint32_t doc, int width, int data_type) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(fwd);
+  if (width == 4) {
+    uint32_t u = pb_bswap32(__ldg(w + doc));
+    return data_type == 2 ? (double)__uint_as_float(u) : (double)(int32_t)u;
+  }
+  uint32_t hi = pb_bswap32(__ldg(w + 2ull * doc)), lo = pb_bswap32(__ldg(w + 2ull * doc + 1));
+  unsigned long long u = ((unsigned long long)hi << 32) | lo;
+  return data_type == 3 ? __longlong_as_double((long long)u) : (double)(long long)u;
+}
+
+
+// ---- global-memory reductions (SASS REDG.*): the table pointers are loaded from descriptors, so the
+// compiler cannot prove the address space; state it explicitly instead of going through generic ATOM + isspacep.
+__device__ __forceinline__ void pb_red_add_f64(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void pb_red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void pb_red_add_u32(unsigned int* p, unsigned int v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void pb_red_min_s64(long long* p, long long v) { asm volatile("red.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void pb_red_max_s64(long long* p, long long v) { asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void pb_red_or_b32(uint32_t* p, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long pb_atom_cas_u64(unsigned long long* p, unsigned long long cmp, unsigned long long val) {
+  unsigned long long old;
+  asm volatile("atom.global.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(cmp), "l"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned long long pb_ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int pb_ld_volatile_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ---- mbarrier / TMA bulk copy (cp.async.bulk -> SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t pb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pb_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pb_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void pb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t pb_mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(pb_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void pb_mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!pb_mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void pb_tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   pb_smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(pb_smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// predicate evaluation on one 1024-doc chunk; every variant returns THIS LANE's 32-bit mask for docs
+// [chunk_doc0 + 32*lane, +32)   (PredicateEvaluator.applySV semantics, CTR/operator/filter/predicate/*)
+// ------------------------------------------------------------------------------------------------
+struct PredCtx {
+  const uint32_t* set;   // resolved bitset pointer (smem or global) for L_DICT_SET
+  uint32_t lo, span;
+  int is_set;
+  int exclusive;
+};
+
+template <bool SET>
+__device__ __forceinline__ bool pb_pred_dict(const PredCtx& pc, uint32_t v) {
+  if (!SET) return (v - pc.lo) < pc.span;
+  bool in = (pc.set[v >> 5] >> (v & 31)) & 1u;
+  return in != (bool)pc.exclusive;
+}
+
+// width-generic path: lane <-> doc, 32 steps, ballot; conflict-free smem reads
+template <bool SET>
+__device__ __forceinline__ uint32_t pb_eval_dict_generic(const uint32_t* __restrict__ p, int bits, const PredCtx& pc, int lane) {
+  uint32_t mine = 0;
+#pragma unroll 4
+  for (int k = 0; k < 32; k++) {
+    uint32_t idx = (uint32_t)(k * 32 + lane);
+    uint32_t bit = idx * (uint32_t)bits;
+    uint32_t wi = bit >> 5, s = bit & 31u;
+    uint32_t hi = pb_bswap32(p[wi]), lo = pb_bswap32(p[wi + 1]);
+    uint32_t v = __funnelshift_l(lo, hi, s) >> (32 - bits);
+    uint32_t b = __ballot_sync(0xffffffffu, pb_pred_dict<SET>(pc, v));
+    if (k == lane) mine = b;
+  }
+  return mine;
+}
+
+// width-specialised path: lane owns 32 consecutive docs == exactly W consecutive 32-bit words.
+// All shifts are compile-time constants (the GPU analogue of FixedBitIntReader's per-width read32 classes,
+// SEGL/io/reader/impl/FixedBitIntReader.java:121-146).
+template <int W, bool SET>
+__device__ __forceinline__ uint32_t pb_eval_dict_w(const uint32_t* __restrict__ p, const PredCtx& pc, int lane) {
+  uint32_t w[W + 1];
+  const uint32_t* q = p + lane * W;
+#pragma unroll
+  for (int k = 0; k < W; k++) w[k] = pb_bswap32(q[k]);
+  w[W] = 0;
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j++) {
+    constexpr uint32_t MASK = (W == 32) ? 0xffffffffu : ((1u << (W & 31)) - 1u);
+    const int bit = j * W;
+    const int k = bit >> 5, s = bit & 31;
+    uint32_t v;
+    if (s + W <= 32) v = (w[k] >> ((32 - s - W) & 31)) & MASK;
+    else v = __funnelshift_l(w[k + 1], w[k], s) >> ((32 - W) & 31);
+    if (pb_pred_dict<SET>(pc, v)) m |= (1u << j);
+  }
+  return m;
+}
+
+__device__ __forceinline__ bool pb_fast_width(int bits) { return bits < 32 && (bits & 7) != 0; }
+
+__device__ __noinline__ uint32_t pb_eval_dict_fast(const uint32_t* __restrict__ p, int bits, const PredCtx& pc, int lane) {
+  switch (bits) {
+#define PB_CASE(W) case W: return pc.is_set ? pb_eval_dict_w<W, true>(p, pc, lane) : pb_eval_dict_w<W, false>(p, pc, lane);
+    PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7)
+    PB_CASE(9) PB_CASE(10) PB_CASE(11) PB_CASE(12) PB_CASE(13) PB_CASE(14) PB_CASE(15)
+    PB_CASE(17) PB_CASE(18) PB_CASE(19) PB_CASE(20) PB_CASE(21) PB_CASE(22) PB_CASE(23)
+    PB_CASE(25) PB_CASE(26) PB_CASE(27) PB_CASE(28) PB_CASE(29) PB_CASE(30) PB_CASE(31)
+#undef PB_CASE
+    default: return 0;
+  }
+}
+
+// raw fixed-width column chunk in smem (big-endian values), lane <-> doc + ballot
+__device__ __forceinline__ uint32_t pb_eval_raw(const uint32_t* __restrict__ p, const DevLeaf& lf, int lane) {
+  uint32_t mine = 0;
+  for (int k = 0; k < 32; k++) {
+    uint32_t idx = (uint32_t)(k * 32 + lane);
+    bool ok;
+    if (lf.raw_width == 4) {
+      uint32_t u = pb_bswap32(p[idx]);
+      if (lf.data_type == 2) {   // FLOAT
+        double v = (double)__uint_as_float(u);
+        if (lf.kind == L_RAW_RANGE_F) ok = (lf.dlo_incl ? v >= lf.dlo : v > lf.dlo) && (lf.dhi_incl ? v <= lf.dhi : v < lf.dhi);
+        else { bool in = false; long long vb = __double_as_longlong(v); for (int i = 0; i < lf.n_raw_set; i++) in |= (lf.raw_set[i] == vb); ok = in != (bool)lf.exclusive; }
+      } else {                   // INT
+        long long v = (long long)(int32_t)u;
+        if (lf.kind == L_RAW_RANGE_I) ok = v >= lf.ilo && v <= lf.ihi;
+        else { bool in = false; for (int i = 0; i < lf.n_raw_set; i++) in |= (lf.raw_set[i] == v); ok = in != (bool)lf.exclusive; }
+      }
+    } else {
+      unsigned long long u = ((unsigned long long)pb_bswap32(p[2 * idx]) << 32) | pb_bswap32(p[2 * idx + 1]);
+      if (lf.data_type == 3) {   // DOUBLE
+        double v = __longlong_as_double((long long)u);
+        if (lf.kind == L_RAW_RANGE_F) ok = (lf.dlo_incl ? v >= lf.dlo : v > lf.dlo) && (lf.dhi_incl ? v <= lf.dhi : v < lf.dhi);
+        else { bool in = false; for (int i = 0; i < lf.n_raw_set; i++) in |= (lf.raw_set[i] == (long long)u); ok = in != (bool)lf.exclusive; }
+      } else {                   // LONG
+        long long v = (long long)u;
+        if (lf.kind == L_RAW_RANGE_I) ok = v >= lf.ilo && v <= lf.ihi;
+        else { bool in = false; for (int i = 0; i < lf.n_raw_set; i++) in |= (lf.raw_set[i] == v); ok = in != (bool)lf.exclusive; }
+      }
+    }
+    uint32_t b = __ballot_sync(0xffffffffu, ok);
+    if (k == lane) mine = b;
+  }
+  return mine;
+}
+
+// ------------------------------------------------------------------------------------------------
+// group table update for one matching doc
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t pb_hash64(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+
+// returns slot, or ~0ull when the key is new and numGroupsLimit is reached
+// (DictionaryBasedGroupKeyGenerator.java:1033-1035: INVALID_ID, rows silently dropped)
+__device__ __forceinline__ uint64_t pb_hash_slot(const DevTable& t, uint64_t key) {
+  if (key == PB_HASH_EMPTY) return t.capacity;          // reserved extra slot for the sentinel value itself
+  uint64_t mask = t.capacity - 1;
+  uint64_t s = pb_hash64(key) & mask;
+  while (true) {
+    unsigned long long cur = pb_ld_volatile_u64(&t.hkeys[s]);
+    if (cur == key) return s;
+    if (cur == PB_HASH_EMPTY) {
+      if (pb_ld_volatile_u32(t.num_groups) >= t.num_groups_limit) { pb_red_add_u32(t.limit_reached, 1u); return ~0ull; }
+      unsigned long long old = pb_atom_cas_u64(&t.hkeys[s], PB_HASH_EMPTY, (unsigned long long)key);
+      if (old == PB_HASH_EMPTY) { pb_red_add_u32(t.num_groups, 1u); return s; }
+      if (old == key) return s;
+    }
+    s = (s + 1) & mask;
+  }
+}
+
+// keyless accumulators live in shared memory, one private cell per thread (no atomics)
+struct KeylessAcc {
+  double* sum;        // [PB_MAX_AGGS][PB_NTHREADS]
+  long long* mm;      // [PB_MAX_AGGS][PB_NTHREADS]
+};
+
+__device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQuery& sq, const DevTable& t, uint32_t doc,
+                                              const KeylessAcc& ka, unsigned long long& keyless_rows) {
+  uint64_t slot = 0;
+  if (Q.table_mode == T_DENSE) {
+    for (int j = 0; j < Q.n_group_by; j++) {
+      const DevKeyCol& kc = sq.keys[j];
+      uint32_t id = pb_unpack_at(kc.fwd, doc, kc.bits);
+      if (kc.remap) id = (uint32_t)__ldg(kc.remap + id);
+      slot += (uint64_t)id * kc.mult;
+    }
+  } else if (Q.table_mode == T_HASH) {
+    uint64_t key = 0;
+    for (int j = 0; j < Q.n_group_by; j++) {
+      const DevKeyCol& kc = sq.keys[j];
+      if (kc.raw_width) {
+        uint64_t v;
+        if (kc.data_type == 2 || kc.data_type == 3) v = (uint64_t)__double_as_longlong(pb_raw_f64(kc.fwd, doc, kc.raw_width, kc.data_type));
+        else v = (uint64_t)pb_raw_i64(kc.fwd, doc, kc.raw_width, kc.data_type);
+        key |= (kc.raw_width == 4 && Q.n_group_by > 1 ? (v & 0xffffffffull) : v) << kc.shift;
+      } else {
+        uint32_t id = pb_unpack_at(kc.fwd, doc, kc.bits);
+        if (kc.remap) id = (uint32_t)__ldg(kc.remap + id);
+        key |= (uint64_t)id << kc.shift;
+      }
+    }
+    slot = pb_hash_slot(t, key);
+    if (slot == ~0ull) return;
+  }
+  if (Q.table_mode == T_KEYLESS) keyless_rows++;
+  else pb_red_add_u64(&t.rowcnt[slot], 1ull);
+
+  for (int a = 0; a < Q.n_aggs; a++) {
+    const int op = Q.agg_op[a];
+    if (op == 0) continue;                       // COUNT(*): the row counter
+    const DevAggCol& ac = sq.aggs[a];
+    if (op == 5) {                               // DISTINCTCOUNT (dictionary column)
+      uint32_t id = pb_unpack_at(ac.fwd, doc, ac.bits);
+      if (ac.remap) id = (uint32_t)__ldg(ac.remap + id);
+      pb_red_or_b32(&t.dc_bits[a][slot * t.dc_words[a] + (id >> 5)], 1u << (id & 31));
+      continue;
+    }
+    // BlockValSet.getDoubleValuesSV: dictionary decode or raw read, widened to double
+    double v = ac.raw_width ? pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type)
+                            : __ldg(ac.dict_f64 + pb_unpack_at(ac.fwd, doc, ac.bits));
+    if (Q.table_mode == T_KEYLESS) {
+      const int tid = threadIdx.x;
+      if (op == 1 || op == 4) ka.sum[a * PB_NTHREADS + tid] += v;
+      else if (v == v) {
+        long long e = pb_enc_f64(v);
+        long long c = ka.mm[a * PB_NTHREADS + tid];
+        if (op == 2 ? e < c : e > c) ka.mm[a * PB_NTHREADS + tid] = e;
+      }
+    } else {
+      if (op == 1 || op == 4) pb_red_add_f64(&t.sum[a][slot], v);            // REDG.E.ADD.F64
+      else if (v == v) {                                                      // NaN never replaces (strict compare)
+        long long e = pb_enc_f64(v);
+        if (op == 2) pb_red_min_s64(&t.mm[a][slot], e); else pb_red_max_s64(&t.mm[a][slot], e);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the scan kernel
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) ScanSmemHeader {
+  uint64_t full[PB_NSTAGE];
+  uint32_t wq[PB_NWARPS][PB_WQ_CAP];
+  uint32_t wq_n[PB_NWARPS];
+  unsigned long long red_u64[PB_NWARPS];
+  double red_f64[PB_NWARPS];
+  long long red_i64[PB_NWARPS];
+  uint32_t set_cache[PB_SET_SMEM_WORDS];
+  DevSegQuery seg;
+};
+
+__device__ __forceinline__ int pb_find_seg(const DevSegQuery* __restrict__ segs, int n_segs, int cur, uint64_t tile) {
+  while (cur + 1 < n_segs && tile >= segs[cur + 1].tile_begin) cur++;
+  return cur;
+}
+
+__global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery* __restrict__ Qp) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  ScanSmemHeader* H = reinterpret_cast<ScanSmemHeader*>(smem_raw);
+  const DevQuery& Q = *Qp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // after the header: keyless accumulators (n_aggs rows), then the stage buffers
+  uint8_t* dyn = smem_raw + ((sizeof(ScanSmemHeader) + 127) & ~(size_t)127);
+  KeylessAcc ka;
+  ka.sum = nullptr; ka.mm = nullptr;
+  const long long ENC_POS_INF = 0x7ff0000000000000LL;                       // enc(+inf)
+  const long long ENC_NEG_INF = (long long)0xfff0000000000000ULL ^ 0x7fffffffffffffffLL;   // enc(-inf)
+  if (Q.table_mode == T_KEYLESS) {
+    ka.sum = reinterpret_cast<double*>(dyn);
+    ka.mm = reinterpret_cast<long long*>(dyn + sizeof(double) * Q.n_aggs * PB_NTHREADS);
+    dyn += ((2 * sizeof(double) * Q.n_aggs * PB_NTHREADS) + 127) & ~(size_t)127;
+    for (int a = 0; a < Q.n_aggs; a++) {
+      ka.sum[a * PB_NTHREADS + tid] = 0.0;
+      ka.mm[a * PB_NTHREADS + tid] = Q.agg_op[a] == 2 ? ENC_POS_INF : ENC_NEG_INF;
+    }
+  }
+  uint8_t* stages = dyn;
+  const int tile_docs = Q.tile_chunks * PB_CHUNK_DOCS;
+  const bool staged = Q.stage_bytes > 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < PB_NSTAGE; s++) pb_mbar_init(&H->full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < PB_NWARPS) H->wq_n[tid] = 0;
+  __syncthreads();
+
+  // producer: issue the loads of this CTA's it-th tile into stage it % NSTAGE
+  auto issue = [&](uint64_t it, int& pseg) {
+    uint64_t tile = (uint64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= Q.n_tiles) return;
+    pseg = pb_find_seg(Q.segs, Q.n_segs, pseg, tile);
+    const DevSegQuery* sg = &Q.segs[pseg];
+    const int st = (int)(it % PB_NSTAGE);
+    uint64_t doc0 = (tile - sg->tile_begin) * (uint64_t)tile_docs;
+    uint32_t total = 0;
+    uint32_t nbytes[PB_MAX_SCAN_SLOTS];
+    const int n_scan = sg->n_scan;
+    for (int c = 0; c < n_scan; c++) {
+      uint64_t off = doc0 * (uint64_t)sg->scan[c].bits_per_doc / 8;             // tile starts are 128-byte multiples
+      uint64_t want = (uint64_t)tile_docs * (uint64_t)sg->scan[c].bits_per_doc / 8 + 16;   // +16: the word after the tile
+      uint64_t avail = sg->scan[c].bytes_total - off;
+      uint64_t n = want < avail ? want : avail;
+      n &= ~(uint64_t)15;
+      nbytes[c] = (uint32_t)n;
+      total += (uint32_t)n;
+    }
+    pb_mbar_expect_tx(&H->full[st], total);
+    for (int c = 0; c < n_scan; c++) {
+      uint64_t off = doc0 * (uint64_t)sg->scan[c].bits_per_doc / 8;
+      pb_tma_load_1d(stages + (size_t)st * Q.stage_bytes + Q.slot_off[c], sg->scan[c].base + off, nbytes[c], &H->full[st]);
+    }
+  };
+
+  int pseg = 0;          // producer's segment cursor (thread 0)
+  int cseg = -1;         // consumer's current segment (smem copy valid when >= 0)
+  int fseg = 0;
+  unsigned long long keyless_rows = 0, matched = 0;
+  if (staged && Q.use_tma && tid == 0) {
+    for (int s = 0; s < PB_NSTAGE - 1; s++) issue((uint64_t)s, pseg);
+  }
+
+  auto drain32 = [&](uint32_t n_take) {
+    // take the first n_take (<= 32) queued docs of this warp, aggregate them, compact the queue
+    uint32_t qn = H->wq_n[warp];
+    uint32_t doc = lane < n_take ? H->wq[warp][lane] : 0u;
+    uint32_t rest = (lane + n_take < qn) ? H->wq[warp][lane + n_take] : 0u;   // qn < 64 => one pass moves the tail
+    __syncwarp();
+    if (lane < n_take) pb_accumulate(Q, H->seg, Q.tables[H->seg.table], doc, ka, keyless_rows);
+    if (lane + n_take < qn) H->wq[warp][lane] = rest;
+    if (lane == 0) H->wq_n[warp] = qn - n_take;
+    __syncwarp();
+  };
+
+  // publish per-table counters of the segment that is being left (CTA-uniform call)
+  auto flush_table = [&]() {
+    const DevTable& t = Q.tables[H->seg.table];
+    unsigned long long m = matched;
+    for (int o = 16; o > 0; o >>= 1) m += __shfl_down_sync(0xffffffffu, m, o);
+    if (lane == 0 && m) pb_red_add_u64(t.docs_matched, m);
+    matched = 0;
+    if (Q.table_mode != T_KEYLESS) return;
+    unsigned long long r = keyless_rows;
+    keyless_rows = 0;
+    for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+    if (lane == 0) H->red_u64[warp] = r;
+    __syncthreads();
+    if (tid == 0) { unsigned long long tot = 0; for (int w = 0; w < PB_NWARPS; w++) tot += H->red_u64[w]; if (tot) pb_red_add_u64(&t.rowcnt[0], tot); }
+    for (int a = 0; a < Q.n_aggs; a++) {
+      const int op = Q.agg_op[a];
+      if (op == 1 || op == 4) {
+        double v = ka.sum[a * PB_NTHREADS + tid];
+        ka.sum[a * PB_NTHREADS + tid] = 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) H->red_f64[warp] = v;
+        __syncthreads();
+        if (tid == 0) { double tot = 0; for (int w = 0; w < PB_NWARPS; w++) tot += H->red_f64[w]; pb_red_add_f64(&t.sum[a][0], tot); }
+        __syncthreads();
+      } else if (op == 2 || op == 3) {
+        long long v = ka.mm[a * PB_NTHREADS + tid];
+        ka.mm[a * PB_NTHREADS + tid] = op == 2 ? ENC_POS_INF : ENC_NEG_INF;
+        for (int o = 16; o > 0; o >>= 1) { long long u = __shfl_down_sync(0xffffffffu, v, o); v = (op == 2) ? (u < v ? u : v) : (u > v ? u : v); }
+        if (lane == 0) H->red_i64[warp] = v;
+        __syncthreads();
+        if (tid == 0) {
+          long long tot = H->red_i64[0];
+          for (int w = 1; w < PB_NWARPS; w++) { long long u = H->red_i64[w]; tot = (op == 2) ? (u < tot ? u : tot) : (u > tot ? u : tot); }
+          if (op == 2) pb_red_min_s64(&t.mm[a][0], tot); else pb_red_max_s64(&t.mm[a][0], tot);
+        }
+        __syncthreads();
+      }
+    }
+  };
+
+  for (uint64_t it = 0;; it++) {
+    const uint64_t tile = (uint64_t)blockIdx.x + it * gridDim.x;
+    if (tile >= Q.n_tiles) break;
+    if (staged && Q.use_tma && tid == 0) issue(it + PB_NSTAGE - 1, pseg);
+
+    fseg = pb_find_seg(Q.segs, Q.n_segs, fseg, tile);
+    if (fseg != cseg) {
+      // segment switch: flush the per-warp queues against the old descriptor, then load the new one
+      if (cseg >= 0) {
+        uint32_t qn = H->wq_n[warp];
+        if (qn) drain32(qn);
+        __syncthreads();
+        flush_table();
+      }
+      __syncthreads();
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&Q.segs[fseg]);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&H->seg);
+      for (int i = tid; i < (int)(sizeof(DevSegQuery) / 4); i += PB_NTHREADS) dst[i] = src[i];
+      __syncthreads();
+      // cache small dictId-set bitsets in shared memory
+      for (int l = 0; l < PB_MAX_LEAVES; l++) {
+        const DevLeaf& lf = H->seg.leaves[l];
+        if (lf.kind == L_DICT_SET && lf.set_smem_off >= 0)
+          for (int i = tid; i < lf.set_words; i += PB_NTHREADS) H->set_cache[lf.set_smem_off + i] = __ldg(lf.set_bits + i);
+      }
+      cseg = fseg;
+      __syncthreads();
+    }
+    const DevSegQuery& sq = H->seg;
+    const int st = (int)(it % PB_NSTAGE);
+    uint8_t* stage = stages + (size_t)st * Q.stage_bytes;
+    const uint64_t tile_doc0 = (tile - sq.tile_begin) * (uint64_t)tile_docs;
+
+    if (staged) {
+      if (Q.use_tma) {
+        pb_mbar_wait(&H->full[st], (uint32_t)((it / PB_NSTAGE) & 1));
+      } else {
+        // fallback staging: cooperative 128-bit loads
+        for (int c = 0; c < sq.n_scan; c++) {
+          uint64_t off = tile_doc0 * (uint64_t)sq.scan[c].bits_per_doc / 8;
+          uint64_t want = (uint64_t)tile_docs * (uint64_t)sq.scan[c].bits_per_doc / 8 + 16;
+          uint64_t avail = sq.scan[c].bytes_total - off;
+          uint64_t n = (want < avail ? want : avail) & ~(uint64_t)15;
+          const uint4* s4 = reinterpret_cast<const uint4*>(sq.scan[c].base + off);
+          uint4* d4 = reinterpret_cast<uint4*>(stage + Q.slot_off[c]);
+          for (uint32_t i = tid; i < (uint32_t)(n / 16); i += PB_NTHREADS) d4[i] = __ldg(s4 + i);
+        }
+        __syncthreads();
+      }
+    }
+
+    // ---- filter: one chunk per warp ----
+    for (int c = warp; c < Q.tile_chunks; c += PB_NWARPS) {
+      const uint64_t chunk_doc0 = tile_doc0 + (uint64_t)c * PB_CHUNK_DOCS;
+      if (chunk_doc0 >= (uint64_t)sq.num_docs) break;
+      // valid-doc mask of this lane
+      long long remaining = (long long)sq.num_docs - (long long)(chunk_doc0 + 32ull * lane);
+      uint32_t valid = remaining >= 32 ? 0xffffffffu : (remaining <= 0 ? 0u : ((1u << remaining) - 1u));
+
+      uint32_t stack[PB_MAX_LEAVES];
+      int sp = 0;
+      for (int n = 0; n < sq.n_nodes; n++) {
+        const int kind = sq.node_kind[n], arg = sq.node_arg[n];
+        if (kind == N_LEAF) {
+          const DevLeaf& lf = sq.leaves[arg];
+          uint32_t m;
+          switch (lf.kind) {
+            case L_TRUE: m = 0xffffffffu; break;
+            case L_FALSE: m = 0u; break;
+            case L_DICT_RANGE:
+            case L_DICT_SET: {
+              const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot] + (size_t)c * (PB_CHUNK_DOCS / 8) * lf.bits);
+              PredCtx pc;
+              pc.is_set = lf.kind == L_DICT_SET;
+              pc.exclusive = lf.exclusive;
+              pc.lo = lf.lo; pc.span = lf.span;
+              pc.set = lf.set_smem_off >= 0 ? &H->set_cache[lf.set_smem_off] : lf.set_bits;
+              if (!Q.generic && pb_fast_width(lf.bits)) m = pb_eval_dict_fast(p, lf.bits, pc, lane);
+              else m = pc.is_set ? pb_eval_dict_generic<true>(p, lf.bits, pc, lane) : pb_eval_dict_generic<false>(p, lf.bits, pc, lane);
+              break;
+            }
+            case L_RAW_RANGE_I:
+            case L_RAW_RANGE_F:
+            case L_RAW_SET: {
+              const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot] + (size_t)c * PB_CHUNK_DOCS * lf.raw_width);
+              m = pb_eval_raw(p, lf, lane);
+              break;
+            }
+            default: {   // L_BITMAP (padded to whole chunks)
+              uint64_t wi = (chunk_doc0 >> 5) + lane;
+              m = __ldg(lf.bitmap + wi);
+              if (lf.exclusive) m = ~m;
+              break;
+            }
+          }
+          stack[sp++] = m;
+        } else if (kind == N_NOT) {
+          stack[sp - 1] = ~stack[sp - 1];
+        } else {
+          uint32_t r = stack[sp - arg];
+          for (int i = 1; i < arg; i++) r = (kind == N_AND) ? (r & stack[sp - arg + i]) : (r | stack[sp - arg + i]);
+          sp -= arg;
+          stack[sp++] = r;
+        }
+      }
+      uint32_t mask = (sp > 0 ? stack[0] : 0xffffffffu) & valid;
+      matched += __popc(mask);
+
+      // ---- matches -> warp queue -> aggregate 32 at a time ----
+      // round r takes the r-th set bit of every lane, so lanes stay full and docs stay clustered
+      while (__any_sync(0xffffffffu, mask != 0)) {
+        bool has = mask != 0;
+        uint32_t b = __ballot_sync(0xffffffffu, has);
+        uint32_t qn = H->wq_n[warp];
+        if (has) {
+          int bit = __ffs(mask) - 1;
+          mask &= mask - 1;
+          H->wq[warp][qn + __popc(b & ((1u << lane) - 1u))] = (uint32_t)(chunk_doc0 + 32ull * lane + bit);
+        }
+        __syncwarp();
+        if (lane == 0) H->wq_n[warp] = qn + __popc(b);
+        __syncwarp();
+        if (qn + __popc(b) >= 32) drain32(32);
+      }
+    }
+    __syncthreads();   // everyone is done with this stage before it is refilled
+  }
+
+  // ---- tail: flush queues and counters of the last segment ----
+  if (cseg >= 0) {
+    uint32_t qn = H->wq_n[warp];
+    if (qn) drain32(qn);
+    __syncthreads();
+    flush_table();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bitmap-producing kernels (inverted index / sorted index / caller bitmaps -> flat doc bitmaps)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pb_ld_le16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+__device__ __forceinline__ uint32_t pb_ld_le32(const uint8_t* p) { return pb_ld_le16(p) | (pb_ld_le16(p + 2) << 16); }
+__device__ __forceinline__ uint32_t pb_ld_be32(const uint8_t* p) {
+  return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
+}
+
+// OR the RoaringBitmaps of ids[] (portable format, inside a .bitmap.inv buffer) into a flat bitmap.
+// grid = (container stride, n_ids).  InvertedIndexFilterOperator.java:60-96 / BitmapInvertedIndexReader.java:45-62.
+__global__ void pb_roaring_expand_kernel(const uint8_t* __restrict__ inv, int32_t card, const int32_t* __restrict__ ids,
+                                         uint32_t* __restrict__ out, uint32_t num_docs) {
+  const int32_t id = ids[blockIdx.y];
+  const uint32_t first = pb_ld_be32(inv);
+  const uint32_t s = pb_ld_be32(inv + 4ull * id), e = pb_ld_be32(inv + 4ull * id + 4);
+  const uint8_t* blob = inv + 4ull * ((uint64_t)card + 1) + (s - first);
+  if (e - s < 8) return;
+  const uint32_t cookie = pb_ld_le32(blob);
+  uint32_t n, p;
+  const uint8_t* run_bitmap = nullptr;
+  bool has_offsets;
+  if ((cookie & 0xffffu) == 12347u) { n = (cookie >> 16) + 1; run_bitmap = blob + 4; p = 4 + (n + 7) / 8; has_offsets = n >= 4; }
+  else if (cookie == 12346u) { n = pb_ld_le32(blob + 4); p = 8; has_offsets = true; }
+  else return;
+  const uint8_t* hdr = blob + p;
+  const uint8_t* offs = hdr + 4ull * n;
+  const uint32_t data0 = p + 4 * n + (has_offsets ? 4 * n : 0);
+  for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+    uint32_t key = pb_ld_le16(hdr + 4 * c), ccard = pb_ld_le16(hdr + 4 * c + 2) + 1;
+    bool is_run = run_bitmap && ((run_bitmap[c >> 3] >> (c & 7)) & 1);
+    uint32_t off;
+    if (has_offsets) off = pb_ld_le32(offs + 4 * c);
+    else {   // < 4 containers, no offset header: walk the sizes
+      off = data0;
+      for (uint32_t k = 0; k < c; k++) {
+        uint32_t kc = pb_ld_le16(hdr + 4 * k + 2) + 1;
+        bool kr = run_bitmap && ((run_bitmap[k >> 3] >> (k & 7)) & 1);
+        off += kr ? 2 + 4 * pb_ld_le16(blob + off) : (kc <= 4096 ? 2 * kc : 8192);
+      }
+    }
+    const uint8_t* d = blob + off;
+    const uint32_t base = key << 16;
+    if (is_run) {
+      uint32_t nr = pb_ld_le16(d);
+      for (uint32_t r = 0; r < nr; r++) {
+        uint32_t st = pb_ld_le16(d + 2 + 4 * r), len = pb_ld_le16(d + 4 + 4 * r);
+        for (uint32_t k = threadIdx.x; k <= len; k += blockDim.x) {
+          uint32_t doc = base | (st + k);
+          if (doc < num_docs) atomicOr(&out[doc >> 5], 1u << (doc & 31));
+        }
+      }
+    } else if (ccard <= 4096) {
+      for (uint32_t k = threadIdx.x; k < ccard; k += blockDim.x) {
+        uint32_t doc = base | pb_ld_le16(d + 2 * k);
+        if (doc < num_docs) atomicOr(&out[doc >> 5], 1u << (doc & 31));
+      }
+    } else {
+      for (uint32_t k = threadIdx.x; k < 2048; k += blockDim.x) {
+        uint32_t w = pb_ld_le32(d + 4 * k);
+        uint32_t wi = (base >> 5) + k;
+        if (w && (uint64_t)wi * 32 < num_docs) atomicOr(&out[wi], w);
+      }
+    }
+  }
+}
+
+// sorted index doc ranges -> flat bitmap (SortedIndexBasedFilterOperator.java:61-131; AndDocIdSet.java:147-151)
+__global__ void pb_ranges_fill_kernel(const int32_t* __restrict__ pairs, int32_t n_pairs, uint32_t* __restrict__ out) {
+  for (int r = blockIdx.x; r < n_pairs; r += gridDim.x) {
+    uint32_t lo = (uint32_t)pairs[2 * r], hi = (uint32_t)pairs[2 * r + 1];   // inclusive
+    uint32_t w0 = lo >> 5, w1 = hi >> 5;
+    for (uint32_t w = w0 + threadIdx.x; w <= w1; w += blockDim.x) {
+      uint32_t m = 0xffffffffu;
+      if (w == w0) m &= 0xffffffffu << (lo & 31);
+      if (w == w1) m &= 0xffffffffu >> (31 - (hi & 31));
+      atomicOr(&out[w], m);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// table init / finalize
+// ------------------------------------------------------------------------------------------------
+__global__ void pb_fill_i64_kernel(long long* p, uint64_t n, long long v) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// count non-empty slots
+__global__ void pb_count_groups_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n, unsigned long long* out) {
+  unsigned long long c = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += rowcnt[i] != 0;
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// compact non-empty slots: out_slot[k] = slot index (keys decoded on the host), out_cnt[k] = rows
+__global__ void pb_compact_slots_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n, unsigned long long* counter,
+                                        unsigned long long* __restrict__ out_slot, unsigned long long* __restrict__ out_cnt) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    unsigned long long c = rowcnt[i];
+    if (c) { unsigned long long k = atomicAdd(counter, 1ull); out_slot[k] = i; out_cnt[k] = c; }
+  }
+}
+
+// gather per-aggregation values of the compacted slots
+__global__ void pb_gather_f64_kernel(const double* __restrict__ src, const unsigned long long* __restrict__ slots, uint64_t n, double* __restrict__ dst) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[slots[i]];
+}
+__global__ void pb_gather_mm_kernel(const long long* __restrict__ src, const unsigned long long* __restrict__ slots, uint64_t n, double* __restrict__ dst) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = pb_dec_f64(src[slots[i]]);
+}
+__global__ void pb_gather_u64_kernel(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ slots, uint64_t n, unsigned long long* __restrict__ dst) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[slots[i]];
+}
+// DISTINCTCOUNT: one warp per compacted group: popcount of its bitset
+__global__ void pb_distinct_count_kernel(const uint32_t* __restrict__ bits, uint64_t words, const unsigned long long* __restrict__ slots,
+                                         uint64_t n, unsigned long long* __restrict__ out) {
+  uint64_t g = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (g >= n) return;
+  const uint32_t* b = bits + slots[g] * words;
+  unsigned long long c = 0;
+  for (uint64_t w = lane; w < words; w += 32) c += __popc(b[w]);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+  if (lane == 0) out[g] = c;
+}
+// DISTINCTCOUNT value sets: one warp per group writes the ascending dictIds at offsets[g]
+__global__ void pb_distinct_ids_kernel(const uint32_t* __restrict__ bits, uint64_t words, const unsigned long long* __restrict__ slots,
+                                       uint64_t n, const unsigned long long* __restrict__ offsets, int32_t* __restrict__ out) {
+  uint64_t g = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (g >= n) return;
+  const uint32_t* b = bits + slots[g] * words;
+  unsigned long long pos = offsets[g];
+  for (uint64_t w0 = 0; w0 < words; w0 += 32) {
+    uint32_t x = (w0 + lane < words) ? b[w0 + lane] : 0u;
+    uint32_t c = __popc(x);
+    uint32_t incl = c;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    unsigned long long my = pos + incl - c;
+    while (x) { int bpos = __ffs(x) - 1; x &= x - 1; out[my++] = (int32_t)((w0 + lane) * 32 + bpos); }
+    pos += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// sorted forward index (docId range pairs) -> big-endian bit-packed dictId stream, so a sorted column can
+// be read like any other dictionary column (SortedIndexReaderImpl doubles as the forward index:
+// SEGL/segment/index/readers/sorted/SortedIndexReaderImpl.java:37-116).  One thread per output word.
+__global__ void pb_sorted_to_packed_kernel(const int32_t* __restrict__ pairs_le, int32_t card, uint32_t num_docs, int bits,
+                                           uint32_t* __restrict__ out_words, uint64_t n_words) {
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t bit0 = w * 32;
+    uint64_t first = bit0 / bits;                       // first value overlapping this word
+    uint32_t acc = 0;
+    for (uint64_t v = first; v * bits < bit0 + 32 && v < num_docs; v++) {
+      // dictId of doc v: binary search on end docIds
+      int lo = 0, hi = card - 1;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if ((uint32_t)pairs_le[2 * mid + 1] < (uint32_t)v) lo = mid + 1; else hi = mid; }
+      uint64_t id = (uint64_t)lo;
+      long long sh = (long long)(bit0 + 32) - (long long)(v * bits + bits);   // left shift to place value's LSB
+      if (sh >= 0) acc |= (uint32_t)(id << sh); else acc |= (uint32_t)(id >> (-sh));
+    }
+    out_words[w] = pb_bswap32(acc);
+  }
+}

@@ -1,0 +1,1248 @@
+// pb_engine.cu — host runtime behind the C ABI in include/pinot_b200.h.
+//
+// Staging (Pinot index buffers -> HBM, once), per-query lowering of the caller's filter tree into the
+// device descriptors of pb_device.cuh, table allocation, the kernel sequence, and result hand-back into
+// pinned host memory.  No CPU implementation of the query path lives here: if the device cannot run a
+// query the call fails with PB_ERR_UNSUPPORTED and the plan maker declines to the stock CPU plan.
+#include "../../include/pinot_b200.h"
+#include "pb_device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024];
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+extern "C" const char* pb_last_error(void) { return g_err; }
+
+#define CU(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) return fail(e__ == cudaErrorMemoryAllocation ? PB_ERR_OOM : PB_ERR_CUDA, \
+                                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct PinnedBlock { void* p; size_t cap; };
+struct Context {
+  std::mutex mu;
+  bool inited = false;
+  std::vector<int> devices;
+  int num_sms = 148;
+  std::vector<PinnedBlock> pinned_free;
+  bool smem_attr_set = false;
+};
+static Context g_ctx;
+
+static int ensure_init() {
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (g_ctx.inited) return PB_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(PB_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  g_ctx.devices.assign(1, dev);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, dev));
+  g_ctx.num_sms = prop.multiProcessorCount;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  g_ctx.inited = true;
+  return PB_OK;
+}
+
+extern "C" int pb_init(const int* device_ids, int n_devices, size_t /*hbm_cache_bytes*/) {
+  if (n_devices > 0 && device_ids) {
+    cudaError_t e = cudaSetDevice(device_ids[0]);
+    if (e != cudaSuccess) return fail(PB_ERR_CUDA, "cudaSetDevice(%d): %s", device_ids[0], cudaGetErrorString(e));
+  }
+  return ensure_init();
+}
+extern "C" int pb_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  for (auto& b : g_ctx.pinned_free) cudaFreeHost(b.p);
+  g_ctx.pinned_free.clear();
+  return PB_OK;
+}
+extern "C" int pb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+static void* pinned_alloc(size_t bytes) {
+  size_t cap = 256;
+  while (cap < bytes) cap <<= 1;
+  {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    for (size_t i = 0; i < g_ctx.pinned_free.size(); i++)
+      if (g_ctx.pinned_free[i].cap == cap) {
+        void* p = g_ctx.pinned_free[i].p;
+        g_ctx.pinned_free.erase(g_ctx.pinned_free.begin() + i);
+        return p;
+      }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+static void pinned_free(void* p, size_t bytes) {
+  if (!p) return;
+  size_t cap = 256;
+  while (cap < bytes) cap <<= 1;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (g_ctx.pinned_free.size() < 256) g_ctx.pinned_free.push_back({p, cap});
+  else cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// segments
+// ------------------------------------------------------------------------------------------------
+static inline uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+static inline uint64_t be64(const uint8_t* p) { return ((uint64_t)be32(p) << 32) | be32(p + 4); }
+
+struct Column {
+  std::string name;
+  int type = 0, has_dict = 0, is_sorted = 0, card = 0, bits = 0, entry_bytes = 0;
+  // caller's buffers (valid until staged; Pinot keeps the mmap alive while the segment is acquired)
+  const uint8_t* h_fwd = nullptr; uint64_t h_fwd_len = 0;
+  const uint8_t* h_inv = nullptr; uint64_t h_inv_len = 0;
+  std::vector<uint8_t> h_dict;          // host copy of the dictionary (big-endian, as stored)
+  uint64_t raw_data_start = 0;
+  int raw_width = 0;
+  // device
+  uint8_t* d_fwd = nullptr; uint64_t d_fwd_bytes = 0;     // bit-packed stream / raw values (16-byte padded)
+  int32_t* d_sorted_pairs = nullptr;                       // sorted column: LE (start,end) pairs
+  std::vector<int32_t> h_sorted_pairs;
+  double* d_dict_f64 = nullptr;
+  uint8_t* d_inv = nullptr;
+  bool fwd_staged = false, dict_staged = false, inv_staged = false;
+};
+
+struct pb_segment_s {
+  std::string name;
+  int num_docs = 0;
+  int device = 0;
+  std::vector<Column> cols;
+  std::mutex mu;
+  int64_t device_bytes = 0;
+};
+
+static int find_col(const pb_segment_s* s, const char* name) {
+  for (size_t i = 0; i < s->cols.size(); i++) if (s->cols[i].name == name) return (int)i;
+  return -1;
+}
+
+extern "C" int pb_segment_stage(const pb_segment_desc* d, int /*device_index*/, pb_segment_handle* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!d || !out || d->num_columns < 0 || d->num_docs < 0) return fail(PB_ERR_INVALID, "bad segment descriptor");
+  std::unique_ptr<pb_segment_s> s(new pb_segment_s());
+  s->name = d->segment_name ? d->segment_name : "";
+  s->num_docs = d->num_docs;
+  s->cols.resize(d->num_columns);
+  for (int i = 0; i < d->num_columns; i++) {
+    const pb_column_desc& cd = d->columns[i];
+    Column& c = s->cols[i];
+    if (!cd.name || !cd.forward_index) return fail(PB_ERR_INVALID, "column %d: name/forward index missing", i);
+    c.name = cd.name;
+    c.type = cd.stored_type; c.has_dict = cd.has_dictionary; c.is_sorted = cd.is_sorted && cd.has_dictionary;
+    c.card = cd.cardinality; c.bits = cd.bits_per_element; c.entry_bytes = cd.dict_entry_bytes;
+    c.h_fwd = (const uint8_t*)cd.forward_index; c.h_fwd_len = cd.forward_index_len;
+    c.h_inv = (const uint8_t*)cd.inverted_index; c.h_inv_len = cd.inverted_index_len;
+    if (c.type < PB_INT || c.type > PB_STRING) return fail(PB_ERR_UNSUPPORTED, "column %s: stored type %d", cd.name, c.type);
+    if (c.has_dict) {
+      if (!cd.dictionary || c.card <= 0 || c.bits < 1 || c.bits > 32) return fail(PB_ERR_INVALID, "column %s: bad dictionary metadata", cd.name);
+      uint64_t need = (uint64_t)c.card * (uint64_t)c.entry_bytes;
+      if (cd.dictionary_len < need) return fail(PB_ERR_INVALID, "column %s: dictionary too short", cd.name);
+      c.h_dict.assign((const uint8_t*)cd.dictionary, (const uint8_t*)cd.dictionary + need);
+      if (c.is_sorted) {
+        if (c.h_fwd_len < 8ull * c.card) return fail(PB_ERR_INVALID, "column %s: sorted index too short", cd.name);
+        c.h_sorted_pairs.resize(2 * (size_t)c.card);
+        for (int k = 0; k < 2 * c.card; k++) c.h_sorted_pairs[k] = (int32_t)be32(c.h_fwd + 4ull * k);
+      } else if (c.h_fwd_len < ((uint64_t)s->num_docs * c.bits + 7) / 8) return fail(PB_ERR_INVALID, "column %s: forward index too short", cd.name);
+    } else {
+      // BaseChunkForwardIndexReader header (SEGL/segment/index/readers/forward/BaseChunkForwardIndexReader.java:61-104)
+      if (c.type == PB_STRING) return fail(PB_ERR_UNSUPPORTED, "column %s: raw STRING forward index", cd.name);
+      if (c.h_fwd_len < 28) return fail(PB_ERR_INVALID, "column %s: raw forward index header", cd.name);
+      int version = (int)be32(c.h_fwd), num_chunks = (int)be32(c.h_fwd + 4);
+      if (version < 2) return fail(PB_ERR_UNSUPPORTED, "column %s: raw index v1 (SNAPPY)", cd.name);
+      int compression = (int)be32(c.h_fwd + 20);
+      if (compression != 0) return fail(PB_ERR_UNSUPPORTED, "column %s: chunk compression %d (only PASS_THROUGH)", cd.name, compression);
+      int data_header_start = (int)be32(c.h_fwd + 24);
+      c.raw_data_start = (uint64_t)data_header_start + (uint64_t)num_chunks * (version <= 2 ? 4 : 8);
+      c.raw_width = (c.type == PB_INT || c.type == PB_FLOAT) ? 4 : 8;
+      if (c.h_fwd_len < c.raw_data_start + (uint64_t)s->num_docs * c.raw_width) return fail(PB_ERR_INVALID, "column %s: raw forward index too short", cd.name);
+    }
+  }
+  *out = s.release();
+  return PB_OK;
+}
+
+// stage what a query needs of one column (under the segment lock)
+static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dict, bool need_inv, cudaStream_t st) {
+  if (need_fwd && !c.fwd_staged) {
+    if (c.has_dict && c.is_sorted) {
+      // pairs -> device, then materialise the bit-packed stream on the device
+      CU(cudaMalloc((void**)&c.d_sorted_pairs, sizeof(int32_t) * 2 * (size_t)c.card));
+      CU(cudaMemcpyAsync(c.d_sorted_pairs, c.h_sorted_pairs.data(), sizeof(int32_t) * 2 * (size_t)c.card, cudaMemcpyHostToDevice, st));
+      uint64_t bytes = ((uint64_t)s->num_docs * c.bits + 7) / 8;
+      uint64_t padded = ((bytes + 15) & ~15ull) + 32;
+      CU(cudaMalloc((void**)&c.d_fwd, padded));
+      CU(cudaMemsetAsync(c.d_fwd, 0, padded, st));
+      uint64_t n_words = (bytes + 3) / 4;
+      int grid = (int)std::min<uint64_t>((n_words + 255) / 256, 4096);
+      if (grid < 1) grid = 1;
+      pb_sorted_to_packed_kernel<<<grid, 256, 0, st>>>(c.d_sorted_pairs, c.card, (uint32_t)s->num_docs, c.bits, (uint32_t*)c.d_fwd, n_words);
+      CU(cudaGetLastError());
+      c.d_fwd_bytes = padded;
+      s->device_bytes += (int64_t)padded;
+    } else {
+      const uint8_t* src = c.has_dict ? c.h_fwd : c.h_fwd + c.raw_data_start;
+      uint64_t bytes = c.has_dict ? ((uint64_t)s->num_docs * c.bits + 7) / 8 : (uint64_t)s->num_docs * c.raw_width;
+      uint64_t padded = ((bytes + 15) & ~15ull) + 32;
+      CU(cudaMalloc((void**)&c.d_fwd, padded));
+      CU(cudaMemsetAsync(c.d_fwd + (bytes & ~15ull), 0, padded - (bytes & ~15ull), st));
+      CU(cudaMemcpyAsync(c.d_fwd, src, bytes, cudaMemcpyHostToDevice, st));
+      c.d_fwd_bytes = padded;
+      s->device_bytes += (int64_t)padded;
+    }
+    c.fwd_staged = true;
+  }
+  if (need_dict && !c.dict_staged && c.has_dict && c.type != PB_STRING) {
+    // BaseImmutableDictionary value reads, widened to double (Dictionary.getDoubleValue)
+    std::vector<double> v((size_t)c.card);
+    for (int i = 0; i < c.card; i++) {
+      const uint8_t* p = c.h_dict.data() + (size_t)i * c.entry_bytes;
+      switch (c.type) {
+        case PB_INT: v[i] = (double)(int32_t)be32(p); break;
+        case PB_LONG: v[i] = (double)(int64_t)be64(p); break;
+        case PB_FLOAT: { uint32_t u = be32(p); float f; memcpy(&f, &u, 4); v[i] = (double)f; break; }
+        default: { uint64_t u = be64(p); double dd; memcpy(&dd, &u, 8); v[i] = dd; break; }
+      }
+    }
+    CU(cudaMalloc((void**)&c.d_dict_f64, sizeof(double) * (size_t)c.card));
+    CU(cudaMemcpyAsync(c.d_dict_f64, v.data(), sizeof(double) * (size_t)c.card, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));   // v is a stack-owned staging buffer
+    s->device_bytes += (int64_t)sizeof(double) * c.card;
+    c.dict_staged = true;
+  }
+  if (need_inv && !c.inv_staged) {
+    if (!c.h_inv) return fail(PB_ERR_INVALID, "column %s has no inverted index", c.name.c_str());
+    CU(cudaMalloc((void**)&c.d_inv, c.h_inv_len + 16));
+    CU(cudaMemcpyAsync(c.d_inv, c.h_inv, c.h_inv_len, cudaMemcpyHostToDevice, st));
+    s->device_bytes += (int64_t)c.h_inv_len;
+    c.inv_staged = true;
+  }
+  return PB_OK;
+}
+
+extern "C" int pb_segment_release(pb_segment_handle s) {
+  if (!s) return PB_OK;
+  for (auto& c : s->cols) {
+    cudaFree(c.d_fwd); cudaFree(c.d_sorted_pairs); cudaFree(c.d_dict_f64); cudaFree(c.d_inv);
+  }
+  delete s;
+  return PB_OK;
+}
+extern "C" int64_t pb_segment_device_bytes(pb_segment_handle s) { return s ? s->device_bytes : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// segment groups and global dictionaries
+// ------------------------------------------------------------------------------------------------
+struct GlobalDict {
+  int type = 0, entry_bytes = 0;
+  int64_t n = 0;
+  std::vector<uint8_t> values;                 // native-endian stored-type values / padded strings, sorted
+  std::vector<std::vector<int32_t>> h_remap;   // per segment: local dictId -> global dictId
+  std::vector<int32_t*> d_remap;
+  bool external = false;                       // installed by pb_segment_group_set_global_dictionary
+};
+
+struct pb_group_s {
+  std::vector<pb_segment_s*> segs;
+  std::map<std::string, GlobalDict> dicts;
+  std::mutex mu;
+};
+
+// dictionary entry -> native-endian comparable form
+static void native_entry(const Column& c, int id, uint8_t* out) {
+  const uint8_t* p = c.h_dict.data() + (size_t)id * c.entry_bytes;
+  if (c.type == PB_STRING) { memcpy(out, p, c.entry_bytes); return; }
+  if (c.entry_bytes == 4) { uint32_t u = be32(p); memcpy(out, &u, 4); } else { uint64_t u = be64(p); memcpy(out, &u, 8); }
+}
+static int cmp_entry(int type, int eb, const uint8_t* a, const uint8_t* b) {
+  switch (type) {
+    case PB_INT: { int32_t x, y; memcpy(&x, a, 4); memcpy(&y, b, 4); return (x > y) - (x < y); }
+    case PB_LONG: { int64_t x, y; memcpy(&x, a, 8); memcpy(&y, b, 8); return (x > y) - (x < y); }
+    case PB_FLOAT: { float x, y; memcpy(&x, a, 4); memcpy(&y, b, 4); return (x > y) - (x < y); }
+    case PB_DOUBLE: { double x, y; memcpy(&x, a, 8); memcpy(&y, b, 8); return (x > y) - (x < y); }
+    default: return memcmp(a, b, eb);
+  }
+}
+
+extern "C" int pb_segment_group_create(const pb_segment_handle* segs, int n, pb_segment_group_handle* out) {
+  if (!segs || n <= 0 || !out) return fail(PB_ERR_INVALID, "bad segment group");
+  pb_group_s* g = new pb_group_s();
+  g->segs.assign(segs, segs + n);
+  *out = g;
+  return PB_OK;
+}
+extern "C" int pb_segment_group_release(pb_segment_group_handle g) {
+  if (!g) return PB_OK;
+  for (auto& kv : g->dicts) for (auto p : kv.second.d_remap) cudaFree(p);
+  delete g;
+  return PB_OK;
+}
+
+// sorted union of the segments' dictionaries (k-way by concatenate + sort + unique; dictionaries are small)
+static int build_union(pb_group_s* g, const char* column, GlobalDict& gd) {
+  int type = -1, eb = 0;
+  for (auto* s : g->segs) {
+    int ci = find_col(s, column);
+    if (ci < 0) return fail(PB_ERR_INVALID, "segment %s has no column %s", s->name.c_str(), column);
+    const Column& c = s->cols[ci];
+    if (!c.has_dict) return fail(PB_ERR_UNSUPPORTED, "column %s has no dictionary", column);
+    if (type < 0) type = c.type;
+    if (type != c.type) return fail(PB_ERR_INVALID, "column %s: stored type differs across segments", column);
+    eb = std::max(eb, c.entry_bytes);
+  }
+  std::vector<uint8_t> all;
+  for (auto* s : g->segs) {
+    const Column& c = s->cols[find_col(s, column)];
+    size_t base = all.size();
+    all.resize(base + (size_t)c.card * eb, 0);
+    for (int i = 0; i < c.card; i++) native_entry(c, i, all.data() + base + (size_t)i * eb);
+  }
+  size_t total = all.size() / eb;
+  std::vector<uint32_t> idx(total);
+  for (size_t i = 0; i < total; i++) idx[i] = (uint32_t)i;
+  std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return cmp_entry(type, eb, all.data() + (size_t)a * eb, all.data() + (size_t)b * eb) < 0; });
+  gd.type = type; gd.entry_bytes = eb; gd.values.clear(); gd.n = 0;
+  for (size_t k = 0; k < total; k++) {
+    const uint8_t* e = all.data() + (size_t)idx[k] * eb;
+    if (gd.n == 0 || cmp_entry(type, eb, gd.values.data() + (size_t)(gd.n - 1) * eb, e) != 0) {
+      gd.values.insert(gd.values.end(), e, e + eb);
+      gd.n++;
+    }
+  }
+  return PB_OK;
+}
+
+static int build_remaps(pb_group_s* g, const char* column, GlobalDict& gd) {
+  for (auto p : gd.d_remap) cudaFree(p);
+  gd.d_remap.assign(g->segs.size(), nullptr);
+  gd.h_remap.assign(g->segs.size(), {});
+  std::vector<uint8_t> tmp((size_t)gd.entry_bytes);
+  for (size_t si = 0; si < g->segs.size(); si++) {
+    pb_segment_s* s = g->segs[si];
+    const Column& c = s->cols[find_col(s, column)];
+    auto& rm = gd.h_remap[si];
+    rm.resize((size_t)c.card);
+    int64_t pos = 0;   // both sides are sorted: merge walk
+    for (int i = 0; i < c.card; i++) {
+      std::fill(tmp.begin(), tmp.end(), 0);
+      native_entry(c, i, tmp.data());
+      while (pos < gd.n && cmp_entry(gd.type, gd.entry_bytes, gd.values.data() + (size_t)pos * gd.entry_bytes, tmp.data()) < 0) pos++;
+      if (pos >= gd.n || cmp_entry(gd.type, gd.entry_bytes, gd.values.data() + (size_t)pos * gd.entry_bytes, tmp.data()) != 0)
+        return fail(PB_ERR_INVALID, "global dictionary of %s misses a value of segment %s", column, s->name.c_str());
+      rm[i] = (int32_t)pos;
+    }
+    CU(cudaMalloc((void**)&gd.d_remap[si], sizeof(int32_t) * (size_t)c.card));
+    CU(cudaMemcpy(gd.d_remap[si], rm.data(), sizeof(int32_t) * (size_t)c.card, cudaMemcpyHostToDevice));
+  }
+  return PB_OK;
+}
+
+static int get_global_dict(pb_group_s* g, const char* column, GlobalDict** out) {
+  std::lock_guard<std::mutex> lk(g->mu);
+  auto it = g->dicts.find(column);
+  if (it == g->dicts.end()) {
+    GlobalDict gd;
+    int rc = build_union(g, column, gd);
+    if (rc) return rc;
+    it = g->dicts.emplace(column, std::move(gd)).first;
+  }
+  if (it->second.d_remap.empty()) {
+    int rc = build_remaps(g, column, it->second);
+    if (rc) return rc;
+  }
+  *out = &it->second;
+  return PB_OK;
+}
+
+extern "C" int pb_segment_group_export_dictionary(pb_segment_group_handle g, const char* column, const void** values,
+                                                  int64_t* num_values, int32_t* entry_bytes) {
+  if (!g || !column) return fail(PB_ERR_INVALID, "bad arguments");
+  std::lock_guard<std::mutex> lk(g->mu);
+  auto it = g->dicts.find(column);
+  if (it == g->dicts.end()) {
+    GlobalDict gd;
+    int rc = build_union(g, column, gd);
+    if (rc) return rc;
+    it = g->dicts.emplace(column, std::move(gd)).first;
+  }
+  *values = it->second.values.data(); *num_values = it->second.n; *entry_bytes = it->second.entry_bytes;
+  return PB_OK;
+}
+extern "C" int pb_segment_group_set_global_dictionary(pb_segment_group_handle g, const char* column, const void* values,
+                                                      int64_t num_values, int32_t entry_bytes) {
+  if (!g || !column || !values || num_values <= 0) return fail(PB_ERR_INVALID, "bad arguments");
+  std::lock_guard<std::mutex> lk(g->mu);
+  GlobalDict& gd = g->dicts[column];
+  int ci = find_col(g->segs[0], column);
+  if (ci < 0) return fail(PB_ERR_INVALID, "no column %s", column);
+  gd.type = g->segs[0]->cols[ci].type;
+  gd.entry_bytes = entry_bytes; gd.n = num_values; gd.external = true;
+  gd.values.assign((const uint8_t*)values, (const uint8_t*)values + (size_t)num_values * entry_bytes);
+  return build_remaps(g, column, gd);
+}
+
+// ------------------------------------------------------------------------------------------------
+// results
+// ------------------------------------------------------------------------------------------------
+struct HostArr {
+  void* p = nullptr; size_t bytes = 0;
+  void alloc(size_t b) { bytes = b ? b : 8; p = pinned_alloc(bytes); }
+  void release() { pinned_free(p, bytes); p = nullptr; }
+};
+
+struct TableMeta {
+  int mode = 0;
+  uint64_t capacity = 0;
+  std::vector<int> seg_idx;                 // segments accumulated into this table
+  std::vector<int64_t> cards;               // per group-by column (global or local)
+  std::vector<int> shifts, widths;          // hash key layout
+  DevTable dev;                             // device pointers (host copy of the struct)
+  // finalize outputs
+  int64_t num_groups = 0;
+  HostArr slots, rows;
+  std::vector<HostArr> dbl, lng, key_ids, key_vals, dc_off, dc_ids;
+  std::vector<int> key_type, key_eb;
+  pb_exec_stats stats{};
+  unsigned long long* d_slots = nullptr;    // compacted slot list on the device
+};
+
+struct pb_result_s {
+  pb_group_s* group = nullptr;
+  cudaStream_t stream = nullptr;
+  int n_gb = 0, n_aggs = 0;
+  int table_mode = 0;
+  bool combine = false, finalized = false;
+  std::vector<int> agg_op;
+  std::vector<std::string> gb_names, agg_cols;
+  std::vector<TableMeta> tables;
+  std::vector<void*> dev_allocs;            // freed (stream-ordered) with the result
+  unsigned long long* d_counters = nullptr; // per table: [num_groups(u32 pair), limit flag, docs_matched, compaction counter]
+  HostArr h_counters;
+  int n_distinct_cols = 0;
+  int n_scan_leaves_total = 0;
+  std::vector<int64_t> seg_scan_leaves;     // per segment: number of scan leaves (for numEntriesScannedInFilter)
+  double device_ms = 0, scan_ms = 0;
+  int launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+};
+
+static void free_result(pb_result_s* r) {
+  if (!r) return;
+  for (void* p : r->dev_allocs) cudaFreeAsync(p, r->stream);
+  for (auto& t : r->tables) {
+    t.slots.release(); t.rows.release();
+    for (auto* v : {&t.dbl, &t.lng, &t.key_ids, &t.key_vals, &t.dc_off, &t.dc_ids}) for (auto& a : *v) a.release();
+  }
+  r->h_counters.release();
+  if (r->ev0) cudaEventDestroy(r->ev0);
+  if (r->ev1) cudaEventDestroy(r->ev1);
+  if (r->ev2) cudaEventDestroy(r->ev2);
+  if (r->ev3) cudaEventDestroy(r->ev3);
+  if (r->stream) { cudaStreamSynchronize(r->stream); cudaStreamDestroy(r->stream); }
+  delete r;
+}
+extern "C" void pb_result_free(pb_result_handle r) { free_result(r); }
+
+// ------------------------------------------------------------------------------------------------
+// query execution
+// ------------------------------------------------------------------------------------------------
+#define PB_DENSE_MAX (1ull << 24)
+#define PB_COUNTERS_PER_TABLE 4   // u64 cells: [0] num_groups(lo u32) [1] limit flag (lo u32) [2] docs matched [3] compaction cursor
+
+struct Arena {   // host mirror of a device allocation; pointers are handed out as device addresses
+  std::vector<uint8_t> host;
+  uint8_t* dev = nullptr;
+  size_t cap = 0, used = 0;
+  template <class T> T* put(const T* src, size_t count, T** host_view = nullptr) {
+    size_t bytes = sizeof(T) * count;
+    used = (used + 15) & ~(size_t)15;
+    if (used + bytes > cap) return nullptr;
+    if (src) memcpy(host.data() + used, src, bytes); else memset(host.data() + used, 0, bytes);
+    if (host_view) *host_view = reinterpret_cast<T*>(host.data() + used);
+    T* d = reinterpret_cast<T*>(dev + used);
+    used += bytes;
+    return d;
+  }
+};
+
+static int finalize_result(pb_result_s* r);
+
+extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_query* sqs, const pb_query_desc* q, pb_result_handle* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!g || !q || !out) return fail(PB_ERR_INVALID, "null argument");
+  const int n_segs = (int)g->segs.size();
+  const int nG = q->num_group_by, nA = q->num_aggregations;
+  if (nG < 0 || nG > PB_MAX_GROUP_BY) return fail(PB_ERR_UNSUPPORTED, "%d group-by columns (max %d)", nG, PB_MAX_GROUP_BY);
+  if (nA <= 0 || nA > PB_MAX_AGGS) return fail(PB_ERR_UNSUPPORTED, "%d aggregations (max %d)", nA, PB_MAX_AGGS);
+  const bool combine = (q->flags & PB_Q_COMBINE) != 0;
+  const int n_tables = combine ? 1 : n_segs;
+
+  std::unique_ptr<pb_result_s, void (*)(pb_result_s*)> R(new pb_result_s(), free_result);
+  pb_result_s* r = R.get();
+  r->group = g; r->n_gb = nG; r->n_aggs = nA; r->combine = combine;
+  CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+  cudaStream_t st = r->stream;
+  CU(cudaEventCreate(&r->ev0)); CU(cudaEventCreate(&r->ev1)); CU(cudaEventCreate(&r->ev2)); CU(cudaEventCreate(&r->ev3));
+  for (int j = 0; j < nG; j++) r->gb_names.push_back(q->group_by_columns[j]);
+  for (int a = 0; a < nA; a++) {
+    r->agg_op.push_back(q->aggregations[a].op);
+    r->agg_cols.push_back(q->aggregations[a].column ? q->aggregations[a].column : "");
+    if (q->aggregations[a].op < PB_AGG_COUNT || q->aggregations[a].op > PB_AGG_DISTINCTCOUNT) return fail(PB_ERR_UNSUPPORTED, "aggregation op %d", q->aggregations[a].op);
+    if (q->aggregations[a].op != PB_AGG_COUNT && !q->aggregations[a].column) return fail(PB_ERR_INVALID, "aggregation %d needs a column", a);
+  }
+
+  // ---- resolve columns, stage what is needed ----
+  std::vector<std::vector<int>> gcol(n_segs, std::vector<int>(nG)), acol(n_segs, std::vector<int>(nA, -1));
+  bool any_raw_key = false;
+  for (int si = 0; si < n_segs; si++) {
+    pb_segment_s* s = g->segs[si];
+    std::lock_guard<std::mutex> lk(s->mu);
+    for (int j = 0; j < nG; j++) {
+      int ci = find_col(s, q->group_by_columns[j]);
+      if (ci < 0) return fail(PB_ERR_INVALID, "segment %s: no column %s", s->name.c_str(), q->group_by_columns[j]);
+      gcol[si][j] = ci;
+      Column& c = s->cols[ci];
+      if (!c.has_dict) any_raw_key = true;
+      if ((rc = stage_column(s, c, true, false, false, st))) return rc;
+    }
+    for (int a = 0; a < nA; a++) {
+      if (q->aggregations[a].op == PB_AGG_COUNT) continue;
+      int ci = find_col(s, q->aggregations[a].column);
+      if (ci < 0) return fail(PB_ERR_INVALID, "segment %s: no column %s", s->name.c_str(), q->aggregations[a].column);
+      acol[si][a] = ci;
+      Column& c = s->cols[ci];
+      if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT) {
+        if (!c.has_dict) return fail(PB_ERR_UNSUPPORTED, "DISTINCTCOUNT on raw column %s", c.name.c_str());
+        if ((rc = stage_column(s, c, true, false, false, st))) return rc;
+      } else {
+        if (c.type == PB_STRING) return fail(PB_ERR_UNSUPPORTED, "numeric aggregation on STRING column %s", c.name.c_str());
+        if ((rc = stage_column(s, c, true, true, false, st))) return rc;
+      }
+    }
+    const pb_segment_query& sq = sqs[si];
+    if (sq.num_filter_nodes > PB_MAX_NODES) return fail(PB_ERR_UNSUPPORTED, "filter has %d nodes (max %d)", sq.num_filter_nodes, PB_MAX_NODES);
+    for (int n = 0; n < sq.num_filter_nodes; n++) {
+      const pb_filter_node& fn = sq.filter[n];
+      if (fn.kind >= PB_F_SCAN_DICT_RANGE && fn.kind <= PB_F_INVERTED) {
+        if (fn.column < 0 || fn.column >= (int)s->cols.size()) return fail(PB_ERR_INVALID, "filter node %d: bad column", n);
+        Column& c = s->cols[fn.column];
+        bool inv = fn.kind == PB_F_INVERTED;
+        if ((fn.kind == PB_F_SCAN_DICT_RANGE || fn.kind == PB_F_SCAN_DICT_SET) && !c.has_dict) return fail(PB_ERR_INVALID, "filter node %d: dictionary scan on raw column", n);
+        if ((fn.kind == PB_F_SCAN_RAW_RANGE || fn.kind == PB_F_SCAN_RAW_SET) && c.has_dict) return fail(PB_ERR_INVALID, "filter node %d: raw scan on dictionary column", n);
+        if ((rc = stage_column(s, c, !inv, false, inv, st))) return rc;
+      }
+    }
+  }
+
+  // ---- global dictionaries (combined mode) ----
+  std::vector<GlobalDict*> gdict(nG, nullptr), adict(nA, nullptr);
+  if (combine) {
+    for (int j = 0; j < nG; j++) {
+      if (!g->segs[0]->cols[gcol[0][j]].has_dict) continue;
+      if ((rc = get_global_dict(g, q->group_by_columns[j], &gdict[j]))) return rc;
+    }
+    for (int a = 0; a < nA; a++)
+      if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT && (rc = get_global_dict(g, q->aggregations[a].column, &adict[a]))) return rc;
+  }
+
+  // ---- table mode and layout ----
+  r->tables.resize(n_tables);
+  int table_mode = nG == 0 ? T_KEYLESS : T_DENSE;
+  if (nG > 0) {
+    for (int t = 0; t < n_tables; t++) {
+      TableMeta& tm = r->tables[t];
+      int si0 = combine ? 0 : t;
+      tm.cards.resize(nG); tm.shifts.resize(nG); tm.widths.resize(nG);
+      unsigned __int128 prod = 1;
+      int total_bits = 0;
+      for (int j = 0; j < nG; j++) {
+        const Column& c = g->segs[si0]->cols[gcol[si0][j]];
+        int64_t card; int width;
+        if (c.has_dict) {
+          card = combine ? gdict[j]->n : c.card;
+          width = 1; while ((1ll << width) < card) width++;
+        } else {
+          card = -1;
+          width = (c.type == PB_INT || c.type == PB_FLOAT) ? 32 : 64;
+          if (nG == 1) width = 64;
+        }
+        tm.cards[j] = card; tm.widths[j] = width; tm.shifts[j] = total_bits; total_bits += width;
+        if (card > 0 && prod <= ((unsigned __int128)1 << 70)) prod *= (unsigned __int128)card;
+      }
+      bool dense_ok = !any_raw_key && prod <= PB_DENSE_MAX;
+      if (!dense_ok) {
+        if (total_bits > 64) return fail(PB_ERR_UNSUPPORTED, "group key needs %d bits (> 64): decline to the CPU plan", total_bits);
+        table_mode = T_HASH;
+      }
+      tm.capacity = dense_ok ? (uint64_t)prod : 0;
+    }
+  }
+  if (table_mode == T_HASH) {
+    for (int t = 0; t < n_tables; t++) {
+      TableMeta& tm = r->tables[t];
+      uint64_t docs = 0;
+      if (combine) for (auto* s : g->segs) docs += (uint64_t)s->num_docs; else docs = (uint64_t)g->segs[t]->num_docs;
+      uint64_t want = std::min<uint64_t>((uint64_t)std::max(1, q->num_groups_limit), std::max<uint64_t>(docs, 1));
+      uint64_t cap = 1024;
+      while (cap < 2 * want) cap <<= 1;
+      tm.capacity = cap;
+    }
+  }
+  if (table_mode == T_KEYLESS) for (auto& tm : r->tables) tm.capacity = 1;
+  r->table_mode = table_mode;
+  for (int t = 0; t < n_tables; t++) {
+    TableMeta& tm = r->tables[t];
+    tm.mode = table_mode;
+    if (combine) for (int si = 0; si < n_segs; si++) tm.seg_idx.push_back(si); else tm.seg_idx.push_back(t);
+  }
+
+  // ---- device table arenas: [zero region][0xFF region][min/max region] ----
+  auto slots_of = [&](const TableMeta& tm) { return tm.capacity + (table_mode == T_HASH ? 1 : 0); };
+  size_t zero_bytes = 0, ff_bytes = 0, mm_elems = 0;
+  std::vector<uint64_t> dc_words(nA, 0);
+  for (int a = 0; a < nA; a++)
+    if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT) {
+      int64_t maxcard = 0;
+      if (combine) maxcard = adict[a]->n; else for (int si = 0; si < n_segs; si++) maxcard = std::max<int64_t>(maxcard, g->segs[si]->cols[acol[si][a]].card);
+      dc_words[a] = ((uint64_t)maxcard + 31) / 32;
+    }
+  for (auto& tm : r->tables) {
+    uint64_t S = slots_of(tm);
+    zero_bytes += 8 * S;                                     // rowcnt
+    for (int a = 0; a < nA; a++) {
+      int op = q->aggregations[a].op;
+      if (op == PB_AGG_SUM || op == PB_AGG_AVG) zero_bytes += 8 * S;
+      if (op == PB_AGG_MIN || op == PB_AGG_MAX) mm_elems += S;
+      if (op == PB_AGG_DISTINCTCOUNT) zero_bytes += 4 * S * dc_words[a];
+    }
+    zero_bytes = (zero_bytes + 255) & ~(size_t)255;
+    if (table_mode == T_HASH) ff_bytes += 8 * S;
+  }
+  zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 256;
+  if (zero_bytes > (64ull << 30)) return fail(PB_ERR_UNSUPPORTED, "group table needs %zu bytes: decline to the CPU plan", zero_bytes);
+  uint8_t *d_zero = nullptr, *d_ff = nullptr; long long* d_mm = nullptr;
+  CU(cudaMallocAsync((void**)&d_zero, zero_bytes, st)); r->dev_allocs.push_back(d_zero);
+  if (ff_bytes) { CU(cudaMallocAsync((void**)&d_ff, ff_bytes, st)); r->dev_allocs.push_back(d_ff); }
+  if (mm_elems) { CU(cudaMallocAsync((void**)&d_mm, 8 * mm_elems, st)); r->dev_allocs.push_back(d_mm); }
+
+  CU(cudaEventRecord(r->ev0, st));
+  CU(cudaMemsetAsync(d_zero, 0, zero_bytes, st));
+  if (ff_bytes) CU(cudaMemsetAsync(d_ff, 0xFF, ff_bytes, st));
+  {
+    size_t zo = 0, fo = 0, mo = 0;
+    r->d_counters = reinterpret_cast<unsigned long long*>(d_zero);
+    zo += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables; zo = (zo + 255) & ~(size_t)255;
+    const long long ENC_POS_INF = 0x7ff0000000000000LL;
+    const long long ENC_NEG_INF = (long long)0xfff0000000000000ULL ^ 0x7fffffffffffffffLL;
+    for (int t = 0; t < n_tables; t++) {
+      TableMeta& tm = r->tables[t];
+      uint64_t S = slots_of(tm);
+      DevTable& dt = tm.dev;
+      memset(&dt, 0, sizeof dt);
+      dt.mode = table_mode; dt.capacity = tm.capacity;
+      dt.rowcnt = reinterpret_cast<unsigned long long*>(d_zero + zo); zo += 8 * S;
+      for (int a = 0; a < nA; a++) {
+        int op = q->aggregations[a].op;
+        if (op == PB_AGG_SUM || op == PB_AGG_AVG) { dt.sum[a] = reinterpret_cast<double*>(d_zero + zo); zo += 8 * S; }
+        if (op == PB_AGG_DISTINCTCOUNT) { dt.dc_bits[a] = reinterpret_cast<uint32_t*>(d_zero + zo); dt.dc_words[a] = dc_words[a]; zo += 4 * S * dc_words[a]; }
+        if (op == PB_AGG_MIN || op == PB_AGG_MAX) {
+          dt.mm[a] = d_mm + mo; mo += S;
+          int grid = (int)std::min<uint64_t>((S + 255) / 256, 1024);
+          pb_fill_i64_kernel<<<grid, 256, 0, st>>>(dt.mm[a], S, op == PB_AGG_MIN ? ENC_POS_INF : ENC_NEG_INF);
+          r->launches++;
+        }
+      }
+      zo = (zo + 255) & ~(size_t)255;
+      if (table_mode == T_HASH) { dt.hkeys = reinterpret_cast<unsigned long long*>(d_ff + fo); fo += 8 * S; }
+      unsigned long long* cnt = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE;
+      dt.num_groups = reinterpret_cast<unsigned int*>(cnt + 0);
+      dt.limit_reached = reinterpret_cast<unsigned int*>(cnt + 1);
+      dt.docs_matched = cnt + 2;
+      dt.num_groups_limit = (uint32_t)std::max(1, q->num_groups_limit);
+    }
+    CU(cudaGetLastError());
+  }
+
+  // ---- query arena (descriptors + leaf payloads) ----
+  size_t arena_cap = sizeof(DevQuery) + 256 + (sizeof(DevSegQuery) + 64) * (size_t)n_segs + (sizeof(DevTable) + 64) * (size_t)n_tables;
+  size_t bitmap_words_total = 0;
+  for (int si = 0; si < n_segs; si++) {
+    const pb_segment_query& sq = sqs[si];
+    pb_segment_s* s = g->segs[si];
+    for (int n = 0; n < sq.num_filter_nodes; n++) {
+      const pb_filter_node& fn = sq.filter[n];
+      if (fn.kind == PB_F_SCAN_DICT_SET) arena_cap += 4 * (((size_t)s->cols[fn.column].card + 31) / 32) + 32;
+      if (fn.kind == PB_F_SCAN_RAW_SET) arena_cap += 8 * (size_t)fn.num_raw_values + 32;
+      if (fn.kind == PB_F_INVERTED) arena_cap += 4 * (size_t)fn.num_ids + 32;
+      if (fn.kind == PB_F_SORTED) arena_cap += 8 * (size_t)fn.num_ids + 32;
+      if (fn.kind == PB_F_BITMAP) arena_cap += fn.blob_len + 64;
+      if (fn.kind == PB_F_INVERTED || fn.kind == PB_F_SORTED || fn.kind == PB_F_BITMAP) bitmap_words_total += (((size_t)s->num_docs + 1023) / 1024) * 32;
+    }
+  }
+  Arena ar;
+  ar.cap = arena_cap; ar.host.resize(arena_cap);
+  CU(cudaMallocAsync((void**)&ar.dev, arena_cap, st)); r->dev_allocs.push_back(ar.dev);
+  uint32_t* d_bitmaps = nullptr;
+  if (bitmap_words_total) {
+    CU(cudaMallocAsync((void**)&d_bitmaps, 4 * bitmap_words_total, st)); r->dev_allocs.push_back(d_bitmaps);
+    CU(cudaMemsetAsync(d_bitmaps, 0, 4 * bitmap_words_total, st));
+  }
+
+  DevQuery* hq = nullptr;
+  DevQuery* dq = ar.put<DevQuery>(nullptr, 1, &hq);
+  DevSegQuery* hsegs = nullptr;
+  DevSegQuery* dsegs = ar.put<DevSegQuery>(nullptr, (size_t)n_segs, &hsegs);
+  DevTable* htabs = nullptr;
+  DevTable* dtabs = ar.put<DevTable>(nullptr, (size_t)n_tables, &htabs);
+  for (int t = 0; t < n_tables; t++) htabs[t] = r->tables[t].dev;
+
+  struct PendingExpand { int kind; const uint8_t* inv; int card; const int32_t* ids; int n_ids; uint32_t* out; uint32_t num_docs; };
+  std::vector<PendingExpand> expands;
+  int slot_bits_max[PB_MAX_SCAN_SLOTS] = {0};
+  int n_slots_max = 0;
+  size_t bm_off = 0;
+  r->seg_scan_leaves.assign(n_segs, 0);
+
+  for (int si = 0; si < n_segs; si++) {
+    pb_segment_s* s = g->segs[si];
+    const pb_segment_query& sq = sqs[si];
+    DevSegQuery& ds = hsegs[si];
+    ds.num_docs = s->num_docs;
+    ds.table = combine ? 0 : si;
+    int n_leaves = 0, n_scan = 0, set_smem_used = 0;
+    int slot_of_col[PB_MAX_SCAN_SLOTS];
+    ds.n_nodes = sq.num_filter_nodes;
+    for (int n = 0; n < sq.num_filter_nodes; n++) {
+      const pb_filter_node& fn = sq.filter[n];
+      if (fn.kind == PB_F_AND || fn.kind == PB_F_OR) {
+        if (fn.num_children < 1 || fn.num_children > PB_MAX_LEAVES) return fail(PB_ERR_UNSUPPORTED, "AND/OR with %d children", fn.num_children);
+        ds.node_kind[n] = fn.kind == PB_F_AND ? N_AND : N_OR; ds.node_arg[n] = (int8_t)fn.num_children; continue;
+      }
+      if (fn.kind == PB_F_NOT) { ds.node_kind[n] = N_NOT; ds.node_arg[n] = 1; continue; }
+      if (n_leaves >= PB_MAX_LEAVES) return fail(PB_ERR_UNSUPPORTED, "more than %d filter leaves", PB_MAX_LEAVES);
+      DevLeaf& lf = ds.leaves[n_leaves];
+      memset(&lf, 0, sizeof lf);
+      lf.set_smem_off = -1;
+      ds.node_kind[n] = N_LEAF; ds.node_arg[n] = (int8_t)n_leaves; n_leaves++;
+      auto scan_slot = [&](const Column& c) -> int {
+        for (int k = 0; k < n_scan; k++) if (slot_of_col[k] == fn.column) return k;
+        if (n_scan >= PB_MAX_SCAN_SLOTS) return -1;
+        slot_of_col[n_scan] = fn.column;
+        DevScanCol& sc = ds.scan[n_scan];
+        sc.base = c.d_fwd; sc.bits_per_doc = c.has_dict ? c.bits : 8 * c.raw_width; sc.bytes_total = c.d_fwd_bytes;
+        slot_bits_max[n_scan] = std::max(slot_bits_max[n_scan], sc.bits_per_doc);
+        return n_scan++;
+      };
+      switch (fn.kind) {
+        case PB_F_MATCH_ALL: lf.kind = L_TRUE; break;
+        case PB_F_EMPTY: lf.kind = L_FALSE; break;
+        case PB_F_SCAN_DICT_RANGE: {
+          const Column& c = s->cols[fn.column];
+          int64_t lo = std::max<int64_t>(fn.lo, 0), hi = std::min<int64_t>(fn.hi, c.card);
+          if (hi <= lo) { lf.kind = L_FALSE; break; }
+          lf.kind = L_DICT_RANGE; lf.bits = c.bits; lf.lo = (uint32_t)lo; lf.span = (uint32_t)(hi - lo);
+          if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
+          r->seg_scan_leaves[si]++;
+          break;
+        }
+        case PB_F_SCAN_DICT_SET: {
+          const Column& c = s->cols[fn.column];
+          if (fn.num_ids <= 0) { lf.kind = fn.exclusive ? L_TRUE : L_FALSE; break; }
+          size_t words = ((size_t)c.card + 31) / 32;
+          uint32_t* hbits = nullptr;
+          const uint32_t* dbits = ar.put<uint32_t>(nullptr, words, &hbits);
+          if (!dbits) return fail(PB_ERR_STATE, "query arena overflow");
+          for (int k = 0; k < fn.num_ids; k++) {
+            int32_t id = fn.ids[k];
+            if (id < 0 || id >= c.card) return fail(PB_ERR_INVALID, "filter node %d: dictId %d out of range", n, id);
+            hbits[id >> 5] |= 1u << (id & 31);
+          }
+          lf.kind = L_DICT_SET; lf.bits = c.bits; lf.exclusive = fn.exclusive ? 1 : 0;
+          lf.set_bits = dbits; lf.set_words = (int32_t)words;
+          if (set_smem_used + (int)words <= PB_SET_SMEM_WORDS) { lf.set_smem_off = set_smem_used; set_smem_used += (int)words; }
+          if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
+          r->seg_scan_leaves[si]++;
+          break;
+        }
+        case PB_F_SCAN_RAW_RANGE: {
+          const Column& c = s->cols[fn.column];
+          lf.raw_width = c.raw_width; lf.data_type = c.type;
+          if (c.type == PB_INT || c.type == PB_LONG) { lf.kind = L_RAW_RANGE_I; lf.ilo = fn.lo; lf.ihi = fn.hi; }
+          else { lf.kind = L_RAW_RANGE_F; lf.dlo = fn.dlo; lf.dhi = fn.dhi; lf.dlo_incl = fn.dlo_inclusive; lf.dhi_incl = fn.dhi_inclusive; }
+          if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
+          r->seg_scan_leaves[si]++;
+          break;
+        }
+        case PB_F_SCAN_RAW_SET: {
+          const Column& c = s->cols[fn.column];
+          if (fn.num_raw_values <= 0) { lf.kind = fn.exclusive ? L_TRUE : L_FALSE; break; }
+          lf.kind = L_RAW_SET; lf.raw_width = c.raw_width; lf.data_type = c.type; lf.exclusive = fn.exclusive ? 1 : 0;
+          lf.raw_set = ar.put<int64_t>(fn.raw_values, (size_t)fn.num_raw_values);
+          lf.n_raw_set = fn.num_raw_values;
+          if (!lf.raw_set) return fail(PB_ERR_STATE, "query arena overflow");
+          if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
+          r->seg_scan_leaves[si]++;
+          break;
+        }
+        case PB_F_INVERTED: case PB_F_SORTED: case PB_F_BITMAP: {
+          size_t words = (((size_t)s->num_docs + 1023) / 1024) * 32;
+          uint32_t* bm = d_bitmaps + bm_off; bm_off += words;
+          lf.kind = L_BITMAP; lf.bitmap = bm; lf.exclusive = fn.exclusive ? 1 : 0;
+          if (fn.kind == PB_F_INVERTED) {
+            const Column& c = s->cols[fn.column];
+            if (fn.num_ids <= 0) { lf.kind = fn.exclusive ? L_TRUE : L_FALSE; break; }
+            for (int k = 0; k < fn.num_ids; k++) if (fn.ids[k] < 0 || fn.ids[k] >= c.card) return fail(PB_ERR_INVALID, "filter node %d: dictId out of range", n);
+            const int32_t* dids = ar.put<int32_t>(fn.ids, (size_t)fn.num_ids);
+            if (!dids) return fail(PB_ERR_STATE, "query arena overflow");
+            expands.push_back({0, c.d_inv, c.card, dids, fn.num_ids, bm, (uint32_t)s->num_docs});
+          } else if (fn.kind == PB_F_SORTED) {
+            lf.exclusive = 0;
+            if (fn.num_ids <= 0) { lf.kind = L_FALSE; break; }
+            for (int k = 0; k < fn.num_ids; k++) {
+              int32_t lo = fn.ids[2 * k], hi = fn.ids[2 * k + 1];
+              if (lo < 0 || hi < lo || hi >= s->num_docs) return fail(PB_ERR_INVALID, "filter node %d: bad docId range [%d,%d]", n, lo, hi);
+            }
+            const int32_t* dp = ar.put<int32_t>(fn.ids, 2 * (size_t)fn.num_ids);
+            if (!dp) return fail(PB_ERR_STATE, "query arena overflow");
+            expands.push_back({1, nullptr, 0, dp, fn.num_ids, bm, (uint32_t)s->num_docs});
+          } else {
+            // wrap the caller's Roaring blob as a one-entry inverted index: [BE off0][BE off1][blob]
+            if (!fn.blob || fn.blob_len < 8) return fail(PB_ERR_INVALID, "filter node %d: bitmap blob missing", n);
+            std::vector<uint8_t> tmp(8 + fn.blob_len);
+            uint32_t o0 = 8, o1 = (uint32_t)(8 + fn.blob_len);
+            tmp[0] = o0 >> 24; tmp[1] = o0 >> 16; tmp[2] = o0 >> 8; tmp[3] = (uint8_t)o0;
+            tmp[4] = o1 >> 24; tmp[5] = o1 >> 16; tmp[6] = o1 >> 8; tmp[7] = (uint8_t)o1;
+            memcpy(tmp.data() + 8, fn.blob, fn.blob_len);
+            const uint8_t* dblob = ar.put<uint8_t>(tmp.data(), tmp.size());
+            static const int32_t zero_id = 0;
+            const int32_t* dids = ar.put<int32_t>(&zero_id, 1);
+            if (!dblob || !dids) return fail(PB_ERR_STATE, "query arena overflow");
+            expands.push_back({0, dblob, 1, dids, 1, bm, (uint32_t)s->num_docs});
+          }
+          break;
+        }
+        default: return fail(PB_ERR_INVALID, "filter node %d: unknown kind %d", n, fn.kind);
+      }
+    }
+    ds.n_scan = n_scan;
+    n_slots_max = std::max(n_slots_max, n_scan);
+    r->n_scan_leaves_total += (int)r->seg_scan_leaves[si];
+
+    // group-by / aggregation columns
+    const TableMeta& tm = r->tables[ds.table];
+    uint64_t mult = 1;
+    for (int j = 0; j < nG; j++) {
+      const Column& c = s->cols[gcol[si][j]];
+      DevKeyCol& kc = ds.keys[j];
+      kc.fwd = c.d_fwd; kc.bits = c.bits; kc.raw_width = c.has_dict ? 0 : c.raw_width; kc.data_type = c.type;
+      kc.remap = (combine && gdict[j]) ? gdict[j]->d_remap[si] : nullptr;
+      kc.shift = tm.shifts[j];
+      kc.mult = mult;
+      if (tm.cards[j] > 0) mult *= (uint64_t)tm.cards[j];
+      if (!c.has_dict && (c.type == PB_FLOAT) && nG > 1) return fail(PB_ERR_UNSUPPORTED, "raw FLOAT key in a multi-column group-by");
+    }
+    for (int a = 0; a < nA; a++) {
+      if (acol[si][a] < 0) continue;
+      const Column& c = s->cols[acol[si][a]];
+      DevAggCol& ac = ds.aggs[a];
+      ac.fwd = c.d_fwd; ac.dict_f64 = c.d_dict_f64; ac.bits = c.bits; ac.raw_width = c.has_dict ? 0 : c.raw_width; ac.data_type = c.type;
+      ac.remap = (combine && adict[a]) ? adict[a]->d_remap[si] : nullptr;
+    }
+  }
+
+  // ---- tile geometry ----
+  int sum_bits = 0;
+  for (int k = 0; k < n_slots_max; k++) sum_bits += slot_bits_max[k];
+  int tile_chunks = 8;
+  const size_t stage_budget = 96 * 1024;   // 3 stages; keeps two CTAs resident per SM for typical filters
+  auto stage_bytes_for = [&](int chunks) {
+    size_t b = 0;
+    for (int k = 0; k < n_slots_max; k++) b += (((size_t)chunks * PB_CHUNK_DOCS * slot_bits_max[k] / 8 + 16) + 127) & ~(size_t)127;
+    return b;
+  };
+  while (tile_chunks > 1 && stage_bytes_for(tile_chunks) * PB_NSTAGE > stage_budget) tile_chunks >>= 1;
+  size_t stage_bytes = stage_bytes_for(tile_chunks);
+  if (stage_bytes * PB_NSTAGE > 160 * 1024) return fail(PB_ERR_UNSUPPORTED, "scan predicates touch %d bits per row: tile does not fit shared memory", sum_bits);
+  const uint64_t tile_docs = (uint64_t)tile_chunks * PB_CHUNK_DOCS;
+  uint64_t n_tiles = 0;
+  for (int si = 0; si < n_segs; si++) { hsegs[si].tile_begin = n_tiles; n_tiles += ((uint64_t)g->segs[si]->num_docs + tile_docs - 1) / tile_docs; }
+
+  hq->n_segs = n_segs; hq->n_group_by = nG; hq->n_aggs = nA; hq->table_mode = table_mode;
+  for (int a = 0; a < nA; a++) hq->agg_op[a] = q->aggregations[a].op;
+  { size_t off = 0; for (int k = 0; k < n_slots_max; k++) { hq->slot_off[k] = (int32_t)off; off += (((size_t)tile_chunks * PB_CHUNK_DOCS * slot_bits_max[k] / 8 + 16) + 127) & ~(size_t)127; } }
+  hq->stage_bytes = (int32_t)stage_bytes; hq->tile_chunks = tile_chunks;
+  hq->use_tma = (q->flags & PB_Q_NO_TMA) ? 0 : 1;
+  hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
+  hq->n_tiles = n_tiles; hq->segs = dsegs; hq->tables = dtabs;
+
+  CU(cudaMemcpyAsync(ar.dev, ar.host.data(), ar.used, cudaMemcpyHostToDevice, st));
+
+  // ---- index leaves -> flat bitmaps ----
+  for (auto& e : expands) {
+    if (e.kind == 0) {
+      dim3 grid(32, (unsigned)e.n_ids);
+      pb_roaring_expand_kernel<<<grid, 256, 0, st>>>(e.inv, e.card, e.ids, e.out, e.num_docs);
+    } else {
+      pb_ranges_fill_kernel<<<std::min(e.n_ids, 1024), 256, 0, st>>>(e.ids, e.n_ids, e.out);
+    }
+    r->launches++;
+  }
+  CU(cudaGetLastError());
+
+  // ---- the scan ----
+  size_t smem = ((sizeof(ScanSmemHeader) + 127) & ~(size_t)127) + stage_bytes * PB_NSTAGE;
+  if (table_mode == T_KEYLESS) smem += ((2 * sizeof(double) * (size_t)nA * PB_NTHREADS) + 127) & ~(size_t)127;
+  if (smem > 227 * 1024) return fail(PB_ERR_UNSUPPORTED, "scan kernel needs %zu bytes of shared memory", smem);
+  {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (!g_ctx.smem_attr_set) {
+      CU(cudaFuncSetAttribute(pb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      g_ctx.smem_attr_set = true;
+    }
+  }
+  int occ = 1;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_scan_kernel, PB_NTHREADS, smem));
+  if (occ < 1) return fail(PB_ERR_CUDA, "scan kernel does not fit an SM (smem %zu)", smem);
+  uint64_t max_ctas = (uint64_t)g_ctx.num_sms * (uint64_t)occ;
+  int grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), max_ctas);
+  CU(cudaEventRecord(r->ev1, st));
+  if (n_tiles > 0) {
+    pb_scan_kernel<<<grid, PB_NTHREADS, smem, st>>>(dq);
+    r->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(r->ev2, st));
+
+  if (q->flags & PB_Q_DEFER_FINALIZE) {
+    CU(cudaEventRecord(r->ev3, st));
+    *out = R.release();
+    return PB_OK;
+  }
+  rc = finalize_result(r);
+  if (rc) return rc;
+  *out = R.release();
+  return PB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize: compaction of non-empty groups, device -> pinned host, key decode
+// ------------------------------------------------------------------------------------------------
+static void decode_key_value(const pb_group_s* g, const pb_result_s* r, const TableMeta& tm, int j, int32_t id, uint8_t* out, int eb) {
+  if (r->combine) {
+    const GlobalDict& gd = g->dicts.at(r->gb_names[j]);
+    memcpy(out, gd.values.data() + (size_t)id * gd.entry_bytes, (size_t)gd.entry_bytes);
+  } else {
+    const pb_segment_s* s = g->segs[tm.seg_idx[0]];
+    const Column& c = s->cols[find_col(s, r->gb_names[j].c_str())];
+    native_entry(c, id, out);
+  }
+  (void)eb;
+}
+
+static int finalize_result(pb_result_s* r) {
+  if (r->finalized) return PB_OK;
+  cudaStream_t st = r->stream;
+  pb_group_s* g = r->group;
+  const int nT = (int)r->tables.size(), nG = r->n_gb, nA = r->n_aggs;
+  const int mode = r->table_mode;
+  r->h_counters.alloc(8 * PB_COUNTERS_PER_TABLE * (size_t)nT);
+  unsigned long long* hc = (unsigned long long*)r->h_counters.p;
+
+  // pass 1: number of non-empty groups per table
+  if (mode != T_KEYLESS) {
+    for (int t = 0; t < nT; t++) {
+      TableMeta& tm = r->tables[t];
+      uint64_t S = tm.capacity + (mode == T_HASH ? 1 : 0);
+      int grid = (int)std::min<uint64_t>((S + 255) / 256, 2048);
+      // counters[3] doubles as the group counter here, then as the compaction cursor (reset below)
+      pb_count_groups_kernel<<<grid, 256, 0, st>>>(tm.dev.rowcnt, S, r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3);
+      r->launches++;
+    }
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(hc, r->d_counters, 8 * PB_COUNTERS_PER_TABLE * (size_t)nT, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+
+  // pass 2: compaction + gathers
+  for (int t = 0; t < nT; t++) {
+    TableMeta& tm = r->tables[t];
+    const uint64_t S = tm.capacity + (mode == T_HASH ? 1 : 0);
+    const int64_t ng = mode == T_KEYLESS ? 1 : (int64_t)hc[(size_t)t * PB_COUNTERS_PER_TABLE + 3];
+    tm.num_groups = ng;
+    tm.dbl.resize(nA); tm.lng.resize(nA); tm.dc_off.resize(nA); tm.dc_ids.resize(nA);
+    const size_t n = (size_t)std::max<int64_t>(ng, 1);
+    tm.slots.alloc(8 * n); tm.rows.alloc(8 * n);
+    unsigned long long *d_slots = nullptr, *d_rows = nullptr;
+    CU(cudaMallocAsync((void**)&d_slots, 8 * n, st)); r->dev_allocs.push_back(d_slots);
+    CU(cudaMallocAsync((void**)&d_rows, 8 * n, st)); r->dev_allocs.push_back(d_rows);
+    tm.d_slots = d_slots;
+    if (mode == T_KEYLESS) {
+      CU(cudaMemsetAsync(d_slots, 0, 8, st));
+      CU(cudaMemcpyAsync(d_rows, tm.dev.rowcnt, 8, cudaMemcpyDeviceToDevice, st));
+    } else if (ng > 0) {
+      unsigned long long* cursor = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3;
+      CU(cudaMemsetAsync(cursor, 0, 8, st));
+      int grid = (int)std::min<uint64_t>((S + 255) / 256, 2048);
+      pb_compact_slots_kernel<<<grid, 256, 0, st>>>(tm.dev.rowcnt, S, cursor, d_slots, d_rows);
+      r->launches++;
+    }
+    CU(cudaMemcpyAsync(tm.slots.p, d_slots, 8 * n, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(tm.rows.p, d_rows, 8 * n, cudaMemcpyDeviceToHost, st));
+    const int ggrid = (int)std::min<uint64_t>((n + 255) / 256, 2048);
+    for (int a = 0; a < nA; a++) {
+      const int op = r->agg_op[a];
+      tm.dbl[a].alloc(8 * n); tm.lng[a].alloc(8 * n);
+      memset(tm.dbl[a].p, 0, 8 * n); memset(tm.lng[a].p, 0, 8 * n);
+      if (ng == 0) continue;
+      if (op == PB_AGG_SUM || op == PB_AGG_AVG || op == PB_AGG_MIN || op == PB_AGG_MAX) {
+        double* d_out = nullptr;
+        CU(cudaMallocAsync((void**)&d_out, 8 * n, st)); r->dev_allocs.push_back(d_out);
+        if (op == PB_AGG_MIN || op == PB_AGG_MAX) pb_gather_mm_kernel<<<ggrid, 256, 0, st>>>(tm.dev.mm[a], d_slots, (uint64_t)ng, d_out);
+        else pb_gather_f64_kernel<<<ggrid, 256, 0, st>>>(tm.dev.sum[a], d_slots, (uint64_t)ng, d_out);
+        r->launches++;
+        CU(cudaMemcpyAsync(tm.dbl[a].p, d_out, 8 * n, cudaMemcpyDeviceToHost, st));
+      }
+      if (op == PB_AGG_DISTINCTCOUNT) {
+        unsigned long long* d_cnt = nullptr;
+        CU(cudaMallocAsync((void**)&d_cnt, 8 * n, st)); r->dev_allocs.push_back(d_cnt);
+        int wgrid = (int)((n * 32 + 255) / 256);
+        pb_distinct_count_kernel<<<wgrid, 256, 0, st>>>(tm.dev.dc_bits[a], tm.dev.dc_words[a], d_slots, (uint64_t)ng, d_cnt);
+        r->launches++;
+        CU(cudaMemcpyAsync(tm.lng[a].p, d_cnt, 8 * n, cudaMemcpyDeviceToHost, st));
+      }
+    }
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(r->ev3, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, r->ev0, r->ev3); r->device_ms = ms;
+  cudaEventElapsedTime(&ms, r->ev1, r->ev2); r->scan_ms = ms;
+
+  // host side: counts, keys, stats, distinct value sets
+  for (int t = 0; t < nT; t++) {
+    TableMeta& tm = r->tables[t];
+    const int64_t ng = tm.num_groups;
+    const unsigned long long* slots = (const unsigned long long*)tm.slots.p;
+    const unsigned long long* rows = (const unsigned long long*)tm.rows.p;
+    for (int a = 0; a < nA; a++) {
+      const int op = r->agg_op[a];
+      int64_t* L = (int64_t*)tm.lng[a].p;
+      if (op == PB_AGG_COUNT || op == PB_AGG_AVG) for (int64_t k = 0; k < ng; k++) L[k] = (int64_t)rows[k];
+      if (op == PB_AGG_COUNT) { double* D = (double*)tm.dbl[a].p; for (int64_t k = 0; k < ng; k++) D[k] = (double)rows[k]; }
+    }
+    // distinct value sets (second device pass needs the counts as offsets)
+    for (int a = 0; a < nA; a++) {
+      if (r->agg_op[a] != PB_AGG_DISTINCTCOUNT) continue;
+      const int64_t* L = (const int64_t*)tm.lng[a].p;
+      tm.dc_off[a].alloc(8 * (size_t)(ng + 1));
+      int64_t* off = (int64_t*)tm.dc_off[a].p;
+      off[0] = 0;
+      for (int64_t k = 0; k < ng; k++) off[k + 1] = off[k] + L[k];
+      const int64_t total = off[ng];
+      tm.dc_ids[a].alloc(4 * (size_t)std::max<int64_t>(total, 1));
+      if (total > 0) {
+        unsigned long long* d_off = nullptr; int32_t* d_ids = nullptr;
+        CU(cudaMallocAsync((void**)&d_off, 8 * (size_t)(ng + 1), st)); r->dev_allocs.push_back(d_off);
+        CU(cudaMallocAsync((void**)&d_ids, 4 * (size_t)total, st)); r->dev_allocs.push_back(d_ids);
+        CU(cudaMemcpyAsync(d_off, off, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
+        int wgrid = (int)(((size_t)ng * 32 + 255) / 256);
+        pb_distinct_ids_kernel<<<wgrid, 256, 0, st>>>(tm.dev.dc_bits[a], tm.dev.dc_words[a], tm.d_slots, (uint64_t)ng, d_off, d_ids);
+        r->launches++;
+        CU(cudaMemcpyAsync(tm.dc_ids[a].p, d_ids, 4 * (size_t)total, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+      }
+    }
+    // keys
+    tm.key_ids.resize(nG); tm.key_vals.resize(nG); tm.key_type.assign(nG, 0); tm.key_eb.assign(nG, 0);
+    for (int j = 0; j < nG; j++) {
+      const pb_segment_s* s0 = g->segs[tm.seg_idx[0]];
+      const Column& c0 = s0->cols[find_col(s0, r->gb_names[j].c_str())];
+      const bool is_dict = c0.has_dict;
+      int eb = is_dict ? (r->combine ? g->dicts.at(r->gb_names[j]).entry_bytes : c0.entry_bytes) : (c0.type == PB_INT || c0.type == PB_FLOAT ? 4 : 8);
+      tm.key_type[j] = c0.type; tm.key_eb[j] = eb;
+      tm.key_ids[j].alloc(4 * (size_t)std::max<int64_t>(ng, 1));
+      tm.key_vals[j].alloc((size_t)eb * (size_t)std::max<int64_t>(ng, 1));
+      int32_t* ids = (int32_t*)tm.key_ids[j].p;
+      uint8_t* vals = (uint8_t*)tm.key_vals[j].p;
+      if (mode == T_DENSE) {   // DictionaryBasedGroupKeyGenerator.java:578-591 (mixed radix decode)
+        for (int64_t k = 0; k < ng; k++) {
+          uint64_t raw = slots[k];
+          for (int jj = 0; jj < j; jj++) raw /= (uint64_t)tm.cards[jj];
+          uint64_t field = raw % (uint64_t)tm.cards[j];
+          ids[k] = (int32_t)field;
+          decode_key_value(g, r, tm, j, (int32_t)field, vals + (size_t)k * eb, eb);
+        }
+      }
+    }
+    if (mode == T_HASH && ng > 0) {
+      // fetch the keys of the compacted slots
+      std::vector<unsigned long long> keys((size_t)ng);
+      unsigned long long* d_k = nullptr;
+      CU(cudaMallocAsync((void**)&d_k, 8 * (size_t)ng, st)); r->dev_allocs.push_back(d_k);
+      int ggrid = (int)std::min<uint64_t>(((uint64_t)ng + 255) / 256, 2048);
+      // slot == capacity (the sentinel cell) has no stored key: patched on the host
+      pb_gather_u64_kernel<<<ggrid, 256, 0, st>>>(tm.dev.hkeys, tm.d_slots, (uint64_t)ng, d_k);
+      r->launches++;
+      CU(cudaMemcpyAsync(keys.data(), d_k, 8 * (size_t)ng, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      for (int64_t k = 0; k < ng; k++) if (slots[k] == tm.capacity) keys[(size_t)k] = PB_HASH_EMPTY;
+      for (int j = 0; j < nG; j++) {
+        const pb_segment_s* s0 = g->segs[tm.seg_idx[0]];
+        const Column& c0 = s0->cols[find_col(s0, r->gb_names[j].c_str())];
+        int eb = tm.key_eb[j];
+        int32_t* ids = (int32_t*)tm.key_ids[j].p;
+        uint8_t* vals = (uint8_t*)tm.key_vals[j].p;
+        const int width = tm.widths[j], shift = tm.shifts[j];
+        for (int64_t k = 0; k < ng; k++) {
+          uint64_t f = keys[(size_t)k] >> shift;
+          if (width < 64) f &= ((1ull << width) - 1ull);
+          if (c0.has_dict) { ids[k] = (int32_t)f; decode_key_value(g, r, tm, j, (int32_t)f, vals + (size_t)k * eb, eb); }
+          else {
+            ids[k] = -1;
+            if (c0.type == PB_INT) { int32_t v = (int32_t)(uint32_t)f; memcpy(vals + (size_t)k * eb, &v, 4); }
+            else if (c0.type == PB_LONG) { int64_t v = (int64_t)f; memcpy(vals + (size_t)k * eb, &v, 8); }
+            else if (c0.type == PB_FLOAT) { double dv; memcpy(&dv, &f, 8); float fv = (float)dv; memcpy(vals + (size_t)k * eb, &fv, 4); }
+            else memcpy(vals + (size_t)k * eb, &f, 8);
+          }
+        }
+      }
+    }
+    // ExecutionStatistics (GroupByOperator.java:148-153; ProjectPlanNode.java:69-78)
+    std::vector<std::string> proj;
+    for (auto& nme : r->gb_names) if (std::find(proj.begin(), proj.end(), nme) == proj.end()) proj.push_back(nme);
+    for (auto& nme : r->agg_cols) if (!nme.empty() && std::find(proj.begin(), proj.end(), nme) == proj.end()) proj.push_back(nme);
+    tm.stats.num_docs_scanned = (int64_t)hc[(size_t)t * PB_COUNTERS_PER_TABLE + 2];
+    tm.stats.num_entries_scanned_post_filter = tm.stats.num_docs_scanned * (int64_t)proj.size();
+    tm.stats.num_total_docs = 0; tm.stats.num_entries_scanned_in_filter = 0;
+    for (int si : tm.seg_idx) {
+      tm.stats.num_total_docs += g->segs[si]->num_docs;
+      // every scan leaf reads every doc of the segment on the device (no restricted scans)
+      tm.stats.num_entries_scanned_in_filter += r->seg_scan_leaves[si] * (int64_t)g->segs[si]->num_docs;
+    }
+    tm.stats.num_segments = (int32_t)tm.seg_idx.size();
+    tm.stats.num_groups_limit_reached = 0;
+    if (nG > 0) {
+      bool flag = (uint32_t)hc[(size_t)t * PB_COUNTERS_PER_TABLE + 1] != 0;
+      tm.stats.num_groups_limit_reached = (flag || ng >= (int64_t)tm.dev.num_groups_limit) ? 1 : 0;   // GroupByOperator.java:116
+    }
+  }
+  r->finalized = true;
+  return PB_OK;
+}
+
+extern "C" int pb_result_finalize(pb_result_handle r) {
+  if (!r) return fail(PB_ERR_INVALID, "null result");
+  return finalize_result(r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// accessors
+// ------------------------------------------------------------------------------------------------
+#define TAB(r, t) ((r) && (t) >= 0 && (t) < (int)(r)->tables.size() && (r)->finalized ? &(r)->tables[(t)] : nullptr)
+extern "C" int32_t pb_result_num_tables(pb_result_handle r) { return r ? (int32_t)r->tables.size() : 0; }
+extern "C" int64_t pb_result_num_groups(pb_result_handle r, int32_t t) { auto* tm = TAB(r, t); return tm ? tm->num_groups : -1; }
+extern "C" const int32_t* pb_result_group_dict_ids(pb_result_handle r, int32_t t, int32_t gb) {
+  auto* tm = TAB(r, t); if (!tm || gb < 0 || gb >= r->n_gb) return nullptr; return (const int32_t*)tm->key_ids[gb].p;
+}
+extern "C" const void* pb_result_group_key_values(pb_result_handle r, int32_t t, int32_t gb, int32_t* stored_type, int32_t* entry_bytes) {
+  auto* tm = TAB(r, t); if (!tm || gb < 0 || gb >= r->n_gb) return nullptr;
+  if (stored_type) *stored_type = tm->key_type[gb];
+  if (entry_bytes) *entry_bytes = tm->key_eb[gb];
+  return tm->key_vals[gb].p;
+}
+extern "C" const double* pb_result_double(pb_result_handle r, int32_t t, int32_t a) { auto* tm = TAB(r, t); return (tm && a >= 0 && a < r->n_aggs) ? (const double*)tm->dbl[a].p : nullptr; }
+extern "C" const int64_t* pb_result_long(pb_result_handle r, int32_t t, int32_t a) { auto* tm = TAB(r, t); return (tm && a >= 0 && a < r->n_aggs) ? (const int64_t*)tm->lng[a].p : nullptr; }
+extern "C" const int64_t* pb_result_distinct_offsets(pb_result_handle r, int32_t t, int32_t a) { auto* tm = TAB(r, t); return (tm && a >= 0 && a < r->n_aggs) ? (const int64_t*)tm->dc_off[a].p : nullptr; }
+extern "C" const int32_t* pb_result_distinct_dict_ids(pb_result_handle r, int32_t t, int32_t a) { auto* tm = TAB(r, t); return (tm && a >= 0 && a < r->n_aggs) ? (const int32_t*)tm->dc_ids[a].p : nullptr; }
+extern "C" const pb_exec_stats* pb_result_stats(pb_result_handle r, int32_t t) { auto* tm = TAB(r, t); return tm ? &tm->stats : nullptr; }
+extern "C" double pb_result_device_ms(pb_result_handle r) { return r ? r->device_ms : 0; }
+extern "C" double pb_result_scan_kernel_ms(pb_result_handle r) {
+  if (!r) return 0;
+  if (!r->finalized) { float ms = 0; cudaEventSynchronize(r->ev2); cudaEventElapsedTime(&ms, r->ev1, r->ev2); return ms; }
+  return r->scan_ms;
+}
+extern "C" int32_t pb_result_kernel_launches(pb_result_handle r) { return r ? r->launches : 0; }
+extern "C" void* pb_result_stream(pb_result_handle r) { return r ? (void*)r->stream : nullptr; }
+
+extern "C" int pb_result_device_buffer(pb_result_handle r, int32_t which, int32_t agg, void** device_ptr, int64_t* num_elements) {
+  if (!r || !device_ptr || !num_elements) return fail(PB_ERR_INVALID, "null argument");
+  if (!r->combine || r->tables.size() != 1) return fail(PB_ERR_STATE, "device buffers are exposed for PB_Q_COMBINE results only");
+  if (r->table_mode == T_HASH) return fail(PB_ERR_UNSUPPORTED, "hash tables cannot be all-reduced in place");
+  TableMeta& tm = r->tables[0];
+  const int64_t S = (int64_t)tm.capacity;
+  switch (which) {
+    case 0: *device_ptr = tm.dev.rowcnt; *num_elements = S; return PB_OK;
+    case 1: if (agg < 0 || agg >= r->n_aggs || !tm.dev.sum[agg]) break; *device_ptr = tm.dev.sum[agg]; *num_elements = S; return PB_OK;
+    case 2: if (agg < 0 || agg >= r->n_aggs || !tm.dev.mm[agg]) break; *device_ptr = tm.dev.mm[agg]; *num_elements = S; return PB_OK;
+    case 3: if (agg < 0 || agg >= r->n_aggs || !tm.dev.dc_bits[agg]) break; *device_ptr = tm.dev.dc_bits[agg]; *num_elements = S * (int64_t)tm.dev.dc_words[agg]; return PB_OK;
+    case 4: *device_ptr = r->d_counters; *num_elements = PB_COUNTERS_PER_TABLE; return PB_OK;
+    default: break;
+  }
+  return fail(PB_ERR_INVALID, "no such device buffer (which=%d agg=%d)", which, agg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// internal views for the host planning layer
+// ------------------------------------------------------------------------------------------------
+#include "pb_internal.h"
+int pbi_segment_view(pb_segment_handle s, PbSegmentView* out) {
+  if (!s || !out) return fail(PB_ERR_INVALID, "null segment");
+  out->name = s->name; out->num_docs = s->num_docs;
+  out->cols.resize(s->cols.size());
+  for (size_t i = 0; i < s->cols.size(); i++) {
+    const Column& c = s->cols[i];
+    PbColumnView& v = out->cols[i];
+    v.name = c.name; v.type = c.type; v.has_dict = c.has_dict; v.is_sorted = c.is_sorted; v.card = c.card; v.bits = c.bits;
+    v.entry_bytes = c.entry_bytes; v.dict = c.h_dict.empty() ? nullptr : c.h_dict.data();
+    v.sorted_pairs = c.h_sorted_pairs.empty() ? nullptr : c.h_sorted_pairs.data();
+    v.has_inverted = c.h_inv != nullptr;
+  }
+  return PB_OK;
+}
+int pbi_group_segments(pb_segment_group_handle g, std::vector<pb_segment_handle>* out) {
+  if (!g || !out) return fail(PB_ERR_INVALID, "null group");
+  out->assign(g->segs.begin(), g->segs.end());
+  return PB_OK;
+}
+int pbi_fail(int code, const char* msg) { return fail(code, "%s", msg); }

@@ -1,0 +1,381 @@
+"""ctypes binding of libpinot_b200.so (include/pinot_b200.h + include/pinot_b200_host.h).
+
+This is what tests and bench.py call; it is the Python twin of the JNI shim (jni/pinot_b200_jni.c).  There is no
+fallback: if the shared library is missing or no CUDA device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from .query import AggOp, QueryContext
+from .segment_writer import DataType, Segment
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpinot_b200.so")
+
+PB_Q_COMBINE = 1
+PB_Q_DEFER_FINALIZE = 2
+PB_Q_GENERIC_KERNEL = 4
+PB_Q_NO_TMA = 8
+
+
+class PbColumnDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("stored_type", C.c_int32), ("has_dictionary", C.c_int32),
+                ("is_sorted", C.c_int32), ("cardinality", C.c_int32), ("bits_per_element", C.c_int32),
+                ("dict_entry_bytes", C.c_int32),
+                ("forward_index", C.c_void_p), ("forward_index_len", C.c_uint64),
+                ("dictionary", C.c_void_p), ("dictionary_len", C.c_uint64),
+                ("inverted_index", C.c_void_p), ("inverted_index_len", C.c_uint64)]
+
+
+class PbSegmentDesc(C.Structure):
+    _fields_ = [("segment_name", C.c_char_p), ("num_docs", C.c_int32), ("num_columns", C.c_int32),
+                ("columns", C.POINTER(PbColumnDesc))]
+
+
+class PbAggregationDesc(C.Structure):
+    _fields_ = [("op", C.c_int32), ("column", C.c_char_p)]
+
+
+class PbExecStats(C.Structure):
+    _fields_ = [("num_docs_scanned", C.c_int64), ("num_entries_scanned_in_filter", C.c_int64),
+                ("num_entries_scanned_post_filter", C.c_int64), ("num_total_docs", C.c_int64),
+                ("num_groups_limit_reached", C.c_int32), ("num_segments", C.c_int32)]
+
+
+class PbhPredicate(C.Structure):
+    _fields_ = [("type", C.c_int32), ("column", C.c_char_p), ("num_values", C.c_int32),
+                ("values", C.POINTER(C.c_char_p)), ("lower", C.c_char_p), ("upper", C.c_char_p),
+                ("lower_inclusive", C.c_int32), ("upper_inclusive", C.c_int32)]
+
+
+class PbhFilterNode(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("num_children", C.c_int32), ("predicate", C.c_int32)]
+
+
+class PbhQueryContext(C.Structure):
+    _fields_ = [("num_filter_nodes", C.c_int32), ("filter_nodes", C.POINTER(PbhFilterNode)),
+                ("predicates", C.POINTER(PbhPredicate)),
+                ("num_group_by", C.c_int32), ("group_by_columns", C.POINTER(C.c_char_p)),
+                ("num_aggregations", C.c_int32), ("aggregations", C.POINTER(PbAggregationDesc)),
+                ("num_groups_limit", C.c_int32), ("max_initial_result_holder_capacity", C.c_int32),
+                ("num_skip_inverted", C.c_int32), ("skip_inverted_columns", C.POINTER(C.c_char_p))]
+
+
+_lib = None
+
+
+def lib():
+    """Load the native library; raises if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the executor has no CPU fallback)")
+    l = C.CDLL(LIB_PATH)
+    l.pb_last_error.restype = C.c_char_p
+    l.pb_init.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_size_t]
+    l.pb_device_count.restype = C.c_int
+    l.pb_segment_stage.argtypes = [C.POINTER(PbSegmentDesc), C.c_int, C.POINTER(C.c_void_p)]
+    l.pb_segment_release.argtypes = [C.c_void_p]
+    l.pb_segment_device_bytes.argtypes = [C.c_void_p]
+    l.pb_segment_device_bytes.restype = C.c_int64
+    l.pb_segment_group_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
+    l.pb_segment_group_release.argtypes = [C.c_void_p]
+    l.pb_segment_group_export_dictionary.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p),
+                                                     C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    l.pb_segment_group_set_global_dictionary.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]
+    l.pbh_execute.argtypes = [C.c_void_p, C.POINTER(PbhQueryContext), C.c_uint32, C.POINTER(C.c_void_p)]
+    l.pbh_is_eligible.argtypes = [C.c_void_p, C.POINTER(PbhQueryContext)]
+    l.pbh_explain_filter.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PbhQueryContext), C.c_char_p, C.c_int32]
+    l.pb_result_free.argtypes = [C.c_void_p]
+    l.pb_result_finalize.argtypes = [C.c_void_p]
+    l.pb_result_num_tables.argtypes = [C.c_void_p]
+    l.pb_result_num_tables.restype = C.c_int32
+    l.pb_result_num_groups.argtypes = [C.c_void_p, C.c_int32]
+    l.pb_result_num_groups.restype = C.c_int64
+    l.pb_result_group_dict_ids.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    l.pb_result_group_dict_ids.restype = C.POINTER(C.c_int32)
+    l.pb_result_group_key_values.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    l.pb_result_group_key_values.restype = C.c_void_p
+    l.pb_result_double.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    l.pb_result_double.restype = C.POINTER(C.c_double)
+    l.pb_result_long.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    l.pb_result_long.restype = C.POINTER(C.c_int64)
+    l.pb_result_distinct_offsets.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    l.pb_result_distinct_offsets.restype = C.POINTER(C.c_int64)
+    l.pb_result_distinct_dict_ids.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    l.pb_result_distinct_dict_ids.restype = C.POINTER(C.c_int32)
+    l.pb_result_stats.argtypes = [C.c_void_p, C.c_int32]
+    l.pb_result_stats.restype = C.POINTER(PbExecStats)
+    l.pb_result_device_ms.argtypes = [C.c_void_p]
+    l.pb_result_device_ms.restype = C.c_double
+    l.pb_result_scan_kernel_ms.argtypes = [C.c_void_p]
+    l.pb_result_scan_kernel_ms.restype = C.c_double
+    l.pb_result_kernel_launches.argtypes = [C.c_void_p]
+    l.pb_result_kernel_launches.restype = C.c_int32
+    l.pb_result_stream.argtypes = [C.c_void_p]
+    l.pb_result_stream.restype = C.c_void_p
+    l.pb_result_device_buffer.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    _lib = l
+    return l
+
+
+class PinotB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pinot_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise PinotB200Error(rc, lib().pb_last_error().decode("utf-8", "replace"))
+
+
+def init(device: Optional[int] = None):
+    if device is None:
+        _check(lib().pb_init(None, 0, 0))
+    else:
+        arr = (C.c_int * 1)(device)
+        _check(lib().pb_init(arr, 1, 0))
+
+
+class StagedSegment:
+    """IndexSegment handle on the device (pb_segment_stage).  Keeps the host buffers alive."""
+
+    def __init__(self, seg: Segment, columns: Optional[Sequence[str]] = None):
+        self.segment = seg
+        names = list(columns) if columns is not None else seg.column_names()
+        self._keep = []
+        cols = (PbColumnDesc * len(names))()
+        for i, n in enumerate(names):
+            c = seg.columns[n]
+            d = cols[i]
+            d.name = n.encode()
+            d.stored_type = int(c.data_type)
+            d.has_dictionary = int(c.has_dictionary)
+            d.is_sorted = int(c.is_sorted)
+            d.cardinality = c.cardinality
+            d.bits_per_element = c.bits_per_element
+            d.dict_entry_bytes = c.dict_entry_bytes
+            d.forward_index = c.forward_index.ctypes.data
+            d.forward_index_len = c.forward_index.size
+            if c.dictionary is not None:
+                d.dictionary = c.dictionary.ctypes.data
+                d.dictionary_len = c.dictionary.size
+            if c.inverted_index is not None:
+                d.inverted_index = c.inverted_index.ctypes.data
+                d.inverted_index_len = c.inverted_index.size
+        desc = PbSegmentDesc(seg.name.encode(), seg.num_docs, len(names), cols)
+        self._keep.append((cols, desc))
+        h = C.c_void_p()
+        _check(lib().pb_segment_stage(C.byref(desc), 0, C.byref(h)))
+        self.handle = h
+
+    def device_bytes(self) -> int:
+        return lib().pb_segment_device_bytes(self.handle)
+
+    def release(self):
+        if self.handle:
+            lib().pb_segment_release(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+class SegmentGroup:
+    def __init__(self, staged: Sequence[StagedSegment]):
+        self.staged = list(staged)
+        arr = (C.c_void_p * len(self.staged))(*[s.handle for s in self.staged])
+        h = C.c_void_p()
+        _check(lib().pb_segment_group_create(arr, len(self.staged), C.byref(h)))
+        self.handle = h
+
+    def export_dictionary(self, column: str) -> np.ndarray:
+        p, n, eb = C.c_void_p(), C.c_int64(), C.c_int32()
+        _check(lib().pb_segment_group_export_dictionary(self.handle, column.encode(), C.byref(p), C.byref(n), C.byref(eb)))
+        raw = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n.value * eb.value,)).copy()
+        return raw.reshape(n.value, eb.value)
+
+    def set_global_dictionary(self, column: str, entries: np.ndarray):
+        e = np.ascontiguousarray(entries, dtype=np.uint8)
+        _check(lib().pb_segment_group_set_global_dictionary(self.handle, column.encode(), e.ctypes.data, e.shape[0], e.shape[1]))
+
+    def release(self):
+        if self.handle:
+            lib().pb_segment_group_release(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+
+_KEY_DT = {0: np.int32, 1: np.int64, 2: np.float32, 3: np.float64}
+
+
+class ResultTable:
+    """One GroupByResultsBlock / AggregationResultsBlock."""
+
+    def __init__(self, rh, t: int, q: QueryContext):
+        l = lib()
+        ng = l.pb_result_num_groups(rh, t)
+        self.num_groups = int(ng)
+        n = max(self.num_groups, 1)
+        st = l.pb_result_stats(rh, t).contents
+        self.stats = {k: getattr(st, k) for k, _ in PbExecStats._fields_}
+        self.key_dict_ids, self.key_values = [], []
+        for j in range(len(q.group_by)):
+            ids = np.ctypeslib.as_array(l.pb_result_group_dict_ids(rh, t, j), shape=(n,))[:self.num_groups].copy()
+            ty, eb = C.c_int32(), C.c_int32()
+            p = l.pb_result_group_key_values(rh, t, j, C.byref(ty), C.byref(eb))
+            raw = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * eb.value,))[:self.num_groups * eb.value].copy()
+            if ty.value == 4:
+                vals = np.array([bytes(r).rstrip(b"\0") for r in raw.reshape(self.num_groups, eb.value)], dtype=object)
+            else:
+                vals = raw.view(_KEY_DT[ty.value])
+            self.key_dict_ids.append(ids)
+            self.key_values.append(vals)
+        self.doubles, self.longs, self.distinct = [], [], []
+        for a, agg in enumerate(q.aggregations):
+            self.doubles.append(np.ctypeslib.as_array(l.pb_result_double(rh, t, a), shape=(n,))[:self.num_groups].copy())
+            self.longs.append(np.ctypeslib.as_array(l.pb_result_long(rh, t, a), shape=(n,))[:self.num_groups].copy())
+            if agg.op == AggOp.DISTINCTCOUNT:
+                off = np.ctypeslib.as_array(l.pb_result_distinct_offsets(rh, t, a), shape=(self.num_groups + 1,)).copy()
+                tot = int(off[-1])
+                ids = np.ctypeslib.as_array(l.pb_result_distinct_dict_ids(rh, t, a), shape=(max(tot, 1),))[:tot].copy()
+                self.distinct.append((off, ids))
+            else:
+                self.distinct.append(None)
+        self.query = q
+
+    def keys(self) -> List[tuple]:
+        out = []
+        for g in range(self.num_groups):
+            out.append(tuple(v[g].item() if hasattr(v[g], "item") else v[g] for v in self.key_values))
+        return out
+
+    def rows(self) -> Dict[tuple, list]:
+        """key -> [per-aggregation value]: COUNT int, SUM/MIN/MAX float, AVG (sum, count), DISTINCTCOUNT count."""
+        ks = self.keys() if self.query.group_by else [()]
+        out = {}
+        for g, k in enumerate(ks):
+            row = []
+            for a, agg in enumerate(self.query.aggregations):
+                if agg.op in (AggOp.COUNT, AggOp.DISTINCTCOUNT):
+                    row.append(int(self.longs[a][g]))
+                elif agg.op == AggOp.AVG:
+                    row.append((float(self.doubles[a][g]), int(self.longs[a][g])))
+                else:
+                    row.append(float(self.doubles[a][g]))
+            out[k] = row
+        return out
+
+
+class Result:
+    def __init__(self, rh, q: QueryContext, deferred: bool = False):
+        self._rh = rh
+        self.query = q
+        self.tables: List[ResultTable] = []
+        if not deferred:
+            self._load()
+
+    def _load(self):
+        l = lib()
+        self.tables = [ResultTable(self._rh, t, self.query) for t in range(l.pb_result_num_tables(self._rh))]
+        self.device_ms = l.pb_result_device_ms(self._rh)
+        self.scan_kernel_ms = l.pb_result_scan_kernel_ms(self._rh)
+        self.kernel_launches = l.pb_result_kernel_launches(self._rh)
+
+    def device_buffer(self, which: int, agg: int = 0):
+        p, n = C.c_void_p(), C.c_int64()
+        _check(lib().pb_result_device_buffer(self._rh, which, agg, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def stream(self) -> int:
+        return lib().pb_result_stream(self._rh) or 0
+
+    def scan_ms(self) -> float:
+        return lib().pb_result_scan_kernel_ms(self._rh)
+
+    def finalize(self):
+        _check(lib().pb_result_finalize(self._rh))
+        self._load()
+
+    def free(self):
+        if self._rh:
+            lib().pb_result_free(self._rh)
+            self._rh = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _MarshalledQuery:
+    def __init__(self, q: QueryContext):
+        nodes, preds = q.filter_postfix()
+        self.keep = []
+        self.nodes = (PbhFilterNode * max(1, len(nodes)))()
+        for i, (k, n, p) in enumerate(nodes):
+            self.nodes[i].kind, self.nodes[i].num_children, self.nodes[i].predicate = k, n, p
+        self.preds = (PbhPredicate * max(1, len(preds)))()
+        for i, p in enumerate(preds):
+            o = self.preds[i]
+            o.type = int(p.type)
+            o.column = p.column.encode()
+            if int(p.type) == 4:
+                o.lower = p.lower.encode() if p.lower is not None else None
+                o.upper = p.upper.encode() if p.upper is not None else None
+                o.lower_inclusive = int(p.lower_inclusive)
+                o.upper_inclusive = int(p.upper_inclusive)
+            else:
+                arr = (C.c_char_p * len(p.values))(*[v.encode() for v in p.values])
+                self.keep.append(arr)
+                o.values = arr
+                o.num_values = len(p.values)
+        self.gb = (C.c_char_p * max(1, len(q.group_by)))(*[c.encode() for c in q.group_by])
+        self.aggs = (PbAggregationDesc * max(1, len(q.aggregations)))()
+        for i, a in enumerate(q.aggregations):
+            self.aggs[i].op = int(a.op)
+            self.aggs[i].column = a.column.encode() if a.column is not None else None
+        skip = [c for c, kinds in q.skip_indexes.items() if "inverted" in kinds]
+        self.skip = (C.c_char_p * max(1, len(skip)))(*[c.encode() for c in skip])
+        self.ctx = PbhQueryContext(len(nodes), self.nodes, self.preds, len(q.group_by), self.gb,
+                                   len(q.aggregations), self.aggs, q.num_groups_limit,
+                                   q.max_initial_result_holder_capacity, len(skip), self.skip)
+
+
+def execute(group: SegmentGroup, q: QueryContext, flags: int = 0) -> Result:
+    """Plan (host layer) + run (device) a query over every segment of the group."""
+    m = _MarshalledQuery(q)
+    rh = C.c_void_p()
+    _check(lib().pbh_execute(group.handle, C.byref(m.ctx), flags, C.byref(rh)))
+    return Result(rh, q, deferred=bool(flags & PB_Q_DEFER_FINALIZE))
+
+
+def is_eligible(group: SegmentGroup, q: QueryContext) -> bool:
+    m = _MarshalledQuery(q)
+    return lib().pbh_is_eligible(group.handle, C.byref(m.ctx)) == 0
+
+
+def explain_filter(group: SegmentGroup, q: QueryContext, segment_index: int = 0) -> str:
+    m = _MarshalledQuery(q)
+    buf = C.create_string_buffer(8192)
+    n = lib().pbh_explain_filter(group.handle, segment_index, C.byref(m.ctx), buf, 8192)
+    if n < 0:
+        _check(n)
+    return buf.value.decode()

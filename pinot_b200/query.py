@@ -114,7 +114,7 @@ class QueryContext:
 
 _TOKEN = re.compile(r"\s*(?:(?P<num>-?\d+\.\d*(?:[eE][-+]?\d+)?|-?\.\d+|-?\d+(?:[eE][-+]?\d+)?)"
                     r"|(?P<str>'(?:[^']|'')*')|(?P<id>[A-Za-z_][A-Za-z_0-9$]*|\"[^\"]+\")"
-                    r"|(?P<op><=|>=|<>|!=|=|<|>|\(|\)|,|\*))")
+                    r"|(?P<op><=|>=|<>|!=|=|<|>|\(|\)|,|\*|;))")
 
 
 def _tokenize(sql: str):
@@ -256,6 +256,8 @@ def parse_sql(sql: str) -> QueryContext:
         k = p.ident()
         p.eat_op("=")
         options[k.lower()] = p.literal()
+        if p.peek() == ("op", ";"):
+            p.i += 1
     p.eat_kw("SELECT")
     aggs: List[Aggregation] = []
     select_idents: List[str] = []

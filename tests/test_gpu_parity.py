@@ -1,0 +1,194 @@
+"""Parity of the CUDA path (called through the C ABI) against the oracle and the reference's goldens.  -m gpu."""
+import numpy as np
+import pytest
+
+from pinot_b200 import datagen, native
+from pinot_b200.query import parse_sql
+from pinot_b200.segment_writer import DataType, build_column, build_dict_column, make_segment
+from tests.fixtures import FILTER, sv_segment
+from tests.parity import check_query
+
+pytestmark = pytest.mark.gpu
+
+AGG = "SELECT COUNT(*), SUM(column1), MAX(column3), MIN(column6), AVG(column7) FROM testTable"
+ALL_FLAGS = (0, native.PB_Q_GENERIC_KERNEL, native.PB_Q_NO_TMA)
+
+
+@pytest.fixture(scope="module")
+def sv_group():
+    native.init()
+    seg = sv_segment()
+    staged = [native.StagedSegment(seg) for _ in range(4)]
+    g = native.SegmentGroup(staged)
+    yield seg, g
+    g.release()
+
+
+def _row(res_table, key=()):
+    return res_table.rows()[key]
+
+
+def test_golden_aggregation_only(sv_group):   # InnerSegmentAggregationSingleValueQueriesTest.java:43-60
+    seg, g = sv_group
+    r = native.execute(g, parse_sql(AGG))
+    row = _row(r.tables[0])
+    assert (row[0], int(row[1]), int(row[2]), int(row[3]), int(row[4][0]), row[4][1]) == \
+        (30000, 32317185437847, 2147419555, 1689277, 28175373944314, 30000)
+    st = r.tables[0].stats
+    assert (st["num_docs_scanned"], st["num_entries_scanned_post_filter"], st["num_total_docs"]) == (30000, 120000, 30000)
+    r = native.execute(g, parse_sql(AGG + FILTER))
+    row = _row(r.tables[0])
+    assert (row[0], int(row[1]), int(row[2]), int(row[3]), int(row[4][0]), row[4][1]) == \
+        (6129, 6875947596072, 999813884, 1980174, 4699510391301, 6129)
+    st = r.tables[0].stats
+    assert (st["num_docs_scanned"], st["num_entries_scanned_post_filter"], st["num_total_docs"]) == (6129, 24516, 30000)
+    # 4 identical segments merged on the device == InterSegment goldens (x4)
+    r = native.execute(g, parse_sql(AGG + FILTER), native.PB_Q_COMBINE)
+    row = _row(r.tables[0])
+    assert (row[0], int(row[1]), int(row[2]), int(row[3])) == (24516, 4 * 6875947596072, 999813884, 1980174)
+
+
+@pytest.mark.parametrize("group_by,key,exp,key_f,exp_f", [
+    (" GROUP BY column9", (11270,), (1, 815409257, 1215316262, 1328642550, 788414092, 1),
+     (242920,), (3, 4348938306, 407993712, 296467636, 5803888725, 3)),
+    (" GROUP BY column9, column11, column12", (1813102948, b"P", b"HEuxNvH"),
+     (4, 2062187196, 1988589001, 394608493, 4782388964, 4),
+     (1176631727, b"P", b"KrNxpdycSiwoRohEiTIlLqDHnx"), (1, 716185211, 489993380, 371110078, 487714191, 1)),
+    (" GROUP BY column1, column6, column9, column11, column12",
+     (484569489, 16200443, 1159557463, b"P", b"MaztCmmxxgguBUxPti"), (2, 969138978, 995355481, 16200443, 2222394270, 2),
+     (1318761745, 353175528, 1172307870, b"P", b"HEuxNvH"), (2, 2637523490, 557154208, 353175528, 2427862396, 2)),
+])
+def test_golden_group_by(sv_group, group_by, key, exp, key_f, exp_f):   # :96-152
+    seg, g = sv_group
+    for sql, k, e in ((AGG + group_by, key, exp), (AGG + FILTER + group_by, key_f, exp_f)):
+        r = native.execute(g, parse_sql(sql))
+        row = _row(r.tables[0], k)
+        assert (row[0], int(row[1]), int(row[2]), int(row[3]), int(row[4][0]), row[4][1]) == e
+
+
+def test_golden_very_large_group_by_declines(sv_group):   # :156-174 — ARRAY_MAP keys (> 64 bits): plan maker declines
+    seg, g = sv_group
+    q = parse_sql(AGG + " GROUP BY column1, column3, column6, column7, column9, column11, column12, column17, column18")
+    with pytest.raises(native.PinotB200Error) as ei:
+        native.execute(g, q)
+    assert ei.value.code == -2
+
+
+def test_golden_inter_segment(sv_group):   # InterSegmentAggregationSingleValueQueriesTest.java:47-258
+    seg, g = sv_group
+    C = native.PB_Q_COMBINE
+    assert _row(native.execute(g, parse_sql("SELECT COUNT(*) FROM testTable"), C).tables[0])[0] == 120000
+    assert _row(native.execute(g, parse_sql("SELECT COUNT(*) FROM testTable" + FILTER), C).tables[0])[0] == 24516
+    t = native.execute(g, parse_sql("SELECT COUNT(*) FROM testTable GROUP BY column9"), C).tables[0]
+    assert max(v[0] for v in t.rows().values()) == 64420
+    t = native.execute(g, parse_sql("SELECT COUNT(*) FROM testTable" + FILTER + " GROUP BY column9"), C).tables[0]
+    assert max(v[0] for v in t.rows().values()) == 17080
+    assert _row(native.execute(g, parse_sql("SELECT MAX(column1), MAX(column3) FROM testTable" + FILTER), C).tables[0]) == [2146952047.0, 999813884.0]
+    assert _row(native.execute(g, parse_sql("SELECT MIN(column1), MIN(column3) FROM testTable"), C).tables[0]) == [240528.0, 17891.0]
+    dc = "SELECT DISTINCTCOUNT(column1), DISTINCTCOUNT(column3) FROM testTable"
+    assert _row(native.execute(g, parse_sql(dc), C).tables[0]) == [6582, 21910]
+    assert _row(native.execute(g, parse_sql(dc + FILTER), C).tables[0]) == [1872, 4556]
+    t = native.execute(g, parse_sql(dc + " GROUP BY column9"), C).tables[0]
+    assert (max(v[0] for v in t.rows().values()), max(v[1] for v in t.rows().values())) == (3495, 11961)
+    t = native.execute(g, parse_sql(dc + FILTER + " GROUP BY column9"), C).tables[0]
+    assert (max(v[0] for v in t.rows().values()), max(v[1] for v in t.rows().values())) == (1272, 3289)
+
+
+def test_sv_segment_vs_oracle_all_kernels():
+    seg = sv_segment()
+    for sql in (AGG, AGG + FILTER, AGG + FILTER + " GROUP BY column9, column11",
+                "SELECT COUNT(*), DISTINCTCOUNT(column17) FROM testTable WHERE column6 < 500000000 OR column11 NOT IN ('t','P') GROUP BY column12",
+                "SELECT SUM(column18) FROM testTable WHERE NOT (column7 IN (1111197135, 296467636)) AND column17 <> 635942547",
+                "SELECT COUNT(*) FROM testTable WHERE column5 = 'nope'",
+                "SELECT COUNT(*), MIN(column1) FROM testTable WHERE daysSinceEpoch > 126164076 GROUP BY daysSinceEpoch"):
+        check_query([seg, seg], sql, flags_list=ALL_FLAGS)
+
+
+@pytest.fixture(scope="module")
+def synth():
+    native.init()
+    segs = [datagen.make_segment_synth(i, n) for i, n in enumerate((100_003, 65_536, 8_192 * 3 + 1))]
+    staged = [native.StagedSegment(s) for s in segs]
+    g = native.SegmentGroup(staged)
+    yield segs, g
+    g.release()
+
+
+def test_config1_keyless_sum(synth):
+    segs, g = synth
+    check_query(segs, datagen.config1_sql(segs[0]), group=g, flags_list=ALL_FLAGS)
+
+
+def test_config2_filter_group_by(synth):
+    segs, g = synth
+    check_query(segs, datagen.config2_sql(segs, 16), group=g, flags_list=ALL_FLAGS)
+    check_query(segs, datagen.config2_sql(segs, 500), group=g, flags_list=(0,))
+
+
+def test_config3_inverted_index_and_or(synth):
+    segs, g = synth
+    d1 = segs[0].columns["c1"].dictionary_values()
+    d3 = segs[0].columns["c3"].dictionary_values()
+    d0 = segs[0].columns["d0"].dictionary_values()
+    sql = (f"SELECT d0, d1, d2, d3, d4, SUM(m0), COUNT(*), MIN(m1), MAX(m2) FROM t WHERE (c1 IN ({', '.join(str(int(v)) for v in d1[:8])}) "
+           f"OR c3 = {int(d3[5])}) AND d0 IN ({int(d0[1])}, {int(d0[6])}) GROUP BY d0, d1, d2, d3, d4 LIMIT 100000")
+    check_query(segs, sql, group=g, flags_list=(0, native.PB_Q_GENERIC_KERNEL))
+
+
+def test_config4_string_key_distinct_raw_double(synth):
+    segs, g = synth
+    d2 = segs[0].columns["c2"].dictionary_values()
+    sql = f"SELECT s0, DISTINCTCOUNT(c0), SUM(x0), AVG(x1) FROM t WHERE c2 < {int(d2[len(d2) // 2])} GROUP BY s0 LIMIT 100000"
+    check_query(segs, sql, group=g, exact_float=False)
+
+
+def test_config5_raw_long_key_hash(synth):
+    segs, g = synth
+    check_query(segs, "SET numGroupsLimit = 20000000; SELECT k0, SUM(m0), COUNT(*) FROM t GROUP BY k0 LIMIT 100000000", group=g)
+
+
+def test_sorted_column_and_raw_predicates(synth):
+    segs, g = synth
+    check_query(segs, "SELECT t0, COUNT(*), MAX(m0) FROM t WHERE t0 BETWEEN 20010 AND 20040 AND x0 < 0.5 GROUP BY t0", group=g)
+    check_query(segs, "SELECT COUNT(*), SUM(x1), MIN(x0), MAX(k0) FROM t WHERE k0 > 5000000000000 AND t0 <> 20003", group=g, exact_float=False)
+    check_query(segs, "SELECT c5, c6, COUNT(*) FROM t WHERE t0 IN (20001, 20005, 20006, 20050) OR c7 = 0 GROUP BY c5, c6", group=g)
+
+
+def test_empty_and_match_all(synth):
+    segs, g = synth
+    check_query(segs, "SELECT COUNT(*), SUM(m0), MIN(m1), MAX(m2) FROM t WHERE c1 < -5", group=g)
+    check_query(segs, "SELECT COUNT(*), SUM(m0), MIN(m1), MAX(m2) FROM t WHERE c1 > -5", group=g)
+    check_query(segs, "SELECT d1, COUNT(*) FROM t WHERE c1 < -5 GROUP BY d1", group=g)
+
+
+@pytest.mark.parametrize("bits", list(range(1, 21)) + [24])
+def test_every_bit_width(bits):
+    """Forward index widths 1..20 and 24 through both predicate paths (range + IN) and the gather path."""
+    native.init()
+    rng = np.random.default_rng(bits)
+    n = 40_000 + bits
+    if bits == 1:
+        card = 2
+    elif bits < 17:
+        card = (1 << bits) - 1
+    else:
+        card = (1 << (bits - 1)) + 5          # bitsPerElement = bit length of (card - 1)
+    if bits <= 20:
+        dvals = np.sort(rng.choice(max(card * 4, 64), size=card, replace=False)).astype(np.int32)
+    else:
+        dvals = (np.arange(card, dtype=np.int64) * 3).astype(np.int32)
+    ids = rng.integers(0, card, n, dtype=np.uint32)
+    k = min(card, n)
+    ids[rng.choice(n, size=k, replace=False)] = rng.choice(card, size=k, replace=False).astype(np.uint32)
+    ids[0] = card - 1
+    col = build_dict_column("w", DataType.INT, dvals, ids)
+    assert col.bits_per_element == bits
+    g_ids = rng.integers(0, 7, n, dtype=np.uint32)
+    gcol = build_dict_column("g", DataType.INT, np.arange(7, dtype=np.int32) * 11, g_ids)
+    seg = make_segment(f"w{bits}", [col, gcol])
+    lo, hi = int(dvals[card // 4]), int(dvals[(3 * card) // 4])
+    pick = ", ".join(str(int(v)) for v in dvals[:: max(1, card // 9)][:9])
+    for sql in (f"SELECT g, COUNT(*), SUM(w), MIN(w), MAX(w) FROM t WHERE w BETWEEN {lo} AND {hi} GROUP BY g",
+                f"SELECT COUNT(*), SUM(w) FROM t WHERE w IN ({pick})",
+                f"SELECT w, COUNT(*) FROM t WHERE w NOT IN ({pick}) AND g <> 11 GROUP BY w LIMIT 10000000"):
+        check_query([seg], sql, flags_list=(0, native.PB_Q_GENERIC_KERNEL), check_combined=(bits <= 20))
