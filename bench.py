@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py — scanned rows/s of the per-segment filter + group-by hot path (BASELINE.json metric).
+
+Workload at N=1 (BASELINE.json configs[1]): 8 segments x 12.5 M rows = 100 M rows of the 20-column synthetic table
+(only the 8 columns the query touches are materialised), inverted index on c1 disabled so both predicates scan:
+
+    SELECT d0,d1,d2, SUM(m0), COUNT(*), MIN(m1), MAX(m2) FROM t
+    WHERE c1 IN (16 values) AND c2 < k(50 %) GROUP BY d0,d1,d2            -- 4 096 groups, ~0.8 % selectivity
+
+A step = one pass of the whole query over all segments of this rank through the C ABI (host planning layer ->
+pb_query_execute, merged result table back in pinned host memory).  `value` = rows / wall time of K steps with the
+segments already resident in HBM; `e2e` = the same call sequence starting from HOST buffers (pb_segment_stage of
+the touched columns + execute + result read-back inside the timed region).  N > 1: every rank owns its own 8
+segments (weak scaling), per-rank dense tables are all-reduced over NCCL, rank 0 finalises.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/, the one place this file may run it
+besides the cpu_baseline leg) on the host cores, one thread per segment.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "scanned rows/sec for filter+groupby(3 dims,4 aggs) @1/2/4/8 B200; %HBM BW"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--segments", type=int, default=8)
+    ap.add_argument("--docs-per-segment", type=int, default=12_500_000)
+    ap.add_argument("--in-values", type=int, default=16)
+    ap.add_argument("--flags", type=int, default=0, help="extra PB_Q_* flags (A/B: 4 = generic predicate path, 8 = no TMA)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smmax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_table(args, rank):
+    from pinot_b200 import datagen
+    segs = datagen.make_table(args.segments, args.docs_per_segment, columns=datagen.CONFIG2_COLUMNS,
+                              first_index=rank * args.segments)
+    return segs
+
+
+def algorithmic_bytes(segs, q):
+    """sum over segments of numDocs x sum over touched columns of storedBits / 8 (full-scan convention)."""
+    touched = set(q.group_by) | {a.column for a in q.aggregations if a.column}
+    _, preds = q.filter_postfix()
+    touched |= {p.column for p in preds}
+    total = 0.0
+    for s in segs:
+        bits = 0
+        for c in touched:
+            col = s.columns[c]
+            bits += col.bits_per_element if col.has_dictionary else 8 * col.dict_entry_bytes
+        total += s.num_docs * bits / 8.0
+    return total
+
+
+def oracle_query_all_threads(segs, q, threads):
+    """One CombineOperator-style pass on the CPU: one task per segment on `threads` threads, then the merge."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        res = list(ex.map(lambda s: oracle.execute(s, q), segs))
+    return oracle.combine_numeric(res)
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU path (restated in C: oracle/) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    from pinot_b200 import datagen
+    from pinot_b200.query import parse_sql
+    oracle.build()
+    segs = build_table(args, 0)
+    q = parse_sql(datagen.config2_sql(segs, args.in_values))
+    threads = min(len(segs), os.cpu_count() or 1)
+    rows = sum(s.num_docs for s in segs)
+    for _ in range(args.warmup):
+        oracle_query_all_threads(segs, q, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_query_all_threads(segs, q, threads)
+    dt = time.perf_counter() - t0
+    value = rows * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, segs),
+            "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
+                             "sample": f"full {rows} row query per step, one thread per segment ({threads} threads), {args.steps} steps"},
+            "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, segs):
+    return {"workload": f"BASELINE.json configs[1]: {len(segs)} segments x {segs[0].num_docs} rows, "
+                        f"WHERE c1 IN({args.in_values}) AND c2<k GROUP BY d0,d1,d2 SUM/COUNT/MIN/MAX, skipIndexes c1=inverted",
+            "segments_per_gpu": len(segs), "rows_per_gpu": sum(s.num_docs for s in segs),
+            "columns_materialised": "8 touched of the 20-column table", "l2_policy": "inputs (>1 GB/GPU) larger than the 126 MB L2",
+            "parallelism": f"segments sharded over {args.gpus} GPU(s); dense group tables all-reduced over NCCL" if args.gpus > 1 else "1 GPU"}
+
+
+class _DevBuf:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from pinot_b200 import datagen, native
+    from pinot_b200.query import AggOp, parse_sql
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    native.init(local_rank)
+
+    segs = build_table(args, rank)
+    # table-wide literals must agree on every rank: dimension dictionaries are table-wide (datagen), so they do
+    q = parse_sql(datagen.config2_sql(segs, args.in_values))
+    rows_rank = sum(s.num_docs for s in segs)
+    flags = native.PB_Q_COMBINE | args.flags
+
+    # page-lock the host copies of the touched columns (what a server does once for its mmap'd segments)
+    for s in segs:
+        for c in s.columns.values():
+            native.host_register(c.forward_index)
+
+    staged = [native.StagedSegment(s) for s in segs]
+    group = native.SegmentGroup(staged)
+
+    if world > 1:
+        # agree on the global dictionaries of the group-by columns (dense tables must line up across ranks)
+        for col in q.group_by:
+            mine = group.export_dictionary(col)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            allv = np.concatenate(gathered, axis=0)
+            vals = np.unique(allv.view(np.int32).reshape(-1))
+            group.set_global_dictionary(col, vals.astype(np.int32).view(np.uint8).reshape(-1, 4))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def step(g=None):
+        """one pass of the hot path over this rank's segments; returns the Result"""
+        g = g or group
+        if world == 1:
+            return native.execute(g, q, flags)
+        r = native.execute(g, q, flags | native.PB_Q_DEFER_FINALIZE)
+        r.wait()
+        # fused reduce: counts + sums (SUM), min (MIN), max (MAX) — <= 4 small collectives over NVLink
+        ptr, n = r.device_buffer(0)
+        dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.SUM)
+        ptr, n = r.device_buffer(4)
+        dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.SUM)
+        for a, agg in enumerate(q.aggregations):
+            if agg.op in (AggOp.SUM, AggOp.AVG):
+                ptr, n = r.device_buffer(1, a)
+                dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<f8"), device="cuda"), op=dist.ReduceOp.SUM)
+            elif agg.op in (AggOp.MIN, AggOp.MAX):
+                ptr, n = r.device_buffer(2, a)
+                dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"),
+                                op=dist.ReduceOp.MIN if agg.op == AggOp.MIN else dist.ReduceOp.MAX)
+        torch.cuda.synchronize()
+        if rank == 0:
+            r.finalize()
+        return r
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        r = step()
+        r.free()
+
+    # ---- timed: K steps, barrier + synchronize on both sides, max over ranks ----
+    sampler = ClockSampler(local_rank)
+    scan_ms, device_ms, launches = [], [], 0
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t0 = time.perf_counter()
+    last = None
+    for _ in range(args.steps):
+        r = step()
+        scan_ms.append(r.scan_ms())
+        if world == 1 or rank == 0:
+            launches += lib_launches(r)
+            device_ms.append(getattr(r, "device_ms", 0.0))
+        if last is not None:
+            last.free()
+        last = r
+    torch.cuda.synchronize()
+    barrier()
+    elapsed = time.perf_counter() - t0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed = float(t.item())
+        sk = torch.tensor([float(np.mean(scan_ms))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(sk, op=dist.ReduceOp.MAX)
+        scan_mean = float(sk.item())
+    else:
+        scan_mean = float(np.mean(scan_ms))
+    rows_total = rows_rank * world
+    value = rows_total * args.steps / elapsed
+
+    num_groups = last.tables[0].num_groups if (rank == 0 and last.tables) else 0
+    docs_matched = last.tables[0].stats["num_docs_scanned"] if (rank == 0 and last.tables) else 0
+    d2h_bytes = 0
+    if rank == 0 and last.tables:
+        t0_ = last.tables[0]
+        d2h_bytes = int(t0_.num_groups * (16 + 16 * len(q.aggregations)) + 64)
+    last.free()
+
+    # ---- e2e: same call sequence from HOST buffers (stage + execute + read-back) ----
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(2, min(args.steps, 5))
+        h2d_bytes = 0
+
+        def e2e_step():
+            nonlocal h2d_bytes
+            st = [native.StagedSegment(s) for s in segs]
+            g2 = native.SegmentGroup(st)
+            if world > 1:
+                for col in q.group_by:
+                    g2.set_global_dictionary(col, group.export_dictionary(col))
+            r2 = step(g2)
+            h2d_bytes = sum(s.device_bytes() for s in st)
+            r2.free()
+            g2.release()
+            for s in st:
+                s.release()
+
+        e2e_step()   # warm
+        barrier()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        barrier()
+        e2e_elapsed = time.perf_counter() - t1
+        if world > 1:
+            t = torch.tensor([e2e_elapsed], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_elapsed = float(t.item())
+        e2e = {"value": rows_total * e2e_steps / e2e_elapsed, "unit": "rows/s", "h2d_bytes_per_step": int(h2d_bytes),
+               "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps, "ms_per_step": 1000 * e2e_elapsed / e2e_steps,
+               "note": "pb_segment_stage of the touched columns from page-locked host buffers + execute + result read-back, per step"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (pb_scan_kernel), CUDA events on its launching stream ----
+    peak, peak_src = measured_peak_gbs()
+    alg_bytes = algorithmic_bytes(segs, q)
+    achieved = alg_bytes / (scan_mean * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "pb_scan_kernel", "kernel_ms": scan_mean, "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": peak_src,
+                "note": "algorithmic bytes use the full-scan convention (87 bits/row); the kernel skips group/metric sectors of rows "
+                        "the filter rejects, so frac can exceed 1 at low selectivity — see traffic"}
+
+    # ---- CPU baseline: the oracle (port of the reference algorithm) on this box's host cores ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        threads = min(len(segs), os.cpu_count() or 1)
+        oracle_query_all_threads(segs[:1], q, 1)   # warm
+        reps, t2 = 0, time.perf_counter()
+        while True:
+            oracle_query_all_threads(segs, q, threads)
+            reps += 1
+            if time.perf_counter() - t2 > 10.0 or reps >= 200:
+                break
+        cdt = time.perf_counter() - t2
+        cpu = {"value": rows_rank * reps / cdt, "unit": "rows/s", "cores": threads, "kind": "port",
+               "sample": f"{reps} passes of the full {rows_rank}-row query, one thread per segment ({threads} threads of {os.cpu_count()} cores), {cdt:.1f} s"}
+
+    line = {"metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": 1000 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, segs),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "device_ms_per_step": float(np.mean(device_ms)) if device_ms else None,
+            "scan_kernel_ms": scan_mean, "num_groups": int(num_groups), "docs_matched": int(docs_matched),
+            "kernel_variant": {0: "tma+width-specialised", 4: "tma+generic", 8: "ldg+width-specialised", 12: "ldg+generic"}.get(args.flags & 12)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def lib_launches(r):
+    from pinot_b200 import native
+    return native.lib().pb_result_kernel_launches(r._rh)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

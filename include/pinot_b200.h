@@ -205,8 +205,14 @@ void pb_result_free(pb_result_handle r);
  *        3 = per-aggregation distinct bitset words (int32; OR == MAX over 0/1 is NOT valid — all-gather + pb_or) -------- */
 int pb_result_device_buffer(pb_result_handle r, int32_t which, int32_t agg, void** device_ptr, int64_t* num_elements);
 int pb_result_finalize(pb_result_handle r);
-/* the CUDA stream (cudaStream_t) this result's work was issued on */
+/* the CUDA stream (cudaStream_t) this result's work was issued on, and a host-side wait for it */
 void* pb_result_stream(pb_result_handle r);
+int pb_result_wait(pb_result_handle r);
+
+/* Page-lock a caller-owned buffer (e.g. the mmap'd columns.psf of a segment) so staging runs at full PCIe
+ * rate; optional.  Wraps cudaHostRegister / cudaHostUnregister. */
+int pb_host_register(const void* ptr, size_t bytes);
+int pb_host_unregister(const void* ptr);
 
 #ifdef __cplusplus
 }

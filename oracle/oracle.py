@@ -295,3 +295,51 @@ def combine(results: List[OracleResult]) -> Dict[tuple, list]:
                 else:
                     cur[a] = cur[a] | row[a]
     return table
+
+
+def combine_numeric(results: List[OracleResult]):
+    """Vectorised cross-segment merge for numeric group keys and COUNT/SUM/MIN/MAX/AVG (same semantics as
+    combine(); used where the merge itself is timed).  Returns (keys[n, nG], [per-aggregation arrays])."""
+    q = results[0].query
+    cols = [results[0].segment.columns[c] for c in q.group_by]
+    if any(int(a.op) == 5 for a in q.aggregations) or any(c.data_type.name == "STRING" for c in cols):
+        return combine(results)
+    key_blocks = []
+    for r in results:
+        if not q.group_by:
+            key_blocks.append(np.zeros((1, 0), dtype=np.int64))
+            continue
+        blk = np.empty((r.num_groups, len(q.group_by)), dtype=np.float64)
+        for j, cname in enumerate(q.group_by):
+            c = r.segment.columns[cname]
+            if c.has_dictionary:
+                blk[:, j] = c.dictionary_values()[r.group_keys[:, j]]
+            elif c.data_type.name in ("FLOAT", "DOUBLE"):
+                blk[:, j] = r.group_keys[:, j].view(np.float64)
+            else:
+                blk[:, j] = r.group_keys[:, j]
+        key_blocks.append(blk)
+    allk = np.concatenate(key_blocks, axis=0)
+    if allk.shape[1] == 0:
+        uniq, inv = np.zeros((1, 0)), np.zeros(allk.shape[0], dtype=np.int64)
+    else:
+        uniq, inv = np.unique(allk, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+    n = uniq.shape[0]
+    out = []
+    for a, agg in enumerate(q.aggregations):
+        op = int(agg.op)
+        d = np.concatenate([r.doubles[a] for r in results])
+        l = np.concatenate([r.longs[a] for r in results])
+        if op == 0:
+            acc = np.zeros(n, dtype=np.int64); np.add.at(acc, inv, l); out.append(acc)
+        elif op == 1:
+            acc = np.zeros(n); np.add.at(acc, inv, d); out.append(acc)
+        elif op == 2:
+            acc = np.full(n, np.inf); np.minimum.at(acc, inv, d); out.append(acc)
+        elif op == 3:
+            acc = np.full(n, -np.inf); np.maximum.at(acc, inv, d); out.append(acc)
+        else:
+            acc = np.zeros(n); np.add.at(acc, inv, d)
+            cnt = np.zeros(n, dtype=np.int64); np.add.at(cnt, inv, l); out.append((acc, cnt))
+    return uniq, out

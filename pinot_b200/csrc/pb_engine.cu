@@ -1205,6 +1205,22 @@ extern "C" double pb_result_scan_kernel_ms(pb_result_handle r) {
 extern "C" int32_t pb_result_kernel_launches(pb_result_handle r) { return r ? r->launches : 0; }
 extern "C" void* pb_result_stream(pb_result_handle r) { return r ? (void*)r->stream : nullptr; }
 
+extern "C" int pb_result_wait(pb_result_handle r) {
+  if (!r) return fail(PB_ERR_INVALID, "null result");
+  CU(cudaStreamSynchronize(r->stream));
+  return PB_OK;
+}
+extern "C" int pb_host_register(const void* ptr, size_t bytes) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  CU(cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault));
+  return PB_OK;
+}
+extern "C" int pb_host_unregister(const void* ptr) {
+  CU(cudaHostUnregister(const_cast<void*>(ptr)));
+  return PB_OK;
+}
+
 extern "C" int pb_result_device_buffer(pb_result_handle r, int32_t which, int32_t agg, void** device_ptr, int64_t* num_elements) {
   if (!r || !device_ptr || !num_elements) return fail(PB_ERR_INVALID, "null argument");
   if (!r->combine || r->tables.size() != 1) return fail(PB_ERR_STATE, "device buffers are exposed for PB_Q_COMBINE results only");

@@ -41,11 +41,15 @@ def _int_dictionary(rng, card: int, value_range: int) -> np.ndarray:
     return np.sort(rng.choice(value_range, size=card, replace=False)).astype(np.int32)
 
 
-def make_column(name: str, n: int, rng, inverted: Optional[bool] = None) -> ColumnIndex:
+def make_column(name: str, n: int, rng, inverted: Optional[bool] = None, dict_rng=None) -> ColumnIndex:
+    """dict_rng draws the dictionary of a dimension column (shared by all segments of a table unless the caller
+    passes the per-segment stream, see make_segment_synth(vary_dim_dictionaries=True))."""
     inv = (name in INVERTED) if inverted is None else inverted
+    if dict_rng is None:
+        dict_rng = rng
     if name in DIM_CARDS:
         card = min(DIM_CARDS[name], n)
-        dvals = _int_dictionary(rng, card, max(card * 10, 1000))
+        dvals = _int_dictionary(dict_rng, card, max(card * 10, 1000))
         return build_dict_column(name, DataType.INT, dvals, _ids(rng, card, n), inverted=inv)
     if name in ("m0", "m1", "m2"):
         card = min(METRIC_CARD, n)
@@ -53,7 +57,7 @@ def make_column(name: str, n: int, rng, inverted: Optional[bool] = None) -> Colu
         return build_dict_column(name, DataType.INT, dvals, _ids(rng, card, n), inverted=False)
     if name == "s0":
         card = min(10_000, n)
-        raw = rng.choice(26 ** 4, size=card, replace=False)
+        raw = dict_rng.choice(26 ** 4, size=card, replace=False)
         letters = np.array(list(b"abcdefghijklmnopqrstuvwxyz"), dtype=np.uint8)
         strs = []
         for v in np.sort(raw):
@@ -75,19 +79,25 @@ def make_column(name: str, n: int, rng, inverted: Optional[bool] = None) -> Colu
 
 
 def make_segment_synth(index: int, num_docs: int, columns: Optional[Sequence[str]] = None, seed: int = 42,
-                       name_prefix: str = "synth") -> Segment:
+                       name_prefix: str = "synth", vary_dim_dictionaries: bool = False) -> Segment:
+    """Dimension dictionaries (c*, d*, s0) are table-wide, as dimension values are in a real table; metric
+    dictionaries are per segment.  vary_dim_dictionaries=True draws the dimension dictionaries per segment too
+    (exercises the local->global dictId remap of the combined mode)."""
     cols = list(columns) if columns is not None else ALL_COLUMNS
     out = []
     for cname in cols:
+        ci = ALL_COLUMNS.index(cname)
         # one independent stream per (segment, column) so a column looks the same whichever subset is built
-        rng = np.random.Generator(np.random.PCG64([seed + index, ALL_COLUMNS.index(cname)]))
-        out.append(make_column(cname, num_docs, rng))
+        rng = np.random.Generator(np.random.PCG64([seed + index, ci]))
+        dict_rng = None if vary_dim_dictionaries else np.random.Generator(np.random.PCG64([seed, 1000 + ci]))
+        out.append(make_column(cname, num_docs, rng, dict_rng=dict_rng))
     return make_segment(f"{name_prefix}_{index}", out)
 
 
 def make_table(num_segments: int, docs_per_segment: int, columns: Optional[Sequence[str]] = None, seed: int = 42,
-               first_index: int = 0) -> List[Segment]:
-    return [make_segment_synth(first_index + i, docs_per_segment, columns, seed) for i in range(num_segments)]
+               first_index: int = 0, vary_dim_dictionaries: bool = False) -> List[Segment]:
+    return [make_segment_synth(first_index + i, docs_per_segment, columns, seed, vary_dim_dictionaries=vary_dim_dictionaries)
+            for i in range(num_segments)]
 
 
 # ---- BASELINE.json configs as SQL (literals are chosen per table, see helpers) ----

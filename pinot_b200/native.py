@@ -121,6 +121,9 @@ def lib():
     l.pb_result_kernel_launches.restype = C.c_int32
     l.pb_result_stream.argtypes = [C.c_void_p]
     l.pb_result_stream.restype = C.c_void_p
+    l.pb_result_wait.argtypes = [C.c_void_p]
+    l.pb_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    l.pb_host_unregister.argtypes = [C.c_void_p]
     l.pb_result_device_buffer.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     _lib = l
     return l
@@ -306,6 +309,9 @@ class Result:
     def stream(self) -> int:
         return lib().pb_result_stream(self._rh) or 0
 
+    def wait(self):
+        _check(lib().pb_result_wait(self._rh))
+
     def scan_ms(self) -> float:
         return lib().pb_result_scan_kernel_ms(self._rh)
 
@@ -365,6 +371,14 @@ def execute(group: SegmentGroup, q: QueryContext, flags: int = 0) -> Result:
     rh = C.c_void_p()
     _check(lib().pbh_execute(group.handle, C.byref(m.ctx), flags, C.byref(rh)))
     return Result(rh, q, deferred=bool(flags & PB_Q_DEFER_FINALIZE))
+
+
+def host_register(arr: np.ndarray):
+    _check(lib().pb_host_register(arr.ctypes.data, arr.nbytes))
+
+
+def host_unregister(arr: np.ndarray):
+    _check(lib().pb_host_unregister(arr.ctypes.data))
 
 
 def is_eligible(group: SegmentGroup, q: QueryContext) -> bool:

@@ -107,7 +107,7 @@ def test_sv_segment_vs_oracle_all_kernels():
 @pytest.fixture(scope="module")
 def synth():
     native.init()
-    segs = [datagen.make_segment_synth(i, n) for i, n in enumerate((100_003, 65_536, 8_192 * 3 + 1))]
+    segs = [datagen.make_segment_synth(i, n, vary_dim_dictionaries=(i > 0)) for i, n in enumerate((100_003, 65_536, 8_192 * 3 + 1))]
     staged = [native.StagedSegment(s) for s in segs]
     g = native.SegmentGroup(staged)
     yield segs, g
