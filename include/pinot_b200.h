@@ -196,6 +196,10 @@ const pb_exec_stats* pb_result_stats(pb_result_handle r, int32_t table);
 double pb_result_device_ms(pb_result_handle r);
 double pb_result_scan_kernel_ms(pb_result_handle r);
 int32_t pb_result_kernel_launches(pb_result_handle r);
+/* host-side microseconds spent in this call, by phase: [0] resolve + stage, [1] table allocation + init,
+ * [2] descriptor build + upload, [3] kernel launches, [4] wait for the scan + group count, [5] compaction,
+ * gathers and read-back, [6] host key decode / stats; [7] reserved */
+int pb_result_host_timing(pb_result_handle r, double* out8);
 void pb_result_free(pb_result_handle r);
 
 /* -------- multi-GPU (PB_Q_COMBINE | PB_Q_DEFER_FINALIZE): device-resident table arrays for an

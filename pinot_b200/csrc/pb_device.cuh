@@ -25,7 +25,7 @@
 #define PB_MAX_GROUP_BY 16
 #define PB_MAX_AGGS 16
 #define PB_MAX_SCAN_SLOTS 8
-#define PB_SET_SMEM_WORDS 1024      // 4 KB of dictId-set bitsets cached in smem per segment
+#define PB_SET_SMEM_BYTES 8192      // dictId-set membership LUTs (one byte per dictId) cached in smem per segment
 #define PB_WQ_CAP 64                // per-warp match queue entries
 
 enum { L_TRUE = 0, L_FALSE = 1, L_DICT_RANGE = 2, L_DICT_SET = 3, L_RAW_RANGE_I = 4, L_RAW_RANGE_F = 5,
@@ -43,8 +43,8 @@ struct DevLeaf {
   int32_t data_type;
   int32_t exclusive;
   uint32_t lo, span;       // L_DICT_RANGE: match iff (dictId - lo) < span (unsigned)
-  int32_t set_smem_off;    // L_DICT_SET: word offset into the smem set cache, -1 = read from global
-  int32_t set_words;
+  int32_t set_smem_off;    // L_DICT_SET: byte offset of the membership LUT in the smem set cache, -1 = bitset in global
+  int32_t set_card;        // dictionary cardinality (LUT length)
   const uint32_t* set_bits;   // L_DICT_SET: bitset over dictIds
   int64_t ilo, ihi;        // L_RAW_RANGE_I inclusive
   double dlo, dhi;         // L_RAW_RANGE_F
@@ -87,7 +87,8 @@ struct DevSegQuery {
   int32_t n_nodes;
   int32_t n_scan;
   int32_t table;           // result table index
-  uint64_t tile_begin;     // global index of this segment's first tile
+  uint64_t chunk_begin;    // global index of this segment's first 1024-doc chunk
+  uint64_t n_chunks;       // ceil(num_docs / 1024)
   int8_t node_kind[PB_MAX_NODES];
   int8_t node_arg[PB_MAX_NODES];
   DevLeaf leaves[PB_MAX_LEAVES];
@@ -120,11 +121,11 @@ struct DevQuery {
   int32_t table_mode;
   int32_t agg_op[PB_MAX_AGGS];
   int32_t slot_off[PB_MAX_SCAN_SLOTS];   // byte offset of each scan slot inside a stage
-  int32_t stage_bytes;                   // bytes per stage
-  int32_t tile_chunks;                   // chunks (1024 docs) per tile
+  int32_t stage_bytes;                   // bytes per warp stage (one 1024-doc chunk of every scan slot)
+  int32_t pad_q;
   int32_t use_tma;
   int32_t generic;                       // 1 = width-generic predicate path only
-  uint64_t n_tiles;
+  uint64_t n_chunks;
   const DevSegQuery* segs;
   DevTable* tables;
 };
@@ -182,12 +183,12 @@ __device__ __forceinline__ double pb_raw_f64(const uint8_t* __restrict__ fwd, ui
 
 // ---- global-memory reductions (SASS REDG.*): the table pointers are loaded from descriptors, so the
 // compiler cannot prove the address space; state it explicitly instead of going through generic ATOM + isspacep.
-__device__ __forceinline__ void pb_red_add_f64(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
-__device__ __forceinline__ void pb_red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ void pb_red_add_u32(unsigned int* p, unsigned int v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void pb_red_min_s64(long long* p, long long v) { asm volatile("red.global.min.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ void pb_red_max_s64(long long* p, long long v) { asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ void pb_red_or_b32(uint32_t* p, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void pb_red_add_f64(double* p, double v) { asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v)); }
+__device__ __forceinline__ void pb_red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v)); }
+__device__ __forceinline__ void pb_red_add_u32(unsigned int* p, unsigned int v) { asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v)); }
+__device__ __forceinline__ void pb_red_min_s64(long long* p, long long v) { asm volatile("red.global.min.s64 [%0], %1;" ::"l"(p), "l"(v)); }
+__device__ __forceinline__ void pb_red_max_s64(long long* p, long long v) { asm volatile("red.global.max.s64 [%0], %1;" ::"l"(p), "l"(v)); }
+__device__ __forceinline__ void pb_red_or_b32(uint32_t* p, uint32_t v) { asm volatile("red.global.or.b32 [%0], %1;" ::"l"(p), "r"(v)); }
 __device__ __forceinline__ unsigned long long pb_atom_cas_u64(unsigned long long* p, unsigned long long cmp, unsigned long long val) {
   unsigned long long old;
   asm volatile("atom.global.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(cmp), "l"(val) : "memory");
@@ -239,23 +240,23 @@ __device__ __forceinline__ void pb_tma_load_1d(void* smem_dst, const void* gmem_
 // predicate evaluation on one 1024-doc chunk; every variant returns THIS LANE's 32-bit mask for docs
 // [chunk_doc0 + 32*lane, +32)   (PredicateEvaluator.applySV semantics, CTR/operator/filter/predicate/*)
 // ------------------------------------------------------------------------------------------------
-struct PredCtx {
-  const uint32_t* set;   // resolved bitset pointer (smem or global) for L_DICT_SET
+struct PredRange {      // SortedDictionaryBasedRangePredicateEvaluator.applySV: start <= dictId < end
   uint32_t lo, span;
-  int is_set;
-  int exclusive;
+  __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return (v - lo) < span ? 1u : 0u; }
+};
+struct PredLut8 {       // IN / NOT_IN / EQ / NEQ with the (exclusive-folded) membership table in shared memory
+  const uint8_t* lut;
+  __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return lut[v]; }
+};
+struct PredBits {       // same, large dictionaries: bitset in global memory (L1-resident)
+  const uint32_t* bits;
+  uint32_t excl;
+  __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return (__funnelshift_r(__ldg(bits + (v >> 5)), 0u, v) & 1u) ^ excl; }
 };
 
-template <bool SET>
-__device__ __forceinline__ bool pb_pred_dict(const PredCtx& pc, uint32_t v) {
-  if (!SET) return (v - pc.lo) < pc.span;
-  bool in = (pc.set[v >> 5] >> (v & 31)) & 1u;
-  return in != (bool)pc.exclusive;
-}
-
 // width-generic path: lane <-> doc, 32 steps, ballot; conflict-free smem reads
-template <bool SET>
-__device__ __forceinline__ uint32_t pb_eval_dict_generic(const uint32_t* __restrict__ p, int bits, const PredCtx& pc, int lane) {
+template <class Pred>
+__device__ __forceinline__ uint32_t pb_eval_dict_generic(const uint32_t* __restrict__ p, int bits, const Pred& pred, int lane) {
   uint32_t mine = 0;
 #pragma unroll 4
   for (int k = 0; k < 32; k++) {
@@ -264,7 +265,7 @@ __device__ __forceinline__ uint32_t pb_eval_dict_generic(const uint32_t* __restr
     uint32_t wi = bit >> 5, s = bit & 31u;
     uint32_t hi = pb_bswap32(p[wi]), lo = pb_bswap32(p[wi + 1]);
     uint32_t v = __funnelshift_l(lo, hi, s) >> (32 - bits);
-    uint32_t b = __ballot_sync(0xffffffffu, pb_pred_dict<SET>(pc, v));
+    uint32_t b = __ballot_sync(0xffffffffu, pred(v) != 0);
     if (k == lane) mine = b;
   }
   return mine;
@@ -272,9 +273,9 @@ __device__ __forceinline__ uint32_t pb_eval_dict_generic(const uint32_t* __restr
 
 // width-specialised path: lane owns 32 consecutive docs == exactly W consecutive 32-bit words.
 // All shifts are compile-time constants (the GPU analogue of FixedBitIntReader's per-width read32 classes,
-// SEGL/io/reader/impl/FixedBitIntReader.java:121-146).
-template <int W, bool SET>
-__device__ __forceinline__ uint32_t pb_eval_dict_w(const uint32_t* __restrict__ p, const PredCtx& pc, int lane) {
+// SEGL/io/reader/impl/FixedBitIntReader.java:121-146).  The mask is built MSB-first by shift-accumulate.
+template <int W, class Pred>
+__device__ __forceinline__ uint32_t pb_eval_dict_w(const uint32_t* __restrict__ p, const Pred& pred, int lane) {
   uint32_t w[W + 1];
   const uint32_t* q = p + lane * W;
 #pragma unroll
@@ -282,23 +283,24 @@ __device__ __forceinline__ uint32_t pb_eval_dict_w(const uint32_t* __restrict__ 
   w[W] = 0;
   uint32_t m = 0;
 #pragma unroll
-  for (int j = 0; j < 32; j++) {
+  for (int j = 31; j >= 0; j--) {
     constexpr uint32_t MASK = (W == 32) ? 0xffffffffu : ((1u << (W & 31)) - 1u);
     const int bit = j * W;
     const int k = bit >> 5, s = bit & 31;
     uint32_t v;
     if (s + W <= 32) v = (w[k] >> ((32 - s - W) & 31)) & MASK;
     else v = __funnelshift_l(w[k + 1], w[k], s) >> ((32 - W) & 31);
-    if (pb_pred_dict<SET>(pc, v)) m |= (1u << j);
+    m = (m << 1) | pred(v);
   }
   return m;
 }
 
 __device__ __forceinline__ bool pb_fast_width(int bits) { return bits < 32 && (bits & 7) != 0; }
 
-__device__ __noinline__ uint32_t pb_eval_dict_fast(const uint32_t* __restrict__ p, int bits, const PredCtx& pc, int lane) {
+template <class Pred>
+__device__ __noinline__ uint32_t pb_eval_dict_fast(const uint32_t* __restrict__ p, int bits, const Pred& pred, int lane) {
   switch (bits) {
-#define PB_CASE(W) case W: return pc.is_set ? pb_eval_dict_w<W, true>(p, pc, lane) : pb_eval_dict_w<W, false>(p, pc, lane);
+#define PB_CASE(W) case W: return pb_eval_dict_w<W, Pred>(p, pred, lane);
     PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7)
     PB_CASE(9) PB_CASE(10) PB_CASE(11) PB_CASE(12) PB_CASE(13) PB_CASE(14) PB_CASE(15)
     PB_CASE(17) PB_CASE(18) PB_CASE(19) PB_CASE(20) PB_CASE(21) PB_CASE(22) PB_CASE(23)
@@ -308,8 +310,14 @@ __device__ __noinline__ uint32_t pb_eval_dict_fast(const uint32_t* __restrict__ 
   }
 }
 
+template <class Pred>
+__device__ __forceinline__ uint32_t pb_eval_dict(const uint32_t* __restrict__ p, int bits, const Pred& pred, int lane, bool generic) {
+  if (!generic && pb_fast_width(bits)) return pb_eval_dict_fast<Pred>(p, bits, pred, lane);
+  return pb_eval_dict_generic<Pred>(p, bits, pred, lane);
+}
+
 // raw fixed-width column chunk in smem (big-endian values), lane <-> doc + ballot
-__device__ __forceinline__ uint32_t pb_eval_raw(const uint32_t* __restrict__ p, const DevLeaf& lf, int lane) {
+__device__ __noinline__ uint32_t pb_eval_raw(const uint32_t* __restrict__ p, const DevLeaf& lf, int lane) {
   uint32_t mine = 0;
   for (int k = 0; k < 32; k++) {
     uint32_t idx = (uint32_t)(k * 32 + lane);
@@ -372,54 +380,86 @@ __device__ __forceinline__ uint64_t pb_hash_slot(const DevTable& t, uint64_t key
 
 // keyless accumulators live in shared memory, one private cell per thread (no atomics)
 struct KeylessAcc {
-  double* sum;        // [PB_MAX_AGGS][PB_NTHREADS]
-  long long* mm;      // [PB_MAX_AGGS][PB_NTHREADS]
+  double* sum;        // [n_aggs][PB_NTHREADS]
+  long long* mm;      // [n_aggs][PB_NTHREADS]
 };
+
+__device__ __forceinline__ uint64_t pb_key_field(const DevKeyCol& kc, uint32_t doc, bool multi) {
+  if (kc.raw_width) {
+    uint64_t v;
+    if (kc.data_type == 2 || kc.data_type == 3) v = (uint64_t)__double_as_longlong(pb_raw_f64(kc.fwd, doc, kc.raw_width, kc.data_type));
+    else v = (uint64_t)pb_raw_i64(kc.fwd, doc, kc.raw_width, kc.data_type);
+    return (kc.raw_width == 4 && multi) ? (v & 0xffffffffull) : v;
+  }
+  uint32_t id = pb_unpack_at(kc.fwd, doc, kc.bits);
+  if (kc.remap) id = (uint32_t)__ldg(kc.remap + id);
+  return id;
+}
+
+// value of aggregation column a for `doc`: BlockValSet.getDoubleValuesSV (dictionary decode or raw read, widened
+// to double); for DISTINCTCOUNT the (global) dictId, returned through the same 64-bit channel
+__device__ __forceinline__ double pb_agg_input(const DevAggCol& ac, int op, uint32_t doc) {
+  if (op == 5) {
+    uint32_t id = pb_unpack_at(ac.fwd, doc, ac.bits);
+    if (ac.remap) id = (uint32_t)__ldg(ac.remap + id);
+    return __longlong_as_double((long long)id);
+  }
+  return ac.raw_width ? pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type)
+                      : __ldg(ac.dict_f64 + pb_unpack_at(ac.fwd, doc, ac.bits));
+}
 
 __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQuery& sq, const DevTable& t, uint32_t doc,
                                               const KeylessAcc& ka, unsigned long long& keyless_rows) {
+  // ---- phase 1: every gather of this doc is issued before anything is reduced, four independent chains at a
+  // time (index clamping instead of branches keeps the loads unconditional, so they overlap) ----
+  const int nG = Q.n_group_by, nA = Q.n_aggs;
   uint64_t slot = 0;
-  if (Q.table_mode == T_DENSE) {
-    for (int j = 0; j < Q.n_group_by; j++) {
-      const DevKeyCol& kc = sq.keys[j];
-      uint32_t id = pb_unpack_at(kc.fwd, doc, kc.bits);
-      if (kc.remap) id = (uint32_t)__ldg(kc.remap + id);
-      slot += (uint64_t)id * kc.mult;
-    }
-  } else if (Q.table_mode == T_HASH) {
-    uint64_t key = 0;
-    for (int j = 0; j < Q.n_group_by; j++) {
-      const DevKeyCol& kc = sq.keys[j];
-      if (kc.raw_width) {
-        uint64_t v;
-        if (kc.data_type == 2 || kc.data_type == 3) v = (uint64_t)__double_as_longlong(pb_raw_f64(kc.fwd, doc, kc.raw_width, kc.data_type));
-        else v = (uint64_t)pb_raw_i64(kc.fwd, doc, kc.raw_width, kc.data_type);
-        key |= (kc.raw_width == 4 && Q.n_group_by > 1 ? (v & 0xffffffffull) : v) << kc.shift;
-      } else {
-        uint32_t id = pb_unpack_at(kc.fwd, doc, kc.bits);
-        if (kc.remap) id = (uint32_t)__ldg(kc.remap + id);
-        key |= (uint64_t)id << kc.shift;
+  if (Q.table_mode != T_KEYLESS) {
+    const bool dense = Q.table_mode == T_DENSE;
+    const bool multi = nG > 1;
+    for (int j = 0; j < nG; j += 4) {
+      uint64_t f[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) f[k] = pb_key_field(sq.keys[min(j + k, nG - 1)], doc, multi);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (j + k < nG) {
+          const DevKeyCol& kc = sq.keys[j + k];
+          slot += dense ? f[k] * kc.mult : (f[k] << kc.shift);
+        }
       }
     }
-    slot = pb_hash_slot(t, key);
+  }
+  double vals[PB_MAX_AGGS];
+  for (int a = 0; a < nA; a += 4) {
+    double v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int aa = min(a + k, nA - 1);
+      const int op = Q.agg_op[aa];
+      v[k] = op == 0 ? 0.0 : pb_agg_input(sq.aggs[aa], op, doc);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (a + k < nA) vals[a + k] = v[k];
+  }
+
+  // ---- phase 2: table update ----
+  if (Q.table_mode == T_HASH) {
+    slot = pb_hash_slot(t, slot);
     if (slot == ~0ull) return;
   }
   if (Q.table_mode == T_KEYLESS) keyless_rows++;
   else pb_red_add_u64(&t.rowcnt[slot], 1ull);
 
-  for (int a = 0; a < Q.n_aggs; a++) {
+  for (int a = 0; a < nA; a++) {
     const int op = Q.agg_op[a];
     if (op == 0) continue;                       // COUNT(*): the row counter
-    const DevAggCol& ac = sq.aggs[a];
+    const double v = vals[a];
     if (op == 5) {                               // DISTINCTCOUNT (dictionary column)
-      uint32_t id = pb_unpack_at(ac.fwd, doc, ac.bits);
-      if (ac.remap) id = (uint32_t)__ldg(ac.remap + id);
+      uint32_t id = (uint32_t)__double_as_longlong(v);
       pb_red_or_b32(&t.dc_bits[a][slot * t.dc_words[a] + (id >> 5)], 1u << (id & 31));
       continue;
     }
-    // BlockValSet.getDoubleValuesSV: dictionary decode or raw read, widened to double
-    double v = ac.raw_width ? pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type)
-                            : __ldg(ac.dict_f64 + pb_unpack_at(ac.fwd, doc, ac.bits));
     if (Q.table_mode == T_KEYLESS) {
       const int tid = threadIdx.x;
       if (op == 1 || op == 4) ka.sum[a * PB_NTHREADS + tid] += v;
@@ -440,29 +480,29 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 
 // ------------------------------------------------------------------------------------------------
 // the scan kernel
+//
+// A CTA owns a contiguous range of 1024-doc chunks; inside it every WARP is an independent worker with its
+// own 3-stage TMA pipeline (cp.async.bulk + mbarrier) over its chunks: no block-wide barrier in the steady
+// state, so a warp that is busy gathering/aggregating its matches never stalls the other seven.  The only
+// block-level synchronisation is at segment boundaries inside the CTA's range (descriptor + LUT reload).
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) ScanSmemHeader {
-  uint64_t full[PB_NSTAGE];
+  uint64_t full[PB_NWARPS][PB_NSTAGE];
   uint32_t wq[PB_NWARPS][PB_WQ_CAP];
   uint32_t wq_n[PB_NWARPS];
   unsigned long long red_u64[PB_NWARPS];
   double red_f64[PB_NWARPS];
   long long red_i64[PB_NWARPS];
-  uint32_t set_cache[PB_SET_SMEM_WORDS];
+  uint8_t set_cache[PB_SET_SMEM_BYTES];
   DevSegQuery seg;
 };
-
-__device__ __forceinline__ int pb_find_seg(const DevSegQuery* __restrict__ segs, int n_segs, int cur, uint64_t tile) {
-  while (cur + 1 < n_segs && tile >= segs[cur + 1].tile_begin) cur++;
-  return cur;
-}
 
 __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery* __restrict__ Qp) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   ScanSmemHeader* H = reinterpret_cast<ScanSmemHeader*>(smem_raw);
   const DevQuery& Q = *Qp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // after the header: keyless accumulators (n_aggs rows), then the stage buffers
+  // after the header: keyless accumulators (n_aggs rows), then the per-warp stage buffers
   uint8_t* dyn = smem_raw + ((sizeof(ScanSmemHeader) + 127) & ~(size_t)127);
   KeylessAcc ka;
   ka.sum = nullptr; ka.mm = nullptr;
@@ -477,51 +517,26 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
       ka.mm[a * PB_NTHREADS + tid] = Q.agg_op[a] == 2 ? ENC_POS_INF : ENC_NEG_INF;
     }
   }
-  uint8_t* stages = dyn;
-  const int tile_docs = Q.tile_chunks * PB_CHUNK_DOCS;
+  uint8_t* my_stages = dyn + (size_t)warp * PB_NSTAGE * Q.stage_bytes;
   const bool staged = Q.stage_bytes > 0;
 
-  if (tid == 0) {
-    for (int s = 0; s < PB_NSTAGE; s++) pb_mbar_init(&H->full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (lane == 0) {
+    for (int s = 0; s < PB_NSTAGE; s++) pb_mbar_init(&H->full[warp][s], 1);
+    H->wq_n[warp] = 0;
   }
-  if (tid < PB_NWARPS) H->wq_n[tid] = 0;
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  // producer: issue the loads of this CTA's it-th tile into stage it % NSTAGE
-  auto issue = [&](uint64_t it, int& pseg) {
-    uint64_t tile = (uint64_t)blockIdx.x + it * gridDim.x;
-    if (tile >= Q.n_tiles) return;
-    pseg = pb_find_seg(Q.segs, Q.n_segs, pseg, tile);
-    const DevSegQuery* sg = &Q.segs[pseg];
-    const int st = (int)(it % PB_NSTAGE);
-    uint64_t doc0 = (tile - sg->tile_begin) * (uint64_t)tile_docs;
-    uint32_t total = 0;
-    uint32_t nbytes[PB_MAX_SCAN_SLOTS];
-    const int n_scan = sg->n_scan;
-    for (int c = 0; c < n_scan; c++) {
-      uint64_t off = doc0 * (uint64_t)sg->scan[c].bits_per_doc / 8;             // tile starts are 128-byte multiples
-      uint64_t want = (uint64_t)tile_docs * (uint64_t)sg->scan[c].bits_per_doc / 8 + 16;   // +16: the word after the tile
-      uint64_t avail = sg->scan[c].bytes_total - off;
-      uint64_t n = want < avail ? want : avail;
-      n &= ~(uint64_t)15;
-      nbytes[c] = (uint32_t)n;
-      total += (uint32_t)n;
-    }
-    pb_mbar_expect_tx(&H->full[st], total);
-    for (int c = 0; c < n_scan; c++) {
-      uint64_t off = doc0 * (uint64_t)sg->scan[c].bits_per_doc / 8;
-      pb_tma_load_1d(stages + (size_t)st * Q.stage_bytes + Q.slot_off[c], sg->scan[c].base + off, nbytes[c], &H->full[st]);
-    }
-  };
+  // this CTA's contiguous chunk range
+  const uint64_t per = (Q.n_chunks + gridDim.x - 1) / gridDim.x;
+  const uint64_t cta_lo = (uint64_t)blockIdx.x * per;
+  const uint64_t cta_hi = cta_lo + per < Q.n_chunks ? cta_lo + per : Q.n_chunks;
+  if (cta_lo >= cta_hi) return;
+  int seg_first = 0;
+  while (seg_first + 1 < Q.n_segs && cta_lo >= Q.segs[seg_first + 1].chunk_begin) seg_first++;
 
-  int pseg = 0;          // producer's segment cursor (thread 0)
-  int cseg = -1;         // consumer's current segment (smem copy valid when >= 0)
-  int fseg = 0;
   unsigned long long keyless_rows = 0, matched = 0;
-  if (staged && Q.use_tma && tid == 0) {
-    for (int s = 0; s < PB_NSTAGE - 1; s++) issue((uint64_t)s, pseg);
-  }
+  uint32_t consumed = 0;   // chunks this warp has consumed so far: stage = consumed % NSTAGE, parity from consumed / NSTAGE
 
   auto drain32 = [&](uint32_t n_take) {
     // take the first n_take (<= 32) queued docs of this warp, aggregate them, compact the queue
@@ -575,65 +590,85 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
     }
   };
 
-  for (uint64_t it = 0;; it++) {
-    const uint64_t tile = (uint64_t)blockIdx.x + it * gridDim.x;
-    if (tile >= Q.n_tiles) break;
-    if (staged && Q.use_tma && tid == 0) issue(it + PB_NSTAGE - 1, pseg);
-
-    fseg = pb_find_seg(Q.segs, Q.n_segs, fseg, tile);
-    if (fseg != cseg) {
-      // segment switch: flush the per-warp queues against the old descriptor, then load the new one
-      if (cseg >= 0) {
-        uint32_t qn = H->wq_n[warp];
-        if (qn) drain32(qn);
-        __syncthreads();
-        flush_table();
-      }
-      __syncthreads();
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(&Q.segs[fseg]);
+  for (int sgi = seg_first; sgi < Q.n_segs; sgi++) {
+    if (Q.segs[sgi].chunk_begin >= cta_hi) break;
+    // ---- segment entry: descriptor and LUTs into shared memory (everyone has left the previous segment) ----
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&Q.segs[sgi]);
       uint32_t* dst = reinterpret_cast<uint32_t*>(&H->seg);
       for (int i = tid; i < (int)(sizeof(DevSegQuery) / 4); i += PB_NTHREADS) dst[i] = src[i];
       __syncthreads();
-      // cache small dictId-set bitsets in shared memory
       for (int l = 0; l < PB_MAX_LEAVES; l++) {
         const DevLeaf& lf = H->seg.leaves[l];
-        if (lf.kind == L_DICT_SET && lf.set_smem_off >= 0)
-          for (int i = tid; i < lf.set_words; i += PB_NTHREADS) H->set_cache[lf.set_smem_off + i] = __ldg(lf.set_bits + i);
+        if (lf.kind == L_DICT_SET && lf.set_smem_off >= 0) {
+          // membership bytes with the exclusive flag folded in (NOT_IN / NEQ)
+          for (int i = tid; i < lf.set_card; i += PB_NTHREADS)
+            H->set_cache[lf.set_smem_off + i] = (uint8_t)(((__ldg(lf.set_bits + (i >> 5)) >> (i & 31)) & 1u) ^ (uint32_t)lf.exclusive);
+        }
       }
-      cseg = fseg;
       __syncthreads();
     }
     const DevSegQuery& sq = H->seg;
-    const int st = (int)(it % PB_NSTAGE);
-    uint8_t* stage = stages + (size_t)st * Q.stage_bytes;
-    const uint64_t tile_doc0 = (tile - sq.tile_begin) * (uint64_t)tile_docs;
+    const uint64_t seg_lo = sq.chunk_begin > cta_lo ? sq.chunk_begin : cta_lo;
+    const uint64_t seg_end = sq.chunk_begin + sq.n_chunks;
+    const uint64_t seg_hi = seg_end < cta_hi ? seg_end : cta_hi;
+    // this warp's chunks in this segment: seg_lo + warp, + NWARPS, ...
+    const uint64_t first = seg_lo + warp;
+    const uint32_t n_mine = first < seg_hi ? (uint32_t)((seg_hi - first + PB_NWARPS - 1) / PB_NWARPS) : 0u;
 
-    if (staged) {
-      if (Q.use_tma) {
-        pb_mbar_wait(&H->full[st], (uint32_t)((it / PB_NSTAGE) & 1));
-      } else {
-        // fallback staging: cooperative 128-bit loads
-        for (int c = 0; c < sq.n_scan; c++) {
-          uint64_t off = tile_doc0 * (uint64_t)sq.scan[c].bits_per_doc / 8;
-          uint64_t want = (uint64_t)tile_docs * (uint64_t)sq.scan[c].bits_per_doc / 8 + 16;
-          uint64_t avail = sq.scan[c].bytes_total - off;
-          uint64_t n = (want < avail ? want : avail) & ~(uint64_t)15;
-          const uint4* s4 = reinterpret_cast<const uint4*>(sq.scan[c].base + off);
-          uint4* d4 = reinterpret_cast<uint4*>(stage + Q.slot_off[c]);
-          for (uint32_t i = tid; i < (uint32_t)(n / 16); i += PB_NTHREADS) d4[i] = __ldg(s4 + i);
-        }
-        __syncthreads();
+    // producer side (lane 0 of each warp): load this warp's k-th chunk of the segment into its stage
+    auto issue = [&](uint32_t k, uint32_t seq) {
+      const uint64_t chunk = first + (uint64_t)k * PB_NWARPS;
+      const uint64_t doc0 = (chunk - sq.chunk_begin) * PB_CHUNK_DOCS;
+      const int st = (int)(seq % PB_NSTAGE);
+      uint32_t total = 0;
+      uint32_t nbytes[PB_MAX_SCAN_SLOTS];
+      for (int c = 0; c < sq.n_scan; c++) {
+        uint64_t off = doc0 * (uint64_t)sq.scan[c].bits_per_doc / 8;              // chunk starts are 128-byte multiples
+        uint64_t want = (uint64_t)PB_CHUNK_DOCS * (uint64_t)sq.scan[c].bits_per_doc / 8 + 16;   // +16: the word after the chunk
+        uint64_t avail = sq.scan[c].bytes_total - off;
+        uint64_t n = (want < avail ? want : avail) & ~(uint64_t)15;
+        nbytes[c] = (uint32_t)n;
+        total += (uint32_t)n;
       }
-    }
+      pb_mbar_expect_tx(&H->full[warp][st], total);
+      for (int c = 0; c < sq.n_scan; c++) {
+        uint64_t off = doc0 * (uint64_t)sq.scan[c].bits_per_doc / 8;
+        pb_tma_load_1d(my_stages + (size_t)st * Q.stage_bytes + Q.slot_off[c], sq.scan[c].base + off, nbytes[c], &H->full[warp][st]);
+      }
+    };
 
-    // ---- filter: one chunk per warp ----
-    for (int c = warp; c < Q.tile_chunks; c += PB_NWARPS) {
-      const uint64_t chunk_doc0 = tile_doc0 + (uint64_t)c * PB_CHUNK_DOCS;
-      if (chunk_doc0 >= (uint64_t)sq.num_docs) break;
-      // valid-doc mask of this lane
+    if (staged && Q.use_tma && lane == 0)
+      for (uint32_t k = 0; k < PB_NSTAGE - 1 && k < n_mine; k++) issue(k, consumed + k);
+
+    for (uint32_t k = 0; k < n_mine; k++) {
+      const uint64_t chunk = first + (uint64_t)k * PB_NWARPS;
+      const uint64_t chunk_doc0 = (chunk - sq.chunk_begin) * PB_CHUNK_DOCS;
+      const int st = (int)(consumed % PB_NSTAGE);
+      uint8_t* stage = my_stages + (size_t)st * Q.stage_bytes;
+      if (staged) {
+        if (Q.use_tma) {
+          // the stage being refilled was consumed one iteration ago by this same warp
+          if (lane == 0 && k + PB_NSTAGE - 1 < n_mine) issue(k + PB_NSTAGE - 1, consumed + PB_NSTAGE - 1);
+          pb_mbar_wait(&H->full[warp][st], (consumed / PB_NSTAGE) & 1u);
+        } else {
+          for (int c = 0; c < sq.n_scan; c++) {
+            uint64_t off = chunk_doc0 * (uint64_t)sq.scan[c].bits_per_doc / 8;
+            uint64_t want = (uint64_t)PB_CHUNK_DOCS * (uint64_t)sq.scan[c].bits_per_doc / 8 + 16;
+            uint64_t avail = sq.scan[c].bytes_total - off;
+            uint64_t n = (want < avail ? want : avail) & ~(uint64_t)15;
+            const uint4* s4 = reinterpret_cast<const uint4*>(sq.scan[c].base + off);
+            uint4* d4 = reinterpret_cast<uint4*>(stage + Q.slot_off[c]);
+            for (uint32_t i = lane; i < (uint32_t)(n / 16); i += 32) d4[i] = __ldg(s4 + i);
+          }
+          __syncwarp();
+        }
+      }
+      consumed++;
+
+      // ---- filter ----
       long long remaining = (long long)sq.num_docs - (long long)(chunk_doc0 + 32ull * lane);
       uint32_t valid = remaining >= 32 ? 0xffffffffu : (remaining <= 0 ? 0u : ((1u << remaining) - 1u));
-
       uint32_t stack[PB_MAX_LEAVES];
       int sp = 0;
       for (int n = 0; n < sq.n_nodes; n++) {
@@ -644,22 +679,22 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
           switch (lf.kind) {
             case L_TRUE: m = 0xffffffffu; break;
             case L_FALSE: m = 0u; break;
-            case L_DICT_RANGE:
+            case L_DICT_RANGE: {
+              const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
+              PredRange pr; pr.lo = lf.lo; pr.span = lf.span;
+              m = pb_eval_dict<PredRange>(p, lf.bits, pr, lane, Q.generic);
+              break;
+            }
             case L_DICT_SET: {
-              const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot] + (size_t)c * (PB_CHUNK_DOCS / 8) * lf.bits);
-              PredCtx pc;
-              pc.is_set = lf.kind == L_DICT_SET;
-              pc.exclusive = lf.exclusive;
-              pc.lo = lf.lo; pc.span = lf.span;
-              pc.set = lf.set_smem_off >= 0 ? &H->set_cache[lf.set_smem_off] : lf.set_bits;
-              if (!Q.generic && pb_fast_width(lf.bits)) m = pb_eval_dict_fast(p, lf.bits, pc, lane);
-              else m = pc.is_set ? pb_eval_dict_generic<true>(p, lf.bits, pc, lane) : pb_eval_dict_generic<false>(p, lf.bits, pc, lane);
+              const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
+              if (lf.set_smem_off >= 0) { PredLut8 pl; pl.lut = &H->set_cache[lf.set_smem_off]; m = pb_eval_dict<PredLut8>(p, lf.bits, pl, lane, Q.generic); }
+              else { PredBits pb; pb.bits = lf.set_bits; pb.excl = (uint32_t)lf.exclusive; m = pb_eval_dict<PredBits>(p, lf.bits, pb, lane, Q.generic); }
               break;
             }
             case L_RAW_RANGE_I:
             case L_RAW_RANGE_F:
             case L_RAW_SET: {
-              const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot] + (size_t)c * PB_CHUNK_DOCS * lf.raw_width);
+              const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
               m = pb_eval_raw(p, lf, lane);
               break;
             }
@@ -682,6 +717,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
       }
       uint32_t mask = (sp > 0 ? stack[0] : 0xffffffffu) & valid;
       matched += __popc(mask);
+      __syncwarp();   // all lanes are done reading this stage before lane 0 may refill it next iteration
 
       // ---- matches -> warp queue -> aggregate 32 at a time ----
       // round r takes the r-th set bit of every lane, so lanes stay full and docs stay clustered
@@ -700,15 +736,11 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
         if (qn + __popc(b) >= 32) drain32(32);
       }
     }
-    __syncthreads();   // everyone is done with this stage before it is refilled
-  }
-
-  // ---- tail: flush queues and counters of the last segment ----
-  if (cseg >= 0) {
-    uint32_t qn = H->wq_n[warp];
-    if (qn) drain32(qn);
+    // ---- segment exit: flush this warp's queue, then the block publishes its counters ----
+    { uint32_t qn = H->wq_n[warp]; if (qn) drain32(qn); }
     __syncthreads();
     flush_table();
+    __syncthreads();
   }
 }
 

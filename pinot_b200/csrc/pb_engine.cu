@@ -8,6 +8,7 @@
 #include "pb_device.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -461,6 +462,7 @@ struct pb_result_s {
   int n_scan_leaves_total = 0;
   std::vector<int64_t> seg_scan_leaves;     // per segment: number of scan leaves (for numEntriesScannedInFilter)
   double device_ms = 0, scan_ms = 0;
+  double host_us[8] = {0};   // [0] stage+resolve [1] tables [2] descriptors [3] launches [4] finalize: count [5] gather+D2H wait [6] host decode
   int launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
 };
@@ -505,6 +507,7 @@ struct Arena {   // host mirror of a device allocation; pointers are handed out 
 };
 
 static int finalize_result(pb_result_s* r);
+static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_query* sqs, const pb_query_desc* q, pb_result_handle* out) {
   int rc = ensure_init();
@@ -531,6 +534,8 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     if (q->aggregations[a].op != PB_AGG_COUNT && !q->aggregations[a].column) return fail(PB_ERR_INVALID, "aggregation %d needs a column", a);
   }
 
+  double t_prev = now_us();
+  auto lap = [&](int i) { double t = now_us(); r->host_us[i] += t - t_prev; t_prev = t; };
   // ---- resolve columns, stage what is needed ----
   std::vector<std::vector<int>> gcol(n_segs, std::vector<int>(nG)), acol(n_segs, std::vector<int>(nA, -1));
   bool any_raw_key = false;
@@ -585,6 +590,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT && (rc = get_global_dict(g, q->aggregations[a].column, &adict[a]))) return rc;
   }
 
+  lap(0);
   // ---- table mode and layout ----
   r->tables.resize(n_tables);
   int table_mode = nG == 0 ? T_KEYLESS : T_DENSE;
@@ -703,6 +709,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     CU(cudaGetLastError());
   }
 
+  lap(1);
   // ---- query arena (descriptors + leaf payloads) ----
   size_t arena_cap = sizeof(DevQuery) + 256 + (sizeof(DevSegQuery) + 64) * (size_t)n_segs + (sizeof(DevTable) + 64) * (size_t)n_tables;
   size_t bitmap_words_total = 0;
@@ -798,8 +805,8 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
             hbits[id >> 5] |= 1u << (id & 31);
           }
           lf.kind = L_DICT_SET; lf.bits = c.bits; lf.exclusive = fn.exclusive ? 1 : 0;
-          lf.set_bits = dbits; lf.set_words = (int32_t)words;
-          if (set_smem_used + (int)words <= PB_SET_SMEM_WORDS) { lf.set_smem_off = set_smem_used; set_smem_used += (int)words; }
+          lf.set_bits = dbits; lf.set_card = c.card;
+          if (set_smem_used + c.card <= PB_SET_SMEM_BYTES) { lf.set_smem_off = set_smem_used; set_smem_used += (c.card + 15) & ~15; }
           if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
           r->seg_scan_leaves[si]++;
           break;
@@ -890,32 +897,34 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     }
   }
 
-  // ---- tile geometry ----
+  // ---- chunk geometry: one stage = one 1024-doc chunk of every scan slot, per warp ----
   int sum_bits = 0;
   for (int k = 0; k < n_slots_max; k++) sum_bits += slot_bits_max[k];
-  int tile_chunks = 8;
-  const size_t stage_budget = 96 * 1024;   // 3 stages; keeps two CTAs resident per SM for typical filters
-  auto stage_bytes_for = [&](int chunks) {
-    size_t b = 0;
-    for (int k = 0; k < n_slots_max; k++) b += (((size_t)chunks * PB_CHUNK_DOCS * slot_bits_max[k] / 8 + 16) + 127) & ~(size_t)127;
-    return b;
-  };
-  while (tile_chunks > 1 && stage_bytes_for(tile_chunks) * PB_NSTAGE > stage_budget) tile_chunks >>= 1;
-  size_t stage_bytes = stage_bytes_for(tile_chunks);
-  if (stage_bytes * PB_NSTAGE > 160 * 1024) return fail(PB_ERR_UNSUPPORTED, "scan predicates touch %d bits per row: tile does not fit shared memory", sum_bits);
-  const uint64_t tile_docs = (uint64_t)tile_chunks * PB_CHUNK_DOCS;
-  uint64_t n_tiles = 0;
-  for (int si = 0; si < n_segs; si++) { hsegs[si].tile_begin = n_tiles; n_tiles += ((uint64_t)g->segs[si]->num_docs + tile_docs - 1) / tile_docs; }
+  size_t stage_bytes = 0;
+  int32_t slot_offs[PB_MAX_SCAN_SLOTS] = {0};
+  for (int k = 0; k < n_slots_max; k++) {
+    slot_offs[k] = (int32_t)stage_bytes;
+    stage_bytes += (((size_t)PB_CHUNK_DOCS * slot_bits_max[k] / 8 + 16) + 127) & ~(size_t)127;
+  }
+  if (stage_bytes * PB_NSTAGE * PB_NWARPS > 200 * 1024)
+    return fail(PB_ERR_UNSUPPORTED, "scan predicates touch %d bits per row: chunk stages do not fit shared memory", sum_bits);
+  uint64_t n_chunks = 0;
+  for (int si = 0; si < n_segs; si++) {
+    hsegs[si].chunk_begin = n_chunks;
+    hsegs[si].n_chunks = ((uint64_t)g->segs[si]->num_docs + PB_CHUNK_DOCS - 1) / PB_CHUNK_DOCS;
+    n_chunks += hsegs[si].n_chunks;
+  }
 
   hq->n_segs = n_segs; hq->n_group_by = nG; hq->n_aggs = nA; hq->table_mode = table_mode;
   for (int a = 0; a < nA; a++) hq->agg_op[a] = q->aggregations[a].op;
-  { size_t off = 0; for (int k = 0; k < n_slots_max; k++) { hq->slot_off[k] = (int32_t)off; off += (((size_t)tile_chunks * PB_CHUNK_DOCS * slot_bits_max[k] / 8 + 16) + 127) & ~(size_t)127; } }
-  hq->stage_bytes = (int32_t)stage_bytes; hq->tile_chunks = tile_chunks;
+  for (int k = 0; k < n_slots_max; k++) hq->slot_off[k] = slot_offs[k];
+  hq->stage_bytes = (int32_t)stage_bytes;
   hq->use_tma = (q->flags & PB_Q_NO_TMA) ? 0 : 1;
   hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
-  hq->n_tiles = n_tiles; hq->segs = dsegs; hq->tables = dtabs;
+  hq->n_chunks = n_chunks; hq->segs = dsegs; hq->tables = dtabs;
 
   CU(cudaMemcpyAsync(ar.dev, ar.host.data(), ar.used, cudaMemcpyHostToDevice, st));
+  lap(2);
 
   // ---- index leaves -> flat bitmaps ----
   for (auto& e : expands) {
@@ -930,7 +939,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   CU(cudaGetLastError());
 
   // ---- the scan ----
-  size_t smem = ((sizeof(ScanSmemHeader) + 127) & ~(size_t)127) + stage_bytes * PB_NSTAGE;
+  size_t smem = ((sizeof(ScanSmemHeader) + 127) & ~(size_t)127) + stage_bytes * PB_NSTAGE * PB_NWARPS;
   if (table_mode == T_KEYLESS) smem += ((2 * sizeof(double) * (size_t)nA * PB_NTHREADS) + 127) & ~(size_t)127;
   if (smem > 227 * 1024) return fail(PB_ERR_UNSUPPORTED, "scan kernel needs %zu bytes of shared memory", smem);
   {
@@ -944,14 +953,16 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_scan_kernel, PB_NTHREADS, smem));
   if (occ < 1) return fail(PB_ERR_CUDA, "scan kernel does not fit an SM (smem %zu)", smem);
   uint64_t max_ctas = (uint64_t)g_ctx.num_sms * (uint64_t)occ;
-  int grid = (int)std::min<uint64_t>(std::max<uint64_t>(n_tiles, 1), max_ctas);
+  // every CTA gets a contiguous range of chunks; keep at least one chunk per warp
+  int grid = (int)std::min<uint64_t>(std::max<uint64_t>((n_chunks + PB_NWARPS - 1) / PB_NWARPS, 1), max_ctas);
   CU(cudaEventRecord(r->ev1, st));
-  if (n_tiles > 0) {
+  if (n_chunks > 0) {
     pb_scan_kernel<<<grid, PB_NTHREADS, smem, st>>>(dq);
     r->launches++;
   }
   CU(cudaGetLastError());
   CU(cudaEventRecord(r->ev2, st));
+  lap(3);
 
   if (q->flags & PB_Q_DEFER_FINALIZE) {
     CU(cudaEventRecord(r->ev3, st));
@@ -1000,8 +1011,11 @@ static int finalize_result(pb_result_s* r) {
     }
   }
   CU(cudaGetLastError());
+  double t_prev = now_us();
+  auto lap = [&](int i) { double t = now_us(); r->host_us[i] += t - t_prev; t_prev = t; };
   CU(cudaMemcpyAsync(hc, r->d_counters, 8 * PB_COUNTERS_PER_TABLE * (size_t)nT, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  lap(4);
 
   // pass 2: compaction + gathers
   for (int t = 0; t < nT; t++) {
@@ -1055,6 +1069,7 @@ static int finalize_result(pb_result_s* r) {
   CU(cudaGetLastError());
   CU(cudaEventRecord(r->ev3, st));
   CU(cudaStreamSynchronize(st));
+  lap(5);
   float ms = 0;
   cudaEventElapsedTime(&ms, r->ev0, r->ev3); r->device_ms = ms;
   cudaEventElapsedTime(&ms, r->ev1, r->ev2); r->scan_ms = ms;
@@ -1167,6 +1182,7 @@ static int finalize_result(pb_result_s* r) {
       tm.stats.num_groups_limit_reached = (flag || ng >= (int64_t)tm.dev.num_groups_limit) ? 1 : 0;   // GroupByOperator.java:116
     }
   }
+  lap(6);
   r->finalized = true;
   return PB_OK;
 }
@@ -1205,6 +1221,11 @@ extern "C" double pb_result_scan_kernel_ms(pb_result_handle r) {
 extern "C" int32_t pb_result_kernel_launches(pb_result_handle r) { return r ? r->launches : 0; }
 extern "C" void* pb_result_stream(pb_result_handle r) { return r ? (void*)r->stream : nullptr; }
 
+extern "C" int pb_result_host_timing(pb_result_handle r, double* out8) {
+  if (!r || !out8) return fail(PB_ERR_INVALID, "null argument");
+  for (int i = 0; i < 8; i++) out8[i] = r->host_us[i];
+  return PB_OK;
+}
 extern "C" int pb_result_wait(pb_result_handle r) {
   if (!r) return fail(PB_ERR_INVALID, "null result");
   CU(cudaStreamSynchronize(r->stream));

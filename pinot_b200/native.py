@@ -122,6 +122,7 @@ def lib():
     l.pb_result_stream.argtypes = [C.c_void_p]
     l.pb_result_stream.restype = C.c_void_p
     l.pb_result_wait.argtypes = [C.c_void_p]
+    l.pb_result_host_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     l.pb_host_register.argtypes = [C.c_void_p, C.c_size_t]
     l.pb_host_unregister.argtypes = [C.c_void_p]
     l.pb_result_device_buffer.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
@@ -308,6 +309,11 @@ class Result:
 
     def stream(self) -> int:
         return lib().pb_result_stream(self._rh) or 0
+
+    def host_timing_us(self):
+        arr = (C.c_double * 8)()
+        _check(lib().pb_result_host_timing(self._rh, arr))
+        return list(arr)
 
     def wait(self):
         _check(lib().pb_result_wait(self._rh))
