@@ -19,14 +19,15 @@
 #define PB_NTHREADS 256
 #define PB_NWARPS 8
 #define PB_CHUNK_DOCS 1024          // docs per warp-chunk (lane owns 32)
-#define PB_NSTAGE 3
+#define PB_NSTAGE 2
 #define PB_MAX_LEAVES 16
 #define PB_MAX_NODES 32
 #define PB_MAX_GROUP_BY 16
 #define PB_MAX_AGGS 16
 #define PB_MAX_SCAN_SLOTS 8
 #define PB_SET_SMEM_BYTES 8192      // dictId-set membership LUTs (one byte per dictId) cached in smem per segment
-#define PB_WQ_CAP 64                // per-warp match queue entries
+#define PB_WQ_CAP 128               // per-warp match queue (ring buffer, power of two)
+#define PB_MAX_GATHER 32             // gather columns prefetched at enqueue time
 
 enum { L_TRUE = 0, L_FALSE = 1, L_DICT_RANGE = 2, L_DICT_SET = 3, L_RAW_RANGE_I = 4, L_RAW_RANGE_F = 5,
        L_RAW_SET = 6, L_BITMAP = 7 };
@@ -122,7 +123,7 @@ struct DevQuery {
   int32_t agg_op[PB_MAX_AGGS];
   int32_t slot_off[PB_MAX_SCAN_SLOTS];   // byte offset of each scan slot inside a stage
   int32_t stage_bytes;                   // bytes per warp stage (one 1024-doc chunk of every scan slot)
-  int32_t pad_q;
+  int32_t set_cache_bytes;               // shared-memory bytes reserved for IN-set membership LUTs
   int32_t use_tma;
   int32_t generic;                       // 1 = width-generic predicate path only
   uint64_t n_chunks;
@@ -240,17 +241,24 @@ __device__ __forceinline__ void pb_tma_load_1d(void* smem_dst, const void* gmem_
 // predicate evaluation on one 1024-doc chunk; every variant returns THIS LANE's 32-bit mask for docs
 // [chunk_doc0 + 32*lane, +32)   (PredicateEvaluator.applySV semantics, CTR/operator/filter/predicate/*)
 // ------------------------------------------------------------------------------------------------
+// Each functor sees the value TOP-ALIGNED in 32 bits (vt = dictId << (32-W) | garbage below the field) so a
+// range test needs no masking; returns 0/1.
 struct PredRange {      // SortedDictionaryBasedRangePredicateEvaluator.applySV: start <= dictId < end
   uint32_t lo, span;
+  template <int W> __device__ __forceinline__ uint32_t test(uint32_t vt) const {
+    return ((vt - (lo << (32 - W))) < (span << (32 - W))) ? 1u : 0u;
+  }
   __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return (v - lo) < span ? 1u : 0u; }
 };
 struct PredLut8 {       // IN / NOT_IN / EQ / NEQ with the (exclusive-folded) membership table in shared memory
   const uint8_t* lut;
+  template <int W> __device__ __forceinline__ uint32_t test(uint32_t vt) const { return lut[vt >> (32 - W)]; }
   __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return lut[v]; }
 };
 struct PredBits {       // same, large dictionaries: bitset in global memory (L1-resident)
   const uint32_t* bits;
   uint32_t excl;
+  template <int W> __device__ __forceinline__ uint32_t test(uint32_t vt) const { return (*this)(vt >> (32 - W)); }
   __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return (__funnelshift_r(__ldg(bits + (v >> 5)), 0u, v) & 1u) ^ excl; }
 };
 
@@ -284,13 +292,10 @@ __device__ __forceinline__ uint32_t pb_eval_dict_w(const uint32_t* __restrict__ 
   uint32_t m = 0;
 #pragma unroll
   for (int j = 31; j >= 0; j--) {
-    constexpr uint32_t MASK = (W == 32) ? 0xffffffffu : ((1u << (W & 31)) - 1u);
     const int bit = j * W;
     const int k = bit >> 5, s = bit & 31;
-    uint32_t v;
-    if (s + W <= 32) v = (w[k] >> ((32 - s - W) & 31)) & MASK;
-    else v = __funnelshift_l(w[k + 1], w[k], s) >> ((32 - W) & 31);
-    m = (m << 1) | pred(v);
+    const uint32_t vt = (s == 0) ? w[k] : __funnelshift_l(w[k + 1], w[k], s);   // value in the top W bits
+    m = (m << 1) + pred.template test<W>(vt);
   }
   return m;
 }
@@ -486,24 +491,39 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 // state, so a warp that is busy gathering/aggregating its matches never stalls the other seven.  The only
 // block-level synchronisation is at segment boundaries inside the CTA's range (descriptor + LUT reload).
 // ------------------------------------------------------------------------------------------------
+struct GatherCol {          // a column the aggregation step will gather from; used to prefetch at enqueue time
+  const uint8_t* fwd;
+  int32_t bits;             // dictionary column: bits per element; raw: 0
+  int32_t width;            // raw column: bytes per value
+};
+
 struct __align__(16) ScanSmemHeader {
   uint64_t full[PB_NWARPS][PB_NSTAGE];
   uint32_t wq[PB_NWARPS][PB_WQ_CAP];
+  uint32_t wq_head[PB_NWARPS];        // ring buffer: entries [head, head + n)
   uint32_t wq_n[PB_NWARPS];
   unsigned long long red_u64[PB_NWARPS];
   double red_f64[PB_NWARPS];
   long long red_i64[PB_NWARPS];
-  uint8_t set_cache[PB_SET_SMEM_BYTES];
+  // per-segment constants derived at segment entry
+  uint32_t slot_stride[PB_MAX_SCAN_SLOTS];   // bytes of one chunk of the slot (128 * bits)
+  int32_t n_gather;
+  int32_t flat_and;                          // program is AND(leaf, leaf, ...) (or a single leaf): no stack needed
+  int32_t n_flat;
+  int32_t flat_leaf[PB_MAX_LEAVES];
+  GatherCol gather[PB_MAX_GATHER];
   DevSegQuery seg;
 };
 
-__global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery* __restrict__ Qp) {
+__global__ void __launch_bounds__(PB_NTHREADS, 3) pb_scan_kernel(const DevQuery* __restrict__ Qp) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   ScanSmemHeader* H = reinterpret_cast<ScanSmemHeader*>(smem_raw);
   const DevQuery& Q = *Qp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // after the header: keyless accumulators (n_aggs rows), then the per-warp stage buffers
+  // after the header: IN-set LUTs, keyless accumulators (n_aggs rows), then the per-warp stage buffers
   uint8_t* dyn = smem_raw + ((sizeof(ScanSmemHeader) + 127) & ~(size_t)127);
+  uint8_t* set_cache = dyn;
+  dyn += (Q.set_cache_bytes + 127) & ~127;
   KeylessAcc ka;
   ka.sum = nullptr; ka.mm = nullptr;
   const long long ENC_POS_INF = 0x7ff0000000000000LL;                       // enc(+inf)
@@ -523,6 +543,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
   if (lane == 0) {
     for (int s = 0; s < PB_NSTAGE; s++) pb_mbar_init(&H->full[warp][s], 1);
     H->wq_n[warp] = 0;
+    H->wq_head[warp] = 0;
   }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
@@ -538,15 +559,14 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
   unsigned long long keyless_rows = 0, matched = 0;
   uint32_t consumed = 0;   // chunks this warp has consumed so far: stage = consumed % NSTAGE, parity from consumed / NSTAGE
 
+  // aggregate the n_take (<= 32) OLDEST queued docs of this warp (their gather lines were prefetched when they
+  // were enqueued, at least one chunk ago)
   auto drain32 = [&](uint32_t n_take) {
-    // take the first n_take (<= 32) queued docs of this warp, aggregate them, compact the queue
-    uint32_t qn = H->wq_n[warp];
-    uint32_t doc = lane < n_take ? H->wq[warp][lane] : 0u;
-    uint32_t rest = (lane + n_take < qn) ? H->wq[warp][lane + n_take] : 0u;   // qn < 64 => one pass moves the tail
+    const uint32_t head = H->wq_head[warp], qn = H->wq_n[warp];
+    uint32_t doc = lane < n_take ? H->wq[warp][(head + lane) & (PB_WQ_CAP - 1)] : 0u;
     __syncwarp();
+    if (lane == 0) { H->wq_head[warp] = (head + n_take) & (PB_WQ_CAP - 1); H->wq_n[warp] = qn - n_take; }
     if (lane < n_take) pb_accumulate(Q, H->seg, Q.tables[H->seg.table], doc, ka, keyless_rows);
-    if (lane + n_take < qn) H->wq[warp][lane] = rest;
-    if (lane == 0) H->wq_n[warp] = qn - n_take;
     __syncwarp();
   };
 
@@ -590,20 +610,73 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
     }
   };
 
+  // evaluate one filter leaf on the staged chunk; returns this lane's 32-doc mask
+  auto eval_leaf = [&](const DevLeaf& lf, const uint8_t* stage, uint64_t chunk_doc0) -> uint32_t {
+    switch (lf.kind) {
+      case L_TRUE: return 0xffffffffu;
+      case L_FALSE: return 0u;
+      case L_DICT_RANGE: {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
+        PredRange pr; pr.lo = lf.lo; pr.span = lf.span;
+        return pb_eval_dict<PredRange>(p, lf.bits, pr, lane, Q.generic);
+      }
+      case L_DICT_SET: {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
+        if (lf.set_smem_off >= 0) { PredLut8 pl; pl.lut = set_cache + lf.set_smem_off; return pb_eval_dict<PredLut8>(p, lf.bits, pl, lane, Q.generic); }
+        PredBits pb; pb.bits = lf.set_bits; pb.excl = (uint32_t)lf.exclusive;
+        return pb_eval_dict<PredBits>(p, lf.bits, pb, lane, Q.generic);
+      }
+      case L_RAW_RANGE_I:
+      case L_RAW_RANGE_F:
+      case L_RAW_SET: {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
+        return pb_eval_raw(p, lf, lane);
+      }
+      default: {   // L_BITMAP (padded to whole chunks)
+        uint32_t m = __ldg(lf.bitmap + (chunk_doc0 >> 5) + lane);
+        return lf.exclusive ? ~m : m;
+      }
+    }
+  };
+
   for (int sgi = seg_first; sgi < Q.n_segs; sgi++) {
     if (Q.segs[sgi].chunk_begin >= cta_hi) break;
-    // ---- segment entry: descriptor and LUTs into shared memory (everyone has left the previous segment) ----
+    // ---- segment entry: descriptor, derived constants and LUTs into shared memory ----
     {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(&Q.segs[sgi]);
       uint32_t* dst = reinterpret_cast<uint32_t*>(&H->seg);
       for (int i = tid; i < (int)(sizeof(DevSegQuery) / 4); i += PB_NTHREADS) dst[i] = src[i];
       __syncthreads();
+      const DevSegQuery& g = H->seg;
+      if (tid < g.n_scan) H->slot_stride[tid] = (uint32_t)(PB_CHUNK_DOCS / 8) * (uint32_t)g.scan[tid].bits_per_doc;
+      if (tid == 32) {
+        // gather list (deduplicated by forward-index pointer)
+        int n = 0;
+        auto add = [&](const uint8_t* fwd, int bits, int width) {
+          for (int i = 0; i < n; i++) if (H->gather[i].fwd == fwd) return;
+          if (n < PB_MAX_GATHER && fwd) { H->gather[n].fwd = fwd; H->gather[n].bits = bits; H->gather[n].width = width; n++; }
+        };
+        for (int j = 0; j < Q.n_group_by; j++) add(g.keys[j].fwd, g.keys[j].raw_width ? 0 : g.keys[j].bits, g.keys[j].raw_width);
+        for (int a = 0; a < Q.n_aggs; a++) if (Q.agg_op[a] != 0) add(g.aggs[a].fwd, g.aggs[a].raw_width ? 0 : g.aggs[a].bits, g.aggs[a].raw_width);
+        H->n_gather = n;
+      }
+      if (tid == 64) {
+        // flat conjunction?  postfix == leaf* AND(n)   or a single leaf   or empty (match all)
+        int nl = 0; bool flat = true;
+        for (int n = 0; n < g.n_nodes; n++) {
+          if (g.node_kind[n] == N_LEAF) { if (nl < PB_MAX_LEAVES) H->flat_leaf[nl] = g.node_arg[n]; nl++; }
+          else if (!(g.node_kind[n] == N_AND && n == g.n_nodes - 1 && g.node_arg[n] == nl)) flat = false;
+        }
+        if (g.n_nodes > 1 && g.node_kind[g.n_nodes - 1] != N_AND) flat = false;
+        H->flat_and = flat ? 1 : 0;
+        H->n_flat = nl;
+      }
       for (int l = 0; l < PB_MAX_LEAVES; l++) {
-        const DevLeaf& lf = H->seg.leaves[l];
+        const DevLeaf& lf = g.leaves[l];
         if (lf.kind == L_DICT_SET && lf.set_smem_off >= 0) {
           // membership bytes with the exclusive flag folded in (NOT_IN / NEQ)
           for (int i = tid; i < lf.set_card; i += PB_NTHREADS)
-            H->set_cache[lf.set_smem_off + i] = (uint8_t)(((__ldg(lf.set_bits + (i >> 5)) >> (i & 31)) & 1u) ^ (uint32_t)lf.exclusive);
+            set_cache[lf.set_smem_off + i] = (uint8_t)(((__ldg(lf.set_bits + (i >> 5)) >> (i & 31)) & 1u) ^ (uint32_t)lf.exclusive);
         }
       }
       __syncthreads();
@@ -615,35 +688,33 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
     // this warp's chunks in this segment: seg_lo + warp, + NWARPS, ...
     const uint64_t first = seg_lo + warp;
     const uint32_t n_mine = first < seg_hi ? (uint32_t)((seg_hi - first + PB_NWARPS - 1) / PB_NWARPS) : 0u;
+    const uint32_t rel0 = (uint32_t)(first - sq.chunk_begin);     // chunk index inside the segment
+    const int n_scan = sq.n_scan;
 
     // producer side (lane 0 of each warp): load this warp's k-th chunk of the segment into its stage
     auto issue = [&](uint32_t k, uint32_t seq) {
-      const uint64_t chunk = first + (uint64_t)k * PB_NWARPS;
-      const uint64_t doc0 = (chunk - sq.chunk_begin) * PB_CHUNK_DOCS;
+      const uint32_t rel = rel0 + k * PB_NWARPS;
       const int st = (int)(seq % PB_NSTAGE);
+      uint8_t* dst = my_stages + (size_t)st * Q.stage_bytes;
       uint32_t total = 0;
       uint32_t nbytes[PB_MAX_SCAN_SLOTS];
-      for (int c = 0; c < sq.n_scan; c++) {
-        uint64_t off = doc0 * (uint64_t)sq.scan[c].bits_per_doc / 8;              // chunk starts are 128-byte multiples
-        uint64_t want = (uint64_t)PB_CHUNK_DOCS * (uint64_t)sq.scan[c].bits_per_doc / 8 + 16;   // +16: the word after the chunk
-        uint64_t avail = sq.scan[c].bytes_total - off;
-        uint64_t n = (want < avail ? want : avail) & ~(uint64_t)15;
-        nbytes[c] = (uint32_t)n;
-        total += (uint32_t)n;
+      for (int c = 0; c < n_scan; c++) {
+        const uint64_t off = (uint64_t)rel * H->slot_stride[c];                   // chunk starts are 128-byte multiples
+        const uint64_t want = (uint64_t)H->slot_stride[c] + 16;                   // +16: the word after the chunk
+        const uint64_t avail = sq.scan[c].bytes_total - off;
+        nbytes[c] = (uint32_t)((want < avail ? want : avail) & ~(uint64_t)15);
+        total += nbytes[c];
       }
       pb_mbar_expect_tx(&H->full[warp][st], total);
-      for (int c = 0; c < sq.n_scan; c++) {
-        uint64_t off = doc0 * (uint64_t)sq.scan[c].bits_per_doc / 8;
-        pb_tma_load_1d(my_stages + (size_t)st * Q.stage_bytes + Q.slot_off[c], sq.scan[c].base + off, nbytes[c], &H->full[warp][st]);
-      }
+      for (int c = 0; c < n_scan; c++)
+        pb_tma_load_1d(dst + Q.slot_off[c], sq.scan[c].base + (uint64_t)rel * H->slot_stride[c], nbytes[c], &H->full[warp][st]);
     };
 
     if (staged && Q.use_tma && lane == 0)
       for (uint32_t k = 0; k < PB_NSTAGE - 1 && k < n_mine; k++) issue(k, consumed + k);
 
     for (uint32_t k = 0; k < n_mine; k++) {
-      const uint64_t chunk = first + (uint64_t)k * PB_NWARPS;
-      const uint64_t chunk_doc0 = (chunk - sq.chunk_begin) * PB_CHUNK_DOCS;
+      const uint64_t chunk_doc0 = (uint64_t)(rel0 + k * PB_NWARPS) * PB_CHUNK_DOCS;
       const int st = (int)(consumed % PB_NSTAGE);
       uint8_t* stage = my_stages + (size_t)st * Q.stage_bytes;
       if (staged) {
@@ -652,11 +723,11 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
           if (lane == 0 && k + PB_NSTAGE - 1 < n_mine) issue(k + PB_NSTAGE - 1, consumed + PB_NSTAGE - 1);
           pb_mbar_wait(&H->full[warp][st], (consumed / PB_NSTAGE) & 1u);
         } else {
-          for (int c = 0; c < sq.n_scan; c++) {
-            uint64_t off = chunk_doc0 * (uint64_t)sq.scan[c].bits_per_doc / 8;
-            uint64_t want = (uint64_t)PB_CHUNK_DOCS * (uint64_t)sq.scan[c].bits_per_doc / 8 + 16;
-            uint64_t avail = sq.scan[c].bytes_total - off;
-            uint64_t n = (want < avail ? want : avail) & ~(uint64_t)15;
+          for (int c = 0; c < n_scan; c++) {
+            const uint64_t off = (uint64_t)(rel0 + k * PB_NWARPS) * H->slot_stride[c];
+            const uint64_t want = (uint64_t)H->slot_stride[c] + 16;
+            const uint64_t avail = sq.scan[c].bytes_total - off;
+            const uint64_t n = (want < avail ? want : avail) & ~(uint64_t)15;
             const uint4* s4 = reinterpret_cast<const uint4*>(sq.scan[c].base + off);
             uint4* d4 = reinterpret_cast<uint4*>(stage + Q.slot_off[c]);
             for (uint32_t i = lane; i < (uint32_t)(n / 16); i += 32) d4[i] = __ldg(s4 + i);
@@ -667,77 +738,62 @@ __global__ void __launch_bounds__(PB_NTHREADS, 2) pb_scan_kernel(const DevQuery*
       consumed++;
 
       // ---- filter ----
-      long long remaining = (long long)sq.num_docs - (long long)(chunk_doc0 + 32ull * lane);
-      uint32_t valid = remaining >= 32 ? 0xffffffffu : (remaining <= 0 ? 0u : ((1u << remaining) - 1u));
-      uint32_t stack[PB_MAX_LEAVES];
-      int sp = 0;
-      for (int n = 0; n < sq.n_nodes; n++) {
-        const int kind = sq.node_kind[n], arg = sq.node_arg[n];
-        if (kind == N_LEAF) {
-          const DevLeaf& lf = sq.leaves[arg];
-          uint32_t m;
-          switch (lf.kind) {
-            case L_TRUE: m = 0xffffffffu; break;
-            case L_FALSE: m = 0u; break;
-            case L_DICT_RANGE: {
-              const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
-              PredRange pr; pr.lo = lf.lo; pr.span = lf.span;
-              m = pb_eval_dict<PredRange>(p, lf.bits, pr, lane, Q.generic);
-              break;
-            }
-            case L_DICT_SET: {
-              const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
-              if (lf.set_smem_off >= 0) { PredLut8 pl; pl.lut = &H->set_cache[lf.set_smem_off]; m = pb_eval_dict<PredLut8>(p, lf.bits, pl, lane, Q.generic); }
-              else { PredBits pb; pb.bits = lf.set_bits; pb.excl = (uint32_t)lf.exclusive; m = pb_eval_dict<PredBits>(p, lf.bits, pb, lane, Q.generic); }
-              break;
-            }
-            case L_RAW_RANGE_I:
-            case L_RAW_RANGE_F:
-            case L_RAW_SET: {
-              const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
-              m = pb_eval_raw(p, lf, lane);
-              break;
-            }
-            default: {   // L_BITMAP (padded to whole chunks)
-              uint64_t wi = (chunk_doc0 >> 5) + lane;
-              m = __ldg(lf.bitmap + wi);
-              if (lf.exclusive) m = ~m;
-              break;
-            }
+      const long long remaining = (long long)sq.num_docs - (long long)(chunk_doc0 + 32ull * lane);
+      uint32_t mask = remaining >= 32 ? 0xffffffffu : (remaining <= 0 ? 0u : ((1u << remaining) - 1u));
+      if (H->flat_and) {
+        const int nl = H->n_flat;
+        for (int i = 0; i < nl; i++) mask &= eval_leaf(sq.leaves[H->flat_leaf[i]], stage, chunk_doc0);
+      } else {
+        uint32_t stack[PB_MAX_LEAVES];
+        int sp = 0;
+        for (int n = 0; n < sq.n_nodes; n++) {
+          const int kind = sq.node_kind[n], arg = sq.node_arg[n];
+          if (kind == N_LEAF) stack[sp++] = eval_leaf(sq.leaves[arg], stage, chunk_doc0);
+          else if (kind == N_NOT) stack[sp - 1] = ~stack[sp - 1];
+          else {
+            uint32_t r = stack[sp - arg];
+            for (int i = 1; i < arg; i++) r = (kind == N_AND) ? (r & stack[sp - arg + i]) : (r | stack[sp - arg + i]);
+            sp -= arg;
+            stack[sp++] = r;
           }
-          stack[sp++] = m;
-        } else if (kind == N_NOT) {
-          stack[sp - 1] = ~stack[sp - 1];
-        } else {
-          uint32_t r = stack[sp - arg];
-          for (int i = 1; i < arg; i++) r = (kind == N_AND) ? (r & stack[sp - arg + i]) : (r | stack[sp - arg + i]);
-          sp -= arg;
-          stack[sp++] = r;
         }
+        if (sp > 0) mask &= stack[0];
       }
-      uint32_t mask = (sp > 0 ? stack[0] : 0xffffffffu) & valid;
       matched += __popc(mask);
       __syncwarp();   // all lanes are done reading this stage before lane 0 may refill it next iteration
 
-      // ---- matches -> warp queue -> aggregate 32 at a time ----
+      // ---- matches -> warp ring queue (+ L2 prefetch of their gather lines); aggregate the oldest 32 once 64 wait ----
       // round r takes the r-th set bit of every lane, so lanes stay full and docs stay clustered
       while (__any_sync(0xffffffffu, mask != 0)) {
-        bool has = mask != 0;
-        uint32_t b = __ballot_sync(0xffffffffu, has);
-        uint32_t qn = H->wq_n[warp];
+        const bool has = mask != 0;
+        const uint32_t b = __ballot_sync(0xffffffffu, has);
+        const uint32_t head = H->wq_head[warp], qn = H->wq_n[warp];
         if (has) {
-          int bit = __ffs(mask) - 1;
+          const int bit = __ffs(mask) - 1;
           mask &= mask - 1;
-          H->wq[warp][qn + __popc(b & ((1u << lane) - 1u))] = (uint32_t)(chunk_doc0 + 32ull * lane + bit);
+          const uint32_t doc = (uint32_t)(chunk_doc0 + 32ull * lane + bit);
+          H->wq[warp][(head + qn + __popc(b & ((1u << lane) - 1u))) & (PB_WQ_CAP - 1)] = doc;
+          const int ng = H->n_gather;
+          for (int i = 0; i < ng; i++) {
+            const GatherCol gc = H->gather[i];
+            const uint8_t* a = gc.bits ? gc.fwd + ((((unsigned long long)doc * (unsigned)gc.bits) >> 5) << 2)
+                                       : gc.fwd + (unsigned long long)doc * (unsigned)gc.width;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          }
         }
         __syncwarp();
-        if (lane == 0) H->wq_n[warp] = qn + __popc(b);
+        const uint32_t nq = qn + __popc(b);
+        if (lane == 0) H->wq_n[warp] = nq;
         __syncwarp();
-        if (qn + __popc(b) >= 32) drain32(32);
+        if (nq >= 64) drain32(32);
       }
     }
     // ---- segment exit: flush this warp's queue, then the block publishes its counters ----
-    { uint32_t qn = H->wq_n[warp]; if (qn) drain32(qn); }
+    while (true) {
+      const uint32_t qn = H->wq_n[warp];
+      if (!qn) break;
+      drain32(qn < 32 ? qn : 32);
+    }
     __syncthreads();
     flush_table();
     __syncthreads();

@@ -746,6 +746,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   struct PendingExpand { int kind; const uint8_t* inv; int card; const int32_t* ids; int n_ids; uint32_t* out; uint32_t num_docs; };
   std::vector<PendingExpand> expands;
   int slot_bits_max[PB_MAX_SCAN_SLOTS] = {0};
+  int set_cache_max = 0;
   int n_slots_max = 0;
   size_t bm_off = 0;
   r->seg_scan_leaves.assign(n_segs, 0);
@@ -872,6 +873,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       }
     }
     ds.n_scan = n_scan;
+    set_cache_max = std::max(set_cache_max, set_smem_used);
     n_slots_max = std::max(n_slots_max, n_scan);
     r->n_scan_leaves_total += (int)r->seg_scan_leaves[si];
 
@@ -919,6 +921,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   for (int a = 0; a < nA; a++) hq->agg_op[a] = q->aggregations[a].op;
   for (int k = 0; k < n_slots_max; k++) hq->slot_off[k] = slot_offs[k];
   hq->stage_bytes = (int32_t)stage_bytes;
+  hq->set_cache_bytes = set_cache_max;
   hq->use_tma = (q->flags & PB_Q_NO_TMA) ? 0 : 1;
   hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
   hq->n_chunks = n_chunks; hq->segs = dsegs; hq->tables = dtabs;
@@ -939,7 +942,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   CU(cudaGetLastError());
 
   // ---- the scan ----
-  size_t smem = ((sizeof(ScanSmemHeader) + 127) & ~(size_t)127) + stage_bytes * PB_NSTAGE * PB_NWARPS;
+  size_t smem = ((sizeof(ScanSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + stage_bytes * PB_NSTAGE * PB_NWARPS;
   if (table_mode == T_KEYLESS) smem += ((2 * sizeof(double) * (size_t)nA * PB_NTHREADS) + 127) & ~(size_t)127;
   if (smem > 227 * 1024) return fail(PB_ERR_UNSUPPORTED, "scan kernel needs %zu bytes of shared memory", smem);
   {
@@ -978,17 +981,25 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
 // ------------------------------------------------------------------------------------------------
 // finalize: compaction of non-empty groups, device -> pinned host, key decode
 // ------------------------------------------------------------------------------------------------
-static void decode_key_value(const pb_group_s* g, const pb_result_s* r, const TableMeta& tm, int j, int32_t id, uint8_t* out, int eb) {
-  if (r->combine) {
-    const GlobalDict& gd = g->dicts.at(r->gb_names[j]);
-    memcpy(out, gd.values.data() + (size_t)id * gd.entry_bytes, (size_t)gd.entry_bytes);
-  } else {
-    const pb_segment_s* s = g->segs[tm.seg_idx[0]];
-    const Column& c = s->cols[find_col(s, r->gb_names[j].c_str())];
-    native_entry(c, id, out);
+// resolves, once per (table, group-by column), where decoded key values come from
+struct KeyDecoder {
+  const uint8_t* global_values = nullptr;   // combined mode: native-endian entries of the global dictionary
+  int global_eb = 0;
+  const Column* col = nullptr;              // per-segment mode: the segment's own dictionary (big-endian)
+  void init(const pb_group_s* g, const pb_result_s* r, const TableMeta& tm, int j) {
+    if (r->combine) {
+      const GlobalDict& gd = g->dicts.at(r->gb_names[j]);
+      global_values = gd.values.data(); global_eb = gd.entry_bytes;
+    } else {
+      const pb_segment_s* s = g->segs[tm.seg_idx[0]];
+      col = &s->cols[find_col(s, r->gb_names[j].c_str())];
+    }
   }
-  (void)eb;
-}
+  inline void decode(int32_t id, uint8_t* out) const {
+    if (global_values) memcpy(out, global_values + (size_t)id * global_eb, (size_t)global_eb);
+    else native_entry(*col, id, out);
+  }
+};
 
 static int finalize_result(pb_result_s* r) {
   if (r->finalized) return PB_OK;
@@ -1121,12 +1132,14 @@ static int finalize_result(pb_result_s* r) {
       int32_t* ids = (int32_t*)tm.key_ids[j].p;
       uint8_t* vals = (uint8_t*)tm.key_vals[j].p;
       if (mode == T_DENSE) {   // DictionaryBasedGroupKeyGenerator.java:578-591 (mixed radix decode)
+        KeyDecoder kd; kd.init(g, r, tm, j);
+        uint64_t div = 1;
+        for (int jj = 0; jj < j; jj++) div *= (uint64_t)tm.cards[jj];
+        const uint64_t card = (uint64_t)tm.cards[j];
         for (int64_t k = 0; k < ng; k++) {
-          uint64_t raw = slots[k];
-          for (int jj = 0; jj < j; jj++) raw /= (uint64_t)tm.cards[jj];
-          uint64_t field = raw % (uint64_t)tm.cards[j];
+          const uint64_t field = (slots[k] / div) % card;
           ids[k] = (int32_t)field;
-          decode_key_value(g, r, tm, j, (int32_t)field, vals + (size_t)k * eb, eb);
+          kd.decode((int32_t)field, vals + (size_t)k * eb);
         }
       }
     }
@@ -1149,10 +1162,12 @@ static int finalize_result(pb_result_s* r) {
         int32_t* ids = (int32_t*)tm.key_ids[j].p;
         uint8_t* vals = (uint8_t*)tm.key_vals[j].p;
         const int width = tm.widths[j], shift = tm.shifts[j];
+        KeyDecoder kd;
+        if (c0.has_dict) kd.init(g, r, tm, j);
         for (int64_t k = 0; k < ng; k++) {
           uint64_t f = keys[(size_t)k] >> shift;
           if (width < 64) f &= ((1ull << width) - 1ull);
-          if (c0.has_dict) { ids[k] = (int32_t)f; decode_key_value(g, r, tm, j, (int32_t)f, vals + (size_t)k * eb, eb); }
+          if (c0.has_dict) { ids[k] = (int32_t)f; kd.decode((int32_t)f, vals + (size_t)k * eb); }
           else {
             ids[k] = -1;
             if (c0.type == PB_INT) { int32_t v = (int32_t)(uint32_t)f; memcpy(vals + (size_t)k * eb, &v, 4); }
