@@ -192,9 +192,11 @@ const int64_t* pb_result_long(pb_result_handle r, int32_t table, int32_t agg);
 const int64_t* pb_result_distinct_offsets(pb_result_handle r, int32_t table, int32_t agg);
 const int32_t* pb_result_distinct_dict_ids(pb_result_handle r, int32_t table, int32_t agg);
 const pb_exec_stats* pb_result_stats(pb_result_handle r, int32_t table);
-/* device time (CUDA events around the kernels of this call), and the scan kernel alone */
+/* device time (CUDA events on the call's stream): the whole call (table init .. result read-back), the two hot
+ * kernels together (pb_filter_kernel + pb_agg_kernel), and each of them */
 double pb_result_device_ms(pb_result_handle r);
 double pb_result_scan_kernel_ms(pb_result_handle r);
+int pb_result_phase_ms(pb_result_handle r, double* filter_kernel_ms, double* agg_kernel_ms);
 int32_t pb_result_kernel_launches(pb_result_handle r);
 /* host-side microseconds spent in this call, by phase: [0] resolve + stage, [1] table allocation + init,
  * [2] descriptor build + upload, [3] kernel launches, [4] wait for the scan + group count, [5] compaction,

@@ -1,15 +1,16 @@
 // pb_device.cuh — device-side data model and kernels of the B200 segment executor (sm_100a).
 //
-// One persistent kernel (pb_scan_kernel) runs the whole per-segment operator chain for every segment of
-// a query:  DocIdSetOperator/filter operators -> ProjectionOperator -> GroupByOperator/AggregationOperator
-// (reference: CTR/operator/query/GroupByOperator.java:101-140 and the call stack in SURVEY.md §3.1).
+// Two kernels run the per-segment operator chain for every segment of a query in one launch each
+// (reference: CTR/operator/query/GroupByOperator.java:101-140 and the call stack in SURVEY.md §3.1):
 //
-//   tile (8 x 1024 docs) of every scan-predicate column  --cp.async.bulk (TMA) + mbarrier, 3 stages-->  smem
-//   warp = 1024-doc chunk, lane = 32 consecutive docs: unpack big-endian bit-packed dictIds from smem,
-//     evaluate the predicate tree on 32-bit doc masks (one mask word per lane == packed docId bitmap)
-//   matching docs -> per-warp queue -> 32 at a time: gather group-key / metric dictIds straight from HBM
-//     (only the sectors that hold matching rows are touched), dictionary decode, accumulate into the
-//     group table with native L2 reductions (RED.ADD.F64 / RED.MIN.S64 / RED.MAX.S64 / RED.OR.B32).
+//   pb_filter_kernel   DocIdSetOperator + filter operators.  Per warp: a 1024-doc chunk of every scan-predicate
+//     column --cp.async.bulk (TMA) + mbarrier, 2 stages--> smem; lane = 32 consecutive docs: unpack big-endian
+//     bit-packed dictIds, evaluate the predicate tree on 32-bit doc masks (one mask word per lane == packed docId
+//     bitmap), append matching docIds to the global match list.
+//   pb_agg_kernel      ProjectionOperator + GroupByOperator/AggregationOperator.  One thread per matching doc:
+//     gather group-key / metric dictIds straight from HBM (only the sectors that hold matching rows are touched),
+//     dictionary decode, accumulate into the group table with native L2 reductions
+//     (RED.ADD.F64 / RED.MIN.S64 / RED.MAX.S64 / RED.OR.B32).
 //
 // No tensor cores: the path is integer / gather / atomic bound (BASELINE.json north_star).
 #pragma once
@@ -26,8 +27,6 @@
 #define PB_MAX_AGGS 16
 #define PB_MAX_SCAN_SLOTS 8
 #define PB_SET_SMEM_BYTES 8192      // dictId-set membership LUTs (one byte per dictId) cached in smem per segment
-#define PB_WQ_CAP 128               // per-warp match queue (ring buffer, power of two)
-#define PB_MAX_GATHER 32             // gather columns prefetched at enqueue time
 
 enum { L_TRUE = 0, L_FALSE = 1, L_DICT_RANGE = 2, L_DICT_SET = 3, L_RAW_RANGE_I = 4, L_RAW_RANGE_F = 5,
        L_RAW_SET = 6, L_BITMAP = 7 };
@@ -90,13 +89,16 @@ struct DevSegQuery {
   int32_t table;           // result table index
   uint64_t chunk_begin;    // global index of this segment's first 1024-doc chunk
   uint64_t n_chunks;       // ceil(num_docs / 1024)
+  uint64_t doc_base;       // global doc number of this segment's doc 0 (match list numbering)
   int8_t node_kind[PB_MAX_NODES];
   int8_t node_arg[PB_MAX_NODES];
   DevLeaf leaves[PB_MAX_LEAVES];
   DevScanCol scan[PB_MAX_SCAN_SLOTS];
+  // ---- everything above is the filter part (copied to shared memory by pb_filter_kernel) ----
   DevKeyCol keys[PB_MAX_GROUP_BY];
   DevAggCol aggs[PB_MAX_AGGS];
 };
+#define PB_SEG_FILTER_BYTES (sizeof(DevSegQuery) - sizeof(DevKeyCol) * PB_MAX_GROUP_BY - sizeof(DevAggCol) * PB_MAX_AGGS)
 
 struct DevTable {
   int32_t mode;
@@ -127,6 +129,11 @@ struct DevQuery {
   int32_t use_tma;
   int32_t generic;                       // 1 = width-generic predicate path only
   uint64_t n_chunks;
+  uint64_t n_docs_total;
+  int32_t match_all;                     // no filter: pb_agg_kernel walks every doc, no match list
+  int32_t pad_m;
+  uint32_t* match_list;                  // global doc numbers of the docs that pass the filter
+  unsigned long long* match_count;
   const DevSegQuery* segs;
   DevTable* tables;
 };
@@ -491,60 +498,37 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 // state, so a warp that is busy gathering/aggregating its matches never stalls the other seven.  The only
 // block-level synchronisation is at segment boundaries inside the CTA's range (descriptor + LUT reload).
 // ------------------------------------------------------------------------------------------------
-struct GatherCol {          // a column the aggregation step will gather from; used to prefetch at enqueue time
-  const uint8_t* fwd;
-  int32_t bits;             // dictionary column: bits per element; raw: 0
-  int32_t width;            // raw column: bytes per value
-};
-
-struct __align__(16) ScanSmemHeader {
+// ------------------------------------------------------------------------------------------------
+// Kernel 1: pb_filter_kernel  (DocIdSetOperator + filter operators: SURVEY.md §3.2)
+//
+// A CTA owns a contiguous range of 1024-doc chunks; inside it every WARP is an independent worker with its
+// own 2-stage TMA pipeline (cp.async.bulk + mbarrier) over its chunks — no block-wide barrier in the steady
+// state.  Per chunk: unpack + predicate tree on 32-bit doc masks, then the matching docIds are appended to the
+// global match list (one atomicAdd per warp-chunk, ascending docIds inside a block).  The instruction stream is
+// short and identical for all warps, which keeps the instruction cache warm.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) FilterSmemHeader {
   uint64_t full[PB_NWARPS][PB_NSTAGE];
-  uint32_t wq[PB_NWARPS][PB_WQ_CAP];
-  uint32_t wq_head[PB_NWARPS];        // ring buffer: entries [head, head + n)
-  uint32_t wq_n[PB_NWARPS];
-  unsigned long long red_u64[PB_NWARPS];
-  double red_f64[PB_NWARPS];
-  long long red_i64[PB_NWARPS];
-  // per-segment constants derived at segment entry
   uint32_t slot_stride[PB_MAX_SCAN_SLOTS];   // bytes of one chunk of the slot (128 * bits)
-  int32_t n_gather;
   int32_t flat_and;                          // program is AND(leaf, leaf, ...) (or a single leaf): no stack needed
   int32_t n_flat;
   int32_t flat_leaf[PB_MAX_LEAVES];
-  GatherCol gather[PB_MAX_GATHER];
-  DevSegQuery seg;
+  uint8_t seg[PB_SEG_FILTER_BYTES];          // the filter part of the current DevSegQuery
 };
 
-__global__ void __launch_bounds__(PB_NTHREADS, 3) pb_scan_kernel(const DevQuery* __restrict__ Qp) {
+__global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  ScanSmemHeader* H = reinterpret_cast<ScanSmemHeader*>(smem_raw);
+  FilterSmemHeader* H = reinterpret_cast<FilterSmemHeader*>(smem_raw);
   const DevQuery& Q = *Qp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // after the header: IN-set LUTs, keyless accumulators (n_aggs rows), then the per-warp stage buffers
-  uint8_t* dyn = smem_raw + ((sizeof(ScanSmemHeader) + 127) & ~(size_t)127);
+  uint8_t* dyn = smem_raw + ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127);
   uint8_t* set_cache = dyn;
   dyn += (Q.set_cache_bytes + 127) & ~127;
-  KeylessAcc ka;
-  ka.sum = nullptr; ka.mm = nullptr;
-  const long long ENC_POS_INF = 0x7ff0000000000000LL;                       // enc(+inf)
-  const long long ENC_NEG_INF = (long long)0xfff0000000000000ULL ^ 0x7fffffffffffffffLL;   // enc(-inf)
-  if (Q.table_mode == T_KEYLESS) {
-    ka.sum = reinterpret_cast<double*>(dyn);
-    ka.mm = reinterpret_cast<long long*>(dyn + sizeof(double) * Q.n_aggs * PB_NTHREADS);
-    dyn += ((2 * sizeof(double) * Q.n_aggs * PB_NTHREADS) + 127) & ~(size_t)127;
-    for (int a = 0; a < Q.n_aggs; a++) {
-      ka.sum[a * PB_NTHREADS + tid] = 0.0;
-      ka.mm[a * PB_NTHREADS + tid] = Q.agg_op[a] == 2 ? ENC_POS_INF : ENC_NEG_INF;
-    }
-  }
   uint8_t* my_stages = dyn + (size_t)warp * PB_NSTAGE * Q.stage_bytes;
   const bool staged = Q.stage_bytes > 0;
 
-  if (lane == 0) {
+  if (lane == 0)
     for (int s = 0; s < PB_NSTAGE; s++) pb_mbar_init(&H->full[warp][s], 1);
-    H->wq_n[warp] = 0;
-    H->wq_head[warp] = 0;
-  }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
@@ -556,59 +540,8 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_scan_kernel(const DevQuery*
   int seg_first = 0;
   while (seg_first + 1 < Q.n_segs && cta_lo >= Q.segs[seg_first + 1].chunk_begin) seg_first++;
 
-  unsigned long long keyless_rows = 0, matched = 0;
   uint32_t consumed = 0;   // chunks this warp has consumed so far: stage = consumed % NSTAGE, parity from consumed / NSTAGE
-
-  // aggregate the n_take (<= 32) OLDEST queued docs of this warp (their gather lines were prefetched when they
-  // were enqueued, at least one chunk ago)
-  auto drain32 = [&](uint32_t n_take) {
-    const uint32_t head = H->wq_head[warp], qn = H->wq_n[warp];
-    uint32_t doc = lane < n_take ? H->wq[warp][(head + lane) & (PB_WQ_CAP - 1)] : 0u;
-    __syncwarp();
-    if (lane == 0) { H->wq_head[warp] = (head + n_take) & (PB_WQ_CAP - 1); H->wq_n[warp] = qn - n_take; }
-    if (lane < n_take) pb_accumulate(Q, H->seg, Q.tables[H->seg.table], doc, ka, keyless_rows);
-    __syncwarp();
-  };
-
-  // publish per-table counters of the segment that is being left (CTA-uniform call)
-  auto flush_table = [&]() {
-    const DevTable& t = Q.tables[H->seg.table];
-    unsigned long long m = matched;
-    for (int o = 16; o > 0; o >>= 1) m += __shfl_down_sync(0xffffffffu, m, o);
-    if (lane == 0 && m) pb_red_add_u64(t.docs_matched, m);
-    matched = 0;
-    if (Q.table_mode != T_KEYLESS) return;
-    unsigned long long r = keyless_rows;
-    keyless_rows = 0;
-    for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
-    if (lane == 0) H->red_u64[warp] = r;
-    __syncthreads();
-    if (tid == 0) { unsigned long long tot = 0; for (int w = 0; w < PB_NWARPS; w++) tot += H->red_u64[w]; if (tot) pb_red_add_u64(&t.rowcnt[0], tot); }
-    for (int a = 0; a < Q.n_aggs; a++) {
-      const int op = Q.agg_op[a];
-      if (op == 1 || op == 4) {
-        double v = ka.sum[a * PB_NTHREADS + tid];
-        ka.sum[a * PB_NTHREADS + tid] = 0.0;
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) H->red_f64[warp] = v;
-        __syncthreads();
-        if (tid == 0) { double tot = 0; for (int w = 0; w < PB_NWARPS; w++) tot += H->red_f64[w]; pb_red_add_f64(&t.sum[a][0], tot); }
-        __syncthreads();
-      } else if (op == 2 || op == 3) {
-        long long v = ka.mm[a * PB_NTHREADS + tid];
-        ka.mm[a * PB_NTHREADS + tid] = op == 2 ? ENC_POS_INF : ENC_NEG_INF;
-        for (int o = 16; o > 0; o >>= 1) { long long u = __shfl_down_sync(0xffffffffu, v, o); v = (op == 2) ? (u < v ? u : v) : (u > v ? u : v); }
-        if (lane == 0) H->red_i64[warp] = v;
-        __syncthreads();
-        if (tid == 0) {
-          long long tot = H->red_i64[0];
-          for (int w = 1; w < PB_NWARPS; w++) { long long u = H->red_i64[w]; tot = (op == 2) ? (u < tot ? u : tot) : (u > tot ? u : tot); }
-          if (op == 2) pb_red_min_s64(&t.mm[a][0], tot); else pb_red_max_s64(&t.mm[a][0], tot);
-        }
-        __syncthreads();
-      }
-    }
-  };
+  const DevSegQuery& sq = *reinterpret_cast<const DevSegQuery*>(H->seg);   // only the filter part is valid
 
   // evaluate one filter leaf on the staged chunk; returns this lane's 32-doc mask
   auto eval_leaf = [&](const DevLeaf& lf, const uint8_t* stage, uint64_t chunk_doc0) -> uint32_t {
@@ -641,38 +574,26 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_scan_kernel(const DevQuery*
 
   for (int sgi = seg_first; sgi < Q.n_segs; sgi++) {
     if (Q.segs[sgi].chunk_begin >= cta_hi) break;
-    // ---- segment entry: descriptor, derived constants and LUTs into shared memory ----
+    // ---- segment entry: filter descriptor, derived constants and LUTs into shared memory ----
+    __syncthreads();   // everyone has left the previous segment
     {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(&Q.segs[sgi]);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(&H->seg);
-      for (int i = tid; i < (int)(sizeof(DevSegQuery) / 4); i += PB_NTHREADS) dst[i] = src[i];
+      uint32_t* dst = reinterpret_cast<uint32_t*>(H->seg);
+      for (int i = tid; i < (int)(PB_SEG_FILTER_BYTES / 4); i += PB_NTHREADS) dst[i] = src[i];
       __syncthreads();
-      const DevSegQuery& g = H->seg;
-      if (tid < g.n_scan) H->slot_stride[tid] = (uint32_t)(PB_CHUNK_DOCS / 8) * (uint32_t)g.scan[tid].bits_per_doc;
-      if (tid == 32) {
-        // gather list (deduplicated by forward-index pointer)
-        int n = 0;
-        auto add = [&](const uint8_t* fwd, int bits, int width) {
-          for (int i = 0; i < n; i++) if (H->gather[i].fwd == fwd) return;
-          if (n < PB_MAX_GATHER && fwd) { H->gather[n].fwd = fwd; H->gather[n].bits = bits; H->gather[n].width = width; n++; }
-        };
-        for (int j = 0; j < Q.n_group_by; j++) add(g.keys[j].fwd, g.keys[j].raw_width ? 0 : g.keys[j].bits, g.keys[j].raw_width);
-        for (int a = 0; a < Q.n_aggs; a++) if (Q.agg_op[a] != 0) add(g.aggs[a].fwd, g.aggs[a].raw_width ? 0 : g.aggs[a].bits, g.aggs[a].raw_width);
-        H->n_gather = n;
-      }
+      if (tid < sq.n_scan) H->slot_stride[tid] = (uint32_t)(PB_CHUNK_DOCS / 8) * (uint32_t)sq.scan[tid].bits_per_doc;
       if (tid == 64) {
         // flat conjunction?  postfix == leaf* AND(n)   or a single leaf   or empty (match all)
         int nl = 0; bool flat = true;
-        for (int n = 0; n < g.n_nodes; n++) {
-          if (g.node_kind[n] == N_LEAF) { if (nl < PB_MAX_LEAVES) H->flat_leaf[nl] = g.node_arg[n]; nl++; }
-          else if (!(g.node_kind[n] == N_AND && n == g.n_nodes - 1 && g.node_arg[n] == nl)) flat = false;
+        for (int n = 0; n < sq.n_nodes; n++) {
+          if (sq.node_kind[n] == N_LEAF) { if (nl < PB_MAX_LEAVES) H->flat_leaf[nl] = sq.node_arg[n]; nl++; }
+          else if (!(sq.node_kind[n] == N_AND && n == sq.n_nodes - 1 && sq.node_arg[n] == nl)) flat = false;
         }
-        if (g.n_nodes > 1 && g.node_kind[g.n_nodes - 1] != N_AND) flat = false;
         H->flat_and = flat ? 1 : 0;
         H->n_flat = nl;
       }
       for (int l = 0; l < PB_MAX_LEAVES; l++) {
-        const DevLeaf& lf = g.leaves[l];
+        const DevLeaf& lf = sq.leaves[l];
         if (lf.kind == L_DICT_SET && lf.set_smem_off >= 0) {
           // membership bytes with the exclusive flag folded in (NOT_IN / NEQ)
           for (int i = tid; i < lf.set_card; i += PB_NTHREADS)
@@ -681,7 +602,6 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_scan_kernel(const DevQuery*
       }
       __syncthreads();
     }
-    const DevSegQuery& sq = H->seg;
     const uint64_t seg_lo = sq.chunk_begin > cta_lo ? sq.chunk_begin : cta_lo;
     const uint64_t seg_end = sq.chunk_begin + sq.n_chunks;
     const uint64_t seg_hi = seg_end < cta_hi ? seg_end : cta_hi;
@@ -690,6 +610,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_scan_kernel(const DevQuery*
     const uint32_t n_mine = first < seg_hi ? (uint32_t)((seg_hi - first + PB_NWARPS - 1) / PB_NWARPS) : 0u;
     const uint32_t rel0 = (uint32_t)(first - sq.chunk_begin);     // chunk index inside the segment
     const int n_scan = sq.n_scan;
+    unsigned long long matched = 0;
 
     // producer side (lane 0 of each warp): load this warp's k-th chunk of the segment into its stage
     auto issue = [&](uint32_t k, uint32_t seq) {
@@ -737,7 +658,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_scan_kernel(const DevQuery*
       }
       consumed++;
 
-      // ---- filter ----
+      // ---- predicate tree on 32-doc masks ----
       const long long remaining = (long long)sq.num_docs - (long long)(chunk_doc0 + 32ull * lane);
       uint32_t mask = remaining >= 32 ? 0xffffffffu : (remaining <= 0 ? 0u : ((1u << remaining) - 1u));
       if (H->flat_and) {
@@ -759,44 +680,140 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_scan_kernel(const DevQuery*
         }
         if (sp > 0) mask &= stack[0];
       }
-      matched += __popc(mask);
       __syncwarp();   // all lanes are done reading this stage before lane 0 may refill it next iteration
 
-      // ---- matches -> warp ring queue (+ L2 prefetch of their gather lines); aggregate the oldest 32 once 64 wait ----
-      // round r takes the r-th set bit of every lane, so lanes stay full and docs stay clustered
-      while (__any_sync(0xffffffffu, mask != 0)) {
-        const bool has = mask != 0;
-        const uint32_t b = __ballot_sync(0xffffffffu, has);
-        const uint32_t head = H->wq_head[warp], qn = H->wq_n[warp];
-        if (has) {
+      // ---- append the matching docIds (global doc numbering) to the match list ----
+      const uint32_t cnt = (uint32_t)__popc(mask);
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+      if (total) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        unsigned long long pos = base + incl - cnt;
+        const uint32_t gdoc0 = (uint32_t)(sq.doc_base + chunk_doc0) + 32u * (uint32_t)lane;
+        while (mask) {
           const int bit = __ffs(mask) - 1;
           mask &= mask - 1;
-          const uint32_t doc = (uint32_t)(chunk_doc0 + 32ull * lane + bit);
-          H->wq[warp][(head + qn + __popc(b & ((1u << lane) - 1u))) & (PB_WQ_CAP - 1)] = doc;
-          const int ng = H->n_gather;
-          for (int i = 0; i < ng; i++) {
-            const GatherCol gc = H->gather[i];
-            const uint8_t* a = gc.bits ? gc.fwd + ((((unsigned long long)doc * (unsigned)gc.bits) >> 5) << 2)
-                                       : gc.fwd + (unsigned long long)doc * (unsigned)gc.width;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-          }
+          Q.match_list[pos++] = gdoc0 + (uint32_t)bit;
         }
-        __syncwarp();
-        const uint32_t nq = qn + __popc(b);
-        if (lane == 0) H->wq_n[warp] = nq;
-        __syncwarp();
-        if (nq >= 64) drain32(32);
+        matched += total;
       }
     }
-    // ---- segment exit: flush this warp's queue, then the block publishes its counters ----
-    while (true) {
-      const uint32_t qn = H->wq_n[warp];
-      if (!qn) break;
-      drain32(qn < 32 ? qn : 32);
+    // ---- segment exit: numDocsScanned of this segment's table (matched is warp-uniform) ----
+    if (lane == 0 && matched) pb_red_add_u64(Q.tables[sq.table].docs_matched, matched);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 2: pb_agg_kernel  (ProjectionOperator + GroupByOperator / AggregationOperator: SURVEY.md §3.1)
+//
+// One thread per matching doc, grid-strided over the match list written by pb_filter_kernel (or over all docs
+// when there is no filter).  Each thread gathers the group-key / metric dictIds of its doc straight from the
+// bit-packed forward indexes in HBM (only the sectors holding matching rows are touched), decodes through the
+// dictionary, and reduces into the table with native L2 reductions.  With every match in flight at once the
+// dependent-load latency of the gathers is hidden by thread-level parallelism.
+// ------------------------------------------------------------------------------------------------
+#define PB_AGG_MAX_SEGS_SMEM 1024
+
+__global__ void __launch_bounds__(PB_NTHREADS, 4) pb_agg_kernel(const DevQuery* __restrict__ Qp) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const DevQuery& Q = *Qp;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ unsigned long long s_doc_base[PB_AGG_MAX_SEGS_SMEM + 1];
+  __shared__ unsigned long long s_red_u64[PB_NWARPS];
+  __shared__ double s_red_f64[PB_NWARPS];
+  __shared__ long long s_red_i64[PB_NWARPS];
+  __shared__ int s_table0;
+  const int n_segs = Q.n_segs;
+  const int n_smem = n_segs < PB_AGG_MAX_SEGS_SMEM ? n_segs : PB_AGG_MAX_SEGS_SMEM;
+  for (int i = tid; i < n_smem; i += PB_NTHREADS) s_doc_base[i] = Q.segs[i].doc_base;
+  KeylessAcc ka;
+  ka.sum = nullptr; ka.mm = nullptr;
+  const long long ENC_POS_INF = 0x7ff0000000000000LL;
+  const long long ENC_NEG_INF = (long long)0xfff0000000000000ULL ^ 0x7fffffffffffffffLL;
+  const bool keyless = Q.table_mode == T_KEYLESS;
+  if (keyless) {
+    ka.sum = reinterpret_cast<double*>(smem_raw);
+    ka.mm = reinterpret_cast<long long*>(smem_raw + sizeof(double) * Q.n_aggs * PB_NTHREADS);
+    for (int a = 0; a < Q.n_aggs; a++) {
+      ka.sum[a * PB_NTHREADS + tid] = 0.0;
+      ka.mm[a * PB_NTHREADS + tid] = Q.agg_op[a] == 2 ? ENC_POS_INF : ENC_NEG_INF;
     }
-    __syncthreads();
-    flush_table();
-    __syncthreads();
+  }
+  __syncthreads();
+
+  const unsigned long long n = Q.match_all ? Q.n_docs_total : *Q.match_count;
+  unsigned long long keyless_rows = 0;
+  int my_table = -1;      // keyless: table the private accumulators currently belong to
+
+  auto keyless_flush_thread = [&]() {   // rare path: this thread moves on to another table
+    if (my_table < 0) return;
+    const DevTable& t = Q.tables[my_table];
+    if (keyless_rows) pb_red_add_u64(&t.rowcnt[0], keyless_rows);
+    keyless_rows = 0;
+    for (int a = 0; a < Q.n_aggs; a++) {
+      const int op = Q.agg_op[a];
+      if (op == 1 || op == 4) { pb_red_add_f64(&t.sum[a][0], ka.sum[a * PB_NTHREADS + tid]); ka.sum[a * PB_NTHREADS + tid] = 0.0; }
+      else if (op == 2) { pb_red_min_s64(&t.mm[a][0], ka.mm[a * PB_NTHREADS + tid]); ka.mm[a * PB_NTHREADS + tid] = ENC_POS_INF; }
+      else if (op == 3) { pb_red_max_s64(&t.mm[a][0], ka.mm[a * PB_NTHREADS + tid]); ka.mm[a * PB_NTHREADS + tid] = ENC_NEG_INF; }
+    }
+  };
+
+  for (unsigned long long i = (unsigned long long)blockIdx.x * PB_NTHREADS + tid; i < n; i += (unsigned long long)gridDim.x * PB_NTHREADS) {
+    const unsigned long long gdoc = Q.match_all ? i : (unsigned long long)__ldg(Q.match_list + i);
+    // segment of this doc: last doc_base <= gdoc
+    int lo = 0, hi = n_segs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      const unsigned long long b = mid < PB_AGG_MAX_SEGS_SMEM ? s_doc_base[mid] : Q.segs[mid].doc_base;
+      if (b <= gdoc) lo = mid; else hi = mid - 1;
+    }
+    const DevSegQuery& sg = Q.segs[lo];
+    const uint32_t doc = (uint32_t)(gdoc - (lo < PB_AGG_MAX_SEGS_SMEM ? s_doc_base[lo] : sg.doc_base));
+    const int table = sg.table;
+    if (keyless && table != my_table) { keyless_flush_thread(); my_table = table; }
+    pb_accumulate(Q, sg, Q.tables[table], doc, ka, keyless_rows);
+  }
+
+  if (!keyless) return;
+  // ---- keyless: merge the private accumulators; one reduction per CTA when the whole CTA saw one table ----
+  if (tid == 0) s_table0 = -1;
+  __syncthreads();
+  if (my_table >= 0) atomicMax(&s_table0, my_table);
+  __syncthreads();
+  const int t0 = s_table0;
+  const int uniform = __syncthreads_and(my_table < 0 || my_table == t0);
+  if (!uniform || t0 < 0) { keyless_flush_thread(); return; }
+  const DevTable& t = Q.tables[t0];
+  unsigned long long r = keyless_rows;
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
+  if (lane == 0) s_red_u64[warp] = r;
+  __syncthreads();
+  if (tid == 0) { unsigned long long tot = 0; for (int w = 0; w < PB_NWARPS; w++) tot += s_red_u64[w]; if (tot) pb_red_add_u64(&t.rowcnt[0], tot); }
+  for (int a = 0; a < Q.n_aggs; a++) {
+    const int op = Q.agg_op[a];
+    if (op == 1 || op == 4) {
+      double v = ka.sum[a * PB_NTHREADS + tid];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_red_f64[warp] = v;
+      __syncthreads();
+      if (tid == 0) { double tot = 0; for (int w = 0; w < PB_NWARPS; w++) tot += s_red_f64[w]; pb_red_add_f64(&t.sum[a][0], tot); }
+      __syncthreads();
+    } else if (op == 2 || op == 3) {
+      long long v = ka.mm[a * PB_NTHREADS + tid];
+      for (int o = 16; o > 0; o >>= 1) { long long u = __shfl_down_sync(0xffffffffu, v, o); v = (op == 2) ? (u < v ? u : v) : (u > v ? u : v); }
+      if (lane == 0) s_red_i64[warp] = v;
+      __syncthreads();
+      if (tid == 0) {
+        long long tot = s_red_i64[0];
+        for (int w = 1; w < PB_NWARPS; w++) { long long u = s_red_i64[w]; tot = (op == 2) ? (u < tot ? u : tot) : (u > tot ? u : tot); }
+        if (op == 2) pb_red_min_s64(&t.mm[a][0], tot); else pb_red_max_s64(&t.mm[a][0], tot);
+      }
+      __syncthreads();
+    }
   }
 }
 

@@ -464,7 +464,9 @@ struct pb_result_s {
   double device_ms = 0, scan_ms = 0;
   double host_us[8] = {0};   // [0] stage+resolve [1] tables [2] descriptors [3] launches [4] finalize: count [5] gather+D2H wait [6] host decode
   int launches = 0;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr, ev2 = nullptr, ev3 = nullptr;
+  bool match_all = false;
+  double filter_ms = 0, agg_ms = 0;
 };
 
 static void free_result(pb_result_s* r) {
@@ -477,6 +479,7 @@ static void free_result(pb_result_s* r) {
   r->h_counters.release();
   if (r->ev0) cudaEventDestroy(r->ev0);
   if (r->ev1) cudaEventDestroy(r->ev1);
+  if (r->evm) cudaEventDestroy(r->evm);
   if (r->ev2) cudaEventDestroy(r->ev2);
   if (r->ev3) cudaEventDestroy(r->ev3);
   if (r->stream) { cudaStreamSynchronize(r->stream); cudaStreamDestroy(r->stream); }
@@ -525,7 +528,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   r->group = g; r->n_gb = nG; r->n_aggs = nA; r->combine = combine;
   CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
   cudaStream_t st = r->stream;
-  CU(cudaEventCreate(&r->ev0)); CU(cudaEventCreate(&r->ev1)); CU(cudaEventCreate(&r->ev2)); CU(cudaEventCreate(&r->ev3));
+  CU(cudaEventCreate(&r->ev0)); CU(cudaEventCreate(&r->ev1)); CU(cudaEventCreate(&r->evm)); CU(cudaEventCreate(&r->ev2)); CU(cudaEventCreate(&r->ev3));
   for (int j = 0; j < nG; j++) r->gb_names.push_back(q->group_by_columns[j]);
   for (int a = 0; a < nA; a++) {
     r->agg_op.push_back(q->aggregations[a].op);
@@ -664,7 +667,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     zero_bytes = (zero_bytes + 255) & ~(size_t)255;
     if (table_mode == T_HASH) ff_bytes += 8 * S;
   }
-  zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 256;
+  zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 + 256;
   if (zero_bytes > (64ull << 30)) return fail(PB_ERR_UNSUPPORTED, "group table needs %zu bytes: decline to the CPU plan", zero_bytes);
   uint8_t *d_zero = nullptr, *d_ff = nullptr; long long* d_mm = nullptr;
   CU(cudaMallocAsync((void**)&d_zero, zero_bytes, st)); r->dev_allocs.push_back(d_zero);
@@ -677,7 +680,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   {
     size_t zo = 0, fo = 0, mo = 0;
     r->d_counters = reinterpret_cast<unsigned long long*>(d_zero);
-    zo += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables; zo = (zo + 255) & ~(size_t)255;
+    zo += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8; zo = (zo + 255) & ~(size_t)255;
     const long long ENC_POS_INF = 0x7ff0000000000000LL;
     const long long ENC_NEG_INF = (long long)0xfff0000000000000ULL ^ 0x7fffffffffffffffLL;
     for (int t = 0; t < n_tables; t++) {
@@ -910,12 +913,22 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   }
   if (stage_bytes * PB_NSTAGE * PB_NWARPS > 200 * 1024)
     return fail(PB_ERR_UNSUPPORTED, "scan predicates touch %d bits per row: chunk stages do not fit shared memory", sum_bits);
-  uint64_t n_chunks = 0;
+  uint64_t n_chunks = 0, n_docs_total = 0;
+  bool match_all = true;
   for (int si = 0; si < n_segs; si++) {
     hsegs[si].chunk_begin = n_chunks;
     hsegs[si].n_chunks = ((uint64_t)g->segs[si]->num_docs + PB_CHUNK_DOCS - 1) / PB_CHUNK_DOCS;
+    hsegs[si].doc_base = n_docs_total;
     n_chunks += hsegs[si].n_chunks;
+    n_docs_total += (uint64_t)g->segs[si]->num_docs;
+    if (sqs[si].num_filter_nodes != 0) match_all = false;
   }
+  if (n_docs_total >= (1ull << 32)) return fail(PB_ERR_UNSUPPORTED, "%llu docs in one call (match list is 32-bit): split the segment group", (unsigned long long)n_docs_total);
+  uint32_t* d_match_list = nullptr;
+  if (!match_all && n_docs_total > 0) {
+    CU(cudaMallocAsync((void**)&d_match_list, 4 * (size_t)n_docs_total + 256, st)); r->dev_allocs.push_back(d_match_list);
+  }
+  r->match_all = match_all;
 
   hq->n_segs = n_segs; hq->n_group_by = nG; hq->n_aggs = nA; hq->table_mode = table_mode;
   for (int a = 0; a < nA; a++) hq->agg_op[a] = q->aggregations[a].op;
@@ -925,6 +938,9 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   hq->use_tma = (q->flags & PB_Q_NO_TMA) ? 0 : 1;
   hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
   hq->n_chunks = n_chunks; hq->segs = dsegs; hq->tables = dtabs;
+  hq->n_docs_total = n_docs_total; hq->match_all = match_all ? 1 : 0;
+  hq->match_list = d_match_list;
+  hq->match_count = r->d_counters + (size_t)n_tables * PB_COUNTERS_PER_TABLE;   // one extra zeroed cell after the per-table counters
 
   CU(cudaMemcpyAsync(ar.dev, ar.host.data(), ar.used, cudaMemcpyHostToDevice, st));
   lap(2);
@@ -941,29 +957,50 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   }
   CU(cudaGetLastError());
 
-  // ---- the scan ----
-  size_t smem = ((sizeof(ScanSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + stage_bytes * PB_NSTAGE * PB_NWARPS;
-  if (table_mode == T_KEYLESS) smem += ((2 * sizeof(double) * (size_t)nA * PB_NTHREADS) + 127) & ~(size_t)127;
-  if (smem > 227 * 1024) return fail(PB_ERR_UNSUPPORTED, "scan kernel needs %zu bytes of shared memory", smem);
-  {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    if (!g_ctx.smem_attr_set) {
-      CU(cudaFuncSetAttribute(pb_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      g_ctx.smem_attr_set = true;
-    }
-  }
-  int occ = 1;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_scan_kernel, PB_NTHREADS, smem));
-  if (occ < 1) return fail(PB_ERR_CUDA, "scan kernel does not fit an SM (smem %zu)", smem);
-  uint64_t max_ctas = (uint64_t)g_ctx.num_sms * (uint64_t)occ;
-  // every CTA gets a contiguous range of chunks; keep at least one chunk per warp
-  int grid = (int)std::min<uint64_t>(std::max<uint64_t>((n_chunks + PB_NWARPS - 1) / PB_NWARPS, 1), max_ctas);
+  // ---- kernel 1: filter -> match list ----
   CU(cudaEventRecord(r->ev1, st));
-  if (n_chunks > 0) {
-    pb_scan_kernel<<<grid, PB_NTHREADS, smem, st>>>(dq);
+  if (!match_all && n_chunks > 0) {
+    size_t smem = ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + stage_bytes * PB_NSTAGE * PB_NWARPS;
+    if (smem > 227 * 1024) return fail(PB_ERR_UNSUPPORTED, "filter kernel needs %zu bytes of shared memory", smem);
+    {
+      std::lock_guard<std::mutex> lk(g_ctx.mu);
+      if (!g_ctx.smem_attr_set) {
+        CU(cudaFuncSetAttribute(pb_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(pb_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        g_ctx.smem_attr_set = true;
+      }
+    }
+    int occ = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel, PB_NTHREADS, smem));
+    if (occ < 1) return fail(PB_ERR_CUDA, "filter kernel does not fit an SM (smem %zu)", smem);
+    uint64_t max_ctas = (uint64_t)g_ctx.num_sms * (uint64_t)occ;
+    // every CTA gets a contiguous range of chunks; keep at least one chunk per warp
+    int grid = (int)std::min<uint64_t>(std::max<uint64_t>((n_chunks + PB_NWARPS - 1) / PB_NWARPS, 1), max_ctas);
+    pb_filter_kernel<<<grid, PB_NTHREADS, smem, st>>>(dq);
     r->launches++;
+    CU(cudaGetLastError());
   }
-  CU(cudaGetLastError());
+  CU(cudaEventRecord(r->evm, st));
+  // ---- kernel 2: gather + aggregate the matching docs ----
+  if (n_docs_total > 0) {
+    {
+      std::lock_guard<std::mutex> lk(g_ctx.mu);
+      if (!g_ctx.smem_attr_set) {
+        CU(cudaFuncSetAttribute(pb_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(pb_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        g_ctx.smem_attr_set = true;
+      }
+    }
+    size_t smem2 = table_mode == T_KEYLESS ? 2 * sizeof(double) * (size_t)nA * PB_NTHREADS : 0;
+    int occ2 = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pb_agg_kernel, PB_NTHREADS, smem2));
+    if (occ2 < 1) return fail(PB_ERR_CUDA, "aggregation kernel does not fit an SM");
+    uint64_t max2 = (uint64_t)g_ctx.num_sms * (uint64_t)occ2;
+    int grid2 = (int)std::min<uint64_t>(std::max<uint64_t>((n_docs_total + PB_NTHREADS - 1) / PB_NTHREADS, 1), max2);
+    pb_agg_kernel<<<grid2, PB_NTHREADS, smem2, st>>>(dq);
+    r->launches++;
+    CU(cudaGetLastError());
+  }
   CU(cudaEventRecord(r->ev2, st));
   lap(3);
 
@@ -1084,6 +1121,8 @@ static int finalize_result(pb_result_s* r) {
   float ms = 0;
   cudaEventElapsedTime(&ms, r->ev0, r->ev3); r->device_ms = ms;
   cudaEventElapsedTime(&ms, r->ev1, r->ev2); r->scan_ms = ms;
+  cudaEventElapsedTime(&ms, r->ev1, r->evm); r->filter_ms = ms;
+  cudaEventElapsedTime(&ms, r->evm, r->ev2); r->agg_ms = ms;
 
   // host side: counts, keys, stats, distinct value sets
   for (int t = 0; t < nT; t++) {
@@ -1183,6 +1222,7 @@ static int finalize_result(pb_result_s* r) {
     for (auto& nme : r->gb_names) if (std::find(proj.begin(), proj.end(), nme) == proj.end()) proj.push_back(nme);
     for (auto& nme : r->agg_cols) if (!nme.empty() && std::find(proj.begin(), proj.end(), nme) == proj.end()) proj.push_back(nme);
     tm.stats.num_docs_scanned = (int64_t)hc[(size_t)t * PB_COUNTERS_PER_TABLE + 2];
+    if (r->match_all) { tm.stats.num_docs_scanned = 0; for (int si : tm.seg_idx) tm.stats.num_docs_scanned += g->segs[si]->num_docs; }
     tm.stats.num_entries_scanned_post_filter = tm.stats.num_docs_scanned * (int64_t)proj.size();
     tm.stats.num_total_docs = 0; tm.stats.num_entries_scanned_in_filter = 0;
     for (int si : tm.seg_idx) {
@@ -1236,6 +1276,18 @@ extern "C" double pb_result_scan_kernel_ms(pb_result_handle r) {
 extern "C" int32_t pb_result_kernel_launches(pb_result_handle r) { return r ? r->launches : 0; }
 extern "C" void* pb_result_stream(pb_result_handle r) { return r ? (void*)r->stream : nullptr; }
 
+extern "C" int pb_result_phase_ms(pb_result_handle r, double* filter_ms, double* agg_ms) {
+  if (!r) return fail(PB_ERR_INVALID, "null result");
+  if (!r->finalized) {
+    float ms = 0;
+    cudaEventSynchronize(r->ev2);
+    cudaEventElapsedTime(&ms, r->ev1, r->evm); r->filter_ms = ms;
+    cudaEventElapsedTime(&ms, r->evm, r->ev2); r->agg_ms = ms;
+  }
+  if (filter_ms) *filter_ms = r->filter_ms;
+  if (agg_ms) *agg_ms = r->agg_ms;
+  return PB_OK;
+}
 extern "C" int pb_result_host_timing(pb_result_handle r, double* out8) {
   if (!r || !out8) return fail(PB_ERR_INVALID, "null argument");
   for (int i = 0; i < 8; i++) out8[i] = r->host_us[i];

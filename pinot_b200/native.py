@@ -122,6 +122,7 @@ def lib():
     l.pb_result_stream.argtypes = [C.c_void_p]
     l.pb_result_stream.restype = C.c_void_p
     l.pb_result_wait.argtypes = [C.c_void_p]
+    l.pb_result_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     l.pb_result_host_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     l.pb_host_register.argtypes = [C.c_void_p, C.c_size_t]
     l.pb_host_unregister.argtypes = [C.c_void_p]
@@ -309,6 +310,11 @@ class Result:
 
     def stream(self) -> int:
         return lib().pb_result_stream(self._rh) or 0
+
+    def phase_ms(self):
+        f, a = C.c_double(), C.c_double()
+        _check(lib().pb_result_phase_ms(self._rh, C.byref(f), C.byref(a)))
+        return f.value, a.value
 
     def host_timing_us(self):
         arr = (C.c_double * 8)()
