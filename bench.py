@@ -242,12 +242,14 @@ def main():
         if world > 1:
             dist.barrier()
 
+    prepared = native.prepare(q)
+
     def step(g=None):
         """one pass of the hot path over this rank's segments; returns the Result"""
         g = g or group
         if world == 1:
-            return native.execute(g, q, flags)
-        r = native.execute(g, q, flags | native.PB_Q_DEFER_FINALIZE)
+            return native.execute(g, q, flags, prepared)
+        r = native.execute(g, q, flags | native.PB_Q_DEFER_FINALIZE, prepared)
         r.wait()
         # fused reduce: counts + sums (SUM), min (MIN), max (MAX) — <= 4 small collectives over NVLink
         ptr, n = r.device_buffer(0)

@@ -26,6 +26,7 @@
 #define PB_MAX_GROUP_BY 16
 #define PB_MAX_AGGS 16
 #define PB_MAX_SCAN_SLOTS 8
+#define PB_SPARSE_MAX 128            // survivors per 1024-doc chunk below which later AND leaves use the restricted scan
 #define PB_SET_SMEM_BYTES 8192      // dictId-set membership LUTs (one byte per dictId) cached in smem per segment
 
 enum { L_TRUE = 0, L_FALSE = 1, L_DICT_RANGE = 2, L_DICT_SET = 3, L_RAW_RANGE_I = 4, L_RAW_RANGE_F = 5,
@@ -51,7 +52,7 @@ struct DevLeaf {
   int32_t dlo_incl, dhi_incl;
   const int64_t* raw_set;  // L_RAW_SET
   int32_t n_raw_set;
-  int32_t pad0;
+  int32_t est_permille;    // host estimate of the leaf's selectivity (0..1000), used to order AND chains
   const uint32_t* bitmap;  // L_BITMAP: flat doc bitmap of this segment (bit d&31 of word d>>5)
 };
 
@@ -296,15 +297,34 @@ __device__ __forceinline__ uint32_t pb_eval_dict_w(const uint32_t* __restrict__ 
 #pragma unroll
   for (int k = 0; k < W; k++) w[k] = pb_bswap32(q[k]);
   w[W] = 0;
-  uint32_t m = 0;
+  // four independent shift-accumulate chains (8 docs each) instead of one 32-deep dependency chain
+  uint32_t m[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int j = 31; j >= 0; j--) {
     const int bit = j * W;
     const int k = bit >> 5, s = bit & 31;
     const uint32_t vt = (s == 0) ? w[k] : __funnelshift_l(w[k + 1], w[k], s);   // value in the top W bits
-    m = (m << 1) + pred.template test<W>(vt);
+    m[j >> 3] = (m[j >> 3] << 1) + pred.template test<W>(vt);
   }
-  return m;
+  return (m[3] << 24) | (m[2] << 16) | (m[1] << 8) | m[0];
+}
+
+// restricted scan: only the docs still set in `mask` are decoded and tested (the device analogue of
+// SVScanDocIdIterator.applyAnd over the surviving docIds, CTR/operator/dociditerators/SVScanDocIdIterator.java:115-142)
+template <class Pred>
+__device__ __forceinline__ uint32_t pb_eval_dict_sparse(const uint32_t* __restrict__ p, int bits, const Pred& pred, int lane, uint32_t mask) {
+  const uint32_t* q = p + lane * bits;
+  uint32_t rem = mask;
+  while (rem) {
+    const int j = __ffs(rem) - 1;
+    rem &= rem - 1;
+    const uint32_t bit = (uint32_t)j * (uint32_t)bits;
+    const uint32_t k = bit >> 5, s = bit & 31u;
+    const uint32_t hi = pb_bswap32(q[k]), lo = pb_bswap32(q[k + 1]);
+    const uint32_t v = __funnelshift_l(lo, hi, s) >> (32 - bits);
+    if (!pred(v)) mask &= ~(1u << j);
+  }
+  return mask;
 }
 
 __device__ __forceinline__ bool pb_fast_width(int bits) { return bits < 32 && (bits & 7) != 0; }
@@ -543,20 +563,27 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
   uint32_t consumed = 0;   // chunks this warp has consumed so far: stage = consumed % NSTAGE, parity from consumed / NSTAGE
   const DevSegQuery& sq = *reinterpret_cast<const DevSegQuery*>(H->seg);   // only the filter part is valid
 
-  // evaluate one filter leaf on the staged chunk; returns this lane's 32-doc mask
-  auto eval_leaf = [&](const DevLeaf& lf, const uint8_t* stage, uint64_t chunk_doc0) -> uint32_t {
+  // evaluate one filter leaf on the staged chunk; returns this lane's 32-doc mask.  `restrict_to` != 0xffffffff
+  // with sparse == true means only those docs matter (AND chain with few survivors): decode just them.
+  auto eval_leaf = [&](const DevLeaf& lf, const uint8_t* stage, uint64_t chunk_doc0, uint32_t restrict_to, bool sparse) -> uint32_t {
     switch (lf.kind) {
       case L_TRUE: return 0xffffffffu;
       case L_FALSE: return 0u;
       case L_DICT_RANGE: {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
         PredRange pr; pr.lo = lf.lo; pr.span = lf.span;
+        if (sparse) return pb_eval_dict_sparse<PredRange>(p, lf.bits, pr, lane, restrict_to);
         return pb_eval_dict<PredRange>(p, lf.bits, pr, lane, Q.generic);
       }
       case L_DICT_SET: {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
-        if (lf.set_smem_off >= 0) { PredLut8 pl; pl.lut = set_cache + lf.set_smem_off; return pb_eval_dict<PredLut8>(p, lf.bits, pl, lane, Q.generic); }
+        if (lf.set_smem_off >= 0) {
+          PredLut8 pl; pl.lut = set_cache + lf.set_smem_off;
+          if (sparse) return pb_eval_dict_sparse<PredLut8>(p, lf.bits, pl, lane, restrict_to);
+          return pb_eval_dict<PredLut8>(p, lf.bits, pl, lane, Q.generic);
+        }
         PredBits pb; pb.bits = lf.set_bits; pb.excl = (uint32_t)lf.exclusive;
+        if (sparse) return pb_eval_dict_sparse<PredBits>(p, lf.bits, pb, lane, restrict_to);
         return pb_eval_dict<PredBits>(p, lf.bits, pb, lane, Q.generic);
       }
       case L_RAW_RANGE_I:
@@ -589,6 +616,13 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
           if (sq.node_kind[n] == N_LEAF) { if (nl < PB_MAX_LEAVES) H->flat_leaf[nl] = sq.node_arg[n]; nl++; }
           else if (!(sq.node_kind[n] == N_AND && n == sq.n_nodes - 1 && sq.node_arg[n] == nl)) flat = false;
         }
+        // most selective leaf first (insertion sort on the host's estimate)
+        if (flat && nl <= PB_MAX_LEAVES)
+          for (int a = 1; a < nl; a++) {
+            int x = H->flat_leaf[a]; int b = a - 1;
+            while (b >= 0 && sq.leaves[H->flat_leaf[b]].est_permille > sq.leaves[x].est_permille) { H->flat_leaf[b + 1] = H->flat_leaf[b]; b--; }
+            H->flat_leaf[b + 1] = x;
+          }
         H->flat_and = flat ? 1 : 0;
         H->n_flat = nl;
       }
@@ -663,13 +697,19 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
       uint32_t mask = remaining >= 32 ? 0xffffffffu : (remaining <= 0 ? 0u : ((1u << remaining) - 1u));
       if (H->flat_and) {
         const int nl = H->n_flat;
-        for (int i = 0; i < nl; i++) mask &= eval_leaf(sq.leaves[H->flat_leaf[i]], stage, chunk_doc0);
+        for (int i = 0; i < nl; i++) {
+          // few survivors in the whole chunk -> restricted scan of the remaining leaves (leaves arrive ordered by
+          // estimated selectivity from the host)
+          const bool sparse = i > 0 && !Q.generic && __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mask)) <= PB_SPARSE_MAX;
+          mask &= eval_leaf(sq.leaves[H->flat_leaf[i]], stage, chunk_doc0, mask, sparse);
+          if (sparse && !__any_sync(0xffffffffu, mask != 0)) break;
+        }
       } else {
         uint32_t stack[PB_MAX_LEAVES];
         int sp = 0;
         for (int n = 0; n < sq.n_nodes; n++) {
           const int kind = sq.node_kind[n], arg = sq.node_arg[n];
-          if (kind == N_LEAF) stack[sp++] = eval_leaf(sq.leaves[arg], stage, chunk_doc0);
+          if (kind == N_LEAF) stack[sp++] = eval_leaf(sq.leaves[arg], stage, chunk_doc0, 0xffffffffu, false);
           else if (kind == N_NOT) stack[sp - 1] = ~stack[sp - 1];
           else {
             uint32_t r = stack[sp - arg];
@@ -913,22 +953,91 @@ __global__ void pb_count_groups_kernel(const unsigned long long* __restrict__ ro
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
-// compact non-empty slots: out_slot[k] = slot index (keys decoded on the host), out_cnt[k] = rows
-__global__ void pb_compact_slots_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n, unsigned long long* counter,
-                                        unsigned long long* __restrict__ out_slot, unsigned long long* __restrict__ out_cnt) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    unsigned long long c = rowcnt[i];
-    if (c) { unsigned long long k = atomicAdd(counter, 1ull); out_slot[k] = i; out_cnt[k] = c; }
+// Result hand-back in one pass: compaction of the non-empty groups, aggregate extraction, and group-key decode
+// (DictionaryBasedGroupKeyGenerator.getKeys: rawKey -> dictIds -> dictionary values, :578-591) straight into
+// page-locked host memory.  Warp-aggregated cursor => each warp writes consecutive rows (coalesced PCIe writes).
+struct DevFinKey {
+  const uint8_t* dict_vals;   // native-endian dictionary entries on the device (dictionary key columns)
+  int32_t eb;                 // bytes per decoded value
+  int32_t is_dict;
+  int32_t type;               // PB_INT .. PB_STRING
+  int32_t shift, width;       // T_HASH: field position in the composite key
+  int32_t pad;
+  uint64_t div, card;         // T_DENSE: field = (slot / div) % card
+  int32_t* out_ids;
+  uint8_t* out_vals;
+};
+struct DevFinAgg {
+  int32_t op, pad;
+  const double* sum;
+  const long long* mm;
+  double* out;
+};
+struct DevFinalize {
+  int32_t mode, n_gb, n_aggs, always_emit;
+  uint64_t S;                 // slots to scan
+  uint64_t capacity;          // T_HASH: index of the reserved sentinel slot
+  uint64_t cap_out;
+  const unsigned long long* rowcnt;
+  const unsigned long long* hkeys;
+  unsigned long long* cursor;
+  const unsigned long long* counters;      // per-table device counters [4]
+  unsigned long long* out_counters;        // host copy [4] + [4] = number of groups written
+  unsigned long long* out_slots;
+  unsigned long long* out_rows;
+  DevFinKey keys[PB_MAX_GROUP_BY];
+  DevFinAgg aggs[PB_MAX_AGGS];
+};
+
+__global__ void pb_finalize_kernel(const DevFinalize F) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t S_round = (F.S + 31) & ~(uint64_t)31;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < S_round; i += stride) {
+    const unsigned long long c = i < F.S ? F.rowcnt[i] : 0ull;
+    const bool emit = i < F.S && (c != 0 || F.always_emit);
+    const uint32_t b = __ballot_sync(0xffffffffu, emit);
+    if (!b) continue;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(F.cursor, (unsigned long long)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!emit) continue;
+    const uint64_t k = base + __popc(b & ((1u << lane) - 1u));
+    if (k >= F.cap_out) continue;
+    F.out_slots[k] = i;
+    F.out_rows[k] = c;
+    for (int a = 0; a < F.n_aggs; a++) {
+      const DevFinAgg& fa = F.aggs[a];
+      if (fa.sum) fa.out[k] = fa.sum[i];
+      else if (fa.mm) fa.out[k] = pb_dec_f64(fa.mm[i]);
+      else if (fa.op == 0) fa.out[k] = (double)c;
+    }
+    unsigned long long key = 0;
+    if (F.mode == T_HASH) key = (i == F.capacity) ? PB_HASH_EMPTY : F.hkeys[i];
+    for (int j = 0; j < F.n_gb; j++) {
+      const DevFinKey& fk = F.keys[j];
+      uint64_t field;
+      if (F.mode == T_DENSE) field = (i / fk.div) % fk.card;
+      else { field = key >> fk.shift; if (fk.width < 64) field &= ((1ull << fk.width) - 1ull); }
+      uint8_t* o = fk.out_vals + k * (uint64_t)fk.eb;
+      if (fk.is_dict) {
+        fk.out_ids[k] = (int32_t)field;
+        const uint8_t* src = fk.dict_vals + field * (uint64_t)fk.eb;
+        if (fk.eb == 4) *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<const uint32_t*>(src);
+        else if (fk.eb == 8) *reinterpret_cast<unsigned long long*>(o) = *reinterpret_cast<const unsigned long long*>(src);
+        else for (int q = 0; q < fk.eb; q++) o[q] = src[q];
+      } else {
+        fk.out_ids[k] = -1;
+        if (fk.type == 0) *reinterpret_cast<int32_t*>(o) = (int32_t)(uint32_t)field;
+        else if (fk.type == 2) *reinterpret_cast<float*>(o) = (float)__longlong_as_double((long long)field);
+        else *reinterpret_cast<unsigned long long*>(o) = field;
+      }
+    }
   }
+  if (blockIdx.x == 0 && threadIdx.x < 4) F.out_counters[threadIdx.x] = F.counters[threadIdx.x];
 }
 
-// gather per-aggregation values of the compacted slots
-__global__ void pb_gather_f64_kernel(const double* __restrict__ src, const unsigned long long* __restrict__ slots, uint64_t n, double* __restrict__ dst) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[slots[i]];
-}
-__global__ void pb_gather_mm_kernel(const long long* __restrict__ src, const unsigned long long* __restrict__ slots, uint64_t n, double* __restrict__ dst) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = pb_dec_f64(src[slots[i]]);
-}
+// gather kernels used by the two-pass path of very large tables
 __global__ void pb_gather_u64_kernel(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ slots, uint64_t n, unsigned long long* __restrict__ dst) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[slots[i]];
 }

@@ -49,6 +49,7 @@ struct Context {
   std::vector<int> devices;
   int num_sms = 148;
   std::vector<PinnedBlock> pinned_free;
+  std::vector<PinnedBlock> scratch_free;      // large device scratch buffers (match lists), reused across calls
   bool smem_attr_set = false;
 };
 static Context g_ctx;
@@ -70,6 +71,13 @@ static int ensure_init() {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
+  // the aggregation kernel gathers 4-8 bytes at random docIds: fetch single 32-byte sectors from DRAM instead of
+  // the default 64 (PB_L2_FETCH=64|128 restores the larger granularity for A/B measurements)
+  {
+    size_t gran = 32;
+    if (const char* e = getenv("PB_L2_FETCH")) gran = (size_t)atoi(e);
+    if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+  }
   g_ctx.inited = true;
   return PB_OK;
 }
@@ -85,6 +93,8 @@ extern "C" int pb_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_ctx.mu);
   for (auto& b : g_ctx.pinned_free) cudaFreeHost(b.p);
   g_ctx.pinned_free.clear();
+  for (auto& b : g_ctx.scratch_free) cudaFree(b.p);
+  g_ctx.scratch_free.clear();
   return PB_OK;
 }
 extern "C" int pb_device_count(void) {
@@ -106,7 +116,7 @@ static void* pinned_alloc(size_t bytes) {
       }
   }
   void* p = nullptr;
-  if (cudaHostAlloc(&p, cap, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  if (cudaHostAlloc(&p, cap, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
   return p;
 }
 static void pinned_free(void* p, size_t bytes) {
@@ -116,6 +126,33 @@ static void pinned_free(void* p, size_t bytes) {
   std::lock_guard<std::mutex> lk(g_ctx.mu);
   if (g_ctx.pinned_free.size() < 256) g_ctx.pinned_free.push_back({p, cap});
   else cudaFreeHost(p);
+}
+
+// large device scratch (the match list): cudaMallocAsync of hundreds of MB is not free even from the pool
+static void* scratch_alloc(size_t bytes, size_t* cap_out) {
+  {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    int best = -1;
+    for (size_t i = 0; i < g_ctx.scratch_free.size(); i++)
+      if (g_ctx.scratch_free[i].cap >= bytes && (best < 0 || g_ctx.scratch_free[i].cap < g_ctx.scratch_free[best].cap)) best = (int)i;
+    if (best >= 0) {
+      PinnedBlock b = g_ctx.scratch_free[best];
+      g_ctx.scratch_free.erase(g_ctx.scratch_free.begin() + best);
+      *cap_out = b.cap;
+      return b.p;
+    }
+  }
+  size_t cap = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+  void* p = nullptr;
+  if (cudaMalloc(&p, cap) != cudaSuccess) return nullptr;
+  *cap_out = cap;
+  return p;
+}
+static void scratch_free(void* p, size_t cap) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_ctx.mu);
+  if (g_ctx.scratch_free.size() < 8) g_ctx.scratch_free.push_back({p, cap});
+  else cudaFree(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -138,8 +175,9 @@ struct Column {
   int32_t* d_sorted_pairs = nullptr;                       // sorted column: LE (start,end) pairs
   std::vector<int32_t> h_sorted_pairs;
   double* d_dict_f64 = nullptr;
+  uint8_t* d_dict_native = nullptr;                       // native-endian entries (group-key decode on the device)
   uint8_t* d_inv = nullptr;
-  bool fwd_staged = false, dict_staged = false, inv_staged = false;
+  bool fwd_staged = false, dict_staged = false, inv_staged = false, native_staged = false;
 };
 
 struct pb_segment_s {
@@ -203,7 +241,8 @@ extern "C" int pb_segment_stage(const pb_segment_desc* d, int /*device_index*/, 
 }
 
 // stage what a query needs of one column (under the segment lock)
-static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dict, bool need_inv, cudaStream_t st) {
+static void native_entry(const Column& c, int id, uint8_t* out);
+static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dict, bool need_inv, cudaStream_t st, bool need_native = false) {
   if (need_fwd && !c.fwd_staged) {
     if (c.has_dict && c.is_sorted) {
       // pairs -> device, then materialise the bit-packed stream on the device
@@ -250,6 +289,14 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
     s->device_bytes += (int64_t)sizeof(double) * c.card;
     c.dict_staged = true;
   }
+  if (need_native && !c.native_staged && c.has_dict) {
+    std::vector<uint8_t> v((size_t)c.card * c.entry_bytes);
+    for (int i = 0; i < c.card; i++) native_entry(c, i, v.data() + (size_t)i * c.entry_bytes);
+    CU(cudaMalloc((void**)&c.d_dict_native, v.size() + 16));
+    CU(cudaMemcpy(c.d_dict_native, v.data(), v.size(), cudaMemcpyHostToDevice));
+    s->device_bytes += (int64_t)v.size();
+    c.native_staged = true;
+  }
   if (need_inv && !c.inv_staged) {
     if (!c.h_inv) return fail(PB_ERR_INVALID, "column %s has no inverted index", c.name.c_str());
     CU(cudaMalloc((void**)&c.d_inv, c.h_inv_len + 16));
@@ -263,7 +310,7 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
 extern "C" int pb_segment_release(pb_segment_handle s) {
   if (!s) return PB_OK;
   for (auto& c : s->cols) {
-    cudaFree(c.d_fwd); cudaFree(c.d_sorted_pairs); cudaFree(c.d_dict_f64); cudaFree(c.d_inv);
+    cudaFree(c.d_fwd); cudaFree(c.d_sorted_pairs); cudaFree(c.d_dict_f64); cudaFree(c.d_dict_native); cudaFree(c.d_inv);
   }
   delete s;
   return PB_OK;
@@ -279,6 +326,7 @@ struct GlobalDict {
   std::vector<uint8_t> values;                 // native-endian stored-type values / padded strings, sorted
   std::vector<std::vector<int32_t>> h_remap;   // per segment: local dictId -> global dictId
   std::vector<int32_t*> d_remap;
+  uint8_t* d_values = nullptr;                 // device copy of `values`
   bool external = false;                       // installed by pb_segment_group_set_global_dictionary
 };
 
@@ -313,7 +361,7 @@ extern "C" int pb_segment_group_create(const pb_segment_handle* segs, int n, pb_
 }
 extern "C" int pb_segment_group_release(pb_segment_group_handle g) {
   if (!g) return PB_OK;
-  for (auto& kv : g->dicts) for (auto p : kv.second.d_remap) cudaFree(p);
+  for (auto& kv : g->dicts) { for (auto p : kv.second.d_remap) cudaFree(p); cudaFree(kv.second.d_values); }
   delete g;
   return PB_OK;
 }
@@ -354,6 +402,9 @@ static int build_union(pb_group_s* g, const char* column, GlobalDict& gd) {
 
 static int build_remaps(pb_group_s* g, const char* column, GlobalDict& gd) {
   for (auto p : gd.d_remap) cudaFree(p);
+  cudaFree(gd.d_values); gd.d_values = nullptr;
+  CU(cudaMalloc((void**)&gd.d_values, gd.values.size() + 16));
+  CU(cudaMemcpy(gd.d_values, gd.values.data(), gd.values.size(), cudaMemcpyHostToDevice));
   gd.d_remap.assign(g->segs.size(), nullptr);
   gd.h_remap.assign(g->segs.size(), {});
   std::vector<uint8_t> tmp((size_t)gd.entry_bytes);
@@ -443,7 +494,7 @@ struct TableMeta {
   std::vector<HostArr> dbl, lng, key_ids, key_vals, dc_off, dc_ids;
   std::vector<int> key_type, key_eb;
   pb_exec_stats stats{};
-  unsigned long long* d_slots = nullptr;    // compacted slot list on the device
+  uint64_t out_cap = 0;                     // capacity of the pinned output arrays
 };
 
 struct pb_result_s {
@@ -456,6 +507,7 @@ struct pb_result_s {
   std::vector<std::string> gb_names, agg_cols;
   std::vector<TableMeta> tables;
   std::vector<void*> dev_allocs;            // freed (stream-ordered) with the result
+  void* scratch = nullptr; size_t scratch_cap = 0;   // cached large scratch (match list)
   unsigned long long* d_counters = nullptr; // per table: [num_groups(u32 pair), limit flag, docs_matched, compaction counter]
   HostArr h_counters;
   int n_distinct_cols = 0;
@@ -471,6 +523,8 @@ struct pb_result_s {
 
 static void free_result(pb_result_s* r) {
   if (!r) return;
+  if (r->stream) cudaStreamSynchronize(r->stream);
+  scratch_free(r->scratch, r->scratch_cap);
   for (void* p : r->dev_allocs) cudaFreeAsync(p, r->stream);
   for (auto& t : r->tables) {
     t.slots.release(); t.rows.release();
@@ -551,7 +605,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       gcol[si][j] = ci;
       Column& c = s->cols[ci];
       if (!c.has_dict) any_raw_key = true;
-      if ((rc = stage_column(s, c, true, false, false, st))) return rc;
+      if ((rc = stage_column(s, c, true, false, false, st, !combine))) return rc;
     }
     for (int a = 0; a < nA; a++) {
       if (q->aggregations[a].op == PB_AGG_COUNT) continue;
@@ -774,6 +828,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       DevLeaf& lf = ds.leaves[n_leaves];
       memset(&lf, 0, sizeof lf);
       lf.set_smem_off = -1;
+      lf.est_permille = 500;
       ds.node_kind[n] = N_LEAF; ds.node_arg[n] = (int8_t)n_leaves; n_leaves++;
       auto scan_slot = [&](const Column& c) -> int {
         for (int k = 0; k < n_scan; k++) if (slot_of_col[k] == fn.column) return k;
@@ -792,6 +847,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
           int64_t lo = std::max<int64_t>(fn.lo, 0), hi = std::min<int64_t>(fn.hi, c.card);
           if (hi <= lo) { lf.kind = L_FALSE; break; }
           lf.kind = L_DICT_RANGE; lf.bits = c.bits; lf.lo = (uint32_t)lo; lf.span = (uint32_t)(hi - lo);
+          lf.est_permille = (int32_t)(1000.0 * (double)(hi - lo) / (double)c.card);
           if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
           r->seg_scan_leaves[si]++;
           break;
@@ -810,6 +866,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
           }
           lf.kind = L_DICT_SET; lf.bits = c.bits; lf.exclusive = fn.exclusive ? 1 : 0;
           lf.set_bits = dbits; lf.set_card = c.card;
+          { double f = (double)fn.num_ids / (double)c.card; lf.est_permille = (int32_t)(1000.0 * (fn.exclusive ? 1.0 - f : f)); }
           if (set_smem_used + c.card <= PB_SET_SMEM_BYTES) { lf.set_smem_off = set_smem_used; set_smem_used += (c.card + 15) & ~15; }
           if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
           r->seg_scan_leaves[si]++;
@@ -926,7 +983,9 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   if (n_docs_total >= (1ull << 32)) return fail(PB_ERR_UNSUPPORTED, "%llu docs in one call (match list is 32-bit): split the segment group", (unsigned long long)n_docs_total);
   uint32_t* d_match_list = nullptr;
   if (!match_all && n_docs_total > 0) {
-    CU(cudaMallocAsync((void**)&d_match_list, 4 * (size_t)n_docs_total + 256, st)); r->dev_allocs.push_back(d_match_list);
+    r->scratch = scratch_alloc(4 * (size_t)n_docs_total + 256, &r->scratch_cap);
+    if (!r->scratch) return fail(PB_ERR_OOM, "match list allocation (%zu bytes) failed", 4 * (size_t)n_docs_total + 256);
+    d_match_list = (uint32_t*)r->scratch;
   }
   r->match_all = match_all;
 
@@ -1018,26 +1077,6 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
 // ------------------------------------------------------------------------------------------------
 // finalize: compaction of non-empty groups, device -> pinned host, key decode
 // ------------------------------------------------------------------------------------------------
-// resolves, once per (table, group-by column), where decoded key values come from
-struct KeyDecoder {
-  const uint8_t* global_values = nullptr;   // combined mode: native-endian entries of the global dictionary
-  int global_eb = 0;
-  const Column* col = nullptr;              // per-segment mode: the segment's own dictionary (big-endian)
-  void init(const pb_group_s* g, const pb_result_s* r, const TableMeta& tm, int j) {
-    if (r->combine) {
-      const GlobalDict& gd = g->dicts.at(r->gb_names[j]);
-      global_values = gd.values.data(); global_eb = gd.entry_bytes;
-    } else {
-      const pb_segment_s* s = g->segs[tm.seg_idx[0]];
-      col = &s->cols[find_col(s, r->gb_names[j].c_str())];
-    }
-  }
-  inline void decode(int32_t id, uint8_t* out) const {
-    if (global_values) memcpy(out, global_values + (size_t)id * global_eb, (size_t)global_eb);
-    else native_entry(*col, id, out);
-  }
-};
-
 static int finalize_result(pb_result_s* r) {
   if (r->finalized) return PB_OK;
   cudaStream_t st = r->stream;
@@ -1046,75 +1085,79 @@ static int finalize_result(pb_result_s* r) {
   const int mode = r->table_mode;
   r->h_counters.alloc(8 * PB_COUNTERS_PER_TABLE * (size_t)nT);
   unsigned long long* hc = (unsigned long long*)r->h_counters.p;
+  double t_prev = now_us();
+  auto lap = [&](int i) { double t = now_us(); r->host_us[i] += t - t_prev; t_prev = t; };
 
-  // pass 1: number of non-empty groups per table
-  if (mode != T_KEYLESS) {
-    for (int t = 0; t < nT; t++) {
-      TableMeta& tm = r->tables[t];
-      uint64_t S = tm.capacity + (mode == T_HASH ? 1 : 0);
+  // very large tables: count the non-empty groups first so the host arrays can be sized exactly
+  const uint64_t SMALL_TABLE = 1ull << 20;
+  bool any_big = false;
+  for (int t = 0; t < nT; t++) {
+    TableMeta& tm = r->tables[t];
+    const uint64_t S = tm.capacity + (mode == T_HASH ? 1 : 0);
+    if (mode != T_KEYLESS && S > SMALL_TABLE) {
+      any_big = true;
       int grid = (int)std::min<uint64_t>((S + 255) / 256, 2048);
-      // counters[3] doubles as the group counter here, then as the compaction cursor (reset below)
       pb_count_groups_kernel<<<grid, 256, 0, st>>>(tm.dev.rowcnt, S, r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3);
       r->launches++;
     }
   }
-  CU(cudaGetLastError());
-  double t_prev = now_us();
-  auto lap = [&](int i) { double t = now_us(); r->host_us[i] += t - t_prev; t_prev = t; };
-  CU(cudaMemcpyAsync(hc, r->d_counters, 8 * PB_COUNTERS_PER_TABLE * (size_t)nT, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  if (any_big) {
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hc, r->d_counters, 8 * PB_COUNTERS_PER_TABLE * (size_t)nT, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
   lap(4);
 
-  // pass 2: compaction + gathers
+  // one pass per table: compaction + aggregate extraction + key decode, written straight into pinned host memory
   for (int t = 0; t < nT; t++) {
     TableMeta& tm = r->tables[t];
     const uint64_t S = tm.capacity + (mode == T_HASH ? 1 : 0);
-    const int64_t ng = mode == T_KEYLESS ? 1 : (int64_t)hc[(size_t)t * PB_COUNTERS_PER_TABLE + 3];
-    tm.num_groups = ng;
+    uint64_t cap = mode == T_KEYLESS ? 1 : S;
+    if (mode != T_KEYLESS && S > SMALL_TABLE) {
+      cap = std::max<uint64_t>(hc[(size_t)t * PB_COUNTERS_PER_TABLE + 3], 1);
+      CU(cudaMemsetAsync(r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3, 0, 8, st));
+    }
+    tm.out_cap = cap;
     tm.dbl.resize(nA); tm.lng.resize(nA); tm.dc_off.resize(nA); tm.dc_ids.resize(nA);
-    const size_t n = (size_t)std::max<int64_t>(ng, 1);
-    tm.slots.alloc(8 * n); tm.rows.alloc(8 * n);
-    unsigned long long *d_slots = nullptr, *d_rows = nullptr;
-    CU(cudaMallocAsync((void**)&d_slots, 8 * n, st)); r->dev_allocs.push_back(d_slots);
-    CU(cudaMallocAsync((void**)&d_rows, 8 * n, st)); r->dev_allocs.push_back(d_rows);
-    tm.d_slots = d_slots;
-    if (mode == T_KEYLESS) {
-      CU(cudaMemsetAsync(d_slots, 0, 8, st));
-      CU(cudaMemcpyAsync(d_rows, tm.dev.rowcnt, 8, cudaMemcpyDeviceToDevice, st));
-    } else if (ng > 0) {
-      unsigned long long* cursor = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3;
-      CU(cudaMemsetAsync(cursor, 0, 8, st));
-      int grid = (int)std::min<uint64_t>((S + 255) / 256, 2048);
-      pb_compact_slots_kernel<<<grid, 256, 0, st>>>(tm.dev.rowcnt, S, cursor, d_slots, d_rows);
-      r->launches++;
-    }
-    CU(cudaMemcpyAsync(tm.slots.p, d_slots, 8 * n, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(tm.rows.p, d_rows, 8 * n, cudaMemcpyDeviceToHost, st));
-    const int ggrid = (int)std::min<uint64_t>((n + 255) / 256, 2048);
+    tm.key_ids.resize(nG); tm.key_vals.resize(nG); tm.key_type.assign(nG, 0); tm.key_eb.assign(nG, 0);
+    tm.slots.alloc(8 * cap); tm.rows.alloc(8 * cap);
+    if (!tm.slots.p || !tm.rows.p) return fail(PB_ERR_OOM, "pinned host allocation failed");
+    DevFinalize F;
+    memset(&F, 0, sizeof F);
+    F.mode = mode; F.n_gb = nG; F.n_aggs = nA; F.always_emit = mode == T_KEYLESS ? 1 : 0;
+    F.S = mode == T_KEYLESS ? 1 : S; F.capacity = tm.capacity; F.cap_out = cap;
+    F.rowcnt = tm.dev.rowcnt; F.hkeys = tm.dev.hkeys;
+    F.cursor = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3;
+    F.out_slots = (unsigned long long*)tm.slots.p; F.out_rows = (unsigned long long*)tm.rows.p;
     for (int a = 0; a < nA; a++) {
-      const int op = r->agg_op[a];
-      tm.dbl[a].alloc(8 * n); tm.lng[a].alloc(8 * n);
-      memset(tm.dbl[a].p, 0, 8 * n); memset(tm.lng[a].p, 0, 8 * n);
-      if (ng == 0) continue;
-      if (op == PB_AGG_SUM || op == PB_AGG_AVG || op == PB_AGG_MIN || op == PB_AGG_MAX) {
-        double* d_out = nullptr;
-        CU(cudaMallocAsync((void**)&d_out, 8 * n, st)); r->dev_allocs.push_back(d_out);
-        if (op == PB_AGG_MIN || op == PB_AGG_MAX) pb_gather_mm_kernel<<<ggrid, 256, 0, st>>>(tm.dev.mm[a], d_slots, (uint64_t)ng, d_out);
-        else pb_gather_f64_kernel<<<ggrid, 256, 0, st>>>(tm.dev.sum[a], d_slots, (uint64_t)ng, d_out);
-        r->launches++;
-        CU(cudaMemcpyAsync(tm.dbl[a].p, d_out, 8 * n, cudaMemcpyDeviceToHost, st));
-      }
-      if (op == PB_AGG_DISTINCTCOUNT) {
-        unsigned long long* d_cnt = nullptr;
-        CU(cudaMallocAsync((void**)&d_cnt, 8 * n, st)); r->dev_allocs.push_back(d_cnt);
-        int wgrid = (int)((n * 32 + 255) / 256);
-        pb_distinct_count_kernel<<<wgrid, 256, 0, st>>>(tm.dev.dc_bits[a], tm.dev.dc_words[a], d_slots, (uint64_t)ng, d_cnt);
-        r->launches++;
-        CU(cudaMemcpyAsync(tm.lng[a].p, d_cnt, 8 * n, cudaMemcpyDeviceToHost, st));
-      }
+      tm.dbl[a].alloc(8 * cap); tm.lng[a].alloc(8 * cap);
+      if (!tm.dbl[a].p || !tm.lng[a].p) return fail(PB_ERR_OOM, "pinned host allocation failed");
+      F.aggs[a].op = r->agg_op[a]; F.aggs[a].sum = tm.dev.sum[a]; F.aggs[a].mm = tm.dev.mm[a]; F.aggs[a].out = (double*)tm.dbl[a].p;
     }
+    uint64_t div = 1;
+    for (int j = 0; j < nG; j++) {
+      const pb_segment_s* s0 = g->segs[tm.seg_idx[0]];
+      const Column& c0 = s0->cols[find_col(s0, r->gb_names[j].c_str())];
+      DevFinKey& fk = F.keys[j];
+      fk.is_dict = c0.has_dict; fk.type = c0.type;
+      if (c0.has_dict) {
+        if (r->combine) { const GlobalDict& gd = g->dicts.at(r->gb_names[j]); fk.dict_vals = gd.d_values; fk.eb = gd.entry_bytes; }
+        else { fk.dict_vals = c0.d_dict_native; fk.eb = c0.entry_bytes; }
+        if (!fk.dict_vals) return fail(PB_ERR_STATE, "dictionary of %s is not staged", c0.name.c_str());
+      } else fk.eb = (c0.type == PB_INT || c0.type == PB_FLOAT) ? 4 : 8;
+      if (mode == T_DENSE) { fk.div = div; fk.card = (uint64_t)tm.cards[j]; div *= (uint64_t)tm.cards[j]; }
+      else if (mode == T_HASH) { fk.shift = tm.shifts[j]; fk.width = tm.widths[j]; }
+      tm.key_type[j] = c0.type; tm.key_eb[j] = fk.eb;
+      tm.key_ids[j].alloc(4 * cap); tm.key_vals[j].alloc((size_t)fk.eb * cap);
+      if (!tm.key_ids[j].p || !tm.key_vals[j].p) return fail(PB_ERR_OOM, "pinned host allocation failed");
+      fk.out_ids = (int32_t*)tm.key_ids[j].p; fk.out_vals = (uint8_t*)tm.key_vals[j].p;
+    }
+    int grid = (int)std::min<uint64_t>((F.S + 255) / 256, 1184);
+    pb_finalize_kernel<<<grid, 256, 0, st>>>(F);
+    r->launches++;
   }
   CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(hc, r->d_counters, 8 * PB_COUNTERS_PER_TABLE * (size_t)nT, cudaMemcpyDeviceToHost, st));
   CU(cudaEventRecord(r->ev3, st));
   CU(cudaStreamSynchronize(st));
   lap(5);
@@ -1124,97 +1167,42 @@ static int finalize_result(pb_result_s* r) {
   cudaEventElapsedTime(&ms, r->ev1, r->evm); r->filter_ms = ms;
   cudaEventElapsedTime(&ms, r->evm, r->ev2); r->agg_ms = ms;
 
-  // host side: counts, keys, stats, distinct value sets
+  // host side: counts, stats, distinct value sets
   for (int t = 0; t < nT; t++) {
     TableMeta& tm = r->tables[t];
-    const int64_t ng = tm.num_groups;
-    const unsigned long long* slots = (const unsigned long long*)tm.slots.p;
+    const int64_t ng = (int64_t)std::min<uint64_t>(hc[(size_t)t * PB_COUNTERS_PER_TABLE + 3], tm.out_cap);
+    tm.num_groups = ng;
     const unsigned long long* rows = (const unsigned long long*)tm.rows.p;
     for (int a = 0; a < nA; a++) {
       const int op = r->agg_op[a];
       int64_t* L = (int64_t*)tm.lng[a].p;
       if (op == PB_AGG_COUNT || op == PB_AGG_AVG) for (int64_t k = 0; k < ng; k++) L[k] = (int64_t)rows[k];
-      if (op == PB_AGG_COUNT) { double* D = (double*)tm.dbl[a].p; for (int64_t k = 0; k < ng; k++) D[k] = (double)rows[k]; }
+      else if (op != PB_AGG_DISTINCTCOUNT) memset(L, 0, 8 * (size_t)std::max<int64_t>(ng, 1));
     }
-    // distinct value sets (second device pass needs the counts as offsets)
+    // DISTINCTCOUNT: sizes, then the value sets (BaseDistinctAggregateAggregationFunction intermediate result)
     for (int a = 0; a < nA; a++) {
       if (r->agg_op[a] != PB_AGG_DISTINCTCOUNT) continue;
-      const int64_t* L = (const int64_t*)tm.lng[a].p;
+      int64_t* L = (int64_t*)tm.lng[a].p;
       tm.dc_off[a].alloc(8 * (size_t)(ng + 1));
       int64_t* off = (int64_t*)tm.dc_off[a].p;
       off[0] = 0;
+      if (ng > 0) {
+        int wgrid = (int)(((size_t)ng * 32 + 255) / 256);
+        pb_distinct_count_kernel<<<wgrid, 256, 0, st>>>(tm.dev.dc_bits[a], tm.dev.dc_words[a], (const unsigned long long*)tm.slots.p, (uint64_t)ng, (unsigned long long*)L);
+        r->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(st));
+      }
       for (int64_t k = 0; k < ng; k++) off[k + 1] = off[k] + L[k];
       const int64_t total = off[ng];
       tm.dc_ids[a].alloc(4 * (size_t)std::max<int64_t>(total, 1));
       if (total > 0) {
-        unsigned long long* d_off = nullptr; int32_t* d_ids = nullptr;
-        CU(cudaMallocAsync((void**)&d_off, 8 * (size_t)(ng + 1), st)); r->dev_allocs.push_back(d_off);
-        CU(cudaMallocAsync((void**)&d_ids, 4 * (size_t)total, st)); r->dev_allocs.push_back(d_ids);
-        CU(cudaMemcpyAsync(d_off, off, 8 * (size_t)(ng + 1), cudaMemcpyHostToDevice, st));
         int wgrid = (int)(((size_t)ng * 32 + 255) / 256);
-        pb_distinct_ids_kernel<<<wgrid, 256, 0, st>>>(tm.dev.dc_bits[a], tm.dev.dc_words[a], tm.d_slots, (uint64_t)ng, d_off, d_ids);
+        pb_distinct_ids_kernel<<<wgrid, 256, 0, st>>>(tm.dev.dc_bits[a], tm.dev.dc_words[a], (const unsigned long long*)tm.slots.p, (uint64_t)ng,
+                                                      (const unsigned long long*)off, (int32_t*)tm.dc_ids[a].p);
         r->launches++;
-        CU(cudaMemcpyAsync(tm.dc_ids[a].p, d_ids, 4 * (size_t)total, cudaMemcpyDeviceToHost, st));
+        CU(cudaGetLastError());
         CU(cudaStreamSynchronize(st));
-      }
-    }
-    // keys
-    tm.key_ids.resize(nG); tm.key_vals.resize(nG); tm.key_type.assign(nG, 0); tm.key_eb.assign(nG, 0);
-    for (int j = 0; j < nG; j++) {
-      const pb_segment_s* s0 = g->segs[tm.seg_idx[0]];
-      const Column& c0 = s0->cols[find_col(s0, r->gb_names[j].c_str())];
-      const bool is_dict = c0.has_dict;
-      int eb = is_dict ? (r->combine ? g->dicts.at(r->gb_names[j]).entry_bytes : c0.entry_bytes) : (c0.type == PB_INT || c0.type == PB_FLOAT ? 4 : 8);
-      tm.key_type[j] = c0.type; tm.key_eb[j] = eb;
-      tm.key_ids[j].alloc(4 * (size_t)std::max<int64_t>(ng, 1));
-      tm.key_vals[j].alloc((size_t)eb * (size_t)std::max<int64_t>(ng, 1));
-      int32_t* ids = (int32_t*)tm.key_ids[j].p;
-      uint8_t* vals = (uint8_t*)tm.key_vals[j].p;
-      if (mode == T_DENSE) {   // DictionaryBasedGroupKeyGenerator.java:578-591 (mixed radix decode)
-        KeyDecoder kd; kd.init(g, r, tm, j);
-        uint64_t div = 1;
-        for (int jj = 0; jj < j; jj++) div *= (uint64_t)tm.cards[jj];
-        const uint64_t card = (uint64_t)tm.cards[j];
-        for (int64_t k = 0; k < ng; k++) {
-          const uint64_t field = (slots[k] / div) % card;
-          ids[k] = (int32_t)field;
-          kd.decode((int32_t)field, vals + (size_t)k * eb);
-        }
-      }
-    }
-    if (mode == T_HASH && ng > 0) {
-      // fetch the keys of the compacted slots
-      std::vector<unsigned long long> keys((size_t)ng);
-      unsigned long long* d_k = nullptr;
-      CU(cudaMallocAsync((void**)&d_k, 8 * (size_t)ng, st)); r->dev_allocs.push_back(d_k);
-      int ggrid = (int)std::min<uint64_t>(((uint64_t)ng + 255) / 256, 2048);
-      // slot == capacity (the sentinel cell) has no stored key: patched on the host
-      pb_gather_u64_kernel<<<ggrid, 256, 0, st>>>(tm.dev.hkeys, tm.d_slots, (uint64_t)ng, d_k);
-      r->launches++;
-      CU(cudaMemcpyAsync(keys.data(), d_k, 8 * (size_t)ng, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      for (int64_t k = 0; k < ng; k++) if (slots[k] == tm.capacity) keys[(size_t)k] = PB_HASH_EMPTY;
-      for (int j = 0; j < nG; j++) {
-        const pb_segment_s* s0 = g->segs[tm.seg_idx[0]];
-        const Column& c0 = s0->cols[find_col(s0, r->gb_names[j].c_str())];
-        int eb = tm.key_eb[j];
-        int32_t* ids = (int32_t*)tm.key_ids[j].p;
-        uint8_t* vals = (uint8_t*)tm.key_vals[j].p;
-        const int width = tm.widths[j], shift = tm.shifts[j];
-        KeyDecoder kd;
-        if (c0.has_dict) kd.init(g, r, tm, j);
-        for (int64_t k = 0; k < ng; k++) {
-          uint64_t f = keys[(size_t)k] >> shift;
-          if (width < 64) f &= ((1ull << width) - 1ull);
-          if (c0.has_dict) { ids[k] = (int32_t)f; kd.decode((int32_t)f, vals + (size_t)k * eb); }
-          else {
-            ids[k] = -1;
-            if (c0.type == PB_INT) { int32_t v = (int32_t)(uint32_t)f; memcpy(vals + (size_t)k * eb, &v, 4); }
-            else if (c0.type == PB_LONG) { int64_t v = (int64_t)f; memcpy(vals + (size_t)k * eb, &v, 8); }
-            else if (c0.type == PB_FLOAT) { double dv; memcpy(&dv, &f, 8); float fv = (float)dv; memcpy(vals + (size_t)k * eb, &fv, 4); }
-            else memcpy(vals + (size_t)k * eb, &f, 8);
-          }
-        }
       }
     }
     // ExecutionStatistics (GroupByOperator.java:148-153; ProjectPlanNode.java:69-78)

@@ -231,59 +231,90 @@ _KEY_DT = {0: np.int32, 1: np.int64, 2: np.float32, 3: np.float64}
 
 
 class ResultTable:
-    """One GroupByResultsBlock / AggregationResultsBlock."""
+    """One GroupByResultsBlock / AggregationResultsBlock.  Arrays are zero-copy views of the result handle's pinned
+    host memory, created on first access (valid until Result.free())."""
 
     def __init__(self, rh, t: int, q: QueryContext):
         l = lib()
-        ng = l.pb_result_num_groups(rh, t)
-        self.num_groups = int(ng)
-        n = max(self.num_groups, 1)
+        self._rh, self._t, self.query = rh, t, q
+        self.num_groups = int(l.pb_result_num_groups(rh, t))
         st = l.pb_result_stats(rh, t).contents
         self.stats = {k: getattr(st, k) for k, _ in PbExecStats._fields_}
-        self.key_dict_ids, self.key_values = [], []
-        for j in range(len(q.group_by)):
-            ids = np.ctypeslib.as_array(l.pb_result_group_dict_ids(rh, t, j), shape=(n,))[:self.num_groups].copy()
-            ty, eb = C.c_int32(), C.c_int32()
-            p = l.pb_result_group_key_values(rh, t, j, C.byref(ty), C.byref(eb))
-            raw = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * eb.value,))[:self.num_groups * eb.value].copy()
-            if ty.value == 4:
-                vals = np.array([bytes(r).rstrip(b"\0") for r in raw.reshape(self.num_groups, eb.value)], dtype=object)
-            else:
-                vals = raw.view(_KEY_DT[ty.value])
-            self.key_dict_ids.append(ids)
-            self.key_values.append(vals)
-        self.doubles, self.longs, self.distinct = [], [], []
-        for a, agg in enumerate(q.aggregations):
-            self.doubles.append(np.ctypeslib.as_array(l.pb_result_double(rh, t, a), shape=(n,))[:self.num_groups].copy())
-            self.longs.append(np.ctypeslib.as_array(l.pb_result_long(rh, t, a), shape=(n,))[:self.num_groups].copy())
-            if agg.op == AggOp.DISTINCTCOUNT:
-                off = np.ctypeslib.as_array(l.pb_result_distinct_offsets(rh, t, a), shape=(self.num_groups + 1,)).copy()
-                tot = int(off[-1])
-                ids = np.ctypeslib.as_array(l.pb_result_distinct_dict_ids(rh, t, a), shape=(max(tot, 1),))[:tot].copy()
-                self.distinct.append((off, ids))
-            else:
-                self.distinct.append(None)
-        self.query = q
+        self._cache = {}
+
+    def _view(self, name, fn):
+        if name not in self._cache:
+            self._cache[name] = fn()
+        return self._cache[name]
+
+    @property
+    def key_dict_ids(self):
+        def load():
+            n = max(self.num_groups, 1)
+            return [np.ctypeslib.as_array(lib().pb_result_group_dict_ids(self._rh, self._t, j), shape=(n,))[:self.num_groups]
+                    for j in range(len(self.query.group_by))]
+        return self._view("ids", load)
+
+    @property
+    def key_values(self):
+        def load():
+            out, n = [], max(self.num_groups, 1)
+            for j in range(len(self.query.group_by)):
+                ty, eb = C.c_int32(), C.c_int32()
+                p = lib().pb_result_group_key_values(self._rh, self._t, j, C.byref(ty), C.byref(eb))
+                raw = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n * eb.value,))[:self.num_groups * eb.value]
+                if ty.value == 4:
+                    out.append(np.array([bytes(r).rstrip(b"\0") for r in raw.reshape(self.num_groups, eb.value)], dtype=object))
+                else:
+                    out.append(raw.view(_KEY_DT[ty.value]))
+            return out
+        return self._view("vals", load)
+
+    @property
+    def doubles(self):
+        n = max(self.num_groups, 1)
+        return self._view("dbl", lambda: [np.ctypeslib.as_array(lib().pb_result_double(self._rh, self._t, a), shape=(n,))[:self.num_groups]
+                                          for a in range(len(self.query.aggregations))])
+
+    @property
+    def longs(self):
+        n = max(self.num_groups, 1)
+        return self._view("lng", lambda: [np.ctypeslib.as_array(lib().pb_result_long(self._rh, self._t, a), shape=(n,))[:self.num_groups]
+                                          for a in range(len(self.query.aggregations))])
+
+    @property
+    def distinct(self):
+        def load():
+            out = []
+            for a, agg in enumerate(self.query.aggregations):
+                if agg.op == AggOp.DISTINCTCOUNT:
+                    off = np.ctypeslib.as_array(lib().pb_result_distinct_offsets(self._rh, self._t, a), shape=(self.num_groups + 1,))
+                    tot = int(off[-1])
+                    ids = np.ctypeslib.as_array(lib().pb_result_distinct_dict_ids(self._rh, self._t, a), shape=(max(tot, 1),))[:tot]
+                    out.append((off, ids))
+                else:
+                    out.append(None)
+            return out
+        return self._view("dc", load)
 
     def keys(self) -> List[tuple]:
-        out = []
-        for g in range(self.num_groups):
-            out.append(tuple(v[g].item() if hasattr(v[g], "item") else v[g] for v in self.key_values))
-        return out
+        vals = self.key_values
+        return [tuple(v[g].item() if hasattr(v[g], "item") else v[g] for v in vals) for g in range(self.num_groups)]
 
     def rows(self) -> Dict[tuple, list]:
         """key -> [per-aggregation value]: COUNT int, SUM/MIN/MAX float, AVG (sum, count), DISTINCTCOUNT count."""
         ks = self.keys() if self.query.group_by else [()]
+        dbl, lng = self.doubles, self.longs
         out = {}
         for g, k in enumerate(ks):
             row = []
             for a, agg in enumerate(self.query.aggregations):
                 if agg.op in (AggOp.COUNT, AggOp.DISTINCTCOUNT):
-                    row.append(int(self.longs[a][g]))
+                    row.append(int(lng[a][g]))
                 elif agg.op == AggOp.AVG:
-                    row.append((float(self.doubles[a][g]), int(self.longs[a][g])))
+                    row.append((float(dbl[a][g]), int(lng[a][g])))
                 else:
-                    row.append(float(self.doubles[a][g]))
+                    row.append(float(dbl[a][g]))
             out[k] = row
         return out
 
@@ -377,9 +408,14 @@ class _MarshalledQuery:
                                    q.max_initial_result_holder_capacity, len(skip), self.skip)
 
 
-def execute(group: SegmentGroup, q: QueryContext, flags: int = 0) -> Result:
+def prepare(q: QueryContext) -> "_MarshalledQuery":
+    """Marshal a QueryContext once; pass it to execute(prepared=...) when the same query runs many times."""
+    return _MarshalledQuery(q)
+
+
+def execute(group: SegmentGroup, q: QueryContext, flags: int = 0, prepared: Optional["_MarshalledQuery"] = None) -> Result:
     """Plan (host layer) + run (device) a query over every segment of the group."""
-    m = _MarshalledQuery(q)
+    m = prepared if prepared is not None else _MarshalledQuery(q)
     rh = C.c_void_p()
     _check(lib().pbh_execute(group.handle, C.byref(m.ctx), flags, C.byref(rh)))
     return Result(rh, q, deferred=bool(flags & PB_Q_DEFER_FINALIZE))
