@@ -981,8 +981,6 @@ struct DevFinalize {
   const unsigned long long* rowcnt;
   const unsigned long long* hkeys;
   unsigned long long* cursor;
-  const unsigned long long* counters;      // per-table device counters [4]
-  unsigned long long* out_counters;        // host copy [4] + [4] = number of groups written
   unsigned long long* out_slots;
   unsigned long long* out_rows;
   DevFinKey keys[PB_MAX_GROUP_BY];
@@ -1034,7 +1032,6 @@ __global__ void pb_finalize_kernel(const DevFinalize F) {
       }
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x < 4) F.out_counters[threadIdx.x] = F.counters[threadIdx.x];
 }
 
 // gather kernels used by the two-pass path of very large tables
