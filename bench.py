@@ -262,8 +262,8 @@ def main():
                 dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<f8"), device="cuda"), op=dist.ReduceOp.SUM)
             elif agg.op in (AggOp.MIN, AggOp.MAX):
                 ptr, n = r.device_buffer(2, a)
-                dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"),
-                                op=dist.ReduceOp.MIN if agg.op == AggOp.MIN else dist.ReduceOp.MAX)
+                # MAX tables hold the bit-complement of the encoded value, so both reduce with MIN
+                dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.MIN)
         torch.cuda.synchronize()
         if rank == 0:
             r.finalize()

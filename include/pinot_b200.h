@@ -207,7 +207,8 @@ void pb_result_free(pb_result_handle r);
 /* -------- multi-GPU (PB_Q_COMBINE | PB_Q_DEFER_FINALIZE): device-resident table arrays for an
  * NCCL all-reduce issued by the caller (torch.distributed), then finalize on the root.
  * which: 0 = row counts (int64, SUM); 1 = per-aggregation double sums (float64, SUM);
- *        2 = per-aggregation min/max in order-preserving int64 encoding (int64, MIN or MAX);
+ *        2 = per-aggregation min/max in order-preserving int64 encoding (int64; reduce with MIN for both:
+ *            MAX tables hold the bit-complement);
  *        3 = per-aggregation distinct bitset words (int32; OR == MAX over 0/1 is NOT valid — all-gather + pb_or) -------- */
 int pb_result_device_buffer(pb_result_handle r, int32_t which, int32_t agg, void** device_ptr, int64_t* num_elements);
 int pb_result_finalize(pb_result_handle r);

@@ -504,7 +504,7 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
       if (op == 1 || op == 4) pb_red_add_f64(&t.sum[a][slot], v);            // REDG.E.ADD.F64
       else if (v == v) {                                                      // NaN never replaces (strict compare)
         long long e = pb_enc_f64(v);
-        if (op == 2) pb_red_min_s64(&t.mm[a][slot], e); else pb_red_max_s64(&t.mm[a][slot], e);
+        pb_red_min_s64(&t.mm[a][slot], op == 2 ? e : ~e);   // MAX is kept as MIN of the bit-complement (one init value for all)
       }
     }
   }
@@ -530,13 +530,15 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 struct __align__(16) FilterSmemHeader {
   uint64_t full[PB_NWARPS][PB_NSTAGE];
   uint32_t slot_stride[PB_MAX_SCAN_SLOTS];   // bytes of one chunk of the slot (128 * bits)
+  uint32_t slot_last_rel[PB_MAX_SCAN_SLOTS]; // first chunk index whose load must be clipped to the buffer end
+  uint32_t n_scan_full_bytes;                // expect_tx total of an unclipped chunk
   int32_t flat_and;                          // program is AND(leaf, leaf, ...) (or a single leaf): no stack needed
   int32_t n_flat;
   int32_t flat_leaf[PB_MAX_LEAVES];
   uint8_t seg[PB_SEG_FILTER_BYTES];          // the filter part of the current DevSegQuery
 };
 
-__global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
+__global__ void __launch_bounds__(PB_NTHREADS, 4) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   FilterSmemHeader* H = reinterpret_cast<FilterSmemHeader*>(smem_raw);
   const DevQuery& Q = *Qp;
@@ -608,7 +610,18 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
       uint32_t* dst = reinterpret_cast<uint32_t*>(H->seg);
       for (int i = tid; i < (int)(PB_SEG_FILTER_BYTES / 4); i += PB_NTHREADS) dst[i] = src[i];
       __syncthreads();
-      if (tid < sq.n_scan) H->slot_stride[tid] = (uint32_t)(PB_CHUNK_DOCS / 8) * (uint32_t)sq.scan[tid].bits_per_doc;
+      if (tid < sq.n_scan) {
+        const uint32_t stride = (uint32_t)(PB_CHUNK_DOCS / 8) * (uint32_t)sq.scan[tid].bits_per_doc;
+        H->slot_stride[tid] = stride;
+        // chunks rel < last_rel can load stride + 16 bytes without leaving the (16-byte padded) buffer
+        const uint64_t total = sq.scan[tid].bytes_total;
+        H->slot_last_rel[tid] = total >= (uint64_t)stride + 16 ? (uint32_t)((total - stride - 16) / stride) + 1 : 0u;
+      }
+      if (tid == 96) {
+        uint32_t t = 0;
+        for (int c = 0; c < sq.n_scan; c++) t += (uint32_t)(PB_CHUNK_DOCS / 8) * (uint32_t)sq.scan[c].bits_per_doc + 16;
+        H->n_scan_full_bytes = t;
+      }
       if (tid == 64) {
         // flat conjunction?  postfix == leaf* AND(n)   or a single leaf   or empty (match all)
         int nl = 0; bool flat = true;
@@ -651,6 +664,17 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
       const uint32_t rel = rel0 + k * PB_NWARPS;
       const int st = (int)(seq % PB_NSTAGE);
       uint8_t* dst = my_stages + (size_t)st * Q.stage_bytes;
+      uint64_t* bar = &H->full[warp][st];
+      bool clipped = false;
+      for (int c = 0; c < n_scan; c++) clipped |= rel >= H->slot_last_rel[c];
+      if (!clipped) {                                   // steady state: constant sizes
+        pb_mbar_expect_tx(bar, H->n_scan_full_bytes);
+        for (int c = 0; c < n_scan; c++) {
+          const uint32_t stride = H->slot_stride[c];
+          pb_tma_load_1d(dst + Q.slot_off[c], sq.scan[c].base + (uint64_t)rel * stride, stride + 16, bar);
+        }
+        return;
+      }
       uint32_t total = 0;
       uint32_t nbytes[PB_MAX_SCAN_SLOTS];
       for (int c = 0; c < n_scan; c++) {
@@ -660,9 +684,9 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
         nbytes[c] = (uint32_t)((want < avail ? want : avail) & ~(uint64_t)15);
         total += nbytes[c];
       }
-      pb_mbar_expect_tx(&H->full[warp][st], total);
+      pb_mbar_expect_tx(bar, total);
       for (int c = 0; c < n_scan; c++)
-        pb_tma_load_1d(dst + Q.slot_off[c], sq.scan[c].base + (uint64_t)rel * H->slot_stride[c], nbytes[c], &H->full[warp][st]);
+        pb_tma_load_1d(dst + Q.slot_off[c], sq.scan[c].base + (uint64_t)rel * H->slot_stride[c], nbytes[c], bar);
     };
 
     if (staged && Q.use_tma && lane == 0)
@@ -798,7 +822,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, 4) pb_agg_kernel(const DevQuery* 
       const int op = Q.agg_op[a];
       if (op == 1 || op == 4) { pb_red_add_f64(&t.sum[a][0], ka.sum[a * PB_NTHREADS + tid]); ka.sum[a * PB_NTHREADS + tid] = 0.0; }
       else if (op == 2) { pb_red_min_s64(&t.mm[a][0], ka.mm[a * PB_NTHREADS + tid]); ka.mm[a * PB_NTHREADS + tid] = ENC_POS_INF; }
-      else if (op == 3) { pb_red_max_s64(&t.mm[a][0], ka.mm[a * PB_NTHREADS + tid]); ka.mm[a * PB_NTHREADS + tid] = ENC_NEG_INF; }
+      else if (op == 3) { pb_red_min_s64(&t.mm[a][0], ~ka.mm[a * PB_NTHREADS + tid]); ka.mm[a * PB_NTHREADS + tid] = ENC_NEG_INF; }
     }
   };
 
@@ -850,7 +874,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, 4) pb_agg_kernel(const DevQuery* 
       if (tid == 0) {
         long long tot = s_red_i64[0];
         for (int w = 1; w < PB_NWARPS; w++) { long long u = s_red_i64[w]; tot = (op == 2) ? (u < tot ? u : tot) : (u > tot ? u : tot); }
-        if (op == 2) pb_red_min_s64(&t.mm[a][0], tot); else pb_red_max_s64(&t.mm[a][0], tot);
+        pb_red_min_s64(&t.mm[a][0], op == 2 ? tot : ~tot);
       }
       __syncthreads();
     }
@@ -941,8 +965,14 @@ __global__ void pb_ranges_fill_kernel(const int32_t* __restrict__ pairs, int32_t
 // ------------------------------------------------------------------------------------------------
 // table init / finalize
 // ------------------------------------------------------------------------------------------------
-__global__ void pb_fill_i64_kernel(long long* p, uint64_t n, long long v) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+// one launch initialises every table of the query: zero region (row counts, sums, distinct bitsets, counters),
+// 0xFF region (hash keys = PB_HASH_EMPTY) and the min/max region (INT64_MAX: larger than any encoded value)
+__global__ void pb_init_tables_kernel(uint4* zero, uint64_t zero_n16, uint4* ff, uint64_t ff_n16, uint4* mm, uint64_t mm_n16) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u), f = make_uint4(~0u, ~0u, ~0u, ~0u), m = make_uint4(~0u, 0x7fffffffu, ~0u, 0x7fffffffu);
+  for (uint64_t i = t0; i < zero_n16; i += stride) zero[i] = z;
+  for (uint64_t i = t0; i < ff_n16; i += stride) ff[i] = f;
+  for (uint64_t i = t0; i < mm_n16; i += stride) mm[i] = m;
 }
 
 // count non-empty slots
@@ -1007,7 +1037,11 @@ __global__ void pb_finalize_kernel(const DevFinalize F) {
     for (int a = 0; a < F.n_aggs; a++) {
       const DevFinAgg& fa = F.aggs[a];
       if (fa.sum) fa.out[k] = fa.sum[i];
-      else if (fa.mm) fa.out[k] = pb_dec_f64(fa.mm[i]);
+      else if (fa.mm) {
+        // empty group (keyless query without matches): MIN = +inf, MAX = -inf (MinAggregationFunction.java:37 defaults)
+        if (c == 0) fa.out[k] = fa.op == 2 ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double((long long)0xfff0000000000000ULL);
+        else fa.out[k] = pb_dec_f64(fa.op == 2 ? fa.mm[i] : ~fa.mm[i]);
+      }
       else if (fa.op == 0) fa.out[k] = (double)c;
     }
     unsigned long long key = 0;

@@ -724,19 +724,25 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 + 256;
   if (zero_bytes > (64ull << 30)) return fail(PB_ERR_UNSUPPORTED, "group table needs %zu bytes: decline to the CPU plan", zero_bytes);
   uint8_t *d_zero = nullptr, *d_ff = nullptr; long long* d_mm = nullptr;
-  CU(cudaMallocAsync((void**)&d_zero, zero_bytes, st)); r->dev_allocs.push_back(d_zero);
-  if (ff_bytes) { CU(cudaMallocAsync((void**)&d_ff, ff_bytes, st)); r->dev_allocs.push_back(d_ff); }
-  if (mm_elems) { CU(cudaMallocAsync((void**)&d_mm, 8 * mm_elems, st)); r->dev_allocs.push_back(d_mm); }
+  CU(cudaMallocAsync((void**)&d_zero, zero_bytes + 16, st)); r->dev_allocs.push_back(d_zero);
+  if (ff_bytes) { CU(cudaMallocAsync((void**)&d_ff, ff_bytes + 16, st)); r->dev_allocs.push_back(d_ff); }
+  if (mm_elems) { CU(cudaMallocAsync((void**)&d_mm, 8 * mm_elems + 16, st)); r->dev_allocs.push_back(d_mm); }
 
   CU(cudaEventRecord(r->ev0, st));
-  CU(cudaMemsetAsync(d_zero, 0, zero_bytes, st));
-  if (ff_bytes) CU(cudaMemsetAsync(d_ff, 0xFF, ff_bytes, st));
+  {
+    // all three regions are 16-byte multiples (cudaMallocAsync alignment is 256)
+    const uint64_t zn = (zero_bytes + 15) / 16, fn = (ff_bytes + 15) / 16, mn = (8 * mm_elems + 15) / 16;
+    const uint64_t mx = std::max(zn, std::max(fn, mn));
+    int grid = (int)std::min<uint64_t>((mx + 255) / 256, (uint64_t)g_ctx.num_sms * 8);
+    if (grid < 1) grid = 1;
+    pb_init_tables_kernel<<<grid, 256, 0, st>>>((uint4*)d_zero, zn, (uint4*)d_ff, fn, (uint4*)d_mm, mn);
+    r->launches++;
+    CU(cudaGetLastError());
+  }
   {
     size_t zo = 0, fo = 0, mo = 0;
     r->d_counters = reinterpret_cast<unsigned long long*>(d_zero);
     zo += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8; zo = (zo + 255) & ~(size_t)255;
-    const long long ENC_POS_INF = 0x7ff0000000000000LL;
-    const long long ENC_NEG_INF = (long long)0xfff0000000000000ULL ^ 0x7fffffffffffffffLL;
     for (int t = 0; t < n_tables; t++) {
       TableMeta& tm = r->tables[t];
       uint64_t S = slots_of(tm);
@@ -750,9 +756,6 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
         if (op == PB_AGG_DISTINCTCOUNT) { dt.dc_bits[a] = reinterpret_cast<uint32_t*>(d_zero + zo); dt.dc_words[a] = dc_words[a]; zo += 4 * S * dc_words[a]; }
         if (op == PB_AGG_MIN || op == PB_AGG_MAX) {
           dt.mm[a] = d_mm + mo; mo += S;
-          int grid = (int)std::min<uint64_t>((S + 255) / 256, 1024);
-          pb_fill_i64_kernel<<<grid, 256, 0, st>>>(dt.mm[a], S, op == PB_AGG_MIN ? ENC_POS_INF : ENC_NEG_INF);
-          r->launches++;
         }
       }
       zo = (zo + 255) & ~(size_t)255;
@@ -966,7 +969,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   int32_t slot_offs[PB_MAX_SCAN_SLOTS] = {0};
   for (int k = 0; k < n_slots_max; k++) {
     slot_offs[k] = (int32_t)stage_bytes;
-    stage_bytes += (((size_t)PB_CHUNK_DOCS * slot_bits_max[k] / 8 + 16) + 127) & ~(size_t)127;
+    stage_bytes += (((size_t)PB_CHUNK_DOCS * slot_bits_max[k] / 8 + 16) + 15) & ~(size_t)15;
   }
   if (stage_bytes * PB_NSTAGE * PB_NWARPS > 200 * 1024)
     return fail(PB_ERR_UNSUPPORTED, "scan predicates touch %d bits per row: chunk stages do not fit shared memory", sum_bits);

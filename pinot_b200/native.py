@@ -234,9 +234,10 @@ class ResultTable:
     """One GroupByResultsBlock / AggregationResultsBlock.  Arrays are zero-copy views of the result handle's pinned
     host memory, created on first access (valid until Result.free())."""
 
-    def __init__(self, rh, t: int, q: QueryContext):
+    def __init__(self, rh, t: int, q: QueryContext, parent=None):
         l = lib()
         self._rh, self._t, self.query = rh, t, q
+        self._parent = parent          # the views below point into the Result's pinned memory: keep it alive
         self.num_groups = int(l.pb_result_num_groups(rh, t))
         st = l.pb_result_stats(rh, t).contents
         self.stats = {k: getattr(st, k) for k, _ in PbExecStats._fields_}
@@ -329,7 +330,7 @@ class Result:
 
     def _load(self):
         l = lib()
-        self.tables = [ResultTable(self._rh, t, self.query) for t in range(l.pb_result_num_tables(self._rh))]
+        self.tables = [ResultTable(self._rh, t, self.query, self) for t in range(l.pb_result_num_tables(self._rh))]
         self.device_ms = l.pb_result_device_ms(self._rh)
         self.scan_kernel_ms = l.pb_result_scan_kernel_ms(self._rh)
         self.kernel_launches = l.pb_result_kernel_launches(self._rh)
