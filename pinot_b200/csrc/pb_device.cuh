@@ -535,7 +535,7 @@ struct __align__(16) FilterSmemHeader {
   int32_t flat_and;                          // program is AND(leaf, leaf, ...) (or a single leaf): no stack needed
   int32_t n_flat;
   int32_t flat_leaf[PB_MAX_LEAVES];
-  uint8_t seg[PB_SEG_FILTER_BYTES];          // the filter part of the current DevSegQuery
+  alignas(16) uint8_t seg[PB_SEG_FILTER_BYTES];   // the filter part of the current DevSegQuery
 };
 
 __global__ void __launch_bounds__(PB_NTHREADS, 4) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
