@@ -190,11 +190,6 @@ def workload_config(args, segs):
             "parallelism": f"segments sharded over {args.gpus} GPU(s); dense group tables all-reduced over NCCL" if args.gpus > 1 else "1 GPU"}
 
 
-class _DevBuf:
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -230,13 +225,8 @@ def main():
 
     if world > 1:
         # agree on the global dictionaries of the group-by columns (dense tables must line up across ranks)
-        for col in q.group_by:
-            mine = group.export_dictionary(col)
-            gathered = [None] * world
-            dist.all_gather_object(gathered, mine)
-            allv = np.concatenate(gathered, axis=0)
-            vals = np.unique(allv.view(np.int32).reshape(-1))
-            group.set_global_dictionary(col, vals.astype(np.int32).view(np.uint8).reshape(-1, 4))
+        from pinot_b200.distributed import agree_global_dictionaries, all_reduce_tables
+        agree_global_dictionaries(group, q.group_by, [int(segs[0].columns[c].data_type) for c in q.group_by], dist)
 
     def barrier():
         if world > 1:
@@ -250,21 +240,7 @@ def main():
         if world == 1:
             return native.execute(g, q, flags, prepared)
         r = native.execute(g, q, flags | native.PB_Q_DEFER_FINALIZE, prepared)
-        r.wait()
-        # fused reduce: counts + sums (SUM), min (MIN), max (MAX) — <= 4 small collectives over NVLink
-        ptr, n = r.device_buffer(0)
-        dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.SUM)
-        ptr, n = r.device_buffer(4)
-        dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.SUM)
-        for a, agg in enumerate(q.aggregations):
-            if agg.op in (AggOp.SUM, AggOp.AVG):
-                ptr, n = r.device_buffer(1, a)
-                dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<f8"), device="cuda"), op=dist.ReduceOp.SUM)
-            elif agg.op in (AggOp.MIN, AggOp.MAX):
-                ptr, n = r.device_buffer(2, a)
-                # MAX tables hold the bit-complement of the encoded value, so both reduce with MIN
-                dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.MIN)
-        torch.cuda.synchronize()
+        all_reduce_tables(r, q, dist, torch)        # counts + sums (SUM), min/max (MIN): small collectives over NVLink
         if rank == 0:
             r.finalize()
         return r

@@ -165,6 +165,9 @@ int pb_segment_group_export_dictionary(pb_segment_group_handle g, const char* co
 int pb_segment_group_set_global_dictionary(pb_segment_group_handle g, const char* column, const void* values,
                                            int64_t num_values, int32_t entry_bytes);
 
+/* host view of segment `segment_index`'s local -> global dictId remap for `column` (length = local cardinality) */
+int pb_segment_group_remap(pb_segment_group_handle g, const char* column, int32_t segment_index, const int32_t** remap, int32_t* n);
+
 /* -------- execution: replaces GroupByOperator.getNextBlock / AggregationOperator.getNextBlock
  * (CTR/operator/query/GroupByOperator.java:101-140, AggregationOperator.java:64-80) for every segment of
  * the group in one call.  seg_queries[i] belongs to the i-th segment of the group. -------- */

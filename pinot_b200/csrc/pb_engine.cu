@@ -195,8 +195,8 @@ static int find_col(const pb_segment_s* s, const char* name) {
 }
 
 extern "C" int pb_segment_stage(const pb_segment_desc* d, int /*device_index*/, pb_segment_handle* out) {
-  int rc = ensure_init();
-  if (rc) return rc;
+  // registers the buffers and validates the layouts; columns are copied to HBM on first use by a query
+  // (or eagerly by pb_segment_prefetch), so planning-only callers never touch the device
   if (!d || !out || d->num_columns < 0 || d->num_docs < 0) return fail(PB_ERR_INVALID, "bad segment descriptor");
   std::unique_ptr<pb_segment_s> s(new pb_segment_s());
   s->name = d->segment_name ? d->segment_name : "";
@@ -327,7 +327,8 @@ struct GlobalDict {
   std::vector<std::vector<int32_t>> h_remap;   // per segment: local dictId -> global dictId
   std::vector<int32_t*> d_remap;
   uint8_t* d_values = nullptr;                 // device copy of `values`
-  bool external = false;                       // installed by pb_segment_group_set_global_dictionary
+  bool external = false;
+  bool uploaded = false;                       // remaps + values are on the device                       // installed by pb_segment_group_set_global_dictionary
 };
 
 struct pb_group_s {
@@ -400,12 +401,24 @@ static int build_union(pb_group_s* g, const char* column, GlobalDict& gd) {
   return PB_OK;
 }
 
-static int build_remaps(pb_group_s* g, const char* column, GlobalDict& gd) {
+static int upload_remaps(pb_group_s* g, GlobalDict& gd) {
+  if (gd.uploaded) return PB_OK;
   for (auto p : gd.d_remap) cudaFree(p);
   cudaFree(gd.d_values); gd.d_values = nullptr;
   CU(cudaMalloc((void**)&gd.d_values, gd.values.size() + 16));
   CU(cudaMemcpy(gd.d_values, gd.values.data(), gd.values.size(), cudaMemcpyHostToDevice));
   gd.d_remap.assign(g->segs.size(), nullptr);
+  for (size_t si = 0; si < g->segs.size(); si++) {
+    const auto& rm = gd.h_remap[si];
+    CU(cudaMalloc((void**)&gd.d_remap[si], sizeof(int32_t) * std::max<size_t>(rm.size(), 1)));
+    CU(cudaMemcpy(gd.d_remap[si], rm.data(), sizeof(int32_t) * rm.size(), cudaMemcpyHostToDevice));
+  }
+  gd.uploaded = true;
+  return PB_OK;
+}
+
+static int build_remaps(pb_group_s* g, const char* column, GlobalDict& gd) {
+  gd.uploaded = false;
   gd.h_remap.assign(g->segs.size(), {});
   std::vector<uint8_t> tmp((size_t)gd.entry_bytes);
   for (size_t si = 0; si < g->segs.size(); si++) {
@@ -422,8 +435,6 @@ static int build_remaps(pb_group_s* g, const char* column, GlobalDict& gd) {
         return fail(PB_ERR_INVALID, "global dictionary of %s misses a value of segment %s", column, s->name.c_str());
       rm[i] = (int32_t)pos;
     }
-    CU(cudaMalloc((void**)&gd.d_remap[si], sizeof(int32_t) * (size_t)c.card));
-    CU(cudaMemcpy(gd.d_remap[si], rm.data(), sizeof(int32_t) * (size_t)c.card, cudaMemcpyHostToDevice));
   }
   return PB_OK;
 }
@@ -437,11 +448,30 @@ static int get_global_dict(pb_group_s* g, const char* column, GlobalDict** out) 
     if (rc) return rc;
     it = g->dicts.emplace(column, std::move(gd)).first;
   }
-  if (it->second.d_remap.empty()) {
+  if (it->second.h_remap.empty()) {
     int rc = build_remaps(g, column, it->second);
     if (rc) return rc;
   }
+  int rc = upload_remaps(g, it->second);
+  if (rc) return rc;
   *out = &it->second;
+  return PB_OK;
+}
+
+// host view of a remap (tests / multi-process agreement checks)
+extern "C" int pb_segment_group_remap(pb_segment_group_handle g, const char* column, int32_t segment_index, const int32_t** remap, int32_t* n) {
+  if (!g || !column || !remap || !n) return fail(PB_ERR_INVALID, "bad arguments");
+  std::lock_guard<std::mutex> lk(g->mu);
+  auto it = g->dicts.find(column);
+  if (it == g->dicts.end()) {
+    GlobalDict gd;
+    int rc = build_union(g, column, gd);
+    if (rc) return rc;
+    it = g->dicts.emplace(column, std::move(gd)).first;
+  }
+  if (it->second.h_remap.empty()) { int rc = build_remaps(g, column, it->second); if (rc) return rc; }
+  if (segment_index < 0 || segment_index >= (int)it->second.h_remap.size()) return fail(PB_ERR_INVALID, "segment index");
+  *remap = it->second.h_remap[segment_index].data(); *n = (int32_t)it->second.h_remap[segment_index].size();
   return PB_OK;
 }
 

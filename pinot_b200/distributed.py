@@ -1,0 +1,60 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed): segments shard across ranks with no data-path
+collective; the only exchange step is the merge of the per-rank group tables — the device-side equivalent of
+GroupByCombineOperator's IndexedTable merge (CTR/operator/combine/GroupByCombineOperator.java:132-147).
+
+  1. agree_global_dictionaries: every rank exports the sorted union of its segments' dictionaries for each
+     group-by column, all-gathers them, and installs the union over all ranks, so dense tables line up.
+  2. all_reduce_tables: in-place NCCL all-reduce of the dense table arrays left on the device by
+     PB_Q_COMBINE | PB_Q_DEFER_FINALIZE (row counts + sums: SUM; min/max: MIN — MAX tables hold complements).
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import numpy as np
+
+from . import native
+from .query import AggOp, QueryContext
+
+
+def merge_sorted_dictionaries(blocks: Sequence[np.ndarray], stored_type: int) -> np.ndarray:
+    """blocks: [n_i, entry_bytes] uint8 arrays of native-endian entries -> sorted unique union (same layout)."""
+    eb = blocks[0].shape[1]
+    allv = np.concatenate([np.ascontiguousarray(b, dtype=np.uint8) for b in blocks], axis=0)
+    if stored_type == 4:          # STRING: fixed-width padded entries compare bytewise
+        keys = [bytes(r) for r in allv]
+        uniq = sorted(set(keys))
+        return np.frombuffer(b"".join(uniq), dtype=np.uint8).reshape(len(uniq), eb).copy()
+    dt = {0: np.int32, 1: np.int64, 2: np.float32, 3: np.float64}[stored_type]
+    vals = np.unique(allv.reshape(-1).view(dt))
+    return vals.astype(dt).view(np.uint8).reshape(-1, eb).copy()
+
+
+def agree_global_dictionaries(group: native.SegmentGroup, columns: Sequence[str], stored_types: Sequence[int], dist) -> None:
+    for col, ty in zip(columns, stored_types):
+        mine = group.export_dictionary(col)
+        gathered = [None] * dist.get_world_size()
+        dist.all_gather_object(gathered, mine)
+        group.set_global_dictionary(col, merge_sorted_dictionaries(gathered, ty))
+
+
+class _DevBuf:
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def all_reduce_tables(result: native.Result, q: QueryContext, dist, torch) -> None:
+    """NCCL all-reduce of a deferred, combined, dense result's device tables (in place)."""
+    result.wait()
+    ptr, n = result.device_buffer(0)                    # rows per group
+    dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.SUM)
+    ptr, n = result.device_buffer(4)                    # counters (numDocsScanned)
+    dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.SUM)
+    for a, agg in enumerate(q.aggregations):
+        if agg.op in (AggOp.SUM, AggOp.AVG):
+            ptr, n = result.device_buffer(1, a)
+            dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<f8"), device="cuda"), op=dist.ReduceOp.SUM)
+        elif agg.op in (AggOp.MIN, AggOp.MAX):
+            ptr, n = result.device_buffer(2, a)
+            dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.MIN)
+    torch.cuda.synchronize()

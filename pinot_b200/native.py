@@ -90,6 +90,7 @@ def lib():
     l.pb_segment_group_export_dictionary.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p),
                                                      C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     l.pb_segment_group_set_global_dictionary.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]
+    l.pb_segment_group_remap.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int32)]
     l.pbh_execute.argtypes = [C.c_void_p, C.POINTER(PbhQueryContext), C.c_uint32, C.POINTER(C.c_void_p)]
     l.pbh_is_eligible.argtypes = [C.c_void_p, C.POINTER(PbhQueryContext)]
     l.pbh_explain_filter.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PbhQueryContext), C.c_char_p, C.c_int32]
@@ -214,6 +215,11 @@ class SegmentGroup:
     def set_global_dictionary(self, column: str, entries: np.ndarray):
         e = np.ascontiguousarray(entries, dtype=np.uint8)
         _check(lib().pb_segment_group_set_global_dictionary(self.handle, column.encode(), e.ctypes.data, e.shape[0], e.shape[1]))
+
+    def remap(self, column: str, segment_index: int) -> np.ndarray:
+        p, n = C.POINTER(C.c_int32)(), C.c_int32()
+        _check(lib().pb_segment_group_remap(self.handle, column.encode(), segment_index, C.byref(p), C.byref(n)))
+        return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
 
     def release(self):
         if self.handle:

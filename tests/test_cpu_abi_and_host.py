@@ -1,0 +1,97 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the headers declare; the host planning layer
+(FilterPlanNode / PredicateEvaluator / FilterOperatorUtils restatement) lowers filters as the reference does.  No
+compute call is made here (there is no GPU)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pinot_b200 import datagen, native
+from pinot_b200.query import parse_sql
+from tests.fixtures import FILTER, sv_segment
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(pbh?_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = native.lib()
+    names = _declared("pinot_b200.h") + _declared("pinot_b200_host.h")
+    assert len(names) > 35
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"symbols declared in include/*.h but not exported: {missing}"
+
+
+def test_errors_are_reported_not_fatal():
+    lib = native.lib()
+    assert lib.pb_result_num_tables(None) == 0
+    assert lib.pb_segment_release(None) == 0
+    assert native.PinotB200Error(-2, "x").code == -2
+
+
+@pytest.fixture(scope="module")
+def sv_group():
+    seg = sv_segment()
+    st = native.StagedSegment(seg)       # registers buffers only: no device needed for planning
+    g = native.SegmentGroup([st])
+    yield seg, g
+    g.release()
+
+
+def test_filter_plan_matches_reference_operator_selection(sv_group):
+    """BaseSingleValueQueriesTest FILTER: column5='gFuH' matches all (cardinality 1) and is dropped; daysSinceEpoch is
+    sorted -> sorted index; column11 NOT IN uses the inverted index; column1/column3/column6 ranges scan; AND children
+    ordered sorted < OR < scans (FilterOperatorUtils.java:205-252)."""
+    seg, g = sv_group
+    q = parse_sql("SELECT COUNT(*) FROM testTable" + FILTER)
+    plan = native.explain_filter(g, q).splitlines()
+    assert plan[0] == "FILTER_AND"
+    kinds = [ln.strip().split("(")[0] for ln in plan[1:]]
+    assert kinds == ["FILTER_SORTED_INDEX", "FILTER_OR", "FILTER_FULL_SCAN", "FILTER_INVERTED_INDEX", "FILTER_FULL_SCAN", "FILTER_FULL_SCAN"]
+    assert "column6 RANGE" in plan[3] and "column11 NOT_IN" in plan[4]
+    assert "column1 RANGE" in plan[5] and "column3 RANGE" in plan[6]
+    assert native.is_eligible(g, q)
+
+
+def test_predicate_lowering_edge_cases(sv_group):
+    seg, g = sv_group
+    # value absent from the dictionary: EQ -> empty, NOT_EQ -> match all
+    assert native.explain_filter(g, parse_sql("SELECT COUNT(*) FROM t WHERE column1 = 1")).strip() == "FILTER_EMPTY"
+    assert native.explain_filter(g, parse_sql("SELECT COUNT(*) FROM t WHERE column1 <> 1")).strip() == "FILTER_MATCH_ENTIRE_SEGMENT"
+    # range covering the whole dictionary -> match all; AND with an empty child -> empty; OR with match-all -> match all
+    assert native.explain_filter(g, parse_sql("SELECT COUNT(*) FROM t WHERE column1 > 0")).strip() == "FILTER_MATCH_ENTIRE_SEGMENT"
+    assert native.explain_filter(g, parse_sql("SELECT COUNT(*) FROM t WHERE column1 = 1 AND column3 > 5")).strip() == "FILTER_EMPTY"
+    assert native.explain_filter(g, parse_sql("SELECT COUNT(*) FROM t WHERE column1 > 0 OR column3 = 5")).strip() == "FILTER_MATCH_ENTIRE_SEGMENT"
+    # NOT of an inverted-index leaf keeps the index; skipIndexes forces a scan
+    assert "FILTER_INVERTED_INDEX" in native.explain_filter(g, parse_sql("SELECT COUNT(*) FROM t WHERE NOT column7 = 296467636"))
+    assert "FILTER_FULL_SCAN" in native.explain_filter(g, parse_sql("SET skipIndexes='column7=inverted'; SELECT COUNT(*) FROM t WHERE column7 = 296467636"))
+    # dictId range of a sorted-dictionary RANGE equals numpy's searchsorted on the dictionary
+    d = seg.columns["column3"].dictionary_values()
+    txt = native.explain_filter(g, parse_sql("SELECT COUNT(*) FROM t WHERE column3 BETWEEN 20000000 AND 1000000000"))
+    lo, hi = int(np.searchsorted(d, 20000000, "left")), int(np.searchsorted(d, 1000000000, "right"))
+    assert f"dictIds[{lo},{hi})" in txt
+
+
+def test_ineligible_queries_decline(sv_group):
+    seg, g = sv_group
+    assert not native.is_eligible(g, parse_sql("SELECT SUM(column11) FROM t"))          # numeric aggregation on STRING
+    assert not native.is_eligible(g, parse_sql("SELECT COUNT(*) FROM t WHERE nosuch = 3"))
+
+
+def test_global_dictionary_remaps_on_host():
+    segs = [datagen.make_segment_synth(i, 5000, columns=["d1", "m0"], vary_dim_dictionaries=True) for i in range(3)]
+    staged = [native.StagedSegment(s) for s in segs]
+    g = native.SegmentGroup(staged)
+    union = g.export_dictionary("d1").view(np.int32).reshape(-1)
+    exp = np.unique(np.concatenate([s.columns["d1"].dictionary_values() for s in segs]))
+    assert (union == exp).all()
+    for i, s in enumerate(segs):
+        rm = g.remap("d1", i)
+        assert (union[rm] == s.columns["d1"].dictionary_values()).all()
+    g.release()
