@@ -538,7 +538,7 @@ struct __align__(16) FilterSmemHeader {
   alignas(16) uint8_t seg[PB_SEG_FILTER_BYTES];   // the filter part of the current DevSegQuery
 };
 
-__global__ void __launch_bounds__(PB_NTHREADS, 4) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
+__global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   FilterSmemHeader* H = reinterpret_cast<FilterSmemHeader*>(smem_raw);
   const DevQuery& Q = *Qp;
@@ -658,6 +658,8 @@ __global__ void __launch_bounds__(PB_NTHREADS, 4) pb_filter_kernel(const DevQuer
     const uint32_t rel0 = (uint32_t)(first - sq.chunk_begin);     // chunk index inside the segment
     const int n_scan = sq.n_scan;
     unsigned long long matched = 0;
+    uint32_t min_last_rel = 0xffffffffu;               // first chunk whose load must be clipped to the buffer end
+    for (int c = 0; c < n_scan; c++) min_last_rel = min(min_last_rel, H->slot_last_rel[c]);
 
     // producer side (lane 0 of each warp): load this warp's k-th chunk of the segment into its stage
     auto issue = [&](uint32_t k, uint32_t seq) {
@@ -665,9 +667,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, 4) pb_filter_kernel(const DevQuer
       const int st = (int)(seq % PB_NSTAGE);
       uint8_t* dst = my_stages + (size_t)st * Q.stage_bytes;
       uint64_t* bar = &H->full[warp][st];
-      bool clipped = false;
-      for (int c = 0; c < n_scan; c++) clipped |= rel >= H->slot_last_rel[c];
-      if (!clipped) {                                   // steady state: constant sizes
+      if (rel < min_last_rel) {                         // steady state: constant sizes
         pb_mbar_expect_tx(bar, H->n_scan_full_bytes);
         for (int c = 0; c < n_scan; c++) {
           const uint32_t stride = H->slot_stride[c];
@@ -748,15 +748,28 @@ __global__ void __launch_bounds__(PB_NTHREADS, 4) pb_filter_kernel(const DevQuer
 
       // ---- append the matching docIds (global doc numbering) to the match list ----
       const uint32_t cnt = (uint32_t)__popc(mask);
-      uint32_t incl = cnt;
+      const uint32_t mx = __reduce_max_sync(0xffffffffu, cnt);
+      uint32_t excl = 0, total = 0;
+      if (mx <= 4) {
+        // few matches per lane: exclusive prefix from ballots (no shuffle dependency chain)
+        const uint32_t lt = (1u << lane) - 1u;
+        for (uint32_t kk = 1; kk <= mx; kk++) {
+          const uint32_t b = __ballot_sync(0xffffffffu, cnt >= kk);
+          excl += __popc(b & lt);
+          total += __popc(b);
+        }
+      } else {
+        uint32_t incl = cnt;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-      const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        excl = incl - cnt;
+      }
       if (total) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)total);
         base = __shfl_sync(0xffffffffu, base, 0);
-        unsigned long long pos = base + incl - cnt;
+        unsigned long long pos = base + excl;
         const uint32_t gdoc0 = (uint32_t)(sq.doc_base + chunk_doc0) + 32u * (uint32_t)lane;
         while (mask) {
           const int bit = __ffs(mask) - 1;
