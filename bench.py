@@ -240,7 +240,7 @@ def main():
         if world == 1:
             return native.execute(g, q, flags, prepared)
         r = native.execute(g, q, flags | native.PB_Q_DEFER_FINALIZE, prepared)
-        all_reduce_tables(r, q, dist, torch)        # counts + sums (SUM), min/max (MIN): small collectives over NVLink
+        all_reduce_tables(r, q, dist, torch)        # 3 small collectives on the call's stream: no host sync in between
         if rank == 0:
             r.finalize()
         return r

@@ -212,6 +212,8 @@ void pb_result_free(pb_result_handle r);
  * which: 0 = row counts (int64, SUM); 1 = per-aggregation double sums (float64, SUM);
  *        2 = per-aggregation min/max in order-preserving int64 encoding (int64; reduce with MIN for both:
  *            MAX tables hold the bit-complement);
+ *        5 / 6 / 7 = the same data as three contiguous spans, one collective each: 5 = counters + row counts
+ *            (int64, SUM), 6 = all sums (float64, SUM; may be empty), 7 = all min/max tables (int64, MIN; may be empty);
  *        3 = per-aggregation distinct bitset words (int32; OR == MAX over 0/1 is NOT valid — all-gather + pb_or) -------- */
 int pb_result_device_buffer(pb_result_handle r, int32_t which, int32_t agg, void** device_ptr, int64_t* num_elements);
 int pb_result_finalize(pb_result_handle r);

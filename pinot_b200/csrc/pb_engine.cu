@@ -549,6 +549,10 @@ struct pb_result_s {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr, ev2 = nullptr, ev3 = nullptr;
   bool match_all = false;
   double filter_ms = 0, agg_ms = 0;
+  // contiguous spans of table 0 for the cross-GPU reduce: [counters .. row counts] int64 SUM, sums float64 SUM, min/max int64 MIN
+  unsigned long long* span_i64 = nullptr; int64_t span_i64_n = 0;
+  double* span_f64 = nullptr; int64_t span_f64_n = 0;
+  long long* span_mm = nullptr; int64_t span_mm_n = 0;
 };
 
 static void free_result(pb_result_s* r) {
@@ -780,14 +784,22 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       memset(&dt, 0, sizeof dt);
       dt.mode = table_mode; dt.capacity = tm.capacity;
       dt.rowcnt = reinterpret_cast<unsigned long long*>(d_zero + zo); zo += 8 * S;
+      if (t == 0) { r->span_i64 = r->d_counters; r->span_i64_n = (int64_t)((d_zero + zo - (uint8_t*)r->d_counters) / 8); }
+      // sums first (one contiguous float64 span for the cross-GPU reduce), then the distinct bitsets
+      if (t == 0) r->span_f64 = reinterpret_cast<double*>(d_zero + zo);
       for (int a = 0; a < nA; a++) {
         int op = q->aggregations[a].op;
         if (op == PB_AGG_SUM || op == PB_AGG_AVG) { dt.sum[a] = reinterpret_cast<double*>(d_zero + zo); zo += 8 * S; }
+      }
+      if (t == 0) r->span_f64_n = (int64_t)((d_zero + zo - (uint8_t*)r->span_f64) / 8);
+      for (int a = 0; a < nA; a++) {
+        int op = q->aggregations[a].op;
         if (op == PB_AGG_DISTINCTCOUNT) { dt.dc_bits[a] = reinterpret_cast<uint32_t*>(d_zero + zo); dt.dc_words[a] = dc_words[a]; zo += 4 * S * dc_words[a]; }
         if (op == PB_AGG_MIN || op == PB_AGG_MAX) {
           dt.mm[a] = d_mm + mo; mo += S;
         }
       }
+      if (t == 0) { r->span_mm = d_mm; r->span_mm_n = (int64_t)mo; }
       zo = (zo + 255) & ~(size_t)255;
       if (table_mode == T_HASH) { dt.hkeys = reinterpret_cast<unsigned long long*>(d_ff + fo); fo += 8 * S; }
       unsigned long long* cnt = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE;
@@ -1342,6 +1354,9 @@ extern "C" int pb_result_device_buffer(pb_result_handle r, int32_t which, int32_
     case 2: if (agg < 0 || agg >= r->n_aggs || !tm.dev.mm[agg]) break; *device_ptr = tm.dev.mm[agg]; *num_elements = S; return PB_OK;
     case 3: if (agg < 0 || agg >= r->n_aggs || !tm.dev.dc_bits[agg]) break; *device_ptr = tm.dev.dc_bits[agg]; *num_elements = S * (int64_t)tm.dev.dc_words[agg]; return PB_OK;
     case 4: *device_ptr = r->d_counters; *num_elements = PB_COUNTERS_PER_TABLE; return PB_OK;
+    case 5: *device_ptr = r->span_i64; *num_elements = r->span_i64_n; return PB_OK;
+    case 6: *device_ptr = r->span_f64; *num_elements = r->span_f64_n; return PB_OK;
+    case 7: *device_ptr = r->span_mm; *num_elements = r->span_mm_n; return PB_OK;
     default: break;
   }
   return fail(PB_ERR_INVALID, "no such device buffer (which=%d agg=%d)", which, agg);

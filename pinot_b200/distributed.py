@@ -44,17 +44,12 @@ class _DevBuf:
 
 
 def all_reduce_tables(result: native.Result, q: QueryContext, dist, torch) -> None:
-    """NCCL all-reduce of a deferred, combined, dense result's device tables (in place)."""
-    result.wait()
-    ptr, n = result.device_buffer(0)                    # rows per group
-    dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.SUM)
-    ptr, n = result.device_buffer(4)                    # counters (numDocsScanned)
-    dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.SUM)
-    for a, agg in enumerate(q.aggregations):
-        if agg.op in (AggOp.SUM, AggOp.AVG):
-            ptr, n = result.device_buffer(1, a)
-            dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<f8"), device="cuda"), op=dist.ReduceOp.SUM)
-        elif agg.op in (AggOp.MIN, AggOp.MAX):
-            ptr, n = result.device_buffer(2, a)
-            dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, "<i8"), device="cuda"), op=dist.ReduceOp.MIN)
-    torch.cuda.synchronize()
+    """NCCL all-reduce of a deferred, combined, dense result's device tables, in place, enqueued on the result's own
+    CUDA stream (so it runs after the kernels and before pb_result_finalize without any host synchronisation).
+    Three small collectives: counters + row counts (int64 SUM), sums (float64 SUM), min/max (int64 MIN)."""
+    ext = torch.cuda.ExternalStream(result.stream())
+    with torch.cuda.stream(ext):
+        for which, typestr, op in ((5, "<i8", dist.ReduceOp.SUM), (6, "<f8", dist.ReduceOp.SUM), (7, "<i8", dist.ReduceOp.MIN)):
+            ptr, n = result.device_buffer(which)
+            if n > 0 and ptr:
+                dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, typestr), device="cuda"), op=op)
