@@ -204,6 +204,7 @@ def main():
     from pinot_b200 import datagen, native
     from pinot_b200.query import AggOp, parse_sql
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep NCCL's banner off stdout (one JSON line only)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -255,6 +256,9 @@ def main():
     sampler.start()
     time.sleep(0.05)
     scan_ms, device_ms, launches, host_us, filt_ms, agg_ms, step_wall = [], [], 0, [], [], [], []
+    import gc
+    gc.collect()
+    gc.disable()          # no cyclic-GC pauses inside the timed region (re-enabled right after)
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -277,6 +281,7 @@ def main():
     torch.cuda.synchronize()
     barrier()
     elapsed = time.perf_counter() - t0
+    gc.enable()
     clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
@@ -386,7 +391,8 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "device_ms_per_step": float(np.mean(device_ms)) if device_ms else None,
             "scan_kernel_ms": scan_mean, "filter_kernel_ms": f_mean, "agg_kernel_ms": a_mean,
-            "step_wall_ms": {"min": float(np.min(step_wall)), "median": float(np.median(step_wall)), "max": float(np.max(step_wall))}, "host_us_by_phase": [round(float(x), 1) for x in np.mean(np.array(host_us), axis=0)] if host_us else None, "num_groups": int(num_groups), "docs_matched": int(docs_matched),
+            "step_wall_ms": {"min": float(np.min(step_wall)), "median": float(np.median(step_wall)), "max": float(np.max(step_wall)),
+                             "all": [round(float(x), 3) for x in step_wall]}, "host_us_by_phase": [round(float(x), 1) for x in np.mean(np.array(host_us), axis=0)] if host_us else None, "num_groups": int(num_groups), "docs_matched": int(docs_matched),
             "kernel_variant": {0: "tma+width-specialised", 4: "tma+generic", 8: "ldg+width-specialised", 12: "ldg+generic"}.get(args.flags & 12)}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -795,7 +795,8 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
 // ------------------------------------------------------------------------------------------------
 #define PB_AGG_MAX_SEGS_SMEM 1024
 
-__global__ void __launch_bounds__(PB_NTHREADS, 4) pb_agg_kernel(const DevQuery* __restrict__ Qp) {
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_agg_kernel(const DevQuery* __restrict__ Qp) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const DevQuery& Q = *Qp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -1070,7 +1070,8 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       std::lock_guard<std::mutex> lk(g_ctx.mu);
       if (!g_ctx.smem_attr_set) {
         CU(cudaFuncSetAttribute(pb_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CU(cudaFuncSetAttribute(pb_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CU(cudaFuncSetAttribute(pb_agg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CU(cudaFuncSetAttribute(pb_agg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         g_ctx.smem_attr_set = true;
       }
     }
@@ -1091,17 +1092,22 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       std::lock_guard<std::mutex> lk(g_ctx.mu);
       if (!g_ctx.smem_attr_set) {
         CU(cudaFuncSetAttribute(pb_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CU(cudaFuncSetAttribute(pb_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CU(cudaFuncSetAttribute(pb_agg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CU(cudaFuncSetAttribute(pb_agg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         g_ctx.smem_attr_set = true;
       }
     }
     size_t smem2 = table_mode == T_KEYLESS ? 2 * sizeof(double) * (size_t)nA * PB_NTHREADS : 0;
+    // more resident threads = more gathers in flight (the kernel is DRAM-latency bound); 6 CTAs/SM costs a 4-byte spill
+    static const int agg_occ = []() { const char* e = getenv("PB_AGG_OCC"); int v = e ? atoi(e) : 6; return v == 4 ? 4 : 6; }();
     int occ2 = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pb_agg_kernel, PB_NTHREADS, smem2));
+    if (agg_occ == 4) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pb_agg_kernel<4>, PB_NTHREADS, smem2));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pb_agg_kernel<6>, PB_NTHREADS, smem2));
     if (occ2 < 1) return fail(PB_ERR_CUDA, "aggregation kernel does not fit an SM");
     uint64_t max2 = (uint64_t)g_ctx.num_sms * (uint64_t)occ2;
     int grid2 = (int)std::min<uint64_t>(std::max<uint64_t>((n_docs_total + PB_NTHREADS - 1) / PB_NTHREADS, 1), max2);
-    pb_agg_kernel<<<grid2, PB_NTHREADS, smem2, st>>>(dq);
+    if (agg_occ == 4) pb_agg_kernel<4><<<grid2, PB_NTHREADS, smem2, st>>>(dq);
+    else pb_agg_kernel<6><<<grid2, PB_NTHREADS, smem2, st>>>(dq);
     r->launches++;
     CU(cudaGetLastError());
   }

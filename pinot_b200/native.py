@@ -330,13 +330,21 @@ class Result:
     def __init__(self, rh, q: QueryContext, deferred: bool = False):
         self._rh = rh
         self.query = q
-        self.tables: List[ResultTable] = []
+        self._finalized = not deferred
         if not deferred:
             self._load()
 
+    @property
+    def tables(self) -> List[ResultTable]:
+        """Built on access and not cached: a table keeps its Result alive (its arrays are views of the Result's pinned
+        memory) but the Result does not reference its tables, so no reference cycle is left for the GC."""
+        if not self._finalized:
+            return []
+        return [ResultTable(self._rh, t, self.query, self) for t in range(lib().pb_result_num_tables(self._rh))]
+
     def _load(self):
         l = lib()
-        self.tables = [ResultTable(self._rh, t, self.query, self) for t in range(l.pb_result_num_tables(self._rh))]
+        self._finalized = True
         self.device_ms = l.pb_result_device_ms(self._rh)
         self.scan_kernel_ms = l.pb_result_scan_kernel_ms(self._rh)
         self.kernel_launches = l.pb_result_kernel_launches(self._rh)
