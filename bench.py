@@ -68,6 +68,11 @@ class ClockSampler:
         self.t = None
         self.err = None
 
+    def mark(self):
+        """samples taken before this call (warm-up) are dropped"""
+        self.sm = []
+        self.reasons = set()
+
     def start(self):
         try:
             import pynvml
@@ -246,21 +251,21 @@ def main():
             r.finalize()
         return r
 
-    # ---- warm-up ----
+    # ---- warm-up (the clock sampler and GC state are set up before it so nothing new starts inside the timed region) ----
+    import gc
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    gc.collect()
+    gc.disable()          # no cyclic-GC pauses inside the timed region (re-enabled right after)
     for _ in range(max(args.warmup, 3)):
         r = step()
         r.free()
 
     # ---- timed: K steps, barrier + synchronize on both sides, max over ranks ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.05)
     scan_ms, device_ms, launches, host_us, filt_ms, agg_ms, step_wall = [], [], 0, [], [], [], []
-    import gc
-    gc.collect()
-    gc.disable()          # no cyclic-GC pauses inside the timed region (re-enabled right after)
     barrier()
     torch.cuda.synchronize()
+    sampler.mark()
     t0 = time.perf_counter()
     last = None
     for _ in range(args.steps):

@@ -88,8 +88,8 @@ struct DevSegQuery {
   int32_t n_nodes;
   int32_t n_scan;
   int32_t table;           // result table index
-  uint64_t chunk_begin;    // global index of this segment's first 1024-doc chunk
-  uint64_t n_chunks;       // ceil(num_docs / 1024)
+  uint64_t unit_begin;     // global index of this segment's first work unit (U x 1024 docs)
+  uint64_t n_units;        // ceil(num_docs / (U * 1024))
   uint64_t doc_base;       // global doc number of this segment's doc 0 (match list numbering)
   int8_t node_kind[PB_MAX_NODES];
   int8_t node_arg[PB_MAX_NODES];
@@ -129,7 +129,7 @@ struct DevQuery {
   int32_t set_cache_bytes;               // shared-memory bytes reserved for IN-set membership LUTs
   int32_t use_tma;
   int32_t generic;                       // 1 = width-generic predicate path only
-  uint64_t n_chunks;
+  uint64_t n_units;
   uint64_t n_docs_total;
   int32_t match_all;                     // no filter: pb_agg_kernel walks every doc, no match list
   int32_t pad_m;
@@ -329,23 +329,24 @@ __device__ __forceinline__ uint32_t pb_eval_dict_sparse(const uint32_t* __restri
 
 __device__ __forceinline__ bool pb_fast_width(int bits) { return bits < 32 && (bits & 7) != 0; }
 
+// evaluates nu (<= 2) consecutive 1024-doc chunks with one dispatch: out[u] = this lane's mask of sub-chunk u
 template <class Pred>
-__device__ __noinline__ uint32_t pb_eval_dict_fast(const uint32_t* __restrict__ p, int bits, const Pred& pred, int lane) {
+__device__ __noinline__ void pb_eval_dict_fast(const uint32_t* __restrict__ p, int bits, const Pred& pred, int lane, int nu, uint32_t* out) {
   switch (bits) {
-#define PB_CASE(W) case W: return pb_eval_dict_w<W, Pred>(p, pred, lane);
+#define PB_CASE(W) case W: for (int u = 0; u < nu; u++) out[u] = pb_eval_dict_w<W, Pred>(p + u * 32 * W, pred, lane); return;
     PB_CASE(1) PB_CASE(2) PB_CASE(3) PB_CASE(4) PB_CASE(5) PB_CASE(6) PB_CASE(7)
     PB_CASE(9) PB_CASE(10) PB_CASE(11) PB_CASE(12) PB_CASE(13) PB_CASE(14) PB_CASE(15)
     PB_CASE(17) PB_CASE(18) PB_CASE(19) PB_CASE(20) PB_CASE(21) PB_CASE(22) PB_CASE(23)
     PB_CASE(25) PB_CASE(26) PB_CASE(27) PB_CASE(28) PB_CASE(29) PB_CASE(30) PB_CASE(31)
 #undef PB_CASE
-    default: return 0;
+    default: for (int u = 0; u < nu; u++) out[u] = 0; return;
   }
 }
 
 template <class Pred>
-__device__ __forceinline__ uint32_t pb_eval_dict(const uint32_t* __restrict__ p, int bits, const Pred& pred, int lane, bool generic) {
-  if (!generic && pb_fast_width(bits)) return pb_eval_dict_fast<Pred>(p, bits, pred, lane);
-  return pb_eval_dict_generic<Pred>(p, bits, pred, lane);
+__device__ __forceinline__ void pb_eval_dict(const uint32_t* __restrict__ p, int bits, const Pred& pred, int lane, bool generic, int nu, uint32_t* out) {
+  if (!generic && pb_fast_width(bits)) { pb_eval_dict_fast<Pred>(p, bits, pred, lane, nu, out); return; }
+  for (int u = 0; u < nu; u++) out[u] = pb_eval_dict_generic<Pred>(p + u * 32 * bits, bits, pred, lane);
 }
 
 // raw fixed-width column chunk in smem (big-endian values), lane <-> doc + ballot
@@ -529,16 +530,18 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) FilterSmemHeader {
   uint64_t full[PB_NWARPS][PB_NSTAGE];
-  uint32_t slot_stride[PB_MAX_SCAN_SLOTS];   // bytes of one chunk of the slot (128 * bits)
-  uint32_t slot_last_rel[PB_MAX_SCAN_SLOTS]; // first chunk index whose load must be clipped to the buffer end
-  uint32_t n_scan_full_bytes;                // expect_tx total of an unclipped chunk
+  uint32_t slot_stride[PB_MAX_SCAN_SLOTS];   // bytes of one work unit of the slot (U * 128 * bits)
+  uint32_t slot_last_rel[PB_MAX_SCAN_SLOTS]; // first unit index whose load must be clipped to the buffer end
+  uint32_t n_scan_full_bytes;                // expect_tx total of an unclipped unit
   int32_t flat_and;                          // program is AND(leaf, leaf, ...) (or a single leaf): no stack needed
   int32_t n_flat;
   int32_t flat_leaf[PB_MAX_LEAVES];
   alignas(16) uint8_t seg[PB_SEG_FILTER_BYTES];   // the filter part of the current DevSegQuery
 };
 
-__global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
+// U = 1024-doc chunks per work unit (one TMA load + one dispatch per predicate leaf per unit)
+template <int U>
+__global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   FilterSmemHeader* H = reinterpret_cast<FilterSmemHeader*>(smem_raw);
   const DevQuery& Q = *Qp;
@@ -548,61 +551,69 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
   dyn += (Q.set_cache_bytes + 127) & ~127;
   uint8_t* my_stages = dyn + (size_t)warp * PB_NSTAGE * Q.stage_bytes;
   const bool staged = Q.stage_bytes > 0;
+  constexpr uint32_t UNIT_DOCS = U * PB_CHUNK_DOCS;
 
   if (lane == 0)
     for (int s = 0; s < PB_NSTAGE; s++) pb_mbar_init(&H->full[warp][s], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
 
-  // this CTA's contiguous chunk range
-  const uint64_t per = (Q.n_chunks + gridDim.x - 1) / gridDim.x;
+  // this CTA's contiguous range of work units
+  const uint64_t per = (Q.n_units + gridDim.x - 1) / gridDim.x;
   const uint64_t cta_lo = (uint64_t)blockIdx.x * per;
-  const uint64_t cta_hi = cta_lo + per < Q.n_chunks ? cta_lo + per : Q.n_chunks;
+  const uint64_t cta_hi = cta_lo + per < Q.n_units ? cta_lo + per : Q.n_units;
   if (cta_lo >= cta_hi) return;
   int seg_first = 0;
-  while (seg_first + 1 < Q.n_segs && cta_lo >= Q.segs[seg_first + 1].chunk_begin) seg_first++;
+  while (seg_first + 1 < Q.n_segs && cta_lo >= Q.segs[seg_first + 1].unit_begin) seg_first++;
 
-  uint32_t consumed = 0;   // chunks this warp has consumed so far: stage = consumed % NSTAGE, parity from consumed / NSTAGE
+  uint32_t consumed = 0;   // units this warp has consumed so far: stage = consumed % NSTAGE, parity from consumed / NSTAGE
   const DevSegQuery& sq = *reinterpret_cast<const DevSegQuery*>(H->seg);   // only the filter part is valid
 
-  // evaluate one filter leaf on the staged chunk; returns this lane's 32-doc mask.  `restrict_to` != 0xffffffff
-  // with sparse == true means only those docs matter (AND chain with few survivors): decode just them.
-  auto eval_leaf = [&](const DevLeaf& lf, const uint8_t* stage, uint64_t chunk_doc0, uint32_t restrict_to, bool sparse) -> uint32_t {
+  // evaluate one filter leaf on the staged unit: m[u] = this lane's 32-doc mask of sub-chunk u.  With sparse == true only
+  // the docs still set in restrict_to[u] matter (AND chain with few survivors): decode just them.
+  auto eval_leaf = [&](const DevLeaf& lf, const uint8_t* stage, uint64_t unit_doc0, int nu, const uint32_t* restrict_to, bool sparse, uint32_t* m) {
     switch (lf.kind) {
-      case L_TRUE: return 0xffffffffu;
-      case L_FALSE: return 0u;
+      case L_TRUE: for (int u = 0; u < nu; u++) m[u] = 0xffffffffu; return;
+      case L_FALSE: for (int u = 0; u < nu; u++) m[u] = 0u; return;
       case L_DICT_RANGE: {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
         PredRange pr; pr.lo = lf.lo; pr.span = lf.span;
-        if (sparse) return pb_eval_dict_sparse<PredRange>(p, lf.bits, pr, lane, restrict_to);
-        return pb_eval_dict<PredRange>(p, lf.bits, pr, lane, Q.generic);
+        if (sparse) { for (int u = 0; u < nu; u++) m[u] = pb_eval_dict_sparse<PredRange>(p + u * 32 * lf.bits, lf.bits, pr, lane, restrict_to[u]); return; }
+        pb_eval_dict<PredRange>(p, lf.bits, pr, lane, Q.generic, nu, m);
+        return;
       }
       case L_DICT_SET: {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
         if (lf.set_smem_off >= 0) {
           PredLut8 pl; pl.lut = set_cache + lf.set_smem_off;
-          if (sparse) return pb_eval_dict_sparse<PredLut8>(p, lf.bits, pl, lane, restrict_to);
-          return pb_eval_dict<PredLut8>(p, lf.bits, pl, lane, Q.generic);
+          if (sparse) { for (int u = 0; u < nu; u++) m[u] = pb_eval_dict_sparse<PredLut8>(p + u * 32 * lf.bits, lf.bits, pl, lane, restrict_to[u]); return; }
+          pb_eval_dict<PredLut8>(p, lf.bits, pl, lane, Q.generic, nu, m);
+          return;
         }
         PredBits pb; pb.bits = lf.set_bits; pb.excl = (uint32_t)lf.exclusive;
-        if (sparse) return pb_eval_dict_sparse<PredBits>(p, lf.bits, pb, lane, restrict_to);
-        return pb_eval_dict<PredBits>(p, lf.bits, pb, lane, Q.generic);
+        if (sparse) { for (int u = 0; u < nu; u++) m[u] = pb_eval_dict_sparse<PredBits>(p + u * 32 * lf.bits, lf.bits, pb, lane, restrict_to[u]); return; }
+        pb_eval_dict<PredBits>(p, lf.bits, pb, lane, Q.generic, nu, m);
+        return;
       }
       case L_RAW_RANGE_I:
       case L_RAW_RANGE_F:
       case L_RAW_SET: {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
-        return pb_eval_raw(p, lf, lane);
+        for (int u = 0; u < nu; u++) m[u] = pb_eval_raw(p + u * (PB_CHUNK_DOCS / 4) * lf.raw_width, lf, lane);
+        return;
       }
-      default: {   // L_BITMAP (padded to whole chunks)
-        uint32_t m = __ldg(lf.bitmap + (chunk_doc0 >> 5) + lane);
-        return lf.exclusive ? ~m : m;
+      default: {   // L_BITMAP (padded to whole units)
+        for (int u = 0; u < nu; u++) {
+          uint32_t w = __ldg(lf.bitmap + (unit_doc0 >> 5) + u * 32 + lane);
+          m[u] = lf.exclusive ? ~w : w;
+        }
+        return;
       }
     }
   };
 
   for (int sgi = seg_first; sgi < Q.n_segs; sgi++) {
-    if (Q.segs[sgi].chunk_begin >= cta_hi) break;
+    if (Q.segs[sgi].unit_begin >= cta_hi) break;
     // ---- segment entry: filter descriptor, derived constants and LUTs into shared memory ----
     __syncthreads();   // everyone has left the previous segment
     {
@@ -611,15 +622,15 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
       for (int i = tid; i < (int)(PB_SEG_FILTER_BYTES / 4); i += PB_NTHREADS) dst[i] = src[i];
       __syncthreads();
       if (tid < sq.n_scan) {
-        const uint32_t stride = (uint32_t)(PB_CHUNK_DOCS / 8) * (uint32_t)sq.scan[tid].bits_per_doc;
+        const uint32_t stride = (uint32_t)(UNIT_DOCS / 8) * (uint32_t)sq.scan[tid].bits_per_doc;
         H->slot_stride[tid] = stride;
-        // chunks rel < last_rel can load stride + 16 bytes without leaving the (16-byte padded) buffer
+        // units rel < last_rel can load stride + 16 bytes without leaving the (16-byte padded) buffer
         const uint64_t total = sq.scan[tid].bytes_total;
         H->slot_last_rel[tid] = total >= (uint64_t)stride + 16 ? (uint32_t)((total - stride - 16) / stride) + 1 : 0u;
       }
       if (tid == 96) {
         uint32_t t = 0;
-        for (int c = 0; c < sq.n_scan; c++) t += (uint32_t)(PB_CHUNK_DOCS / 8) * (uint32_t)sq.scan[c].bits_per_doc + 16;
+        for (int c = 0; c < sq.n_scan; c++) t += (uint32_t)(UNIT_DOCS / 8) * (uint32_t)sq.scan[c].bits_per_doc + 16;
         H->n_scan_full_bytes = t;
       }
       if (tid == 64) {
@@ -649,19 +660,19 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
       }
       __syncthreads();
     }
-    const uint64_t seg_lo = sq.chunk_begin > cta_lo ? sq.chunk_begin : cta_lo;
-    const uint64_t seg_end = sq.chunk_begin + sq.n_chunks;
+    const uint64_t seg_lo = sq.unit_begin > cta_lo ? sq.unit_begin : cta_lo;
+    const uint64_t seg_end = sq.unit_begin + sq.n_units;
     const uint64_t seg_hi = seg_end < cta_hi ? seg_end : cta_hi;
-    // this warp's chunks in this segment: seg_lo + warp, + NWARPS, ...
+    // this warp's units in this segment: seg_lo + warp, + NWARPS, ...
     const uint64_t first = seg_lo + warp;
     const uint32_t n_mine = first < seg_hi ? (uint32_t)((seg_hi - first + PB_NWARPS - 1) / PB_NWARPS) : 0u;
-    const uint32_t rel0 = (uint32_t)(first - sq.chunk_begin);     // chunk index inside the segment
+    const uint32_t rel0 = (uint32_t)(first - sq.unit_begin);     // unit index inside the segment
     const int n_scan = sq.n_scan;
     unsigned long long matched = 0;
-    uint32_t min_last_rel = 0xffffffffu;               // first chunk whose load must be clipped to the buffer end
+    uint32_t min_last_rel = 0xffffffffu;               // first unit whose load must be clipped to the buffer end
     for (int c = 0; c < n_scan; c++) min_last_rel = min(min_last_rel, H->slot_last_rel[c]);
 
-    // producer side (lane 0 of each warp): load this warp's k-th chunk of the segment into its stage
+    // producer side (lane 0 of each warp): load this warp's k-th unit of the segment into its stage
     auto issue = [&](uint32_t k, uint32_t seq) {
       const uint32_t rel = rel0 + k * PB_NWARPS;
       const int st = (int)(seq % PB_NSTAGE);
@@ -678,8 +689,8 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
       uint32_t total = 0;
       uint32_t nbytes[PB_MAX_SCAN_SLOTS];
       for (int c = 0; c < n_scan; c++) {
-        const uint64_t off = (uint64_t)rel * H->slot_stride[c];                   // chunk starts are 128-byte multiples
-        const uint64_t want = (uint64_t)H->slot_stride[c] + 16;                   // +16: the word after the chunk
+        const uint64_t off = (uint64_t)rel * H->slot_stride[c];                   // unit starts are 128-byte multiples
+        const uint64_t want = (uint64_t)H->slot_stride[c] + 16;                   // +16: the word after the unit
         const uint64_t avail = sq.scan[c].bytes_total - off;
         nbytes[c] = (uint32_t)((want < avail ? want : avail) & ~(uint64_t)15);
         total += nbytes[c];
@@ -693,7 +704,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
       for (uint32_t k = 0; k < PB_NSTAGE - 1 && k < n_mine; k++) issue(k, consumed + k);
 
     for (uint32_t k = 0; k < n_mine; k++) {
-      const uint64_t chunk_doc0 = (uint64_t)(rel0 + k * PB_NWARPS) * PB_CHUNK_DOCS;
+      const uint64_t unit_doc0 = (uint64_t)(rel0 + k * PB_NWARPS) * UNIT_DOCS;
       const int st = (int)(consumed % PB_NSTAGE);
       uint8_t* stage = my_stages + (size_t)st * Q.stage_bytes;
       if (staged) {
@@ -716,38 +727,55 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
       }
       consumed++;
 
-      // ---- predicate tree on 32-doc masks ----
-      const long long remaining = (long long)sq.num_docs - (long long)(chunk_doc0 + 32ull * lane);
-      uint32_t mask = remaining >= 32 ? 0xffffffffu : (remaining <= 0 ? 0u : ((1u << remaining) - 1u));
+      // ---- predicate tree on 32-doc masks (one mask word per lane per sub-chunk) ----
+      uint32_t mask[U], tmp[U];
+      int nu = 0;
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const long long remaining = (long long)sq.num_docs - (long long)(unit_doc0 + (uint64_t)u * PB_CHUNK_DOCS + 32ull * lane);
+        mask[u] = remaining >= 32 ? 0xffffffffu : (remaining <= 0 ? 0u : ((1u << remaining) - 1u));
+        if ((long long)sq.num_docs > (long long)(unit_doc0 + (uint64_t)u * PB_CHUNK_DOCS)) nu = u + 1;
+      }
       if (H->flat_and) {
         const int nl = H->n_flat;
         for (int i = 0; i < nl; i++) {
-          // few survivors in the whole chunk -> restricted scan of the remaining leaves (leaves arrive ordered by
+          // few survivors in the whole unit -> restricted scan of the remaining leaves (leaves arrive ordered by
           // estimated selectivity from the host)
-          const bool sparse = i > 0 && !Q.generic && __reduce_add_sync(0xffffffffu, (uint32_t)__popc(mask)) <= PB_SPARSE_MAX;
-          mask &= eval_leaf(sq.leaves[H->flat_leaf[i]], stage, chunk_doc0, mask, sparse);
-          if (sparse && !__any_sync(0xffffffffu, mask != 0)) break;
+          uint32_t pc = 0;
+#pragma unroll
+          for (int u = 0; u < U; u++) pc += (uint32_t)__popc(mask[u]);
+          const bool sparse = i > 0 && !Q.generic && __reduce_add_sync(0xffffffffu, pc) <= PB_SPARSE_MAX * U;
+          eval_leaf(sq.leaves[H->flat_leaf[i]], stage, unit_doc0, nu, mask, sparse, tmp);
+          uint32_t any = 0;
+#pragma unroll
+          for (int u = 0; u < U; u++) { if (u < nu) mask[u] &= tmp[u]; any |= mask[u]; }
+          if (sparse && !__any_sync(0xffffffffu, any != 0)) break;
         }
       } else {
-        uint32_t stack[PB_MAX_LEAVES];
+        uint32_t stack[PB_MAX_LEAVES][U];
+        const uint32_t all[2] = {0xffffffffu, 0xffffffffu};
         int sp = 0;
         for (int n = 0; n < sq.n_nodes; n++) {
           const int kind = sq.node_kind[n], arg = sq.node_arg[n];
-          if (kind == N_LEAF) stack[sp++] = eval_leaf(sq.leaves[arg], stage, chunk_doc0, 0xffffffffu, false);
-          else if (kind == N_NOT) stack[sp - 1] = ~stack[sp - 1];
+          if (kind == N_LEAF) { eval_leaf(sq.leaves[arg], stage, unit_doc0, nu, all, false, stack[sp]); sp++; }
+          else if (kind == N_NOT) { for (int u = 0; u < nu; u++) stack[sp - 1][u] = ~stack[sp - 1][u]; }
           else {
-            uint32_t r = stack[sp - arg];
-            for (int i = 1; i < arg; i++) r = (kind == N_AND) ? (r & stack[sp - arg + i]) : (r | stack[sp - arg + i]);
-            sp -= arg;
-            stack[sp++] = r;
+            for (int u = 0; u < nu; u++) {
+              uint32_t r = stack[sp - arg][u];
+              for (int i = 1; i < arg; i++) r = (kind == N_AND) ? (r & stack[sp - arg + i][u]) : (r | stack[sp - arg + i][u]);
+              stack[sp - arg][u] = r;
+            }
+            sp -= arg - 1;
           }
         }
-        if (sp > 0) mask &= stack[0];
+        if (sp > 0) for (int u = 0; u < nu; u++) mask[u] &= stack[0][u];
       }
       __syncwarp();   // all lanes are done reading this stage before lane 0 may refill it next iteration
 
       // ---- append the matching docIds (global doc numbering) to the match list ----
-      const uint32_t cnt = (uint32_t)__popc(mask);
+      uint32_t cnt = 0;
+#pragma unroll
+      for (int u = 0; u < U; u++) cnt += (uint32_t)__popc(mask[u]);
       const uint32_t mx = __reduce_max_sync(0xffffffffu, cnt);
       uint32_t excl = 0, total = 0;
       if (mx <= 4) {
@@ -770,11 +798,15 @@ __global__ void __launch_bounds__(PB_NTHREADS, 3) pb_filter_kernel(const DevQuer
         if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)total);
         base = __shfl_sync(0xffffffffu, base, 0);
         unsigned long long pos = base + excl;
-        const uint32_t gdoc0 = (uint32_t)(sq.doc_base + chunk_doc0) + 32u * (uint32_t)lane;
-        while (mask) {
-          const int bit = __ffs(mask) - 1;
-          mask &= mask - 1;
-          Q.match_list[pos++] = gdoc0 + (uint32_t)bit;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const uint32_t gdoc0 = (uint32_t)(sq.doc_base + unit_doc0) + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
+          uint32_t mm = mask[u];
+          while (mm) {
+            const int bit = __ffs(mm) - 1;
+            mm &= mm - 1;
+            Q.match_list[pos++] = gdoc0 + (uint32_t)bit;
+          }
         }
         matched += total;
       }

@@ -825,7 +825,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       if (fn.kind == PB_F_INVERTED) arena_cap += 4 * (size_t)fn.num_ids + 32;
       if (fn.kind == PB_F_SORTED) arena_cap += 8 * (size_t)fn.num_ids + 32;
       if (fn.kind == PB_F_BITMAP) arena_cap += fn.blob_len + 64;
-      if (fn.kind == PB_F_INVERTED || fn.kind == PB_F_SORTED || fn.kind == PB_F_BITMAP) bitmap_words_total += (((size_t)s->num_docs + 1023) / 1024) * 32;
+      if (fn.kind == PB_F_INVERTED || fn.kind == PB_F_SORTED || fn.kind == PB_F_BITMAP) bitmap_words_total += (((size_t)s->num_docs + 2047) / 2048) * 64;
     }
   }
   Arena ar;
@@ -938,7 +938,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
           break;
         }
         case PB_F_INVERTED: case PB_F_SORTED: case PB_F_BITMAP: {
-          size_t words = (((size_t)s->num_docs + 1023) / 1024) * 32;
+          size_t words = (((size_t)s->num_docs + 2047) / 2048) * 64;
           uint32_t* bm = d_bitmaps + bm_off; bm_off += words;
           lf.kind = L_BITMAP; lf.bitmap = bm; lf.exclusive = fn.exclusive ? 1 : 0;
           if (fn.kind == PB_F_INVERTED) {
@@ -1004,24 +1004,33 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     }
   }
 
-  // ---- chunk geometry: one stage = one 1024-doc chunk of every scan slot, per warp ----
+  // ---- work-unit geometry: one stage = one unit (U x 1024 docs) of every scan slot, per warp ----
   int sum_bits = 0;
   for (int k = 0; k < n_slots_max; k++) sum_bits += slot_bits_max[k];
-  size_t stage_bytes = 0;
+  static const int unit_env = []() { const char* e = getenv("PB_UNIT"); return e ? atoi(e) : 2; }();
+  auto stage_bytes_for = [&](int U, int32_t* offs) {
+    size_t b = 0;
+    for (int k = 0; k < n_slots_max; k++) {
+      if (offs) offs[k] = (int32_t)b;
+      b += (((size_t)U * PB_CHUNK_DOCS * slot_bits_max[k] / 8 + 16) + 15) & ~(size_t)15;
+    }
+    return b;
+  };
+  // two chunks per unit halve the per-unit overhead (dispatch, TMA issue, list append) when two CTAs still fit an SM
+  int U = (unit_env == 1) ? 1 : 2;
+  if (U == 2 && stage_bytes_for(2, nullptr) * PB_NSTAGE * PB_NWARPS > 100 * 1024) U = 1;
   int32_t slot_offs[PB_MAX_SCAN_SLOTS] = {0};
-  for (int k = 0; k < n_slots_max; k++) {
-    slot_offs[k] = (int32_t)stage_bytes;
-    stage_bytes += (((size_t)PB_CHUNK_DOCS * slot_bits_max[k] / 8 + 16) + 15) & ~(size_t)15;
-  }
+  size_t stage_bytes = stage_bytes_for(U, slot_offs);
   if (stage_bytes * PB_NSTAGE * PB_NWARPS > 200 * 1024)
-    return fail(PB_ERR_UNSUPPORTED, "scan predicates touch %d bits per row: chunk stages do not fit shared memory", sum_bits);
+    return fail(PB_ERR_UNSUPPORTED, "scan predicates touch %d bits per row: unit stages do not fit shared memory", sum_bits);
+  const uint64_t unit_docs = (uint64_t)U * PB_CHUNK_DOCS;
   uint64_t n_chunks = 0, n_docs_total = 0;
   bool match_all = true;
   for (int si = 0; si < n_segs; si++) {
-    hsegs[si].chunk_begin = n_chunks;
-    hsegs[si].n_chunks = ((uint64_t)g->segs[si]->num_docs + PB_CHUNK_DOCS - 1) / PB_CHUNK_DOCS;
+    hsegs[si].unit_begin = n_chunks;
+    hsegs[si].n_units = ((uint64_t)g->segs[si]->num_docs + unit_docs - 1) / unit_docs;
     hsegs[si].doc_base = n_docs_total;
-    n_chunks += hsegs[si].n_chunks;
+    n_chunks += hsegs[si].n_units;
     n_docs_total += (uint64_t)g->segs[si]->num_docs;
     if (sqs[si].num_filter_nodes != 0) match_all = false;
   }
@@ -1041,7 +1050,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   hq->set_cache_bytes = set_cache_max;
   hq->use_tma = (q->flags & PB_Q_NO_TMA) ? 0 : 1;
   hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
-  hq->n_chunks = n_chunks; hq->segs = dsegs; hq->tables = dtabs;
+  hq->n_units = n_chunks; hq->segs = dsegs; hq->tables = dtabs;
   hq->n_docs_total = n_docs_total; hq->match_all = match_all ? 1 : 0;
   hq->match_list = d_match_list;
   hq->match_count = r->d_counters + (size_t)n_tables * PB_COUNTERS_PER_TABLE;   // one extra zeroed cell after the per-table counters
@@ -1069,19 +1078,22 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     {
       std::lock_guard<std::mutex> lk(g_ctx.mu);
       if (!g_ctx.smem_attr_set) {
-        CU(cudaFuncSetAttribute(pb_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(pb_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(pb_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CU(cudaFuncSetAttribute(pb_agg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         CU(cudaFuncSetAttribute(pb_agg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         g_ctx.smem_attr_set = true;
       }
     }
     int occ = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel, PB_NTHREADS, smem));
+    if (U == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<1>, PB_NTHREADS, smem));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<2>, PB_NTHREADS, smem));
     if (occ < 1) return fail(PB_ERR_CUDA, "filter kernel does not fit an SM (smem %zu)", smem);
     uint64_t max_ctas = (uint64_t)g_ctx.num_sms * (uint64_t)occ;
     // every CTA gets a contiguous range of chunks; keep at least one chunk per warp
     int grid = (int)std::min<uint64_t>(std::max<uint64_t>((n_chunks + PB_NWARPS - 1) / PB_NWARPS, 1), max_ctas);
-    pb_filter_kernel<<<grid, PB_NTHREADS, smem, st>>>(dq);
+    if (U == 1) pb_filter_kernel<1><<<grid, PB_NTHREADS, smem, st>>>(dq);
+    else pb_filter_kernel<2><<<grid, PB_NTHREADS, smem, st>>>(dq);
     r->launches++;
     CU(cudaGetLastError());
   }
@@ -1091,7 +1103,8 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     {
       std::lock_guard<std::mutex> lk(g_ctx.mu);
       if (!g_ctx.smem_attr_set) {
-        CU(cudaFuncSetAttribute(pb_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(pb_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        CU(cudaFuncSetAttribute(pb_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         CU(cudaFuncSetAttribute(pb_agg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         CU(cudaFuncSetAttribute(pb_agg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         g_ctx.smem_attr_set = true;
