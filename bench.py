@@ -268,8 +268,10 @@ def main():
     sampler.mark()
     t0 = time.perf_counter()
     last = None
-    for _ in range(args.steps):
+    for it in range(args.steps):
         ts = time.perf_counter()
+        if last is not None:
+            last.free()            # the operator frees a result before it runs the next query (same as the warm-up)
         r = step()
         step_wall.append(1000 * (time.perf_counter() - ts))
         scan_ms.append(r.scan_ms())
@@ -280,8 +282,6 @@ def main():
             launches += lib_launches(r)
             device_ms.append(getattr(r, "device_ms", 0.0))
             host_us.append(r.host_timing_us())
-        if last is not None:
-            last.free()
         last = r
     torch.cuda.synchronize()
     barrier()

@@ -132,7 +132,7 @@ struct DevQuery {
   uint64_t n_units;
   uint64_t n_docs_total;
   int32_t match_all;                     // no filter: pb_agg_kernel walks every doc, no match list
-  int32_t pad_m;
+  int32_t prefetch;                      // pb_filter_kernel prefetches the gather sectors of matching docs into L2
   uint32_t* match_list;                  // global doc numbers of the docs that pass the filter
   unsigned long long* match_count;
   const DevSegQuery* segs;
@@ -238,6 +238,20 @@ __device__ __forceinline__ uint32_t pb_mbar_try_wait(uint64_t* bar, uint32_t par
 __device__ __forceinline__ void pb_mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!pb_mbar_try_wait(bar, parity)) {}
 }
+// streaming variant: the scanned columns are read once, keep them from evicting the L2 lines prefetched for the
+// aggregation gathers
+__device__ __forceinline__ uint64_t pb_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void pb_tma_load_1d_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   pb_smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(pb_smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void pb_prefetch_l2_keep(const void* p) { asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p)); }
 __device__ __forceinline__ void pb_tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    pb_smem_u32(smem_dst)),
@@ -528,6 +542,13 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 // global match list (one atomicAdd per warp-chunk, ascending docIds inside a block).  The instruction stream is
 // short and identical for all warps, which keeps the instruction cache warm.
 // ------------------------------------------------------------------------------------------------
+#define PB_MAX_GATHER 16
+struct GatherCol {          // a column the aggregation kernel will gather from
+  const uint8_t* fwd;
+  int32_t bits;             // dictionary column: bits per element; raw: 0
+  int32_t width;            // raw column: bytes per value
+};
+
 struct __align__(16) FilterSmemHeader {
   uint64_t full[PB_NWARPS][PB_NSTAGE];
   uint32_t slot_stride[PB_MAX_SCAN_SLOTS];   // bytes of one work unit of the slot (U * 128 * bits)
@@ -536,6 +557,9 @@ struct __align__(16) FilterSmemHeader {
   int32_t flat_and;                          // program is AND(leaf, leaf, ...) (or a single leaf): no stack needed
   int32_t n_flat;
   int32_t flat_leaf[PB_MAX_LEAVES];
+  int32_t n_gather;                          // columns pb_agg_kernel will gather from (L2 prefetch at match time)
+  int32_t pad_g;
+  GatherCol gather[PB_MAX_GATHER];
   alignas(16) uint8_t seg[PB_SEG_FILTER_BYTES];   // the filter part of the current DevSegQuery
 };
 
@@ -568,6 +592,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
 
   uint32_t consumed = 0;   // units this warp has consumed so far: stage = consumed % NSTAGE, parity from consumed / NSTAGE
   const DevSegQuery& sq = *reinterpret_cast<const DevSegQuery*>(H->seg);   // only the filter part is valid
+  const uint64_t l2_stream = pb_policy_evict_first();
 
   // evaluate one filter leaf on the staged unit: m[u] = this lane's 32-doc mask of sub-chunk u.  With sparse == true only
   // the docs still set in restrict_to[u] matter (AND chain with few survivors): decode just them.
@@ -633,6 +658,21 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
         for (int c = 0; c < sq.n_scan; c++) t += (uint32_t)(UNIT_DOCS / 8) * (uint32_t)sq.scan[c].bits_per_doc + 16;
         H->n_scan_full_bytes = t;
       }
+      if (tid == 32) {
+        // gather list (deduplicated by forward-index pointer); read from the full descriptor in global memory
+        const DevSegQuery& full = Q.segs[sgi];
+        int n = 0;
+        auto add = [&](const uint8_t* fwd, int bits, int width) {
+          if (!fwd) return;
+          for (int i = 0; i < n; i++) if (H->gather[i].fwd == fwd) return;
+          if (n < PB_MAX_GATHER) { H->gather[n].fwd = fwd; H->gather[n].bits = bits; H->gather[n].width = width; n++; }
+        };
+        if (Q.prefetch) {
+          for (int j = 0; j < Q.n_group_by; j++) add(full.keys[j].fwd, full.keys[j].raw_width ? 0 : full.keys[j].bits, full.keys[j].raw_width);
+          for (int a = 0; a < Q.n_aggs; a++) if (Q.agg_op[a] != 0) add(full.aggs[a].fwd, full.aggs[a].raw_width ? 0 : full.aggs[a].bits, full.aggs[a].raw_width);
+        }
+        H->n_gather = n;
+      }
       if (tid == 64) {
         // flat conjunction?  postfix == leaf* AND(n)   or a single leaf   or empty (match all)
         int nl = 0; bool flat = true;
@@ -668,6 +708,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
     const uint32_t n_mine = first < seg_hi ? (uint32_t)((seg_hi - first + PB_NWARPS - 1) / PB_NWARPS) : 0u;
     const uint32_t rel0 = (uint32_t)(first - sq.unit_begin);     // unit index inside the segment
     const int n_scan = sq.n_scan;
+    const int n_gather = H->n_gather;
     unsigned long long matched = 0;
     uint32_t min_last_rel = 0xffffffffu;               // first unit whose load must be clipped to the buffer end
     for (int c = 0; c < n_scan; c++) min_last_rel = min(min_last_rel, H->slot_last_rel[c]);
@@ -682,7 +723,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
         pb_mbar_expect_tx(bar, H->n_scan_full_bytes);
         for (int c = 0; c < n_scan; c++) {
           const uint32_t stride = H->slot_stride[c];
-          pb_tma_load_1d(dst + Q.slot_off[c], sq.scan[c].base + (uint64_t)rel * stride, stride + 16, bar);
+          pb_tma_load_1d_hint(dst + Q.slot_off[c], sq.scan[c].base + (uint64_t)rel * stride, stride + 16, bar, l2_stream);
         }
         return;
       }
@@ -802,10 +843,19 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
         for (int u = 0; u < U; u++) {
           const uint32_t gdoc0 = (uint32_t)(sq.doc_base + unit_doc0) + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
           uint32_t mm = mask[u];
+          const uint32_t ldoc0 = (uint32_t)unit_doc0 + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
           while (mm) {
             const int bit = __ffs(mm) - 1;
             mm &= mm - 1;
             Q.match_list[pos++] = gdoc0 + (uint32_t)bit;
+            // start pulling this doc's group-key / metric sectors into L2 now: pb_agg_kernel finds them there
+            const uint32_t doc = ldoc0 + (uint32_t)bit;
+            for (int i = 0; i < n_gather; i++) {
+              const GatherCol gc = H->gather[i];
+              const uint8_t* a = gc.bits ? gc.fwd + ((((unsigned long long)doc * (unsigned)gc.bits) >> 5) << 2)
+                                         : gc.fwd + (unsigned long long)doc * (unsigned)gc.width;
+              pb_prefetch_l2_keep(a);
+            }
           }
         }
         matched += total;
