@@ -1244,27 +1244,14 @@ static int finalize_result(pb_result_s* r) {
       if (op == PB_AGG_COUNT || op == PB_AGG_AVG) for (int64_t k = 0; k < ng; k++) L[k] = (int64_t)rows[k];
       else if (op != PB_AGG_DISTINCTCOUNT) memset(L, 0, 8 * (size_t)std::max<int64_t>(ng, 1));
     }
-    // DISTINCTCOUNT: sizes, then the value sets (BaseDistinctAggregateAggregationFunction intermediate result)
+    // DISTINCTCOUNT: the sizes now; the value sets (BaseDistinctAggregateAggregationFunction intermediate result) are
+    // materialised on first access (pb_result_distinct_offsets / _dict_ids) — a merged result usually needs the sizes only
     for (int a = 0; a < nA; a++) {
       if (r->agg_op[a] != PB_AGG_DISTINCTCOUNT) continue;
       int64_t* L = (int64_t*)tm.lng[a].p;
-      tm.dc_off[a].alloc(8 * (size_t)(ng + 1));
-      int64_t* off = (int64_t*)tm.dc_off[a].p;
-      off[0] = 0;
       if (ng > 0) {
         int wgrid = (int)(((size_t)ng * 32 + 255) / 256);
         pb_distinct_count_kernel<<<wgrid, 256, 0, st>>>(tm.dev.dc_bits[a], tm.dev.dc_words[a], (const unsigned long long*)tm.slots.p, (uint64_t)ng, (unsigned long long*)L);
-        r->launches++;
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(st));
-      }
-      for (int64_t k = 0; k < ng; k++) off[k + 1] = off[k] + L[k];
-      const int64_t total = off[ng];
-      tm.dc_ids[a].alloc(4 * (size_t)std::max<int64_t>(total, 1));
-      if (total > 0) {
-        int wgrid = (int)(((size_t)ng * 32 + 255) / 256);
-        pb_distinct_ids_kernel<<<wgrid, 256, 0, st>>>(tm.dev.dc_bits[a], tm.dev.dc_words[a], (const unsigned long long*)tm.slots.p, (uint64_t)ng,
-                                                      (const unsigned long long*)off, (int32_t*)tm.dc_ids[a].p);
         r->launches++;
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(st));
@@ -1317,8 +1304,40 @@ extern "C" const void* pb_result_group_key_values(pb_result_handle r, int32_t t,
 }
 extern "C" const double* pb_result_double(pb_result_handle r, int32_t t, int32_t a) { auto* tm = TAB(r, t); return (tm && a >= 0 && a < r->n_aggs) ? (const double*)tm->dbl[a].p : nullptr; }
 extern "C" const int64_t* pb_result_long(pb_result_handle r, int32_t t, int32_t a) { auto* tm = TAB(r, t); return (tm && a >= 0 && a < r->n_aggs) ? (const int64_t*)tm->lng[a].p : nullptr; }
-extern "C" const int64_t* pb_result_distinct_offsets(pb_result_handle r, int32_t t, int32_t a) { auto* tm = TAB(r, t); return (tm && a >= 0 && a < r->n_aggs) ? (const int64_t*)tm->dc_off[a].p : nullptr; }
-extern "C" const int32_t* pb_result_distinct_dict_ids(pb_result_handle r, int32_t t, int32_t a) { auto* tm = TAB(r, t); return (tm && a >= 0 && a < r->n_aggs) ? (const int32_t*)tm->dc_ids[a].p : nullptr; }
+// DISTINCTCOUNT value sets, materialised on first access
+static int materialize_distinct(pb_result_s* r, TableMeta& tm, int a) {
+  if (tm.dc_off[a].p) return PB_OK;
+  if (r->agg_op[a] != PB_AGG_DISTINCTCOUNT) return fail(PB_ERR_INVALID, "aggregation %d is not DISTINCTCOUNT", a);
+  cudaStream_t st = r->stream;
+  const int64_t ng = tm.num_groups;
+  const int64_t* L = (const int64_t*)tm.lng[a].p;
+  tm.dc_off[a].alloc(8 * (size_t)(ng + 1));
+  int64_t* off = (int64_t*)tm.dc_off[a].p;
+  off[0] = 0;
+  for (int64_t k = 0; k < ng; k++) off[k + 1] = off[k] + L[k];
+  const int64_t total = off[ng];
+  tm.dc_ids[a].alloc(4 * (size_t)std::max<int64_t>(total, 1));
+  if (!tm.dc_ids[a].p) return fail(PB_ERR_OOM, "pinned host allocation failed");
+  if (total > 0) {
+    int wgrid = (int)(((size_t)ng * 32 + 255) / 256);
+    pb_distinct_ids_kernel<<<wgrid, 256, 0, st>>>(tm.dev.dc_bits[a], tm.dev.dc_words[a], (const unsigned long long*)tm.slots.p, (uint64_t)ng,
+                                                  (const unsigned long long*)off, (int32_t*)tm.dc_ids[a].p);
+    r->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+  }
+  return PB_OK;
+}
+extern "C" const int64_t* pb_result_distinct_offsets(pb_result_handle r, int32_t t, int32_t a) {
+  auto* tm = TAB(r, t);
+  if (!tm || a < 0 || a >= r->n_aggs || materialize_distinct(r, *tm, a) != PB_OK) return nullptr;
+  return (const int64_t*)tm->dc_off[a].p;
+}
+extern "C" const int32_t* pb_result_distinct_dict_ids(pb_result_handle r, int32_t t, int32_t a) {
+  auto* tm = TAB(r, t);
+  if (!tm || a < 0 || a >= r->n_aggs || materialize_distinct(r, *tm, a) != PB_OK) return nullptr;
+  return (const int32_t*)tm->dc_ids[a].p;
+}
 extern "C" const pb_exec_stats* pb_result_stats(pb_result_handle r, int32_t t) { auto* tm = TAB(r, t); return tm ? &tm->stats : nullptr; }
 extern "C" double pb_result_device_ms(pb_result_handle r) { return r ? r->device_ms : 0; }
 extern "C" double pb_result_scan_kernel_ms(pb_result_handle r) {
