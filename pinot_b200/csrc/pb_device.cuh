@@ -133,6 +133,8 @@ struct DevQuery {
   uint64_t n_docs_total;
   int32_t match_all;                     // no filter: pb_agg_kernel walks every doc, no match list
   int32_t prefetch;                      // pb_filter_kernel prefetches the gather sectors of matching docs into L2
+  int32_t sparse_max;                    // survivors per 1024 docs below which later AND leaves use the restricted scan
+  int32_t pad_s;
   uint32_t* match_list;                  // global doc numbers of the docs that pass the filter
   unsigned long long* match_count;
   const DevSegQuery* segs;
@@ -785,7 +787,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
           uint32_t pc = 0;
 #pragma unroll
           for (int u = 0; u < U; u++) pc += (uint32_t)__popc(mask[u]);
-          const bool sparse = i > 0 && !Q.generic && __reduce_add_sync(0xffffffffu, pc) <= PB_SPARSE_MAX * U;
+          const bool sparse = i > 0 && !Q.generic && __reduce_add_sync(0xffffffffu, pc) <= (uint32_t)Q.sparse_max * U;
           eval_leaf(sq.leaves[H->flat_leaf[i]], stage, unit_doc0, nu, mask, sparse, tmp);
           uint32_t any = 0;
 #pragma unroll

@@ -1052,6 +1052,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
   hq->n_units = n_chunks; hq->segs = dsegs; hq->tables = dtabs;
   hq->n_docs_total = n_docs_total; hq->match_all = match_all ? 1 : 0;
+  { static const int sm = []() { const char* e = getenv("PB_SPARSE_MAX"); return e ? atoi(e) : PB_SPARSE_MAX; }(); hq->sparse_max = sm; }
   { static const int pf = []() { const char* e = getenv("PB_PREFETCH"); return e ? atoi(e) : 0; }(); hq->prefetch = pf; }   // off: measured no gain (profiles/r1_experiments.md)
   hq->match_list = d_match_list;
   hq->match_count = r->d_counters + (size_t)n_tables * PB_COUNTERS_PER_TABLE;   // one extra zeroed cell after the per-table counters
