@@ -274,10 +274,16 @@ struct PredRange {      // SortedDictionaryBasedRangePredicateEvaluator.applySV:
   }
   __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return (v - lo) < span ? 1u : 0u; }
 };
-struct PredLut8 {       // IN / NOT_IN / EQ / NEQ with the (exclusive-folded) membership table in shared memory
-  const uint8_t* lut;
-  template <int W> __device__ __forceinline__ uint32_t test(uint32_t vt) const { return lut[vt >> (32 - W)]; }
-  __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return lut[v]; }
+struct PredLut8 {       // IN / NOT_IN / EQ / NEQ: membership BITSET in shared memory, exclusive flag folded in, bit b of word i
+                        // stored at position 31-b (so `word << dictId` brings it to the sign bit).  One 32-bit word per 32
+                        // dictIds: a 1024-entry dictionary maps one word per bank => conflict-free lookups (a byte table costs
+                        // ~3.4 wavefronts per LDS and made the shared-memory pipe the bottleneck).
+  const uint32_t* lut;
+  template <int W> __device__ __forceinline__ uint32_t test(uint32_t vt) const {
+    const uint32_t v = vt >> (32 - W);
+    return (lut[v >> 5] << (v & 31)) >> 31;
+  }
+  __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return (lut[v >> 5] << (v & 31)) >> 31; }
 };
 struct PredBits {       // same, large dictionaries: bitset in global memory (L1-resident)
   const uint32_t* bits;
@@ -612,7 +618,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
       case L_DICT_SET: {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
         if (lf.set_smem_off >= 0) {
-          PredLut8 pl; pl.lut = set_cache + lf.set_smem_off;
+          PredLut8 pl; pl.lut = reinterpret_cast<const uint32_t*>(set_cache + lf.set_smem_off);
           if (sparse) { for (int u = 0; u < nu; u++) m[u] = pb_eval_dict_sparse<PredLut8>(p + u * 32 * lf.bits, lf.bits, pl, lane, restrict_to[u]); return; }
           pb_eval_dict<PredLut8>(p, lf.bits, pl, lane, Q.generic, nu, m);
           return;
@@ -695,9 +701,13 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
       for (int l = 0; l < PB_MAX_LEAVES; l++) {
         const DevLeaf& lf = sq.leaves[l];
         if (lf.kind == L_DICT_SET && lf.set_smem_off >= 0) {
-          // membership bytes with the exclusive flag folded in (NOT_IN / NEQ)
-          for (int i = tid; i < lf.set_card; i += PB_NTHREADS)
-            set_cache[lf.set_smem_off + i] = (uint8_t)(((__ldg(lf.set_bits + (i >> 5)) >> (i & 31)) & 1u) ^ (uint32_t)lf.exclusive);
+          // membership bitset, MSB-first inside each word, exclusive flag (NOT_IN / NEQ) folded in
+          uint32_t* dstw = reinterpret_cast<uint32_t*>(set_cache + lf.set_smem_off);
+          const int nw = (lf.set_card + 31) >> 5;
+          for (int i = tid; i < nw; i += PB_NTHREADS) {
+            uint32_t w = __brev(__ldg(lf.set_bits + i));
+            dstw[i] = lf.exclusive ? ~w : w;
+          }
         }
       }
       __syncthreads();
@@ -988,14 +998,42 @@ __device__ __forceinline__ uint32_t pb_ld_be32(const uint8_t* p) {
   return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3];
 }
 
-// OR the RoaringBitmaps of ids[] (portable format, inside a .bitmap.inv buffer) into a flat bitmap.
-// grid = (container stride, n_ids).  InvertedIndexFilterOperator.java:60-96 / BitmapInvertedIndexReader.java:45-62.
-__global__ void pb_roaring_expand_kernel(const uint8_t* __restrict__ inv, int32_t card, const int32_t* __restrict__ ids,
-                                         uint32_t* __restrict__ out, uint32_t num_docs) {
-  const int32_t id = ids[blockIdx.y];
+// One item = one RoaringBitmap of a .bitmap.inv buffer (portable format) OR one list of sorted-index docId ranges, ORed
+// into a flat doc bitmap.  All index leaves of all segments of a query are expanded by ONE launch: grid = (32, n_items).
+// InvertedIndexFilterOperator.java:60-96 / BitmapInvertedIndexReader.java:45-62 / SortedIndexBasedFilterOperator.java:61-131.
+struct DevExpandItem {
+  const uint8_t* inv;      // kind 0: the inverted index buffer
+  const int32_t* pairs;    // kind 1: inclusive (start,end) docId pairs
+  uint32_t* out;           // flat bitmap (bit d&31 of word d>>5)
+  int32_t kind;            // 0 = roaring bitmap of dictId `id`, 1 = docId ranges
+  int32_t card;
+  int32_t id;
+  int32_t n_pairs;
+  uint32_t num_docs;
+  uint32_t pad;
+};
+
+__global__ void pb_expand_kernel(const DevExpandItem* __restrict__ items) {
+  const DevExpandItem it = items[blockIdx.y];
+  uint32_t* __restrict__ out = it.out;
+  if (it.kind == 1) {
+    for (int r = blockIdx.x; r < it.n_pairs; r += gridDim.x) {
+      uint32_t lo = (uint32_t)it.pairs[2 * r], hi = (uint32_t)it.pairs[2 * r + 1];   // inclusive
+      uint32_t w0 = lo >> 5, w1 = hi >> 5;
+      for (uint32_t w = w0 + threadIdx.x; w <= w1; w += blockDim.x) {
+        uint32_t m = 0xffffffffu;
+        if (w == w0) m &= 0xffffffffu << (lo & 31);
+        if (w == w1) m &= 0xffffffffu >> (31 - (hi & 31));
+        atomicOr(&out[w], m);
+      }
+    }
+    return;
+  }
+  const uint8_t* inv = it.inv;
+  const uint32_t num_docs = it.num_docs;
   const uint32_t first = pb_ld_be32(inv);
-  const uint32_t s = pb_ld_be32(inv + 4ull * id), e = pb_ld_be32(inv + 4ull * id + 4);
-  const uint8_t* blob = inv + 4ull * ((uint64_t)card + 1) + (s - first);
+  const uint32_t s = pb_ld_be32(inv + 4ull * it.id), e = pb_ld_be32(inv + 4ull * it.id + 4);
+  const uint8_t* blob = inv + 4ull * ((uint64_t)it.card + 1) + (s - first);
   if (e - s < 8) return;
   const uint32_t cookie = pb_ld_le32(blob);
   uint32_t n, p;
@@ -1042,20 +1080,6 @@ __global__ void pb_roaring_expand_kernel(const uint8_t* __restrict__ inv, int32_
         uint32_t wi = (base >> 5) + k;
         if (w && (uint64_t)wi * 32 < num_docs) atomicOr(&out[wi], w);
       }
-    }
-  }
-}
-
-// sorted index doc ranges -> flat bitmap (SortedIndexBasedFilterOperator.java:61-131; AndDocIdSet.java:147-151)
-__global__ void pb_ranges_fill_kernel(const int32_t* __restrict__ pairs, int32_t n_pairs, uint32_t* __restrict__ out) {
-  for (int r = blockIdx.x; r < n_pairs; r += gridDim.x) {
-    uint32_t lo = (uint32_t)pairs[2 * r], hi = (uint32_t)pairs[2 * r + 1];   // inclusive
-    uint32_t w0 = lo >> 5, w1 = hi >> 5;
-    for (uint32_t w = w0 + threadIdx.x; w <= w1; w += blockDim.x) {
-      uint32_t m = 0xffffffffu;
-      if (w == w0) m &= 0xffffffffu << (lo & 31);
-      if (w == w1) m &= 0xffffffffu >> (31 - (hi & 31));
-      atomicOr(&out[w], m);
     }
   }
 }

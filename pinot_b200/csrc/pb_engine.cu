@@ -822,9 +822,9 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       const pb_filter_node& fn = sq.filter[n];
       if (fn.kind == PB_F_SCAN_DICT_SET) arena_cap += 4 * (((size_t)s->cols[fn.column].card + 31) / 32) + 32;
       if (fn.kind == PB_F_SCAN_RAW_SET) arena_cap += 8 * (size_t)fn.num_raw_values + 32;
-      if (fn.kind == PB_F_INVERTED) arena_cap += 4 * (size_t)fn.num_ids + 32;
-      if (fn.kind == PB_F_SORTED) arena_cap += 8 * (size_t)fn.num_ids + 32;
-      if (fn.kind == PB_F_BITMAP) arena_cap += fn.blob_len + 64;
+      if (fn.kind == PB_F_INVERTED) arena_cap += (4 + sizeof(DevExpandItem)) * (size_t)std::max(fn.num_ids, 0) + 64;
+      if (fn.kind == PB_F_SORTED) arena_cap += 8 * (size_t)std::max(fn.num_ids, 0) + sizeof(DevExpandItem) + 64;
+      if (fn.kind == PB_F_BITMAP) arena_cap += fn.blob_len + sizeof(DevExpandItem) + 128;
       if (fn.kind == PB_F_INVERTED || fn.kind == PB_F_SORTED || fn.kind == PB_F_BITMAP) bitmap_words_total += (((size_t)s->num_docs + 2047) / 2048) * 64;
     }
   }
@@ -845,7 +845,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   DevTable* dtabs = ar.put<DevTable>(nullptr, (size_t)n_tables, &htabs);
   for (int t = 0; t < n_tables; t++) htabs[t] = r->tables[t].dev;
 
-  struct PendingExpand { int kind; const uint8_t* inv; int card; const int32_t* ids; int n_ids; uint32_t* out; uint32_t num_docs; };
+  struct PendingExpand { int kind; const uint8_t* inv; int card; const int32_t* ids; int n_ids; uint32_t* out; uint32_t num_docs; std::vector<int32_t> host_ids; };
   std::vector<PendingExpand> expands;
   int slot_bits_max[PB_MAX_SCAN_SLOTS] = {0};
   int set_cache_max = 0;
@@ -912,7 +912,8 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
           lf.kind = L_DICT_SET; lf.bits = c.bits; lf.exclusive = fn.exclusive ? 1 : 0;
           lf.set_bits = dbits; lf.set_card = c.card;
           { double f = (double)fn.num_ids / (double)c.card; lf.est_permille = (int32_t)(1000.0 * (fn.exclusive ? 1.0 - f : f)); }
-          if (set_smem_used + c.card <= PB_SET_SMEM_BYTES) { lf.set_smem_off = set_smem_used; set_smem_used += (c.card + 15) & ~15; }
+          const int lut_bytes = (int)(((c.card + 31) / 32) * 4);
+          if (set_smem_used + lut_bytes <= PB_SET_SMEM_BYTES) { lf.set_smem_off = set_smem_used; set_smem_used += (lut_bytes + 15) & ~15; }
           if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
           r->seg_scan_leaves[si]++;
           break;
@@ -947,7 +948,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
             for (int k = 0; k < fn.num_ids; k++) if (fn.ids[k] < 0 || fn.ids[k] >= c.card) return fail(PB_ERR_INVALID, "filter node %d: dictId out of range", n);
             const int32_t* dids = ar.put<int32_t>(fn.ids, (size_t)fn.num_ids);
             if (!dids) return fail(PB_ERR_STATE, "query arena overflow");
-            expands.push_back({0, c.d_inv, c.card, dids, fn.num_ids, bm, (uint32_t)s->num_docs});
+            expands.push_back({0, c.d_inv, c.card, dids, fn.num_ids, bm, (uint32_t)s->num_docs, std::vector<int32_t>(fn.ids, fn.ids + fn.num_ids)});
           } else if (fn.kind == PB_F_SORTED) {
             lf.exclusive = 0;
             if (fn.num_ids <= 0) { lf.kind = L_FALSE; break; }
@@ -957,7 +958,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
             }
             const int32_t* dp = ar.put<int32_t>(fn.ids, 2 * (size_t)fn.num_ids);
             if (!dp) return fail(PB_ERR_STATE, "query arena overflow");
-            expands.push_back({1, nullptr, 0, dp, fn.num_ids, bm, (uint32_t)s->num_docs});
+            expands.push_back({1, nullptr, 0, dp, fn.num_ids, bm, (uint32_t)s->num_docs, {}});
           } else {
             // wrap the caller's Roaring blob as a one-entry inverted index: [BE off0][BE off1][blob]
             if (!fn.blob || fn.blob_len < 8) return fail(PB_ERR_INVALID, "filter node %d: bitmap blob missing", n);
@@ -970,7 +971,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
             static const int32_t zero_id = 0;
             const int32_t* dids = ar.put<int32_t>(&zero_id, 1);
             if (!dblob || !dids) return fail(PB_ERR_STATE, "query arena overflow");
-            expands.push_back({0, dblob, 1, dids, 1, bm, (uint32_t)s->num_docs});
+            expands.push_back({0, dblob, 1, dids, 1, bm, (uint32_t)s->num_docs, std::vector<int32_t>(1, 0)});
           }
           break;
         }
@@ -1057,20 +1058,41 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   hq->match_list = d_match_list;
   hq->match_count = r->d_counters + (size_t)n_tables * PB_COUNTERS_PER_TABLE;   // one extra zeroed cell after the per-table counters
 
+  // expand items (one per inverted-index bitmap / per sorted-index range list)
+  int n_expand_items = 0;
+  for (auto& e : expands) n_expand_items += e.kind == 0 ? e.n_ids : 1;
+  const DevExpandItem* d_expand_items = nullptr;
+  if (n_expand_items > 0) {
+    std::vector<DevExpandItem> items;
+    items.reserve((size_t)n_expand_items);
+    for (auto& e : expands) {
+      if (e.kind == 0) {
+        for (int k = 0; k < e.n_ids; k++) {
+          DevExpandItem it; memset(&it, 0, sizeof it);
+          it.inv = e.inv; it.out = e.out; it.kind = 0; it.card = e.card; it.id = e.host_ids[k]; it.num_docs = e.num_docs;
+          items.push_back(it);
+        }
+      } else {
+        DevExpandItem it; memset(&it, 0, sizeof it);
+        it.pairs = e.ids; it.out = e.out; it.kind = 1; it.n_pairs = e.n_ids; it.num_docs = e.num_docs;
+        items.push_back(it);
+      }
+    }
+    d_expand_items = ar.put<DevExpandItem>(items.data(), items.size());
+    if (!d_expand_items) return fail(PB_ERR_STATE, "query arena overflow");
+  }
   CU(cudaMemcpyAsync(ar.dev, ar.host.data(), ar.used, cudaMemcpyHostToDevice, st));
   lap(2);
 
-  // ---- index leaves -> flat bitmaps ----
-  for (auto& e : expands) {
-    if (e.kind == 0) {
-      dim3 grid(32, (unsigned)e.n_ids);
-      pb_roaring_expand_kernel<<<grid, 256, 0, st>>>(e.inv, e.card, e.ids, e.out, e.num_docs);
-    } else {
-      pb_ranges_fill_kernel<<<std::min(e.n_ids, 1024), 256, 0, st>>>(e.ids, e.n_ids, e.out);
+  // ---- index leaves -> flat bitmaps: one launch for every bitmap / range list of every segment ----
+  if (n_expand_items > 0) {
+    for (int y0 = 0; y0 < n_expand_items; y0 += 65535) {
+      dim3 grid(32, (unsigned)std::min(65535, n_expand_items - y0));
+      pb_expand_kernel<<<grid, 256, 0, st>>>(d_expand_items + y0);
+      r->launches++;
     }
-    r->launches++;
+    CU(cudaGetLastError());
   }
-  CU(cudaGetLastError());
 
   // ---- kernel 1: filter -> match list ----
   CU(cudaEventRecord(r->ev1, st));
