@@ -274,16 +274,12 @@ struct PredRange {      // SortedDictionaryBasedRangePredicateEvaluator.applySV:
   }
   __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return (v - lo) < span ? 1u : 0u; }
 };
-struct PredLut8 {       // IN / NOT_IN / EQ / NEQ: membership BITSET in shared memory, exclusive flag folded in, bit b of word i
-                        // stored at position 31-b (so `word << dictId` brings it to the sign bit).  One 32-bit word per 32
-                        // dictIds: a 1024-entry dictionary maps one word per bank => conflict-free lookups (a byte table costs
-                        // ~3.4 wavefronts per LDS and made the shared-memory pipe the bottleneck).
-  const uint32_t* lut;
-  template <int W> __device__ __forceinline__ uint32_t test(uint32_t vt) const {
-    const uint32_t v = vt >> (32 - W);
-    return (lut[v >> 5] << (v & 31)) >> 31;
-  }
-  __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return (lut[v >> 5] << (v & 31)) >> 31; }
+struct PredLut8 {       // IN / NOT_IN / EQ / NEQ: one membership byte per dictId in shared memory, exclusive flag folded in.
+                        // (A bitset is conflict-free but costs ~3 more ALU instructions per value; the kernel is issue-bound,
+                        // the shared-memory pipe is only ~25 % busy: profiles/r1_experiments.md.)
+  const uint8_t* lut;
+  template <int W> __device__ __forceinline__ uint32_t test(uint32_t vt) const { return lut[vt >> (32 - W)]; }
+  __device__ __forceinline__ uint32_t operator()(uint32_t v) const { return lut[v]; }
 };
 struct PredBits {       // same, large dictionaries: bitset in global memory (L1-resident)
   const uint32_t* bits;
@@ -326,7 +322,7 @@ __device__ __forceinline__ uint32_t pb_eval_dict_w(const uint32_t* __restrict__ 
     const int bit = j * W;
     const int k = bit >> 5, s = bit & 31;
     const uint32_t vt = (s == 0) ? w[k] : __funnelshift_l(w[k + 1], w[k], s);   // value in the top W bits
-    m[j >> 3] = (m[j >> 3] << 1) + pred.template test<W>(vt);
+    m[j >> 3] = m[j >> 3] * 2 + pred.template test<W>(vt);
   }
   return (m[3] << 24) | (m[2] << 16) | (m[1] << 8) | m[0];
 }
@@ -618,7 +614,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
       case L_DICT_SET: {
         const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
         if (lf.set_smem_off >= 0) {
-          PredLut8 pl; pl.lut = reinterpret_cast<const uint32_t*>(set_cache + lf.set_smem_off);
+          PredLut8 pl; pl.lut = set_cache + lf.set_smem_off;
           if (sparse) { for (int u = 0; u < nu; u++) m[u] = pb_eval_dict_sparse<PredLut8>(p + u * 32 * lf.bits, lf.bits, pl, lane, restrict_to[u]); return; }
           pb_eval_dict<PredLut8>(p, lf.bits, pl, lane, Q.generic, nu, m);
           return;
@@ -701,13 +697,9 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
       for (int l = 0; l < PB_MAX_LEAVES; l++) {
         const DevLeaf& lf = sq.leaves[l];
         if (lf.kind == L_DICT_SET && lf.set_smem_off >= 0) {
-          // membership bitset, MSB-first inside each word, exclusive flag (NOT_IN / NEQ) folded in
-          uint32_t* dstw = reinterpret_cast<uint32_t*>(set_cache + lf.set_smem_off);
-          const int nw = (lf.set_card + 31) >> 5;
-          for (int i = tid; i < nw; i += PB_NTHREADS) {
-            uint32_t w = __brev(__ldg(lf.set_bits + i));
-            dstw[i] = lf.exclusive ? ~w : w;
-          }
+          // membership bytes with the exclusive flag (NOT_IN / NEQ) folded in
+          for (int i = tid; i < lf.set_card; i += PB_NTHREADS)
+            set_cache[lf.set_smem_off + i] = (uint8_t)(((__ldg(lf.set_bits + (i >> 5)) >> (i & 31)) & 1u) ^ (uint32_t)lf.exclusive);
         }
       }
       __syncthreads();

@@ -50,6 +50,7 @@ struct Context {
   int num_sms = 148;
   std::vector<PinnedBlock> pinned_free;
   std::vector<PinnedBlock> scratch_free;      // large device scratch buffers (match lists), reused across calls
+  cudaStream_t util_stream = nullptr;         // stream-ordered allocations / frees of staged data
   bool smem_attr_set = false;
 };
 static Context g_ctx;
@@ -78,8 +79,21 @@ static int ensure_init() {
     if (const char* e = getenv("PB_L2_FETCH")) gran = (size_t)atoi(e);
     if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
   }
+  CU(cudaStreamCreateWithFlags(&g_ctx.util_stream, cudaStreamNonBlocking));
   g_ctx.inited = true;
   return PB_OK;
+}
+
+// staged data comes from the stream-ordered pool (release threshold = keep everything): re-staging a segment reuses
+// pool memory instead of paying cudaMalloc / cudaFree (hundreds of microseconds each)
+static cudaError_t dev_alloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMallocAsync(p, bytes, g_ctx.util_stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(g_ctx.util_stream);
+}
+static void dev_free(void* p) {
+  if (p && g_ctx.util_stream) cudaFreeAsync(p, g_ctx.util_stream);
+  else if (p) cudaFree(p);
 }
 
 extern "C" int pb_init(const int* device_ids, int n_devices, size_t /*hbm_cache_bytes*/) {
@@ -246,11 +260,11 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
   if (need_fwd && !c.fwd_staged) {
     if (c.has_dict && c.is_sorted) {
       // pairs -> device, then materialise the bit-packed stream on the device
-      CU(cudaMalloc((void**)&c.d_sorted_pairs, sizeof(int32_t) * 2 * (size_t)c.card));
+      CU(dev_alloc((void**)&c.d_sorted_pairs, sizeof(int32_t) * 2 * (size_t)c.card));
       CU(cudaMemcpyAsync(c.d_sorted_pairs, c.h_sorted_pairs.data(), sizeof(int32_t) * 2 * (size_t)c.card, cudaMemcpyHostToDevice, st));
       uint64_t bytes = ((uint64_t)s->num_docs * c.bits + 7) / 8;
       uint64_t padded = ((bytes + 15) & ~15ull) + 32;
-      CU(cudaMalloc((void**)&c.d_fwd, padded));
+      CU(dev_alloc((void**)&c.d_fwd, padded));
       CU(cudaMemsetAsync(c.d_fwd, 0, padded, st));
       uint64_t n_words = (bytes + 3) / 4;
       int grid = (int)std::min<uint64_t>((n_words + 255) / 256, 4096);
@@ -263,7 +277,7 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
       const uint8_t* src = c.has_dict ? c.h_fwd : c.h_fwd + c.raw_data_start;
       uint64_t bytes = c.has_dict ? ((uint64_t)s->num_docs * c.bits + 7) / 8 : (uint64_t)s->num_docs * c.raw_width;
       uint64_t padded = ((bytes + 15) & ~15ull) + 32;
-      CU(cudaMalloc((void**)&c.d_fwd, padded));
+      CU(dev_alloc((void**)&c.d_fwd, padded));
       CU(cudaMemsetAsync(c.d_fwd + (bytes & ~15ull), 0, padded - (bytes & ~15ull), st));
       CU(cudaMemcpyAsync(c.d_fwd, src, bytes, cudaMemcpyHostToDevice, st));
       c.d_fwd_bytes = padded;
@@ -283,7 +297,7 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
         default: { uint64_t u = be64(p); double dd; memcpy(&dd, &u, 8); v[i] = dd; break; }
       }
     }
-    CU(cudaMalloc((void**)&c.d_dict_f64, sizeof(double) * (size_t)c.card));
+    CU(dev_alloc((void**)&c.d_dict_f64, sizeof(double) * (size_t)c.card));
     CU(cudaMemcpyAsync(c.d_dict_f64, v.data(), sizeof(double) * (size_t)c.card, cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));   // v is a stack-owned staging buffer
     s->device_bytes += (int64_t)sizeof(double) * c.card;
@@ -292,14 +306,14 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
   if (need_native && !c.native_staged && c.has_dict) {
     std::vector<uint8_t> v((size_t)c.card * c.entry_bytes);
     for (int i = 0; i < c.card; i++) native_entry(c, i, v.data() + (size_t)i * c.entry_bytes);
-    CU(cudaMalloc((void**)&c.d_dict_native, v.size() + 16));
+    CU(dev_alloc((void**)&c.d_dict_native, v.size() + 16));
     CU(cudaMemcpy(c.d_dict_native, v.data(), v.size(), cudaMemcpyHostToDevice));
     s->device_bytes += (int64_t)v.size();
     c.native_staged = true;
   }
   if (need_inv && !c.inv_staged) {
     if (!c.h_inv) return fail(PB_ERR_INVALID, "column %s has no inverted index", c.name.c_str());
-    CU(cudaMalloc((void**)&c.d_inv, c.h_inv_len + 16));
+    CU(dev_alloc((void**)&c.d_inv, c.h_inv_len + 16));
     CU(cudaMemcpyAsync(c.d_inv, c.h_inv, c.h_inv_len, cudaMemcpyHostToDevice, st));
     s->device_bytes += (int64_t)c.h_inv_len;
     c.inv_staged = true;
@@ -310,7 +324,7 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
 extern "C" int pb_segment_release(pb_segment_handle s) {
   if (!s) return PB_OK;
   for (auto& c : s->cols) {
-    cudaFree(c.d_fwd); cudaFree(c.d_sorted_pairs); cudaFree(c.d_dict_f64); cudaFree(c.d_dict_native); cudaFree(c.d_inv);
+    dev_free(c.d_fwd); dev_free(c.d_sorted_pairs); dev_free(c.d_dict_f64); dev_free(c.d_dict_native); dev_free(c.d_inv);
   }
   delete s;
   return PB_OK;
@@ -362,7 +376,7 @@ extern "C" int pb_segment_group_create(const pb_segment_handle* segs, int n, pb_
 }
 extern "C" int pb_segment_group_release(pb_segment_group_handle g) {
   if (!g) return PB_OK;
-  for (auto& kv : g->dicts) { for (auto p : kv.second.d_remap) cudaFree(p); cudaFree(kv.second.d_values); }
+  for (auto& kv : g->dicts) { for (auto p : kv.second.d_remap) dev_free(p); dev_free(kv.second.d_values); }
   delete g;
   return PB_OK;
 }
@@ -403,14 +417,14 @@ static int build_union(pb_group_s* g, const char* column, GlobalDict& gd) {
 
 static int upload_remaps(pb_group_s* g, GlobalDict& gd) {
   if (gd.uploaded) return PB_OK;
-  for (auto p : gd.d_remap) cudaFree(p);
-  cudaFree(gd.d_values); gd.d_values = nullptr;
-  CU(cudaMalloc((void**)&gd.d_values, gd.values.size() + 16));
+  for (auto p : gd.d_remap) dev_free(p);
+  dev_free(gd.d_values); gd.d_values = nullptr;
+  CU(dev_alloc((void**)&gd.d_values, gd.values.size() + 16));
   CU(cudaMemcpy(gd.d_values, gd.values.data(), gd.values.size(), cudaMemcpyHostToDevice));
   gd.d_remap.assign(g->segs.size(), nullptr);
   for (size_t si = 0; si < g->segs.size(); si++) {
     const auto& rm = gd.h_remap[si];
-    CU(cudaMalloc((void**)&gd.d_remap[si], sizeof(int32_t) * std::max<size_t>(rm.size(), 1)));
+    CU(dev_alloc((void**)&gd.d_remap[si], sizeof(int32_t) * std::max<size_t>(rm.size(), 1)));
     CU(cudaMemcpy(gd.d_remap[si], rm.data(), sizeof(int32_t) * rm.size(), cudaMemcpyHostToDevice));
   }
   gd.uploaded = true;
@@ -912,8 +926,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
           lf.kind = L_DICT_SET; lf.bits = c.bits; lf.exclusive = fn.exclusive ? 1 : 0;
           lf.set_bits = dbits; lf.set_card = c.card;
           { double f = (double)fn.num_ids / (double)c.card; lf.est_permille = (int32_t)(1000.0 * (fn.exclusive ? 1.0 - f : f)); }
-          const int lut_bytes = (int)(((c.card + 31) / 32) * 4);
-          if (set_smem_used + lut_bytes <= PB_SET_SMEM_BYTES) { lf.set_smem_off = set_smem_used; set_smem_used += (lut_bytes + 15) & ~15; }
+          if (set_smem_used + c.card <= PB_SET_SMEM_BYTES) { lf.set_smem_off = set_smem_used; set_smem_used += (c.card + 15) & ~15; }
           if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
           r->seg_scan_leaves[si]++;
           break;
