@@ -231,7 +231,7 @@ def main():
 
     if world > 1:
         # agree on the global dictionaries of the group-by columns (dense tables must line up across ranks)
-        from pinot_b200.distributed import agree_global_dictionaries, all_reduce_tables
+        from pinot_b200.distributed import agree_global_dictionaries, all_gather_merge_tables
         agree_global_dictionaries(group, q.group_by, [int(segs[0].columns[c].data_type) for c in q.group_by], dist)
 
     def barrier():
@@ -246,7 +246,7 @@ def main():
         if world == 1:
             return native.execute(g, q, flags, prepared)
         r = native.execute(g, q, flags | native.PB_Q_DEFER_FINALIZE, prepared)
-        all_reduce_tables(r, q, dist, torch)        # 3 small collectives on the call's stream: no host sync in between
+        all_gather_merge_tables(r, dist, torch)     # ONE collective on the call's stream + a device-side merge kernel
         if rank == 0:
             r.finalize()
         return r

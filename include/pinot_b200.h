@@ -216,6 +216,11 @@ void pb_result_free(pb_result_handle r);
  *            (int64, SUM), 6 = all sums (float64, SUM; may be empty), 7 = all min/max tables (int64, MIN; may be empty);
  *        3 = per-aggregation distinct bitset words (int32; OR == MAX over 0/1 is NOT valid — all-gather + pb_or) -------- */
 int pb_result_device_buffer(pb_result_handle r, int32_t which, int32_t agg, void** device_ptr, int64_t* num_elements);
+/* which = 8: the whole reducible state of the table as one byte block (num_elements = bytes).  all-gather it across
+ * ranks (one collective) and hand the rank-major copies to pb_result_merge_gathered, which reduces them into this result on
+ * the result's stream with the right operator per region (u64 SUM | f64 SUM | bitset OR | i64 MIN) — this also merges
+ * DISTINCTCOUNT bitsets, which no NCCL reduction operator can. */
+int pb_result_merge_gathered(pb_result_handle r, const void* gathered_device_ptr, int32_t n_ranks);
 int pb_result_finalize(pb_result_handle r);
 /* the CUDA stream (cudaStream_t) this result's work was issued on, and a host-side wait for it */
 void* pb_result_stream(pb_result_handle r);

@@ -1089,6 +1089,20 @@ __global__ void pb_init_tables_kernel(uint4* zero, uint64_t zero_n16, uint4* ff,
   for (uint64_t i = t0; i < mm_n16; i += stride) mm[i] = m;
 }
 
+// cross-GPU merge: `gathered` holds n_ranks copies of the table block (rank-major); reduce them element-wise into `dst`
+// with the operator of each region: counters + row counts u64 SUM | sums f64 SUM | distinct bitsets OR | min/max i64 MIN
+__global__ void pb_merge_blocks_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ gathered, int n_ranks,
+                                       uint64_t n_words, uint64_t sum_off, uint64_t dc_off, uint64_t mm_off) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x) {
+    unsigned long long v = gathered[i];
+    if (i < sum_off) { for (int r = 1; r < n_ranks; r++) v += gathered[(uint64_t)r * n_words + i]; }
+    else if (i < dc_off) { double d = __longlong_as_double((long long)v); for (int r = 1; r < n_ranks; r++) d += __longlong_as_double((long long)gathered[(uint64_t)r * n_words + i]); v = (unsigned long long)__double_as_longlong(d); }
+    else if (i < mm_off) { for (int r = 1; r < n_ranks; r++) v |= gathered[(uint64_t)r * n_words + i]; }
+    else { long long m = (long long)v; for (int r = 1; r < n_ranks; r++) { long long o = (long long)gathered[(uint64_t)r * n_words + i]; m = o < m ? o : m; } v = (unsigned long long)m; }
+    dst[i] = v;
+  }
+}
+
 // count non-empty slots
 __global__ void pb_count_groups_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n, unsigned long long* out) {
   unsigned long long c = 0;

@@ -567,6 +567,9 @@ struct pb_result_s {
   unsigned long long* span_i64 = nullptr; int64_t span_i64_n = 0;
   double* span_f64 = nullptr; int64_t span_f64_n = 0;
   long long* span_mm = nullptr; int64_t span_mm_n = 0;
+  // the whole reducible state of table 0 as one block: [0, sum_off) counters + row counts (u64 SUM), [sum_off, dc_off) sums
+  // (f64 SUM), [dc_off, mm_off) distinct bitsets (OR), [mm_off, bytes) min/max (i64 MIN)
+  uint8_t* block = nullptr; int64_t block_bytes = 0, block_sum_off = 0, block_dc_off = 0, block_mm_off = 0;
 };
 
 static void free_result(pb_result_s* r) {
@@ -772,9 +775,13 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 + 256;
   if (zero_bytes > (64ull << 30)) return fail(PB_ERR_UNSUPPORTED, "group table needs %zu bytes: decline to the CPU plan", zero_bytes);
   uint8_t *d_zero = nullptr, *d_ff = nullptr; long long* d_mm = nullptr;
-  CU(cudaMallocAsync((void**)&d_zero, zero_bytes + 16, st)); r->dev_allocs.push_back(d_zero);
+  // one block: [zero region | min/max region] so that a cross-GPU merge can ship the whole table in one collective
+  zero_bytes = (zero_bytes + 255) & ~(size_t)255;
+  CU(cudaMallocAsync((void**)&d_zero, zero_bytes + 8 * mm_elems + 16, st)); r->dev_allocs.push_back(d_zero);
   if (ff_bytes) { CU(cudaMallocAsync((void**)&d_ff, ff_bytes + 16, st)); r->dev_allocs.push_back(d_ff); }
-  if (mm_elems) { CU(cudaMallocAsync((void**)&d_mm, 8 * mm_elems + 16, st)); r->dev_allocs.push_back(d_mm); }
+  if (mm_elems) d_mm = reinterpret_cast<long long*>(d_zero + zero_bytes);
+  r->block = d_zero; r->block_bytes = (int64_t)(zero_bytes + 8 * mm_elems);
+  r->block_mm_off = (int64_t)zero_bytes;
 
   CU(cudaEventRecord(r->ev0, st));
   {
@@ -806,6 +813,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
         if (op == PB_AGG_SUM || op == PB_AGG_AVG) { dt.sum[a] = reinterpret_cast<double*>(d_zero + zo); zo += 8 * S; }
       }
       if (t == 0) r->span_f64_n = (int64_t)((d_zero + zo - (uint8_t*)r->span_f64) / 8);
+      if (t == 0) { r->block_sum_off = (int64_t)((uint8_t*)r->span_f64 - d_zero); r->block_dc_off = (int64_t)zo; }
       for (int a = 0; a < nA; a++) {
         int op = q->aggregations[a].op;
         if (op == PB_AGG_DISTINCTCOUNT) { dt.dc_bits[a] = reinterpret_cast<uint32_t*>(d_zero + zo); dt.dc_words[a] = dc_words[a]; zo += 4 * S * dc_words[a]; }
@@ -1384,6 +1392,18 @@ extern "C" double pb_result_scan_kernel_ms(pb_result_handle r) {
 extern "C" int32_t pb_result_kernel_launches(pb_result_handle r) { return r ? r->launches : 0; }
 extern "C" void* pb_result_stream(pb_result_handle r) { return r ? (void*)r->stream : nullptr; }
 
+// merge the gathered table blocks of all ranks (rank-major copies of pb_result_device_buffer(which = 8)) into this result
+extern "C" int pb_result_merge_gathered(pb_result_handle r, const void* gathered, int32_t n_ranks) {
+  if (!r || !gathered || n_ranks < 1) return fail(PB_ERR_INVALID, "bad arguments");
+  if (!r->combine || r->tables.size() != 1 || r->table_mode == T_HASH) return fail(PB_ERR_UNSUPPORTED, "merge needs a combined dense / keyless result");
+  const uint64_t n_words = (uint64_t)r->block_bytes / 8;
+  int grid = (int)std::min<uint64_t>((n_words + 255) / 256, 1184);
+  pb_merge_blocks_kernel<<<grid, 256, 0, r->stream>>>((unsigned long long*)r->block, (const unsigned long long*)gathered, n_ranks, n_words,
+                                                      (uint64_t)r->block_sum_off / 8, (uint64_t)r->block_dc_off / 8, (uint64_t)r->block_mm_off / 8);
+  r->launches++;
+  CU(cudaGetLastError());
+  return PB_OK;
+}
 extern "C" int pb_result_phase_ms(pb_result_handle r, double* filter_ms, double* agg_ms) {
   if (!r) return fail(PB_ERR_INVALID, "null result");
   if (!r->finalized) {
@@ -1432,6 +1452,7 @@ extern "C" int pb_result_device_buffer(pb_result_handle r, int32_t which, int32_
     case 5: *device_ptr = r->span_i64; *num_elements = r->span_i64_n; return PB_OK;
     case 6: *device_ptr = r->span_f64; *num_elements = r->span_f64_n; return PB_OK;
     case 7: *device_ptr = r->span_mm; *num_elements = r->span_mm_n; return PB_OK;
+    case 8: *device_ptr = r->block; *num_elements = r->block_bytes; return PB_OK;
     default: break;
   }
   return fail(PB_ERR_INVALID, "no such device buffer (which=%d agg=%d)", which, agg);

@@ -53,3 +53,16 @@ def all_reduce_tables(result: native.Result, q: QueryContext, dist, torch) -> No
             ptr, n = result.device_buffer(which)
             if n > 0 and ptr:
                 dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, typestr), device="cuda"), op=op)
+
+
+def all_gather_merge_tables(result: native.Result, dist, torch) -> None:
+    """One collective instead of three: all-gather the whole table block of every rank on the result's stream, then
+    pb_result_merge_gathered reduces the copies on the device (u64 SUM | f64 SUM | bitset OR | i64 MIN per region)."""
+    ext = torch.cuda.ExternalStream(result.stream())
+    with torch.cuda.stream(ext):
+        ptr, nbytes = result.device_buffer(8)
+        local = torch.as_tensor(_DevBuf(ptr, nbytes // 8, "<i8"), device="cuda")
+        gathered = torch.empty(dist.get_world_size() * (nbytes // 8), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(gathered, local)
+        result.merge_gathered(gathered.data_ptr(), dist.get_world_size())
+        gathered.record_stream(ext)

@@ -123,6 +123,7 @@ def lib():
     l.pb_result_stream.argtypes = [C.c_void_p]
     l.pb_result_stream.restype = C.c_void_p
     l.pb_result_wait.argtypes = [C.c_void_p]
+    l.pb_result_merge_gathered.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     l.pb_result_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     l.pb_result_host_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     l.pb_host_register.argtypes = [C.c_void_p, C.c_size_t]
@@ -353,6 +354,9 @@ class Result:
         p, n = C.c_void_p(), C.c_int64()
         _check(lib().pb_result_device_buffer(self._rh, which, agg, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def merge_gathered(self, gathered_ptr: int, n_ranks: int):
+        _check(lib().pb_result_merge_gathered(self._rh, gathered_ptr, n_ranks))
 
     def stream(self) -> int:
         return lib().pb_result_stream(self._rh) or 0

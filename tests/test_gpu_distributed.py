@@ -18,7 +18,7 @@ faulthandler.enable()
 def test_deferred_reduce_then_finalize():
     import torch
     import torch.distributed as dist
-    from pinot_b200.distributed import agree_global_dictionaries, all_reduce_tables
+    from pinot_b200.distributed import agree_global_dictionaries, all_gather_merge_tables, all_reduce_tables
 
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -35,9 +35,12 @@ def test_deferred_reduce_then_finalize():
         q = parse_sql(datagen.config2_sql(segs, 200))
         agree_global_dictionaries(group, q.group_by, [0, 0, 0], dist)
         exp = combined_rows(oracle.combine([oracle.execute(x, q) for x in segs]), q)
-        for _ in range(3):
+        for it in range(4):
             r = native.execute(group, q, native.PB_Q_COMBINE | native.PB_Q_DEFER_FINALIZE)
-            all_reduce_tables(r, q, dist, torch)
+            if it % 2 == 0:
+                all_reduce_tables(r, q, dist, torch)
+            else:
+                all_gather_merge_tables(r, dist, torch)
             r.finalize()
             assert_rows_equal(r.tables[0].rows(), exp, q, exact_float=True, what="deferred + all-reduce")
             r.free()
