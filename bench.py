@@ -231,7 +231,8 @@ def main():
 
     if world > 1:
         # agree on the global dictionaries of the group-by columns (dense tables must line up across ranks)
-        from pinot_b200.distributed import agree_global_dictionaries, all_gather_merge_tables
+        from pinot_b200.distributed import agree_global_dictionaries, all_gather_merge_tables, all_reduce_tables
+        merge_mode = os.environ.get("PB_MERGE", "allreduce")
         agree_global_dictionaries(group, q.group_by, [int(segs[0].columns[c].data_type) for c in q.group_by], dist)
 
     def barrier():
@@ -246,7 +247,10 @@ def main():
         if world == 1:
             return native.execute(g, q, flags, prepared)
         r = native.execute(g, q, flags | native.PB_Q_DEFER_FINALIZE, prepared)
-        all_gather_merge_tables(r, dist, torch)     # ONE collective on the call's stream + a device-side merge kernel
+        if merge_mode == "allgather":
+            all_gather_merge_tables(r, dist, torch)     # ONE collective on the call's stream + a device-side merge kernel
+        else:
+            all_reduce_tables(r, q, dist, torch)        # three small all-reduces on the call's stream
         if rank == 0:
             r.finalize()
         return r

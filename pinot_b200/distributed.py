@@ -55,14 +55,21 @@ def all_reduce_tables(result: native.Result, q: QueryContext, dist, torch) -> No
                 dist.all_reduce(torch.as_tensor(_DevBuf(ptr, n, typestr), device="cuda"), op=op)
 
 
+_gather_buffers = {}
+
+
 def all_gather_merge_tables(result: native.Result, dist, torch) -> None:
     """One collective instead of three: all-gather the whole table block of every rank on the result's stream, then
-    pb_result_merge_gathered reduces the copies on the device (u64 SUM | f64 SUM | bitset OR | i64 MIN per region)."""
+    pb_result_merge_gathered reduces the copies on the device (u64 SUM | f64 SUM | bitset OR | i64 MIN per region).
+    The receive buffer is allocated once per size and reused (no allocator traffic on the hot path)."""
     ext = torch.cuda.ExternalStream(result.stream())
+    ptr, nbytes = result.device_buffer(8)
+    words, world = nbytes // 8, dist.get_world_size()
+    gathered = _gather_buffers.get((words, world))
+    if gathered is None:
+        gathered = torch.empty(world * words, dtype=torch.int64, device="cuda")
+        _gather_buffers[(words, world)] = gathered
     with torch.cuda.stream(ext):
-        ptr, nbytes = result.device_buffer(8)
-        local = torch.as_tensor(_DevBuf(ptr, nbytes // 8, "<i8"), device="cuda")
-        gathered = torch.empty(dist.get_world_size() * (nbytes // 8), dtype=torch.int64, device="cuda")
+        local = torch.as_tensor(_DevBuf(ptr, words, "<i8"), device="cuda")
         dist.all_gather_into_tensor(gathered, local)
-        result.merge_gathered(gathered.data_ptr(), dist.get_world_size())
-        gathered.record_stream(ext)
+        result.merge_gathered(gathered.data_ptr(), world)
