@@ -11,7 +11,8 @@ A step = one pass of the whole query over all segments of this rank through the 
 pb_query_execute, merged result table back in pinned host memory).  `value` = rows / wall time of K steps with the
 segments already resident in HBM; `e2e` = the same call sequence starting from HOST buffers (pb_segment_stage of
 the touched columns + execute + result read-back inside the timed region).  N > 1: every rank owns its own 8
-segments (weak scaling), per-rank dense tables are all-reduced over NCCL, rank 0 finalises.
+segments (weak scaling), per-rank dense tables are merged over NCCL (one all-gather of the table block + a merge kernel;
+PB_MERGE=allreduce selects three in-place all-reduces instead), rank 0 finalises.
 
 `--impl reference` times the CPU restatement of the reference path (oracle/, the one place this file may run it
 besides the cpu_baseline leg) on the host cores, one thread per segment.
@@ -192,7 +193,7 @@ def workload_config(args, segs):
                         f"WHERE c1 IN({args.in_values}) AND c2<k GROUP BY d0,d1,d2 SUM/COUNT/MIN/MAX, skipIndexes c1=inverted",
             "segments_per_gpu": len(segs), "rows_per_gpu": sum(s.num_docs for s in segs),
             "columns_materialised": "8 touched of the 20-column table", "l2_policy": "inputs (>1 GB/GPU) larger than the 126 MB L2",
-            "parallelism": f"segments sharded over {args.gpus} GPU(s); dense group tables all-reduced over NCCL" if args.gpus > 1 else "1 GPU"}
+            "parallelism": f"segments sharded over {args.gpus} GPU(s); dense group tables merged over NCCL ({os.environ.get('PB_MERGE', 'allgather')})" if args.gpus > 1 else "1 GPU"}
 
 
 def main():
@@ -232,7 +233,7 @@ def main():
     if world > 1:
         # agree on the global dictionaries of the group-by columns (dense tables must line up across ranks)
         from pinot_b200.distributed import agree_global_dictionaries, all_gather_merge_tables, all_reduce_tables
-        merge_mode = os.environ.get("PB_MERGE", "allreduce")
+        merge_mode = os.environ.get("PB_MERGE", "allgather")
         agree_global_dictionaries(group, q.group_by, [int(segs[0].columns[c].data_type) for c in q.group_by], dist)
 
     def barrier():

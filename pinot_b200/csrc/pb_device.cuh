@@ -103,7 +103,7 @@ struct DevSegQuery {
 
 struct DevTable {
   int32_t mode;
-  int32_t pad;
+  int32_t key_words;                 // hash: 1 = 64-bit composite key, 2 = 128-bit (ARRAY_MAP-sized key spaces)
   uint64_t capacity;                 // dense: number of groups; hash: slots (power of two)
   unsigned long long* hkeys;         // hash: slot keys (PB_HASH_EMPTY = free)
   unsigned long long* rowcnt;        // rows per slot
@@ -429,6 +429,34 @@ __device__ __forceinline__ uint64_t pb_hash_slot(const DevTable& t, uint64_t key
   }
 }
 
+// 128-bit composite keys (more than 64 bits of dictIds: the reference's ArrayMapBasedHolder,
+// DictionaryBasedGroupKeyGenerator.java:809-885): slots are 16-byte pairs claimed with ATOMG.CAS.128
+__device__ __forceinline__ void pb_atom_cas_u128(unsigned long long* p, unsigned long long clo, unsigned long long chi, unsigned long long vlo,
+                                                 unsigned long long vhi, unsigned long long& olo, unsigned long long& ohi) {
+  asm volatile("{\n.reg .b128 c, v, o;\nmov.b128 c, {%2, %3};\nmov.b128 v, {%4, %5};\natom.global.cas.b128 o, [%6], c, v;\nmov.b128 {%0, %1}, o;\n}\n"
+               : "=l"(olo), "=l"(ohi) : "l"(clo), "l"(chi), "l"(vlo), "l"(vhi), "l"(p) : "memory");
+}
+__device__ __forceinline__ uint64_t pb_hash_slot2(const DevTable& t, uint64_t lo, uint64_t hi) {
+  if (lo == PB_HASH_EMPTY && hi == PB_HASH_EMPTY) return t.capacity;     // reserved slot for the sentinel pattern itself
+  const uint64_t mask = t.capacity - 1;
+  uint64_t s = pb_hash64(lo ^ pb_hash64(hi)) & mask;
+  while (true) {
+    if (pb_ld_volatile_u32(t.num_groups) >= t.num_groups_limit) {
+      // limit reached: only existing keys may still be updated -> probe without inserting
+      unsigned long long clo, chi;   // one 16-byte transaction, so a concurrent CAS.128 is seen whole or not at all
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(clo), "=l"(chi) : "l"(&t.hkeys[2 * s]));
+      if (clo == lo && chi == hi) return s;
+      if (clo == PB_HASH_EMPTY && chi == PB_HASH_EMPTY) { pb_red_add_u32(t.limit_reached, 1u); return ~0ull; }
+    } else {
+      unsigned long long olo, ohi;
+      pb_atom_cas_u128(&t.hkeys[2 * s], PB_HASH_EMPTY, PB_HASH_EMPTY, lo, hi, olo, ohi);
+      if (olo == PB_HASH_EMPTY && ohi == PB_HASH_EMPTY) { pb_red_add_u32(t.num_groups, 1u); return s; }
+      if (olo == lo && ohi == hi) return s;
+    }
+    s = (s + 1) & mask;
+  }
+}
+
 // keyless accumulators live in shared memory, one private cell per thread (no atomics)
 struct KeylessAcc {
   double* sum;        // [n_aggs][PB_NTHREADS]
@@ -464,7 +492,7 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
   // ---- phase 1: every gather of this doc is issued before anything is reduced, four independent chains at a
   // time (index clamping instead of branches keeps the loads unconditional, so they overlap) ----
   const int nG = Q.n_group_by, nA = Q.n_aggs;
-  uint64_t slot = 0;
+  uint64_t slot = 0, slot_hi = 0;
   if (Q.table_mode != T_KEYLESS) {
     const bool dense = Q.table_mode == T_DENSE;
     const bool multi = nG > 1;
@@ -476,7 +504,9 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
       for (int k = 0; k < 4; k++) {
         if (j + k < nG) {
           const DevKeyCol& kc = sq.keys[j + k];
-          slot += dense ? f[k] * kc.mult : (f[k] << kc.shift);
+          if (dense) slot += f[k] * kc.mult;
+          else if (kc.shift < 64) { slot |= f[k] << kc.shift; if (kc.shift) slot_hi |= f[k] >> (64 - kc.shift); }
+          else slot_hi |= f[k] << (kc.shift - 64);
         }
       }
     }
@@ -496,7 +526,7 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 
   // ---- phase 2: table update ----
   if (Q.table_mode == T_HASH) {
-    slot = pb_hash_slot(t, slot);
+    slot = t.key_words == 2 ? pb_hash_slot2(t, slot, slot_hi) : pb_hash_slot(t, slot);
     if (slot == ~0ull) return;
   }
   if (Q.table_mode == T_KEYLESS) keyless_rows++;
@@ -1134,6 +1164,7 @@ struct DevFinAgg {
 struct DevFinalize {
   int32_t mode, n_gb, n_aggs, always_emit;
   uint64_t S;                 // slots to scan
+  int32_t key_words, pad_k;
   uint64_t capacity;          // T_HASH: index of the reserved sentinel slot
   uint64_t cap_out;
   const unsigned long long* rowcnt;
@@ -1172,13 +1203,20 @@ __global__ void pb_finalize_kernel(const DevFinalize F) {
       }
       else if (fa.op == 0) fa.out[k] = (double)c;
     }
-    unsigned long long key = 0;
-    if (F.mode == T_HASH) key = (i == F.capacity) ? PB_HASH_EMPTY : F.hkeys[i];
+    unsigned long long key = 0, key_hi = 0;
+    if (F.mode == T_HASH) {
+      if (F.key_words == 2) { key = (i == F.capacity) ? PB_HASH_EMPTY : F.hkeys[2 * i]; key_hi = (i == F.capacity) ? PB_HASH_EMPTY : F.hkeys[2 * i + 1]; }
+      else key = (i == F.capacity) ? PB_HASH_EMPTY : F.hkeys[i];
+    }
     for (int j = 0; j < F.n_gb; j++) {
       const DevFinKey& fk = F.keys[j];
       uint64_t field;
       if (F.mode == T_DENSE) field = (i / fk.div) % fk.card;
-      else { field = key >> fk.shift; if (fk.width < 64) field &= ((1ull << fk.width) - 1ull); }
+      else {
+        if (fk.shift < 64) { field = key >> fk.shift; if (fk.shift && fk.shift + fk.width > 64) field |= key_hi << (64 - fk.shift); }
+        else field = key_hi >> (fk.shift - 64);
+        if (fk.width < 64) field &= ((1ull << fk.width) - 1ull);
+      }
       uint8_t* o = fk.out_vals + k * (uint64_t)fk.eb;
       if (fk.is_dict) {
         fk.out_ids[k] = (int32_t)field;

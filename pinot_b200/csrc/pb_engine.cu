@@ -702,6 +702,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   // ---- table mode and layout ----
   r->tables.resize(n_tables);
   int table_mode = nG == 0 ? T_KEYLESS : T_DENSE;
+  int key_words = 1;
   if (nG > 0) {
     for (int t = 0; t < n_tables; t++) {
       TableMeta& tm = r->tables[t];
@@ -725,7 +726,8 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       }
       bool dense_ok = !any_raw_key && prod <= PB_DENSE_MAX;
       if (!dense_ok) {
-        if (total_bits > 64) return fail(PB_ERR_UNSUPPORTED, "group key needs %d bits (> 64): decline to the CPU plan", total_bits);
+        if (total_bits > 128) return fail(PB_ERR_UNSUPPORTED, "group key needs %d bits (> 128): decline to the CPU plan", total_bits);
+        if (total_bits > 64) key_words = 2;
         table_mode = T_HASH;
       }
       tm.capacity = dense_ok ? (uint64_t)prod : 0;
@@ -770,7 +772,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       if (op == PB_AGG_DISTINCTCOUNT) zero_bytes += 4 * S * dc_words[a];
     }
     zero_bytes = (zero_bytes + 255) & ~(size_t)255;
-    if (table_mode == T_HASH) ff_bytes += 8 * S;
+    if (table_mode == T_HASH) ff_bytes += 8 * S * (size_t)key_words;
   }
   zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 + 256;
   if (zero_bytes > (64ull << 30)) return fail(PB_ERR_UNSUPPORTED, "group table needs %zu bytes: decline to the CPU plan", zero_bytes);
@@ -823,7 +825,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       }
       if (t == 0) { r->span_mm = d_mm; r->span_mm_n = (int64_t)mo; }
       zo = (zo + 255) & ~(size_t)255;
-      if (table_mode == T_HASH) { dt.hkeys = reinterpret_cast<unsigned long long*>(d_ff + fo); fo += 8 * S; }
+      if (table_mode == T_HASH) { dt.hkeys = reinterpret_cast<unsigned long long*>(d_ff + fo); fo += 8 * S * (size_t)key_words; dt.key_words = key_words; }
       unsigned long long* cnt = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE;
       dt.num_groups = reinterpret_cast<unsigned int*>(cnt + 0);
       dt.limit_reached = reinterpret_cast<unsigned int*>(cnt + 1);
@@ -1234,7 +1236,7 @@ static int finalize_result(pb_result_s* r) {
     DevFinalize F;
     memset(&F, 0, sizeof F);
     F.mode = mode; F.n_gb = nG; F.n_aggs = nA; F.always_emit = mode == T_KEYLESS ? 1 : 0;
-    F.S = mode == T_KEYLESS ? 1 : S; F.capacity = tm.capacity; F.cap_out = cap;
+    F.S = mode == T_KEYLESS ? 1 : S; F.capacity = tm.capacity; F.cap_out = cap; F.key_words = tm.dev.key_words;
     F.rowcnt = tm.dev.rowcnt; F.hkeys = tm.dev.hkeys;
     F.cursor = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3;
     F.out_slots = (unsigned long long*)tm.slots.p; F.out_rows = (unsigned long long*)tm.rows.p;

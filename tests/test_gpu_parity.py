@@ -66,9 +66,28 @@ def test_golden_group_by(sv_group, group_by, key, exp, key_f, exp_f):   # :96-15
         assert (row[0], int(row[1]), int(row[2]), int(row[3]), int(row[4][0]), row[4][1]) == e
 
 
-def test_golden_very_large_group_by_declines(sv_group):   # :156-174 — ARRAY_MAP keys (> 64 bits): plan maker declines
+VERY_LARGE = " GROUP BY column1, column3, column6, column7, column9, column11, column12, column17, column18"
+
+
+def test_golden_very_large_group_by(sv_group):   # :156-174 — the ARRAY_MAP holder's key space (> 64 bits of dictIds): 128-bit keys
     seg, g = sv_group
-    q = parse_sql(AGG + " GROUP BY column1, column3, column6, column7, column9, column11, column12, column17, column18")
+    for sql, k, e, st_e in (
+            (AGG + VERY_LARGE, (1784773968, 204243323, 628170461, 1985159279, 296467636, b"P", b"HEuxNvH", 402773817, 2047180536),
+             (1, 1784773968, 204243323, 628170461, 1985159279, 1), (30000, 0, 270000, 30000)),
+            (AGG + FILTER + VERY_LARGE, (1361199163, 178133991, 296467636, 788414092, 1719301234, b"P", b"MaztCmmxxgguBUxPti", 1284373442, 752388855),
+             (1, 1361199163, 178133991, 296467636, 788414092, 1), (6129, 63064, 55161, 30000))):
+        r = native.execute(g, parse_sql(sql))
+        row = _row(r.tables[0], k)
+        assert (row[0], int(row[1]), int(row[2]), int(row[3]), int(row[4][0]), row[4][1]) == e
+        st = r.tables[0].stats
+        assert (st["num_docs_scanned"], st["num_entries_scanned_post_filter"], st["num_total_docs"]) == (st_e[0], st_e[2], st_e[3])
+    check_query([seg, seg], AGG + FILTER + VERY_LARGE, flags_list=ALL_FLAGS)
+    check_query([seg, seg], "SELECT COUNT(*), DISTINCTCOUNT(column5) FROM testTable" + VERY_LARGE)
+
+
+def test_group_key_wider_than_128_bits_declines(sv_group):   # plan maker declines: PB_ERR_UNSUPPORTED, never a CPU fallback
+    seg, g = sv_group
+    q = parse_sql("SELECT COUNT(*) FROM testTable" + VERY_LARGE + ", column5, daysSinceEpoch, column1, column3, column6, column7")
     with pytest.raises(native.PinotB200Error) as ei:
         native.execute(g, q)
     assert ei.value.code == -2
