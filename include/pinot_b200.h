@@ -117,6 +117,10 @@ typedef struct pb_aggregation_desc {
 #define PB_Q_COMBINE 1u            /* one merged table over all segments (GroupByCombineOperator semantics, on device) */
 #define PB_Q_DEFER_FINALIZE 2u     /* leave tables on the device for a cross-GPU reduce; call pb_result_finalize */
 #define PB_Q_GENERIC_KERNEL 4u     /* force the width-generic predicate path (testing / A-B measurement) */
+#define PB_Q_GATHER_IN_PLACE 16u   /* cold segments: columns that are only gathered (group-by keys, aggregation inputs) and are not
+                                    * resident in HBM yet are read in place from the caller's pb_host_register'd buffers (a few
+                                    * PCIe sectors per matching row) instead of being copied whole; predicate columns are staged.
+                                    * Buffers that are not page-locked/mapped or not 4-byte aligned are staged as usual. */
 #define PB_Q_NO_TMA 8u             /* stage tiles with ld.global/st.shared instead of cp.async.bulk (testing) */
 
 typedef struct pb_query_desc {
@@ -201,6 +205,7 @@ double pb_result_device_ms(pb_result_handle r);
 double pb_result_scan_kernel_ms(pb_result_handle r);
 int pb_result_phase_ms(pb_result_handle r, double* filter_kernel_ms, double* agg_kernel_ms);
 int32_t pb_result_kernel_launches(pb_result_handle r);
+int32_t pb_result_in_place_columns(pb_result_handle r);   /* (segment, column) pairs this query gathered in place from host memory */
 /* host-side microseconds spent in this call, by phase: [0] resolve + stage, [1] table allocation + init,
  * [2] descriptor build + upload, [3] kernel launches, [4] wait for the scan + group count, [5] compaction,
  * gathers and read-back, [6] host key decode / stats; [7] reserved */
@@ -228,7 +233,7 @@ int pb_result_wait(pb_result_handle r);
 
 /* Page-lock a caller-owned buffer (e.g. the mmap'd columns.psf of a segment) so staging runs at full PCIe
  * rate; optional.  Wraps cudaHostRegister / cudaHostUnregister. */
-int pb_host_register(const void* ptr, size_t bytes);
+int pb_host_register(const void* ptr, size_t bytes);   /* cudaHostRegisterPortable | cudaHostRegisterMapped */
 int pb_host_unregister(const void* ptr);
 
 #ifdef __cplusplus

@@ -71,6 +71,8 @@ struct DevKeyCol {         // group-by column (gathered per matching doc)
   int32_t data_type;
   int32_t shift;           // T_HASH: bit position of this column in the composite key
   uint64_t mult;           // T_DENSE: mixed-radix multiplier
+  uint32_t n_full_words;   // words wholly inside the buffer (0xFFFFFFFF: padded HBM copy, no bound needed)
+  uint32_t tail_word;      // in-place host buffer: the trailing partial word, zero-padded (as stored, big-endian)
 };
 
 struct DevAggCol {
@@ -80,7 +82,9 @@ struct DevAggCol {
   int32_t bits;
   int32_t raw_width;
   int32_t data_type;
-  int32_t pad;
+  uint32_t n_full_words;   // see DevKeyCol
+  uint32_t tail_word;
+  uint32_t pad;
 };
 
 struct DevSegQuery {
@@ -171,6 +175,19 @@ __device__ __forceinline__ uint32_t pb_unpack_at(const uint8_t* __restrict__ fwd
   uint32_t hi = pb_bswap32(__ldg(w + wi));
   uint32_t lo = pb_bswap32(__ldg(w + wi + 1));
   return __funnelshift_l(lo, hi, s) >> (32 - bits);
+}
+
+// Same, for a gathered column that may be read IN PLACE from the caller's page-locked host buffer (PB_Q_GATHER_IN_PLACE):
+// that buffer has no padding, so words past its last whole word come from the descriptor instead of memory.
+__device__ __forceinline__ uint32_t pb_unpack_at_bounded(const uint8_t* __restrict__ fwd, uint32_t doc, int bits, uint32_t n_full, uint32_t tail) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(fwd);
+  unsigned long long bit = (unsigned long long)doc * (unsigned)bits;
+  unsigned long long wi = bit >> 5;
+  uint32_t s = (uint32_t)bit & 31u;
+  uint32_t hi = tail, lo = tail;
+  if (wi < n_full) hi = __ldg(w + wi);
+  if (wi + 1 < n_full) lo = __ldg(w + wi + 1);
+  return __funnelshift_l(pb_bswap32(lo), pb_bswap32(hi), s) >> (32 - bits);
 }
 
 // raw PASS_THROUGH forward index value (FixedByteChunkSVForwardIndexReader.java:53-61): big-endian
@@ -470,7 +487,7 @@ __device__ __forceinline__ uint64_t pb_key_field(const DevKeyCol& kc, uint32_t d
     else v = (uint64_t)pb_raw_i64(kc.fwd, doc, kc.raw_width, kc.data_type);
     return (kc.raw_width == 4 && multi) ? (v & 0xffffffffull) : v;
   }
-  uint32_t id = pb_unpack_at(kc.fwd, doc, kc.bits);
+  uint32_t id = pb_unpack_at_bounded(kc.fwd, doc, kc.bits, kc.n_full_words, kc.tail_word);
   if (kc.remap) id = (uint32_t)__ldg(kc.remap + id);
   return id;
 }
@@ -479,12 +496,12 @@ __device__ __forceinline__ uint64_t pb_key_field(const DevKeyCol& kc, uint32_t d
 // to double); for DISTINCTCOUNT the (global) dictId, returned through the same 64-bit channel
 __device__ __forceinline__ double pb_agg_input(const DevAggCol& ac, int op, uint32_t doc) {
   if (op == 5) {
-    uint32_t id = pb_unpack_at(ac.fwd, doc, ac.bits);
+    uint32_t id = pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word);
     if (ac.remap) id = (uint32_t)__ldg(ac.remap + id);
     return __longlong_as_double((long long)id);
   }
   return ac.raw_width ? pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type)
-                      : __ldg(ac.dict_f64 + pb_unpack_at(ac.fwd, doc, ac.bits));
+                      : __ldg(ac.dict_f64 + pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word));
 }
 
 __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQuery& sq, const DevTable& t, uint32_t doc,

@@ -191,6 +191,8 @@ struct Column {
   double* d_dict_f64 = nullptr;
   uint8_t* d_dict_native = nullptr;                       // native-endian entries (group-key decode on the device)
   uint8_t* d_inv = nullptr;
+  // PB_Q_GATHER_IN_PLACE: device-visible alias of the caller's page-locked forward index (no HBM copy)
+  const uint8_t* d_fwd_host = nullptr; uint32_t host_full_words = 0, host_tail_word = 0;
   bool fwd_staged = false, dict_staged = false, inv_staged = false, native_staged = false;
 };
 
@@ -256,7 +258,31 @@ extern "C" int pb_segment_stage(const pb_segment_desc* d, int /*device_index*/, 
 
 // stage what a query needs of one column (under the segment lock)
 static void native_entry(const Column& c, int id, uint8_t* out);
-static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dict, bool need_inv, cudaStream_t st, bool need_native = false) {
+// Columns that a query only GATHERS (group-by keys, aggregation inputs) can be read in place from the caller's
+// page-locked, device-mapped host buffer: for a selective query that moves a few sectors per matching row over PCIe
+// instead of the whole column.  Needs pb_host_register'd memory and 4-byte alignment; otherwise the column is staged.
+static bool map_column_in_place(pb_segment_s* s, Column& c) {
+  if (c.d_fwd_host) return true;
+  if (c.has_dict && c.is_sorted) return false;
+  const uint8_t* src = c.has_dict ? c.h_fwd : c.h_fwd + c.raw_data_start;
+  uint64_t bytes = c.has_dict ? ((uint64_t)s->num_docs * c.bits + 7) / 8 : (uint64_t)s->num_docs * c.raw_width;
+  if (!src || bytes == 0 || (reinterpret_cast<uintptr_t>(src) & 3u) || bytes / 4 >= 0xFFFFFFFFull) return false;
+  void* dp = nullptr;
+  if (cudaHostGetDevicePointer(&dp, const_cast<uint8_t*>(src), 0) != cudaSuccess || !dp) { cudaGetLastError(); return false; }
+  // the last byte must be mapped too
+  void* dp_end = nullptr;
+  if (cudaHostGetDevicePointer(&dp_end, const_cast<uint8_t*>(src + bytes - 1), 0) != cudaSuccess) { cudaGetLastError(); return false; }
+  c.d_fwd_host = static_cast<const uint8_t*>(dp);
+  c.host_full_words = (uint32_t)(bytes / 4);
+  uint8_t tail[4] = {0, 0, 0, 0};
+  memcpy(tail, src + (bytes & ~3ull), (size_t)(bytes & 3ull));
+  memcpy(&c.host_tail_word, tail, 4);
+  return true;
+}
+
+static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dict, bool need_inv, cudaStream_t st, bool need_native = false,
+                        bool in_place_ok = false) {
+  if (need_fwd && !c.fwd_staged && in_place_ok && map_column_in_place(s, c)) need_fwd = false;
   if (need_fwd && !c.fwd_staged) {
     if (c.has_dict && c.is_sorted) {
       // pairs -> device, then materialise the bit-packed stream on the device
@@ -547,6 +573,7 @@ struct pb_result_s {
   int n_gb = 0, n_aggs = 0;
   int table_mode = 0;
   bool combine = false, finalized = false;
+  int in_place_columns = 0;                 // (segment, column) pairs gathered from mapped host memory (PB_Q_GATHER_IN_PLACE)
   std::vector<int> agg_op;
   std::vector<std::string> gb_names, agg_cols;
   std::vector<TableMeta> tables;
@@ -626,6 +653,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   if (nG < 0 || nG > PB_MAX_GROUP_BY) return fail(PB_ERR_UNSUPPORTED, "%d group-by columns (max %d)", nG, PB_MAX_GROUP_BY);
   if (nA <= 0 || nA > PB_MAX_AGGS) return fail(PB_ERR_UNSUPPORTED, "%d aggregations (max %d)", nA, PB_MAX_AGGS);
   const bool combine = (q->flags & PB_Q_COMBINE) != 0;
+  const bool in_place = (q->flags & PB_Q_GATHER_IN_PLACE) != 0;
   const int n_tables = combine ? 1 : n_segs;
 
   std::unique_ptr<pb_result_s, void (*)(pb_result_s*)> R(new pb_result_s(), free_result);
@@ -656,7 +684,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       gcol[si][j] = ci;
       Column& c = s->cols[ci];
       if (!c.has_dict) any_raw_key = true;
-      if ((rc = stage_column(s, c, true, false, false, st, !combine))) return rc;
+      if ((rc = stage_column(s, c, true, false, false, st, !combine, in_place))) return rc;
     }
     for (int a = 0; a < nA; a++) {
       if (q->aggregations[a].op == PB_AGG_COUNT) continue;
@@ -666,10 +694,10 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       Column& c = s->cols[ci];
       if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT) {
         if (!c.has_dict) return fail(PB_ERR_UNSUPPORTED, "DISTINCTCOUNT on raw column %s", c.name.c_str());
-        if ((rc = stage_column(s, c, true, false, false, st))) return rc;
+        if ((rc = stage_column(s, c, true, false, false, st, false, in_place))) return rc;
       } else {
         if (c.type == PB_STRING) return fail(PB_ERR_UNSUPPORTED, "numeric aggregation on STRING column %s", c.name.c_str());
-        if ((rc = stage_column(s, c, true, true, false, st))) return rc;
+        if ((rc = stage_column(s, c, true, true, false, st, false, in_place))) return rc;
       }
     }
     const pb_segment_query& sq = sqs[si];
@@ -1012,7 +1040,9 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     for (int j = 0; j < nG; j++) {
       const Column& c = s->cols[gcol[si][j]];
       DevKeyCol& kc = ds.keys[j];
-      kc.fwd = c.d_fwd; kc.bits = c.bits; kc.raw_width = c.has_dict ? 0 : c.raw_width; kc.data_type = c.type;
+      kc.fwd = c.fwd_staged ? c.d_fwd : c.d_fwd_host; kc.n_full_words = c.fwd_staged ? 0xFFFFFFFFu : c.host_full_words;
+      kc.tail_word = c.fwd_staged ? 0u : c.host_tail_word; if (!c.fwd_staged) r->in_place_columns++;
+      kc.bits = c.bits; kc.raw_width = c.has_dict ? 0 : c.raw_width; kc.data_type = c.type;
       kc.remap = (combine && gdict[j]) ? gdict[j]->d_remap[si] : nullptr;
       kc.shift = tm.shifts[j];
       kc.mult = mult;
@@ -1023,7 +1053,9 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       if (acol[si][a] < 0) continue;
       const Column& c = s->cols[acol[si][a]];
       DevAggCol& ac = ds.aggs[a];
-      ac.fwd = c.d_fwd; ac.dict_f64 = c.d_dict_f64; ac.bits = c.bits; ac.raw_width = c.has_dict ? 0 : c.raw_width; ac.data_type = c.type;
+      ac.fwd = c.fwd_staged ? c.d_fwd : c.d_fwd_host; ac.n_full_words = c.fwd_staged ? 0xFFFFFFFFu : c.host_full_words;
+      ac.tail_word = c.fwd_staged ? 0u : c.host_tail_word; if (!c.fwd_staged) r->in_place_columns++;
+      ac.dict_f64 = c.d_dict_f64; ac.bits = c.bits; ac.raw_width = c.has_dict ? 0 : c.raw_width; ac.data_type = c.type;
       ac.remap = (combine && adict[a]) ? adict[a]->d_remap[si] : nullptr;
     }
   }
@@ -1428,10 +1460,12 @@ extern "C" int pb_result_wait(pb_result_handle r) {
   CU(cudaStreamSynchronize(r->stream));
   return PB_OK;
 }
+extern "C" int32_t pb_result_in_place_columns(pb_result_handle r) { return r ? r->in_place_columns : 0; }
+
 extern "C" int pb_host_register(const void* ptr, size_t bytes) {
   int rc = ensure_init();
   if (rc) return rc;
-  CU(cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterDefault));
+  CU(cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
   return PB_OK;
 }
 extern "C" int pb_host_unregister(const void* ptr) {

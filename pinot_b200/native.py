@@ -21,6 +21,7 @@ PB_Q_COMBINE = 1
 PB_Q_DEFER_FINALIZE = 2
 PB_Q_GENERIC_KERNEL = 4
 PB_Q_NO_TMA = 8
+PB_Q_GATHER_IN_PLACE = 16
 
 
 class PbColumnDesc(C.Structure):
@@ -120,6 +121,8 @@ def lib():
     l.pb_result_scan_kernel_ms.restype = C.c_double
     l.pb_result_kernel_launches.argtypes = [C.c_void_p]
     l.pb_result_kernel_launches.restype = C.c_int32
+    l.pb_result_in_place_columns.argtypes = [C.c_void_p]
+    l.pb_result_in_place_columns.restype = C.c_int32
     l.pb_result_stream.argtypes = [C.c_void_p]
     l.pb_result_stream.restype = C.c_void_p
     l.pb_result_wait.argtypes = [C.c_void_p]
@@ -349,6 +352,7 @@ class Result:
         self.device_ms = l.pb_result_device_ms(self._rh)
         self.scan_kernel_ms = l.pb_result_scan_kernel_ms(self._rh)
         self.kernel_launches = l.pb_result_kernel_launches(self._rh)
+        self.in_place_columns = l.pb_result_in_place_columns(self._rh)
 
     def device_buffer(self, which: int, agg: int = 0):
         p, n = C.c_void_p(), C.c_int64()

@@ -87,7 +87,9 @@ def test_golden_very_large_group_by(sv_group):   # :156-174 — the ARRAY_MAP ho
 
 def test_group_key_wider_than_128_bits_declines(sv_group):   # plan maker declines: PB_ERR_UNSUPPORTED, never a CPU fallback
     seg, g = sv_group
-    q = parse_sql("SELECT COUNT(*) FROM testTable" + VERY_LARGE + ", column5, daysSinceEpoch, column1, column3, column6, column7")
+    # exactly 128 bits of dictIds (15 columns) still runs
+    check_query([seg], "SELECT COUNT(*), SUM(column1) FROM testTable" + FILTER + VERY_LARGE + ", column5, daysSinceEpoch, column1, column3, column6, column7")
+    q = parse_sql("SELECT COUNT(*) FROM testTable" + VERY_LARGE + ", column5, daysSinceEpoch, column1, column3, column6, column7, column9")   # 139 bits
     with pytest.raises(native.PinotB200Error) as ei:
         native.execute(g, q)
     assert ei.value.code == -2
@@ -178,6 +180,39 @@ def test_empty_and_match_all(synth):
     check_query(segs, "SELECT COUNT(*), SUM(m0), MIN(m1), MAX(m2) FROM t WHERE c1 < -5", group=g)
     check_query(segs, "SELECT COUNT(*), SUM(m0), MIN(m1), MAX(m2) FROM t WHERE c1 > -5", group=g)
     check_query(segs, "SELECT d1, COUNT(*) FROM t WHERE c1 < -5 GROUP BY d1", group=g)
+
+
+def test_gather_in_place_from_mapped_host_buffers():
+    """PB_Q_GATHER_IN_PLACE: group-by / aggregation columns of cold segments are read from the caller's page-locked
+    buffers (no HBM copy); predicate columns are staged.  Row counts chosen so the bit streams end mid-word."""
+    native.init()
+    segs = [datagen.make_segment_synth(i, n, vary_dim_dictionaries=(i > 0)) for i, n in enumerate((70_001, 33_333, 1_027))]
+    registered = []
+    for s in segs:
+        for c in s.columns.values():
+            if c.forward_index is not None and c.forward_index.nbytes:
+                native.host_register(c.forward_index)
+                registered.append(c.forward_index)
+    try:
+        for sql, exact, min_cols in (
+                (datagen.config2_sql(segs, 16), True, 6 * 3),
+                ("SELECT s0, d3, DISTINCTCOUNT(c0), SUM(x0), MAX(k0) FROM t WHERE c2 > 100 GROUP BY s0, d3 LIMIT 100000", False, 5 * 3),
+                ("SELECT d0, COUNT(*), SUM(m0) FROM t WHERE d0 > 2 AND c1 > 10 GROUP BY d0", True, 1 * 3),   # d0: predicate AND key
+                ("SELECT MIN(m1), MAX(m2), AVG(m0) FROM t", True, 3 * 3)):
+            staged = [native.StagedSegment(s) for s in segs]       # cold: nothing resident yet
+            g = native.SegmentGroup(staged)
+            q = parse_sql(sql)
+            for flags in (native.PB_Q_GATHER_IN_PLACE, native.PB_Q_GATHER_IN_PLACE | native.PB_Q_COMBINE):
+                r = native.execute(g, q, flags)
+                assert r.in_place_columns >= min_cols, (sql, r.in_place_columns)
+                r.free()
+            check_query(segs, q, group=g, flags_list=(native.PB_Q_GATHER_IN_PLACE,), exact_float=exact)
+            g.release()
+            for st_ in staged:
+                st_.release()
+    finally:
+        for a in registered:
+            native.host_unregister(a)
 
 
 @pytest.mark.parametrize("bits", list(range(1, 21)) + [24])
