@@ -139,6 +139,7 @@ struct DevQuery {
   int32_t prefetch;                      // pb_filter_kernel prefetches the gather sectors of matching docs into L2
   int32_t sparse_max;                    // survivors per 1024 docs below which later AND leaves use the restricted scan
   int32_t pad_s;
+  uint64_t unit_lo;                      // this launch covers work units [unit_lo, unit_lo + n_units) (a wave of segments)
   uint32_t* match_list;                  // global doc numbers of the docs that pass the filter
   unsigned long long* match_count;
   const DevSegQuery* segs;
@@ -635,8 +636,8 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
 
   // this CTA's contiguous range of work units
   const uint64_t per = (Q.n_units + gridDim.x - 1) / gridDim.x;
-  const uint64_t cta_lo = (uint64_t)blockIdx.x * per;
-  const uint64_t cta_hi = cta_lo + per < Q.n_units ? cta_lo + per : Q.n_units;
+  const uint64_t cta_lo = Q.unit_lo + (uint64_t)blockIdx.x * per;
+  const uint64_t cta_hi = cta_lo + per < Q.unit_lo + Q.n_units ? cta_lo + per : Q.unit_lo + Q.n_units;
   if (cta_lo >= cta_hi) return;
   int seg_first = 0;
   while (seg_first + 1 < Q.n_segs && cta_lo >= Q.segs[seg_first + 1].unit_begin) seg_first++;

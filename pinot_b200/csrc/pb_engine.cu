@@ -51,6 +51,7 @@ struct Context {
   std::vector<PinnedBlock> pinned_free;
   std::vector<PinnedBlock> scratch_free;      // large device scratch buffers (match lists), reused across calls
   cudaStream_t util_stream = nullptr;         // stream-ordered allocations / frees of staged data
+  cudaStream_t copy_stream = nullptr;         // host -> HBM staging copies (queries wait on per-segment events)
   bool smem_attr_set = false;
 };
 static Context g_ctx;
@@ -80,6 +81,7 @@ static int ensure_init() {
     if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
   }
   CU(cudaStreamCreateWithFlags(&g_ctx.util_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
   g_ctx.inited = true;
   return PB_OK;
 }
@@ -203,6 +205,11 @@ struct pb_segment_s {
   std::vector<Column> cols;
   std::mutex mu;
   int64_t device_bytes = 0;
+  // staging copies run on the context's copy stream; `staged_ev` marks the last one enqueued for this segment and
+  // every query that touches the segment orders its kernels after it (until it is known to have completed)
+  cudaEvent_t staged_ev = nullptr;
+  bool staged_pending = false, stage_dirty = false;
+  std::vector<PinnedBlock> staging_bufs;   // pinned sources of in-flight dictionary uploads (freed with the segment)
 };
 
 static int find_col(const pb_segment_s* s, const char* name) {
@@ -310,10 +317,14 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
       s->device_bytes += (int64_t)padded;
     }
     c.fwd_staged = true;
+    s->stage_dirty = true;
   }
   if (need_dict && !c.dict_staged && c.has_dict && c.type != PB_STRING) {
     // BaseImmutableDictionary value reads, widened to double (Dictionary.getDoubleValue)
-    std::vector<double> v((size_t)c.card);
+    const size_t vbytes = sizeof(double) * (size_t)std::max(c.card, 1);
+    double* v = static_cast<double*>(pinned_alloc(vbytes));       // pinned so the upload never synchronises the copy stream
+    if (!v) return fail(PB_ERR_OOM, "pinned host allocation failed");
+    s->staging_bufs.push_back({v, vbytes});
     for (int i = 0; i < c.card; i++) {
       const uint8_t* p = c.h_dict.data() + (size_t)i * c.entry_bytes;
       switch (c.type) {
@@ -324,8 +335,8 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
       }
     }
     CU(dev_alloc((void**)&c.d_dict_f64, sizeof(double) * (size_t)c.card));
-    CU(cudaMemcpyAsync(c.d_dict_f64, v.data(), sizeof(double) * (size_t)c.card, cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));   // v is a stack-owned staging buffer
+    CU(cudaMemcpyAsync(c.d_dict_f64, v, sizeof(double) * (size_t)c.card, cudaMemcpyHostToDevice, st));
+    s->stage_dirty = true;
     s->device_bytes += (int64_t)sizeof(double) * c.card;
     c.dict_staged = true;
   }
@@ -343,12 +354,15 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
     CU(cudaMemcpyAsync(c.d_inv, c.h_inv, c.h_inv_len, cudaMemcpyHostToDevice, st));
     s->device_bytes += (int64_t)c.h_inv_len;
     c.inv_staged = true;
+    s->stage_dirty = true;
   }
   return PB_OK;
 }
 
 extern "C" int pb_segment_release(pb_segment_handle s) {
   if (!s) return PB_OK;
+  if (s->staged_ev) { cudaEventSynchronize(s->staged_ev); cudaEventDestroy(s->staged_ev); }
+  for (auto& b : s->staging_bufs) pinned_free(b.p, b.cap);
   for (auto& c : s->cols) {
     dev_free(c.d_fwd); dev_free(c.d_sorted_pairs); dev_free(c.d_dict_f64); dev_free(c.d_dict_native); dev_free(c.d_inv);
   }
@@ -573,6 +587,7 @@ struct pb_result_s {
   int n_gb = 0, n_aggs = 0;
   int table_mode = 0;
   bool combine = false, finalized = false;
+  int waves = 1;                            // launches were split into this many waves behind the staging copies
   int in_place_columns = 0;                 // (segment, column) pairs gathered from mapped host memory (PB_Q_GATHER_IN_PLACE)
   std::vector<int> agg_op;
   std::vector<std::string> gb_names, agg_cols;
@@ -623,6 +638,7 @@ extern "C" void pb_result_free(pb_result_handle r) { free_result(r); }
 // query execution
 // ------------------------------------------------------------------------------------------------
 #define PB_DENSE_MAX (1ull << 24)
+#define PB_MAX_WAVES 8            // cold segments: launches are split into waves that follow the staging copies
 #define PB_COUNTERS_PER_TABLE 4   // u64 cells: [0] num_groups(lo u32) [1] limit flag (lo u32) [2] docs matched [3] compaction cursor
 
 struct Arena {   // host mirror of a device allocation; pointers are handed out as device addresses
@@ -640,6 +656,41 @@ struct Arena {   // host mirror of a device allocation; pointers are handed out 
     return d;
   }
 };
+
+// Expected fraction of a segment's docs that pass the filter (postfix tree), from dictionary cardinalities: the same
+// uniform-value estimate the AND ordering uses.  Drives the stage-or-gather choice of PB_Q_GATHER_IN_PLACE.
+static double estimate_selectivity(const pb_segment_s* s, const pb_segment_query& sq) {
+  if (sq.num_filter_nodes <= 0) return 1.0;
+  std::vector<double> stk;
+  for (int n = 0; n < sq.num_filter_nodes; n++) {
+    const pb_filter_node& fn = sq.filter[n];
+    const Column* c = (fn.column >= 0 && fn.column < (int)s->cols.size()) ? &s->cols[fn.column] : nullptr;
+    const double card = c && c->card > 0 ? (double)c->card : 1.0;
+    auto excl = [&](double f) { return fn.exclusive ? 1.0 - f : f; };
+    switch (fn.kind) {
+      case PB_F_AND: case PB_F_OR: {
+        int k = std::min<int>(fn.num_children, (int)stk.size());
+        double v = fn.kind == PB_F_AND ? 1.0 : 0.0;
+        for (int i = 0; i < k; i++) { double x = stk.back(); stk.pop_back(); v = fn.kind == PB_F_AND ? v * x : v + x; }
+        stk.push_back(std::min(1.0, v));
+        break;
+      }
+      case PB_F_NOT: if (!stk.empty()) stk.back() = 1.0 - stk.back(); break;
+      case PB_F_MATCH_ALL: stk.push_back(1.0); break;
+      case PB_F_EMPTY: stk.push_back(0.0); break;
+      case PB_F_SCAN_DICT_RANGE: stk.push_back(std::min(1.0, std::max(0.0, (double)(fn.hi - fn.lo) / card))); break;
+      case PB_F_SCAN_DICT_SET: case PB_F_INVERTED: stk.push_back(excl(std::min(1.0, (double)fn.num_ids / card))); break;
+      case PB_F_SORTED: {
+        double docs = 0;
+        for (int i = 0; i + 1 < fn.num_ids; i += 2) docs += (double)(fn.ids[i + 1] - fn.ids[i] + 1);
+        stk.push_back(excl(std::min(1.0, docs / std::max(1, s->num_docs))));
+        break;
+      }
+      default: stk.push_back(0.5); break;     // raw-value predicates, serialized bitmaps: no statistics
+    }
+  }
+  return stk.empty() ? 1.0 : std::min(1.0, std::max(0.0, stk.back()));
+}
 
 static int finalize_result(pb_result_s* r);
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -675,16 +726,31 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   // ---- resolve columns, stage what is needed ----
   std::vector<std::vector<int>> gcol(n_segs, std::vector<int>(nG)), acol(n_segs, std::vector<int>(nA, -1));
   bool any_raw_key = false;
+  cudaStream_t cs = g_ctx.copy_stream;
+  std::vector<cudaEvent_t> seg_wait(n_segs, nullptr);   // staging events this call's kernels must wait for
+  int n_pending = 0;
   for (int si = 0; si < n_segs; si++) {
     pb_segment_s* s = g->segs[si];
     std::lock_guard<std::mutex> lk(s->mu);
+    // PB_Q_GATHER_IN_PLACE, per column: a gathered value costs one 32-byte PCIe read (about the link time of ~100 streamed
+    // bytes, measured: ~0.5 G reads/s vs ~50 GB/s); copying the column costs bits/8 bytes per doc.  Gather in place only
+    // where that is cheaper: expected matches x 100 B < column bytes.
+    // (PB_IN_PLACE_COST overrides the 100 B; 0 = always gather: used by the tests to reach every code path.)
+    const double sel = in_place ? estimate_selectivity(s, sqs[si]) : 1.0;
+    double gather_cost = 100.0;
+    if (in_place) if (const char* e = getenv("PB_IN_PLACE_COST")) gather_cost = atof(e);
+    auto gather_ok = [&](const Column& c) {
+      if (!in_place) return false;
+      const double col_bytes_per_doc = c.has_dict ? c.bits / 8.0 : (double)c.raw_width;
+      return sel * gather_cost < col_bytes_per_doc;
+    };
     for (int j = 0; j < nG; j++) {
       int ci = find_col(s, q->group_by_columns[j]);
       if (ci < 0) return fail(PB_ERR_INVALID, "segment %s: no column %s", s->name.c_str(), q->group_by_columns[j]);
       gcol[si][j] = ci;
       Column& c = s->cols[ci];
       if (!c.has_dict) any_raw_key = true;
-      if ((rc = stage_column(s, c, true, false, false, st, !combine, in_place))) return rc;
+      if ((rc = stage_column(s, c, true, false, false, cs, !combine, gather_ok(c)))) return rc;
     }
     for (int a = 0; a < nA; a++) {
       if (q->aggregations[a].op == PB_AGG_COUNT) continue;
@@ -694,10 +760,10 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       Column& c = s->cols[ci];
       if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT) {
         if (!c.has_dict) return fail(PB_ERR_UNSUPPORTED, "DISTINCTCOUNT on raw column %s", c.name.c_str());
-        if ((rc = stage_column(s, c, true, false, false, st, false, in_place))) return rc;
+        if ((rc = stage_column(s, c, true, false, false, cs, false, gather_ok(c)))) return rc;
       } else {
         if (c.type == PB_STRING) return fail(PB_ERR_UNSUPPORTED, "numeric aggregation on STRING column %s", c.name.c_str());
-        if ((rc = stage_column(s, c, true, true, false, st, false, in_place))) return rc;
+        if ((rc = stage_column(s, c, true, true, false, cs, false, gather_ok(c)))) return rc;
       }
     }
     const pb_segment_query& sq = sqs[si];
@@ -710,8 +776,19 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
         bool inv = fn.kind == PB_F_INVERTED;
         if ((fn.kind == PB_F_SCAN_DICT_RANGE || fn.kind == PB_F_SCAN_DICT_SET) && !c.has_dict) return fail(PB_ERR_INVALID, "filter node %d: dictionary scan on raw column", n);
         if ((fn.kind == PB_F_SCAN_RAW_RANGE || fn.kind == PB_F_SCAN_RAW_SET) && c.has_dict) return fail(PB_ERR_INVALID, "filter node %d: raw scan on dictionary column", n);
-        if ((rc = stage_column(s, c, !inv, false, inv, st))) return rc;
+        if ((rc = stage_column(s, c, !inv, false, inv, cs))) return rc;
       }
+    }
+    // order this (and every later) query's kernels after the copies just enqueued for the segment
+    if (s->stage_dirty) {
+      if (!s->staged_ev) CU(cudaEventCreateWithFlags(&s->staged_ev, cudaEventDisableTiming));
+      CU(cudaEventRecord(s->staged_ev, cs));
+      s->stage_dirty = false; s->staged_pending = true;
+    }
+    if (s->staged_pending) {
+      if (cudaEventQuery(s->staged_ev) == cudaSuccess) s->staged_pending = false;
+      else { seg_wait[si] = s->staged_ev; n_pending++; }
+      cudaGetLastError();   // cudaErrorNotReady is not an error
     }
   }
 
@@ -802,7 +879,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     zero_bytes = (zero_bytes + 255) & ~(size_t)255;
     if (table_mode == T_HASH) ff_bytes += 8 * S * (size_t)key_words;
   }
-  zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 + 256;
+  zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 * PB_MAX_WAVES + 256;
   if (zero_bytes > (64ull << 30)) return fail(PB_ERR_UNSUPPORTED, "group table needs %zu bytes: decline to the CPU plan", zero_bytes);
   uint8_t *d_zero = nullptr, *d_ff = nullptr; long long* d_mm = nullptr;
   // one block: [zero region | min/max region] so that a cross-GPU merge can ship the whole table in one collective
@@ -827,7 +904,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   {
     size_t zo = 0, fo = 0, mo = 0;
     r->d_counters = reinterpret_cast<unsigned long long*>(d_zero);
-    zo += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8; zo = (zo + 255) & ~(size_t)255;
+    zo += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 * PB_MAX_WAVES; zo = (zo + 255) & ~(size_t)255;
     for (int t = 0; t < n_tables; t++) {
       TableMeta& tm = r->tables[t];
       uint64_t S = slots_of(tm);
@@ -1111,7 +1188,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   { static const int sm = []() { const char* e = getenv("PB_SPARSE_MAX"); return e ? atoi(e) : PB_SPARSE_MAX; }(); hq->sparse_max = sm; }
   { static const int pf = []() { const char* e = getenv("PB_PREFETCH"); return e ? atoi(e) : 0; }(); hq->prefetch = pf; }   // off: measured no gain (profiles/r1_experiments.md)
   hq->match_list = d_match_list;
-  hq->match_count = r->d_counters + (size_t)n_tables * PB_COUNTERS_PER_TABLE;   // one extra zeroed cell after the per-table counters
+  hq->match_count = r->d_counters + (size_t)n_tables * PB_COUNTERS_PER_TABLE;   // PB_MAX_WAVES zeroed cells after the per-table counters
 
   // expand items (one per inverted-index bitmap / per sorted-index range list)
   int n_expand_items = 0;
@@ -1136,6 +1213,29 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     d_expand_items = ar.put<DevExpandItem>(items.data(), items.size());
     if (!d_expand_items) return fail(PB_ERR_STATE, "query arena overflow");
   }
+  // ---- waves: when some segments are still being copied to HBM, launch per run of segments so that the kernels of
+  // one wave (and its in-place gathers over PCIe) overlap the staging copies of the next ----
+  struct Wave { int seg_lo, seg_hi; const DevQuery* dq; uint64_t n_units, n_docs; };
+  std::vector<Wave> waves;
+  if (n_pending > 0 && !match_all && n_expand_items == 0 && n_segs > 1 && n_chunks > 0) {
+    const int per_wave = (n_segs + PB_MAX_WAVES - 1) / PB_MAX_WAVES;
+    for (int lo = 0; lo < n_segs; lo += per_wave) {
+      const int hi = std::min(n_segs, lo + per_wave);
+      DevQuery w = *hq;
+      w.unit_lo = hsegs[lo].unit_begin;
+      w.n_units = hsegs[hi - 1].unit_begin + hsegs[hi - 1].n_units - w.unit_lo;
+      w.n_docs_total = hsegs[hi - 1].doc_base + (uint64_t)g->segs[hi - 1]->num_docs - hsegs[lo].doc_base;
+      w.match_list = d_match_list + hsegs[lo].doc_base;
+      w.match_count = hq->match_count + waves.size();
+      const DevQuery* dw = ar.put<DevQuery>(&w, 1);
+      if (!dw) return fail(PB_ERR_STATE, "query arena overflow");
+      waves.push_back({lo, hi, dw, w.n_units, w.n_docs_total});
+    }
+  } else {
+    for (int si = 0; si < n_segs; si++) if (seg_wait[si]) CU(cudaStreamWaitEvent(st, seg_wait[si], 0));
+    waves.push_back({0, n_segs, dq, n_chunks, n_docs_total});
+  }
+  r->waves = (int)waves.size();
   CU(cudaMemcpyAsync(ar.dev, ar.host.data(), ar.used, cudaMemcpyHostToDevice, st));
   lap(2);
 
@@ -1149,59 +1249,60 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     CU(cudaGetLastError());
   }
 
-  // ---- kernel 1: filter -> match list ----
+  // ---- kernel 1: filter -> match list;  kernel 2: gather + aggregate the matching docs (per wave) ----
   CU(cudaEventRecord(r->ev1, st));
-  if (!match_all && n_chunks > 0) {
-    size_t smem = ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + stage_bytes * PB_NSTAGE * PB_NWARPS;
-    if (smem > 227 * 1024) return fail(PB_ERR_UNSUPPORTED, "filter kernel needs %zu bytes of shared memory", smem);
-    {
-      std::lock_guard<std::mutex> lk(g_ctx.mu);
-      if (!g_ctx.smem_attr_set) {
-        CU(cudaFuncSetAttribute(pb_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CU(cudaFuncSetAttribute(pb_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CU(cudaFuncSetAttribute(pb_agg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        CU(cudaFuncSetAttribute(pb_agg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        g_ctx.smem_attr_set = true;
-      }
+  {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (!g_ctx.smem_attr_set) {
+      CU(cudaFuncSetAttribute(pb_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CU(cudaFuncSetAttribute(pb_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CU(cudaFuncSetAttribute(pb_agg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      CU(cudaFuncSetAttribute(pb_agg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      g_ctx.smem_attr_set = true;
     }
+  }
+  size_t smem = 0;
+  uint64_t max_ctas = 0;
+  if (!match_all && n_chunks > 0) {
+    smem = ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + stage_bytes * PB_NSTAGE * PB_NWARPS;
+    if (smem > 227 * 1024) return fail(PB_ERR_UNSUPPORTED, "filter kernel needs %zu bytes of shared memory", smem);
     int occ = 1;
     if (U == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<1>, PB_NTHREADS, smem));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<2>, PB_NTHREADS, smem));
     if (occ < 1) return fail(PB_ERR_CUDA, "filter kernel does not fit an SM (smem %zu)", smem);
-    uint64_t max_ctas = (uint64_t)g_ctx.num_sms * (uint64_t)occ;
-    // every CTA gets a contiguous range of chunks; keep at least one chunk per warp
-    int grid = (int)std::min<uint64_t>(std::max<uint64_t>((n_chunks + PB_NWARPS - 1) / PB_NWARPS, 1), max_ctas);
-    if (U == 1) pb_filter_kernel<1><<<grid, PB_NTHREADS, smem, st>>>(dq);
-    else pb_filter_kernel<2><<<grid, PB_NTHREADS, smem, st>>>(dq);
-    r->launches++;
-    CU(cudaGetLastError());
+    max_ctas = (uint64_t)g_ctx.num_sms * (uint64_t)occ;
   }
-  CU(cudaEventRecord(r->evm, st));
-  // ---- kernel 2: gather + aggregate the matching docs ----
+  const size_t smem2 = table_mode == T_KEYLESS ? 2 * sizeof(double) * (size_t)nA * PB_NTHREADS : 0;
+  // more resident threads = more gathers in flight (the kernel is DRAM-latency bound); 6 CTAs/SM costs a 4-byte spill
+  static const int agg_occ = []() { const char* e = getenv("PB_AGG_OCC"); int v = e ? atoi(e) : 6; return v == 4 ? 4 : 6; }();
+  uint64_t max2 = 0;
   if (n_docs_total > 0) {
-    {
-      std::lock_guard<std::mutex> lk(g_ctx.mu);
-      if (!g_ctx.smem_attr_set) {
-        CU(cudaFuncSetAttribute(pb_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CU(cudaFuncSetAttribute(pb_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        CU(cudaFuncSetAttribute(pb_agg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        CU(cudaFuncSetAttribute(pb_agg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        g_ctx.smem_attr_set = true;
-      }
-    }
-    size_t smem2 = table_mode == T_KEYLESS ? 2 * sizeof(double) * (size_t)nA * PB_NTHREADS : 0;
-    // more resident threads = more gathers in flight (the kernel is DRAM-latency bound); 6 CTAs/SM costs a 4-byte spill
-    static const int agg_occ = []() { const char* e = getenv("PB_AGG_OCC"); int v = e ? atoi(e) : 6; return v == 4 ? 4 : 6; }();
     int occ2 = 1;
     if (agg_occ == 4) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pb_agg_kernel<4>, PB_NTHREADS, smem2));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pb_agg_kernel<6>, PB_NTHREADS, smem2));
     if (occ2 < 1) return fail(PB_ERR_CUDA, "aggregation kernel does not fit an SM");
-    uint64_t max2 = (uint64_t)g_ctx.num_sms * (uint64_t)occ2;
-    int grid2 = (int)std::min<uint64_t>(std::max<uint64_t>((n_docs_total + PB_NTHREADS - 1) / PB_NTHREADS, 1), max2);
-    if (agg_occ == 4) pb_agg_kernel<4><<<grid2, PB_NTHREADS, smem2, st>>>(dq);
-    else pb_agg_kernel<6><<<grid2, PB_NTHREADS, smem2, st>>>(dq);
-    r->launches++;
-    CU(cudaGetLastError());
+    max2 = (uint64_t)g_ctx.num_sms * (uint64_t)occ2;
+  }
+  for (size_t wi = 0; wi < waves.size(); wi++) {
+    const Wave& w = waves[wi];
+    if (waves.size() > 1)
+      for (int si = w.seg_lo; si < w.seg_hi; si++) if (seg_wait[si]) CU(cudaStreamWaitEvent(st, seg_wait[si], 0));
+    if (!match_all && w.n_units > 0) {
+      // every CTA gets a contiguous range of chunks; keep at least one chunk per warp
+      int grid = (int)std::min<uint64_t>(std::max<uint64_t>((w.n_units + PB_NWARPS - 1) / PB_NWARPS, 1), max_ctas);
+      if (U == 1) pb_filter_kernel<1><<<grid, PB_NTHREADS, smem, st>>>(w.dq);
+      else pb_filter_kernel<2><<<grid, PB_NTHREADS, smem, st>>>(w.dq);
+      r->launches++;
+      CU(cudaGetLastError());
+    }
+    if (wi + 1 == waves.size() || waves.size() == 1) CU(cudaEventRecord(r->evm, st));   // (waves interleave: the split is only exact for one wave)
+    if (w.n_docs > 0) {
+      int grid2 = (int)std::min<uint64_t>(std::max<uint64_t>((w.n_docs + PB_NTHREADS - 1) / PB_NTHREADS, 1), max2);
+      if (agg_occ == 4) pb_agg_kernel<4><<<grid2, PB_NTHREADS, smem2, st>>>(w.dq);
+      else pb_agg_kernel<6><<<grid2, PB_NTHREADS, smem2, st>>>(w.dq);
+      r->launches++;
+      CU(cudaGetLastError());
+    }
   }
   CU(cudaEventRecord(r->ev2, st));
   lap(3);

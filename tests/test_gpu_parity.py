@@ -6,7 +6,7 @@ from pinot_b200 import datagen, native
 from pinot_b200.query import parse_sql
 from pinot_b200.segment_writer import DataType, build_column, build_dict_column, make_segment
 from tests.fixtures import FILTER, sv_segment
-from tests.parity import check_query
+from tests.parity import assert_rows_equal, check_query
 
 pytestmark = pytest.mark.gpu
 
@@ -182,31 +182,48 @@ def test_empty_and_match_all(synth):
     check_query(segs, "SELECT d1, COUNT(*) FROM t WHERE c1 < -5 GROUP BY d1", group=g)
 
 
-def test_gather_in_place_from_mapped_host_buffers():
+def test_gather_in_place_from_mapped_host_buffers(monkeypatch):
     """PB_Q_GATHER_IN_PLACE: group-by / aggregation columns of cold segments are read from the caller's page-locked
-    buffers (no HBM copy); predicate columns are staged.  Row counts chosen so the bit streams end mid-word."""
+    buffers (no HBM copy) where that is cheaper than copying them; predicate columns are staged on the copy stream and
+    the kernels follow in per-segment waves.  Row counts chosen so the bit streams end mid-word."""
     native.init()
-    segs = [datagen.make_segment_synth(i, n, vary_dim_dictionaries=(i > 0)) for i, n in enumerate((70_001, 33_333, 1_027))]
+    segs = [datagen.make_segment_synth(i, n, vary_dim_dictionaries=(i > 0)) for i, n in enumerate((150_001, 120_011, 100_003))]
     registered = []
     for s in segs:
         for c in s.columns.values():
             if c.forward_index is not None and c.forward_index.nbytes:
                 native.host_register(c.forward_index)
                 registered.append(c.forward_index)
+    d1 = segs[0].columns["c1"].dictionary_values()
+    in3 = ", ".join(str(int(v)) for v in d1[10:13])
+    d0v = int(segs[0].columns["d0"].dictionary_values()[3])
     try:
-        for sql, exact, min_cols in (
-                (datagen.config2_sql(segs, 16), True, 6 * 3),
-                ("SELECT s0, d3, DISTINCTCOUNT(c0), SUM(x0), MAX(k0) FROM t WHERE c2 > 100 GROUP BY s0, d3 LIMIT 100000", False, 5 * 3),
-                ("SELECT d0, COUNT(*), SUM(m0) FROM t WHERE d0 > 2 AND c1 > 10 GROUP BY d0", True, 1 * 3),   # d0: predicate AND key
-                ("SELECT MIN(m1), MAX(m2), AVG(m0) FROM t", True, 3 * 3)):
+        for cost, sql, exact, min_cols in (
+                (None, datagen.config2_sql(segs, 16), True, 3 * 3),          # cost rule: wide metric columns in place, narrow keys copied
+                ("0", datagen.config2_sql(segs, 16), True, 6 * 3),           # forced: every gathered column in place
+                ("0", f"SELECT s0, d3, DISTINCTCOUNT(c0), SUM(x0), MAX(k0) FROM t WHERE c1 IN ({in3}) GROUP BY s0, d3 LIMIT 100000", False, 5 * 3),
+                ("0", f"SELECT d0, COUNT(*), SUM(m0) FROM t WHERE d0 = {d0v} AND c1 > 10 GROUP BY d0", True, 1 * 3),   # d0: predicate AND key
+                ("0", "SELECT MIN(m1), MAX(m2), AVG(m0) FROM t", True, 3 * 3),
+                (None, "SELECT d1, MIN(m1), MAX(m2), AVG(m0) FROM t WHERE c2 > 100 GROUP BY d1", True, 0)):   # unselective: everything is copied
+            if cost is None:
+                monkeypatch.delenv("PB_IN_PLACE_COST", raising=False)
+            else:
+                monkeypatch.setenv("PB_IN_PLACE_COST", cost)
             staged = [native.StagedSegment(s) for s in segs]       # cold: nothing resident yet
             g = native.SegmentGroup(staged)
             q = parse_sql(sql)
-            for flags in (native.PB_Q_GATHER_IN_PLACE, native.PB_Q_GATHER_IN_PLACE | native.PB_Q_COMBINE):
-                r = native.execute(g, q, flags)
-                assert r.in_place_columns >= min_cols, (sql, r.in_place_columns)
-                r.free()
+            r = native.execute(g, q, native.PB_Q_GATHER_IN_PLACE | native.PB_Q_COMBINE)
+            assert r.in_place_columns >= min_cols, (sql, r.in_place_columns)
+            if min_cols == 0:
+                assert r.in_place_columns == 0
+            rows_cold = r.tables[0].rows()       # computed in waves behind the staging copies
+            cold_stats = dict(r.tables[0].stats)
+            r.free()
             check_query(segs, q, group=g, flags_list=(native.PB_Q_GATHER_IN_PLACE,), exact_float=exact)
+            r = native.execute(g, q, native.PB_Q_COMBINE)      # warm, single wave; same path check_query just verified
+            assert_rows_equal(rows_cold, r.tables[0].rows(), q, exact, what="cold (waves) vs warm")
+            assert cold_stats["num_docs_scanned"] == r.tables[0].stats["num_docs_scanned"]
+            r.free()
             g.release()
             for st_ in staged:
                 st_.release()
