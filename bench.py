@@ -331,7 +331,6 @@ def main():
     if not args.no_e2e:
         e2e_steps = max(2, min(args.steps, 5))
         docs_matched_rank = docs_matched // max(world, 1)       # merged statistics are totals over ranks; per-rank data is iid
-        gather_values = docs_matched_rank * (len(q.group_by) + len({a.column for a in q.aggregations if a.column}))
 
         def e2e_leg(in_place):
             """stage from the page-locked host buffers + execute + read the result back, K times.  in_place: only the
@@ -370,7 +369,8 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 el = float(t.item())
             # in place: every gathered value is one or two 4-byte words; PCIe moves them as 32-byte sectors
-            h2d = int(staged_bytes + (32 * gather_values if in_place_cols else 0))
+            gather_values = docs_matched_rank * in_place_cols // max(len(segs), 1)     # matching rows x columns read in place
+            h2d = int(staged_bytes + 32 * gather_values)
             return {"value": rows_total * e2e_steps / el, "ms_per_step": 1000 * el / e2e_steps, "h2d_bytes_per_step": h2d,
                     "staged_bytes_per_step": int(staged_bytes), "in_place_columns": int(in_place_cols)}
 

@@ -27,6 +27,7 @@
 #define PB_MAX_AGGS 16
 #define PB_MAX_SCAN_SLOTS 8
 #define PB_SPARSE_MAX 128            // survivors per 1024-doc chunk below which later AND leaves use the restricted scan
+#define PB_CAND_CAP 512              // candidates per warp list (u16 offsets inside the unit); more = extra passes
 #define PB_SET_SMEM_BYTES 8192      // dictId-set membership LUTs (one byte per dictId) cached in smem per segment
 
 enum { L_TRUE = 0, L_FALSE = 1, L_DICT_RANGE = 2, L_DICT_SET = 3, L_RAW_RANGE_I = 4, L_RAW_RANGE_F = 5,
@@ -54,6 +55,15 @@ struct DevLeaf {
   int32_t n_raw_set;
   int32_t est_permille;    // host estimate of the leaf's selectivity (0..1000), used to order AND chains
   const uint32_t* bitmap;  // L_BITMAP: flat doc bitmap of this segment (bit d&31 of word d>>5)
+  // Candidate evaluation (flat AND chains whose earlier leaves leave few survivors): the column of this leaf is NOT
+  // streamed through shared memory; the leaf is tested only on the surviving docs, one lane per candidate, reading the
+  // forward index where it lies (HBM copy, or the caller's mapped host buffer for cold segments).  The device analogue of
+  // SVScanDocIdIterator.applyAnd (CTR/operator/dociditerators/SVScanDocIdIterator.java:115-142).
+  int32_t gather;
+  uint32_t g_full_words;   // see DevKeyCol::n_full_words
+  uint32_t g_tail_word;
+  int32_t pad_l;
+  const uint8_t* gfwd;
 };
 
 struct DevScanCol {        // a column staged tile-by-tile through smem
@@ -136,9 +146,9 @@ struct DevQuery {
   uint64_t n_units;
   uint64_t n_docs_total;
   int32_t match_all;                     // no filter: pb_agg_kernel walks every doc, no match list
-  int32_t prefetch;                      // pb_filter_kernel prefetches the gather sectors of matching docs into L2
+  int32_t pad_p;
   int32_t sparse_max;                    // survivors per 1024 docs below which later AND leaves use the restricted scan
-  int32_t pad_s;
+  int32_t cand_bytes;                    // shared memory for the per-warp candidate lists (0: no leaf runs on candidates)
   uint64_t unit_lo;                      // this launch covers work units [unit_lo, unit_lo + n_units) (a wave of segments)
   uint32_t* match_list;                  // global doc numbers of the docs that pass the filter
   unsigned long long* match_count;
@@ -420,6 +430,37 @@ __device__ __noinline__ uint32_t pb_eval_raw(const uint32_t* __restrict__ p, con
   return mine;
 }
 
+// one doc against one scan leaf, reading the forward index in place (candidate evaluation, see DevLeaf::gather)
+__device__ __forceinline__ bool pb_leaf_test_doc(const DevLeaf& lf, const uint8_t* __restrict__ set_cache, uint32_t doc) {
+  switch (lf.kind) {
+    case L_TRUE: return true;
+    case L_FALSE: return false;
+    case L_DICT_RANGE: {
+      const uint32_t id = pb_unpack_at_bounded(lf.gfwd, doc, lf.bits, lf.g_full_words, lf.g_tail_word);
+      return (id - lf.lo) < lf.span;
+    }
+    case L_DICT_SET: {
+      const uint32_t id = pb_unpack_at_bounded(lf.gfwd, doc, lf.bits, lf.g_full_words, lf.g_tail_word);
+      if (lf.set_smem_off >= 0) return set_cache[lf.set_smem_off + id] != 0;         // exclusive flag folded in
+      return (((__ldg(lf.set_bits + (id >> 5)) >> (id & 31)) & 1u) ^ (uint32_t)lf.exclusive) != 0;
+    }
+    case L_RAW_RANGE_I: { const long long v = pb_raw_i64(lf.gfwd, doc, lf.raw_width, lf.data_type); return v >= lf.ilo && v <= lf.ihi; }
+    case L_RAW_RANGE_F: {
+      const double v = pb_raw_f64(lf.gfwd, doc, lf.raw_width, lf.data_type);
+      return (lf.dlo_incl ? v >= lf.dlo : v > lf.dlo) && (lf.dhi_incl ? v <= lf.dhi : v < lf.dhi);
+    }
+    case L_RAW_SET: {
+      long long vb;
+      if (lf.data_type == 2 || lf.data_type == 3) vb = __double_as_longlong(pb_raw_f64(lf.gfwd, doc, lf.raw_width, lf.data_type));
+      else vb = pb_raw_i64(lf.gfwd, doc, lf.raw_width, lf.data_type);
+      bool in = false;
+      for (int i = 0; i < lf.n_raw_set; i++) in |= (lf.raw_set[i] == vb);
+      return in != (bool)lf.exclusive;
+    }
+    default: return false;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // group table update for one matching doc
 // ------------------------------------------------------------------------------------------------
@@ -594,13 +635,6 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 // global match list (one atomicAdd per warp-chunk, ascending docIds inside a block).  The instruction stream is
 // short and identical for all warps, which keeps the instruction cache warm.
 // ------------------------------------------------------------------------------------------------
-#define PB_MAX_GATHER 16
-struct GatherCol {          // a column the aggregation kernel will gather from
-  const uint8_t* fwd;
-  int32_t bits;             // dictionary column: bits per element; raw: 0
-  int32_t width;            // raw column: bytes per value
-};
-
 struct __align__(16) FilterSmemHeader {
   uint64_t full[PB_NWARPS][PB_NSTAGE];
   uint32_t slot_stride[PB_MAX_SCAN_SLOTS];   // bytes of one work unit of the slot (U * 128 * bits)
@@ -609,15 +643,14 @@ struct __align__(16) FilterSmemHeader {
   int32_t flat_and;                          // program is AND(leaf, leaf, ...) (or a single leaf): no stack needed
   int32_t n_flat;
   int32_t flat_leaf[PB_MAX_LEAVES];
-  int32_t n_gather;                          // columns pb_agg_kernel will gather from (L2 prefetch at match time)
+  int32_t n_dense;                           // flat_leaf[0 .. n_dense) run on the staged unit, the rest on the candidates
   int32_t pad_g;
-  GatherCol gather[PB_MAX_GATHER];
   alignas(16) uint8_t seg[PB_SEG_FILTER_BYTES];   // the filter part of the current DevSegQuery
 };
 
 // U = 1024-doc chunks per work unit (one TMA load + one dispatch per predicate leaf per unit)
-template <int U>
-__global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
+template <int U, int MIN_CTAS>
+__global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   FilterSmemHeader* H = reinterpret_cast<FilterSmemHeader*>(smem_raw);
   const DevQuery& Q = *Qp;
@@ -625,6 +658,8 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
   uint8_t* dyn = smem_raw + ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127);
   uint8_t* set_cache = dyn;
   dyn += (Q.set_cache_bytes + 127) & ~127;
+  uint16_t* cand = reinterpret_cast<uint16_t*>(dyn);     // per-warp candidate lists (only when some leaf is evaluated on candidates)
+  dyn += Q.cand_bytes;
   uint8_t* my_stages = dyn + (size_t)warp * PB_NSTAGE * Q.stage_bytes;
   const bool staged = Q.stage_bytes > 0;
   constexpr uint32_t UNIT_DOCS = U * PB_CHUNK_DOCS;
@@ -710,21 +745,6 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
         for (int c = 0; c < sq.n_scan; c++) t += (uint32_t)(UNIT_DOCS / 8) * (uint32_t)sq.scan[c].bits_per_doc + 16;
         H->n_scan_full_bytes = t;
       }
-      if (tid == 32) {
-        // gather list (deduplicated by forward-index pointer); read from the full descriptor in global memory
-        const DevSegQuery& full = Q.segs[sgi];
-        int n = 0;
-        auto add = [&](const uint8_t* fwd, int bits, int width) {
-          if (!fwd) return;
-          for (int i = 0; i < n; i++) if (H->gather[i].fwd == fwd) return;
-          if (n < PB_MAX_GATHER) { H->gather[n].fwd = fwd; H->gather[n].bits = bits; H->gather[n].width = width; n++; }
-        };
-        if (Q.prefetch) {
-          for (int j = 0; j < Q.n_group_by; j++) add(full.keys[j].fwd, full.keys[j].raw_width ? 0 : full.keys[j].bits, full.keys[j].raw_width);
-          for (int a = 0; a < Q.n_aggs; a++) if (Q.agg_op[a] != 0) add(full.aggs[a].fwd, full.aggs[a].raw_width ? 0 : full.aggs[a].bits, full.aggs[a].raw_width);
-        }
-        H->n_gather = n;
-      }
       if (tid == 64) {
         // flat conjunction?  postfix == leaf* AND(n)   or a single leaf   or empty (match all)
         int nl = 0; bool flat = true;
@@ -732,15 +752,20 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
           if (sq.node_kind[n] == N_LEAF) { if (nl < PB_MAX_LEAVES) H->flat_leaf[nl] = sq.node_arg[n]; nl++; }
           else if (!(sq.node_kind[n] == N_AND && n == sq.n_nodes - 1 && sq.node_arg[n] == nl)) flat = false;
         }
-        // most selective leaf first (insertion sort on the host's estimate)
-        if (flat && nl <= PB_MAX_LEAVES)
+        // most selective leaf first (insertion sort on the host's estimate); leaves evaluated on candidates go last
+        int nd = 0;
+        if (flat && nl <= PB_MAX_LEAVES) {
+          auto key = [&](int l) { return sq.leaves[l].est_permille + (sq.leaves[l].gather ? 4096 : 0); };
           for (int a = 1; a < nl; a++) {
             int x = H->flat_leaf[a]; int b = a - 1;
-            while (b >= 0 && sq.leaves[H->flat_leaf[b]].est_permille > sq.leaves[x].est_permille) { H->flat_leaf[b + 1] = H->flat_leaf[b]; b--; }
+            while (b >= 0 && key(H->flat_leaf[b]) > key(x)) { H->flat_leaf[b + 1] = H->flat_leaf[b]; b--; }
             H->flat_leaf[b + 1] = x;
           }
+          for (int a = 0; a < nl; a++) if (!sq.leaves[H->flat_leaf[a]].gather) nd++;
+        }
         H->flat_and = flat ? 1 : 0;
         H->n_flat = nl;
+        H->n_dense = nd;
       }
       for (int l = 0; l < PB_MAX_LEAVES; l++) {
         const DevLeaf& lf = sq.leaves[l];
@@ -760,7 +785,6 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
     const uint32_t n_mine = first < seg_hi ? (uint32_t)((seg_hi - first + PB_NWARPS - 1) / PB_NWARPS) : 0u;
     const uint32_t rel0 = (uint32_t)(first - sq.unit_begin);     // unit index inside the segment
     const int n_scan = sq.n_scan;
-    const int n_gather = H->n_gather;
     unsigned long long matched = 0;
     uint32_t min_last_rel = 0xffffffffu;               // first unit whose load must be clipped to the buffer end
     for (int c = 0; c < n_scan; c++) min_last_rel = min(min_last_rel, H->slot_last_rel[c]);
@@ -825,12 +849,14 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
       int nu = 0;
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        const long long remaining = (long long)sq.num_docs - (long long)(unit_doc0 + (uint64_t)u * PB_CHUNK_DOCS + 32ull * lane);
-        mask[u] = remaining >= 32 ? 0xffffffffu : (remaining <= 0 ? 0u : ((1u << remaining) - 1u));
-        if ((long long)sq.num_docs > (long long)(unit_doc0 + (uint64_t)u * PB_CHUNK_DOCS)) nu = u + 1;
+        // docs of a segment fit 31 bits: plain 32-bit arithmetic
+        const uint32_t nd = (uint32_t)sq.num_docs, c0 = (uint32_t)unit_doc0 + (uint32_t)u * PB_CHUNK_DOCS, d0 = c0 + 32u * (uint32_t)lane;
+        mask[u] = d0 + 32u <= nd ? 0xffffffffu : (d0 >= nd ? 0u : ((1u << (nd - d0)) - 1u));
+        if (nd > c0) nu = u + 1;
       }
+      const int n_cand_leaves = H->flat_and ? H->n_flat - H->n_dense : 0;
       if (H->flat_and) {
-        const int nl = H->n_flat;
+        const int nl = H->n_dense;
         for (int i = 0; i < nl; i++) {
           // few survivors in the whole unit -> restricted scan of the remaining leaves (leaves arrive ordered by
           // estimated selectivity from the host)
@@ -870,10 +896,11 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
 #pragma unroll
       for (int u = 0; u < U; u++) cnt += (uint32_t)__popc(mask[u]);
       const uint32_t mx = __reduce_max_sync(0xffffffffu, cnt);
+      if (mx == 0) continue;                                   // warp-uniform
       uint32_t excl = 0, total = 0;
+      const uint32_t lt = (1u << lane) - 1u;
       if (mx <= 4) {
         // few matches per lane: exclusive prefix from ballots (no shuffle dependency chain)
-        const uint32_t lt = (1u << lane) - 1u;
         for (uint32_t kk = 1; kk <= mx; kk++) {
           const uint32_t b = __ballot_sync(0xffffffffu, cnt >= kk);
           excl += __popc(b & lt);
@@ -886,31 +913,66 @@ __global__ void __launch_bounds__(PB_NTHREADS, U == 1 ? 3 : 2) pb_filter_kernel(
         total = __shfl_sync(0xffffffffu, incl, 31);
         excl = incl - cnt;
       }
-      if (total) {
+      const uint32_t gunit0 = (uint32_t)(sq.doc_base + unit_doc0);
+      if (n_cand_leaves == 0) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)total);
         base = __shfl_sync(0xffffffffu, base, 0);
-        unsigned long long pos = base + excl;
+        uint32_t* out = Q.match_list + base + excl;
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          const uint32_t gdoc0 = (uint32_t)(sq.doc_base + unit_doc0) + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
+          const uint32_t gdoc0 = gunit0 + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
           uint32_t mm = mask[u];
-          const uint32_t ldoc0 = (uint32_t)unit_doc0 + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
           while (mm) {
             const int bit = __ffs(mm) - 1;
             mm &= mm - 1;
-            Q.match_list[pos++] = gdoc0 + (uint32_t)bit;
-            // start pulling this doc's group-key / metric sectors into L2 now: pb_agg_kernel finds them there
-            const uint32_t doc = ldoc0 + (uint32_t)bit;
-            for (int i = 0; i < n_gather; i++) {
-              const GatherCol gc = H->gather[i];
-              const uint8_t* a = gc.bits ? gc.fwd + ((((unsigned long long)doc * (unsigned)gc.bits) >> 5) << 2)
-                                         : gc.fwd + (unsigned long long)doc * (unsigned)gc.width;
-              pb_prefetch_l2_keep(a);
-            }
+            *out++ = gdoc0 + (uint32_t)bit;
           }
         }
         matched += total;
+      } else {
+        // ---- candidates: survivors of the staged leaves, compacted into this warp's list, then one lane per candidate
+        // tests the remaining leaves straight from their forward indexes (all 32 gathers of a round in flight at once) ----
+        uint16_t* cl = cand + (size_t)warp * PB_CAND_CAP;
+        for (uint32_t pass0 = 0; pass0 < total; pass0 += PB_CAND_CAP) {     // one pass unless the estimate was far off
+          if (pass0) __syncwarp();
+          {
+            uint32_t pos = excl - pass0;                                     // (wraps below the window: unsigned compare)
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              const uint32_t off0 = (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
+              uint32_t mm = mask[u];
+              while (mm) {
+                const int bit = __ffs(mm) - 1;
+                mm &= mm - 1;
+                if (pos < PB_CAND_CAP) cl[pos] = (uint16_t)(off0 + (uint32_t)bit);
+                pos++;
+              }
+            }
+          }
+          __syncwarp();
+          const uint32_t n_pass = total - pass0 < PB_CAND_CAP ? total - pass0 : PB_CAND_CAP;
+          for (uint32_t b0 = 0; b0 < n_pass; b0 += 32) {
+            const uint32_t idx = b0 + (uint32_t)lane;
+            bool alive = idx < n_pass;
+            const uint32_t off = alive ? (uint32_t)cl[idx] : 0u;
+            const uint32_t doc = (uint32_t)unit_doc0 + off;          // doc inside the segment
+            for (int i = 0; i < n_cand_leaves; i++) {
+              if (alive) alive = pb_leaf_test_doc(sq.leaves[H->flat_leaf[H->n_dense + i]], set_cache, doc);
+              if (!__any_sync(0xffffffffu, alive)) break;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+            if (bal) {
+              const uint32_t n = (uint32_t)__popc(bal);
+              unsigned long long base = 0;
+              if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)n);
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (alive) Q.match_list[base + __popc(bal & lt)] = gunit0 + off;
+              matched += n;
+            }
+          }
+        }
+        __syncwarp();   // the list is rewritten by the next unit
       }
     }
     // ---- segment exit: numDocsScanned of this segment's table (matched is warp-uniform) ----

@@ -657,16 +657,69 @@ struct Arena {   // host mirror of a device allocation; pointers are handed out 
   }
 };
 
-// Expected fraction of a segment's docs that pass the filter (postfix tree), from dictionary cardinalities: the same
-// uniform-value estimate the AND ordering uses.  Drives the stage-or-gather choice of PB_Q_GATHER_IN_PLACE.
+// Expected fraction of a segment's docs that pass one filter leaf, from dictionary cardinalities (uniform values).
+static double estimate_leaf(const pb_segment_s* s, const pb_filter_node& fn) {
+  const Column* c = (fn.column >= 0 && fn.column < (int)s->cols.size()) ? &s->cols[fn.column] : nullptr;
+  const double card = c && c->card > 0 ? (double)c->card : 1.0;
+  auto excl = [&](double f) { return fn.exclusive ? 1.0 - f : f; };
+  switch (fn.kind) {
+    case PB_F_MATCH_ALL: return 1.0;
+    case PB_F_EMPTY: return 0.0;
+    case PB_F_SCAN_DICT_RANGE: return std::min(1.0, std::max(0.0, (double)(fn.hi - fn.lo) / card));
+    case PB_F_SCAN_DICT_SET: case PB_F_INVERTED: return excl(std::min(1.0, (double)fn.num_ids / card));
+    case PB_F_SORTED: {
+      double docs = 0;
+      for (int i = 0; i + 1 < fn.num_ids; i += 2) docs += (double)(fn.ids[i + 1] - fn.ids[i] + 1);
+      return excl(std::min(1.0, docs / std::max(1, s->num_docs)));
+    }
+    default: return 0.5;     // raw-value predicates, serialized bitmaps: no statistics
+  }
+}
+
+// Which scan leaves of a flat conjunction run on CANDIDATES instead of on the streamed column (DevLeaf::gather): leaves are
+// taken most-selective first (as the kernel orders them); once the expected survivors drop to PB_GATHER_LEAF_PERMILLE
+// (default 30 = 3 %), every later scan leaf costs less as one 32-byte sector read per surviving doc than as bits/8 bytes
+// of stream per doc, and its column no longer occupies shared-memory stages.  cand_frac[n] = expected fraction of docs
+// that reach leaf n.  (The reference does the same on the CPU: AndDocIdSet drives later scan iterators through applyAnd.)
+static void plan_candidate_leaves(const pb_segment_s* s, const pb_segment_query& sq, std::vector<char>& gather, std::vector<double>& cand_frac) {
+  const int nn = sq.num_filter_nodes;
+  gather.assign((size_t)std::max(nn, 0), 0);
+  cand_frac.assign((size_t)std::max(nn, 0), 1.0);
+  static const int permille_max = []() { const char* e = getenv("PB_GATHER_LEAF_PERMILLE"); return e ? atoi(e) : 30; }();
+  if (permille_max <= 0 || nn < 3) return;
+  const pb_filter_node& root = sq.filter[nn - 1];
+  if (root.kind != PB_F_AND || root.num_children != nn - 1) return;
+  struct L { int n; double est; bool scan; };
+  std::vector<L> ls;
+  for (int n = 0; n + 1 < nn; n++) {
+    const int k = sq.filter[n].kind;
+    if (k == PB_F_AND || k == PB_F_OR || k == PB_F_NOT) return;
+    const bool scan = k == PB_F_SCAN_DICT_RANGE || k == PB_F_SCAN_DICT_SET || k == PB_F_SCAN_RAW_RANGE || k == PB_F_SCAN_RAW_SET;
+    ls.push_back({n, estimate_leaf(s, sq.filter[n]), scan});
+  }
+  std::stable_sort(ls.begin(), ls.end(), [](const L& a, const L& b) { return a.est < b.est; });
+  double p = 1.0;
+  bool have_dense = false;
+  for (const L& l : ls) {
+    cand_frac[l.n] = p;
+    if (have_dense && l.scan && p * 1000.0 <= (double)permille_max) gather[l.n] = 1;
+    else have_dense = true;
+    p *= l.est;
+  }
+  // a column that is streamed anyway (another leaf on it runs dense) is not gathered as well
+  for (const L& l : ls)
+    if (gather[l.n])
+      for (const L& o : ls)
+        if (!gather[o.n] && o.scan && sq.filter[o.n].column == sq.filter[l.n].column) { gather[l.n] = 0; break; }
+}
+
+// Expected fraction of a segment's docs that pass the filter (postfix tree).  Drives the stage-or-gather choice of
+// PB_Q_GATHER_IN_PLACE.
 static double estimate_selectivity(const pb_segment_s* s, const pb_segment_query& sq) {
   if (sq.num_filter_nodes <= 0) return 1.0;
   std::vector<double> stk;
   for (int n = 0; n < sq.num_filter_nodes; n++) {
     const pb_filter_node& fn = sq.filter[n];
-    const Column* c = (fn.column >= 0 && fn.column < (int)s->cols.size()) ? &s->cols[fn.column] : nullptr;
-    const double card = c && c->card > 0 ? (double)c->card : 1.0;
-    auto excl = [&](double f) { return fn.exclusive ? 1.0 - f : f; };
     switch (fn.kind) {
       case PB_F_AND: case PB_F_OR: {
         int k = std::min<int>(fn.num_children, (int)stk.size());
@@ -676,17 +729,7 @@ static double estimate_selectivity(const pb_segment_s* s, const pb_segment_query
         break;
       }
       case PB_F_NOT: if (!stk.empty()) stk.back() = 1.0 - stk.back(); break;
-      case PB_F_MATCH_ALL: stk.push_back(1.0); break;
-      case PB_F_EMPTY: stk.push_back(0.0); break;
-      case PB_F_SCAN_DICT_RANGE: stk.push_back(std::min(1.0, std::max(0.0, (double)(fn.hi - fn.lo) / card))); break;
-      case PB_F_SCAN_DICT_SET: case PB_F_INVERTED: stk.push_back(excl(std::min(1.0, (double)fn.num_ids / card))); break;
-      case PB_F_SORTED: {
-        double docs = 0;
-        for (int i = 0; i + 1 < fn.num_ids; i += 2) docs += (double)(fn.ids[i + 1] - fn.ids[i] + 1);
-        stk.push_back(excl(std::min(1.0, docs / std::max(1, s->num_docs))));
-        break;
-      }
-      default: stk.push_back(0.5); break;     // raw-value predicates, serialized bitmaps: no statistics
+      default: stk.push_back(estimate_leaf(s, fn)); break;
     }
   }
   return stk.empty() ? 1.0 : std::min(1.0, std::max(0.0, stk.back()));
@@ -729,15 +772,19 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   cudaStream_t cs = g_ctx.copy_stream;
   std::vector<cudaEvent_t> seg_wait(n_segs, nullptr);   // staging events this call's kernels must wait for
   int n_pending = 0;
+  std::vector<std::vector<char>> cand_leaf(n_segs);     // per filter node: scan leaf evaluated on candidates (DevLeaf::gather)
+  std::vector<std::vector<double>> cand_frac(n_segs);
+  for (int si = 0; si < n_segs; si++) plan_candidate_leaves(g->segs[si], sqs[si], cand_leaf[si], cand_frac[si]);
   for (int si = 0; si < n_segs; si++) {
     pb_segment_s* s = g->segs[si];
     std::lock_guard<std::mutex> lk(s->mu);
-    // PB_Q_GATHER_IN_PLACE, per column: a gathered value costs one 32-byte PCIe read (about the link time of ~100 streamed
-    // bytes, measured: ~0.5 G reads/s vs ~50 GB/s); copying the column costs bits/8 bytes per doc.  Gather in place only
-    // where that is cheaper: expected matches x 100 B < column bytes.
-    // (PB_IN_PLACE_COST overrides the 100 B; 0 = always gather: used by the tests to reach every code path.)
+    // PB_Q_GATHER_IN_PLACE, per column: a gathered value costs one 32-byte PCIe read = 32 B payload + ~24 B of TLP
+    // overhead of link time (measured on B200 / PCIe Gen5: the cold query is link-bound and each in-place value costs
+    // ~56 streamed bytes); copying the column costs bits/8 bytes per doc.  Gather in place only where that is cheaper:
+    // expected matches x 56 B < column bytes.
+    // (PB_IN_PLACE_COST overrides the 56 B; 0 = always gather: used by the tests to reach every code path.)
     const double sel = in_place ? estimate_selectivity(s, sqs[si]) : 1.0;
-    double gather_cost = 100.0;
+    double gather_cost = 56.0;
     if (in_place) if (const char* e = getenv("PB_IN_PLACE_COST")) gather_cost = atof(e);
     auto gather_ok = [&](const Column& c) {
       if (!in_place) return false;
@@ -776,7 +823,13 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
         bool inv = fn.kind == PB_F_INVERTED;
         if ((fn.kind == PB_F_SCAN_DICT_RANGE || fn.kind == PB_F_SCAN_DICT_SET) && !c.has_dict) return fail(PB_ERR_INVALID, "filter node %d: dictionary scan on raw column", n);
         if ((fn.kind == PB_F_SCAN_RAW_RANGE || fn.kind == PB_F_SCAN_RAW_SET) && c.has_dict) return fail(PB_ERR_INVALID, "filter node %d: raw scan on dictionary column", n);
-        if ((rc = stage_column(s, c, !inv, false, inv, cs))) return rc;
+        // a leaf that runs on candidates only reads the rows that reach it: cold segments can leave its column in host memory
+        bool leaf_in_place = false;
+        if (in_place && !inv && cand_leaf[si][n]) {
+          const double col_bytes_per_doc = c.has_dict ? c.bits / 8.0 : (double)c.raw_width;
+          leaf_in_place = cand_frac[si][n] * gather_cost < col_bytes_per_doc;
+        }
+        if ((rc = stage_column(s, c, !inv, false, inv, cs, false, leaf_in_place))) return rc;
       }
     }
     // order this (and every later) query's kernels after the copies just enqueued for the segment
@@ -942,7 +995,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
 
   lap(1);
   // ---- query arena (descriptors + leaf payloads) ----
-  size_t arena_cap = sizeof(DevQuery) + 256 + (sizeof(DevSegQuery) + 64) * (size_t)n_segs + (sizeof(DevTable) + 64) * (size_t)n_tables;
+  size_t arena_cap = (sizeof(DevQuery) + 16) * (1 + PB_MAX_WAVES) + 256 + (sizeof(DevSegQuery) + 64) * (size_t)n_segs + (sizeof(DevTable) + 64) * (size_t)n_tables;
   size_t bitmap_words_total = 0;
   for (int si = 0; si < n_segs; si++) {
     const pb_segment_query& sq = sqs[si];
@@ -979,6 +1032,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   int slot_bits_max[PB_MAX_SCAN_SLOTS] = {0};
   int set_cache_max = 0;
   int n_slots_max = 0;
+  bool any_cand_leaf = false;
   size_t bm_off = 0;
   r->seg_scan_leaves.assign(n_segs, 0);
 
@@ -990,6 +1044,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     ds.table = combine ? 0 : si;
     int n_leaves = 0, n_scan = 0, set_smem_used = 0;
     int slot_of_col[PB_MAX_SCAN_SLOTS];
+    (void)0;
     ds.n_nodes = sq.num_filter_nodes;
     for (int n = 0; n < sq.num_filter_nodes; n++) {
       const pb_filter_node& fn = sq.filter[n];
@@ -1005,6 +1060,15 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       lf.est_permille = 500;
       ds.node_kind[n] = N_LEAF; ds.node_arg[n] = (int8_t)n_leaves; n_leaves++;
       auto scan_slot = [&](const Column& c) -> int {
+        if (cand_leaf[si][n]) {          // evaluated on candidates: no stage slot, read where the column lies
+          lf.gather = 1;
+          lf.gfwd = c.fwd_staged ? c.d_fwd : c.d_fwd_host;
+          lf.g_full_words = c.fwd_staged ? 0xFFFFFFFFu : c.host_full_words;
+          lf.g_tail_word = c.fwd_staged ? 0u : c.host_tail_word;
+          if (!c.fwd_staged) r->in_place_columns++;
+          any_cand_leaf = true;
+          return PB_MAX_SCAN_SLOTS;      // not a slot index (>= 0 = success)
+        }
         for (int k = 0; k < n_scan; k++) if (slot_of_col[k] == fn.column) return k;
         if (n_scan >= PB_MAX_SCAN_SLOTS) return -1;
         slot_of_col[n_scan] = fn.column;
@@ -1105,6 +1169,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
         }
         default: return fail(PB_ERR_INVALID, "filter node %d: unknown kind %d", n, fn.kind);
       }
+      if (lf.gather) lf.slot = -1;
     }
     ds.n_scan = n_scan;
     set_cache_max = std::max(set_cache_max, set_smem_used);
@@ -1181,12 +1246,12 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   for (int k = 0; k < n_slots_max; k++) hq->slot_off[k] = slot_offs[k];
   hq->stage_bytes = (int32_t)stage_bytes;
   hq->set_cache_bytes = set_cache_max;
+  hq->cand_bytes = any_cand_leaf ? (int32_t)(2 * PB_CAND_CAP * PB_NWARPS) : 0;   // u16 offsets inside the unit, one list per warp
   hq->use_tma = (q->flags & PB_Q_NO_TMA) ? 0 : 1;
   hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
   hq->n_units = n_chunks; hq->segs = dsegs; hq->tables = dtabs;
   hq->n_docs_total = n_docs_total; hq->match_all = match_all ? 1 : 0;
   { static const int sm = []() { const char* e = getenv("PB_SPARSE_MAX"); return e ? atoi(e) : PB_SPARSE_MAX; }(); hq->sparse_max = sm; }
-  { static const int pf = []() { const char* e = getenv("PB_PREFETCH"); return e ? atoi(e) : 0; }(); hq->prefetch = pf; }   // off: measured no gain (profiles/r1_experiments.md)
   hq->match_list = d_match_list;
   hq->match_count = r->d_counters + (size_t)n_tables * PB_COUNTERS_PER_TABLE;   // PB_MAX_WAVES zeroed cells after the per-table counters
 
@@ -1254,8 +1319,9 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   {
     std::lock_guard<std::mutex> lk(g_ctx.mu);
     if (!g_ctx.smem_attr_set) {
-      CU(cudaFuncSetAttribute(pb_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      CU(cudaFuncSetAttribute(pb_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CU(cudaFuncSetAttribute(pb_filter_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CU(cudaFuncSetAttribute(pb_filter_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CU(cudaFuncSetAttribute(pb_filter_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       CU(cudaFuncSetAttribute(pb_agg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       CU(cudaFuncSetAttribute(pb_agg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       g_ctx.smem_attr_set = true;
@@ -1263,12 +1329,16 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   }
   size_t smem = 0;
   uint64_t max_ctas = 0;
+  bool u2_three = false;
   if (!match_all && n_chunks > 0) {
-    smem = ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + stage_bytes * PB_NSTAGE * PB_NWARPS;
+    smem = ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + (size_t)hq->cand_bytes + stage_bytes * PB_NSTAGE * PB_NWARPS;
     if (smem > 227 * 1024) return fail(PB_ERR_UNSUPPORTED, "filter kernel needs %zu bytes of shared memory", smem);
     int occ = 1;
-    if (U == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<1>, PB_NTHREADS, smem));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<2>, PB_NTHREADS, smem));
+    // U = 2 comes in two register budgets: 3 CTAs/SM (80 registers) when three stages sets fit shared memory, else 2 CTAs/SM
+    u2_three = U == 2 && 3 * (smem + 1024) <= 227 * 1024;
+    if (U == 1) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<1, 3>, PB_NTHREADS, smem));
+    else if (u2_three) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<2, 3>, PB_NTHREADS, smem));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<2, 2>, PB_NTHREADS, smem));
     if (occ < 1) return fail(PB_ERR_CUDA, "filter kernel does not fit an SM (smem %zu)", smem);
     max_ctas = (uint64_t)g_ctx.num_sms * (uint64_t)occ;
   }
@@ -1290,8 +1360,9 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     if (!match_all && w.n_units > 0) {
       // every CTA gets a contiguous range of chunks; keep at least one chunk per warp
       int grid = (int)std::min<uint64_t>(std::max<uint64_t>((w.n_units + PB_NWARPS - 1) / PB_NWARPS, 1), max_ctas);
-      if (U == 1) pb_filter_kernel<1><<<grid, PB_NTHREADS, smem, st>>>(w.dq);
-      else pb_filter_kernel<2><<<grid, PB_NTHREADS, smem, st>>>(w.dq);
+      if (U == 1) pb_filter_kernel<1, 3><<<grid, PB_NTHREADS, smem, st>>>(w.dq);
+      else if (u2_three) pb_filter_kernel<2, 3><<<grid, PB_NTHREADS, smem, st>>>(w.dq);
+      else pb_filter_kernel<2, 2><<<grid, PB_NTHREADS, smem, st>>>(w.dq);
       r->launches++;
       CU(cudaGetLastError());
     }

@@ -263,3 +263,49 @@ def test_every_bit_width(bits):
                 f"SELECT COUNT(*), SUM(w) FROM t WHERE w IN ({pick})",
                 f"SELECT w, COUNT(*) FROM t WHERE w NOT IN ({pick}) AND g <> 11 GROUP BY w LIMIT 10000000"):
         check_query([seg], sql, flags_list=(0, native.PB_Q_GENERIC_KERNEL), check_combined=(bits <= 20))
+
+
+def test_candidate_leaves_of_a_flat_conjunction():
+    """Flat AND whose most selective leaf leaves <= 3 % of the docs (by dictionary statistics): the other scan leaves run
+    on the candidates only, one lane per surviving doc, reading their forward index in place (DevLeaf::gather) — the
+    device form of AndDocIdSet + SVScanDocIdIterator.applyAnd.  Covers dictionary range / IN (smem LUT and global
+    bitset) / NOT IN, raw LONG and DOUBLE ranges, a raw IN, and a skewed column whose estimate is far off (the candidate
+    list then takes several passes)."""
+    native.init()
+    rng = np.random.default_rng(7)
+    n = 300_017
+    # a: 1000 values, heavily skewed: 70 % of the docs carry dictId 3 (the statistics say 0.1 %)
+    a_ids = rng.integers(0, 1000, n, dtype=np.uint32)
+    a_ids[rng.random(n) < 0.7] = 3
+    a_ids[:1000] = np.arange(1000, dtype=np.uint32)
+    a = build_dict_column("a", DataType.INT, np.arange(1000, dtype=np.int32) * 7 + 1, a_ids)
+    b_ids = rng.integers(0, 5000, n, dtype=np.uint32); b_ids[:5000] = np.arange(5000, dtype=np.uint32)
+    b = build_dict_column("b", DataType.INT, np.arange(5000, dtype=np.int32) * 3, b_ids)
+    c_ids = rng.integers(0, 20000, n, dtype=np.uint32); c_ids[:20000] = np.arange(20000, dtype=np.uint32)   # > 8192: bitset in global memory
+    c = build_dict_column("c", DataType.LONG, np.arange(20000, dtype=np.int64) * 1_000_003, c_ids)
+    d_ids = rng.integers(0, 6, n, dtype=np.uint32)
+    d = build_dict_column("d", DataType.INT, np.arange(6, dtype=np.int32) + 10, d_ids)
+    x = build_column("x", DataType.DOUBLE, rng.random(n), dictionary=False)
+    k = build_column("k", DataType.LONG, rng.integers(0, 1_000_000, n, dtype=np.int64), dictionary=False)
+    m = build_dict_column("m", DataType.INT, np.arange(50_000, dtype=np.int32) * 2,
+                          np.concatenate([np.arange(50_000, dtype=np.uint32), rng.integers(0, 50_000, n - 50_000, dtype=np.uint32)]))
+    seg = make_segment("cand", [a, b, c, d, x, k, m])
+    seg2 = make_segment("cand2", [build_dict_column("a", DataType.INT, np.arange(1000, dtype=np.int32) * 7 + 1, a_ids[::-1].copy()),
+                                  b, c, d, x, k, m])
+    c_in = ", ".join(str(int(v) * 1_000_003) for v in range(0, 20000, 3))
+    k_in = ", ".join(str(int(v)) for v in np.unique(k_raw_sample(seg, 40)))
+    for sql in (
+            "SELECT d, COUNT(*), SUM(m), MIN(m), MAX(m) FROM t WHERE a IN (8, 15, 29, 701) AND b < 9000 GROUP BY d",
+            "SELECT d, COUNT(*), SUM(m) FROM t WHERE a = 22 AND b BETWEEN 300 AND 12000 AND d <> 12 AND x < 0.75 AND k > 200000 GROUP BY d",
+            f"SELECT COUNT(*), SUM(m) FROM t WHERE a IN (8, 15) AND c IN ({c_in}) AND b NOT IN (3, 6, 9, 12)",
+            f"SELECT COUNT(*), MAX(m) FROM t WHERE a = 71 AND k IN ({k_in})",
+            "SELECT d, COUNT(*), SUM(m) FROM t WHERE a = 22 AND b < 9000 GROUP BY d",      # a = 22 is dictId 3: 70 % of the docs are candidates
+            "SELECT COUNT(*) FROM t WHERE a = 22 AND b < 3 AND x > 2.0"):
+        check_query([seg, seg2], sql, flags_list=ALL_FLAGS, exact_float=True)
+
+
+def k_raw_sample(seg, count):
+    from pinot_b200.segment_writer import DataType as _DT   # noqa: F401
+    col = seg.columns["k"]
+    vals = np.frombuffer(col.forward_index[col.forward_index.nbytes - 8 * seg.num_docs:].tobytes(), dtype=">i8")
+    return vals[:count].astype(np.int64)
