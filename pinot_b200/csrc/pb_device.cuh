@@ -27,6 +27,7 @@
 #define PB_MAX_AGGS 16
 #define PB_MAX_SCAN_SLOTS 8
 #define PB_SPARSE_MAX 128            // survivors per 1024-doc chunk below which later AND leaves use the restricted scan
+#define PB_OUT_CAP 256               // matches buffered per warp before one ATOMG reserves their place in the match list
 #define PB_CAND_CAP 512              // candidates per warp list (u16 offsets inside the unit); more = extra passes
 #define PB_SET_SMEM_BYTES 8192      // dictId-set membership LUTs (one byte per dictId) cached in smem per segment
 
@@ -650,16 +651,28 @@ struct __align__(16) FilterSmemHeader {
 
 // U = 1024-doc chunks per work unit (one TMA load + one dispatch per predicate leaf per unit)
 template <int U, int MIN_CTAS>
-__global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const DevQuery* __restrict__ Qp) {
+__global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const __grid_constant__ DevQuery Q) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   FilterSmemHeader* H = reinterpret_cast<FilterSmemHeader*>(smem_raw);
-  const DevQuery& Q = *Qp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint8_t* dyn = smem_raw + ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127);
   uint8_t* set_cache = dyn;
   dyn += (Q.set_cache_bytes + 127) & ~127;
   uint16_t* cand = reinterpret_cast<uint16_t*>(dyn);     // per-warp candidate lists (only when some leaf is evaluated on candidates)
   dyn += Q.cand_bytes;
+  uint32_t* ob = reinterpret_cast<uint32_t*>(dyn) + (size_t)warp * PB_OUT_CAP;   // this warp's output buffer
+  dyn += (size_t)PB_NWARPS * PB_OUT_CAP * sizeof(uint32_t);
+  uint32_t out_n = 0;                                     // buffered matches (warp-uniform)
+  auto flush_out = [&]() {
+    if (out_n == 0) return;
+    __syncwarp();
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)out_n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t i = (uint32_t)lane; i < out_n; i += 32) Q.match_list[base + i] = ob[i];
+    __syncwarp();
+    out_n = 0;
+  };
   uint8_t* my_stages = dyn + (size_t)warp * PB_NSTAGE * Q.stage_bytes;
   const bool staged = Q.stage_bytes > 0;
   constexpr uint32_t UNIT_DOCS = U * PB_CHUNK_DOCS;
@@ -892,6 +905,8 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       __syncwarp();   // all lanes are done reading this stage before lane 0 may refill it next iteration
 
       // ---- append the matching docIds (global doc numbering) to the match list ----
+      // Matches go through a per-warp output buffer in shared memory and reach the global list in batches: one
+      // ATOMG (whose ~1 us round trip used to sit on every unit's critical path) per ~PB_OUT_CAP matches.
       uint32_t cnt = 0;
 #pragma unroll
       for (int u = 0; u < U; u++) cnt += (uint32_t)__popc(mask[u]);
@@ -915,19 +930,36 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       }
       const uint32_t gunit0 = (uint32_t)(sq.doc_base + unit_doc0);
       if (n_cand_leaves == 0) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        uint32_t* out = Q.match_list + base + excl;
+        if (total > PB_OUT_CAP) {
+          // dense matches: straight to the list
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          uint32_t* out = Q.match_list + base + excl;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const uint32_t gdoc0 = gunit0 + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
-          uint32_t mm = mask[u];
-          while (mm) {
-            const int bit = __ffs(mm) - 1;
-            mm &= mm - 1;
-            *out++ = gdoc0 + (uint32_t)bit;
+          for (int u = 0; u < U; u++) {
+            const uint32_t gdoc0 = gunit0 + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
+            uint32_t mm = mask[u];
+            while (mm) {
+              const int bit = __ffs(mm) - 1;
+              mm &= mm - 1;
+              *out++ = gdoc0 + (uint32_t)bit;
+            }
           }
+        } else {
+          if (out_n + total > PB_OUT_CAP) flush_out();
+          uint32_t* out = ob + out_n + excl;
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const uint32_t gdoc0 = gunit0 + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
+            uint32_t mm = mask[u];
+            while (mm) {
+              const int bit = __ffs(mm) - 1;
+              mm &= mm - 1;
+              *out++ = gdoc0 + (uint32_t)bit;
+            }
+          }
+          out_n += total;
         }
         matched += total;
       } else {
@@ -964,10 +996,9 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
             const uint32_t bal = __ballot_sync(0xffffffffu, alive);
             if (bal) {
               const uint32_t n = (uint32_t)__popc(bal);
-              unsigned long long base = 0;
-              if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)n);
-              base = __shfl_sync(0xffffffffu, base, 0);
-              if (alive) Q.match_list[base + __popc(bal & lt)] = gunit0 + off;
+              if (out_n + n > PB_OUT_CAP) flush_out();
+              if (alive) ob[out_n + __popc(bal & lt)] = gunit0 + off;
+              out_n += n;
               matched += n;
             }
           }
@@ -975,6 +1006,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
         __syncwarp();   // the list is rewritten by the next unit
       }
     }
+    flush_out();
     // ---- segment exit: numDocsScanned of this segment's table (matched is warp-uniform) ----
     if (lane == 0 && matched) pb_red_add_u64(Q.tables[sq.table].docs_matched, matched);
   }
@@ -992,9 +1024,8 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
 #define PB_AGG_MAX_SEGS_SMEM 1024
 
 template <int MIN_CTAS>
-__global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_agg_kernel(const DevQuery* __restrict__ Qp) {
+__global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_agg_kernel(const __grid_constant__ DevQuery Q) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const DevQuery& Q = *Qp;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ unsigned long long s_doc_base[PB_AGG_MAX_SEGS_SMEM + 1];
   __shared__ unsigned long long s_red_u64[PB_NWARPS];

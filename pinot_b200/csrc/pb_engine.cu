@@ -43,6 +43,7 @@ extern "C" const char* pb_last_error(void) { return g_err; }
 // context
 // ------------------------------------------------------------------------------------------------
 struct PinnedBlock { void* p; size_t cap; };
+struct StreamSet { cudaStream_t stream = nullptr; cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; };   // one per in-flight call, pooled
 struct Context {
   std::mutex mu;
   bool inited = false;
@@ -50,6 +51,7 @@ struct Context {
   int num_sms = 148;
   std::vector<PinnedBlock> pinned_free;
   std::vector<PinnedBlock> scratch_free;      // large device scratch buffers (match lists), reused across calls
+  std::vector<StreamSet> streams_free;        // stream + timing events of finished calls (creation costs ~10 us per call)
   cudaStream_t util_stream = nullptr;         // stream-ordered allocations / frees of staged data
   cudaStream_t copy_stream = nullptr;         // host -> HBM staging copies (queries wait on per-segment events)
   bool smem_attr_set = false;
@@ -111,6 +113,8 @@ extern "C" int pb_shutdown(void) {
   g_ctx.pinned_free.clear();
   for (auto& b : g_ctx.scratch_free) cudaFree(b.p);
   g_ctx.scratch_free.clear();
+  for (auto& ss : g_ctx.streams_free) { for (int i = 0; i < 5; i++) if (ss.ev[i]) cudaEventDestroy(ss.ev[i]); cudaStreamDestroy(ss.stream); }
+  g_ctx.streams_free.clear();
   return PB_OK;
 }
 extern "C" int pb_device_count(void) {
@@ -142,6 +146,27 @@ static void pinned_free(void* p, size_t bytes) {
   std::lock_guard<std::mutex> lk(g_ctx.mu);
   if (g_ctx.pinned_free.size() < 256) g_ctx.pinned_free.push_back({p, cap});
   else cudaFreeHost(p);
+}
+
+static int stream_set_acquire(StreamSet* out) {
+  {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (!g_ctx.streams_free.empty()) { *out = g_ctx.streams_free.back(); g_ctx.streams_free.pop_back(); return PB_OK; }
+  }
+  StreamSet s;
+  CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 5; i++) CU(cudaEventCreate(&s.ev[i]));
+  *out = s;
+  return PB_OK;
+}
+static void stream_set_release(const StreamSet& s) {   // the stream must be idle
+  if (!s.stream) return;
+  {
+    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    if (g_ctx.streams_free.size() < 64) { g_ctx.streams_free.push_back(s); return; }
+  }
+  for (int i = 0; i < 5; i++) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+  cudaStreamDestroy(s.stream);
 }
 
 // large device scratch (the match list): cudaMallocAsync of hundreds of MB is not free even from the pool
@@ -603,6 +628,7 @@ struct pb_result_s {
   double host_us[8] = {0};   // [0] stage+resolve [1] tables [2] descriptors [3] launches [4] finalize: count [5] gather+D2H wait [6] host decode
   int launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm = nullptr, ev2 = nullptr, ev3 = nullptr;
+  StreamSet sset;
   bool match_all = false;
   double filter_ms = 0, agg_ms = 0;
   // contiguous spans of table 0 for the cross-GPU reduce: [counters .. row counts] int64 SUM, sums float64 SUM, min/max int64 MIN
@@ -624,12 +650,7 @@ static void free_result(pb_result_s* r) {
     for (auto* v : {&t.dbl, &t.lng, &t.key_ids, &t.key_vals, &t.dc_off, &t.dc_ids}) for (auto& a : *v) a.release();
   }
   r->h_counters.release();
-  if (r->ev0) cudaEventDestroy(r->ev0);
-  if (r->ev1) cudaEventDestroy(r->ev1);
-  if (r->evm) cudaEventDestroy(r->evm);
-  if (r->ev2) cudaEventDestroy(r->ev2);
-  if (r->ev3) cudaEventDestroy(r->ev3);
-  if (r->stream) { cudaStreamSynchronize(r->stream); cudaStreamDestroy(r->stream); }
+  if (r->stream) { cudaStreamSynchronize(r->stream); stream_set_release(r->sset); }
   delete r;
 }
 extern "C" void pb_result_free(pb_result_handle r) { free_result(r); }
@@ -753,9 +774,10 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   std::unique_ptr<pb_result_s, void (*)(pb_result_s*)> R(new pb_result_s(), free_result);
   pb_result_s* r = R.get();
   r->group = g; r->n_gb = nG; r->n_aggs = nA; r->combine = combine;
-  CU(cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking));
+  if ((rc = stream_set_acquire(&r->sset))) return rc;
+  r->stream = r->sset.stream;
   cudaStream_t st = r->stream;
-  CU(cudaEventCreate(&r->ev0)); CU(cudaEventCreate(&r->ev1)); CU(cudaEventCreate(&r->evm)); CU(cudaEventCreate(&r->ev2)); CU(cudaEventCreate(&r->ev3));
+  r->ev0 = r->sset.ev[0]; r->ev1 = r->sset.ev[1]; r->evm = r->sset.ev[2]; r->ev2 = r->sset.ev[3]; r->ev3 = r->sset.ev[4];
   for (int j = 0; j < nG; j++) r->gb_names.push_back(q->group_by_columns[j]);
   for (int a = 0; a < nA; a++) {
     r->agg_op.push_back(q->aggregations[a].op);
@@ -1280,7 +1302,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   }
   // ---- waves: when some segments are still being copied to HBM, launch per run of segments so that the kernels of
   // one wave (and its in-place gathers over PCIe) overlap the staging copies of the next ----
-  struct Wave { int seg_lo, seg_hi; const DevQuery* dq; uint64_t n_units, n_docs; };
+  struct Wave { int seg_lo, seg_hi; DevQuery dq; uint64_t n_units, n_docs; };   // the descriptor travels as a __grid_constant__ kernel parameter
   std::vector<Wave> waves;
   if (n_pending > 0 && !match_all && n_expand_items == 0 && n_segs > 1 && n_chunks > 0) {
     const int per_wave = (n_segs + PB_MAX_WAVES - 1) / PB_MAX_WAVES;
@@ -1292,13 +1314,11 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       w.n_docs_total = hsegs[hi - 1].doc_base + (uint64_t)g->segs[hi - 1]->num_docs - hsegs[lo].doc_base;
       w.match_list = d_match_list + hsegs[lo].doc_base;
       w.match_count = hq->match_count + waves.size();
-      const DevQuery* dw = ar.put<DevQuery>(&w, 1);
-      if (!dw) return fail(PB_ERR_STATE, "query arena overflow");
-      waves.push_back({lo, hi, dw, w.n_units, w.n_docs_total});
+      waves.push_back({lo, hi, w, w.n_units, w.n_docs_total});
     }
   } else {
     for (int si = 0; si < n_segs; si++) if (seg_wait[si]) CU(cudaStreamWaitEvent(st, seg_wait[si], 0));
-    waves.push_back({0, n_segs, dq, n_chunks, n_docs_total});
+    waves.push_back({0, n_segs, *hq, n_chunks, n_docs_total});
   }
   r->waves = (int)waves.size();
   CU(cudaMemcpyAsync(ar.dev, ar.host.data(), ar.used, cudaMemcpyHostToDevice, st));
@@ -1331,7 +1351,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   uint64_t max_ctas = 0;
   bool u2_three = false;
   if (!match_all && n_chunks > 0) {
-    smem = ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + (size_t)hq->cand_bytes + stage_bytes * PB_NSTAGE * PB_NWARPS;
+    smem = ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + (size_t)hq->cand_bytes + (size_t)PB_NWARPS * PB_OUT_CAP * 4 + stage_bytes * PB_NSTAGE * PB_NWARPS;
     if (smem > 227 * 1024) return fail(PB_ERR_UNSUPPORTED, "filter kernel needs %zu bytes of shared memory", smem);
     int occ = 1;
     // U = 2 comes in two register budgets: 3 CTAs/SM (80 registers) when three stages sets fit shared memory, else 2 CTAs/SM
