@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       const int st = (int)(seq % PB_NSTAGE);
       uint8_t* dst = my_stages + (size_t)st * Q.stage_bytes;
       uint64_t* bar = &H->full[warp][st];
-      if (rel < min_last_rel) {                         // steady state: constant sizes
+      if (__builtin_expect(rel < min_last_rel, 1)) {    // steady state: constant sizes
         pb_mbar_expect_tx(bar, H->n_scan_full_bytes);
         for (int c = 0; c < n_scan; c++) {
           const uint32_t stride = H->slot_stride[c];
@@ -838,7 +838,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       const int st = (int)(consumed % PB_NSTAGE);
       uint8_t* stage = my_stages + (size_t)st * Q.stage_bytes;
       if (staged) {
-        if (Q.use_tma) {
+        if (__builtin_expect(Q.use_tma != 0, 1)) {
           // the stage being refilled was consumed one iteration ago by this same warp
           if (lane == 0 && k + PB_NSTAGE - 1 < n_mine) issue(k + PB_NSTAGE - 1, consumed + PB_NSTAGE - 1);
           pb_mbar_wait(&H->full[warp][st], (consumed / PB_NSTAGE) & 1u);
@@ -860,15 +860,15 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       // ---- predicate tree on 32-doc masks (one mask word per lane per sub-chunk) ----
       uint32_t mask[U], tmp[U];
       int nu = 0;
+      const uint32_t nd_rel = (uint32_t)sq.num_docs - (uint32_t)unit_doc0;      // docs from the start of this unit (>= 1; docs of a segment fit 31 bits)
+      nu = nd_rel >= (uint32_t)U * PB_CHUNK_DOCS ? U : (int)((nd_rel + PB_CHUNK_DOCS - 1) / PB_CHUNK_DOCS);
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        // docs of a segment fit 31 bits: plain 32-bit arithmetic
-        const uint32_t nd = (uint32_t)sq.num_docs, c0 = (uint32_t)unit_doc0 + (uint32_t)u * PB_CHUNK_DOCS, d0 = c0 + 32u * (uint32_t)lane;
-        mask[u] = d0 + 32u <= nd ? 0xffffffffu : (d0 >= nd ? 0u : ((1u << (nd - d0)) - 1u));
-        if (nd > c0) nu = u + 1;
+        const uint32_t d = (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
+        mask[u] = nd_rel >= d + 32u ? 0xffffffffu : (nd_rel <= d ? 0u : ((1u << (nd_rel - d)) - 1u));
       }
       const int n_cand_leaves = H->flat_and ? H->n_flat - H->n_dense : 0;
-      if (H->flat_and) {
+      if (__builtin_expect(H->flat_and != 0, 1)) {
         const int nl = H->n_dense;
         for (int i = 0; i < nl; i++) {
           // few survivors in the whole unit -> restricted scan of the remaining leaves (leaves arrive ordered by
@@ -930,7 +930,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       }
       const uint32_t gunit0 = (uint32_t)(sq.doc_base + unit_doc0);
       if (n_cand_leaves == 0) {
-        if (total > PB_OUT_CAP) {
+        if (__builtin_expect(total > PB_OUT_CAP, 0)) {
           // dense matches: straight to the list
           unsigned long long base = 0;
           if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)total);
