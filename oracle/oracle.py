@@ -51,12 +51,19 @@ class OrcAggregation(C.Structure):
     _fields_ = [("op", C.c_int32), ("column", C.c_int32)]
 
 
+class OrcFilterProgram(C.Structure):
+    _fields_ = [("num_nodes", C.c_int32), ("_pad", C.c_int32),
+                ("nodes", C.POINTER(OrcFilterNode)), ("predicates", C.POINTER(OrcPredicate))]
+
+
 class OrcQuery(C.Structure):
     _fields_ = [("num_filter_nodes", C.c_int32), ("num_group_by", C.c_int32), ("num_aggregations", C.c_int32),
                 ("num_groups_limit", C.c_int32), ("max_initial_result_holder_capacity", C.c_int32),
                 ("skip_inverted_index", C.c_int32),
                 ("filter_nodes", C.POINTER(OrcFilterNode)), ("predicates", C.POINTER(OrcPredicate)),
-                ("group_by_columns", C.POINTER(C.c_int32)), ("aggregations", C.POINTER(OrcAggregation))]
+                ("group_by_columns", C.POINTER(C.c_int32)), ("aggregations", C.POINTER(OrcAggregation)),
+                ("num_agg_filters", C.c_int32), ("_pad2", C.c_int32),
+                ("agg_filters", C.POINTER(OrcFilterProgram)), ("agg_filter_of", C.POINTER(C.c_int32))]
 
 
 class OrcStats(C.Structure):
@@ -134,10 +141,12 @@ def marshal_segment(seg, m: _Marshalled, skip_inverted=()) -> OrcSegment:
     return m.hold(s)
 
 
-def marshal_query(seg, q, m: _Marshalled) -> OrcQuery:
+def _marshal_filter(seg, flt, m: _Marshalled):
+    """postfix nodes + predicates of one filter expression -> (n_nodes, OrcFilterNode[], OrcPredicate[])"""
+    from pinot_b200.query import postfix_of
     from pinot_b200.segment_writer import DataType
     names = seg.column_names()
-    nodes, preds = q.filter_postfix()
+    nodes, preds = postfix_of(flt)
     cn = (OrcFilterNode * max(1, len(nodes)))()
     for i, (k, n, p) in enumerate(nodes):
         cn[i].kind, cn[i].n_children, cn[i].predicate = k, n, p
@@ -157,22 +166,37 @@ def marshal_query(seg, q, m: _Marshalled) -> OrcQuery:
             vals = list(p.values)
         o.num_values = len(vals)
         if col.data_type in (DataType.INT, DataType.LONG):
-            arr = (C.c_int64 * len(vals))(*[int(float(v)) if ("." in v or "e" in v.lower()) else int(v) for v in vals])
+            arr = (C.c_int64 * max(1, len(vals)))(*[int(float(v)) if ("." in v or "e" in v.lower()) else int(v) for v in vals])
             o.int_values = m.hold(arr)
         elif col.data_type in (DataType.FLOAT, DataType.DOUBLE):
-            arr = (C.c_double * len(vals))(*[float(v) for v in vals])
+            arr = (C.c_double * max(1, len(vals)))(*[float(v) for v in vals])
             o.double_values = m.hold(arr)
         else:
-            arr = (C.c_char_p * len(vals))(*[v.encode("utf-8") for v in vals])
+            arr = (C.c_char_p * max(1, len(vals)))(*[v.encode("utf-8") for v in vals])
             o.string_values = m.hold(arr)
+    m.hold((cn, cp))
+    return len(nodes), cn, cp
+
+
+def marshal_query(seg, q, m: _Marshalled) -> OrcQuery:
+    names = seg.column_names()
+    n_nodes, cn, cp = _marshal_filter(seg, q.filter, m)
+    nodes = [None] * n_nodes
     gb = (C.c_int32 * max(1, len(q.group_by)))(*[names.index(c) for c in q.group_by])
     ag = (OrcAggregation * max(1, len(q.aggregations)))()
     for i, a in enumerate(q.aggregations):
         ag[i].op = int(a.op)
         ag[i].column = -1 if a.column is None else names.index(a.column)
+    filters, filter_of = q.agg_filters()
+    progs = (OrcFilterProgram * max(1, len(filters)))()
+    for i, f in enumerate(filters):
+        n, fn_, fp_ = _marshal_filter(seg, f, m)
+        progs[i].num_nodes, progs[i].nodes, progs[i].predicates = n, fn_, fp_
+    fo = (C.c_int32 * max(1, len(filter_of)))(*filter_of)
     oq = OrcQuery(len(nodes), len(q.group_by), len(q.aggregations), q.num_groups_limit,
-                  q.max_initial_result_holder_capacity, int(q.skip_inverted_all), cn, cp, gb, ag)
-    m.hold((cn, cp, gb, ag))
+                  q.max_initial_result_holder_capacity, int(q.skip_inverted_all), cn, cp, gb, ag,
+                  len(filters), 0, progs, fo)
+    m.hold((cn, cp, gb, ag, progs, fo))
     return m.hold(oq)
 
 

@@ -477,6 +477,9 @@ static fop* make_inverted_op(pred_eval* e, int32_t num_docs) {
 
 /* CTR/operator/filter/FilterOperatorUtils.java:74-133 (index selection) */
 static fop* make_leaf_op(const orc_segment* seg, const orc_query* q, const orc_predicate* p) {
+  /* FilterPlanNode.java:294-307: no null-value vector on this path */
+  if (p->type == ORC_IS_NULL) return fop_new(OP_EMPTY, seg->num_docs);
+  if (p->type == ORC_IS_NOT_NULL) return fop_new(OP_MATCH_ALL, seg->num_docs);
   pred_eval* e = (pred_eval*)malloc(sizeof(pred_eval));
   if (pred_eval_init(e, seg, p) != 0) { free(e); return NULL; }
   int32_t n = seg->num_docs;
@@ -946,10 +949,59 @@ static void bholder_ensure(bholder* h, int64_t n) {
 orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
   g_err[0] = 0;
   const int32_t nG = q->num_group_by, nA = q->num_aggregations, num_docs = seg->num_docs;
-  fop* root = build_filter(seg, q);
-  if (!root) return NULL;
-  int64_t extra_entries = 0;
-  dit* it = make_iterator(root, &extra_entries);
+  /* ---- swim-lanes: AggregationFunctionUtils.buildFilteredAggregationInfos
+   * (CTR/query/aggregation/function/AggregationFunctionUtils.java:312-400).  A plain query is one lane. ---- */
+  typedef struct { fop* root; dit* it; uint8_t* has; int64_t docs, extra; int32_t ncols; } lane_t;
+  const int32_t nF = q->num_agg_filters;
+  lane_t* lanes = (lane_t*)calloc((size_t)nF + 2, sizeof(lane_t));
+  int32_t n_lanes = 0;
+  {
+    fop* main_root = build_filter(seg, q);
+    if (!main_root) { free(lanes); return NULL; }
+    uint8_t* in_main = (uint8_t*)calloc((size_t)(nA > 0 ? nA : 1), 1);   /* functions of the non-filtered lane */
+    int any_main = 0;
+    if (nF == 0 || main_root->kind == OP_EMPTY) {
+      /* no FILTER clause, or ":317-326": an empty main filter needs no sub-filters: one lane, every function */
+      for (int32_t a = 0; a < nA; a++) in_main[a] = 1;
+      any_main = 1;
+    } else {
+      for (int32_t f = 0; f < nF; f++) {
+        orc_query sub = *q;
+        sub.num_filter_nodes = q->agg_filters[f].num_nodes; sub.filter_nodes = q->agg_filters[f].nodes; sub.predicates = q->agg_filters[f].predicates;
+        fop* sub_root = build_filter(seg, &sub);
+        if (!sub_root) { fop_free(main_root); free(in_main); free(lanes); return NULL; }
+        fop* combined;
+        if (main_root->kind == OP_MATCH_ALL || sub_root->kind == OP_EMPTY) combined = sub_root;                 /* :346-347 */
+        else if (sub_root->kind == OP_MATCH_ALL) {                                                            /* :348-349, 370-372 */
+          for (int32_t a = 0; a < nA; a++) if (q->agg_filter_of[a] == f) { in_main[a] = 1; any_main = 1; }
+          fop_free(sub_root);
+          continue;
+        } else {                                                                                              /* CombinedFilterOperator: AND of the two docId sets */
+          fop* kids[2]; kids[0] = build_filter(seg, q); kids[1] = sub_root;
+          combined = make_and_op(kids, 2, num_docs);
+        }
+        lane_t* L = &lanes[n_lanes++];
+        L->root = combined;
+        L->has = (uint8_t*)calloc((size_t)(nA > 0 ? nA : 1), 1);
+        for (int32_t a = 0; a < nA; a++) if (q->agg_filter_of[a] == f) L->has[a] = 1;
+      }
+      for (int32_t a = 0; a < nA; a++) if (q->agg_filter_of[a] < 0) { in_main[a] = 1; any_main = 1; }
+    }
+    /* :381-396: the non-filtered lane; a group-by keeps it even without functions so that every group of the main filter exists */
+    if (any_main || nG > 0) {
+      lane_t* L = &lanes[n_lanes++];
+      L->root = main_root; L->has = in_main;
+    } else { fop_free(main_root); free(in_main); }
+    for (int32_t l = 0; l < n_lanes; l++) {
+      lanes[l].it = make_iterator(lanes[l].root, &lanes[l].extra);
+      /* ProjectPlanNode.java:69-78: distinct columns projected by the lane = group-by columns + inputs of its functions */
+      int32_t cols[128]; int32_t nc = 0;
+      for (int32_t j = 0; j < nG; j++) { int32_t c = q->group_by_columns[j]; int seen = 0; for (int32_t k = 0; k < nc; k++) if (cols[k] == c) seen = 1; if (!seen && nc < 128) cols[nc++] = c; }
+      for (int32_t a = 0; a < nA; a++) { if (!lanes[l].has[a]) continue; int32_t c = q->aggregations[a].column; if (c < 0) continue; int seen = 0; for (int32_t k = 0; k < nc; k++) if (cols[k] == c) seen = 1; if (!seen && nc < 128) cols[nc++] = c; }
+      lanes[l].ncols = nc;
+    }
+  }
+  fop* root = NULL; dit* it = NULL;     /* (owned by the lanes) */
 
   col_reader* greaders = (col_reader*)calloc((size_t)(nG > 0 ? nG : 1), sizeof(col_reader));
   col_reader* areaders = (col_reader*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(col_reader));
@@ -1014,12 +1066,19 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
 
   /* GroupByOperator.getNextBlock (CTR/operator/query/GroupByOperator.java:101-140) /
    * AggregationOperator.getNextBlock (CTR/operator/query/AggregationOperator.java:64-80) */
+  /* FilteredGroupByOperator.getNextBlock (CTR/operator/query/FilteredGroupByOperator.java:108-159) /
+   * FilteredAggregationOperator.getNextBlock (FilteredAggregationOperator.java:68-103): lane after lane, one shared
+   * group-key generator, result holders indexed by function */
+  for (int32_t lane = 0; lane < n_lanes; lane++) {
+  const uint8_t* lane_has = lanes[lane].has;
+  it = lanes[lane].it;
   while (1) {
     /* DocIdSetOperator.getNextBlock: CTR/operator/DocIdSetOperator.java:59-86 */
     int32_t len = 0;
     for (; len < MAX_DOC_PER_CALL; len++) { int32_t d = dit_next(it); if (d == ORC_EOF) break; doc_ids[len] = d; }
     if (len == 0) break;
     num_docs_scanned += len;
+    lanes[lane].docs += len;
 
     if (nG > 0) {
       /* generateKeysForBlock: DictionaryBasedGroupKeyGenerator.java:210-217, 290-305, 341-347, 424-446 */
@@ -1046,6 +1105,7 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
         dholder_ensure(&dh[a], need);
         if (op == ORC_AVG) dholder_ensure(&ch[a], need);
         if (op == ORC_DISTINCTCOUNT) bholder_ensure(&bh[a], need);
+        if (!lane_has[a]) continue;
         if (op == ORC_COUNT) {   /* CountAggregationFunction.java:178-185 */
           for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0) dh[a].v[group_ids[i]] += 1.0;
           continue;
@@ -1081,6 +1141,7 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
       kl_count += len;
       for (int32_t a = 0; a < nA; a++) {
         int op = q->aggregations[a].op;
+        if (!lane_has[a]) continue;
         if (op == ORC_COUNT) { dh[a].v[0] += (double)len; continue; }   /* CountAggregationFunction.java:110-116 */
         const col_reader* r = &areaders[a];
         if (op == ORC_DISTINCTCOUNT) {   /* BaseDistinctAggregateAggregationFunction.java:144-155 */
@@ -1108,6 +1169,11 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
         (void)dict_buf;
       }
     }
+  }
+  }   /* lanes */
+  if (nG > 0) {   /* holders of functions whose lane saw no block still cover every group (FilteredGroupByOperator.java:161-163) */
+    int64_t need = holder == 1 ? card_product : map.size;
+    for (int32_t a = 0; a < nA; a++) { dholder_ensure(&dh[a], need); dholder_ensure(&ch[a], need); bholder_ensure(&bh[a], need); }
   }
 
   /* ---- build the result ---- */
@@ -1169,9 +1235,12 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
     int32_t cols[128]; int32_t nc = 0;
     for (int32_t j = 0; j < nG; j++) { int32_t c = q->group_by_columns[j]; int seen = 0; for (int32_t k = 0; k < nc; k++) if (cols[k] == c) seen = 1; if (!seen && nc < 128) cols[nc++] = c; }
     for (int32_t a = 0; a < nA; a++) { int32_t c = q->aggregations[a].column; if (c < 0) continue; int seen = 0; for (int32_t k = 0; k < nc; k++) if (cols[k] == c) seen = 1; if (!seen && nc < 128) cols[nc++] = c; }
+    (void)nc;
+    int64_t in_filter = 0, post_filter = 0;
+    for (int32_t l = 0; l < n_lanes; l++) { in_filter += lanes[l].extra + dit_entries(lanes[l].it); post_filter += lanes[l].docs * lanes[l].ncols; }
     res->stats.num_docs_scanned = num_docs_scanned;
-    res->stats.num_entries_scanned_in_filter = extra_entries + dit_entries(it);
-    res->stats.num_entries_scanned_post_filter = num_docs_scanned * nc;
+    res->stats.num_entries_scanned_in_filter = in_filter;
+    res->stats.num_entries_scanned_post_filter = post_filter;
     res->stats.num_total_docs = num_docs;
     res->stats.num_groups_limit_reached = (nG > 0 && ng >= limit) ? 1 : 0;   /* GroupByOperator.java:116 */
     res->stats.key_holder = holder;
@@ -1186,8 +1255,9 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
   free(dh); free(ch); free(bh); free(kl_long); free(kl_long_set);
   if (have_map) gmap_free(&map);
   free(array_flags); free(greaders); free(areaders);
-  dit_free(it); fop_free(root);
-  (void)kl_count;
+  for (int32_t l = 0; l < n_lanes; l++) { dit_free(lanes[l].it); fop_free(lanes[l].root); free(lanes[l].has); }
+  free(lanes);
+  (void)kl_count; (void)root;
   return res;
 
 fail2:
@@ -1197,6 +1267,8 @@ fail2:
   free(array_flags);
 fail:
   free(greaders); free(areaders);
-  dit_free(it); fop_free(root);
+  for (int32_t l = 0; l < n_lanes; l++) { if (lanes[l].it) dit_free(lanes[l].it); if (lanes[l].root) fop_free(lanes[l].root); free(lanes[l].has); }
+  free(lanes);
+  (void)it;
   return NULL;
 }

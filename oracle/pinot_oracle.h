@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 enum { ORC_INT = 0, ORC_LONG = 1, ORC_FLOAT = 2, ORC_DOUBLE = 3, ORC_STRING = 4 };
-enum { ORC_EQ = 0, ORC_NEQ = 1, ORC_IN = 2, ORC_NOT_IN = 3, ORC_RANGE = 4 };
+enum { ORC_EQ = 0, ORC_NEQ = 1, ORC_IN = 2, ORC_NOT_IN = 3, ORC_RANGE = 4, ORC_IS_NULL = 5, ORC_IS_NOT_NULL = 6 };
 enum { ORC_AND = 0, ORC_OR = 1, ORC_NOT = 2, ORC_PRED = 3 };
 enum { ORC_COUNT = 0, ORC_SUM = 1, ORC_MIN = 2, ORC_MAX = 3, ORC_AVG = 4, ORC_DISTINCTCOUNT = 5 };
 
@@ -68,6 +68,14 @@ typedef struct orc_filter_node {
   int32_t predicate;     /* index into predicates for ORC_PRED */
 } orc_filter_node;
 
+/* A filter of its own: the FILTER(WHERE ...) clause of one or more aggregations. */
+typedef struct orc_filter_program {
+  int32_t num_nodes;
+  int32_t _pad;
+  const orc_filter_node* nodes;
+  const orc_predicate* predicates;
+} orc_filter_program;
+
 typedef struct orc_aggregation {
   int32_t op;            /* ORC_COUNT .. ORC_DISTINCTCOUNT */
   int32_t column;        /* -1 for COUNT(*) */
@@ -84,6 +92,12 @@ typedef struct orc_query {
   const orc_predicate* predicates;
   const int32_t* group_by_columns;
   const orc_aggregation* aggregations;
+  /* filtered aggregations (FilteredGroupByOperator / FilteredAggregationOperator): distinct FILTER clauses and, per
+   * aggregation, the index of its clause (-1 = not filtered).  num_agg_filters = 0: the plain operators. */
+  int32_t num_agg_filters;
+  int32_t _pad2;
+  const orc_filter_program* agg_filters;
+  const int32_t* agg_filter_of;
 } orc_query;
 
 typedef struct orc_stats {

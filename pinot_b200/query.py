@@ -5,8 +5,9 @@ build: SURVEY.md §2b "run unchanged before the hot path").  Tests and the bench
 starting point, so this module parses the SQL subset the hot path covers
 
     SELECT <agg | ident>, ... FROM <table> [WHERE <bool-expr>] [GROUP BY ident, ...] [LIMIT n]
-    agg   := COUNT(*) | SUM|MIN|MAX|AVG|DISTINCTCOUNT(ident)
+    agg   := (COUNT(*) | SUM|MIN|MAX|AVG|DISTINCTCOUNT(ident)) [FILTER(WHERE <bool-expr>)]
     pred  := ident (=|!=|<>|<|<=|>|>=) literal | ident [NOT] IN (lit, ...) | ident BETWEEN lit AND lit
+           | ident IS [NOT] NULL
 
 into the logical `QueryContext` below (predicate literals are still strings, as in Pinot's
 `Predicate` classes: pinot-common/.../request/context/predicate/*.java).  Lowering to dictIds and
@@ -26,6 +27,8 @@ class PredicateType(IntEnum):
     IN = 2
     NOT_IN = 3
     RANGE = 4
+    IS_NULL = 5          # no null-value vectors on this path: EmptyFilterOperator (FilterPlanNode.java:294-300)
+    IS_NOT_NULL = 6      # ... MatchAllFilterOperator (FilterPlanNode.java:301-307)
 
 
 class AggOp(IntEnum):
@@ -70,9 +73,31 @@ FilterNode = Union[And, Or, Not, Predicate]
 class Aggregation:
     op: AggOp
     column: Optional[str]        # None for COUNT(*)
+    filter: Optional["FilterNode"] = None    # AGG(...) FILTER(WHERE ...): QueryContext.getFilteredAggregationFunctions()
 
     def __str__(self):
         return f"{self.op.name.lower()}({self.column or '*'})"
+
+
+def postfix_of(flt: Optional["FilterNode"]):
+    """[(kind, n_children, predicate_index)], [Predicate] — AND=0 OR=1 NOT=2 PRED=3."""
+    nodes, preds = [], []
+
+    def walk(n):
+        if isinstance(n, Predicate):
+            preds.append(n)
+            nodes.append((3, 0, len(preds) - 1))
+        elif isinstance(n, Not):
+            walk(n.child)
+            nodes.append((2, 1, -1))
+        else:
+            for c in n.children:
+                walk(c)
+            nodes.append((0 if isinstance(n, And) else 1, len(n.children), -1))
+
+    if flt is not None:
+        walk(flt)
+    return nodes, preds
 
 
 @dataclass
@@ -91,23 +116,24 @@ class QueryContext:
 
     def filter_postfix(self):
         """[(kind, n_children, predicate_index)], [Predicate] — AND=0 OR=1 NOT=2 PRED=3."""
-        nodes, preds = [], []
+        return postfix_of(self.filter)
 
-        def walk(n):
-            if isinstance(n, Predicate):
-                preds.append(n)
-                nodes.append((3, 0, len(preds) - 1))
-            elif isinstance(n, Not):
-                walk(n.child)
-                nodes.append((2, 1, -1))
+    def agg_filters(self):
+        """Distinct aggregation filters (equal filter expressions share a swim-lane, AggregationFunctionUtils.java:333-366)
+        and, per aggregation, the index of its filter (-1 = not filtered)."""
+        filters, index = [], []
+        for a in self.aggregations:
+            if a.filter is None:
+                index.append(-1)
+                continue
+            for i, f in enumerate(filters):
+                if f == a.filter:
+                    index.append(i)
+                    break
             else:
-                for c in n.children:
-                    walk(c)
-                nodes.append((0 if isinstance(n, And) else 1, len(n.children), -1))
-
-        if self.filter is not None:
-            walk(self.filter)
-        return nodes, preds
+                filters.append(a.filter)
+                index.append(len(filters) - 1)
+        return filters, index
 
 
 # --------------------------------------------------------------------------- SQL subset parser
@@ -209,6 +235,14 @@ class _Parser:
             self.eat_kw("AND")
             hi = self.literal()
             return Predicate(PredicateType.RANGE, col, lower=lo, upper=hi, lower_inclusive=True, upper_inclusive=True)
+        if self.kw("IS"):
+            self.i += 1
+            neg = False
+            if self.kw("NOT"):
+                self.i += 1
+                neg = True
+            self.eat_kw("NULL")
+            return Predicate(PredicateType.IS_NOT_NULL if neg else PredicateType.IS_NULL, col)
         negate = False
         if self.kw("NOT"):
             self.i += 1
@@ -274,7 +308,14 @@ def parse_sql(sql: str) -> QueryContext:
             else:
                 col = p.ident()
             p.eat_op(")")
-            aggs.append(Aggregation(op, col))
+            agg_filter = None
+            if p.kw("FILTER"):
+                p.i += 1
+                p.eat_op("(")
+                p.eat_kw("WHERE")
+                agg_filter = p.or_expr()
+                p.eat_op(")")
+            aggs.append(Aggregation(op, col, agg_filter))
         else:
             select_idents.append(name)
         if p.peek() == ("op", ","):

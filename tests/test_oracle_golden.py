@@ -118,3 +118,57 @@ def test_inter_segment_distinct_count():   # :235-258
     t, _ = _inter("SELECT DISTINCTCOUNT(column1), DISTINCTCOUNT(column3) FROM testTable" + FILTER + " GROUP BY column9")
     assert max(len(v[0]) for v in t.values()) == 1272
     assert max(len(v[1]) for v in t.values()) == 3289
+
+
+FILTERED = ("SELECT SUM(column6) FILTER(WHERE column6 > 5), COUNT(*) FILTER(WHERE column1 IS NOT NULL), "
+            "MAX(column3) FILTER(WHERE column3 IS NOT NULL), SUM(column3), AVG(column7) FILTER(WHERE column7 > 0) FROM testTable")
+FILTERED_3 = ("SELECT SUM(column6) FILTER(WHERE column6 > 5 OR column6 < 15), COUNT(*) FILTER(WHERE column1 IS NOT NULL), "
+              "MAX(column3) FILTER(WHERE column3 IS NOT NULL AND column3 > 0), SUM(column3), "
+              "AVG(column7) FILTER(WHERE column7 > 0 AND column7 < 100) FROM testTable")
+
+
+def filtered_row(r, g=0):
+    return (int(r.doubles[0][g]), int(r.longs[1][g]), int(r.doubles[2][g]), int(r.doubles[3][g]), int(r.doubles[4][g]), int(r.longs[4][g]))
+
+
+def test_filtered_aggregations():   # InnerSegment...Test.java:62-93 (FilteredAggregationOperator, one swim-lane per FILTER clause)
+    r = _inner(FILTERED + " WHERE column3 > 0")
+    assert _stats(r) == (150000, 0, 120000, 30000)
+    assert filtered_row(r) == (22266008882250, 30000, 2147419555, 32289159189150, 28175373944314, 30000)
+    r = _inner(FILTERED)
+    assert _stats(r) == (150000, 0, 120000, 30000)
+    assert filtered_row(r) == (22266008882250, 30000, 2147419555, 32289159189150, 28175373944314, 30000)
+    r = _inner(FILTERED_3)
+    assert _stats(r) == (120000, 0, 90000, 30000)
+    assert filtered_row(r) == (22266008882250, 30000, 2147419555, 32289159189150, 0, 0)
+
+
+def test_filtered_aggregations_equal_separate_queries():
+    """FilteredAggregationsTest.java's property: AGG(x) FILTER(WHERE p) under WHERE m == AGG(x) WHERE m AND p, keyless
+    and grouped (every group of the main filter is present; functions without a matching doc keep their default)."""
+    seg = sv_segment()
+    main, p1, p2 = "column6 < 1500000000", "column1 > 100000000 AND column11 <> 'P'", "column7 IN (1111197135, 296467636, 675163196) OR column17 < 100000000"
+    q = parse_sql(f"SELECT SUM(column1) FILTER(WHERE {p1}), COUNT(*) FILTER(WHERE {p2}), MIN(column3) FILTER(WHERE {p1}), COUNT(*), "
+                  f"AVG(column6) FILTER(WHERE {p2}), DISTINCTCOUNT(column9) FILTER(WHERE {p1}), MAX(column18) FROM testTable WHERE {main}")
+    r = oracle.execute(seg, q)
+    a = oracle.execute(seg, parse_sql(f"SELECT SUM(column1), MIN(column3), DISTINCTCOUNT(column9), COUNT(*) FROM testTable WHERE {main} AND ({p1})"))
+    b = oracle.execute(seg, parse_sql(f"SELECT COUNT(*), AVG(column6) FROM testTable WHERE {main} AND ({p2})"))
+    c = oracle.execute(seg, parse_sql(f"SELECT COUNT(*), MAX(column18) FROM testTable WHERE {main}"))
+    assert r.doubles[0][0] == a.doubles[0][0] and r.doubles[2][0] == a.doubles[1][0] and r.longs[5][0] == a.longs[2][0]
+    assert r.longs[1][0] == b.longs[0][0] and r.doubles[4][0] == b.doubles[1][0] and r.longs[4][0] == b.longs[1][0]
+    assert r.longs[3][0] == c.longs[0][0] and r.doubles[6][0] == c.doubles[1][0]
+    assert r.stats["num_docs_scanned"] == a.longs[3][0] + b.longs[0][0] + c.longs[0][0]
+    # grouped
+    gq = parse_sql(f"SELECT column11, SUM(column1) FILTER(WHERE {p1}), COUNT(*) FILTER(WHERE {p2}), MAX(column3) FILTER(WHERE {p1}) "
+                   f"FROM testTable WHERE {main} GROUP BY column11")
+    g = oracle.execute(seg, gq)
+    gm = oracle.execute(seg, parse_sql(f"SELECT column11, COUNT(*) FROM testTable WHERE {main} GROUP BY column11"))
+    ga = oracle.execute(seg, parse_sql(f"SELECT column11, SUM(column1), MAX(column3) FROM testTable WHERE {main} AND ({p1}) GROUP BY column11"))
+    gb = oracle.execute(seg, parse_sql(f"SELECT column11, COUNT(*) FROM testTable WHERE {main} AND ({p2}) GROUP BY column11"))
+    assert sorted(g.decoded_keys()) == sorted(gm.decoded_keys())          # the main lane creates every group
+    ka = {k: i for i, k in enumerate(ga.decoded_keys())}
+    kb = {k: i for i, k in enumerate(gb.decoded_keys())}
+    for i, k in enumerate(g.decoded_keys()):
+        assert g.doubles[0][i] == (ga.doubles[0][ka[k]] if k in ka else 0.0)
+        assert g.doubles[2][i] == (ga.doubles[1][ka[k]] if k in ka else -np.inf)
+        assert g.longs[1][i] == (gb.longs[0][kb[k]] if k in kb else 0)
