@@ -107,6 +107,12 @@ typedef struct pb_filter_node {
 typedef struct pb_segment_query {
   const pb_filter_node* filter;
   int32_t num_filter_nodes;
+  /* Filtered aggregations (FilteredGroupByOperator / FilteredAggregationOperator, CTR/operator/query/
+   * FilteredGroupByOperator.java:108-159): the FILTER(WHERE ...) clause f of the query, lowered for this segment,
+   * is agg_filters[f] with agg_filter_nodes[f] postfix nodes (0 nodes = matches all).  pb_query_desc.num_agg_filters
+   * entries; both pointers may be NULL when that is 0. */
+  const pb_filter_node* const* agg_filters;
+  const int32_t* agg_filter_nodes;
 } pb_segment_query;
 
 typedef struct pb_aggregation_desc {
@@ -131,6 +137,10 @@ typedef struct pb_query_desc {
   int32_t num_groups_limit;                     /* InstancePlanMakerImplV2.java:79 (default 100000) */
   int32_t max_initial_result_holder_capacity;   /* InstancePlanMakerImplV2.java:70 (default 10000) */
   uint32_t flags;                               /* PB_Q_* */
+  /* filtered aggregations: number of distinct FILTER(WHERE ...) clauses (<= 8) and, per aggregation, the index of its
+   * clause (-1 = none; NULL when num_agg_filters = 0).  QueryContext.getFilteredAggregationFunctions(). */
+  int32_t num_agg_filters;
+  const int32_t* agg_filter_of;
 } pb_query_desc;
 
 /* ExecutionStatistics (CTR/operator/ExecutionStatistics.java:28-65) */

@@ -22,7 +22,8 @@ extern "C" {
 #endif
 
 /* Predicate.Type (pinot-common/.../request/context/predicate/Predicate.java) */
-enum { PBH_EQ = 0, PBH_NOT_EQ = 1, PBH_IN = 2, PBH_NOT_IN = 3, PBH_RANGE = 4 };
+enum { PBH_EQ = 0, PBH_NOT_EQ = 1, PBH_IN = 2, PBH_NOT_IN = 3, PBH_RANGE = 4,
+       PBH_IS_NULL = 5, PBH_IS_NOT_NULL = 6 };   /* no null-value vectors here: EmptyFilterOperator / MatchAllFilterOperator (CTR/plan/FilterPlanNode.java:294-307) */
 /* FilterContext.Type */
 enum { PBH_AND = 0, PBH_OR = 1, PBH_NOT = 2, PBH_PREDICATE = 3 };
 
@@ -44,6 +45,13 @@ typedef struct pbh_filter_node {  /* postfix */
   int32_t predicate;              /* index into predicates */
 } pbh_filter_node;
 
+/* One FILTER(WHERE ...) clause of a filtered aggregation (QueryContext.getFilteredAggregationFunctions()). */
+typedef struct pbh_filter_program {
+  int32_t num_filter_nodes;
+  const pbh_filter_node* filter_nodes;
+  const pbh_predicate* predicates;
+} pbh_filter_program;
+
 /* The part of QueryContext (CTR/query/request/context/QueryContext.java) this path reads. */
 typedef struct pbh_query_context {
   int32_t num_filter_nodes;       /* 0 = no WHERE clause */
@@ -57,6 +65,11 @@ typedef struct pbh_query_context {
   int32_t max_initial_result_holder_capacity;
   int32_t num_skip_inverted;      /* query option skipIndexes: columns whose inverted index must not be used */
   const char* const* skip_inverted_columns;
+  /* filtered aggregations: the distinct FILTER clauses (equal clauses share a swim-lane,
+   * AggregationFunctionUtils.java:333-366) and, per aggregation, the index of its clause (-1 = none) */
+  int32_t num_agg_filters;
+  const pbh_filter_program* agg_filters;
+  const int32_t* agg_filter_of;
 } pbh_query_context;
 
 /* B200PlanMaker.makeSegmentPlanNode eligibility (InstancePlanMakerImplV2.java:275-294 override):

@@ -249,15 +249,20 @@ static int findColumn(const PbSegmentView& s, const char* name) {
 class FilterPlanNode {
  public:
   // constructPhysicalOperator over the postfix FilterContext
-  static OpPtr run(const PbSegmentView& seg, const pbh_query_context& q) {
-    if (q.num_filter_nodes == 0) return mk(OP_MATCH_ALL);
+  static OpPtr run(const PbSegmentView& seg, const pbh_query_context& q) { return run(seg, q, q.num_filter_nodes, q.filter_nodes, q.predicates); }
+  // (the FILTER clause of a filtered aggregation is planned on its own: AggregationFunctionUtils.java:343-344)
+  static OpPtr run(const PbSegmentView& seg, const pbh_query_context& q, int num_filter_nodes, const pbh_filter_node* filter_nodes, const pbh_predicate* predicates) {
+    if (num_filter_nodes == 0) return mk(OP_MATCH_ALL);
     std::vector<OpPtr> stack;
-    for (int i = 0; i < q.num_filter_nodes; i++) {
-      const pbh_filter_node& n = q.filter_nodes[i];
+    for (int i = 0; i < num_filter_nodes; i++) {
+      const pbh_filter_node& n = filter_nodes[i];
       if (n.kind == PBH_PREDICATE) {
-        const pbh_predicate& p = q.predicates[n.predicate];
+        const pbh_predicate& p = predicates[n.predicate];
         int ci = findColumn(seg, p.column);
         if (ci < 0) throw BadQuery{std::string("unknown column ") + p.column};
+        // FilterPlanNode.java:294-307: without a null-value vector IS NULL is empty and IS NOT NULL matches all
+        if (p.type == PBH_IS_NULL) { stack.push_back(mk(OP_EMPTY)); continue; }
+        if (p.type == PBH_IS_NOT_NULL) { stack.push_back(mk(OP_MATCH_ALL)); continue; }
         bool skipInv = false;
         for (int k = 0; k < q.num_skip_inverted; k++) if (seg.cols[ci].name == q.skip_inverted_columns[k]) skipInv = true;
         PredicateEvaluator ev = PredicateEvaluatorProvider::getPredicateEvaluator(p, seg.cols[ci], ci);
@@ -382,6 +387,7 @@ extern "C" int pbh_is_eligible(pb_segment_group_handle g, const pbh_query_contex
       if ((rc = pbi_segment_view(s, &v))) return rc;
       B200PlanMaker::checkEligible(v, *q);
       FilterPlanNode::run(v, *q);
+      for (int f = 0; f < q->num_agg_filters; f++) FilterPlanNode::run(v, *q, q->agg_filters[f].num_filter_nodes, q->agg_filters[f].filter_nodes, q->agg_filters[f].predicates);
     }
   } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
   return PB_OK;
@@ -394,6 +400,11 @@ extern "C" int pbh_execute(pb_segment_group_handle g, const pbh_query_context* q
   if (!q || !out) return pbi_fail(PB_ERR_INVALID, "null argument");
   std::vector<LoweredSegment> lowered(segs.size());
   std::vector<pb_segment_query> sq(segs.size());
+  if (q->num_agg_filters < 0 || (q->num_agg_filters > 0 && (!q->agg_filters || !q->agg_filter_of))) return pbi_fail(PB_ERR_INVALID, "bad FILTER clauses");
+  std::vector<LoweredSegment> clauseLowered(segs.size() * (size_t)q->num_agg_filters);
+  std::vector<std::vector<const pb_filter_node*>> clausePtr(segs.size());
+  std::vector<std::vector<int32_t>> clauseLen(segs.size());
+  for (auto& sqi : sq) memset(&sqi, 0, sizeof sqi);
   try {
     for (size_t i = 0; i < segs.size(); i++) {
       PbSegmentView v;
@@ -403,6 +414,17 @@ extern "C" int pbh_execute(pb_segment_group_handle g, const pbh_query_context* q
       if (root->kind != OP_MATCH_ALL) emit(*root, v, lowered[i]);
       sq[i].filter = lowered[i].nodes.data();
       sq[i].num_filter_nodes = (int32_t)lowered[i].nodes.size();
+      // FILTER clauses, each planned like a filter of its own for this segment
+      for (int f = 0; f < q->num_agg_filters; f++) {
+        const pbh_filter_program& fp = q->agg_filters[f];
+        OpPtr sub = FilterPlanNode::run(v, *q, fp.num_filter_nodes, fp.filter_nodes, fp.predicates);
+        LoweredSegment& ls = clauseLowered[i * (size_t)q->num_agg_filters + f];
+        if (sub->kind != OP_MATCH_ALL) emit(*sub, v, ls);
+        clausePtr[i].push_back(ls.nodes.data());
+        clauseLen[i].push_back((int32_t)ls.nodes.size());
+      }
+      sq[i].agg_filters = clausePtr[i].data();
+      sq[i].agg_filter_nodes = clauseLen[i].data();
     }
   } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
   pb_query_desc d;
@@ -412,6 +434,7 @@ extern "C" int pbh_execute(pb_segment_group_handle g, const pbh_query_context* q
   d.num_groups_limit = q->num_groups_limit > 0 ? q->num_groups_limit : 100000;
   d.max_initial_result_holder_capacity = q->max_initial_result_holder_capacity > 0 ? q->max_initial_result_holder_capacity : 10000;
   d.flags = flags;
+  d.num_agg_filters = q->num_agg_filters; d.agg_filter_of = q->agg_filter_of;
   return pb_query_execute(g, sq.data(), &d, out);
 }
 

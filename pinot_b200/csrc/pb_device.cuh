@@ -26,6 +26,9 @@
 #define PB_MAX_GROUP_BY 16
 #define PB_MAX_AGGS 16
 #define PB_MAX_SCAN_SLOTS 8
+#define PB_MAX_AGG_FILTERS 8         // distinct FILTER(WHERE ...) clauses per query (swim-lanes of FilteredGroupByOperator)
+#define PB_MAX_AF_LEAVES 16          // leaves of all FILTER clauses of a segment together
+#define PB_MAX_AF_NODES 48
 #define PB_SPARSE_MAX 128            // survivors per 1024-doc chunk below which later AND leaves use the restricted scan
 #define PB_OUT_CAP 256               // matches buffered per warp before one ATOMG reserves their place in the match list
 #define PB_CAND_CAP 512              // candidates per warp list (u16 offsets inside the unit); more = extra passes
@@ -113,8 +116,18 @@ struct DevSegQuery {
   // ---- everything above is the filter part (copied to shared memory by pb_filter_kernel) ----
   DevKeyCol keys[PB_MAX_GROUP_BY];
   DevAggCol aggs[PB_MAX_AGGS];
+  // ---- filtered aggregations: the FILTER(WHERE ...) clauses as postfix programs over leaves that are tested per doc by
+  // pb_agg_kernel (clause f = nodes [af_begin[f], af_begin[f+1])); af_docs: docs of this segment that reach the aggregation
+  // kernel [0] and that pass clause f [1 + f] (ExecutionStatistics of the swim-lanes) ----
+  int32_t n_agg_filters;
+  int32_t pad_af;
+  int32_t af_begin[PB_MAX_AGG_FILTERS + 1];
+  int8_t af_node_kind[PB_MAX_AF_NODES];
+  int8_t af_node_arg[PB_MAX_AF_NODES];
+  unsigned long long* af_docs;
+  DevLeaf af_leaves[PB_MAX_AF_LEAVES];
 };
-#define PB_SEG_FILTER_BYTES (sizeof(DevSegQuery) - sizeof(DevKeyCol) * PB_MAX_GROUP_BY - sizeof(DevAggCol) * PB_MAX_AGGS)
+#define PB_SEG_FILTER_BYTES offsetof(DevSegQuery, keys)
 
 struct DevTable {
   int32_t mode;
@@ -124,6 +137,7 @@ struct DevTable {
   unsigned long long* rowcnt;        // rows per slot
   double* sum[PB_MAX_AGGS];
   long long* mm[PB_MAX_AGGS];        // order-preserving int64 encoding of the double min / max
+  unsigned long long* fcnt[PB_MAX_AGGS];   // COUNT / AVG with a FILTER clause: their own row count (others use rowcnt)
   uint32_t* dc_bits[PB_MAX_AGGS];    // DISTINCTCOUNT: per-slot bitset over (global) dictIds
   uint64_t dc_words[PB_MAX_AGGS];
   unsigned int* num_groups;          // hash: groups created so far
@@ -139,6 +153,9 @@ struct DevQuery {
   int32_t n_aggs;
   int32_t table_mode;
   int32_t agg_op[PB_MAX_AGGS];
+  int32_t agg_filter_of[PB_MAX_AGGS];    // FILTER clause of each aggregation (-1 = none)
+  int32_t n_agg_filters;
+  int32_t pad_f;
   int32_t slot_off[PB_MAX_SCAN_SLOTS];   // byte offset of each scan slot inside a stage
   int32_t stage_bytes;                   // bytes per warp stage (one 1024-doc chunk of every scan slot)
   int32_t set_cache_bytes;               // shared-memory bytes reserved for IN-set membership LUTs
@@ -445,6 +462,7 @@ __device__ __forceinline__ bool pb_leaf_test_doc(const DevLeaf& lf, const uint8_
       if (lf.set_smem_off >= 0) return set_cache[lf.set_smem_off + id] != 0;         // exclusive flag folded in
       return (((__ldg(lf.set_bits + (id >> 5)) >> (id & 31)) & 1u) ^ (uint32_t)lf.exclusive) != 0;
     }
+    case L_BITMAP: return (((__ldg(lf.bitmap + (doc >> 5)) >> (doc & 31)) & 1u) ^ (uint32_t)lf.exclusive) != 0;
     case L_RAW_RANGE_I: { const long long v = pb_raw_i64(lf.gfwd, doc, lf.raw_width, lf.data_type); return v >= lf.ilo && v <= lf.ihi; }
     case L_RAW_RANGE_F: {
       const double v = pb_raw_f64(lf.gfwd, doc, lf.raw_width, lf.data_type);
@@ -519,9 +537,31 @@ __device__ __forceinline__ uint64_t pb_hash_slot2(const DevTable& t, uint64_t lo
 
 // keyless accumulators live in shared memory, one private cell per thread (no atomics)
 struct KeylessAcc {
-  double* sum;        // [n_aggs][PB_NTHREADS]
-  long long* mm;      // [n_aggs][PB_NTHREADS]
+  double* sum;               // [n_aggs][PB_NTHREADS]
+  long long* mm;             // [n_aggs][PB_NTHREADS]
+  unsigned long long* cnt;   // [n_aggs][PB_NTHREADS]: row counts of COUNT / AVG with a FILTER clause (null without clauses)
 };
+
+// FILTER(WHERE ...) clauses of the query against one doc: bit f of the result = clause f passes
+// (the swim-lane filters of FilteredGroupByOperator.java:108-159, evaluated per doc instead of per lane)
+__device__ __forceinline__ uint32_t pb_agg_filter_bits(const DevSegQuery& sq, uint32_t doc) {
+  uint32_t bits = 0;
+  for (int f = 0; f < sq.n_agg_filters; f++) {
+    uint32_t stack = 0;       // boolean stack, top = bit 0
+    for (int n = sq.af_begin[f]; n < sq.af_begin[f + 1]; n++) {
+      const int kind = sq.af_node_kind[n], arg = sq.af_node_arg[n];
+      if (kind == N_LEAF) stack = (stack << 1) | (pb_leaf_test_doc(sq.af_leaves[arg], nullptr, doc) ? 1u : 0u);
+      else if (kind == N_NOT) stack ^= 1u;
+      else {
+        const uint32_t m = (1u << arg) - 1u, top = stack & m;
+        const uint32_t r = kind == N_AND ? (top == m ? 1u : 0u) : (top != 0u ? 1u : 0u);
+        stack = ((stack >> arg) << 1) | r;
+      }
+    }
+    if (sq.af_begin[f + 1] == sq.af_begin[f] || (stack & 1u)) bits |= 1u << f;      // an empty program matches all
+  }
+  return bits;
+}
 
 __device__ __forceinline__ uint64_t pb_key_field(const DevKeyCol& kc, uint32_t doc, bool multi) {
   if (kc.raw_width) {
@@ -548,7 +588,7 @@ __device__ __forceinline__ double pb_agg_input(const DevAggCol& ac, int op, uint
 }
 
 __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQuery& sq, const DevTable& t, uint32_t doc,
-                                              const KeylessAcc& ka, unsigned long long& keyless_rows) {
+                                              const KeylessAcc& ka, unsigned long long& keyless_rows, uint32_t fpass) {
   // ---- phase 1: every gather of this doc is issued before anything is reduced, four independent chains at a
   // time (index clamping instead of branches keeps the loads unconditional, so they overlap) ----
   const int nG = Q.n_group_by, nA = Q.n_aggs;
@@ -594,6 +634,14 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 
   for (int a = 0; a < nA; a++) {
     const int op = Q.agg_op[a];
+    const int fo = Q.agg_filter_of[a];
+    if (fo >= 0) {                               // FILTER clause: the function only sees docs that pass it
+      if (!((fpass >> fo) & 1u)) continue;
+      if (op == 0 || op == 4) {                  // its own row count (COUNT value / AVG denominator)
+        if (Q.table_mode == T_KEYLESS) ka.cnt[a * PB_NTHREADS + threadIdx.x]++;
+        else pb_red_add_u64(&t.fcnt[a][slot], 1ull);
+      }
+    }
     if (op == 0) continue;                       // COUNT(*): the row counter
     const double v = vals[a];
     if (op == 5) {                               // DISTINCTCOUNT (dictionary column)
@@ -1036,16 +1084,18 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_agg_kernel(const __g
   const int n_smem = n_segs < PB_AGG_MAX_SEGS_SMEM ? n_segs : PB_AGG_MAX_SEGS_SMEM;
   for (int i = tid; i < n_smem; i += PB_NTHREADS) s_doc_base[i] = Q.segs[i].doc_base;
   KeylessAcc ka;
-  ka.sum = nullptr; ka.mm = nullptr;
+  ka.sum = nullptr; ka.mm = nullptr; ka.cnt = nullptr;
   const long long ENC_POS_INF = 0x7ff0000000000000LL;
   const long long ENC_NEG_INF = (long long)0xfff0000000000000ULL ^ 0x7fffffffffffffffLL;
   const bool keyless = Q.table_mode == T_KEYLESS;
   if (keyless) {
     ka.sum = reinterpret_cast<double*>(smem_raw);
     ka.mm = reinterpret_cast<long long*>(smem_raw + sizeof(double) * Q.n_aggs * PB_NTHREADS);
+    if (Q.n_agg_filters > 0) ka.cnt = reinterpret_cast<unsigned long long*>(smem_raw + 2 * sizeof(double) * Q.n_aggs * PB_NTHREADS);
     for (int a = 0; a < Q.n_aggs; a++) {
       ka.sum[a * PB_NTHREADS + tid] = 0.0;
       ka.mm[a * PB_NTHREADS + tid] = Q.agg_op[a] == 2 ? ENC_POS_INF : ENC_NEG_INF;
+      if (ka.cnt) ka.cnt[a * PB_NTHREADS + tid] = 0ull;
     }
   }
   __syncthreads();
@@ -1064,7 +1114,21 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_agg_kernel(const __g
       if (op == 1 || op == 4) { pb_red_add_f64(&t.sum[a][0], ka.sum[a * PB_NTHREADS + tid]); ka.sum[a * PB_NTHREADS + tid] = 0.0; }
       else if (op == 2) { pb_red_min_s64(&t.mm[a][0], ka.mm[a * PB_NTHREADS + tid]); ka.mm[a * PB_NTHREADS + tid] = ENC_POS_INF; }
       else if (op == 3) { pb_red_min_s64(&t.mm[a][0], ~ka.mm[a * PB_NTHREADS + tid]); ka.mm[a * PB_NTHREADS + tid] = ENC_NEG_INF; }
+      if (ka.cnt && t.fcnt[a]) { if (ka.cnt[a * PB_NTHREADS + tid]) pb_red_add_u64(&t.fcnt[a][0], ka.cnt[a * PB_NTHREADS + tid]); ka.cnt[a * PB_NTHREADS + tid] = 0ull; }
     }
+  };
+  // swim-lane statistics: docs of the current segment that reached this kernel [0] / passed clause f [1 + f], kept per
+  // thread and flushed when the thread moves to another segment
+  const int nF = Q.n_agg_filters;
+  int stat_seg = -1;
+  unsigned int stat_cnt[1 + PB_MAX_AGG_FILTERS];
+#pragma unroll
+  for (int f = 0; f <= PB_MAX_AGG_FILTERS; f++) stat_cnt[f] = 0;
+  auto stat_flush = [&]() {
+    if (stat_seg < 0) return;
+    unsigned long long* dst = Q.segs[stat_seg].af_docs;
+#pragma unroll
+    for (int f = 0; f <= PB_MAX_AGG_FILTERS; f++) if (f <= nF && stat_cnt[f]) { pb_red_add_u64(dst + f, (unsigned long long)stat_cnt[f]); stat_cnt[f] = 0; }
   };
 
   for (unsigned long long i = (unsigned long long)blockIdx.x * PB_NTHREADS + tid; i < n; i += (unsigned long long)gridDim.x * PB_NTHREADS) {
@@ -1080,8 +1144,17 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_agg_kernel(const __g
     const uint32_t doc = (uint32_t)(gdoc - (lo < PB_AGG_MAX_SEGS_SMEM ? s_doc_base[lo] : sg.doc_base));
     const int table = sg.table;
     if (keyless && table != my_table) { keyless_flush_thread(); my_table = table; }
-    pb_accumulate(Q, sg, Q.tables[table], doc, ka, keyless_rows);
+    uint32_t fpass = 0;
+    if (nF > 0) {
+      fpass = pb_agg_filter_bits(sg, doc);
+      if (lo != stat_seg) { stat_flush(); stat_seg = lo; }
+      stat_cnt[0]++;
+#pragma unroll
+      for (int f = 0; f < PB_MAX_AGG_FILTERS; f++) if (f < nF) stat_cnt[1 + f] += (fpass >> f) & 1u;
+    }
+    pb_accumulate(Q, sg, Q.tables[table], doc, ka, keyless_rows, fpass);
   }
+  if (nF > 0) stat_flush();
 
   if (!keyless) return;
   // ---- keyless: merge the private accumulators; one reduction per CTA when the whole CTA saw one table ----
@@ -1100,6 +1173,14 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_agg_kernel(const __g
   if (tid == 0) { unsigned long long tot = 0; for (int w = 0; w < PB_NWARPS; w++) tot += s_red_u64[w]; if (tot) pb_red_add_u64(&t.rowcnt[0], tot); }
   for (int a = 0; a < Q.n_aggs; a++) {
     const int op = Q.agg_op[a];
+    if (ka.cnt && t.fcnt[a]) {
+      unsigned long long c = ka.cnt[a * PB_NTHREADS + tid];
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+      if (lane == 0) s_red_u64[warp] = c;
+      __syncthreads();
+      if (tid == 0) { unsigned long long tot = 0; for (int w = 0; w < PB_NWARPS; w++) tot += s_red_u64[w]; if (tot) pb_red_add_u64(&t.fcnt[a][0], tot); }
+      __syncthreads();
+    }
     if (op == 1 || op == 4) {
       double v = ka.sum[a * PB_NTHREADS + tid];
       for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -1270,7 +1351,9 @@ struct DevFinAgg {
   int32_t op, pad;
   const double* sum;
   const long long* mm;
+  const unsigned long long* fcnt;   // COUNT / AVG with a FILTER clause: row count of the function (else the group's)
   double* out;
+  long long* out_cnt;               // where fcnt goes (the aggregation's long array)
 };
 struct DevFinalize {
   int32_t mode, n_gb, n_aggs, always_emit;
@@ -1312,7 +1395,8 @@ __global__ void pb_finalize_kernel(const DevFinalize F) {
         if (c == 0) fa.out[k] = fa.op == 2 ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double((long long)0xfff0000000000000ULL);
         else fa.out[k] = pb_dec_f64(fa.op == 2 ? fa.mm[i] : ~fa.mm[i]);
       }
-      else if (fa.op == 0) fa.out[k] = (double)c;
+      else if (fa.op == 0) fa.out[k] = fa.fcnt ? (double)fa.fcnt[i] : (double)c;
+      if (fa.fcnt) fa.out_cnt[k] = (long long)fa.fcnt[i];
     }
     unsigned long long key = 0, key_hi = 0;
     if (F.mode == T_HASH) {

@@ -612,6 +612,10 @@ struct pb_result_s {
   int n_gb = 0, n_aggs = 0;
   int table_mode = 0;
   bool combine = false, finalized = false;
+  unsigned long long* d_seg_stats = nullptr;   // filtered aggregations: [n_segs][1 + PB_MAX_AGG_FILTERS] docs per swim-lane
+  int n_agg_filters = 0;
+  std::vector<int> agg_filter_of;
+  std::vector<std::vector<int>> seg_clause_kind;   // per segment, per FILTER clause: 0 = general, 1 = matches all, 2 = empty; [nF] = the main filter
   int waves = 1;                            // launches were split into this many waves behind the staging copies
   int in_place_columns = 0;                 // (segment, column) pairs gathered from mapped host memory (PB_Q_GATHER_IN_PLACE)
   std::vector<int> agg_op;
@@ -770,6 +774,13 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   const bool combine = (q->flags & PB_Q_COMBINE) != 0;
   const bool in_place = (q->flags & PB_Q_GATHER_IN_PLACE) != 0;
   const int n_tables = combine ? 1 : n_segs;
+  const int nF = q->num_agg_filters;
+  if (nF < 0 || nF > PB_MAX_AGG_FILTERS) return fail(PB_ERR_UNSUPPORTED, "%d FILTER clauses (max %d)", nF, PB_MAX_AGG_FILTERS);
+  if (nF > 0) {
+    if (!q->agg_filter_of) return fail(PB_ERR_INVALID, "agg_filter_of missing");
+    for (int a = 0; a < nA; a++) if (q->agg_filter_of[a] < -1 || q->agg_filter_of[a] >= nF) return fail(PB_ERR_INVALID, "aggregation %d: bad FILTER clause index", a);
+    for (int si = 0; si < n_segs; si++) if (!sqs[si].agg_filters || !sqs[si].agg_filter_nodes) return fail(PB_ERR_INVALID, "segment %d: FILTER clause programs missing", si);
+  }
 
   std::unique_ptr<pb_result_s, void (*)(pb_result_s*)> R(new pb_result_s(), free_result);
   pb_result_s* r = R.get();
@@ -852,6 +863,21 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
           leaf_in_place = cand_frac[si][n] * gather_cost < col_bytes_per_doc;
         }
         if ((rc = stage_column(s, c, !inv, false, inv, cs, false, leaf_in_place))) return rc;
+      }
+    }
+    // FILTER(WHERE ...) clauses: their leaves are tested per matching doc by the aggregation kernel (gathers)
+    for (int f = 0; f < nF; f++) {
+      if (sq.agg_filter_nodes[f] < 0 || sq.agg_filter_nodes[f] > PB_MAX_AF_NODES) return fail(PB_ERR_UNSUPPORTED, "FILTER clause %d has %d nodes (max %d)", f, sq.agg_filter_nodes[f], PB_MAX_AF_NODES);
+      for (int n = 0; n < sq.agg_filter_nodes[f]; n++) {
+        const pb_filter_node& fn = sq.agg_filters[f][n];
+        if (fn.kind >= PB_F_SCAN_DICT_RANGE && fn.kind <= PB_F_INVERTED) {
+          if (fn.column < 0 || fn.column >= (int)s->cols.size()) return fail(PB_ERR_INVALID, "FILTER clause %d node %d: bad column", f, n);
+          Column& c = s->cols[fn.column];
+          bool inv = fn.kind == PB_F_INVERTED;
+          if ((fn.kind == PB_F_SCAN_DICT_RANGE || fn.kind == PB_F_SCAN_DICT_SET) && !c.has_dict) return fail(PB_ERR_INVALID, "FILTER clause %d node %d: dictionary scan on raw column", f, n);
+          if ((fn.kind == PB_F_SCAN_RAW_RANGE || fn.kind == PB_F_SCAN_RAW_SET) && c.has_dict) return fail(PB_ERR_INVALID, "FILTER clause %d node %d: raw scan on dictionary column", f, n);
+          if ((rc = stage_column(s, c, !inv, false, inv, cs, false, !inv && gather_ok(c)))) return rc;
+        }
       }
     }
     // order this (and every later) query's kernels after the copies just enqueued for the segment
@@ -947,6 +973,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     zero_bytes += 8 * S;                                     // rowcnt
     for (int a = 0; a < nA; a++) {
       int op = q->aggregations[a].op;
+      if (nF > 0 && q->agg_filter_of[a] >= 0 && (op == PB_AGG_COUNT || op == PB_AGG_AVG)) zero_bytes += 8 * S;   // fcnt
       if (op == PB_AGG_SUM || op == PB_AGG_AVG) zero_bytes += 8 * S;
       if (op == PB_AGG_MIN || op == PB_AGG_MAX) mm_elems += S;
       if (op == PB_AGG_DISTINCTCOUNT) zero_bytes += 4 * S * dc_words[a];
@@ -954,9 +981,11 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     zero_bytes = (zero_bytes + 255) & ~(size_t)255;
     if (table_mode == T_HASH) ff_bytes += 8 * S * (size_t)key_words;
   }
-  zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 * PB_MAX_WAVES + 256;
+  const size_t seg_stats_bytes = nF > 0 ? 8 * (size_t)(1 + PB_MAX_AGG_FILTERS) * (size_t)n_segs : 0;   // swim-lane statistics per segment
+  zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 * PB_MAX_WAVES + seg_stats_bytes + 256;
   if (zero_bytes > (64ull << 30)) return fail(PB_ERR_UNSUPPORTED, "group table needs %zu bytes: decline to the CPU plan", zero_bytes);
   uint8_t *d_zero = nullptr, *d_ff = nullptr; long long* d_mm = nullptr;
+  unsigned long long* d_seg_stats = nullptr;
   // one block: [zero region | min/max region] so that a cross-GPU merge can ship the whole table in one collective
   zero_bytes = (zero_bytes + 255) & ~(size_t)255;
   CU(cudaMallocAsync((void**)&d_zero, zero_bytes + 8 * mm_elems + 16, st)); r->dev_allocs.push_back(d_zero);
@@ -979,7 +1008,10 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   {
     size_t zo = 0, fo = 0, mo = 0;
     r->d_counters = reinterpret_cast<unsigned long long*>(d_zero);
-    zo += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 * PB_MAX_WAVES; zo = (zo + 255) & ~(size_t)255;
+    zo += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 * PB_MAX_WAVES;
+    if (seg_stats_bytes) { d_seg_stats = reinterpret_cast<unsigned long long*>(d_zero + zo); zo += seg_stats_bytes; }
+    r->d_seg_stats = d_seg_stats;
+    zo = (zo + 255) & ~(size_t)255;
     for (int t = 0; t < n_tables; t++) {
       TableMeta& tm = r->tables[t];
       uint64_t S = slots_of(tm);
@@ -987,6 +1019,10 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       memset(&dt, 0, sizeof dt);
       dt.mode = table_mode; dt.capacity = tm.capacity;
       dt.rowcnt = reinterpret_cast<unsigned long long*>(d_zero + zo); zo += 8 * S;
+      for (int a = 0; a < nA; a++) {   // row counts of COUNT / AVG with a FILTER clause (u64, summed across GPUs with the row counts)
+        int op = q->aggregations[a].op;
+        if (nF > 0 && q->agg_filter_of[a] >= 0 && (op == PB_AGG_COUNT || op == PB_AGG_AVG)) { dt.fcnt[a] = reinterpret_cast<unsigned long long*>(d_zero + zo); zo += 8 * S; }
+      }
       if (t == 0) { r->span_i64 = r->d_counters; r->span_i64_n = (int64_t)((d_zero + zo - (uint8_t*)r->d_counters) / 8); }
       // sums first (one contiguous float64 span for the cross-GPU reduce), then the distinct bitsets
       if (t == 0) r->span_f64 = reinterpret_cast<double*>(d_zero + zo);
@@ -1022,15 +1058,19 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   for (int si = 0; si < n_segs; si++) {
     const pb_segment_query& sq = sqs[si];
     pb_segment_s* s = g->segs[si];
-    for (int n = 0; n < sq.num_filter_nodes; n++) {
-      const pb_filter_node& fn = sq.filter[n];
-      if (fn.kind == PB_F_SCAN_DICT_SET) arena_cap += 4 * (((size_t)s->cols[fn.column].card + 31) / 32) + 32;
-      if (fn.kind == PB_F_SCAN_RAW_SET) arena_cap += 8 * (size_t)fn.num_raw_values + 32;
-      if (fn.kind == PB_F_INVERTED) arena_cap += (4 + sizeof(DevExpandItem)) * (size_t)std::max(fn.num_ids, 0) + 64;
-      if (fn.kind == PB_F_SORTED) arena_cap += 8 * (size_t)std::max(fn.num_ids, 0) + sizeof(DevExpandItem) + 64;
-      if (fn.kind == PB_F_BITMAP) arena_cap += fn.blob_len + sizeof(DevExpandItem) + 128;
-      if (fn.kind == PB_F_INVERTED || fn.kind == PB_F_SORTED || fn.kind == PB_F_BITMAP) bitmap_words_total += (((size_t)s->num_docs + 2047) / 2048) * 64;
-    }
+    auto account = [&](const pb_filter_node* nodes, int n_nodes) {
+      for (int n = 0; n < n_nodes; n++) {
+        const pb_filter_node& fn = nodes[n];
+        if (fn.kind == PB_F_SCAN_DICT_SET) arena_cap += 4 * (((size_t)s->cols[fn.column].card + 31) / 32) + 32;
+        if (fn.kind == PB_F_SCAN_RAW_SET) arena_cap += 8 * (size_t)fn.num_raw_values + 32;
+        if (fn.kind == PB_F_INVERTED) arena_cap += (4 + sizeof(DevExpandItem)) * (size_t)std::max(fn.num_ids, 0) + 64;
+        if (fn.kind == PB_F_SORTED) arena_cap += 8 * (size_t)std::max(fn.num_ids, 0) + sizeof(DevExpandItem) + 64;
+        if (fn.kind == PB_F_BITMAP) arena_cap += fn.blob_len + sizeof(DevExpandItem) + 128;
+        if (fn.kind == PB_F_INVERTED || fn.kind == PB_F_SORTED || fn.kind == PB_F_BITMAP) bitmap_words_total += (((size_t)s->num_docs + 2047) / 2048) * 64;
+      }
+    };
+    account(sq.filter, sq.num_filter_nodes);
+    for (int f = 0; f < nF; f++) account(sq.agg_filters[f], sq.agg_filter_nodes[f]);
   }
   Arena ar;
   ar.cap = arena_cap; ar.host.resize(arena_cap);
@@ -1064,25 +1104,27 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     DevSegQuery& ds = hsegs[si];
     ds.num_docs = s->num_docs;
     ds.table = combine ? 0 : si;
-    int n_leaves = 0, n_scan = 0, set_smem_used = 0;
+    int n_scan = 0, set_smem_used = 0;
     int slot_of_col[PB_MAX_SCAN_SLOTS];
-    (void)0;
-    ds.n_nodes = sq.num_filter_nodes;
-    for (int n = 0; n < sq.num_filter_nodes; n++) {
-      const pb_filter_node& fn = sq.filter[n];
+    // one postfix filter program -> device nodes + leaves.  force_gather: every scan leaf is tested per doc from its forward
+    // index (FILTER clauses, evaluated by pb_agg_kernel); otherwise the candidate plan decides per leaf.
+    auto build_program = [&](const pb_filter_node* nodes, int n_nodes, int8_t* node_kind, int8_t* node_arg, DevLeaf* leaves, int max_leaves,
+                             int& n_leaves, bool force_gather) -> int {
+    for (int n = 0; n < n_nodes; n++) {
+      const pb_filter_node& fn = nodes[n];
       if (fn.kind == PB_F_AND || fn.kind == PB_F_OR) {
         if (fn.num_children < 1 || fn.num_children > PB_MAX_LEAVES) return fail(PB_ERR_UNSUPPORTED, "AND/OR with %d children", fn.num_children);
-        ds.node_kind[n] = fn.kind == PB_F_AND ? N_AND : N_OR; ds.node_arg[n] = (int8_t)fn.num_children; continue;
+        node_kind[n] = fn.kind == PB_F_AND ? N_AND : N_OR; node_arg[n] = (int8_t)fn.num_children; continue;
       }
-      if (fn.kind == PB_F_NOT) { ds.node_kind[n] = N_NOT; ds.node_arg[n] = 1; continue; }
-      if (n_leaves >= PB_MAX_LEAVES) return fail(PB_ERR_UNSUPPORTED, "more than %d filter leaves", PB_MAX_LEAVES);
-      DevLeaf& lf = ds.leaves[n_leaves];
+      if (fn.kind == PB_F_NOT) { node_kind[n] = N_NOT; node_arg[n] = 1; continue; }
+      if (n_leaves >= max_leaves) return fail(PB_ERR_UNSUPPORTED, "more than %d filter leaves", max_leaves);
+      DevLeaf& lf = leaves[n_leaves];
       memset(&lf, 0, sizeof lf);
       lf.set_smem_off = -1;
       lf.est_permille = 500;
-      ds.node_kind[n] = N_LEAF; ds.node_arg[n] = (int8_t)n_leaves; n_leaves++;
+      node_kind[n] = N_LEAF; node_arg[n] = (int8_t)n_leaves; n_leaves++;
       auto scan_slot = [&](const Column& c) -> int {
-        if (cand_leaf[si][n]) {          // evaluated on candidates: no stage slot, read where the column lies
+        if (force_gather || cand_leaf[si][n]) {          // evaluated on candidates: no stage slot, read where the column lies
           lf.gather = 1;
           lf.gfwd = c.fwd_staged ? c.d_fwd : c.d_fwd_host;
           lf.g_full_words = c.fwd_staged ? 0xFFFFFFFFu : c.host_full_words;
@@ -1127,7 +1169,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
           lf.kind = L_DICT_SET; lf.bits = c.bits; lf.exclusive = fn.exclusive ? 1 : 0;
           lf.set_bits = dbits; lf.set_card = c.card;
           { double f = (double)fn.num_ids / (double)c.card; lf.est_permille = (int32_t)(1000.0 * (fn.exclusive ? 1.0 - f : f)); }
-          if (set_smem_used + c.card <= PB_SET_SMEM_BYTES) { lf.set_smem_off = set_smem_used; set_smem_used += (c.card + 15) & ~15; }
+          if (!force_gather && set_smem_used + c.card <= PB_SET_SMEM_BYTES) { lf.set_smem_off = set_smem_used; set_smem_used += (c.card + 15) & ~15; }
           if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
           r->seg_scan_leaves[si]++;
           break;
@@ -1192,6 +1234,26 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
         default: return fail(PB_ERR_INVALID, "filter node %d: unknown kind %d", n, fn.kind);
       }
       if (lf.gather) lf.slot = -1;
+    }
+    return PB_OK;
+    };
+    ds.n_nodes = sq.num_filter_nodes;
+    {
+      int nl = 0;
+      if ((rc = build_program(sq.filter, sq.num_filter_nodes, ds.node_kind, ds.node_arg, ds.leaves, PB_MAX_LEAVES, nl, false))) return rc;
+    }
+    // FILTER(WHERE ...) clauses
+    ds.n_agg_filters = nF;
+    {
+      int nl = 0, nn = 0;
+      for (int f = 0; f < nF; f++) {
+        ds.af_begin[f] = nn;
+        if (nn + sq.agg_filter_nodes[f] > PB_MAX_AF_NODES) return fail(PB_ERR_UNSUPPORTED, "FILTER clauses have more than %d nodes", PB_MAX_AF_NODES);
+        if ((rc = build_program(sq.agg_filters[f], sq.agg_filter_nodes[f], ds.af_node_kind + nn, ds.af_node_arg + nn, ds.af_leaves, PB_MAX_AF_LEAVES, nl, true))) return rc;
+        nn += sq.agg_filter_nodes[f];
+      }
+      for (int f = nF; f <= PB_MAX_AGG_FILTERS; f++) ds.af_begin[f] = nn;
+      ds.af_docs = d_seg_stats ? d_seg_stats + (size_t)si * (1 + PB_MAX_AGG_FILTERS) : nullptr;
     }
     ds.n_scan = n_scan;
     set_cache_max = std::max(set_cache_max, set_smem_used);
@@ -1262,9 +1324,21 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     d_match_list = (uint32_t*)r->scratch;
   }
   r->match_all = match_all;
+  r->n_agg_filters = nF;
+  if (nF > 0) {
+    r->agg_filter_of.assign(q->agg_filter_of, q->agg_filter_of + nA);
+    auto classify = [](const pb_filter_node* nodes, int n) { return n == 0 ? 1 : (n == 1 && nodes[0].kind == PB_F_MATCH_ALL ? 1 : (n == 1 && nodes[0].kind == PB_F_EMPTY ? 2 : 0)); };
+    r->seg_clause_kind.resize(n_segs);
+    for (int si = 0; si < n_segs; si++) {
+      for (int f = 0; f < nF; f++) r->seg_clause_kind[si].push_back(classify(sqs[si].agg_filters[f], sqs[si].agg_filter_nodes[f]));
+      r->seg_clause_kind[si].push_back(classify(sqs[si].filter, sqs[si].num_filter_nodes));
+    }
+  }
 
   hq->n_segs = n_segs; hq->n_group_by = nG; hq->n_aggs = nA; hq->table_mode = table_mode;
   for (int a = 0; a < nA; a++) hq->agg_op[a] = q->aggregations[a].op;
+  for (int a = 0; a < PB_MAX_AGGS; a++) hq->agg_filter_of[a] = (nF > 0 && a < nA) ? q->agg_filter_of[a] : -1;
+  hq->n_agg_filters = nF;
   for (int k = 0; k < n_slots_max; k++) hq->slot_off[k] = slot_offs[k];
   hq->stage_bytes = (int32_t)stage_bytes;
   hq->set_cache_bytes = set_cache_max;
@@ -1362,7 +1436,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     if (occ < 1) return fail(PB_ERR_CUDA, "filter kernel does not fit an SM (smem %zu)", smem);
     max_ctas = (uint64_t)g_ctx.num_sms * (uint64_t)occ;
   }
-  const size_t smem2 = table_mode == T_KEYLESS ? 2 * sizeof(double) * (size_t)nA * PB_NTHREADS : 0;
+  const size_t smem2 = table_mode == T_KEYLESS ? (nF > 0 ? 3 : 2) * sizeof(double) * (size_t)nA * PB_NTHREADS : 0;
   // more resident threads = more gathers in flight (the kernel is DRAM-latency bound); 6 CTAs/SM costs a 4-byte spill
   static const int agg_occ = []() { const char* e = getenv("PB_AGG_OCC"); int v = e ? atoi(e) : 6; return v == 4 ? 4 : 6; }();
   uint64_t max2 = 0;
@@ -1468,6 +1542,7 @@ static int finalize_result(pb_result_s* r) {
       tm.dbl[a].alloc(8 * cap); tm.lng[a].alloc(8 * cap);
       if (!tm.dbl[a].p || !tm.lng[a].p) return fail(PB_ERR_OOM, "pinned host allocation failed");
       F.aggs[a].op = r->agg_op[a]; F.aggs[a].sum = tm.dev.sum[a]; F.aggs[a].mm = tm.dev.mm[a]; F.aggs[a].out = (double*)tm.dbl[a].p;
+      F.aggs[a].fcnt = tm.dev.fcnt[a]; F.aggs[a].out_cnt = (long long*)tm.lng[a].p;
     }
     uint64_t div = 1;
     for (int j = 0; j < nG; j++) {
@@ -1511,6 +1586,7 @@ static int finalize_result(pb_result_s* r) {
     for (int a = 0; a < nA; a++) {
       const int op = r->agg_op[a];
       int64_t* L = (int64_t*)tm.lng[a].p;
+      if (tm.dev.fcnt[a]) continue;      // COUNT / AVG with a FILTER clause: written by the finalize kernel
       if (op == PB_AGG_COUNT || op == PB_AGG_AVG) for (int64_t k = 0; k < ng; k++) L[k] = (int64_t)rows[k];
       else if (op != PB_AGG_DISTINCTCOUNT) memset(L, 0, 8 * (size_t)std::max<int64_t>(ng, 1));
     }
@@ -1534,6 +1610,44 @@ static int finalize_result(pb_result_s* r) {
     tm.stats.num_docs_scanned = (int64_t)hc[(size_t)t * PB_COUNTERS_PER_TABLE + 2];
     if (r->match_all) { tm.stats.num_docs_scanned = 0; for (int si : tm.seg_idx) tm.stats.num_docs_scanned += g->segs[si]->num_docs; }
     tm.stats.num_entries_scanned_post_filter = tm.stats.num_docs_scanned * (int64_t)proj.size();
+    if (r->n_agg_filters > 0) {
+      // swim-lanes (AggregationFunctionUtils.buildFilteredAggregationInfos :312-400; statistics summed lane by lane,
+      // FilteredGroupByOperator.java:146-149): per segment, one lane per FILTER clause over (main AND clause) -- unless the
+      // clause matches all under a real main filter, then its functions join the non-filtered lane -- plus the
+      // non-filtered lane when it has functions or the query groups
+      const int nF = r->n_agg_filters;
+      auto lane_cols = [&](const std::vector<char>& in_lane) {
+        std::vector<std::string> cols;
+        for (auto& nme : r->gb_names) if (std::find(cols.begin(), cols.end(), nme) == cols.end()) cols.push_back(nme);
+        for (int a = 0; a < nA; a++) if (in_lane[a] && !r->agg_cols[a].empty() && std::find(cols.begin(), cols.end(), r->agg_cols[a]) == cols.end()) cols.push_back(r->agg_cols[a]);
+        return (int64_t)cols.size();
+      };
+      std::vector<unsigned long long> hs((size_t)(1 + PB_MAX_AGG_FILTERS) * g->segs.size());
+      CU(cudaMemcpyAsync(hs.data(), r->d_seg_stats, 8 * hs.size(), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      int64_t docs = 0, post = 0;
+      for (int si : tm.seg_idx) {
+        const unsigned long long* ss = hs.data() + (size_t)si * (1 + PB_MAX_AGG_FILTERS);
+        const std::vector<int>& ck = r->seg_clause_kind[si];
+        const int main_kind = ck[nF];
+        std::vector<char> in_main(nA, 0);
+        bool any_main = false;
+        if (main_kind == 2) {                      // empty main filter: one lane with every function, no docs
+          continue;
+        }
+        for (int f = 0; f < nF; f++) {
+          std::vector<char> in_lane(nA, 0);
+          for (int a = 0; a < nA; a++) if (r->agg_filter_of[a] == f) in_lane[a] = 1;
+          if (main_kind != 1 && ck[f] == 1) { for (int a = 0; a < nA; a++) if (in_lane[a]) { in_main[a] = 1; any_main = true; } continue; }
+          docs += (int64_t)ss[1 + f];
+          post += (int64_t)ss[1 + f] * lane_cols(in_lane);
+        }
+        for (int a = 0; a < nA; a++) if (r->agg_filter_of[a] < 0) { in_main[a] = 1; any_main = true; }
+        if (any_main || nG > 0) { docs += (int64_t)ss[0]; post += (int64_t)ss[0] * lane_cols(in_main); }
+      }
+      tm.stats.num_docs_scanned = docs;
+      tm.stats.num_entries_scanned_post_filter = post;
+    }
     tm.stats.num_total_docs = 0; tm.stats.num_entries_scanned_in_filter = 0;
     for (int si : tm.seg_idx) {
       tm.stats.num_total_docs += g->segs[si]->num_docs;

@@ -58,13 +58,20 @@ class PbhFilterNode(C.Structure):
     _fields_ = [("kind", C.c_int32), ("num_children", C.c_int32), ("predicate", C.c_int32)]
 
 
+class PbhFilterProgram(C.Structure):
+    _fields_ = [("num_filter_nodes", C.c_int32), ("filter_nodes", C.POINTER(PbhFilterNode)),
+                ("predicates", C.POINTER(PbhPredicate))]
+
+
 class PbhQueryContext(C.Structure):
     _fields_ = [("num_filter_nodes", C.c_int32), ("filter_nodes", C.POINTER(PbhFilterNode)),
                 ("predicates", C.POINTER(PbhPredicate)),
                 ("num_group_by", C.c_int32), ("group_by_columns", C.POINTER(C.c_char_p)),
                 ("num_aggregations", C.c_int32), ("aggregations", C.POINTER(PbAggregationDesc)),
                 ("num_groups_limit", C.c_int32), ("max_initial_result_holder_capacity", C.c_int32),
-                ("num_skip_inverted", C.c_int32), ("skip_inverted_columns", C.POINTER(C.c_char_p))]
+                ("num_skip_inverted", C.c_int32), ("skip_inverted_columns", C.POINTER(C.c_char_p)),
+                ("num_agg_filters", C.c_int32), ("agg_filters", C.POINTER(PbhFilterProgram)),
+                ("agg_filter_of", C.POINTER(C.c_int32))]
 
 
 _lib = None
@@ -398,15 +405,16 @@ class Result:
 
 
 class _MarshalledQuery:
-    def __init__(self, q: QueryContext):
-        nodes, preds = q.filter_postfix()
-        self.keep = []
-        self.nodes = (PbhFilterNode * max(1, len(nodes)))()
+    def _filter(self, flt):
+        """one filter expression -> (n_nodes, PbhFilterNode[], PbhPredicate[])"""
+        from .query import postfix_of
+        nodes, preds = postfix_of(flt)
+        cn = (PbhFilterNode * max(1, len(nodes)))()
         for i, (k, n, p) in enumerate(nodes):
-            self.nodes[i].kind, self.nodes[i].num_children, self.nodes[i].predicate = k, n, p
-        self.preds = (PbhPredicate * max(1, len(preds)))()
+            cn[i].kind, cn[i].num_children, cn[i].predicate = k, n, p
+        cp = (PbhPredicate * max(1, len(preds)))()
         for i, p in enumerate(preds):
-            o = self.preds[i]
+            o = cp[i]
             o.type = int(p.type)
             o.column = p.column.encode()
             if int(p.type) == 4:
@@ -415,10 +423,17 @@ class _MarshalledQuery:
                 o.lower_inclusive = int(p.lower_inclusive)
                 o.upper_inclusive = int(p.upper_inclusive)
             else:
-                arr = (C.c_char_p * len(p.values))(*[v.encode() for v in p.values])
+                arr = (C.c_char_p * max(1, len(p.values)))(*[v.encode() for v in p.values])
                 self.keep.append(arr)
                 o.values = arr
                 o.num_values = len(p.values)
+        self.keep.append((cn, cp))
+        return len(nodes), cn, cp
+
+    def __init__(self, q: QueryContext):
+        self.keep = []
+        n_nodes, self.nodes, self.preds = self._filter(q.filter)
+        nodes = [None] * n_nodes
         self.gb = (C.c_char_p * max(1, len(q.group_by)))(*[c.encode() for c in q.group_by])
         self.aggs = (PbAggregationDesc * max(1, len(q.aggregations)))()
         for i, a in enumerate(q.aggregations):
@@ -426,9 +441,16 @@ class _MarshalledQuery:
             self.aggs[i].column = a.column.encode() if a.column is not None else None
         skip = [c for c, kinds in q.skip_indexes.items() if "inverted" in kinds]
         self.skip = (C.c_char_p * max(1, len(skip)))(*[c.encode() for c in skip])
+        filters, filter_of = q.agg_filters()
+        self.progs = (PbhFilterProgram * max(1, len(filters)))()
+        for i, f in enumerate(filters):
+            n, cn, cp = self._filter(f)
+            self.progs[i].num_filter_nodes, self.progs[i].filter_nodes, self.progs[i].predicates = n, cn, cp
+        self.filter_of = (C.c_int32 * max(1, len(filter_of)))(*filter_of)
         self.ctx = PbhQueryContext(len(nodes), self.nodes, self.preds, len(q.group_by), self.gb,
                                    len(q.aggregations), self.aggs, q.num_groups_limit,
-                                   q.max_initial_result_holder_capacity, len(skip), self.skip)
+                                   q.max_initial_result_holder_capacity, len(skip), self.skip,
+                                   len(filters), self.progs, self.filter_of)
 
 
 def prepare(q: QueryContext) -> "_MarshalledQuery":

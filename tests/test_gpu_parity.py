@@ -309,3 +309,40 @@ def k_raw_sample(seg, count):
     col = seg.columns["k"]
     vals = np.frombuffer(col.forward_index[col.forward_index.nbytes - 8 * seg.num_docs:].tobytes(), dtype=">i8")
     return vals[:count].astype(np.int64)
+
+
+FILTERED = ("SELECT SUM(column6) FILTER(WHERE column6 > 5), COUNT(*) FILTER(WHERE column1 IS NOT NULL), "
+            "MAX(column3) FILTER(WHERE column3 IS NOT NULL), SUM(column3), AVG(column7) FILTER(WHERE column7 > 0) FROM testTable")
+FILTERED_3 = ("SELECT SUM(column6) FILTER(WHERE column6 > 5 OR column6 < 15), COUNT(*) FILTER(WHERE column1 IS NOT NULL), "
+              "MAX(column3) FILTER(WHERE column3 IS NOT NULL AND column3 > 0), SUM(column3), "
+              "AVG(column7) FILTER(WHERE column7 > 0 AND column7 < 100) FROM testTable")
+
+
+def test_golden_filtered_aggregations(sv_group):   # InnerSegmentAggregationSingleValueQueriesTest.java:62-93
+    seg, g = sv_group
+    for sql, exp, st_e in ((FILTERED + " WHERE column3 > 0", (22266008882250, 30000, 2147419555, 32289159189150, 28175373944314, 30000), (150000, 120000, 30000)),
+                           (FILTERED, (22266008882250, 30000, 2147419555, 32289159189150, 28175373944314, 30000), (150000, 120000, 30000)),
+                           (FILTERED_3, (22266008882250, 30000, 2147419555, 32289159189150, 0, 0), (120000, 90000, 30000))):
+        r = native.execute(g, parse_sql(sql))
+        row = _row(r.tables[0])
+        assert (int(row[0]), row[1], int(row[2]), int(row[3]), int(row[4][0]), row[4][1]) == exp
+        st = r.tables[0].stats
+        assert (st["num_docs_scanned"], st["num_entries_scanned_post_filter"], st["num_total_docs"]) == st_e
+        r.free()
+
+
+def test_filtered_aggregations_vs_oracle(synth):
+    """FILTER(WHERE ...) clauses: keyless and grouped, dense and hash tables, index-backed and raw clause leaves, per segment
+    and merged; every group of the main filter exists and functions without a passing doc keep their defaults."""
+    segs, g = synth
+    d1 = segs[0].columns["c1"].dictionary_values()
+    d3 = segs[0].columns["c3"].dictionary_values()
+    in4 = ", ".join(str(int(v)) for v in d1[5:9])
+    for sql, exact in (
+            (f"SELECT d0, d1, SUM(m0) FILTER(WHERE c2 < {int(segs[0].columns['c2'].dictionary_values()[3000])}), COUNT(*) FILTER(WHERE c1 IN ({in4})), "
+             f"MIN(m1) FILTER(WHERE c1 IN ({in4})), COUNT(*), AVG(m2) FILTER(WHERE x0 < 0.25 OR c3 = {int(d3[5])}), MAX(m2) FROM t WHERE c1 > {int(d1[100])} GROUP BY d0, d1 LIMIT 100000", True),
+            (f"SELECT SUM(m0) FILTER(WHERE x0 < 0.5), COUNT(*) FILTER(WHERE x0 < 0.5), AVG(x1) FILTER(WHERE k0 > 5000000000000), DISTINCTCOUNT(c0) FILTER(WHERE c1 IN ({in4})), "
+             f"MAX(m1) FILTER(WHERE c1 < -5) FROM t WHERE c3 <> {int(d3[2])}", False),
+            (f"SELECT s0, COUNT(*) FILTER(WHERE t0 BETWEEN 20010 AND 20030), SUM(x0) FILTER(WHERE NOT (c1 IN ({in4}))), DISTINCTCOUNT(d3) FILTER(WHERE x1 > 0.9) FROM t GROUP BY s0 LIMIT 100000", False),
+            ("SET numGroupsLimit = 20000000; SELECT k0, COUNT(*) FILTER(WHERE x0 < 0.3), SUM(m0) FILTER(WHERE m0 > 500000) FROM t WHERE x1 < 0.02 GROUP BY k0 LIMIT 100000000", True)):
+        check_query(segs, sql, group=g, exact_float=exact)
