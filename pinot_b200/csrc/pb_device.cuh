@@ -1392,7 +1392,8 @@ __global__ void pb_finalize_kernel(const DevFinalize F) {
       if (fa.sum) fa.out[k] = fa.sum[i];
       else if (fa.mm) {
         // empty group (keyless query without matches): MIN = +inf, MAX = -inf (MinAggregationFunction.java:37 defaults)
-        if (c == 0) fa.out[k] = fa.op == 2 ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double((long long)0xfff0000000000000ULL);
+        // (same for a group none of whose docs passes the function's FILTER clause: the cell still holds the init pattern)
+        if (c == 0 || fa.mm[i] == 0x7fffffffffffffffLL) fa.out[k] = fa.op == 2 ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double((long long)0xfff0000000000000ULL);
         else fa.out[k] = pb_dec_f64(fa.op == 2 ? fa.mm[i] : ~fa.mm[i]);
       }
       else if (fa.op == 0) fa.out[k] = fa.fcnt ? (double)fa.fcnt[i] : (double)c;
