@@ -349,6 +349,8 @@ def parse_sql(sql: str) -> QueryContext:
         q.num_groups_limit = int(options["numgroupslimit"])
     if "maxinitialresultholdercapacity" in options:
         q.max_initial_result_holder_capacity = int(options["maxinitialresultholdercapacity"])
+    if options.get("filteredaggregationsskipemptygroups", "false").lower() == "true":
+        raise ValueError("filteredAggregationsSkipEmptyGroups is not offloaded (the plan maker declines)")
     if "skipindexes" in options:     # e.g. 'c1=inverted,c2=inverted'
         for part in options["skipindexes"].split(","):
             if "=" in part:
