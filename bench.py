@@ -407,6 +407,8 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "pb_filter_kernel", "kernel_ms": f_mean, "algorithmic_bytes_per_launch": alg_filter,
                 "peak_source": peak_src,
+                "traffic_note": "DRAM bytes of one launch from ncu (profiles/scan_kernel_traffic.json); below the algorithmic bytes because "
+                                "later predicates of a selective conjunction are evaluated on the surviving rows only, their columns are not streamed",
                 "whole_query": {"kernels": "pb_filter_kernel + pb_agg_kernel", "ms": f_mean + a_mean,
                                 "algorithmic_bytes": alg_all, "achieved": alg_all / ((f_mean + a_mean) * 1e-3) / 1e9,
                                 "frac": alg_all / ((f_mean + a_mean) * 1e-3) / 1e9 / peak,
