@@ -187,7 +187,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port",
                              "sample": f"full {rows} row query per step, one thread per segment ({threads} threads), {args.steps} steps"},
             "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, segs):
@@ -198,8 +198,28 @@ def workload_config(args, segs):
             "parallelism": f"segments sharded over {args.gpus} GPU(s); dense group tables merged over NCCL ({os.environ.get('PB_MERGE', 'allgather')})" if args.gpus > 1 else "1 GPU"}
 
 
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries loaded later write banners to file descriptor 1 from C (NCCL prints
+    its version there): keep a private duplicate of the real stdout for the JSON line and point fd 1 at stderr for everyone else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -442,7 +462,7 @@ def main():
             "step_wall_ms": {"min": float(np.min(step_wall)), "median": float(np.median(step_wall)), "max": float(np.max(step_wall)),
                              "all": [round(float(x), 3) for x in step_wall]}, "host_us_by_phase": [round(float(x), 1) for x in np.mean(np.array(host_us), axis=0)] if host_us else None, "num_groups": int(num_groups), "docs_matched": int(docs_matched),
             "kernel_variant": {0: "tma+width-specialised", 4: "tma+generic", 8: "ldg+width-specialised", 12: "ldg+generic"}.get(args.flags & 12)}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

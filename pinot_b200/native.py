@@ -342,6 +342,7 @@ class Result:
         self._rh = rh
         self.query = q
         self._finalized = not deferred
+        self.in_place_columns = lib().pb_result_in_place_columns(rh)     # known as soon as the call is planned
         if not deferred:
             self._load()
 
