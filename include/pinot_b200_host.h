@@ -85,6 +85,8 @@ int pbh_execute(pb_segment_group_handle g, const pbh_query_context* q, uint32_t 
 /* EXPLAIN-style dump of the lowered filter of one segment (Operator.toExplainString analogue); returns the
  * number of bytes written (excluding the terminator). */
 int pbh_explain_filter(pb_segment_group_handle g, int32_t segment_index, const pbh_query_context* q, char* buf, int32_t cap);
+/* Same for FILTER clause `clause` of a filtered aggregation (planned on its own, AggregationFunctionUtils.java:343-344). */
+int pbh_explain_agg_filter(pb_segment_group_handle g, int32_t segment_index, const pbh_query_context* q, int32_t clause, char* buf, int32_t cap);
 
 #ifdef __cplusplus
 }

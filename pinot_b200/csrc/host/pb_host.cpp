@@ -454,3 +454,21 @@ extern "C" int pbh_explain_filter(pb_segment_group_handle g, int32_t si, const p
     return n;
   } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
 }
+
+extern "C" int pbh_explain_agg_filter(pb_segment_group_handle g, int32_t si, const pbh_query_context* q, int32_t clause, char* buf, int32_t cap) {
+  std::vector<pb_segment_handle> segs;
+  int rc = pbi_group_segments(g, &segs);
+  if (rc) return rc;
+  if (!q || !buf || cap <= 0 || si < 0 || si >= (int)segs.size() || clause < 0 || clause >= q->num_agg_filters) return pbi_fail(PB_ERR_INVALID, "bad argument");
+  try {
+    PbSegmentView v;
+    if ((rc = pbi_segment_view(segs[si], &v))) return rc;
+    const pbh_filter_program& fp = q->agg_filters[clause];
+    OpPtr root = FilterPlanNode::run(v, *q, fp.num_filter_nodes, fp.filter_nodes, fp.predicates);
+    std::string s;
+    explain(*root, v, 0, s);
+    int n = (int)std::min<size_t>(s.size(), (size_t)cap - 1);
+    memcpy(buf, s.data(), (size_t)n); buf[n] = 0;
+    return n;
+  } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
+}

@@ -102,6 +102,7 @@ def lib():
     l.pbh_execute.argtypes = [C.c_void_p, C.POINTER(PbhQueryContext), C.c_uint32, C.POINTER(C.c_void_p)]
     l.pbh_is_eligible.argtypes = [C.c_void_p, C.POINTER(PbhQueryContext)]
     l.pbh_explain_filter.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PbhQueryContext), C.c_char_p, C.c_int32]
+    l.pbh_explain_agg_filter.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PbhQueryContext), C.c_int32, C.c_char_p, C.c_int32]
     l.pb_result_free.argtypes = [C.c_void_p]
     l.pb_result_finalize.argtypes = [C.c_void_p]
     l.pb_result_num_tables.argtypes = [C.c_void_p]
@@ -478,6 +479,16 @@ def host_unregister(arr: np.ndarray):
 def is_eligible(group: SegmentGroup, q: QueryContext) -> bool:
     m = _MarshalledQuery(q)
     return lib().pbh_is_eligible(group.handle, C.byref(m.ctx)) == 0
+
+
+def explain_agg_filter(group: SegmentGroup, q: QueryContext, clause: int, segment_index: int = 0) -> str:
+    """EXPLAIN of FILTER clause `clause` (index into QueryContext.agg_filters()[0]) as planned for one segment."""
+    m = _MarshalledQuery(q)
+    buf = C.create_string_buffer(8192)
+    n = lib().pbh_explain_agg_filter(group.handle, segment_index, C.byref(m.ctx), clause, buf, 8192)
+    if n < 0:
+        _check(n)
+    return buf.value.decode()
 
 
 def explain_filter(group: SegmentGroup, q: QueryContext, segment_index: int = 0) -> str:

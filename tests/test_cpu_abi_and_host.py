@@ -78,6 +78,25 @@ def test_predicate_lowering_edge_cases(sv_group):
     assert f"dictIds[{lo},{hi})" in txt
 
 
+def test_filtered_aggregation_clauses_are_planned_on_their_own(sv_group):
+    """AggregationFunctionUtils.buildFilteredAggregationInfos (:312-400): every FILTER clause gets a FilterPlanNode of its own;
+    IS [NOT] NULL without a null-value vector is EmptyFilterOperator / MatchAllFilterOperator (FilterPlanNode.java:294-307)."""
+    seg, g = sv_group
+    q = parse_sql("SELECT SUM(column6) FILTER(WHERE column6 > 5 OR column6 < 15), COUNT(*) FILTER(WHERE column1 IS NOT NULL), "
+                  "MAX(column3) FILTER(WHERE column3 IS NULL), SUM(column3), AVG(column7) FILTER(WHERE column7 IN (296467636, 1111197135) AND column3 > 100000000), "
+                  "COUNT(*) FILTER(WHERE column1 IS NOT NULL) FROM testTable WHERE daysSinceEpoch > 126164076")
+    filters, index = q.agg_filters()
+    assert index == [0, 1, 2, -1, 3, 1] and len(filters) == 4          # equal clauses share a swim-lane
+    assert native.is_eligible(g, q)
+    assert native.explain_agg_filter(g, q, 0).strip() == "FILTER_MATCH_ENTIRE_SEGMENT"
+    assert native.explain_agg_filter(g, q, 1).strip() == "FILTER_MATCH_ENTIRE_SEGMENT"
+    assert native.explain_agg_filter(g, q, 2).strip() == "FILTER_EMPTY"
+    txt = native.explain_agg_filter(g, q, 3)
+    assert txt.splitlines()[0] == "FILTER_AND" and "FILTER_INVERTED_INDEX(column7 IN n=2)" in txt and "FILTER_FULL_SCAN(column3 RANGE" in txt
+    assert "FILTER_SORTED_INDEX" in native.explain_filter(g, q)        # the main filter is unaffected
+    assert not native.is_eligible(g, parse_sql("SELECT COUNT(*) FILTER(WHERE nosuch > 3) FROM testTable"))
+
+
 def test_ineligible_queries_decline(sv_group):
     seg, g = sv_group
     assert not native.is_eligible(g, parse_sql("SELECT SUM(column11) FROM t"))          # numeric aggregation on STRING
