@@ -3,14 +3,15 @@
 // Two kernels run the per-segment operator chain for every segment of a query in one launch each
 // (reference: CTR/operator/query/GroupByOperator.java:101-140 and the call stack in SURVEY.md §3.1):
 //
-//   pb_filter_kernel   DocIdSetOperator + filter operators.  Per warp: a 1024-doc chunk of every scan-predicate
-//     column --cp.async.bulk (TMA) + mbarrier, 2 stages--> smem; lane = 32 consecutive docs: unpack big-endian
+//   pb_filter_kernel   DocIdSetOperator + filter operators.  Per warp: a unit (1-2 x 1024 docs) of every streamed
+//     predicate column --cp.async.bulk (TMA) + mbarrier, 2 stages--> smem; lane = 32 consecutive docs: unpack big-endian
 //     bit-packed dictIds, evaluate the predicate tree on 32-bit doc masks (one mask word per lane == packed docId
-//     bitmap), append matching docIds to the global match list.
-//   pb_agg_kernel      ProjectionOperator + GroupByOperator/AggregationOperator.  One thread per matching doc:
-//     gather group-key / metric dictIds straight from HBM (only the sectors that hold matching rows are touched),
-//     dictionary decode, accumulate into the group table with native L2 reductions
-//     (RED.ADD.F64 / RED.MIN.S64 / RED.MAX.S64 / RED.OR.B32).
+//     bitmap); later leaves of a selective conjunction are tested on the surviving docs only, straight from their forward
+//     index; matching docIds reach the global match list in batches through a per-warp shared-memory buffer.
+//   pb_agg_kernel      ProjectionOperator + GroupByOperator/AggregationOperator (+ the FILTER clauses of filtered
+//     aggregations).  One thread per matching doc: gather group-key / metric dictIds straight from HBM (only the sectors
+//     that hold matching rows are touched), dictionary decode, accumulate into the group table with native L2 reductions
+//     (RED.ADD.F64 / RED.MIN.S64 / RED.OR.B32).
 //
 // No tensor cores: the path is integer / gather / atomic bound (BASELINE.json north_star).
 #pragma once
@@ -286,8 +287,7 @@ __device__ __forceinline__ uint32_t pb_mbar_try_wait(uint64_t* bar, uint32_t par
 __device__ __forceinline__ void pb_mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!pb_mbar_try_wait(bar, parity)) {}
 }
-// streaming variant: the scanned columns are read once, keep them from evicting the L2 lines prefetched for the
-// aggregation gathers
+// streaming variant: the scanned columns are read once (evict-first), the gathered sectors and tables stay in L2
 __device__ __forceinline__ uint64_t pb_policy_evict_first() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -299,7 +299,6 @@ __device__ __forceinline__ void pb_tma_load_1d_hint(void* smem_dst, const void* 
                "l"(gmem_src), "r"(bytes), "r"(pb_smem_u32(bar)), "l"(policy)
                : "memory");
 }
-__device__ __forceinline__ void pb_prefetch_l2_keep(const void* p) { asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p)); }
 __device__ __forceinline__ void pb_tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    pb_smem_u32(smem_dst)),
@@ -668,21 +667,12 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 }
 
 // ------------------------------------------------------------------------------------------------
-// the scan kernel
-//
-// A CTA owns a contiguous range of 1024-doc chunks; inside it every WARP is an independent worker with its
-// own 3-stage TMA pipeline (cp.async.bulk + mbarrier) over its chunks: no block-wide barrier in the steady
-// state, so a warp that is busy gathering/aggregating its matches never stalls the other seven.  The only
-// block-level synchronisation is at segment boundaries inside the CTA's range (descriptor + LUT reload).
-// ------------------------------------------------------------------------------------------------
-// ------------------------------------------------------------------------------------------------
 // Kernel 1: pb_filter_kernel  (DocIdSetOperator + filter operators: SURVEY.md §3.2)
 //
 // A CTA owns a contiguous range of 1024-doc chunks; inside it every WARP is an independent worker with its
 // own 2-stage TMA pipeline (cp.async.bulk + mbarrier) over its chunks — no block-wide barrier in the steady
-// state.  Per chunk: unpack + predicate tree on 32-bit doc masks, then the matching docIds are appended to the
-// global match list (one atomicAdd per warp-chunk, ascending docIds inside a block).  The instruction stream is
-// short and identical for all warps, which keeps the instruction cache warm.
+// state.  Per unit: unpack + predicate tree on 32-bit doc masks (dense leaves), candidate leaves on the survivors, then the
+// matching docIds go to the warp's output buffer (one ATOMG per ~256 matches reserves their place in the match list).
 // ------------------------------------------------------------------------------------------------
 struct __align__(16) FilterSmemHeader {
   uint64_t full[PB_NWARPS][PB_NSTAGE];
