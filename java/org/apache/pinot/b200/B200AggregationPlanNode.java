@@ -14,6 +14,12 @@ import org.apache.pinot.segment.spi.SegmentContext;
  * that tree and emits the postfix pb_filter_node list (ScanBasedFilterOperator -> SCAN_DICT_RANGE / SCAN_DICT_SET / SCAN_RAW_*,
  * InvertedIndexFilterOperator -> INVERTED with getMatchingDictIds()/getNonMatchingDictIds(), SortedIndexBasedFilterOperator
  * -> SORTED docId ranges, BitmapBasedFilterOperator -> BITMAP); (3) returns a B200GroupByOperator / B200AggregationOperator.
+ *
+ * Filtered aggregations (QueryContext.getFilteredAggregationFunctions(), AGG(x) FILTER(WHERE ...)): every distinct
+ * FilterContext gets a FilterPlanNode of its own, exactly as AggregationFunctionUtils.buildFilteredAggregationInfos does
+ * (:343-344), and is lowered the same way into pb_segment_query.agg_filters[f]; pb_query_desc.agg_filter_of maps each
+ * aggregation function to its clause.  The device evaluates the clauses per matching doc instead of running one
+ * projection per swim-lane (DESIGN.md 4.5).
  */
 public class B200AggregationPlanNode implements PlanNode {
   private final SegmentContext _segmentContext;
@@ -28,6 +34,9 @@ public class B200AggregationPlanNode implements PlanNode {
   public BaseOperator<? extends BaseResultsBlock> run() {
     FilterPlanNode filterPlanNode = new FilterPlanNode(_segmentContext, _queryContext);
     long[] lowered = B200FilterLowering.lower(filterPlanNode.run(), _segmentContext.getIndexSegment());
-    return new B200GroupByOperator(_segmentContext.getIndexSegment(), _queryContext, lowered);
+    // FILTER clauses of filtered aggregations: B200FilterLowering.lowerClauses plans each distinct FilterContext with
+    // new FilterPlanNode(_segmentContext, _queryContext, filter).run() and appends the lowered programs
+    long[][] clauses = B200FilterLowering.lowerClauses(_segmentContext, _queryContext);
+    return new B200GroupByOperator(_segmentContext.getIndexSegment(), _queryContext, lowered, clauses);
   }
 }

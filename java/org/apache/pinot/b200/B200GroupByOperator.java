@@ -22,10 +22,13 @@ public class B200GroupByOperator extends BaseOperator<GroupByResultsBlock> {
   private final IndexSegment _indexSegment;
   private final QueryContext _queryContext;
   private final long[] _loweredFilter;
+  private final long[][] _loweredClauses;   // FILTER(WHERE ...) clauses of filtered aggregations, one program each
   private long _numDocsScanned;
   private long _numEntriesScannedPostFilter;
 
-  public B200GroupByOperator(IndexSegment indexSegment, QueryContext queryContext, long[] loweredFilter) {
+  public B200GroupByOperator(IndexSegment indexSegment, QueryContext queryContext, long[] loweredFilter,
+      long[][] loweredClauses) {
+    _loweredClauses = loweredClauses;
     _indexSegment = indexSegment;
     _queryContext = queryContext;
     _loweredFilter = loweredFilter;
@@ -34,7 +37,7 @@ public class B200GroupByOperator extends BaseOperator<GroupByResultsBlock> {
   @Override
   protected GroupByResultsBlock getNextBlock() {
     long seg = B200SegmentCache.stage(_indexSegment);
-    long result = Native.execute(seg, _loweredFilter, _queryContext);
+    long result = Native.execute(seg, _loweredFilter, _loweredClauses, _queryContext);
     try {
       _numDocsScanned = Native.statNumDocsScanned(result);
       _numEntriesScannedPostFilter = Native.statNumEntriesScannedPostFilter(result);
