@@ -346,3 +346,23 @@ def test_filtered_aggregations_vs_oracle(synth):
             (f"SELECT s0, COUNT(*) FILTER(WHERE t0 BETWEEN 20010 AND 20030), SUM(x0) FILTER(WHERE NOT (c1 IN ({in4}))), DISTINCTCOUNT(d3) FILTER(WHERE x1 > 0.9) FROM t GROUP BY s0 LIMIT 100000", False),
             ("SET numGroupsLimit = 20000000; SELECT k0, COUNT(*) FILTER(WHERE x0 < 0.3), SUM(m0) FILTER(WHERE m0 > 500000) FROM t WHERE x1 < 0.02 GROUP BY k0 LIMIT 100000000", True)):
         check_query(segs, sql, group=g, exact_float=exact)
+
+
+def test_golden_inter_segment_group_by(sv_group):
+    """InterSegmentGroupBySingleValueQueriesTest.java:61-288: the (group -> value) literals of the reference's 4-segment
+    group-by results (its ORDER BY / LIMIT are broker-side), from the device-side merge (PB_Q_COMBINE)."""
+    from tests.test_oracle_golden import G11_12_SUM1, G11_AVG6, G11_MIN6, G11_SUM1, G12_MIN6, G17_COUNT
+    seg, g = sv_group
+    C = native.PB_Q_COMBINE
+    t = native.execute(g, parse_sql("SELECT column11, SUM(column1), MIN(column6) FROM testTable GROUP BY column11"), C).tables[0].rows()
+    assert {k[0]: v[0] for k, v in t.items()} == G11_SUM1 and {k[0]: v[1] for k, v in t.items()} == G11_MIN6
+    t = native.execute(g, parse_sql("SELECT column11, column12, SUM(column1) FROM testTable GROUP BY column11, column12"), C).tables[0].rows()
+    got = {k: v[0] for k, v in t.items()}
+    assert all(got[k] == v for k, v in G11_12_SUM1.items())
+    t = native.execute(g, parse_sql("SELECT column12, MIN(column6) FROM testTable GROUP BY column12"), C).tables[0].rows()
+    assert {k[0]: v[0] for k, v in t.items()} == G12_MIN6
+    t = native.execute(g, parse_sql("SELECT column17, COUNT(*) FROM testTable GROUP BY column17"), C).tables[0].rows()
+    got = {k[0]: v[0] for k, v in t.items()}
+    assert [(k, got[k]) for k in sorted(got)[:15]] == sorted(G17_COUNT.items())
+    t = native.execute(g, parse_sql("SELECT column11, AVG(column6) FROM testTable GROUP BY column11"), C).tables[0].rows()
+    assert {k[0]: v[0][0] / v[0][1] for k, v in t.items()} == G11_AVG6

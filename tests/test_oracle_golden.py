@@ -202,3 +202,48 @@ def test_filtered_aggregations_vs_numpy():
     # ExecutionStatistics lane by lane: three clause lanes + the non-filtered lane (FilteredGroupByOperator.java:146-149)
     assert r.stats["num_docs_scanned"] == int(f1.sum() + f2.sum() + f3.sum() + main.sum())
     assert r.stats["num_entries_scanned_post_filter"] == int(f1.sum() * 2 + f2.sum() * 2 + f3.sum() * 2 + main.sum() * 2)
+
+
+# InterSegmentGroupBySingleValueQueriesTest.java:61-288: 4 identical segments merged by GroupByCombineOperator; the ORDER BY /
+# LIMIT of those queries is broker-side and out of scope, the (group -> value) literals are not
+G11_SUM1 = {b"": 5935285005452.0, b"P": 88832999206836.0, b"gFuH": 63202785888.0, b"o": 18105331533948.0, b"t": 16331923219264.0}
+G11_12_SUM1 = {(b"", b"HEuxNvH"): 3789390396216.0, (b"", b"KrNxpdycSiwoRohEiTIlLqDHnx"): 733802350944.0,
+               (b"", b"MaztCmmxxgguBUxPti"): 1333941430664.0, (b"", b"dJWwFk"): 55470665124.0, (b"", b"oZgnrlDEtjjVpUoFLol"): 22680162504.0,
+               (b"P", b"HEuxNvH"): 21998672845052.0, (b"P", b"KrNxpdycSiwoRohEiTIlLqDHnx"): 18069909216728.0,
+               (b"P", b"MaztCmmxxgguBUxPti"): 27177029040008.0, (b"P", b"TTltMtFiRqUjvOG"): 4462670055540.0, (b"P", b"XcBNHe"): 120021767504.0,
+               (b"P", b"dJWwFk"): 6224665921376.0, (b"P", b"fykKFqiw"): 1574451324140.0, (b"P", b"gFuH"): 860077643636.0,
+               (b"P", b"oZgnrlDEtjjVpUoFLol"): 8345501392852.0, (b"gFuH", b"HEuxNvH"): 29872400856.0,
+               (b"o", b"MaztCmmxxgguBUxPti"): 6905624581072.0, (b"o", b"HEuxNvH"): 5026384681784.0, (b"t", b"MaztCmmxxgguBUxPti"): 4492405624940.0,
+               (b"t", b"HEuxNvH"): 4424489490364.0, (b"o", b"KrNxpdycSiwoRohEiTIlLqDHnx"): 4051812250524.0,
+               (b"t", b"KrNxpdycSiwoRohEiTIlLqDHnx"): 3529048341192.0, (b"t", b"dJWwFk"): 1349058948804.0, (b"o", b"dJWwFk"): 1152689463360.0,
+               (b"t", b"oZgnrlDEtjjVpUoFLol"): 1039101333316.0, (b"o", b"oZgnrlDEtjjVpUoFLol"): 699381633640.0,
+               (b"t", b"TTltMtFiRqUjvOG"): 675238030848.0, (b"t", b"fykKFqiw"): 480973878052.0, (b"t", b"gFuH"): 330331507792.0,
+               (b"o", b"TTltMtFiRqUjvOG"): 203835153352.0, (b"o", b"fykKFqiw"): 62975165296.0, (b"gFuH", b"MaztCmmxxgguBUxPti"): 29170832184.0,
+               (b"t", b"XcBNHe"): 11276063956.0, (b"gFuH", b"KrNxpdycSiwoRohEiTIlLqDHnx"): 4159552848.0, (b"o", b"gFuH"): 2628604920.0}
+G11_MIN6 = {b"": 296467636.0, b"P": 1689277.0, b"gFuH": 296467636.0, b"o": 296467636.0, b"t": 1980174.0}
+G12_MIN6 = {b"XcBNHe": 329467557.0, b"fykKFqiw": 296467636.0, b"gFuH": 296467636.0, b"HEuxNvH": 6043515.0, b"MaztCmmxxgguBUxPti": 6043515.0,
+            b"dJWwFk": 6043515.0, b"KrNxpdycSiwoRohEiTIlLqDHnx": 1980174.0, b"TTltMtFiRqUjvOG": 1980174.0, b"oZgnrlDEtjjVpUoFLol": 1689277.0}
+G17_COUNT = {83386499: 2924, 217787432: 3892, 227908817: 6564, 402773817: 7304, 423049234: 6556, 561673250: 7420, 635942547: 3308,
+             638936844: 3816, 939479517: 3116, 984091268: 3824, 1230252339: 5620, 1284373442: 7428, 1555255521: 2900, 1618904660: 2744,
+             1670085862: 3388}
+G11_AVG6 = {b"": 296467636.0, b"P": 909380310.3521485, b"gFuH": 296467636.0, b"o": 296467636.0, b"t": 526245333.3900426}
+G12_DC11 = {b"HEuxNvH": 5, b"KrNxpdycSiwoRohEiTIlLqDHnx": 5, b"MaztCmmxxgguBUxPti": 5, b"TTltMtFiRqUjvOG": 3, b"XcBNHe": 2, b"dJWwFk": 4,
+            b"fykKFqiw": 3, b"gFuH": 3, b"oZgnrlDEtjjVpUoFLol": 4}
+
+
+def test_inter_segment_group_by():
+    t, _ = _inter("SELECT column11, SUM(column1), MIN(column6) FROM testTable GROUP BY column11")
+    assert {k[0]: v[0] for k, v in t.items()} == G11_SUM1 and {k[0]: v[1] for k, v in t.items()} == G11_MIN6
+    t, _ = _inter("SELECT column11, column12, SUM(column1) FROM testTable GROUP BY column11, column12")
+    got = {k: v[0] for k, v in t.items()}
+    assert all(got[k] == v for k, v in G11_12_SUM1.items())
+    assert sorted(got.values(), reverse=True)[:len(G11_12_SUM1)] == sorted(G11_12_SUM1.values(), reverse=True)     # the top of ORDER BY SUM DESC LIMIT 50
+    t, _ = _inter("SELECT column12, MIN(column6) FROM testTable GROUP BY column12")
+    assert {k[0]: v[0] for k, v in t.items()} == G12_MIN6
+    t, _ = _inter("SELECT column17, COUNT(*) FROM testTable GROUP BY column17")
+    got = {k[0]: v[0] for k, v in t.items()}
+    assert [(k, got[k]) for k in sorted(got)[:15]] == sorted(G17_COUNT.items())
+    t, _ = _inter("SELECT column11, AVG(column6) FROM testTable GROUP BY column11")
+    assert {k[0]: v[0][0] / v[0][1] for k, v in t.items()} == G11_AVG6
+    t, _ = _inter("SELECT column12, DISTINCTCOUNT(column11) FROM testTable GROUP BY column12")
+    assert {k[0]: len(v[0]) for k, v in t.items()} == G12_DC11
