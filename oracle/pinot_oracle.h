@@ -8,8 +8,9 @@
  *
  * Parity status: PINNED against the reference's own golden values
  * (pinot-core/src/test/java/org/apache/pinot/queries/
- *  InnerSegmentAggregationSingleValueQueriesTest.java:43-177,
- *  InterSegmentAggregationSingleValueQueriesTest.java:47-258) through
+ *  InnerSegmentAggregationSingleValueQueriesTest.java:43-177 incl. the filtered aggregations :62-93,
+ *  InterSegmentAggregationSingleValueQueriesTest.java:47-258,
+ *  InterSegmentGroupBySingleValueQueriesTest.java:61-288) through
  * tests/test_oracle_golden.py over tests/golden/test_data_sv.npz (derived from
  * the reference's test_data-sv.avro by tests/golden/make_golden.py).
  * RoaringBitmap byte-format parity is UNPINNED (no golden bytes exist in the
