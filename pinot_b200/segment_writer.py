@@ -292,3 +292,50 @@ def write_v3(seg: Segment, out_dir: str, table_name: str = "testTable") -> str:
     with open(os.path.join(v3, "metadata.properties"), "w") as f:
         f.write("\n".join(md) + "\n")
     return os.path.join(out_dir, seg.name)
+
+
+def load_v3(segment_dir: str) -> Segment:
+    """Open a v3 segment directory the way Pinot's SingleFileIndexDirectory does (SEGL/segment/store/
+    SingleFileIndexDirectory.java:72-73, 174-204): `index_map` gives (startOffset, size) of every index inside
+    `columns.psf`, each slice starts with the 8-byte magic marker 0xdeadbeefdeafbead, and the index buffer is the view
+    after the marker.  Buffers are zero-copy read-only views of one np.memmap (like PinotDataBuffer views of the mmap'd
+    file), so they sit at arbitrary byte offsets — exactly what the stager has to cope with in a server."""
+    v3 = os.path.join(segment_dir, "v3")
+    props: Dict[str, str] = {}
+    with open(os.path.join(v3, "metadata.properties")) as f:
+        for line in f:
+            if "=" in line:
+                k, v = line.split("=", 1)
+                props[k.strip()] = v.strip()
+    slices: Dict[tuple, List[int]] = {}
+    with open(os.path.join(v3, "index_map")) as f:
+        for line in f:
+            if "=" not in line:
+                continue
+            k, v = (x.strip() for x in line.split("=", 1))
+            col, kind, what = k.rsplit(".", 2)
+            slices.setdefault((col, kind), [0, 0])[0 if what == "startOffset" else 1] = int(v)
+    psf = np.memmap(os.path.join(v3, "columns.psf"), dtype=np.uint8, mode="r")
+    magic = np.frombuffer(MAGIC_MARKER.to_bytes(8, "big"), dtype=np.uint8)
+
+    def view(col: str, kind: str) -> Optional[np.ndarray]:
+        if (col, kind) not in slices:
+            return None
+        off, size = slices[(col, kind)]
+        if not (psf[off:off + 8] == magic).all():
+            raise ValueError(f"{col}.{kind}: magic marker missing at offset {off}")
+        return psf[off + 8:off + size]
+
+    seg = Segment(props["segment.name"], int(props["segment.total.docs"]))
+    for name in props["segment.dimension.column.names"].split(","):
+        p = f"column.{name}."
+        dt = DataType[props[p + "dataType"]]
+        has_dict = props[p + "hasDictionary"] == "true"
+        width = int(props[p + "lengthOfEachEntry"]) if dt == DataType.STRING else _WIDTH[dt]
+        seg.columns[name] = ColumnIndex(
+            name=name, data_type=dt, num_docs=int(props[p + "totalDocs"]), has_dictionary=has_dict,
+            is_sorted=props[p + "isSorted"] == "true", cardinality=int(props[p + "cardinality"]),
+            bits_per_element=int(props[p + "bitsPerElement"]), dict_entry_bytes=width,
+            forward_index=view(name, "forward_index"), dictionary=view(name, "dictionary") if has_dict else None,
+            inverted_index=view(name, "inverted_index"))
+    return seg

@@ -114,3 +114,26 @@ def test_global_dictionary_remaps_on_host():
         rm = g.remap("d1", i)
         assert (union[rm] == s.columns["d1"].dictionary_values()).all()
     g.release()
+
+
+def test_stage_and_plan_from_an_mmapped_v3_directory(tmp_path):
+    """pb_segment_stage + host planning over index buffers that are views of one mmap'd columns.psf (arbitrary byte offsets,
+    read-only pages) — what SegmentDirectory.Reader.getIndexFor hands out in a server.  No device work happens here:
+    columns are copied to HBM on first use by a query."""
+    from pinot_b200.segment_writer import load_v3, write_v3
+    seg = datagen.make_segment_synth(4, 30_011, columns=["c1", "c3", "d0", "s0", "t0", "m0", "x0", "k0"])
+    back = load_v3(write_v3(seg, str(tmp_path)))
+    g_mem = native.SegmentGroup([native.StagedSegment(seg)])
+    g_map = native.SegmentGroup([native.StagedSegment(back)])
+    d1, d3 = seg.columns["c1"].dictionary_values(), seg.columns["c3"].dictionary_values()
+    for sql in (f"SELECT s0, COUNT(*), SUM(m0) FROM t WHERE c3 IN ({int(d3[2])}, {int(d3[9])}) AND c1 BETWEEN {int(d1[40])} AND {int(d1[700])} GROUP BY s0",
+                "SELECT COUNT(*) FROM t WHERE t0 BETWEEN 20003 AND 20011 OR x0 < 0.25 OR k0 IN (7, 1000010)",
+                f"SELECT MAX(k0) FILTER(WHERE s0 = 'aaaa_key' OR c1 > {int(d1[990])}) FROM t WHERE NOT c3 = {int(d3[1])}"):
+        q = parse_sql(sql)
+        assert native.is_eligible(g_map, q)
+        assert native.explain_filter(g_map, q) == native.explain_filter(g_mem, q)
+    q = parse_sql(f"SELECT MAX(k0) FILTER(WHERE s0 = 'aaaa_key' OR c1 > {int(d1[990])}) FROM t")
+    assert native.explain_agg_filter(g_map, q, 0) == native.explain_agg_filter(g_mem, q, 0)
+    assert np.array_equal(np.asarray(g_map.export_dictionary("s0")), np.asarray(g_mem.export_dictionary("s0")))
+    g_mem.release()
+    g_map.release()

@@ -366,3 +366,16 @@ def test_golden_inter_segment_group_by(sv_group):
     assert [(k, got[k]) for k in sorted(got)[:15]] == sorted(G17_COUNT.items())
     t = native.execute(g, parse_sql("SELECT column11, AVG(column6) FROM testTable GROUP BY column11"), C).tables[0].rows()
     assert {k[0]: v[0][0] / v[0][1] for k, v in t.items()} == G11_AVG6
+
+
+def test_query_from_mmapped_v3_directory(tmp_path):
+    """The index buffers handed to pb_segment_stage are views of one mmap'd columns.psf (SingleFileIndexDirectory layout:
+    index_map + magic markers): arbitrary byte offsets, read-only, file-backed pages."""
+    from pinot_b200.segment_writer import load_v3, write_v3
+    native.init()
+    seg = datagen.make_segment_synth(4, 70_003, columns=["c1", "c3", "d0", "s0", "t0", "m0", "x0", "k0"])
+    back = load_v3(write_v3(seg, str(tmp_path)))
+    d1, d3 = seg.columns["c1"].dictionary_values(), seg.columns["c3"].dictionary_values()
+    for sql, exact in ((f"SELECT s0, d0, COUNT(*), SUM(m0), MAX(x0) FROM t WHERE c3 IN ({int(d3[2])}, {int(d3[9])}) OR c1 BETWEEN {int(d1[40])} AND {int(d1[90])} GROUP BY s0, d0 LIMIT 100000", False),
+                       ("SELECT COUNT(*), MIN(k0), AVG(m0) FROM t WHERE t0 BETWEEN 20003 AND 20011 OR x0 < 0.25", True)):
+        check_query([back], sql, exact_float=exact)
