@@ -9,8 +9,10 @@ Workload at N=1 (BASELINE.json configs[1]): 8 segments x 12.5 M rows = 100 M row
 
 A step = one pass of the whole query over all segments of this rank through the C ABI (host planning layer ->
 pb_query_execute, merged result table back in pinned host memory).  `value` = rows / wall time of K steps with the
-segments already resident in HBM; `e2e` = the same call sequence starting from HOST buffers (pb_segment_stage of
-the touched columns + execute + result read-back inside the timed region).  N > 1: every rank owns its own 8
+segments already resident in HBM; `e2e` = the same call sequence starting from page-locked HOST buffers inside the timed
+region (pb_segment_stage + execute + result read-back; headline policy PB_Q_GATHER_IN_PLACE = copy the predicate columns,
+gather the group-by / aggregation columns of the matching rows over PCIe; the copy-every-touched-column policy is
+measured alongside as e2e.legs.stage_all).  N > 1: every rank owns its own 8
 segments (weak scaling), per-rank dense tables are merged over NCCL (one all-gather of the table block + a merge kernel;
 PB_MERGE=allreduce selects three in-place all-reduces instead), rank 0 finalises.
 
