@@ -10,8 +10,8 @@ import org.apache.pinot.segment.spi.SegmentContext;
 
 /**
  * run(): (1) FilterPlanNode.run() builds the reference's own filter operator tree (predicate evaluators, index
- * selection, AND re-ordering: FilterPlanNode.java:195-320, FilterOperatorUtils.java:74-252); (2) B200FilterLowering walks
- * that tree and emits the postfix pb_filter_node list (ScanBasedFilterOperator -> SCAN_DICT_RANGE / SCAN_DICT_SET / SCAN_RAW_*,
+ * selection, AND re-ordering: FilterPlanNode.java:195-320, FilterOperatorUtils.java:74-252) while B200FilterOperatorUtils
+ * records which evaluator each leaf came from; (2) B200FilterLowering walks that tree and emits the postfix pb_filter_node list (ScanBasedFilterOperator -> SCAN_DICT_RANGE / SCAN_DICT_SET / SCAN_RAW_*,
  * InvertedIndexFilterOperator -> INVERTED with getMatchingDictIds()/getNonMatchingDictIds(), SortedIndexBasedFilterOperator
  * -> SORTED docId ranges, BitmapBasedFilterOperator -> BITMAP); (3) returns a B200GroupByOperator / B200AggregationOperator.
  *
@@ -32,11 +32,20 @@ public class B200AggregationPlanNode implements PlanNode {
 
   @Override
   public BaseOperator<? extends BaseResultsBlock> run() {
-    FilterPlanNode filterPlanNode = new FilterPlanNode(_segmentContext, _queryContext);
-    long[] lowered = B200FilterLowering.lower(filterPlanNode.run(), _segmentContext.getIndexSegment());
-    // FILTER clauses of filtered aggregations: B200FilterLowering.lowerClauses plans each distinct FilterContext with
-    // new FilterPlanNode(_segmentContext, _queryContext, filter).run() and appends the lowered programs
-    long[][] clauses = B200FilterLowering.lowerClauses(_segmentContext, _queryContext);
-    return new B200GroupByOperator(_segmentContext.getIndexSegment(), _queryContext, lowered, clauses);
+    B200FilterLowering.LoweredProgram where = B200FilterLowering.lower(_segmentContext, _queryContext);
+    // FILTER clauses of filtered aggregations: one program per distinct FilterContext, each planned with its own
+    // FilterPlanNode(_segmentContext, _queryContext, filter)
+    java.util.List<B200FilterLowering.LoweredProgram> clauses = new java.util.ArrayList<>();
+    java.util.Map<org.apache.pinot.common.request.context.FilterContext, Integer> clauseIndex = new java.util.HashMap<>();
+    if (_queryContext.getFilteredAggregationFunctions() != null) {
+      for (org.apache.commons.lang3.tuple.Pair<?, org.apache.pinot.common.request.context.FilterContext> pair
+          : _queryContext.getFilteredAggregationFunctions()) {
+        if (pair.getRight() != null && !clauseIndex.containsKey(pair.getRight())) {
+          clauseIndex.put(pair.getRight(), clauses.size());
+          clauses.add(B200FilterLowering.lower(_segmentContext, _queryContext, pair.getRight()));
+        }
+      }
+    }
+    return new B200GroupByOperator(_segmentContext.getIndexSegment(), _queryContext, where, clauses, clauseIndex);
   }
 }

@@ -21,26 +21,30 @@ import org.apache.pinot.segment.spi.IndexSegment;
 public class B200GroupByOperator extends BaseOperator<GroupByResultsBlock> {
   private final IndexSegment _indexSegment;
   private final QueryContext _queryContext;
-  private final long[] _loweredFilter;
-  private final long[][] _loweredClauses;   // FILTER(WHERE ...) clauses of filtered aggregations, one program each
-  private long _numDocsScanned;
-  private long _numEntriesScannedPostFilter;
+  private final B200FilterLowering.LoweredProgram _where;
+  private final java.util.List<B200FilterLowering.LoweredProgram> _clauses;   // FILTER(WHERE ...) clauses, one program each
+  private final java.util.Map<org.apache.pinot.common.request.context.FilterContext, Integer> _clauseIndex;
+  private long[] _stats = new long[5];
 
-  public B200GroupByOperator(IndexSegment indexSegment, QueryContext queryContext, long[] loweredFilter,
-      long[][] loweredClauses) {
-    _loweredClauses = loweredClauses;
+  public B200GroupByOperator(IndexSegment indexSegment, QueryContext queryContext, B200FilterLowering.LoweredProgram where,
+      java.util.List<B200FilterLowering.LoweredProgram> clauses,
+      java.util.Map<org.apache.pinot.common.request.context.FilterContext, Integer> clauseIndex) {
     _indexSegment = indexSegment;
     _queryContext = queryContext;
-    _loweredFilter = loweredFilter;
+    _where = where;
+    _clauses = clauses;
+    _clauseIndex = clauseIndex;
   }
 
   @Override
   protected GroupByResultsBlock getNextBlock() {
-    long seg = B200SegmentCache.stage(_indexSegment);
-    long result = Native.execute(seg, _loweredFilter, _loweredClauses, _queryContext);
+    // one-segment group: GroupByCombineOperator keeps merging per-segment blocks exactly as today.  (A combine-level
+    // plug-in would hand all segments of the server to one call with PB_Q_COMBINE and skip that merge.)
+    long group = B200SegmentCache.groupOf(_indexSegment);     // stages the segment on first use, cached until destroy()
+    long result = B200Flatten.execute(group, _where, _clauses, _clauseIndex, _queryContext, /*flags=*/0);
     try {
-      _numDocsScanned = Native.statNumDocsScanned(result);
-      _numEntriesScannedPostFilter = Native.statNumEntriesScannedPostFilter(result);
+      _stats = Native.resultStats(result, 0);
+      // wraps the pinned arrays in GroupKeyGenerator / GroupByResultHolder implementations (AggregationGroupByResult.java:31-57)
       return DeviceResults.toGroupByResultsBlock(result, _indexSegment, _queryContext);
     } finally {
       Native.freeResult(result);
@@ -64,7 +68,6 @@ public class B200GroupByOperator extends BaseOperator<GroupByResultsBlock> {
 
   @Override
   public ExecutionStatistics getExecutionStatistics() {
-    return new ExecutionStatistics(_numDocsScanned, 0, _numEntriesScannedPostFilter,
-        _indexSegment.getSegmentMetadata().getTotalDocs());
+    return new ExecutionStatistics(_stats[0], _stats[1], _stats[2], _stats[3]);
   }
 }

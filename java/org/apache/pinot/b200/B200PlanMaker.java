@@ -16,6 +16,13 @@ import org.apache.pinot.segment.spi.SegmentContext;
  */
 public class B200PlanMaker extends InstancePlanMakerImplV2 {
   @Override
+  public void init(org.apache.pinot.spi.env.PinotConfiguration queryExecutorConfig) {
+    super.init(queryExecutorConfig);
+    // record (leaf operator -> predicate evaluator, data source) while the stock factory builds filter operators
+    org.apache.pinot.core.operator.filter.FilterOperatorUtils.setImplementation(new B200FilterOperatorUtils());
+  }
+
+  @Override
   public PlanNode makeSegmentPlanNode(SegmentContext segmentContext, QueryContext queryContext) {
     if (QueryContextUtils.isAggregationQuery(queryContext) && B200Eligibility.isEligible(segmentContext, queryContext)) {
       return new B200AggregationPlanNode(segmentContext, queryContext);

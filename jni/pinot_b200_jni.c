@@ -72,10 +72,130 @@ JNIEXPORT jlong JNICALL Java_org_apache_pinot_b200_Native_createGroup(JNIEnv* en
   return (jlong)(intptr_t)g;
 }
 
-/* long execute(long group, int[] nodeInts /\* 8 ints per node: segment, kind, column, numChildren, exclusive, numIds,
- * dloIncl, dhiIncl *\/, long[] nodeLongs /\* lo, hi per node *\/, double[] nodeDoubles /\* dlo, dhi per node *\/,
- * int[][] nodeIds, String[] groupBy, int[] aggOps, String[] aggCols, int numGroupsLimit, int maxInitCapacity, int flags) —
- * flattening / unflattening is mechanical and elided here for brevity of the shim; see Native.java for the layout. */
+/* long execute(long group, int numSegments, int numAggFilters,
+ *              int[] nodeInts, long[] nodeLongs, double[] nodeDoubles, int[] idPool, long[] rawPool,
+ *              String[] groupBy, int[] aggOps, String[] aggCols, int[] aggFilterOf,
+ *              int numGroupsLimit, int maxInitCapacity, int flags)
+ *
+ * The lowered filter programs of ALL segments, flattened by B200FilterLowering (Native.java documents the same layout):
+ *   nodeInts    12 ints per node: segment, program (0 = the WHERE filter, 1 + f = FILTER clause f), kind (PB_F_*), column,
+ *               numChildren, exclusive, numIds, idOffset (into idPool; SORTED: 2 * numIds ints), numRaw, rawOffset (into
+ *               rawPool), dloInclusive, dhiInclusive
+ *   nodeLongs   2 per node: lo, hi          nodeDoubles  2 per node: dlo, dhi
+ * Nodes arrive grouped by (segment, program), each program in postfix order — the order FilterPlanNode's operator tree is
+ * walked in.  PB_F_BITMAP leaves (caller-supplied bitmaps) are not produced by the Java side. */
+JNIEXPORT jlong JNICALL Java_org_apache_pinot_b200_Native_execute(JNIEnv* env, jclass cls, jlong group, jint numSegments,
+    jint numAggFilters, jintArray nodeInts, jlongArray nodeLongs, jdoubleArray nodeDoubles, jintArray idPool, jlongArray rawPool,
+    jobjectArray groupBy, jintArray aggOps, jobjectArray aggCols, jintArray aggFilterOf, jint numGroupsLimit, jint maxInitCapacity,
+    jint flags) {
+  enum { NI = 12 };
+  const jsize nNodes = (*env)->GetArrayLength(env, nodeInts) / NI;
+  jint* ni = (*env)->GetIntArrayElements(env, nodeInts, NULL);
+  jlong* nl = (*env)->GetLongArrayElements(env, nodeLongs, NULL);
+  jdouble* nd = (*env)->GetDoubleArrayElements(env, nodeDoubles, NULL);
+  jint* ids = (*env)->GetIntArrayElements(env, idPool, NULL);
+  jlong* raws = (*env)->GetLongArrayElements(env, rawPool, NULL);
+  const int nProg = 1 + numAggFilters;
+  pb_filter_node* nodes = (pb_filter_node*)calloc((size_t)(nNodes > 0 ? nNodes : 1), sizeof(pb_filter_node));
+  pb_segment_query* sq = (pb_segment_query*)calloc((size_t)numSegments, sizeof(pb_segment_query));
+  /* per (segment, program): first node and node count */
+  const pb_filter_node** progFirst = (const pb_filter_node**)calloc((size_t)numSegments * nProg, sizeof(void*));
+  int32_t* progLen = (int32_t*)calloc((size_t)numSegments * nProg, sizeof(int32_t));
+  for (jsize i = 0; i < nNodes; i++) {
+    const jint* v = ni + (size_t)i * NI;
+    pb_filter_node* n = &nodes[i];
+    n->kind = v[2]; n->column = v[3]; n->num_children = v[4]; n->exclusive = v[5];
+    n->num_ids = v[6]; n->ids = v[6] > 0 ? (const int32_t*)(ids + v[7]) : NULL;
+    n->num_raw_values = v[8]; n->raw_values = v[8] > 0 ? (const int64_t*)(raws + v[9]) : NULL;
+    n->dlo_inclusive = v[10]; n->dhi_inclusive = v[11];
+    n->lo = nl[2 * i]; n->hi = nl[2 * i + 1]; n->dlo = nd[2 * i]; n->dhi = nd[2 * i + 1];
+    const size_t slot = (size_t)v[0] * nProg + (size_t)v[1];
+    if (progLen[slot] == 0) progFirst[slot] = n;
+    progLen[slot]++;
+  }
+  for (jint s = 0; s < numSegments; s++) {
+    sq[s].filter = progFirst[(size_t)s * nProg];
+    sq[s].num_filter_nodes = progLen[(size_t)s * nProg];
+    sq[s].agg_filters = numAggFilters > 0 ? &progFirst[(size_t)s * nProg + 1] : NULL;
+    sq[s].agg_filter_nodes = numAggFilters > 0 ? &progLen[(size_t)s * nProg + 1] : NULL;
+  }
+  const jsize nG = (*env)->GetArrayLength(env, groupBy), nA = (*env)->GetArrayLength(env, aggOps);
+  const char** gb = (const char**)calloc((size_t)(nG > 0 ? nG : 1), sizeof(char*));
+  for (jsize j = 0; j < nG; j++) gb[j] = (*env)->GetStringUTFChars(env, (jstring)(*env)->GetObjectArrayElement(env, groupBy, j), NULL);
+  jint* ops = (*env)->GetIntArrayElements(env, aggOps, NULL);
+  jint* fof = numAggFilters > 0 ? (*env)->GetIntArrayElements(env, aggFilterOf, NULL) : NULL;
+  pb_aggregation_desc* aggs = (pb_aggregation_desc*)calloc((size_t)nA, sizeof(pb_aggregation_desc));
+  for (jsize a = 0; a < nA; a++) {
+    jstring c = (jstring)(*env)->GetObjectArrayElement(env, aggCols, a);
+    aggs[a].op = ops[a];
+    aggs[a].column = c ? (*env)->GetStringUTFChars(env, c, NULL) : NULL;     /* NULL for COUNT(*) */
+  }
+  pb_query_desc d;
+  memset(&d, 0, sizeof d);
+  d.num_group_by = (int32_t)nG; d.group_by_columns = gb;
+  d.num_aggregations = (int32_t)nA; d.aggregations = aggs;
+  d.num_groups_limit = numGroupsLimit; d.max_initial_result_holder_capacity = maxInitCapacity;
+  d.flags = (uint32_t)flags;
+  d.num_agg_filters = numAggFilters; d.agg_filter_of = (const int32_t*)fof;
+  pb_result_handle r = NULL;
+  int rc = pb_query_execute((pb_segment_group_handle)(intptr_t)group, sq, &d, &r);
+  for (jsize a = 0; a < nA; a++) {
+    jstring c = (jstring)(*env)->GetObjectArrayElement(env, aggCols, a);
+    if (c && aggs[a].column) (*env)->ReleaseStringUTFChars(env, c, aggs[a].column);
+  }
+  for (jsize j = 0; j < nG; j++) (*env)->ReleaseStringUTFChars(env, (jstring)(*env)->GetObjectArrayElement(env, groupBy, j), gb[j]);
+  if (fof) (*env)->ReleaseIntArrayElements(env, aggFilterOf, fof, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, aggOps, ops, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, rawPool, raws, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, idPool, ids, JNI_ABORT);
+  (*env)->ReleaseDoubleArrayElements(env, nodeDoubles, nd, JNI_ABORT);
+  (*env)->ReleaseLongArrayElements(env, nodeLongs, nl, JNI_ABORT);
+  (*env)->ReleaseIntArrayElements(env, nodeInts, ni, JNI_ABORT);
+  free(aggs); free(gb); free(progLen); free(progFirst); free(sq); free(nodes);
+  if (rc != PB_OK) { throw_last(env); return 0; }   /* PB_ERR_UNSUPPORTED here means the eligibility check and the engine disagree */
+  return (jlong)(intptr_t)r;
+}
+
+JNIEXPORT void JNICALL Java_org_apache_pinot_b200_Native_releaseGroup(JNIEnv* env, jclass cls, jlong g) {
+  pb_segment_group_release((pb_segment_group_handle)(intptr_t)g);
+}
+
+/* long[] resultStats(long result, int table): numDocsScanned, numEntriesScannedInFilter, numEntriesScannedPostFilter,
+ * numTotalDocs, numGroupsLimitReached (ExecutionStatistics, CTR/operator/ExecutionStatistics.java:28-65) */
+JNIEXPORT jlongArray JNICALL Java_org_apache_pinot_b200_Native_resultStats(JNIEnv* env, jclass cls, jlong r, jint table) {
+  const pb_exec_stats* st = pb_result_stats((pb_result_handle)(intptr_t)r, table);
+  jlongArray out = (*env)->NewLongArray(env, 5);
+  if (!st) { throw_last(env); return out; }
+  jlong v[5] = { st->num_docs_scanned, st->num_entries_scanned_in_filter, st->num_entries_scanned_post_filter, st->num_total_docs,
+                 st->num_groups_limit_reached };
+  (*env)->SetLongArrayRegion(env, out, 0, 5, v);
+  return out;
+}
+
+/* ByteBuffer resultGroupKeyValues(long result, int table, int groupByColumn): decoded key values, native-endian, fixed width
+ * (INT 4, LONG 8, FLOAT 4, DOUBLE 8, STRING lengthOfEachEntry zero-padded) — GroupKeyGenerator.GroupKey._keys */
+JNIEXPORT jobject JNICALL Java_org_apache_pinot_b200_Native_resultGroupKeyValues(JNIEnv* env, jclass cls, jlong r, jint table, jint gb) {
+  pb_result_handle h = (pb_result_handle)(intptr_t)r;
+  int32_t type = 0, eb = 0;
+  const void* p = pb_result_group_key_values(h, table, gb, &type, &eb);
+  if (!p) { throw_last(env); return NULL; }
+  return (*env)->NewDirectByteBuffer(env, (void*)p, (jlong)eb * pb_result_num_groups(h, table));
+}
+
+/* DISTINCTCOUNT value sets (the intermediate result the combine layer merges): offsets[numGroups + 1] into dictIds[] */
+JNIEXPORT jobject JNICALL Java_org_apache_pinot_b200_Native_resultDistinctOffsets(JNIEnv* env, jclass cls, jlong r, jint table, jint agg) {
+  pb_result_handle h = (pb_result_handle)(intptr_t)r;
+  const int64_t* p = pb_result_distinct_offsets(h, table, agg);
+  if (!p) { throw_last(env); return NULL; }
+  return (*env)->NewDirectByteBuffer(env, (void*)p, 8 * (pb_result_num_groups(h, table) + 1));
+}
+JNIEXPORT jobject JNICALL Java_org_apache_pinot_b200_Native_resultDistinctDictIds(JNIEnv* env, jclass cls, jlong r, jint table, jint agg) {
+  pb_result_handle h = (pb_result_handle)(intptr_t)r;
+  const int64_t* off = pb_result_distinct_offsets(h, table, agg);
+  const int32_t* p = pb_result_distinct_dict_ids(h, table, agg);
+  if (!off || !p) { throw_last(env); return NULL; }
+  return (*env)->NewDirectByteBuffer(env, (void*)p, 4 * off[pb_result_num_groups(h, table)]);
+}
 
 JNIEXPORT jlong JNICALL Java_org_apache_pinot_b200_Native_resultNumGroups(JNIEnv* env, jclass cls, jlong r, jint table) {
   return (jlong)pb_result_num_groups((pb_result_handle)(intptr_t)r, table);
