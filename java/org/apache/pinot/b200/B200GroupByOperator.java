@@ -24,6 +24,7 @@ public class B200GroupByOperator extends BaseOperator<GroupByResultsBlock> {
   private final B200FilterLowering.LoweredProgram _where;
   private final java.util.List<B200FilterLowering.LoweredProgram> _clauses;   // FILTER(WHERE ...) clauses, one program each
   private final java.util.Map<org.apache.pinot.common.request.context.FilterContext, Integer> _clauseIndex;
+  private final org.apache.pinot.common.utils.DataSchema _dataSchema = null;   // built in the ctor exactly like GroupByOperator.java:65-98 (elided)
   private long[] _stats = new long[5];
 
   public B200GroupByOperator(IndexSegment indexSegment, QueryContext queryContext, B200FilterLowering.LoweredProgram where,
@@ -45,7 +46,7 @@ public class B200GroupByOperator extends BaseOperator<GroupByResultsBlock> {
     try {
       _stats = Native.resultStats(result, 0);
       // wraps the pinned arrays in GroupKeyGenerator / GroupByResultHolder implementations (AggregationGroupByResult.java:31-57)
-      return DeviceResults.toGroupByResultsBlock(result, _indexSegment, _queryContext);
+      return DeviceResults.toGroupByResultsBlock(result, _indexSegment, _queryContext, _dataSchema);   // _dataSchema as in GroupByOperator.java:65-98
     } finally {
       Native.freeResult(result);
     }
