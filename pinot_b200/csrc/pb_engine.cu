@@ -244,7 +244,7 @@ static int find_col(const pb_segment_s* s, const char* name) {
 
 extern "C" int pb_segment_stage(const pb_segment_desc* d, int /*device_index*/, pb_segment_handle* out) {
   // registers the buffers and validates the layouts; columns are copied to HBM on first use by a query
-  // (or eagerly by pb_segment_prefetch), so planning-only callers never touch the device
+  // so planning-only callers never touch the device
   if (!d || !out || d->num_columns < 0 || d->num_docs < 0) return fail(PB_ERR_INVALID, "bad segment descriptor");
   std::unique_ptr<pb_segment_s> s(new pb_segment_s());
   s->name = d->segment_name ? d->segment_name : "";
