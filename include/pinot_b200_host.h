@@ -88,6 +88,12 @@ int pbh_explain_filter(pb_segment_group_handle g, int32_t segment_index, const p
 /* Same for FILTER clause `clause` of a filtered aggregation (planned on its own, AggregationFunctionUtils.java:343-344). */
 int pbh_explain_agg_filter(pb_segment_group_handle g, int32_t segment_index, const pbh_query_context* q, int32_t clause, char* buf, int32_t cap);
 
+/* The lowered program itself — exactly the pb_filter_node list pbh_execute would hand to pb_query_execute for that segment
+ * (clause = -1: the WHERE filter, >= 0: that FILTER clause) — as text, one postfix node per line with every dictId / docId /
+ * raw value spelled out.  For tests and debugging of the lowering; returns the full length needed (excluding the terminator),
+ * truncating to cap - 1 bytes. */
+int pbh_dump_lowered(pb_segment_group_handle g, int32_t segment_index, const pbh_query_context* q, int32_t clause, char* buf, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

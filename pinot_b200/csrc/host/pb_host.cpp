@@ -472,3 +472,54 @@ extern "C" int pbh_explain_agg_filter(pb_segment_group_handle g, int32_t si, con
     return n;
   } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
 }
+
+extern "C" int pbh_dump_lowered(pb_segment_group_handle g, int32_t si, const pbh_query_context* q, int32_t clause, char* buf, int32_t cap) {
+  std::vector<pb_segment_handle> segs;
+  int rc = pbi_group_segments(g, &segs);
+  if (rc) return rc;
+  if (!q || !buf || cap <= 0 || si < 0 || si >= (int)segs.size() || clause < -1 || clause >= q->num_agg_filters) return pbi_fail(PB_ERR_INVALID, "bad argument");
+  try {
+    PbSegmentView v;
+    if ((rc = pbi_segment_view(segs[si], &v))) return rc;
+    OpPtr root = clause < 0 ? FilterPlanNode::run(v, *q)
+                            : FilterPlanNode::run(v, *q, q->agg_filters[clause].num_filter_nodes, q->agg_filters[clause].filter_nodes, q->agg_filters[clause].predicates);
+    LoweredSegment ls;
+    if (root->kind != OP_MATCH_ALL) emit(*root, v, ls);
+    std::string s;
+    char tmp[256];
+    auto ids = [&](const int32_t* p, int n) { for (int i = 0; i < n; i++) { snprintf(tmp, sizeof tmp, i ? ",%d" : "%d", p[i]); s += tmp; } };
+    for (const pb_filter_node& n : ls.nodes) {
+      const char* col = (n.column >= 0 && n.column < (int)v.cols.size()) ? v.cols[n.column].name.c_str() : "";
+      switch (n.kind) {
+        case PB_F_AND: snprintf(tmp, sizeof tmp, "AND n=%d", n.num_children); s += tmp; break;
+        case PB_F_OR: snprintf(tmp, sizeof tmp, "OR n=%d", n.num_children); s += tmp; break;
+        case PB_F_NOT: s += "NOT"; break;
+        case PB_F_MATCH_ALL: s += "MATCH_ALL"; break;
+        case PB_F_EMPTY: s += "EMPTY"; break;
+        case PB_F_SCAN_DICT_RANGE: snprintf(tmp, sizeof tmp, "SCAN_DICT_RANGE col=%s lo=%lld hi=%lld", col, (long long)n.lo, (long long)n.hi); s += tmp; break;
+        case PB_F_SCAN_DICT_SET: case PB_F_INVERTED:
+          snprintf(tmp, sizeof tmp, "%s col=%s excl=%d ids=", n.kind == PB_F_INVERTED ? "INVERTED" : "SCAN_DICT_SET", col, n.exclusive); s += tmp;
+          ids(n.ids, n.num_ids);
+          break;
+        case PB_F_SCAN_RAW_RANGE:
+          snprintf(tmp, sizeof tmp, "SCAN_RAW_RANGE col=%s ilo=%lld ihi=%lld dlo=%.17g dhi=%.17g dlo_incl=%d dhi_incl=%d", col, (long long)n.lo, (long long)n.hi,
+                   n.dlo, n.dhi, n.dlo_inclusive, n.dhi_inclusive);
+          s += tmp;
+          break;
+        case PB_F_SCAN_RAW_SET:
+          snprintf(tmp, sizeof tmp, "SCAN_RAW_SET col=%s excl=%d vals=", col, n.exclusive); s += tmp;
+          for (int i = 0; i < n.num_raw_values; i++) { snprintf(tmp, sizeof tmp, i ? ",%lld" : "%lld", (long long)n.raw_values[i]); s += tmp; }
+          break;
+        case PB_F_SORTED:
+          s += "SORTED ranges=";
+          for (int i = 0; i < n.num_ids; i++) { snprintf(tmp, sizeof tmp, i ? ",%d-%d" : "%d-%d", n.ids[2 * i], n.ids[2 * i + 1]); s += tmp; }
+          break;
+        default: s += "?"; break;
+      }
+      s += "\n";
+    }
+    int n = (int)std::min<size_t>(s.size(), (size_t)cap - 1);
+    memcpy(buf, s.data(), (size_t)n); buf[n] = 0;
+    return (int)s.size();
+  } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
+}

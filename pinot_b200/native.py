@@ -103,6 +103,7 @@ def lib():
     l.pbh_is_eligible.argtypes = [C.c_void_p, C.POINTER(PbhQueryContext)]
     l.pbh_explain_filter.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PbhQueryContext), C.c_char_p, C.c_int32]
     l.pbh_explain_agg_filter.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PbhQueryContext), C.c_int32, C.c_char_p, C.c_int32]
+    l.pbh_dump_lowered.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PbhQueryContext), C.c_int32, C.c_char_p, C.c_int32]
     l.pb_result_free.argtypes = [C.c_void_p]
     l.pb_result_finalize.argtypes = [C.c_void_p]
     l.pb_result_num_tables.argtypes = [C.c_void_p]
@@ -479,6 +480,20 @@ def host_unregister(arr: np.ndarray):
 def is_eligible(group: SegmentGroup, q: QueryContext) -> bool:
     m = _MarshalledQuery(q)
     return lib().pbh_is_eligible(group.handle, C.byref(m.ctx)) == 0
+
+
+def dump_lowered(group: SegmentGroup, q: QueryContext, clause: int = -1, segment_index: int = 0) -> List[str]:
+    """The lowered pb_filter_node program of one segment (clause -1 = WHERE filter), one postfix node per line."""
+    m = _MarshalledQuery(q)
+    cap = 1 << 16
+    while True:
+        buf = C.create_string_buffer(cap)
+        n = lib().pbh_dump_lowered(group.handle, segment_index, C.byref(m.ctx), clause, buf, cap)
+        if n < 0:
+            _check(n)
+        if n < cap:
+            return buf.value.decode().splitlines()
+        cap = n + 1
 
 
 def explain_agg_filter(group: SegmentGroup, q: QueryContext, clause: int, segment_index: int = 0) -> str:

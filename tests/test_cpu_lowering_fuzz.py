@@ -1,0 +1,153 @@
+"""Differential test of the host planning layer (pinot_b200/csrc/host/pb_host.cpp: PredicateEvaluatorProvider, FilterOperatorUtils,
+FilterPlanNode, SortedIndexBasedFilterOperator) against the oracle, on CPU.
+
+The lowered pb_filter_node program of a query (pbh_dump_lowered: exactly what pbh_execute hands to the device) is evaluated by a
+few lines of numpy over the decoded columns, and the resulting docId set must equal the oracle's DocIdSetOperator output
+(orc_filter_doc_ids) — two independent restatements of the reference's predicate lowering (C++ vs C) meeting in the middle.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from pinot_b200 import datagen, native
+from pinot_b200.query import parse_sql
+from pinot_b200.segment_writer import DataType, unpack_bits_be
+
+
+def _dict_ids(c):
+    if c.is_sorted:
+        pairs = np.frombuffer(c.forward_index.tobytes(), dtype=">i4").reshape(-1, 2)
+        ids = np.zeros(c.num_docs, np.int64)
+        for d, (s, e) in enumerate(pairs):
+            ids[s:e + 1] = d
+        return ids
+    return unpack_bits_be(c.forward_index, c.num_docs, c.bits_per_element).astype(np.int64)
+
+
+def _raw_values(c):
+    dt = {DataType.INT: ">i4", DataType.LONG: ">i8", DataType.FLOAT: ">f4", DataType.DOUBLE: ">f8"}[c.data_type]
+    width = np.dtype(dt).itemsize
+    return np.frombuffer(c.forward_index.tobytes()[-width * c.num_docs:], dtype=dt)
+
+
+def evaluate_lowered(seg, lines):
+    """numpy interpreter of the postfix program printed by pbh_dump_lowered; an empty program matches all."""
+    n = seg.num_docs
+    if not lines:
+        return np.ones(n, bool)
+    stack = []
+    for line in lines:
+        op, _, rest = line.partition(" ")
+        kv = dict(p.split("=", 1) for p in rest.split()) if rest else {}
+        if op == "AND" or op == "OR":
+            k = int(kv["n"])
+            args, stack = stack[-k:], stack[:-k]
+            stack.append(np.logical_and.reduce(args) if op == "AND" else np.logical_or.reduce(args))
+        elif op == "NOT":
+            stack.append(~stack.pop())
+        elif op == "MATCH_ALL":
+            stack.append(np.ones(n, bool))
+        elif op == "EMPTY":
+            stack.append(np.zeros(n, bool))
+        elif op == "SCAN_DICT_RANGE":
+            ids = _dict_ids(seg.columns[kv["col"]])
+            stack.append((ids >= int(kv["lo"])) & (ids < int(kv["hi"])))
+        elif op in ("SCAN_DICT_SET", "INVERTED"):
+            ids = _dict_ids(seg.columns[kv["col"]])
+            member = np.isin(ids, np.array([int(x) for x in kv["ids"].split(",") if x], dtype=np.int64))
+            stack.append(~member if kv["excl"] == "1" else member)
+        elif op == "SCAN_RAW_RANGE":
+            c = seg.columns[kv["col"]]
+            v = _raw_values(c)
+            if c.data_type in (DataType.INT, DataType.LONG):
+                stack.append((v >= int(kv["ilo"])) & (v <= int(kv["ihi"])))
+            else:
+                v = v.astype(np.float64)
+                lo, hi = float(kv["dlo"]), float(kv["dhi"])
+                stack.append((v >= lo if kv["dlo_incl"] == "1" else v > lo) & (v <= hi if kv["dhi_incl"] == "1" else v < hi))
+        elif op == "SCAN_RAW_SET":
+            c = seg.columns[kv["col"]]
+            v = _raw_values(c)
+            vals = [int(x) for x in kv["vals"].split(",") if x]
+            if c.data_type in (DataType.FLOAT, DataType.DOUBLE):      # doubles travel as IEEE-754 bits
+                member = np.isin(v.astype(np.float64).view(np.int64), np.array(vals, dtype=np.int64))
+            else:
+                member = np.isin(v.astype(np.int64), np.array(vals, dtype=np.int64))
+            stack.append(~member if kv["excl"] == "1" else member)
+        elif op == "SORTED":
+            m = np.zeros(n, bool)
+            for r in kv["ranges"].split(","):
+                if r:
+                    s, e = r.split("-")
+                    m[int(s):int(e) + 1] = True
+            stack.append(m)
+        else:
+            raise AssertionError(f"unknown node {line!r}")
+    assert len(stack) == 1
+    return stack[0]
+
+
+@pytest.fixture(scope="module")
+def fuzz_segment():
+    seg = datagen.make_segment_synth(7, 30_011, columns=["c1", "c3", "c5", "d0", "s0", "t0", "m0", "x0", "k0"])
+    g = native.SegmentGroup([native.StagedSegment(seg)])
+    yield seg, g
+    g.release()
+
+
+def _literal(rng, seg, col):
+    """a literal for `col`: mostly a value that exists, sometimes one between / outside the dictionary or the value range"""
+    c = seg.columns[col]
+    if c.has_dictionary:
+        d = c.dictionary_values()
+        v = d[rng.integers(0, len(d))]
+        if c.data_type == DataType.STRING:
+            s = v.decode()
+            r = rng.random()
+            return "'" + (s if r < 0.6 else (s[:2] if r < 0.8 else s + "x")) + "'"
+        v = int(v) + int(rng.choice([0, 0, 0, 1, -1, 10**9, -10**9]))
+        return str(v)
+    if c.data_type in (DataType.DOUBLE, DataType.FLOAT):
+        return repr(float(rng.choice([rng.random(), rng.random(), -0.5, 1.5, 0.0])))
+    vals = _raw_values(c)
+    return str(int(vals[rng.integers(0, len(vals))]) + int(rng.choice([0, 0, 1, -1])))
+
+
+def _predicate(rng, seg, cols):
+    col = str(rng.choice(cols))
+    kind = rng.choice(["eq", "neq", "in", "notin", "lt", "le", "gt", "ge", "between"])
+    lit = lambda: _literal(rng, seg, col)
+    if kind == "eq":
+        return f"{col} = {lit()}"
+    if kind == "neq":
+        return f"{col} <> {lit()}"
+    if kind in ("in", "notin"):
+        vals = ", ".join(lit() for _ in range(int(rng.integers(1, 6))))
+        return f"{col} {'NOT IN' if kind == 'notin' else 'IN'} ({vals})"
+    if kind == "between":
+        a, b = lit(), lit()
+        return f"{col} BETWEEN {a} AND {b}"
+    return f"{col} {dict(lt='<', le='<=', gt='>', ge='>=')[kind]} {lit()}"
+
+
+def _expr(rng, seg, cols, depth):
+    if depth == 0 or rng.random() < 0.35:
+        p = _predicate(rng, seg, cols)
+        return f"NOT {p}" if rng.random() < 0.15 and " IN " not in p and "BETWEEN" not in p else p
+    k = int(rng.integers(2, 4))
+    op = " AND " if rng.random() < 0.5 else " OR "
+    return "(" + op.join(_expr(rng, seg, cols, depth - 1) for _ in range(k)) + ")"
+
+
+@pytest.mark.parametrize("seed", range(100))
+def test_lowered_program_matches_oracle(fuzz_segment, seed):
+    seg, g = fuzz_segment
+    rng = np.random.default_rng(1000 + seed)
+    cols = ["c1", "c3", "c5", "d0", "s0", "t0", "m0", "x0", "k0"]
+    for _ in range(6):
+        where = _expr(rng, seg, cols, depth=2)
+        opts = "SET skipIndexes='c3=inverted'; " if rng.random() < 0.3 else ""
+        q = parse_sql(f"{opts}SELECT COUNT(*) FROM t WHERE {where}")
+        docs, _ = oracle.filter_doc_ids(seg, q)
+        got = np.nonzero(evaluate_lowered(seg, native.dump_lowered(g, q)))[0]
+        assert got.tolist() == docs.tolist(), where
