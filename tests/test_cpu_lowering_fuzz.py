@@ -87,6 +87,54 @@ def evaluate_lowered(seg, lines):
     return stack[0]
 
 
+def _column_values(seg, col):
+    c = seg.columns[col]
+    if not c.has_dictionary:
+        v = _raw_values(c)
+        return v.astype(np.float64) if c.data_type in (DataType.FLOAT, DataType.DOUBLE) else v.astype(np.int64)
+    d = c.dictionary_values()
+    ids = _dict_ids(c)
+    if c.data_type == DataType.STRING:
+        return np.array([d[i] for i in ids], dtype=object)           # bytes: same order as Java compareTo for ASCII
+    return d.astype(np.int64)[ids] if c.data_type in (DataType.INT, DataType.LONG) else d.astype(np.float64)[ids]
+
+
+def evaluate_sql(seg, node):
+    """Third opinion: the WHERE tree straight from the SQL semantics on the decoded column values (no dictIds, no indexes)."""
+    from pinot_b200.query import And, Not, Or, PredicateType
+    if isinstance(node, (And, Or)):
+        parts = [evaluate_sql(seg, c) for c in node.children]
+        return np.logical_and.reduce(parts) if isinstance(node, And) else np.logical_or.reduce(parts)
+    if isinstance(node, Not):
+        return ~evaluate_sql(seg, node.child)
+    c = seg.columns[node.column]
+    v = _column_values(seg, node.column)
+
+    def lit(s):
+        if c.data_type == DataType.STRING:
+            return s.encode()
+        return float(s) if c.data_type in (DataType.FLOAT, DataType.DOUBLE) else int(s)
+
+    def cmp(op, x):
+        if c.data_type == DataType.STRING:
+            return np.array([op(e, x) for e in v], dtype=bool)
+        return op(v, x)
+    import operator as o
+    t = node.type
+    if t in (PredicateType.EQ, PredicateType.NOT_EQ):
+        m = cmp(o.eq, lit(node.values[0]))
+        return ~m if t == PredicateType.NOT_EQ else m
+    if t in (PredicateType.IN, PredicateType.NOT_IN):
+        m = np.logical_or.reduce([cmp(o.eq, lit(x)) for x in node.values])
+        return ~m if t == PredicateType.NOT_IN else m
+    m = np.ones(seg.num_docs, bool)
+    if node.lower is not None:
+        m &= cmp(o.ge if node.lower_inclusive else o.gt, lit(node.lower))
+    if node.upper is not None:
+        m &= cmp(o.le if node.upper_inclusive else o.lt, lit(node.upper))
+    return m
+
+
 @pytest.fixture(scope="module")
 def fuzz_segment():
     seg = datagen.make_segment_synth(7, 30_011, columns=["c1", "c3", "c5", "d0", "s0", "t0", "m0", "x0", "k0"])
@@ -151,3 +199,4 @@ def test_lowered_program_matches_oracle(fuzz_segment, seed):
         docs, _ = oracle.filter_doc_ids(seg, q)
         got = np.nonzero(evaluate_lowered(seg, native.dump_lowered(g, q)))[0]
         assert got.tolist() == docs.tolist(), where
+        assert np.nonzero(evaluate_sql(seg, q.filter))[0].tolist() == docs.tolist(), where      # ... and both equal the SQL semantics
