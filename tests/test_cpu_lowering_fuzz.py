@@ -95,7 +95,7 @@ def _column_values(seg, col):
     d = c.dictionary_values()
     ids = _dict_ids(c)
     if c.data_type == DataType.STRING:
-        return np.array([d[i] for i in ids], dtype=object)           # bytes: same order as Java compareTo for ASCII
+        return np.array(list(d), dtype="S")[ids]                     # bytes: same order as Java compareTo for ASCII
     return d.astype(np.int64)[ids] if c.data_type in (DataType.INT, DataType.LONG) else d.astype(np.float64)[ids]
 
 
@@ -116,9 +116,7 @@ def evaluate_sql(seg, node):
         return float(s) if c.data_type in (DataType.FLOAT, DataType.DOUBLE) else int(s)
 
     def cmp(op, x):
-        if c.data_type == DataType.STRING:
-            return np.array([op(e, x) for e in v], dtype=bool)
-        return op(v, x)
+        return op(v, np.bytes_(x)) if c.data_type == DataType.STRING else op(v, x)
     import operator as o
     t = node.type
     if t in (PredicateType.EQ, PredicateType.NOT_EQ):

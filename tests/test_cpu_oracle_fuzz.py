@@ -1,0 +1,131 @@
+"""The oracle (the checker of every GPU parity test) against an independent pandas restatement of group-by / aggregation on
+random queries — on top of the reference's golden literals in test_oracle_golden.py.  CPU only."""
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import oracle
+from pinot_b200 import datagen
+from pinot_b200.query import AggOp, parse_sql
+from tests.test_cpu_lowering_fuzz import _column_values, _expr, evaluate_sql
+
+COLS = ["c1", "c3", "d0", "d1", "d3", "s0", "t0", "m0", "m1", "x0", "k0"]
+
+
+@pytest.fixture(scope="module")
+def table():
+    seg = datagen.make_segment_synth(11, 120_011, columns=COLS)
+    frame = pd.DataFrame({c: ([bytes(x) for x in v] if v.dtype.kind == "S" else v) for c, v in ((c, _column_values(seg, c)) for c in COLS)})
+    return seg, frame
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_group_by_aggregations_vs_pandas(table, seed):
+    seg, frame = table
+    rng = np.random.default_rng(500 + seed)
+    keys = list(rng.choice(["d0", "d1", "d3", "s0", "t0", "k0", "c3"], size=int(rng.integers(0, 4)), replace=False))
+    metrics = ["m0", "m1", "x0", "k0", "c1"]
+    aggs = []
+    for _ in range(int(rng.integers(1, 5))):
+        op = str(rng.choice(["COUNT", "SUM", "MIN", "MAX", "AVG", "DISTINCTCOUNT"]))
+        col = str(rng.choice(["c1", "d3", "c3"])) if op == "DISTINCTCOUNT" else str(rng.choice(metrics))
+        aggs.append((op, None if op == "COUNT" else col))
+    where = _expr(rng, seg, ["c1", "c3", "d0", "t0", "x0", "s0"], depth=1) if rng.random() < 0.8 else None
+    select = ", ".join(f"{op}({col or '*'})" for op, col in aggs)
+    sql = f"SET numGroupsLimit = 10000000; SELECT {select} FROM t" + (f" WHERE {where}" if where else "") + \
+          (f" GROUP BY {', '.join(keys)} LIMIT 10000000" if keys else "")
+    q = parse_sql(sql)
+    r = oracle.execute(seg, q)
+    sub = frame[evaluate_sql(seg, q.filter)] if q.filter is not None else frame
+    assert r.stats["num_docs_scanned"] == len(sub), sql
+    got_keys = [tuple(x) for x in r.decoded_keys()] if keys else [()]
+    grouped = sub.groupby(keys, sort=False) if keys else None
+    if keys:
+        sizes = grouped.size()
+        exp_keys = [k if isinstance(k, tuple) else (k,) for k in sizes.index.tolist()]
+        assert sorted(map(repr, got_keys)) == sorted(map(repr, exp_keys)), sql
+        pos = {k: i for i, k in enumerate(exp_keys)}
+        order = np.array([pos[k] for k in got_keys], dtype=np.int64)          # oracle row -> pandas row
+    for a, (op, col) in enumerate(aggs):
+        if keys:
+            if op == "COUNT":
+                exp = sizes.to_numpy()
+            elif op == "DISTINCTCOUNT":
+                exp = grouped[col].nunique().to_numpy()
+            else:
+                exp = getattr(grouped[col], {"SUM": "sum", "AVG": "sum", "MIN": "min", "MAX": "max"}[op])().to_numpy(dtype=np.float64)
+            exp = exp[order]
+            cnt = sizes.to_numpy()[order]
+        else:
+            n = len(sub)
+            cnt = np.array([n])
+            if op == "COUNT":
+                exp = np.array([n])
+            elif op == "DISTINCTCOUNT":
+                exp = np.array([sub[col].nunique()])
+            elif n == 0:                                                 # keyless query without matching docs: the defaults
+                exp = np.array([{"SUM": 0.0, "AVG": 0.0, "MIN": np.inf, "MAX": -np.inf}[op]])
+            else:
+                v = sub[col].to_numpy(dtype=np.float64)
+                exp = np.array([{"SUM": v.sum(), "AVG": v.sum(), "MIN": v.min(), "MAX": v.max()}[op]])
+        if op in ("COUNT", "DISTINCTCOUNT"):
+            assert (r.longs[a] == exp).all(), (sql, op, col)
+        else:
+            assert np.allclose(r.doubles[a], exp, rtol=1e-9, atol=0.0, equal_nan=False), (sql, op, col)
+            if op == "AVG":
+                assert (r.longs[a] == cnt).all(), (sql, op, col)
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_filtered_aggregations_vs_pandas(table, seed):
+    """Random FILTER(WHERE ...) clauses: every group of the main filter exists; a function sees only the docs that pass its
+    clause and keeps its default where none does (FilteredGroupByOperator.java:108-159)."""
+    seg, frame = table
+    rng = np.random.default_rng(9000 + seed)
+    keys = list(rng.choice(["d0", "d1", "d3", "t0"], size=int(rng.integers(0, 3)), replace=False))
+    clause_cols = ["c1", "c3", "d0", "x0", "t0"]
+    clauses = [_expr(rng, seg, clause_cols, depth=1) for _ in range(int(rng.integers(1, 4)))]
+    aggs = []
+    for _ in range(int(rng.integers(1, 5))):
+        op = str(rng.choice(["COUNT", "SUM", "MIN", "MAX", "AVG", "DISTINCTCOUNT"]))
+        col = str(rng.choice(["c1", "d3"])) if op == "DISTINCTCOUNT" else str(rng.choice(["m0", "m1", "x0", "k0"]))
+        clause = int(rng.integers(-1, len(clauses)))
+        aggs.append((op, None if op == "COUNT" else col, clause))
+    where = _expr(rng, seg, ["c1", "d0", "x0"], depth=1) if rng.random() < 0.7 else None
+    select = ", ".join(f"{op}({col or '*'})" + (f" FILTER(WHERE {clauses[cl]})" if cl >= 0 else "") for op, col, cl in aggs)
+    sql = f"SELECT {select} FROM t" + (f" WHERE {where}" if where else "") + (f" GROUP BY {', '.join(keys)} LIMIT 10000000" if keys else "")
+    q = parse_sql(sql)
+    r = oracle.execute(seg, q)
+    main = evaluate_sql(seg, q.filter) if q.filter is not None else np.ones(seg.num_docs, bool)
+    sub = frame[main]
+    got_keys = [tuple(x) for x in r.decoded_keys()] if keys else [()]
+    if keys:
+        exp_keys = [k if isinstance(k, tuple) else (k,) for k in sub.groupby(keys, sort=False).size().index.tolist()]
+        assert sorted(map(repr, got_keys)) == sorted(map(repr, exp_keys)), sql
+    defaults = {"COUNT": 0, "DISTINCTCOUNT": 0, "SUM": 0.0, "AVG": 0.0, "MIN": np.inf, "MAX": -np.inf}
+    for a, (op, col, cl) in enumerate(aggs):
+        lane = frame[main & evaluate_sql(seg, q.aggregations[a].filter)] if cl >= 0 else sub
+        if keys:
+            g = lane.groupby(keys, sort=False)
+            if op == "COUNT":
+                ser = g.size()
+            elif op == "DISTINCTCOUNT":
+                ser = g[col].nunique()
+            else:
+                ser = getattr(g[col], {"SUM": "sum", "AVG": "sum", "MIN": "min", "MAX": "max"}[op])()
+            lut = {(k if isinstance(k, tuple) else (k,)): v for k, v in ser.items()}
+            cnt = {(k if isinstance(k, tuple) else (k,)): v for k, v in g.size().items()}
+        else:
+            n = len(lane)
+            v = lane[col].to_numpy(dtype=np.float64) if col and op not in ("COUNT", "DISTINCTCOUNT") and n else None
+            val = n if op == "COUNT" else (lane[col].nunique() if op == "DISTINCTCOUNT" else
+                                           (defaults[op] if n == 0 else {"SUM": v.sum(), "AVG": v.sum(), "MIN": v.min(), "MAX": v.max()}[op]))
+            lut, cnt = {(): val}, {(): n}
+        for gi, key in enumerate(got_keys):
+            exp = lut.get(key, defaults[op])
+            if op in ("COUNT", "DISTINCTCOUNT"):
+                assert r.longs[a][gi] == exp, (sql, key, op)
+            else:
+                assert r.doubles[a][gi] == pytest.approx(exp, rel=1e-9), (sql, key, op, col)
+                if op == "AVG":
+                    assert r.longs[a][gi] == cnt.get(key, 0), (sql, key)
