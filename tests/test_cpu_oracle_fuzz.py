@@ -129,3 +129,28 @@ def test_filtered_aggregations_vs_pandas(table, seed):
                 assert r.doubles[a][gi] == pytest.approx(exp, rel=1e-9), (sql, key, op, col)
                 if op == "AVG":
                     assert r.longs[a][gi] == cnt.get(key, 0), (sql, key)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_cross_segment_merge_vs_pandas(seed):
+    """oracle.combine (GroupByCombineOperator / IndexedTable merge by decoded key: the checker of PB_Q_COMBINE) against pandas
+    over the concatenated rows of three segments whose dimension dictionaries differ."""
+    rng = np.random.default_rng(40 + seed)
+    cols = ["c1", "d1", "d3", "s0", "m0", "x0"]
+    segs = [datagen.make_segment_synth(20 + i, n, columns=cols, vary_dim_dictionaries=True) for i, n in enumerate((30_011, 20_003, 12_345))]
+    frames = [pd.DataFrame({c: ([bytes(x) for x in v] if v.dtype.kind == "S" else v) for c, v in ((c, _column_values(s, c)) for c in cols)})
+              for s in segs]
+    keys = list(rng.choice(["d1", "d3", "s0"], size=int(rng.integers(1, 3)), replace=False))
+    where = _expr(rng, segs[0], ["c1", "x0"], depth=1)
+    q = parse_sql(f"SET numGroupsLimit = 10000000; SELECT COUNT(*), SUM(m0), MIN(x0), MAX(m0), AVG(x0), DISTINCTCOUNT(c1) FROM t "
+                  f"WHERE {where} GROUP BY {', '.join(keys)} LIMIT 10000000")
+    merged = oracle.combine([oracle.execute(s, q) for s in segs])
+    sub = pd.concat([f[evaluate_sql(s, q.filter)] for s, f in zip(segs, frames)], ignore_index=True)
+    g = sub.groupby(keys, sort=False)
+    exp = pd.DataFrame({"n": g.size(), "sum": g["m0"].sum(), "min": g["x0"].min(), "max": g["m0"].max(), "avg": g["x0"].sum(), "dc": g["c1"].nunique()})
+    assert len(merged) == len(exp)
+    for k, row in exp.iterrows():
+        key = k if isinstance(k, tuple) else (k,)
+        got = merged[key]
+        assert got[0] == row["n"] and got[1] == float(row["sum"]) and got[2] == row["min"] and got[3] == float(row["max"])
+        assert got[4][1] == row["n"] and got[4][0] == pytest.approx(row["avg"], rel=1e-12) and len(got[5]) == row["dc"]
