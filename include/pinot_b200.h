@@ -128,6 +128,12 @@ typedef struct pb_aggregation_desc {
                                     * PCIe sectors per matching row) instead of being copied whole; predicate columns are staged.
                                     * Buffers that are not page-locked/mapped or not 4-byte aligned are staged as usual. */
 #define PB_Q_NO_TMA 8u             /* stage tiles with ld.global/st.shared instead of cp.async.bulk (testing) */
+#define PB_Q_ALL_RANKS 32u         /* collective call (needs PB_Q_COMBINE and pb_comm_init): every rank runs the same query over its own
+                                    * segments, the per-rank tables are merged over NCCL on the call's stream inside the library
+                                    * (all-gather of the table block + one merge kernel; hash tables: hash-partitioned all-to-all),
+                                    * and every rank gets the merged result.  The ranks must agree on the global dictionaries of the
+                                    * group-by / DISTINCTCOUNT columns first (pb_segment_group_export_dictionary /
+                                    * _set_global_dictionary) and must issue their PB_Q_ALL_RANKS calls in the same order. */
 
 typedef struct pb_query_desc {
   int32_t num_group_by;
@@ -154,10 +160,30 @@ typedef struct pb_exec_stats {
 } pb_exec_stats;
 
 /* -------- lifecycle -------- */
+/* device_ids: the CUDA devices this process drives (NULL / 0 = the calling thread's current device).  Every later entry
+ * point selects the device of the handle it works on, so calls may come from any thread (nextBlock() runs on
+ * the query executor's worker threads, BaseCombineOperator.java:100-141).  hbm_cache_bytes bounds the staged segment data
+ * per device (0 = unlimited): least-recently-used segments that no query is using are dropped from HBM and re-staged from
+ * the caller's buffers on their next use. */
 int pb_init(const int* device_ids, int n_devices, size_t hbm_cache_bytes);
 int pb_shutdown(void);
 const char* pb_last_error(void);
 int pb_device_count(void);
+
+/* -------- multi-GPU.  Two deployments:
+ *   (a) one process driving several GPUs (one JVM, pb_init with n_devices > 1): stage each segment on a device_index of
+ *       your choice; a query over a group whose segments span devices runs every device's part concurrently and merges the
+ *       tables on the first device over NVLink -- nothing else to call.  This is BaseCombineOperator's segment parallelism
+ *       (CTR/operator/combine/BaseCombineOperator.java:97-142) across GPUs instead of threads.
+ *   (b) one process per GPU (torchrun, or several server JVMs on one box): every process calls pb_comm_init with the same
+ *       128-byte id (made by pb_comm_unique_id on one rank and distributed by the caller: a file, a socket, torch.distributed)
+ *       and then passes PB_Q_ALL_RANKS to pb_query_execute.  NCCL is loaded at run time (PB_NCCL_LIB overrides the search);
+ *       single-GPU servers never need it. -------- */
+#define PB_COMM_ID_BYTES 128
+int pb_comm_unique_id(void* out, size_t cap);                                     /* ncclGetUniqueId */
+int pb_comm_init(int n_ranks, int rank, const void* unique_id, size_t id_bytes);  /* ncclCommInitRank on this process's device */
+int pb_comm_info(int* n_ranks, int* rank);                                        /* returns 1 when a communicator exists */
+int pb_comm_destroy(void);
 
 /* -------- segment staging: replaces the DataSource / ForwardIndexReader / Dictionary / InvertedIndexReader
  * objects the operators pull from IndexSegment.getDataSource (SPI/datasource/DataSource.java:38-60).

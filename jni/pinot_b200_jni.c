@@ -30,8 +30,10 @@ JNIEXPORT jlong JNICALL Java_org_apache_pinot_b200_Native_stageSegment(JNIEnv* e
   pb_column_desc* cols = (pb_column_desc*)calloc((size_t)n, sizeof(pb_column_desc));
   jint* m = (*env)->GetIntArrayElements(env, meta, NULL);
   const char** names = (const char**)calloc((size_t)n, sizeof(char*));
+  jstring* jnames = (jstring*)calloc((size_t)n, sizeof(jstring));
   for (jsize i = 0; i < n; i++) {
     jstring s = (jstring)(*env)->GetObjectArrayElement(env, colNames, i);
+    jnames[i] = s;
     names[i] = (*env)->GetStringUTFChars(env, s, NULL);
     cols[i].name = names[i];
     cols[i].stored_type = m[6 * i]; cols[i].has_dictionary = m[6 * i + 1]; cols[i].is_sorted = m[6 * i + 2];
@@ -39,18 +41,20 @@ JNIEXPORT jlong JNICALL Java_org_apache_pinot_b200_Native_stageSegment(JNIEnv* e
     jobject b = (*env)->GetObjectArrayElement(env, fwd, i);
     cols[i].forward_index = (*env)->GetDirectBufferAddress(env, b);
     cols[i].forward_index_len = (uint64_t)(*env)->GetDirectBufferCapacity(env, b);
+    (*env)->DeleteLocalRef(env, b);      /* the ByteBuffer stays referenced by the array; a wide table must not fill the local-ref table */
     b = (*env)->GetObjectArrayElement(env, dict, i);
-    if (b) { cols[i].dictionary = (*env)->GetDirectBufferAddress(env, b); cols[i].dictionary_len = (uint64_t)(*env)->GetDirectBufferCapacity(env, b); }
+    if (b) { cols[i].dictionary = (*env)->GetDirectBufferAddress(env, b); cols[i].dictionary_len = (uint64_t)(*env)->GetDirectBufferCapacity(env, b); (*env)->DeleteLocalRef(env, b); }
     b = (*env)->GetObjectArrayElement(env, inv, i);
-    if (b) { cols[i].inverted_index = (*env)->GetDirectBufferAddress(env, b); cols[i].inverted_index_len = (uint64_t)(*env)->GetDirectBufferCapacity(env, b); }
+    if (b) { cols[i].inverted_index = (*env)->GetDirectBufferAddress(env, b); cols[i].inverted_index_len = (uint64_t)(*env)->GetDirectBufferCapacity(env, b); (*env)->DeleteLocalRef(env, b); }
   }
   const char* sname = (*env)->GetStringUTFChars(env, name, NULL);
   pb_segment_desc d = { sname, numDocs, (int32_t)n, cols };
   pb_segment_handle h = NULL;
-  int rc = pb_segment_stage(&d, 0, &h);
+  int rc = pb_segment_stage(&d, 0, &h);       /* copies the names; the buffers stay owned by Pinot (mmap) */
   (*env)->ReleaseStringUTFChars(env, name, sname);
+  for (jsize i = 0; i < n; i++) { (*env)->ReleaseStringUTFChars(env, jnames[i], names[i]); (*env)->DeleteLocalRef(env, jnames[i]); }
   (*env)->ReleaseIntArrayElements(env, meta, m, JNI_ABORT);
-  free(names); free(cols);
+  free(jnames); free(names); free(cols);
   if (rc != PB_OK) { throw_last(env); return 0; }
   return (jlong)(intptr_t)h;
 }

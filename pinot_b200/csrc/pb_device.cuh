@@ -145,7 +145,7 @@ struct DevTable {
   unsigned int* limit_reached;
   unsigned long long* docs_matched;  // numDocsScanned
   uint32_t num_groups_limit;
-  uint32_t pad2;
+  uint32_t limit_active;             // 0: the table can never reach numGroupsLimit (limit >= docs), inserts need no ticket
 };
 
 struct DevQuery {
@@ -487,23 +487,47 @@ __device__ __forceinline__ uint64_t pb_hash64(uint64_t k) {
   return k;
 }
 
+// ---- numGroupsLimit (DictionaryBasedGroupKeyGenerator.java:1033-1035: a NEW key past the limit gets INVALID_ID and its
+// rows are dropped; existing keys keep aggregating).  A thread may insert only while it holds a ticket: tickets are taken
+// from num_groups with a returning atomic BEFORE the slot is claimed and handed back when the claim is lost to another
+// thread, so the table never holds more than `limit` keys however many threads race (the check-then-insert of round 1 let
+// every resident thread pass the check at once and could fill the table, after which absent keys probed forever).  Lanes of
+// a warp that need a ticket at the same time share one atomic.  Probing is bounded by the capacity. ----
+__device__ __forceinline__ bool pb_group_ticket(const DevTable& t) {
+  if (!t.limit_active) { pb_red_add_u32(t.num_groups, 1u); return true; }
+  const unsigned m = __activemask();
+  const int leader = __ffs(m) - 1, lane = (int)(threadIdx.x & 31);
+  const unsigned rank = __popc(m & ((1u << lane) - 1u)), need = __popc(m);
+  unsigned base = 0;
+  if (lane == leader) base = atomicAdd(t.num_groups, need);
+  base = __shfl_sync(m, base, leader);
+  if (base + rank < t.num_groups_limit) return true;
+  atomicSub(t.num_groups, 1u);                           // over the limit: hand the ticket back
+  pb_red_add_u32(t.limit_reached, 1u);
+  return false;
+}
+__device__ __forceinline__ void pb_group_ticket_return(const DevTable& t) { atomicSub(t.num_groups, 1u); }
+
 // returns slot, or ~0ull when the key is new and numGroupsLimit is reached
-// (DictionaryBasedGroupKeyGenerator.java:1033-1035: INVALID_ID, rows silently dropped)
 __device__ __forceinline__ uint64_t pb_hash_slot(const DevTable& t, uint64_t key) {
   if (key == PB_HASH_EMPTY) return t.capacity;          // reserved extra slot for the sentinel value itself
   uint64_t mask = t.capacity - 1;
   uint64_t s = pb_hash64(key) & mask;
-  while (true) {
+  for (uint64_t probes = 0; probes <= mask; probes++) {
     unsigned long long cur = pb_ld_volatile_u64(&t.hkeys[s]);
     if (cur == key) return s;
     if (cur == PB_HASH_EMPTY) {
-      if (pb_ld_volatile_u32(t.num_groups) >= t.num_groups_limit) { pb_red_add_u32(t.limit_reached, 1u); return ~0ull; }
+      // the key is not in the table (linear probing never skips an empty slot): inserting needs a ticket
+      if (!pb_group_ticket(t)) return ~0ull;
       unsigned long long old = pb_atom_cas_u64(&t.hkeys[s], PB_HASH_EMPTY, (unsigned long long)key);
-      if (old == PB_HASH_EMPTY) { pb_red_add_u32(t.num_groups, 1u); return s; }
+      if (old == PB_HASH_EMPTY) return s;
+      pb_group_ticket_return(t);                         // somebody else claimed the slot first
       if (old == key) return s;
     }
     s = (s + 1) & mask;
   }
+  pb_red_add_u32(t.limit_reached, 1u);                   // table full (cannot happen while capacity >= 2 x limit): drop the row
+  return ~0ull;
 }
 
 // 128-bit composite keys (more than 64 bits of dictIds: the reference's ArrayMapBasedHolder,
@@ -517,21 +541,22 @@ __device__ __forceinline__ uint64_t pb_hash_slot2(const DevTable& t, uint64_t lo
   if (lo == PB_HASH_EMPTY && hi == PB_HASH_EMPTY) return t.capacity;     // reserved slot for the sentinel pattern itself
   const uint64_t mask = t.capacity - 1;
   uint64_t s = pb_hash64(lo ^ pb_hash64(hi)) & mask;
-  while (true) {
-    if (pb_ld_volatile_u32(t.num_groups) >= t.num_groups_limit) {
-      // limit reached: only existing keys may still be updated -> probe without inserting
-      unsigned long long clo, chi;   // one 16-byte transaction, so a concurrent CAS.128 is seen whole or not at all
-      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(clo), "=l"(chi) : "l"(&t.hkeys[2 * s]));
-      if (clo == lo && chi == hi) return s;
-      if (clo == PB_HASH_EMPTY && chi == PB_HASH_EMPTY) { pb_red_add_u32(t.limit_reached, 1u); return ~0ull; }
-    } else {
+  for (uint64_t probes = 0; probes <= mask; probes++) {
+    unsigned long long clo, chi;   // one 16-byte transaction, so a concurrent CAS.128 is seen whole or not at all
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(clo), "=l"(chi) : "l"(&t.hkeys[2 * s]));
+    if (clo == lo && chi == hi) return s;
+    if (clo == PB_HASH_EMPTY && chi == PB_HASH_EMPTY) {
+      if (!pb_group_ticket(t)) return ~0ull;
       unsigned long long olo, ohi;
       pb_atom_cas_u128(&t.hkeys[2 * s], PB_HASH_EMPTY, PB_HASH_EMPTY, lo, hi, olo, ohi);
-      if (olo == PB_HASH_EMPTY && ohi == PB_HASH_EMPTY) { pb_red_add_u32(t.num_groups, 1u); return s; }
+      if (olo == PB_HASH_EMPTY && ohi == PB_HASH_EMPTY) return s;
+      pb_group_ticket_return(t);
       if (olo == lo && ohi == hi) return s;
     }
     s = (s + 1) & mask;
   }
+  pb_red_add_u32(t.limit_reached, 1u);
+  return ~0ull;
 }
 
 // keyless accumulators live in shared memory, one private cell per thread (no atomics)
@@ -1293,24 +1318,55 @@ __global__ void pb_expand_kernel(const DevExpandItem* __restrict__ items) {
 // ------------------------------------------------------------------------------------------------
 // one launch initialises every table of the query: zero region (row counts, sums, distinct bitsets, counters),
 // 0xFF region (hash keys = PB_HASH_EMPTY) and the min/max region (INT64_MAX: larger than any encoded value)
-__global__ void pb_init_tables_kernel(uint4* zero, uint64_t zero_n16, uint4* ff, uint64_t ff_n16, uint4* mm, uint64_t mm_n16) {
+// The first head_n16 16-byte words of the zero region are the per-table counter cells: they start from the host-known
+// values in `head` (total docs, entries scanned in filter, docs matched of a match-all query) instead of zero, so that a
+// cross-GPU merge sums them like every other counter.  `aux` is a second zero region (per-wave match counters and
+// per-segment swim-lane statistics) that is not part of the merged block.
+__global__ void pb_init_tables_kernel(uint4* zero, uint64_t zero_n16, uint4* ff, uint64_t ff_n16, uint4* mm, uint64_t mm_n16,
+                                      uint4* aux, uint64_t aux_n16, const uint4* __restrict__ head, uint64_t head_n16) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u), f = make_uint4(~0u, ~0u, ~0u, ~0u), m = make_uint4(~0u, 0x7fffffffu, ~0u, 0x7fffffffu);
-  for (uint64_t i = t0; i < zero_n16; i += stride) zero[i] = z;
+  for (uint64_t i = t0; i < zero_n16; i += stride) zero[i] = i < head_n16 ? head[i] : z;
   for (uint64_t i = t0; i < ff_n16; i += stride) ff[i] = f;
   for (uint64_t i = t0; i < mm_n16; i += stride) mm[i] = m;
+  for (uint64_t i = t0; i < aux_n16; i += stride) aux[i] = z;
 }
 
-// cross-GPU merge: `gathered` holds n_ranks copies of the table block (rank-major); reduce them element-wise into `dst`
-// with the operator of each region: counters + row counts u64 SUM | sums f64 SUM | distinct bitsets OR | min/max i64 MIN
-__global__ void pb_merge_blocks_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ gathered, int n_ranks,
-                                       uint64_t n_words, uint64_t sum_off, uint64_t dc_off, uint64_t mm_off) {
+// Filtered aggregations: ExecutionStatistics of the swim-lanes (FilteredGroupByOperator.java:146-149), reduced from the
+// per-segment counters to two cells of the segment's table so that they merge across GPUs with the other counters.
+// Per segment and lane l (0 = the non-filtered lane, 1 + f = FILTER clause f): docs_w = 1 when the lane's docs count
+// towards numDocsScanned, post_w = the lane's projected columns (numEntriesScannedPostFilter = docs x columns).
+struct DevLaneWeights { int32_t table; int32_t docs_w[1 + PB_MAX_AGG_FILTERS]; int32_t post_w[1 + PB_MAX_AGG_FILTERS]; int32_t pad; };
+__global__ void pb_lane_stats_kernel(const DevLaneWeights* __restrict__ w, const unsigned long long* __restrict__ seg_stats, int n_segs,
+                                     int n_lanes, unsigned long long* counters, int cells_per_table) {
+  for (int si = blockIdx.x * blockDim.x + threadIdx.x; si < n_segs; si += gridDim.x * blockDim.x) {
+    const unsigned long long* ss = seg_stats + (size_t)si * (1 + PB_MAX_AGG_FILTERS);
+    unsigned long long docs = 0, post = 0;
+    for (int l = 0; l < n_lanes; l++) { docs += ss[l] * (unsigned long long)w[si].docs_w[l]; post += ss[l] * (unsigned long long)w[si].post_w[l]; }
+    unsigned long long* c = counters + (size_t)w[si].table * cells_per_table;
+    if (docs) atomicAdd(c + 4, docs);
+    if (post) atomicAdd(c + 5, post);
+  }
+}
+
+// cross-GPU merge: reduce n_rows copies of the table block element-wise into `dst` with the operator of each region:
+// counters + row counts u64 SUM | sums f64 SUM | distinct bitsets OR | min/max i64 MIN.  The copies are either the rows of one
+// buffer (`gathered`, row-major: the receive buffer of an all-gather, which includes this rank's own block) or, when
+// `peers` is set, blocks read in place from the peer GPUs over NVLink (one process driving several devices); with
+// base_is_dst the copy already in `dst` is the first operand.  Sums are added in row order, so every rank computes the same
+// bits from the same gathered buffer.
+#define PB_MERGE_MAX_PEERS 16
+struct DevMergePeers { const unsigned long long* p[PB_MERGE_MAX_PEERS]; };
+__global__ void pb_merge_blocks_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ gathered, const DevMergePeers peers,
+                                       int n_rows, int base_is_dst, uint64_t n_words, uint64_t sum_off, uint64_t dc_off, uint64_t mm_off) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x) {
-    unsigned long long v = gathered[i];
-    if (i < sum_off) { for (int r = 1; r < n_ranks; r++) v += gathered[(uint64_t)r * n_words + i]; }
-    else if (i < dc_off) { double d = __longlong_as_double((long long)v); for (int r = 1; r < n_ranks; r++) d += __longlong_as_double((long long)gathered[(uint64_t)r * n_words + i]); v = (unsigned long long)__double_as_longlong(d); }
-    else if (i < mm_off) { for (int r = 1; r < n_ranks; r++) v |= gathered[(uint64_t)r * n_words + i]; }
-    else { long long m = (long long)v; for (int r = 1; r < n_ranks; r++) { long long o = (long long)gathered[(uint64_t)r * n_words + i]; m = o < m ? o : m; } v = (unsigned long long)m; }
+    auto row = [&](int r) -> unsigned long long { return gathered ? gathered[(uint64_t)r * n_words + i] : peers.p[r][i]; };
+    unsigned long long v = base_is_dst ? dst[i] : row(0);
+    const int r0 = base_is_dst ? 0 : 1;
+    if (i < sum_off) { for (int r = r0; r < n_rows; r++) v += row(r); }
+    else if (i < dc_off) { double d = __longlong_as_double((long long)v); for (int r = r0; r < n_rows; r++) d += __longlong_as_double((long long)row(r)); v = (unsigned long long)__double_as_longlong(d); }
+    else if (i < mm_off) { for (int r = r0; r < n_rows; r++) v |= row(r); }
+    else { long long m = (long long)v; for (int r = r0; r < n_rows; r++) { long long o = (long long)row(r); m = o < m ? o : m; } v = (unsigned long long)m; }
     dst[i] = v;
   }
 }

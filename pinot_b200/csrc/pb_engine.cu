@@ -7,6 +7,9 @@
 #include "../../include/pinot_b200.h"
 #include "pb_device.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -43,35 +46,51 @@ extern "C" const char* pb_last_error(void) { return g_err; }
 // context
 // ------------------------------------------------------------------------------------------------
 struct PinnedBlock { void* p; size_t cap; };
-struct StreamSet { cudaStream_t stream = nullptr; cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; };   // one per in-flight call, pooled
+#define PB_N_EVENTS 7
+struct StreamSet { cudaStream_t stream = nullptr; cudaEvent_t ev[PB_N_EVENTS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; };   // one per in-flight call, pooled
+
+// One Context per device handed to pb_init (SURVEY.md §8b threading contract: every entry point selects the device of the
+// handle it works on; a JVM worker thread that never called pb_init itself still runs on the right GPU).
 struct Context {
   std::mutex mu;
-  bool inited = false;
-  std::vector<int> devices;
+  int device = 0;                             // CUDA device ordinal
+  int index = 0;                              // position in pb_init's device_ids (the device_index of pb_segment_stage)
   int num_sms = 148;
-  std::vector<PinnedBlock> pinned_free;
   std::vector<PinnedBlock> scratch_free;      // large device scratch buffers (match lists), reused across calls
   std::vector<StreamSet> streams_free;        // stream + timing events of finished calls (creation costs ~10 us per call)
   cudaStream_t util_stream = nullptr;         // stream-ordered allocations / frees of staged data
   cudaStream_t copy_stream = nullptr;         // host -> HBM staging copies (queries wait on per-segment events)
   bool smem_attr_set = false;
+  // segment cache accounting (hbm_cache_bytes of pb_init): staged bytes on this device and the LRU clock
+  int64_t staged_bytes = 0;
+  uint64_t lru_clock = 0;
+  std::vector<struct pb_segment_s*> segments; // every live segment staged on this device (eviction candidates)
+  // cross-rank merge (pb_comm_init): receive buffer of the table all-gather, grown on demand
+  void* gather_buf = nullptr; size_t gather_cap = 0;
 };
-static Context g_ctx;
+struct Global {
+  std::mutex mu;
+  bool inited = false;
+  std::vector<std::unique_ptr<Context>> ctxs;
+  size_t hbm_cache_bytes = 0;                 // 0 = unlimited
+  std::vector<PinnedBlock> pinned_free;       // page-locked host blocks (portable: usable from every device)
+};
+static Global g_all;
 
-static int ensure_init() {
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (g_ctx.inited) return PB_OK;
-  int n = 0;
-  cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0) return fail(PB_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
-  int dev = 0;
-  cudaGetDevice(&dev);
-  g_ctx.devices.assign(1, dev);
+// cudaSetDevice for the duration of one entry point (restores the caller's device)
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const Context* c) { cudaGetDevice(&prev); if (c && prev != c->device) cudaSetDevice(c->device); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int init_context(Context* c) {
+  CU(cudaSetDevice(c->device));
   cudaDeviceProp prop;
-  CU(cudaGetDeviceProperties(&prop, dev));
-  g_ctx.num_sms = prop.multiProcessorCount;
+  CU(cudaGetDeviceProperties(&prop, c->device));
+  c->num_sms = prop.multiProcessorCount;
   cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+  if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
@@ -82,39 +101,95 @@ static int ensure_init() {
     if (const char* e = getenv("PB_L2_FETCH")) gran = (size_t)atoi(e);
     if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
   }
-  CU(cudaStreamCreateWithFlags(&g_ctx.util_stream, cudaStreamNonBlocking));
-  CU(cudaStreamCreateWithFlags(&g_ctx.copy_stream, cudaStreamNonBlocking));
-  g_ctx.inited = true;
+  CU(cudaStreamCreateWithFlags(&c->util_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   return PB_OK;
 }
 
+static int init_devices(const int* device_ids, int n_devices, size_t hbm_cache_bytes) {
+  std::lock_guard<std::mutex> lk(g_all.mu);
+  if (g_all.inited) {
+    // a second pb_init may only restate the devices it already has (the JVM calls it once per server)
+    if (n_devices > 0 && device_ids) {
+      if ((size_t)n_devices != g_all.ctxs.size()) return fail(PB_ERR_STATE, "pb_init: already initialised with %zu devices", g_all.ctxs.size());
+      for (int i = 0; i < n_devices; i++) if (g_all.ctxs[i]->device != device_ids[i]) return fail(PB_ERR_STATE, "pb_init: already initialised with device %d at index %d", g_all.ctxs[i]->device, i);
+    }
+    if (hbm_cache_bytes) g_all.hbm_cache_bytes = hbm_cache_bytes;
+    return PB_OK;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) return fail(PB_ERR_CUDA, "no CUDA device: %s", cudaGetErrorString(e));
+  int prev = 0;
+  cudaGetDevice(&prev);
+  std::vector<int> ids;
+  if (n_devices > 0 && device_ids) ids.assign(device_ids, device_ids + n_devices); else ids.push_back(prev);
+  for (size_t i = 0; i < ids.size(); i++) {
+    if (ids[i] < 0 || ids[i] >= n) return fail(PB_ERR_INVALID, "pb_init: device %d does not exist (%d devices)", ids[i], n);
+    for (size_t k = 0; k < i; k++) if (ids[k] == ids[i]) return fail(PB_ERR_INVALID, "pb_init: device %d listed twice", ids[i]);
+  }
+  std::vector<std::unique_ptr<Context>> ctxs;
+  for (size_t i = 0; i < ids.size(); i++) {
+    std::unique_ptr<Context> c(new Context());
+    c->device = ids[i]; c->index = (int)i;
+    int rc = init_context(c.get());
+    if (rc) { cudaSetDevice(prev); return rc; }
+    ctxs.push_back(std::move(c));
+  }
+  // one JVM driving several GPUs: the cross-device table merge reads the peers' blocks over NVLink
+  for (size_t i = 0; i < ctxs.size(); i++)
+    for (size_t k = 0; k < ctxs.size(); k++) {
+      if (i == k) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, ctxs[i]->device, ctxs[k]->device) == cudaSuccess && can) {
+        cudaSetDevice(ctxs[i]->device);
+        cudaError_t pe = cudaDeviceEnablePeerAccess(ctxs[k]->device, 0);
+        if (pe != cudaSuccess) cudaGetLastError();   // already enabled / unsupported: the merge falls back to copies
+      }
+    }
+  cudaSetDevice(prev);
+  g_all.ctxs = std::move(ctxs);
+  g_all.hbm_cache_bytes = hbm_cache_bytes;
+  g_all.inited = true;
+  return PB_OK;
+}
+
+static int ensure_init() {
+  if (g_all.inited) return PB_OK;
+  return init_devices(nullptr, 0, 0);
+}
+static Context* ctx_at(int index) { return (index >= 0 && index < (int)g_all.ctxs.size()) ? g_all.ctxs[index].get() : nullptr; }
+
 // staged data comes from the stream-ordered pool (release threshold = keep everything): re-staging a segment reuses
 // pool memory instead of paying cudaMalloc / cudaFree (hundreds of microseconds each)
-static cudaError_t dev_alloc(void** p, size_t bytes) {
-  cudaError_t e = cudaMallocAsync(p, bytes, g_ctx.util_stream);
+static cudaError_t dev_alloc(Context* c, void** p, size_t bytes) {
+  cudaError_t e = cudaMallocAsync(p, bytes, c->util_stream);
   if (e != cudaSuccess) return e;
-  return cudaStreamSynchronize(g_ctx.util_stream);
+  return cudaStreamSynchronize(c->util_stream);
 }
-static void dev_free(void* p) {
-  if (p && g_ctx.util_stream) cudaFreeAsync(p, g_ctx.util_stream);
+static void dev_free(Context* c, void* p) {
+  if (p && c && c->util_stream) cudaFreeAsync(p, c->util_stream);
   else if (p) cudaFree(p);
 }
 
-extern "C" int pb_init(const int* device_ids, int n_devices, size_t /*hbm_cache_bytes*/) {
-  if (n_devices > 0 && device_ids) {
-    cudaError_t e = cudaSetDevice(device_ids[0]);
-    if (e != cudaSuccess) return fail(PB_ERR_CUDA, "cudaSetDevice(%d): %s", device_ids[0], cudaGetErrorString(e));
-  }
-  return ensure_init();
+extern "C" int pb_init(const int* device_ids, int n_devices, size_t hbm_cache_bytes) {
+  return init_devices(device_ids, n_devices, hbm_cache_bytes);
 }
+static void comm_shutdown();
 extern "C" int pb_shutdown(void) {
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  for (auto& b : g_ctx.pinned_free) cudaFreeHost(b.p);
-  g_ctx.pinned_free.clear();
-  for (auto& b : g_ctx.scratch_free) cudaFree(b.p);
-  g_ctx.scratch_free.clear();
-  for (auto& ss : g_ctx.streams_free) { for (int i = 0; i < 5; i++) if (ss.ev[i]) cudaEventDestroy(ss.ev[i]); cudaStreamDestroy(ss.stream); }
-  g_ctx.streams_free.clear();
+  comm_shutdown();
+  std::lock_guard<std::mutex> lk(g_all.mu);
+  for (auto& b : g_all.pinned_free) cudaFreeHost(b.p);
+  g_all.pinned_free.clear();
+  for (auto& c : g_all.ctxs) {
+    DeviceGuard dg(c.get());
+    std::lock_guard<std::mutex> lk2(c->mu);
+    for (auto& b : c->scratch_free) cudaFree(b.p);
+    c->scratch_free.clear();
+    for (auto& ss : c->streams_free) { for (int i = 0; i < PB_N_EVENTS; i++) if (ss.ev[i]) cudaEventDestroy(ss.ev[i]); cudaStreamDestroy(ss.stream); }
+    c->streams_free.clear();
+    if (c->gather_buf) { cudaFree(c->gather_buf); c->gather_buf = nullptr; c->gather_cap = 0; }
+  }
   return PB_OK;
 }
 extern "C" int pb_device_count(void) {
@@ -127,11 +202,11 @@ static void* pinned_alloc(size_t bytes) {
   size_t cap = 256;
   while (cap < bytes) cap <<= 1;
   {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    for (size_t i = 0; i < g_ctx.pinned_free.size(); i++)
-      if (g_ctx.pinned_free[i].cap == cap) {
-        void* p = g_ctx.pinned_free[i].p;
-        g_ctx.pinned_free.erase(g_ctx.pinned_free.begin() + i);
+    std::lock_guard<std::mutex> lk(g_all.mu);
+    for (size_t i = 0; i < g_all.pinned_free.size(); i++)
+      if (g_all.pinned_free[i].cap == cap) {
+        void* p = g_all.pinned_free[i].p;
+        g_all.pinned_free.erase(g_all.pinned_free.begin() + i);
         return p;
       }
   }
@@ -143,42 +218,42 @@ static void pinned_free(void* p, size_t bytes) {
   if (!p) return;
   size_t cap = 256;
   while (cap < bytes) cap <<= 1;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (g_ctx.pinned_free.size() < 256) g_ctx.pinned_free.push_back({p, cap});
+  std::lock_guard<std::mutex> lk(g_all.mu);
+  if (g_all.pinned_free.size() < 256) g_all.pinned_free.push_back({p, cap});
   else cudaFreeHost(p);
 }
 
-static int stream_set_acquire(StreamSet* out) {
+static int stream_set_acquire(Context* c, StreamSet* out) {
   {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    if (!g_ctx.streams_free.empty()) { *out = g_ctx.streams_free.back(); g_ctx.streams_free.pop_back(); return PB_OK; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->streams_free.empty()) { *out = c->streams_free.back(); c->streams_free.pop_back(); return PB_OK; }
   }
   StreamSet s;
   CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 5; i++) CU(cudaEventCreate(&s.ev[i]));
+  for (int i = 0; i < PB_N_EVENTS; i++) CU(cudaEventCreate(&s.ev[i]));
   *out = s;
   return PB_OK;
 }
-static void stream_set_release(const StreamSet& s) {   // the stream must be idle
+static void stream_set_release(Context* c, const StreamSet& s) {   // the stream must be idle
   if (!s.stream) return;
   {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    if (g_ctx.streams_free.size() < 64) { g_ctx.streams_free.push_back(s); return; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->streams_free.size() < 64) { c->streams_free.push_back(s); return; }
   }
-  for (int i = 0; i < 5; i++) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+  for (int i = 0; i < PB_N_EVENTS; i++) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
   cudaStreamDestroy(s.stream);
 }
 
 // large device scratch (the match list): cudaMallocAsync of hundreds of MB is not free even from the pool
-static void* scratch_alloc(size_t bytes, size_t* cap_out) {
+static void* scratch_alloc(Context* c, size_t bytes, size_t* cap_out) {
   {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
+    std::lock_guard<std::mutex> lk(c->mu);
     int best = -1;
-    for (size_t i = 0; i < g_ctx.scratch_free.size(); i++)
-      if (g_ctx.scratch_free[i].cap >= bytes && (best < 0 || g_ctx.scratch_free[i].cap < g_ctx.scratch_free[best].cap)) best = (int)i;
+    for (size_t i = 0; i < c->scratch_free.size(); i++)
+      if (c->scratch_free[i].cap >= bytes && (best < 0 || c->scratch_free[i].cap < c->scratch_free[best].cap)) best = (int)i;
     if (best >= 0) {
-      PinnedBlock b = g_ctx.scratch_free[best];
-      g_ctx.scratch_free.erase(g_ctx.scratch_free.begin() + best);
+      PinnedBlock b = c->scratch_free[best];
+      c->scratch_free.erase(c->scratch_free.begin() + best);
       *cap_out = b.cap;
       return b.p;
     }
@@ -189,10 +264,10 @@ static void* scratch_alloc(size_t bytes, size_t* cap_out) {
   *cap_out = cap;
   return p;
 }
-static void scratch_free(void* p, size_t cap) {
+static void scratch_free(Context* c, void* p, size_t cap) {
   if (!p) return;
-  std::lock_guard<std::mutex> lk(g_ctx.mu);
-  if (g_ctx.scratch_free.size() < 8) g_ctx.scratch_free.push_back({p, cap});
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (c->scratch_free.size() < 8) c->scratch_free.push_back({p, cap});
   else cudaFree(p);
 }
 
@@ -226,10 +301,14 @@ struct Column {
 struct pb_segment_s {
   std::string name;
   int num_docs = 0;
-  int device = 0;
+  Context* ctx = nullptr;                   // the device this segment is staged on (device_index of pb_segment_stage)
   std::vector<Column> cols;
   std::mutex mu;
   int64_t device_bytes = 0;
+  // segment cache (hbm_cache_bytes): queries in flight pin the segment; epoch changes whenever device buffers are dropped,
+  // which invalidates cached query plans that hold pointers into them
+  int inflight = 0;
+  uint64_t last_used = 0, epoch = 0;
   // staging copies run on the context's copy stream; `staged_ev` marks the last one enqueued for this segment and
   // every query that touches the segment orders its kernels after it (until it is known to have completed)
   cudaEvent_t staged_ev = nullptr;
@@ -242,11 +321,15 @@ static int find_col(const pb_segment_s* s, const char* name) {
   return -1;
 }
 
-extern "C" int pb_segment_stage(const pb_segment_desc* d, int /*device_index*/, pb_segment_handle* out) {
+extern "C" int pb_segment_stage(const pb_segment_desc* d, int device_index, pb_segment_handle* out) {
   // registers the buffers and validates the layouts; columns are copied to HBM on first use by a query
   // so planning-only callers never touch the device
   if (!d || !out || d->num_columns < 0 || d->num_docs < 0) return fail(PB_ERR_INVALID, "bad segment descriptor");
+  { int rc0 = ensure_init(); if (rc0) return rc0; }
+  Context* ctx = ctx_at(device_index);
+  if (!ctx) return fail(PB_ERR_INVALID, "pb_segment_stage: device_index %d is not one of the %zu devices given to pb_init", device_index, g_all.ctxs.size());
   std::unique_ptr<pb_segment_s> s(new pb_segment_s());
+  s->ctx = ctx;
   s->name = d->segment_name ? d->segment_name : "";
   s->num_docs = d->num_docs;
   s->cols.resize(d->num_columns);
@@ -284,6 +367,7 @@ extern "C" int pb_segment_stage(const pb_segment_desc* d, int /*device_index*/, 
       if (c.h_fwd_len < c.raw_data_start + (uint64_t)s->num_docs * c.raw_width) return fail(PB_ERR_INVALID, "column %s: raw forward index too short", cd.name);
     }
   }
+  { std::lock_guard<std::mutex> lk(ctx->mu); ctx->segments.push_back(s.get()); }
   *out = s.release();
   return PB_OK;
 }
@@ -318,11 +402,11 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
   if (need_fwd && !c.fwd_staged) {
     if (c.has_dict && c.is_sorted) {
       // pairs -> device, then materialise the bit-packed stream on the device
-      CU(dev_alloc((void**)&c.d_sorted_pairs, sizeof(int32_t) * 2 * (size_t)c.card));
+      CU(dev_alloc(s->ctx, (void**)&c.d_sorted_pairs, sizeof(int32_t) * 2 * (size_t)c.card));
       CU(cudaMemcpyAsync(c.d_sorted_pairs, c.h_sorted_pairs.data(), sizeof(int32_t) * 2 * (size_t)c.card, cudaMemcpyHostToDevice, st));
       uint64_t bytes = ((uint64_t)s->num_docs * c.bits + 7) / 8;
       uint64_t padded = ((bytes + 15) & ~15ull) + 32;
-      CU(dev_alloc((void**)&c.d_fwd, padded));
+      CU(dev_alloc(s->ctx, (void**)&c.d_fwd, padded));
       CU(cudaMemsetAsync(c.d_fwd, 0, padded, st));
       uint64_t n_words = (bytes + 3) / 4;
       int grid = (int)std::min<uint64_t>((n_words + 255) / 256, 4096);
@@ -335,7 +419,7 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
       const uint8_t* src = c.has_dict ? c.h_fwd : c.h_fwd + c.raw_data_start;
       uint64_t bytes = c.has_dict ? ((uint64_t)s->num_docs * c.bits + 7) / 8 : (uint64_t)s->num_docs * c.raw_width;
       uint64_t padded = ((bytes + 15) & ~15ull) + 32;
-      CU(dev_alloc((void**)&c.d_fwd, padded));
+      CU(dev_alloc(s->ctx, (void**)&c.d_fwd, padded));
       CU(cudaMemsetAsync(c.d_fwd + (bytes & ~15ull), 0, padded - (bytes & ~15ull), st));
       CU(cudaMemcpyAsync(c.d_fwd, src, bytes, cudaMemcpyHostToDevice, st));
       c.d_fwd_bytes = padded;
@@ -359,7 +443,7 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
         default: { uint64_t u = be64(p); double dd; memcpy(&dd, &u, 8); v[i] = dd; break; }
       }
     }
-    CU(dev_alloc((void**)&c.d_dict_f64, sizeof(double) * (size_t)c.card));
+    CU(dev_alloc(s->ctx, (void**)&c.d_dict_f64, sizeof(double) * (size_t)c.card));
     CU(cudaMemcpyAsync(c.d_dict_f64, v, sizeof(double) * (size_t)c.card, cudaMemcpyHostToDevice, st));
     s->stage_dirty = true;
     s->device_bytes += (int64_t)sizeof(double) * c.card;
@@ -368,14 +452,14 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
   if (need_native && !c.native_staged && c.has_dict) {
     std::vector<uint8_t> v((size_t)c.card * c.entry_bytes);
     for (int i = 0; i < c.card; i++) native_entry(c, i, v.data() + (size_t)i * c.entry_bytes);
-    CU(dev_alloc((void**)&c.d_dict_native, v.size() + 16));
+    CU(dev_alloc(s->ctx, (void**)&c.d_dict_native, v.size() + 16));
     CU(cudaMemcpy(c.d_dict_native, v.data(), v.size(), cudaMemcpyHostToDevice));
     s->device_bytes += (int64_t)v.size();
     c.native_staged = true;
   }
   if (need_inv && !c.inv_staged) {
     if (!c.h_inv) return fail(PB_ERR_INVALID, "column %s has no inverted index", c.name.c_str());
-    CU(dev_alloc((void**)&c.d_inv, c.h_inv_len + 16));
+    CU(dev_alloc(s->ctx, (void**)&c.d_inv, c.h_inv_len + 16));
     CU(cudaMemcpyAsync(c.d_inv, c.h_inv, c.h_inv_len, cudaMemcpyHostToDevice, st));
     s->device_bytes += (int64_t)c.h_inv_len;
     c.inv_staged = true;
@@ -386,10 +470,17 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
 
 extern "C" int pb_segment_release(pb_segment_handle s) {
   if (!s) return PB_OK;
+  DeviceGuard dg(s->ctx);
+  {
+    std::lock_guard<std::mutex> lk(s->ctx->mu);
+    auto& v = s->ctx->segments;
+    v.erase(std::remove(v.begin(), v.end(), s), v.end());
+    s->ctx->staged_bytes -= s->device_bytes;
+  }
   if (s->staged_ev) { cudaEventSynchronize(s->staged_ev); cudaEventDestroy(s->staged_ev); }
   for (auto& b : s->staging_bufs) pinned_free(b.p, b.cap);
   for (auto& c : s->cols) {
-    dev_free(c.d_fwd); dev_free(c.d_sorted_pairs); dev_free(c.d_dict_f64); dev_free(c.d_dict_native); dev_free(c.d_inv);
+    dev_free(s->ctx, c.d_fwd); dev_free(s->ctx, c.d_sorted_pairs); dev_free(s->ctx, c.d_dict_f64); dev_free(s->ctx, c.d_dict_native); dev_free(s->ctx, c.d_inv);
   }
   delete s;
   return PB_OK;
@@ -410,10 +501,20 @@ struct GlobalDict {
   bool uploaded = false;                       // remaps + values are on the device                       // installed by pb_segment_group_set_global_dictionary
 };
 
+struct QueryPlan;
 struct pb_group_s {
   std::vector<pb_segment_s*> segs;
   std::map<std::string, GlobalDict> dicts;
   std::mutex mu;
+  Context* ctx = nullptr;                      // device of the segments; nullptr when they span several devices
+  // segments on several devices of this process (one JVM driving N GPUs): one child group per device, in order of first
+  // appearance; child_of[i] / index_in_child[i] locate segment i.  Children run the per-device part of a query and the
+  // parent merges their tables over NVLink (pb_query_execute).
+  std::vector<pb_group_s*> children;
+  std::vector<int> child_of, index_in_child;
+  std::map<std::string, uint64_t> child_dict_version;   // global dictionaries already installed in the children
+  uint64_t dict_version = 0;                   // bumps whenever a global dictionary changes (cached plans depend on it)
+  std::vector<QueryPlan*> plans;               // cached query plans (CUDA graphs) of this group
 };
 
 // dictionary entry -> native-endian comparable form
@@ -434,14 +535,38 @@ static int cmp_entry(int type, int eb, const uint8_t* a, const uint8_t* b) {
 
 extern "C" int pb_segment_group_create(const pb_segment_handle* segs, int n, pb_segment_group_handle* out) {
   if (!segs || n <= 0 || !out) return fail(PB_ERR_INVALID, "bad segment group");
+  for (int i = 0; i < n; i++) if (!segs[i]) return fail(PB_ERR_INVALID, "segment %d of the group is null", i);
   pb_group_s* g = new pb_group_s();
   g->segs.assign(segs, segs + n);
+  g->ctx = segs[0]->ctx;
+  for (int i = 1; i < n; i++) if (segs[i]->ctx != g->ctx) g->ctx = nullptr;
+  if (!g->ctx) {
+    std::vector<Context*> order;
+    std::vector<std::vector<pb_segment_s*>> parts;
+    g->child_of.resize(n); g->index_in_child.resize(n);
+    for (int i = 0; i < n; i++) {
+      size_t k = 0;
+      while (k < order.size() && order[k] != segs[i]->ctx) k++;
+      if (k == order.size()) { order.push_back(segs[i]->ctx); parts.emplace_back(); }
+      g->child_of[i] = (int)k; g->index_in_child[i] = (int)parts[k].size();
+      parts[k].push_back(segs[i]);
+    }
+    for (size_t k = 0; k < order.size(); k++) {
+      pb_group_s* c = new pb_group_s();
+      c->segs = parts[k]; c->ctx = order[k];
+      g->children.push_back(c);
+    }
+  }
   *out = g;
   return PB_OK;
 }
+static void free_plans(pb_group_s* g) { (void)g; }   // (plan cache: see below)
 extern "C" int pb_segment_group_release(pb_segment_group_handle g) {
   if (!g) return PB_OK;
-  for (auto& kv : g->dicts) { for (auto p : kv.second.d_remap) dev_free(p); dev_free(kv.second.d_values); }
+  for (auto* c : g->children) pb_segment_group_release(c);
+  DeviceGuard dg(g->ctx);
+  free_plans(g);
+  for (auto& kv : g->dicts) { for (auto p : kv.second.d_remap) dev_free(g->ctx, p); dev_free(g->ctx, kv.second.d_values); }
   delete g;
   return PB_OK;
 }
@@ -482,14 +607,15 @@ static int build_union(pb_group_s* g, const char* column, GlobalDict& gd) {
 
 static int upload_remaps(pb_group_s* g, GlobalDict& gd) {
   if (gd.uploaded) return PB_OK;
-  for (auto p : gd.d_remap) dev_free(p);
-  dev_free(gd.d_values); gd.d_values = nullptr;
-  CU(dev_alloc((void**)&gd.d_values, gd.values.size() + 16));
+  if (!g->ctx) return fail(PB_ERR_STATE, "global dictionaries are uploaded per device group");
+  for (auto p : gd.d_remap) dev_free(g->ctx, p);
+  dev_free(g->ctx, gd.d_values); gd.d_values = nullptr;
+  CU(dev_alloc(g->ctx, (void**)&gd.d_values, gd.values.size() + 16));
   CU(cudaMemcpy(gd.d_values, gd.values.data(), gd.values.size(), cudaMemcpyHostToDevice));
   gd.d_remap.assign(g->segs.size(), nullptr);
   for (size_t si = 0; si < g->segs.size(); si++) {
     const auto& rm = gd.h_remap[si];
-    CU(dev_alloc((void**)&gd.d_remap[si], sizeof(int32_t) * std::max<size_t>(rm.size(), 1)));
+    CU(dev_alloc(g->ctx, (void**)&gd.d_remap[si], sizeof(int32_t) * std::max<size_t>(rm.size(), 1)));
     CU(cudaMemcpy(gd.d_remap[si], rm.data(), sizeof(int32_t) * rm.size(), cudaMemcpyHostToDevice));
   }
   gd.uploaded = true;
@@ -572,9 +698,17 @@ extern "C" int pb_segment_group_set_global_dictionary(pb_segment_group_handle g,
                                                       int64_t num_values, int32_t entry_bytes) {
   if (!g || !column || !values || num_values <= 0) return fail(PB_ERR_INVALID, "bad arguments");
   std::lock_guard<std::mutex> lk(g->mu);
-  GlobalDict& gd = g->dicts[column];
   int ci = find_col(g->segs[0], column);
   if (ci < 0) return fail(PB_ERR_INVALID, "no column %s", column);
+  for (auto* sg : g->segs) {
+    int cj = find_col(sg, column);
+    if (cj < 0) return fail(PB_ERR_INVALID, "segment %s has no column %s", sg->name.c_str(), column);
+    // build_remaps writes each segment entry into an entry_bytes-sized buffer: a narrower global entry would overflow it
+    if (!sg->cols[cj].has_dict) return fail(PB_ERR_UNSUPPORTED, "column %s has no dictionary", column);
+    if (entry_bytes < sg->cols[cj].entry_bytes) return fail(PB_ERR_INVALID, "global dictionary of %s: entry_bytes %d < %d of segment %s", column, entry_bytes, sg->cols[cj].entry_bytes, sg->name.c_str());
+  }
+  GlobalDict& gd = g->dicts[column];
+  g->dict_version++;
   gd.type = g->segs[0]->cols[ci].type;
   gd.entry_bytes = entry_bytes; gd.n = num_values; gd.external = true;
   gd.values.assign((const uint8_t*)values, (const uint8_t*)values + (size_t)num_values * entry_bytes);
@@ -615,7 +749,6 @@ struct pb_result_s {
   unsigned long long* d_seg_stats = nullptr;   // filtered aggregations: [n_segs][1 + PB_MAX_AGG_FILTERS] docs per swim-lane
   int n_agg_filters = 0;
   std::vector<int> agg_filter_of;
-  std::vector<std::vector<int>> seg_clause_kind;   // per segment, per FILTER clause: 0 = general, 1 = matches all, 2 = empty; [nF] = the main filter
   int waves = 1;                            // launches were split into this many waves behind the staging copies
   int in_place_columns = 0;                 // (segment, column) pairs gathered from mapped host memory (PB_Q_GATHER_IN_PLACE)
   std::vector<int> agg_op;
@@ -642,19 +775,40 @@ struct pb_result_s {
   // the whole reducible state of table 0 as one block: [0, sum_off) counters + row counts (u64 SUM), [sum_off, dc_off) sums
   // (f64 SUM), [dc_off, mm_off) distinct bitsets (OR), [mm_off, bytes) min/max (i64 MIN)
   uint8_t* block = nullptr; int64_t block_bytes = 0, block_sum_off = 0, block_dc_off = 0, block_mm_off = 0;
+  unsigned long long fingerprint = 0;       // of the block layout (counter cell [9])
+  int merged_ranks = 1;                     // blocks summed into this one (cross-GPU merges)
+  int pinned_segments = 0;                  // the first k segments of the group are pinned by this call
+  bool comm_timed = false;                  // events [5],[6] bracket the cross-rank merge
+  double comm_ms = 0;
+  Context* ctx = nullptr;
+  std::vector<pb_result_s*> parts;          // multi-device group: the per-device results merged into this one (freed with it)
+  std::vector<std::pair<int, int>> table_map;   // shell result of a multi-device per-segment query: table -> (part, table of the part)
 };
 
+// queries in flight pin their segments against eviction from the HBM segment cache
+static void release_segments(pb_result_s* r) {
+  if (!r->pinned_segments || !r->group) return;
+  for (int i = 0; i < r->pinned_segments && i < (int)r->group->segs.size(); i++) {
+    pb_segment_s* s = r->group->segs[(size_t)i];
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->inflight > 0) s->inflight--;
+  }
+  r->pinned_segments = 0;
+}
 static void free_result(pb_result_s* r) {
   if (!r) return;
+  for (auto* p : r->parts) free_result(p);
+  DeviceGuard dg(r->ctx);
   if (r->stream) cudaStreamSynchronize(r->stream);
-  scratch_free(r->scratch, r->scratch_cap);
+  release_segments(r);
+  if (r->ctx) scratch_free(r->ctx, r->scratch, r->scratch_cap);
   for (void* p : r->dev_allocs) cudaFreeAsync(p, r->stream);
   for (auto& t : r->tables) {
     t.slots.release(); t.rows.release();
     for (auto* v : {&t.dbl, &t.lng, &t.key_ids, &t.key_vals, &t.dc_off, &t.dc_ids}) for (auto& a : *v) a.release();
   }
   r->h_counters.release();
-  if (r->stream) { cudaStreamSynchronize(r->stream); stream_set_release(r->sset); }
+  if (r->stream) { cudaStreamSynchronize(r->stream); stream_set_release(r->ctx, r->sset); }
   delete r;
 }
 extern "C" void pb_result_free(pb_result_handle r) { free_result(r); }
@@ -664,7 +818,13 @@ extern "C" void pb_result_free(pb_result_handle r) { free_result(r); }
 // ------------------------------------------------------------------------------------------------
 #define PB_DENSE_MAX (1ull << 24)
 #define PB_MAX_WAVES 8            // cold segments: launches are split into waves that follow the staging copies
-#define PB_COUNTERS_PER_TABLE 4   // u64 cells: [0] num_groups(lo u32) [1] limit flag (lo u32) [2] docs matched [3] compaction cursor
+// u64 cells per table at the head of the table block (summed by cross-GPU merges like the row counts):
+//   [0] num_groups (lo u32)  [1] limit flag (lo u32)  [2] docs matched  [3] compaction cursor (0 until finalize)
+//   [4] swim-lane docs  [5] swim-lane entries scanned post filter (filtered aggregations, pb_lane_stats_kernel)
+//   [6] total docs  [7] entries scanned in filter  [8] segments        (host-known; injected by pb_init_tables_kernel)
+//   [9] layout fingerprint of the block: after a merge over n ranks it must read n x the local value, else the ranks
+//       did not run the same query over the same global dictionaries
+#define PB_COUNTERS_PER_TABLE 10
 
 struct Arena {   // host mirror of a device allocation; pointers are handed out as device addresses
   std::vector<uint8_t> host;
@@ -763,10 +923,165 @@ static double estimate_selectivity(const pb_segment_s* s, const pb_segment_query
 static int finalize_result(pb_result_s* r);
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_query* sqs, const pb_query_desc* q, pb_result_handle* out) {
+
+// ------------------------------------------------------------------------------------------------
+// cross-rank communicator (one process per GPU): NCCL, loaded at run time so that a single-GPU server needs no NCCL at all.
+// The merge of the per-rank group tables is the device-side equivalent of GroupByCombineOperator's IndexedTable merge
+// (CTR/operator/combine/GroupByCombineOperator.java:132-147) across the servers' GPUs.
+// ------------------------------------------------------------------------------------------------
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+};
+struct Comm {
+  std::mutex mu;
+  NcclApi api;
+  ncclComm_t comm = nullptr;
+  int n_ranks = 1, rank = 0;
+  Context* ctx = nullptr;
+  int64_t checked_block_bytes = -1;      // block size the ranks last agreed on (sizes must match before an all-gather)
+};
+static Comm g_comm;
+
+static int nccl_load() {
+  NcclApi& a = g_comm.api;
+  if (a.handle) return PB_OK;
+  // (1) PB_NCCL_LIB, (2) a libnccl already mapped into the process (e.g. by torch: two NCCL copies in one process work but
+  // waste memory), (3) the system library
+  const char* env = getenv("PB_NCCL_LIB");
+  void* h = env ? dlopen(env, RTLD_NOW | RTLD_LOCAL) : nullptr;
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!h) return fail(PB_ERR_STATE, "NCCL not found (%s); set PB_NCCL_LIB", dlerror());
+#define PB_NCCL_SYM(field, name)                                                                   \
+  *(void**)(&a.field) = dlsym(h, name);                                                            \
+  if (!a.field) { dlclose(h); return fail(PB_ERR_STATE, "NCCL symbol %s missing", name); }
+  PB_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") PB_NCCL_SYM(CommInitRank, "ncclCommInitRank") PB_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  PB_NCCL_SYM(AllGather, "ncclAllGather") PB_NCCL_SYM(Send, "ncclSend") PB_NCCL_SYM(Recv, "ncclRecv")
+  PB_NCCL_SYM(GroupStart, "ncclGroupStart") PB_NCCL_SYM(GroupEnd, "ncclGroupEnd") PB_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+  PB_NCCL_SYM(GetVersion, "ncclGetVersion")
+#undef PB_NCCL_SYM
+  a.handle = h;
+  return PB_OK;
+}
+#define NC(call)                                                                                     \
+  do {                                                                                               \
+    ncclResult_t e__ = (call);                                                                       \
+    if (e__ != ncclSuccess) return fail(PB_ERR_CUDA, "%s failed: %s", #call, g_comm.api.GetErrorString(e__)); \
+  } while (0)
+
+extern "C" int pb_comm_unique_id(void* out, size_t cap) {
+  if (!out || cap < sizeof(ncclUniqueId)) return fail(PB_ERR_INVALID, "pb_comm_unique_id: need %zu bytes", sizeof(ncclUniqueId));
+  std::lock_guard<std::mutex> lk(g_comm.mu);
+  int rc = nccl_load();
+  if (rc) return rc;
+  ncclUniqueId id;
+  NC(g_comm.api.GetUniqueId(&id));
+  memcpy(out, &id, sizeof id);
+  return PB_OK;
+}
+extern "C" int pb_comm_init(int n_ranks, int rank, const void* unique_id, size_t id_bytes) {
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(PB_ERR_INVALID, "pb_comm_init: rank %d of %d", rank, n_ranks);
+  if (!unique_id || id_bytes < sizeof(ncclUniqueId)) return fail(PB_ERR_INVALID, "pb_comm_init: unique id of %zu bytes expected", sizeof(ncclUniqueId));
   int rc = ensure_init();
   if (rc) return rc;
-  if (!g || !q || !out) return fail(PB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(g_comm.mu);
+  if (g_comm.comm) return fail(PB_ERR_STATE, "pb_comm_init: communicator already initialised (rank %d of %d)", g_comm.rank, g_comm.n_ranks);
+  if (g_all.ctxs.size() != 1) return fail(PB_ERR_UNSUPPORTED, "pb_comm_init: one device per process (this process drives %zu)", g_all.ctxs.size());
+  if ((rc = nccl_load())) return rc;
+  Context* ctx = g_all.ctxs[0].get();
+  DeviceGuard dg(ctx);
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof id);
+  NC(g_comm.api.CommInitRank(&g_comm.comm, n_ranks, id, rank));
+  g_comm.n_ranks = n_ranks; g_comm.rank = rank; g_comm.ctx = ctx; g_comm.checked_block_bytes = -1;
+  return PB_OK;
+}
+extern "C" int pb_comm_info(int* n_ranks, int* rank) {
+  std::lock_guard<std::mutex> lk(g_comm.mu);
+  if (n_ranks) *n_ranks = g_comm.comm ? g_comm.n_ranks : 1;
+  if (rank) *rank = g_comm.comm ? g_comm.rank : 0;
+  return g_comm.comm ? 1 : 0;
+}
+static void comm_shutdown() {
+  std::lock_guard<std::mutex> lk(g_comm.mu);
+  if (g_comm.comm) {
+    DeviceGuard dg(g_comm.ctx);
+    cudaDeviceSynchronize();
+    g_comm.api.CommDestroy(g_comm.comm);
+    g_comm.comm = nullptr; g_comm.n_ranks = 1; g_comm.rank = 0;
+  }
+}
+extern "C" int pb_comm_destroy(void) { comm_shutdown(); return PB_OK; }
+
+static int ensure_gather_buf(Context* ctx, size_t bytes, cudaStream_t st) {
+  if (ctx->gather_cap >= bytes) return PB_OK;
+  // the old buffer may still be read by a merge kernel in flight on another stream: let the device drain first (rare: growth only)
+  if (ctx->gather_buf) { CU(cudaDeviceSynchronize()); CU(cudaFree(ctx->gather_buf)); ctx->gather_buf = nullptr; ctx->gather_cap = 0; }
+  size_t cap = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+  CU(cudaMalloc(&ctx->gather_buf, cap));
+  ctx->gather_cap = cap;
+  (void)st;
+  return PB_OK;
+}
+
+static int launch_merge(pb_result_s* r, const void* gathered, int n_rows, bool base_is_dst);
+static int launch_merge_rows(pb_result_s* r, const void* gathered, const DevMergePeers* peers, int n_rows, bool base_is_dst);
+static int comm_merge_hash(pb_result_s* r);
+
+// All ranks call with the same query (PB_Q_ALL_RANKS): all-gather of the table blocks + one merge kernel, on the call's own
+// stream.  Every rank ends up with the merged table.
+static int comm_merge(pb_result_s* r) {
+  std::lock_guard<std::mutex> lk(g_comm.mu);       // collectives of one communicator must be issued in the same order on every rank
+  if (!g_comm.comm) return fail(PB_ERR_STATE, "PB_Q_ALL_RANKS without pb_comm_init");
+  if (g_comm.n_ranks == 1) return PB_OK;
+  if (!r->combine || r->tables.size() != 1) return fail(PB_ERR_UNSUPPORTED, "PB_Q_ALL_RANKS needs PB_Q_COMBINE (one table per rank)");
+  if (r->ctx != g_comm.ctx) return fail(PB_ERR_STATE, "PB_Q_ALL_RANKS: the result is not on the communicator's device");
+  if (r->table_mode == T_HASH) return comm_merge_hash(r);
+  const int n = g_comm.n_ranks;
+  cudaStream_t st = r->stream;
+  if (g_comm.checked_block_bytes != r->block_bytes) {
+    // first query of this shape: the ranks compare their block sizes before anything is shipped (a size mismatch inside
+    // ncclAllGather would corrupt memory or hang); same-size layouts are told apart later by the fingerprint cell
+    int rc = ensure_gather_buf(r->ctx, 8 * (size_t)n + 8, st);
+    if (rc) return rc;
+    long long mine = r->block_bytes;
+    long long* d = reinterpret_cast<long long*>(r->ctx->gather_buf);
+    CU(cudaMemcpyAsync(d + n, &mine, 8, cudaMemcpyHostToDevice, st));
+    NC(g_comm.api.AllGather(d + n, d, 8, ncclChar, g_comm.comm, st));
+    std::vector<long long> all((size_t)n);
+    CU(cudaMemcpyAsync(all.data(), d, 8 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int k = 0; k < n; k++)
+      if (all[k] != mine) return fail(PB_ERR_STATE, "PB_Q_ALL_RANKS: rank %d's table block is %lld bytes, rank %d's %lld (different query or global dictionaries)", k, all[k], g_comm.rank, mine);
+    g_comm.checked_block_bytes = r->block_bytes;
+  }
+  int rc = ensure_gather_buf(r->ctx, (size_t)n * (size_t)r->block_bytes, st);
+  if (rc) return rc;
+  CU(cudaEventRecord(r->sset.ev[5], st));
+  NC(g_comm.api.AllGather(r->block, r->ctx->gather_buf, (size_t)r->block_bytes, ncclChar, g_comm.comm, st));
+  if ((rc = launch_merge(r, r->ctx->gather_buf, n, false))) return rc;
+  CU(cudaEventRecord(r->sset.ev[6], st));
+  r->comm_timed = true;
+  r->merged_ranks *= n;
+  return PB_OK;
+}
+
+// One device's part of a query: every segment of `g` lives on g->ctx.  Leaves the tables on the device when
+// PB_Q_DEFER_FINALIZE is set; otherwise merges across ranks (PB_Q_ALL_RANKS) and finalizes.
+static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, const pb_query_desc* q, pb_result_handle* out) {
+  int rc = PB_OK;
+  Context* ctx = g->ctx;
   const int n_segs = (int)g->segs.size();
   const int nG = q->num_group_by, nA = q->num_aggregations;
   if (nG < 0 || nG > PB_MAX_GROUP_BY) return fail(PB_ERR_UNSUPPORTED, "%d group-by columns (max %d)", nG, PB_MAX_GROUP_BY);
@@ -784,8 +1099,8 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
 
   std::unique_ptr<pb_result_s, void (*)(pb_result_s*)> R(new pb_result_s(), free_result);
   pb_result_s* r = R.get();
-  r->group = g; r->n_gb = nG; r->n_aggs = nA; r->combine = combine;
-  if ((rc = stream_set_acquire(&r->sset))) return rc;
+  r->group = g; r->n_gb = nG; r->n_aggs = nA; r->combine = combine; r->ctx = ctx;
+  if ((rc = stream_set_acquire(ctx, &r->sset))) return rc;
   r->stream = r->sset.stream;
   cudaStream_t st = r->stream;
   r->ev0 = r->sset.ev[0]; r->ev1 = r->sset.ev[1]; r->evm = r->sset.ev[2]; r->ev2 = r->sset.ev[3]; r->ev3 = r->sset.ev[4];
@@ -802,7 +1117,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   // ---- resolve columns, stage what is needed ----
   std::vector<std::vector<int>> gcol(n_segs, std::vector<int>(nG)), acol(n_segs, std::vector<int>(nA, -1));
   bool any_raw_key = false;
-  cudaStream_t cs = g_ctx.copy_stream;
+  cudaStream_t cs = ctx->copy_stream;
   std::vector<cudaEvent_t> seg_wait(n_segs, nullptr);   // staging events this call's kernels must wait for
   int n_pending = 0;
   std::vector<std::vector<char>> cand_leaf(n_segs);     // per filter node: scan leaf evaluated on candidates (DevLeaf::gather)
@@ -811,6 +1126,8 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   for (int si = 0; si < n_segs; si++) {
     pb_segment_s* s = g->segs[si];
     std::lock_guard<std::mutex> lk(s->mu);
+    s->inflight++; r->pinned_segments = si + 1;
+    { std::lock_guard<std::mutex> lk2(ctx->mu); s->last_used = ++ctx->lru_clock; }
     // PB_Q_GATHER_IN_PLACE, per column: a gathered value costs one 32-byte PCIe read = 32 B payload + ~24 B of TLP
     // overhead of link time (measured on B200 / PCIe Gen5: the cold query is link-bound and each in-place value costs
     // ~56 streamed bytes); copying the column costs bits/8 bytes per doc.  Gather in place only where that is cheaper:
@@ -982,34 +1299,28 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     if (table_mode == T_HASH) ff_bytes += 8 * S * (size_t)key_words;
   }
   const size_t seg_stats_bytes = nF > 0 ? 8 * (size_t)(1 + PB_MAX_AGG_FILTERS) * (size_t)n_segs : 0;   // swim-lane statistics per segment
-  zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 * PB_MAX_WAVES + seg_stats_bytes + 256;
+  zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 256;
   if (zero_bytes > (64ull << 30)) return fail(PB_ERR_UNSUPPORTED, "group table needs %zu bytes: decline to the CPU plan", zero_bytes);
   uint8_t *d_zero = nullptr, *d_ff = nullptr; long long* d_mm = nullptr;
   unsigned long long* d_seg_stats = nullptr;
-  // one block: [zero region | min/max region] so that a cross-GPU merge can ship the whole table in one collective
+  // one block: [zero region | min/max region] so that a cross-GPU merge can ship the whole table in one collective.  Its size
+  // and layout depend on the query and the (global) dictionaries only -- never on how many segments this rank holds: the
+  // per-wave match counters and per-segment swim-lane statistics live in an aux region behind it that is not shipped.
   zero_bytes = (zero_bytes + 255) & ~(size_t)255;
-  CU(cudaMallocAsync((void**)&d_zero, zero_bytes + 8 * mm_elems + 16, st)); r->dev_allocs.push_back(d_zero);
+  const size_t mm_bytes = (8 * mm_elems + 255) & ~(size_t)255;
+  const size_t aux_bytes = (8 * PB_MAX_WAVES + seg_stats_bytes + 255) & ~(size_t)255;
+  CU(cudaMallocAsync((void**)&d_zero, zero_bytes + mm_bytes + aux_bytes + 16, st)); r->dev_allocs.push_back(d_zero);
   if (ff_bytes) { CU(cudaMallocAsync((void**)&d_ff, ff_bytes + 16, st)); r->dev_allocs.push_back(d_ff); }
   if (mm_elems) d_mm = reinterpret_cast<long long*>(d_zero + zero_bytes);
+  uint8_t* d_aux = d_zero + zero_bytes + mm_bytes;
   r->block = d_zero; r->block_bytes = (int64_t)(zero_bytes + 8 * mm_elems);
   r->block_mm_off = (int64_t)zero_bytes;
 
-  CU(cudaEventRecord(r->ev0, st));
-  {
-    // all three regions are 16-byte multiples (cudaMallocAsync alignment is 256)
-    const uint64_t zn = (zero_bytes + 15) / 16, fn = (ff_bytes + 15) / 16, mn = (8 * mm_elems + 15) / 16;
-    const uint64_t mx = std::max(zn, std::max(fn, mn));
-    int grid = (int)std::min<uint64_t>((mx + 255) / 256, (uint64_t)g_ctx.num_sms * 8);
-    if (grid < 1) grid = 1;
-    pb_init_tables_kernel<<<grid, 256, 0, st>>>((uint4*)d_zero, zn, (uint4*)d_ff, fn, (uint4*)d_mm, mn);
-    r->launches++;
-    CU(cudaGetLastError());
-  }
   {
     size_t zo = 0, fo = 0, mo = 0;
     r->d_counters = reinterpret_cast<unsigned long long*>(d_zero);
-    zo += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 8 * PB_MAX_WAVES;
-    if (seg_stats_bytes) { d_seg_stats = reinterpret_cast<unsigned long long*>(d_zero + zo); zo += seg_stats_bytes; }
+    zo += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables;
+    if (seg_stats_bytes) d_seg_stats = reinterpret_cast<unsigned long long*>(d_aux + 8 * PB_MAX_WAVES);
     r->d_seg_stats = d_seg_stats;
     zo = (zo + 255) & ~(size_t)255;
     for (int t = 0; t < n_tables; t++) {
@@ -1047,13 +1358,19 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
       dt.limit_reached = reinterpret_cast<unsigned int*>(cnt + 1);
       dt.docs_matched = cnt + 2;
       dt.num_groups_limit = (uint32_t)std::max(1, q->num_groups_limit);
+      {
+        uint64_t docs = 0;
+        for (int si : tm.seg_idx) docs += (uint64_t)g->segs[si]->num_docs;
+        dt.limit_active = (uint64_t)dt.num_groups_limit < docs ? 1u : 0u;    // groups <= docs: an unreachable limit needs no tickets
+      }
     }
     CU(cudaGetLastError());
   }
 
   lap(1);
   // ---- query arena (descriptors + leaf payloads) ----
-  size_t arena_cap = (sizeof(DevQuery) + 16) * (1 + PB_MAX_WAVES) + 256 + (sizeof(DevSegQuery) + 64) * (size_t)n_segs + (sizeof(DevTable) + 64) * (size_t)n_tables;
+  size_t arena_cap = (sizeof(DevQuery) + 16) * (1 + PB_MAX_WAVES) + 256 + (sizeof(DevSegQuery) + 64) * (size_t)n_segs + (sizeof(DevTable) + 64) * (size_t)n_tables
+                     + 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 64 + (nF > 0 ? (sizeof(DevLaneWeights) + 16) * (size_t)n_segs : 0);
   size_t bitmap_words_total = 0;
   for (int si = 0; si < n_segs; si++) {
     const pb_segment_query& sq = sqs[si];
@@ -1148,6 +1465,8 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
           const Column& c = s->cols[fn.column];
           int64_t lo = std::max<int64_t>(fn.lo, 0), hi = std::min<int64_t>(fn.hi, c.card);
           if (hi <= lo) { lf.kind = L_FALSE; break; }
+          // the whole dictionary: no scan (and span == 2^bits would overflow the top-aligned compare of PredRange::test<W>)
+          if (lo == 0 && hi >= c.card) { lf.kind = L_TRUE; break; }
           lf.kind = L_DICT_RANGE; lf.bits = c.bits; lf.lo = (uint32_t)lo; lf.span = (uint32_t)(hi - lo);
           lf.est_permille = (int32_t)(1000.0 * (double)(hi - lo) / (double)c.card);
           if ((lf.slot = scan_slot(c)) < 0) return fail(PB_ERR_UNSUPPORTED, "more than %d scanned columns", PB_MAX_SCAN_SLOTS);
@@ -1319,19 +1638,71 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   if (n_docs_total >= (1ull << 32)) return fail(PB_ERR_UNSUPPORTED, "%llu docs in one call (match list is 32-bit): split the segment group", (unsigned long long)n_docs_total);
   uint32_t* d_match_list = nullptr;
   if (!match_all && n_docs_total > 0) {
-    r->scratch = scratch_alloc(4 * (size_t)n_docs_total + 256, &r->scratch_cap);
+    r->scratch = scratch_alloc(ctx, 4 * (size_t)n_docs_total + 256, &r->scratch_cap);
     if (!r->scratch) return fail(PB_ERR_OOM, "match list allocation (%zu bytes) failed", 4 * (size_t)n_docs_total + 256);
     d_match_list = (uint32_t*)r->scratch;
   }
   r->match_all = match_all;
   r->n_agg_filters = nF;
+  // ---- counter cells that the host knows up front (ExecutionStatistics; see PB_COUNTERS_PER_TABLE) ----
+  unsigned long long* h_head = nullptr;
+  const unsigned long long* d_head = ar.put<unsigned long long>(nullptr, (size_t)PB_COUNTERS_PER_TABLE * n_tables, &h_head);
+  if (!d_head) return fail(PB_ERR_STATE, "query arena overflow");
+  for (int si = 0; si < n_segs; si++) {
+    unsigned long long* c = h_head + (size_t)hsegs[si].table * PB_COUNTERS_PER_TABLE;
+    const unsigned long long nd = (unsigned long long)g->segs[si]->num_docs;
+    if (match_all) c[2] += nd;                                   // numDocsScanned of a match-all query (no filter kernel)
+    c[6] += nd;                                                  // numTotalDocs
+    c[7] += (unsigned long long)r->seg_scan_leaves[si] * nd;     // every scan leaf reads every doc of the segment on the device
+    c[8] += 1;
+  }
+  {
+    // what must agree across ranks for the blocks to be mergeable element by element
+    unsigned long long fp = 0xcbf29ce484222325ull;
+    auto mix = [&](unsigned long long v) { fp ^= v; fp *= 0x100000001b3ull; fp ^= fp >> 29; };
+    mix((unsigned long long)r->block_bytes); mix((unsigned long long)r->block_sum_off); mix((unsigned long long)r->block_dc_off); mix((unsigned long long)r->block_mm_off);
+    mix((unsigned long long)table_mode); mix((unsigned long long)nG); mix((unsigned long long)nA); mix((unsigned long long)nF);
+    for (int a = 0; a < nA; a++) mix((unsigned long long)q->aggregations[a].op * 131 + dc_words[a]);
+    for (auto& tm : r->tables) { mix(tm.capacity); for (auto cd : tm.cards) mix((unsigned long long)cd); }
+    r->fingerprint = fp >> 8;                               // head room: n_ranks x fp must not wrap
+    for (int t = 0; t < n_tables; t++) h_head[(size_t)t * PB_COUNTERS_PER_TABLE + 9] = r->fingerprint;
+  }
+  // ---- filtered aggregations: which swim-lanes exist per segment, and how many columns each projects
+  // (AggregationFunctionUtils.buildFilteredAggregationInfos :312-400; statistics are summed lane by lane,
+  // FilteredGroupByOperator.java:146-149): one lane per FILTER clause over (main AND clause) -- unless the clause matches all
+  // under a real main filter, then its functions join the non-filtered lane -- plus the non-filtered lane when it has
+  // functions or the query groups; an empty main filter is a single lane without docs ----
+  const DevLaneWeights* d_lane_w = nullptr;
   if (nF > 0) {
     r->agg_filter_of.assign(q->agg_filter_of, q->agg_filter_of + nA);
     auto classify = [](const pb_filter_node* nodes, int n) { return n == 0 ? 1 : (n == 1 && nodes[0].kind == PB_F_MATCH_ALL ? 1 : (n == 1 && nodes[0].kind == PB_F_EMPTY ? 2 : 0)); };
-    r->seg_clause_kind.resize(n_segs);
+    auto lane_cols = [&](const std::vector<char>& in_lane) {
+      std::vector<std::string> cols;
+      for (auto& nme : r->gb_names) if (std::find(cols.begin(), cols.end(), nme) == cols.end()) cols.push_back(nme);
+      for (int a = 0; a < nA; a++) if (in_lane[a] && !r->agg_cols[a].empty() && std::find(cols.begin(), cols.end(), r->agg_cols[a]) == cols.end()) cols.push_back(r->agg_cols[a]);
+      return (int32_t)cols.size();
+    };
+    DevLaneWeights* h_lw = nullptr;
+    d_lane_w = ar.put<DevLaneWeights>(nullptr, (size_t)n_segs, &h_lw);
+    if (!d_lane_w) return fail(PB_ERR_STATE, "query arena overflow");
     for (int si = 0; si < n_segs; si++) {
-      for (int f = 0; f < nF; f++) r->seg_clause_kind[si].push_back(classify(sqs[si].agg_filters[f], sqs[si].agg_filter_nodes[f]));
-      r->seg_clause_kind[si].push_back(classify(sqs[si].filter, sqs[si].num_filter_nodes));
+      DevLaneWeights& lw = h_lw[si];
+      lw.table = hsegs[si].table;
+      const int main_kind = classify(sqs[si].filter, sqs[si].num_filter_nodes);
+      if (main_kind == 2) continue;                        // empty main filter: no docs in any lane
+      std::vector<char> in_main(nA, 0);
+      bool any_main = false;
+      for (int f = 0; f < nF; f++) {
+        std::vector<char> in_lane(nA, 0);
+        for (int a = 0; a < nA; a++) if (q->agg_filter_of[a] == f) in_lane[a] = 1;
+        if (main_kind != 1 && classify(sqs[si].agg_filters[f], sqs[si].agg_filter_nodes[f]) == 1) {
+          for (int a = 0; a < nA; a++) if (in_lane[a]) { in_main[a] = 1; any_main = true; }
+          continue;
+        }
+        lw.docs_w[1 + f] = 1; lw.post_w[1 + f] = lane_cols(in_lane);
+      }
+      for (int a = 0; a < nA; a++) if (q->agg_filter_of[a] < 0) { in_main[a] = 1; any_main = true; }
+      if (any_main || nG > 0) { lw.docs_w[0] = 1; lw.post_w[0] = lane_cols(in_main); }
     }
   }
 
@@ -1349,7 +1720,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   hq->n_docs_total = n_docs_total; hq->match_all = match_all ? 1 : 0;
   { static const int sm = []() { const char* e = getenv("PB_SPARSE_MAX"); return e ? atoi(e) : PB_SPARSE_MAX; }(); hq->sparse_max = sm; }
   hq->match_list = d_match_list;
-  hq->match_count = r->d_counters + (size_t)n_tables * PB_COUNTERS_PER_TABLE;   // PB_MAX_WAVES zeroed cells after the per-table counters
+  hq->match_count = reinterpret_cast<unsigned long long*>(d_aux);   // PB_MAX_WAVES zeroed cells (aux region)
 
   // expand items (one per inverted-index bitmap / per sorted-index range list)
   int n_expand_items = 0;
@@ -1395,7 +1766,19 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     waves.push_back({0, n_segs, *hq, n_chunks, n_docs_total});
   }
   r->waves = (int)waves.size();
+  CU(cudaEventRecord(r->ev0, st));
   CU(cudaMemcpyAsync(ar.dev, ar.host.data(), ar.used, cudaMemcpyHostToDevice, st));
+  {
+    // table init: all regions are 16-byte multiples (cudaMallocAsync alignment is 256)
+    const uint64_t zn = (zero_bytes + 15) / 16, fn = (ff_bytes + 15) / 16, mn = (8 * mm_elems + 15) / 16, an = (aux_bytes + 15) / 16;
+    const uint64_t mx = std::max(std::max(zn, an), std::max(fn, mn));
+    int grid = (int)std::min<uint64_t>((mx + 255) / 256, (uint64_t)ctx->num_sms * 8);
+    if (grid < 1) grid = 1;
+    pb_init_tables_kernel<<<grid, 256, 0, st>>>((uint4*)d_zero, zn, (uint4*)d_ff, fn, (uint4*)d_mm, mn, (uint4*)d_aux, an,
+                                                reinterpret_cast<const uint4*>(d_head), (uint64_t)PB_COUNTERS_PER_TABLE * n_tables / 2);
+    r->launches++;
+    CU(cudaGetLastError());
+  }
   lap(2);
 
   // ---- index leaves -> flat bitmaps: one launch for every bitmap / range list of every segment ----
@@ -1411,14 +1794,14 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   // ---- kernel 1: filter -> match list;  kernel 2: gather + aggregate the matching docs (per wave) ----
   CU(cudaEventRecord(r->ev1, st));
   {
-    std::lock_guard<std::mutex> lk(g_ctx.mu);
-    if (!g_ctx.smem_attr_set) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->smem_attr_set) {
       CU(cudaFuncSetAttribute(pb_filter_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       CU(cudaFuncSetAttribute(pb_filter_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       CU(cudaFuncSetAttribute(pb_filter_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       CU(cudaFuncSetAttribute(pb_agg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       CU(cudaFuncSetAttribute(pb_agg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      g_ctx.smem_attr_set = true;
+      ctx->smem_attr_set = true;
     }
   }
   size_t smem = 0;
@@ -1434,7 +1817,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     else if (u2_three) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<2, 3>, PB_NTHREADS, smem));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pb_filter_kernel<2, 2>, PB_NTHREADS, smem));
     if (occ < 1) return fail(PB_ERR_CUDA, "filter kernel does not fit an SM (smem %zu)", smem);
-    max_ctas = (uint64_t)g_ctx.num_sms * (uint64_t)occ;
+    max_ctas = (uint64_t)ctx->num_sms * (uint64_t)occ;
   }
   const size_t smem2 = table_mode == T_KEYLESS ? (nF > 0 ? 3 : 2) * sizeof(double) * (size_t)nA * PB_NTHREADS : 0;
   // more resident threads = more gathers in flight (the kernel is DRAM-latency bound); 6 CTAs/SM costs a 4-byte spill
@@ -1445,7 +1828,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     if (agg_occ == 4) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pb_agg_kernel<4>, PB_NTHREADS, smem2));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, pb_agg_kernel<6>, PB_NTHREADS, smem2));
     if (occ2 < 1) return fail(PB_ERR_CUDA, "aggregation kernel does not fit an SM");
-    max2 = (uint64_t)g_ctx.num_sms * (uint64_t)occ2;
+    max2 = (uint64_t)ctx->num_sms * (uint64_t)occ2;
   }
   for (size_t wi = 0; wi < waves.size(); wi++) {
     const Wave& w = waves[wi];
@@ -1470,6 +1853,11 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     }
   }
   CU(cudaEventRecord(r->ev2, st));
+  if (nF > 0 && n_segs > 0) {
+    pb_lane_stats_kernel<<<(n_segs + 127) / 128, 128, 0, st>>>(d_lane_w, d_seg_stats, n_segs, 1 + nF, r->d_counters, PB_COUNTERS_PER_TABLE);
+    r->launches++;
+    CU(cudaGetLastError());
+  }
   lap(3);
 
   if (q->flags & PB_Q_DEFER_FINALIZE) {
@@ -1477,9 +1865,123 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
     *out = R.release();
     return PB_OK;
   }
+  if ((q->flags & PB_Q_ALL_RANKS) && (rc = comm_merge(r))) return rc;
   rc = finalize_result(r);
   if (rc) return rc;
   *out = R.release();
+  return PB_OK;
+}
+
+// hash tables across ranks: see comm_merge_hash further down (hash-partitioned all-to-all)
+
+// Install the global dictionary of `column` (sorted union over ALL segments of the parent group) in every per-device child.
+static int sync_child_dictionary(pb_group_s* g, const char* column) {
+  std::lock_guard<std::mutex> lk(g->mu);
+  auto it = g->dicts.find(column);
+  if (it == g->dicts.end()) {
+    GlobalDict gd;
+    int rc = build_union(g, column, gd);
+    if (rc) return rc;
+    it = g->dicts.emplace(column, std::move(gd)).first;
+    g->dict_version++;
+  }
+  auto ver = g->child_dict_version.find(column);
+  if (ver != g->child_dict_version.end() && ver->second == g->dict_version) return PB_OK;
+  const GlobalDict& gd = it->second;
+  for (auto* c : g->children) {
+    int rc = pb_segment_group_set_global_dictionary(c, column, gd.values.data(), gd.n, gd.entry_bytes);
+    if (rc) return rc;
+  }
+  g->child_dict_version[column] = g->dict_version;
+  return PB_OK;
+}
+
+extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_query* sqs, const pb_query_desc* q, pb_result_handle* out) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  if (!g || !q || !out || !sqs) return fail(PB_ERR_INVALID, "null argument");
+  if (g->children.empty()) {
+    DeviceGuard dg(g->ctx);          // the calling thread may never have selected this device
+    return exec_single(g, sqs, q, out);
+  }
+  // ---- one process driving several GPUs: every device runs its segments (asynchronously, one stream per device), then the
+  // tables are merged on the first device, which reads its peers' blocks in place over NVLink.  Same role as
+  // BaseCombineOperator's worker threads + the IndexedTable merge (CTR/operator/combine/BaseCombineOperator.java:97-142). ----
+  const int nc = (int)g->children.size();
+  const bool combine = (q->flags & PB_Q_COMBINE) != 0;
+  if (nc > PB_MERGE_MAX_PEERS) return fail(PB_ERR_UNSUPPORTED, "segment group spans %d devices (max %d)", nc, PB_MERGE_MAX_PEERS);
+  if (combine) {
+    for (int j = 0; j < q->num_group_by; j++) {
+      int ci = find_col(g->segs[0], q->group_by_columns[j]);
+      if (ci < 0) return fail(PB_ERR_INVALID, "segment %s: no column %s", g->segs[0]->name.c_str(), q->group_by_columns[j]);
+      if (g->segs[0]->cols[ci].has_dict && (rc = sync_child_dictionary(g, q->group_by_columns[j]))) return rc;
+    }
+    for (int a = 0; a < q->num_aggregations; a++)
+      if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT && q->aggregations[a].column) {
+        int ci = find_col(g->segs[0], q->aggregations[a].column);
+        if (ci >= 0 && g->segs[0]->cols[ci].has_dict && (rc = sync_child_dictionary(g, q->aggregations[a].column))) return rc;
+      }
+  }
+  std::vector<std::vector<pb_segment_query>> csq((size_t)nc);
+  for (size_t i = 0; i < g->segs.size(); i++) csq[(size_t)g->child_of[i]].push_back(sqs[i]);
+  pb_query_desc cq = *q;
+  cq.flags = q->flags & ~PB_Q_ALL_RANKS;
+  if (combine) cq.flags |= PB_Q_DEFER_FINALIZE;
+  std::vector<pb_result_s*> parts((size_t)nc, nullptr);
+  auto free_parts = [&]() { for (auto* p : parts) if (p) free_result(p); };
+  for (int k = 0; k < nc; k++) {
+    DeviceGuard dg(g->children[k]->ctx);
+    if ((rc = exec_single(g->children[k], csq[(size_t)k].data(), &cq, &parts[(size_t)k]))) { free_parts(); return rc; }
+  }
+  if (!combine) {
+    // one table per segment, in the caller's segment order: a shell result that maps table t to (device part, local table)
+    pb_result_s* shell = new pb_result_s();
+    shell->group = g; shell->n_gb = parts[0]->n_gb; shell->n_aggs = parts[0]->n_aggs; shell->agg_op = parts[0]->agg_op;
+    shell->table_mode = parts[0]->table_mode; shell->finalized = true;
+    for (size_t i = 0; i < g->segs.size(); i++) shell->table_map.push_back({g->child_of[i], g->index_in_child[i]});
+    for (auto* p : parts) { shell->device_ms = std::max(shell->device_ms, p->device_ms); shell->scan_ms = std::max(shell->scan_ms, p->scan_ms); shell->launches += p->launches; }
+    shell->parts = parts;
+    *out = shell;
+    return PB_OK;
+  }
+  pb_result_s* root = parts[0];
+  {
+    DeviceGuard dg(root->ctx);
+    for (int k = 1; k < nc; k++) {
+      if (parts[(size_t)k]->block_bytes != root->block_bytes || parts[(size_t)k]->fingerprint != root->fingerprint || root->table_mode == T_HASH) {
+        free_parts();
+        return fail(PB_ERR_UNSUPPORTED, root->table_mode == T_HASH ? "hash group tables are not merged across the devices of one process yet: use one process per GPU"
+                                                                    : "per-device table layouts differ");
+      }
+    }
+    // the peers' kernels must have finished before their blocks are read
+    for (int k = 1; k < nc; k++) {
+      cudaError_t e = cudaStreamWaitEvent(root->stream, parts[(size_t)k]->ev3, 0);
+      if (e != cudaSuccess) { free_parts(); return fail(PB_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e)); }
+    }
+    bool p2p = true;
+    for (int k = 1; k < nc; k++) { int can = 0; cudaDeviceCanAccessPeer(&can, root->ctx->device, parts[(size_t)k]->ctx->device); if (!can) p2p = false; }
+    if (p2p) {
+      DevMergePeers peers; memset(&peers, 0, sizeof peers);
+      for (int k = 1; k < nc; k++) peers.p[k - 1] = reinterpret_cast<const unsigned long long*>(parts[(size_t)k]->block);
+      rc = launch_merge_rows(root, nullptr, &peers, nc - 1, true);
+    } else {
+      // no peer access (e.g. across PCIe switches): stage the blocks through copies
+      rc = ensure_gather_buf(root->ctx, (size_t)(nc - 1) * (size_t)root->block_bytes, root->stream);
+      for (int k = 1; k < nc && !rc; k++) {
+        cudaError_t e = cudaMemcpyPeerAsync((uint8_t*)root->ctx->gather_buf + (size_t)(k - 1) * (size_t)root->block_bytes, root->ctx->device,
+                                            parts[(size_t)k]->block, parts[(size_t)k]->ctx->device, (size_t)root->block_bytes, root->stream);
+        if (e != cudaSuccess) rc = fail(PB_ERR_CUDA, "cudaMemcpyPeerAsync: %s", cudaGetErrorString(e));
+      }
+      if (!rc) rc = launch_merge_rows(root, root->ctx->gather_buf, nullptr, nc - 1, true);
+    }
+    if (rc) { free_parts(); return rc; }
+    root->merged_ranks *= nc;
+    for (int k = 1; k < nc; k++) { root->parts.push_back(parts[(size_t)k]); root->launches += parts[(size_t)k]->launches; }
+    if ((q->flags & PB_Q_ALL_RANKS) && (rc = comm_merge(root))) { free_result(root); return rc; }
+    if (!(q->flags & PB_Q_DEFER_FINALIZE) && (rc = finalize_result(root))) { free_result(root); return rc; }
+  }
+  *out = root;
   return PB_OK;
 }
 
@@ -1607,54 +2109,20 @@ static int finalize_result(pb_result_s* r) {
     std::vector<std::string> proj;
     for (auto& nme : r->gb_names) if (std::find(proj.begin(), proj.end(), nme) == proj.end()) proj.push_back(nme);
     for (auto& nme : r->agg_cols) if (!nme.empty() && std::find(proj.begin(), proj.end(), nme) == proj.end()) proj.push_back(nme);
-    tm.stats.num_docs_scanned = (int64_t)hc[(size_t)t * PB_COUNTERS_PER_TABLE + 2];
-    if (r->match_all) { tm.stats.num_docs_scanned = 0; for (int si : tm.seg_idx) tm.stats.num_docs_scanned += g->segs[si]->num_docs; }
+    // every statistic is a counter cell of the table block (PB_COUNTERS_PER_TABLE): device-accumulated or injected by the
+    // host at init, and summed by the cross-GPU merges -- a merged result reports the totals over all ranks' segments
+    const unsigned long long* cc = hc + (size_t)t * PB_COUNTERS_PER_TABLE;
+    tm.stats.num_docs_scanned = (int64_t)cc[2];
     tm.stats.num_entries_scanned_post_filter = tm.stats.num_docs_scanned * (int64_t)proj.size();
-    if (r->n_agg_filters > 0) {
-      // swim-lanes (AggregationFunctionUtils.buildFilteredAggregationInfos :312-400; statistics summed lane by lane,
-      // FilteredGroupByOperator.java:146-149): per segment, one lane per FILTER clause over (main AND clause) -- unless the
-      // clause matches all under a real main filter, then its functions join the non-filtered lane -- plus the
-      // non-filtered lane when it has functions or the query groups
-      const int nF = r->n_agg_filters;
-      auto lane_cols = [&](const std::vector<char>& in_lane) {
-        std::vector<std::string> cols;
-        for (auto& nme : r->gb_names) if (std::find(cols.begin(), cols.end(), nme) == cols.end()) cols.push_back(nme);
-        for (int a = 0; a < nA; a++) if (in_lane[a] && !r->agg_cols[a].empty() && std::find(cols.begin(), cols.end(), r->agg_cols[a]) == cols.end()) cols.push_back(r->agg_cols[a]);
-        return (int64_t)cols.size();
-      };
-      std::vector<unsigned long long> hs((size_t)(1 + PB_MAX_AGG_FILTERS) * g->segs.size());
-      CU(cudaMemcpyAsync(hs.data(), r->d_seg_stats, 8 * hs.size(), cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-      int64_t docs = 0, post = 0;
-      for (int si : tm.seg_idx) {
-        const unsigned long long* ss = hs.data() + (size_t)si * (1 + PB_MAX_AGG_FILTERS);
-        const std::vector<int>& ck = r->seg_clause_kind[si];
-        const int main_kind = ck[nF];
-        std::vector<char> in_main(nA, 0);
-        bool any_main = false;
-        if (main_kind == 2) {                      // empty main filter: one lane with every function, no docs
-          continue;
-        }
-        for (int f = 0; f < nF; f++) {
-          std::vector<char> in_lane(nA, 0);
-          for (int a = 0; a < nA; a++) if (r->agg_filter_of[a] == f) in_lane[a] = 1;
-          if (main_kind != 1 && ck[f] == 1) { for (int a = 0; a < nA; a++) if (in_lane[a]) { in_main[a] = 1; any_main = true; } continue; }
-          docs += (int64_t)ss[1 + f];
-          post += (int64_t)ss[1 + f] * lane_cols(in_lane);
-        }
-        for (int a = 0; a < nA; a++) if (r->agg_filter_of[a] < 0) { in_main[a] = 1; any_main = true; }
-        if (any_main || nG > 0) { docs += (int64_t)ss[0]; post += (int64_t)ss[0] * lane_cols(in_main); }
-      }
-      tm.stats.num_docs_scanned = docs;
-      tm.stats.num_entries_scanned_post_filter = post;
+    if (r->n_agg_filters > 0) {        // swim-lanes of filtered aggregations (pb_lane_stats_kernel)
+      tm.stats.num_docs_scanned = (int64_t)cc[4];
+      tm.stats.num_entries_scanned_post_filter = (int64_t)cc[5];
     }
-    tm.stats.num_total_docs = 0; tm.stats.num_entries_scanned_in_filter = 0;
-    for (int si : tm.seg_idx) {
-      tm.stats.num_total_docs += g->segs[si]->num_docs;
-      // every scan leaf reads every doc of the segment on the device (no restricted scans)
-      tm.stats.num_entries_scanned_in_filter += r->seg_scan_leaves[si] * (int64_t)g->segs[si]->num_docs;
-    }
-    tm.stats.num_segments = (int32_t)tm.seg_idx.size();
+    tm.stats.num_total_docs = (int64_t)cc[6];
+    tm.stats.num_entries_scanned_in_filter = (int64_t)cc[7];
+    tm.stats.num_segments = (int32_t)cc[8];
+    if (cc[9] != r->fingerprint * (unsigned long long)r->merged_ranks)
+      return fail(PB_ERR_STATE, "cross-GPU merge: table layouts differ across ranks (different query or global dictionaries)");
     tm.stats.num_groups_limit_reached = 0;
     if (nG > 0) {
       bool flag = (uint32_t)hc[(size_t)t * PB_COUNTERS_PER_TABLE + 1] != 0;
@@ -1668,14 +2136,26 @@ static int finalize_result(pb_result_s* r) {
 
 extern "C" int pb_result_finalize(pb_result_handle r) {
   if (!r) return fail(PB_ERR_INVALID, "null result");
+  DeviceGuard dg(r->ctx);
   return finalize_result(r);
 }
 
 // ------------------------------------------------------------------------------------------------
 // accessors
 // ------------------------------------------------------------------------------------------------
-#define TAB(r, t) ((r) && (t) >= 0 && (t) < (int)(r)->tables.size() && (r)->finalized ? &(r)->tables[(t)] : nullptr)
-extern "C" int32_t pb_result_num_tables(pb_result_handle r) { return r ? (int32_t)r->tables.size() : 0; }
+static TableMeta* tab_of(pb_result_s*& r, int t) {     // resolves a shell result's table to the part that owns it (r is updated)
+  if (!r || t < 0 || !r->finalized) return nullptr;
+  if (!r->table_map.empty()) {
+    if (t >= (int)r->table_map.size()) return nullptr;
+    const auto m = r->table_map[(size_t)t];
+    r = r->parts[(size_t)m.first];
+    t = m.second;
+    if (!r->finalized) return nullptr;
+  }
+  return t < (int)r->tables.size() ? &r->tables[(size_t)t] : nullptr;
+}
+#define TAB(r, t) tab_of(r, t)
+extern "C" int32_t pb_result_num_tables(pb_result_handle r) { return r ? (int32_t)(r->table_map.empty() ? r->tables.size() : r->table_map.size()) : 0; }
 extern "C" int64_t pb_result_num_groups(pb_result_handle r, int32_t t) { auto* tm = TAB(r, t); return tm ? tm->num_groups : -1; }
 extern "C" const int32_t* pb_result_group_dict_ids(pb_result_handle r, int32_t t, int32_t gb) {
   auto* tm = TAB(r, t); if (!tm || gb < 0 || gb >= r->n_gb) return nullptr; return (const int32_t*)tm->key_ids[gb].p;
@@ -1692,6 +2172,7 @@ extern "C" const int64_t* pb_result_long(pb_result_handle r, int32_t t, int32_t 
 static int materialize_distinct(pb_result_s* r, TableMeta& tm, int a) {
   if (tm.dc_off[a].p) return PB_OK;
   if (r->agg_op[a] != PB_AGG_DISTINCTCOUNT) return fail(PB_ERR_INVALID, "aggregation %d is not DISTINCTCOUNT", a);
+  DeviceGuard dg(r->ctx);
   cudaStream_t st = r->stream;
   const int64_t ng = tm.num_groups;
   const int64_t* L = (const int64_t*)tm.lng[a].p;
@@ -1732,16 +2213,28 @@ extern "C" double pb_result_scan_kernel_ms(pb_result_handle r) {
 extern "C" int32_t pb_result_kernel_launches(pb_result_handle r) { return r ? r->launches : 0; }
 extern "C" void* pb_result_stream(pb_result_handle r) { return r ? (void*)r->stream : nullptr; }
 
-// merge the gathered table blocks of all ranks (rank-major copies of pb_result_device_buffer(which = 8)) into this result
-extern "C" int pb_result_merge_gathered(pb_result_handle r, const void* gathered, int32_t n_ranks) {
-  if (!r || !gathered || n_ranks < 1) return fail(PB_ERR_INVALID, "bad arguments");
+static int comm_merge_hash(pb_result_s* r) { (void)r; return fail(PB_ERR_UNSUPPORTED, "hash group tables are not merged across ranks yet"); }
+static int launch_merge_rows(pb_result_s* r, const void* gathered, const DevMergePeers* peers, int n_rows, bool base_is_dst) {
   if (!r->combine || r->tables.size() != 1 || r->table_mode == T_HASH) return fail(PB_ERR_UNSUPPORTED, "merge needs a combined dense / keyless result");
   const uint64_t n_words = (uint64_t)r->block_bytes / 8;
-  int grid = (int)std::min<uint64_t>((n_words + 255) / 256, 1184);
-  pb_merge_blocks_kernel<<<grid, 256, 0, r->stream>>>((unsigned long long*)r->block, (const unsigned long long*)gathered, n_ranks, n_words,
-                                                      (uint64_t)r->block_sum_off / 8, (uint64_t)r->block_dc_off / 8, (uint64_t)r->block_mm_off / 8);
+  int grid = (int)std::min<uint64_t>((n_words + 255) / 256, (uint64_t)r->ctx->num_sms * 8);
+  DevMergePeers none; memset(&none, 0, sizeof none);
+  pb_merge_blocks_kernel<<<grid, 256, 0, r->stream>>>((unsigned long long*)r->block, (const unsigned long long*)gathered, peers ? *peers : none, n_rows,
+                                                      base_is_dst ? 1 : 0, n_words, (uint64_t)r->block_sum_off / 8, (uint64_t)r->block_dc_off / 8,
+                                                      (uint64_t)r->block_mm_off / 8);
   r->launches++;
   CU(cudaGetLastError());
+  return PB_OK;
+}
+static int launch_merge(pb_result_s* r, const void* gathered, int n_rows, bool base_is_dst) { return launch_merge_rows(r, gathered, nullptr, n_rows, base_is_dst); }
+// merge the gathered table blocks of all ranks (rank-major copies of pb_result_device_buffer(which = 8)) into this result:
+// for callers that run the collective themselves (PB_Q_DEFER_FINALIZE); PB_Q_ALL_RANKS does all of it inside the library
+extern "C" int pb_result_merge_gathered(pb_result_handle r, const void* gathered, int32_t n_ranks) {
+  if (!r || !gathered || n_ranks < 1) return fail(PB_ERR_INVALID, "bad arguments");
+  DeviceGuard dg(r->ctx);
+  int rc = launch_merge(r, gathered, n_ranks, false);
+  if (rc) return rc;
+  r->merged_ranks *= n_ranks;
   return PB_OK;
 }
 extern "C" int pb_result_phase_ms(pb_result_handle r, double* filter_ms, double* agg_ms) {
@@ -1763,7 +2256,8 @@ extern "C" int pb_result_host_timing(pb_result_handle r, double* out8) {
 }
 extern "C" int pb_result_wait(pb_result_handle r) {
   if (!r) return fail(PB_ERR_INVALID, "null result");
-  CU(cudaStreamSynchronize(r->stream));
+  for (auto* p : r->parts) if (p->stream) { DeviceGuard dgp(p->ctx); CU(cudaStreamSynchronize(p->stream)); }
+  if (r->stream) { DeviceGuard dg(r->ctx); CU(cudaStreamSynchronize(r->stream)); }
   return PB_OK;
 }
 extern "C" int32_t pb_result_in_place_columns(pb_result_handle r) { return r ? r->in_place_columns : 0; }
@@ -1771,6 +2265,7 @@ extern "C" int32_t pb_result_in_place_columns(pb_result_handle r) { return r ? r
 extern "C" int pb_host_register(const void* ptr, size_t bytes) {
   int rc = ensure_init();
   if (rc) return rc;
+  DeviceGuard dg(g_all.ctxs[0].get());
   CU(cudaHostRegister(const_cast<void*>(ptr), bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
   return PB_OK;
 }
