@@ -325,9 +325,13 @@ extern "C" int pb_segment_stage(const pb_segment_desc* d, int device_index, pb_s
   // registers the buffers and validates the layouts; columns are copied to HBM on first use by a query
   // so planning-only callers never touch the device
   if (!d || !out || d->num_columns < 0 || d->num_docs < 0) return fail(PB_ERR_INVALID, "bad segment descriptor");
-  { int rc0 = ensure_init(); if (rc0) return rc0; }
-  Context* ctx = ctx_at(device_index);
-  if (!ctx) return fail(PB_ERR_INVALID, "pb_segment_stage: device_index %d is not one of the %zu devices given to pb_init", device_index, g_all.ctxs.size());
+  // registration itself never touches the device (planning-only callers: eligibility checks, EXPLAIN); without any CUDA
+  // device the handle is still valid for the host planning layer and queries on it fail with PB_ERR_CUDA
+  Context* ctx = nullptr;
+  if (ensure_init() == PB_OK) {
+    ctx = ctx_at(device_index);
+    if (!ctx) return fail(PB_ERR_INVALID, "pb_segment_stage: device_index %d is not one of the %zu devices given to pb_init", device_index, g_all.ctxs.size());
+  } else if (device_index != 0) return PB_ERR_CUDA;
   std::unique_ptr<pb_segment_s> s(new pb_segment_s());
   s->ctx = ctx;
   s->name = d->segment_name ? d->segment_name : "";
@@ -367,7 +371,7 @@ extern "C" int pb_segment_stage(const pb_segment_desc* d, int device_index, pb_s
       if (c.h_fwd_len < c.raw_data_start + (uint64_t)s->num_docs * c.raw_width) return fail(PB_ERR_INVALID, "column %s: raw forward index too short", cd.name);
     }
   }
-  { std::lock_guard<std::mutex> lk(ctx->mu); ctx->segments.push_back(s.get()); }
+  if (ctx) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->segments.push_back(s.get()); }
   *out = s.release();
   return PB_OK;
 }
@@ -471,7 +475,7 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
 extern "C" int pb_segment_release(pb_segment_handle s) {
   if (!s) return PB_OK;
   DeviceGuard dg(s->ctx);
-  {
+  if (s->ctx) {
     std::lock_guard<std::mutex> lk(s->ctx->mu);
     auto& v = s->ctx->segments;
     v.erase(std::remove(v.begin(), v.end(), s), v.end());
@@ -1901,6 +1905,7 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
   if (rc) return rc;
   if (!g || !q || !out || !sqs) return fail(PB_ERR_INVALID, "null argument");
   if (g->children.empty()) {
+    if (!g->ctx) return fail(PB_ERR_STATE, "the segments of this group were registered while no CUDA device was available");
     DeviceGuard dg(g->ctx);          // the calling thread may never have selected this device
     return exec_single(g, sqs, q, out);
   }
@@ -2261,6 +2266,11 @@ extern "C" int pb_result_wait(pb_result_handle r) {
   return PB_OK;
 }
 extern "C" int32_t pb_result_in_place_columns(pb_result_handle r) { return r ? r->in_place_columns : 0; }
+extern "C" double pb_result_comm_ms(pb_result_handle r) {
+  if (!r || !r->comm_timed) return 0;
+  if (r->comm_ms == 0) { float ms = 0; cudaEventSynchronize(r->sset.ev[6]); if (cudaEventElapsedTime(&ms, r->sset.ev[5], r->sset.ev[6]) == cudaSuccess) r->comm_ms = ms; }
+  return r->comm_ms;
+}
 
 extern "C" int pb_host_register(const void* ptr, size_t bytes) {
   int rc = ensure_init();

@@ -22,6 +22,8 @@ PB_Q_DEFER_FINALIZE = 2
 PB_Q_GENERIC_KERNEL = 4
 PB_Q_NO_TMA = 8
 PB_Q_GATHER_IN_PLACE = 16
+PB_Q_ALL_RANKS = 32
+PB_COMM_ID_BYTES = 128
 
 
 class PbColumnDesc(C.Structure):
@@ -89,6 +91,11 @@ def lib():
     l.pb_last_error.restype = C.c_char_p
     l.pb_init.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_size_t]
     l.pb_device_count.restype = C.c_int
+    l.pb_comm_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+    l.pb_comm_init.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    l.pb_comm_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    l.pb_result_comm_ms.argtypes = [C.c_void_p]
+    l.pb_result_comm_ms.restype = C.c_double
     l.pb_segment_stage.argtypes = [C.POINTER(PbSegmentDesc), C.c_int, C.POINTER(C.c_void_p)]
     l.pb_segment_release.argtypes = [C.c_void_p]
     l.pb_segment_device_bytes.argtypes = [C.c_void_p]
@@ -156,19 +163,46 @@ def _check(rc: int):
         raise PinotB200Error(rc, lib().pb_last_error().decode("utf-8", "replace"))
 
 
-def init(device: Optional[int] = None):
+def init(device=None, hbm_cache_bytes: int = 0):
+    """pb_init.  device: None = the current CUDA device, an int, or a list of CUDA device ordinals driven by this process
+    (segments are then staged on a device_index into that list)."""
     if device is None:
-        _check(lib().pb_init(None, 0, 0))
+        _check(lib().pb_init(None, 0, hbm_cache_bytes))
     else:
-        arr = (C.c_int * 1)(device)
-        _check(lib().pb_init(arr, 1, 0))
+        ids = [device] if isinstance(device, int) else list(device)
+        arr = (C.c_int * len(ids))(*ids)
+        _check(lib().pb_init(arr, len(ids), hbm_cache_bytes))
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(PB_COMM_ID_BYTES)
+    _check(lib().pb_comm_unique_id(buf, PB_COMM_ID_BYTES))
+    return buf.raw
+
+
+def comm_init(n_ranks: int, rank: int, unique_id: bytes):
+    """ncclCommInitRank inside libpinot_b200.so (collective: every rank calls it with rank 0's id)."""
+    assert len(unique_id) == PB_COMM_ID_BYTES
+    buf = C.create_string_buffer(unique_id, PB_COMM_ID_BYTES)
+    _check(lib().pb_comm_init(n_ranks, rank, buf, PB_COMM_ID_BYTES))
+
+
+def comm_info():
+    n, r = C.c_int(), C.c_int()
+    has = lib().pb_comm_info(C.byref(n), C.byref(r))
+    return bool(has), n.value, r.value
+
+
+def comm_destroy():
+    _check(lib().pb_comm_destroy())
 
 
 class StagedSegment:
     """IndexSegment handle on the device (pb_segment_stage).  Keeps the host buffers alive."""
 
-    def __init__(self, seg: Segment, columns: Optional[Sequence[str]] = None):
+    def __init__(self, seg: Segment, columns: Optional[Sequence[str]] = None, device_index: int = 0):
         self.segment = seg
+        self.device_index = device_index
         names = list(columns) if columns is not None else seg.column_names()
         self._keep = []
         cols = (PbColumnDesc * len(names))()
@@ -193,7 +227,7 @@ class StagedSegment:
         desc = PbSegmentDesc(seg.name.encode(), seg.num_docs, len(names), cols)
         self._keep.append((cols, desc))
         h = C.c_void_p()
-        _check(lib().pb_segment_stage(C.byref(desc), 0, C.byref(h)))
+        _check(lib().pb_segment_stage(C.byref(desc), device_index, C.byref(h)))
         self.handle = h
 
     def device_bytes(self) -> int:
@@ -387,6 +421,10 @@ class Result:
 
     def wait(self):
         _check(lib().pb_result_wait(self._rh))
+
+    def comm_ms(self) -> float:
+        """device time of the cross-rank merge of this call (collective + merge kernel), 0 without PB_Q_ALL_RANKS"""
+        return lib().pb_result_comm_ms(self._rh)
 
     def scan_ms(self) -> float:
         return lib().pb_result_scan_kernel_ms(self._rh)
