@@ -161,12 +161,18 @@ def algorithmic_bytes(segs, q, part="all"):
     return total
 
 
+_oracle_prepared = {}
+
+
 def oracle_query_all_threads(segs, q, threads):
-    """One CombineOperator-style pass on the CPU: one task per segment on `threads` threads, then the merge."""
-    from concurrent.futures import ThreadPoolExecutor
+    """One CombineOperator-style pass on the CPU: the segments on `threads` native worker threads (pthreads inside
+    liboracle.so, the segments and the query marshalled once), then the cross-segment merge."""
     from oracle import oracle
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        res = list(ex.map(lambda s: oracle.execute(s, q), segs))
+    key = (id(segs[0]), len(segs), id(q))
+    prep = _oracle_prepared.get(key)
+    if prep is None:
+        prep = _oracle_prepared[key] = oracle.PreparedBatch(segs, q)
+    res = oracle.execute_batch(prep, threads)
     return oracle.combine_numeric(res)
 
 

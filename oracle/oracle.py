@@ -19,7 +19,7 @@ _SRC = [os.path.join(_HERE, "pinot_oracle.c"), os.path.join(_HERE, "pinot_oracle
 
 def build(force: bool = False) -> str:
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(s) for s in _SRC if os.path.exists(s)):
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-std=gnu11", "-shared", "-fPIC", "-o", _SO, _SRC[0], "-lm"])
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-std=gnu11", "-shared", "-fPIC", "-pthread", "-o", _SO, _SRC[0], "-lm"])
     return _SO
 
 
@@ -97,6 +97,8 @@ def lib():
                                          C.POINTER(C.c_int64)]
         l.orc_filter_doc_ids.restype = C.c_int64
         l.orc_free.argtypes = [C.c_void_p]
+        l.orc_execute_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        l.orc_execute_batch.restype = C.c_int32
         l.orc_num_bits_per_value.argtypes = [C.c_int32]
         l.orc_num_bits_per_value.restype = C.c_int32
         l.orc_read_dict_id.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
@@ -259,6 +261,37 @@ def execute(seg, q) -> OracleResult:
         return OracleResult(seg, q, rp)
     finally:
         lib().orc_result_free(rp)
+
+
+class PreparedBatch:
+    """segments + query marshalled once (what a server does at plan time), for execute_batch"""
+
+    def __init__(self, segs, q):
+        self.segs, self.q, self.m = list(segs), q, _Marshalled()
+        skip = [c for c, kinds in q.skip_indexes.items() if "inverted" in kinds]
+        ss = [marshal_segment(s, self.m, skip_inverted=skip) for s in self.segs]
+        qs = [marshal_query(s, q, self.m) for s in self.segs]
+        n = len(self.segs)
+        self.seg_ptrs = (C.POINTER(OrcSegment) * n)(*[C.pointer(x) for x in ss])
+        self.q_ptrs = (C.POINTER(OrcQuery) * n)(*[C.pointer(x) for x in qs])
+        self.out = (C.c_void_p * n)()
+
+
+def execute_batch(prep: "PreparedBatch", threads: int) -> List["OracleResult"]:
+    """All segments of the query on `threads` native worker threads (pthreads inside liboracle.so: no interpreter in the
+    loop), like one GroupByCombineOperator pass before the merge."""
+    l = lib()
+    n = len(prep.segs)
+    failed = l.orc_execute_batch(prep.seg_ptrs, prep.q_ptrs, n, threads, prep.out)
+    try:
+        if failed:
+            raise RuntimeError("oracle: " + l.orc_last_error().decode())
+        return [OracleResult(s, prep.q, prep.out[i]) for i, s in enumerate(prep.segs)]
+    finally:
+        for i in range(n):
+            if prep.out[i]:
+                l.orc_result_free(prep.out[i])
+                prep.out[i] = None
 
 
 def filter_doc_ids(seg, q):

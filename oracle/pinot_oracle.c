@@ -1272,3 +1272,34 @@ fail:
   (void)it;
   return NULL;
 }
+
+
+/* ---- CombineOperator-style driver: the segments of one query on `threads` worker threads (a shared work queue, as
+ * BaseCombineOperator hands segments to its tasks: CTR/operator/combine/BaseCombineOperator.java:100-141).  Test / bench
+ * infrastructure: lets the CPU baseline use every host core without the Python interpreter in the timed loop. ---- */
+#include <pthread.h>
+typedef struct { const orc_segment* const* segs; const orc_query* const* qs; orc_result** out; int32_t n; volatile int32_t next; } orc_batch;
+static void* orc_batch_worker(void* arg) {
+  orc_batch* b = (orc_batch*)arg;
+  for (;;) {
+    int32_t i = __sync_fetch_and_add(&b->next, 1);
+    if (i >= b->n) break;
+    b->out[i] = orc_execute(b->segs[i], b->qs[i]);
+  }
+  return NULL;
+}
+int32_t orc_execute_batch(const orc_segment* const* segs, const orc_query* const* qs, int32_t n, int32_t threads, orc_result** out) {
+  if (n <= 0) return 0;
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = n;
+  orc_batch b = { segs, qs, out, n, 0 };
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
+  int32_t started = 0;
+  for (int32_t t = 1; t < threads; t++) if (pthread_create(&th[started], NULL, orc_batch_worker, &b) == 0) started++;
+  orc_batch_worker(&b);                        /* the calling thread works too */
+  for (int32_t t = 0; t < started; t++) pthread_join(th[t], NULL);
+  free(th);
+  int32_t failed = 0;
+  for (int32_t i = 0; i < n; i++) if (!out[i]) failed++;
+  return failed;
+}

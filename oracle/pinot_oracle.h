@@ -117,6 +117,9 @@ typedef struct orc_result orc_result;
 orc_result* orc_execute(const orc_segment* seg, const orc_query* q);
 void orc_result_free(orc_result* r);
 const char* orc_last_error(void);
+/* the segments of one query on `threads` worker threads (shared work queue); out[i] = result of segment i; returns the number
+ * of segments that failed */
+int32_t orc_execute_batch(const orc_segment* const* segs, const orc_query* const* qs, int32_t n, int32_t threads, orc_result** out);
 
 int32_t orc_result_num_groups(const orc_result* r);        /* 1 for keyless */
 const orc_stats* orc_result_stats(const orc_result* r);

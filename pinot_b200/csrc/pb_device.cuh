@@ -169,6 +169,12 @@ struct DevQuery {
   int32_t sparse_max;                    // survivors per 1024 docs below which later AND leaves use the restricted scan
   int32_t cand_bytes;                    // shared memory for the per-warp candidate lists (0: no leaf runs on candidates)
   uint64_t unit_lo;                      // this launch covers work units [unit_lo, unit_lo + n_units) (a wave of segments)
+  int32_t fuse;                          // pb_filter_kernel aggregates its matches itself (no match list, no pb_agg_kernel)
+  int32_t st_slots;                      // pb_agg_smem_kernel: slots of the CTA-private dense table (= table capacity), 0 = not used
+  int32_t st_replicas;                   //   replicas of it per CTA (power of two)
+  int32_t fuse_batch;                    // fused: buffered matches at which a warp aggregates (a warp only sees ~14 units per query:
+                                         // waiting for a full buffer would put all the gathers at the end of the kernel)
+  uint64_t st_min_docs;                  //   matches below which the kernel updates the global table directly (merging 148 private tables costs more)
   uint32_t* match_list;                  // global doc numbers of the docs that pass the filter
   unsigned long long* match_count;
   const DevSegQuery* segs;
@@ -250,6 +256,11 @@ __device__ __forceinline__ void pb_red_or_b32(uint32_t* p, uint32_t v) { asm vol
 __device__ __forceinline__ unsigned long long pb_atom_cas_u64(unsigned long long* p, unsigned long long cmp, unsigned long long val) {
   unsigned long long old;
   asm volatile("atom.global.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "l"(p), "l"(cmp), "l"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned int pb_atom_add_u32(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
   return old;
 }
 __device__ __forceinline__ unsigned long long pb_ld_volatile_u64(const unsigned long long* p) {
@@ -499,14 +510,14 @@ __device__ __forceinline__ bool pb_group_ticket(const DevTable& t) {
   const int leader = __ffs(m) - 1, lane = (int)(threadIdx.x & 31);
   const unsigned rank = __popc(m & ((1u << lane) - 1u)), need = __popc(m);
   unsigned base = 0;
-  if (lane == leader) base = atomicAdd(t.num_groups, need);
+  if (lane == leader) base = pb_atom_add_u32(t.num_groups, need);
   base = __shfl_sync(m, base, leader);
   if (base + rank < t.num_groups_limit) return true;
-  atomicSub(t.num_groups, 1u);                           // over the limit: hand the ticket back
+  pb_red_add_u32(t.num_groups, 0xffffffffu);              // over the limit: hand the ticket back (-1)
   pb_red_add_u32(t.limit_reached, 1u);
   return false;
 }
-__device__ __forceinline__ void pb_group_ticket_return(const DevTable& t) { atomicSub(t.num_groups, 1u); }
+__device__ __forceinline__ void pb_group_ticket_return(const DevTable& t) { pb_red_add_u32(t.num_groups, 0xffffffffu); }
 
 // returns slot, or ~0ull when the key is new and numGroupsLimit is reached
 __device__ __forceinline__ uint64_t pb_hash_slot(const DevTable& t, uint64_t key) {
@@ -611,12 +622,12 @@ __device__ __forceinline__ double pb_agg_input(const DevAggCol& ac, int op, uint
                       : __ldg(ac.dict_f64 + pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word));
 }
 
-__device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQuery& sq, const DevTable& t, uint32_t doc,
-                                              const KeylessAcc& ka, unsigned long long& keyless_rows, uint32_t fpass) {
-  // ---- phase 1: every gather of this doc is issued before anything is reduced, four independent chains at a
-  // time (index clamping instead of branches keeps the loads unconditional, so they overlap) ----
+// ---- phase 1 of a matching doc: every gather is issued before anything is reduced, four independent chains at a
+// time (index clamping instead of branches keeps the loads unconditional, so they overlap).  slot = dense table index,
+// or the 64 / 128-bit composite key of a hash table. ----
+__device__ __forceinline__ void pb_gather_doc(const DevQuery& Q, const DevSegQuery& sq, uint32_t doc, uint64_t& slot, uint64_t& slot_hi, double* vals) {
   const int nG = Q.n_group_by, nA = Q.n_aggs;
-  uint64_t slot = 0, slot_hi = 0;
+  slot = 0; slot_hi = 0;
   if (Q.table_mode != T_KEYLESS) {
     const bool dense = Q.table_mode == T_DENSE;
     const bool multi = nG > 1;
@@ -635,7 +646,6 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
       }
     }
   }
-  double vals[PB_MAX_AGGS];
   for (int a = 0; a < nA; a += 4) {
     double v[4];
 #pragma unroll
@@ -647,6 +657,14 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 #pragma unroll
     for (int k = 0; k < 4; k++) if (a + k < nA) vals[a + k] = v[k];
   }
+}
+
+__device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQuery& sq, const DevTable& t, uint32_t doc,
+                                              const KeylessAcc& ka, unsigned long long& keyless_rows, uint32_t fpass) {
+  const int nA = Q.n_aggs;
+  uint64_t slot, slot_hi;
+  double vals[PB_MAX_AGGS];
+  pb_gather_doc(Q, sq, doc, slot, slot_hi, vals);
 
   // ---- phase 2: table update ----
   if (Q.table_mode == T_HASH) {
@@ -692,6 +710,82 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-private group table in shared memory (BASELINE.json north_star: "group-by hashes into a shared-memory table reduced
+// ... then a global atomic merge"; the reference keeps such key spaces in a dense array too:
+// DictionaryBasedGroupKeyGenerator.java:285-414 ArrayBasedHolder, DoubleGroupByResultHolder.java:74-98).
+// A dense table of S slots is replicated R times per CTA (warp w updates replica w % R): row counts are native 32-bit
+// ATOMS, sums / min / max are 64-bit compare-and-swap loops on shared memory (SASS ATOMS.CAST.SPIN.64) -- an order of
+// magnitude above the ~77 G/s of same-line L2 reductions that bounded the global-table kernel at 25 % selectivity.  At the
+// end every CTA merges its non-empty slots into the global table with one RED per cell.
+// Layout of one replica: cnt u32[S] | fcnt u32[n_fc][S] | acc u64[n_acc][S]   (acc: f64 sum, or order-encoded i64 min/max).
+// ------------------------------------------------------------------------------------------------
+// The cells are addressed in the shared STATE SPACE (32-bit addresses, atom.shared / red.shared / ld.shared PTX): through
+// generic pointers the compiler emits generic ATOM.E instructions that resolve the address window at run time -- measured
+// no faster than the L2 reductions they were meant to replace.
+__device__ __forceinline__ void pb_sh_add_u32(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long pb_sh_ld_u64(uint32_t a) { unsigned long long v; asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t pb_sh_ld_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void pb_sh_st_u64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ void pb_sh_st_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long pb_sh_cas_u64(uint32_t a, unsigned long long cmp, unsigned long long val) {
+  unsigned long long old;
+  asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(a), "l"(cmp), "l"(val) : "memory");
+  return old;
+}
+struct SmemTable {
+  uint32_t base;            // shared-space address of this warp's replica
+  uint32_t S, n_fc;
+  int8_t acc_of[PB_MAX_AGGS];   // aggregation -> accumulator array (SUM / AVG / MIN / MAX), -1 = none
+  int8_t fc_of[PB_MAX_AGGS];    // aggregation -> filtered row counter (COUNT / AVG under a FILTER clause), -1 = none
+  __device__ __forceinline__ uint32_t cnt(uint32_t slot) const { return base + 4u * slot; }
+  __device__ __forceinline__ uint32_t fcnt(int k, uint32_t slot) const { return base + 4u * ((uint32_t)(1 + k) * S + slot); }
+  __device__ __forceinline__ uint32_t acc(int k, uint32_t slot) const { return base + ((((1u + n_fc) * S * 4u) + 7u) & ~7u) + 8u * ((uint32_t)k * S + slot); }
+};
+__host__ __device__ __forceinline__ size_t pb_smem_table_bytes(uint32_t S, int n_fc, int n_acc) {
+  return ((((size_t)(1 + n_fc) * S * 4 + 7) & ~(size_t)7) + (size_t)n_acc * S * 8 + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ void pb_accumulate_smem(const DevQuery& Q, const DevSegQuery& sq, const DevTable& t, const SmemTable& st, uint32_t doc, uint32_t fpass) {
+  const int nA = Q.n_aggs;
+  uint64_t slot, slot_hi;
+  double vals[PB_MAX_AGGS];
+  pb_gather_doc(Q, sq, doc, slot, slot_hi, vals);
+  const uint32_t sl = (uint32_t)slot;
+  pb_sh_add_u32(st.cnt(sl), 1u);
+  for (int a = 0; a < nA; a++) {
+    const int op = Q.agg_op[a];
+    const int fo = Q.agg_filter_of[a];
+    if (fo >= 0) {
+      if (!((fpass >> fo) & 1u)) continue;
+      if (st.fc_of[a] >= 0) pb_sh_add_u32(st.fcnt(st.fc_of[a], sl), 1u);
+    }
+    if (op == 0) continue;
+    const double v = vals[a];
+    if (op == 5) {                               // distinct bitsets stay in global memory (OR is idempotent: no contention cost)
+      uint32_t id = (uint32_t)__double_as_longlong(v);
+      pb_red_or_b32(&t.dc_bits[a][slot * t.dc_words[a] + (id >> 5)], 1u << (id & 31));
+      continue;
+    }
+    const uint32_t cell = st.acc(st.acc_of[a], sl);
+    if (op == 1 || op == 4) {
+      unsigned long long old = pb_sh_ld_u64(cell), assumed;
+      do {
+        assumed = old;
+        old = pb_sh_cas_u64(cell, assumed, (unsigned long long)__double_as_longlong(__longlong_as_double((long long)assumed) + v));
+      } while (old != assumed);
+    } else if (v == v) {
+      const long long e = op == 2 ? pb_enc_f64(v) : ~pb_enc_f64(v);
+      long long old = (long long)pb_sh_ld_u64(cell);
+      while (e < old) {                          // most docs do not improve the extreme: a plain load
+        const long long seen = (long long)pb_sh_cas_u64(cell, (unsigned long long)old, (unsigned long long)e);
+        if (seen == old) break;
+        old = seen;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Kernel 1: pb_filter_kernel  (DocIdSetOperator + filter operators: SURVEY.md §3.2)
 //
 // A CTA owns a contiguous range of 1024-doc chunks; inside it every WARP is an independent worker with its
@@ -712,6 +806,18 @@ struct __align__(16) FilterSmemHeader {
   alignas(16) uint8_t seg[PB_SEG_FILTER_BYTES];   // the filter part of the current DevSegQuery
 };
 
+// Fused aggregation (DevQuery::fuse): the warp that found the matches aggregates them itself -- ob[0..cnt) are global doc
+// numbers of one segment; one lane per doc, every gather of the round in flight at once.  The random-sector gathers of
+// the aggregation then overlap the streaming of the predicate columns by the other warps instead of running as a second
+// kernel behind it.  Not inlined: the filter loop keeps its own register budget.
+__device__ __noinline__ void pb_warp_aggregate(const DevQuery& Q, const DevSegQuery& sgq, const uint32_t* ob, uint32_t cnt, int lane) {
+  const DevTable& tb = Q.tables[sgq.table];
+  const uint32_t base = (uint32_t)sgq.doc_base;
+  KeylessAcc ka; ka.sum = nullptr; ka.mm = nullptr; ka.cnt = nullptr;
+  unsigned long long unused = 0;
+  for (uint32_t i = (uint32_t)lane; i < cnt; i += 32) pb_accumulate(Q, sgq, tb, ob[i] - base, ka, unused, 0u);
+}
+
 // U = 1024-doc chunks per work unit (one TMA load + one dispatch per predicate leaf per unit)
 template <int U, int MIN_CTAS>
 __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const __grid_constant__ DevQuery Q) {
@@ -726,9 +832,16 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
   uint32_t* ob = reinterpret_cast<uint32_t*>(dyn) + (size_t)warp * PB_OUT_CAP;   // this warp's output buffer
   dyn += (size_t)PB_NWARPS * PB_OUT_CAP * sizeof(uint32_t);
   uint32_t out_n = 0;                                     // buffered matches (warp-uniform)
+  int cur_seg = 0;                                        // segment the buffered matches belong to
   auto flush_out = [&]() {
     if (out_n == 0) return;
     __syncwarp();
+    if (Q.fuse) {
+      pb_warp_aggregate(Q, Q.segs[cur_seg], ob, out_n, lane);
+      __syncwarp();
+      out_n = 0;
+      return;
+    }
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)out_n);
     base = __shfl_sync(0xffffffffu, base, 0);
@@ -802,6 +915,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
 
   for (int sgi = seg_first; sgi < Q.n_segs; sgi++) {
     if (Q.segs[sgi].unit_begin >= cta_hi) break;
+    cur_seg = sgi;
     // ---- segment entry: filter descriptor, derived constants and LUTs into shared memory ----
     __syncthreads();   // everyone has left the previous segment
     {
@@ -993,7 +1107,26 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       }
       const uint32_t gunit0 = (uint32_t)(sq.doc_base + unit_doc0);
       if (n_cand_leaves == 0) {
-        if (__builtin_expect(total > PB_OUT_CAP, 0)) {
+        if (__builtin_expect(total > PB_OUT_CAP && Q.fuse, 0)) {
+          // dense matches, fused aggregation: through the buffer, PB_OUT_CAP docs at a time
+          flush_out();
+          for (uint32_t base0 = 0; base0 < total; base0 += PB_OUT_CAP) {
+            uint32_t pos = excl - base0;                                   // (wraps below the window: unsigned compare)
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              const uint32_t gdoc0 = gunit0 + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
+              uint32_t mm = mask[u];
+              while (mm) {
+                const int bit = __ffs(mm) - 1;
+                mm &= mm - 1;
+                if (pos < PB_OUT_CAP) ob[pos] = gdoc0 + (uint32_t)bit;
+                pos++;
+              }
+            }
+            out_n = total - base0 < PB_OUT_CAP ? total - base0 : PB_OUT_CAP;
+            flush_out();
+          }
+        } else if (__builtin_expect(total > PB_OUT_CAP, 0)) {
           // dense matches: straight to the list
           unsigned long long base = 0;
           if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)total);
@@ -1023,6 +1156,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
             }
           }
           out_n += total;
+          if (Q.fuse && out_n >= (uint32_t)Q.fuse_batch) flush_out();
         }
         matched += total;
       } else {
@@ -1065,6 +1199,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
               matched += n;
             }
           }
+          if (Q.fuse && out_n >= (uint32_t)Q.fuse_batch) flush_out();
         }
         __syncwarp();   // the list is rewritten by the next unit
       }
@@ -1214,6 +1349,114 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_agg_kernel(const __g
         pb_red_min_s64(&t.mm[a][0], op == 2 ? tot : ~tot);
       }
       __syncthreads();
+    }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 2b: pb_agg_smem_kernel — pb_agg_kernel for ONE dense table whose slots fit shared memory: one CTA of 1024 threads
+// per SM, CTA-private replicas of the table (see SmemTable), one merge into the global table at the end.  With few matches
+// (< st_min_docs, known on the device only) it updates the global table directly like pb_agg_kernel.
+// ------------------------------------------------------------------------------------------------
+#define PB_AGG_SMEM_THREADS 1024
+__global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_smem_kernel(const __grid_constant__ DevQuery Q) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ unsigned long long s_doc_base[PB_AGG_MAX_SEGS_SMEM + 1];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_segs = Q.n_segs;
+  const int n_smem = n_segs < PB_AGG_MAX_SEGS_SMEM ? n_segs : PB_AGG_MAX_SEGS_SMEM;
+  for (int i = tid; i < n_smem; i += PB_AGG_SMEM_THREADS) s_doc_base[i] = Q.segs[i].doc_base;
+  const unsigned long long n = Q.match_all ? Q.n_docs_total : *Q.match_count;
+  const DevTable& t = Q.tables[0];
+  const uint32_t S = (uint32_t)Q.st_slots, R = (uint32_t)Q.st_replicas;
+  SmemTable st;
+  st.S = S;
+  int n_acc = 0, n_fc = 0;
+  for (int a = 0; a < PB_MAX_AGGS; a++) {
+    const int op = a < Q.n_aggs ? Q.agg_op[a] : 0;
+    st.acc_of[a] = (a < Q.n_aggs && op >= 1 && op <= 4) ? (int8_t)n_acc++ : (int8_t)-1;
+    st.fc_of[a] = (a < Q.n_aggs && Q.agg_filter_of[a] >= 0 && (op == 0 || op == 4)) ? (int8_t)n_fc++ : (int8_t)-1;
+  }
+  st.n_fc = (uint32_t)n_fc;
+  const size_t rep_bytes = pb_smem_table_bytes(S, n_fc, n_acc);
+  const uint32_t smem0 = pb_smem_u32(smem_raw);
+  st.base = smem0 + ((uint32_t)warp & (R - 1)) * (uint32_t)rep_bytes;
+  const bool use_smem = n >= Q.st_min_docs;
+  if (use_smem) {
+    for (uint32_t r = 0; r < R; r++) {
+      SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes;
+      for (uint32_t i = tid; i < (1 + (uint32_t)n_fc) * S; i += PB_AGG_SMEM_THREADS) pb_sh_st_u32(z.cnt(i), 0u);
+      for (int a = 0; a < Q.n_aggs; a++) {
+        if (st.acc_of[a] < 0) continue;
+        const unsigned long long init = (Q.agg_op[a] == 1 || Q.agg_op[a] == 4) ? 0ull : 0x7fffffffffffffffull;
+        for (uint32_t i = tid; i < S; i += PB_AGG_SMEM_THREADS) pb_sh_st_u64(z.acc(st.acc_of[a], i), init);
+      }
+    }
+  }
+  __syncthreads();
+
+  const int nF = Q.n_agg_filters;
+  int stat_seg = -1;
+  unsigned int stat_cnt[1 + PB_MAX_AGG_FILTERS];
+#pragma unroll
+  for (int f = 0; f <= PB_MAX_AGG_FILTERS; f++) stat_cnt[f] = 0;
+  auto stat_flush = [&]() {
+    if (stat_seg < 0) return;
+    unsigned long long* dst = Q.segs[stat_seg].af_docs;
+#pragma unroll
+    for (int f = 0; f <= PB_MAX_AGG_FILTERS; f++) if (f <= nF && stat_cnt[f]) { pb_red_add_u64(dst + f, (unsigned long long)stat_cnt[f]); stat_cnt[f] = 0; }
+  };
+  KeylessAcc ka; ka.sum = nullptr; ka.mm = nullptr; ka.cnt = nullptr;
+  unsigned long long unused_rows = 0;
+
+  for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += (unsigned long long)gridDim.x * PB_AGG_SMEM_THREADS) {
+    const unsigned long long gdoc = Q.match_all ? i : (unsigned long long)__ldg(Q.match_list + i);
+    int lo = 0, hi = n_segs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      const unsigned long long b = mid < PB_AGG_MAX_SEGS_SMEM ? s_doc_base[mid] : Q.segs[mid].doc_base;
+      if (b <= gdoc) lo = mid; else hi = mid - 1;
+    }
+    const DevSegQuery& sg = Q.segs[lo];
+    const uint32_t doc = (uint32_t)(gdoc - (lo < PB_AGG_MAX_SEGS_SMEM ? s_doc_base[lo] : sg.doc_base));
+    uint32_t fpass = 0;
+    if (nF > 0) {
+      fpass = pb_agg_filter_bits(sg, doc);
+      if (lo != stat_seg) { stat_flush(); stat_seg = lo; }
+      stat_cnt[0]++;
+#pragma unroll
+      for (int f = 0; f < PB_MAX_AGG_FILTERS; f++) if (f < nF) stat_cnt[1 + f] += (fpass >> f) & 1u;
+    }
+    if (use_smem) pb_accumulate_smem(Q, sg, t, st, doc, fpass);
+    else pb_accumulate(Q, sg, t, doc, ka, unused_rows, fpass);
+  }
+  if (nF > 0) stat_flush();
+  if (!use_smem) return;
+  __syncthreads();
+  // ---- merge the CTA's replicas into the global table: one RED per non-empty cell ----
+  for (uint32_t i = tid; i < S; i += PB_AGG_SMEM_THREADS) {
+    unsigned long long c = 0;
+    for (uint32_t r = 0; r < R; r++) { SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes; c += pb_sh_ld_u32(z.cnt(i)); }
+    if (c == 0) continue;
+    pb_red_add_u64(&t.rowcnt[i], c);
+    for (int a = 0; a < Q.n_aggs; a++) {
+      if (st.fc_of[a] >= 0) {
+        unsigned long long fc = 0;
+        for (uint32_t r = 0; r < R; r++) { SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes; fc += pb_sh_ld_u32(z.fcnt(st.fc_of[a], i)); }
+        if (fc) pb_red_add_u64(&t.fcnt[a][i], fc);
+      }
+      if (st.acc_of[a] < 0) continue;
+      const int op = Q.agg_op[a];
+      if (op == 1 || op == 4) {
+        double v = 0.0;
+        for (uint32_t r = 0; r < R; r++) { SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes; v += __longlong_as_double((long long)pb_sh_ld_u64(z.acc(st.acc_of[a], i))); }
+        pb_red_add_f64(&t.sum[a][i], v);
+      } else {
+        long long m = 0x7fffffffffffffffLL;
+        for (uint32_t r = 0; r < R; r++) { SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes; const long long o = (long long)pb_sh_ld_u64(z.acc(st.acc_of[a], i)); m = o < m ? o : m; }
+        if (m != 0x7fffffffffffffffLL) pb_red_min_s64(&t.mm[a][i], m);
+      }
     }
   }
 }
@@ -1369,6 +1612,99 @@ __global__ void pb_merge_blocks_kernel(unsigned long long* __restrict__ dst, con
     else { long long m = (long long)v; for (int r = r0; r < n_rows; r++) { long long o = (long long)row(r); m = o < m ? o : m; } v = (unsigned long long)m; }
     dst[i] = v;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hash tables across ranks ("partition tuples by hash(key) % nGPU, one all-to-all, local merge kernel"; the
+// reference merges by key in IndexedTable.upsert, CTR/data/table/IndexedTable.java:99-125).  A tuple is
+// [key words | row count | one u64 per aggregation (f64 sum bits / encoded min-max / filtered row count)].
+// ------------------------------------------------------------------------------------------------
+struct DevHashXfer {
+  int32_t n_ranks, key_words, n_aggs, tuple_words;
+  uint64_t S;                                   // slots to scan (capacity + the sentinel slot)
+  uint64_t capacity;
+  const unsigned long long* hkeys;
+  const unsigned long long* rowcnt;
+  const double* sum[PB_MAX_AGGS];
+  const long long* mm[PB_MAX_AGGS];
+  const unsigned long long* fcnt[PB_MAX_AGGS];
+  unsigned long long* counts;                   // [n_ranks] tuples per destination
+  unsigned long long* cursors;                  // [n_ranks] running positions while packing
+  const unsigned long long* offsets;            // [n_ranks] first tuple of each destination in `out`
+  unsigned long long* out;                      // packed tuples, grouped by destination
+};
+__device__ __forceinline__ uint32_t pb_owner_rank(unsigned long long klo, unsigned long long khi, int key_words, int n_ranks) {
+  // a different mix than the slot hash, so that a rank's partition still spreads over its whole table
+  unsigned long long h = pb_hash64((key_words == 2 ? (klo ^ pb_hash64(khi)) : klo) ^ 0x9e3779b97f4a7c15ull);
+  return (uint32_t)((h >> 32) % (unsigned)n_ranks);
+}
+__device__ __forceinline__ void pb_slot_key(const DevHashXfer& X, uint64_t i, unsigned long long& klo, unsigned long long& khi) {
+  if (X.key_words == 2) { klo = i == X.capacity ? PB_HASH_EMPTY : X.hkeys[2 * i]; khi = i == X.capacity ? PB_HASH_EMPTY : X.hkeys[2 * i + 1]; }
+  else { klo = i == X.capacity ? PB_HASH_EMPTY : X.hkeys[i]; khi = 0; }
+}
+__global__ void pb_hash_count_kernel(const DevHashXfer X) {
+  __shared__ unsigned int s_cnt[64];
+  for (int k = threadIdx.x; k < X.n_ranks; k += blockDim.x) s_cnt[k] = 0;
+  __syncthreads();
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < X.S; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (X.rowcnt[i] == 0) continue;
+    unsigned long long klo, khi;
+    pb_slot_key(X, i, klo, khi);
+    atomicAdd(&s_cnt[pb_owner_rank(klo, khi, X.key_words, X.n_ranks)], 1u);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < X.n_ranks; k += blockDim.x) if (s_cnt[k]) atomicAdd(&X.counts[k], (unsigned long long)s_cnt[k]);
+}
+__global__ void pb_hash_pack_kernel(const DevHashXfer X) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t S_round = (X.S + 31) & ~(uint64_t)31;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < S_round; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long c = i < X.S ? X.rowcnt[i] : 0ull;
+    unsigned long long klo = 0, khi = 0;
+    uint32_t dest = 0xffffffffu;
+    if (c) { pb_slot_key(X, i, klo, khi); dest = pb_owner_rank(klo, khi, X.key_words, X.n_ranks); }
+    // lanes bound for the same destination share one atomic
+    const unsigned peers = __match_any_sync(0xffffffffu, dest);
+    if (!c) continue;
+    const int leader = __ffs(peers) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(&X.cursors[dest], (unsigned long long)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    unsigned long long* o = X.out + (X.offsets[dest] + base + __popc(peers & ((1u << lane) - 1u))) * (uint64_t)X.tuple_words;
+    int w = 0;
+    o[w++] = klo;
+    if (X.key_words == 2) o[w++] = khi;
+    o[w++] = c;
+    for (int a = 0; a < X.n_aggs; a++)
+      o[w++] = X.sum[a] ? (unsigned long long)__double_as_longlong(X.sum[a][i]) : X.mm[a] ? (unsigned long long)X.mm[a][i] : X.fcnt[a] ? X.fcnt[a][i] : 0ull;
+  }
+}
+// received tuples -> this rank's (re-initialised) table
+__global__ void pb_hash_merge_kernel(const DevTable t, const unsigned long long* __restrict__ in, uint64_t n_tuples, int key_words, int n_aggs, int tuple_words) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_tuples; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long* p = in + i * (uint64_t)tuple_words;
+    int w = 0;
+    const unsigned long long klo = p[w++];
+    const unsigned long long khi = key_words == 2 ? p[w++] : 0ull;
+    const unsigned long long c = p[w++];
+    const uint64_t slot = key_words == 2 ? pb_hash_slot2(t, klo, khi) : pb_hash_slot(t, klo);
+    if (slot == ~0ull) continue;                 // numGroupsLimit of the merged table (IndexedTable drops new keys past its limit too)
+    pb_red_add_u64(&t.rowcnt[slot], c);
+    for (int a = 0; a < n_aggs; a++) {
+      const unsigned long long v = p[w++];
+      if (t.sum[a]) pb_red_add_f64(&t.sum[a][slot], __longlong_as_double((long long)v));
+      else if (t.mm[a]) pb_red_min_s64(&t.mm[a][slot], (long long)v);
+      else if (t.fcnt[a]) pb_red_add_u64(&t.fcnt[a][slot], v);
+    }
+  }
+}
+// counter cells of all ranks (rank-major) summed into this rank's; the group count [0] and the cursor [3] stay local
+__global__ void pb_sum_counters_kernel(unsigned long long* cells, const unsigned long long* __restrict__ gathered, int n_ranks, int n_cells) {
+  const int i = threadIdx.x;
+  if (i >= n_cells || i == 0 || i == 3) return;
+  unsigned long long v = 0;
+  for (int r = 0; r < n_ranks; r++) v += gathered[r * n_cells + i];
+  cells[i] = v;
 }
 
 // count non-empty slots

@@ -87,7 +87,20 @@ def run_ranks(rank, world, xdir):
     q = parse_sql("SET numGroupsLimit = 10000000; SELECT k0, SUM(m0), COUNT(*) FROM t GROUP BY k0 LIMIT 10000000")
     exp, orc = expected(all_segs, q)
     res = native.execute(group, q, flags)
-    check(f"rank {rank}: hash table", res, exp, orc, q, True, len(all_segs))
+    # hash tables are merged by a hash-partitioned all-to-all: every rank holds the groups whose key hashes to it (disjoint
+    # partitions whose union is the merged table) and the statistics of the whole query
+    t = res.tables[0]
+    parts = ex.all_gather(t.rows())
+    assert sum(len(p) for p in parts) == len(exp), (sum(len(p) for p in parts), len(exp))
+    union = {}
+    for p in parts:
+        assert not (set(p) & set(union)), "partitions overlap"
+        union.update(p)
+    assert_rows_equal(union, exp, q, exact_float=True, what=f"rank {rank}: hash table (union of the partitions)")
+    assert all(len(p) > 0 for p in parts), "a rank ended up without groups"
+    st = t.stats
+    assert st["num_docs_scanned"] == sum(o.stats["num_docs_scanned"] for o in orc) and st["num_segments"] == len(all_segs), st
+    assert res.comm_ms() > 0
     res.free()
     ex.barrier()
     native.comm_destroy()
@@ -117,8 +130,27 @@ def run_devices(n_dev):
     print("MULTI_GPU_OK devices")
 
 
+def run_single():
+    """a communicator of ONE rank on one GPU: NCCL is loaded, ncclCommInitRank runs, PB_Q_ALL_RANKS is a no-op merge"""
+    native.init(0)
+    native.comm_init(1, 0, native.comm_unique_id())
+    assert native.comm_info() == (True, 1, 0)
+    all_segs = [segment(i) for i in range(3)]
+    group = native.SegmentGroup([native.StagedSegment(s) for s in all_segs])
+    for name, sql, exact in queries(all_segs):
+        q = parse_sql(sql)
+        exp, orc = expected(all_segs, q)
+        res = native.execute(group, q, native.PB_Q_COMBINE | native.PB_Q_ALL_RANKS)
+        check(f"single rank: {name}", res, exp, orc, q, exact, len(all_segs))
+        res.free()
+    native.comm_destroy()
+    print("MULTI_GPU_OK single")
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "ranks":
+    if sys.argv[1] == "single":
+        run_single()
+    elif sys.argv[1] == "ranks":
         run_ranks(int(sys.argv[2]), int(sys.argv[3]), sys.argv[4])
     else:
         run_devices(int(sys.argv[2]))

@@ -50,3 +50,8 @@ def test_one_process_driving_two_devices_matches_oracle():
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
     _run([subprocess.Popen([sys.executable, WORKER, "devices", "2"], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)])
+
+
+@pytest.mark.timeout(600)
+def test_single_rank_communicator_on_one_gpu():
+    _run([subprocess.Popen([sys.executable, WORKER, "single"], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)])
