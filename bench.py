@@ -390,7 +390,7 @@ def run_timed(w, steps, warmup, torch, dist, sampler=None):
         r = w.step()
         rec["wall"].append(1000 * (time.perf_counter() - ts))
         rec["scan"].append(r.scan_ms())
-        f_, a_ = r.phase_ms()
+        f_, a_ = r.phase_ms()      # CUDA events on the call's stream (a cached plan samples them on every 8th replay and repeats the sample in between)
         rec["filt"].append(f_)
         rec["agg"].append(a_)
         rec["comm"].append(r.comm_ms())
@@ -480,7 +480,8 @@ def main():
                  "value": T25["value"], "filter_kernel_ms": T25["filter_ms"], "agg_kernel_ms": T25["agg_ms"], "docs_matched": p25["docs_matched"],
                  "parity_checked": True,
                  "whole_query_frac_on_step_time": alg25 / (T25["ms_per_step"] * 1e-3) / 1e9 / (measured_peak_gbs()[0] * world),
-                 "whole_query_frac_on_kernel_time": algorithmic_bytes(segs, w25.q, "all") / ((T25["filter_ms"] + T25["agg_ms"]) * 1e-3) / 1e9 / measured_peak_gbs()[0]}
+                 "whole_query_frac_on_kernel_time": (algorithmic_bytes(segs, w25.q, "all") / ((T25["filter_ms"] + T25["agg_ms"]) * 1e-3) / 1e9 / measured_peak_gbs()[0]
+                                                     if T25["filter_ms"] + T25["agg_ms"] > 0 else None)}
 
     # ---- the other scaling curve (both are reported at every N; `scaling` names the headline's) ----
     other = None
@@ -575,7 +576,7 @@ def main():
     alg_all = algorithmic_bytes(segs, q, "all")
     dom = "pb_filter_kernel" if f_mean >= a_mean else "pb_agg_kernel"
     dom_ms, dom_alg = (f_mean, alg_filter) if dom == "pb_filter_kernel" else (a_mean, alg_agg)
-    achieved = dom_alg / (dom_ms * 1e-3) / 1e9
+    achieved = dom_alg / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "scan_kernel_traffic.json")
     if os.path.exists(tp):
@@ -595,7 +596,7 @@ def main():
                                                       "fraction is not a bandwidth utilisation at low selectivity"}},
                 "whole_query": {"algorithmic_bytes": alg_all * world, "step_ms": step_ms,
                                 "frac_on_step_time": alg_all * world / (step_ms * 1e-3) / 1e9 / (peak * world),
-                                "kernel_ms": f_mean + a_mean, "frac_on_kernel_time": alg_all / ((f_mean + a_mean) * 1e-3) / 1e9 / peak,
+                                "kernel_ms": f_mean + a_mean, "frac_on_kernel_time": alg_all / ((f_mean + a_mean) * 1e-3) / 1e9 / peak if f_mean + a_mean > 0 else None,
                                 "note": "BASELINE.md full-scan convention (87 bits/row); frac_on_step_time divides by the driver-visible step "
                                         "(launch gaps, finalize, host and the NCCL merge included)"}}
 

@@ -191,6 +191,8 @@ int pb_comm_destroy(void);
 int pb_segment_stage(const pb_segment_desc* desc, int device_index, pb_segment_handle* out);
 int pb_segment_release(pb_segment_handle seg);
 int64_t pb_segment_device_bytes(pb_segment_handle seg);
+/* segment cache of one device: bytes staged right now and segments evicted so far (hbm_cache_bytes of pb_init) */
+int pb_cache_stats(int device_index, int64_t* staged_bytes, int64_t* evictions);
 
 /* A set of segments queried together.  Holds the per-column global dictionaries (sorted union of the
  * segment dictionaries) and local->global dictId remaps that make a device-side cross-segment merge

@@ -173,12 +173,31 @@ static int32_t dict_insertion_index_double(const orc_column* c, double v) {
   }
   return -(lo + 1);
 }
-/* padded fixed-width string compare (pad byte 0 sorts first, as in the sorted dictionary) */
-static int str_cmp_entry(const orc_column* c, int32_t id, const char* s) {
+/* STRING dictionary entry `id` as (pointer, length).  Two on-disk forms (BaseImmutableDictionary picks the ValueReader:
+ * SEGL/segment/index/readers/BaseImmutableDictionary.java:45-58):
+ *   fixed width  FixedByteValueReaderWriter: entries of lengthOfEachEntry bytes, padded with 0
+ *   var length   VarLengthValueReader (SEGL/io/util/VarLengthValueReader.java:41-96): magic ".vl;", int version = 1,
+ *                int numValues, int dataSectionStartOffset, then numValues + 1 big-endian offsets, then the bytes */
+static int dict_is_var_length(const orc_column* c) {
+  return c->dictionary_len >= 20 && memcmp(c->dictionary, ".vl;", 4) == 0 && be32(c->dictionary + 4) == 1;
+}
+static const uint8_t* str_entry(const orc_column* c, int32_t id, int32_t* len) {
+  if (dict_is_var_length(c)) {
+    const uint32_t data0 = be32(c->dictionary + 12);
+    const uint32_t a = be32(c->dictionary + data0 + 4 * (int64_t)id), b = be32(c->dictionary + data0 + 4 * (int64_t)id + 4);
+    *len = (int32_t)(b - a);
+    return c->dictionary + a;
+  }
   const uint8_t* e = c->dictionary + (int64_t)id * c->dict_entry_bytes;
-  int32_t n = c->dict_entry_bytes;
-  int32_t elen = 0;
+  int32_t n = c->dict_entry_bytes, elen = 0;
   while (elen < n && e[elen] != 0) elen++;
+  *len = elen;
+  return e;
+}
+/* string compare against a dictionary entry (pad byte 0 sorts first, as in the sorted dictionary) */
+static int str_cmp_entry(const orc_column* c, int32_t id, const char* s) {
+  int32_t elen = 0;
+  const uint8_t* e = str_entry(c, id, &elen);
   size_t slen = strlen(s);
   size_t m = (size_t)elen < slen ? (size_t)elen : slen;
   int r = memcmp(e, s, m);

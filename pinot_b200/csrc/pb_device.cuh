@@ -144,6 +144,10 @@ struct DevTable {
   unsigned int* num_groups;          // hash: groups created so far
   unsigned int* limit_reached;
   unsigned long long* docs_matched;  // numDocsScanned
+  // dense table whose key space exceeds numGroupsLimit (the reference's IntMapBasedHolder, first come first served in doc
+  // order: DictionaryBasedGroupKeyGenerator.java:1023-1058): first_doc[slot] = smallest doc that produced the group; the
+  // hand-back keeps the numGroupsLimit groups that appeared first -- exactly the groups the reference would have created
+  uint32_t* first_doc;
   uint32_t num_groups_limit;
   uint32_t limit_active;             // 0: the table can never reach numGroupsLimit (limit >= docs), inserts need no ticket
 };
@@ -499,13 +503,15 @@ __device__ __forceinline__ uint64_t pb_hash64(uint64_t k) {
 }
 
 // ---- numGroupsLimit (DictionaryBasedGroupKeyGenerator.java:1033-1035: a NEW key past the limit gets INVALID_ID and its
-// rows are dropped; existing keys keep aggregating).  A thread may insert only while it holds a ticket: tickets are taken
-// from num_groups with a returning atomic BEFORE the slot is claimed and handed back when the claim is lost to another
-// thread, so the table never holds more than `limit` keys however many threads race (the check-then-insert of round 1 let
-// every resident thread pass the check at once and could fill the table, after which absent keys probed forever).  Lanes of
-// a warp that need a ticket at the same time share one atomic.  Probing is bounded by the capacity. ----
+// rows are dropped; existing keys keep aggregating).  A thread may insert only while it holds a ticket, taken from
+// num_groups with a returning atomic BEFORE the slot is claimed (the check-then-insert of round 1 let every resident thread
+// pass the check at once and could fill the table, after which absent keys probed forever).  Tickets are never handed
+// back: once one request has been refused every later one is refused too, so a key can never be created after some of its
+// rows were dropped (no partially aggregated group) and the table never holds more than `limit` keys; a claim lost to a
+// concurrent insert of the same slot wastes its ticket, so a limited result may hold a few groups fewer than the limit.
+// Lanes of a warp that need a ticket at the same time share one atomic.  Probing is bounded by the capacity. ----
 __device__ __forceinline__ bool pb_group_ticket(const DevTable& t) {
-  if (!t.limit_active) { pb_red_add_u32(t.num_groups, 1u); return true; }
+  if (!t.limit_active) return true;                      // groups <= docs <= limit: cannot be reached, nothing to count
   const unsigned m = __activemask();
   const int leader = __ffs(m) - 1, lane = (int)(threadIdx.x & 31);
   const unsigned rank = __popc(m & ((1u << lane) - 1u)), need = __popc(m);
@@ -513,11 +519,10 @@ __device__ __forceinline__ bool pb_group_ticket(const DevTable& t) {
   if (lane == leader) base = pb_atom_add_u32(t.num_groups, need);
   base = __shfl_sync(m, base, leader);
   if (base + rank < t.num_groups_limit) return true;
-  pb_red_add_u32(t.num_groups, 0xffffffffu);              // over the limit: hand the ticket back (-1)
   pb_red_add_u32(t.limit_reached, 1u);
   return false;
 }
-__device__ __forceinline__ void pb_group_ticket_return(const DevTable& t) { pb_red_add_u32(t.num_groups, 0xffffffffu); }
+__device__ __forceinline__ void pb_group_ticket_return(const DevTable&) {}
 
 // returns slot, or ~0ull when the key is new and numGroupsLimit is reached
 __device__ __forceinline__ uint64_t pb_hash_slot(const DevTable& t, uint64_t key) {
@@ -673,6 +678,7 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
   }
   if (Q.table_mode == T_KEYLESS) keyless_rows++;
   else pb_red_add_u64(&t.rowcnt[slot], 1ull);
+  if (t.first_doc) asm volatile("red.global.min.u32 [%0], %1;" ::"l"(t.first_doc + slot), "r"(doc));
 
   for (int a = 0; a < nA; a++) {
     const int op = Q.agg_op[a];
@@ -1707,6 +1713,35 @@ __global__ void pb_sum_counters_kernel(unsigned long long* cells, const unsigned
   cells[i] = v;
 }
 
+// numGroupsLimit in doc order: *thr = the limit-th smallest first_doc among the existing groups (first docs are distinct: a
+// doc belongs to one group), or 0xFFFFFFFE when fewer groups exist.  One CTA, four 8-bit radix-select passes.
+__global__ void pb_select_first_kernel(const uint32_t* __restrict__ first_doc, uint64_t S, uint32_t limit, uint32_t* thr) {
+  __shared__ unsigned int hist[256];
+  __shared__ uint32_t s_prefix, s_k, s_done;
+  if (threadIdx.x == 0) { s_prefix = 0; s_k = limit; s_done = 0; }
+  __syncthreads();
+  for (int pass = 3; pass >= 0; pass--) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix, hi_mask = pass == 3 ? 0u : (0xffffffffu << (8 * (pass + 1)));
+    for (uint64_t i = threadIdx.x; i < S; i += blockDim.x) {
+      const uint32_t v = first_doc[i];
+      if (v != 0xffffffffu && (v & hi_mask) == (prefix & hi_mask)) atomicAdd(&hist[(v >> (8 * pass)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t k = s_k, cum = 0;
+      int b = 0;
+      for (; b < 256; b++) { if (cum + hist[b] >= k) break; cum += hist[b]; }
+      if (b == 256) s_done = 1;                       // fewer than `limit` groups exist: everything survives
+      else { s_prefix = prefix | ((uint32_t)b << (8 * pass)); s_k = k - cum; }
+    }
+    __syncthreads();
+    if (s_done) break;
+  }
+  if (threadIdx.x == 0) *thr = s_done ? 0xfffffffeu : s_prefix;
+}
+
 // count non-empty slots
 __global__ void pb_count_groups_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n, unsigned long long* out) {
   unsigned long long c = 0;
@@ -1745,6 +1780,8 @@ struct DevFinalize {
   uint64_t cap_out;
   const unsigned long long* rowcnt;
   const unsigned long long* hkeys;
+  const uint32_t* first_doc;      // numGroupsLimit in doc order: emit only groups whose first doc is <= *first_thr
+  const uint32_t* first_thr;
   unsigned long long* cursor;
   unsigned long long* out_slots;
   unsigned long long* out_rows;
@@ -1758,7 +1795,8 @@ __global__ void pb_finalize_kernel(const DevFinalize F) {
   const uint64_t S_round = (F.S + 31) & ~(uint64_t)31;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < S_round; i += stride) {
     const unsigned long long c = i < F.S ? F.rowcnt[i] : 0ull;
-    const bool emit = i < F.S && (c != 0 || F.always_emit);
+    bool emit = i < F.S && (c != 0 || F.always_emit);
+    if (emit && F.first_doc && F.first_doc[i] > *F.first_thr) emit = false;
     const uint32_t b = __ballot_sync(0xffffffffu, emit);
     if (!b) continue;
     unsigned long long base = 0;
@@ -1779,7 +1817,8 @@ __global__ void pb_finalize_kernel(const DevFinalize F) {
         else fa.out[k] = pb_dec_f64(fa.op == 2 ? fa.mm[i] : ~fa.mm[i]);
       }
       else if (fa.op == 0) fa.out[k] = fa.fcnt ? (double)fa.fcnt[i] : (double)c;
-      if (fa.fcnt) fa.out_cnt[k] = (long long)fa.fcnt[i];
+      // the aggregation's long array: COUNT value / AVG denominator (the function's own row count under a FILTER clause), 0 otherwise
+      if (fa.op != 5) fa.out_cnt[k] = (fa.op == 0 || fa.op == 4) ? (fa.fcnt ? (long long)fa.fcnt[i] : (long long)c) : 0ll;
     }
     unsigned long long key = 0, key_hi = 0;
     if (F.mode == T_HASH) {

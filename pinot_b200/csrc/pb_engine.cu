@@ -64,6 +64,7 @@ struct Context {
   // segment cache accounting (hbm_cache_bytes of pb_init): staged bytes on this device and the LRU clock
   int64_t staged_bytes = 0;
   uint64_t lru_clock = 0;
+  uint64_t evictions = 0;
   std::vector<struct pb_segment_s*> segments; // every live segment staged on this device (eviction candidates)
   // cross-rank merge (pb_comm_init): receive buffer of the table all-gather, grown on demand
   void* gather_buf = nullptr; size_t gather_cap = 0;
@@ -309,6 +310,7 @@ struct pb_segment_s {
   // which invalidates cached query plans that hold pointers into them
   int inflight = 0;
   uint64_t last_used = 0, epoch = 0;
+  int64_t accounted_bytes = 0;              // part of device_bytes already added to the context's staged_bytes
   // staging copies run on the context's copy stream; `staged_ev` marks the last one enqueued for this segment and
   // every query that touches the segment orders its kernels after it (until it is known to have completed)
   cudaEvent_t staged_ev = nullptr;
@@ -349,9 +351,33 @@ extern "C" int pb_segment_stage(const pb_segment_desc* d, int device_index, pb_s
     if (c.type < PB_INT || c.type > PB_STRING) return fail(PB_ERR_UNSUPPORTED, "column %s: stored type %d", cd.name, c.type);
     if (c.has_dict) {
       if (!cd.dictionary || c.card <= 0 || c.bits < 1 || c.bits > 32) return fail(PB_ERR_INVALID, "column %s: bad dictionary metadata", cd.name);
-      uint64_t need = (uint64_t)c.card * (uint64_t)c.entry_bytes;
-      if (cd.dictionary_len < need) return fail(PB_ERR_INVALID, "column %s: dictionary too short", cd.name);
-      c.h_dict.assign((const uint8_t*)cd.dictionary, (const uint8_t*)cd.dictionary + need);
+      const uint8_t* db = (const uint8_t*)cd.dictionary;
+      if (c.type == PB_STRING && cd.dictionary_len >= 20 && memcmp(db, ".vl;", 4) == 0 && be32(db + 4) == 1) {
+        // var-length dictionary (VarLengthValueReader, SEGL/io/util/VarLengthValueReader.java:41-96: magic, version, numValues,
+        // dataSectionStartOffset, numValues + 1 offsets, bytes): kept on this side as zero-padded entries of the longest
+        // value's width, the layout every later step (global dictionaries, key decode) works on
+        const uint32_t nv = be32(db + 8), data0 = be32(db + 12);
+        if ((int64_t)nv != (int64_t)c.card) return fail(PB_ERR_INVALID, "column %s: var-length dictionary holds %u values, metadata says %d", cd.name, nv, c.card);
+        if ((uint64_t)data0 + 4ull * ((uint64_t)nv + 1) > cd.dictionary_len) return fail(PB_ERR_INVALID, "column %s: var-length dictionary offsets out of bounds", cd.name);
+        uint32_t width = 1;
+        for (uint32_t k = 0; k < nv; k++) {
+          const uint32_t a = be32(db + data0 + 4ull * k), b = be32(db + data0 + 4ull * k + 4);
+          if (b < a || b > cd.dictionary_len) return fail(PB_ERR_INVALID, "column %s: var-length dictionary entry %u out of bounds", cd.name, k);
+          width = std::max(width, b - a);
+        }
+        if (width > (1u << 20)) return fail(PB_ERR_UNSUPPORTED, "column %s: %u-byte dictionary values", cd.name, width);
+        c.entry_bytes = (int)width;
+        c.h_dict.assign((size_t)nv * width, 0);
+        for (uint32_t k = 0; k < nv; k++) {
+          const uint32_t a = be32(db + data0 + 4ull * k), b = be32(db + data0 + 4ull * k + 4);
+          memcpy(c.h_dict.data() + (size_t)k * width, db + a, b - a);
+        }
+      } else {
+        if (c.entry_bytes <= 0) return fail(PB_ERR_INVALID, "column %s: dictionary entry width %d", cd.name, c.entry_bytes);
+        uint64_t need = (uint64_t)c.card * (uint64_t)c.entry_bytes;
+        if (cd.dictionary_len < need) return fail(PB_ERR_INVALID, "column %s: dictionary too short", cd.name);
+        c.h_dict.assign(db, db + need);
+      }
       if (c.is_sorted) {
         if (c.h_fwd_len < 8ull * c.card) return fail(PB_ERR_INVALID, "column %s: sorted index too short", cd.name);
         c.h_sorted_pairs.resize(2 * (size_t)c.card);
@@ -472,6 +498,51 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
   return PB_OK;
 }
 
+
+// ---- segment cache (hbm_cache_bytes of pb_init): when the staged bytes of a device exceed the limit, the least recently
+// used segments that no query is using lose their HBM copies (their host buffers are still the caller's mmap: the next
+// query on them stages again).  Every eviction bumps the segment's epoch, which retires cached plans that point into it. ----
+static void drop_device_copies(pb_segment_s* s) {     // under s->mu, inflight == 0, no staging copy pending
+  for (auto& c : s->cols) {
+    dev_free(s->ctx, c.d_fwd); dev_free(s->ctx, c.d_sorted_pairs); dev_free(s->ctx, c.d_dict_f64); dev_free(s->ctx, c.d_dict_native); dev_free(s->ctx, c.d_inv);
+    c.d_fwd = nullptr; c.d_sorted_pairs = nullptr; c.d_dict_f64 = nullptr; c.d_dict_native = nullptr; c.d_inv = nullptr;
+    c.d_fwd_bytes = 0;
+    c.fwd_staged = c.dict_staged = c.inv_staged = c.native_staged = false;
+  }
+  for (auto& b : s->staging_bufs) pinned_free(b.p, b.cap);
+  s->staging_bufs.clear();
+  s->device_bytes = 0; s->accounted_bytes = 0;
+  s->epoch++;
+}
+static void enforce_cache_limit(Context* ctx) {
+  const size_t limit = g_all.hbm_cache_bytes;
+  if (!limit) return;
+  std::vector<pb_segment_s*> cand;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((size_t)std::max<int64_t>(ctx->staged_bytes, 0) <= limit) return;
+    cand = ctx->segments;
+  }
+  std::sort(cand.begin(), cand.end(), [](const pb_segment_s* a, const pb_segment_s* b) { return a->last_used < b->last_used; });
+  for (pb_segment_s* s : cand) {
+    {
+      std::lock_guard<std::mutex> lk(ctx->mu);
+      if ((size_t)std::max<int64_t>(ctx->staged_bytes, 0) <= limit) return;
+    }
+    std::unique_lock<std::mutex> sl(s->mu, std::try_to_lock);
+    if (!sl.owns_lock() || s->inflight > 0 || s->device_bytes == 0) continue;
+    if (s->staged_pending) {
+      if (cudaEventQuery(s->staged_ev) != cudaSuccess) { cudaGetLastError(); continue; }
+      s->staged_pending = false;
+    }
+    const int64_t freed = s->accounted_bytes;
+    drop_device_copies(s);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->staged_bytes -= freed;
+    ctx->evictions++;
+  }
+}
+
 extern "C" int pb_segment_release(pb_segment_handle s) {
   if (!s) return PB_OK;
   DeviceGuard dg(s->ctx);
@@ -479,7 +550,7 @@ extern "C" int pb_segment_release(pb_segment_handle s) {
     std::lock_guard<std::mutex> lk(s->ctx->mu);
     auto& v = s->ctx->segments;
     v.erase(std::remove(v.begin(), v.end(), s), v.end());
-    s->ctx->staged_bytes -= s->device_bytes;
+    s->ctx->staged_bytes -= s->accounted_bytes;
   }
   if (s->staged_ev) { cudaEventSynchronize(s->staged_ev); cudaEventDestroy(s->staged_ev); }
   for (auto& b : s->staging_bufs) pinned_free(b.p, b.cap);
@@ -490,6 +561,14 @@ extern "C" int pb_segment_release(pb_segment_handle s) {
   return PB_OK;
 }
 extern "C" int64_t pb_segment_device_bytes(pb_segment_handle s) { return s ? s->device_bytes : 0; }
+extern "C" int pb_cache_stats(int device_index, int64_t* staged_bytes, int64_t* evictions) {
+  Context* c = ctx_at(device_index);
+  if (!c) return fail(PB_ERR_INVALID, "pb_cache_stats: no device at index %d", device_index);
+  std::lock_guard<std::mutex> lk(c->mu);
+  if (staged_bytes) *staged_bytes = c->staged_bytes;
+  if (evictions) *evictions = (int64_t)c->evictions;
+  return PB_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // segment groups and global dictionaries
@@ -803,6 +882,7 @@ struct pb_result_s {
   struct InitArgs { uint4* zero = nullptr; uint64_t zn = 0; uint4* ff = nullptr; uint64_t fn = 0; uint4* mm = nullptr; uint64_t mn = 0;
                     uint4* aux = nullptr; uint64_t an = 0; const uint4* head = nullptr; uint64_t head_n16 = 0; int grid = 1; } init;   // pb_init_tables_kernel
   int key_words = 1;
+  bool track_first = false; uint32_t* d_first_thr = nullptr;   // numGroupsLimit in doc order (dense per-segment tables)
   bool fused = false, smem_table = false;   // how the matches reached the table (see exec_single)
   bool comm_timed = false;                  // events [5],[6] bracket the cross-rank merge
   double comm_ms = 0;
@@ -1261,7 +1341,6 @@ static int replay_plan(pb_result_s* r, const pb_query_desc* q) {
   cudaStream_t st = r->stream;
   const double t0 = now_us();
   r->finalized = false; r->launches = 0; r->comm_timed = false; r->comm_ms = 0; r->merged_ranks = 1;
-  r->device_ms = r->scan_ms = r->filter_ms = r->agg_ms = 0;
   for (int i = 0; i < 8; i++) r->host_us[i] = 0;
   for (auto& tm : r->tables) {
     tm.num_groups = 0;
@@ -1294,8 +1373,11 @@ static int replay_plan(pb_result_s* r, const pb_query_desc* q) {
       rp.graph_launches = r->launches;
       r->launches = 0;
     }
-    if (rp.graph) { CU(cudaGraphLaunch(rp.graph, st)); r->launches = rp.graph_launches; r->graph_replayed = true; }
-    else { if ((rc = enqueue_all(r, nullptr))) return rc; if ((rc = enqueue_finalize(r))) return rc; }
+    // CUDA events recorded inside a graph cannot be timed: every 8th replay is enqueued kernel by kernel instead, which
+    // keeps the per-kernel CUDA-event times (pb_result_phase_ms) of a cached plan live; the others report the last sample
+    const bool sample = rp.graph && (rp.uses & 7) == 7;
+    if (rp.graph && !sample) { CU(cudaGraphLaunch(rp.graph, st)); r->launches = rp.graph_launches; r->graph_replayed = true; }
+    else { r->graph_replayed = false; if ((rc = enqueue_all(r, nullptr))) return rc; if ((rc = enqueue_finalize(r))) return rc; }
   } else {
     if ((rc = enqueue_all(r, nullptr))) return rc;
     if (all_ranks && (rc = comm_merge(r))) return rc;
@@ -1437,6 +1519,11 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
         }
       }
     }
+    if (s->device_bytes != s->accounted_bytes) {
+      std::lock_guard<std::mutex> lk2(ctx->mu);
+      ctx->staged_bytes += s->device_bytes - s->accounted_bytes;
+      s->accounted_bytes = s->device_bytes;
+    }
     // order this (and every later) query's kernels after the copies just enqueued for the segment
     if (s->stage_dirty) {
       if (!s->staged_ev) CU(cudaEventCreateWithFlags(&s->staged_ev, cudaEventDisableTiming));
@@ -1449,6 +1536,8 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       cudaGetLastError();   // cudaErrorNotReady is not an error
     }
   }
+
+  enforce_cache_limit(ctx);      // this call's segments are pinned: only others can go
 
   // ---- global dictionaries (combined mode) ----
   std::vector<GlobalDict*> gdict(nG, nullptr), adict(nA, nullptr);
@@ -1518,6 +1607,12 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   // ---- device table arenas: [zero region][0xFF region][min/max region] ----
   auto slots_of = [&](const TableMeta& tm) { return tm.capacity + (table_mode == T_HASH ? 1 : 0); };
   size_t zero_bytes = 0, ff_bytes = 0, mm_elems = 0;
+  // numGroupsLimit below the key space of a dense table: the reference creates groups first come first served in doc order
+  // (IntMapBasedHolder); kept exact for per-segment tables (a merged table reports the superset and the flag)
+  bool track_first = false;
+  if (table_mode == T_DENSE && (!combine || n_segs == 1))
+    for (auto& tm : r->tables) if ((uint64_t)std::max(1, q->num_groups_limit) < tm.capacity) track_first = true;
+  r->track_first = track_first;
   std::vector<uint64_t> dc_words(nA, 0);
   for (int a = 0; a < nA; a++)
     if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT) {
@@ -1537,6 +1632,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     }
     zero_bytes = (zero_bytes + 255) & ~(size_t)255;
     if (table_mode == T_HASH) ff_bytes += 8 * S * (size_t)key_words;
+    if (track_first) ff_bytes += (4 * S + 15) & ~(size_t)15;
   }
   const size_t seg_stats_bytes = nF > 0 ? 8 * (size_t)(1 + PB_MAX_AGG_FILTERS) * (size_t)n_segs : 0;   // swim-lane statistics per segment
   zero_bytes += 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 256;
@@ -1548,11 +1644,13 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   // per-wave match counters and per-segment swim-lane statistics live in an aux region behind it that is not shipped.
   zero_bytes = (zero_bytes + 255) & ~(size_t)255;
   const size_t mm_bytes = (8 * mm_elems + 255) & ~(size_t)255;
-  const size_t aux_bytes = (8 * PB_MAX_WAVES + seg_stats_bytes + 255) & ~(size_t)255;
+  const size_t thr_off = 8 * PB_MAX_WAVES + seg_stats_bytes;          // numGroupsLimit thresholds (one u32 per table), after the statistics
+  const size_t aux_bytes = (thr_off + (track_first ? 4 * (size_t)n_tables : 0) + 255) & ~(size_t)255;
   CU(cudaMallocAsync((void**)&d_zero, zero_bytes + mm_bytes + aux_bytes + 16, st)); r->dev_allocs.push_back(d_zero);
   if (ff_bytes) { CU(cudaMallocAsync((void**)&d_ff, ff_bytes + 16, st)); r->dev_allocs.push_back(d_ff); }
   if (mm_elems) d_mm = reinterpret_cast<long long*>(d_zero + zero_bytes);
   uint8_t* d_aux = d_zero + zero_bytes + mm_bytes;
+  r->d_first_thr = track_first ? reinterpret_cast<uint32_t*>(d_aux + thr_off) : nullptr;
   r->block = d_zero; r->block_bytes = (int64_t)(zero_bytes + 8 * mm_elems);
   r->block_mm_off = (int64_t)zero_bytes;
 
@@ -1593,6 +1691,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       if (t == 0) { r->span_mm = d_mm; r->span_mm_n = (int64_t)mo; }
       zo = (zo + 255) & ~(size_t)255;
       if (table_mode == T_HASH) { dt.hkeys = reinterpret_cast<unsigned long long*>(d_ff + fo); fo += 8 * S * (size_t)key_words; dt.key_words = key_words; }
+      if (track_first) { dt.first_doc = reinterpret_cast<uint32_t*>(d_ff + fo); fo += (4 * S + 15) & ~(size_t)15; }
       unsigned long long* cnt = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE;
       dt.num_groups = reinterpret_cast<unsigned int*>(cnt + 0);
       dt.limit_reached = reinterpret_cast<unsigned int*>(cnt + 1);
@@ -1883,7 +1982,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   double est_sel = 0.0;
   for (int si = 0; si < n_segs; si++) est_sel += estimate_selectivity(g->segs[si], sqs[si]) * (double)g->segs[si]->num_docs;
   est_sel = n_docs_total ? est_sel / (double)n_docs_total : 0.0;
-  static const int fuse_permille = []() { const char* e = getenv("PB_FUSE_PERMILLE"); return e ? atoi(e) : 50; }();
+  static const int fuse_permille = []() { const char* e = getenv("PB_FUSE_PERMILLE"); return e ? atoi(e) : -1; }();   // (measured: no gain on B200 while every matching row costs six random DRAM sectors; see profiles/r2_experiments.md)
   const bool fuse = !match_all && table_mode != T_KEYLESS && nF == 0 && n_docs_total > 0 && est_sel * 1000.0 <= (double)fuse_permille;
   int n_acc = 0, n_fc = 0;
   for (int a = 0; a < nA; a++) {
@@ -1894,7 +1993,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   static const int smem_table_env = []() { const char* e = getenv("PB_AGG_SMEM"); return e ? atoi(e) : 1; }();
   static const size_t smem_table_budget = 200 * 1024;
   size_t st_rep_bytes = 0; int st_replicas = 0;
-  if (smem_table_env && !fuse && table_mode == T_DENSE && n_tables == 1 && r->tables[0].capacity <= (1u << 20)) {
+  if (smem_table_env && !fuse && !track_first && table_mode == T_DENSE && n_tables == 1 && r->tables[0].capacity <= (1u << 20)) {
     st_rep_bytes = pb_smem_table_bytes((uint32_t)r->tables[0].capacity, n_fc, n_acc);
     if (st_rep_bytes <= smem_table_budget) { st_replicas = 1; while (st_replicas < 32 && (size_t)(2 * st_replicas) * st_rep_bytes <= smem_table_budget) st_replicas *= 2; }
   }
@@ -2297,6 +2396,7 @@ static int prepare_finalize(pb_result_s* r) {
     F.mode = mode; F.n_gb = nG; F.n_aggs = nA; F.always_emit = mode == T_KEYLESS ? 1 : 0;
     F.S = mode == T_KEYLESS ? 1 : S; F.capacity = tm.capacity; F.cap_out = cap; F.key_words = tm.dev.key_words;
     F.rowcnt = tm.dev.rowcnt; F.hkeys = tm.dev.hkeys;
+    if (tm.dev.first_doc) { F.first_doc = tm.dev.first_doc; F.first_thr = r->d_first_thr + t; }
     F.cursor = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3;
     F.out_slots = (unsigned long long*)tm.slots.p; F.out_rows = (unsigned long long*)tm.rows.p;
     for (int a = 0; a < nA; a++) {
@@ -2334,7 +2434,12 @@ static int enqueue_finalize(pb_result_s* r) {
   cudaStream_t st = r->stream;
   const int nT = (int)r->tables.size();
   for (int t = 0; t < nT; t++) {
-    pb_finalize_kernel<<<r->rp.fin_grid[(size_t)t], 256, 0, st>>>(r->rp.fin[(size_t)t]);
+    const DevFinalize& F = r->rp.fin[(size_t)t];
+    if (F.first_doc) {
+      pb_select_first_kernel<<<1, 1024, 0, st>>>(F.first_doc, F.S, r->tables[(size_t)t].dev.num_groups_limit, r->d_first_thr + t);
+      r->launches++;
+    }
+    pb_finalize_kernel<<<r->rp.fin_grid[(size_t)t], 256, 0, st>>>(F);
     r->launches++;
   }
   CU(cudaGetLastError());
@@ -2351,12 +2456,14 @@ static int finish_finalize(pb_result_s* r) {
   auto lap = [&](int i) { double t = now_us(); r->host_us[i] += t - t_prev; t_prev = t; };
   CU(cudaStreamSynchronize(st));
   lap(5);
-  float ms = 0;
-  if (cudaEventElapsedTime(&ms, r->ev0, r->ev3) == cudaSuccess) r->device_ms = ms;
-  if (cudaEventElapsedTime(&ms, r->ev1, r->ev2) == cudaSuccess) r->scan_ms = ms;
-  if (cudaEventElapsedTime(&ms, r->ev1, r->evm) == cudaSuccess) r->filter_ms = ms;
-  if (cudaEventElapsedTime(&ms, r->evm, r->ev2) == cudaSuccess) r->agg_ms = ms;
-  cudaGetLastError();
+  if (!r->graph_replayed) {      // (a graph replay keeps the times of the plan's last kernel-by-kernel run)
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r->ev0, r->ev3) == cudaSuccess) r->device_ms = ms;
+    if (cudaEventElapsedTime(&ms, r->ev1, r->ev2) == cudaSuccess) r->scan_ms = ms;
+    if (cudaEventElapsedTime(&ms, r->ev1, r->evm) == cudaSuccess) r->filter_ms = ms;
+    if (cudaEventElapsedTime(&ms, r->evm, r->ev2) == cudaSuccess) r->agg_ms = ms;
+    cudaGetLastError();
+  }
 
   // host side: counts, stats, distinct value sets
   for (int t = 0; t < nT; t++) {
@@ -2367,9 +2474,7 @@ static int finish_finalize(pb_result_s* r) {
     for (int a = 0; a < nA; a++) {
       const int op = r->agg_op[a];
       int64_t* L = (int64_t*)tm.lng[a].p;
-      if (tm.dev.fcnt[a]) continue;      // COUNT / AVG with a FILTER clause: written by the finalize kernel
-      if (op == PB_AGG_COUNT || op == PB_AGG_AVG) for (int64_t k = 0; k < ng; k++) L[k] = (int64_t)rows[k];
-      else if (op != PB_AGG_DISTINCTCOUNT) memset(L, 0, 8 * (size_t)std::max<int64_t>(ng, 1));
+      (void)L; (void)rows; (void)op;     // COUNT / AVG counts and the zeros of SUM / MIN / MAX are written by the finalize kernel
     }
     // DISTINCTCOUNT: the sizes now; the value sets (BaseDistinctAggregateAggregationFunction intermediate result) are
     // materialised on first access (pb_result_distinct_offsets / _dict_ids) — a merged result usually needs the sizes only

@@ -98,6 +98,7 @@ def lib():
     l.pb_result_comm_ms.restype = C.c_double
     l.pb_segment_stage.argtypes = [C.POINTER(PbSegmentDesc), C.c_int, C.POINTER(C.c_void_p)]
     l.pb_segment_release.argtypes = [C.c_void_p]
+    l.pb_cache_stats.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     l.pb_segment_device_bytes.argtypes = [C.c_void_p]
     l.pb_segment_device_bytes.restype = C.c_int64
     l.pb_segment_group_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]
@@ -172,6 +173,13 @@ def init(device=None, hbm_cache_bytes: int = 0):
         ids = [device] if isinstance(device, int) else list(device)
         arr = (C.c_int * len(ids))(*ids)
         _check(lib().pb_init(arr, len(ids), hbm_cache_bytes))
+
+
+def cache_stats(device_index: int = 0):
+    """(bytes staged in HBM right now, segments evicted so far) of one device's segment cache"""
+    b, e = C.c_int64(), C.c_int64()
+    _check(lib().pb_cache_stats(device_index, C.byref(b), C.byref(e)))
+    return b.value, e.value
 
 
 def comm_unique_id() -> bytes:

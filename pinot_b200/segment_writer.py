@@ -150,6 +150,11 @@ class ColumnIndex:
     def dictionary_values(self) -> np.ndarray:
         """Decoded dictionary (native numpy array; bytes objects for STRING)."""
         assert self.has_dictionary
+        if self.data_type == DataType.STRING and is_var_length_dictionary(self.dictionary):
+            d = self.dictionary
+            data0 = int(d[12:16].view(">i4")[0])
+            offs = d[data0:data0 + 4 * (self.cardinality + 1)].view(">i4").astype(np.int64)
+            return np.array([bytes(d[offs[i]:offs[i + 1]]) for i in range(self.cardinality)], dtype=object)
         if self.data_type == DataType.STRING:
             raw = self.dictionary.reshape(self.cardinality, self.dict_entry_bytes)
             return np.array([bytes(r).rstrip(b"\0") for r in raw], dtype=object)
@@ -166,7 +171,27 @@ class Segment:
         return list(self.columns.keys())
 
 
-def _encode_dictionary(values_sorted: np.ndarray, data_type: DataType):
+VAR_LENGTH_MAGIC = b".vl;"
+
+
+def _encode_var_length_dictionary(values_sorted) -> np.ndarray:
+    """VarLengthValueWriter (SEGL/io/util/VarLengthValueWriter.java:78-125): magic, version 1, numValues,
+    dataSectionStartOffset (= header length 16), numValues + 1 big-endian int offsets from the buffer start, the bytes."""
+    n = len(values_sorted)
+    off0 = 16 + 4 * (n + 1)
+    lens = np.array([len(v) for v in values_sorted], dtype=np.int64)
+    offs = off0 + np.concatenate([[0], np.cumsum(lens)])
+    head = VAR_LENGTH_MAGIC + np.array([1, n, 16], dtype=">i4").tobytes() + offs.astype(">i4").tobytes()
+    return np.frombuffer(head + b"".join(bytes(v) for v in values_sorted), dtype=np.uint8).copy()
+
+
+def is_var_length_dictionary(buf: np.ndarray) -> bool:
+    return buf is not None and buf.size >= 20 and bytes(buf[:4]) == VAR_LENGTH_MAGIC and int(buf[4:8].view(">i4")[0]) == 1
+
+
+def _encode_dictionary(values_sorted: np.ndarray, data_type: DataType, var_length: bool = False):
+    if data_type == DataType.STRING and var_length:
+        return _encode_var_length_dictionary(values_sorted), max(1, max(len(v) for v in values_sorted))
     if data_type == DataType.STRING:
         width = max(1, max(len(v) for v in values_sorted))
         buf = np.zeros((len(values_sorted), width), dtype=np.uint8)
@@ -206,13 +231,13 @@ def _raw_forward_index(values: np.ndarray, data_type: DataType) -> np.ndarray:
 
 
 def build_dict_column(name: str, data_type: DataType, dict_values_sorted: np.ndarray, dict_ids: np.ndarray,
-                      inverted: bool = False, run_optimize: bool = True) -> ColumnIndex:
+                      inverted: bool = False, run_optimize: bool = True, var_length_dictionary: bool = False) -> ColumnIndex:
     """Column from an already-known sorted dictionary and per-doc dictIds."""
     card = len(dict_values_sorted)
     dict_ids = np.ascontiguousarray(dict_ids, dtype=np.uint32)
     n = dict_ids.size
     bits = num_bits_per_value(card - 1)
-    dbuf, width = _encode_dictionary(dict_values_sorted, data_type)
+    dbuf, width = _encode_dictionary(dict_values_sorted, data_type, var_length_dictionary)
     is_sorted = bool(n <= 1 or (dict_ids[1:] >= dict_ids[:-1]).all())
     fwd = _sorted_pairs(dict_ids, card) if is_sorted else pack_bits_be(dict_ids, bits)
     inv = build_inverted_index(dict_ids, card, run_optimize) if (inverted and not is_sorted) else None
@@ -223,13 +248,13 @@ def build_dict_column(name: str, data_type: DataType, dict_values_sorted: np.nda
 
 
 def build_column(name: str, data_type: DataType, values, dictionary: bool = True, inverted: bool = False,
-                 run_optimize: bool = True) -> ColumnIndex:
+                 run_optimize: bool = True, var_length_dictionary: bool = False) -> ColumnIndex:
     """Column from per-doc values (what SegmentIndexCreationDriverImpl does per column)."""
     if data_type == DataType.STRING:
         vals = np.array([v if isinstance(v, bytes) else str(v).encode("utf-8") for v in values], dtype=object)
         assert dictionary, "raw STRING columns are out of scope"
         uniq, inv_ids = np.unique(vals, return_inverse=True)   # bytes order == Java compareTo for ASCII
-        return build_dict_column(name, data_type, uniq, inv_ids.astype(np.uint32), inverted, run_optimize)
+        return build_dict_column(name, data_type, uniq, inv_ids.astype(np.uint32), inverted, run_optimize, var_length_dictionary)
     vals = np.asarray(values).astype(_NP_NATIVE[data_type])
     if dictionary:
         uniq, inv_ids = np.unique(vals, return_inverse=True)

@@ -6,7 +6,8 @@ from pinot_b200 import datagen, native
 from pinot_b200.query import parse_sql
 from pinot_b200.segment_writer import DataType, build_column, build_dict_column, make_segment
 from tests.fixtures import FILTER, sv_segment
-from tests.parity import assert_rows_equal, check_query
+from oracle import oracle
+from tests.parity import assert_rows_equal, check_query, oracle_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -379,3 +380,69 @@ def test_query_from_mmapped_v3_directory(tmp_path):
     for sql, exact in ((f"SELECT s0, d0, COUNT(*), SUM(m0), MAX(x0) FROM t WHERE c3 IN ({int(d3[2])}, {int(d3[9])}) OR c1 BETWEEN {int(d1[40])} AND {int(d1[90])} GROUP BY s0, d0 LIMIT 100000", False),
                        ("SELECT COUNT(*), MIN(k0), AVG(m0) FROM t WHERE t0 BETWEEN 20003 AND 20011 OR x0 < 0.25", True)):
         check_query([back], sql, exact_float=exact)
+
+
+def test_var_length_string_dictionary():
+    """a .vl; dictionary (VarLengthValueReader.java:41-96) is staged as padded entries: group keys, predicates and
+    DISTINCTCOUNT on such a column equal the oracle's"""
+    rng = np.random.Generator(np.random.PCG64(11))
+    words = [b"a", b"ab", b"abc", b"zebra", b"pinot-b200", b"x" * 37, b"mid", b"", b"q"]
+    segs = []
+    for i in range(2):
+        vals = [words[j] for j in rng.integers(0, len(words) - i, size=20000)]      # the second segment misses a value
+        segs.append(make_segment(f"vl{i}", [build_column("s", DataType.STRING, vals, var_length_dictionary=True, inverted=True),
+                                            build_column("v", DataType.INT, rng.integers(0, 1000, size=20000))]))
+    for sql in ("SELECT s, COUNT(*), SUM(v) FROM t WHERE s > 'ab' AND s <= 'pinot-b200' GROUP BY s LIMIT 100",
+                "SELECT COUNT(*), MAX(v) FROM t WHERE s IN ('', 'zebra', 'nosuch') OR s = 'mid'",
+                "SET skipIndexes = 's=inverted'; SELECT s, DISTINCTCOUNT(v), MIN(v) FROM t WHERE s != 'q' GROUP BY s LIMIT 100"):
+        check_query(segs, sql, flags_list=(0, native.PB_Q_GENERIC_KERNEL))
+
+
+def test_num_groups_limit_dense_tables_keep_the_first_groups_in_doc_order():
+    """numGroupsLimit below the key space: the reference's IntMapBasedHolder creates groups first come first served in doc
+    order and drops the rows of later keys (DictionaryBasedGroupKeyGenerator.java:1023-1058).  Per-segment dense tables
+    reproduce exactly that set of groups with their full aggregates."""
+    segs = [datagen.make_segment_synth(i, 30_000, columns=["c2", "c3", "d1", "d2", "m0", "m1"]) for i in range(2)]
+    d2 = segs[0].columns["c2"].dictionary_values()
+    for limit in (1, 7, 100, 500, 512, 100000):
+        for sql in (f"SET numGroupsLimit = {limit}; SELECT d1, d2, COUNT(*), SUM(m0), MIN(m1) FROM t GROUP BY d1, d2 LIMIT 100000",
+                    f"SET numGroupsLimit = {limit}; SELECT c3, d2, COUNT(*), MAX(m0) FROM t WHERE c2 < {int(d2[len(d2) // 3])} GROUP BY c3, d2 LIMIT 100000"):
+            q = parse_sql(sql)
+            staged = [native.StagedSegment(s) for s in segs]
+            g = native.SegmentGroup(staged)
+            for flags in (0, native.PB_Q_GENERIC_KERNEL):
+                res = native.execute(g, q, flags)
+                for i, (t, s) in enumerate(zip(res.tables, segs)):
+                    o = oracle.execute(s, q)
+                    assert_rows_equal(t.rows(), oracle_rows(o), q, exact_float=True, what=f"limit {limit} segment {i}")
+                    assert t.stats["num_groups_limit_reached"] == o.stats["num_groups_limit_reached"], (limit, t.stats, o.stats)
+                    assert t.stats["num_docs_scanned"] == o.stats["num_docs_scanned"]
+                res.free()
+            g.release()
+
+
+def test_num_groups_limit_hash_tables_never_overflow_or_hang():
+    """every resident thread used to pass the limit check at once, fill the table and leave absent keys
+    probing forever.  Hash tables apply the limit in thread order (documented divergence): at most `limit` groups, the flag
+    set, every returned group complete (its aggregates equal the unlimited query's)."""
+    segs = [datagen.make_segment_synth(i, 200_000, columns=["k0", "m0", "c2"]) for i in range(2)]
+    full_q = parse_sql("SET numGroupsLimit = 10000000; SELECT k0, COUNT(*), SUM(m0) FROM t GROUP BY k0 LIMIT 10000000")
+    staged = [native.StagedSegment(s) for s in segs]
+    g = native.SegmentGroup(staged)
+    full = [oracle_rows(oracle.execute(s, full_q)) for s in segs]
+    for limit in (1, 100, 1000, 5000):
+        q = parse_sql(f"SET numGroupsLimit = {limit}; SELECT k0, COUNT(*), SUM(m0) FROM t GROUP BY k0 LIMIT 10000000")
+        for run in range(3):
+            res = native.execute(g, q, 0)
+            for i, t in enumerate(res.tables):
+                rows = t.rows()
+                assert 0 < len(rows) <= limit, (limit, len(rows))
+                assert t.stats["num_groups_limit_reached"] == 1
+                for k, row in rows.items():
+                    assert row == full[i][k], (limit, k, row, full[i][k])      # no partially aggregated group
+            res.free()
+        res = native.execute(g, q, native.PB_Q_COMBINE)
+        rows = res.tables[0].rows()
+        assert 0 < len(rows) <= limit and res.tables[0].stats["num_groups_limit_reached"] == 1
+        res.free()
+    g.release()
