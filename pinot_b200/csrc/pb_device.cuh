@@ -67,6 +67,8 @@ struct DevLeaf {
   int32_t gather;
   uint32_t g_full_words;   // see DevKeyCol::n_full_words
   uint32_t g_tail_word;
+  int32_t g_stride_bits;   // bits between consecutive docs' values at gfwd (= bits for a column's own forward index; the row
+  int32_t g_bit_off;       // stride and the field offset when the value is read from a row group, see DevKeyCol)
   int32_t pad_l;
   const uint8_t* gfwd;
 };
@@ -78,6 +80,11 @@ struct DevScanCol {        // a column staged tile-by-tile through smem
   uint64_t bytes_total;    // readable bytes from base (16-byte padded)
 };
 
+// Gathered columns are read either from their own bit-packed forward index (stride_bits = bits, bit_off = 0) or from a ROW
+// GROUP: a second, row-major copy of the columns a query gathers together (group-by keys, aggregation inputs, candidate
+// predicate columns), built on the device at first use -- doc d's dictIds packed MSB-first into one row of 64 / 128 / 256
+// bits, so that every gather of a matching doc falls into ONE 32-byte DRAM sector instead of one sector per column
+// (the aggregation kernel is bound by the DRAM random-access rate, ~50 G sectors/s: profiles/r1_experiments.md).
 struct DevKeyCol {         // group-by column (gathered per matching doc)
   const uint8_t* fwd;
   const int32_t* remap;    // local -> global dictId (combined mode), may be null
@@ -88,6 +95,8 @@ struct DevKeyCol {         // group-by column (gathered per matching doc)
   uint64_t mult;           // T_DENSE: mixed-radix multiplier
   uint32_t n_full_words;   // words wholly inside the buffer (0xFFFFFFFF: padded HBM copy, no bound needed)
   uint32_t tail_word;      // in-place host buffer: the trailing partial word, zero-padded (as stored, big-endian)
+  int32_t stride_bits;     // bits between consecutive docs' values (bits, or the row stride of a row group)
+  int32_t bit_off;         // position of the field inside the row (0 for a column's own forward index)
 };
 
 struct DevAggCol {
@@ -99,6 +108,7 @@ struct DevAggCol {
   int32_t data_type;
   uint32_t n_full_words;   // see DevKeyCol
   uint32_t tail_word;
+  int32_t stride_bits, bit_off;
   uint32_t pad;
 };
 
@@ -219,9 +229,10 @@ __device__ __forceinline__ uint32_t pb_unpack_at(const uint8_t* __restrict__ fwd
 
 // Same, for a gathered column that may be read IN PLACE from the caller's page-locked host buffer (PB_Q_GATHER_IN_PLACE):
 // that buffer has no padding, so words past its last whole word come from the descriptor instead of memory.
-__device__ __forceinline__ uint32_t pb_unpack_at_bounded(const uint8_t* __restrict__ fwd, uint32_t doc, int bits, uint32_t n_full, uint32_t tail) {
+__device__ __forceinline__ uint32_t pb_unpack_at_bounded(const uint8_t* __restrict__ fwd, uint32_t doc, int bits, uint32_t n_full, uint32_t tail,
+                                                         int stride_bits, int bit_off) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(fwd);
-  unsigned long long bit = (unsigned long long)doc * (unsigned)bits;
+  unsigned long long bit = (unsigned long long)doc * (unsigned)stride_bits + (unsigned)bit_off;
   unsigned long long wi = bit >> 5;
   uint32_t s = (uint32_t)bit & 31u;
   uint32_t hi = tail, lo = tail;
@@ -468,11 +479,11 @@ __device__ __forceinline__ bool pb_leaf_test_doc(const DevLeaf& lf, const uint8_
     case L_TRUE: return true;
     case L_FALSE: return false;
     case L_DICT_RANGE: {
-      const uint32_t id = pb_unpack_at_bounded(lf.gfwd, doc, lf.bits, lf.g_full_words, lf.g_tail_word);
+      const uint32_t id = pb_unpack_at_bounded(lf.gfwd, doc, lf.bits, lf.g_full_words, lf.g_tail_word, lf.g_stride_bits, lf.g_bit_off);
       return (id - lf.lo) < lf.span;
     }
     case L_DICT_SET: {
-      const uint32_t id = pb_unpack_at_bounded(lf.gfwd, doc, lf.bits, lf.g_full_words, lf.g_tail_word);
+      const uint32_t id = pb_unpack_at_bounded(lf.gfwd, doc, lf.bits, lf.g_full_words, lf.g_tail_word, lf.g_stride_bits, lf.g_bit_off);
       if (lf.set_smem_off >= 0) return set_cache[lf.set_smem_off + id] != 0;         // exclusive flag folded in
       return (((__ldg(lf.set_bits + (id >> 5)) >> (id & 31)) & 1u) ^ (uint32_t)lf.exclusive) != 0;
     }
@@ -610,7 +621,7 @@ __device__ __forceinline__ uint64_t pb_key_field(const DevKeyCol& kc, uint32_t d
     else v = (uint64_t)pb_raw_i64(kc.fwd, doc, kc.raw_width, kc.data_type);
     return (kc.raw_width == 4 && multi) ? (v & 0xffffffffull) : v;
   }
-  uint32_t id = pb_unpack_at_bounded(kc.fwd, doc, kc.bits, kc.n_full_words, kc.tail_word);
+  uint32_t id = pb_unpack_at_bounded(kc.fwd, doc, kc.bits, kc.n_full_words, kc.tail_word, kc.stride_bits, kc.bit_off);
   if (kc.remap) id = (uint32_t)__ldg(kc.remap + id);
   return id;
 }
@@ -619,12 +630,12 @@ __device__ __forceinline__ uint64_t pb_key_field(const DevKeyCol& kc, uint32_t d
 // to double); for DISTINCTCOUNT the (global) dictId, returned through the same 64-bit channel
 __device__ __forceinline__ double pb_agg_input(const DevAggCol& ac, int op, uint32_t doc) {
   if (op == 5) {
-    uint32_t id = pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word);
+    uint32_t id = pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word, ac.stride_bits, ac.bit_off);
     if (ac.remap) id = (uint32_t)__ldg(ac.remap + id);
     return __longlong_as_double((long long)id);
   }
   return ac.raw_width ? pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type)
-                      : __ldg(ac.dict_f64 + pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word));
+                      : __ldg(ac.dict_f64 + pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word, ac.stride_bits, ac.bit_off));
 }
 
 // ---- phase 1 of a matching doc: every gather is issued before anything is reduced, four independent chains at a
@@ -1883,6 +1894,39 @@ __global__ void pb_distinct_ids_kernel(const uint32_t* __restrict__ bits, uint64
     unsigned long long my = pos + incl - c;
     while (x) { int bpos = __ffs(x) - 1; x &= x - 1; out[my++] = (int32_t)((w0 + lane) * 32 + bpos); }
     pos += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// Row group build: one thread per doc packs the doc's dictIds of the member columns MSB-first into one row of
+// stride_words 32-bit words, in the same big-endian bit order as Pinot's own forward indexes, so that pb_unpack_at_bounded
+// reads a field of a row exactly like a value of a column (stride_bits = row stride, bit_off = field offset).
+#define PB_ROW_MAX_COLS 16
+#define PB_ROW_MAX_WORDS 8
+struct DevRowBuild {
+  int32_t n_cols, stride_words;
+  uint32_t num_docs, pad;
+  const uint8_t* fwd[PB_ROW_MAX_COLS];
+  int32_t bits[PB_ROW_MAX_COLS];
+  int32_t bit_off[PB_ROW_MAX_COLS];
+  uint32_t* out;
+};
+__global__ void pb_build_rows_kernel(const DevRowBuild B) {
+  for (uint64_t doc = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; doc < B.num_docs; doc += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t w[PB_ROW_MAX_WORDS];
+#pragma unroll
+    for (int k = 0; k < PB_ROW_MAX_WORDS; k++) w[k] = 0;
+    for (int c = 0; c < B.n_cols; c++) {
+      const uint32_t id = pb_unpack_at(B.fwd[c], (uint32_t)doc, B.bits[c]);
+      const int p = B.bit_off[c], k = p >> 5, sft = 32 - B.bits[c] - (p & 31);      // left shift that puts the value's LSB in place
+#pragma unroll
+      for (int kk = 0; kk < PB_ROW_MAX_WORDS; kk++) {
+        if (kk == k) w[kk] |= sft >= 0 ? (id << sft) : (id >> (-sft));
+        if (kk == k + 1 && sft < 0) w[kk] |= id << (32 + sft);
+      }
+    }
+    uint32_t* o = B.out + doc * (uint64_t)B.stride_words;
+#pragma unroll
+    for (int k = 0; k < PB_ROW_MAX_WORDS; k++) if (k < B.stride_words) o[k] = pb_bswap32(w[k]);
   }
 }
 

@@ -299,6 +299,18 @@ struct Column {
   bool fwd_staged = false, dict_staged = false, inv_staged = false, native_staged = false;
 };
 
+// A row-major copy of the dictionary columns some query gathers together (see DevKeyCol in pb_device.cuh)
+struct RowGroup {
+  std::vector<int> cols;          // member columns (indices into the segment's columns, ascending)
+  std::vector<int> bit_off;       // field offset of each member inside a row
+  int stride_bits = 0;            // 64 / 128 / 256: rows never straddle a 32-byte sector
+  uint8_t* d_rows = nullptr;
+  uint64_t bytes = 0;
+  uint64_t last_used = 0;
+  int find(int col) const { for (size_t i = 0; i < cols.size(); i++) if (cols[i] == col) return (int)i; return -1; }
+};
+#define PB_MAX_ROW_GROUPS_PER_SEGMENT 4
+
 struct pb_segment_s {
   std::string name;
   int num_docs = 0;
@@ -316,6 +328,7 @@ struct pb_segment_s {
   cudaEvent_t staged_ev = nullptr;
   bool staged_pending = false, stage_dirty = false;
   std::vector<PinnedBlock> staging_bufs;   // pinned sources of in-flight dictionary uploads (freed with the segment)
+  std::vector<std::unique_ptr<RowGroup>> row_groups;
 };
 
 static int find_col(const pb_segment_s* s, const char* name) {
@@ -511,6 +524,8 @@ static void drop_device_copies(pb_segment_s* s) {     // under s->mu, inflight =
   }
   for (auto& b : s->staging_bufs) pinned_free(b.p, b.cap);
   s->staging_bufs.clear();
+  for (auto& rg : s->row_groups) dev_free(s->ctx, rg->d_rows);
+  s->row_groups.clear();
   s->device_bytes = 0; s->accounted_bytes = 0;
   s->epoch++;
 }
@@ -543,6 +558,53 @@ static void enforce_cache_limit(Context* ctx) {
   }
 }
 
+
+// The row group that holds every column of `want` (ascending column indices, all dictionary columns staged in HBM): an
+// existing one whose members include them, else a new one built on the copy stream behind the column copies it reads.
+// Returns nullptr when rows would not pay (a single column, more than 256 bits) or cannot be built.  Under s->mu.
+static const RowGroup* row_group_for(pb_segment_s* s, const std::vector<int>& want, cudaStream_t cs) {
+  if (want.size() < 2 || want.size() > PB_ROW_MAX_COLS) return nullptr;
+  int sum_bits = 0;
+  for (int ci : want) { const Column& c = s->cols[ci]; if (!c.has_dict || !c.fwd_staged) return nullptr; sum_bits += c.bits; }
+  if (sum_bits > 256) return nullptr;
+  const uint64_t tick = [&]() { std::lock_guard<std::mutex> lk(s->ctx->mu); return ++s->ctx->lru_clock; }();
+  for (auto& rg : s->row_groups) {
+    bool all = true;
+    for (int ci : want) if (rg->find(ci) < 0) { all = false; break; }
+    if (all) { rg->last_used = tick; return rg.get(); }
+  }
+  if (s->row_groups.size() >= PB_MAX_ROW_GROUPS_PER_SEGMENT) {
+    // (a parked plan may still point into the oldest one: the epoch retires those plans)
+    if (s->inflight > 1) return nullptr;          // another query of this segment is in flight and may be reading it
+    size_t old = 0;
+    for (size_t i = 1; i < s->row_groups.size(); i++) if (s->row_groups[i]->last_used < s->row_groups[old]->last_used) old = i;
+    dev_free(s->ctx, s->row_groups[old]->d_rows);
+    s->device_bytes -= (int64_t)s->row_groups[old]->bytes;
+    s->row_groups.erase(s->row_groups.begin() + (long)old);
+    s->epoch++;
+  }
+  std::unique_ptr<RowGroup> rg(new RowGroup());
+  rg->cols = want;
+  rg->stride_bits = sum_bits <= 64 ? 64 : sum_bits <= 128 ? 128 : 256;
+  int off = 0;
+  for (int ci : want) { rg->bit_off.push_back(off); off += s->cols[ci].bits; }
+  rg->bytes = (uint64_t)s->num_docs * (uint64_t)(rg->stride_bits / 8) + 32;
+  if (dev_alloc(s->ctx, (void**)&rg->d_rows, rg->bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  DevRowBuild B; memset(&B, 0, sizeof B);
+  B.n_cols = (int)want.size(); B.stride_words = rg->stride_bits / 32; B.num_docs = (uint32_t)s->num_docs; B.out = (uint32_t*)rg->d_rows;
+  for (size_t i = 0; i < want.size(); i++) { const Column& c = s->cols[want[i]]; B.fwd[i] = c.d_fwd; B.bits[i] = c.bits; B.bit_off[i] = rg->bit_off[i]; }
+  if (cudaMemsetAsync(rg->d_rows + (rg->bytes - 32), 0, 32, cs) != cudaSuccess) { cudaGetLastError(); dev_free(s->ctx, rg->d_rows); return nullptr; }
+  int grid = (int)std::min<uint64_t>(((uint64_t)s->num_docs + 255) / 256, (uint64_t)s->ctx->num_sms * 16);
+  if (grid < 1) grid = 1;
+  pb_build_rows_kernel<<<grid, 256, 0, cs>>>(B);
+  if (cudaGetLastError() != cudaSuccess) { dev_free(s->ctx, rg->d_rows); return nullptr; }
+  rg->last_used = tick;
+  s->device_bytes += (int64_t)rg->bytes;
+  s->stage_dirty = true;                          // the query's kernels wait for the build like for a staging copy
+  s->row_groups.push_back(std::move(rg));
+  return s->row_groups.back().get();
+}
+
 extern "C" int pb_segment_release(pb_segment_handle s) {
   if (!s) return PB_OK;
   DeviceGuard dg(s->ctx);
@@ -557,6 +619,7 @@ extern "C" int pb_segment_release(pb_segment_handle s) {
   for (auto& c : s->cols) {
     dev_free(s->ctx, c.d_fwd); dev_free(s->ctx, c.d_sorted_pairs); dev_free(s->ctx, c.d_dict_f64); dev_free(s->ctx, c.d_dict_native); dev_free(s->ctx, c.d_inv);
   }
+  for (auto& rg : s->row_groups) dev_free(s->ctx, rg->d_rows);
   delete s;
   return PB_OK;
 }
@@ -1442,6 +1505,8 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   cudaStream_t cs = ctx->copy_stream;
   std::vector<cudaEvent_t> seg_wait(n_segs, nullptr);   // staging events this call's kernels must wait for
   int n_pending = 0;
+  static const bool row_groups_on = []() { const char* e = getenv("PB_ROW_GROUPS"); return !e || atoi(e) != 0; }();
+  std::vector<const RowGroup*> seg_rg(n_segs, nullptr);  // row group the gathers of each segment read from (nullptr: the columns themselves)
   std::vector<std::vector<char>> cand_leaf(n_segs);     // per filter node: scan leaf evaluated on candidates (DevLeaf::gather)
   std::vector<std::vector<double>> cand_frac(n_segs);
   for (int si = 0; si < n_segs; si++) plan_candidate_leaves(g->segs[si], sqs[si], cand_leaf[si], cand_frac[si]);
@@ -1517,6 +1582,23 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
           if ((fn.kind == PB_F_SCAN_RAW_RANGE || fn.kind == PB_F_SCAN_RAW_SET) && c.has_dict) return fail(PB_ERR_INVALID, "FILTER clause %d node %d: raw scan on dictionary column", f, n);
           if ((rc = stage_column(s, c, !inv, false, inv, cs, false, !inv && gather_ok(c)))) return rc;
         }
+      }
+    }
+    // ---- row group: the dictionary columns this query gathers per matching doc, side by side in one row ----
+    if (row_groups_on && !in_place) {
+      const double sel_rg = estimate_selectivity(s, sq);
+      if (sel_rg <= 0.5) {
+        std::vector<int> want;
+        auto add = [&](int ci) { if (ci >= 0 && s->cols[ci].has_dict && s->cols[ci].fwd_staged && std::find(want.begin(), want.end(), ci) == want.end()) want.push_back(ci); };
+        for (int j = 0; j < nG; j++) add(gcol[si][j]);
+        for (int a = 0; a < nA; a++) add(acol[si][a]);
+        for (int n = 0; n < sq.num_filter_nodes; n++)
+          if (cand_leaf[si][n] && (sq.filter[n].kind == PB_F_SCAN_DICT_RANGE || sq.filter[n].kind == PB_F_SCAN_DICT_SET)) add(sq.filter[n].column);
+        for (int f = 0; f < nF; f++)
+          for (int n = 0; n < sq.agg_filter_nodes[f]; n++)
+            if (sq.agg_filters[f][n].kind == PB_F_SCAN_DICT_RANGE || sq.agg_filters[f][n].kind == PB_F_SCAN_DICT_SET) add(sq.agg_filters[f][n].column);
+        std::sort(want.begin(), want.end());
+        seg_rg[si] = row_group_for(s, want, cs);
       }
     }
     if (s->device_bytes != s->accounted_bytes) {
@@ -1785,6 +1867,12 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
           lf.gfwd = c.fwd_staged ? c.d_fwd : c.d_fwd_host;
           lf.g_full_words = c.fwd_staged ? 0xFFFFFFFFu : c.host_full_words;
           lf.g_tail_word = c.fwd_staged ? 0u : c.host_tail_word;
+          lf.g_stride_bits = c.bits; lf.g_bit_off = 0;
+          if (c.has_dict && seg_rg[si] && seg_rg[si]->find(fn.column) >= 0) {
+            const RowGroup* rg = seg_rg[si];
+            lf.gfwd = rg->d_rows; lf.g_full_words = 0xFFFFFFFFu; lf.g_tail_word = 0u;
+            lf.g_stride_bits = rg->stride_bits; lf.g_bit_off = rg->bit_off[(size_t)rg->find(fn.column)];
+          }
           if (!c.fwd_staged) r->in_place_columns++;
           any_cand_leaf = true;
           return PB_MAX_SCAN_SLOTS;      // not a slot index (>= 0 = success)
@@ -1927,6 +2015,12 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       kc.fwd = c.fwd_staged ? c.d_fwd : c.d_fwd_host; kc.n_full_words = c.fwd_staged ? 0xFFFFFFFFu : c.host_full_words;
       kc.tail_word = c.fwd_staged ? 0u : c.host_tail_word; if (!c.fwd_staged) r->in_place_columns++;
       kc.bits = c.bits; kc.raw_width = c.has_dict ? 0 : c.raw_width; kc.data_type = c.type;
+      kc.stride_bits = c.bits; kc.bit_off = 0;
+      if (c.has_dict && seg_rg[si] && seg_rg[si]->find(gcol[si][j]) >= 0) {
+        const RowGroup* rg = seg_rg[si];
+        kc.fwd = rg->d_rows; kc.n_full_words = 0xFFFFFFFFu; kc.tail_word = 0u;
+        kc.stride_bits = rg->stride_bits; kc.bit_off = rg->bit_off[(size_t)rg->find(gcol[si][j])];
+      }
       kc.remap = (combine && gdict[j]) ? gdict[j]->d_remap[si] : nullptr;
       kc.shift = tm.shifts[j];
       kc.mult = mult;
@@ -1940,6 +2034,12 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       ac.fwd = c.fwd_staged ? c.d_fwd : c.d_fwd_host; ac.n_full_words = c.fwd_staged ? 0xFFFFFFFFu : c.host_full_words;
       ac.tail_word = c.fwd_staged ? 0u : c.host_tail_word; if (!c.fwd_staged) r->in_place_columns++;
       ac.dict_f64 = c.d_dict_f64; ac.bits = c.bits; ac.raw_width = c.has_dict ? 0 : c.raw_width; ac.data_type = c.type;
+      ac.stride_bits = c.bits; ac.bit_off = 0;
+      if (c.has_dict && seg_rg[si] && seg_rg[si]->find(acol[si][a]) >= 0) {
+        const RowGroup* rg = seg_rg[si];
+        ac.fwd = rg->d_rows; ac.n_full_words = 0xFFFFFFFFu; ac.tail_word = 0u;
+        ac.stride_bits = rg->stride_bits; ac.bit_off = rg->bit_off[(size_t)rg->find(acol[si][a])];
+      }
       ac.remap = (combine && adict[a]) ? adict[a]->d_remap[si] : nullptr;
     }
   }
@@ -2470,12 +2570,7 @@ static int finish_finalize(pb_result_s* r) {
     TableMeta& tm = r->tables[t];
     const int64_t ng = (int64_t)std::min<uint64_t>(hc[(size_t)t * PB_COUNTERS_PER_TABLE + 3], tm.out_cap);
     tm.num_groups = ng;
-    const unsigned long long* rows = (const unsigned long long*)tm.rows.p;
-    for (int a = 0; a < nA; a++) {
-      const int op = r->agg_op[a];
-      int64_t* L = (int64_t*)tm.lng[a].p;
-      (void)L; (void)rows; (void)op;     // COUNT / AVG counts and the zeros of SUM / MIN / MAX are written by the finalize kernel
-    }
+    // (COUNT / AVG counts and the zeros of the other long arrays are written by the finalize kernel)
     // DISTINCTCOUNT: the sizes now; the value sets (BaseDistinctAggregateAggregationFunction intermediate result) are
     // materialised on first access (pb_result_distinct_offsets / _dict_ids) — a merged result usually needs the sizes only
     for (int a = 0; a < nA; a++) {

@@ -100,6 +100,25 @@ def make_table(num_segments: int, docs_per_segment: int, columns: Optional[Seque
             for i in range(num_segments)]
 
 
+def _make_one(args):
+    index, docs, columns, seed, vary = args
+    return make_segment_synth(index, docs, columns, seed, vary_dim_dictionaries=vary)
+
+
+def make_table_parallel(num_segments: int, docs_per_segment: int, columns: Optional[Sequence[str]] = None, seed: int = 42,
+                        first_index: int = 0, vary_dim_dictionaries: bool = False, workers: int = 8,
+                        indices: Optional[Sequence[int]] = None) -> List[Segment]:
+    """make_table with one worker process per segment (spawned: safe after CUDA initialisation).  Every segment is drawn
+    from its own (seed, index, column) streams, so the result is identical to the sequential generator's."""
+    idx = list(indices) if indices is not None else [first_index + i for i in range(num_segments)]
+    if workers <= 1 or len(idx) <= 1:
+        return [_make_one((i, docs_per_segment, columns, seed, vary_dim_dictionaries)) for i in idx]
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    with ProcessPoolExecutor(max_workers=min(workers, len(idx)), mp_context=mp.get_context("spawn")) as ex:
+        return list(ex.map(_make_one, [(i, docs_per_segment, columns, seed, vary_dim_dictionaries) for i in idx]))
+
+
 # ---- BASELINE.json configs as SQL (literals are chosen per table, see helpers) ----
 
 def config1_sql(seg: Segment) -> str:
