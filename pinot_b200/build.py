@@ -1,18 +1,26 @@
-"""In-tree builds: libpinot_b200.so (CUDA, sm_100a) and the CPU-only segment-writer helper."""
+"""In-tree builds: libpinot_b200.so (CUDA, sm_100a) and the CPU-only segment-writer helper.
+
+The library is compiled per translation unit (objects under pinot_b200/build/, rebuilt only when stale, in parallel) and
+linked with nvcc: pb_engine.cu (runtime + generic kernels), pb_filter_spec.cu (the plan-time specialised instantiations of
+the filter kernel: one small kernel per bit width and predicate kind) and host/pb_host.cpp (the planning layer)."""
 from __future__ import annotations
 
 import os
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libpinot_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", "pb_engine.cu"), os.path.join(HERE, "csrc", "host", "pb_host.cpp")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", "pb_device.cuh"), os.path.join(HERE, "csrc", "pb_internal.h"),
-                  os.path.join(ROOT, "include", "pinot_b200.h"), os.path.join(ROOT, "include", "pinot_b200_host.h")]
+OBJ_DIR = os.path.join(HERE, "build")
+SOURCES = [os.path.join(HERE, "csrc", "pb_engine.cu"), os.path.join(HERE, "csrc", "pb_filter_spec.cu"),
+           os.path.join(HERE, "csrc", "host", "pb_host.cpp")]
+HEADERS = [os.path.join(HERE, "csrc", "pb_device.cuh"), os.path.join(HERE, "csrc", "pb_internal.h"),
+           os.path.join(ROOT, "include", "pinot_b200.h"), os.path.join(ROOT, "include", "pinot_b200_host.h")]
+DEPS = SOURCES + HEADERS
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def nvcc_path() -> str:
@@ -22,12 +30,30 @@ def nvcc_path() -> str:
     return "nvcc"
 
 
+def _obj(src: str) -> str:
+    return os.path.join(OBJ_DIR, os.path.basename(src) + ".o")
+
+
 def build_native(force: bool = False, verbose: bool = False) -> str:
     """nvcc cross-compiles for sm_100a without a GPU."""
-    stale = force or not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(d) for d in DEPS)
-    if stale:
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    newest_header = max(os.path.getmtime(h) for h in HEADERS)
+
+    def stale(src):
+        o = _obj(src)
+        return force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(src), newest_header)
+
+    todo = [s for s in SOURCES if stale(s)]
+
+    def compile_one(src):
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", _obj(src), src]
         subprocess.check_call(cmd)
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=len(todo)) as ex:
+            list(ex.map(compile_one, todo))
+    if todo or not os.path.exists(LIB) or any(os.path.getmtime(LIB) < os.path.getmtime(_obj(s)) for s in SOURCES):
+        subprocess.check_call([nvcc_path()] + ARCH + ["-shared", "-Xcompiler", "-fPIC", "-o", LIB] + [_obj(s) for s in SOURCES] + ["-ldl"])
     return LIB
 
 

@@ -439,7 +439,7 @@ __device__ __forceinline__ void pb_eval_dict(const uint32_t* __restrict__ p, int
 }
 
 // raw fixed-width column chunk in smem (big-endian values), lane <-> doc + ballot
-__device__ __noinline__ uint32_t pb_eval_raw(const uint32_t* __restrict__ p, const DevLeaf& lf, int lane) {
+static __device__ __noinline__ uint32_t pb_eval_raw(const uint32_t* __restrict__ p, const DevLeaf& lf, int lane) {
   uint32_t mine = 0;
   for (int k = 0; k < 32; k++) {
     uint32_t idx = (uint32_t)(k * 32 + lane);
@@ -827,7 +827,7 @@ struct __align__(16) FilterSmemHeader {
 // numbers of one segment; one lane per doc, every gather of the round in flight at once.  The random-sector gathers of
 // the aggregation then overlap the streaming of the predicate columns by the other warps instead of running as a second
 // kernel behind it.  Not inlined: the filter loop keeps its own register budget.
-__device__ __noinline__ void pb_warp_aggregate(const DevQuery& Q, const DevSegQuery& sgq, const uint32_t* ob, uint32_t cnt, int lane) {
+static __device__ __noinline__ void pb_warp_aggregate(const DevQuery& Q, const DevSegQuery& sgq, const uint32_t* ob, uint32_t cnt, int lane) {
   const DevTable& tb = Q.tables[sgq.table];
   const uint32_t base = (uint32_t)sgq.doc_base;
   KeylessAcc ka; ka.sum = nullptr; ka.mm = nullptr; ka.cnt = nullptr;
@@ -836,7 +836,14 @@ __device__ __noinline__ void pb_warp_aggregate(const DevQuery& Q, const DevSegQu
 }
 
 // U = 1024-doc chunks per work unit (one TMA load + one dispatch per predicate leaf per unit)
-template <int U, int MIN_CTAS>
+//
+// SW / SPK: plan-time specialisation.  SW = 0 is the general kernel (any predicate tree, every width and predicate kind
+// dispatched at run time: ~27 k SASS instructions, whose instruction-cache misses and dispatch cost were a fifth of the
+// issue slots of the common case).  SW > 0 is a kernel for ONE shape -- a flat conjunction whose only streamed leaf is a
+// dictionary column of SW bits tested with predicate kind SPK (0 = dictId range, 1 = IN / NOT IN membership LUT), every
+// other leaf evaluated on the candidates -- with that leaf's unpack + test inlined and nothing else compiled in.  The host
+// picks it when every segment of the launch has that shape (pb_filter_spec.cu holds the instantiations).
+template <int U, int MIN_CTAS, int SW = 0, int SPK = 0>
 __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const __grid_constant__ DevQuery Q) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   FilterSmemHeader* H = reinterpret_cast<FilterSmemHeader*>(smem_raw);
@@ -1062,7 +1069,20 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
         mask[u] = nd_rel >= d + 32u ? 0xffffffffu : (nd_rel <= d ? 0u : ((1u << (nd_rel - d)) - 1u));
       }
       const int n_cand_leaves = H->flat_and ? H->n_flat - H->n_dense : 0;
-      if (__builtin_expect(H->flat_and != 0, 1)) {
+      if constexpr (SW > 0) {
+        // the one streamed leaf, unpack + predicate inlined for this width and kind
+        const DevLeaf& lf = sq.leaves[H->flat_leaf[0]];
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(stage + Q.slot_off[lf.slot]);
+        if constexpr (SPK == 0) {
+          PredRange pr; pr.lo = lf.lo; pr.span = lf.span;
+#pragma unroll
+          for (int u = 0; u < U; u++) if (u < nu) mask[u] &= pb_eval_dict_w<SW, PredRange>(p + u * 32 * SW, pr, lane);
+        } else {
+          PredLut8 pl; pl.lut = set_cache + lf.set_smem_off;
+#pragma unroll
+          for (int u = 0; u < U; u++) if (u < nu) mask[u] &= pb_eval_dict_w<SW, PredLut8>(p + u * 32 * SW, pl, lane);
+        }
+      } else if (__builtin_expect(H->flat_and != 0, 1)) {
         const int nl = H->n_dense;
         for (int i = 0; i < nl; i++) {
           // few survivors in the whole unit -> restricted scan of the remaining leaves (leaves arrive ordered by
@@ -1377,7 +1397,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_agg_kernel(const __g
 // (< st_min_docs, known on the device only) it updates the global table directly like pb_agg_kernel.
 // ------------------------------------------------------------------------------------------------
 #define PB_AGG_SMEM_THREADS 1024
-__global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_smem_kernel(const __grid_constant__ DevQuery Q) {
+static __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_smem_kernel(const __grid_constant__ DevQuery Q) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ unsigned long long s_doc_base[PB_AGG_MAX_SEGS_SMEM + 1];
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -1502,7 +1522,7 @@ struct DevExpandItem {
   uint32_t pad;
 };
 
-__global__ void pb_expand_kernel(const DevExpandItem* __restrict__ items) {
+static __global__ void pb_expand_kernel(const DevExpandItem* __restrict__ items) {
   const DevExpandItem it = items[blockIdx.y];
   uint32_t* __restrict__ out = it.out;
   if (it.kind == 1) {
@@ -1582,7 +1602,7 @@ __global__ void pb_expand_kernel(const DevExpandItem* __restrict__ items) {
 // values in `head` (total docs, entries scanned in filter, docs matched of a match-all query) instead of zero, so that a
 // cross-GPU merge sums them like every other counter.  `aux` is a second zero region (per-wave match counters and
 // per-segment swim-lane statistics) that is not part of the merged block.
-__global__ void pb_init_tables_kernel(uint4* zero, uint64_t zero_n16, uint4* ff, uint64_t ff_n16, uint4* mm, uint64_t mm_n16,
+static __global__ void pb_init_tables_kernel(uint4* zero, uint64_t zero_n16, uint4* ff, uint64_t ff_n16, uint4* mm, uint64_t mm_n16,
                                       uint4* aux, uint64_t aux_n16, const uint4* __restrict__ head, uint64_t head_n16) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u), f = make_uint4(~0u, ~0u, ~0u, ~0u), m = make_uint4(~0u, 0x7fffffffu, ~0u, 0x7fffffffu);
@@ -1597,7 +1617,7 @@ __global__ void pb_init_tables_kernel(uint4* zero, uint64_t zero_n16, uint4* ff,
 // Per segment and lane l (0 = the non-filtered lane, 1 + f = FILTER clause f): docs_w = 1 when the lane's docs count
 // towards numDocsScanned, post_w = the lane's projected columns (numEntriesScannedPostFilter = docs x columns).
 struct DevLaneWeights { int32_t table; int32_t docs_w[1 + PB_MAX_AGG_FILTERS]; int32_t post_w[1 + PB_MAX_AGG_FILTERS]; int32_t pad; };
-__global__ void pb_lane_stats_kernel(const DevLaneWeights* __restrict__ w, const unsigned long long* __restrict__ seg_stats, int n_segs,
+static __global__ void pb_lane_stats_kernel(const DevLaneWeights* __restrict__ w, const unsigned long long* __restrict__ seg_stats, int n_segs,
                                      int n_lanes, unsigned long long* counters, int cells_per_table) {
   for (int si = blockIdx.x * blockDim.x + threadIdx.x; si < n_segs; si += gridDim.x * blockDim.x) {
     const unsigned long long* ss = seg_stats + (size_t)si * (1 + PB_MAX_AGG_FILTERS);
@@ -1617,7 +1637,7 @@ __global__ void pb_lane_stats_kernel(const DevLaneWeights* __restrict__ w, const
 // bits from the same gathered buffer.
 #define PB_MERGE_MAX_PEERS 16
 struct DevMergePeers { const unsigned long long* p[PB_MERGE_MAX_PEERS]; };
-__global__ void pb_merge_blocks_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ gathered, const DevMergePeers peers,
+static __global__ void pb_merge_blocks_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ gathered, const DevMergePeers peers,
                                        int n_rows, int base_is_dst, uint64_t n_words, uint64_t sum_off, uint64_t dc_off, uint64_t mm_off) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_words; i += (uint64_t)gridDim.x * blockDim.x) {
     auto row = [&](int r) -> unsigned long long { return gathered ? gathered[(uint64_t)r * n_words + i] : peers.p[r][i]; };
@@ -1659,7 +1679,7 @@ __device__ __forceinline__ void pb_slot_key(const DevHashXfer& X, uint64_t i, un
   if (X.key_words == 2) { klo = i == X.capacity ? PB_HASH_EMPTY : X.hkeys[2 * i]; khi = i == X.capacity ? PB_HASH_EMPTY : X.hkeys[2 * i + 1]; }
   else { klo = i == X.capacity ? PB_HASH_EMPTY : X.hkeys[i]; khi = 0; }
 }
-__global__ void pb_hash_count_kernel(const DevHashXfer X) {
+static __global__ void pb_hash_count_kernel(const DevHashXfer X) {
   __shared__ unsigned int s_cnt[64];
   for (int k = threadIdx.x; k < X.n_ranks; k += blockDim.x) s_cnt[k] = 0;
   __syncthreads();
@@ -1672,7 +1692,7 @@ __global__ void pb_hash_count_kernel(const DevHashXfer X) {
   __syncthreads();
   for (int k = threadIdx.x; k < X.n_ranks; k += blockDim.x) if (s_cnt[k]) atomicAdd(&X.counts[k], (unsigned long long)s_cnt[k]);
 }
-__global__ void pb_hash_pack_kernel(const DevHashXfer X) {
+static __global__ void pb_hash_pack_kernel(const DevHashXfer X) {
   const int lane = threadIdx.x & 31;
   const uint64_t S_round = (X.S + 31) & ~(uint64_t)31;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < S_round; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -1697,7 +1717,7 @@ __global__ void pb_hash_pack_kernel(const DevHashXfer X) {
   }
 }
 // received tuples -> this rank's (re-initialised) table
-__global__ void pb_hash_merge_kernel(const DevTable t, const unsigned long long* __restrict__ in, uint64_t n_tuples, int key_words, int n_aggs, int tuple_words) {
+static __global__ void pb_hash_merge_kernel(const DevTable t, const unsigned long long* __restrict__ in, uint64_t n_tuples, int key_words, int n_aggs, int tuple_words) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_tuples; i += (uint64_t)gridDim.x * blockDim.x) {
     const unsigned long long* p = in + i * (uint64_t)tuple_words;
     int w = 0;
@@ -1716,7 +1736,7 @@ __global__ void pb_hash_merge_kernel(const DevTable t, const unsigned long long*
   }
 }
 // counter cells of all ranks (rank-major) summed into this rank's; the group count [0] and the cursor [3] stay local
-__global__ void pb_sum_counters_kernel(unsigned long long* cells, const unsigned long long* __restrict__ gathered, int n_ranks, int n_cells) {
+static __global__ void pb_sum_counters_kernel(unsigned long long* cells, const unsigned long long* __restrict__ gathered, int n_ranks, int n_cells) {
   const int i = threadIdx.x;
   if (i >= n_cells || i == 0 || i == 3) return;
   unsigned long long v = 0;
@@ -1726,7 +1746,7 @@ __global__ void pb_sum_counters_kernel(unsigned long long* cells, const unsigned
 
 // numGroupsLimit in doc order: *thr = the limit-th smallest first_doc among the existing groups (first docs are distinct: a
 // doc belongs to one group), or 0xFFFFFFFE when fewer groups exist.  One CTA, four 8-bit radix-select passes.
-__global__ void pb_select_first_kernel(const uint32_t* __restrict__ first_doc, uint64_t S, uint32_t limit, uint32_t* thr) {
+static __global__ void pb_select_first_kernel(const uint32_t* __restrict__ first_doc, uint64_t S, uint32_t limit, uint32_t* thr) {
   __shared__ unsigned int hist[256];
   __shared__ uint32_t s_prefix, s_k, s_done;
   if (threadIdx.x == 0) { s_prefix = 0; s_k = limit; s_done = 0; }
@@ -1754,7 +1774,7 @@ __global__ void pb_select_first_kernel(const uint32_t* __restrict__ first_doc, u
 }
 
 // count non-empty slots
-__global__ void pb_count_groups_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n, unsigned long long* out) {
+static __global__ void pb_count_groups_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n, unsigned long long* out) {
   unsigned long long c = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += rowcnt[i] != 0;
   for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
@@ -1800,7 +1820,7 @@ struct DevFinalize {
   DevFinAgg aggs[PB_MAX_AGGS];
 };
 
-__global__ void pb_finalize_kernel(const DevFinalize F) {
+static __global__ void pb_finalize_kernel(const DevFinalize F) {
   const int lane = threadIdx.x & 31;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t S_round = (F.S + 31) & ~(uint64_t)31;
@@ -1863,11 +1883,11 @@ __global__ void pb_finalize_kernel(const DevFinalize F) {
 }
 
 // gather kernels used by the two-pass path of very large tables
-__global__ void pb_gather_u64_kernel(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ slots, uint64_t n, unsigned long long* __restrict__ dst) {
+static __global__ void pb_gather_u64_kernel(const unsigned long long* __restrict__ src, const unsigned long long* __restrict__ slots, uint64_t n, unsigned long long* __restrict__ dst) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = src[slots[i]];
 }
 // DISTINCTCOUNT: one warp per compacted group: popcount of its bitset
-__global__ void pb_distinct_count_kernel(const uint32_t* __restrict__ bits, uint64_t words, const unsigned long long* __restrict__ slots,
+static __global__ void pb_distinct_count_kernel(const uint32_t* __restrict__ bits, uint64_t words, const unsigned long long* __restrict__ slots,
                                          uint64_t n, unsigned long long* __restrict__ out) {
   uint64_t g = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -1879,7 +1899,7 @@ __global__ void pb_distinct_count_kernel(const uint32_t* __restrict__ bits, uint
   if (lane == 0) out[g] = c;
 }
 // DISTINCTCOUNT value sets: one warp per group writes the ascending dictIds at offsets[g]
-__global__ void pb_distinct_ids_kernel(const uint32_t* __restrict__ bits, uint64_t words, const unsigned long long* __restrict__ slots,
+static __global__ void pb_distinct_ids_kernel(const uint32_t* __restrict__ bits, uint64_t words, const unsigned long long* __restrict__ slots,
                                        uint64_t n, const unsigned long long* __restrict__ offsets, int32_t* __restrict__ out) {
   uint64_t g = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
@@ -1910,7 +1930,7 @@ struct DevRowBuild {
   int32_t bit_off[PB_ROW_MAX_COLS];
   uint32_t* out;
 };
-__global__ void pb_build_rows_kernel(const DevRowBuild B) {
+static __global__ void pb_build_rows_kernel(const DevRowBuild B) {
   for (uint64_t doc = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; doc < B.num_docs; doc += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t w[PB_ROW_MAX_WORDS];
 #pragma unroll
@@ -1933,7 +1953,7 @@ __global__ void pb_build_rows_kernel(const DevRowBuild B) {
 // sorted forward index (docId range pairs) -> big-endian bit-packed dictId stream, so a sorted column can
 // be read like any other dictionary column (SortedIndexReaderImpl doubles as the forward index:
 // SEGL/segment/index/readers/sorted/SortedIndexReaderImpl.java:37-116).  One thread per output word.
-__global__ void pb_sorted_to_packed_kernel(const int32_t* __restrict__ pairs_le, int32_t card, uint32_t num_docs, int bits,
+static __global__ void pb_sorted_to_packed_kernel(const int32_t* __restrict__ pairs_le, int32_t card, uint32_t num_docs, int bits,
                                            uint32_t* __restrict__ out_words, uint64_t n_words) {
   for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
     uint64_t bit0 = w * 32;

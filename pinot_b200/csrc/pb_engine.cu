@@ -6,6 +6,7 @@
 // query the call fails with PB_ERR_UNSUPPORTED and the plan maker declines to the stock CPU plan.
 #include "../../include/pinot_b200.h"
 #include "pb_device.cuh"
+#include "pb_filter_spec.h"
 
 #include <dlfcn.h>
 #include <nccl.h>
@@ -929,6 +930,7 @@ struct pb_result_s {
     std::vector<WaveLaunch> waves;
     const DevExpandItem* expand_items = nullptr; int n_expand = 0;
     int U = 2; bool u2_three = false; size_t smem_filter = 0;
+    int spec_w = 0, spec_pk = 0;             // > 0: the plan-time specialised filter kernel of that width / predicate kind
     int agg_kind = 0;                        // 0 none (fused), 1 pb_agg_kernel<6>, 2 pb_agg_kernel<4>, 3 pb_agg_smem_kernel
     size_t smem_agg = 0;
     const DevLaneWeights* lane_w = nullptr; int n_lanes = 0, n_segs = 0;
@@ -1370,7 +1372,10 @@ static int enqueue_all(pb_result_s* r, const std::vector<cudaEvent_t>* seg_wait)
     const pb_result_s::WaveLaunch& w = rp.waves[wi];
     if (seg_wait && rp.waves.size() > 1)
       for (int si = w.seg_lo; si < w.seg_hi; si++) if ((*seg_wait)[si]) CU(cudaStreamWaitEvent(st, (*seg_wait)[si], 0));
-    if (w.grid_filter > 0) {
+    if (w.grid_filter > 0 && rp.spec_w > 0) {
+      CU(pb_filter_spec_launch(rp.spec_w, rp.spec_pk, w.grid_filter, rp.smem_filter, st, &w.dq));
+      r->launches++;
+    } else if (w.grid_filter > 0) {
       if (rp.U == 1) pb_filter_kernel<1, 3><<<w.grid_filter, PB_NTHREADS, rp.smem_filter, st>>>(w.dq);
       else if (rp.u2_three) pb_filter_kernel<2, 3><<<w.grid_filter, PB_NTHREADS, rp.smem_filter, st>>>(w.dq);
       else pb_filter_kernel<2, 2><<<w.grid_filter, PB_NTHREADS, rp.smem_filter, st>>>(w.dq);
@@ -2278,6 +2283,37 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     if (occ < 1) return fail(PB_ERR_CUDA, "filter kernel does not fit an SM (smem %zu)", smem);
     max_ctas = (uint64_t)ctx->num_sms * (uint64_t)occ;
   }
+  // ---- plan-time specialisation: every segment of the launch is "one streamed dictionary leaf of the same width and
+  // predicate kind + candidate leaves" -> the small kernel compiled for exactly that (pb_filter_spec.cu) ----
+  int spec_w = 0, spec_pk = 0;
+  {
+    static const bool spec_on = []() { const char* e = getenv("PB_FILTER_SPEC"); return !e || atoi(e) != 0; }();
+    if (spec_on && !match_all && n_chunks > 0 && U == 2 && u2_three && !hq->generic && hq->use_tma) {
+      int w = -1, pk = -1;
+      bool ok = true;
+      for (int si = 0; si < n_segs && ok; si++) {
+        const DevSegQuery& ds = hsegs[si];
+        int nl = 0, dense = -1, n_dense = 0;
+        for (int n = 0; n < ds.n_nodes && ok; n++) {
+          if (ds.node_kind[n] == N_LEAF) {
+            const DevLeaf& lf = ds.leaves[ds.node_arg[n]];
+            if (!lf.gather) { dense = ds.node_arg[n]; n_dense++; }
+            nl++;
+          } else if (!(ds.node_kind[n] == N_AND && n == ds.n_nodes - 1 && ds.node_arg[n] == nl)) ok = false;
+        }
+        if (!ok || n_dense != 1) { ok = false; break; }
+        const DevLeaf& lf = ds.leaves[dense];
+        const int k = lf.kind == L_DICT_RANGE ? 0 : (lf.kind == L_DICT_SET && lf.set_smem_off >= 0) ? 1 : -1;
+        if (k < 0 || (w >= 0 && (w != lf.bits || pk != k))) { ok = false; break; }
+        w = lf.bits; pk = k;
+      }
+      if (ok && w > 0 && pb_filter_spec_available(w, pk)) {
+        int occ = 0;
+        if (pb_filter_spec_prepare(w, pk, smem, &occ) == cudaSuccess && occ >= 1) { spec_w = w; spec_pk = pk; max_ctas = (uint64_t)ctx->num_sms * (uint64_t)occ; }
+        else cudaGetLastError();
+      }
+    }
+  }
   const size_t smem2 = table_mode == T_KEYLESS ? (nF > 0 ? 3 : 2) * sizeof(double) * (size_t)nA * PB_NTHREADS : 0;
   // more resident threads = more gathers in flight (the kernel is DRAM-latency bound); 6 CTAs/SM costs a 4-byte spill
   static const int agg_occ = []() { const char* e = getenv("PB_AGG_OCC"); int v = e ? atoi(e) : 6; return v == 4 ? 4 : 6; }();
@@ -2292,7 +2328,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   {
     pb_result_s::Replay& rp = r->rp;
     rp.expand_items = d_expand_items; rp.n_expand = n_expand_items;
-    rp.U = U; rp.u2_three = u2_three; rp.smem_filter = smem;
+    rp.U = U; rp.u2_three = u2_three; rp.smem_filter = smem; rp.spec_w = spec_w; rp.spec_pk = spec_pk;
     rp.agg_kind = (fuse || n_docs_total == 0) ? 0 : use_smem_table ? 3 : agg_occ == 4 ? 2 : 1;
     rp.smem_agg = use_smem_table ? (size_t)st_replicas * st_rep_bytes : smem2;
     rp.lane_w = d_lane_w; rp.n_lanes = 1 + nF; rp.n_segs = n_segs;

@@ -26,3 +26,4 @@ for f in sorted(glob.glob("gpurun_out/r2d_bench*.json")):
     except Exception as e:
         print(f, "ERR", e)
 PY
+echo "== bench_configs small scale"; timeout 600 python bench_configs.py --only 1,3,4,5 --scale 0.05 --steps 3 > gpurun_out/r2d_configs_small.jsonl 2> gpurun_out/r2d_configs_small.err; tail -c 400 gpurun_out/r2d_configs_small.err; cut -c1-700 gpurun_out/r2d_configs_small.jsonl
