@@ -236,6 +236,9 @@ const int64_t* pb_result_long(pb_result_handle r, int32_t table, int32_t agg);
  * offsets[num_groups+1] into dictIds (ascending per group; local without COMBINE, global with it) */
 const int64_t* pb_result_distinct_offsets(pb_result_handle r, int32_t table, int32_t agg);
 const int32_t* pb_result_distinct_dict_ids(pb_result_handle r, int32_t table, int32_t agg);
+/* DISTINCTCOUNT on a raw (no-dictionary) column: the value sets as bits, ascending per group (INT / LONG: the value;
+ * FLOAT / DOUBLE: IEEE-754 bits of the value widened to double); same offsets.  NULL for dictionary columns. */
+const int64_t* pb_result_distinct_values(pb_result_handle r, int32_t table, int32_t agg);
 const pb_exec_stats* pb_result_stats(pb_result_handle r, int32_t table);
 /* device time (CUDA events on the call's stream): the whole call (table init .. result read-back), the two hot
  * kernels together (pb_filter_kernel + pb_agg_kernel), and each of them */

@@ -97,6 +97,8 @@ def lib():
                                          C.POINTER(C.c_int64)]
         l.orc_filter_doc_ids.restype = C.c_int64
         l.orc_free.argtypes = [C.c_void_p]
+        l.orc_result_distinct_values.argtypes = [C.c_void_p, C.c_int32]
+        l.orc_result_distinct_values.restype = C.POINTER(C.c_int64)
         l.orc_execute_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         l.orc_execute_batch.restype = C.c_int32
         l.orc_num_bits_per_value.argtypes = [C.c_int32]
@@ -220,7 +222,10 @@ class OracleResult:
             if int(agg.op) == 5:
                 off = np.ctypeslib.as_array(l.orc_result_distinct_offsets(rp, a), shape=(ng + 1,)).copy()
                 n = int(off[-1])
-                ids = np.ctypeslib.as_array(l.orc_result_distinct_dict_ids(rp, a), shape=(max(n, 1),))[:n].copy()
+                if seg.columns[agg.column].has_dictionary:      # value sets as dictIds ...
+                    ids = np.ctypeslib.as_array(l.orc_result_distinct_dict_ids(rp, a), shape=(max(n, 1),))[:n].copy()
+                else:                                           # ... or, for a raw column, as value bits (int64)
+                    ids = np.ctypeslib.as_array(l.orc_result_distinct_values(rp, a), shape=(max(n, 1),))[:n].copy()
                 self.distinct.append((off, ids))
             else:
                 self.distinct.append(None)
@@ -318,10 +323,10 @@ def combine(results: List[OracleResult]) -> Dict[tuple, list]:
         keys = r.decoded_keys() if q.group_by else [()]
         dvals = []
         for a, agg in enumerate(q.aggregations):
-            if int(agg.op) == 5:
+            if int(agg.op) == 5 and r.segment.columns[agg.column].has_dictionary:
                 dvals.append(r.segment.columns[agg.column].dictionary_values())
             else:
-                dvals.append(None)
+                dvals.append(None)      # (DISTINCTCOUNT on a raw column: the sets hold the value bits themselves)
         for g, key in enumerate(keys):
             row = []
             for a, agg in enumerate(q.aggregations):
@@ -334,7 +339,7 @@ def combine(results: List[OracleResult]) -> Dict[tuple, list]:
                     row.append((float(r.doubles[a][g]), int(r.longs[a][g])))
                 else:
                     off, ids = r.distinct[a]
-                    row.append(set(dvals[a][ids[off[g]:off[g + 1]]].tolist()))
+                    row.append(set((dvals[a][ids[off[g]:off[g + 1]]] if dvals[a] is not None else ids[off[g]:off[g + 1]]).tolist()))
             cur = table.get(key)
             if cur is None:
                 table[key] = row

@@ -877,6 +877,7 @@ struct orc_result {
   int64_t** lng;                /* per agg */
   int64_t** dc_offsets;         /* per agg (DISTINCTCOUNT) */
   int32_t** dc_ids;
+  int64_t** dc_values;          /* DISTINCTCOUNT on a raw column: value bits, ascending per group */
 };
 
 void orc_result_free(orc_result* r) {
@@ -886,8 +887,9 @@ void orc_result_free(orc_result* r) {
     if (r->lng) free(r->lng[a]);
     if (r->dc_offsets) free(r->dc_offsets[a]);
     if (r->dc_ids) free(r->dc_ids[a]);
+    if (r->dc_values) free(r->dc_values[a]);
   }
-  free(r->dbl); free(r->lng); free(r->dc_offsets); free(r->dc_ids); free(r->group_keys); free(r);
+  free(r->dbl); free(r->lng); free(r->dc_offsets); free(r->dc_ids); free(r->dc_values); free(r->group_keys); free(r);
 }
 int32_t orc_result_num_groups(const orc_result* r) { return r->num_groups; }
 const orc_stats* orc_result_stats(const orc_result* r) { return &r->stats; }
@@ -896,6 +898,7 @@ const double* orc_result_double(const orc_result* r, int32_t a) { return r->dbl[
 const int64_t* orc_result_long(const orc_result* r, int32_t a) { return r->lng[a]; }
 const int64_t* orc_result_distinct_offsets(const orc_result* r, int32_t a) { return r->dc_offsets[a]; }
 const int32_t* orc_result_distinct_dict_ids(const orc_result* r, int32_t a) { return r->dc_ids[a]; }
+const int64_t* orc_result_distinct_values(const orc_result* r, int32_t a) { return r->dc_values[a]; }
 
 /* tuple-keyed open-addressing map, ids in first-seen order — stands in for IntGroupIdMap /
  * Long2IntOpenHashMap / Object2IntOpenHashMap<IntArray> (DictionaryBasedGroupKeyGenerator.java:416-495,
@@ -965,6 +968,32 @@ static void bholder_ensure(bholder* h, int64_t n) {
   h->cap = nc;
 }
 
+/* DISTINCTCOUNT on a raw (no-dictionary) column keeps per-group VALUE sets (IntOpenHashSet / LongOpenHashSet /
+ * FloatOpenHashSet / DoubleOpenHashSet, BaseDistinctAggregateAggregationFunction.java:157-226).  Restated as a list of
+ * (holder index, value bits) pairs, sorted and de-duplicated at the end; float values are widened to double and NaNs
+ * canonicalised, which preserves the sets' notion of equality (Float.floatToIntBits / Double.doubleToLongBits). */
+typedef struct { int64_t* h; int64_t* v; int64_t n, cap; } pholder;
+static void pholder_add(pholder* p, int64_t h, int64_t v) {
+  if (p->n == p->cap) {
+    p->cap = p->cap ? p->cap * 2 : 1024;
+    p->h = (int64_t*)realloc(p->h, sizeof(int64_t) * (size_t)p->cap);
+    p->v = (int64_t*)realloc(p->v, sizeof(int64_t) * (size_t)p->cap);
+  }
+  p->h[p->n] = h; p->v[p->n] = v; p->n++;
+}
+static inline int64_t raw_value_bits(const col_reader* r, int32_t doc) {
+  if (r->c->data_type == ORC_INT || r->c->data_type == ORC_LONG) return raw_long(r, doc);
+  double d = raw_double(r, doc);
+  if (d != d) return 0x7ff8000000000000LL;
+  int64_t b; memcpy(&b, &d, 8); return b;
+}
+typedef struct { int64_t h, v; } hv_pair;
+static int hv_cmp(const void* a, const void* b) {
+  const hv_pair* x = (const hv_pair*)a; const hv_pair* y = (const hv_pair*)b;
+  if (x->h != y->h) return x->h < y->h ? -1 : 1;
+  return x->v < y->v ? -1 : (x->v > y->v ? 1 : 0);
+}
+
 orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
   g_err[0] = 0;
   const int32_t nG = q->num_group_by, nA = q->num_aggregations, num_docs = seg->num_docs;
@@ -1032,7 +1061,7 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
   for (int32_t a = 0; a < nA; a++) {
     if (q->aggregations[a].column >= 0) {
       if (col_reader_init(&areaders[a], &seg->columns[q->aggregations[a].column], num_docs) != 0) goto fail;
-      if (q->aggregations[a].op == ORC_DISTINCTCOUNT && !areaders[a].c->has_dictionary) { set_err("DISTINCTCOUNT on raw column unsupported in oracle"); goto fail; }
+      if (q->aggregations[a].op == ORC_DISTINCTCOUNT && !areaders[a].c->has_dictionary && areaders[a].c->data_type == ORC_STRING) { set_err("DISTINCTCOUNT on raw STRING column unsupported in oracle"); goto fail; }
       if (q->aggregations[a].op != ORC_DISTINCTCOUNT && areaders[a].c->data_type == ORC_STRING) { set_err("numeric aggregation on STRING"); goto fail; }
     }
   }
@@ -1063,11 +1092,12 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
   dholder* dh = (dholder*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(dholder));   /* SUM/MIN/MAX/COUNT(double)/AVG sum */
   dholder* ch = (dholder*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(dholder));   /* AVG count */
   bholder* bh = (bholder*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(bholder));
+  pholder* ph = (pholder*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(pholder));   /* DISTINCTCOUNT on raw columns */
   for (int32_t a = 0; a < nA; a++) {
     int op = q->aggregations[a].op;
     dh[a].dflt = op == ORC_MIN ? INFINITY : (op == ORC_MAX ? -INFINITY : 0.0);
     ch[a].dflt = 0.0;
-    if (op == ORC_DISTINCTCOUNT) bh[a].words = ((int64_t)areaders[a].c->cardinality + 63) / 64;
+    if (op == ORC_DISTINCTCOUNT && areaders[a].c->has_dictionary) bh[a].words = ((int64_t)areaders[a].c->cardinality + 63) / 64;
   }
   /* keyless native-type MIN/MAX state (MinAggregationFunction.java:69-148) */
   int64_t* kl_long = (int64_t*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int64_t));
@@ -1129,6 +1159,10 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
           for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0) dh[a].v[group_ids[i]] += 1.0;
           continue;
         }
+        if (op == ORC_DISTINCTCOUNT && !areaders[a].c->has_dictionary) {   /* BaseDistinctAggregateAggregationFunction.java:323-400 */
+          for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0) pholder_add(&ph[a], group_ids[i], raw_value_bits(&areaders[a], doc_ids[i]));
+          continue;
+        }
         if (op == ORC_DISTINCTCOUNT) {  /* BaseDistinctAggregateAggregationFunction.java:306-321 */
           for (int32_t i = 0; i < len; i++) {
             int32_t g = group_ids[i]; if (g < 0) continue;
@@ -1163,6 +1197,10 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
         if (!lane_has[a]) continue;
         if (op == ORC_COUNT) { dh[a].v[0] += (double)len; continue; }   /* CountAggregationFunction.java:110-116 */
         const col_reader* r = &areaders[a];
+        if (op == ORC_DISTINCTCOUNT && !r->c->has_dictionary) {   /* BaseDistinctAggregateAggregationFunction.java:157-226 */
+          for (int32_t i = 0; i < len; i++) pholder_add(&ph[a], 0, raw_value_bits(r, doc_ids[i]));
+          continue;
+        }
         if (op == ORC_DISTINCTCOUNT) {   /* BaseDistinctAggregateAggregationFunction.java:144-155 */
           if (!bh[a].sets[0]) bh[a].sets[0] = (uint64_t*)calloc((size_t)bh[a].words, 8);
           for (int32_t i = 0; i < len; i++) { int32_t id = dict_id_of(r, doc_ids[i]); bh[a].sets[0][id >> 6] |= 1ull << (id & 63); }
@@ -1219,11 +1257,32 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
   res->lng = (int64_t**)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int64_t*));
   res->dc_offsets = (int64_t**)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int64_t*));
   res->dc_ids = (int32_t**)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int32_t*));
+  res->dc_values = (int64_t**)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int64_t*));
   for (int32_t a = 0; a < nA; a++) {
     int op = q->aggregations[a].op;
     res->dbl[a] = (double*)calloc((size_t)(ng > 0 ? ng : 1), sizeof(double));
     res->lng[a] = (int64_t*)calloc((size_t)(ng > 0 ? ng : 1), sizeof(int64_t));
     if (op == ORC_DISTINCTCOUNT) res->dc_offsets[a] = (int64_t*)calloc((size_t)ng + 1, sizeof(int64_t));
+    if (op == ORC_DISTINCTCOUNT && !areaders[a].c->has_dictionary) {
+      /* sort (holder index, value), drop duplicates, then hand the sets out in result-group order */
+      hv_pair* pr = (hv_pair*)malloc(sizeof(hv_pair) * (size_t)(ph[a].n > 0 ? ph[a].n : 1));
+      for (int64_t i = 0; i < ph[a].n; i++) { pr[i].h = ph[a].h[i]; pr[i].v = ph[a].v[i]; }
+      qsort(pr, (size_t)ph[a].n, sizeof(hv_pair), hv_cmp);
+      int64_t nu = 0;
+      for (int64_t i = 0; i < ph[a].n; i++) if (i == 0 || pr[i].h != pr[i - 1].h || pr[i].v != pr[i - 1].v) pr[nu++] = pr[i];
+      res->dc_values[a] = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nu > 0 ? nu : 1));
+      int64_t k = 0;
+      for (int64_t g = 0; g < ng; g++) {
+        int64_t h = (nG > 0 && holder == 1) ? id_of_group[g] : g;
+        int64_t lo = 0, hi = nu;                       /* first pair with holder index >= h */
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (pr[mid].h < h) lo = mid + 1; else hi = mid; }
+        int64_t n = 0;
+        for (int64_t i = lo; i < nu && pr[i].h == h; i++) { res->dc_values[a][k++] = pr[i].v; n++; }
+        res->lng[a][g] = n; res->dc_offsets[a][g + 1] = k;
+      }
+      free(pr);
+      continue;
+    }
     int64_t total_ids = 0;
     for (int64_t g = 0; g < ng; g++) {
       int64_t h = (nG > 0 && holder == 1) ? id_of_group[g] : g;
@@ -1270,8 +1329,9 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
     free(dh[a].v); free(ch[a].v);
     for (int64_t i = 0; i < bh[a].cap; i++) free(bh[a].sets[i]);
     free(bh[a].sets);
+    free(ph[a].h); free(ph[a].v);
   }
-  free(dh); free(ch); free(bh); free(kl_long); free(kl_long_set);
+  free(dh); free(ch); free(bh); free(ph); free(kl_long); free(kl_long_set);
   if (have_map) gmap_free(&map);
   free(array_flags); free(greaders); free(areaders);
   for (int32_t l = 0; l < n_lanes; l++) { dit_free(lanes[l].it); fop_free(lanes[l].root); free(lanes[l].has); }
@@ -1281,7 +1341,7 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
 
 fail2:
   free(doc_ids); free(group_ids); free(values); free(dict_buf);
-  free(dh); free(ch); free(bh); free(kl_long); free(kl_long_set);
+  free(dh); free(ch); free(bh); free(ph); free(kl_long); free(kl_long_set);
   if (have_map) gmap_free(&map);
   free(array_flags);
 fail:

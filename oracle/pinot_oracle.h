@@ -132,6 +132,8 @@ const int64_t* orc_result_long(const orc_result* r, int32_t agg);    /* COUNT, A
 /* DISTINCTCOUNT value sets: offsets[num_groups+1] into ids[] (dictIds, ascending per group) */
 const int64_t* orc_result_distinct_offsets(const orc_result* r, int32_t agg);
 const int32_t* orc_result_distinct_dict_ids(const orc_result* r, int32_t agg);
+/* DISTINCTCOUNT on a raw column: the value sets as bits (INT / LONG: the value; FLOAT / DOUBLE: IEEE bits of the double), NULL otherwise */
+const int64_t* orc_result_distinct_values(const orc_result* r, int32_t agg);
 
 /* Matching docIds of the filter alone (ascending, as DocIdSetOperator would deliver them);
  * returns the count, *out is malloc'd (orc_free). */

@@ -11,8 +11,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "libpinot_b200.so")
-OBJ_DIR = os.path.join(HERE, "build")
+# PB_SCRATCH_BUILD=<dir>: compile and link into <dir> instead of the tree (a compile check that leaves the in-tree library,
+# which a GPU run in flight may be about to snapshot, untouched)
+_SCRATCH = os.environ.get("PB_SCRATCH_BUILD")
+LIB = os.path.join(_SCRATCH or HERE, "libpinot_b200.so")
+OBJ_DIR = os.path.join(_SCRATCH, "obj") if _SCRATCH else os.path.join(HERE, "build")
 SOURCES = [os.path.join(HERE, "csrc", "pb_engine.cu"), os.path.join(HERE, "csrc", "pb_filter_spec.cu"),
            os.path.join(HERE, "csrc", "host", "pb_host.cpp")]
 HEADERS = [os.path.join(HERE, "csrc", "pb_device.cuh"), os.path.join(HERE, "csrc", "pb_internal.h"),

@@ -151,6 +151,12 @@ struct DevTable {
   unsigned long long* fcnt[PB_MAX_AGGS];   // COUNT / AVG with a FILTER clause: their own row count (others use rowcnt)
   uint32_t* dc_bits[PB_MAX_AGGS];    // DISTINCTCOUNT: per-slot bitset over (global) dictIds
   uint64_t dc_words[PB_MAX_AGGS];
+  // DISTINCTCOUNT on a raw column (the reference keeps a value set per group: BaseDistinctAggregateAggregationFunction.java:
+  // 157-226): ONE open-addressing set of (slot, value bits) pairs for the whole table, 16-byte entries claimed with CAS.128;
+  // dcnt[slot] = distinct values of the slot, counted from the set at hand-back
+  unsigned long long* dset[PB_MAX_AGGS];
+  uint64_t dset_mask[PB_MAX_AGGS];
+  unsigned long long* dcnt[PB_MAX_AGGS];
   unsigned int* num_groups;          // hash: groups created so far
   unsigned int* limit_reached;
   unsigned long long* docs_matched;  // numDocsScanned
@@ -629,6 +635,10 @@ __device__ __forceinline__ uint64_t pb_key_field(const DevKeyCol& kc, uint32_t d
 // value of aggregation column a for `doc`: BlockValSet.getDoubleValuesSV (dictionary decode or raw read, widened
 // to double); for DISTINCTCOUNT the (global) dictId, returned through the same 64-bit channel
 __device__ __forceinline__ double pb_agg_input(const DevAggCol& ac, int op, uint32_t doc) {
+  if (op == 5 && ac.raw_width) {       // raw column: the value itself, as bits (NaNs canonical, like Double.doubleToLongBits)
+    if (ac.data_type == 2 || ac.data_type == 3) { const double d = pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type); return d == d ? d : __longlong_as_double(0x7ff8000000000000LL); }
+    return __longlong_as_double(pb_raw_i64(ac.fwd, doc, ac.raw_width, ac.data_type));
+  }
   if (op == 5) {
     uint32_t id = pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word, ac.stride_bits, ac.bit_off);
     if (ac.remap) id = (uint32_t)__ldg(ac.remap + id);
@@ -636,6 +646,24 @@ __device__ __forceinline__ double pb_agg_input(const DevAggCol& ac, int op, uint
   }
   return ac.raw_width ? pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type)
                       : __ldg(ac.dict_f64 + pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word, ac.stride_bits, ac.bit_off));
+}
+
+// (slot, value) into the table-wide distinct set of aggregation a
+__device__ __forceinline__ void pb_dset_insert(const DevTable& t, int a, uint64_t slot, unsigned long long v) {
+  const uint64_t mask = t.dset_mask[a];
+  unsigned long long* keys = t.dset[a];
+  uint64_t s = pb_hash64(slot * 0x9e3779b97f4a7c15ull ^ pb_hash64(v)) & mask;
+  for (uint64_t probes = 0; probes <= mask; probes++) {
+    unsigned long long clo, chi;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(clo), "=l"(chi) : "l"(&keys[2 * s]));
+    if (clo == slot && chi == v) return;
+    if (clo == PB_HASH_EMPTY && chi == PB_HASH_EMPTY) {
+      unsigned long long olo, ohi;
+      pb_atom_cas_u128(&keys[2 * s], PB_HASH_EMPTY, PB_HASH_EMPTY, slot, v, olo, ohi);
+      if ((olo == PB_HASH_EMPTY && ohi == PB_HASH_EMPTY) || (olo == slot && ohi == v)) return;
+    }
+    s = (s + 1) & mask;
+  }
 }
 
 // ---- phase 1 of a matching doc: every gather is issued before anything is reduced, four independent chains at a
@@ -703,7 +731,8 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
     }
     if (op == 0) continue;                       // COUNT(*): the row counter
     const double v = vals[a];
-    if (op == 5) {                               // DISTINCTCOUNT (dictionary column)
+    if (op == 5) {                               // DISTINCTCOUNT: dictionary column -> bitset over dictIds; raw column -> value set
+      if (t.dset[a]) { pb_dset_insert(t, a, slot, (unsigned long long)__double_as_longlong(v)); continue; }
       uint32_t id = (uint32_t)__double_as_longlong(v);
       pb_red_or_b32(&t.dc_bits[a][slot * t.dc_words[a] + (id >> 5)], 1u << (id & 31));
       continue;
@@ -778,7 +807,8 @@ __device__ __forceinline__ void pb_accumulate_smem(const DevQuery& Q, const DevS
     }
     if (op == 0) continue;
     const double v = vals[a];
-    if (op == 5) {                               // distinct bitsets stay in global memory (OR is idempotent: no contention cost)
+    if (op == 5) {                               // distinct bitsets / value sets stay in global memory (idempotent: no contention cost)
+      if (t.dset[a]) { pb_dset_insert(t, a, slot, (unsigned long long)__double_as_longlong(v)); continue; }
       uint32_t id = (uint32_t)__double_as_longlong(v);
       pb_red_or_b32(&t.dc_bits[a][slot * t.dc_words[a] + (id >> 5)], 1u << (id & 31));
       continue;
@@ -1773,6 +1803,28 @@ static __global__ void pb_select_first_kernel(const uint32_t* __restrict__ first
   if (threadIdx.x == 0) *thr = s_done ? 0xfffffffeu : s_prefix;
 }
 
+// DISTINCTCOUNT on raw columns: distinct values per slot, from the table-wide (slot, value) set
+static __global__ void pb_dset_count_kernel(const unsigned long long* __restrict__ keys, uint64_t cap, unsigned long long* __restrict__ dcnt) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long slot = keys[2 * i];
+    if (slot != PB_HASH_EMPTY || keys[2 * i + 1] != PB_HASH_EMPTY) atomicAdd(&dcnt[slot], 1ull);
+  }
+}
+// ... and the value sets themselves: the values of compacted group k land (unordered) at out[offsets[k] ..)
+static __global__ void pb_dset_scatter_kernel(const unsigned long long* __restrict__ keys, uint64_t cap, const uint32_t* __restrict__ group_of_slot,
+                                              const unsigned long long* __restrict__ offsets, unsigned long long* cursors, long long* __restrict__ out) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long slot = keys[2 * i], v = keys[2 * i + 1];
+    if (slot == PB_HASH_EMPTY && v == PB_HASH_EMPTY) continue;
+    const uint32_t k = group_of_slot[slot];
+    if (k == 0xffffffffu) continue;
+    out[offsets[k] + atomicAdd(&cursors[k], 1ull)] = (long long)v;
+  }
+}
+static __global__ void pb_invert_slots_kernel(const unsigned long long* __restrict__ slots, uint64_t n, uint32_t* __restrict__ group_of_slot) {
+  for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) group_of_slot[slots[k]] = (uint32_t)k;
+}
+
 // count non-empty slots
 static __global__ void pb_count_groups_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n, unsigned long long* out) {
   unsigned long long c = 0;
@@ -1800,6 +1852,7 @@ struct DevFinAgg {
   const double* sum;
   const long long* mm;
   const unsigned long long* fcnt;   // COUNT / AVG with a FILTER clause: row count of the function (else the group's)
+  const unsigned long long* dcnt;   // DISTINCTCOUNT on a raw column: distinct values per slot
   double* out;
   long long* out_cnt;               // where fcnt goes (the aggregation's long array)
 };
@@ -1849,6 +1902,7 @@ static __global__ void pb_finalize_kernel(const DevFinalize F) {
       }
       else if (fa.op == 0) fa.out[k] = fa.fcnt ? (double)fa.fcnt[i] : (double)c;
       // the aggregation's long array: COUNT value / AVG denominator (the function's own row count under a FILTER clause), 0 otherwise
+      if (fa.op == 5 && fa.dcnt) fa.out_cnt[k] = (long long)fa.dcnt[i];
       if (fa.op != 5) fa.out_cnt[k] = (fa.op == 0 || fa.op == 4) ? (fa.fcnt ? (long long)fa.fcnt[i] : (long long)c) : 0ll;
     }
     unsigned long long key = 0, key_hi = 0;

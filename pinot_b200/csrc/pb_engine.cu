@@ -882,6 +882,8 @@ struct TableMeta {
   HostArr slots, rows;
   std::vector<HostArr> dbl, lng, key_ids, key_vals, dc_off, dc_ids;
   std::vector<int> key_type, key_eb;
+  std::vector<uint64_t> dset_cap;           // per aggregation: entries of the raw-column DISTINCTCOUNT value set (0 = none)
+  std::vector<HostArr> dc_vals;             // ... and its value sets, materialised on demand
   pb_exec_stats stats{};
   uint64_t out_cap = 0;                     // capacity of the pinned output arrays
 };
@@ -1060,7 +1062,7 @@ static void destroy_result(pb_result_s* r) {
   for (void* p : r->dev_allocs) cudaFreeAsync(p, r->stream);
   for (auto& t : r->tables) {
     t.slots.release(); t.rows.release();
-    for (auto* v : {&t.dbl, &t.lng, &t.key_ids, &t.key_vals, &t.dc_off, &t.dc_ids}) for (auto& a : *v) a.release();
+    for (auto* v : {&t.dbl, &t.lng, &t.key_ids, &t.key_vals, &t.dc_off, &t.dc_ids, &t.dc_vals}) for (auto& a : *v) a.release();
   }
   r->h_counters.release();
   if (r->stream) { cudaStreamSynchronize(r->stream); stream_set_release(r->ctx, r->sset); }
@@ -1414,6 +1416,7 @@ static int replay_plan(pb_result_s* r, const pb_query_desc* q) {
     tm.num_groups = 0;
     for (auto& a : tm.dc_off) a.release();        // DISTINCTCOUNT value sets of the previous run (materialised on demand)
     for (auto& a : tm.dc_ids) a.release();
+    for (auto& a : tm.dc_vals) a.release();
   }
   for (size_t si = 0; si < g->segs.size(); si++) {
     pb_segment_s* sg = g->segs[si];
@@ -1548,7 +1551,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       acol[si][a] = ci;
       Column& c = s->cols[ci];
       if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT) {
-        if (!c.has_dict) return fail(PB_ERR_UNSUPPORTED, "DISTINCTCOUNT on raw column %s", c.name.c_str());
+        if (!c.has_dict && c.type == PB_STRING) return fail(PB_ERR_UNSUPPORTED, "DISTINCTCOUNT on raw STRING column %s", c.name.c_str());
         if ((rc = stage_column(s, c, true, false, false, cs, false, gather_ok(c)))) return rc;
       } else {
         if (c.type == PB_STRING) return fail(PB_ERR_UNSUPPORTED, "numeric aggregation on STRING column %s", c.name.c_str());
@@ -1634,7 +1637,8 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       if ((rc = get_global_dict(g, q->group_by_columns[j], &gdict[j]))) return rc;
     }
     for (int a = 0; a < nA; a++)
-      if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT && (rc = get_global_dict(g, q->aggregations[a].column, &adict[a]))) return rc;
+      if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT && g->segs[0]->cols[acol[0][a]].has_dict &&
+          (rc = get_global_dict(g, q->aggregations[a].column, &adict[a]))) return rc;
   }
 
   lap(0);
@@ -1701,8 +1705,11 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     for (auto& tm : r->tables) if ((uint64_t)std::max(1, q->num_groups_limit) < tm.capacity) track_first = true;
   r->track_first = track_first;
   std::vector<uint64_t> dc_words(nA, 0);
+  std::vector<char> dc_raw(nA, 0);           // DISTINCTCOUNT on a raw column: a (slot, value) set instead of a dictId bitset
   for (int a = 0; a < nA; a++)
-    if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT) {
+    if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT && !g->segs[0]->cols[acol[0][a]].has_dict) dc_raw[a] = 1;
+  for (int a = 0; a < nA; a++)
+    if (q->aggregations[a].op == PB_AGG_DISTINCTCOUNT && !dc_raw[a]) {
       int64_t maxcard = 0;
       if (combine) maxcard = adict[a]->n; else for (int si = 0; si < n_segs; si++) maxcard = std::max<int64_t>(maxcard, g->segs[si]->cols[acol[si][a]].card);
       dc_words[a] = ((uint64_t)maxcard + 31) / 32;
@@ -1715,7 +1722,17 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       if (nF > 0 && q->agg_filter_of[a] >= 0 && (op == PB_AGG_COUNT || op == PB_AGG_AVG)) zero_bytes += 8 * S;   // fcnt
       if (op == PB_AGG_SUM || op == PB_AGG_AVG) zero_bytes += 8 * S;
       if (op == PB_AGG_MIN || op == PB_AGG_MAX) mm_elems += S;
-      if (op == PB_AGG_DISTINCTCOUNT) zero_bytes += 4 * S * dc_words[a];
+      if (op == PB_AGG_DISTINCTCOUNT && !dc_raw[a]) zero_bytes += 4 * S * dc_words[a];
+      if (op == PB_AGG_DISTINCTCOUNT && dc_raw[a]) {
+        zero_bytes += 8 * S;                                   // dcnt
+        uint64_t docs = 0;
+        for (int si : tm.seg_idx) docs += (uint64_t)g->segs[si]->num_docs;
+        uint64_t cap = 1024;
+        while (cap < 2 * docs) cap <<= 1;                      // at most one entry per doc
+        if (cap > (1ull << 28)) return fail(PB_ERR_UNSUPPORTED, "DISTINCTCOUNT on raw column %s over %llu docs: value set too large", q->aggregations[a].column, (unsigned long long)docs);
+        tm.dset_cap.resize(nA, 0); tm.dset_cap[a] = cap;
+        ff_bytes += 16 * cap;
+      }
     }
     zero_bytes = (zero_bytes + 255) & ~(size_t)255;
     if (table_mode == T_HASH) ff_bytes += 8 * S * (size_t)key_words;
@@ -1770,7 +1787,8 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       if (t == 0) { r->block_sum_off = (int64_t)((uint8_t*)r->span_f64 - d_zero); r->block_dc_off = (int64_t)zo; }
       for (int a = 0; a < nA; a++) {
         int op = q->aggregations[a].op;
-        if (op == PB_AGG_DISTINCTCOUNT) { dt.dc_bits[a] = reinterpret_cast<uint32_t*>(d_zero + zo); dt.dc_words[a] = dc_words[a]; zo += 4 * S * dc_words[a]; }
+        if (op == PB_AGG_DISTINCTCOUNT && !dc_raw[a]) { dt.dc_bits[a] = reinterpret_cast<uint32_t*>(d_zero + zo); dt.dc_words[a] = dc_words[a]; zo += 4 * S * dc_words[a]; }
+        if (op == PB_AGG_DISTINCTCOUNT && dc_raw[a]) { dt.dcnt[a] = reinterpret_cast<unsigned long long*>(d_zero + zo); zo += 8 * S; }
         if (op == PB_AGG_MIN || op == PB_AGG_MAX) {
           dt.mm[a] = d_mm + mo; mo += S;
         }
@@ -1779,6 +1797,8 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       zo = (zo + 255) & ~(size_t)255;
       if (table_mode == T_HASH) { dt.hkeys = reinterpret_cast<unsigned long long*>(d_ff + fo); fo += 8 * S * (size_t)key_words; dt.key_words = key_words; }
       if (track_first) { dt.first_doc = reinterpret_cast<uint32_t*>(d_ff + fo); fo += (4 * S + 15) & ~(size_t)15; }
+      for (int a = 0; a < nA; a++)
+        if (dc_raw[a]) { dt.dset[a] = reinterpret_cast<unsigned long long*>(d_ff + fo); dt.dset_mask[a] = tm.dset_cap[a] - 1; fo += 16 * tm.dset_cap[a]; }
       unsigned long long* cnt = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE;
       dt.num_groups = reinterpret_cast<unsigned int*>(cnt + 0);
       dt.limit_reached = reinterpret_cast<unsigned int*>(cnt + 1);
@@ -2539,7 +2559,7 @@ static int prepare_finalize(pb_result_s* r) {
       tm.dbl[a].alloc(8 * cap); tm.lng[a].alloc(8 * cap);
       if (!tm.dbl[a].p || !tm.lng[a].p) return fail(PB_ERR_OOM, "pinned host allocation failed");
       F.aggs[a].op = r->agg_op[a]; F.aggs[a].sum = tm.dev.sum[a]; F.aggs[a].mm = tm.dev.mm[a]; F.aggs[a].out = (double*)tm.dbl[a].p;
-      F.aggs[a].fcnt = tm.dev.fcnt[a]; F.aggs[a].out_cnt = (long long*)tm.lng[a].p;
+      F.aggs[a].fcnt = tm.dev.fcnt[a]; F.aggs[a].out_cnt = (long long*)tm.lng[a].p; F.aggs[a].dcnt = tm.dev.dcnt[a];
     }
     uint64_t div = 1;
     for (int j = 0; j < nG; j++) {
@@ -2571,6 +2591,13 @@ static int enqueue_finalize(pb_result_s* r) {
   const int nT = (int)r->tables.size();
   for (int t = 0; t < nT; t++) {
     const DevFinalize& F = r->rp.fin[(size_t)t];
+    for (int a = 0; a < r->n_aggs; a++) {
+      const DevTable& dt = r->tables[(size_t)t].dev;
+      if (!dt.dset[a]) continue;
+      const uint64_t cap = dt.dset_mask[a] + 1;
+      pb_dset_count_kernel<<<(int)std::min<uint64_t>((cap + 255) / 256, (uint64_t)r->ctx->num_sms * 8), 256, 0, st>>>(dt.dset[a], cap, dt.dcnt[a]);
+      r->launches++;
+    }
     if (F.first_doc) {
       pb_select_first_kernel<<<1, 1024, 0, st>>>(F.first_doc, F.S, r->tables[(size_t)t].dev.num_groups_limit, r->d_first_thr + t);
       r->launches++;
@@ -2610,7 +2637,7 @@ static int finish_finalize(pb_result_s* r) {
     // DISTINCTCOUNT: the sizes now; the value sets (BaseDistinctAggregateAggregationFunction intermediate result) are
     // materialised on first access (pb_result_distinct_offsets / _dict_ids) — a merged result usually needs the sizes only
     for (int a = 0; a < nA; a++) {
-      if (r->agg_op[a] != PB_AGG_DISTINCTCOUNT) continue;
+      if (r->agg_op[a] != PB_AGG_DISTINCTCOUNT || !tm.dev.dc_bits[a]) continue;      // (raw columns: counted by the finalize pass)
       int64_t* L = (int64_t*)tm.lng[a].p;
       if (ng > 0) {
         int wgrid = (int)(((size_t)ng * 32 + 255) / 256);
@@ -2707,6 +2734,31 @@ static int materialize_distinct(pb_result_s* r, TableMeta& tm, int a) {
   off[0] = 0;
   for (int64_t k = 0; k < ng; k++) off[k + 1] = off[k] + L[k];
   const int64_t total = off[ng];
+  if (tm.dev.dset[a]) {
+    // raw column: scatter the (slot, value) set into per-group runs, then order each run on the host (value sets are an
+    // on-demand hand-back: the merged result of a query usually needs the sizes only)
+    if (tm.dc_vals.size() < (size_t)r->n_aggs) tm.dc_vals.resize((size_t)r->n_aggs);
+    tm.dc_vals[a].alloc(8 * (size_t)std::max<int64_t>(total, 1));
+    if (!tm.dc_vals[a].p) return fail(PB_ERR_OOM, "pinned host allocation failed");
+    if (total > 0) {
+      const uint64_t S = tm.capacity + (r->table_mode == T_HASH ? 1 : 0), cap = tm.dev.dset_mask[a] + 1;
+      uint32_t* d_map = nullptr; unsigned long long* d_cur = nullptr;
+      CU(cudaMallocAsync((void**)&d_map, 4 * S, st));
+      CU(cudaMallocAsync((void**)&d_cur, 8 * (size_t)ng, st));
+      CU(cudaMemsetAsync(d_map, 0xff, 4 * S, st));
+      CU(cudaMemsetAsync(d_cur, 0, 8 * (size_t)ng, st));
+      pb_invert_slots_kernel<<<(int)std::min<int64_t>((ng + 255) / 256, 4096), 256, 0, st>>>((const unsigned long long*)tm.slots.p, (uint64_t)ng, d_map);
+      pb_dset_scatter_kernel<<<(int)std::min<uint64_t>((cap + 255) / 256, (uint64_t)r->ctx->num_sms * 8), 256, 0, st>>>(
+          tm.dev.dset[a], cap, d_map, (const unsigned long long*)off, d_cur, (long long*)tm.dc_vals[a].p);
+      r->launches += 2;
+      CU(cudaGetLastError());
+      CU(cudaFreeAsync(d_map, st)); CU(cudaFreeAsync(d_cur, st));
+      CU(cudaStreamSynchronize(st));
+      int64_t* v = (int64_t*)tm.dc_vals[a].p;
+      for (int64_t k = 0; k < ng; k++) std::sort(v + off[k], v + off[k + 1]);
+    }
+    return PB_OK;
+  }
   tm.dc_ids[a].alloc(4 * (size_t)std::max<int64_t>(total, 1));
   if (!tm.dc_ids[a].p) return fail(PB_ERR_OOM, "pinned host allocation failed");
   if (total > 0) {
@@ -2724,9 +2776,14 @@ extern "C" const int64_t* pb_result_distinct_offsets(pb_result_handle r, int32_t
   if (!tm || a < 0 || a >= r->n_aggs || materialize_distinct(r, *tm, a) != PB_OK) return nullptr;
   return (const int64_t*)tm->dc_off[a].p;
 }
+extern "C" const int64_t* pb_result_distinct_values(pb_result_handle r, int32_t t, int32_t a) {
+  auto* tm = TAB(r, t);
+  if (!tm || a < 0 || a >= r->n_aggs || !tm->dev.dset[a] || materialize_distinct(r, *tm, a) != PB_OK) return nullptr;
+  return (const int64_t*)tm->dc_vals[a].p;
+}
 extern "C" const int32_t* pb_result_distinct_dict_ids(pb_result_handle r, int32_t t, int32_t a) {
   auto* tm = TAB(r, t);
-  if (!tm || a < 0 || a >= r->n_aggs || materialize_distinct(r, *tm, a) != PB_OK) return nullptr;
+  if (!tm || a < 0 || a >= r->n_aggs || tm->dev.dset[a] || materialize_distinct(r, *tm, a) != PB_OK) return nullptr;
   return (const int32_t*)tm->dc_ids[a].p;
 }
 extern "C" const pb_exec_stats* pb_result_stats(pb_result_handle r, int32_t t) { auto* tm = TAB(r, t); return tm ? &tm->stats : nullptr; }
@@ -2816,6 +2873,7 @@ static int comm_merge_hash(pb_result_s* r) {
 }
 static int launch_merge_rows(pb_result_s* r, const void* gathered, const DevMergePeers* peers, int n_rows, bool base_is_dst) {
   if (!r->combine || r->tables.size() != 1 || r->table_mode == T_HASH) return fail(PB_ERR_UNSUPPORTED, "merge needs a combined dense / keyless result");
+  for (int a = 0; a < r->n_aggs; a++) if (r->tables[0].dev.dset[a]) return fail(PB_ERR_UNSUPPORTED, "DISTINCTCOUNT on a raw column is not merged across GPUs");
   const uint64_t n_words = (uint64_t)r->block_bytes / 8;
   int grid = (int)std::min<uint64_t>((n_words + 255) / 256, (uint64_t)r->ctx->num_sms * 8);
   DevMergePeers none; memset(&none, 0, sizeof none);

@@ -130,6 +130,8 @@ def lib():
     l.pb_result_distinct_offsets.restype = C.POINTER(C.c_int64)
     l.pb_result_distinct_dict_ids.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     l.pb_result_distinct_dict_ids.restype = C.POINTER(C.c_int32)
+    l.pb_result_distinct_values.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    l.pb_result_distinct_values.restype = C.POINTER(C.c_int64)
     l.pb_result_stats.argtypes = [C.c_void_p, C.c_int32]
     l.pb_result_stats.restype = C.POINTER(PbExecStats)
     l.pb_result_device_ms.argtypes = [C.c_void_p]
@@ -352,7 +354,10 @@ class ResultTable:
                 if agg.op == AggOp.DISTINCTCOUNT:
                     off = np.ctypeslib.as_array(lib().pb_result_distinct_offsets(self._rh, self._t, a), shape=(self.num_groups + 1,))
                     tot = int(off[-1])
-                    ids = np.ctypeslib.as_array(lib().pb_result_distinct_dict_ids(self._rh, self._t, a), shape=(max(tot, 1),))[:tot]
+                    p = lib().pb_result_distinct_dict_ids(self._rh, self._t, a)
+                    if not p:       # raw column: the value sets as bits (int64)
+                        p = lib().pb_result_distinct_values(self._rh, self._t, a)
+                    ids = np.ctypeslib.as_array(p, shape=(max(tot, 1),))[:tot]
                     out.append((off, ids))
                 else:
                     out.append(None)

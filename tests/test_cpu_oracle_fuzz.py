@@ -154,3 +154,32 @@ def test_cross_segment_merge_vs_pandas(seed):
         got = merged[key]
         assert got[0] == row["n"] and got[1] == float(row["sum"]) and got[2] == row["min"] and got[3] == float(row["max"])
         assert got[4][1] == row["n"] and got[4][0] == pytest.approx(row["avg"], rel=1e-12) and len(got[5]) == row["dc"]
+
+
+def test_distinctcount_on_raw_columns_against_pandas():
+    """BaseDistinctAggregateAggregationFunction.java:157-226: a raw column's DISTINCTCOUNT keeps per-group value sets"""
+    import pandas as pd
+    from pinot_b200.segment_writer import DataType, build_column, make_segment
+    rng = np.random.Generator(np.random.PCG64(3))
+    n = 20_000
+    g = rng.integers(0, 12, size=n)
+    ri = rng.integers(-50, 50, size=n)
+    rl = rng.integers(-10**12, 10**12, size=n) // 10**11 * 10**11
+    rd = np.round(rng.normal(size=n), 1)
+    rd[::97] = -0.0
+    seg = make_segment("rawdc", [build_column("g", DataType.INT, g), build_column("ri", DataType.INT, ri, dictionary=False),
+                                 build_column("rl", DataType.LONG, rl, dictionary=False), build_column("rd", DataType.DOUBLE, rd, dictionary=False),
+                                 build_column("f", DataType.INT, rng.integers(0, 100, size=n))])
+    df = pd.DataFrame({"g": g, "ri": ri, "rl": rl, "rd": rd, "f": seg.columns["f"].dictionary_values()[0] * 0 + rng.integers(0, 1, size=n)})
+    q = parse_sql("SELECT g, DISTINCTCOUNT(ri), DISTINCTCOUNT(rl), DISTINCTCOUNT(rd), COUNT(*) FROM t GROUP BY g LIMIT 1000")
+    o = oracle.execute(seg, q)
+    keys = [k[0] for k in o.decoded_keys()]
+    for gi, k in enumerate(keys):
+        sub = df[df.g == k]
+        assert o.longs[0][gi] == sub.ri.nunique() and o.longs[1][gi] == sub.rl.nunique()
+        # -0.0 and 0.0 are different members of a DoubleOpenHashSet (Double.doubleToLongBits)
+        assert o.longs[2][gi] == len(set(sub.rd.values.view(np.int64).tolist()))
+        off, vals = o.distinct[0]
+        assert sorted(set(sub.ri.tolist())) == vals[off[gi]:off[gi + 1]].tolist()
+    ok = oracle.execute(seg, parse_sql("SELECT DISTINCTCOUNT(ri), DISTINCTCOUNT(rl) FROM t WHERE g < 6"))
+    assert ok.longs[0][0] == df[df.g < 6].ri.nunique() and ok.longs[1][0] == df[df.g < 6].rl.nunique()

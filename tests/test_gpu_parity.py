@@ -446,3 +446,25 @@ def test_num_groups_limit_hash_tables_never_overflow_or_hang():
         assert 0 < len(rows) <= limit and res.tables[0].stats["num_groups_limit_reached"] == 1
         res.free()
     g.release()
+
+
+def test_distinctcount_on_raw_columns():
+    """BaseDistinctAggregateAggregationFunction.java:157-226 (per-group value sets of a no-dictionary column): keyless,
+    dense and hash group tables, per segment and merged; sizes and the value sets themselves"""
+    rng = np.random.Generator(np.random.PCG64(5))
+    segs = []
+    for i in range(2):
+        n = 40_000 + 1000 * i
+        rd = np.round(rng.normal(size=n), 1)
+        rd[::101] = -0.0
+        segs.append(make_segment(f"rawdc{i}", [
+            build_column("g", DataType.INT, rng.integers(0, 12, size=n)), build_column("h", DataType.INT, rng.integers(0, 5, size=n)),
+            build_column("ri", DataType.INT, rng.integers(-50, 50, size=n), dictionary=False),
+            build_column("rl", DataType.LONG, rng.integers(-10**12, 10**12, size=n) // 10**11 * 10**11, dictionary=False),
+            build_column("rd", DataType.DOUBLE, rd, dictionary=False),
+            build_column("k", DataType.LONG, rng.integers(0, 3000, size=n), dictionary=False),
+            build_column("f", DataType.INT, rng.integers(0, 100, size=n))]))
+    for sql in ("SELECT DISTINCTCOUNT(ri), DISTINCTCOUNT(rl), DISTINCTCOUNT(rd), COUNT(*) FROM t WHERE f < 60",
+                "SELECT g, h, DISTINCTCOUNT(ri), DISTINCTCOUNT(rd), DISTINCTCOUNT(f), SUM(f) FROM t WHERE f >= 10 GROUP BY g, h LIMIT 1000",
+                "SELECT k, DISTINCTCOUNT(ri), COUNT(*) FROM t GROUP BY k LIMIT 100000"):
+        check_query(segs, sql)

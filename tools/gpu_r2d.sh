@@ -6,8 +6,8 @@ echo "== tests row groups off, fuse always"; PB_ROW_GROUPS=0 PB_FUSE_PERMILLE=10
 echo "== tests fuse always + row groups, no graph"; PB_GRAPH=0 PB_FUSE_PERMILLE=1000 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r2d_tests_fuse.log 2>&1; tail -3 gpurun_out/r2d_tests_fuse.log
 B="python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline"
 echo "== bench default (full)"; timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/r2d_bench.json 2> gpurun_out/r2d_bench.err; tail -c 300 gpurun_out/r2d_bench.err
-for v in "PB_ROW_GROUPS=0" "PB_GRAPH=0" "PB_FUSE_PERMILLE=50" "PB_FUSE_PERMILLE=50 PB_FUSE_BATCH=128" "PB_AGG_SMEM=0"; do
-  n=$(echo $v | tr '=- ' '___')
+for v in "PB_ROW_GROUPS=0" "PB_GRAPH=0" "PB_FUSE_PERMILLE=50" "PB_FUSE_PERMILLE=50 PB_FUSE_BATCH=128" "PB_FILTER_SPEC=0" "PB_FILTER_SPEC=0 PB_ROW_GROUPS=0"; do
+  n=$(echo "$v" | sed 's/[^A-Za-z0-9]/_/g')
   echo "== bench $v"; env $v timeout 600 $B --no-variants > gpurun_out/r2d_bench_$n.json 2> gpurun_out/r2d_bench_$n.err; tail -c 200 gpurun_out/r2d_bench_$n.err
 done
 echo "== bench sel25 variants"; PB_ROW_GROUPS=0 timeout 600 $B --in-values 500 --no-variants > gpurun_out/r2d_bench_sel25_norg.json 2> gpurun_out/r2d_bench_sel25_norg.err
@@ -26,4 +26,4 @@ for f in sorted(glob.glob("gpurun_out/r2d_bench*.json")):
     except Exception as e:
         print(f, "ERR", e)
 PY
-echo "== bench_configs small scale"; timeout 600 python bench_configs.py --only 1,3,4,5 --scale 0.05 --steps 3 > gpurun_out/r2d_configs_small.jsonl 2> gpurun_out/r2d_configs_small.err; tail -c 400 gpurun_out/r2d_configs_small.err; cut -c1-700 gpurun_out/r2d_configs_small.jsonl
+echo "== bench_configs small scale"; date; timeout 600 python bench_configs.py --only 1,3,4,5 --scale 0.05 --steps 3 > gpurun_out/r2d_configs_small.jsonl 2> gpurun_out/r2d_configs_small.err; tail -c 400 gpurun_out/r2d_configs_small.err; cut -c1-700 gpurun_out/r2d_configs_small.jsonl
