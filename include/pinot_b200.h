@@ -120,6 +120,12 @@ typedef struct pb_aggregation_desc {
   const char* column;          /* NULL for COUNT(*) */
 } pb_aggregation_desc;
 
+typedef struct pb_order_by {
+  int32_t kind;                /* 0 = the index-th group-by column, 1 = the index-th aggregation (COUNT / SUM / MIN / MAX / AVG) */
+  int32_t index;
+  int32_t descending;
+} pb_order_by;
+
 #define PB_Q_COMBINE 1u            /* one merged table over all segments (GroupByCombineOperator semantics, on device) */
 #define PB_Q_DEFER_FINALIZE 2u     /* leave tables on the device for a cross-GPU reduce; call pb_result_finalize */
 #define PB_Q_GENERIC_KERNEL 4u     /* force the width-generic predicate path (testing / A-B measurement) */
@@ -147,6 +153,15 @@ typedef struct pb_query_desc {
    * clause (-1 = none; NULL when num_agg_filters = 0).  QueryContext.getFilteredAggregationFunctions(). */
   int32_t num_agg_filters;
   const int32_t* agg_filter_of;
+  /* ORDER BY ... LIMIT trim of a group-by result, on the device (the combine layer's server-side trim: IndexedTable +
+   * TableResizer keep trim_size = max(5 x LIMIT, minServerGroupTrimSize) groups once a table holds more than
+   * trim_threshold = groupTrimThreshold groups; CTR/util/GroupByUtils.java:44-70, CTR/data/table/TableResizer.java).
+   * order_by[0] selects: the trim_size best groups by it survive, plus every group that ties with the last of them; further
+   * ORDER BY expressions are left to the broker's final sort.  num_order_by = 0 or trim_size <= 0: no trim. */
+  int32_t num_order_by;
+  const struct pb_order_by* order_by;
+  int32_t trim_size;
+  int32_t trim_threshold;
 } pb_query_desc;
 
 /* ExecutionStatistics (CTR/operator/ExecutionStatistics.java:28-65) */

@@ -70,6 +70,12 @@ typedef struct pbh_query_context {
   int32_t num_agg_filters;
   const pbh_filter_program* agg_filters;
   const int32_t* agg_filter_of;
+  /* ORDER BY expressions that name a group-by column or an aggregation of the SELECT list, and the trim the combine layer
+   * would apply (pb_query_desc.order_by / trim_size / trim_threshold; 0 = none) */
+  int32_t num_order_by;
+  const pb_order_by* order_by;
+  int32_t trim_size;
+  int32_t trim_threshold;
 } pbh_query_context;
 
 /* B200PlanMaker.makeSegmentPlanNode eligibility (InstancePlanMakerImplV2.java:275-294 override):

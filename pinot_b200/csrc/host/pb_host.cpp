@@ -435,6 +435,7 @@ extern "C" int pbh_execute(pb_segment_group_handle g, const pbh_query_context* q
   d.max_initial_result_holder_capacity = q->max_initial_result_holder_capacity > 0 ? q->max_initial_result_holder_capacity : 10000;
   d.flags = flags;
   d.num_agg_filters = q->num_agg_filters; d.agg_filter_of = q->agg_filter_of;
+  d.num_order_by = q->num_order_by; d.order_by = q->order_by; d.trim_size = q->trim_size; d.trim_threshold = q->trim_threshold;
   return pb_query_execute(g, sq.data(), &d, out);
 }
 

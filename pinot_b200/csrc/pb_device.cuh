@@ -1825,10 +1825,108 @@ static __global__ void pb_invert_slots_kernel(const unsigned long long* __restri
   for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) group_of_slot[slots[k]] = (uint32_t)k;
 }
 
-// count non-empty slots
-static __global__ void pb_count_groups_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n, unsigned long long* out) {
+// ------------------------------------------------------------------------------------------------
+// ORDER BY ... LIMIT trim of a group table (the server-side trim of the combine layer: IndexedTable + TableResizer keep
+// max(5 x LIMIT, minServerGroupTrimSize) groups once a table passes groupTrimThreshold: CTR/util/GroupByUtils.java:44-70,
+// CTR/data/table/TableResizer.java).  okey[slot] = the first ORDER BY expression as an unsigned 64-bit rank (larger = earlier
+// in the requested order); a grid-wide radix select finds the trim_size-th largest; the hand-back emits the groups at or
+// above it (ties at the boundary are all kept: the broker's final sort decides among them).
+// ------------------------------------------------------------------------------------------------
+struct DevOrderKey {
+  int32_t kind;              // 0 = group-by column, 1 = aggregation
+  int32_t descending;
+  int32_t mode, key_words;   // table mode / hash key words
+  int32_t op;                // aggregation: PB_AGG_*
+  int32_t field_is_signed;   // group column: raw INT / LONG value (signed order)
+  int32_t field_is_double;   // group column: raw FLOAT / DOUBLE value (bits of the double)
+  int32_t shift, width;      // hash: field position
+  uint64_t div, card;        // dense: field = (slot / div) % card
+  uint64_t S, capacity;
+  const unsigned long long* rowcnt;
+  const unsigned long long* hkeys;
+  const double* sum;
+  const long long* mm;
+  const unsigned long long* fcnt;
+  unsigned long long* okey;
+};
+static __global__ void pb_order_key_kernel(const DevOrderKey K) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < K.S; i += (uint64_t)gridDim.x * blockDim.x) {
+    const unsigned long long c = K.rowcnt[i];
+    unsigned long long u = 0;
+    if (c) {
+      if (K.kind == 1) {
+        long long e;
+        if (K.op == 0) e = (long long)(K.fcnt ? K.fcnt[i] : c);                                        // COUNT
+        else if (K.op == 1) e = pb_enc_f64(K.sum[i]);                                                   // SUM
+        else if (K.op == 4) { const unsigned long long n = K.fcnt ? K.fcnt[i] : c; e = pb_enc_f64(n ? K.sum[i] / (double)n : 0.0); }   // AVG
+        else e = K.op == 2 ? K.mm[i] : ~K.mm[i];                                                        // MIN / MAX (encoded; MAX is stored complemented)
+        u = (unsigned long long)e ^ 0x8000000000000000ull;
+      } else {
+        uint64_t field;
+        if (K.mode == T_DENSE) field = (i / K.div) % K.card;
+        else {
+          unsigned long long klo, khi = 0;
+          if (K.key_words == 2) { klo = i == K.capacity ? PB_HASH_EMPTY : K.hkeys[2 * i]; khi = i == K.capacity ? PB_HASH_EMPTY : K.hkeys[2 * i + 1]; }
+          else klo = i == K.capacity ? PB_HASH_EMPTY : K.hkeys[i];
+          if (K.shift < 64) { field = klo >> K.shift; if (K.shift && K.shift + K.width > 64) field |= khi << (64 - K.shift); }
+          else field = khi >> (K.shift - 64);
+          if (K.width < 64) field &= ((1ull << K.width) - 1ull);
+        }
+        if (K.field_is_double) u = (unsigned long long)pb_enc_f64(__longlong_as_double((long long)field)) ^ 0x8000000000000000ull;
+        else if (K.field_is_signed) u = (K.width == 32 ? (unsigned long long)(long long)(int32_t)(uint32_t)field : field) ^ 0x8000000000000000ull;
+        else u = field;                                                                                  // dictId: sorted dictionary order
+      }
+      if (!K.descending) u = ~u;
+    }
+    K.okey[i] = u;
+  }
+}
+// radix select, one 8-bit digit per pass: state = {prefix, k remaining, done, threshold, candidates}
+struct DevSelectState { unsigned long long prefix, k, done, thr, total; unsigned long long hist[256]; };
+static __global__ void pb_rselect_hist_kernel(const unsigned long long* __restrict__ okey, const unsigned long long* __restrict__ rowcnt, uint64_t S, int pass,
+                                              DevSelectState* st) {
+  __shared__ unsigned int h[256];
+  for (int b = threadIdx.x; b < 256; b += blockDim.x) h[b] = 0;
+  __syncthreads();
+  if (!st->done) {
+    const unsigned long long prefix = st->prefix;
+    const unsigned long long hi_mask = pass == 7 ? 0ull : (~0ull << (8 * (pass + 1)));
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < S; i += (uint64_t)gridDim.x * blockDim.x) {
+      if (!rowcnt[i]) continue;
+      const unsigned long long v = okey[i];
+      if ((v & hi_mask) == (prefix & hi_mask)) atomicAdd(&h[(v >> (8 * pass)) & 255u], 1u);
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < 256; b += blockDim.x) if (h[b]) atomicAdd(&st->hist[b], (unsigned long long)h[b]);
+}
+static __global__ void pb_rselect_pick_kernel(DevSelectState* st, int pass, unsigned long long trim_size, unsigned long long trim_threshold) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (pass == 7) { st->prefix = 0; st->k = trim_size; st->done = 0; st->thr = 0; }
+  if (!st->done) {
+    if (pass == 7) {
+      unsigned long long total = 0;
+      for (int b = 0; b < 256; b++) total += st->hist[b];
+      st->total = total;
+      if (total <= trim_threshold || total <= st->k) { st->done = 1; st->thr = 0; }      // the table is small enough: keep everything
+    }
+    if (!st->done) {
+      unsigned long long k = st->k, cum = 0;
+      int b = 255;
+      for (; b >= 0; b--) { if (cum + st->hist[b] >= k) break; cum += st->hist[b]; }      // k-th LARGEST
+      if (b < 0) { st->done = 1; st->thr = 0; }
+      else { st->prefix |= (unsigned long long)b << (8 * pass); st->k = k - cum; if (pass == 0) st->thr = st->prefix; }
+    }
+  }
+  for (int b = 0; b < 256; b++) st->hist[b] = 0;
+}
+
+// count non-empty slots (that survive the ORDER BY trim, if any)
+static __global__ void pb_count_groups_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n, unsigned long long* out,
+                                              const unsigned long long* __restrict__ okey, const unsigned long long* __restrict__ othr) {
   unsigned long long c = 0;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += rowcnt[i] != 0;
+  const unsigned long long thr = othr ? *othr : 0ull;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += rowcnt[i] != 0 && (!okey || okey[i] >= thr);
   for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
@@ -1866,6 +1964,8 @@ struct DevFinalize {
   const unsigned long long* hkeys;
   const uint32_t* first_doc;      // numGroupsLimit in doc order: emit only groups whose first doc is <= *first_thr
   const uint32_t* first_thr;
+  const unsigned long long* okey; // ORDER BY ... LIMIT trim: emit only groups whose order key is >= *othr
+  const unsigned long long* othr;
   unsigned long long* cursor;
   unsigned long long* out_slots;
   unsigned long long* out_rows;
@@ -1881,6 +1981,7 @@ static __global__ void pb_finalize_kernel(const DevFinalize F) {
     const unsigned long long c = i < F.S ? F.rowcnt[i] : 0ull;
     bool emit = i < F.S && (c != 0 || F.always_emit);
     if (emit && F.first_doc && F.first_doc[i] > *F.first_thr) emit = false;
+    if (emit && F.okey && F.okey[i] < *F.othr) emit = false;
     const uint32_t b = __ballot_sync(0xffffffffu, emit);
     if (!b) continue;
     unsigned long long base = 0;

@@ -949,6 +949,9 @@ struct pb_result_s {
   struct InitArgs { uint4* zero = nullptr; uint64_t zn = 0; uint4* ff = nullptr; uint64_t fn = 0; uint4* mm = nullptr; uint64_t mn = 0;
                     uint4* aux = nullptr; uint64_t an = 0; const uint4* head = nullptr; uint64_t head_n16 = 0; int grid = 1; } init;   // pb_init_tables_kernel
   int key_words = 1;
+  // ORDER BY ... LIMIT trim (pb_query_desc.order_by): per table an order-key array and the radix-select state
+  pb_order_by order0{0, 0, 0}; int trim_size = 0, trim_threshold = 0;
+  std::vector<unsigned long long*> d_okey; std::vector<DevSelectState*> d_sel;
   bool track_first = false; uint32_t* d_first_thr = nullptr;   // numGroupsLimit in doc order (dense per-segment tables)
   bool fused = false, smem_table = false;   // how the matches reached the table (see exec_single)
   bool comm_timed = false;                  // events [5],[6] bracket the cross-rank merge
@@ -997,6 +1000,8 @@ static std::string plan_signature(pb_group_s* g, const pb_segment_query* sqs, co
   for (int a = 0; a < q->num_aggregations; a++) { sig_pod(s, q->aggregations[a].op); sig_str(s, q->aggregations[a].column); }
   sig_pod(s, q->num_agg_filters);
   if (q->num_agg_filters > 0) sig_put(s, q->agg_filter_of, sizeof(int32_t) * (size_t)q->num_aggregations);
+  sig_pod(s, q->num_order_by); sig_pod(s, q->trim_size); sig_pod(s, q->trim_threshold);
+  if (q->num_order_by > 0 && q->order_by) sig_put(s, q->order_by, sizeof(pb_order_by) * (size_t)q->num_order_by);
   sig_pod(s, g->dict_version);
   for (size_t si = 0; si < g->segs.size(); si++) {
     sig_pod(s, g->segs[si]->epoch);
@@ -1193,6 +1198,7 @@ static double estimate_selectivity(const pb_segment_s* s, const pb_segment_query
 
 static int finalize_result(pb_result_s* r);
 static int enqueue_finalize(pb_result_s* r);
+static int enqueue_trim(pb_result_s* r);
 static int finish_finalize(pb_result_s* r);
 static inline double now_us() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
@@ -1435,6 +1441,7 @@ static int replay_plan(pb_result_s* r, const pb_query_desc* q) {
       cudaGraph_t graph = nullptr;
       CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       rc = enqueue_all(r, nullptr);
+      if (!rc) rc = enqueue_trim(r);
       if (!rc) rc = enqueue_finalize(r);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (rc || e != cudaSuccess || !graph) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc ? rc : fail(PB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e)); }
@@ -1448,10 +1455,11 @@ static int replay_plan(pb_result_s* r, const pb_query_desc* q) {
     // keeps the per-kernel CUDA-event times (pb_result_phase_ms) of a cached plan live; the others report the last sample
     const bool sample = rp.graph && (rp.uses & 7) == 7;
     if (rp.graph && !sample) { CU(cudaGraphLaunch(rp.graph, st)); r->launches = rp.graph_launches; r->graph_replayed = true; }
-    else { r->graph_replayed = false; if ((rc = enqueue_all(r, nullptr))) return rc; if ((rc = enqueue_finalize(r))) return rc; }
+    else { r->graph_replayed = false; if ((rc = enqueue_all(r, nullptr))) return rc; if ((rc = enqueue_trim(r))) return rc; if ((rc = enqueue_finalize(r))) return rc; }
   } else {
     if ((rc = enqueue_all(r, nullptr))) return rc;
     if (all_ranks && (rc = comm_merge(r))) return rc;
+    if ((rc = enqueue_trim(r))) return rc;
     if ((rc = enqueue_finalize(r))) return rc;
   }
   r->host_us[3] = now_us() - t1;
@@ -1695,6 +1703,15 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     if (combine) for (int si = 0; si < n_segs; si++) tm.seg_idx.push_back(si); else tm.seg_idx.push_back(t);
   }
 
+  // ---- ORDER BY ... LIMIT trim requested? (first ORDER BY expression: a group-by column or a COUNT / SUM / MIN / MAX / AVG) ----
+  if (q->num_order_by > 0 && q->order_by && q->trim_size > 0 && nG > 0) {
+    const pb_order_by& ob = q->order_by[0];
+    const bool ok = (ob.kind == 0 && ob.index >= 0 && ob.index < nG) ||
+                    (ob.kind == 1 && ob.index >= 0 && ob.index < nA && q->aggregations[ob.index].op != PB_AGG_DISTINCTCOUNT);
+    if (!ok) return fail(PB_ERR_UNSUPPORTED, "ORDER BY expression %d/%d cannot drive a device-side trim", ob.kind, ob.index);
+    r->order0 = ob; r->trim_size = q->trim_size; r->trim_threshold = std::max(0, q->trim_threshold);
+  }
+
   // ---- device table arenas: [zero region][0xFF region][min/max region] ----
   auto slots_of = [&](const TableMeta& tm) { return tm.capacity + (table_mode == T_HASH ? 1 : 0); };
   size_t zero_bytes = 0, ff_bytes = 0, mm_elems = 0;
@@ -1813,6 +1830,16 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     CU(cudaGetLastError());
   }
 
+  if (r->trim_size > 0) {
+    for (int t = 0; t < n_tables; t++) {
+      const uint64_t S = slots_of(r->tables[t]);
+      unsigned long long* ok = nullptr; DevSelectState* sel = nullptr;
+      CU(cudaMallocAsync((void**)&ok, 8 * S, st)); r->dev_allocs.push_back(ok);
+      CU(cudaMallocAsync((void**)&sel, sizeof(DevSelectState), st)); r->dev_allocs.push_back(sel);
+      CU(cudaMemsetAsync(sel, 0, sizeof(DevSelectState), st));
+      r->d_okey.push_back(ok); r->d_sel.push_back(sel);
+    }
+  }
   lap(1);
   // ---- query arena (descriptors + leaf payloads) ----
   size_t arena_cap = (sizeof(DevQuery) + 16) * (1 + PB_MAX_WAVES) + 256 + (sizeof(DevSegQuery) + 64) * (size_t)n_segs + (sizeof(DevTable) + 64) * (size_t)n_tables
@@ -2502,6 +2529,42 @@ extern "C" int pb_query_execute(pb_segment_group_handle g, const pb_segment_quer
 // ------------------------------------------------------------------------------------------------
 // finalize: compaction of non-empty groups, device -> pinned host, key decode
 // ------------------------------------------------------------------------------------------------
+
+// ORDER BY ... LIMIT trim: order keys of every table + the grid-wide radix select of the trim_size-th best (8 digit passes)
+static int enqueue_trim(pb_result_s* r) {
+  if (r->trim_size <= 0 || r->table_mode == T_KEYLESS) return PB_OK;
+  cudaStream_t st = r->stream;
+  pb_group_s* g = r->group;
+  for (size_t t = 0; t < r->tables.size(); t++) {
+    TableMeta& tm = r->tables[t];
+    DevOrderKey K; memset(&K, 0, sizeof K);
+    K.kind = r->order0.kind; K.descending = r->order0.descending; K.mode = r->table_mode; K.key_words = tm.dev.key_words;
+    K.S = tm.capacity + (r->table_mode == T_HASH ? 1 : 0); K.capacity = tm.capacity;
+    K.rowcnt = tm.dev.rowcnt; K.hkeys = tm.dev.hkeys; K.okey = r->d_okey[t];
+    if (K.kind == 1) {
+      const int a = r->order0.index;
+      K.op = r->agg_op[a]; K.sum = tm.dev.sum[a]; K.mm = tm.dev.mm[a]; K.fcnt = tm.dev.fcnt[a];
+    } else {
+      const int j = r->order0.index;
+      const pb_segment_s* s0 = g->segs[tm.seg_idx[0]];
+      const Column& c0 = s0->cols[find_col(s0, r->gb_names[j].c_str())];
+      K.field_is_signed = !c0.has_dict && (c0.type == PB_INT || c0.type == PB_LONG);
+      K.field_is_double = !c0.has_dict && (c0.type == PB_FLOAT || c0.type == PB_DOUBLE);
+      if (r->table_mode == T_DENSE) { uint64_t div = 1; for (int k = 0; k < j; k++) div *= (uint64_t)tm.cards[k]; K.div = div; K.card = (uint64_t)tm.cards[j]; }
+      else { K.shift = tm.shifts[j]; K.width = tm.widths[j]; }
+    }
+    const int grid = (int)std::min<uint64_t>((K.S + 255) / 256, (uint64_t)r->ctx->num_sms * 8);
+    pb_order_key_kernel<<<grid, 256, 0, st>>>(K);
+    for (int pass = 7; pass >= 0; pass--) {
+      pb_rselect_hist_kernel<<<grid, 256, 0, st>>>(K.okey, K.rowcnt, K.S, pass, r->d_sel[t]);
+      pb_rselect_pick_kernel<<<1, 32, 0, st>>>(r->d_sel[t], pass, (unsigned long long)r->trim_size, (unsigned long long)r->trim_threshold);
+    }
+    r->launches += 17;
+  }
+  CU(cudaGetLastError());
+  return PB_OK;
+}
+
 // ---- result hand-back in three steps, so that a cached plan can re-enqueue step 2 without redoing step 1 ----
 // (1) pinned host arrays + the finalize descriptor of every table.  Very large tables are counted first (one extra pass
 //     and a synchronisation) so that the host arrays can be sized exactly; such plans are not cached.
@@ -2523,7 +2586,8 @@ static int prepare_finalize(pb_result_s* r) {
     if (mode != T_KEYLESS && S > SMALL_TABLE) {
       any_big = true;
       int grid = (int)std::min<uint64_t>((S + 255) / 256, 2048);
-      pb_count_groups_kernel<<<grid, 256, 0, st>>>(tm.dev.rowcnt, S, r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3);
+      pb_count_groups_kernel<<<grid, 256, 0, st>>>(tm.dev.rowcnt, S, r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3,
+                                                   r->trim_size > 0 ? r->d_okey[(size_t)t] : nullptr, r->trim_size > 0 ? &r->d_sel[(size_t)t]->thr : nullptr);
       r->launches++;
     }
   }
@@ -2553,6 +2617,7 @@ static int prepare_finalize(pb_result_s* r) {
     F.S = mode == T_KEYLESS ? 1 : S; F.capacity = tm.capacity; F.cap_out = cap; F.key_words = tm.dev.key_words;
     F.rowcnt = tm.dev.rowcnt; F.hkeys = tm.dev.hkeys;
     if (tm.dev.first_doc) { F.first_doc = tm.dev.first_doc; F.first_thr = r->d_first_thr + t; }
+    if (r->trim_size > 0 && mode != T_KEYLESS) { F.okey = r->d_okey[(size_t)t]; F.othr = &r->d_sel[(size_t)t]->thr; }
     F.cursor = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3;
     F.out_slots = (unsigned long long*)tm.slots.p; F.out_rows = (unsigned long long*)tm.rows.p;
     for (int a = 0; a < nA; a++) {
@@ -2681,6 +2746,7 @@ static int finalize_result(pb_result_s* r) {
   if (r->finalized) return PB_OK;
   int rc;
   double t0 = now_us();
+  if ((rc = enqueue_trim(r))) return rc;
   if ((rc = prepare_finalize(r))) return rc;
   r->host_us[4] += now_us() - t0;
   if ((rc = enqueue_finalize(r))) return rc;

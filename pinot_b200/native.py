@@ -15,7 +15,7 @@ from .query import AggOp, QueryContext
 from .segment_writer import DataType, Segment
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpinot_b200.so")
+LIB_PATH = os.environ.get("PB_LIB_PATH") or os.path.join(_HERE, "libpinot_b200.so")      # (PB_LIB_PATH: a scratch build, see build.py)
 
 PB_Q_COMBINE = 1
 PB_Q_DEFER_FINALIZE = 2
@@ -65,6 +65,10 @@ class PbhFilterProgram(C.Structure):
                 ("predicates", C.POINTER(PbhPredicate))]
 
 
+class PbOrderBy(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("index", C.c_int32), ("descending", C.c_int32)]
+
+
 class PbhQueryContext(C.Structure):
     _fields_ = [("num_filter_nodes", C.c_int32), ("filter_nodes", C.POINTER(PbhFilterNode)),
                 ("predicates", C.POINTER(PbhPredicate)),
@@ -73,7 +77,8 @@ class PbhQueryContext(C.Structure):
                 ("num_groups_limit", C.c_int32), ("max_initial_result_holder_capacity", C.c_int32),
                 ("num_skip_inverted", C.c_int32), ("skip_inverted_columns", C.POINTER(C.c_char_p)),
                 ("num_agg_filters", C.c_int32), ("agg_filters", C.POINTER(PbhFilterProgram)),
-                ("agg_filter_of", C.POINTER(C.c_int32))]
+                ("agg_filter_of", C.POINTER(C.c_int32)),
+                ("num_order_by", C.c_int32), ("order_by", C.POINTER(PbOrderBy)), ("trim_size", C.c_int32), ("trim_threshold", C.c_int32)]
 
 
 _lib = None
@@ -505,6 +510,11 @@ class _MarshalledQuery:
                                    len(q.aggregations), self.aggs, q.num_groups_limit,
                                    q.max_initial_result_holder_capacity, len(skip), self.skip,
                                    len(filters), self.progs, self.filter_of)
+        self.order = (PbOrderBy * max(1, len(q.order_by)))()
+        for i, (kind, index, desc) in enumerate(q.order_by):
+            self.order[i].kind, self.order[i].index, self.order[i].descending = kind, index, int(desc)
+        self.ctx.num_order_by, self.ctx.order_by = len(q.order_by), self.order
+        self.trims = {True: q.trim(True), False: q.trim(False)}
 
 
 def prepare(q: QueryContext) -> "_MarshalledQuery":
@@ -515,6 +525,8 @@ def prepare(q: QueryContext) -> "_MarshalledQuery":
 def execute(group: SegmentGroup, q: QueryContext, flags: int = 0, prepared: Optional["_MarshalledQuery"] = None) -> Result:
     """Plan (host layer) + run (device) a query over every segment of the group."""
     m = prepared if prepared is not None else _MarshalledQuery(q)
+    # ORDER BY ... LIMIT trim: the server-level trim of the combine layer for a merged table, the segment-level one otherwise
+    m.ctx.trim_size, m.ctx.trim_threshold = m.trims[bool(flags & PB_Q_COMBINE)]
     rh = C.c_void_p()
     _check(lib().pbh_execute(group.handle, C.byref(m.ctx), flags, C.byref(rh)))
     return Result(rh, q, deferred=bool(flags & PB_Q_DEFER_FINALIZE))

@@ -113,6 +113,26 @@ class QueryContext:
     skip_indexes: Dict[str, List[str]] = field(default_factory=dict)   # column -> ["inverted", ...]
     skip_inverted_all: bool = False
     limit: int = 10
+    # ORDER BY expressions that name a group-by column (kind 0, index into group_by) or an aggregation of the SELECT list
+    # (kind 1, index into aggregations): [(kind, index, descending)]
+    order_by: List[tuple] = field(default_factory=list)
+    # CommonConstants.Server defaults: DEFAULT_MIN_SERVER_GROUP_TRIM_SIZE 5000, DEFAULT_MIN_SEGMENT_GROUP_TRIM_SIZE -1,
+    # DEFAULT_GROUPBY_TRIM_THRESHOLD 1_000_000 (query options minServerGroupTrimSize / minSegmentGroupTrimSize / groupTrimThreshold)
+    min_server_group_trim_size: int = 5000
+    min_segment_group_trim_size: int = -1
+    group_trim_threshold: int = 1_000_000
+
+    def trim(self, combined: bool):
+        """(trim_size, trim_threshold) the combine layer (combined) or the segment operator would apply: GroupByUtils.
+        getTableCapacity = max(5 x LIMIT, min trim size); (0, 0) when there is no ORDER BY or trimming is disabled."""
+        m = self.min_server_group_trim_size if combined else self.min_segment_group_trim_size
+        if not self.order_by or not self.group_by or m <= 0:
+            return 0, 0
+        size = max(min(5 * self.limit, 2**31 - 1), m)
+        thr = self.group_trim_threshold if combined else size     # (the segment-level trim has no threshold: GroupByOperator trims whenever it holds more)
+        if combined and (thr <= 0 or thr > 1_000_000_000):
+            return 0, 0
+        return size, max(thr, 2 * size) if combined else size
 
     def filter_postfix(self):
         """[(kind, n_children, predicate_index)], [Predicate] — AND=0 OR=1 NOT=2 PRED=3."""
@@ -336,6 +356,40 @@ def parse_sql(sql: str) -> QueryContext:
         while p.peek() == ("op", ","):
             p.i += 1
             group_by.append(p.ident())
+    order_by = []
+    if p.kw("ORDER"):
+        p.i += 1
+        p.eat_kw("BY")
+        while True:
+            name = p.ident()
+            if p.peek() == ("op", "("):
+                p.i += 1
+                op = _AGGS.get(name.upper())
+                if p.peek() == ("op", "*"):
+                    p.i += 1
+                    col = None
+                else:
+                    col = p.ident()
+                p.eat_op(")")
+                hits = [i for i, a in enumerate(aggs) if a.op == op and a.column == col and a.filter is None]
+                if not hits:
+                    raise ValueError(f"ORDER BY {name}({col or '*'}) is not in the SELECT list")
+                ob = (1, hits[0])
+            else:
+                if name not in group_by:
+                    raise ValueError(f"ORDER BY {name} is not a group-by column")
+                ob = (0, group_by.index(name))
+            desc = False
+            if p.kw("DESC"):
+                p.i += 1
+                desc = True
+            elif p.kw("ASC"):
+                p.i += 1
+            order_by.append((ob[0], ob[1], desc))
+            if p.peek() == ("op", ","):
+                p.i += 1
+                continue
+            break
     limit = 10
     if p.kw("LIMIT"):
         p.i += 1
@@ -344,7 +398,11 @@ def parse_sql(sql: str) -> QueryContext:
         raise ValueError(f"trailing tokens: {p.t[p.i:]}")
     if not aggs:
         raise ValueError("only aggregation / group-by queries are on this path")
-    q = QueryContext(table=table, aggregations=aggs, group_by=group_by, filter=flt, limit=limit)
+    q = QueryContext(table=table, aggregations=aggs, group_by=group_by, filter=flt, limit=limit, order_by=order_by)
+    for opt, attr in (("minservergrouptrimsize", "min_server_group_trim_size"), ("minsegmentgrouptrimsize", "min_segment_group_trim_size"),
+                      ("grouptrimthreshold", "group_trim_threshold")):
+        if opt in options:
+            setattr(q, attr, int(options[opt]))
     if "numgroupslimit" in options:
         q.num_groups_limit = int(options["numgroupslimit"])
     if "maxinitialresultholdercapacity" in options:

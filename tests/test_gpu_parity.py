@@ -7,7 +7,7 @@ from pinot_b200.query import parse_sql
 from pinot_b200.segment_writer import DataType, build_column, build_dict_column, make_segment
 from tests.fixtures import FILTER, sv_segment
 from oracle import oracle
-from tests.parity import assert_rows_equal, check_query, oracle_rows
+from tests.parity import assert_rows_equal, check_query, combined_rows, oracle_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -468,3 +468,59 @@ def test_distinctcount_on_raw_columns():
                 "SELECT g, h, DISTINCTCOUNT(ri), DISTINCTCOUNT(rd), DISTINCTCOUNT(f), SUM(f) FROM t WHERE f >= 10 GROUP BY g, h LIMIT 1000",
                 "SELECT k, DISTINCTCOUNT(ri), COUNT(*) FROM t GROUP BY k LIMIT 100000"):
         check_query(segs, sql)
+
+
+def _expected_trim(rows, q, combined):
+    """what TableResizer keeps: the trim_size best groups by the first ORDER BY expression (+ every tie with the last)"""
+    size, thr = q.trim(combined)
+    if not size or len(rows) <= thr or len(rows) <= size:
+        return rows
+    kind, idx, desc = q.order_by[0]
+
+    def key(item):
+        k, row = item
+        v = k[idx] if kind == 0 else row[idx]
+        if isinstance(v, tuple):          # AVG: (sum, count)
+            v = v[0] / v[1] if v[1] else 0.0
+        return v
+    vals = sorted((key(it) for it in rows.items()), reverse=desc)
+    cut = vals[size - 1]
+    return {k: r for k, r in rows.items() if (key((k, r)) >= cut if desc else key((k, r)) <= cut)}
+
+
+def test_order_by_limit_trim_on_the_device():
+    """ORDER BY ... LIMIT: the server-side trim of the combine layer (GroupByUtils.getTableCapacity = max(5 x LIMIT,
+    minServerGroupTrimSize) groups once the table passes groupTrimThreshold; TableResizer) done at hand-back: the kept groups
+    are exactly the best ones by the first ORDER BY expression (ties with the last kept group included), values untouched."""
+    segs = [datagen.make_segment_synth(i, 60_000, columns=["c2", "c3", "d1", "d2", "m0", "m1", "k0"]) for i in range(2)]
+    staged = [native.StagedSegment(s) for s in segs]
+    g = native.SegmentGroup(staged)
+    opts = "SET groupTrimThreshold = 100; SET minServerGroupTrimSize = 20; SET minSegmentGroupTrimSize = 30; "
+    for tail in ("ORDER BY SUM(m0) DESC LIMIT 3", "ORDER BY SUM(m0) ASC LIMIT 3", "ORDER BY COUNT(*) DESC LIMIT 2", "ORDER BY MIN(m1) ASC LIMIT 1",
+                 "ORDER BY MAX(m1) DESC, d1 LIMIT 4", "ORDER BY AVG(m0) DESC LIMIT 3", "ORDER BY d2 DESC, c3 ASC LIMIT 2", "ORDER BY c3 LIMIT 1"):
+        sql = opts + "SELECT c3, d2, SUM(m0), COUNT(*), MIN(m1), MAX(m1), AVG(m0) FROM t WHERE c2 >= 0 GROUP BY c3, d2 " + tail
+        q = parse_sql(sql)
+        orc = [oracle.execute(s, q) for s in segs]
+        for run in range(3):                       # also through the plan cache / graph replay
+            res = native.execute(g, q, native.PB_Q_COMBINE)
+            exp = _expected_trim(combined_rows(oracle.combine(orc), q), q, True)
+            assert 20 <= len(exp) < 2048
+            assert_rows_equal(res.tables[0].rows(), exp, q, exact_float=True, what=f"combined trim: {tail}")
+            res.free()
+        res = native.execute(g, q, 0)
+        for i, (t, o) in enumerate(zip(res.tables, orc)):
+            assert_rows_equal(t.rows(), _expected_trim(oracle_rows(o), q, False), q, exact_float=True, what=f"segment {i} trim: {tail}")
+        res.free()
+    # a hash table (raw LONG key) ordered by its key and by an aggregate; and no trim below the threshold
+    for tail in ("ORDER BY k0 DESC LIMIT 3", "ORDER BY SUM(m0) DESC LIMIT 2"):
+        q = parse_sql("SET numGroupsLimit = 10000000; " + opts + "SELECT k0, SUM(m0), COUNT(*) FROM t GROUP BY k0 " + tail)
+        orc = [oracle.execute(s, q) for s in segs]
+        res = native.execute(g, q, native.PB_Q_COMBINE)
+        exp = _expected_trim(combined_rows(oracle.combine(orc), q), q, True)
+        assert_rows_equal(res.tables[0].rows(), exp, q, exact_float=True, what=f"hash trim: {tail}")
+        res.free()
+    q = parse_sql("SELECT d1, SUM(m0) FROM t GROUP BY d1 ORDER BY SUM(m0) DESC LIMIT 3")      # 16 groups: far below any threshold
+    res = native.execute(g, q, native.PB_Q_COMBINE)
+    assert len(res.tables[0].rows()) == 16
+    res.free()
+    g.release()
