@@ -159,6 +159,7 @@ struct DevTable {
   unsigned long long* dcnt[PB_MAX_AGGS];
   unsigned int* num_groups;          // hash: groups created so far
   unsigned int* limit_reached;
+  unsigned int* any_limit;           // query-wide: some hash table of this launch refused a key (drives the repair pass)
   unsigned long long* docs_matched;  // numDocsScanned
   // dense table whose key space exceeds numGroupsLimit (the reference's IntMapBasedHolder, first come first served in doc
   // order: DictionaryBasedGroupKeyGenerator.java:1023-1058): first_doc[slot] = smallest doc that produced the group; the
@@ -189,14 +190,14 @@ struct DevQuery {
   int32_t sparse_max;                    // survivors per 1024 docs below which later AND leaves use the restricted scan
   int32_t cand_bytes;                    // shared memory for the per-warp candidate lists (0: no leaf runs on candidates)
   uint64_t unit_lo;                      // this launch covers work units [unit_lo, unit_lo + n_units) (a wave of segments)
-  int32_t fuse;                          // pb_filter_kernel aggregates its matches itself (no match list, no pb_agg_kernel)
+  int32_t phase;                         // pb_agg_kernel: 0 = normal; 2 = repair pass of a hash table that hit numGroupsLimit (see pb_hash_slot)
   int32_t st_slots;                      // pb_agg_smem_kernel: slots of the CTA-private dense table (= table capacity), 0 = not used
   int32_t st_replicas;                   //   replicas of it per CTA (power of two)
-  int32_t fuse_batch;                    // fused: buffered matches at which a warp aggregates (a warp only sees ~14 units per query:
-                                         // waiting for a full buffer would put all the gathers at the end of the kernel)
+  int32_t st_pad;
   uint64_t st_min_docs;                  //   matches below which the kernel updates the global table directly (merging 148 private tables costs more)
   uint32_t* match_list;                  // global doc numbers of the docs that pass the filter
   unsigned long long* match_count;
+  const unsigned int* any_limit;         // see DevTable::any_limit
   const DevSegQuery* segs;
   DevTable* tables;
 };
@@ -248,19 +249,21 @@ __device__ __forceinline__ uint32_t pb_unpack_at_bounded(const uint8_t* __restri
 }
 
 // raw PASS_THROUGH forward index value (FixedByteChunkSVForwardIndexReader.java:53-61): big-endian
-__device__ __forceinline__ long long pb_raw_i64(const uint8_t* __restrict__ fwd, uint32_t doc, int width, int data_type) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(fwd);
-  if (width == 4) return (long long)(int32_t)pb_bswap32(__ldg(w + doc));
-  uint32_t hi = pb_bswap32(__ldg(w + 2ull * doc)), lo = pb_bswap32(__ldg(w + 2ull * doc + 1));
+// stride_bits / bit_off: a column's own raw forward index has stride 8 * width and offset 0; a DECODED VALUE field of a row
+// group (see DevKeyCol) has the row stride and its (32-bit aligned) offset inside the row
+__device__ __forceinline__ long long pb_raw_i64(const uint8_t* __restrict__ fwd, uint32_t doc, int width, int data_type, int stride_bits, int bit_off) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(fwd) + (((unsigned long long)doc * (unsigned)stride_bits + (unsigned)bit_off) >> 5);
+  if (width == 4) return (long long)(int32_t)pb_bswap32(__ldg(w));
+  uint32_t hi = pb_bswap32(__ldg(w)), lo = pb_bswap32(__ldg(w + 1));
   return (long long)(((unsigned long long)hi << 32) | lo);
 }
-__device__ __forceinline__ double pb_raw_f64(const uint8_t* __restrict__ fwd, uint32_t doc, int width, int data_type) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(fwd);
+__device__ __forceinline__ double pb_raw_f64(const uint8_t* __restrict__ fwd, uint32_t doc, int width, int data_type, int stride_bits, int bit_off) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(fwd) + (((unsigned long long)doc * (unsigned)stride_bits + (unsigned)bit_off) >> 5);
   if (width == 4) {
-    uint32_t u = pb_bswap32(__ldg(w + doc));
+    uint32_t u = pb_bswap32(__ldg(w));
     return data_type == 2 ? (double)__uint_as_float(u) : (double)(int32_t)u;
   }
-  uint32_t hi = pb_bswap32(__ldg(w + 2ull * doc)), lo = pb_bswap32(__ldg(w + 2ull * doc + 1));
+  uint32_t hi = pb_bswap32(__ldg(w)), lo = pb_bswap32(__ldg(w + 1));
   unsigned long long u = ((unsigned long long)hi << 32) | lo;
   return data_type == 3 ? __longlong_as_double((long long)u) : (double)(long long)u;
 }
@@ -494,15 +497,15 @@ __device__ __forceinline__ bool pb_leaf_test_doc(const DevLeaf& lf, const uint8_
       return (((__ldg(lf.set_bits + (id >> 5)) >> (id & 31)) & 1u) ^ (uint32_t)lf.exclusive) != 0;
     }
     case L_BITMAP: return (((__ldg(lf.bitmap + (doc >> 5)) >> (doc & 31)) & 1u) ^ (uint32_t)lf.exclusive) != 0;
-    case L_RAW_RANGE_I: { const long long v = pb_raw_i64(lf.gfwd, doc, lf.raw_width, lf.data_type); return v >= lf.ilo && v <= lf.ihi; }
+    case L_RAW_RANGE_I: { const long long v = pb_raw_i64(lf.gfwd, doc, lf.raw_width, lf.data_type, lf.g_stride_bits, lf.g_bit_off); return v >= lf.ilo && v <= lf.ihi; }
     case L_RAW_RANGE_F: {
-      const double v = pb_raw_f64(lf.gfwd, doc, lf.raw_width, lf.data_type);
+      const double v = pb_raw_f64(lf.gfwd, doc, lf.raw_width, lf.data_type, lf.g_stride_bits, lf.g_bit_off);
       return (lf.dlo_incl ? v >= lf.dlo : v > lf.dlo) && (lf.dhi_incl ? v <= lf.dhi : v < lf.dhi);
     }
     case L_RAW_SET: {
       long long vb;
-      if (lf.data_type == 2 || lf.data_type == 3) vb = __double_as_longlong(pb_raw_f64(lf.gfwd, doc, lf.raw_width, lf.data_type));
-      else vb = pb_raw_i64(lf.gfwd, doc, lf.raw_width, lf.data_type);
+      if (lf.data_type == 2 || lf.data_type == 3) vb = __double_as_longlong(pb_raw_f64(lf.gfwd, doc, lf.raw_width, lf.data_type, lf.g_stride_bits, lf.g_bit_off));
+      else vb = pb_raw_i64(lf.gfwd, doc, lf.raw_width, lf.data_type, lf.g_stride_bits, lf.g_bit_off);
       bool in = false;
       for (int i = 0; i < lf.n_raw_set; i++) in |= (lf.raw_set[i] == vb);
       return in != (bool)lf.exclusive;
@@ -526,7 +529,12 @@ __device__ __forceinline__ uint64_t pb_hash64(uint64_t k) {
 // back: once one request has been refused every later one is refused too, so a key can never be created after some of its
 // rows were dropped (no partially aggregated group) and the table never holds more than `limit` keys; a claim lost to a
 // concurrent insert of the same slot wastes its ticket, so a limited result may hold a few groups fewer than the limit.
-// Lanes of a warp that need a ticket at the same time share one atomic.  Probing is bounded by the capacity. ----
+// Lanes of a warp that need a ticket at the same time share one atomic.  Probing is bounded by the capacity.
+// One anomaly is left to a REPAIR PASS: a row can be refused while another thread that already holds a ticket is about to
+// create the very same key, which would leave that group short of the refused row.  When (and only when) some key was
+// refused, the aggregates are zeroed again (the keys stay) and the matches are aggregated a second time in lookup-only mode
+// (DevQuery::phase = 2): every row of a key that made it into the table counts, every other row is dropped -- exactly the
+// reference's "existing groups keep aggregating, new keys are ignored". ----
 __device__ __forceinline__ bool pb_group_ticket(const DevTable& t) {
   if (!t.limit_active) return true;                      // groups <= docs <= limit: cannot be reached, nothing to count
   const unsigned m = __activemask();
@@ -537,12 +545,13 @@ __device__ __forceinline__ bool pb_group_ticket(const DevTable& t) {
   base = __shfl_sync(m, base, leader);
   if (base + rank < t.num_groups_limit) return true;
   pb_red_add_u32(t.limit_reached, 1u);
+  if (t.any_limit) pb_red_add_u32(t.any_limit, 1u);
   return false;
 }
 __device__ __forceinline__ void pb_group_ticket_return(const DevTable&) {}
 
 // returns slot, or ~0ull when the key is new and numGroupsLimit is reached
-__device__ __forceinline__ uint64_t pb_hash_slot(const DevTable& t, uint64_t key) {
+__device__ __forceinline__ uint64_t pb_hash_slot(const DevTable& t, uint64_t key, bool insert = true) {
   if (key == PB_HASH_EMPTY) return t.capacity;          // reserved extra slot for the sentinel value itself
   uint64_t mask = t.capacity - 1;
   uint64_t s = pb_hash64(key) & mask;
@@ -551,7 +560,7 @@ __device__ __forceinline__ uint64_t pb_hash_slot(const DevTable& t, uint64_t key
     if (cur == key) return s;
     if (cur == PB_HASH_EMPTY) {
       // the key is not in the table (linear probing never skips an empty slot): inserting needs a ticket
-      if (!pb_group_ticket(t)) return ~0ull;
+      if (!insert || !pb_group_ticket(t)) return ~0ull;
       unsigned long long old = pb_atom_cas_u64(&t.hkeys[s], PB_HASH_EMPTY, (unsigned long long)key);
       if (old == PB_HASH_EMPTY) return s;
       pb_group_ticket_return(t);                         // somebody else claimed the slot first
@@ -570,7 +579,7 @@ __device__ __forceinline__ void pb_atom_cas_u128(unsigned long long* p, unsigned
   asm volatile("{\n.reg .b128 c, v, o;\nmov.b128 c, {%2, %3};\nmov.b128 v, {%4, %5};\natom.global.cas.b128 o, [%6], c, v;\nmov.b128 {%0, %1}, o;\n}\n"
                : "=l"(olo), "=l"(ohi) : "l"(clo), "l"(chi), "l"(vlo), "l"(vhi), "l"(p) : "memory");
 }
-__device__ __forceinline__ uint64_t pb_hash_slot2(const DevTable& t, uint64_t lo, uint64_t hi) {
+__device__ __forceinline__ uint64_t pb_hash_slot2(const DevTable& t, uint64_t lo, uint64_t hi, bool insert = true) {
   if (lo == PB_HASH_EMPTY && hi == PB_HASH_EMPTY) return t.capacity;     // reserved slot for the sentinel pattern itself
   const uint64_t mask = t.capacity - 1;
   uint64_t s = pb_hash64(lo ^ pb_hash64(hi)) & mask;
@@ -579,7 +588,7 @@ __device__ __forceinline__ uint64_t pb_hash_slot2(const DevTable& t, uint64_t lo
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(clo), "=l"(chi) : "l"(&t.hkeys[2 * s]));
     if (clo == lo && chi == hi) return s;
     if (clo == PB_HASH_EMPTY && chi == PB_HASH_EMPTY) {
-      if (!pb_group_ticket(t)) return ~0ull;
+      if (!insert || !pb_group_ticket(t)) return ~0ull;
       unsigned long long olo, ohi;
       pb_atom_cas_u128(&t.hkeys[2 * s], PB_HASH_EMPTY, PB_HASH_EMPTY, lo, hi, olo, ohi);
       if (olo == PB_HASH_EMPTY && ohi == PB_HASH_EMPTY) return s;
@@ -623,8 +632,8 @@ __device__ __forceinline__ uint32_t pb_agg_filter_bits(const DevSegQuery& sq, ui
 __device__ __forceinline__ uint64_t pb_key_field(const DevKeyCol& kc, uint32_t doc, bool multi) {
   if (kc.raw_width) {
     uint64_t v;
-    if (kc.data_type == 2 || kc.data_type == 3) v = (uint64_t)__double_as_longlong(pb_raw_f64(kc.fwd, doc, kc.raw_width, kc.data_type));
-    else v = (uint64_t)pb_raw_i64(kc.fwd, doc, kc.raw_width, kc.data_type);
+    if (kc.data_type == 2 || kc.data_type == 3) v = (uint64_t)__double_as_longlong(pb_raw_f64(kc.fwd, doc, kc.raw_width, kc.data_type, kc.stride_bits, kc.bit_off));
+    else v = (uint64_t)pb_raw_i64(kc.fwd, doc, kc.raw_width, kc.data_type, kc.stride_bits, kc.bit_off);
     return (kc.raw_width == 4 && multi) ? (v & 0xffffffffull) : v;
   }
   uint32_t id = pb_unpack_at_bounded(kc.fwd, doc, kc.bits, kc.n_full_words, kc.tail_word, kc.stride_bits, kc.bit_off);
@@ -636,15 +645,15 @@ __device__ __forceinline__ uint64_t pb_key_field(const DevKeyCol& kc, uint32_t d
 // to double); for DISTINCTCOUNT the (global) dictId, returned through the same 64-bit channel
 __device__ __forceinline__ double pb_agg_input(const DevAggCol& ac, int op, uint32_t doc) {
   if (op == 5 && ac.raw_width) {       // raw column: the value itself, as bits (NaNs canonical, like Double.doubleToLongBits)
-    if (ac.data_type == 2 || ac.data_type == 3) { const double d = pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type); return d == d ? d : __longlong_as_double(0x7ff8000000000000LL); }
-    return __longlong_as_double(pb_raw_i64(ac.fwd, doc, ac.raw_width, ac.data_type));
+    if (ac.data_type == 2 || ac.data_type == 3) { const double d = pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type, ac.stride_bits, ac.bit_off); return d == d ? d : __longlong_as_double(0x7ff8000000000000LL); }
+    return __longlong_as_double(pb_raw_i64(ac.fwd, doc, ac.raw_width, ac.data_type, ac.stride_bits, ac.bit_off));
   }
   if (op == 5) {
     uint32_t id = pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word, ac.stride_bits, ac.bit_off);
     if (ac.remap) id = (uint32_t)__ldg(ac.remap + id);
     return __longlong_as_double((long long)id);
   }
-  return ac.raw_width ? pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type)
+  return ac.raw_width ? pb_raw_f64(ac.fwd, doc, ac.raw_width, ac.data_type, ac.stride_bits, ac.bit_off)
                       : __ldg(ac.dict_f64 + pb_unpack_at_bounded(ac.fwd, doc, ac.bits, ac.n_full_words, ac.tail_word, ac.stride_bits, ac.bit_off));
 }
 
@@ -712,7 +721,8 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 
   // ---- phase 2: table update ----
   if (Q.table_mode == T_HASH) {
-    slot = t.key_words == 2 ? pb_hash_slot2(t, slot, slot_hi) : pb_hash_slot(t, slot);
+    const bool insert = Q.phase != 2;
+    slot = t.key_words == 2 ? pb_hash_slot2(t, slot, slot_hi, insert) : pb_hash_slot(t, slot, insert);
     if (slot == ~0ull) return;
   }
   if (Q.table_mode == T_KEYLESS) keyless_rows++;
@@ -748,8 +758,10 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
     } else {
       if (op == 1 || op == 4) pb_red_add_f64(&t.sum[a][slot], v);            // REDG.E.ADD.F64
       else if (v == v) {                                                      // NaN never replaces (strict compare)
-        long long e = pb_enc_f64(v);
-        pb_red_min_s64(&t.mm[a][slot], op == 2 ? e : ~e);   // MAX is kept as MIN of the bit-complement (one init value for all)
+        // MAX is kept as MIN of the bit-complement (one init value for all).  Most docs do not improve the extreme: a plain
+        // (possibly stale: the RED still decides) read filters them out before they reach the L2 atomic units
+        const long long e = op == 2 ? pb_enc_f64(v) : ~pb_enc_f64(v);
+        if (e < (long long)pb_ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&t.mm[a][slot]))) pb_red_min_s64(&t.mm[a][slot], e);
       }
     }
   }
@@ -853,18 +865,6 @@ struct __align__(16) FilterSmemHeader {
   alignas(16) uint8_t seg[PB_SEG_FILTER_BYTES];   // the filter part of the current DevSegQuery
 };
 
-// Fused aggregation (DevQuery::fuse): the warp that found the matches aggregates them itself -- ob[0..cnt) are global doc
-// numbers of one segment; one lane per doc, every gather of the round in flight at once.  The random-sector gathers of
-// the aggregation then overlap the streaming of the predicate columns by the other warps instead of running as a second
-// kernel behind it.  Not inlined: the filter loop keeps its own register budget.
-static __device__ __noinline__ void pb_warp_aggregate(const DevQuery& Q, const DevSegQuery& sgq, const uint32_t* ob, uint32_t cnt, int lane) {
-  const DevTable& tb = Q.tables[sgq.table];
-  const uint32_t base = (uint32_t)sgq.doc_base;
-  KeylessAcc ka; ka.sum = nullptr; ka.mm = nullptr; ka.cnt = nullptr;
-  unsigned long long unused = 0;
-  for (uint32_t i = (uint32_t)lane; i < cnt; i += 32) pb_accumulate(Q, sgq, tb, ob[i] - base, ka, unused, 0u);
-}
-
 // U = 1024-doc chunks per work unit (one TMA load + one dispatch per predicate leaf per unit)
 //
 // SW / SPK: plan-time specialisation.  SW = 0 is the general kernel (any predicate tree, every width and predicate kind
@@ -886,16 +886,9 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
   uint32_t* ob = reinterpret_cast<uint32_t*>(dyn) + (size_t)warp * PB_OUT_CAP;   // this warp's output buffer
   dyn += (size_t)PB_NWARPS * PB_OUT_CAP * sizeof(uint32_t);
   uint32_t out_n = 0;                                     // buffered matches (warp-uniform)
-  int cur_seg = 0;                                        // segment the buffered matches belong to
   auto flush_out = [&]() {
     if (out_n == 0) return;
     __syncwarp();
-    if (Q.fuse) {
-      pb_warp_aggregate(Q, Q.segs[cur_seg], ob, out_n, lane);
-      __syncwarp();
-      out_n = 0;
-      return;
-    }
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)out_n);
     base = __shfl_sync(0xffffffffu, base, 0);
@@ -969,7 +962,6 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
 
   for (int sgi = seg_first; sgi < Q.n_segs; sgi++) {
     if (Q.segs[sgi].unit_begin >= cta_hi) break;
-    cur_seg = sgi;
     // ---- segment entry: filter descriptor, derived constants and LUTs into shared memory ----
     __syncthreads();   // everyone has left the previous segment
     {
@@ -1174,26 +1166,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       }
       const uint32_t gunit0 = (uint32_t)(sq.doc_base + unit_doc0);
       if (n_cand_leaves == 0) {
-        if (__builtin_expect(total > PB_OUT_CAP && Q.fuse, 0)) {
-          // dense matches, fused aggregation: through the buffer, PB_OUT_CAP docs at a time
-          flush_out();
-          for (uint32_t base0 = 0; base0 < total; base0 += PB_OUT_CAP) {
-            uint32_t pos = excl - base0;                                   // (wraps below the window: unsigned compare)
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-              const uint32_t gdoc0 = gunit0 + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
-              uint32_t mm = mask[u];
-              while (mm) {
-                const int bit = __ffs(mm) - 1;
-                mm &= mm - 1;
-                if (pos < PB_OUT_CAP) ob[pos] = gdoc0 + (uint32_t)bit;
-                pos++;
-              }
-            }
-            out_n = total - base0 < PB_OUT_CAP ? total - base0 : PB_OUT_CAP;
-            flush_out();
-          }
-        } else if (__builtin_expect(total > PB_OUT_CAP, 0)) {
+        if (__builtin_expect(total > PB_OUT_CAP, 0)) {
           // dense matches: straight to the list
           unsigned long long base = 0;
           if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)total);
@@ -1223,7 +1196,6 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
             }
           }
           out_n += total;
-          if (Q.fuse && out_n >= (uint32_t)Q.fuse_batch) flush_out();
         }
         matched += total;
       } else {
@@ -1266,7 +1238,6 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
               matched += n;
             }
           }
-          if (Q.fuse && out_n >= (uint32_t)Q.fuse_batch) flush_out();
         }
         __syncwarp();   // the list is rewritten by the next unit
       }
@@ -1317,6 +1288,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_agg_kernel(const __g
   }
   __syncthreads();
 
+  if (Q.phase == 2 && *Q.any_limit == 0) return;          // repair pass: nothing was refused, nothing to repair
   const unsigned long long n = Q.match_all ? Q.n_docs_total : *Q.match_count;
   unsigned long long keyless_rows = 0;
   int my_table = -1;      // keyless: table the private accumulators currently belong to
@@ -1633,7 +1605,9 @@ static __global__ void pb_expand_kernel(const DevExpandItem* __restrict__ items)
 // cross-GPU merge sums them like every other counter.  `aux` is a second zero region (per-wave match counters and
 // per-segment swim-lane statistics) that is not part of the merged block.
 static __global__ void pb_init_tables_kernel(uint4* zero, uint64_t zero_n16, uint4* ff, uint64_t ff_n16, uint4* mm, uint64_t mm_n16,
-                                      uint4* aux, uint64_t aux_n16, const uint4* __restrict__ head, uint64_t head_n16) {
+                                      uint4* aux, uint64_t aux_n16, const uint4* __restrict__ head, uint64_t head_n16,
+                                      const unsigned int* only_if = nullptr) {
+  if (only_if && *only_if == 0) return;      // (the conditional re-initialisation of a repair pass)
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint4 z = make_uint4(0u, 0u, 0u, 0u), f = make_uint4(~0u, ~0u, ~0u, ~0u), m = make_uint4(~0u, 0x7fffffffu, ~0u, 0x7fffffffu);
   for (uint64_t i = t0; i < zero_n16; i += stride) zero[i] = i < head_n16 ? head[i] : z;
@@ -2081,6 +2055,8 @@ struct DevRowBuild {
   int32_t n_cols, stride_words;
   uint32_t num_docs, pad;
   const uint8_t* fwd[PB_ROW_MAX_COLS];
+  const uint8_t* dict_native[PB_ROW_MAX_COLS];   // non-null: the field holds the DECODED dictionary value (value_bytes = 4 or 8), not the dictId
+  int32_t value_bytes[PB_ROW_MAX_COLS];
   int32_t bits[PB_ROW_MAX_COLS];
   int32_t bit_off[PB_ROW_MAX_COLS];
   uint32_t* out;
@@ -2092,6 +2068,20 @@ static __global__ void pb_build_rows_kernel(const DevRowBuild B) {
     for (int k = 0; k < PB_ROW_MAX_WORDS; k++) w[k] = 0;
     for (int c = 0; c < B.n_cols; c++) {
       const uint32_t id = pb_unpack_at(B.fwd[c], (uint32_t)doc, B.bits[c]);
+      if (B.dict_native[c]) {
+        // decoded value, stored like a raw forward index entry (big-endian once the words are swapped below): aggregation
+        // inputs then need no dictionary lookup per matching row (a dependent random L2 access each)
+        const int k0 = B.bit_off[c] >> 5;
+        uint32_t v0, v1 = 0;
+        if (B.value_bytes[c] == 4) v0 = reinterpret_cast<const uint32_t*>(B.dict_native[c])[id];
+        else { const unsigned long long v = reinterpret_cast<const unsigned long long*>(B.dict_native[c])[id]; v0 = (uint32_t)(v >> 32); v1 = (uint32_t)v; }
+#pragma unroll
+        for (int kk = 0; kk < PB_ROW_MAX_WORDS; kk++) {
+          if (kk == k0) w[kk] = v0;
+          if (kk == k0 + 1 && B.value_bytes[c] == 8) w[kk] = v1;
+        }
+        continue;
+      }
       const int p = B.bit_off[c], k = p >> 5, sft = 32 - B.bits[c] - (p & 31);      // left shift that puts the value's LSB in place
 #pragma unroll
       for (int kk = 0; kk < PB_ROW_MAX_WORDS; kk++) {

@@ -302,13 +302,15 @@ struct Column {
 
 // A row-major copy of the dictionary columns some query gathers together (see DevKeyCol in pb_device.cuh)
 struct RowGroup {
-  std::vector<int> cols;          // member columns (indices into the segment's columns, ascending)
-  std::vector<int> bit_off;       // field offset of each member inside a row
+  // members: (column index, form) -- form 0: the dictId (bits wide); form 1: the DECODED dictionary value, 4 or 8 bytes,
+  // stored like a raw forward index entry, for aggregation inputs (no dictionary lookup per matching row)
+  std::vector<int> cols, form;
+  std::vector<int> bit_off;       // field offset of each member inside a row (value fields first, 32-bit aligned)
   int stride_bits = 0;            // 64 / 128 / 256: rows never straddle a 32-byte sector
   uint8_t* d_rows = nullptr;
   uint64_t bytes = 0;
   uint64_t last_used = 0;
-  int find(int col) const { for (size_t i = 0; i < cols.size(); i++) if (cols[i] == col) return (int)i; return -1; }
+  int find(int col, int f) const { for (size_t i = 0; i < cols.size(); i++) if (cols[i] == col && form[i] == f) return (int)i; return -1; }
 };
 #define PB_MAX_ROW_GROUPS_PER_SEGMENT 4
 
@@ -560,18 +562,24 @@ static void enforce_cache_limit(Context* ctx) {
 }
 
 
-// The row group that holds every column of `want` (ascending column indices, all dictionary columns staged in HBM): an
-// existing one whose members include them, else a new one built on the copy stream behind the column copies it reads.
-// Returns nullptr when rows would not pay (a single column, more than 256 bits) or cannot be built.  Under s->mu.
-static const RowGroup* row_group_for(pb_segment_s* s, const std::vector<int>& want, cudaStream_t cs) {
+// The row group that holds every (column, form) of `want`: an existing one whose members include them, else a new one
+// built on the copy stream behind the column copies it reads.  Returns nullptr when rows would not pay (a single field, more
+// than 256 bits) or cannot be built.  Under s->mu.
+static int field_bits(const Column& c, int form) { return form ? 8 * c.entry_bytes : c.bits; }
+static const RowGroup* row_group_for(pb_segment_s* s, std::vector<std::pair<int, int>> want, cudaStream_t cs) {
   if (want.size() < 2 || want.size() > PB_ROW_MAX_COLS) return nullptr;
   int sum_bits = 0;
-  for (int ci : want) { const Column& c = s->cols[ci]; if (!c.has_dict || !c.fwd_staged) return nullptr; sum_bits += c.bits; }
+  for (auto& w : want) {
+    const Column& c = s->cols[w.first];
+    if (!c.has_dict || !c.fwd_staged) return nullptr;
+    if (w.second && (!c.native_staged || (c.entry_bytes != 4 && c.entry_bytes != 8) || c.type == PB_STRING)) return nullptr;
+    sum_bits += field_bits(c, w.second);
+  }
   if (sum_bits > 256) return nullptr;
   const uint64_t tick = [&]() { std::lock_guard<std::mutex> lk(s->ctx->mu); return ++s->ctx->lru_clock; }();
   for (auto& rg : s->row_groups) {
     bool all = true;
-    for (int ci : want) if (rg->find(ci) < 0) { all = false; break; }
+    for (auto& w : want) if (rg->find(w.first, w.second) < 0) { all = false; break; }
     if (all) { rg->last_used = tick; return rg.get(); }
   }
   if (s->row_groups.size() >= PB_MAX_ROW_GROUPS_PER_SEGMENT) {
@@ -584,16 +592,24 @@ static const RowGroup* row_group_for(pb_segment_s* s, const std::vector<int>& wa
     s->row_groups.erase(s->row_groups.begin() + (long)old);
     s->epoch++;
   }
+  // value fields first (8-byte ones, then 4-byte ones: all stay 32-bit aligned), then the bit-packed dictIds
+  std::stable_sort(want.begin(), want.end(), [&](const std::pair<int, int>& a, const std::pair<int, int>& b) {
+    const int ka = a.second ? (s->cols[a.first].entry_bytes == 8 ? 0 : 1) : 2, kb = b.second ? (s->cols[b.first].entry_bytes == 8 ? 0 : 1) : 2;
+    return ka < kb;
+  });
   std::unique_ptr<RowGroup> rg(new RowGroup());
-  rg->cols = want;
   rg->stride_bits = sum_bits <= 64 ? 64 : sum_bits <= 128 ? 128 : 256;
   int off = 0;
-  for (int ci : want) { rg->bit_off.push_back(off); off += s->cols[ci].bits; }
+  for (auto& w : want) { rg->cols.push_back(w.first); rg->form.push_back(w.second); rg->bit_off.push_back(off); off += field_bits(s->cols[w.first], w.second); }
   rg->bytes = (uint64_t)s->num_docs * (uint64_t)(rg->stride_bits / 8) + 32;
   if (dev_alloc(s->ctx, (void**)&rg->d_rows, rg->bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   DevRowBuild B; memset(&B, 0, sizeof B);
   B.n_cols = (int)want.size(); B.stride_words = rg->stride_bits / 32; B.num_docs = (uint32_t)s->num_docs; B.out = (uint32_t*)rg->d_rows;
-  for (size_t i = 0; i < want.size(); i++) { const Column& c = s->cols[want[i]]; B.fwd[i] = c.d_fwd; B.bits[i] = c.bits; B.bit_off[i] = rg->bit_off[i]; }
+  for (size_t i = 0; i < want.size(); i++) {
+    const Column& c = s->cols[want[i].first];
+    B.fwd[i] = c.d_fwd; B.bits[i] = c.bits; B.bit_off[i] = rg->bit_off[i];
+    if (want[i].second) { B.dict_native[i] = c.d_dict_native; B.value_bytes[i] = c.entry_bytes; }
+  }
   if (cudaMemsetAsync(rg->d_rows + (rg->bytes - 32), 0, 32, cs) != cudaSuccess) { cudaGetLastError(); dev_free(s->ctx, rg->d_rows); return nullptr; }
   int grid = (int)std::min<uint64_t>(((uint64_t)s->num_docs + 255) / 256, (uint64_t)s->ctx->num_sms * 16);
   if (grid < 1) grid = 1;
@@ -953,6 +969,7 @@ struct pb_result_s {
   pb_order_by order0{0, 0, 0}; int trim_size = 0, trim_threshold = 0;
   std::vector<unsigned long long*> d_okey; std::vector<DevSelectState*> d_sel;
   bool track_first = false; uint32_t* d_first_thr = nullptr;   // numGroupsLimit in doc order (dense per-segment tables)
+  bool repair_pass = false;                 // hash tables with a reachable numGroupsLimit: conditional second aggregation pass
   bool fused = false, smem_table = false;   // how the matches reached the table (see exec_single)
   bool comm_timed = false;                  // events [5],[6] bracket the cross-rank merge
   double comm_ms = 0;
@@ -1397,6 +1414,19 @@ static int enqueue_all(pb_result_s* r, const std::vector<cudaEvent_t>* seg_wait)
       else pb_agg_kernel<6><<<w.grid_agg, PB_NTHREADS, rp.smem_agg, st>>>(w.dq);
       r->launches++;
       CU(cudaGetLastError());
+      if (r->repair_pass && rp.waves.size() == 1 && (rp.agg_kind == 1 || rp.agg_kind == 2)) {
+        // numGroupsLimit was reachable: if some key was refused (device-side check), zero the aggregates (keys and counters
+        // stay) and aggregate the matches again in lookup-only mode, see pb_hash_slot
+        const uint64_t skip16 = (((uint64_t)PB_COUNTERS_PER_TABLE * 8 * r->tables.size() + 255) & ~(uint64_t)255) / 16;
+        pb_init_tables_kernel<<<r->init.grid, 256, 0, st>>>(r->init.zero + skip16, r->init.zn - skip16, nullptr, 0, r->init.mm, r->init.mn, nullptr, 0, nullptr, 0,
+                                                             w.dq.any_limit);
+        DevQuery dq2 = w.dq;
+        dq2.phase = 2;
+        if (rp.agg_kind == 2) pb_agg_kernel<4><<<w.grid_agg, PB_NTHREADS, rp.smem_agg, st>>>(dq2);
+        else pb_agg_kernel<6><<<w.grid_agg, PB_NTHREADS, rp.smem_agg, st>>>(dq2);
+        r->launches += 2;
+        CU(cudaGetLastError());
+      }
     }
   }
   CU(cudaEventRecord(r->ev2, st));
@@ -1604,15 +1634,24 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     if (row_groups_on && !in_place) {
       const double sel_rg = estimate_selectivity(s, sq);
       if (sel_rg <= 0.5) {
-        std::vector<int> want;
-        auto add = [&](int ci) { if (ci >= 0 && s->cols[ci].has_dict && s->cols[ci].fwd_staged && std::find(want.begin(), want.end(), ci) == want.end()) want.push_back(ci); };
-        for (int j = 0; j < nG; j++) add(gcol[si][j]);
-        for (int a = 0; a < nA; a++) add(acol[si][a]);
+        std::vector<std::pair<int, int>> want;      // (column, form): 0 = dictId, 1 = decoded value (numeric aggregation inputs)
+        auto add = [&](int ci, int form) {
+          if (ci < 0 || !s->cols[ci].has_dict || !s->cols[ci].fwd_staged) return;
+          if (std::find(want.begin(), want.end(), std::make_pair(ci, form)) == want.end()) want.push_back({ci, form});
+        };
+        for (int j = 0; j < nG; j++) add(gcol[si][j], 0);
+        for (int a = 0; a < nA; a++) {
+          if (acol[si][a] < 0) continue;
+          Column& c = s->cols[acol[si][a]];
+          const bool decoded = q->aggregations[a].op != PB_AGG_DISTINCTCOUNT && c.has_dict && c.type != PB_STRING;
+          if (decoded && !c.native_staged && (rc = stage_column(s, c, false, false, false, cs, true, false))) return rc;   // the build reads the native dictionary
+          add(acol[si][a], decoded ? 1 : 0);
+        }
         for (int n = 0; n < sq.num_filter_nodes; n++)
-          if (cand_leaf[si][n] && (sq.filter[n].kind == PB_F_SCAN_DICT_RANGE || sq.filter[n].kind == PB_F_SCAN_DICT_SET)) add(sq.filter[n].column);
+          if (cand_leaf[si][n] && (sq.filter[n].kind == PB_F_SCAN_DICT_RANGE || sq.filter[n].kind == PB_F_SCAN_DICT_SET)) add(sq.filter[n].column, 0);
         for (int f = 0; f < nF; f++)
           for (int n = 0; n < sq.agg_filter_nodes[f]; n++)
-            if (sq.agg_filters[f][n].kind == PB_F_SCAN_DICT_RANGE || sq.agg_filters[f][n].kind == PB_F_SCAN_DICT_SET) add(sq.agg_filters[f][n].column);
+            if (sq.agg_filters[f][n].kind == PB_F_SCAN_DICT_RANGE || sq.agg_filters[f][n].kind == PB_F_SCAN_DICT_SET) add(sq.agg_filters[f][n].column, 0);
         std::sort(want.begin(), want.end());
         seg_rg[si] = row_group_for(s, want, cs);
       }
@@ -1765,7 +1804,8 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   // per-wave match counters and per-segment swim-lane statistics live in an aux region behind it that is not shipped.
   zero_bytes = (zero_bytes + 255) & ~(size_t)255;
   const size_t mm_bytes = (8 * mm_elems + 255) & ~(size_t)255;
-  const size_t thr_off = 8 * PB_MAX_WAVES + seg_stats_bytes;          // numGroupsLimit thresholds (one u32 per table), after the statistics
+  const size_t any_limit_off = 8 * PB_MAX_WAVES + seg_stats_bytes;   // query-wide "a key was refused" flag (hash tables)
+  const size_t thr_off = any_limit_off + 8;          // numGroupsLimit thresholds (one u32 per table), after the statistics
   const size_t aux_bytes = (thr_off + (track_first ? 4 * (size_t)n_tables : 0) + 255) & ~(size_t)255;
   CU(cudaMallocAsync((void**)&d_zero, zero_bytes + mm_bytes + aux_bytes + 16, st)); r->dev_allocs.push_back(d_zero);
   if (ff_bytes) { CU(cudaMallocAsync((void**)&d_ff, ff_bytes + 16, st)); r->dev_allocs.push_back(d_ff); }
@@ -1819,6 +1859,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       unsigned long long* cnt = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE;
       dt.num_groups = reinterpret_cast<unsigned int*>(cnt + 0);
       dt.limit_reached = reinterpret_cast<unsigned int*>(cnt + 1);
+      dt.any_limit = reinterpret_cast<unsigned int*>(d_aux + any_limit_off);
       dt.docs_matched = cnt + 2;
       dt.num_groups_limit = (uint32_t)std::max(1, q->num_groups_limit);
       {
@@ -1920,10 +1961,11 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
           lf.g_full_words = c.fwd_staged ? 0xFFFFFFFFu : c.host_full_words;
           lf.g_tail_word = c.fwd_staged ? 0u : c.host_tail_word;
           lf.g_stride_bits = c.bits; lf.g_bit_off = 0;
-          if (c.has_dict && seg_rg[si] && seg_rg[si]->find(fn.column) >= 0) {
+          if (!c.has_dict) lf.g_stride_bits = 8 * c.raw_width;
+          if (c.has_dict && seg_rg[si] && seg_rg[si]->find(fn.column, 0) >= 0) {
             const RowGroup* rg = seg_rg[si];
             lf.gfwd = rg->d_rows; lf.g_full_words = 0xFFFFFFFFu; lf.g_tail_word = 0u;
-            lf.g_stride_bits = rg->stride_bits; lf.g_bit_off = rg->bit_off[(size_t)rg->find(fn.column)];
+            lf.g_stride_bits = rg->stride_bits; lf.g_bit_off = rg->bit_off[(size_t)rg->find(fn.column, 0)];
           }
           if (!c.fwd_staged) r->in_place_columns++;
           any_cand_leaf = true;
@@ -2067,11 +2109,11 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       kc.fwd = c.fwd_staged ? c.d_fwd : c.d_fwd_host; kc.n_full_words = c.fwd_staged ? 0xFFFFFFFFu : c.host_full_words;
       kc.tail_word = c.fwd_staged ? 0u : c.host_tail_word; if (!c.fwd_staged) r->in_place_columns++;
       kc.bits = c.bits; kc.raw_width = c.has_dict ? 0 : c.raw_width; kc.data_type = c.type;
-      kc.stride_bits = c.bits; kc.bit_off = 0;
-      if (c.has_dict && seg_rg[si] && seg_rg[si]->find(gcol[si][j]) >= 0) {
+      kc.stride_bits = c.has_dict ? c.bits : 8 * c.raw_width; kc.bit_off = 0;
+      if (c.has_dict && seg_rg[si] && seg_rg[si]->find(gcol[si][j], 0) >= 0) {
         const RowGroup* rg = seg_rg[si];
         kc.fwd = rg->d_rows; kc.n_full_words = 0xFFFFFFFFu; kc.tail_word = 0u;
-        kc.stride_bits = rg->stride_bits; kc.bit_off = rg->bit_off[(size_t)rg->find(gcol[si][j])];
+        kc.stride_bits = rg->stride_bits; kc.bit_off = rg->bit_off[(size_t)rg->find(gcol[si][j], 0)];
       }
       kc.remap = (combine && gdict[j]) ? gdict[j]->d_remap[si] : nullptr;
       kc.shift = tm.shifts[j];
@@ -2086,11 +2128,17 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       ac.fwd = c.fwd_staged ? c.d_fwd : c.d_fwd_host; ac.n_full_words = c.fwd_staged ? 0xFFFFFFFFu : c.host_full_words;
       ac.tail_word = c.fwd_staged ? 0u : c.host_tail_word; if (!c.fwd_staged) r->in_place_columns++;
       ac.dict_f64 = c.d_dict_f64; ac.bits = c.bits; ac.raw_width = c.has_dict ? 0 : c.raw_width; ac.data_type = c.type;
-      ac.stride_bits = c.bits; ac.bit_off = 0;
-      if (c.has_dict && seg_rg[si] && seg_rg[si]->find(acol[si][a]) >= 0) {
+      ac.stride_bits = c.has_dict ? c.bits : 8 * c.raw_width; ac.bit_off = 0;
+      if (c.has_dict && seg_rg[si]) {
         const RowGroup* rg = seg_rg[si];
-        ac.fwd = rg->d_rows; ac.n_full_words = 0xFFFFFFFFu; ac.tail_word = 0u;
-        ac.stride_bits = rg->stride_bits; ac.bit_off = rg->bit_off[(size_t)rg->find(acol[si][a])];
+        const int fv = q->aggregations[a].op != PB_AGG_DISTINCTCOUNT ? rg->find(acol[si][a], 1) : -1, fi = rg->find(acol[si][a], 0);
+        if (fv >= 0) {            // decoded value field: read like a raw column, no dictionary lookup
+          ac.fwd = rg->d_rows; ac.n_full_words = 0xFFFFFFFFu; ac.tail_word = 0u;
+          ac.raw_width = c.entry_bytes; ac.stride_bits = rg->stride_bits; ac.bit_off = rg->bit_off[(size_t)fv];
+        } else if (fi >= 0) {
+          ac.fwd = rg->d_rows; ac.n_full_words = 0xFFFFFFFFu; ac.tail_word = 0u;
+          ac.stride_bits = rg->stride_bits; ac.bit_off = rg->bit_off[(size_t)fi];
+        }
       }
       ac.remap = (combine && adict[a]) ? adict[a]->d_remap[si] : nullptr;
     }
@@ -2128,14 +2176,11 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   }
   if (n_docs_total >= (1ull << 32)) return fail(PB_ERR_UNSUPPORTED, "%llu docs in one call (match list is 32-bit): split the segment group", (unsigned long long)n_docs_total);
   // ---- how the matches reach the group table (see pb_device.cuh):
-  //   fused     selective filters: the filter kernel aggregates its matches itself (global REDs; no match list, no second kernel)
   //   smem      one dense table that fits shared memory and enough matches to amortise merging 148 private copies
   //   global    everything else: pb_agg_kernel, one thread per match, reductions straight into the global table
-  double est_sel = 0.0;
-  for (int si = 0; si < n_segs; si++) est_sel += estimate_selectivity(g->segs[si], sqs[si]) * (double)g->segs[si]->num_docs;
-  est_sel = n_docs_total ? est_sel / (double)n_docs_total : 0.0;
-  static const int fuse_permille = []() { const char* e = getenv("PB_FUSE_PERMILLE"); return e ? atoi(e) : -1; }();   // (measured: no gain on B200 while every matching row costs six random DRAM sectors; see profiles/r2_experiments.md)
-  const bool fuse = !match_all && table_mode != T_KEYLESS && nF == 0 && n_docs_total > 0 && est_sel * 1000.0 <= (double)fuse_permille;
+  // (a third way -- the filter kernel aggregating its own matches, no match list -- was measured and removed: the two
+  //  kernels are bound by the same memory system and did not overlap, profiles/r2_experiments.md)
+  const bool fuse = false;
   int n_acc = 0, n_fc = 0;
   for (int a = 0; a < nA; a++) {
     const int op = q->aggregations[a].op;
@@ -2234,8 +2279,6 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   hq->n_docs_total = n_docs_total; hq->match_all = match_all ? 1 : 0;
   { static const int sm = []() { const char* e = getenv("PB_SPARSE_MAX"); return e ? atoi(e) : PB_SPARSE_MAX; }(); hq->sparse_max = sm; }
   hq->match_list = d_match_list;
-  hq->fuse = fuse ? 1 : 0;
-  { static const int fb = []() { const char* e = getenv("PB_FUSE_BATCH"); int v = e ? atoi(e) : 32; return v < 1 ? 1 : (v > PB_OUT_CAP ? PB_OUT_CAP : v); }(); hq->fuse_batch = fb; }
   if (use_smem_table) {
     hq->st_slots = (int32_t)r->tables[0].capacity; hq->st_replicas = st_replicas;
     // merging a CTA's private table costs up to one RED per slot and aggregate: it pays once a CTA sees several matches per slot
@@ -2244,6 +2287,9 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   }
   r->fused = fuse; r->smem_table = use_smem_table;
   hq->match_count = reinterpret_cast<unsigned long long*>(d_aux);   // PB_MAX_WAVES zeroed cells (aux region)
+  hq->any_limit = reinterpret_cast<const unsigned int*>(d_aux + any_limit_off);
+  r->repair_pass = false;
+  if (table_mode == T_HASH) for (auto& tm : r->tables) if (tm.dev.limit_active) r->repair_pass = true;
 
   // expand items (one per inverted-index bitmap / per sorted-index range list)
   int n_expand_items = 0;
