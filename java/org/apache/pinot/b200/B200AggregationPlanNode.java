@@ -46,6 +46,9 @@ public class B200AggregationPlanNode implements PlanNode {
         }
       }
     }
+    if (_queryContext.getGroupByExpressions() == null || _queryContext.getGroupByExpressions().isEmpty()) {
+      return new B200AggregationOperator(_segmentContext.getIndexSegment(), _queryContext, where, clauses, clauseIndex);
+    }
     return new B200GroupByOperator(_segmentContext.getIndexSegment(), _queryContext, where, clauses, clauseIndex);
   }
 }

@@ -80,12 +80,131 @@ final class B200Eligibility {
         && (dataSource.getDictionary() != null || dataSource.getDataSourceMetadata().getDataType().getStoredType().isFixedWidth());
   }
 
-  /** docId ranges of a sorted-index leaf, merged like SortedIndexBasedFilterOperator.java:61-131 (inclusive pairs, ascending). */
+  /**
+   * docId ranges of a sorted-index leaf: inclusive (start, end) pairs in ascending order, adjacent ranges merged -- the list
+   * SortedIndexBasedFilterOperator.getNextBlock builds (SortedIndexBasedFilterOperator.java:61-131).
+   */
   static int[] sortedDocIdRanges(PredicateEvaluator evaluator, DataSource dataSource) {
     SortedIndexReader<?> sortedIndexReader = (SortedIndexReader<?>) dataSource.getInvertedIndex();
-    // RANGE: one pair spanning [getDocIds(startDictId).left, getDocIds(endDictId - 1).right]; EQ / IN: one pair per dictId, adjacent
-    // pairs merged; NOT_EQ / NOT_IN: the complement.  (Array bookkeeping elided; pb_host.cpp SortedIndexBasedFilterOperator is the
-    // executable version.)
-    return new int[0];
+    java.util.List<int[]> ranges = new java.util.ArrayList<>();
+    if (evaluator instanceof org.apache.pinot.core.operator.filter.predicate.RangePredicateEvaluatorFactory
+        .SortedDictionaryBasedRangePredicateEvaluator) {
+      org.apache.pinot.core.operator.filter.predicate.RangePredicateEvaluatorFactory.SortedDictionaryBasedRangePredicateEvaluator range =
+          (org.apache.pinot.core.operator.filter.predicate.RangePredicateEvaluatorFactory.SortedDictionaryBasedRangePredicateEvaluator) evaluator;
+      int start = range.getStartDictId();
+      int end = range.getEndDictId();           // exclusive
+      if (end > start) {
+        ranges.add(new int[]{sortedIndexReader.getDocIds(start).getLeft(), sortedIndexReader.getDocIds(end - 1).getRight()});
+      }
+    } else {
+      boolean exclusive = evaluator.getPredicateType() == org.apache.pinot.common.request.context.predicate.Predicate.Type.NOT_EQ
+          || evaluator.getPredicateType() == org.apache.pinot.common.request.context.predicate.Predicate.Type.NOT_IN;
+      int[] dictIds = exclusive ? evaluator.getNonMatchingDictIds() : evaluator.getMatchingDictIds();
+      int[] sorted = dictIds.clone();
+      java.util.Arrays.sort(sorted);
+      java.util.List<int[]> hit = new java.util.ArrayList<>();
+      for (int dictId : sorted) {
+        org.apache.pinot.spi.utils.Pairs.IntPair docIds = sortedIndexReader.getDocIds(dictId);
+        int[] last = hit.isEmpty() ? null : hit.get(hit.size() - 1);
+        if (last != null && last[1] + 1 == docIds.getLeft()) {
+          last[1] = docIds.getRight();           // adjacent dictIds cover adjacent docId ranges: merge
+        } else {
+          hit.add(new int[]{docIds.getLeft(), docIds.getRight()});
+        }
+      }
+      if (!exclusive) {
+        ranges = hit;
+      } else {                                   // NOT_EQ / NOT_IN: the complement over [0, numDocs)
+        int numDocs = dataSource.getDataSourceMetadata().getNumDocs();
+        int next = 0;
+        for (int[] r : hit) {
+          if (r[0] > next) {
+            ranges.add(new int[]{next, r[0] - 1});
+          }
+          next = r[1] + 1;
+        }
+        if (next < numDocs) {
+          ranges.add(new int[]{next, numDocs - 1});
+        }
+      }
+    }
+    int[] flat = new int[2 * ranges.size()];
+    for (int i = 0; i < ranges.size(); i++) {
+      flat[2 * i] = ranges.get(i)[0];
+      flat[2 * i + 1] = ranges.get(i)[1];
+    }
+    return flat;
+  }
+
+  /**
+   * Inclusive bounds of a RANGE predicate on a raw INT / LONG column.  The raw-value evaluators that hold them
+   * (RangePredicateEvaluatorFactory.Int/LongRawValueBasedRangePredicateEvaluator, :326-430) are private, so the bounds are
+   * derived from the predicate's literals the same way the factory does: an exclusive bound moves by one, a fractional
+   * bound rounds towards the inside of the interval, an unbounded side is the type's extreme.
+   */
+  static long inclusiveLowerBound(PredicateEvaluator evaluator) {
+    org.apache.pinot.common.request.context.predicate.RangePredicate range =
+        (org.apache.pinot.common.request.context.predicate.RangePredicate) evaluator.getPredicate();
+    boolean isInt = evaluator.getDataType() == org.apache.pinot.spi.data.FieldSpec.DataType.INT;
+    long min = isInt ? Integer.MIN_VALUE : Long.MIN_VALUE;
+    if (range.getLowerBound().equals(org.apache.pinot.common.request.context.predicate.RangePredicate.UNBOUNDED)) {
+      return min;
+    }
+    java.math.BigDecimal bound = new java.math.BigDecimal(range.getLowerBound());
+    java.math.BigDecimal ceil = bound.setScale(0, java.math.RoundingMode.CEILING);
+    java.math.BigInteger v = ceil.toBigInteger();
+    if (ceil.compareTo(bound) == 0 && !range.isLowerInclusive()) {
+      v = v.add(java.math.BigInteger.ONE);
+    }
+    return clamp(v, isInt);
+  }
+
+  static long inclusiveUpperBound(PredicateEvaluator evaluator) {
+    org.apache.pinot.common.request.context.predicate.RangePredicate range =
+        (org.apache.pinot.common.request.context.predicate.RangePredicate) evaluator.getPredicate();
+    boolean isInt = evaluator.getDataType() == org.apache.pinot.spi.data.FieldSpec.DataType.INT;
+    long max = isInt ? Integer.MAX_VALUE : Long.MAX_VALUE;
+    if (range.getUpperBound().equals(org.apache.pinot.common.request.context.predicate.RangePredicate.UNBOUNDED)) {
+      return max;
+    }
+    java.math.BigDecimal bound = new java.math.BigDecimal(range.getUpperBound());
+    java.math.BigDecimal floor = bound.setScale(0, java.math.RoundingMode.FLOOR);
+    java.math.BigInteger v = floor.toBigInteger();
+    if (floor.compareTo(bound) == 0 && !range.isUpperInclusive()) {
+      v = v.subtract(java.math.BigInteger.ONE);
+    }
+    return clamp(v, isInt);
+  }
+
+  private static long clamp(java.math.BigInteger v, boolean isInt) {
+    java.math.BigInteger lo = java.math.BigInteger.valueOf(isInt ? Integer.MIN_VALUE : Long.MIN_VALUE);
+    java.math.BigInteger hi = java.math.BigInteger.valueOf(isInt ? Integer.MAX_VALUE : Long.MAX_VALUE);
+    return v.max(lo).min(hi).longValue();
+  }
+
+  /** the literal values of an EQ / NOT_EQ / IN / NOT_IN predicate on a raw column: longs, or IEEE-754 bits of the doubles */
+  static long[] rawValueSet(PredicateEvaluator evaluator, boolean integral) {
+    org.apache.pinot.common.request.context.predicate.Predicate predicate = evaluator.getPredicate();
+    java.util.List<String> literals;
+    switch (predicate.getType()) {
+      case EQ:
+        literals = java.util.Collections.singletonList(((org.apache.pinot.common.request.context.predicate.EqPredicate) predicate).getValue());
+        break;
+      case NOT_EQ:
+        literals = java.util.Collections.singletonList(((org.apache.pinot.common.request.context.predicate.NotEqPredicate) predicate).getValue());
+        break;
+      case IN:
+        literals = ((org.apache.pinot.common.request.context.predicate.InPredicate) predicate).getValues();
+        break;
+      default:
+        literals = ((org.apache.pinot.common.request.context.predicate.NotInPredicate) predicate).getValues();
+        break;
+    }
+    long[] out = new long[literals.size()];
+    for (int i = 0; i < out.length; i++) {
+      out[i] = integral ? new java.math.BigDecimal(literals.get(i)).longValueExact()
+          : Double.doubleToLongBits(Double.parseDouble(literals.get(i)));
+    }
+    return out;
   }
 }

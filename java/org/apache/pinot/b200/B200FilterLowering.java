@@ -53,7 +53,7 @@ final class B200FilterLowering {
     B200FilterOperatorUtils.takeLeaves();
     BaseFilterOperator root = new FilterPlanNode(segmentContext, queryContext, filter).run();
     Map<BaseFilterOperator, B200FilterOperatorUtils.Leaf> leaves = B200FilterOperatorUtils.takeLeaves();
-    LoweredProgram program = new LoweredProgram();
+    LoweredProgram program = new LoweredProgram(B200SegmentCache.stagedColumns(segmentContext.getIndexSegment()));
     if (!(root instanceof MatchAllFilterOperator)) {       // an empty program means "matches all" to the device
       emit(root, leaves, program);
     }
@@ -102,20 +102,110 @@ final class B200FilterLowering {
     }
   }
 
-  /** Growable flattened program (see Native.execute). */
+  /**
+   * One postfix program in the flattened layout of Native.execute: per node 12 ints (segment and program are filled in by
+   * B200Flatten; kind, column, numChildren, exclusive, numIds, idOffset, numRaw, rawOffset, dloInclusive, dhiInclusive),
+   * 2 longs (lo, hi) and 2 doubles (dlo, dhi); dictId / docId lists and raw values live in per-program pools whose offsets
+   * B200Flatten rebases when it concatenates the programs of a call.
+   */
   static final class LoweredProgram {
+    static final int INTS_PER_NODE = 12;
     final List<int[]> _ints = new ArrayList<>();
     final List<long[]> _longs = new ArrayList<>();
     final List<double[]> _doubles = new ArrayList<>();
-    final List<int[]> _idLists = new ArrayList<>();
+    final List<int[]> _idLists = new ArrayList<>();       // one entry per node (empty array when the node has none)
     final List<long[]> _rawLists = new ArrayList<>();
-    // addCombinator / addSorted / addDictIdSet / addDictIdRange / addRawPredicate / columnIndex fill one node each;
-    // their bodies are array bookkeeping only.
-    void addCombinator(int kind, int numChildren) { /* ... */ }
-    void addSorted(int column, int[] docIdRangePairs) { /* ... */ }
-    void addDictIdSet(int kind, int column, boolean exclusive, int[] dictIds) { /* ... */ }
-    void addDictIdRange(int column, int startDictId, int endDictIdExclusive) { /* ... */ }
-    void addRawPredicate(int column, PredicateEvaluator evaluator) { /* ... */ }
-    int columnIndex(org.apache.pinot.segment.spi.datasource.DataSource dataSource) { return 0; /* position in the staged segment */ }
+    private final List<String> _columns;                   // column order of the staged segment (B200SegmentCache)
+
+    LoweredProgram() {
+      this(new ArrayList<>());
+    }
+
+    LoweredProgram(List<String> stagedColumns) {
+      _columns = stagedColumns;
+    }
+
+    int numNodes() {
+      return _ints.size();
+    }
+
+    private void add(int kind, int column, int numChildren, boolean exclusive, int[] ids, int numIds, long[] raws, long lo, long hi,
+        double dlo, double dhi, boolean dloInclusive, boolean dhiInclusive) {
+      int[] node = new int[INTS_PER_NODE];
+      node[2] = kind;
+      node[3] = column;
+      node[4] = numChildren;
+      node[5] = exclusive ? 1 : 0;
+      node[6] = numIds;                 // idOffset (7) and rawOffset (9) are assigned when the pools are concatenated
+      node[8] = raws.length;
+      node[10] = dloInclusive ? 1 : 0;
+      node[11] = dhiInclusive ? 1 : 0;
+      _ints.add(node);
+      _longs.add(new long[]{lo, hi});
+      _doubles.add(new double[]{dlo, dhi});
+      _idLists.add(ids);
+      _rawLists.add(raws);
+    }
+
+    void addCombinator(int kind, int numChildren) {
+      add(kind, -1, numChildren, false, new int[0], 0, new long[0], 0, 0, 0, 0, false, false);
+    }
+
+    /** docIdRangePairs: inclusive (start, end) pairs, ascending; pb_filter_node.num_ids counts PAIRS for PB_F_SORTED. */
+    void addSorted(int column, int[] docIdRangePairs) {
+      add(Native.PB_F_SORTED, column, 0, false, docIdRangePairs, docIdRangePairs.length / 2, new long[0], 0, 0, 0, 0, false, false);
+    }
+
+    void addDictIdSet(int kind, int column, boolean exclusive, int[] dictIds) {
+      int[] sorted = dictIds.clone();
+      java.util.Arrays.sort(sorted);      // the C ABI wants ascending dictIds
+      add(kind, column, 0, exclusive, sorted, sorted.length, new long[0], 0, 0, 0, 0, false, false);
+    }
+
+    void addDictIdRange(int column, int startDictId, int endDictIdExclusive) {
+      add(Native.PB_F_SCAN_DICT_RANGE, column, 0, false, new int[0], 0, new long[0], startDictId, endDictIdExclusive, 0, 0, false, false);
+    }
+
+    /**
+     * Raw-value (no-dictionary) scan leaves.  RANGE evaluators expose their bounds (Int/Long/Float/DoubleRawValueBasedRange-
+     * PredicateEvaluator.getLowerBound() / getUpperBound(), already adjusted to INCLUSIVE bounds for the integral types:
+     * RangePredicateEvaluatorFactory.java:331-366); EQ / IN / NOT_EQ / NOT_IN evaluators expose their value sets.
+     */
+    void addRawPredicate(int column, PredicateEvaluator evaluator) {
+      Predicate.Type type = evaluator.getPredicateType();
+      org.apache.pinot.spi.data.FieldSpec.DataType dataType = evaluator.getDataType();
+      boolean integral = dataType == org.apache.pinot.spi.data.FieldSpec.DataType.INT
+          || dataType == org.apache.pinot.spi.data.FieldSpec.DataType.LONG;
+      if (type == Predicate.Type.RANGE) {
+        org.apache.pinot.common.request.context.predicate.RangePredicate range =
+            (org.apache.pinot.common.request.context.predicate.RangePredicate) evaluator.getPredicate();
+        if (integral) {
+          long lo = B200Eligibility.inclusiveLowerBound(evaluator);
+          long hi = B200Eligibility.inclusiveUpperBound(evaluator);
+          add(Native.PB_F_SCAN_RAW_RANGE, column, 0, false, new int[0], 0, new long[0], lo, hi, 0, 0, true, true);
+        } else {
+          double lo = range.getLowerBound().equals(org.apache.pinot.common.request.context.predicate.RangePredicate.UNBOUNDED)
+              ? Double.NEGATIVE_INFINITY : Double.parseDouble(range.getLowerBound());
+          double hi = range.getUpperBound().equals(org.apache.pinot.common.request.context.predicate.RangePredicate.UNBOUNDED)
+              ? Double.POSITIVE_INFINITY : Double.parseDouble(range.getUpperBound());
+          add(Native.PB_F_SCAN_RAW_RANGE, column, 0, false, new int[0], 0, new long[0], 0, 0, lo, hi,
+              range.isLowerInclusive() || Double.isInfinite(lo), range.isUpperInclusive() || Double.isInfinite(hi));
+        }
+        return;
+      }
+      boolean exclusive = type == Predicate.Type.NOT_EQ || type == Predicate.Type.NOT_IN;
+      long[] values = B200Eligibility.rawValueSet(evaluator, integral);      // doubles as IEEE-754 bits
+      add(Native.PB_F_SCAN_RAW_SET, column, 0, exclusive, new int[0], 0, values, 0, 0, 0, 0, false, false);
+    }
+
+    /** position of the data source's column in the staged segment */
+    int columnIndex(org.apache.pinot.segment.spi.datasource.DataSource dataSource) {
+      String name = dataSource.getDataSourceMetadata().getFieldSpec().getName();
+      int index = _columns.indexOf(name);
+      if (index < 0) {
+        throw new B200Eligibility.NotEligibleException("column " + name + " is not staged");
+      }
+      return index;
+    }
   }
 }

@@ -366,7 +366,7 @@ class B200PlanMaker {
       if (ad.op == PB_AGG_COUNT) continue;
       int ci = ad.column ? findColumn(seg, ad.column) : -1;
       if (ci < 0) throw BadQuery{"unknown aggregation column"};
-      if (ad.op == PB_AGG_DISTINCTCOUNT) { if (!seg.cols[ci].has_dict) throw BadQuery{"DISTINCTCOUNT on a raw column"}; }
+      if (ad.op == PB_AGG_DISTINCTCOUNT) { if (!seg.cols[ci].has_dict && seg.cols[ci].type == PB_STRING) throw BadQuery{"DISTINCTCOUNT on a raw STRING column"}; }
       else if (seg.cols[ci].type == PB_STRING) throw BadQuery{"numeric aggregation on STRING"};
     }
   }

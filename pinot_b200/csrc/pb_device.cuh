@@ -31,8 +31,8 @@
 #define PB_MAX_AF_LEAVES 16          // leaves of all FILTER clauses of a segment together
 #define PB_MAX_AF_NODES 48
 #define PB_SPARSE_MAX 128            // survivors per 1024-doc chunk below which later AND leaves use the restricted scan
-#define PB_OUT_CAP 256               // matches buffered per warp before one ATOMG reserves their place in the match list
-#define PB_CAND_CAP 512              // candidates per warp list (u16 offsets inside the unit); more = extra passes
+#define PB_OUT_CAP 256               // (upper bound; DevQuery::out_cap) matches buffered per warp before one ATOMG reserves their place in the match list
+#define PB_CAND_CAP 512              // (upper bound; DevQuery::cand_cap) candidates per warp list (u16 offsets inside the unit); more = extra passes
 #define PB_SET_SMEM_BYTES 8192      // dictId-set membership LUTs (one byte per dictId) cached in smem per segment
 
 enum { L_TRUE = 0, L_FALSE = 1, L_DICT_RANGE = 2, L_DICT_SET = 3, L_RAW_RANGE_I = 4, L_RAW_RANGE_F = 5,
@@ -193,7 +193,7 @@ struct DevQuery {
   int32_t phase;                         // pb_agg_kernel: 0 = normal; 2 = repair pass of a hash table that hit numGroupsLimit (see pb_hash_slot)
   int32_t st_slots;                      // pb_agg_smem_kernel: slots of the CTA-private dense table (= table capacity), 0 = not used
   int32_t st_replicas;                   //   replicas of it per CTA (power of two)
-  int32_t st_pad;
+  int32_t out_cap, cand_cap;             // per-warp output buffer / candidate list entries (smaller caps let a fourth CTA fit an SM)
   uint64_t st_min_docs;                  //   matches below which the kernel updates the global table directly (merging 148 private tables costs more)
   uint32_t* match_list;                  // global doc numbers of the docs that pass the filter
   unsigned long long* match_count;
@@ -883,8 +883,9 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
   dyn += (Q.set_cache_bytes + 127) & ~127;
   uint16_t* cand = reinterpret_cast<uint16_t*>(dyn);     // per-warp candidate lists (only when some leaf is evaluated on candidates)
   dyn += Q.cand_bytes;
-  uint32_t* ob = reinterpret_cast<uint32_t*>(dyn) + (size_t)warp * PB_OUT_CAP;   // this warp's output buffer
-  dyn += (size_t)PB_NWARPS * PB_OUT_CAP * sizeof(uint32_t);
+  const uint32_t OUT_CAP = (uint32_t)Q.out_cap, CAND_CAP = (uint32_t)Q.cand_cap;
+  uint32_t* ob = reinterpret_cast<uint32_t*>(dyn) + (size_t)warp * OUT_CAP;   // this warp's output buffer
+  dyn += (size_t)PB_NWARPS * OUT_CAP * sizeof(uint32_t);
   uint32_t out_n = 0;                                     // buffered matches (warp-uniform)
   auto flush_out = [&]() {
     if (out_n == 0) return;
@@ -1166,7 +1167,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       }
       const uint32_t gunit0 = (uint32_t)(sq.doc_base + unit_doc0);
       if (n_cand_leaves == 0) {
-        if (__builtin_expect(total > PB_OUT_CAP, 0)) {
+        if (__builtin_expect(total > OUT_CAP, 0)) {
           // dense matches: straight to the list
           unsigned long long base = 0;
           if (lane == 0) base = atomicAdd(Q.match_count, (unsigned long long)total);
@@ -1183,7 +1184,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
             }
           }
         } else {
-          if (out_n + total > PB_OUT_CAP) flush_out();
+          if (out_n + total > OUT_CAP) flush_out();
           uint32_t* out = ob + out_n + excl;
 #pragma unroll
           for (int u = 0; u < U; u++) {
@@ -1201,8 +1202,8 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       } else {
         // ---- candidates: survivors of the staged leaves, compacted into this warp's list, then one lane per candidate
         // tests the remaining leaves straight from their forward indexes (all 32 gathers of a round in flight at once) ----
-        uint16_t* cl = cand + (size_t)warp * PB_CAND_CAP;
-        for (uint32_t pass0 = 0; pass0 < total; pass0 += PB_CAND_CAP) {     // one pass unless the estimate was far off
+        uint16_t* cl = cand + (size_t)warp * CAND_CAP;
+        for (uint32_t pass0 = 0; pass0 < total; pass0 += CAND_CAP) {     // one pass unless the estimate was far off
           if (pass0) __syncwarp();
           {
             uint32_t pos = excl - pass0;                                     // (wraps below the window: unsigned compare)
@@ -1213,13 +1214,13 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
               while (mm) {
                 const int bit = __ffs(mm) - 1;
                 mm &= mm - 1;
-                if (pos < PB_CAND_CAP) cl[pos] = (uint16_t)(off0 + (uint32_t)bit);
+                if (pos < CAND_CAP) cl[pos] = (uint16_t)(off0 + (uint32_t)bit);
                 pos++;
               }
             }
           }
           __syncwarp();
-          const uint32_t n_pass = total - pass0 < PB_CAND_CAP ? total - pass0 : PB_CAND_CAP;
+          const uint32_t n_pass = total - pass0 < CAND_CAP ? total - pass0 : CAND_CAP;
           for (uint32_t b0 = 0; b0 < n_pass; b0 += 32) {
             const uint32_t idx = b0 + (uint32_t)lane;
             bool alive = idx < n_pass;
@@ -1232,7 +1233,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
             const uint32_t bal = __ballot_sync(0xffffffffu, alive);
             if (bal) {
               const uint32_t n = (uint32_t)__popc(bal);
-              if (out_n + n > PB_OUT_CAP) flush_out();
+              if (out_n + n > OUT_CAP) flush_out();
               if (alive) ob[out_n + __popc(bal & lt)] = gunit0 + off;
               out_n += n;
               matched += n;
@@ -1485,6 +1486,163 @@ static __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_smem_ker
         for (uint32_t r = 0; r < R; r++) { SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes; fc += pb_sh_ld_u32(z.fcnt(st.fc_of[a], i)); }
         if (fc) pb_red_add_u64(&t.fcnt[a][i], fc);
       }
+      if (st.acc_of[a] < 0) continue;
+      const int op = Q.agg_op[a];
+      if (op == 1 || op == 4) {
+        double v = 0.0;
+        for (uint32_t r = 0; r < R; r++) { SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes; v += __longlong_as_double((long long)pb_sh_ld_u64(z.acc(st.acc_of[a], i))); }
+        pb_red_add_f64(&t.sum[a][i], v);
+      } else {
+        long long m = 0x7fffffffffffffffLL;
+        for (uint32_t r = 0; r < R; r++) { SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes; const long long o = (long long)pb_sh_ld_u64(z.acc(st.acc_of[a], i)); m = o < m ? o : m; }
+        if (m != 0x7fffffffffffffffLL) pb_red_min_s64(&t.mm[a][i], m);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 2c: pb_agg_rows_kernel — the aggregation of the common query shape, specialised at plan time: a dense group table
+// whose keys are dictionary columns and whose aggregation inputs are COUNT(*) or numeric columns, every one of them a field
+// of the segments' ROW GROUPS (dictIds for the keys, decoded values for the inputs).  A matching doc is then one row: no
+// per-column descriptors, no dictionary lookups, no bounds checks -- ~90 instructions per doc instead of the ~400 of the
+// general kernel, which was instruction- and latency-bound (ncu, profiles/r2_kernels.md).  RW = 32-bit words per row.
+// Table update: the CTA-private shared-memory table (SmemTable) when the launch carries one and has enough matches, else
+// reductions into the global table.
+// ------------------------------------------------------------------------------------------------
+struct DevRowKey { uint32_t off, bits; uint64_t mult; const int32_t* remap; };
+struct DevRowAgg { uint32_t off, width, type, pad; };        // width 4 / 8 bytes, type PB_INT .. PB_DOUBLE; unused for COUNT(*)
+struct DevRowSeg {
+  const uint32_t* rows;
+  uint64_t doc_base;
+  int32_t table, pad;
+  DevRowKey keys[PB_MAX_GROUP_BY];
+  DevRowAgg aggs[PB_MAX_AGGS];
+};
+#define PB_ROWS_SMEM_SEGS 16
+
+template <int RW>
+__global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_rows_kernel(const __grid_constant__ DevQuery Q, const DevRowSeg* __restrict__ gsegs) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ DevRowSeg s_segs[PB_ROWS_SMEM_SEGS];
+  __shared__ unsigned long long s_doc_base[PB_AGG_MAX_SEGS_SMEM + 1];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_segs = Q.n_segs, nG = Q.n_group_by, nA = Q.n_aggs;
+  const int n_smem = n_segs < PB_AGG_MAX_SEGS_SMEM ? n_segs : PB_AGG_MAX_SEGS_SMEM;
+  for (int i = tid; i < n_smem; i += PB_AGG_SMEM_THREADS) s_doc_base[i] = gsegs[i].doc_base;
+  const bool segs_in_smem = n_segs <= PB_ROWS_SMEM_SEGS;
+  if (segs_in_smem) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gsegs);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_segs);
+    for (int i = tid; i < (int)(sizeof(DevRowSeg) / 4) * n_segs; i += PB_AGG_SMEM_THREADS) dst[i] = src[i];
+  }
+  const DevRowSeg* segs = segs_in_smem ? s_segs : gsegs;
+  const unsigned long long n = Q.match_all ? Q.n_docs_total : *Q.match_count;
+  // shared-memory table (one table per launch) when it pays
+  const uint32_t S = (uint32_t)Q.st_slots, R = (uint32_t)(Q.st_replicas > 0 ? Q.st_replicas : 1);
+  SmemTable st;
+  st.S = S;
+  int n_acc = 0;
+  for (int a = 0; a < PB_MAX_AGGS; a++) {
+    const int op = a < nA ? Q.agg_op[a] : 0;
+    st.acc_of[a] = (a < nA && op >= 1 && op <= 4) ? (int8_t)n_acc++ : (int8_t)-1;
+    st.fc_of[a] = -1;
+  }
+  st.n_fc = 0;
+  const size_t rep_bytes = pb_smem_table_bytes(S, 0, n_acc);
+  const uint32_t smem0 = pb_smem_u32(smem_raw);
+  st.base = smem0 + ((uint32_t)warp & (R - 1)) * (uint32_t)rep_bytes;
+  const bool use_smem = S > 0 && n >= Q.st_min_docs;
+  if (use_smem) {
+    for (uint32_t r = 0; r < R; r++) {
+      SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes;
+      for (uint32_t i = tid; i < S; i += PB_AGG_SMEM_THREADS) pb_sh_st_u32(z.cnt(i), 0u);
+      for (int a = 0; a < nA; a++) {
+        if (st.acc_of[a] < 0) continue;
+        const unsigned long long init = (Q.agg_op[a] == 1 || Q.agg_op[a] == 4) ? 0ull : 0x7fffffffffffffffull;
+        for (uint32_t i = tid; i < S; i += PB_AGG_SMEM_THREADS) pb_sh_st_u64(z.acc(st.acc_of[a], i), init);
+      }
+    }
+  }
+  __syncthreads();
+
+  for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += (unsigned long long)gridDim.x * PB_AGG_SMEM_THREADS) {
+    const unsigned long long gdoc = Q.match_all ? i : (unsigned long long)__ldg(Q.match_list + i);
+    int lo = 0, hi = n_segs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      const unsigned long long b = mid < PB_AGG_MAX_SEGS_SMEM ? s_doc_base[mid] : gsegs[mid].doc_base;
+      if (b <= gdoc) lo = mid; else hi = mid - 1;
+    }
+    const DevRowSeg& sg = segs[lo];
+    const uint32_t* __restrict__ row = sg.rows + (gdoc - sg.doc_base) * (unsigned long long)RW;
+    // ---- the row's fields: every load below falls into the row's own 32-byte sector ----
+    uint64_t slot = 0;
+    for (int j = 0; j < nG; j++) {
+      const DevRowKey& k = sg.keys[j];
+      const uint32_t wi = k.off >> 5, sh = k.off & 31u;
+      uint32_t id = __funnelshift_l(pb_bswap32(__ldg(row + wi + 1)), pb_bswap32(__ldg(row + wi)), sh) >> (32u - k.bits);
+      if (k.remap) id = (uint32_t)__ldg(k.remap + id);
+      slot += (uint64_t)id * k.mult;
+    }
+    // the row's value field of aggregation a, widened to double like BlockValSet.getDoubleValuesSV
+    auto value_of = [&](int a) -> double {
+      const DevRowAgg& g = sg.aggs[a];
+      const uint32_t w0 = pb_bswap32(__ldg(row + (g.off >> 5)));
+      if (g.width == 4) return g.type == 2 ? (double)__uint_as_float(w0) : (double)(int32_t)w0;
+      const unsigned long long u = ((unsigned long long)w0 << 32) | pb_bswap32(__ldg(row + (g.off >> 5) + 1));
+      return g.type == 3 ? __longlong_as_double((long long)u) : (double)(long long)u;
+    };
+    // ---- table update ----
+    if (use_smem) {
+      const uint32_t sl = (uint32_t)slot;
+      pb_sh_add_u32(st.cnt(sl), 1u);
+      for (int a = 0; a < nA; a++) {
+        const int op = Q.agg_op[a];
+        if (op == 0) continue;
+        const double v = value_of(a);
+        const uint32_t cell = st.acc(st.acc_of[a], sl);
+        if (op == 1 || op == 4) {
+          unsigned long long old = pb_sh_ld_u64(cell), assumed;
+          do {
+            assumed = old;
+            old = pb_sh_cas_u64(cell, assumed, (unsigned long long)__double_as_longlong(__longlong_as_double((long long)assumed) + v));
+          } while (old != assumed);
+        } else if (v == v) {
+          const long long e = op == 2 ? pb_enc_f64(v) : ~pb_enc_f64(v);
+          long long old = (long long)pb_sh_ld_u64(cell);
+          while (e < old) {
+            const long long seen = (long long)pb_sh_cas_u64(cell, (unsigned long long)old, (unsigned long long)e);
+            if (seen == old) break;
+            old = seen;
+          }
+        }
+      }
+    } else {
+      const DevTable& t = Q.tables[sg.table];
+      pb_red_add_u64(&t.rowcnt[slot], 1ull);
+      if (t.first_doc) asm volatile("red.global.min.u32 [%0], %1;" ::"l"(t.first_doc + slot), "r"((uint32_t)(gdoc - sg.doc_base)));
+      for (int a = 0; a < nA; a++) {
+        const int op = Q.agg_op[a];
+        if (op == 0) continue;
+        const double v = value_of(a);
+        if (op == 1 || op == 4) pb_red_add_f64(&t.sum[a][slot], v);
+        else if (v == v) {
+          const long long e = op == 2 ? pb_enc_f64(v) : ~pb_enc_f64(v);
+          if (e < (long long)pb_ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&t.mm[a][slot]))) pb_red_min_s64(&t.mm[a][slot], e);
+        }
+      }
+    }
+  }
+  if (!use_smem) return;
+  __syncthreads();
+  const DevTable& t = Q.tables[0];
+  for (uint32_t i = tid; i < S; i += PB_AGG_SMEM_THREADS) {
+    unsigned long long c = 0;
+    for (uint32_t r = 0; r < R; r++) { SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes; c += pb_sh_ld_u32(z.cnt(i)); }
+    if (c == 0) continue;
+    pb_red_add_u64(&t.rowcnt[i], c);
+    for (int a = 0; a < nA; a++) {
       if (st.acc_of[a] < 0) continue;
       const int op = Q.agg_op[a];
       if (op == 1 || op == 4) {

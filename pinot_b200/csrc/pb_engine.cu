@@ -949,6 +949,7 @@ struct pb_result_s {
     const DevExpandItem* expand_items = nullptr; int n_expand = 0;
     int U = 2; bool u2_three = false; size_t smem_filter = 0;
     int spec_w = 0, spec_pk = 0;             // > 0: the plan-time specialised filter kernel of that width / predicate kind
+    const DevRowSeg* row_segs = nullptr; int rows_rw = 0;   // agg_kind 4: pb_agg_rows_kernel<rows_rw>
     int agg_kind = 0;                        // 0 none (fused), 1 pb_agg_kernel<6>, 2 pb_agg_kernel<4>, 3 pb_agg_smem_kernel
     size_t smem_agg = 0;
     const DevLaneWeights* lane_w = nullptr; int n_lanes = 0, n_segs = 0;
@@ -1409,7 +1410,11 @@ static int enqueue_all(pb_result_s* r, const std::vector<cudaEvent_t>* seg_wait)
     }
     if (wi + 1 == rp.waves.size() || rp.waves.size() == 1) CU(cudaEventRecord(r->evm, st));   // (waves interleave: the split is only exact for one wave)
     if (w.grid_agg > 0) {
-      if (rp.agg_kind == 3) pb_agg_smem_kernel<<<w.grid_agg, PB_AGG_SMEM_THREADS, rp.smem_agg, st>>>(w.dq);
+      if (rp.agg_kind == 4) {
+        if (rp.rows_rw == 2) pb_agg_rows_kernel<2><<<w.grid_agg, PB_AGG_SMEM_THREADS, rp.smem_agg, st>>>(w.dq, rp.row_segs);
+        else if (rp.rows_rw == 4) pb_agg_rows_kernel<4><<<w.grid_agg, PB_AGG_SMEM_THREADS, rp.smem_agg, st>>>(w.dq, rp.row_segs);
+        else pb_agg_rows_kernel<8><<<w.grid_agg, PB_AGG_SMEM_THREADS, rp.smem_agg, st>>>(w.dq, rp.row_segs);
+      } else if (rp.agg_kind == 3) pb_agg_smem_kernel<<<w.grid_agg, PB_AGG_SMEM_THREADS, rp.smem_agg, st>>>(w.dq);
       else if (rp.agg_kind == 2) pb_agg_kernel<4><<<w.grid_agg, PB_NTHREADS, rp.smem_agg, st>>>(w.dq);
       else pb_agg_kernel<6><<<w.grid_agg, PB_NTHREADS, rp.smem_agg, st>>>(w.dq);
       r->launches++;
@@ -1884,7 +1889,8 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   lap(1);
   // ---- query arena (descriptors + leaf payloads) ----
   size_t arena_cap = (sizeof(DevQuery) + 16) * (1 + PB_MAX_WAVES) + 256 + (sizeof(DevSegQuery) + 64) * (size_t)n_segs + (sizeof(DevTable) + 64) * (size_t)n_tables
-                     + 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 64 + (nF > 0 ? (sizeof(DevLaneWeights) + 16) * (size_t)n_segs : 0);
+                     + 8 * PB_COUNTERS_PER_TABLE * (size_t)n_tables + 64 + (nF > 0 ? (sizeof(DevLaneWeights) + 16) * (size_t)n_segs : 0)
+                     + (sizeof(DevRowSeg) + 16) * (size_t)n_segs;
   size_t bitmap_words_total = 0;
   for (int si = 0; si < n_segs; si++) {
     const pb_segment_query& sq = sqs[si];
@@ -2144,6 +2150,50 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     }
   }
 
+  // ---- plan-time specialisation of the aggregation (pb_agg_rows_kernel): a dense table, every key a dictionary column
+  // and every aggregation COUNT(*) or a numeric column, all of them fields of row groups of one stride ----
+  const DevRowSeg* d_row_segs = nullptr;
+  int rows_rw = 0;
+  {
+    static const bool rows_on = []() { const char* e = getenv("PB_AGG_ROWS"); return !e || atoi(e) != 0; }();
+    bool ok = rows_on && table_mode == T_DENSE && nF == 0 && nG > 0 && n_segs > 0;
+    for (int si = 0; si < n_segs && ok; si++) {
+      const RowGroup* rg = seg_rg[si];
+      if (!rg || (rows_rw && rows_rw != rg->stride_bits / 32)) { ok = false; break; }
+      rows_rw = rg->stride_bits / 32;
+      for (int j = 0; j < nG && ok; j++) if (rg->find(gcol[si][j], 0) < 0) ok = false;
+      for (int a = 0; a < nA && ok; a++) {
+        const int op = q->aggregations[a].op;
+        if (op == PB_AGG_COUNT) continue;
+        if (op == PB_AGG_DISTINCTCOUNT || rg->find(acol[si][a], 1) < 0) ok = false;
+      }
+    }
+    if (ok) {
+      DevRowSeg* h_rs = nullptr;
+      d_row_segs = ar.put<DevRowSeg>(nullptr, (size_t)n_segs, &h_rs);
+      if (!d_row_segs) return fail(PB_ERR_STATE, "query arena overflow");
+      for (int si = 0; si < n_segs; si++) {
+        const RowGroup* rg = seg_rg[si];
+        const pb_segment_s* sg = g->segs[si];
+        DevRowSeg& rs = h_rs[si];
+        rs.rows = reinterpret_cast<const uint32_t*>(rg->d_rows);
+        rs.table = hsegs[si].table;
+        for (int j = 0; j < nG; j++) {
+          const DevKeyCol& kc = hsegs[si].keys[j];
+          rs.keys[j].off = (uint32_t)rg->bit_off[(size_t)rg->find(gcol[si][j], 0)];
+          rs.keys[j].bits = (uint32_t)sg->cols[gcol[si][j]].bits;
+          rs.keys[j].mult = kc.mult; rs.keys[j].remap = kc.remap;
+        }
+        for (int a = 0; a < nA; a++) {
+          if (q->aggregations[a].op == PB_AGG_COUNT) continue;
+          const Column& c = sg->cols[acol[si][a]];
+          rs.aggs[a].off = (uint32_t)rg->bit_off[(size_t)rg->find(acol[si][a], 1)];
+          rs.aggs[a].width = (uint32_t)c.entry_bytes; rs.aggs[a].type = (uint32_t)c.type;
+        }
+      }
+    } else rows_rw = 0;
+  }
+
   // ---- work-unit geometry: one stage = one unit (U x 1024 docs) of every scan slot, per warp ----
   int sum_bits = 0;
   for (int k = 0; k < n_slots_max; k++) sum_bits += slot_bits_max[k];
@@ -2173,6 +2223,10 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     n_chunks += hsegs[si].n_units;
     n_docs_total += (uint64_t)g->segs[si]->num_docs;
     if (sqs[si].num_filter_nodes != 0) match_all = false;
+  }
+  if (d_row_segs) {
+    DevRowSeg* h_rs = reinterpret_cast<DevRowSeg*>(ar.host.data() + (reinterpret_cast<const uint8_t*>(d_row_segs) - ar.dev));
+    for (int si = 0; si < n_segs; si++) h_rs[si].doc_base = hsegs[si].doc_base;
   }
   if (n_docs_total >= (1ull << 32)) return fail(PB_ERR_UNSUPPORTED, "%llu docs in one call (match list is 32-bit): split the segment group", (unsigned long long)n_docs_total);
   // ---- how the matches reach the group table (see pb_device.cuh):
@@ -2272,6 +2326,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   for (int k = 0; k < n_slots_max; k++) hq->slot_off[k] = slot_offs[k];
   hq->stage_bytes = (int32_t)stage_bytes;
   hq->set_cache_bytes = set_cache_max;
+  hq->out_cap = PB_OUT_CAP; hq->cand_cap = PB_CAND_CAP;
   hq->cand_bytes = any_cand_leaf ? (int32_t)(2 * PB_CAND_CAP * PB_NWARPS) : 0;   // u16 offsets inside the unit, one list per warp
   hq->use_tma = (q->flags & PB_Q_NO_TMA) ? 0 : 1;
   hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
@@ -2358,14 +2413,21 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       CU(cudaFuncSetAttribute(pb_agg_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       CU(cudaFuncSetAttribute(pb_agg_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       CU(cudaFuncSetAttribute(pb_agg_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 16 * 1024));
+      CU(cudaFuncSetAttribute(pb_agg_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 32 * 1024));
+      CU(cudaFuncSetAttribute(pb_agg_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 32 * 1024));
+      CU(cudaFuncSetAttribute(pb_agg_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 32 * 1024));
       ctx->smem_attr_set = true;
     }
   }
+  auto filter_smem = [&](int out_cap, int cand_cap) {
+    return ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + (any_cand_leaf ? (size_t)2 * cand_cap * PB_NWARPS : 0) +
+           (size_t)PB_NWARPS * out_cap * 4 + stage_bytes * PB_NSTAGE * PB_NWARPS;
+  };
   size_t smem = 0;
   uint64_t max_ctas = 0;
   bool u2_three = false;
   if (!match_all && n_chunks > 0) {
-    smem = ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + (size_t)hq->cand_bytes + (size_t)PB_NWARPS * PB_OUT_CAP * 4 + stage_bytes * PB_NSTAGE * PB_NWARPS;
+    smem = filter_smem(PB_OUT_CAP, PB_CAND_CAP);
     if (smem > 227 * 1024) return fail(PB_ERR_UNSUPPORTED, "filter kernel needs %zu bytes of shared memory", smem);
     int occ = 1;
     // U = 2 comes in two register budgets: 3 CTAs/SM (80 registers) when three stages sets fit shared memory, else 2 CTAs/SM
@@ -2401,9 +2463,17 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
         w = lf.bits; pk = k;
       }
       if (ok && w > 0 && pb_filter_spec_available(w, pk)) {
+        // the specialised kernel needs 64 registers: a fourth CTA fits an SM when its shared memory does -- halve the
+        // per-warp output buffer and candidate list for that (more flushes / candidate passes, both cheap)
+        size_t smem_spec = smem;
+        int oc = PB_OUT_CAP, cc = PB_CAND_CAP;
+        if (4 * (filter_smem(PB_OUT_CAP / 2, PB_CAND_CAP / 2) + 1024) <= 227 * 1024 && 4 * (smem + 1024) > 227 * 1024) { oc /= 2; cc /= 2; smem_spec = filter_smem(oc, cc); }
         int occ = 0;
-        if (pb_filter_spec_prepare(w, pk, smem, &occ) == cudaSuccess && occ >= 1) { spec_w = w; spec_pk = pk; max_ctas = (uint64_t)ctx->num_sms * (uint64_t)occ; }
-        else cudaGetLastError();
+        if (pb_filter_spec_prepare(w, pk, smem_spec, &occ) == cudaSuccess && occ >= 1) {
+          spec_w = w; spec_pk = pk; max_ctas = (uint64_t)ctx->num_sms * (uint64_t)occ; smem = smem_spec;
+          hq->out_cap = oc; hq->cand_cap = cc; hq->cand_bytes = any_cand_leaf ? (int32_t)(2 * cc * PB_NWARPS) : 0;
+          for (auto& wv : waves) { wv.dq.out_cap = oc; wv.dq.cand_cap = cc; wv.dq.cand_bytes = hq->cand_bytes; }
+        } else cudaGetLastError();
       }
     }
   }
@@ -2422,8 +2492,9 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     pb_result_s::Replay& rp = r->rp;
     rp.expand_items = d_expand_items; rp.n_expand = n_expand_items;
     rp.U = U; rp.u2_three = u2_three; rp.smem_filter = smem; rp.spec_w = spec_w; rp.spec_pk = spec_pk;
-    rp.agg_kind = (fuse || n_docs_total == 0) ? 0 : use_smem_table ? 3 : agg_occ == 4 ? 2 : 1;
-    rp.smem_agg = use_smem_table ? (size_t)st_replicas * st_rep_bytes : smem2;
+    rp.agg_kind = (fuse || n_docs_total == 0) ? 0 : d_row_segs ? 4 : use_smem_table ? 3 : agg_occ == 4 ? 2 : 1;
+    rp.smem_agg = (use_smem_table && rp.agg_kind >= 3) ? (size_t)st_replicas * st_rep_bytes : rp.agg_kind == 4 ? 0 : smem2;
+    rp.row_segs = d_row_segs; rp.rows_rw = rows_rw;
     rp.lane_w = d_lane_w; rp.n_lanes = 1 + nF; rp.n_segs = n_segs;
     rp.flags = q->flags;
     for (const Wave& w : waves) {
@@ -2431,7 +2502,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       wl.dq = w.dq; wl.seg_lo = w.seg_lo; wl.seg_hi = w.seg_hi; wl.n_units = w.n_units; wl.n_docs = w.n_docs;
       // every CTA gets a contiguous range of chunks; keep at least one chunk per warp
       wl.grid_filter = (!match_all && w.n_units > 0) ? (int)std::min<uint64_t>(std::max<uint64_t>((w.n_units + PB_NWARPS - 1) / PB_NWARPS, 1), max_ctas) : 0;
-      if (rp.agg_kind == 3) wl.grid_agg = (int)std::min<uint64_t>(std::max<uint64_t>((w.n_docs + PB_AGG_SMEM_THREADS - 1) / PB_AGG_SMEM_THREADS, 1), (uint64_t)ctx->num_sms);
+      if (rp.agg_kind >= 3) wl.grid_agg = (int)std::min<uint64_t>(std::max<uint64_t>((w.n_docs + PB_AGG_SMEM_THREADS - 1) / PB_AGG_SMEM_THREADS, 1), (uint64_t)ctx->num_sms);
       else if (rp.agg_kind) wl.grid_agg = (int)std::min<uint64_t>(std::max<uint64_t>((w.n_docs + PB_NTHREADS - 1) / PB_NTHREADS, 1), max2);
       if (w.n_docs == 0) wl.grid_agg = 0;
       rp.waves.push_back(wl);

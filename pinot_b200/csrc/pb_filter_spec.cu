@@ -1,4 +1,4 @@
-// pb_filter_spec.cu — the specialised instantiations of pb_filter_kernel<2, 3, W, PK> (see the template's comment in
+// pb_filter_spec.cu — the specialised instantiations of pb_filter_kernel<2, 4, W, PK> (see the template's comment in
 // pb_device.cuh): one small kernel per bit width 1..20 that is not a byte multiple and per predicate kind.  The GPU analogue
 // of FixedBitIntReader's one-class-per-width readers (SEGL/io/reader/impl/FixedBitIntReader.java:121-146), taken one step
 // further: the predicate is compiled in as well.
@@ -19,9 +19,9 @@ bool pb_filter_spec_available(int width, int pred_kind) {
 
 template <int W, int PK>
 static cudaError_t prepare_one(size_t smem, int* ctas) {
-  cudaError_t e = cudaFuncSetAttribute(pb_filter_kernel<2, 3, W, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(pb_filter_kernel<2, 4, W, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, pb_filter_kernel<2, 3, W, PK>, PB_NTHREADS, smem);
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas, pb_filter_kernel<2, 4, W, PK>, PB_NTHREADS, smem);
 }
 
 cudaError_t pb_filter_spec_prepare(int width, int pred_kind, size_t smem, int* ctas_per_sm) {
@@ -37,8 +37,8 @@ cudaError_t pb_filter_spec_launch(int width, int pred_kind, int grid, size_t sme
   switch (width) {
 #define X(W)                                                                              \
   case W:                                                                                 \
-    if (pred_kind == 0) pb_filter_kernel<2, 3, W, 0><<<grid, PB_NTHREADS, smem, st>>>(*q); \
-    else pb_filter_kernel<2, 3, W, 1><<<grid, PB_NTHREADS, smem, st>>>(*q);                \
+    if (pred_kind == 0) pb_filter_kernel<2, 4, W, 0><<<grid, PB_NTHREADS, smem, st>>>(*q); \
+    else pb_filter_kernel<2, 4, W, 1><<<grid, PB_NTHREADS, smem, st>>>(*q);                \
     return cudaGetLastError();
     PB_SPEC_WIDTHS(X)
 #undef X

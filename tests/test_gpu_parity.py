@@ -497,7 +497,7 @@ def test_order_by_limit_trim_on_the_device():
     g = native.SegmentGroup(staged)
     opts = "SET groupTrimThreshold = 100; SET minServerGroupTrimSize = 20; SET minSegmentGroupTrimSize = 30; "
     for tail in ("ORDER BY SUM(m0) DESC LIMIT 3", "ORDER BY SUM(m0) ASC LIMIT 3", "ORDER BY COUNT(*) DESC LIMIT 2", "ORDER BY MIN(m1) ASC LIMIT 1",
-                 "ORDER BY MAX(m1) DESC, d1 LIMIT 4", "ORDER BY AVG(m0) DESC LIMIT 3", "ORDER BY d2 DESC, c3 ASC LIMIT 2", "ORDER BY c3 LIMIT 1"):
+                 "ORDER BY MAX(m1) DESC, d2 LIMIT 4", "ORDER BY AVG(m0) DESC LIMIT 3", "ORDER BY d2 DESC, c3 ASC LIMIT 2", "ORDER BY c3 LIMIT 1"):
         sql = opts + "SELECT c3, d2, SUM(m0), COUNT(*), MIN(m1), MAX(m1), AVG(m0) FROM t WHERE c2 >= 0 GROUP BY c3, d2 " + tail
         q = parse_sql(sql)
         orc = [oracle.execute(s, q) for s in segs]
