@@ -1566,34 +1566,32 @@ __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_rows_kernel(con
   }
   __syncthreads();
 
-  for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += (unsigned long long)gridDim.x * PB_AGG_SMEM_THREADS) {
-    const unsigned long long gdoc = Q.match_all ? i : (unsigned long long)__ldg(Q.match_list + i);
-    int lo = 0, hi = n_segs - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      const unsigned long long b = mid < PB_AGG_MAX_SEGS_SMEM ? s_doc_base[mid] : gsegs[mid].doc_base;
-      if (b <= gdoc) lo = mid; else hi = mid - 1;
-    }
-    const DevRowSeg& sg = segs[lo];
-    const uint32_t* __restrict__ row = sg.rows + (gdoc - sg.doc_base) * (unsigned long long)RW;
-    // ---- the row's fields: every load below falls into the row's own 32-byte sector ----
+  // One doc = one row, fetched with ONE vector load (rows never straddle a 32-byte sector) and taken apart in registers:
+  // the aggregation is latency-bound (ncu: 34 warps waiting on memory per issue slot when every field was its own load),
+  // so the chain per doc is kept at match list -> row -> remap, and every thread works on two docs at a time.
+  auto process = [&](unsigned long long gdoc, const uint32_t (&w)[RW], const DevRowSeg& sg) {
+    auto field = [&](uint32_t off, uint32_t bits) -> uint32_t {
+      const uint32_t wi = off >> 5, sh = off & 31u;
+      uint32_t hi = w[0], lo = RW > 1 ? w[1 % RW] : 0u;
+#pragma unroll
+      for (int k = 1; k < RW; k++) if (wi == (uint32_t)k) { hi = w[k]; lo = k + 1 < RW ? w[(k + 1) % RW] : 0u; }
+      return __funnelshift_l(lo, hi, sh) >> (32u - bits);
+    };
     uint64_t slot = 0;
     for (int j = 0; j < nG; j++) {
       const DevRowKey& k = sg.keys[j];
-      const uint32_t wi = k.off >> 5, sh = k.off & 31u;
-      uint32_t id = __funnelshift_l(pb_bswap32(__ldg(row + wi + 1)), pb_bswap32(__ldg(row + wi)), sh) >> (32u - k.bits);
+      uint32_t id = field(k.off, k.bits);
       if (k.remap) id = (uint32_t)__ldg(k.remap + id);
       slot += (uint64_t)id * k.mult;
     }
     // the row's value field of aggregation a, widened to double like BlockValSet.getDoubleValuesSV
     auto value_of = [&](int a) -> double {
       const DevRowAgg& g = sg.aggs[a];
-      const uint32_t w0 = pb_bswap32(__ldg(row + (g.off >> 5)));
+      const uint32_t w0 = field(g.off, 32u);
       if (g.width == 4) return g.type == 2 ? (double)__uint_as_float(w0) : (double)(int32_t)w0;
-      const unsigned long long u = ((unsigned long long)w0 << 32) | pb_bswap32(__ldg(row + (g.off >> 5) + 1));
+      const unsigned long long u = ((unsigned long long)w0 << 32) | field(g.off + 32u, 32u);
       return g.type == 3 ? __longlong_as_double((long long)u) : (double)(long long)u;
     };
-    // ---- table update ----
     if (use_smem) {
       const uint32_t sl = (uint32_t)slot;
       pb_sh_add_u32(st.cnt(sl), 1u);
@@ -1627,12 +1625,44 @@ __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_rows_kernel(con
         if (op == 0) continue;
         const double v = value_of(a);
         if (op == 1 || op == 4) pb_red_add_f64(&t.sum[a][slot], v);
-        else if (v == v) {
-          const long long e = op == 2 ? pb_enc_f64(v) : ~pb_enc_f64(v);
-          if (e < (long long)pb_ld_volatile_u64(reinterpret_cast<const unsigned long long*>(&t.mm[a][slot]))) pb_red_min_s64(&t.mm[a][slot], e);
-        }
+        else if (v == v) pb_red_min_s64(&t.mm[a][slot], op == 2 ? pb_enc_f64(v) : ~pb_enc_f64(v));   // (few matches: a read-before-RED would only add a dependent L2 round trip)
       }
     }
+  };
+  auto seg_of = [&](unsigned long long gdoc) -> int {
+    int lo = 0, hi = n_segs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      const unsigned long long b = mid < PB_AGG_MAX_SEGS_SMEM ? s_doc_base[mid] : gsegs[mid].doc_base;
+      if (b <= gdoc) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+  };
+  auto load_row = [&](const DevRowSeg& sg, unsigned long long gdoc, uint32_t (&w)[RW]) {
+    const uint32_t* __restrict__ row = sg.rows + (gdoc - sg.doc_base) * (unsigned long long)RW;
+    if (RW == 2) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(row)); w[0] = v.x; w[1 % RW] = v.y; }
+    else {
+#pragma unroll
+      for (int q4 = 0; q4 < RW / 4; q4++) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + q4);
+        w[(4 * q4) % RW] = v.x; w[(4 * q4 + 1) % RW] = v.y; w[(4 * q4 + 2) % RW] = v.z; w[(4 * q4 + 3) % RW] = v.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RW; k++) w[k] = pb_bswap32(w[k]);
+  };
+  const unsigned long long stride = (unsigned long long)gridDim.x * PB_AGG_SMEM_THREADS;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += 2 * stride) {
+    const bool two = i + stride < n;
+    const unsigned long long gdoc0 = Q.match_all ? i : (unsigned long long)__ldg(Q.match_list + i);
+    const unsigned long long gdoc1 = !two ? gdoc0 : (Q.match_all ? i + stride : (unsigned long long)__ldg(Q.match_list + i + stride));
+    const DevRowSeg& sg0 = segs[seg_of(gdoc0)];
+    const DevRowSeg& sg1 = segs[seg_of(gdoc1)];
+    uint32_t w0[RW], w1[RW];
+    load_row(sg0, gdoc0, w0);
+    load_row(sg1, gdoc1, w1);
+    process(gdoc0, w0, sg0);
+    if (two) process(gdoc1, w1, sg1);
   }
   if (!use_smem) return;
   __syncthreads();

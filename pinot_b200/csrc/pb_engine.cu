@@ -1796,7 +1796,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       }
     }
     zero_bytes = (zero_bytes + 255) & ~(size_t)255;
-    if (table_mode == T_HASH) ff_bytes += 8 * S * (size_t)key_words;
+    if (table_mode == T_HASH) ff_bytes += (8 * S * (size_t)key_words + 15) & ~(size_t)15;      // (every piece of the 0xFF region starts 16-byte aligned: CAS.128)
     if (track_first) ff_bytes += (4 * S + 15) & ~(size_t)15;
   }
   const size_t seg_stats_bytes = nF > 0 ? 8 * (size_t)(1 + PB_MAX_AGG_FILTERS) * (size_t)n_segs : 0;   // swim-lane statistics per segment
@@ -1857,7 +1857,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       }
       if (t == 0) { r->span_mm = d_mm; r->span_mm_n = (int64_t)mo; }
       zo = (zo + 255) & ~(size_t)255;
-      if (table_mode == T_HASH) { dt.hkeys = reinterpret_cast<unsigned long long*>(d_ff + fo); fo += 8 * S * (size_t)key_words; dt.key_words = key_words; }
+      if (table_mode == T_HASH) { dt.hkeys = reinterpret_cast<unsigned long long*>(d_ff + fo); fo += (8 * S * (size_t)key_words + 15) & ~(size_t)15; dt.key_words = key_words; }
       if (track_first) { dt.first_doc = reinterpret_cast<uint32_t*>(d_ff + fo); fo += (4 * S + 15) & ~(size_t)15; }
       for (int a = 0; a < nA; a++)
         if (dc_raw[a]) { dt.dset[a] = reinterpret_cast<unsigned long long*>(d_ff + fo); dt.dset_mask[a] = tm.dset_cap[a] - 1; fo += 16 * tm.dset_cap[a]; }
