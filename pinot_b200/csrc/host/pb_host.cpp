@@ -401,6 +401,45 @@ extern "C" int pbh_execute(pb_segment_group_handle g, const pbh_query_context* q
   std::vector<LoweredSegment> lowered(segs.size());
   std::vector<pb_segment_query> sq(segs.size());
   if (q->num_agg_filters < 0 || (q->num_agg_filters > 0 && (!q->agg_filters || !q->agg_filter_of))) return pbi_fail(PB_ERR_INVALID, "bad FILTER clauses");
+  // ---- plan cache, host side: the byte image of the unlowered query is the key; a hit replays the parked plan without
+  // running FilterPlanNode / the predicate lowering for any segment ----
+  std::string host_key;
+  {
+    auto put = [&](const void* p, size_t n) { host_key.append(static_cast<const char*>(p), n); };
+    auto pod = [&](int64_t v) { put(&v, sizeof v); };
+    auto str = [&](const char* c) { if (!c) { pod(-1); return; } const size_t n = strlen(c); pod((int64_t)n); put(c, n); };
+    auto program = [&](int32_t n_nodes, const pbh_filter_node* nodes, const pbh_predicate* preds) {
+      pod(n_nodes);
+      for (int32_t i = 0; i < n_nodes; i++) {
+        pod(nodes[i].kind); pod(nodes[i].num_children); pod(nodes[i].predicate);
+        if (nodes[i].kind == PBH_PREDICATE) {
+          const pbh_predicate& p = preds[nodes[i].predicate];
+          pod(p.type); str(p.column); pod(p.num_values);
+          for (int32_t k = 0; k < p.num_values; k++) str(p.values[k]);
+          str(p.lower); str(p.upper); pod(p.lower_inclusive); pod(p.upper_inclusive);
+        }
+      }
+    };
+    pod(flags);
+    program(q->num_filter_nodes, q->filter_nodes, q->predicates);
+    pod(q->num_group_by);
+    for (int32_t j = 0; j < q->num_group_by; j++) str(q->group_by_columns[j]);
+    pod(q->num_aggregations);
+    for (int32_t a = 0; a < q->num_aggregations; a++) { pod(q->aggregations[a].op); str(q->aggregations[a].column); }
+    pod(q->num_groups_limit); pod(q->max_initial_result_holder_capacity);
+    pod(q->num_skip_inverted);
+    for (int32_t k = 0; k < q->num_skip_inverted; k++) str(q->skip_inverted_columns[k]);
+    pod(q->num_agg_filters);
+    for (int32_t f = 0; f < q->num_agg_filters; f++) program(q->agg_filters[f].num_filter_nodes, q->agg_filters[f].filter_nodes, q->agg_filters[f].predicates);
+    if (q->num_agg_filters > 0) for (int32_t a = 0; a < q->num_aggregations; a++) pod(q->agg_filter_of[a]);
+    pod(q->num_order_by); pod(q->trim_size); pod(q->trim_threshold);
+    for (int32_t k = 0; k < q->num_order_by; k++) { pod(q->order_by[k].kind); pod(q->order_by[k].index); pod(q->order_by[k].descending); }
+    pb_query_desc d0;
+    memset(&d0, 0, sizeof d0);
+    d0.flags = flags;
+    const int hit = pbi_plan_replay(g, host_key, &d0, out);
+    if (hit != 0) return hit < 0 ? hit : PB_OK;
+  }
   std::vector<LoweredSegment> clauseLowered(segs.size() * (size_t)q->num_agg_filters);
   std::vector<std::vector<const pb_filter_node*>> clausePtr(segs.size());
   std::vector<std::vector<int32_t>> clauseLen(segs.size());
@@ -436,7 +475,10 @@ extern "C" int pbh_execute(pb_segment_group_handle g, const pbh_query_context* q
   d.flags = flags;
   d.num_agg_filters = q->num_agg_filters; d.agg_filter_of = q->agg_filter_of;
   d.num_order_by = q->num_order_by; d.order_by = q->order_by; d.trim_size = q->trim_size; d.trim_threshold = q->trim_threshold;
-  return pb_query_execute(g, sq.data(), &d, out);
+  pbi_set_pending_host_key(host_key);
+  rc = pb_query_execute(g, sq.data(), &d, out);
+  pbi_set_pending_host_key(std::string());
+  return rc;
 }
 
 extern "C" int pbh_explain_filter(pb_segment_group_handle g, int32_t si, const pbh_query_context* q, char* buf, int32_t cap) {

@@ -2152,7 +2152,7 @@ static __global__ void pb_finalize_kernel(const DevFinalize F) {
     if (!emit) continue;
     const uint64_t k = base + __popc(b & ((1u << lane) - 1u));
     if (k >= F.cap_out) continue;
-    F.out_slots[k] = i;
+    if (F.out_slots) F.out_slots[k] = i;          // (only DISTINCTCOUNT hand-back needs the slot of a row)
     F.out_rows[k] = c;
     for (int a = 0; a < F.n_aggs; a++) {
       const DevFinAgg& fa = F.aggs[a];
@@ -2166,7 +2166,7 @@ static __global__ void pb_finalize_kernel(const DevFinalize F) {
       else if (fa.op == 0) fa.out[k] = fa.fcnt ? (double)fa.fcnt[i] : (double)c;
       // the aggregation's long array: COUNT value / AVG denominator (the function's own row count under a FILTER clause), 0 otherwise
       if (fa.op == 5 && fa.dcnt) fa.out_cnt[k] = (long long)fa.dcnt[i];
-      if (fa.op != 5) fa.out_cnt[k] = (fa.op == 0 || fa.op == 4) ? (fa.fcnt ? (long long)fa.fcnt[i] : (long long)c) : 0ll;
+      if (fa.op != 5 && fa.out_cnt) fa.out_cnt[k] = (fa.op == 0 || fa.op == 4) ? (fa.fcnt ? (long long)fa.fcnt[i] : (long long)c) : 0ll;
     }
     unsigned long long key = 0, key_hi = 0;
     if (F.mode == T_HASH) {

@@ -147,6 +147,17 @@ static int init_devices(const int* device_ids, int n_devices, size_t hbm_cache_b
         cudaSetDevice(ctxs[i]->device);
         cudaError_t pe = cudaDeviceEnablePeerAccess(ctxs[k]->device, 0);
         if (pe != cudaSuccess) cudaGetLastError();   // already enabled / unsupported: the merge falls back to copies
+        // the tables live in device k's stream-ordered memory pool: pools keep their own access lists
+        // (cudaDeviceEnablePeerAccess does not cover them), so device i is granted read / write access to it explicitly
+        cudaMemPool_t pool_k;
+        if (cudaDeviceGetDefaultMemPool(&pool_k, ctxs[k]->device) == cudaSuccess) {
+          cudaMemAccessDesc desc;
+          memset(&desc, 0, sizeof desc);
+          desc.location.type = cudaMemLocationTypeDevice;
+          desc.location.id = ctxs[i]->device;
+          desc.flags = cudaMemAccessFlagsProtReadWrite;
+          if (cudaMemPoolSetAccess(pool_k, &desc, 1) != cudaSuccess) cudaGetLastError();
+        }
       }
     }
   cudaSetDevice(prev);
@@ -957,9 +968,12 @@ struct pb_result_s {
     // plan cache
     bool cacheable = false, busy = false;
     std::string sig;
+    std::string host_sig;                    // key of the UNLOWERED query (host planning layer): a hit skips the lowering too
+    uint64_t dict_version = 0; std::vector<uint64_t> seg_epochs;   // what the plan's pointers depend on (checked on a host-key hit)
     pb_group_s* owner = nullptr;             // group whose plan list holds this result (nullptr: not registered / orphaned)
     cudaGraphExec_t graph = nullptr;
     int uses = 0, graph_launches = 0;
+    double comm_ms_sample = 0;               // cross-rank merge time of the plan's last kernel-by-kernel run (graph replays repeat it)
     uint32_t flags = 0;
   } rp;
   bool graph_replayed = false;
@@ -1038,11 +1052,16 @@ static pb_result_s* plan_take(pb_group_s* g, const std::string& sig) {
   return nullptr;
 }
 static void destroy_result(pb_result_s* r);
+static thread_local std::string g_pending_host_key;      // set by the host planning layer around its pb_query_execute call
 static void plan_register(pb_group_s* g, pb_result_s* r, std::string&& sig) {
   std::vector<pb_result_s*> evict;
   {
     std::lock_guard<std::mutex> lk(g_plan_mu);
     r->rp.sig = std::move(sig); r->rp.owner = g; r->rp.busy = true;
+    r->rp.host_sig = g_pending_host_key;
+    r->rp.dict_version = g->dict_version;
+    r->rp.seg_epochs.clear();
+    for (auto* sg : g->segs) r->rp.seg_epochs.push_back(sg->epoch);
     g->plans.push_back(r);
     for (size_t i = 0; g->plans.size() > PB_MAX_PLANS_PER_GROUP && i < g->plans.size();) {      // oldest idle plans go first
       if (!g->plans[i]->rp.busy) { evict.push_back(g->plans[i]); g->plans[i]->rp.owner = nullptr; g->plans.erase(g->plans.begin() + (long)i); }
@@ -1470,12 +1489,17 @@ static int replay_plan(pb_result_s* r, const pb_query_desc* q) {
   const bool all_ranks = (q->flags & PB_Q_ALL_RANKS) != 0;
   r->host_us[0] = now_us() - t0;
   const double t1 = now_us();
-  if (!all_ranks && plan_graph_enabled()) {
+  // a collective query is captured too (NCCL collectives are graph-capturable): every rank replays the same plan the same
+  // number of times, so all of them capture, sample and launch in step.  Hash tables merge with a host round trip and stay eager.
+  static const bool graph_comm = []() { const char* e = getenv("PB_GRAPH_COMM"); return !e || atoi(e) != 0; }();
+  const bool graph_ok = plan_graph_enabled() && (!all_ranks || (graph_comm && r->table_mode != T_HASH && g_comm.comm && g_comm.checked_block_bytes == r->block_bytes));
+  if (graph_ok) {
     if (!rp.graph && rp.uses >= 1) {
       // second reuse: record the whole sequence once
       cudaGraph_t graph = nullptr;
       CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       rc = enqueue_all(r, nullptr);
+      if (!rc && all_ranks) rc = comm_merge(r);
       if (!rc) rc = enqueue_trim(r);
       if (!rc) rc = enqueue_finalize(r);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
@@ -1485,12 +1509,21 @@ static int replay_plan(pb_result_s* r, const pb_query_desc* q) {
       if (e != cudaSuccess) { rp.graph = nullptr; return fail(PB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
       rp.graph_launches = r->launches;
       r->launches = 0;
+      r->merged_ranks = 1; r->comm_timed = false;       // (the capture ran comm_merge's bookkeeping, not the collective)
     }
     // CUDA events recorded inside a graph cannot be timed: every 8th replay is enqueued kernel by kernel instead, which
     // keeps the per-kernel CUDA-event times (pb_result_phase_ms) of a cached plan live; the others report the last sample
     const bool sample = rp.graph && (rp.uses & 7) == 7;
-    if (rp.graph && !sample) { CU(cudaGraphLaunch(rp.graph, st)); r->launches = rp.graph_launches; r->graph_replayed = true; }
-    else { r->graph_replayed = false; if ((rc = enqueue_all(r, nullptr))) return rc; if ((rc = enqueue_trim(r))) return rc; if ((rc = enqueue_finalize(r))) return rc; }
+    if (rp.graph && !sample) {
+      CU(cudaGraphLaunch(rp.graph, st)); r->launches = rp.graph_launches; r->graph_replayed = true;
+      if (all_ranks) { r->merged_ranks *= g_comm.n_ranks; r->comm_timed = true; r->comm_ms = rp.comm_ms_sample; }
+    } else {
+      r->graph_replayed = false;
+      if ((rc = enqueue_all(r, nullptr))) return rc;
+      if (all_ranks && (rc = comm_merge(r))) return rc;
+      if ((rc = enqueue_trim(r))) return rc;
+      if ((rc = enqueue_finalize(r))) return rc;
+    }
   } else {
     if ((rc = enqueue_all(r, nullptr))) return rc;
     if (all_ranks && (rc = comm_merge(r))) return rc;
@@ -2736,12 +2769,17 @@ static int prepare_finalize(pb_result_s* r) {
     if (tm.dev.first_doc) { F.first_doc = tm.dev.first_doc; F.first_thr = r->d_first_thr + t; }
     if (r->trim_size > 0 && mode != T_KEYLESS) { F.okey = r->d_okey[(size_t)t]; F.othr = &r->d_sel[(size_t)t]->thr; }
     F.cursor = r->d_counters + (size_t)t * PB_COUNTERS_PER_TABLE + 3;
-    F.out_slots = (unsigned long long*)tm.slots.p; F.out_rows = (unsigned long long*)tm.rows.p;
+    // every byte of the hand-back crosses PCIe: the slot of a row is only written when a DISTINCTCOUNT will ask for it, and
+    // the long arrays of SUM / MIN / MAX (all zeros) are made on the host when somebody reads them (pb_result_long)
+    bool any_dc = false;
+    for (int a = 0; a < nA; a++) any_dc |= r->agg_op[a] == PB_AGG_DISTINCTCOUNT;
+    F.out_slots = any_dc ? (unsigned long long*)tm.slots.p : nullptr; F.out_rows = (unsigned long long*)tm.rows.p;
     for (int a = 0; a < nA; a++) {
       tm.dbl[a].alloc(8 * cap); tm.lng[a].alloc(8 * cap);
       if (!tm.dbl[a].p || !tm.lng[a].p) return fail(PB_ERR_OOM, "pinned host allocation failed");
       F.aggs[a].op = r->agg_op[a]; F.aggs[a].sum = tm.dev.sum[a]; F.aggs[a].mm = tm.dev.mm[a]; F.aggs[a].out = (double*)tm.dbl[a].p;
-      F.aggs[a].fcnt = tm.dev.fcnt[a]; F.aggs[a].out_cnt = (long long*)tm.lng[a].p; F.aggs[a].dcnt = tm.dev.dcnt[a];
+      const bool lng_on_device = r->agg_op[a] == PB_AGG_COUNT || r->agg_op[a] == PB_AGG_AVG || r->agg_op[a] == PB_AGG_DISTINCTCOUNT;
+      F.aggs[a].fcnt = tm.dev.fcnt[a]; F.aggs[a].out_cnt = lng_on_device ? (long long*)tm.lng[a].p : nullptr; F.aggs[a].dcnt = tm.dev.dcnt[a];
     }
     uint64_t div = 1;
     for (int j = 0; j < nG; j++) {
@@ -2807,6 +2845,7 @@ static int finish_finalize(pb_result_s* r) {
     if (cudaEventElapsedTime(&ms, r->ev1, r->ev2) == cudaSuccess) r->scan_ms = ms;
     if (cudaEventElapsedTime(&ms, r->ev1, r->evm) == cudaSuccess) r->filter_ms = ms;
     if (cudaEventElapsedTime(&ms, r->evm, r->ev2) == cudaSuccess) r->agg_ms = ms;
+    if (r->comm_timed && cudaEventElapsedTime(&ms, r->sset.ev[5], r->sset.ev[6]) == cudaSuccess) { r->comm_ms = ms; r->rp.comm_ms_sample = ms; }
     cudaGetLastError();
   }
 
@@ -2903,7 +2942,13 @@ extern "C" const void* pb_result_group_key_values(pb_result_handle r, int32_t t,
   return tm->key_vals[gb].p;
 }
 extern "C" const double* pb_result_double(pb_result_handle r, int32_t t, int32_t a) { auto* tm = TAB(r, t); return (tm && a >= 0 && a < r->n_aggs) ? (const double*)tm->dbl[a].p : nullptr; }
-extern "C" const int64_t* pb_result_long(pb_result_handle r, int32_t t, int32_t a) { auto* tm = TAB(r, t); return (tm && a >= 0 && a < r->n_aggs) ? (const int64_t*)tm->lng[a].p : nullptr; }
+extern "C" const int64_t* pb_result_long(pb_result_handle r, int32_t t, int32_t a) {
+  auto* tm = TAB(r, t);
+  if (!tm || a < 0 || a >= r->n_aggs) return nullptr;
+  const int op = r->agg_op[a];
+  if (op == PB_AGG_SUM || op == PB_AGG_MIN || op == PB_AGG_MAX) memset(tm->lng[a].p, 0, 8 * (size_t)std::max<int64_t>(tm->num_groups, 1));   // not written by the device
+  return (const int64_t*)tm->lng[a].p;
+}
 // DISTINCTCOUNT value sets, materialised on first access
 static int materialize_distinct(pb_result_s* r, TableMeta& tm, int a) {
   if (tm.dc_off[a].p) return PB_OK;
@@ -3165,3 +3210,26 @@ int pbi_group_segments(pb_segment_group_handle g, std::vector<pb_segment_handle>
   return PB_OK;
 }
 int pbi_fail(int code, const char* msg) { return fail(code, "%s", msg); }
+void pbi_set_pending_host_key(const std::string& key) { g_pending_host_key = key; }
+// Replay the parked plan of an UNLOWERED query (the host layer's key): 1 = replayed (*out set), 0 = no such plan, < 0 = error
+int pbi_plan_replay(pb_segment_group_handle g, const std::string& host_key, const pb_query_desc* q, pb_result_handle* out) {
+  if (!g || !plan_cache_enabled() || !g->children.empty() || !g->ctx || host_key.empty()) return 0;
+  pb_result_s* p = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    for (auto* c : g->plans) {
+      if (c->rp.busy || c->rp.host_sig != host_key || c->rp.dict_version != g->dict_version || c->rp.seg_epochs.size() != g->segs.size()) continue;
+      bool same = true;
+      for (size_t i = 0; i < g->segs.size(); i++) if (c->rp.seg_epochs[i] != g->segs[i]->epoch) { same = false; break; }
+      if (!same) continue;
+      c->rp.busy = true; p = c;
+      break;
+    }
+  }
+  if (!p) return 0;
+  DeviceGuard dg(g->ctx);
+  int rc = replay_plan(p, q);
+  if (rc) { free_result(p); return rc; }
+  *out = p;
+  return 1;
+}

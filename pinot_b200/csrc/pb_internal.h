@@ -21,3 +21,6 @@ struct PbSegmentView {
 int pbi_segment_view(pb_segment_handle seg, PbSegmentView* out);
 int pbi_group_segments(pb_segment_group_handle g, std::vector<pb_segment_handle>* out);
 int pbi_fail(int code, const char* msg);
+// plan cache, host side: the key of the unlowered query lets a repeated query skip the per-segment lowering as well
+void pbi_set_pending_host_key(const std::string& key);
+int pbi_plan_replay(pb_segment_group_handle g, const std::string& host_key, const pb_query_desc* q, pb_result_handle* out);
