@@ -107,8 +107,36 @@ def lib():
         l.orc_read_dict_id.restype = C.c_int32
         l.orc_roaring_to_doc_ids.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
         l.orc_roaring_to_doc_ids.restype = C.c_int64
+        for f in (l.orc_lz4_block_decode, l.orc_snappy_block_decode):
+            f.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+            f.restype = C.c_int64
+        l.orc_raw_forward_decompress.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64]
+        l.orc_raw_forward_decompress.restype = C.c_int64
         _lib = l
     return _lib
+
+
+def raw_forward_decompress(fwd: np.ndarray, width: int) -> np.ndarray:
+    """A chunk-compressed raw forward index rewritten as the equivalent PASS_THROUGH one (orc_raw_forward_decompress)."""
+    fwd = np.ascontiguousarray(fwd, dtype=np.uint8)
+    need = lib().orc_raw_forward_decompress(fwd.ctypes.data, fwd.size, width, None, 0)
+    if need < 0:
+        raise RuntimeError(lib().orc_last_error().decode())
+    out = np.zeros(need, dtype=np.uint8)
+    if lib().orc_raw_forward_decompress(fwd.ctypes.data, fwd.size, width, out.ctypes.data, out.size) != need:
+        raise RuntimeError(lib().orc_last_error().decode())
+    return out
+
+
+def block_decode(codec: str, data: bytes, decoded_size: int) -> bytes:
+    """One LZ4 block / raw Snappy block through the oracle's decoder (tests pin it against pyarrow's codecs)."""
+    src = np.frombuffer(data, dtype=np.uint8)
+    out = np.zeros(max(decoded_size, 1), dtype=np.uint8)
+    f = lib().orc_lz4_block_decode if codec == "lz4" else lib().orc_snappy_block_decode
+    n = f(src.ctypes.data, src.size, out.ctypes.data, decoded_size)
+    if n < 0:
+        raise ValueError("malformed %s block" % codec)
+    return out[:n].tobytes()
 
 
 class _Marshalled:
@@ -132,8 +160,12 @@ def marshal_segment(seg, m: _Marshalled, skip_inverted=()) -> OrcSegment:
         oc.cardinality = c.cardinality
         oc.bits_per_element = c.bits_per_element
         oc.dict_entry_bytes = c.dict_entry_bytes
-        oc.forward_index = c.forward_index.ctypes.data
-        oc.forward_index_len = c.forward_index.size
+        fwd = c.forward_index
+        if not c.has_dictionary and fwd.size >= 28 and int.from_bytes(fwd[0:4].tobytes(), "big") > 1 \
+                and int.from_bytes(fwd[20:24].tobytes(), "big") != 0:
+            fwd = m.hold(raw_forward_decompress(fwd, c.dict_entry_bytes))      # chunk codec -> plain values
+        oc.forward_index = fwd.ctypes.data
+        oc.forward_index_len = fwd.size
         if c.dictionary is not None:
             oc.dictionary = c.dictionary.ctypes.data
             oc.dictionary_len = c.dictionary.size

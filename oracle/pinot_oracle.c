@@ -60,6 +60,110 @@ int32_t orc_read_dict_id(const uint8_t* fwd, int32_t bits, int64_t doc) {
 }
 
 /* ------------------------------------------------------------------ */
+/* chunk codecs of raw forward indexes                                  */
+/* ------------------------------------------------------------------ */
+/* LZ4 block format, as lz4-java's safeDecompressor reads it (SEGL/io/compression/LZ4Decompressor.java:41-52; the format is
+ * the public "LZ4 Block Format Description"): token = literal length : match length - 4, 15 = more length bytes follow (each
+ * adds 0..255, 255 = another one), literals, 2-byte little-endian offset, match copied byte by byte (it may overlap its own
+ * output).  The last sequence stops after its literals.  Returns the decoded size, -1 on a malformed stream. */
+static int64_t lz4_block_decode(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_cap) {
+  int64_t ip = 0, op = 0;
+  while (ip < in_len) {
+    uint32_t token = in[ip++];
+    int64_t lit = token >> 4;
+    if (lit == 15) { uint32_t b; do { if (ip >= in_len) return -1; b = in[ip++]; lit += b; } while (b == 255); }
+    if (ip + lit > in_len || op + lit > out_cap) return -1;
+    memcpy(out + op, in + ip, (size_t)lit); ip += lit; op += lit;
+    if (ip >= in_len) break;
+    if (ip + 2 > in_len) return -1;
+    int64_t off = (int64_t)in[ip] | ((int64_t)in[ip + 1] << 8); ip += 2;
+    int64_t ml = token & 15u;
+    if (ml == 15) { uint32_t b; do { if (ip >= in_len) return -1; b = in[ip++]; ml += b; } while (b == 255); }
+    ml += 4;
+    if (off == 0 || off > op || op + ml > out_cap) return -1;
+    for (int64_t i = 0; i < ml; i++) out[op + i] = out[op + i - off];
+    op += ml;
+  }
+  return op;
+}
+/* raw Snappy block, as snappy-java's Snappy.uncompress reads it (SEGL/io/compression/SnappyDecompressor.java; public
+ * "Snappy compressed format description"): varint decoded length, then elements tagged in their low two bits --
+ * 00 literal (length - 1 in the upper six bits, 60..63 = that many + 1 - 60 length bytes follow), 01 copy with 11-bit offset
+ * and length 4..11, 10 / 11 copy with 2- / 4-byte little-endian offset and length 1..64. */
+static int64_t snappy_block_decode(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_cap) {
+  int64_t ip = 0, op = 0;
+  uint64_t want = 0; int sh = 0;
+  for (;;) { if (ip >= in_len || sh > 28) return -1; uint32_t b = in[ip++]; want |= (uint64_t)(b & 127u) << sh; sh += 7; if (!(b & 128u)) break; }
+  if ((int64_t)want > out_cap) return -1;
+  while (ip < in_len) {
+    uint32_t tag = in[ip++];
+    int64_t len, off;
+    if ((tag & 3u) == 0) {
+      len = tag >> 2;
+      if (len >= 60) { int nb = (int)len - 59; if (ip + nb > in_len) return -1; len = 0; for (int k = 0; k < nb; k++) len |= (int64_t)in[ip + k] << (8 * k); ip += nb; }
+      len += 1;
+      if (ip + len > in_len || op + len > out_cap) return -1;
+      memcpy(out + op, in + ip, (size_t)len); ip += len; op += len;
+      continue;
+    }
+    if ((tag & 3u) == 1) { if (ip + 1 > in_len) return -1; len = 4 + ((tag >> 2) & 7u); off = ((int64_t)(tag >> 5) << 8) | in[ip]; ip += 1; }
+    else { int nb = (tag & 3u) == 2 ? 2 : 4; if (ip + nb > in_len) return -1; len = (tag >> 2) + 1; off = 0; for (int k = 0; k < nb; k++) off |= (int64_t)in[ip + k] << (8 * k); ip += nb; }
+    if (off == 0 || off > op || op + len > out_cap) return -1;
+    for (int64_t i = 0; i < len; i++) out[op + i] = out[op + i - off];
+    op += len;
+  }
+  return op == (int64_t)want ? op : -1;
+}
+int64_t orc_lz4_block_decode(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_cap) { return lz4_block_decode(in, in_len, out, out_cap); }
+int64_t orc_snappy_block_decode(const uint8_t* in, int64_t in_len, uint8_t* out, int64_t out_cap) { return snappy_block_decode(in, in_len, out, out_cap); }
+
+/* BaseChunkForwardIndexReader.decompressChunk for every chunk of a fixed-width single-value raw forward index
+ * (SEGL/segment/index/readers/forward/BaseChunkForwardIndexReader.java:61-160, FixedByteChunkSVForwardIndexReader.java):
+ * rewrites the index as the equivalent PASS_THROUGH one (same version, same chunking) so that the readers below see
+ * plain values.  out == NULL returns the size needed; -1 = malformed / unsupported codec (ZSTANDARD, GZIP). */
+int64_t orc_raw_forward_decompress(const uint8_t* b, int64_t len, int32_t width, uint8_t* out, int64_t out_cap) {
+  if (len < 16) { set_err("raw forward index header"); return -1; }
+  int32_t version = (int32_t)be32(b), num_chunks = (int32_t)be32(b + 4), docs_per_chunk = (int32_t)be32(b + 8);
+  int32_t total_docs, codec, data_header_start;
+  if (version > 1) { if (len < 28) { set_err("raw forward index header"); return -1; } total_docs = (int32_t)be32(b + 16); codec = (int32_t)be32(b + 20); data_header_start = (int32_t)be32(b + 24); }
+  else { set_err("raw forward index v1 carries no doc count"); return -1; }
+  int32_t entry = version <= 2 ? 4 : 8;
+  int64_t raw_start = (int64_t)data_header_start + (int64_t)num_chunks * entry;
+  int64_t need = 28 + (int64_t)num_chunks * entry + (int64_t)total_docs * width;
+  if (!out) return need;
+  if (out_cap < need || raw_start > len) { set_err("raw forward index: buffer"); return -1; }
+  memcpy(out, b, 16);
+  uint8_t hdr[12] = {0};
+  hdr[0] = (uint8_t)(total_docs >> 24); hdr[1] = (uint8_t)(total_docs >> 16); hdr[2] = (uint8_t)(total_docs >> 8); hdr[3] = (uint8_t)total_docs;
+  hdr[11] = 28;                                   /* compression 0, dataHeaderStart 28 */
+  memcpy(out + 16, hdr, 12);
+  int64_t chunk_bytes = (int64_t)docs_per_chunk * width, vals0 = 28 + (int64_t)num_chunks * entry;
+  for (int32_t k = 0; k < num_chunks; k++) {
+    int64_t o = entry == 4 ? (int64_t)be32(b + data_header_start + 4 * (int64_t)k) : (int64_t)be64(b + data_header_start + 8 * (int64_t)k);
+    int64_t e = k + 1 < num_chunks ? (entry == 4 ? (int64_t)be32(b + data_header_start + 4 * (int64_t)(k + 1)) : (int64_t)be64(b + data_header_start + 8 * (int64_t)(k + 1))) : len;
+    int64_t left = (int64_t)total_docs * width - (int64_t)k * chunk_bytes;
+    int64_t want = left < chunk_bytes ? left : chunk_bytes;
+    uint8_t* dst = out + vals0 + (int64_t)k * chunk_bytes;
+    int64_t po = vals0 + (int64_t)k * chunk_bytes;
+    if (entry == 4) { uint8_t* q = out + 28 + 4 * (int64_t)k; q[0] = (uint8_t)(po >> 24); q[1] = (uint8_t)(po >> 16); q[2] = (uint8_t)(po >> 8); q[3] = (uint8_t)po; }
+    else { uint8_t* q = out + 28 + 8 * (int64_t)k; for (int i = 0; i < 8; i++) q[i] = (uint8_t)((uint64_t)po >> (56 - 8 * i)); }
+    if (o < raw_start || e > len || e < o) { set_err("raw forward index: chunk offsets"); return -1; }
+    int64_t got;
+    switch (codec) {
+      case 0: if (e - o < want) { set_err("raw forward index: short chunk"); return -1; } memcpy(dst, b + o, (size_t)want); got = want; break;
+      case 1: got = snappy_block_decode(b + o, e - o, dst, want); break;
+      case 3: got = lz4_block_decode(b + o, e - o, dst, want); break;
+      case 4:   /* lz4-java LZ4DecompressorWithLength: little-endian decoded length first */
+        if (e - o < 4 || ((int64_t)b[o] | ((int64_t)b[o + 1] << 8) | ((int64_t)b[o + 2] << 16) | ((int64_t)b[o + 3] << 24)) != want) { set_err("raw forward index: LZ4 length prefix"); return -1; }
+        got = lz4_block_decode(b + o + 4, e - o - 4, dst, want); break;
+      default: set_err("raw forward index: codec not restated (ZSTANDARD / GZIP)"); return -1;
+    }
+    if (got != want) { set_err("raw forward index: chunk does not decode to its size"); return -1; }
+  }
+  return need;
+}
+
+/* ------------------------------------------------------------------ */
 /* column readers                                                      */
 /* ------------------------------------------------------------------ */
 typedef struct {

@@ -32,7 +32,7 @@
 #define PB_MAX_AF_NODES 48
 #define PB_SPARSE_MAX 128            // survivors per 1024-doc chunk below which later AND leaves use the restricted scan
 #define PB_OUT_CAP 256               // (upper bound; DevQuery::out_cap) matches buffered per warp before one ATOMG reserves their place in the match list
-#define PB_CAND_CAP 512              // (upper bound; DevQuery::cand_cap) candidates per warp list (u16 offsets inside the unit); more = extra passes
+#define PB_CAND_CAP 256              // (upper bound; DevQuery::cand_cap, a multiple of 32) candidates per warp list (u32 docs inside the segment)
 #define PB_SET_SMEM_BYTES 8192      // dictId-set membership LUTs (one byte per dictId) cached in smem per segment
 
 enum { L_TRUE = 0, L_FALSE = 1, L_DICT_RANGE = 2, L_DICT_SET = 3, L_RAW_RANGE_I = 4, L_RAW_RANGE_F = 5,
@@ -403,6 +403,33 @@ __device__ __forceinline__ uint32_t pb_eval_dict_w(const uint32_t* __restrict__ 
     const int k = bit >> 5, s = bit & 31;
     const uint32_t vt = (s == 0) ? w[k] : __funnelshift_l(w[k + 1], w[k], s);   // value in the top W bits
     m[j >> 3] = m[j >> 3] * 2 + pred.template test<W>(vt);
+  }
+  return (m[3] << 24) | (m[2] << 16) | (m[1] << 8) | m[0];
+}
+
+// IN / NOT IN on a dictionary of <= 1024 values (5 <= W <= 10) without touching shared memory per value: the 2^W membership
+// bits live in ONE REGISTER PER LANE (lane = top five bits of the dictId, bit 31 - (low five bits)) and are fetched with a
+// warp shuffle, which -- unlike the byte LUT, whose random addresses serialise 3.5 ways on the 32 banks -- is conflict-free.
+// Both five-bit fields are read straight out of the packed stream with compile-time funnel shifts (SHFL.IDX and SHF.L.W use
+// only the low five bits of their operand, so nothing is masked): five instructions per value.
+template <int W>
+__device__ __forceinline__ uint32_t pb_eval_dict_w_shfl(const uint32_t* __restrict__ p, uint32_t lutword, int lane) {
+  static_assert(W >= 5 && W <= 10, "shuffle LUT: 5..10-bit dictIds");
+  uint32_t w[W + 1];
+  const uint32_t* q = p + lane * W;
+#pragma unroll
+  for (int k = 0; k < W; k++) w[k] = pb_bswap32(q[k]);
+  w[W] = 0;
+  uint32_t m[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int j = 31; j >= 0; j--) {
+    const int e1 = j * W + 5, e2 = j * W + W;                  // stream bit (exclusive) where each window ends
+    const int k1 = e1 >> 5, s1 = e1 & 31, k2 = e2 >> 5, s2 = e2 & 31;
+    const uint32_t rl = s1 == 0 ? w[k1 - (s1 == 0 ? 1 : 0)] : k1 == 0 ? (w[0] >> (32 - s1)) : __funnelshift_l(w[k1], w[k1 - (k1 > 0 ? 1 : 0)], s1);
+    const uint32_t rb = s2 == 0 ? w[k2 - (s2 == 0 ? 1 : 0)] : k2 == 0 ? (w[0] >> (32 - s2)) : __funnelshift_l(w[k2], w[k2 - (k2 > 0 ? 1 : 0)], s2);
+    const uint32_t word = __shfl_sync(0xffffffffu, lutword, (int)rl);       // lane = rl & 31 = top five bits of the dictId
+    const uint32_t x = __funnelshift_l(0u, word, rb);                       // word << (rb & 31): the member bit on top
+    m[j >> 3] = __funnelshift_l(x, m[j >> 3], 1);                           // (m << 1) | (x >> 31)
   }
   return (m[3] << 24) | (m[2] << 16) | (m[1] << 8) | m[0];
 }
@@ -781,6 +808,7 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
 // generic pointers the compiler emits generic ATOM.E instructions that resolve the address window at run time -- measured
 // no faster than the L2 reductions they were meant to replace.
 __device__ __forceinline__ void pb_sh_add_u32(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t pb_sh_atom_add_u32(uint32_t a, uint32_t v) { uint32_t o; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory"); return o; }
 __device__ __forceinline__ unsigned long long pb_sh_ld_u64(uint32_t a) { unsigned long long v; asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ uint32_t pb_sh_ld_u32(uint32_t a) { uint32_t v; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void pb_sh_st_u64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
@@ -870,7 +898,8 @@ struct __align__(16) FilterSmemHeader {
 // SW / SPK: plan-time specialisation.  SW = 0 is the general kernel (any predicate tree, every width and predicate kind
 // dispatched at run time: ~27 k SASS instructions, whose instruction-cache misses and dispatch cost were a fifth of the
 // issue slots of the common case).  SW > 0 is a kernel for ONE shape -- a flat conjunction whose only streamed leaf is a
-// dictionary column of SW bits tested with predicate kind SPK (0 = dictId range, 1 = IN / NOT IN membership LUT), every
+// dictionary column of SW bits tested with predicate kind SPK (0 = dictId range, 1 = IN / NOT IN byte LUT in shared memory,
+// 2 = IN / NOT IN bit LUT in registers fetched by warp shuffle: dictionaries of <= 1024 values), every
 // other leaf evaluated on the candidates -- with that leaf's unpack + test inlined and nothing else compiled in.  The host
 // picks it when every segment of the launch has that shape (pb_filter_spec.cu holds the instantiations).
 template <int U, int MIN_CTAS, int SW = 0, int SPK = 0>
@@ -881,7 +910,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
   uint8_t* dyn = smem_raw + ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127);
   uint8_t* set_cache = dyn;
   dyn += (Q.set_cache_bytes + 127) & ~127;
-  uint16_t* cand = reinterpret_cast<uint16_t*>(dyn);     // per-warp candidate lists (only when some leaf is evaluated on candidates)
+  uint32_t* cand = reinterpret_cast<uint32_t*>(dyn);     // per-warp candidate lists (only when some leaf is evaluated on candidates)
   dyn += Q.cand_bytes;
   const uint32_t OUT_CAP = (uint32_t)Q.out_cap, CAND_CAP = (uint32_t)Q.cand_cap;
   uint32_t* ob = reinterpret_cast<uint32_t*>(dyn) + (size_t)warp * OUT_CAP;   // this warp's output buffer
@@ -1014,6 +1043,14 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       }
       __syncthreads();
     }
+    [[maybe_unused]] uint32_t shfl_lut = 0;
+    if constexpr (SW > 0 && SPK == 2) {
+      // this lane's 32 membership bits: dictIds whose top five bits are `lane`, bit 31 - (dictId & 31), exclusive flag folded in
+      const DevLeaf& lf = sq.leaves[H->flat_leaf[0]];
+      const uint32_t v0 = (uint32_t)lane << (SW - 5);
+      for (uint32_t v = v0; v < v0 + (1u << (SW - 5)); v++)
+        if (v < (uint32_t)lf.set_card && ((((__ldg(lf.set_bits + (v >> 5)) >> (v & 31)) & 1u) ^ (uint32_t)lf.exclusive) != 0)) shfl_lut |= 0x80000000u >> (v & 31);
+    }
     const uint64_t seg_lo = sq.unit_begin > cta_lo ? sq.unit_begin : cta_lo;
     const uint64_t seg_end = sq.unit_begin + sq.n_units;
     const uint64_t seg_hi = seg_end < cta_hi ? seg_end : cta_hi;
@@ -1023,6 +1060,37 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
     const uint32_t rel0 = (uint32_t)(first - sq.unit_begin);     // unit index inside the segment
     const int n_scan = sq.n_scan;
     unsigned long long matched = 0;
+    uint32_t* const cl = cand + (size_t)warp * CAND_CAP;     // this warp's candidate list
+    uint32_t cand_n = 0;                                     // candidates waiting in it (warp-uniform)
+    // test the first n (a multiple of 32, or everything at segment exit) candidates, then move the rest to the front
+    auto cand_rounds = [&](uint32_t n) {
+      if (n == 0) return;
+      const uint32_t lt = (1u << lane) - 1u;
+      const int n_cand_leaves = H->n_flat - H->n_dense;
+      for (uint32_t b0 = 0; b0 < n; b0 += 32) {
+        const uint32_t idx = b0 + (uint32_t)lane;
+        bool alive = idx < n;
+        const uint32_t doc = alive ? cl[idx] : 0u;                // doc inside the segment
+        for (int i = 0; i < n_cand_leaves; i++) {
+          if (alive) alive = pb_leaf_test_doc(sq.leaves[H->flat_leaf[H->n_dense + i]], set_cache, doc);
+          if (!__any_sync(0xffffffffu, alive)) break;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+        if (bal) {
+          const uint32_t nb = (uint32_t)__popc(bal);
+          if (out_n + nb > OUT_CAP) flush_out();
+          if (alive) ob[out_n + __popc(bal & lt)] = (uint32_t)sq.doc_base + doc;
+          out_n += nb;
+          matched += nb;
+        }
+      }
+      const uint32_t rest = cand_n - n;                             // < 32 unless called at segment exit (then 0)
+      const uint32_t keep = (uint32_t)lane < rest ? cl[n + (uint32_t)lane] : 0u;
+      __syncwarp();
+      if ((uint32_t)lane < rest) cl[lane] = keep;
+      cand_n = rest;
+      __syncwarp();
+    };
     uint32_t min_last_rel = 0xffffffffu;               // first unit whose load must be clipped to the buffer end
     for (int c = 0; c < n_scan; c++) min_last_rel = min(min_last_rel, H->slot_last_rel[c]);
 
@@ -1100,10 +1168,13 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
           PredRange pr; pr.lo = lf.lo; pr.span = lf.span;
 #pragma unroll
           for (int u = 0; u < U; u++) if (u < nu) mask[u] &= pb_eval_dict_w<SW, PredRange>(p + u * 32 * SW, pr, lane);
-        } else {
+        } else if constexpr (SPK == 1) {
           PredLut8 pl; pl.lut = set_cache + lf.set_smem_off;
 #pragma unroll
           for (int u = 0; u < U; u++) if (u < nu) mask[u] &= pb_eval_dict_w<SW, PredLut8>(p + u * 32 * SW, pl, lane);
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; u++) if (u < nu) mask[u] &= pb_eval_dict_w_shfl<SW>(p + u * 32 * SW, shfl_lut, lane);
         }
       } else if (__builtin_expect(H->flat_and != 0, 1)) {
         const int nl = H->n_dense;
@@ -1200,49 +1271,35 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
         }
         matched += total;
       } else {
-        // ---- candidates: survivors of the staged leaves, compacted into this warp's list, then one lane per candidate
-        // tests the remaining leaves straight from their forward indexes (all 32 gathers of a round in flight at once) ----
-        uint16_t* cl = cand + (size_t)warp * CAND_CAP;
-        for (uint32_t pass0 = 0; pass0 < total; pass0 += CAND_CAP) {     // one pass unless the estimate was far off
-          if (pass0) __syncwarp();
+        // ---- candidates: survivors of the staged leaves go to this warp's list (docs inside the segment); whenever the list
+        // holds 32 or more, one lane per candidate tests the remaining leaves straight from their forward indexes / row
+        // groups (all 32 gathers of a round in flight at once).  The list carries over from unit to unit so that rounds
+        // run with all 32 lanes busy (a unit leaves ~33 survivors in the headline query: two half-empty rounds before) ----
+        for (uint32_t done = 0; done < total;) {
+          const uint32_t room = CAND_CAP - cand_n;
+          const uint32_t take = total - done < room ? total - done : room;
           {
-            uint32_t pos = excl - pass0;                                     // (wraps below the window: unsigned compare)
+            uint32_t pos = excl - done;                                      // (wraps below the window: unsigned compare)
 #pragma unroll
             for (int u = 0; u < U; u++) {
-              const uint32_t off0 = (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
+              const uint32_t doc0 = (uint32_t)unit_doc0 + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
               uint32_t mm = mask[u];
               while (mm) {
                 const int bit = __ffs(mm) - 1;
                 mm &= mm - 1;
-                if (pos < CAND_CAP) cl[pos] = (uint16_t)(off0 + (uint32_t)bit);
+                if (pos < take) cl[cand_n + pos] = doc0 + (uint32_t)bit;
                 pos++;
               }
             }
           }
+          cand_n += take;
+          done += take;
           __syncwarp();
-          const uint32_t n_pass = total - pass0 < CAND_CAP ? total - pass0 : CAND_CAP;
-          for (uint32_t b0 = 0; b0 < n_pass; b0 += 32) {
-            const uint32_t idx = b0 + (uint32_t)lane;
-            bool alive = idx < n_pass;
-            const uint32_t off = alive ? (uint32_t)cl[idx] : 0u;
-            const uint32_t doc = (uint32_t)unit_doc0 + off;          // doc inside the segment
-            for (int i = 0; i < n_cand_leaves; i++) {
-              if (alive) alive = pb_leaf_test_doc(sq.leaves[H->flat_leaf[H->n_dense + i]], set_cache, doc);
-              if (!__any_sync(0xffffffffu, alive)) break;
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-            if (bal) {
-              const uint32_t n = (uint32_t)__popc(bal);
-              if (out_n + n > OUT_CAP) flush_out();
-              if (alive) ob[out_n + __popc(bal & lt)] = gunit0 + off;
-              out_n += n;
-              matched += n;
-            }
-          }
+          cand_rounds(cand_n & ~31u);
         }
-        __syncwarp();   // the list is rewritten by the next unit
       }
     }
+    if (cand_n) { __syncwarp(); cand_rounds(cand_n); }
     flush_out();
     // ---- segment exit: numDocsScanned of this segment's table (matched is warp-uniform) ----
     if (lane == 0 && matched) pb_red_add_u64(Q.tables[sq.table].docs_matched, matched);
@@ -1511,7 +1568,8 @@ static __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_smem_ker
 // reductions into the global table.
 // ------------------------------------------------------------------------------------------------
 struct DevRowKey { uint32_t off, bits; uint64_t mult; const int32_t* remap; };
-struct DevRowAgg { uint32_t off, width, type, pad; };        // width 4 / 8 bytes, type PB_INT .. PB_DOUBLE; unused for COUNT(*)
+struct DevRowAgg { uint32_t off, width, type, exact_int; };  // width 4 / 8 bytes, type PB_INT .. PB_DOUBLE; unused for COUNT(*).  exact_int: SUM / AVG
+                                                             // of an integer column whose sums stay below 2^53 (same flag in every segment)
 struct DevRowSeg {
   const uint32_t* rows;
   uint64_t doc_base;
@@ -1592,15 +1650,29 @@ __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_rows_kernel(con
       const unsigned long long u = ((unsigned long long)w0 << 32) | field(g.off + 32u, 32u);
       return g.type == 3 ? __longlong_as_double((long long)u) : (double)(long long)u;
     };
+    auto ivalue_of = [&](int a) -> long long {           // INT / LONG fields only
+      const DevRowAgg& g = sg.aggs[a];
+      const uint32_t w0 = field(g.off, 32u);
+      if (g.width == 4) return (long long)(int32_t)w0;
+      return (long long)(((unsigned long long)w0 << 32) | field(g.off + 32u, 32u));
+    };
     if (use_smem) {
       const uint32_t sl = (uint32_t)slot;
       pb_sh_add_u32(st.cnt(sl), 1u);
       for (int a = 0; a < nA; a++) {
         const int op = Q.agg_op[a];
         if (op == 0) continue;
-        const double v = value_of(a);
+        const double v = ((op == 1 || op == 4) && sg.aggs[a].exact_int) ? 0.0 : value_of(a);
         const uint32_t cell = st.acc(st.acc_of[a], sl);
-        if (op == 1 || op == 4) {
+        if ((op == 1 || op == 4) && sg.aggs[a].exact_int) {
+          // exact integer sum: the cell is an int64 kept as two u32 halves, low half first; the carry out of the low half
+          // (seen in the value the returning add hands back) rides on the add to the high half -- two native ATOMS, no loop
+          const long long iv = ivalue_of(a);
+          const uint32_t vlo = (uint32_t)iv, vhi = (uint32_t)((unsigned long long)iv >> 32);
+          uint32_t add_hi = vhi;
+          if (vlo) { const uint32_t before = pb_sh_atom_add_u32(cell, vlo); add_hi += (before + vlo) < vlo ? 1u : 0u; }
+          if (add_hi) pb_sh_add_u32(cell + 4u, add_hi);
+        } else if (op == 1 || op == 4) {
           unsigned long long old = pb_sh_ld_u64(cell), assumed;
           do {
             assumed = old;
@@ -1652,17 +1724,23 @@ __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_rows_kernel(con
     for (int k = 0; k < RW; k++) w[k] = pb_bswap32(w[k]);
   };
   const unsigned long long stride = (unsigned long long)gridDim.x * PB_AGG_SMEM_THREADS;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += 2 * stride) {
-    const bool two = i + stride < n;
-    const unsigned long long gdoc0 = Q.match_all ? i : (unsigned long long)__ldg(Q.match_list + i);
-    const unsigned long long gdoc1 = !two ? gdoc0 : (Q.match_all ? i + stride : (unsigned long long)__ldg(Q.match_list + i + stride));
-    const DevRowSeg& sg0 = segs[seg_of(gdoc0)];
-    const DevRowSeg& sg1 = segs[seg_of(gdoc1)];
-    uint32_t w0[RW], w1[RW];
-    load_row(sg0, gdoc0, w0);
-    load_row(sg1, gdoc1, w1);
-    process(gdoc0, w0, sg0);
-    if (two) process(gdoc1, w1, sg1);
+  constexpr int ND = RW <= 4 ? 4 : 2;          // docs in flight per thread (their row loads are issued back to back)
+  for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += ND * stride) {
+    unsigned long long gdoc[ND];
+    int sgi[ND];
+    uint32_t w[ND][RW];
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+      const unsigned long long idx = i + (unsigned long long)d * stride;
+      gdoc[d] = idx < n ? (Q.match_all ? idx : (unsigned long long)__ldg(Q.match_list + idx)) : ~0ull;
+    }
+#pragma unroll
+    for (int d = 0; d < ND; d++) {
+      sgi[d] = seg_of(gdoc[d] == ~0ull ? gdoc[0] : gdoc[d]);
+      load_row(segs[sgi[d]], gdoc[d] == ~0ull ? gdoc[0] : gdoc[d], w[d]);
+    }
+#pragma unroll
+    for (int d = 0; d < ND; d++) if (gdoc[d] != ~0ull) process(gdoc[d], w[d], segs[sgi[d]]);
   }
   if (!use_smem) return;
   __syncthreads();
@@ -1675,7 +1753,11 @@ __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_rows_kernel(con
     for (int a = 0; a < nA; a++) {
       if (st.acc_of[a] < 0) continue;
       const int op = Q.agg_op[a];
-      if (op == 1 || op == 4) {
+      if ((op == 1 || op == 4) && segs[0].aggs[a].exact_int) {
+        long long v = 0;
+        for (uint32_t r = 0; r < R; r++) { SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes; v += (long long)pb_sh_ld_u64(z.acc(st.acc_of[a], i)); }
+        pb_red_add_f64(&t.sum[a][i], (double)v);                 // exact: |v| < 2^53
+      } else if (op == 1 || op == 4) {
         double v = 0.0;
         for (uint32_t r = 0; r < R; r++) { SmemTable z = st; z.base = smem0 + r * (uint32_t)rep_bytes; v += __longlong_as_double((long long)pb_sh_ld_u64(z.acc(st.acc_of[a], i))); }
         pb_red_add_f64(&t.sum[a][i], v);
@@ -2281,6 +2363,115 @@ static __global__ void pb_build_rows_kernel(const DevRowBuild B) {
 #pragma unroll
     for (int k = 0; k < PB_ROW_MAX_WORDS; k++) if (k < B.stride_words) o[k] = pb_bswap32(w[k]);
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chunk-compressed raw forward indexes (BaseChunkForwardIndexReader.decompressChunk,
+// SEGL/segment/index/readers/forward/BaseChunkForwardIndexReader.java:120-160; codecs SEGL/io/compression/LZ4Decompressor.java,
+// LZ4WithLengthDecompressor.java, SnappyDecompressor.java): decoded ONCE, at stage time, into the PASS_THROUGH value area the
+// scan / gather kernels read -- the compressed bytes are what crosses PCIe.  One warp per chunk: every lane parses the
+// sequence headers (uniform loads), the warp copies the literal and match bytes cooperatively.  A match may overlap its own
+// output (offset < length = a repeating pattern): byte i of it is byte (i mod offset) of the `offset` bytes before the match,
+// all written by earlier sequences.  Every read and write is bounds-checked; a malformed stream sets *err and stops the chunk.
+// ------------------------------------------------------------------------------------------------
+#define PB_CODEC_SNAPPY 1
+#define PB_CODEC_LZ4 3
+#define PB_CODEC_LZ4_LENGTH_PREFIXED 4
+struct DevChunkDecode {
+  const uint8_t* src;          // the compressed chunks, back to back as in the file
+  const uint64_t* offs;        // n_chunks + 1 offsets into src
+  uint8_t* dst;                // value area: chunk k at k * chunk_bytes
+  uint64_t total_bytes;        // num_docs x width (the last chunk is shorter)
+  uint32_t n_chunks, chunk_bytes;
+  int32_t codec;
+  uint32_t* err;
+};
+static __global__ void __launch_bounds__(256) pb_chunk_decode_kernel(const DevChunkDecode D) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chunk >= D.n_chunks) return;
+  const uint8_t* in = D.src + D.offs[chunk];
+  const uint64_t in_len = D.offs[chunk + 1] - D.offs[chunk];
+  uint8_t* out = D.dst + (uint64_t)chunk * D.chunk_bytes;
+  const uint64_t left = D.total_bytes - (uint64_t)chunk * D.chunk_bytes;
+  const uint64_t out_len = left < D.chunk_bytes ? left : D.chunk_bytes;
+  uint64_t ip = 0, op = 0;
+  bool bad = false;
+  auto copy_literals = [&](uint64_t n) {
+    if (ip + n > in_len || op + n > out_len) { bad = true; return; }
+    for (uint64_t i = (uint64_t)lane; i < n; i += 32) out[op + i] = in[ip + i];
+    ip += n; op += n;
+  };
+  auto copy_match = [&](uint64_t off, uint64_t n) {
+    if (off == 0 || off > op || op + n > out_len) { bad = true; return; }
+    __syncwarp();                                  // the bytes before op are complete
+    const uint8_t* from = out + (op - off);
+    for (uint64_t i = (uint64_t)lane; i < n; i += 32) out[op + i] = from[i % off];
+    op += n;
+    __syncwarp();
+  };
+  if (D.codec == PB_CODEC_SNAPPY) {
+    // preamble: decoded length as a varint, then literal / copy elements (tag in the low two bits)
+    uint64_t want = 0; int sh = 0;
+    for (;;) {
+      if (ip >= in_len || sh > 28) { bad = true; break; }
+      const uint32_t b = in[ip++];
+      want |= (uint64_t)(b & 127u) << sh; sh += 7;
+      if (!(b & 128u)) break;
+    }
+    if (want != out_len) bad = true;
+    while (!bad && ip < in_len) {
+      const uint32_t tag = in[ip++];
+      if ((tag & 3u) == 0) {
+        uint64_t n = tag >> 2;
+        if (n >= 60) {
+          const int nb = (int)n - 59;
+          if (ip + nb > in_len) { bad = true; break; }
+          n = 0;
+          for (int k = 0; k < nb; k++) n |= (uint64_t)in[ip + k] << (8 * k);
+          ip += nb;
+        }
+        copy_literals(n + 1);
+      } else if ((tag & 3u) == 1) {
+        if (ip + 1 > in_len) { bad = true; break; }
+        const uint64_t off = ((uint64_t)(tag >> 5) << 8) | in[ip]; ip += 1;
+        copy_match(off, 4 + ((tag >> 2) & 7u));
+      } else {
+        const int nb = (tag & 3u) == 2 ? 2 : 4;
+        if (ip + nb > in_len) { bad = true; break; }
+        uint64_t off = 0;
+        for (int k = 0; k < nb; k++) off |= (uint64_t)in[ip + k] << (8 * k);
+        ip += nb;
+        copy_match(off, (tag >> 2) + 1);
+      }
+    }
+  } else {
+    if (D.codec == PB_CODEC_LZ4_LENGTH_PREFIXED) {   // lz4-java LZ4CompressorWithLength: decoded length, little-endian int
+      if (in_len < 4) bad = true;
+      else {
+        const uint64_t want = (uint64_t)in[0] | ((uint64_t)in[1] << 8) | ((uint64_t)in[2] << 16) | ((uint64_t)in[3] << 24);
+        if (want != out_len) bad = true;
+        ip = 4;
+      }
+    }
+    // LZ4 block: token (literal length : match length - 4), [length bytes], literals, offset LE16, [length bytes]; the
+    // last sequence ends after its literals
+    while (!bad && ip < in_len) {
+      const uint32_t token = in[ip++];
+      uint64_t lit = token >> 4;
+      if (lit == 15) for (;;) { if (ip >= in_len) { bad = true; break; } const uint32_t b = in[ip++]; lit += b; if (b != 255) break; }
+      if (bad) break;
+      copy_literals(lit);
+      if (bad || ip >= in_len) break;
+      if (ip + 2 > in_len) { bad = true; break; }
+      const uint64_t off = (uint64_t)in[ip] | ((uint64_t)in[ip + 1] << 8); ip += 2;
+      uint64_t ml = token & 15u;
+      if (ml == 15) for (;;) { if (ip >= in_len) { bad = true; break; } const uint32_t b = in[ip++]; ml += b; if (b != 255) break; }
+      if (bad) break;
+      copy_match(off, ml + 4);
+    }
+  }
+  if ((bad || op != out_len) && lane == 0) atomicAdd(D.err, 1u);
 }
 
 // sorted forward index (docId range pairs) -> big-endian bit-packed dictId stream, so a sorted column can

@@ -21,6 +21,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <unordered_set>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------
@@ -299,6 +300,9 @@ struct Column {
   std::vector<uint8_t> h_dict;          // host copy of the dictionary (big-endian, as stored)
   uint64_t raw_data_start = 0;
   int raw_width = 0;
+  // chunk-compressed raw forward index (ChunkCompressionType != PASS_THROUGH): decoded on the device at stage time
+  int raw_codec = 0, raw_num_chunks = 0, raw_docs_per_chunk = 0, raw_offset_bytes = 4;
+  uint64_t raw_header_start = 0;
   // device
   uint8_t* d_fwd = nullptr; uint64_t d_fwd_bytes = 0;     // bit-packed stream / raw values (16-byte padded)
   int32_t* d_sorted_pairs = nullptr;                       // sorted column: LE (start,end) pairs
@@ -415,13 +419,24 @@ extern "C" int pb_segment_stage(const pb_segment_desc* d, int device_index, pb_s
       if (c.type == PB_STRING) return fail(PB_ERR_UNSUPPORTED, "column %s: raw STRING forward index", cd.name);
       if (c.h_fwd_len < 28) return fail(PB_ERR_INVALID, "column %s: raw forward index header", cd.name);
       int version = (int)be32(c.h_fwd), num_chunks = (int)be32(c.h_fwd + 4);
-      if (version < 2) return fail(PB_ERR_UNSUPPORTED, "column %s: raw index v1 (SNAPPY)", cd.name);
-      int compression = (int)be32(c.h_fwd + 20);
-      if (compression != 0) return fail(PB_ERR_UNSUPPORTED, "column %s: chunk compression %d (only PASS_THROUGH)", cd.name, compression);
-      int data_header_start = (int)be32(c.h_fwd + 24);
-      c.raw_data_start = (uint64_t)data_header_start + (uint64_t)num_chunks * (version <= 2 ? 4 : 8);
+      // version 1 has no compression field: always SNAPPY, chunk offsets start right after the four header ints
+      int compression = version > 1 ? (int)be32(c.h_fwd + 20) : PB_CODEC_SNAPPY;
+      if (compression != 0 && compression != PB_CODEC_SNAPPY && compression != PB_CODEC_LZ4 && compression != PB_CODEC_LZ4_LENGTH_PREFIXED)
+        return fail(PB_ERR_UNSUPPORTED, "column %s: chunk compression %d (PASS_THROUGH, SNAPPY, LZ4 and LZ4_LENGTH_PREFIXED are decoded)", cd.name, compression);
+      int data_header_start = version > 1 ? (int)be32(c.h_fwd + 24) : 16;
+      c.raw_offset_bytes = version <= 2 ? 4 : 8;
+      c.raw_data_start = (uint64_t)data_header_start + (uint64_t)num_chunks * (uint64_t)c.raw_offset_bytes;
       c.raw_width = (c.type == PB_INT || c.type == PB_FLOAT) ? 4 : 8;
-      if (c.h_fwd_len < c.raw_data_start + (uint64_t)s->num_docs * c.raw_width) return fail(PB_ERR_INVALID, "column %s: raw forward index too short", cd.name);
+      c.raw_codec = compression; c.raw_num_chunks = num_chunks; c.raw_docs_per_chunk = (int)be32(c.h_fwd + 8); c.raw_header_start = (uint64_t)data_header_start;
+      if (num_chunks < 0 || data_header_start < 16 || c.h_fwd_len < c.raw_data_start) return fail(PB_ERR_INVALID, "column %s: raw forward index header", cd.name);
+      if (compression == 0) {
+        if (c.h_fwd_len < c.raw_data_start + (uint64_t)s->num_docs * c.raw_width) return fail(PB_ERR_INVALID, "column %s: raw forward index too short", cd.name);
+      } else {
+        if ((int)be32(c.h_fwd + 12) != c.raw_width) return fail(PB_ERR_INVALID, "column %s: raw forward index entry size %d", cd.name, (int)be32(c.h_fwd + 12));
+        if (c.raw_docs_per_chunk <= 0 || (uint64_t)c.raw_docs_per_chunk * (uint64_t)c.raw_width > 0x7fffffffull ||
+            (uint64_t)num_chunks != ((uint64_t)s->num_docs + (uint64_t)c.raw_docs_per_chunk - 1) / (uint64_t)c.raw_docs_per_chunk)
+          return fail(PB_ERR_INVALID, "column %s: raw forward index chunking (%d chunks of %d docs for %d docs)", cd.name, num_chunks, c.raw_docs_per_chunk, s->num_docs);
+      }
     }
   }
   if (ctx) { std::lock_guard<std::mutex> lk(ctx->mu); ctx->segments.push_back(s.get()); }
@@ -436,7 +451,7 @@ static void native_entry(const Column& c, int id, uint8_t* out);
 // instead of the whole column.  Needs pb_host_register'd memory and 4-byte alignment; otherwise the column is staged.
 static bool map_column_in_place(pb_segment_s* s, Column& c) {
   if (c.d_fwd_host) return true;
-  if (c.has_dict && c.is_sorted) return false;
+  if ((c.has_dict && c.is_sorted) || (!c.has_dict && c.raw_codec != 0)) return false;
   const uint8_t* src = c.has_dict ? c.h_fwd : c.h_fwd + c.raw_data_start;
   uint64_t bytes = c.has_dict ? ((uint64_t)s->num_docs * c.bits + 7) / 8 : (uint64_t)s->num_docs * c.raw_width;
   if (!src || bytes == 0 || (reinterpret_cast<uintptr_t>(src) & 3u) || bytes / 4 >= 0xFFFFFFFFull) return false;
@@ -470,6 +485,49 @@ static int stage_column(pb_segment_s* s, Column& c, bool need_fwd, bool need_dic
       if (grid < 1) grid = 1;
       pb_sorted_to_packed_kernel<<<grid, 256, 0, st>>>(c.d_sorted_pairs, c.card, (uint32_t)s->num_docs, c.bits, (uint32_t*)c.d_fwd, n_words);
       CU(cudaGetLastError());
+      c.d_fwd_bytes = padded;
+      s->device_bytes += (int64_t)padded;
+    } else if (!c.has_dict && c.raw_codec != 0) {
+      // compressed chunks -> device, decode there into the PASS_THROUGH value area (pb_chunk_decode_kernel)
+      const uint64_t bytes = (uint64_t)s->num_docs * c.raw_width;
+      const uint64_t padded = ((bytes + 15) & ~15ull) + 32;
+      const size_t n_chunks = (size_t)c.raw_num_chunks;
+      const size_t offs_bytes = sizeof(uint64_t) * (n_chunks + 1);
+      uint64_t* offs = static_cast<uint64_t*>(pinned_alloc(offs_bytes + 8));
+      if (!offs) return fail(PB_ERR_OOM, "pinned host allocation failed");
+      s->staging_bufs.push_back({offs, offs_bytes + 8});
+      for (size_t k = 0; k <= n_chunks; k++) {
+        uint64_t o = c.h_fwd_len;                                              // the last chunk ends with the buffer
+        if (k < n_chunks) o = c.raw_offset_bytes == 4 ? (uint64_t)be32(c.h_fwd + c.raw_header_start + 4 * k) : be64(c.h_fwd + c.raw_header_start + 8 * k);
+        if (o < c.raw_data_start || o > c.h_fwd_len || (k > 0 && o - c.raw_data_start < offs[k - 1]))
+          return fail(PB_ERR_INVALID, "column %s: chunk offset %zu of the raw forward index is out of order or out of range", c.name.c_str(), k);
+        offs[k] = o - c.raw_data_start;
+      }
+      const uint64_t comp_bytes = c.h_fwd_len - c.raw_data_start;
+      uint8_t* d_comp = nullptr; uint64_t* d_offs = nullptr; uint32_t* d_err = nullptr;
+      CU(dev_alloc(s->ctx, (void**)&d_comp, comp_bytes + 16));
+      CU(dev_alloc(s->ctx, (void**)&d_offs, offs_bytes + 16));
+      d_err = reinterpret_cast<uint32_t*>(d_offs + n_chunks + 1);
+      CU(dev_alloc(s->ctx, (void**)&c.d_fwd, padded));
+      offs[n_chunks + 1] = 0;                                                  // the error word rides behind the offsets
+      CU(cudaMemsetAsync(c.d_fwd + (bytes & ~15ull), 0, padded - (bytes & ~15ull), st));
+      CU(cudaMemcpyAsync(d_comp, c.h_fwd + c.raw_data_start, comp_bytes, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_offs, offs, offs_bytes + 8, cudaMemcpyHostToDevice, st));
+      DevChunkDecode D;
+      D.src = d_comp; D.offs = d_offs; D.dst = c.d_fwd; D.total_bytes = bytes; D.n_chunks = (uint32_t)n_chunks;
+      D.chunk_bytes = (uint32_t)((uint64_t)c.raw_docs_per_chunk * (uint64_t)c.raw_width); D.codec = c.raw_codec; D.err = d_err;
+      if (n_chunks > 0) {
+        pb_chunk_decode_kernel<<<(unsigned)((n_chunks + 7) / 8), 256, 0, st>>>(D);
+        CU(cudaGetLastError());
+      }
+      uint32_t* h_err = reinterpret_cast<uint32_t*>(offs + n_chunks + 1);
+      CU(cudaMemcpyAsync(h_err, d_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));                                           // one-time cost of a compressed column; frees the temporaries
+      dev_free(s->ctx, d_comp); dev_free(s->ctx, d_offs);
+      if (*h_err != 0) {
+        dev_free(s->ctx, c.d_fwd); c.d_fwd = nullptr;
+        return fail(PB_ERR_INVALID, "column %s: %u chunk(s) of the raw forward index do not decode (codec %d)", c.name.c_str(), *h_err, c.raw_codec);
+      }
       c.d_fwd_bytes = padded;
       s->device_bytes += (int64_t)padded;
     } else {
@@ -1092,10 +1150,15 @@ static void release_segments(pb_result_s* r) {
   }
   r->pinned_segments = 0;
 }
+// CUDA graphs that captured NCCL collectives hold references on the communicator, and ncclCommDestroy waits until the last
+// of them is gone: pb_comm_destroy therefore destroys these graphs first (their plans simply capture again later)
+static std::mutex g_comm_graphs_mu;
+static std::unordered_set<pb_result_s*> g_comm_graphs;
 static void free_result(pb_result_s* r);
 static void destroy_result(pb_result_s* r) {
   if (!r) return;
   for (auto* p : r->parts) free_result(p);
+  { std::lock_guard<std::mutex> lk(g_comm_graphs_mu); g_comm_graphs.erase(r); }
   if (r->rp.graph) { cudaGraphExecDestroy(r->rp.graph); r->rp.graph = nullptr; }
   DeviceGuard dg(r->ctx);
   if (r->stream) cudaStreamSynchronize(r->stream);
@@ -1334,6 +1397,11 @@ static void comm_shutdown() {
   if (g_comm.comm) {
     DeviceGuard dg(g_comm.ctx);
     cudaDeviceSynchronize();
+    {
+      std::lock_guard<std::mutex> lk2(g_comm_graphs_mu);
+      for (pb_result_s* r : g_comm_graphs) if (r->rp.graph) { cudaGraphExecDestroy(r->rp.graph); r->rp.graph = nullptr; }
+      g_comm_graphs.clear();
+    }
     g_comm.api.CommDestroy(g_comm.comm);
     g_comm.comm = nullptr; g_comm.n_ranks = 1; g_comm.rank = 0;
   }
@@ -1507,6 +1575,7 @@ static int replay_plan(pb_result_s* r, const pb_query_desc* q) {
       e = cudaGraphInstantiate(&rp.graph, graph, 0);
       cudaGraphDestroy(graph);
       if (e != cudaSuccess) { rp.graph = nullptr; return fail(PB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+      if (all_ranks) { std::lock_guard<std::mutex> lk(g_comm_graphs_mu); g_comm_graphs.insert(r); }
       rp.graph_launches = r->launches;
       r->launches = 0;
       r->merged_ranks = 1; r->comm_timed = false;       // (the capture ran comm_merge's bookkeeping, not the collective)
@@ -2221,8 +2290,32 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
           if (q->aggregations[a].op == PB_AGG_COUNT) continue;
           const Column& c = sg->cols[acol[si][a]];
           rs.aggs[a].off = (uint32_t)rg->bit_off[(size_t)rg->find(acol[si][a], 1)];
-          rs.aggs[a].width = (uint32_t)c.entry_bytes; rs.aggs[a].type = (uint32_t)c.type;
+          rs.aggs[a].width = (uint32_t)c.entry_bytes; rs.aggs[a].type = (uint32_t)c.type; rs.aggs[a].exact_int = 0;
         }
+      }
+      // SUM / AVG over INT / LONG columns: when max|value| x docs < 2^53 every partial sum is an integer a double holds
+      // exactly, so the CTA-private table may accumulate them as 64-bit integers with two native 32-bit shared-memory
+      // atomics instead of a compare-and-swap loop on a double -- bit-identical to the reference's double accumulation,
+      // whatever the order (DevRowAgg::exact_int)
+      static const bool exact_on = []() { const char* e = getenv("PB_AGG_EXACT_INT"); return !e || atoi(e) != 0; }();
+      uint64_t docs_all = 0;
+      for (int si = 0; si < n_segs; si++) docs_all += (uint64_t)g->segs[si]->num_docs;
+      for (int a = 0; a < nA && exact_on; a++) {
+        const int op = q->aggregations[a].op;
+        if (op != PB_AGG_SUM && op != PB_AGG_AVG) continue;
+        bool exact = true;
+        for (int si = 0; si < n_segs && exact; si++) {
+          const Column& c = g->segs[si]->cols[acol[si][a]];
+          if (!c.has_dict || c.card <= 0 || (c.type != PB_INT && c.type != PB_LONG) || c.h_dict.size() < (size_t)c.card * (size_t)c.entry_bytes) { exact = false; break; }
+          // sorted dictionary: the extremes are its first and last entries
+          const uint8_t* lo = c.h_dict.data(); const uint8_t* hi = c.h_dict.data() + (size_t)(c.card - 1) * (size_t)c.entry_bytes;
+          const int64_t vlo = c.type == PB_INT ? (int64_t)(int32_t)be32(lo) : (int64_t)be64(lo);
+          const int64_t vhi = c.type == PB_INT ? (int64_t)(int32_t)be32(hi) : (int64_t)be64(hi);
+          const uint64_t alo = vlo < 0 ? (uint64_t)0 - (uint64_t)vlo : (uint64_t)vlo, ahi = vhi < 0 ? (uint64_t)0 - (uint64_t)vhi : (uint64_t)vhi;
+          const uint64_t bound = std::max<uint64_t>(std::max(alo, ahi), 1);
+          if (bound >= (1ull << 53) || docs_all >= (1ull << 53) / bound) exact = false;
+        }
+        if (exact) for (int si = 0; si < n_segs; si++) h_rs[si].aggs[a].exact_int = 1;
       }
     } else rows_rw = 0;
   }
@@ -2360,7 +2453,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   hq->stage_bytes = (int32_t)stage_bytes;
   hq->set_cache_bytes = set_cache_max;
   hq->out_cap = PB_OUT_CAP; hq->cand_cap = PB_CAND_CAP;
-  hq->cand_bytes = any_cand_leaf ? (int32_t)(2 * PB_CAND_CAP * PB_NWARPS) : 0;   // u16 offsets inside the unit, one list per warp
+  hq->cand_bytes = any_cand_leaf ? (int32_t)(4 * PB_CAND_CAP * PB_NWARPS) : 0;   // u32 docs inside the segment, one list per warp
   hq->use_tma = (q->flags & PB_Q_NO_TMA) ? 0 : 1;
   hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
   hq->n_units = n_chunks; hq->segs = dsegs; hq->tables = dtabs;
@@ -2453,7 +2546,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     }
   }
   auto filter_smem = [&](int out_cap, int cand_cap) {
-    return ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + (any_cand_leaf ? (size_t)2 * cand_cap * PB_NWARPS : 0) +
+    return ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + (any_cand_leaf ? (size_t)4 * cand_cap * PB_NWARPS : 0) +
            (size_t)PB_NWARPS * out_cap * 4 + stage_bytes * PB_NSTAGE * PB_NWARPS;
   };
   size_t smem = 0;
@@ -2491,7 +2584,12 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
         }
         if (!ok || n_dense != 1) { ok = false; break; }
         const DevLeaf& lf = ds.leaves[dense];
-        const int k = lf.kind == L_DICT_RANGE ? 0 : (lf.kind == L_DICT_SET && lf.set_smem_off >= 0) ? 1 : -1;
+        // IN / NOT IN: dictionaries of <= 1024 values keep the membership bits in registers (warp shuffle), larger ones in a
+        // byte LUT in shared memory
+        static const bool shfl_on = []() { const char* e = getenv("PB_FILTER_SHFL"); return !e || atoi(e) != 0; }();
+        const int k = lf.kind == L_DICT_RANGE ? 0
+                      : (lf.kind == L_DICT_SET && shfl_on && lf.bits >= 5 && lf.bits <= 10 && lf.set_card <= (1 << lf.bits) && pb_filter_spec_available(lf.bits, 2)) ? 2
+                      : (lf.kind == L_DICT_SET && lf.set_smem_off >= 0) ? 1 : -1;
         if (k < 0 || (w >= 0 && (w != lf.bits || pk != k))) { ok = false; break; }
         w = lf.bits; pk = k;
       }
@@ -2504,7 +2602,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
         int occ = 0;
         if (pb_filter_spec_prepare(w, pk, smem_spec, &occ) == cudaSuccess && occ >= 1) {
           spec_w = w; spec_pk = pk; max_ctas = (uint64_t)ctx->num_sms * (uint64_t)occ; smem = smem_spec;
-          hq->out_cap = oc; hq->cand_cap = cc; hq->cand_bytes = any_cand_leaf ? (int32_t)(2 * cc * PB_NWARPS) : 0;
+          hq->out_cap = oc; hq->cand_cap = cc; hq->cand_bytes = any_cand_leaf ? (int32_t)(4 * cc * PB_NWARPS) : 0;
           for (auto& wv : waves) { wv.dq.out_cap = oc; wv.dq.cand_cap = cc; wv.dq.cand_bytes = hq->cand_bytes; }
         } else cudaGetLastError();
       }

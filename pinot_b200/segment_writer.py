@@ -212,22 +212,60 @@ def _sorted_pairs(dict_ids: np.ndarray, card: int) -> np.ndarray:
     return np.frombuffer(pairs.tobytes(), dtype=np.uint8).copy()
 
 
-def _raw_forward_index(values: np.ndarray, data_type: DataType) -> np.ndarray:
+COMPRESSION_SNAPPY = 1           # ChunkCompressionType ordinals (SPI/compression/ChunkCompressionType.java:22)
+COMPRESSION_LZ4 = 3
+COMPRESSION_LZ4_LENGTH_PREFIXED = 4
+_COMPRESSION_BY_NAME = {None: 0, "PASS_THROUGH": 0, "SNAPPY": 1, "LZ4": 3, "LZ4_LENGTH_PREFIXED": 4}
+
+
+def _compress_chunk(raw: bytes, compression: int) -> bytes:
+    """One chunk through the codec Pinot's ChunkCompressorFactory would use.  The compressors are pyarrow's bindings of the
+    stock C libraries (liblz4 block format = lz4-java's fastCompressor output format; raw snappy = snappy-java's): this
+    module only frames them the way the reference's writers do."""
+    import pyarrow as pa
+    if compression == COMPRESSION_SNAPPY:
+        return pa.Codec("snappy").compress(raw, asbytes=True)
+    z = pa.Codec("lz4_raw").compress(raw, asbytes=True)
+    if compression == COMPRESSION_LZ4_LENGTH_PREFIXED:        # lz4-java LZ4CompressorWithLength: little-endian decoded length
+        return len(raw).to_bytes(4, "little") + z
+    return z
+
+
+def _raw_forward_index(values: np.ndarray, data_type: DataType, compression=None, version: int = RAW_WRITER_VERSION,
+                       docs_per_chunk: int = RAW_DOCS_PER_CHUNK) -> np.ndarray:
+    """BaseChunkForwardIndexWriter / FixedByteChunkForwardIndexWriter (SEGL/io/writer/impl/BaseChunkForwardIndexWriter.java:
+    73-190): header of seven big-endian ints (version, numChunks, numDocsPerChunk, sizeOfEntry, totalDocs, compressionType,
+    dataHeaderStart), chunk offsets (int for version 2, long for 3 and 4), then the chunks, each compressed on its own;
+    the last chunk holds only the docs that are left."""
+    comp = _COMPRESSION_BY_NAME[compression] if not isinstance(compression, int) else compression
+    assert version in (2, 3, 4)
     n = values.size
     width = _WIDTH[data_type]
-    num_chunks = (n + RAW_DOCS_PER_CHUNK - 1) // RAW_DOCS_PER_CHUNK
-    header_size = 7 * 4 + num_chunks * 4          # version 2: int chunk offsets
-    header = np.empty(7 + num_chunks, dtype=">i4")
-    header[0] = RAW_WRITER_VERSION
+    num_chunks = (n + docs_per_chunk - 1) // docs_per_chunk
+    off_dtype = ">i4" if version == 2 else ">i8"
+    header_size = 7 * 4 + num_chunks * (4 if version == 2 else 8)
+    header = np.empty(7, dtype=">i4")
+    header[0] = version
     header[1] = num_chunks
-    header[2] = RAW_DOCS_PER_CHUNK
+    header[2] = docs_per_chunk
     header[3] = width
     header[4] = n
-    header[5] = COMPRESSION_PASS_THROUGH
+    header[5] = comp
     header[6] = 7 * 4                              # dataHeaderStart
-    header[7:] = header_size + np.arange(num_chunks, dtype=np.int64) * (RAW_DOCS_PER_CHUNK * width)
     body = np.asarray(values).astype(_NP_BE[data_type]).tobytes()
-    return np.frombuffer(header.tobytes() + body, dtype=np.uint8).copy()
+    if comp == 0:
+        offs = header_size + np.arange(num_chunks, dtype=np.int64) * (docs_per_chunk * width)
+        chunks = [body]
+    else:
+        chunks, offs, pos = [], [], header_size
+        step = docs_per_chunk * width
+        for k in range(num_chunks):
+            z = _compress_chunk(body[k * step:(k + 1) * step], comp)
+            offs.append(pos)
+            chunks.append(z)
+            pos += len(z)
+        offs = np.asarray(offs, dtype=np.int64)
+    return np.frombuffer(header.tobytes() + offs.astype(off_dtype).tobytes() + b"".join(chunks), dtype=np.uint8).copy()
 
 
 def build_dict_column(name: str, data_type: DataType, dict_values_sorted: np.ndarray, dict_ids: np.ndarray,
@@ -248,7 +286,8 @@ def build_dict_column(name: str, data_type: DataType, dict_values_sorted: np.nda
 
 
 def build_column(name: str, data_type: DataType, values, dictionary: bool = True, inverted: bool = False,
-                 run_optimize: bool = True, var_length_dictionary: bool = False) -> ColumnIndex:
+                 run_optimize: bool = True, var_length_dictionary: bool = False, raw_compression=None,
+                 raw_version: int = RAW_WRITER_VERSION, raw_docs_per_chunk: int = RAW_DOCS_PER_CHUNK) -> ColumnIndex:
     """Column from per-doc values (what SegmentIndexCreationDriverImpl does per column)."""
     if data_type == DataType.STRING:
         vals = np.array([v if isinstance(v, bytes) else str(v).encode("utf-8") for v in values], dtype=object)
@@ -263,7 +302,7 @@ def build_column(name: str, data_type: DataType, values, dictionary: bool = True
     is_sorted = bool(n <= 1 or (vals[1:] >= vals[:-1]).all())
     return ColumnIndex(name=name, data_type=data_type, num_docs=n, has_dictionary=False, is_sorted=is_sorted,
                        cardinality=-1, bits_per_element=-1, dict_entry_bytes=_WIDTH[data_type],
-                       forward_index=_raw_forward_index(vals, data_type),
+                       forward_index=_raw_forward_index(vals, data_type, raw_compression, raw_version, raw_docs_per_chunk),
                        min_value=vals.min() if n else None, max_value=vals.max() if n else None)
 
 

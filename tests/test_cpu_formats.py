@@ -195,3 +195,91 @@ def test_var_length_string_dictionary_roundtrip_and_oracle():
         for x, y in zip(a.doubles + a.longs, b.doubles + b.longs):
             assert np.array_equal(x, y)
         assert native.dump_lowered(staged[False], q) == native.dump_lowered(staged[True], q)
+
+
+# ---- chunk codecs of raw forward indexes (ChunkCompressionType LZ4 / LZ4_LENGTH_PREFIXED / SNAPPY) ----
+
+def test_lz4_block_known_answers():
+    """Hand-assembled streams of the public LZ4 block format (what lz4-java's safeDecompressor reads, LZ4Decompressor.java:41-52)."""
+    dec = lambda b, n: oracle.block_decode("lz4", bytes(b), n)
+    assert dec([0x50] + list(b"hello"), 5) == b"hello"                                  # literals only: token 5:0
+    # 'a', then a match at offset 1 of length 4 + 5 that overlaps its own output (run-length), then 5 closing literals
+    assert dec([0x15, ord("a"), 0x01, 0x00, 0x50] + list(b"bcdef"), 15) == b"a" * 10 + b"bcdef"
+    # 'abcd', match offset 4 length 4 + 15 + 7 (length extension byte), closing literal
+    assert dec([0x4F] + list(b"abcd") + [0x04, 0x00, 0x07, 0x10, ord("z")], 31) == b"abcd" * 7 + b"ab" + b"z"
+    # 15 + 255 + 3 literals through two length-extension bytes
+    lit = bytes(range(256)) + bytes(17)
+    assert dec([0xF0, 0xFF, 0x03] + list(lit), len(lit)) == lit
+    for bad in ([0x15, ord("a"), 0x00, 0x00, 0x10, 0], [0x15, ord("a"), 0x05, 0x00, 0x10, 0], [0x60, 1, 2]):   # offset 0, offset before the start, truncated
+        with pytest.raises(ValueError):
+            dec(bad, 64)
+
+
+def test_snappy_block_known_answers():
+    dec = lambda b, n: oracle.block_decode("snappy", bytes(b), n)
+    assert dec([5, (5 - 1) << 2] + list(b"hello"), 5) == b"hello"
+    # literal 'ab', then copy-1 (tag 01) of length 4 + 3 = 7 at offset 2: 'ababababa'
+    assert dec([9, (2 - 1) << 2] + list(b"ab") + [(3 << 2) | 1, 2], 9) == b"ababababa"
+    # literal 'xyz', copy-2 (tag 10) length 6 at offset 3
+    assert dec([9, (3 - 1) << 2] + list(b"xyz") + [((6 - 1) << 2) | 2, 3, 0], 9) == b"xyzxyzxyz"
+    # literal of 100 bytes: length - 1 = 99 in one extra byte (tag 60 << 2)
+    lit = bytes(range(100))
+    assert dec([100, 60 << 2, 99] + list(lit), 100) == lit
+    with pytest.raises(ValueError):
+        dec([9, (2 - 1) << 2] + list(b"ab") + [(3 << 2) | 1, 3], 9)                      # offset before the start
+
+
+@pytest.mark.parametrize("codec", ["lz4", "snappy"])
+def test_block_decoders_against_the_stock_libraries(codec):
+    """The oracle's decoders against liblz4 / libsnappy (through pyarrow): random, repetitive and mixed payloads."""
+    pa = pytest.importorskip("pyarrow")
+    name = {"lz4": "lz4_raw", "snappy": "snappy"}[codec]
+    rng = np.random.default_rng(5)
+    payloads = [b"", b"x", bytes(11), rng.integers(0, 256, 70000, dtype=np.uint8).tobytes(), (b"pinot" * 30000)[:99991],
+                np.repeat(rng.integers(0, 50, 3000), rng.integers(1, 40, 3000)).astype(">i4").tobytes(),
+                np.cumsum(rng.integers(0, 3, 20000)).astype(">i8").tobytes(), bytes(200000)]
+    for p in payloads:
+        z = pa.Codec(name).compress(p, asbytes=True)
+        assert oracle.block_decode(codec, z, len(p)) == p
+
+
+@pytest.mark.parametrize("compression", ["LZ4", "LZ4_LENGTH_PREFIXED", "SNAPPY"])
+@pytest.mark.parametrize("version", [2, 3, 4])
+def test_compressed_raw_forward_index(compression, version):
+    """BaseChunkForwardIndexWriter framing (header, per-chunk offsets, independently compressed chunks, short last chunk) and
+    the oracle's rewrite to PASS_THROUGH: same values as the uncompressed index of the same column."""
+    rng = np.random.default_rng(version)
+    n = 2 * 1000 + 137
+    for dt, vals in ((DataType.LONG, np.cumsum(rng.integers(-3, 50, n)).astype(np.int64)), (DataType.INT, rng.integers(-9, 9, n).astype(np.int32)),
+                     (DataType.DOUBLE, np.round(rng.normal(0, 10, n), 1)), (DataType.FLOAT, rng.integers(0, 4, n).astype(np.float32))):
+        plain = build_column("k", dt, vals, dictionary=False, raw_version=version)
+        comp = build_column("k", dt, vals, dictionary=False, raw_compression=compression, raw_version=version)
+        raw = comp.forward_index.tobytes()
+        v, num_chunks, per_chunk, width, total, codec, header_start = struct.unpack_from(">7i", raw, 0)
+        assert (v, num_chunks, per_chunk, total, header_start) == (version, 3, 1000, n, 28)
+        assert codec == {"LZ4": 3, "LZ4_LENGTH_PREFIXED": 4, "SNAPPY": 1}[compression]
+        offs = struct.unpack_from(">3i" if version == 2 else ">3q", raw, 28)
+        assert offs[0] == 28 + 3 * (4 if version == 2 else 8) and offs[0] < offs[1] < offs[2] < len(raw)
+        assert comp.forward_index.size < plain.forward_index.size or dt == DataType.DOUBLE
+        out = oracle.raw_forward_decompress(comp.forward_index, width)
+        assert out.tobytes() == plain.forward_index.tobytes()
+
+
+def test_oracle_reads_compressed_raw_columns():
+    from pinot_b200.query import parse_sql
+    from pinot_b200.segment_writer import make_segment
+    rng = np.random.default_rng(9)
+    n = 5000
+    d = rng.integers(0, 7, n).astype(np.int32)
+    k = rng.integers(-1000, 1000, n).astype(np.int64)
+    x = np.round(rng.normal(0, 5, n), 2)
+    def seg(compression):
+        return make_segment("s", [build_column("d", DataType.INT, d), build_column("k", DataType.LONG, k, dictionary=False, raw_compression=compression),
+                                  build_column("x", DataType.DOUBLE, x, dictionary=False, raw_compression=compression)])
+    q = parse_sql("SELECT d, COUNT(*), SUM(k), MAX(x), DISTINCTCOUNT(k) FROM t WHERE k > -500 AND x < 4.5 GROUP BY d LIMIT 100")
+    ref = oracle.execute(seg(None), q)
+    for compression in ("LZ4", "LZ4_LENGTH_PREFIXED", "SNAPPY"):
+        got = oracle.execute(seg(compression), q)
+        assert got.stats == ref.stats and got.decoded_keys() == ref.decoded_keys()
+        for a in range(len(q.aggregations)):
+            assert np.array_equal(got.doubles[a], ref.doubles[a]) and np.array_equal(got.longs[a], ref.longs[a])

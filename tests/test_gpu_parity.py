@@ -524,3 +524,45 @@ def test_order_by_limit_trim_on_the_device():
     assert len(res.tables[0].rows()) == 16
     res.free()
     g.release()
+
+
+@pytest.mark.parametrize("compression", ["LZ4", "LZ4_LENGTH_PREFIXED", "SNAPPY"])
+def test_chunk_compressed_raw_columns(compression):
+    """Raw forward indexes written with a chunk codec (ChunkCompressionType LZ4 / LZ4_LENGTH_PREFIXED / SNAPPY, offsets as ints
+    (v2) or longs (v4), short last chunk): the compressed bytes are staged and decoded on the device (pb_chunk_decode_kernel);
+    predicates, group keys, aggregation inputs and DISTINCTCOUNT value sets read from the decoded value area."""
+    native.init()
+    rng = np.random.default_rng(77)
+    segs = []
+    for si, (n, version, per_chunk) in enumerate(((30_123, 2, 1000), (18_001, 4, 4096))):
+        d = rng.integers(0, 9, n).astype(np.int32)
+        k = np.cumsum(rng.integers(-2, 6, n)).astype(np.int64) - 20_000            # compresses into long matches
+        i = rng.integers(-50, 50, n).astype(np.int32)
+        x = np.round(rng.normal(0, 5, n), 1)                                      # few distinct doubles
+        f = rng.integers(0, 1000, n).astype(np.float32) / 8
+        r = rng.integers(-2**62, 2**62, n).astype(np.int64)                       # incompressible: literal-only chunks
+        raw = dict(dictionary=False, raw_compression=compression, raw_version=version, raw_docs_per_chunk=per_chunk)
+        segs.append(make_segment(f"z{si}", [build_column("d", DataType.INT, d), build_column("k", DataType.LONG, k, **raw),
+                                            build_column("i", DataType.INT, i, **raw), build_column("x", DataType.DOUBLE, x, **raw),
+                                            build_column("f", DataType.FLOAT, f, **raw), build_column("r", DataType.LONG, r, **raw)]))
+    check_query(segs, "SELECT d, COUNT(*), SUM(k), MIN(x), MAX(f), AVG(i) FROM t WHERE k > -15000 AND x < 4.5 AND i <> 7 GROUP BY d LIMIT 100")
+    check_query(segs, "SELECT i, COUNT(*), MAX(r), DISTINCTCOUNT(f) FROM t WHERE f BETWEEN 10 AND 90 GROUP BY i LIMIT 1000")
+    check_query(segs, "SELECT COUNT(*), MIN(r), MAX(r), SUM(x) FROM t WHERE r > 0", exact_float=False)
+
+
+def test_malformed_compressed_chunk_is_rejected():
+    native.init()
+    rng = np.random.default_rng(3)
+    n = 5000
+    k = np.cumsum(rng.integers(0, 3, n)).astype(np.int64)
+    col = build_column("k", DataType.LONG, k, dictionary=False, raw_compression="LZ4")
+    fwd = col.forward_index
+    off1 = int.from_bytes(fwd[28 + 4:28 + 8].tobytes(), "big")
+    fwd[off1] = 0x0F                                     # chunk 1 now opens with "no literals, match" before any output exists
+    fwd[off1 + 1:off1 + 3] = (9, 0)
+    seg = make_segment("bad", [build_column("d", DataType.INT, rng.integers(0, 4, n).astype(np.int32)), col])
+    staged = native.StagedSegment(seg)
+    group = native.SegmentGroup([staged])
+    with pytest.raises(native.PinotB200Error) as e:
+        native.execute(group, parse_sql("SELECT d, SUM(k) FROM t GROUP BY d LIMIT 10"), 0)
+    assert "do not decode" in str(e.value)
