@@ -54,7 +54,7 @@ enum {
   PB_F_SCAN_RAW_SET = 8,      /* raw column: value in raw_values[] (exclusive: NOT in); doubles as bits */
   PB_F_INVERTED = 9,          /* bitmap inverted index: OR of the bitmaps of ids[] (exclusive: flipped) */
   PB_F_SORTED = 10,           /* sorted index: ids[] holds num_ids inclusive (start,end) docId pairs    */
-  PB_F_BITMAP = 11            /* caller-supplied RoaringBitmap portable blob (exclusive: flipped)       */
+  PB_F_BITMAP = 11            /* RoaringBitmap portable blob (exclusive: flipped); blob NULL = `column`'s null_value_vector (IS [NOT] NULL) */
 };
 
 typedef struct pb_segment_s* pb_segment_handle;
@@ -71,12 +71,17 @@ typedef struct pb_column_desc {
   int32_t cardinality;         /* column.<name>.cardinality (dictionary columns) */
   int32_t bits_per_element;    /* column.<name>.bitsPerElement */
   int32_t dict_entry_bytes;    /* 4/8 for numerics, lengthOfEachEntry for STRING */
-  const void* forward_index;   /* .sv.unsorted.fwd | .sv.sorted.fwd | .sv.raw.fwd (PASS_THROUGH only) */
+  const void* forward_index;   /* .sv.unsorted.fwd | .sv.sorted.fwd | .sv.raw.fwd (fixed-width values; chunks PASS_THROUGH, or SNAPPY /
+                                * LZ4 / LZ4_LENGTH_PREFIXED compressed: those are decoded on the device when the column is staged) */
   uint64_t forward_index_len;
   const void* dictionary;      /* .dict, NULL for raw columns */
   uint64_t dictionary_len;
   const void* inverted_index;  /* .bitmap.inv, NULL when absent */
   uint64_t inverted_index_len;
+  const void* null_value_vector;   /* .bitmap.nullvalue (DataSource.getNullValueVector(): one RoaringBitmap of the null docIds), NULL when
+                                    * absent.  Only IS NULL / IS NOT NULL read it (FilterPlanNode.java:294-307); queries with
+                                    * enableNullHandling keep the CPU plan */
+  uint64_t null_value_vector_len;
 } pb_column_desc;
 
 typedef struct pb_segment_desc {

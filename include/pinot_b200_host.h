@@ -23,7 +23,7 @@ extern "C" {
 
 /* Predicate.Type (pinot-common/.../request/context/predicate/Predicate.java) */
 enum { PBH_EQ = 0, PBH_NOT_EQ = 1, PBH_IN = 2, PBH_NOT_IN = 3, PBH_RANGE = 4,
-       PBH_IS_NULL = 5, PBH_IS_NOT_NULL = 6 };   /* no null-value vectors here: EmptyFilterOperator / MatchAllFilterOperator (CTR/plan/FilterPlanNode.java:294-307) */
+       PBH_IS_NULL = 5, PBH_IS_NOT_NULL = 6 };   /* BitmapBasedFilterOperator over pb_column_desc.null_value_vector; Empty / MatchAll without one (CTR/plan/FilterPlanNode.java:294-307) */
 /* FilterContext.Type */
 enum { PBH_AND = 0, PBH_OR = 1, PBH_NOT = 2, PBH_PREDICATE = 3 };
 

@@ -12,6 +12,7 @@ import org.apache.pinot.common.request.context.predicate.Predicate;
 import org.apache.pinot.core.common.Operator;
 import org.apache.pinot.core.operator.filter.AndFilterOperator;
 import org.apache.pinot.core.operator.filter.BaseFilterOperator;
+import org.apache.pinot.core.operator.filter.BitmapBasedFilterOperator;
 import org.apache.pinot.core.operator.filter.EmptyFilterOperator;
 import org.apache.pinot.core.operator.filter.InvertedIndexFilterOperator;
 import org.apache.pinot.core.operator.filter.MatchAllFilterOperator;
@@ -35,6 +36,7 @@ import org.apache.pinot.segment.spi.SegmentContext;
  *   InvertedIndexFilterOperator                            -> PB_F_INVERTED  (same dictId lists; the device expands the bitmaps)
  *   SortedIndexBasedFilterOperator                         -> PB_F_SORTED    docId ranges from SortedIndexReader.getDocIds(dictId),
  *                                                            merged exactly as SortedIndexBasedFilterOperator.java:61-131 does
+ *   BitmapBasedFilterOperator (IS NULL / IS NOT NULL)       -> PB_F_BITMAP without a blob: the column's staged null-value vector
  *   MatchAllFilterOperator / EmptyFilterOperator            -> PB_F_MATCH_ALL / PB_F_EMPTY
  *   And / Or / NotFilterOperator                            -> PB_F_AND / PB_F_OR / PB_F_NOT after their children
  * Anything else (range / text / JSON / H3 index operators, expression filters) makes the segment ineligible.
@@ -54,6 +56,7 @@ final class B200FilterLowering {
     BaseFilterOperator root = new FilterPlanNode(segmentContext, queryContext, filter).run();
     Map<BaseFilterOperator, B200FilterOperatorUtils.Leaf> leaves = B200FilterOperatorUtils.takeLeaves();
     LoweredProgram program = new LoweredProgram(B200SegmentCache.stagedColumns(segmentContext.getIndexSegment()));
+    program._segment = segmentContext.getIndexSegment();
     if (!(root instanceof MatchAllFilterOperator)) {       // an empty program means "matches all" to the device
       emit(root, leaves, program);
     }
@@ -75,6 +78,15 @@ final class B200FilterLowering {
       out.addCombinator(Native.PB_F_MATCH_ALL, 0);
     } else if (op instanceof EmptyFilterOperator) {
       out.addCombinator(Native.PB_F_EMPTY, 0);
+    } else if (op instanceof BitmapBasedFilterOperator) {
+      // FilterPlanNode.java:294-307 builds these itself for IS NULL / IS NOT NULL from DataSource.getNullValueVector() and the
+      // operator keeps (bitmap, exclusive) private: B200FilterOperatorUtils.nullVectorLeaf recovers which staged column's null
+      // bitmap it holds.  The device reads the vector staged with that column (pb_column_desc.null_value_vector).
+      B200FilterOperatorUtils.NullVectorLeaf leaf = B200FilterOperatorUtils.nullVectorLeaf((BitmapBasedFilterOperator) op, out.segment(), out.stagedColumns());
+      if (leaf == null) {
+        throw new B200Eligibility.NotEligibleException("bitmap filter that is not a null-value vector");
+      }
+      out.addNullVector(leaf._column, leaf._exclusive);
     } else {
       B200FilterOperatorUtils.Leaf leaf = leaves.get(op);
       if (leaf == null) {
@@ -116,6 +128,11 @@ final class B200FilterLowering {
     final List<int[]> _idLists = new ArrayList<>();       // one entry per node (empty array when the node has none)
     final List<long[]> _rawLists = new ArrayList<>();
     private final List<String> _columns;                   // column order of the staged segment (B200SegmentCache)
+    org.apache.pinot.segment.spi.IndexSegment _segment;    // the segment this program was lowered for
+
+    org.apache.pinot.segment.spi.IndexSegment segment() {
+      return _segment;
+    }
 
     LoweredProgram() {
       this(new ArrayList<>());
@@ -160,6 +177,15 @@ final class B200FilterLowering {
       int[] sorted = dictIds.clone();
       java.util.Arrays.sort(sorted);      // the C ABI wants ascending dictIds
       add(kind, column, 0, exclusive, sorted, sorted.length, new long[0], 0, 0, 0, 0, false, false);
+    }
+
+    /** IS NULL (exclusive = false) / IS NOT NULL (true): PB_F_BITMAP with no blob = the column's own null-value vector. */
+    void addNullVector(int column, boolean exclusive) {
+      add(Native.PB_F_BITMAP, column, 0, exclusive, new int[0], 0, new long[0], 0, 0, 0, 0, false, false);
+    }
+
+    List<String> stagedColumns() {
+      return _columns;
     }
 
     void addDictIdRange(int column, int startDictId, int endDictIdExclusive) {

@@ -31,6 +31,44 @@ public final class B200FilterOperatorUtils implements FilterOperatorUtils.Implem
     }
   }
 
+  /** A BitmapBasedFilterOperator that FilterPlanNode built from a column's null-value vector (IS NULL / IS NOT NULL). */
+  static final class NullVectorLeaf {
+    final int _column;          // index into the staged column list
+    final boolean _exclusive;   // IS NOT NULL
+
+    NullVectorLeaf(int column, boolean exclusive) {
+      _column = column;
+      _exclusive = exclusive;
+    }
+  }
+
+  /**
+   * FilterPlanNode.java:294-307 creates these operators itself (no FilterOperatorUtils call to intercept) and the operator
+   * keeps its bitmap private, so the column is recovered by value: the operator's matching docs (getBitmaps().reduce()) equal
+   * either some staged column's null bitmap (IS NULL) or its complement over [0, numDocs) (IS NOT NULL).  Null vectors are
+   * small and this runs once per (segment, query).  Returns null when no column matches.
+   */
+  static NullVectorLeaf nullVectorLeaf(org.apache.pinot.core.operator.filter.BitmapBasedFilterOperator op,
+      org.apache.pinot.segment.spi.IndexSegment segment, java.util.List<String> stagedColumns) {
+    org.roaringbitmap.buffer.ImmutableRoaringBitmap trues = op.getBitmaps().reduce();
+    int numDocs = segment.getSegmentMetadata().getTotalDocs();
+    for (int i = 0; i < stagedColumns.size(); i++) {
+      org.apache.pinot.segment.spi.index.reader.NullValueVectorReader reader =
+          segment.getDataSource(stagedColumns.get(i)).getNullValueVector();
+      if (reader == null) {
+        continue;
+      }
+      org.roaringbitmap.buffer.ImmutableRoaringBitmap nulls = reader.getNullBitmap();
+      if (nulls.equals(trues)) {
+        return new NullVectorLeaf(i, false);
+      }
+      if (org.roaringbitmap.buffer.ImmutableRoaringBitmap.flip(nulls, 0L, numDocs).equals(trues)) {
+        return new NullVectorLeaf(i, true);
+      }
+    }
+    return null;
+  }
+
   private static final ThreadLocal<Map<BaseFilterOperator, Leaf>> LEAVES = ThreadLocal.withInitial(IdentityHashMap::new);
   private final FilterOperatorUtils.Implementation _stock = new FilterOperatorUtils.DefaultImplementation();
 

@@ -62,6 +62,7 @@ final class B200SegmentCache {
     ByteBuffer[] forward = new ByteBuffer[n];
     ByteBuffer[] dictionary = new ByteBuffer[n];
     ByteBuffer[] inverted = new ByteBuffer[n];
+    ByteBuffer[] nullVectors = new ByteBuffer[n];      // IS NULL / IS NOT NULL leaves (FilterPlanNode: BitmapBasedFilterOperator)
     try {
       for (int i = 0; i < n; i++) {
         String column = columns.get(i);
@@ -80,6 +81,9 @@ final class B200SegmentCache {
         if (!cm.isSorted() && reader.hasIndexFor(column, StandardIndexes.inverted())) {
           inverted[i] = view(reader.getIndexFor(column, StandardIndexes.inverted()));
         }
+        if (reader.hasIndexFor(column, StandardIndexes.nullValueVector())) {
+          nullVectors[i] = view(reader.getIndexFor(column, StandardIndexes.nullValueVector()));
+        }
       }
     } catch (java.io.IOException e) {
       throw new RuntimeException("cannot read the index buffers of " + segment.getSegmentName(), e);
@@ -87,7 +91,7 @@ final class B200SegmentCache {
     Entry e = new Entry();
     e._columns = columns;
     e._segment = Native.stageSegment(segment.getSegmentName(), segment.getSegmentMetadata().getTotalDocs(),
-        columns.toArray(new String[0]), meta, forward, dictionary, inverted);
+        columns.toArray(new String[0]), meta, forward, dictionary, inverted, nullVectors);
     e._group = Native.createGroup(new long[]{e._segment});
     return e;
   }

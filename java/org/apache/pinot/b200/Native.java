@@ -15,14 +15,14 @@ final class Native {
 
   // pb_filter_node kinds (include/pinot_b200.h)
   static final int PB_F_AND = 0, PB_F_OR = 1, PB_F_NOT = 2, PB_F_MATCH_ALL = 3, PB_F_EMPTY = 4, PB_F_SCAN_DICT_RANGE = 5,
-      PB_F_SCAN_DICT_SET = 6, PB_F_SCAN_RAW_RANGE = 7, PB_F_SCAN_RAW_SET = 8, PB_F_INVERTED = 9, PB_F_SORTED = 10;
+      PB_F_SCAN_DICT_SET = 6, PB_F_SCAN_RAW_RANGE = 7, PB_F_SCAN_RAW_SET = 8, PB_F_INVERTED = 9, PB_F_SORTED = 10, PB_F_BITMAP = 11;
   // pb_query_desc.flags
   static final int PB_Q_COMBINE = 1, PB_Q_GATHER_IN_PLACE = 16;
 
   /** meta: 6 ints per column (storedType, hasDictionary, isSorted, cardinality, bitsPerElement, dictEntryBytes); the buffers
    * are PinotDataBuffer.toDirectByteBuffer views of the mmap'd columns.psf (zero copy). */
   static native long stageSegment(String name, int numDocs, String[] columns, int[] meta, ByteBuffer[] forwardIndexes,
-      ByteBuffer[] dictionaries, ByteBuffer[] invertedIndexes);
+      ByteBuffer[] dictionaries, ByteBuffer[] invertedIndexes, ByteBuffer[] nullValueVectors);
 
   static native void releaseSegment(long segment);
 

@@ -23,9 +23,9 @@ static void throw_last(JNIEnv* env) {
 
 /* long stageSegment(String name, int numDocs, String[] colNames, int[] meta /\* 6 ints per column: storedType,
  * hasDictionary, isSorted, cardinality, bitsPerElement, dictEntryBytes *\/, ByteBuffer[] fwd, ByteBuffer[] dict,
- * ByteBuffer[] inv) */
+ * ByteBuffer[] inv, ByteBuffer[] nullVectors) */
 JNIEXPORT jlong JNICALL Java_org_apache_pinot_b200_Native_stageSegment(JNIEnv* env, jclass cls, jstring name, jint numDocs,
-    jobjectArray colNames, jintArray meta, jobjectArray fwd, jobjectArray dict, jobjectArray inv) {
+    jobjectArray colNames, jintArray meta, jobjectArray fwd, jobjectArray dict, jobjectArray inv, jobjectArray nullVectors) {
   jsize n = (*env)->GetArrayLength(env, colNames);
   pb_column_desc* cols = (pb_column_desc*)calloc((size_t)n, sizeof(pb_column_desc));
   jint* m = (*env)->GetIntArrayElements(env, meta, NULL);
@@ -46,6 +46,8 @@ JNIEXPORT jlong JNICALL Java_org_apache_pinot_b200_Native_stageSegment(JNIEnv* e
     if (b) { cols[i].dictionary = (*env)->GetDirectBufferAddress(env, b); cols[i].dictionary_len = (uint64_t)(*env)->GetDirectBufferCapacity(env, b); (*env)->DeleteLocalRef(env, b); }
     b = (*env)->GetObjectArrayElement(env, inv, i);
     if (b) { cols[i].inverted_index = (*env)->GetDirectBufferAddress(env, b); cols[i].inverted_index_len = (uint64_t)(*env)->GetDirectBufferCapacity(env, b); (*env)->DeleteLocalRef(env, b); }
+    b = (*env)->GetObjectArrayElement(env, nullVectors, i);
+    if (b) { cols[i].null_value_vector = (*env)->GetDirectBufferAddress(env, b); cols[i].null_value_vector_len = (uint64_t)(*env)->GetDirectBufferCapacity(env, b); (*env)->DeleteLocalRef(env, b); }
   }
   const char* sname = (*env)->GetStringUTFChars(env, name, NULL);
   pb_segment_desc d = { sname, numDocs, (int32_t)n, cols };

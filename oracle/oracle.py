@@ -28,7 +28,8 @@ class OrcColumn(C.Structure):
                 ("cardinality", C.c_int32), ("bits_per_element", C.c_int32), ("dict_entry_bytes", C.c_int32),
                 ("forward_index", C.c_void_p), ("forward_index_len", C.c_int64),
                 ("dictionary", C.c_void_p), ("dictionary_len", C.c_int64),
-                ("inverted_index", C.c_void_p), ("inverted_index_len", C.c_int64)]
+                ("inverted_index", C.c_void_p), ("inverted_index_len", C.c_int64),
+                ("null_value_vector", C.c_void_p), ("null_value_vector_len", C.c_int64)]
 
 
 class OrcSegment(C.Structure):
@@ -172,6 +173,9 @@ def marshal_segment(seg, m: _Marshalled, skip_inverted=()) -> OrcSegment:
         if c.inverted_index is not None and c.name not in skip_inverted:
             oc.inverted_index = c.inverted_index.ctypes.data
             oc.inverted_index_len = c.inverted_index.size
+        if getattr(c, "null_value_vector", None) is not None:
+            oc.null_value_vector = c.null_value_vector.ctypes.data
+            oc.null_value_vector_len = c.null_value_vector.size
     m.hold(cols)
     s = OrcSegment(seg.num_docs, len(seg.columns), cols)
     return m.hold(s)

@@ -600,9 +600,18 @@ static fop* make_inverted_op(pred_eval* e, int32_t num_docs) {
 
 /* CTR/operator/filter/FilterOperatorUtils.java:74-133 (index selection) */
 static fop* make_leaf_op(const orc_segment* seg, const orc_query* q, const orc_predicate* p) {
-  /* FilterPlanNode.java:294-307: no null-value vector on this path */
-  if (p->type == ORC_IS_NULL) return fop_new(OP_EMPTY, seg->num_docs);
-  if (p->type == ORC_IS_NOT_NULL) return fop_new(OP_MATCH_ALL, seg->num_docs);
+  /* FilterPlanNode.java:294-307: IS NULL / IS NOT NULL are a BitmapBasedFilterOperator over the column's null-value vector
+   * (NullValueVectorReaderImpl: one RoaringBitmap of the null docIds; BitmapBasedFilterOperator.java:35-47 flips it over
+   * [0, numDocs) when exclusive); without a vector IS NULL is empty and IS NOT NULL matches all */
+  if (p->type == ORC_IS_NULL || p->type == ORC_IS_NOT_NULL) {
+    const orc_column* nc = &seg->columns[p->column];
+    if (!nc->null_value_vector) return fop_new(p->type == ORC_IS_NULL ? OP_EMPTY : OP_MATCH_ALL, seg->num_docs);
+    fop* f = fop_new(OP_BITMAP, seg->num_docs);
+    f->bm = bm_new(seg->num_docs);
+    if (roaring_for_each(nc->null_value_vector, nc->null_value_vector_len, bm_sink, &f->bm) != 0) { set_err("malformed null-value vector"); fop_free(f); return NULL; }
+    if (p->type == ORC_IS_NOT_NULL) bm_flip(&f->bm);
+    return f;
+  }
   pred_eval* e = (pred_eval*)malloc(sizeof(pred_eval));
   if (pred_eval_init(e, seg, p) != 0) { free(e); return NULL; }
   int32_t n = seg->num_docs;

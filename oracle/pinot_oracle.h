@@ -42,6 +42,7 @@ typedef struct orc_column {
   const uint8_t* forward_index;  int64_t forward_index_len;
   const uint8_t* dictionary;     int64_t dictionary_len;
   const uint8_t* inverted_index; int64_t inverted_index_len;   /* NULL when absent */
+  const uint8_t* null_value_vector; int64_t null_value_vector_len;   /* .bitmap.nullvalue: RoaringBitmap of the null docIds, NULL when absent */
 } orc_column;
 
 typedef struct orc_segment {

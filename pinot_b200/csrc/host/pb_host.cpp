@@ -158,11 +158,15 @@ class PredicateEvaluatorProvider {
 };
 
 // ---------------------------------------------------------------------------------------------- filter operators
-enum OpKind { OP_EMPTY, OP_MATCH_ALL, OP_SORTED, OP_INVERTED, OP_SCAN, OP_AND, OP_OR, OP_NOT };
+enum OpKind { OP_EMPTY, OP_MATCH_ALL, OP_SORTED, OP_INVERTED, OP_SCAN, OP_AND, OP_OR, OP_NOT, OP_BITMAP };
 struct FilterOperator {
   OpKind kind = OP_EMPTY;
   PredicateEvaluator ev;
   std::vector<int32_t> docIdRanges;   // OP_SORTED: inclusive (start,end) pairs
+  const uint8_t* bitmap = nullptr;    // OP_BITMAP (BitmapBasedFilterOperator): serialized RoaringBitmap, flipped over [0, numDocs) when exclusive
+  uint64_t bitmapLen = 0;
+  bool bitmapExclusive = false;
+  int bitmapColumn = -1;
   std::vector<std::unique_ptr<FilterOperator>> children;
 };
 using OpPtr = std::unique_ptr<FilterOperator>;
@@ -210,6 +214,7 @@ class FilterOperatorUtils {
     switch (f.kind) {
       case OP_SORTED: return 0;
       case OP_INVERTED: return 100;
+      case OP_BITMAP: return 100;     // BitmapBasedFilterOperator
       case OP_AND: return 300;
       case OP_OR: return 400;
       case OP_NOT: return getPriority(*f.children[0]);
@@ -260,9 +265,16 @@ class FilterPlanNode {
         const pbh_predicate& p = predicates[n.predicate];
         int ci = findColumn(seg, p.column);
         if (ci < 0) throw BadQuery{std::string("unknown column ") + p.column};
-        // FilterPlanNode.java:294-307: without a null-value vector IS NULL is empty and IS NOT NULL matches all
-        if (p.type == PBH_IS_NULL) { stack.push_back(mk(OP_EMPTY)); continue; }
-        if (p.type == PBH_IS_NOT_NULL) { stack.push_back(mk(OP_MATCH_ALL)); continue; }
+        // FilterPlanNode.java:294-307: a BitmapBasedFilterOperator over the column's null-value vector (exclusive for IS NOT
+        // NULL); without a vector IS NULL is empty and IS NOT NULL matches all
+        if (p.type == PBH_IS_NULL || p.type == PBH_IS_NOT_NULL) {
+          const PbColumnView& nc = seg.cols[ci];
+          if (!nc.null_vector) { stack.push_back(mk(p.type == PBH_IS_NULL ? OP_EMPTY : OP_MATCH_ALL)); continue; }
+          OpPtr op = mk(OP_BITMAP);
+          op->bitmap = nc.null_vector; op->bitmapLen = nc.null_vector_len; op->bitmapExclusive = p.type == PBH_IS_NOT_NULL; op->bitmapColumn = ci;
+          stack.push_back(std::move(op));
+          continue;
+        }
         bool skipInv = false;
         for (int k = 0; k < q.num_skip_inverted; k++) if (seg.cols[ci].name == q.skip_inverted_columns[k]) skipInv = true;
         PredicateEvaluator ev = PredicateEvaluatorProvider::getPredicateEvaluator(p, seg.cols[ci], ci);
@@ -307,6 +319,7 @@ static void emit(const FilterOperator& f, const PbSegmentView& seg, LoweredSegme
       n.kind = PB_F_INVERTED; n.column = f.ev.column; n.exclusive = f.ev.exclusive; n.ids = out.idStore.back()->data(); n.num_ids = (int32_t)f.ev.dictIds.size();
       break;
     }
+    case OP_BITMAP: n.kind = PB_F_BITMAP; n.column = f.bitmapColumn; n.exclusive = f.bitmapExclusive ? 1 : 0; break;   // no blob: the column's staged null-value vector
     case OP_SCAN: {
       const PredicateEvaluator& e = f.ev;
       n.column = e.column;
@@ -334,7 +347,7 @@ static void emit(const FilterOperator& f, const PbSegmentView& seg, LoweredSegme
 }
 
 static void explain(const FilterOperator& f, const PbSegmentView& seg, int depth, std::string& out) {
-  static const char* names[] = {"FILTER_EMPTY", "FILTER_MATCH_ENTIRE_SEGMENT", "FILTER_SORTED_INDEX", "FILTER_INVERTED_INDEX", "FILTER_FULL_SCAN", "FILTER_AND", "FILTER_OR", "FILTER_NOT"};
+  static const char* names[] = {"FILTER_EMPTY", "FILTER_MATCH_ENTIRE_SEGMENT", "FILTER_SORTED_INDEX", "FILTER_INVERTED_INDEX", "FILTER_FULL_SCAN", "FILTER_AND", "FILTER_OR", "FILTER_NOT", "FILTER_BITMAP"};
   out.append((size_t)depth * 2, ' ');
   out += names[f.kind];
   if (f.kind == OP_SCAN || f.kind == OP_INVERTED) {

@@ -32,7 +32,7 @@
 #define PB_MAX_AF_NODES 48
 #define PB_SPARSE_MAX 128            // survivors per 1024-doc chunk below which later AND leaves use the restricted scan
 #define PB_OUT_CAP 256               // (upper bound; DevQuery::out_cap) matches buffered per warp before one ATOMG reserves their place in the match list
-#define PB_CAND_CAP 256              // (upper bound; DevQuery::cand_cap, a multiple of 32) candidates per warp list (u32 docs inside the segment)
+#define PB_CAND_CAP 512              // (upper bound; DevQuery::cand_cap) candidates per warp list (u16 offsets inside the unit); more = extra passes
 #define PB_SET_SMEM_BYTES 8192      // dictId-set membership LUTs (one byte per dictId) cached in smem per segment
 
 enum { L_TRUE = 0, L_FALSE = 1, L_DICT_RANGE = 2, L_DICT_SET = 3, L_RAW_RANGE_I = 4, L_RAW_RANGE_F = 5,
@@ -403,33 +403,6 @@ __device__ __forceinline__ uint32_t pb_eval_dict_w(const uint32_t* __restrict__ 
     const int k = bit >> 5, s = bit & 31;
     const uint32_t vt = (s == 0) ? w[k] : __funnelshift_l(w[k + 1], w[k], s);   // value in the top W bits
     m[j >> 3] = m[j >> 3] * 2 + pred.template test<W>(vt);
-  }
-  return (m[3] << 24) | (m[2] << 16) | (m[1] << 8) | m[0];
-}
-
-// IN / NOT IN on a dictionary of <= 1024 values (5 <= W <= 10) without touching shared memory per value: the 2^W membership
-// bits live in ONE REGISTER PER LANE (lane = top five bits of the dictId, bit 31 - (low five bits)) and are fetched with a
-// warp shuffle, which -- unlike the byte LUT, whose random addresses serialise 3.5 ways on the 32 banks -- is conflict-free.
-// Both five-bit fields are read straight out of the packed stream with compile-time funnel shifts (SHFL.IDX and SHF.L.W use
-// only the low five bits of their operand, so nothing is masked): five instructions per value.
-template <int W>
-__device__ __forceinline__ uint32_t pb_eval_dict_w_shfl(const uint32_t* __restrict__ p, uint32_t lutword, int lane) {
-  static_assert(W >= 5 && W <= 10, "shuffle LUT: 5..10-bit dictIds");
-  uint32_t w[W + 1];
-  const uint32_t* q = p + lane * W;
-#pragma unroll
-  for (int k = 0; k < W; k++) w[k] = pb_bswap32(q[k]);
-  w[W] = 0;
-  uint32_t m[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int j = 31; j >= 0; j--) {
-    const int e1 = j * W + 5, e2 = j * W + W;                  // stream bit (exclusive) where each window ends
-    const int k1 = e1 >> 5, s1 = e1 & 31, k2 = e2 >> 5, s2 = e2 & 31;
-    const uint32_t rl = s1 == 0 ? w[k1 - (s1 == 0 ? 1 : 0)] : k1 == 0 ? (w[0] >> (32 - s1)) : __funnelshift_l(w[k1], w[k1 - (k1 > 0 ? 1 : 0)], s1);
-    const uint32_t rb = s2 == 0 ? w[k2 - (s2 == 0 ? 1 : 0)] : k2 == 0 ? (w[0] >> (32 - s2)) : __funnelshift_l(w[k2], w[k2 - (k2 > 0 ? 1 : 0)], s2);
-    const uint32_t word = __shfl_sync(0xffffffffu, lutword, (int)rl);       // lane = rl & 31 = top five bits of the dictId
-    const uint32_t x = __funnelshift_l(0u, word, rb);                       // word << (rb & 31): the member bit on top
-    m[j >> 3] = __funnelshift_l(x, m[j >> 3], 1);                           // (m << 1) | (x >> 31)
   }
   return (m[3] << 24) | (m[2] << 16) | (m[1] << 8) | m[0];
 }
@@ -898,8 +871,7 @@ struct __align__(16) FilterSmemHeader {
 // SW / SPK: plan-time specialisation.  SW = 0 is the general kernel (any predicate tree, every width and predicate kind
 // dispatched at run time: ~27 k SASS instructions, whose instruction-cache misses and dispatch cost were a fifth of the
 // issue slots of the common case).  SW > 0 is a kernel for ONE shape -- a flat conjunction whose only streamed leaf is a
-// dictionary column of SW bits tested with predicate kind SPK (0 = dictId range, 1 = IN / NOT IN byte LUT in shared memory,
-// 2 = IN / NOT IN bit LUT in registers fetched by warp shuffle: dictionaries of <= 1024 values), every
+// dictionary column of SW bits tested with predicate kind SPK (0 = dictId range, 1 = IN / NOT IN membership LUT), every
 // other leaf evaluated on the candidates -- with that leaf's unpack + test inlined and nothing else compiled in.  The host
 // picks it when every segment of the launch has that shape (pb_filter_spec.cu holds the instantiations).
 template <int U, int MIN_CTAS, int SW = 0, int SPK = 0>
@@ -910,7 +882,7 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
   uint8_t* dyn = smem_raw + ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127);
   uint8_t* set_cache = dyn;
   dyn += (Q.set_cache_bytes + 127) & ~127;
-  uint32_t* cand = reinterpret_cast<uint32_t*>(dyn);     // per-warp candidate lists (only when some leaf is evaluated on candidates)
+  uint16_t* cand = reinterpret_cast<uint16_t*>(dyn);     // per-warp candidate lists (only when some leaf is evaluated on candidates)
   dyn += Q.cand_bytes;
   const uint32_t OUT_CAP = (uint32_t)Q.out_cap, CAND_CAP = (uint32_t)Q.cand_cap;
   uint32_t* ob = reinterpret_cast<uint32_t*>(dyn) + (size_t)warp * OUT_CAP;   // this warp's output buffer
@@ -1043,14 +1015,6 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
       }
       __syncthreads();
     }
-    [[maybe_unused]] uint32_t shfl_lut = 0;
-    if constexpr (SW > 0 && SPK == 2) {
-      // this lane's 32 membership bits: dictIds whose top five bits are `lane`, bit 31 - (dictId & 31), exclusive flag folded in
-      const DevLeaf& lf = sq.leaves[H->flat_leaf[0]];
-      const uint32_t v0 = (uint32_t)lane << (SW - 5);
-      for (uint32_t v = v0; v < v0 + (1u << (SW - 5)); v++)
-        if (v < (uint32_t)lf.set_card && ((((__ldg(lf.set_bits + (v >> 5)) >> (v & 31)) & 1u) ^ (uint32_t)lf.exclusive) != 0)) shfl_lut |= 0x80000000u >> (v & 31);
-    }
     const uint64_t seg_lo = sq.unit_begin > cta_lo ? sq.unit_begin : cta_lo;
     const uint64_t seg_end = sq.unit_begin + sq.n_units;
     const uint64_t seg_hi = seg_end < cta_hi ? seg_end : cta_hi;
@@ -1060,37 +1024,6 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
     const uint32_t rel0 = (uint32_t)(first - sq.unit_begin);     // unit index inside the segment
     const int n_scan = sq.n_scan;
     unsigned long long matched = 0;
-    uint32_t* const cl = cand + (size_t)warp * CAND_CAP;     // this warp's candidate list
-    uint32_t cand_n = 0;                                     // candidates waiting in it (warp-uniform)
-    // test the first n (a multiple of 32, or everything at segment exit) candidates, then move the rest to the front
-    auto cand_rounds = [&](uint32_t n) {
-      if (n == 0) return;
-      const uint32_t lt = (1u << lane) - 1u;
-      const int n_cand_leaves = H->n_flat - H->n_dense;
-      for (uint32_t b0 = 0; b0 < n; b0 += 32) {
-        const uint32_t idx = b0 + (uint32_t)lane;
-        bool alive = idx < n;
-        const uint32_t doc = alive ? cl[idx] : 0u;                // doc inside the segment
-        for (int i = 0; i < n_cand_leaves; i++) {
-          if (alive) alive = pb_leaf_test_doc(sq.leaves[H->flat_leaf[H->n_dense + i]], set_cache, doc);
-          if (!__any_sync(0xffffffffu, alive)) break;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-        if (bal) {
-          const uint32_t nb = (uint32_t)__popc(bal);
-          if (out_n + nb > OUT_CAP) flush_out();
-          if (alive) ob[out_n + __popc(bal & lt)] = (uint32_t)sq.doc_base + doc;
-          out_n += nb;
-          matched += nb;
-        }
-      }
-      const uint32_t rest = cand_n - n;                             // < 32 unless called at segment exit (then 0)
-      const uint32_t keep = (uint32_t)lane < rest ? cl[n + (uint32_t)lane] : 0u;
-      __syncwarp();
-      if ((uint32_t)lane < rest) cl[lane] = keep;
-      cand_n = rest;
-      __syncwarp();
-    };
     uint32_t min_last_rel = 0xffffffffu;               // first unit whose load must be clipped to the buffer end
     for (int c = 0; c < n_scan; c++) min_last_rel = min(min_last_rel, H->slot_last_rel[c]);
 
@@ -1168,13 +1101,10 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
           PredRange pr; pr.lo = lf.lo; pr.span = lf.span;
 #pragma unroll
           for (int u = 0; u < U; u++) if (u < nu) mask[u] &= pb_eval_dict_w<SW, PredRange>(p + u * 32 * SW, pr, lane);
-        } else if constexpr (SPK == 1) {
+        } else {
           PredLut8 pl; pl.lut = set_cache + lf.set_smem_off;
 #pragma unroll
           for (int u = 0; u < U; u++) if (u < nu) mask[u] &= pb_eval_dict_w<SW, PredLut8>(p + u * 32 * SW, pl, lane);
-        } else {
-#pragma unroll
-          for (int u = 0; u < U; u++) if (u < nu) mask[u] &= pb_eval_dict_w_shfl<SW>(p + u * 32 * SW, shfl_lut, lane);
         }
       } else if (__builtin_expect(H->flat_and != 0, 1)) {
         const int nl = H->n_dense;
@@ -1271,35 +1201,49 @@ __global__ void __launch_bounds__(PB_NTHREADS, MIN_CTAS) pb_filter_kernel(const 
         }
         matched += total;
       } else {
-        // ---- candidates: survivors of the staged leaves go to this warp's list (docs inside the segment); whenever the list
-        // holds 32 or more, one lane per candidate tests the remaining leaves straight from their forward indexes / row
-        // groups (all 32 gathers of a round in flight at once).  The list carries over from unit to unit so that rounds
-        // run with all 32 lanes busy (a unit leaves ~33 survivors in the headline query: two half-empty rounds before) ----
-        for (uint32_t done = 0; done < total;) {
-          const uint32_t room = CAND_CAP - cand_n;
-          const uint32_t take = total - done < room ? total - done : room;
+        // ---- candidates: survivors of the staged leaves, compacted into this warp's list, then one lane per candidate
+        // tests the remaining leaves straight from their forward indexes (all 32 gathers of a round in flight at once) ----
+        uint16_t* cl = cand + (size_t)warp * CAND_CAP;
+        for (uint32_t pass0 = 0; pass0 < total; pass0 += CAND_CAP) {     // one pass unless the estimate was far off
+          if (pass0) __syncwarp();
           {
-            uint32_t pos = excl - done;                                      // (wraps below the window: unsigned compare)
+            uint32_t pos = excl - pass0;                                     // (wraps below the window: unsigned compare)
 #pragma unroll
             for (int u = 0; u < U; u++) {
-              const uint32_t doc0 = (uint32_t)unit_doc0 + (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
+              const uint32_t off0 = (uint32_t)u * PB_CHUNK_DOCS + 32u * (uint32_t)lane;
               uint32_t mm = mask[u];
               while (mm) {
                 const int bit = __ffs(mm) - 1;
                 mm &= mm - 1;
-                if (pos < take) cl[cand_n + pos] = doc0 + (uint32_t)bit;
+                if (pos < CAND_CAP) cl[pos] = (uint16_t)(off0 + (uint32_t)bit);
                 pos++;
               }
             }
           }
-          cand_n += take;
-          done += take;
           __syncwarp();
-          cand_rounds(cand_n & ~31u);
+          const uint32_t n_pass = total - pass0 < CAND_CAP ? total - pass0 : CAND_CAP;
+          for (uint32_t b0 = 0; b0 < n_pass; b0 += 32) {
+            const uint32_t idx = b0 + (uint32_t)lane;
+            bool alive = idx < n_pass;
+            const uint32_t off = alive ? (uint32_t)cl[idx] : 0u;
+            const uint32_t doc = (uint32_t)unit_doc0 + off;          // doc inside the segment
+            for (int i = 0; i < n_cand_leaves; i++) {
+              if (alive) alive = pb_leaf_test_doc(sq.leaves[H->flat_leaf[H->n_dense + i]], set_cache, doc);
+              if (!__any_sync(0xffffffffu, alive)) break;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+            if (bal) {
+              const uint32_t n = (uint32_t)__popc(bal);
+              if (out_n + n > OUT_CAP) flush_out();
+              if (alive) ob[out_n + __popc(bal & lt)] = gunit0 + off;
+              out_n += n;
+              matched += n;
+            }
+          }
         }
+        __syncwarp();   // the list is rewritten by the next unit
       }
     }
-    if (cand_n) { __syncwarp(); cand_rounds(cand_n); }
     flush_out();
     // ---- segment exit: numDocsScanned of this segment's table (matched is warp-uniform) ----
     if (lane == 0 && matched) pb_red_add_u64(Q.tables[sq.table].docs_matched, matched);
@@ -1724,23 +1668,17 @@ __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_rows_kernel(con
     for (int k = 0; k < RW; k++) w[k] = pb_bswap32(w[k]);
   };
   const unsigned long long stride = (unsigned long long)gridDim.x * PB_AGG_SMEM_THREADS;
-  constexpr int ND = RW <= 4 ? 4 : 2;          // docs in flight per thread (their row loads are issued back to back)
-  for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += ND * stride) {
-    unsigned long long gdoc[ND];
-    int sgi[ND];
-    uint32_t w[ND][RW];
-#pragma unroll
-    for (int d = 0; d < ND; d++) {
-      const unsigned long long idx = i + (unsigned long long)d * stride;
-      gdoc[d] = idx < n ? (Q.match_all ? idx : (unsigned long long)__ldg(Q.match_list + idx)) : ~0ull;
-    }
-#pragma unroll
-    for (int d = 0; d < ND; d++) {
-      sgi[d] = seg_of(gdoc[d] == ~0ull ? gdoc[0] : gdoc[d]);
-      load_row(segs[sgi[d]], gdoc[d] == ~0ull ? gdoc[0] : gdoc[d], w[d]);
-    }
-#pragma unroll
-    for (int d = 0; d < ND; d++) if (gdoc[d] != ~0ull) process(gdoc[d], w[d], segs[sgi[d]]);
+  for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += 2 * stride) {
+    const bool two = i + stride < n;
+    const unsigned long long gdoc0 = Q.match_all ? i : (unsigned long long)__ldg(Q.match_list + i);
+    const unsigned long long gdoc1 = !two ? gdoc0 : (Q.match_all ? i + stride : (unsigned long long)__ldg(Q.match_list + i + stride));
+    const DevRowSeg& sg0 = segs[seg_of(gdoc0)];
+    const DevRowSeg& sg1 = segs[seg_of(gdoc1)];
+    uint32_t w0[RW], w1[RW];
+    load_row(sg0, gdoc0, w0);
+    load_row(sg1, gdoc1, w1);
+    process(gdoc0, w0, sg0);
+    if (two) process(gdoc1, w1, sg1);
   }
   if (!use_smem) return;
   __syncthreads();

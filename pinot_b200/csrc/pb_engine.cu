@@ -297,6 +297,7 @@ struct Column {
   // caller's buffers (valid until staged; Pinot keeps the mmap alive while the segment is acquired)
   const uint8_t* h_fwd = nullptr; uint64_t h_fwd_len = 0;
   const uint8_t* h_inv = nullptr; uint64_t h_inv_len = 0;
+  const uint8_t* h_null = nullptr; uint64_t h_null_len = 0;   // null-value vector (a RoaringBitmap): IS [NOT] NULL leaves arrive as PB_F_BITMAP
   std::vector<uint8_t> h_dict;          // host copy of the dictionary (big-endian, as stored)
   uint64_t raw_data_start = 0;
   int raw_width = 0;
@@ -379,6 +380,7 @@ extern "C" int pb_segment_stage(const pb_segment_desc* d, int device_index, pb_s
     c.card = cd.cardinality; c.bits = cd.bits_per_element; c.entry_bytes = cd.dict_entry_bytes;
     c.h_fwd = (const uint8_t*)cd.forward_index; c.h_fwd_len = cd.forward_index_len;
     c.h_inv = (const uint8_t*)cd.inverted_index; c.h_inv_len = cd.inverted_index_len;
+    c.h_null = (const uint8_t*)cd.null_value_vector; c.h_null_len = cd.null_value_vector ? cd.null_value_vector_len : 0;
     if (c.type < PB_INT || c.type > PB_STRING) return fail(PB_ERR_UNSUPPORTED, "column %s: stored type %d", cd.name, c.type);
     if (c.has_dict) {
       if (!cd.dictionary || c.card <= 0 || c.bits < 1 || c.bits > 32) return fail(PB_ERR_INVALID, "column %s: bad dictionary metadata", cd.name);
@@ -1247,7 +1249,7 @@ static void plan_candidate_leaves(const pb_segment_s* s, const pb_segment_query&
   gather.assign((size_t)std::max(nn, 0), 0);
   cand_frac.assign((size_t)std::max(nn, 0), 1.0);
   static const int permille_max = []() { const char* e = getenv("PB_GATHER_LEAF_PERMILLE"); return e ? atoi(e) : 30; }();
-  if (permille_max <= 0 || nn < 3) return;
+  if (nn < 3) return;
   const pb_filter_node& root = sq.filter[nn - 1];
   if (root.kind != PB_F_AND || root.num_children != nn - 1) return;
   struct L { int n; double est; bool scan; };
@@ -1263,7 +1265,7 @@ static void plan_candidate_leaves(const pb_segment_s* s, const pb_segment_query&
   bool have_dense = false;
   for (const L& l : ls) {
     cand_frac[l.n] = p;
-    if (have_dense && l.scan && p * 1000.0 <= (double)permille_max) gather[l.n] = 1;
+    if (have_dense && l.scan && permille_max > 0 && p * 1000.0 <= (double)permille_max) gather[l.n] = 1;
     else have_dense = true;
     p *= l.est;
   }
@@ -1272,6 +1274,26 @@ static void plan_candidate_leaves(const pb_segment_s* s, const pb_segment_query&
     if (gather[l.n])
       for (const L& o : ls)
         if (!gather[o.n] && o.scan && sq.filter[o.n].column == sq.filter[l.n].column) { gather[l.n] = 0; break; }
+  // shared-memory budget: every streamed column takes 2 stages x 8 warps x 1024 docs x its width.  Predicates on several wide
+  // (raw LONG / DOUBLE) columns do not fit; the most selective leaves stay streamed, the rest run on the candidates whatever
+  // the expected survivors (slower than streaming at low selectivity, but it runs -- and exactly the reference's applyAnd)
+  const int budget_bits = 96;
+  int used = 0;
+  std::vector<int> streamed_cols;
+  auto width_of = [&](int n) {
+    const int col = sq.filter[n].column;
+    if (col < 0 || col >= (int)s->cols.size()) return 0;          // (rejected later, when the leaf is lowered)
+    const Column& c = s->cols[(size_t)col];
+    return c.has_dict ? c.bits : 8 * c.raw_width;
+  };
+  for (const L& l : ls) {
+    if (!l.scan || gather[l.n]) continue;
+    const int col = sq.filter[l.n].column;
+    if (std::find(streamed_cols.begin(), streamed_cols.end(), col) != streamed_cols.end()) continue;     // shares a streamed column
+    const int w = width_of(l.n);
+    if (!streamed_cols.empty() && used + w > budget_bits) { gather[l.n] = 1; continue; }
+    used += w; streamed_cols.push_back(col);
+  }
 }
 
 // Expected fraction of a segment's docs that pass the filter (postfix tree).  Drives the stage-or-gather choice of
@@ -2004,7 +2026,11 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
         if (fn.kind == PB_F_SCAN_RAW_SET) arena_cap += 8 * (size_t)fn.num_raw_values + 32;
         if (fn.kind == PB_F_INVERTED) arena_cap += (4 + sizeof(DevExpandItem)) * (size_t)std::max(fn.num_ids, 0) + 64;
         if (fn.kind == PB_F_SORTED) arena_cap += 8 * (size_t)std::max(fn.num_ids, 0) + sizeof(DevExpandItem) + 64;
-        if (fn.kind == PB_F_BITMAP) arena_cap += fn.blob_len + sizeof(DevExpandItem) + 128;
+        if (fn.kind == PB_F_BITMAP) {
+          uint64_t bl = fn.blob ? fn.blob_len : 0;
+          if (!fn.blob && fn.column >= 0 && fn.column < (int)s->cols.size()) bl = s->cols[(size_t)fn.column].h_null_len;   // the column's null-value vector
+          arena_cap += bl + sizeof(DevExpandItem) + 128;
+        }
         if (fn.kind == PB_F_INVERTED || fn.kind == PB_F_SORTED || fn.kind == PB_F_BITMAP) bitmap_words_total += (((size_t)s->num_docs + 2047) / 2048) * 64;
       }
     };
@@ -2165,12 +2191,15 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
             expands.push_back({1, nullptr, 0, dp, fn.num_ids, bm, (uint32_t)s->num_docs, {}});
           } else {
             // wrap the caller's Roaring blob as a one-entry inverted index: [BE off0][BE off1][blob]
-            if (!fn.blob || fn.blob_len < 8) return fail(PB_ERR_INVALID, "filter node %d: bitmap blob missing", n);
-            std::vector<uint8_t> tmp(8 + fn.blob_len);
-            uint32_t o0 = 8, o1 = (uint32_t)(8 + fn.blob_len);
+            // (no blob: the null-value vector staged with the node's column -- IS NULL / IS NOT NULL, FilterPlanNode.java:294-307)
+            const uint8_t* blob = (const uint8_t*)fn.blob; uint64_t blob_len = fn.blob_len;
+            if (!blob && fn.column >= 0 && fn.column < (int)s->cols.size()) { blob = s->cols[(size_t)fn.column].h_null; blob_len = s->cols[(size_t)fn.column].h_null_len; }
+            if (!blob || blob_len < 8) return fail(PB_ERR_INVALID, "filter node %d: bitmap blob missing (and column %d has no null-value vector)", n, fn.column);
+            std::vector<uint8_t> tmp(8 + blob_len);
+            uint32_t o0 = 8, o1 = (uint32_t)(8 + blob_len);
             tmp[0] = o0 >> 24; tmp[1] = o0 >> 16; tmp[2] = o0 >> 8; tmp[3] = (uint8_t)o0;
             tmp[4] = o1 >> 24; tmp[5] = o1 >> 16; tmp[6] = o1 >> 8; tmp[7] = (uint8_t)o1;
-            memcpy(tmp.data() + 8, fn.blob, fn.blob_len);
+            memcpy(tmp.data() + 8, blob, blob_len);
             const uint8_t* dblob = ar.put<uint8_t>(tmp.data(), tmp.size());
             static const int32_t zero_id = 0;
             const int32_t* dids = ar.put<int32_t>(&zero_id, 1);
@@ -2453,7 +2482,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   hq->stage_bytes = (int32_t)stage_bytes;
   hq->set_cache_bytes = set_cache_max;
   hq->out_cap = PB_OUT_CAP; hq->cand_cap = PB_CAND_CAP;
-  hq->cand_bytes = any_cand_leaf ? (int32_t)(4 * PB_CAND_CAP * PB_NWARPS) : 0;   // u32 docs inside the segment, one list per warp
+  hq->cand_bytes = any_cand_leaf ? (int32_t)(2 * PB_CAND_CAP * PB_NWARPS) : 0;   // u16 offsets inside the unit, one list per warp
   hq->use_tma = (q->flags & PB_Q_NO_TMA) ? 0 : 1;
   hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
   hq->n_units = n_chunks; hq->segs = dsegs; hq->tables = dtabs;
@@ -2546,7 +2575,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     }
   }
   auto filter_smem = [&](int out_cap, int cand_cap) {
-    return ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + (any_cand_leaf ? (size_t)4 * cand_cap * PB_NWARPS : 0) +
+    return ((sizeof(FilterSmemHeader) + 127) & ~(size_t)127) + (((size_t)set_cache_max + 127) & ~(size_t)127) + (any_cand_leaf ? (size_t)2 * cand_cap * PB_NWARPS : 0) +
            (size_t)PB_NWARPS * out_cap * 4 + stage_bytes * PB_NSTAGE * PB_NWARPS;
   };
   size_t smem = 0;
@@ -2584,12 +2613,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
         }
         if (!ok || n_dense != 1) { ok = false; break; }
         const DevLeaf& lf = ds.leaves[dense];
-        // IN / NOT IN: dictionaries of <= 1024 values keep the membership bits in registers (warp shuffle), larger ones in a
-        // byte LUT in shared memory
-        static const bool shfl_on = []() { const char* e = getenv("PB_FILTER_SHFL"); return !e || atoi(e) != 0; }();
-        const int k = lf.kind == L_DICT_RANGE ? 0
-                      : (lf.kind == L_DICT_SET && shfl_on && lf.bits >= 5 && lf.bits <= 10 && lf.set_card <= (1 << lf.bits) && pb_filter_spec_available(lf.bits, 2)) ? 2
-                      : (lf.kind == L_DICT_SET && lf.set_smem_off >= 0) ? 1 : -1;
+        const int k = lf.kind == L_DICT_RANGE ? 0 : (lf.kind == L_DICT_SET && lf.set_smem_off >= 0) ? 1 : -1;
         if (k < 0 || (w >= 0 && (w != lf.bits || pk != k))) { ok = false; break; }
         w = lf.bits; pk = k;
       }
@@ -2602,7 +2626,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
         int occ = 0;
         if (pb_filter_spec_prepare(w, pk, smem_spec, &occ) == cudaSuccess && occ >= 1) {
           spec_w = w; spec_pk = pk; max_ctas = (uint64_t)ctx->num_sms * (uint64_t)occ; smem = smem_spec;
-          hq->out_cap = oc; hq->cand_cap = cc; hq->cand_bytes = any_cand_leaf ? (int32_t)(4 * cc * PB_NWARPS) : 0;
+          hq->out_cap = oc; hq->cand_cap = cc; hq->cand_bytes = any_cand_leaf ? (int32_t)(2 * cc * PB_NWARPS) : 0;
           for (auto& wv : waves) { wv.dq.out_cap = oc; wv.dq.cand_cap = cc; wv.dq.cand_bytes = hq->cand_bytes; }
         } else cudaGetLastError();
       }
@@ -3299,6 +3323,7 @@ int pbi_segment_view(pb_segment_handle s, PbSegmentView* out) {
     v.entry_bytes = c.entry_bytes; v.dict = c.h_dict.empty() ? nullptr : c.h_dict.data();
     v.sorted_pairs = c.h_sorted_pairs.empty() ? nullptr : c.h_sorted_pairs.data();
     v.has_inverted = c.h_inv != nullptr;
+    v.null_vector = c.h_null; v.null_vector_len = c.h_null_len;
   }
   return PB_OK;
 }

@@ -7,10 +7,7 @@
 
 #define PB_SPEC_WIDTHS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(17) X(18) X(19) X(20)
 
-#define PB_SPEC_SHFL_WIDTHS(X) X(5) X(6) X(7) X(9) X(10)
-
 bool pb_filter_spec_available(int width, int pred_kind) {
-  if (pred_kind == 2) return width == 5 || width == 6 || width == 7 || width == 9 || width == 10;
   if (pred_kind != 0 && pred_kind != 1) return false;
   switch (width) {
 #define X(W) case W: return true;
@@ -28,14 +25,6 @@ static cudaError_t prepare_one(size_t smem, int* ctas) {
 }
 
 cudaError_t pb_filter_spec_prepare(int width, int pred_kind, size_t smem, int* ctas_per_sm) {
-  if (pred_kind == 2) {
-    switch (width) {
-#define X(W) case W: return prepare_one<W, 2>(smem, ctas_per_sm);
-      PB_SPEC_SHFL_WIDTHS(X)
-#undef X
-      default: return cudaErrorInvalidValue;
-    }
-  }
   switch (width) {
 #define X(W) case W: return pred_kind == 0 ? prepare_one<W, 0>(smem, ctas_per_sm) : prepare_one<W, 1>(smem, ctas_per_sm);
     PB_SPEC_WIDTHS(X)
@@ -45,14 +34,6 @@ cudaError_t pb_filter_spec_prepare(int width, int pred_kind, size_t smem, int* c
 }
 
 cudaError_t pb_filter_spec_launch(int width, int pred_kind, int grid, size_t smem, cudaStream_t st, const DevQuery* q) {
-  if (pred_kind == 2) {
-    switch (width) {
-#define X(W) case W: pb_filter_kernel<2, 4, W, 2><<<grid, PB_NTHREADS, smem, st>>>(*q); return cudaGetLastError();
-      PB_SPEC_SHFL_WIDTHS(X)
-#undef X
-      default: return cudaErrorInvalidValue;
-    }
-  }
   switch (width) {
 #define X(W)                                                                              \
   case W:                                                                                 \

@@ -3,7 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 struct DevQuery;
-// PK: 0 = dictId range, 1 = IN / NOT IN membership LUT in shared memory, 2 = IN / NOT IN bit LUT in registers (5..10-bit dictIds)
+// PK: 0 = dictId range, 1 = IN / NOT IN membership LUT in shared memory
 bool pb_filter_spec_available(int width, int pred_kind);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) on the current device + resident CTAs per SM for `smem` bytes
 cudaError_t pb_filter_spec_prepare(int width, int pred_kind, size_t smem, int* ctas_per_sm);

@@ -12,6 +12,8 @@ struct PbColumnView {
   const uint8_t* dict = nullptr;          // big-endian dictionary bytes (host copy)
   const int32_t* sorted_pairs = nullptr;  // sorted column: little-endian (start,end) inclusive docId pairs
   bool has_inverted = false;
+  const uint8_t* null_vector = nullptr;   // DataSource.getNullValueVector(): RoaringBitmap of the null docIds (caller's buffer)
+  uint64_t null_vector_len = 0;
 };
 struct PbSegmentView {
   std::string name;

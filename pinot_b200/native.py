@@ -32,7 +32,8 @@ class PbColumnDesc(C.Structure):
                 ("dict_entry_bytes", C.c_int32),
                 ("forward_index", C.c_void_p), ("forward_index_len", C.c_uint64),
                 ("dictionary", C.c_void_p), ("dictionary_len", C.c_uint64),
-                ("inverted_index", C.c_void_p), ("inverted_index_len", C.c_uint64)]
+                ("inverted_index", C.c_void_p), ("inverted_index_len", C.c_uint64),
+                ("null_value_vector", C.c_void_p), ("null_value_vector_len", C.c_uint64)]
 
 
 class PbSegmentDesc(C.Structure):
@@ -239,6 +240,9 @@ class StagedSegment:
             if c.inverted_index is not None:
                 d.inverted_index = c.inverted_index.ctypes.data
                 d.inverted_index_len = c.inverted_index.size
+            if getattr(c, "null_value_vector", None) is not None:
+                d.null_value_vector = c.null_value_vector.ctypes.data
+                d.null_value_vector_len = c.null_value_vector.size
         desc = PbSegmentDesc(seg.name.encode(), seg.num_docs, len(names), cols)
         self._keep.append((cols, desc))
         h = C.c_void_p()

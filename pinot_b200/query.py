@@ -27,8 +27,8 @@ class PredicateType(IntEnum):
     IN = 2
     NOT_IN = 3
     RANGE = 4
-    IS_NULL = 5          # no null-value vectors on this path: EmptyFilterOperator (FilterPlanNode.java:294-300)
-    IS_NOT_NULL = 6      # ... MatchAllFilterOperator (FilterPlanNode.java:301-307)
+    IS_NULL = 5          # BitmapBasedFilterOperator over the null-value vector; EmptyFilterOperator without one (FilterPlanNode.java:294-300)
+    IS_NOT_NULL = 6      # ... exclusive; MatchAllFilterOperator without one (FilterPlanNode.java:301-307)
 
 
 class AggOp(IntEnum):

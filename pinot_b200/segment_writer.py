@@ -138,6 +138,7 @@ class ColumnIndex:
     forward_index: np.ndarray                # uint8
     dictionary: Optional[np.ndarray] = None  # uint8
     inverted_index: Optional[np.ndarray] = None
+    null_value_vector: Optional[np.ndarray] = None   # <col>.bitmap.nullvalue: RoaringBitmap of the null docIds (absent when none)
     min_value: object = None
     max_value: object = None
 
@@ -306,6 +307,16 @@ def build_column(name: str, data_type: DataType, values, dictionary: bool = True
                        min_value=vals.min() if n else None, max_value=vals.max() if n else None)
 
 
+def with_nulls(col: ColumnIndex, null_mask) -> ColumnIndex:
+    """Attach a null-value vector (NullValueVectorCreator: SEGL/segment/creator/impl/nullvalue/NullValueVectorCreator.java --
+    one run-compressed RoaringBitmap of the docIds whose value was null; the forward index holds the column's default null
+    value at those docs, which is the caller's business; no file when nothing is null)."""
+    docs = np.flatnonzero(np.asarray(null_mask, dtype=bool)).astype(np.uint32)
+    assert np.asarray(null_mask).size == col.num_docs
+    col.null_value_vector = roaring_serialize(docs, run_optimize=True) if docs.size else None
+    return col
+
+
 def make_segment(name: str, columns: List[ColumnIndex]) -> Segment:
     n = columns[0].num_docs
     assert all(c.num_docs == n for c in columns)
@@ -333,6 +344,8 @@ def write_v3(seg: Segment, out_dir: str, table_name: str = "testTable") -> str:
             parts.append(("forward_index", c.forward_index))
             if c.inverted_index is not None:
                 parts.append(("inverted_index", c.inverted_index))
+            if c.null_value_vector is not None:
+                parts.append(("nullvalue_vector", c.null_value_vector))     # StandardIndexes.nullValueVector() id
             for kind, buf in parts:
                 f.write(magic)
                 f.write(buf.tobytes())
@@ -401,5 +414,5 @@ def load_v3(segment_dir: str) -> Segment:
             is_sorted=props[p + "isSorted"] == "true", cardinality=int(props[p + "cardinality"]),
             bits_per_element=int(props[p + "bitsPerElement"]), dict_entry_bytes=width,
             forward_index=view(name, "forward_index"), dictionary=view(name, "dictionary") if has_dict else None,
-            inverted_index=view(name, "inverted_index"))
+            inverted_index=view(name, "inverted_index"), null_value_vector=view(name, "nullvalue_vector"))
     return seg

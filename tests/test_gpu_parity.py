@@ -566,3 +566,36 @@ def test_malformed_compressed_chunk_is_rejected():
     with pytest.raises(native.PinotB200Error) as e:
         native.execute(group, parse_sql("SELECT d, SUM(k) FROM t GROUP BY d LIMIT 10"), 0)
     assert "do not decode" in str(e.value)
+
+
+def test_predicates_on_several_wide_raw_columns():
+    """Three scan leaves over raw LONG / DOUBLE / INT columns (160 bits per row) do not fit the per-warp stages of shared
+    memory: the most selective one is streamed, the others run on its survivors (DevLeaf::gather) whatever the selectivity."""
+    native.init()
+    rng = np.random.default_rng(12)
+    n = 40_007
+    cols = [build_column("d", DataType.INT, rng.integers(0, 5, n).astype(np.int32)),
+            build_column("k", DataType.LONG, rng.integers(-10**12, 10**12, n).astype(np.int64), dictionary=False),
+            build_column("x", DataType.DOUBLE, rng.normal(0, 5, n), dictionary=False),
+            build_column("y", DataType.DOUBLE, rng.normal(0, 5, n), dictionary=False),
+            build_column("i", DataType.INT, rng.integers(-50, 50, n).astype(np.int32), dictionary=False)]
+    segs = [make_segment("wide", cols)]
+    check_query(segs, "SELECT d, COUNT(*), SUM(i), MIN(x) FROM t WHERE k > -900000000000 AND x < 6.5 AND y > -7 AND i <> 7 GROUP BY d LIMIT 100")
+    check_query(segs, "SELECT COUNT(*), MAX(k) FROM t WHERE k > 0 AND x < 0 AND y > 0")
+
+
+def test_is_null_predicates_over_null_value_vectors():
+    """IS NULL / IS NOT NULL = BitmapBasedFilterOperator over the column's null-value vector (FilterPlanNode.java:294-307;
+    the counts of SegmentWithNullValueVectorTest :242-273 on generated data), combined with scan leaves, OR and NOT."""
+    from tests.test_cpu_formats import _null_segment
+    native.init()
+    seg, d, i, k, i_null, k_null = _null_segment(60_000, seed=8)
+    segs = [seg]
+    for sql in ("SELECT COUNT(*) FROM t WHERE i IS NOT NULL", "SELECT COUNT(*) FROM t WHERE i IS NULL",
+                "SELECT COUNT(*) FROM t WHERE i IS NOT NULL AND k > 500000", "SELECT COUNT(*), SUM(k) FROM t WHERE i IS NULL OR k IS NULL",
+                "SELECT d, COUNT(*), MAX(k) FROM t WHERE NOT (i IS NULL) AND k IS NULL AND d < 3 GROUP BY d LIMIT 10",
+                "SELECT COUNT(*) FROM t WHERE z IS NULL", "SELECT d, COUNT(*) FROM t WHERE z IS NOT NULL AND i IS NULL GROUP BY d LIMIT 10"):
+        check_query(segs, sql)
+    res = native.execute(native.SegmentGroup([native.StagedSegment(seg)]), parse_sql("SELECT COUNT(*) FROM t WHERE i IS NULL"), 0)
+    assert res.tables[0].rows()[()][0] == int(i_null.sum())
+    res.free()
