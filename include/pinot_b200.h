@@ -145,6 +145,13 @@ typedef struct pb_order_by {
                                     * and every rank gets the merged result.  The ranks must agree on the global dictionaries of the
                                     * group-by / DISTINCTCOUNT columns first (pb_segment_group_export_dictionary /
                                     * _set_global_dictionary) and must issue their PB_Q_ALL_RANKS calls in the same order. */
+#define PB_Q_NULL_HANDLING 64u     /* the query runs with enableNullHandling (QueryContext.isNullHandlingEnabled): the caller has folded the
+                                    * three-valued filter into its "trues" program (BaseFilterOperator.getTrues / getFalses) and given
+                                    * every aggregation over a nullable column the implicit clause "<column> IS NOT NULL" as its FILTER
+                                    * clause (NullableSingleInputAggregationFunction.java:72-134 skips null docs) -- pbh_execute does both.
+                                    * The device then keeps the row count of EVERY aggregation (pb_result_long: COUNT value, AVG
+                                    * denominator, and for SUM / MIN / MAX the number of non-null inputs): 0 means the function's result
+                                    * is SQL NULL for that group */
 
 typedef struct pb_query_desc {
   int32_t num_group_by;

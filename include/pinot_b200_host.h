@@ -76,6 +76,13 @@ typedef struct pbh_query_context {
   const pb_order_by* order_by;
   int32_t trim_size;
   int32_t trim_threshold;
+  /* query option enableNullHandling (QueryContext.isNullHandlingEnabled).  The filter is planned three-valued -- the trues of
+   * the root, BaseFilterOperator.getTrues / getNulls / getFalses and the And / Or / Not / BaseColumnFilterOperator overrides --
+   * and every aggregation whose input column has a null-value vector only sees its non-null docs
+   * (NullableSingleInputAggregationFunction.java:63-134), which the device runs as the implicit FILTER clause
+   * "<column> IS NOT NULL" (ANDed with the function's own clause); pb_result_long then carries the number of inputs every
+   * function saw, 0 = SQL NULL (PB_Q_NULL_HANDLING).  Group-by columns with a null-value vector are declined. */
+  int32_t null_handling;
 } pbh_query_context;
 
 /* B200PlanMaker.makeSegmentPlanNode eligibility (InstancePlanMakerImplV2.java:275-294 override):

@@ -18,6 +18,7 @@ import org.apache.pinot.core.operator.filter.InvertedIndexFilterOperator;
 import org.apache.pinot.core.operator.filter.MatchAllFilterOperator;
 import org.apache.pinot.core.operator.filter.NotFilterOperator;
 import org.apache.pinot.core.operator.filter.OrFilterOperator;
+import org.apache.pinot.core.operator.filter.RangeIndexBasedFilterOperator;
 import org.apache.pinot.core.operator.filter.ScanBasedFilterOperator;
 import org.apache.pinot.core.operator.filter.SortedIndexBasedFilterOperator;
 import org.apache.pinot.core.operator.filter.predicate.PredicateEvaluator;
@@ -39,7 +40,9 @@ import org.apache.pinot.segment.spi.SegmentContext;
  *   BitmapBasedFilterOperator (IS NULL / IS NOT NULL)       -> PB_F_BITMAP without a blob: the column's staged null-value vector
  *   MatchAllFilterOperator / EmptyFilterOperator            -> PB_F_MATCH_ALL / PB_F_EMPTY
  *   And / Or / NotFilterOperator                            -> PB_F_AND / PB_F_OR / PB_F_NOT after their children
- * Anything else (range / text / JSON / H3 index operators, expression filters) makes the segment ineligible.
+ *   RangeIndexBasedFilterOperator                           -> the same leaf as the scan operator of that predicate (the index is exact;
+ *                                                            the device scans the column instead of reading it)
+ * Anything else (text / JSON / H3 index operators, expression filters) makes the segment ineligible.
  */
 final class B200FilterLowering {
   private B200FilterLowering() {
@@ -99,14 +102,17 @@ final class B200FilterLowering {
         out.addSorted(column, B200Eligibility.sortedDocIdRanges(ev, leaf._dataSource));
       } else if (op instanceof InvertedIndexFilterOperator) {
         out.addDictIdSet(Native.PB_F_INVERTED, column, exclusive, exclusive ? ev.getNonMatchingDictIds() : ev.getMatchingDictIds());
-      } else if (op instanceof ScanBasedFilterOperator && ev.isDictionaryBased()) {
+      } else if ((op instanceof ScanBasedFilterOperator || op instanceof RangeIndexBasedFilterOperator) && ev.isDictionaryBased()) {
         if (ev instanceof SortedDictionaryBasedRangePredicateEvaluator) {
           SortedDictionaryBasedRangePredicateEvaluator range = (SortedDictionaryBasedRangePredicateEvaluator) ev;
           out.addDictIdRange(column, range.getStartDictId(), range.getEndDictId());
         } else {
           out.addDictIdSet(Native.PB_F_SCAN_DICT_SET, column, exclusive, exclusive ? ev.getNonMatchingDictIds() : ev.getMatchingDictIds());
         }
-      } else if (op instanceof ScanBasedFilterOperator) {
+      } else if (op instanceof ScanBasedFilterOperator || op instanceof RangeIndexBasedFilterOperator) {
+        // a range index (RangeIndexBasedFilterOperator.java: BitSlicedRangeIndexReader.getMatchingDocIds) returns exactly the
+        // docs the predicate matches: the device gets the same set by scanning the column, which it does faster than the CPU
+        // walks the bit slices, so the index is simply not read (numEntriesScannedInFilter then reports the scan)
         out.addRawPredicate(column, ev);        // inclusive bounds / value set of the raw-value evaluators
       } else {
         throw new B200Eligibility.NotEligibleException("filter operator " + op.toExplainString());

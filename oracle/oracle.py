@@ -63,7 +63,7 @@ class OrcQuery(C.Structure):
                 ("skip_inverted_index", C.c_int32),
                 ("filter_nodes", C.POINTER(OrcFilterNode)), ("predicates", C.POINTER(OrcPredicate)),
                 ("group_by_columns", C.POINTER(C.c_int32)), ("aggregations", C.POINTER(OrcAggregation)),
-                ("num_agg_filters", C.c_int32), ("_pad2", C.c_int32),
+                ("num_agg_filters", C.c_int32), ("null_handling", C.c_int32),
                 ("agg_filters", C.POINTER(OrcFilterProgram)), ("agg_filter_of", C.POINTER(C.c_int32))]
 
 
@@ -226,7 +226,8 @@ def marshal_query(seg, q, m: _Marshalled) -> OrcQuery:
     ag = (OrcAggregation * max(1, len(q.aggregations)))()
     for i, a in enumerate(q.aggregations):
         ag[i].op = int(a.op)
-        ag[i].column = -1 if a.column is None else names.index(a.column)
+        keep_col = a.column is not None and (int(a.op) != 0 or getattr(q, "null_handling", False))   # COUNT(col) = COUNT(*) unless nulls are handled
+        ag[i].column = names.index(a.column) if keep_col else -1
     filters, filter_of = q.agg_filters()
     progs = (OrcFilterProgram * max(1, len(filters)))()
     for i, f in enumerate(filters):
@@ -235,7 +236,7 @@ def marshal_query(seg, q, m: _Marshalled) -> OrcQuery:
     fo = (C.c_int32 * max(1, len(filter_of)))(*filter_of)
     oq = OrcQuery(len(nodes), len(q.group_by), len(q.aggregations), q.num_groups_limit,
                   q.max_initial_result_holder_capacity, int(q.skip_inverted_all), cn, cp, gb, ag,
-                  len(filters), 0, progs, fo)
+                  len(filters), int(getattr(q, "null_handling", False)), progs, fo)
     m.hold((cn, cp, gb, ag, progs, fo))
     return m.hold(oq)
 
@@ -363,6 +364,7 @@ def combine(results: List[OracleResult]) -> Dict[tuple, list]:
                 dvals.append(r.segment.columns[agg.column].dictionary_values())
             else:
                 dvals.append(None)      # (DISTINCTCOUNT on a raw column: the sets hold the value bits themselves)
+        nh = getattr(q, "null_handling", False)     # longs hold the inputs every function saw; 0 = SQL NULL (merge: SumAggregationFunction.java:222-233)
         for g, key in enumerate(keys):
             row = []
             for a, agg in enumerate(q.aggregations):
@@ -370,7 +372,7 @@ def combine(results: List[OracleResult]) -> Dict[tuple, list]:
                 if op == 0:
                     row.append(int(r.longs[a][g]))
                 elif op in (1, 2, 3):
-                    row.append(float(r.doubles[a][g]))
+                    row.append(None if nh and int(r.longs[a][g]) == 0 else float(r.doubles[a][g]))
                 elif op == 4:
                     row.append((float(r.doubles[a][g]), int(r.longs[a][g])))
                 else:
@@ -382,7 +384,9 @@ def combine(results: List[OracleResult]) -> Dict[tuple, list]:
                 continue
             for a, agg in enumerate(q.aggregations):
                 op = int(agg.op)
-                if op in (0, 1):
+                if cur[a] is None or row[a] is None:
+                    cur[a] = row[a] if cur[a] is None else cur[a]
+                elif op in (0, 1):
                     cur[a] = cur[a] + row[a]
                 elif op == 2:
                     cur[a] = min(cur[a], row[a])
@@ -392,6 +396,11 @@ def combine(results: List[OracleResult]) -> Dict[tuple, list]:
                     cur[a] = (cur[a][0] + row[a][0], cur[a][1] + row[a][1])
                 else:
                     cur[a] = cur[a] | row[a]
+    if results and getattr(results[0].query, "null_handling", False):
+        for row in table.values():
+            for a, agg in enumerate(results[0].query.aggregations):
+                if int(agg.op) == 4 and row[a][1] == 0:
+                    row[a] = None
     return table
 
 

@@ -679,9 +679,117 @@ static fop* make_not_op(fop* kid, int32_t num_docs) {
 }
 
 /* CTR/plan/FilterPlanNode.java:195-320 (constructPhysicalOperator) from the postfix tree */
+/* ---- enableNullHandling: three-valued filters.  The operator tree is the same; what changes is how its doc sets are
+ * taken: BaseFilterOperator.getTrues() / getNulls() / getFalses() (CTR/operator/filter/BaseFilterOperator.java:88-113).
+ *   column leaf (BaseColumnFilterOperator.java:46-70)  trues = matches AND NOT nulls; nulls = the null-value vector
+ *   IS [NOT] NULL (BitmapBasedFilterOperator), Empty, MatchAll: no nulls; falses = NOT trues
+ *   AND (AndFilterOperator.java:52-88)  trues = AND trues_i;  falses = NOT AND_i (trues_i OR nulls_i)
+ *   OR  (OrFilterOperator.java:51-87)   trues = OR trues_i;   falses = NOT OR_i (trues_i OR nulls_i)
+ *   NOT (NotFilterOperator.java:52-63)  trues = falses of the child; falses = its trues
+ * nulls_i is taken from DIRECT column-leaf children only (And / Or / Not do not override getNulls()).  The filter of the
+ * query is the trues of the root.  Built here as an ordinary two-valued operator tree over the same leaves. ---- */
+typedef struct nexpr { int kind; int pred; int32_t n; struct nexpr** kids; } nexpr;
+static void nexpr_free(nexpr* e) { if (!e) return; for (int32_t i = 0; i < e->n; i++) nexpr_free(e->kids[i]); free(e->kids); free(e); }
+static fop* null_bitmap_op(const orc_segment* seg, int32_t column, int not_null) {
+  const orc_column* nc = &seg->columns[column];
+  if (!nc->null_value_vector) return NULL;
+  fop* f = fop_new(OP_BITMAP, seg->num_docs);
+  f->bm = bm_new(seg->num_docs);
+  if (roaring_for_each(nc->null_value_vector, nc->null_value_vector_len, bm_sink, &f->bm) != 0) { set_err("malformed null-value vector"); fop_free(f); return NULL; }
+  if (not_null) bm_flip(&f->bm);
+  return f;
+}
+static fop* nh_trues(const orc_segment* seg, const orc_query* q, const nexpr* e);
+/* nulls of a node: non-NULL only for a column leaf whose column has a (non-empty) null-value vector and whose own operator is
+ * neither Empty nor MatchAll (those are EmptyFilterOperator / MatchAllFilterOperator, not column operators) */
+static fop* nh_nulls(const orc_segment* seg, const orc_query* q, const nexpr* e) {
+  if (e->kind != ORC_PRED) return NULL;
+  const orc_predicate* p = &q->predicates[e->pred];
+  if (p->type == ORC_IS_NULL || p->type == ORC_IS_NOT_NULL) return NULL;
+  if (!seg->columns[p->column].null_value_vector) return NULL;
+  fop* base = make_leaf_op(seg, q, p);
+  if (!base) return NULL;
+  int trivial = base->kind == OP_EMPTY || base->kind == OP_MATCH_ALL;
+  fop_free(base);
+  return trivial ? NULL : null_bitmap_op(seg, p->column, 0);
+}
+/* trues_i OR nulls_i of one child, as And / OrFilterOperator.getFalses() collect them */
+static fop* nh_trues_or_nulls(const orc_segment* seg, const orc_query* q, const nexpr* e) {
+  fop* t = nh_trues(seg, q, e);
+  if (!t) return NULL;
+  fop* nl = nh_nulls(seg, q, e);
+  if (!nl) return t;
+  fop* kids[2] = { t, nl };
+  return make_or_op(kids, 2, seg->num_docs);
+}
+static fop* nh_falses(const orc_segment* seg, const orc_query* q, const nexpr* e) {
+  const int32_t n = seg->num_docs;
+  if (e->kind == ORC_NOT) return nh_trues(seg, q, e->kids[0]);
+  if (e->kind == ORC_PRED) {   /* BaseFilterOperator.getFalses: NOT (trues OR nulls) */
+    fop* x = nh_trues_or_nulls(seg, q, e);
+    return x ? make_not_op(x, n) : NULL;
+  }
+  fop** kids = (fop**)malloc(sizeof(fop*) * (size_t)e->n);
+  for (int32_t i = 0; i < e->n; i++) {
+    kids[i] = nh_trues_or_nulls(seg, q, e->kids[i]);
+    if (!kids[i]) { for (int32_t j = 0; j < i; j++) fop_free(kids[j]); free(kids); return NULL; }
+  }
+  fop* inner = e->kind == ORC_AND ? make_and_op(kids, e->n, n) : make_or_op(kids, e->n, n);
+  free(kids);
+  return make_not_op(inner, n);
+}
+static fop* nh_trues(const orc_segment* seg, const orc_query* q, const nexpr* e) {
+  const int32_t n = seg->num_docs;
+  if (e->kind == ORC_NOT) return nh_falses(seg, q, e->kids[0]);
+  if (e->kind == ORC_PRED) {
+    const orc_predicate* p = &q->predicates[e->pred];
+    fop* base = make_leaf_op(seg, q, p);
+    if (!base || p->type == ORC_IS_NULL || p->type == ORC_IS_NOT_NULL || base->kind == OP_EMPTY) return base;
+    if (base->kind == OP_MATCH_ALL) {
+      /* FilterOperatorUtils.java:78-88: an always-true predicate on a column with nulls is a BitmapBasedFilterOperator over
+       * the flipped null bitmap (which, not being a column operator, reports no nulls of its own) */
+      fop* nn0 = seg->columns[p->column].null_value_vector ? null_bitmap_op(seg, p->column, 1) : NULL;
+      if (!nn0) return base;
+      fop_free(base);
+      return nn0;
+    }
+    fop* nn = seg->columns[p->column].null_value_vector ? null_bitmap_op(seg, p->column, 1) : NULL;
+    if (!nn) return base;
+    fop* kids[2] = { base, nn };                       /* excludeNulls: AND(matches, flip(nullBitmap)) */
+    return make_and_op(kids, 2, n);
+  }
+  fop** kids = (fop**)malloc(sizeof(fop*) * (size_t)e->n);
+  for (int32_t i = 0; i < e->n; i++) {
+    kids[i] = nh_trues(seg, q, e->kids[i]);
+    if (!kids[i]) { for (int32_t j = 0; j < i; j++) fop_free(kids[j]); free(kids); return NULL; }
+  }
+  fop* f = e->kind == ORC_AND ? make_and_op(kids, e->n, n) : make_or_op(kids, e->n, n);
+  free(kids);
+  return f;
+}
+static fop* build_filter_null_handling(const orc_segment* seg, const orc_query* q) {
+  nexpr** stack = (nexpr**)calloc((size_t)q->num_filter_nodes, sizeof(nexpr*));
+  int32_t sp = 0;
+  for (int32_t i = 0; i < q->num_filter_nodes; i++) {
+    const orc_filter_node* nd = &q->filter_nodes[i];
+    nexpr* e = (nexpr*)calloc(1, sizeof(nexpr));
+    e->kind = nd->kind; e->pred = nd->predicate;
+    int32_t k = nd->kind == ORC_PRED ? 0 : nd->kind == ORC_NOT ? 1 : nd->n_children;
+    e->n = k; e->kids = (nexpr**)malloc(sizeof(nexpr*) * (size_t)(k > 0 ? k : 1));
+    for (int32_t j = 0; j < k; j++) e->kids[j] = stack[sp - k + j];
+    sp -= k; stack[sp++] = e;
+  }
+  nexpr* root = stack[0];
+  free(stack);
+  fop* f = nh_trues(seg, q, root);
+  nexpr_free(root);
+  return f;
+}
+
 static fop* build_filter(const orc_segment* seg, const orc_query* q) {
   int32_t n = seg->num_docs;
   if (q->num_filter_nodes == 0) return fop_new(OP_MATCH_ALL, n);
+  if (q->null_handling) return build_filter_null_handling(seg, q);
   fop** stack = (fop**)malloc(sizeof(fop*) * (size_t)q->num_filter_nodes);
   int32_t sp = 0;
   for (int32_t i = 0; i < q->num_filter_nodes; i++) {
@@ -1212,6 +1320,22 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
     ch[a].dflt = 0.0;
     if (op == ORC_DISTINCTCOUNT && areaders[a].c->has_dictionary) bh[a].words = ((int64_t)areaders[a].c->cardinality + 63) / 64;
   }
+  /* enableNullHandling (NullableSingleInputAggregationFunction.java:63-134 forEachNotNull / foldNotNull): a function only
+   * sees the docs of a block whose input is not null -- the null docs of its column (anull, none = w NULL) are dropped from
+   * the block before the function's loop runs -- and nn counts the inputs it saw per group: 0 = the result is SQL NULL
+   * (ObjectGroupByResultHolder never set, e.g. SumAggregationFunction.java:160-179, 206-220) */
+  bitmap* anull = (bitmap*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(bitmap));
+  dholder* nn = (dholder*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(dholder));
+  int32_t* nn_docs = (int32_t*)malloc(sizeof(int32_t) * MAX_DOC_PER_CALL);
+  int32_t* nn_groups = (int32_t*)malloc(sizeof(int32_t) * MAX_DOC_PER_CALL);
+  uint8_t* nn_brk = (uint8_t*)malloc(MAX_DOC_PER_CALL);     /* element starts a new non-null range of the block */
+  if (q->null_handling)
+    for (int32_t a = 0; a < nA; a++) {
+      int32_t c = q->aggregations[a].column;
+      if (c < 0 || !seg->columns[c].null_value_vector) continue;
+      anull[a] = bm_new(num_docs);
+      roaring_for_each(seg->columns[c].null_value_vector, seg->columns[c].null_value_vector_len, bm_sink, &anull[a]);
+    }
   /* keyless native-type MIN/MAX state (MinAggregationFunction.java:69-148) */
   int64_t* kl_long = (int64_t*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int64_t));
   int* kl_long_set = (int*)calloc((size_t)(nA > 0 ? nA : 1), sizeof(int));
@@ -1224,7 +1348,7 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
   int64_t key[64];
   if (nG > 64) { set_err("too many group-by columns"); goto fail2; }
   int64_t num_docs_scanned = 0;
-  if (nG == 0) for (int32_t a = 0; a < nA; a++) { dholder_ensure(&dh[a], 1); dholder_ensure(&ch[a], 1); bholder_ensure(&bh[a], 1); }
+  if (nG == 0) for (int32_t a = 0; a < nA; a++) { dholder_ensure(&dh[a], 1); dholder_ensure(&ch[a], 1); bholder_ensure(&bh[a], 1); dholder_ensure(&nn[a], 1); }
 
   /* GroupByOperator.getNextBlock (CTR/operator/query/GroupByOperator.java:101-140) /
    * AggregationOperator.getNextBlock (CTR/operator/query/AggregationOperator.java:64-80) */
@@ -1234,10 +1358,12 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
   for (int32_t lane = 0; lane < n_lanes; lane++) {
   const uint8_t* lane_has = lanes[lane].has;
   it = lanes[lane].it;
-  while (1) {
-    /* DocIdSetOperator.getNextBlock: CTR/operator/DocIdSetOperator.java:59-86 */
+  int lane_eof = 0;
+  while (!lane_eof) {
+    /* DocIdSetOperator.getNextBlock: CTR/operator/DocIdSetOperator.java:59-86 (":63 if (_currentDocId == Constants.EOF) return
+     * null": the iterator is never asked again once it has returned EOF -- And / Not iterators are not idempotent there) */
     int32_t len = 0;
-    for (; len < MAX_DOC_PER_CALL; len++) { int32_t d = dit_next(it); if (d == ORC_EOF) break; doc_ids[len] = d; }
+    for (; len < MAX_DOC_PER_CALL; len++) { int32_t d = dit_next(it); if (d == ORC_EOF) { lane_eof = 1; break; } doc_ids[len] = d; }
     if (len == 0) break;
     num_docs_scanned += len;
     lanes[lane].docs += len;
@@ -1268,37 +1394,44 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
         if (op == ORC_AVG) dholder_ensure(&ch[a], need);
         if (op == ORC_DISTINCTCOUNT) bholder_ensure(&bh[a], need);
         if (!lane_has[a]) continue;
+        const int32_t* D = doc_ids; const int32_t* G = group_ids; int32_t L = len;
+        if (anull[a].w) {   /* forEachNotNull: only the non-null docs of the block reach the function */
+          L = 0;
+          for (int32_t i = 0; i < len; i++) if (!bm_get(&anull[a], doc_ids[i])) { nn_docs[L] = doc_ids[i]; nn_groups[L] = group_ids[i]; L++; }
+          D = nn_docs; G = nn_groups;
+        }
+        if (q->null_handling) { dholder_ensure(&nn[a], need); for (int32_t i = 0; i < L; i++) if (G[i] >= 0) nn[a].v[G[i]] += 1.0; }
         if (op == ORC_COUNT) {   /* CountAggregationFunction.java:178-185 */
-          for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0) dh[a].v[group_ids[i]] += 1.0;
+          for (int32_t i = 0; i < L; i++) if (G[i] >= 0) dh[a].v[G[i]] += 1.0;
           continue;
         }
         if (op == ORC_DISTINCTCOUNT && !areaders[a].c->has_dictionary) {   /* BaseDistinctAggregateAggregationFunction.java:323-400 */
-          for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0) pholder_add(&ph[a], group_ids[i], raw_value_bits(&areaders[a], doc_ids[i]));
+          for (int32_t i = 0; i < L; i++) if (G[i] >= 0) pholder_add(&ph[a], G[i], raw_value_bits(&areaders[a], D[i]));
           continue;
         }
         if (op == ORC_DISTINCTCOUNT) {  /* BaseDistinctAggregateAggregationFunction.java:306-321 */
-          for (int32_t i = 0; i < len; i++) {
-            int32_t g = group_ids[i]; if (g < 0) continue;
+          for (int32_t i = 0; i < L; i++) {
+            int32_t g = G[i]; if (g < 0) continue;
             if (!bh[a].sets[g]) bh[a].sets[g] = (uint64_t*)calloc((size_t)bh[a].words, 8);
-            int32_t id = dict_id_of(&areaders[a], doc_ids[i]);
+            int32_t id = dict_id_of(&areaders[a], D[i]);
             bh[a].sets[g][id >> 6] |= 1ull << (id & 63);
           }
           continue;
         }
-        for (int32_t i = 0; i < len; i++) values[i] = value_as_double(&areaders[a], doc_ids[i]);
+        for (int32_t i = 0; i < L; i++) values[i] = value_as_double(&areaders[a], D[i]);
         double* hv = dh[a].v;
         switch (op) {
           case ORC_SUM:  /* SumAggregationFunction.java:160-179 */
-            for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0) hv[group_ids[i]] += values[i];
+            for (int32_t i = 0; i < L; i++) if (G[i] >= 0) hv[G[i]] += values[i];
             break;
           case ORC_MIN:  /* MinAggregationFunction.java:163-188: strict < in double */
-            for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0 && values[i] < hv[group_ids[i]]) hv[group_ids[i]] = values[i];
+            for (int32_t i = 0; i < L; i++) if (G[i] >= 0 && values[i] < hv[G[i]]) hv[G[i]] = values[i];
             break;
           case ORC_MAX:
-            for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0 && values[i] > hv[group_ids[i]]) hv[group_ids[i]] = values[i];
+            for (int32_t i = 0; i < L; i++) if (G[i] >= 0 && values[i] > hv[G[i]]) hv[G[i]] = values[i];
             break;
           case ORC_AVG:  /* AvgAggregationFunction.java:106-127 */
-            for (int32_t i = 0; i < len; i++) if (group_ids[i] >= 0) { hv[group_ids[i]] += values[i]; ch[a].v[group_ids[i]] += 1.0; }
+            for (int32_t i = 0; i < L; i++) if (G[i] >= 0) { hv[G[i]] += values[i]; ch[a].v[G[i]] += 1.0; }
             break;
           default: break;
         }
@@ -1308,34 +1441,58 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
       for (int32_t a = 0; a < nA; a++) {
         int op = q->aggregations[a].op;
         if (!lane_has[a]) continue;
-        if (op == ORC_COUNT) { dh[a].v[0] += (double)len; continue; }   /* CountAggregationFunction.java:110-116 */
+        const int32_t* D = doc_ids; int32_t L = len;
+        if (anull[a].w) {   /* foldNotNull over the non-null ranges of the block */
+          L = 0;
+          int prev_null = 1;
+          for (int32_t i = 0; i < len; i++) {
+            if (bm_get(&anull[a], doc_ids[i])) { prev_null = 1; continue; }
+            nn_docs[L] = doc_ids[i]; nn_brk[L] = (uint8_t)prev_null; prev_null = 0; L++;
+          }
+          D = nn_docs;
+        }
+        if (q->null_handling) nn[a].v[0] += (double)L;
+        if (L == 0 && anull[a].w) continue;          /* the entire block is null: the holder is not touched */
+        if (op == ORC_COUNT) { dh[a].v[0] += (double)L; continue; }   /* CountAggregationFunction.java:110-116 */
         const col_reader* r = &areaders[a];
         if (op == ORC_DISTINCTCOUNT && !r->c->has_dictionary) {   /* BaseDistinctAggregateAggregationFunction.java:157-226 */
-          for (int32_t i = 0; i < len; i++) pholder_add(&ph[a], 0, raw_value_bits(r, doc_ids[i]));
+          for (int32_t i = 0; i < L; i++) pholder_add(&ph[a], 0, raw_value_bits(r, D[i]));
           continue;
         }
         if (op == ORC_DISTINCTCOUNT) {   /* BaseDistinctAggregateAggregationFunction.java:144-155 */
           if (!bh[a].sets[0]) bh[a].sets[0] = (uint64_t*)calloc((size_t)bh[a].words, 8);
-          for (int32_t i = 0; i < len; i++) { int32_t id = dict_id_of(r, doc_ids[i]); bh[a].sets[0][id >> 6] |= 1ull << (id & 63); }
+          for (int32_t i = 0; i < L; i++) { int32_t id = dict_id_of(r, D[i]); bh[a].sets[0][id >> 6] |= 1ull << (id & 63); }
           continue;
         }
         int is_long_typed = (r->c->data_type == ORC_INT || r->c->data_type == ORC_LONG);
         if ((op == ORC_MIN || op == ORC_MAX) && is_long_typed) {
           /* keyless MIN/MAX fold in the native type, then doubleValue() */
-          for (int32_t i = 0; i < len; i++) {
-            int64_t v = r->c->has_dictionary ? dict_long(r->c, dict_id_of(r, doc_ids[i])) : raw_long(r, doc_ids[i]);
+          for (int32_t i = 0; i < L; i++) {
+            int64_t v = r->c->has_dictionary ? dict_long(r->c, dict_id_of(r, D[i])) : raw_long(r, D[i]);
             if (!kl_long_set[a] || (op == ORC_MIN ? v < kl_long[a] : v > kl_long[a])) { kl_long[a] = v; kl_long_set[a] = 1; }
           }
           dh[a].v[0] = (double)kl_long[a];
           continue;
         }
-        for (int32_t i = 0; i < len; i++) values[i] = value_as_double(r, doc_ids[i]);
+        for (int32_t i = 0; i < L; i++) values[i] = value_as_double(r, D[i]);
         if (op == ORC_SUM || op == ORC_AVG) {   /* SumAggregationFunction.java:69-145: per-block innerSum */
-          double inner = 0; for (int32_t i = 0; i < len; i++) inner += values[i];
+          if (anull[a].w) {
+            /* foldNotNull: one innerSum per non-null range, acum == null ? innerSum : acum + innerSum; then sum + otherSum */
+            double acc = 0; int have = 0;
+            for (int32_t i = 0; i < L;) {
+              double inner = values[i]; int32_t k = i + 1;
+              while (k < L && !nn_brk[k]) inner += values[k++];
+              acc = have ? acc + inner : inner; have = 1; i = k;
+            }
+            dh[a].v[0] = acc + dh[a].v[0];
+            if (op == ORC_AVG) ch[a].v[0] += (double)L;
+            continue;
+          }
+          double inner = 0; for (int32_t i = 0; i < L; i++) inner += values[i];
           dh[a].v[0] += inner;
-          if (op == ORC_AVG) ch[a].v[0] += (double)len;
-        } else if (op == ORC_MIN) { for (int32_t i = 0; i < len; i++) if (values[i] < dh[a].v[0]) dh[a].v[0] = values[i]; }
-        else if (op == ORC_MAX) { for (int32_t i = 0; i < len; i++) if (values[i] > dh[a].v[0]) dh[a].v[0] = values[i]; }
+          if (op == ORC_AVG) ch[a].v[0] += (double)L;
+        } else if (op == ORC_MIN) { for (int32_t i = 0; i < L; i++) if (values[i] < dh[a].v[0]) dh[a].v[0] = values[i]; }
+        else if (op == ORC_MAX) { for (int32_t i = 0; i < L; i++) if (values[i] > dh[a].v[0]) dh[a].v[0] = values[i]; }
         (void)dict_buf;
       }
     }
@@ -1343,7 +1500,7 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
   }   /* lanes */
   if (nG > 0) {   /* holders of functions whose lane saw no block still cover every group (FilteredGroupByOperator.java:161-163) */
     int64_t need = holder == 1 ? card_product : map.size;
-    for (int32_t a = 0; a < nA; a++) { dholder_ensure(&dh[a], need); dholder_ensure(&ch[a], need); bholder_ensure(&bh[a], need); }
+    for (int32_t a = 0; a < nA; a++) { dholder_ensure(&dh[a], need); dholder_ensure(&ch[a], need); bholder_ensure(&bh[a], need); dholder_ensure(&nn[a], need); }
   }
 
   /* ---- build the result ---- */
@@ -1408,7 +1565,7 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
           res->lng[a][g] = n; total_ids += n; res->dc_offsets[a][g + 1] = total_ids;
           break;
         }
-        default: res->dbl[a][g] = dh[a].v[h]; break;
+        default: res->dbl[a][g] = dh[a].v[h]; if (q->null_handling) res->lng[a][g] = (int64_t)nn[a].v[h]; break;   /* 0 inputs = SQL NULL */
       }
     }
     if (op == ORC_DISTINCTCOUNT) {
@@ -1444,6 +1601,8 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
     free(bh[a].sets);
     free(ph[a].h); free(ph[a].v);
   }
+  for (int32_t a = 0; a < nA; a++) { free(nn[a].v); if (anull[a].w) bm_free(&anull[a]); }
+  free(nn); free(anull); free(nn_docs); free(nn_groups); free(nn_brk);
   free(dh); free(ch); free(bh); free(ph); free(kl_long); free(kl_long_set);
   if (have_map) gmap_free(&map);
   free(array_flags); free(greaders); free(areaders);
@@ -1454,6 +1613,8 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
 
 fail2:
   free(doc_ids); free(group_ids); free(values); free(dict_buf);
+  for (int32_t a = 0; a < nA; a++) if (anull[a].w) bm_free(&anull[a]);
+  free(nn); free(anull); free(nn_docs); free(nn_groups); free(nn_brk);
   free(dh); free(ch); free(bh); free(ph); free(kl_long); free(kl_long_set);
   if (have_map) gmap_free(&map);
   free(array_flags);

@@ -97,7 +97,7 @@ typedef struct orc_query {
   /* filtered aggregations (FilteredGroupByOperator / FilteredAggregationOperator): distinct FILTER clauses and, per
    * aggregation, the index of its clause (-1 = not filtered).  num_agg_filters = 0: the plain operators. */
   int32_t num_agg_filters;
-  int32_t _pad2;
+  int32_t null_handling;                 /* query option enableNullHandling (QueryContext.isNullHandlingEnabled) */
   const orc_filter_program* agg_filters;
   const int32_t* agg_filter_of;
 } orc_query;

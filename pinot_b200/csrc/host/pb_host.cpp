@@ -256,8 +256,104 @@ class FilterPlanNode {
   // constructPhysicalOperator over the postfix FilterContext
   static OpPtr run(const PbSegmentView& seg, const pbh_query_context& q) { return run(seg, q, q.num_filter_nodes, q.filter_nodes, q.predicates); }
   // (the FILTER clause of a filtered aggregation is planned on its own: AggregationFunctionUtils.java:343-344)
+  // IS NULL / IS NOT NULL leaf: a BitmapBasedFilterOperator over the column's null-value vector (exclusive for IS NOT NULL);
+  // without a vector IS NULL is empty and IS NOT NULL matches all (FilterPlanNode.java:294-307)
+  static OpPtr nullVectorOp(const PbSegmentView& seg, int ci, bool notNull) {
+    const PbColumnView& nc = seg.cols[ci];
+    if (!nc.null_vector) return mk(notNull ? OP_MATCH_ALL : OP_EMPTY);
+    OpPtr op = mk(OP_BITMAP);
+    op->bitmap = nc.null_vector; op->bitmapLen = nc.null_vector_len; op->bitmapExclusive = notNull; op->bitmapColumn = ci;
+    return op;
+  }
+  static OpPtr leafOp(const PbSegmentView& seg, const pbh_query_context& q, const pbh_predicate& p, int ci) {
+    if (p.type == PBH_IS_NULL || p.type == PBH_IS_NOT_NULL) return nullVectorOp(seg, ci, p.type == PBH_IS_NOT_NULL);
+    bool skipInv = false;
+    for (int k = 0; k < q.num_skip_inverted; k++) if (seg.cols[ci].name == q.skip_inverted_columns[k]) skipInv = true;
+    PredicateEvaluator ev = PredicateEvaluatorProvider::getPredicateEvaluator(p, seg.cols[ci], ci);
+    return FilterOperatorUtils::getLeafFilterOperator(ev, seg.cols[ci], seg.num_docs, skipInv);
+  }
+
+  // ---- enableNullHandling: three-valued doc sets of the operator tree (BaseFilterOperator.java:88-113 and the overrides in
+  // BaseColumnFilterOperator.java:46-70, AndFilterOperator.java:52-88, OrFilterOperator.java:51-87, NotFilterOperator.java:
+  // 52-63), folded into an ordinary operator tree:
+  //   column leaf   trues = matches AND NOT nulls;  nulls = the null-value vector;  falses = NOT (trues OR nulls)
+  //   IS [NOT] NULL, Empty, MatchAll: no nulls
+  //   AND  trues = AND trues_i;  falses = NOT AND_i (trues_i OR nulls_i)        (nulls_i of DIRECT column-leaf children only:
+  //   OR   trues = OR trues_i;   falses = NOT OR_i (trues_i OR nulls_i)          And / Or / Not do not override getNulls())
+  //   NOT  trues = falses of the child;  falses = its trues
+  struct Expr { int kind = 0; int pred = -1; std::vector<std::unique_ptr<Expr>> kids; };
+  struct NullAware {
+    const PbSegmentView& seg; const pbh_query_context& q; const pbh_predicate* preds;
+    int col(const Expr& e) const {
+      int ci = findColumn(seg, preds[e.pred].column);
+      if (ci < 0) throw BadQuery{std::string("unknown column ") + preds[e.pred].column};
+      return ci;
+    }
+    // the null-value vector of a column leaf that is a real column operator (not folded to Empty / MatchAll), else -1
+    int nullsOf(const Expr& e) const {
+      if (e.kind != PBH_PREDICATE) return -1;
+      const pbh_predicate& p = preds[e.pred];
+      if (p.type == PBH_IS_NULL || p.type == PBH_IS_NOT_NULL) return -1;
+      const int ci = col(e);
+      if (!seg.cols[ci].null_vector) return -1;
+      OpPtr base = leafOp(seg, q, p, ci);
+      return (base->kind == OP_EMPTY || base->kind == OP_MATCH_ALL) ? -1 : ci;
+    }
+    OpPtr truesOrNulls(const Expr& e) const {
+      OpPtr t = trues(e);
+      const int ci = nullsOf(e);
+      if (ci < 0) return t;
+      std::vector<OpPtr> kids;
+      kids.push_back(std::move(t)); kids.push_back(nullVectorOp(seg, ci, false));
+      return FilterOperatorUtils::getOrFilterOperator(std::move(kids));
+    }
+    OpPtr trues(const Expr& e) const {
+      if (e.kind == PBH_NOT) return falses(*e.kids[0]);
+      if (e.kind == PBH_PREDICATE) {
+        const pbh_predicate& p = preds[e.pred];
+        const int ci = col(e);
+        OpPtr base = leafOp(seg, q, p, ci);
+        if (p.type == PBH_IS_NULL || p.type == PBH_IS_NOT_NULL || base->kind == OP_EMPTY || !seg.cols[ci].null_vector) return base;
+        // FilterOperatorUtils.java:78-88: an always-true predicate on a column with nulls becomes a BitmapBasedFilterOperator over
+        // the flipped null bitmap (not a column operator: it reports no nulls of its own)
+        if (base->kind == OP_MATCH_ALL) return nullVectorOp(seg, ci, true);
+        std::vector<OpPtr> kids;                                     // excludeNulls: AND(matches, flip(nullBitmap))
+        kids.push_back(std::move(base)); kids.push_back(nullVectorOp(seg, ci, true));
+        return FilterOperatorUtils::getAndFilterOperator(std::move(kids));
+      }
+      std::vector<OpPtr> kids;
+      for (auto& k : e.kids) kids.push_back(trues(*k));
+      return e.kind == PBH_AND ? FilterOperatorUtils::getAndFilterOperator(std::move(kids)) : FilterOperatorUtils::getOrFilterOperator(std::move(kids));
+    }
+    OpPtr falses(const Expr& e) const {
+      if (e.kind == PBH_NOT) return trues(*e.kids[0]);
+      if (e.kind == PBH_PREDICATE) return FilterOperatorUtils::getNotFilterOperator(truesOrNulls(e));
+      std::vector<OpPtr> kids;
+      for (auto& k : e.kids) kids.push_back(truesOrNulls(*k));
+      OpPtr inner = e.kind == PBH_AND ? FilterOperatorUtils::getAndFilterOperator(std::move(kids)) : FilterOperatorUtils::getOrFilterOperator(std::move(kids));
+      return FilterOperatorUtils::getNotFilterOperator(std::move(inner));
+    }
+  };
+  static OpPtr runNullHandling(const PbSegmentView& seg, const pbh_query_context& q, int num_filter_nodes, const pbh_filter_node* filter_nodes, const pbh_predicate* predicates) {
+    std::vector<std::unique_ptr<Expr>> stack;
+    for (int i = 0; i < num_filter_nodes; i++) {
+      const pbh_filter_node& n = filter_nodes[i];
+      std::unique_ptr<Expr> e(new Expr());
+      e->kind = n.kind; e->pred = n.predicate;
+      const int k = n.kind == PBH_PREDICATE ? 0 : n.kind == PBH_NOT ? 1 : n.num_children;
+      if ((int)stack.size() < k || (n.kind != PBH_PREDICATE && k < 1)) throw BadQuery{"malformed filter"};
+      for (size_t j = stack.size() - (size_t)k; j < stack.size(); j++) e->kids.push_back(std::move(stack[j]));
+      stack.resize(stack.size() - (size_t)k);
+      stack.push_back(std::move(e));
+    }
+    if (stack.size() != 1) throw BadQuery{"malformed filter"};
+    NullAware na{seg, q, predicates};
+    return na.trues(*stack[0]);
+  }
+
   static OpPtr run(const PbSegmentView& seg, const pbh_query_context& q, int num_filter_nodes, const pbh_filter_node* filter_nodes, const pbh_predicate* predicates) {
     if (num_filter_nodes == 0) return mk(OP_MATCH_ALL);
+    if (q.null_handling) return runNullHandling(seg, q, num_filter_nodes, filter_nodes, predicates);
     std::vector<OpPtr> stack;
     for (int i = 0; i < num_filter_nodes; i++) {
       const pbh_filter_node& n = filter_nodes[i];
@@ -265,20 +361,7 @@ class FilterPlanNode {
         const pbh_predicate& p = predicates[n.predicate];
         int ci = findColumn(seg, p.column);
         if (ci < 0) throw BadQuery{std::string("unknown column ") + p.column};
-        // FilterPlanNode.java:294-307: a BitmapBasedFilterOperator over the column's null-value vector (exclusive for IS NOT
-        // NULL); without a vector IS NULL is empty and IS NOT NULL matches all
-        if (p.type == PBH_IS_NULL || p.type == PBH_IS_NOT_NULL) {
-          const PbColumnView& nc = seg.cols[ci];
-          if (!nc.null_vector) { stack.push_back(mk(p.type == PBH_IS_NULL ? OP_EMPTY : OP_MATCH_ALL)); continue; }
-          OpPtr op = mk(OP_BITMAP);
-          op->bitmap = nc.null_vector; op->bitmapLen = nc.null_vector_len; op->bitmapExclusive = p.type == PBH_IS_NOT_NULL; op->bitmapColumn = ci;
-          stack.push_back(std::move(op));
-          continue;
-        }
-        bool skipInv = false;
-        for (int k = 0; k < q.num_skip_inverted; k++) if (seg.cols[ci].name == q.skip_inverted_columns[k]) skipInv = true;
-        PredicateEvaluator ev = PredicateEvaluatorProvider::getPredicateEvaluator(p, seg.cols[ci], ci);
-        stack.push_back(FilterOperatorUtils::getLeafFilterOperator(ev, seg.cols[ci], seg.num_docs, skipInv));
+        stack.push_back(leafOp(seg, q, p, ci));
       } else if (n.kind == PBH_NOT) {
         if (stack.empty()) throw BadQuery{"malformed filter"};
         OpPtr c = std::move(stack.back()); stack.pop_back();
@@ -372,18 +455,60 @@ class B200PlanMaker {
       int ci = findColumn(seg, q.group_by_columns[j]);
       if (ci < 0) throw BadQuery{std::string("unknown group-by column ") + q.group_by_columns[j]};
       if (!seg.cols[ci].has_dict && seg.cols[ci].type == PB_STRING) throw BadQuery{"raw STRING group-by key"};
+      if (q.null_handling && seg.cols[ci].null_vector) throw BadQuery{"enableNullHandling with a nullable group-by column (null group keys stay on the CPU plan)"};
     }
     for (int a = 0; a < q.num_aggregations; a++) {
       const pb_aggregation_desc& ad = q.aggregations[a];
       if (ad.op < PB_AGG_COUNT || ad.op > PB_AGG_DISTINCTCOUNT) throw BadQuery{"aggregation function not offloaded"};
-      if (ad.op == PB_AGG_COUNT) continue;
+      if (ad.op == PB_AGG_COUNT && !(q.null_handling && ad.column)) continue;      // COUNT(col) = COUNT(*) unless nulls are handled
       int ci = ad.column ? findColumn(seg, ad.column) : -1;
       if (ci < 0) throw BadQuery{"unknown aggregation column"};
+      if (ad.op == PB_AGG_COUNT) continue;
       if (ad.op == PB_AGG_DISTINCTCOUNT) { if (!seg.cols[ci].has_dict && seg.cols[ci].type == PB_STRING) throw BadQuery{"DISTINCTCOUNT on a raw STRING column"}; }
       else if (seg.cols[ci].type == PB_STRING) throw BadQuery{"numeric aggregation on STRING"};
     }
   }
 };
+
+// ---- enableNullHandling, aggregation side.  NullableSingleInputAggregationFunction.forEachNotNull / foldNotNull
+// (CTR/query/aggregation/function/NullableSingleInputAggregationFunction.java:63-134) hand a function only the docs of a block
+// whose input is not null.  On the device that is a FILTER clause: every aggregation over a column that has a null-value
+// vector in some segment of the call gets the clause "<column> IS NOT NULL", ANDed with its own FILTER clause if it has one.
+// Clauses are shared between functions with the same (own clause, column) pair, like the swim-lanes of filtered aggregations.
+struct NullClause { int userClause; std::string column; };
+struct NullClausePlan {
+  std::vector<NullClause> clauses;
+  std::vector<int32_t> of;            // per aggregation: index into clauses, -1 = none
+};
+static NullClausePlan planNullClauses(const std::vector<PbSegmentView>& views, const pbh_query_context& q) {
+  NullClausePlan plan;
+  plan.of.assign((size_t)q.num_aggregations, -1);
+  for (int a = 0; a < q.num_aggregations; a++) {
+    const int user = q.num_agg_filters > 0 ? q.agg_filter_of[a] : -1;
+    std::string column;
+    if (q.aggregations[a].column)
+      for (const PbSegmentView& v : views) {
+        const int ci = findColumn(v, q.aggregations[a].column);
+        if (ci >= 0 && v.cols[ci].null_vector) { column = q.aggregations[a].column; break; }
+      }
+    if (user < 0 && column.empty()) continue;
+    int hit = -1;
+    for (size_t k = 0; k < plan.clauses.size(); k++) if (plan.clauses[k].userClause == user && plan.clauses[k].column == column) hit = (int)k;
+    if (hit < 0) { plan.clauses.push_back({user, column}); hit = (int)plan.clauses.size() - 1; }
+    plan.of[(size_t)a] = hit;
+  }
+  return plan;
+}
+static OpPtr nullClauseOp(const PbSegmentView& v, const pbh_query_context& q, const NullClause& c) {
+  OpPtr op = c.userClause >= 0 ? FilterPlanNode::run(v, q, q.agg_filters[c.userClause].num_filter_nodes, q.agg_filters[c.userClause].filter_nodes, q.agg_filters[c.userClause].predicates)
+                               : mk(OP_MATCH_ALL);
+  if (c.column.empty()) return op;
+  const int ci = findColumn(v, c.column.c_str());
+  if (ci < 0) throw BadQuery{std::string("unknown aggregation column ") + c.column};
+  std::vector<OpPtr> kids;
+  kids.push_back(std::move(op)); kids.push_back(FilterPlanNode::nullVectorOp(v, ci, true));
+  return FilterOperatorUtils::getAndFilterOperator(std::move(kids));
+}
 
 }  // namespace pinot_b200
 
@@ -445,32 +570,47 @@ extern "C" int pbh_execute(pb_segment_group_handle g, const pbh_query_context* q
     pod(q->num_agg_filters);
     for (int32_t f = 0; f < q->num_agg_filters; f++) program(q->agg_filters[f].num_filter_nodes, q->agg_filters[f].filter_nodes, q->agg_filters[f].predicates);
     if (q->num_agg_filters > 0) for (int32_t a = 0; a < q->num_aggregations; a++) pod(q->agg_filter_of[a]);
-    pod(q->num_order_by); pod(q->trim_size); pod(q->trim_threshold);
+    pod(q->num_order_by); pod(q->trim_size); pod(q->trim_threshold); pod(q->null_handling);
     for (int32_t k = 0; k < q->num_order_by; k++) { pod(q->order_by[k].kind); pod(q->order_by[k].index); pod(q->order_by[k].descending); }
     pb_query_desc d0;
     memset(&d0, 0, sizeof d0);
-    d0.flags = flags;
+    d0.flags = flags | (q->null_handling ? PB_Q_NULL_HANDLING : 0u);
     const int hit = pbi_plan_replay(g, host_key, &d0, out);
     if (hit != 0) return hit < 0 ? hit : PB_OK;
   }
-  std::vector<LoweredSegment> clauseLowered(segs.size() * (size_t)q->num_agg_filters);
+  // views of all segments first: with enableNullHandling the clause list depends on which columns are nullable anywhere
+  std::vector<PbSegmentView> views(segs.size());
+  for (size_t i = 0; i < segs.size(); i++) if ((rc = pbi_segment_view(segs[i], &views[i]))) return rc;
+  NullClausePlan nullPlan;
+  int numClauses = q->num_agg_filters;
+  const int32_t* clauseOf = q->agg_filter_of;
+  std::vector<LoweredSegment> clauseLowered;
   std::vector<std::vector<const pb_filter_node*>> clausePtr(segs.size());
   std::vector<std::vector<int32_t>> clauseLen(segs.size());
   for (auto& sqi : sq) memset(&sqi, 0, sizeof sqi);
   try {
+    if (q->null_handling) {
+      nullPlan = planNullClauses(views, *q);
+      numClauses = (int)nullPlan.clauses.size();
+      clauseOf = nullPlan.of.data();
+    }
+    clauseLowered.resize(segs.size() * (size_t)numClauses);
     for (size_t i = 0; i < segs.size(); i++) {
-      PbSegmentView v;
-      if ((rc = pbi_segment_view(segs[i], &v))) return rc;
+      const PbSegmentView& v = views[i];
       B200PlanMaker::checkEligible(v, *q);
       OpPtr root = FilterPlanNode::run(v, *q);
       if (root->kind != OP_MATCH_ALL) emit(*root, v, lowered[i]);
       sq[i].filter = lowered[i].nodes.data();
       sq[i].num_filter_nodes = (int32_t)lowered[i].nodes.size();
       // FILTER clauses, each planned like a filter of its own for this segment
-      for (int f = 0; f < q->num_agg_filters; f++) {
-        const pbh_filter_program& fp = q->agg_filters[f];
-        OpPtr sub = FilterPlanNode::run(v, *q, fp.num_filter_nodes, fp.filter_nodes, fp.predicates);
-        LoweredSegment& ls = clauseLowered[i * (size_t)q->num_agg_filters + f];
+      for (int f = 0; f < numClauses; f++) {
+        OpPtr sub;
+        if (q->null_handling) sub = nullClauseOp(v, *q, nullPlan.clauses[(size_t)f]);
+        else {
+          const pbh_filter_program& fp = q->agg_filters[f];
+          sub = FilterPlanNode::run(v, *q, fp.num_filter_nodes, fp.filter_nodes, fp.predicates);
+        }
+        LoweredSegment& ls = clauseLowered[i * (size_t)numClauses + f];
         if (sub->kind != OP_MATCH_ALL) emit(*sub, v, ls);
         clausePtr[i].push_back(ls.nodes.data());
         clauseLen[i].push_back((int32_t)ls.nodes.size());
@@ -485,8 +625,8 @@ extern "C" int pbh_execute(pb_segment_group_handle g, const pbh_query_context* q
   d.num_aggregations = q->num_aggregations; d.aggregations = q->aggregations;
   d.num_groups_limit = q->num_groups_limit > 0 ? q->num_groups_limit : 100000;
   d.max_initial_result_holder_capacity = q->max_initial_result_holder_capacity > 0 ? q->max_initial_result_holder_capacity : 10000;
-  d.flags = flags;
-  d.num_agg_filters = q->num_agg_filters; d.agg_filter_of = q->agg_filter_of;
+  d.flags = flags | (q->null_handling ? PB_Q_NULL_HANDLING : 0u);
+  d.num_agg_filters = numClauses; d.agg_filter_of = numClauses > 0 ? clauseOf : nullptr;
   d.num_order_by = q->num_order_by; d.order_by = q->order_by; d.trim_size = q->trim_size; d.trim_threshold = q->trim_threshold;
   pbi_set_pending_host_key(host_key);
   rc = pb_query_execute(g, sq.data(), &d, out);
@@ -570,6 +710,7 @@ extern "C" int pbh_dump_lowered(pb_segment_group_handle g, int32_t si, const pbh
           s += "SORTED ranges=";
           for (int i = 0; i < n.num_ids; i++) { snprintf(tmp, sizeof tmp, i ? ",%d-%d" : "%d-%d", n.ids[2 * i], n.ids[2 * i + 1]); s += tmp; }
           break;
+        case PB_F_BITMAP: snprintf(tmp, sizeof tmp, "BITMAP col=%s excl=%d %s", col, n.exclusive, n.blob ? "blob" : "null_value_vector"); s += tmp; break;
         default: s += "?"; break;
       }
       s += "\n";

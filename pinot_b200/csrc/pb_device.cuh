@@ -734,7 +734,7 @@ __device__ __forceinline__ void pb_accumulate(const DevQuery& Q, const DevSegQue
     const int fo = Q.agg_filter_of[a];
     if (fo >= 0) {                               // FILTER clause: the function only sees docs that pass it
       if (!((fpass >> fo) & 1u)) continue;
-      if (op == 0 || op == 4) {                  // its own row count (COUNT value / AVG denominator)
+      if (t.fcnt[a]) {                           // its own row count (COUNT value / AVG denominator; every function with PB_Q_NULL_HANDLING)
         if (Q.table_mode == T_KEYLESS) ka.cnt[a * PB_NTHREADS + threadIdx.x]++;
         else pb_red_add_u64(&t.fcnt[a][slot], 1ull);
       }
@@ -1417,7 +1417,7 @@ static __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_smem_ker
   for (int a = 0; a < PB_MAX_AGGS; a++) {
     const int op = a < Q.n_aggs ? Q.agg_op[a] : 0;
     st.acc_of[a] = (a < Q.n_aggs && op >= 1 && op <= 4) ? (int8_t)n_acc++ : (int8_t)-1;
-    st.fc_of[a] = (a < Q.n_aggs && Q.agg_filter_of[a] >= 0 && (op == 0 || op == 4)) ? (int8_t)n_fc++ : (int8_t)-1;
+    st.fc_of[a] = (a < Q.n_aggs && Q.agg_filter_of[a] >= 0 && t.fcnt[a] != nullptr) ? (int8_t)n_fc++ : (int8_t)-1;
   }
   st.n_fc = (uint32_t)n_fc;
   const size_t rep_bytes = pb_smem_table_bytes(S, n_fc, n_acc);
@@ -2139,7 +2139,7 @@ struct DevFinAgg {
 struct DevFinalize {
   int32_t mode, n_gb, n_aggs, always_emit;
   uint64_t S;                 // slots to scan
-  int32_t key_words, pad_k;
+  int32_t key_words, count_all;   // count_all (PB_Q_NULL_HANDLING): every aggregation's long array carries its row count
   uint64_t capacity;          // T_HASH: index of the reserved sentinel slot
   uint64_t cap_out;
   const unsigned long long* rowcnt;
@@ -2186,7 +2186,7 @@ static __global__ void pb_finalize_kernel(const DevFinalize F) {
       else if (fa.op == 0) fa.out[k] = fa.fcnt ? (double)fa.fcnt[i] : (double)c;
       // the aggregation's long array: COUNT value / AVG denominator (the function's own row count under a FILTER clause), 0 otherwise
       if (fa.op == 5 && fa.dcnt) fa.out_cnt[k] = (long long)fa.dcnt[i];
-      if (fa.op != 5 && fa.out_cnt) fa.out_cnt[k] = (fa.op == 0 || fa.op == 4) ? (fa.fcnt ? (long long)fa.fcnt[i] : (long long)c) : 0ll;
+      if (fa.op != 5 && fa.out_cnt) fa.out_cnt[k] = (fa.op == 0 || fa.op == 4 || F.count_all) ? (fa.fcnt ? (long long)fa.fcnt[i] : (long long)c) : 0ll;
     }
     unsigned long long key = 0, key_hi = 0;
     if (F.mode == T_HASH) {

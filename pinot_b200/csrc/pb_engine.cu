@@ -983,6 +983,7 @@ struct pb_result_s {
   bool combine = false, finalized = false;
   unsigned long long* d_seg_stats = nullptr;   // filtered aggregations: [n_segs][1 + PB_MAX_AGG_FILTERS] docs per swim-lane
   int n_agg_filters = 0;
+  bool count_all = false;                   // PB_Q_NULL_HANDLING: every aggregation keeps its own (non-null) row count
   std::vector<int> agg_filter_of;
   int waves = 1;                            // launches were split into this many waves behind the staging copies
   int in_place_columns = 0;                 // (segment, column) pairs gathered from mapped host memory (PB_Q_GATHER_IN_PLACE)
@@ -1639,6 +1640,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   const bool in_place = (q->flags & PB_Q_GATHER_IN_PLACE) != 0;
   const int n_tables = combine ? 1 : n_segs;
   const int nF = q->num_agg_filters;
+  const bool count_all = (q->flags & PB_Q_NULL_HANDLING) != 0;
   if (nF < 0 || nF > PB_MAX_AGG_FILTERS) return fail(PB_ERR_UNSUPPORTED, "%d FILTER clauses (max %d)", nF, PB_MAX_AGG_FILTERS);
   if (nF > 0) {
     if (!q->agg_filter_of) return fail(PB_ERR_INVALID, "agg_filter_of missing");
@@ -1904,7 +1906,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     zero_bytes += 8 * S;                                     // rowcnt
     for (int a = 0; a < nA; a++) {
       int op = q->aggregations[a].op;
-      if (nF > 0 && q->agg_filter_of[a] >= 0 && (op == PB_AGG_COUNT || op == PB_AGG_AVG)) zero_bytes += 8 * S;   // fcnt
+      if (nF > 0 && q->agg_filter_of[a] >= 0 && (op == PB_AGG_COUNT || op == PB_AGG_AVG || count_all)) zero_bytes += 8 * S;   // fcnt
       if (op == PB_AGG_SUM || op == PB_AGG_AVG) zero_bytes += 8 * S;
       if (op == PB_AGG_MIN || op == PB_AGG_MAX) mm_elems += S;
       if (op == PB_AGG_DISTINCTCOUNT && !dc_raw[a]) zero_bytes += 4 * S * dc_words[a];
@@ -1960,7 +1962,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
       dt.rowcnt = reinterpret_cast<unsigned long long*>(d_zero + zo); zo += 8 * S;
       for (int a = 0; a < nA; a++) {   // row counts of COUNT / AVG with a FILTER clause (u64, summed across GPUs with the row counts)
         int op = q->aggregations[a].op;
-        if (nF > 0 && q->agg_filter_of[a] >= 0 && (op == PB_AGG_COUNT || op == PB_AGG_AVG)) { dt.fcnt[a] = reinterpret_cast<unsigned long long*>(d_zero + zo); zo += 8 * S; }
+        if (nF > 0 && q->agg_filter_of[a] >= 0 && (op == PB_AGG_COUNT || op == PB_AGG_AVG || count_all)) { dt.fcnt[a] = reinterpret_cast<unsigned long long*>(d_zero + zo); zo += 8 * S; }
       }
       if (t == 0) { r->span_i64 = r->d_counters; r->span_i64_n = (int64_t)((d_zero + zo - (uint8_t*)r->d_counters) / 8); }
       // sums first (one contiguous float64 span for the cross-GPU reduce), then the distinct bitsets
@@ -2394,7 +2396,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   for (int a = 0; a < nA; a++) {
     const int op = q->aggregations[a].op;
     if (op >= PB_AGG_SUM && op <= PB_AGG_AVG) n_acc++;
-    if (nF > 0 && q->agg_filter_of[a] >= 0 && (op == PB_AGG_COUNT || op == PB_AGG_AVG)) n_fc++;
+    if (nF > 0 && q->agg_filter_of[a] >= 0 && (op == PB_AGG_COUNT || op == PB_AGG_AVG || count_all)) n_fc++;
   }
   static const int smem_table_env = []() { const char* e = getenv("PB_AGG_SMEM"); return e ? atoi(e) : 1; }();
   static const size_t smem_table_budget = 200 * 1024;
@@ -2411,7 +2413,7 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
     d_match_list = (uint32_t*)r->scratch;
   }
   r->match_all = match_all;
-  r->n_agg_filters = nF;
+  r->n_agg_filters = nF; r->count_all = count_all;
   // ---- counter cells that the host knows up front (ExecutionStatistics; see PB_COUNTERS_PER_TABLE) ----
   unsigned long long* h_head = nullptr;
   const unsigned long long* d_head = ar.put<unsigned long long>(nullptr, (size_t)PB_COUNTERS_PER_TABLE * n_tables, &h_head);
@@ -2885,7 +2887,7 @@ static int prepare_finalize(pb_result_s* r) {
     if (!tm.slots.p || !tm.rows.p) return fail(PB_ERR_OOM, "pinned host allocation failed");
     DevFinalize& F = rp.fin[(size_t)t];
     memset(&F, 0, sizeof F);
-    F.mode = mode; F.n_gb = nG; F.n_aggs = nA; F.always_emit = mode == T_KEYLESS ? 1 : 0;
+    F.mode = mode; F.n_gb = nG; F.n_aggs = nA; F.always_emit = mode == T_KEYLESS ? 1 : 0; F.count_all = r->count_all ? 1 : 0;
     F.S = mode == T_KEYLESS ? 1 : S; F.capacity = tm.capacity; F.cap_out = cap; F.key_words = tm.dev.key_words;
     F.rowcnt = tm.dev.rowcnt; F.hkeys = tm.dev.hkeys;
     if (tm.dev.first_doc) { F.first_doc = tm.dev.first_doc; F.first_thr = r->d_first_thr + t; }
@@ -2900,7 +2902,7 @@ static int prepare_finalize(pb_result_s* r) {
       tm.dbl[a].alloc(8 * cap); tm.lng[a].alloc(8 * cap);
       if (!tm.dbl[a].p || !tm.lng[a].p) return fail(PB_ERR_OOM, "pinned host allocation failed");
       F.aggs[a].op = r->agg_op[a]; F.aggs[a].sum = tm.dev.sum[a]; F.aggs[a].mm = tm.dev.mm[a]; F.aggs[a].out = (double*)tm.dbl[a].p;
-      const bool lng_on_device = r->agg_op[a] == PB_AGG_COUNT || r->agg_op[a] == PB_AGG_AVG || r->agg_op[a] == PB_AGG_DISTINCTCOUNT;
+      const bool lng_on_device = r->agg_op[a] == PB_AGG_COUNT || r->agg_op[a] == PB_AGG_AVG || r->agg_op[a] == PB_AGG_DISTINCTCOUNT || r->count_all;
       F.aggs[a].fcnt = tm.dev.fcnt[a]; F.aggs[a].out_cnt = lng_on_device ? (long long*)tm.lng[a].p : nullptr; F.aggs[a].dcnt = tm.dev.dcnt[a];
     }
     uint64_t div = 1;
@@ -2999,7 +3001,10 @@ static int finish_finalize(pb_result_s* r) {
     const unsigned long long* cc = hc + (size_t)t * PB_COUNTERS_PER_TABLE;
     tm.stats.num_docs_scanned = (int64_t)cc[2];
     tm.stats.num_entries_scanned_post_filter = tm.stats.num_docs_scanned * (int64_t)proj.size();
-    if (r->n_agg_filters > 0) {        // swim-lanes of filtered aggregations (pb_lane_stats_kernel)
+    // (PB_Q_NULL_HANDLING: the clauses are the implicit "<column> IS NOT NULL" of null-skipping functions, which the reference
+    //  evaluates inside the functions, not as swim-lanes: the plain figures apply.  A query that ALSO has FILTER clauses of
+    //  its own reports the plain figures too, where the reference would count its lanes)
+    if (r->n_agg_filters > 0 && !r->count_all) {        // swim-lanes of filtered aggregations (pb_lane_stats_kernel)
       tm.stats.num_docs_scanned = (int64_t)cc[4];
       tm.stats.num_entries_scanned_post_filter = (int64_t)cc[5];
     }
@@ -3068,7 +3073,7 @@ extern "C" const int64_t* pb_result_long(pb_result_handle r, int32_t t, int32_t 
   auto* tm = TAB(r, t);
   if (!tm || a < 0 || a >= r->n_aggs) return nullptr;
   const int op = r->agg_op[a];
-  if (op == PB_AGG_SUM || op == PB_AGG_MIN || op == PB_AGG_MAX) memset(tm->lng[a].p, 0, 8 * (size_t)std::max<int64_t>(tm->num_groups, 1));   // not written by the device
+  if ((op == PB_AGG_SUM || op == PB_AGG_MIN || op == PB_AGG_MAX) && !r->count_all) memset(tm->lng[a].p, 0, 8 * (size_t)std::max<int64_t>(tm->num_groups, 1));   // not written by the device
   return (const int64_t*)tm->lng[a].p;
 }
 // DISTINCTCOUNT value sets, materialised on first access

@@ -79,7 +79,8 @@ class PbhQueryContext(C.Structure):
                 ("num_skip_inverted", C.c_int32), ("skip_inverted_columns", C.POINTER(C.c_char_p)),
                 ("num_agg_filters", C.c_int32), ("agg_filters", C.POINTER(PbhFilterProgram)),
                 ("agg_filter_of", C.POINTER(C.c_int32)),
-                ("num_order_by", C.c_int32), ("order_by", C.POINTER(PbOrderBy)), ("trim_size", C.c_int32), ("trim_threshold", C.c_int32)]
+                ("num_order_by", C.c_int32), ("order_by", C.POINTER(PbOrderBy)), ("trim_size", C.c_int32), ("trim_threshold", C.c_int32),
+                ("null_handling", C.c_int32)]
 
 
 _lib = None
@@ -382,11 +383,14 @@ class ResultTable:
         ks = self.keys() if self.query.group_by else [()]
         dbl, lng = self.doubles, self.longs
         out = {}
+        nh = getattr(self.query, "null_handling", False)      # the long array then holds the inputs every function saw: 0 = SQL NULL
         for g, k in enumerate(ks):
             row = []
             for a, agg in enumerate(self.query.aggregations):
                 if agg.op in (AggOp.COUNT, AggOp.DISTINCTCOUNT):
                     row.append(int(lng[a][g]))
+                elif nh and int(lng[a][g]) == 0:
+                    row.append(None)
                 elif agg.op == AggOp.AVG:
                     row.append((float(dbl[a][g]), int(lng[a][g])))
                 else:
@@ -501,7 +505,8 @@ class _MarshalledQuery:
         self.aggs = (PbAggregationDesc * max(1, len(q.aggregations)))()
         for i, a in enumerate(q.aggregations):
             self.aggs[i].op = int(a.op)
-            self.aggs[i].column = a.column.encode() if a.column is not None else None
+            keep_col = a.column is not None and (int(a.op) != 0 or getattr(q, "null_handling", False))   # COUNT(col) = COUNT(*) unless nulls are handled
+            self.aggs[i].column = a.column.encode() if keep_col else None
         skip = [c for c, kinds in q.skip_indexes.items() if "inverted" in kinds]
         self.skip = (C.c_char_p * max(1, len(skip)))(*[c.encode() for c in skip])
         filters, filter_of = q.agg_filters()
@@ -518,6 +523,7 @@ class _MarshalledQuery:
         for i, (kind, index, desc) in enumerate(q.order_by):
             self.order[i].kind, self.order[i].index, self.order[i].descending = kind, index, int(desc)
         self.ctx.num_order_by, self.ctx.order_by = len(q.order_by), self.order
+        self.ctx.null_handling = int(getattr(q, "null_handling", False))
         self.trims = {True: q.trim(True), False: q.trim(False)}
 
 

@@ -121,6 +121,8 @@ class QueryContext:
     min_server_group_trim_size: int = 5000
     min_segment_group_trim_size: int = -1
     group_trim_threshold: int = 1_000_000
+    # query option enableNullHandling (QueryContext.isNullHandlingEnabled): three-valued filters, aggregations skip null inputs
+    null_handling: bool = False
 
     def trim(self, combined: bool):
         """(trim_size, trim_threshold) the combine layer (combined) or the segment operator would apply: GroupByUtils.
@@ -309,7 +311,11 @@ def parse_sql(sql: str) -> QueryContext:
         p.i += 1
         k = p.ident()
         p.eat_op("=")
-        options[k.lower()] = p.literal()
+        if p.peek()[0] == "id":           # SET enableNullHandling = true
+            options[k.lower()] = p.peek()[1]
+            p.i += 1
+        else:
+            options[k.lower()] = p.literal()
         if p.peek() == ("op", ";"):
             p.i += 1
     p.eat_kw("SELECT")
@@ -403,6 +409,7 @@ def parse_sql(sql: str) -> QueryContext:
                       ("grouptrimthreshold", "group_trim_threshold")):
         if opt in options:
             setattr(q, attr, int(options[opt]))
+    q.null_handling = str(options.get("enablenullhandling", "false")).lower() == "true"
     if "numgroupslimit" in options:
         q.num_groups_limit = int(options["numgroupslimit"])
     if "maxinitialresultholdercapacity" in options:

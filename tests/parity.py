@@ -14,12 +14,15 @@ def oracle_rows(r: "oracle.OracleResult") -> Dict[tuple, list]:
     """key -> per-aggregation value in the same shape as native.ResultTable.rows()."""
     q = r.query
     keys = r.decoded_keys() if q.group_by else [()]
+    nh = getattr(q, "null_handling", False)      # longs then hold the inputs every function saw: 0 = SQL NULL
     out = {}
     for g, k in enumerate(keys):
         row = []
         for a, agg in enumerate(q.aggregations):
             if agg.op in (AggOp.COUNT, AggOp.DISTINCTCOUNT):
                 row.append(int(r.longs[a][g]))
+            elif nh and int(r.longs[a][g]) == 0:
+                row.append(None)
             elif agg.op == AggOp.AVG:
                 row.append((float(r.doubles[a][g]), int(r.longs[a][g])))
             else:
@@ -49,7 +52,9 @@ def assert_rows_equal(got: Dict[tuple, list], exp: Dict[tuple, list], q: QueryCo
     for k, erow in exp.items():
         grow = got[k]
         for a, agg in enumerate(q.aggregations):
-            if agg.op == AggOp.AVG:
+            if grow[a] is None or erow[a] is None:
+                assert grow[a] is None and erow[a] is None, f"{what}: {k} {agg}: {grow[a]!r} != {erow[a]!r} (SQL NULL)"
+            elif agg.op == AggOp.AVG:
                 assert grow[a][1] == erow[a][1], f"{what}: {k} {agg}: count {grow[a][1]} != {erow[a][1]}"
                 assert _close(grow[a][0], erow[a][0], exact_float), f"{what}: {k} {agg}: sum {grow[a][0]!r} != {erow[a][0]!r}"
             elif agg.op in (AggOp.COUNT, AggOp.DISTINCTCOUNT):
@@ -59,7 +64,7 @@ def assert_rows_equal(got: Dict[tuple, list], exp: Dict[tuple, list], q: QueryCo
                 assert _close(grow[a], erow[a], ex), f"{what}: {k} {agg}: {grow[a]!r} != {erow[a]!r}"
 
 
-def check_query(segments, sql_or_q, group=None, flags_list=(0,), exact_float=True, check_combined=True):
+def check_query(segments, sql_or_q, group=None, flags_list=(0,), exact_float=True, check_combined=True, check_stats=True):
     """Run per-segment and combined on the device and compare with the oracle.  Returns the last native Result."""
     q = parse_sql(sql_or_q) if isinstance(sql_or_q, str) else sql_or_q
     own = group is None
@@ -73,7 +78,7 @@ def check_query(segments, sql_or_q, group=None, flags_list=(0,), exact_float=Tru
         assert len(res.tables) == len(segments)
         for i, (t, o) in enumerate(zip(res.tables, orc)):
             assert_rows_equal(t.rows(), oracle_rows(o), q, exact_float, what=f"segment {i} flags={flags}")
-            for key in ("num_docs_scanned", "num_entries_scanned_post_filter", "num_total_docs"):
+            for key in ("num_docs_scanned", "num_entries_scanned_post_filter", "num_total_docs") if check_stats else ("num_total_docs",):
                 assert t.stats[key] == o.stats[key], f"segment {i}: {key}: {t.stats[key]} != {o.stats[key]}"
             # DISTINCTCOUNT value sets (intermediate result) as dictId sets
             for a, agg in enumerate(q.aggregations):
@@ -91,7 +96,7 @@ def check_query(segments, sql_or_q, group=None, flags_list=(0,), exact_float=Tru
             assert len(res.tables) == 1
             exp = combined_rows(oracle.combine(orc), q)
             assert_rows_equal(res.tables[0].rows(), exp, q, exact_float, what=f"combined flags={flags}")
-            assert res.tables[0].stats["num_docs_scanned"] == sum(o.stats["num_docs_scanned"] for o in orc)
+            assert not check_stats or res.tables[0].stats["num_docs_scanned"] == sum(o.stats["num_docs_scanned"] for o in orc)
             assert res.tables[0].stats["num_total_docs"] == sum(s.num_docs for s in segments)
             last = res
     if own:

@@ -9,6 +9,7 @@ import pytest
 
 from pinot_b200 import datagen, native
 from pinot_b200.query import parse_sql
+from pinot_b200.segment_writer import DataType, build_column, make_segment
 from tests.fixtures import FILTER, sv_segment
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -137,3 +138,32 @@ def test_stage_and_plan_from_an_mmapped_v3_directory(tmp_path):
     assert np.array_equal(np.asarray(g_map.export_dictionary("s0")), np.asarray(g_mem.export_dictionary("s0")))
     g_mem.release()
     g_map.release()
+
+
+def test_null_handling_is_lowered_to_trues_programs():
+    """enableNullHandling: the host layer hands the device the TRUES of the three-valued operator tree (BaseFilterOperator.
+    getTrues / getNulls / getFalses and the And / Or / Not / BaseColumnFilterOperator overrides) as an ordinary program, and
+    the clause "<column> IS NOT NULL" for every aggregation over a nullable column."""
+    from pinot_b200.segment_writer import with_nulls
+    rng = np.random.default_rng(1)
+    n = 200
+    a = rng.integers(0, 5, n).astype(np.int32); an = rng.random(n) < 0.3
+    seg = make_segment("nh", [with_nulls(build_column("a", DataType.INT, a), an), build_column("b", DataType.INT, rng.integers(0, 9, n).astype(np.int32))])
+    g = native.SegmentGroup([native.StagedSegment(seg)])
+    nh = "SET enableNullHandling=true; "
+    low = lambda sql, clause=-1: native.dump_lowered(g, parse_sql(sql), clause)
+    # column leaf: matches AND NOT nulls (BaseColumnFilterOperator.java:46-54)
+    assert low(nh + "SELECT COUNT(*) FROM t WHERE a > 2") == ["BITMAP col=a excl=1 null_value_vector", "SCAN_DICT_RANGE col=a lo=3 hi=5", "AND n=2"]
+    # NOT leaf: NOT (trues OR nulls) (BaseFilterOperator.java:97-113)
+    assert low(nh + "SELECT COUNT(*) FROM t WHERE NOT (a > 2)") == ["BITMAP col=a excl=1 null_value_vector", "SCAN_DICT_RANGE col=a lo=3 hi=5", "AND n=2",
+                                                                  "BITMAP col=a excl=0 null_value_vector", "OR n=2", "NOT"]
+    # a column without a null-value vector plans as before; so does everything without the option
+    assert low(nh + "SELECT COUNT(*) FROM t WHERE NOT (b > 2)") == low("SELECT COUNT(*) FROM t WHERE NOT (b > 2)")
+    assert low("SELECT COUNT(*) FROM t WHERE NOT (a > 2)") == ["SCAN_DICT_RANGE col=a lo=3 hi=5", "NOT"]
+    # an always-true predicate on a nullable column is the flipped null bitmap (FilterOperatorUtils.java:78-88)
+    assert low(nh + "SELECT COUNT(*) FROM t WHERE a >= 0") == ["BITMAP col=a excl=1 null_value_vector"]
+    # nullable group-by keys keep the CPU plan
+    assert not native.is_eligible(g, parse_sql(nh + "SELECT a, COUNT(*) FROM t GROUP BY a LIMIT 10"))
+    assert native.is_eligible(g, parse_sql("SELECT a, COUNT(*) FROM t GROUP BY a LIMIT 10"))
+    assert native.is_eligible(g, parse_sql(nh + "SELECT b, SUM(a) FROM t GROUP BY b LIMIT 10"))
+    g.release()
