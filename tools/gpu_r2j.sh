@@ -3,6 +3,7 @@
 mkdir -p gpurun_out
 nvidia-smi -L
 echo "== multi-GPU tests"; timeout 600 python -m pytest tests/test_gpu_multi.py -q > gpurun_out/r2j_tests_multi.log 2>&1; tail -3 gpurun_out/r2j_tests_multi.log
+echo "== null-handling + filtered-aggregation tests"; timeout 400 python -m pytest tests/test_gpu_null_handling.py tests/test_gpu_parity.py -q -k "null or filtered or FILTER or golden" > gpurun_out/r2j_tests_null.log 2>&1; tail -3 gpurun_out/r2j_tests_null.log
 echo "== bench N=2 (torchrun)"; /usr/bin/time -f "wall %e s" timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2j_bench_n2.json 2> gpurun_out/r2j_bench_n2.err; echo "rc=$?"; tail -c 400 gpurun_out/r2j_bench_n2.err
 echo "== bench N=2 reference arm"; timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r2j_ref_n2.json 2> gpurun_out/r2j_ref_n2.err; echo "rc=$?"; tail -c 300 gpurun_out/r2j_ref_n2.json
 echo "== bench_configs N=2 (scaled)"; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench_configs.py --only 3,4,5 --scale 0.1 --steps 5 > gpurun_out/r2j_configs_n2.jsonl 2> gpurun_out/r2j_configs_n2.err; echo "rc=$?"; tail -c 300 gpurun_out/r2j_configs_n2.err
