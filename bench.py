@@ -165,13 +165,17 @@ _oracle_prepared = {}
 
 
 def oracle_query_all_threads(segs, q, threads):
-    """One CombineOperator-style pass on the CPU: the segments on `threads` native worker threads (pthreads inside
-    liboracle.so, the segments and the query marshalled once), then the cross-segment merge."""
+    """One CombineOperator-style pass on the CPU: the segments on `threads` pooled native worker threads (pthreads inside
+    liboracle.so, the segments and the query marshalled once), every worker folding its segments' results into an IndexedTable
+    of its own, tables merged at the end -- GroupByCombineOperator without the interpreter anywhere in the timed loop."""
     from oracle import oracle
     key = (id(segs[0]), len(segs), id(q))
     prep = _oracle_prepared.get(key)
     if prep is None:
         prep = _oracle_prepared[key] = oracle.PreparedBatch(segs, q)
+    merged = oracle.execute_combined(prep, threads)      # segments AND merge on native worker threads
+    if merged is not None:
+        return merged
     res = oracle.execute_batch(prep, threads)
     return oracle.combine_numeric(res)
 
@@ -222,6 +226,16 @@ def workload_config(args, segs, w=None):
             "columns_materialised": "8 touched of the 20-column table", "l2_policy": "inputs (>1 GB/GPU) larger than the 126 MB L2",
             "parallelism": (f"segments sharded over {args.gpus} GPUs, one process per GPU; per-rank group tables merged inside libpinot_b200.so "
                             f"(PB_Q_ALL_RANKS: one ncclAllGather of the table block + pb_merge_blocks_kernel on the call's stream)") if args.gpus > 1 else "1 GPU"}
+
+
+def _teardown(native, dist):
+    """Communicator and process-group teardown after the line is out.  Every rank has finished its work by now; a teardown that
+    cannot complete (a peer that died, a collective library waiting for a resource) must not keep the job alive: a watchdog
+    ends the process 20 s later whatever happens."""
+    import threading
+    threading.Thread(target=lambda: (time.sleep(20), os._exit(0)), daemon=True).start()
+    native.comm_destroy()
+    dist.destroy_process_group()
 
 
 _JSON_OUT = None
@@ -564,8 +578,7 @@ def main():
 
     if rank != 0:
         if world > 1:
-            native.comm_destroy()
-            dist.destroy_process_group()
+            _teardown(native, dist)
         return 0
 
     # ---- roofline: the longer of the two hot kernels is the dominant one; CUDA events on the call's own stream ----
@@ -643,8 +656,7 @@ def main():
             "kernel_variant": {0: "tma+width-specialised", 4: "tma+generic", 8: "ldg+width-specialised", 12: "ldg+generic"}.get(args.flags & 12)}
     _emit(line)
     if world > 1:
-        native.comm_destroy()
-        dist.destroy_process_group()
+        _teardown(native, dist)
     return 0
 
 

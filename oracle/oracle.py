@@ -102,6 +102,9 @@ def lib():
         l.orc_result_distinct_values.restype = C.POINTER(C.c_int64)
         l.orc_execute_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         l.orc_execute_batch.restype = C.c_int32
+        l.orc_execute_combined.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.orc_execute_combined.restype = C.c_int64
+        l.orc_free.argtypes = [C.c_void_p]
         l.orc_num_bits_per_value.argtypes = [C.c_int32]
         l.orc_num_bits_per_value.restype = C.c_int32
         l.orc_read_dict_id.argtypes = [C.c_void_p, C.c_int32, C.c_int64]
@@ -334,6 +337,27 @@ def execute_batch(prep: "PreparedBatch", threads: int) -> List["OracleResult"]:
             if prep.out[i]:
                 l.orc_result_free(prep.out[i])
                 prep.out[i] = None
+
+
+def execute_combined(prep: "PreparedBatch", threads: int):
+    """One GroupByCombineOperator-style pass entirely in native code: the segments on `threads` pooled worker threads, each
+    folding its results into an IndexedTable keyed by the decoded group key, tables merged at the end (orc_execute_combined).
+    Returns (keys[n, nG] int64 -- FLOAT / DOUBLE keys as bit patterns --, doubles[n, nA], longs[n, nA]), or None when the query
+    needs the Python merge (DISTINCTCOUNT, STRING keys)."""
+    l = lib()
+    kp, dp, lp = C.POINTER(C.c_int64)(), C.POINTER(C.c_double)(), C.POINTER(C.c_int64)()
+    n = l.orc_execute_combined(prep.seg_ptrs, prep.q_ptrs, len(prep.segs), threads, C.byref(kp), C.byref(dp), C.byref(lp))
+    if n < 0:
+        return None
+    nG, nA = len(prep.q.group_by), len(prep.q.aggregations)
+    try:
+        keys = np.ctypeslib.as_array(kp, shape=(max(n, 1) * max(nG, 1),))[:n * nG].reshape(n, nG).copy()
+        dbl = np.ctypeslib.as_array(dp, shape=(max(n, 1) * nA,))[:n * nA].reshape(n, nA).copy()
+        lng = np.ctypeslib.as_array(lp, shape=(max(n, 1) * nA,))[:n * nA].reshape(n, nA).copy()
+    finally:
+        for ptr in (kp, dp, lp):
+            l.orc_free(ptr)
+    return keys, dbl, lng
 
 
 def filter_doc_ids(seg, q):

@@ -1631,27 +1631,180 @@ fail:
  * BaseCombineOperator hands segments to its tasks: CTR/operator/combine/BaseCombineOperator.java:100-141).  Test / bench
  * infrastructure: lets the CPU baseline use every host core without the Python interpreter in the timed loop. ---- */
 #include <pthread.h>
-typedef struct { const orc_segment* const* segs; const orc_query* const* qs; orc_result** out; int32_t n; volatile int32_t next; } orc_batch;
-static void* orc_batch_worker(void* arg) {
-  orc_batch* b = (orc_batch*)arg;
+/* ---- the same pass WITH the cross-segment merge done natively, the way GroupByCombineOperator does it: every worker thread
+ * folds the result of the segment it just executed into an IndexedTable keyed by the DECODED group key (CTR/operator/combine/
+ * GroupByCombineOperator.java:132-147 -> IndexedTable.upsert, CTR/data/table/IndexedTable.java:99-125: SUM / COUNT add, MIN
+ * min, MAX max, AVG (sum, count) add).  Here each worker owns a private table and the tables are merged at the end (the
+ * reference's workers share one ConcurrentIndexedTable; the result is the same).  Numeric group keys and COUNT / SUM / MIN /
+ * MAX / AVG only: what the CPU baseline of the benchmark needs.  Worker threads are created once and kept (a query server
+ * runs a thread pool; fresh threads would pay for fresh malloc arenas on every query). ---- */
+typedef struct { int64_t* keys; double* dbl; int64_t* lng; uint8_t* used; int64_t cap, size; int32_t nG, nA; } ctable;
+static void ctable_init(ctable* t, int32_t nG, int32_t nA) {
+  t->nG = nG; t->nA = nA; t->cap = 1024; t->size = 0;
+  t->keys = (int64_t*)malloc(sizeof(int64_t) * (size_t)(t->cap * (nG > 0 ? nG : 1)));
+  t->dbl = (double*)malloc(sizeof(double) * (size_t)(t->cap * nA)); t->lng = (int64_t*)malloc(sizeof(int64_t) * (size_t)(t->cap * nA));
+  t->used = (uint8_t*)calloc((size_t)t->cap, 1);
+}
+static void ctable_free(ctable* t) { free(t->keys); free(t->dbl); free(t->lng); free(t->used); }
+static int64_t ctable_slot(ctable* t, const int64_t* key) {
+  uint64_t h = 1469598103934665603ull;
+  for (int32_t j = 0; j < t->nG; j++) { h ^= (uint64_t)key[j]; h *= 1099511628211ull; h ^= h >> 29; }
+  int64_t i = (int64_t)(h & (uint64_t)(t->cap - 1));
+  while (t->used[i] && memcmp(t->keys + i * t->nG, key, sizeof(int64_t) * (size_t)t->nG) != 0) i = (i + 1) & (t->cap - 1);
+  return i;
+}
+static void ctable_upsert(ctable* t, const int32_t* ops, const int64_t* key, const double* d, const int64_t* l);
+static void ctable_grow(ctable* t, const int32_t* ops) {
+  ctable o = *t;
+  t->cap = o.cap * 2; t->size = 0;
+  t->keys = (int64_t*)malloc(sizeof(int64_t) * (size_t)(t->cap * (t->nG > 0 ? t->nG : 1)));
+  t->dbl = (double*)malloc(sizeof(double) * (size_t)(t->cap * t->nA)); t->lng = (int64_t*)malloc(sizeof(int64_t) * (size_t)(t->cap * t->nA));
+  t->used = (uint8_t*)calloc((size_t)t->cap, 1);
+  for (int64_t i = 0; i < o.cap; i++) if (o.used[i]) ctable_upsert(t, ops, o.keys + i * o.nG, o.dbl + i * o.nA, o.lng + i * o.nA);
+  ctable_free(&o);
+}
+static void ctable_upsert(ctable* t, const int32_t* ops, const int64_t* key, const double* d, const int64_t* l) {
+  if ((t->size + 1) * 2 > t->cap) ctable_grow(t, ops);
+  int64_t i = ctable_slot(t, key);
+  double* td = t->dbl + i * t->nA; int64_t* tl = t->lng + i * t->nA;
+  if (!t->used[i]) {
+    t->used[i] = 1; t->size++;
+    memcpy(t->keys + i * t->nG, key, sizeof(int64_t) * (size_t)t->nG);
+    memcpy(td, d, sizeof(double) * (size_t)t->nA); memcpy(tl, l, sizeof(int64_t) * (size_t)t->nA);
+    return;
+  }
+  for (int32_t a = 0; a < t->nA; a++) {
+    switch (ops[a]) {
+      case ORC_COUNT: tl[a] += l[a]; td[a] += d[a]; break;
+      case ORC_SUM: td[a] += d[a]; break;
+      case ORC_MIN: if (d[a] < td[a]) td[a] = d[a]; break;
+      case ORC_MAX: if (d[a] > td[a]) td[a] = d[a]; break;
+      default: td[a] += d[a]; tl[a] += l[a]; break;     /* AVG */
+    }
+  }
+}
+/* fold one segment's result into a table, decoding dictIds to values (keys of FLOAT / DOUBLE columns as their bit patterns) */
+static void ctable_fold(ctable* t, const orc_segment* seg, const orc_query* q, const orc_result* r, const int32_t* ops) {
+  int64_t key[64]; double d[64]; int64_t l[64];
+  for (int32_t g = 0; g < r->num_groups; g++) {
+    for (int32_t j = 0; j < q->num_group_by; j++) {
+      const orc_column* c = &seg->columns[q->group_by_columns[j]];
+      int64_t k = r->group_keys[(int64_t)g * q->num_group_by + j];
+      if (c->has_dictionary) {
+        if (c->data_type == ORC_INT || c->data_type == ORC_LONG) k = dict_long(c, (int32_t)k);
+        else { double v = dict_double(c, (int32_t)k); memcpy(&k, &v, 8); }
+      }
+      key[j] = k;
+    }
+    for (int32_t a = 0; a < q->num_aggregations; a++) { d[a] = r->dbl[a][g]; l[a] = r->lng[a][g]; }
+    ctable_upsert(t, ops, key, d, l);
+  }
+}
+
+typedef struct orc_pool orc_pool;
+typedef struct { const orc_segment* const* segs; const orc_query* const* qs; orc_result** out; int32_t n; volatile int32_t next;
+                 ctable* tables; const int32_t* ops; volatile int32_t failed; } orc_job;
+struct orc_pool {
+  pthread_mutex_t mu; pthread_cond_t wake, done;
+  pthread_t* th; int32_t n_threads;
+  orc_job* job; int64_t epoch; int32_t want, busy;      /* `want` workers take part in the current job */
+};
+static orc_pool g_pool = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, NULL, 0, NULL, 0, 0, 0 };
+static void orc_job_run(orc_job* b, int32_t worker) {
   for (;;) {
     int32_t i = __sync_fetch_and_add(&b->next, 1);
     if (i >= b->n) break;
-    b->out[i] = orc_execute(b->segs[i], b->qs[i]);
+    orc_result* r = orc_execute(b->segs[i], b->qs[i]);
+    if (!r) { __sync_fetch_and_add(&b->failed, 1); continue; }
+    if (b->tables) { ctable_fold(&b->tables[worker], b->segs[i], b->qs[i], r, b->ops); orc_result_free(r); }
+    else b->out[i] = r;
+  }
+}
+static void* orc_pool_worker(void* arg) {
+  const int32_t id = (int32_t)(intptr_t)arg;            /* worker 0 is the calling thread */
+  int64_t seen = 0;
+  pthread_mutex_lock(&g_pool.mu);
+  for (;;) {
+    while (g_pool.epoch == seen) pthread_cond_wait(&g_pool.wake, &g_pool.mu);
+    seen = g_pool.epoch;
+    orc_job* job = g_pool.job;
+    if (!job || id >= g_pool.want) continue;
+    pthread_mutex_unlock(&g_pool.mu);
+    orc_job_run(job, id);
+    pthread_mutex_lock(&g_pool.mu);
+    if (--g_pool.busy == 0) pthread_cond_signal(&g_pool.done);
   }
   return NULL;
 }
+/* run a job on `threads` threads: the caller plus threads - 1 pooled workers */
+static void orc_pool_run(orc_job* job, int32_t threads) {
+  pthread_mutex_lock(&g_pool.mu);
+  if (g_pool.n_threads < threads) {
+    g_pool.th = (pthread_t*)realloc(g_pool.th, sizeof(pthread_t) * (size_t)threads);
+    for (int32_t t = g_pool.n_threads; t < threads; t++) {
+      if (t == 0) continue;
+      if (pthread_create(&g_pool.th[t], NULL, orc_pool_worker, (void*)(intptr_t)t) != 0) { threads = t; break; }
+    }
+    if (g_pool.n_threads < threads) g_pool.n_threads = threads;
+  }
+  g_pool.job = job; g_pool.want = threads; g_pool.busy = threads - 1; g_pool.epoch++;
+  pthread_cond_broadcast(&g_pool.wake);
+  pthread_mutex_unlock(&g_pool.mu);
+  orc_job_run(job, 0);
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.busy > 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+  g_pool.job = NULL;
+  pthread_mutex_unlock(&g_pool.mu);
+}
+
+/* One combine pass: executes the n segments on `threads` threads and merges their results.  Returns the number of groups
+ * (or -1), and hands out malloc'ed arrays: keys[num_groups][num_group_by] (decoded values), dbl / lng [num_groups][num_aggs].
+ * orc_free() them. */
+int64_t orc_execute_combined(const orc_segment* const* segs, const orc_query* const* qs, int32_t n, int32_t threads,
+                             int64_t** keys_out, double** dbl_out, int64_t** lng_out) {
+  if (n <= 0) return -1;
+  const orc_query* q0 = qs[0];
+  const int32_t nG = q0->num_group_by, nA = q0->num_aggregations;
+  if (nG > 64 || nA > 64) { set_err("orc_execute_combined: too many columns"); return -1; }
+  int32_t ops[64];
+  for (int32_t a = 0; a < nA; a++) {
+    ops[a] = q0->aggregations[a].op;
+    if (ops[a] == ORC_DISTINCTCOUNT) { set_err("orc_execute_combined: DISTINCTCOUNT is merged by the Python combine"); return -1; }
+  }
+  for (int32_t i = 0; i < n; i++)
+    for (int32_t j = 0; j < nG; j++) if (segs[i]->columns[qs[i]->group_by_columns[j]].data_type == ORC_STRING) { set_err("orc_execute_combined: STRING group keys are merged by the Python combine"); return -1; }
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = n;
+  ctable* tables = (ctable*)malloc(sizeof(ctable) * (size_t)threads);
+  for (int32_t t = 0; t < threads; t++) ctable_init(&tables[t], nG, nA);
+  orc_job job = { segs, qs, NULL, n, 0, tables, ops, 0 };
+  orc_pool_run(&job, threads);
+  for (int32_t t = 1; t < threads; t++) {                 /* merge the workers' tables into the first */
+    for (int64_t i = 0; i < tables[t].cap; i++) if (tables[t].used[i]) ctable_upsert(&tables[0], ops, tables[t].keys + i * nG, tables[t].dbl + i * nA, tables[t].lng + i * nA);
+    ctable_free(&tables[t]);
+  }
+  int64_t ng = job.failed ? -1 : tables[0].size;
+  if (ng >= 0) {
+    *keys_out = (int64_t*)malloc(sizeof(int64_t) * (size_t)((ng > 0 ? ng : 1) * (nG > 0 ? nG : 1)));
+    *dbl_out = (double*)malloc(sizeof(double) * (size_t)((ng > 0 ? ng : 1) * nA)); *lng_out = (int64_t*)malloc(sizeof(int64_t) * (size_t)((ng > 0 ? ng : 1) * nA));
+    int64_t k = 0;
+    for (int64_t i = 0; i < tables[0].cap; i++) if (tables[0].used[i]) {
+      memcpy(*keys_out + k * nG, tables[0].keys + i * nG, sizeof(int64_t) * (size_t)nG);
+      memcpy(*dbl_out + k * nA, tables[0].dbl + i * nA, sizeof(double) * (size_t)nA); memcpy(*lng_out + k * nA, tables[0].lng + i * nA, sizeof(int64_t) * (size_t)nA);
+      k++;
+    }
+  }
+  ctable_free(&tables[0]); free(tables);
+  return ng;
+}
+
 int32_t orc_execute_batch(const orc_segment* const* segs, const orc_query* const* qs, int32_t n, int32_t threads, orc_result** out) {
   if (n <= 0) return 0;
   if (threads < 1) threads = 1;
   if (threads > n) threads = n;
-  orc_batch b = { segs, qs, out, n, 0 };
-  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
-  int32_t started = 0;
-  for (int32_t t = 1; t < threads; t++) if (pthread_create(&th[started], NULL, orc_batch_worker, &b) == 0) started++;
-  orc_batch_worker(&b);                        /* the calling thread works too */
-  for (int32_t t = 0; t < started; t++) pthread_join(th[t], NULL);
-  free(th);
+  for (int32_t i = 0; i < n; i++) out[i] = NULL;
+  orc_job job = { segs, qs, out, n, 0, NULL, NULL, 0 };
+  orc_pool_run(&job, threads);
   int32_t failed = 0;
   for (int32_t i = 0; i < n; i++) if (!out[i]) failed++;
   return failed;

@@ -121,6 +121,9 @@ const char* orc_last_error(void);
 /* the segments of one query on `threads` worker threads (shared work queue); out[i] = result of segment i; returns the number
  * of segments that failed */
 int32_t orc_execute_batch(const orc_segment* const* segs, const orc_query* const* qs, int32_t n, int32_t threads, orc_result** out);
+/* the same pass with the cross-segment merge (GroupByCombineOperator / IndexedTable) done natively by the worker threads */
+int64_t orc_execute_combined(const orc_segment* const* segs, const orc_query* const* qs, int32_t n, int32_t threads,
+                             int64_t** keys_out, double** dbl_out, int64_t** lng_out);
 
 int32_t orc_result_num_groups(const orc_result* r);        /* 1 for keyless */
 const orc_stats* orc_result_stats(const orc_result* r);

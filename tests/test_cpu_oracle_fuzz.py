@@ -183,3 +183,25 @@ def test_distinctcount_on_raw_columns_against_pandas():
         assert sorted(set(sub.ri.tolist())) == vals[off[gi]:off[gi + 1]].tolist()
     ok = oracle.execute(seg, parse_sql("SELECT DISTINCTCOUNT(ri), DISTINCTCOUNT(rl) FROM t WHERE g < 6"))
     assert ok.longs[0][0] == df[df.g < 6].ri.nunique() and ok.longs[1][0] == df[df.g < 6].rl.nunique()
+
+
+def test_native_combine_matches_the_python_merge():
+    """orc_execute_combined (worker threads fold their segments' results into IndexedTables keyed by the decoded group key:
+    GroupByCombineOperator.java:132-147, IndexedTable.java:99-125) against oracle.combine over the same per-segment results,
+    with segment-local dictionaries that differ, on 1 and 5 threads, repeatedly (the worker pool is reused)."""
+    from pinot_b200 import datagen
+    segs = [datagen.make_segment_synth(700 + i, 30_000 + 1000 * i, vary_dim_dictionaries=(i % 2 == 1)) for i in range(7)]
+    q = parse_sql("SELECT d1, d2, COUNT(*), SUM(m0), MIN(m1), MAX(m2), AVG(m0) FROM t WHERE c1 < 400 GROUP BY d1, d2 LIMIT 100000")
+    prep = oracle.PreparedBatch(segs, q)
+    exp = oracle.combine([oracle.execute(s, q) for s in segs])
+    for threads in (1, 5, 5, 3):
+        keys, dbl, lng = oracle.execute_combined(prep, threads)
+        assert len(keys) == len(exp)
+        for k, d, l in zip(keys, dbl, lng):
+            row = exp[tuple(int(x) for x in k)]
+            assert int(l[0]) == row[0] and d[1] == row[1] and d[2] == row[2] and d[3] == row[3] and (d[4], int(l[4])) == row[4]
+    # batches on the pool still return per-segment results
+    res = oracle.execute_batch(prep, 4)
+    assert [r.num_groups for r in res] == [oracle.execute(s, q).num_groups for s in segs]
+    # DISTINCTCOUNT is left to the Python merge
+    assert oracle.execute_combined(oracle.PreparedBatch(segs, parse_sql("SELECT d1, DISTINCTCOUNT(c1) FROM t GROUP BY d1 LIMIT 10")), 2) is None
