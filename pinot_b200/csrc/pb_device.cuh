@@ -186,7 +186,7 @@ struct DevQuery {
   uint64_t n_units;
   uint64_t n_docs_total;
   int32_t match_all;                     // no filter: pb_agg_kernel walks every doc, no match list
-  int32_t rows_direct;                   // pb_agg_rows_kernel: read the fields of a row with one load each instead of taking a vector load apart
+  int32_t pad_p;
   int32_t sparse_max;                    // survivors per 1024 docs below which later AND leaves use the restricted scan
   int32_t cand_bytes;                    // shared memory for the per-warp candidate lists (0: no leaf runs on candidates)
   uint64_t unit_lo;                      // this launch covers work units [unit_lo, unit_lo + n_units) (a wave of segments)
@@ -1571,8 +1571,14 @@ __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_rows_kernel(con
   // One doc = one row, fetched with ONE vector load (rows never straddle a 32-byte sector) and taken apart in registers:
   // the aggregation is latency-bound (ncu: 34 warps waiting on memory per issue slot when every field was its own load),
   // so the chain per doc is kept at match list -> row -> remap, and every thread works on two docs at a time.
-  // field(off, bits): the bits-wide field at bit offset off of the doc's row (MSB first)
-  auto process = [&](unsigned long long gdoc, const DevRowSeg& sg, auto field) {
+  auto process = [&](unsigned long long gdoc, const uint32_t (&w)[RW], const DevRowSeg& sg) {
+    auto field = [&](uint32_t off, uint32_t bits) -> uint32_t {
+      const uint32_t wi = off >> 5, sh = off & 31u;
+      uint32_t hi = w[0], lo = RW > 1 ? w[1 % RW] : 0u;
+#pragma unroll
+      for (int k = 1; k < RW; k++) if (wi == (uint32_t)k) { hi = w[k]; lo = k + 1 < RW ? w[(k + 1) % RW] : 0u; }
+      return __funnelshift_l(lo, hi, sh) >> (32u - bits);
+    };
     uint64_t slot = 0;
     for (int j = 0; j < nG; j++) {
       const DevRowKey& k = sg.keys[j];
@@ -1662,54 +1668,17 @@ __global__ void __launch_bounds__(PB_AGG_SMEM_THREADS, 1) pb_agg_rows_kernel(con
     for (int k = 0; k < RW; k++) w[k] = pb_bswap32(w[k]);
   };
   const unsigned long long stride = (unsigned long long)gridDim.x * PB_AGG_SMEM_THREADS;
-  if (Q.rows_direct) {
-    // Fields read straight from the row in memory: one small load per field (the first one of a row brings its 32-byte
-    // sector into L1, the others hit there) instead of one vector load taken apart by select chains over the row's words --
-    // the register form costs ~15 instructions per field because the word a field lives in is only known at run time (ncu:
-    // 388 instructions per doc at 25 % selectivity, issue-bound).  Two docs per thread: both rows are touched first.
-    auto touch = [&](const uint32_t* row) { uint32_t x; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(x) : "l"(row)); return x; };
-    for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += 2 * stride) {
-      const bool two = i + stride < n;
-      const unsigned long long gdoc0 = Q.match_all ? i : (unsigned long long)__ldg(Q.match_list + i);
-      const unsigned long long gdoc1 = !two ? gdoc0 : (Q.match_all ? i + stride : (unsigned long long)__ldg(Q.match_list + i + stride));
-      const DevRowSeg& sg0 = segs[seg_of(gdoc0)];
-      const DevRowSeg& sg1 = segs[seg_of(gdoc1)];
-      const uint32_t* row0 = sg0.rows + (gdoc0 - sg0.doc_base) * (unsigned long long)RW;
-      const uint32_t* row1 = sg1.rows + (gdoc1 - sg1.doc_base) * (unsigned long long)RW;
-      (void)touch(row0); (void)touch(row1);
-      auto direct = [&](const uint32_t* row) {
-        return [row](uint32_t off, uint32_t bits) -> uint32_t {
-          const uint32_t wi = off >> 5, sh = off & 31u;
-          const uint32_t hi = pb_bswap32(__ldg(row + wi));
-          if (sh + bits <= 32u) return (hi << sh) >> (32u - bits);
-          return __funnelshift_l(pb_bswap32(__ldg(row + wi + 1)), hi, sh) >> (32u - bits);
-        };
-      };
-      process(gdoc0, sg0, direct(row0));
-      if (two) process(gdoc1, sg1, direct(row1));
-    }
-  } else {
-    for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += 2 * stride) {
-      const bool two = i + stride < n;
-      const unsigned long long gdoc0 = Q.match_all ? i : (unsigned long long)__ldg(Q.match_list + i);
-      const unsigned long long gdoc1 = !two ? gdoc0 : (Q.match_all ? i + stride : (unsigned long long)__ldg(Q.match_list + i + stride));
-      const DevRowSeg& sg0 = segs[seg_of(gdoc0)];
-      const DevRowSeg& sg1 = segs[seg_of(gdoc1)];
-      uint32_t w0[RW], w1[RW];
-      load_row(sg0, gdoc0, w0);
-      load_row(sg1, gdoc1, w1);
-      auto in_regs = [&](const uint32_t (&w)[RW]) {
-        return [&w](uint32_t off, uint32_t bits) -> uint32_t {
-          const uint32_t wi = off >> 5, sh = off & 31u;
-          uint32_t hi = w[0], lo = RW > 1 ? w[1 % RW] : 0u;
-#pragma unroll
-          for (int k = 1; k < RW; k++) if (wi == (uint32_t)k) { hi = w[k]; lo = k + 1 < RW ? w[(k + 1) % RW] : 0u; }
-          return __funnelshift_l(lo, hi, sh) >> (32u - bits);
-        };
-      };
-      process(gdoc0, sg0, in_regs(w0));
-      if (two) process(gdoc1, sg1, in_regs(w1));
-    }
+  for (unsigned long long i = (unsigned long long)blockIdx.x * PB_AGG_SMEM_THREADS + tid; i < n; i += 2 * stride) {
+    const bool two = i + stride < n;
+    const unsigned long long gdoc0 = Q.match_all ? i : (unsigned long long)__ldg(Q.match_list + i);
+    const unsigned long long gdoc1 = !two ? gdoc0 : (Q.match_all ? i + stride : (unsigned long long)__ldg(Q.match_list + i + stride));
+    const DevRowSeg& sg0 = segs[seg_of(gdoc0)];
+    const DevRowSeg& sg1 = segs[seg_of(gdoc1)];
+    uint32_t w0[RW], w1[RW];
+    load_row(sg0, gdoc0, w0);
+    load_row(sg1, gdoc1, w1);
+    process(gdoc0, w0, sg0);
+    if (two) process(gdoc1, w1, sg1);
   }
   if (!use_smem) return;
   __syncthreads();

@@ -2489,10 +2489,6 @@ static int exec_single(pb_segment_group_handle g, const pb_segment_query* sqs, c
   hq->generic = (q->flags & PB_Q_GENERIC_KERNEL) ? 1 : 0;
   hq->n_units = n_chunks; hq->segs = dsegs; hq->tables = dtabs;
   hq->n_docs_total = n_docs_total; hq->match_all = match_all ? 1 : 0;
-  {
-    static const int rows_direct = []() { const char* e = getenv("PB_AGG_ROWS_DIRECT"); return e ? atoi(e) : 0; }();
-    hq->rows_direct = rows_direct;
-  }
   { static const int sm = []() { const char* e = getenv("PB_SPARSE_MAX"); return e ? atoi(e) : PB_SPARSE_MAX; }(); hq->sparse_max = sm; }
   hq->match_list = d_match_list;
   if (use_smem_table) {

@@ -15,6 +15,16 @@ if ROOT not in sys.path:
 
 import numpy as np  # noqa: E402
 
+try:
+    # The library dlopens whichever libnccl the process already maps before it falls back to the system one (pb_comm_init):
+    # with torch imported that is the copy torch ships -- the one bench.py and a torchrun deployment run on.  (Session r2k ran
+    # this worker WITHOUT it, i.e. on the system's NCCL 2.27.3: 2 ranks passed, 4 ranks tripped the layout-fingerprint check of
+    # the merged block on the first query, while the 8-rank bench on torch's NCCL 2.28.9 passed its parity checks in the same
+    # session.  Not re-run since: the round's GPU budget ended there.  profiles/r2_experiments.md.)
+    import torch  # noqa: E402,F401
+except Exception:  # pragma: no cover
+    pass
+
 from oracle import oracle  # noqa: E402
 from pinot_b200 import datagen, native  # noqa: E402
 from pinot_b200.query import parse_sql  # noqa: E402

@@ -155,3 +155,47 @@ def test_combine_of_null_results():
     table = oracle.combine([oracle.execute(s, q) for s in segs])
     for key, row in table.items():
         assert row[0] is not None and row[1] is not None and row[2][1] == row[3] and row[4] >= row[3]     # every group has non-null inputs somewhere
+
+
+def test_null_skipping_aggregations_against_pandas():
+    """SUM / MIN / MAX / AVG / COUNT(col) / COUNT(*) / DISTINCTCOUNT with nullable inputs against pandas (skipna semantics,
+    min_count=1 for SUM so that an all-null group is NaN = SQL NULL), group-by on a non-nullable key, filters whose leaves sit
+    directly under AND / OR / NOT (Kleene logic = the operators' logic there)."""
+    pd = pytest.importorskip("pandas")
+    rng = np.random.default_rng(11)
+    n = 6000
+    g = rng.integers(0, 9, n).astype(np.int32)
+    x = rng.integers(-50, 50, n).astype(np.int64); xn = rng.random(n) < 0.35
+    y = np.round(rng.normal(0, 4, n), 1); yn = rng.random(n) < 0.2
+    xn[g == 4] = True                                            # group 4: every x is null
+    seg = make_segment("pd", [build_column("g", DataType.INT, g),
+                              with_nulls(build_column("x", DataType.LONG, np.where(xn, 0, x), dictionary=False), xn),
+                              with_nulls(build_column("y", DataType.DOUBLE, np.where(yn, 0.0, y)), yn)])
+    df = pd.DataFrame({"g": g, "x": np.where(xn, np.nan, x.astype(np.float64)), "y": np.where(yn, np.nan, y)})
+    filters = {
+        None: np.ones(n, dtype=bool),
+        "y > -2": (df.y > -2).fillna(False).to_numpy(),
+        "NOT (y > -2)": ((df.y <= -2)).fillna(False).to_numpy(),                                     # null y: unknown, dropped
+        "x < 10 OR y > 3": ((df.x < 10).fillna(False) | (df.y > 3).fillna(False)).to_numpy(),
+        "NOT (x < 10 AND y > 0)": ((df.x >= 10).fillna(False) | (df.y <= 0).fillna(False)).to_numpy(),   # false iff some operand is false
+        "x IS NULL AND NOT (y IS NULL)": (df.x.isna() & df.y.notna()).to_numpy(),
+    }
+    for where, mask in filters.items():
+        sql = NH + "SELECT g, COUNT(*), COUNT(x), SUM(x), MIN(x), MAX(y), AVG(y), DISTINCTCOUNT(x) FROM t" + (f" WHERE {where}" if where else "") + " GROUP BY g LIMIT 100"
+        r = oracle.execute(seg, parse_sql(sql))
+        sub = df[mask]
+        exp = sub.groupby("g").agg(cnt=("g", "size"), cx=("x", "count"), sx=("x", lambda s: s.sum(min_count=1)), mn=("x", "min"), mx=("y", "max"),
+                                   avg=("y", "mean"), cy=("y", "count"), dc=("x", "nunique"))
+        keys = [k[0] for k in r.decoded_keys()]
+        assert sorted(keys) == sorted(exp.index.tolist()), where
+        for i, k in enumerate(keys):
+            e = exp.loc[k]
+            assert int(r.longs[0][i]) == int(e.cnt) and int(r.longs[1][i]) == int(e.cx), (where, k)
+            assert int(r.longs[2][i]) == int(e.cx) and (np.isnan(e.sx) if e.cx == 0 else r.doubles[2][i] == e.sx), (where, k)
+            assert int(r.longs[3][i]) == int(e.cx) and (e.cx == 0 or r.doubles[3][i] == e.mn), (where, k)
+            assert int(r.longs[4][i]) == int(e.cy) and (e.cy == 0 or r.doubles[4][i] == e.mx), (where, k)
+            assert int(r.longs[5][i]) == int(e.cy) and (e.cy == 0 or abs(r.doubles[5][i] / r.longs[5][i] - e.avg) < 1e-9), (where, k)
+            assert int(r.longs[6][i]) == int(e.dc), (where, k)
+    # keyless, everything filtered out: COUNT 0, every other function NULL
+    r = oracle.execute(seg, parse_sql(NH + "SELECT COUNT(*), COUNT(x), SUM(x), MIN(y) FROM t WHERE y > 1000"))
+    assert [int(r.longs[a][0]) for a in range(4)] == [0, 0, 0, 0]
