@@ -523,10 +523,19 @@ static int pred_match_doc(const pred_eval* e, int32_t doc) {
       int hi_ok = e->dhi_incl ? v <= e->dhi : v < e->dhi;
       return lo_ok && hi_ok;
     }
+    /* EQ / NOT_EQ compare with == / != (EqualsPredicateEvaluatorFactory.java:336-337, NotEqualsPredicateEvaluatorFactory.java:
+     * 298-299: 0.0 equals -0.0, NaN equals nothing); IN / NOT_IN ask a fastutil DoubleSet / FloatSet, which compares
+     * Double.doubleToLongBits (InPredicateEvaluatorFactory.java:341-362: -0.0 is not in {0.0}; every NaN is the canonical NaN) */
+    const int by_bits = p->type == ORC_IN || p->type == ORC_NOT_IN;
     int found = 0;
     for (int32_t i = 0; i < p->num_values; i++) {
       double q = c->data_type == ORC_FLOAT ? (double)(float)p->double_values[i] : p->double_values[i];
-      if (q == v) { found = 1; break; }
+      if (by_bits) {
+        uint64_t a, b; memcpy(&a, &q, 8); memcpy(&b, &v, 8);
+        if (q != q) a = 0x7ff8000000000000ull;
+        if (v != v) b = 0x7ff8000000000000ull;
+        if (a == b) { found = 1; break; }
+      } else if (q == v) { found = 1; break; }
     }
     return e->exclusive ? !found : found;
   }

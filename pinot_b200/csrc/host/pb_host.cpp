@@ -20,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -150,7 +151,18 @@ class PredicateEvaluatorProvider {
     } else {
       for (int i = 0; i < p.num_values; i++) {
         if (integral) { long long v; if (!Dictionary::parseIntegral(p.values[i], &v)) throw BadQuery{std::string("cannot parse integral literal '") + p.values[i] + "'"}; e.rawValues.push_back(v); }
-        else { double d = Dictionary::parseDouble(p.values[i]); if (c.type == PB_FLOAT) d = (double)(float)d; int64_t b; memcpy(&b, &d, 8); e.rawValues.push_back(b); }
+        else {
+          // The device compares IEEE-754 bit patterns.  That IS the reference for IN / NOT_IN (fastutil DoubleSet / FloatSet
+          // compare Double.doubleToLongBits: -0.0 is not in {0.0}; InPredicateEvaluatorFactory.java:341-362), but EQ / NOT_EQ
+          // compare with == / != (EqualsPredicateEvaluatorFactory.java:336-337): 0.0 and -0.0 are equal, NaN equals nothing.
+          double d = Dictionary::parseDouble(p.values[i]);
+          if (c.type == PB_FLOAT) d = (double)(float)d;
+          const bool eq = p.type == PBH_EQ || p.type == PBH_NOT_EQ;
+          if (eq && d != d) continue;                               // x = NaN matches nothing, x <> NaN everything
+          if (d != d) d = std::numeric_limits<double>::quiet_NaN(); // doubleToLongBits collapses every NaN to the canonical one
+          int64_t b; memcpy(&b, &d, 8); e.rawValues.push_back(b);
+          if (eq && d == 0.0) { const double z = -d; memcpy(&b, &z, 8); e.rawValues.push_back(b); }   // the other zero
+        }
       }
     }
     return e;

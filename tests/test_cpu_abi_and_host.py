@@ -167,3 +167,24 @@ def test_null_handling_is_lowered_to_trues_programs():
     assert native.is_eligible(g, parse_sql("SELECT a, COUNT(*) FROM t GROUP BY a LIMIT 10"))
     assert native.is_eligible(g, parse_sql(nh + "SELECT b, SUM(a) FROM t GROUP BY b LIMIT 10"))
     g.release()
+
+
+def test_signed_zero_and_nan_in_raw_float_predicates():
+    """Raw FLOAT / DOUBLE columns: EQ / NOT_EQ compare with == / != (0.0 equals -0.0; EqualsPredicateEvaluatorFactory.java:336-337),
+    IN / NOT_IN ask a fastutil DoubleSet, i.e. compare Double.doubleToLongBits (-0.0 is not in {0.0}; InPredicateEvaluatorFactory.
+    java:341-362).  The device compares bit patterns, so the host layer hands EQ both zeros; the oracle follows the same rules."""
+    import struct
+    from oracle import oracle
+    x = np.array([0.0, -0.0, 1.5, -1.5, 0.0, -0.0, 2.0], dtype=np.float64)
+    seg = make_segment("z", [build_column("x", DataType.DOUBLE, x, dictionary=False), build_column("f", DataType.FLOAT, x.astype(np.float32), dictionary=False)])
+    g = native.SegmentGroup([native.StagedSegment(seg)])
+    pos, neg = struct.unpack("<q", struct.pack("<d", 0.0))[0], struct.unpack("<q", struct.pack("<d", -0.0))[0]
+    cnt = lambda where: int(oracle.execute(seg, parse_sql(f"SELECT COUNT(*) FROM t WHERE {where}")).longs[0][0])
+    low = lambda where: native.dump_lowered(g, parse_sql(f"SELECT COUNT(*) FROM t WHERE {where}"))
+    for col in ("x", "f"):
+        assert low(f"{col} = 0.0") == [f"SCAN_RAW_SET col={col} excl=0 vals={pos},{neg}"] and cnt(f"{col} = 0.0") == 4
+        assert low(f"{col} = -0.0") == [f"SCAN_RAW_SET col={col} excl=0 vals={neg},{pos}"] and cnt(f"{col} = -0.0") == 4
+        assert low(f"{col} <> 0.0") == [f"SCAN_RAW_SET col={col} excl=1 vals={pos},{neg}"] and cnt(f"{col} <> 0.0") == 3
+        assert low(f"{col} IN (0.0, 1.5)")[0].startswith(f"SCAN_RAW_SET col={col} excl=0 vals={pos},") and cnt(f"{col} IN (0.0, 1.5)") == 3
+        assert cnt(f"{col} NOT IN (0.0)") == 5 and cnt(f"{col} IN (-0.0)") == 2
+    g.release()

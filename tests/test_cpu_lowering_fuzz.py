@@ -123,7 +123,13 @@ def evaluate_sql(seg, node):
         m = cmp(o.eq, lit(node.values[0]))
         return ~m if t == PredicateType.NOT_EQ else m
     if t in (PredicateType.IN, PredicateType.NOT_IN):
-        m = np.logical_or.reduce([cmp(o.eq, lit(x)) for x in node.values])
+        if not c.has_dictionary and c.data_type in (DataType.FLOAT, DataType.DOUBLE):
+            # a fastutil DoubleSet compares Double.doubleToLongBits (-0.0 is not in {0.0}); EQ / NOT_EQ above compare with ==
+            bits = v.astype(np.float64).view(np.int64)
+            lits = [np.float32(x) if c.data_type == DataType.FLOAT else np.float64(x) for x in node.values]
+            m = np.isin(bits, np.array([np.float64(x) for x in lits]).view(np.int64))
+        else:
+            m = np.logical_or.reduce([cmp(o.eq, lit(x)) for x in node.values])
         return ~m if t == PredicateType.NOT_IN else m
     m = np.ones(seg.num_docs, bool)
     if node.lower is not None:
@@ -198,3 +204,140 @@ def test_lowered_program_matches_oracle(fuzz_segment, seed):
         got = np.nonzero(evaluate_lowered(seg, native.dump_lowered(g, q)))[0]
         assert got.tolist() == docs.tolist(), where
         assert np.nonzero(evaluate_sql(seg, q.filter))[0].tolist() == docs.tolist(), where      # ... and both equal the SQL semantics
+
+
+# ---- enableNullHandling: three restatements of the operators' three-valued doc sets ----
+
+def _null_mask(seg, col):
+    v = getattr(seg.columns[col], "null_value_vector", None)
+    m = np.zeros(seg.num_docs, bool)
+    if v is not None:
+        out = np.zeros(seg.num_docs, dtype=np.uint32)
+        n = oracle.lib().orc_roaring_to_doc_ids(v.ctypes.data, v.size, out.ctypes.data, out.size)
+        m[out[:n]] = True
+    return m
+
+
+def evaluate_lowered_nh(seg, lines):
+    """evaluate_lowered plus the BITMAP leaves of null-value vectors"""
+    plain, patched = [], {}
+    for i, line in enumerate(lines):
+        if line.startswith("BITMAP "):
+            kv = dict(p.split("=", 1) for p in line.split()[1:3])
+            m = _null_mask(seg, kv["col"])
+            patched[i] = ~m if kv["excl"] == "1" else m
+    # run the stock interpreter with the bitmap leaves swapped for a marker it understands
+    n = seg.num_docs
+    stack = []
+    for i, line in enumerate(lines):
+        if i in patched:
+            stack.append(patched[i])
+            continue
+        op = line.split(" ", 1)[0]
+        if op in ("AND", "OR"):
+            k = int(line.split("n=")[1])
+            args, stack = stack[-k:], stack[:-k]
+            stack.append(np.logical_and.reduce(args) if op == "AND" else np.logical_or.reduce(args))
+        elif op == "NOT":
+            stack.append(~stack.pop())
+        else:
+            stack.append(evaluate_lowered(seg, [line]))
+    if not lines:
+        return np.ones(n, bool)
+    assert len(stack) == 1
+    return stack[0]
+
+
+def operator_model(seg, node):
+    """(trues, nulls, falses) of a filter node as the reference's operators define them: BaseFilterOperator.java:88-113,
+    BaseColumnFilterOperator.java:46-70, And / Or / NotFilterOperator, FilterOperatorUtils.java:74-88 -- in numpy over the
+    decoded values."""
+    from pinot_b200.query import And, Not, Or, PredicateType
+    n = seg.num_docs
+    zero = np.zeros(n, bool)
+    if isinstance(node, Not):
+        t, _, f = operator_model(seg, node.child)
+        return f, zero, t
+    if isinstance(node, (And, Or)):
+        kids = [operator_model(seg, c) for c in node.children]
+        if isinstance(node, And):
+            t = np.logical_and.reduce([k[0] for k in kids])
+            f = ~np.logical_and.reduce([k[0] | k[1] for k in kids])
+        else:
+            t = np.logical_or.reduce([k[0] for k in kids])
+            f = ~np.logical_or.reduce([k[0] | k[1] for k in kids])
+        return t, zero, f                                   # (And / Or do not override getNulls())
+    nulls = _null_mask(seg, node.column)
+    if node.type in (PredicateType.IS_NULL, PredicateType.IS_NOT_NULL):
+        t = nulls if node.type == PredicateType.IS_NULL else ~nulls
+        return t, zero, ~t
+    base = evaluate_sql(seg, node)                          # two-valued, on the stored values (default null values included)
+    c = seg.columns[node.column]
+    if not c.has_dictionary and node.type == PredicateType.RANGE and c.data_type in (DataType.INT, DataType.LONG):
+        # the raw integral range evaluator folds its bounds to inclusive ones and is alwaysFalse when they cross
+        # (RangePredicateEvaluatorFactory.java:331-366): an EmptyFilterOperator, which has no nulls
+        lo = None if node.lower is None else int(node.lower) + (0 if node.lower_inclusive else 1)
+        hi = None if node.upper is None else int(node.upper) - (0 if node.upper_inclusive else 1)
+        if lo is not None and hi is not None and lo > hi:
+            return zero, zero, ~zero
+    if c.has_dictionary and not base.any():                 # alwaysFalse: EmptyFilterOperator
+        return zero, zero, ~zero
+    if c.has_dictionary and base.all():                     # alwaysTrue: the flipped null bitmap (or MatchAll), no nulls of its own
+        t = ~nulls
+        return t, zero, ~t
+    t = base & ~nulls
+    return t, nulls, ~(t | nulls)
+
+
+@pytest.fixture(scope="module")
+def nullable_fuzz_segment():
+    from pinot_b200.segment_writer import build_column, make_segment, with_nulls
+    rng = np.random.default_rng(77)
+    n = 9_001
+    int_null = np.iinfo(np.int32).min
+    def nullable(name, dt, values, p, default, **kw):
+        nl = rng.random(n) < p
+        return with_nulls(build_column(name, dt, np.where(nl, default, values), **kw), nl)
+    s_vals = np.sort(rng.integers(0, 30, n)).astype(np.int32)
+    s_null = np.zeros(n, bool); s_null[:40] = True                                      # the nulls of the sorted column carry its smallest value
+    cols = [nullable("a", DataType.INT, rng.integers(-4, 5, n).astype(np.int32), 0.25, int_null),
+            nullable("b", DataType.INT, rng.integers(0, 12, n).astype(np.int32), 0.15, int_null, inverted=True),
+            nullable("r", DataType.LONG, rng.integers(-20, 20, n).astype(np.int64), 0.2, 0, dictionary=False),
+            nullable("x", DataType.DOUBLE, np.round(rng.normal(0, 2, n), 1), 0.3, 0.0, dictionary=False),
+            with_nulls(build_column("s", DataType.INT, np.where(s_null, s_vals.min(), s_vals).astype(np.int32)), s_null),
+            build_column("d", DataType.INT, rng.integers(0, 5, n).astype(np.int32))]
+    seg = make_segment("nhfuzz", cols)
+    g = native.SegmentGroup([native.StagedSegment(seg)])
+    yield seg, g
+    g.release()
+
+
+def _expr_nh(rng, seg, cols, depth):
+    r = rng.random()
+    if depth == 0 or r < 0.3:
+        col = str(rng.choice(cols))
+        if rng.random() < 0.2:
+            return f"{col} IS {'NOT ' if rng.random() < 0.5 else ''}NULL"
+        return _predicate(rng, seg, [col])
+    if r < 0.5:
+        return "NOT (" + _expr_nh(rng, seg, cols, depth - 1) + ")"
+    k = int(rng.integers(2, 4))
+    op = " AND " if rng.random() < 0.5 else " OR "
+    return "(" + op.join(_expr_nh(rng, seg, cols, depth - 1) for _ in range(k)) + ")"
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_null_handling_lowering_matches_oracle_and_operator_model(nullable_fuzz_segment, seed):
+    """enableNullHandling: the trues program of the host layer (C++), the oracle's operator tree (C) and a numpy model of the
+    operators' getTrues / getNulls / getFalses must select the same docs -- on trees with NOT at any depth, IS [NOT] NULL
+    leaves, sorted / inverted / raw / plain dictionary columns, always-true and always-false predicates."""
+    seg, g = nullable_fuzz_segment
+    rng = np.random.default_rng(5000 + seed)
+    cols = ["a", "b", "r", "x", "s", "d"]
+    for _ in range(6):
+        where = _expr_nh(rng, seg, cols, depth=3)
+        q = parse_sql(f"SET enableNullHandling=true; SELECT COUNT(*) FROM t WHERE {where}")
+        docs, _ = oracle.filter_doc_ids(seg, q)
+        got = np.nonzero(evaluate_lowered_nh(seg, native.dump_lowered(g, q)))[0]
+        assert got.tolist() == docs.tolist(), where
+        assert np.nonzero(operator_model(seg, q.filter)[0])[0].tolist() == docs.tolist(), where
