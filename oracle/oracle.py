@@ -209,7 +209,10 @@ def _marshal_filter(seg, flt, m: _Marshalled):
             vals = list(p.values)
         o.num_values = len(vals)
         if col.data_type in (DataType.INT, DataType.LONG):
-            arr = (C.c_int64 * max(1, len(vals)))(*[int(float(v)) if ("." in v or "e" in v.lower()) else int(v) for v in vals])
+            ints = [int(float(v)) if ("." in v or "e" in v.lower()) else int(v) for v in vals]
+            if any(not -2**63 <= x < 2**63 for x in ints):      # Long.parseLong would throw: the query fails in the reference
+                raise ValueError(f"integral literal out of range in a predicate on {p.column}")
+            arr = (C.c_int64 * max(1, len(vals)))(*ints)
             o.int_values = m.hold(arr)
         elif col.data_type in (DataType.FLOAT, DataType.DOUBLE):
             arr = (C.c_double * max(1, len(vals)))(*[float(v) for v in vals])

@@ -268,6 +268,9 @@ static int32_t dict_insertion_index_long(const orc_column* c, int64_t v) {
   return -(lo + 1);
 }
 static int32_t dict_insertion_index_double(const orc_column* c, double v) {
+  /* FloatDictionary.insertionIndexOf: binarySearch(Float.parseFloat(stringValue)) -- the literal is rounded to float first
+   * (SEGL/segment/index/readers/FloatDictionary.java:43-45), so "0.1" finds the entry 0.1f */
+  if (c->data_type == ORC_FLOAT) v = (double)(float)v;
   int32_t lo = 0, hi = c->cardinality - 1;
   while (lo <= hi) {
     int32_t mid = (int32_t)(((uint32_t)lo + (uint32_t)hi) >> 1);

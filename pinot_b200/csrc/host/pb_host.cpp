@@ -47,6 +47,8 @@ class Dictionary {
       case PB_INT: case PB_LONG: {
         long long iv; double dv;
         if (parseIntegral(v, &iv)) return search([&](int m) { long long x = getLong(m); return (x > iv) - (x < iv); });
+        if (v.find_first_not_of("+-0123456789") == std::string::npos)      // an integer that does not fit a long: Long.parseLong throws
+          throw BadQuery{"integral literal out of range: '" + v + "'"};
         dv = parseDouble(v);   // fractional literal against an integral dictionary: never equal
         return search([&](int m) { double x = (double)getLong(m); return (x > dv) - (x < dv); });
       }

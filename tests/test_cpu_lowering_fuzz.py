@@ -341,3 +341,50 @@ def test_null_handling_lowering_matches_oracle_and_operator_model(nullable_fuzz_
         got = np.nonzero(evaluate_lowered_nh(seg, native.dump_lowered(g, q)))[0]
         assert got.tolist() == docs.tolist(), where
         assert np.nonzero(operator_model(seg, q.filter)[0])[0].tolist() == docs.tolist(), where
+
+
+def test_edge_literals_on_dictionary_columns():
+    """Literals at the edges of the types, on dictionaries that hold both zeros, infinities, denormals and the extremes of
+    long: the host layer (C++) and the oracle (C) must lower them to the same docs, and to what the reference's dictionaries
+    do -- Float.parseFloat rounds the literal before the search (FloatDictionary.java:43-45: "0.1" finds 0.1f), comparisons are
+    numeric (0.0 finds the first zero the binary search meets), a long that does not parse fails the query."""
+    from pinot_b200.segment_writer import build_dict_column, make_segment
+    rng = np.random.default_rng(0)
+    n = 5000
+    xv = np.array([-np.inf, -1e308, -1.5, -0.0, 0.0, 1e-320, 2.5, 1e308, np.inf])
+    kv = np.array([np.iinfo(np.int64).min, -5, 0, 7, np.iinfo(np.int64).max], dtype=np.int64)
+    fv = np.array([-3.25, -0.0, 0.0, 0.1, 16777216.0, 16777218.0], dtype=np.float32)
+    xi, ki, fi = (rng.integers(0, len(v), n).astype(np.uint32) for v in (xv, kv, fv))
+    seg = make_segment("edge", [build_dict_column("x", DataType.DOUBLE, xv, xi), build_dict_column("k", DataType.LONG, kv, ki),
+                                build_dict_column("f", DataType.FLOAT, fv, fi)])
+    g = native.SegmentGroup([native.StagedSegment(seg)])
+    x, k, f = xv[xi], kv[ki], fv[fi]
+    F = np.float32
+    cases = {
+        "x > -0.0": x > 0, "x <= -0.0": x <= 0,
+        "x > 1e308": x > 1e308, "x >= 1e309": np.isinf(x) & (x > 0), "x < -1e309": np.zeros(n, bool), "x = 1e-320": x == 1e-320,
+        "x > 1e-321": x > 1e-321, "x NOT IN (2.5, 1e308)": ~np.isin(x, [2.5, 1e308]),
+        "k = -9223372036854775808": k == np.iinfo(np.int64).min, "k <= 9223372036854775807": np.ones(n, bool),
+        "k > 9223372036854775806": k == np.iinfo(np.int64).max, "k BETWEEN -5 AND 7": (k >= -5) & (k <= 7),
+        "k IN (0, 9223372036854775807)": np.isin(k, [0, np.iinfo(np.int64).max]), "k > 6": k > 6,
+        "f = 0.1": f == F(0.1), "f > 0.1": f > F(0.1), "f >= 0.1": f >= F(0.1), "f < 0.1": f < F(0.1),
+        "f = 16777217": f == F(16777217), "f > 16777217": f > F(16777217), "f BETWEEN 16777216 AND 16777217": (f >= F(16777216)) & (f <= F(16777217)),
+        "f <> 0.1": f != F(0.1), "f = 0.10000000149011612": f == F(0.1),
+    }
+    for where, exp in cases.items():
+        q = parse_sql("SELECT COUNT(*) FROM t WHERE " + where)
+        docs, _ = oracle.filter_doc_ids(seg, q)
+        got = np.nonzero(evaluate_lowered(seg, native.dump_lowered(g, q)))[0]
+        assert got.tolist() == docs.tolist() == np.nonzero(exp)[0].tolist(), where
+    # equality with a zero: whichever zero the reference's binary search meets first -- the two restatements must agree
+    # (the same for a range that starts or ends AT a zero: the found entry is the boundary, the other zero falls on one side)
+    for where in ("x = 0.0", "x = -0.0", "x <> 0.0", "x IN (0.0)", "x IN (-0.0, 2.5)", "f IN (0.1, -0.0)", "f <> 0.0",
+                  "x >= 0.0", "x < 0.0", "x BETWEEN -0.0 AND 0.0"):
+        q = parse_sql("SELECT COUNT(*) FROM t WHERE " + where)
+        assert np.nonzero(evaluate_lowered(seg, native.dump_lowered(g, q)))[0].tolist() == oracle.filter_doc_ids(seg, q)[0].tolist(), where
+    # Long.parseLong("9223372036854775808") throws in the reference: the plan maker declines, the oracle refuses
+    q = parse_sql("SELECT COUNT(*) FROM t WHERE k = 9223372036854775808")
+    assert not native.is_eligible(g, q)
+    with pytest.raises(ValueError):
+        oracle.filter_doc_ids(seg, q)
+    g.release()
