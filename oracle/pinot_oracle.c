@@ -496,6 +496,8 @@ static int pred_eval_init(pred_eval* e, const orc_segment* seg, const orc_predic
       } else {
         e->dlo = p->lower_unbounded ? -INFINITY : p->double_values[0];
         e->dhi = p->upper_unbounded ? INFINITY : p->double_values[1];
+        /* FloatRawValueBasedRangePredicateEvaluator holds Float.parseFloat(bound) (RangePredicateEvaluatorFactory.java) */
+        if (c->data_type == ORC_FLOAT) { e->dlo = (double)(float)e->dlo; e->dhi = (double)(float)e->dhi; }
         e->dlo_incl = p->lower_unbounded || p->lower_inclusive;
         e->dhi_incl = p->upper_unbounded || p->upper_inclusive;
       }

@@ -388,3 +388,44 @@ def test_edge_literals_on_dictionary_columns():
     with pytest.raises(ValueError):
         oracle.filter_doc_ids(seg, q)
     g.release()
+
+
+def test_edge_literals_on_raw_columns():
+    """The same on raw (no-dictionary) INT / LONG / FLOAT / DOUBLE columns holding the extremes, both zeros, infinities, NaN
+    and the smallest denormal: integral ranges are folded to inclusive bounds (RangePredicateEvaluatorFactory.java:331-366),
+    FLOAT bounds are Float.parseFloat(bound), NaN matches no range and no equality."""
+    from pinot_b200.segment_writer import build_column, make_segment
+    rng = np.random.default_rng(1)
+    n = 4000
+    i = rng.choice(np.array([np.iinfo(np.int32).min, -7, 0, 5, np.iinfo(np.int32).max], dtype=np.int32), n)
+    l = rng.choice(np.array([np.iinfo(np.int64).min, -7, 0, 5, np.iinfo(np.int64).max], dtype=np.int64), n)
+    f = rng.choice(np.array([-np.inf, -0.0, 0.0, 0.1, 16777216.0, 3.4e38, np.inf, np.nan], dtype=np.float32), n)
+    d = rng.choice(np.array([-np.inf, -0.0, 0.0, 0.1, 1e308, np.inf, np.nan, 5e-324]), n)
+    seg = make_segment("rawedge", [build_column("i", DataType.INT, i, dictionary=False), build_column("l", DataType.LONG, l, dictionary=False),
+                                   build_column("f", DataType.FLOAT, f, dictionary=False), build_column("d", DataType.DOUBLE, d, dictionary=False)])
+    g = native.SegmentGroup([native.StagedSegment(seg)])
+    F = np.float32
+    imax, imin, lmax, lmin = np.iinfo(np.int32).max, np.iinfo(np.int32).min, np.iinfo(np.int64).max, np.iinfo(np.int64).min
+    with np.errstate(invalid="ignore"):
+        cases = {
+            "i > 2147483646": i == imax, "i >= 2147483647": i == imax, "i > 2147483647": np.zeros(n, bool), "i < -2147483648": np.zeros(n, bool),
+            "i <= -2147483648": i == imin, "i = 2147483647": i == imax, "i <> -2147483648": i != imin, "i IN (5, 2147483647)": np.isin(i, [5, imax]),
+            "i BETWEEN 5 AND 4": np.zeros(n, bool), "i > -8 AND i < 6": (i > -8) & (i < 6),
+            "l > 9223372036854775806": l == lmax, "l > 9223372036854775807": np.zeros(n, bool), "l < -9223372036854775808": np.zeros(n, bool),
+            "l = -9223372036854775808": l == lmin, "l NOT IN (0, 5)": ~np.isin(l, [0, 5]),
+            "f > 0.1": f > F(0.1), "f >= 0.1": f >= F(0.1), "f = 0.1": f == F(0.1), "f < 0.1": f < F(0.1), "f <> 0.1": f != F(0.1),
+            "f > 3.4e38": f > F(3.4e38), "f >= 3.5e38": f >= F(np.inf), "f = 16777217": f == F(16777217), "f > -0.0": f > 0, "f >= 0.0": f >= 0,
+            "f < 0.0": f < 0, "f <= -0.0": f <= 0, "f BETWEEN 0 AND 0.1": (f >= 0) & (f <= F(0.1)),
+            "d > 0.1": d > 0.1, "d = 0.1": d == 0.1, "d >= 1e308": d >= 1e308, "d > 1e308": d > 1e308, "d < 5e-324": d < 5e-324,
+            "d <= 5e-324": d <= 5e-324, "d = 5e-324": d == 5e-324, "d > -0.0": d > 0, "d >= 0.0": d >= 0, "d < 0.0": d < 0, "d <= -0.0": d <= 0,
+            "d <> 0.1": d != 0.1, "d BETWEEN -1 AND 1": (d >= -1) & (d <= 1),
+            "d = 0.0": d == 0, "d <> -0.0": d != 0, "f = -0.0": f == 0,                                      # == : both zeros
+            "d IN (0.0, 0.1)": np.isin(d.view(np.int64), np.array([0.0, 0.1]).view(np.int64)),                   # DoubleSet: by bit pattern
+            "d NOT IN (0.1, 1e308)": ~np.isin(d.view(np.int64), np.array([0.1, 1e308]).view(np.int64)),
+        }
+    for where, exp in cases.items():
+        q = parse_sql("SELECT COUNT(*) FROM t WHERE " + where)
+        docs, _ = oracle.filter_doc_ids(seg, q)
+        got = np.nonzero(evaluate_lowered(seg, native.dump_lowered(g, q)))[0]
+        assert got.tolist() == docs.tolist() == np.nonzero(exp)[0].tolist(), where
+    g.release()
