@@ -107,6 +107,12 @@ int pbh_explain_agg_filter(pb_segment_group_handle g, int32_t segment_index, con
  * truncating to cap - 1 bytes. */
 int pbh_dump_lowered(pb_segment_group_handle g, int32_t segment_index, const pbh_query_context* q, int32_t clause, char* buf, int32_t cap);
 
+/* The FILTER clauses the device will run for `q` and, per aggregation, the index of its clause (-1 = none), written to
+ * clause_of[0 .. min(cap, num_aggregations)).  Without enableNullHandling these are the query's own clauses; with it, one
+ * clause per distinct (own clause, nullable input column) pair -- the function's clause ANDed with "<column> IS NOT NULL"
+ * (see pbh_query_context.null_handling).  pbh_dump_lowered / clause indices refer to this list.  Returns the number of clauses. */
+int pbh_null_clause_plan(pb_segment_group_handle g, const pbh_query_context* q, int32_t* clause_of, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -687,12 +687,23 @@ extern "C" int pbh_dump_lowered(pb_segment_group_handle g, int32_t si, const pbh
   std::vector<pb_segment_handle> segs;
   int rc = pbi_group_segments(g, &segs);
   if (rc) return rc;
-  if (!q || !buf || cap <= 0 || si < 0 || si >= (int)segs.size() || clause < -1 || clause >= q->num_agg_filters) return pbi_fail(PB_ERR_INVALID, "bad argument");
+  if (!q || !buf || cap <= 0 || si < 0 || si >= (int)segs.size() || clause < -1) return pbi_fail(PB_ERR_INVALID, "bad argument");
   try {
     PbSegmentView v;
     if ((rc = pbi_segment_view(segs[si], &v))) return rc;
-    OpPtr root = clause < 0 ? FilterPlanNode::run(v, *q)
-                            : FilterPlanNode::run(v, *q, q->agg_filters[clause].num_filter_nodes, q->agg_filters[clause].filter_nodes, q->agg_filters[clause].predicates);
+    OpPtr root;
+    if (clause < 0) root = FilterPlanNode::run(v, *q);
+    else if (q->null_handling) {
+      // the clauses the device runs with enableNullHandling: (own FILTER clause, nullable input column) pairs, pbh_null_clause_plan
+      std::vector<PbSegmentView> views(segs.size());
+      for (size_t i = 0; i < segs.size(); i++) if ((rc = pbi_segment_view(segs[i], &views[i]))) return rc;
+      NullClausePlan plan = planNullClauses(views, *q);
+      if (clause >= (int)plan.clauses.size()) return pbi_fail(PB_ERR_INVALID, "bad clause index");
+      root = nullClauseOp(v, *q, plan.clauses[(size_t)clause]);
+    } else {
+      if (clause >= q->num_agg_filters) return pbi_fail(PB_ERR_INVALID, "bad clause index");
+      root = FilterPlanNode::run(v, *q, q->agg_filters[clause].num_filter_nodes, q->agg_filters[clause].filter_nodes, q->agg_filters[clause].predicates);
+    }
     LoweredSegment ls;
     if (root->kind != OP_MATCH_ALL) emit(*root, v, ls);
     std::string s;
@@ -732,5 +743,21 @@ extern "C" int pbh_dump_lowered(pb_segment_group_handle g, int32_t si, const pbh
     int n = (int)std::min<size_t>(s.size(), (size_t)cap - 1);
     memcpy(buf, s.data(), (size_t)n); buf[n] = 0;
     return (int)s.size();
+  } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
+}
+
+extern "C" int pbh_null_clause_plan(pb_segment_group_handle g, const pbh_query_context* q, int32_t* clause_of, int32_t cap) {
+  std::vector<pb_segment_handle> segs;
+  int rc = pbi_group_segments(g, &segs);
+  if (rc) return rc;
+  if (!q || (cap > 0 && !clause_of)) return pbi_fail(PB_ERR_INVALID, "bad argument");
+  try {
+    std::vector<PbSegmentView> views(segs.size());
+    for (size_t i = 0; i < segs.size(); i++) if ((rc = pbi_segment_view(segs[i], &views[i]))) return rc;
+    NullClausePlan plan;
+    if (q->null_handling) plan = planNullClauses(views, *q);
+    else { plan.of.assign((size_t)q->num_aggregations, -1); for (int a = 0; a < q->num_aggregations && q->num_agg_filters > 0; a++) plan.of[(size_t)a] = q->agg_filter_of[a]; }
+    for (int a = 0; a < q->num_aggregations && a < cap; a++) clause_of[a] = plan.of[(size_t)a];
+    return q->null_handling ? (int)plan.clauses.size() : q->num_agg_filters;
   } catch (const BadQuery& e) { return pbi_fail(PB_ERR_UNSUPPORTED, e.msg.c_str()); }
 }

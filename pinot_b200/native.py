@@ -119,6 +119,8 @@ def lib():
     l.pbh_explain_filter.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PbhQueryContext), C.c_char_p, C.c_int32]
     l.pbh_explain_agg_filter.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PbhQueryContext), C.c_int32, C.c_char_p, C.c_int32]
     l.pbh_dump_lowered.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PbhQueryContext), C.c_int32, C.c_char_p, C.c_int32]
+    l.pbh_null_clause_plan.argtypes = [C.c_void_p, C.POINTER(PbhQueryContext), C.POINTER(C.c_int32), C.c_int32]
+    l.pbh_null_clause_plan.restype = C.c_int32
     l.pb_result_free.argtypes = [C.c_void_p]
     l.pb_result_finalize.argtypes = [C.c_void_p]
     l.pb_result_num_tables.argtypes = [C.c_void_p]
@@ -567,6 +569,18 @@ def dump_lowered(group: SegmentGroup, q: QueryContext, clause: int = -1, segment
         if n < cap:
             return buf.value.decode().splitlines()
         cap = n + 1
+
+
+def clause_plan(group: SegmentGroup, q: QueryContext):
+    """(number of FILTER clauses the device runs for q, clause index per aggregation): the query's own clauses, or with
+    enableNullHandling the (own clause, nullable input column) pairs (pbh_null_clause_plan)."""
+    m = _MarshalledQuery(q)
+    n = len(q.aggregations)
+    of = (C.c_int32 * max(1, n))()
+    k = lib().pbh_null_clause_plan(group.handle, C.byref(m.ctx), of, n)
+    if k < 0:
+        _check(k)
+    return k, list(of)[:n]
 
 
 def explain_agg_filter(group: SegmentGroup, q: QueryContext, clause: int, segment_index: int = 0) -> str:

@@ -429,3 +429,37 @@ def test_edge_literals_on_raw_columns():
         got = np.nonzero(evaluate_lowered(seg, native.dump_lowered(g, q)))[0]
         assert got.tolist() == docs.tolist() == np.nonzero(exp)[0].tolist(), where
     g.release()
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_null_handling_clause_programs(nullable_fuzz_segment, seed):
+    """enableNullHandling, aggregation side: every aggregation over a nullable column runs under the clause "its own FILTER
+    clause (trues) AND <column> IS NOT NULL"; functions with the same pair share a clause.  The lowered clause programs against
+    the numpy model of the operators."""
+    seg, g = nullable_fuzz_segment
+    rng = np.random.default_rng(9000 + seed)
+    cols = ["a", "b", "r", "x", "s", "d"]
+    aggs = []
+    for _ in range(int(rng.integers(2, 6))):
+        fn = str(rng.choice(["SUM", "MIN", "MAX", "AVG", "COUNT"]))
+        col = str(rng.choice(["a", "r", "x", "d", "*"] if fn == "COUNT" else ["a", "r", "x", "d"]))
+        flt = f" FILTER(WHERE {_expr_nh(rng, seg, cols, depth=2)})" if rng.random() < 0.5 else ""
+        aggs.append(f"{fn}({col}){flt}")
+    q = parse_sql(f"SET enableNullHandling=true; SELECT {', '.join(aggs)} FROM t WHERE d >= 0")
+    n_clauses, clause_of = native.clause_plan(g, q)
+    seen = {}
+    for a, agg in enumerate(q.aggregations):
+        nullable = agg.column is not None and getattr(seg.columns[agg.column], "null_value_vector", None) is not None
+        if agg.filter is None and not nullable:
+            assert clause_of[a] == -1, aggs[a]
+            continue
+        k = clause_of[a]
+        assert 0 <= k < n_clauses, aggs[a]
+        exp = operator_model(seg, agg.filter)[0] if agg.filter is not None else np.ones(seg.num_docs, bool)
+        if nullable:
+            exp = exp & ~_null_mask(seg, agg.column)
+        got = evaluate_lowered_nh(seg, native.dump_lowered(g, q, k))
+        assert np.array_equal(got, exp), aggs[a]
+        key = (repr(agg.filter), agg.column if nullable else None)
+        assert seen.setdefault(key, k) == k, "functions with the same (clause, column) pair share a clause"
+    assert n_clauses == len(set(seen.values()))
