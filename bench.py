@@ -625,7 +625,7 @@ def main():
             while True:
                 oracle_query_all_threads(osegs, oq, threads)
                 reps += 1
-                if time.perf_counter() - t2 > budget_s or reps >= 200:
+                if time.perf_counter() - t2 > budget_s or reps >= 5000:
                     break
             return reps, time.perf_counter() - t2
 
