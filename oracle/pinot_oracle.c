@@ -301,15 +301,38 @@ static const uint8_t* str_entry(const orc_column* c, int32_t id, int32_t* len) {
   *len = elen;
   return e;
 }
-/* string compare against a dictionary entry (pad byte 0 sorts first, as in the sorted dictionary) */
+/* String compare against a dictionary entry, in the order the dictionary was sorted in: String.compareTo, i.e. by UTF-16
+ * code units (ValueReaderComparisons.compareUtf8Bytes, SEGL/io/util/ValueReaderComparisons.java:68-139: find the first byte
+ * that differs, step back to the start of its UTF-8 sequence, decode both sides and compare the UTF-16 units).  Byte order
+ * and UTF-16 order differ only between a supplementary character (4-byte UTF-8 = a surrogate pair, 0xD800-0xDFFF) and a BMP
+ * character at or above U+E000.  A shorter string that is a prefix sorts first (the padding byte 0 is the smallest unit). */
+static void utf16_units_at(const uint8_t* p, int64_t avail, uint32_t* u1, uint32_t* u2) {
+  *u1 = 0xfffd; *u2 = 0xfffd;
+  if (avail <= 0) { *u1 = 0; return; }
+  uint8_t b = p[0];
+  if (b < 0x80) *u1 = b;
+  else if ((b & 0xF0) < 0xE0) *u1 = ((uint32_t)(b & 0x1F) << 6) | (avail > 1 ? (p[1] & 0x3Fu) : 0);
+  else if ((b & 0xF0) == 0xE0) *u1 = ((uint32_t)(b & 0x0F) << 12) | ((avail > 1 ? (p[1] & 0x3Fu) : 0) << 6) | (avail > 2 ? (p[2] & 0x3Fu) : 0);
+  else {
+    uint32_t cp = ((uint32_t)(b & 0x07) << 18) | ((avail > 1 ? (p[1] & 0x3Fu) : 0) << 12) | ((avail > 2 ? (p[2] & 0x3Fu) : 0) << 6) | (avail > 3 ? (p[3] & 0x3Fu) : 0);
+    if (cp >= 0x10000 && cp <= 0x10FFFF) { *u1 = 0xD800 + ((cp - 0x10000) >> 10); *u2 = 0xDC00 + ((cp - 0x10000) & 0x3FF); }
+  }
+}
+static int utf8_cmp_utf16_order(const uint8_t* a, int64_t alen, const uint8_t* b, int64_t blen) {
+  int64_t m = alen < blen ? alen : blen, i = 0;
+  while (i < m && a[i] == b[i]) i++;
+  if (i == m) return (alen > blen) - (alen < blen);
+  while (i > 0 && (b[i] & 0xC0) == 0x80) i--;            /* back to the start of the sequence (identical before the mismatch) */
+  uint32_t a1, a2, b1, b2;
+  utf16_units_at(a + i, alen - i, &a1, &a2);
+  utf16_units_at(b + i, blen - i, &b1, &b2);
+  if (a1 != b1) return a1 < b1 ? -1 : 1;
+  return (a2 > b2) - (a2 < b2);
+}
 static int str_cmp_entry(const orc_column* c, int32_t id, const char* s) {
   int32_t elen = 0;
   const uint8_t* e = str_entry(c, id, &elen);
-  size_t slen = strlen(s);
-  size_t m = (size_t)elen < slen ? (size_t)elen : slen;
-  int r = memcmp(e, s, m);
-  if (r != 0) return r;
-  return (elen > (int32_t)slen) - (elen < (int32_t)slen);
+  return utf8_cmp_utf16_order(e, elen, (const uint8_t*)s, (int64_t)strlen(s));
 }
 static int32_t dict_insertion_index_string(const orc_column* c, const char* s) {
   int32_t lo = 0, hi = c->cardinality - 1;

@@ -58,14 +58,41 @@ class Dictionary {
         return search([&](int m) {
           const uint8_t* e = _c.dict + (size_t)m * _c.entry_bytes;
           size_t el = 0; while (el < (size_t)_c.entry_bytes && e[el]) el++;
-          size_t n = std::min(el, v.size());
-          int r = memcmp(e, v.data(), n);
-          if (r) return r;
-          return (el > v.size()) - (el < v.size());
+          return compareUtf8(e, el, (const uint8_t*)v.data(), v.size());
         });
     }
   }
   int indexOf(const std::string& v) const { int i = insertionIndexOf(v); return i >= 0 ? i : -1; }
+
+  // ValueReaderComparisons.compareUtf8Bytes (SEGL/io/util/ValueReaderComparisons.java:68-139): the dictionary is sorted by
+  // String.compareTo, i.e. by UTF-16 code units -- find the first byte that differs, step back to the start of its UTF-8
+  // sequence, decode both sides, compare the units.  Differs from byte order only between a supplementary character (a
+  // surrogate pair, 0xD800-0xDFFF) and a BMP character at or above U+E000; a prefix sorts first.
+  static void utf16UnitsAt(const uint8_t* p, size_t avail, uint32_t* u1, uint32_t* u2) {
+    *u1 = 0xfffd; *u2 = 0xfffd;
+    if (avail == 0) { *u1 = 0; return; }
+    auto cont = [&](size_t k) -> uint32_t { return k < avail ? (p[k] & 0x3Fu) : 0u; };
+    const uint8_t b = p[0];
+    if (b < 0x80) *u1 = b;
+    else if ((b & 0xF0) < 0xE0) *u1 = ((uint32_t)(b & 0x1F) << 6) | cont(1);
+    else if ((b & 0xF0) == 0xE0) *u1 = ((uint32_t)(b & 0x0F) << 12) | (cont(1) << 6) | cont(2);
+    else {
+      const uint32_t cp = ((uint32_t)(b & 0x07) << 18) | (cont(1) << 12) | (cont(2) << 6) | cont(3);
+      if (cp >= 0x10000 && cp <= 0x10FFFF) { *u1 = 0xD800 + ((cp - 0x10000) >> 10); *u2 = 0xDC00 + ((cp - 0x10000) & 0x3FF); }
+    }
+  }
+  static int compareUtf8(const uint8_t* a, size_t alen, const uint8_t* b, size_t blen) {
+    const size_t m = std::min(alen, blen);
+    size_t i = 0;
+    while (i < m && a[i] == b[i]) i++;
+    if (i == m) return (alen > blen) - (alen < blen);
+    while (i > 0 && (b[i] & 0xC0) == 0x80) i--;
+    uint32_t a1, a2, b1, b2;
+    utf16UnitsAt(a + i, alen - i, &a1, &a2);
+    utf16UnitsAt(b + i, blen - i, &b1, &b2);
+    if (a1 != b1) return a1 < b1 ? -1 : 1;
+    return (a2 > b2) - (a2 < b2);
+  }
 
   static bool parseIntegral(const std::string& s, long long* out) {
     errno = 0; char* end = nullptr;

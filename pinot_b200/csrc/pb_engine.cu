@@ -756,13 +756,41 @@ static void native_entry(const Column& c, int id, uint8_t* out) {
   if (c.type == PB_STRING) { memcpy(out, p, c.entry_bytes); return; }
   if (c.entry_bytes == 4) { uint32_t u = be32(p); memcpy(out, &u, 4); } else { uint64_t u = be64(p); memcpy(out, &u, 8); }
 }
+// Strings compare the way their dictionaries are sorted: String.compareTo, i.e. by UTF-16 code units
+// (ValueReaderComparisons.compareUtf8Bytes, SEGL/io/util/ValueReaderComparisons.java:68-139).  Byte order differs from that
+// only between a supplementary character (a surrogate pair) and a BMP character at or above U+E000 -- but a segment
+// dictionary holding both IS sorted the Java way, and the merge walk of build_remaps relies on one order on both sides.
+static void utf16_units_at(const uint8_t* p, size_t avail, uint32_t* u1, uint32_t* u2) {
+  *u1 = 0xfffd; *u2 = 0xfffd;
+  if (avail == 0) { *u1 = 0; return; }
+  auto cont = [&](size_t k) -> uint32_t { return k < avail ? (p[k] & 0x3Fu) : 0u; };
+  const uint8_t b = p[0];
+  if (b < 0x80) *u1 = b;
+  else if ((b & 0xF0) < 0xE0) *u1 = ((uint32_t)(b & 0x1F) << 6) | cont(1);
+  else if ((b & 0xF0) == 0xE0) *u1 = ((uint32_t)(b & 0x0F) << 12) | (cont(1) << 6) | cont(2);
+  else {
+    const uint32_t cp = ((uint32_t)(b & 0x07) << 18) | (cont(1) << 12) | (cont(2) << 6) | cont(3);
+    if (cp >= 0x10000 && cp <= 0x10FFFF) { *u1 = 0xD800 + ((cp - 0x10000) >> 10); *u2 = 0xDC00 + ((cp - 0x10000) & 0x3FF); }
+  }
+}
+static int cmp_utf8_java_order(const uint8_t* a, const uint8_t* b, size_t n) {     // two zero-padded entries of n bytes
+  size_t i = 0;
+  while (i < n && a[i] == b[i]) i++;
+  if (i == n) return 0;
+  while (i > 0 && (b[i] & 0xC0) == 0x80) i--;
+  uint32_t a1, a2, b1, b2;
+  utf16_units_at(a + i, n - i, &a1, &a2);
+  utf16_units_at(b + i, n - i, &b1, &b2);
+  if (a1 != b1) return a1 < b1 ? -1 : 1;
+  return (a2 > b2) - (a2 < b2);
+}
 static int cmp_entry(int type, int eb, const uint8_t* a, const uint8_t* b) {
   switch (type) {
     case PB_INT: { int32_t x, y; memcpy(&x, a, 4); memcpy(&y, b, 4); return (x > y) - (x < y); }
     case PB_LONG: { int64_t x, y; memcpy(&x, a, 8); memcpy(&y, b, 8); return (x > y) - (x < y); }
     case PB_FLOAT: { float x, y; memcpy(&x, a, 4); memcpy(&y, b, 4); return (x > y) - (x < y); }
     case PB_DOUBLE: { double x, y; memcpy(&x, a, 8); memcpy(&y, b, 8); return (x > y) - (x < y); }
-    default: return memcmp(a, b, eb);
+    default: return cmp_utf8_java_order(a, b, (size_t)eb);
   }
 }
 

@@ -78,12 +78,13 @@ def init_comm(exchange) -> None:
 def merge_sorted_dictionaries(blocks: Sequence[np.ndarray], stored_type: int) -> np.ndarray:
     """blocks: [n_i, entry_bytes] uint8 arrays of native-endian entries -> sorted unique union (same layout)."""
     eb = max(b.shape[1] for b in blocks)
-    if stored_type == 4:          # STRING: fixed-width zero-padded entries compare bytewise
+    if stored_type == 4:          # STRING: fixed-width zero-padded entries, ordered like String.compareTo (UTF-16 code units)
+        from .segment_writer import java_string_key
         keys = set()
         for b in blocks:
             for r in np.ascontiguousarray(b, dtype=np.uint8):
                 keys.add(bytes(r).ljust(eb, b"\0"))
-        uniq = sorted(keys)
+        uniq = sorted(keys, key=lambda e: java_string_key(e.rstrip(b"\0")))
         return np.frombuffer(b"".join(uniq), dtype=np.uint8).reshape(len(uniq), eb).copy()
     allv = np.concatenate([np.ascontiguousarray(b, dtype=np.uint8) for b in blocks], axis=0)
     dt = {0: np.int32, 1: np.int64, 2: np.float32, 3: np.float64}[stored_type]

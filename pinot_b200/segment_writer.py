@@ -269,6 +269,14 @@ def _raw_forward_index(values: np.ndarray, data_type: DataType, compression=None
     return np.frombuffer(header.tobytes() + offs.astype(off_dtype).tobytes() + b"".join(chunks), dtype=np.uint8).copy()
 
 
+def java_string_key(b: bytes) -> bytes:
+    """Sort key that orders UTF-8 byte strings like java.lang.String.compareTo (by UTF-16 code units)."""
+    try:
+        return b.decode("utf-8").encode("utf-16-be", "surrogatepass")
+    except UnicodeDecodeError:
+        return b
+
+
 def build_dict_column(name: str, data_type: DataType, dict_values_sorted: np.ndarray, dict_ids: np.ndarray,
                       inverted: bool = False, run_optimize: bool = True, var_length_dictionary: bool = False) -> ColumnIndex:
     """Column from an already-known sorted dictionary and per-doc dictIds."""
@@ -293,8 +301,14 @@ def build_column(name: str, data_type: DataType, values, dictionary: bool = True
     if data_type == DataType.STRING:
         vals = np.array([v if isinstance(v, bytes) else str(v).encode("utf-8") for v in values], dtype=object)
         assert dictionary, "raw STRING columns are out of scope"
-        uniq, inv_ids = np.unique(vals, return_inverse=True)   # bytes order == Java compareTo for ASCII
-        return build_dict_column(name, data_type, uniq, inv_ids.astype(np.uint32), inverted, run_optimize, var_length_dictionary)
+        # the dictionary is sorted by String.compareTo = UTF-16 code units (SegmentDictionaryCreator sorts the Java strings);
+        # for anything below U+10000 that is the byte order of the UTF-8 encodings as well
+        uniq_b, inv_ids = np.unique(vals, return_inverse=True)
+        order = sorted(range(len(uniq_b)), key=lambda i: java_string_key(uniq_b[i]))
+        rank = np.empty(len(order), dtype=np.int64)
+        rank[np.asarray(order, dtype=np.int64)] = np.arange(len(order))
+        uniq = np.array([uniq_b[i] for i in order], dtype=object)
+        return build_dict_column(name, data_type, uniq, rank[inv_ids].astype(np.uint32), inverted, run_optimize, var_length_dictionary)
     vals = np.asarray(values).astype(_NP_NATIVE[data_type])
     if dictionary:
         uniq, inv_ids = np.unique(vals, return_inverse=True)

@@ -188,3 +188,50 @@ def test_signed_zero_and_nan_in_raw_float_predicates():
         assert low(f"{col} IN (0.0, 1.5)")[0].startswith(f"SCAN_RAW_SET col={col} excl=0 vals={pos},") and cnt(f"{col} IN (0.0, 1.5)") == 3
         assert cnt(f"{col} NOT IN (0.0)") == 5 and cnt(f"{col} IN (-0.0)") == 2
     g.release()
+
+
+def test_strings_compare_like_java_strings():
+    """A STRING dictionary is sorted by String.compareTo -- UTF-16 code units -- and searched with ValueReaderComparisons.
+    compareUtf8Bytes (SEGL/io/util/ValueReaderComparisons.java:68-139).  That differs from the byte order of the UTF-8
+    encodings exactly between supplementary characters (surrogate pairs) and BMP characters from U+E000 up: a dictionary that
+    holds both an emoji and a full-width letter.  Host layer, oracle, the writer and the global-dictionary merge of the
+    engine must all use the Java order, or values are not found."""
+    from oracle import oracle
+    from pinot_b200.distributed import merge_sorted_dictionaries
+    from pinot_b200.segment_writer import java_string_key
+    words = ["apple", "zebra", "\U0001F600", "\U0001F600x", "Ａ", "Ａb", "", "中", "\U00020000", "z\U0001F600", "zＡ", ""]
+    java_order = sorted(words, key=lambda w: w.encode("utf-16-be", "surrogatepass"))
+    assert java_order != sorted(words, key=lambda w: w.encode("utf-8"))              # the two orders really differ here
+    rng = np.random.default_rng(3)
+    def seg(name, subset, n):
+        vals = [subset[i] for i in rng.integers(0, len(subset), n)]
+        c = build_column("s", DataType.STRING, vals)
+        assert [v.decode() for v in c.dictionary_values()] == sorted(set(vals), key=lambda w: w.encode("utf-16-be", "surrogatepass"))
+        return make_segment(name, [c, build_column("d", DataType.INT, rng.integers(0, 3, n).astype(np.int32))]), np.array(vals, dtype=object)
+    s0, v0 = seg("u0", words, 3000)
+    s1, v1 = seg("u1", words[2:9], 2000)
+    g = native.SegmentGroup([native.StagedSegment(s0), native.StagedSegment(s1)])
+    key = lambda w: w.encode("utf-16-be", "surrogatepass")
+    cases = {f"s = '{w}'": (lambda v, w=w: v == w) for w in words if w}
+    cases.update({f"s > '{w}'": (lambda v, w=w: np.array([key(x) > key(w) for x in v])) for w in ("Ａ", "\U0001F600", "zebra", "中")})
+    cases.update({f"s <= '{w}'": (lambda v, w=w: np.array([key(x) <= key(w) for x in v])) for w in ("\U0001F600x", "")})
+    cases["s IN ('\U0001F600', 'Ａ', 'nope')"] = lambda v: np.isin(v, ["\U0001F600", "Ａ"])
+    cases["s BETWEEN '\U0001F600' AND 'Ａ'"] = lambda v: np.array([key("\U0001F600") <= key(x) <= key("Ａ") for x in v])
+    from tests.test_cpu_lowering_fuzz import evaluate_lowered
+    for si, (sg, v) in enumerate(((s0, v0), (s1, v1))):
+        for where, f in cases.items():
+            q = parse_sql("SELECT COUNT(*) FROM t WHERE " + where)
+            exp = np.nonzero(np.asarray(f(v), dtype=bool))[0].tolist()
+            assert oracle.filter_doc_ids(sg, q)[0].tolist() == exp, (si, where)
+            assert np.nonzero(evaluate_lowered(sg, native.dump_lowered(g, q, -1, si)))[0].tolist() == exp, (si, where)
+    # the engine's union of the two dictionaries and its local -> global remaps
+    union = g.export_dictionary("s")
+    got = [bytes(r).rstrip(b"\0").decode() for r in union]
+    assert got == java_order
+    for si, sg in enumerate((s0, s1)):
+        local = [x.decode() for x in sg.columns["s"].dictionary_values()]
+        assert [got[j] for j in g.remap("s", si)] == local
+    merged = merge_sorted_dictionaries([union, union[2:5]], 4)
+    assert [bytes(r).rstrip(b"\0").decode() for r in merged] == java_order
+    g.set_global_dictionary("s", merged)
+    g.release()
