@@ -251,6 +251,17 @@ static inline double raw_double(const col_reader* r, int32_t doc) {
     default: return be_f64(p + 8 * (int64_t)doc);
   }
 }
+/* java.lang.Math.min / max on doubles: NaN if either is NaN; -0.0 < 0.0 */
+static inline double java_math_min(double a, double b) {
+  if (a != a || b != b) return NAN;
+  if (a == 0.0 && b == 0.0) return signbit(a) ? a : b;
+  return a < b ? a : b;
+}
+static inline double java_math_max(double a, double b) {
+  if (a != a || b != b) return NAN;
+  if (a == 0.0 && b == 0.0) return signbit(a) ? b : a;
+  return a > b ? a : b;
+}
 /* BlockValSet.getDoubleValuesSV for one doc (CTR/common/DataFetcher.java:376-386) */
 static inline double value_as_double(const col_reader* r, int32_t doc) {
   return r->c->has_dictionary ? dict_double(r->c, dict_id_of(r, doc)) : raw_double(r, doc);
@@ -1528,8 +1539,14 @@ orc_result* orc_execute(const orc_segment* seg, const orc_query* q) {
           double inner = 0; for (int32_t i = 0; i < L; i++) inner += values[i];
           dh[a].v[0] += inner;
           if (op == ORC_AVG) ch[a].v[0] += (double)L;
-        } else if (op == ORC_MIN) { for (int32_t i = 0; i < L; i++) if (values[i] < dh[a].v[0]) dh[a].v[0] = values[i]; }
-        else if (op == ORC_MAX) { for (int32_t i = 0; i < L; i++) if (values[i] > dh[a].v[0]) dh[a].v[0] = values[i]; }
+        } else if (op == ORC_MIN || op == ORC_MAX) {
+          /* keyless MIN / MAX of a FLOAT / DOUBLE column fold with Math.min / Math.max (MinAggregationFunction.java:97-124,
+           * 147-157): a NaN input makes the result NaN, and -0.0 is smaller than 0.0 -- unlike the strict "<" of the
+           * group-by path (:163-188), which never lets a NaN in */
+          double acc = dh[a].v[0];
+          for (int32_t i = 0; i < L; i++) acc = op == ORC_MIN ? java_math_min(acc, values[i]) : java_math_max(acc, values[i]);
+          dh[a].v[0] = acc;
+        }
         (void)dict_buf;
       }
     }

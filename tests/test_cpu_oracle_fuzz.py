@@ -205,3 +205,20 @@ def test_native_combine_matches_the_python_merge():
     assert [r.num_groups for r in res] == [oracle.execute(s, q).num_groups for s in segs]
     # DISTINCTCOUNT is left to the Python merge
     assert oracle.execute_combined(oracle.PreparedBatch(segs, parse_sql("SELECT d1, DISTINCTCOUNT(c1) FROM t GROUP BY d1 LIMIT 10")), 2) is None
+
+
+def test_nan_and_signed_zero_in_min_max():
+    """MinAggregationFunction / MaxAggregationFunction: the keyless path folds with Math.min / Math.max (a NaN input makes the
+    result NaN, -0.0 < 0.0; MinAggregationFunction.java:97-124), the group-by path compares with a strict "<" against the
+    holder (:163-188), which never lets a NaN in."""
+    from pinot_b200.segment_writer import DataType, build_column, make_segment
+    x = np.array([1.5, np.nan, -2.0, 0.0, -0.0, 7.0])
+    g = np.array([0, 0, 0, 1, 1, 1], dtype=np.int32)
+    seg = make_segment("nan", [build_column("x", DataType.DOUBLE, x, dictionary=False), build_column("g", DataType.INT, g)])
+    r = oracle.execute(seg, parse_sql("SELECT MIN(x), MAX(x) FROM t"))
+    assert np.isnan(r.doubles[0][0]) and np.isnan(r.doubles[1][0])
+    r = oracle.execute(seg, parse_sql("SELECT MIN(x), MAX(x) FROM t WHERE g = 1"))
+    assert r.doubles[0][0] == 0.0 and np.signbit(r.doubles[0][0]) and r.doubles[1][0] == 7.0            # Math.min(0.0, -0.0) = -0.0
+    r = oracle.execute(seg, parse_sql("SELECT g, MIN(x), MAX(x) FROM t GROUP BY g LIMIT 10"))
+    rows = {k[0]: (r.doubles[0][i], r.doubles[1][i]) for i, k in enumerate(r.decoded_keys())}
+    assert rows[0] == (-2.0, 1.5) and rows[1][1] == 7.0 and rows[1][0] == 0.0 and not np.signbit(rows[1][0])   # strict <: the first zero stays
